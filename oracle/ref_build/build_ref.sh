@@ -1,0 +1,124 @@
+#!/usr/bin/env bash
+# Build the UNMODIFIED reference (PLUTO 4.3, serial, gcc -O3, no FMA) from the
+# sources where they lie under $PLUTO_DIR (default /root/reference) for one
+# compile-time scheme variant, with oracle/ref_build/problem/init.c as the
+# user problem file.  Output: oracle/_ref/pluto_<variant>  (git-ignored).
+#
+# Mirrors Src/Templates/makefile (base OBJ lists :22-37) + the module
+# makefiles Src/{Math_Tools,MHD,MHD/CT,EOS/Ideal}/makefile + the objects
+# Tools/Python/define_problem.py:506-550 would add.  setup.py itself is
+# interactive (curses) and is bypassed.  Nothing is copied from the
+# reference: the makefile VPATHs into it.
+#
+# usage: build_ref.sh <variant> [<variant> ...]
+#   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ORACLE="$(cd "$HERE/.." && pwd)"
+PLUTO_DIR="${PLUTO_DIR:-/root/reference}"
+if [ ! -d "$PLUTO_DIR/Src" ]; then
+  echo "build_ref.sh: reference sources not found at $PLUTO_DIR (skipping)" >&2
+  exit 0
+fi
+mkdir -p "$ORACLE/_ref" "$ORACLE/_build"
+
+for VARIANT in "$@"; do
+  case "$VARIANT" in
+    2d_*) DIMS=2 ;;
+    3d_*) DIMS=3 ;;
+    *) echo "unknown variant $VARIANT" >&2; exit 1 ;;
+  esac
+  case "$VARIANT" in
+    *_ppm*) RECON=PARABOLIC; STATES_OBJ="ppm_states.o ppm_coeffs.o"; EXTRA_HDR="ppm_coeffs.h" ;;
+    *)      RECON=LINEAR;    STATES_OBJ="plm_states.o";               EXTRA_HDR="" ;;
+  esac
+  case "$VARIANT" in
+    *_rk3) TSTEP=RK3 ;;
+    *)     TSTEP=RK2 ;;
+  esac
+  B="$ORACLE/_build/$VARIANT"
+  mkdir -p "$B"
+  cp "$HERE/problem/init.c" "$B/init.c"
+
+  cat > "$B/definitions.h" <<EOF
+#define  PHYSICS                        MHD
+#define  DIMENSIONS                     $DIMS
+#define  COMPONENTS                     $DIMS
+#define  GEOMETRY                       CARTESIAN
+#define  BODY_FORCE                     NO
+#define  FORCED_TURB                    NO
+#define  COOLING                        NO
+#define  RECONSTRUCTION                 $RECON
+#define  TIME_STEPPING                  $TSTEP
+#define  DIMENSIONAL_SPLITTING          NO
+#define  NTRACER                        0
+#define  USER_DEF_PARAMETERS            9
+
+/* -- physics dependent declarations -- */
+
+#define  EOS                            IDEAL
+#define  ENTROPY_SWITCH                 NO
+#define  DIVB_CONTROL                   CONSTRAINED_TRANSPORT
+#define  BACKGROUND_FIELD               NO
+#define  AMBIPOLAR_DIFFUSION            NO
+#define  RESISTIVITY                    NO
+#define  HALL_MHD                       NO
+#define  THERMAL_CONDUCTION             NO
+#define  VISCOSITY                      NO
+#define  ROTATING_FRAME                 NO
+
+/* -- user-defined parameters (labels) -- */
+
+#define  PROBLEM                        0
+#define  GAMMA_EOS                      1
+#define  P_IN                           2
+#define  P_OUT                          3
+#define  BMAG                           4
+#define  THETA                          5
+#define  PHI                            6
+#define  RADIUS                         7
+#define  SEED                           8
+
+/* [Beg] user-defined constants (do not change this line) */
+
+#define  CT_EMF_AVERAGE                 UCT_CONTACT
+#define  CT_EN_CORRECTION               NO
+#define  ASSIGN_VECTOR_POTENTIAL        YES
+#define  CHECK_DIVB_CONDITION           NO
+#define  WARNING_MESSAGES               NO
+
+/* [End] user-defined constants (do not change this line) */
+EOF
+
+  cat > "$B/makefile" <<EOF
+pluto:
+PLUTO_DIR = $PLUTO_DIR
+SRC = \$(PLUTO_DIR)/Src
+INCLUDE_DIRS = -I. -I\$(SRC)
+VPATH = ./:\$(SRC):\$(SRC)/Time_Stepping:\$(SRC)/States
+CC = gcc
+CFLAGS = -c -O3
+LDFLAGS = -lm
+HEADERS = pluto.h prototypes.h structs.h definitions.h macros.h mod_defs.h plm_coeffs.h $EXTRA_HDR
+OBJ = adv_flux.o arrays.o boundary.o check_states.o cmd_line_opt.o entropy_switch.o \\
+      flag_shock.o flatten.o get_nghost.o init.o int_bound_reset.o input_data.o \\
+      mappers3D.o mean_mol_weight.o parse_file.o plm_coeffs.o rbox.o set_indexes.o \\
+      set_geometry.o set_output.o tools.o var_names.o
+OBJ += bin_io.o colortable.o initialize.o jet_domain.o main.o output_log.o restart.o \\
+       runtime_setup.o set_image.o show_config.o set_grid.o startup.o split_source.o \\
+       userdef_output.o write_data.o write_tab.o write_img.o write_vtk.o write_vtk_proc.o
+include \$(SRC)/Math_Tools/makefile
+OBJ += $STATES_OBJ vec_pot_diff.o vec_pot_update.o rk_step.o update_stage.o
+include \$(SRC)/MHD/makefile
+include \$(SRC)/MHD/CT/makefile
+include \$(SRC)/EOS/Ideal/makefile
+pluto: \$(OBJ)
+	\$(CC) \$(OBJ) \$(LDFLAGS) -o \$@
+.c.o:
+	\$(CC) \$(CFLAGS) \$(INCLUDE_DIRS) \$<
+\$(OBJ): definitions.h
+EOF
+  ( cd "$B" && make -j"$(nproc)" pluto >make.log 2>&1 ) || { tail -30 "$B/make.log"; exit 1; }
+  cp "$B/pluto" "$ORACLE/_ref/pluto_$VARIANT"
+  echo "built oracle/_ref/pluto_$VARIANT"
+done
