@@ -1,0 +1,1070 @@
+/*
+ * mhd_oracle.c -- CPU restatement of the PLUTO 4.3 unsplit RK + CT ideal-MHD
+ * step (see mhd_oracle.h for scope and parity status).  TEST INFRASTRUCTURE.
+ *
+ * The restatement follows the reference's arithmetic operation by operation
+ * (same association order, same comparisons) so that, compiled with plain
+ * `gcc -O2` on x86-64 (no FMA contraction, no -ffast-math), it reproduces the
+ * reference's double-precision results bit for bit.  All `file:line`
+ * citations are relative to /root/reference/Src.
+ *
+ * Internal storage: every 3-D scalar array is padded by one layer on each
+ * side so that indices -1 .. T are addressable:
+ *     idx(k,j,i) = ((k+1)*S2 + (j+1))*S1 + (i+1),   S = T + 2.
+ * Staggered components use the reference's convention: Vs[d] at index i is
+ * the face i+1/2 in direction d (valid from -1).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "mhd_oracle.h"
+
+#define NV   ORC_NV
+#define RHO  ORC_RHO
+#define VX1  ORC_VX1
+#define VX2  ORC_VX2
+#define VX3  ORC_VX3
+#define BX1  ORC_BX1
+#define BX2  ORC_BX2
+#define BX3  ORC_BX3
+#define PRS  ORC_PRS
+#define MX1  VX1
+#define ENG  PRS
+
+/* reference macros.h:140-151 */
+#define MAXV(a,b)     ((a) >= (b) ? (a) : (b))
+#define MINV(a,b)     ((a) <= (b) ? (a) : (b))
+#define ABS_MIN(a,b)  (fabs(a) < fabs(b) ? (a) : (b))
+#define MINMOD(a,b)   ((a)*(b) > 0.0 ? (fabs(a) < fabs(b) ? (a):(b)):0.0)
+
+struct Oracle {
+  OracleConfig c;
+  int ng, T[3], S1, S2, S3, tot;
+  int beg[3], end[3];                  /* IBEG..KEND */
+  double *Vc[NV], *Uc[NV], *U0[NV];
+  double *Vs[3], *Bs0[3];
+  double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
+  double *ex, *ey, *ez, *Ex1, *Ex2, *Ex3;
+  signed char *svx, *svy, *svz;
+  double *C_dt;
+  /* pencil scratch */
+  int np;
+  double (*v)[NV], (*vp)[NV], (*vm)[NV], (*dv)[NV];
+  double (*flux)[NV], *press, *cmax, *bn;
+  double max_mach, inv_dt_hyp;
+  int    stage, floor_events;
+  int    emf_ibeg, emf_iend, emf_jbeg, emf_jend, emf_kbeg, emf_kend;
+};
+
+#define IDX(o,k,j,i) ((((k)+1)*(o)->S2 + ((j)+1))*(o)->S1 + ((i)+1))
+
+static double *dalloc (int n) { return (double *)calloc((size_t)n, sizeof(double)); }
+
+int oracle_nghost (const Oracle *o) { return o->ng; }
+
+/* ********************************************************************* */
+Oracle *oracle_create (const OracleConfig *cfg)
+/* ghost count: reference get_nghost.c:32-50 (2 for LINEAR, 3 for
+   PARABOLIC with MHD).                                                 */
+{
+  int d, nv;
+  Oracle *o = (Oracle *)calloc(1, sizeof(Oracle));
+  o->c  = *cfg;
+  o->ng = (cfg->recon == ORC_RECON_PPM ? 3 : 2);
+  for (d = 0; d < 3; d++){
+    if (d < cfg->dims){
+      o->T[d]   = cfg->n[d] + 2*o->ng;
+      o->beg[d] = o->ng;
+      o->end[d] = o->ng + cfg->n[d] - 1;
+    }else{
+      o->T[d] = 1; o->beg[d] = o->end[d] = 0;
+    }
+  }
+  o->S1 = o->T[0] + 2; o->S2 = o->T[1] + 2; o->S3 = o->T[2] + 2;
+  o->tot = o->S1*o->S2*o->S3;
+  for (nv = 0; nv < NV; nv++){
+    o->Vc[nv] = dalloc(o->tot); o->Uc[nv] = dalloc(o->tot); o->U0[nv] = dalloc(o->tot);
+  }
+  for (d = 0; d < 3; d++){ o->Vs[d] = dalloc(o->tot); o->Bs0[d] = dalloc(o->tot); }
+  o->exj = dalloc(o->tot); o->exk = dalloc(o->tot); o->eyi = dalloc(o->tot);
+  o->eyk = dalloc(o->tot); o->ezi = dalloc(o->tot); o->ezj = dalloc(o->tot);
+  o->ex  = dalloc(o->tot); o->ey  = dalloc(o->tot); o->ez  = dalloc(o->tot);
+  o->Ex1 = dalloc(o->tot); o->Ex2 = dalloc(o->tot); o->Ex3 = dalloc(o->tot);
+  o->svx = (signed char *)calloc((size_t)o->tot, 1);
+  o->svy = (signed char *)calloc((size_t)o->tot, 1);
+  o->svz = (signed char *)calloc((size_t)o->tot, 1);
+  o->C_dt = dalloc(o->tot);
+  o->np = o->T[0];
+  if (o->T[1] > o->np) o->np = o->T[1];
+  if (o->T[2] > o->np) o->np = o->T[2];
+  o->np += 8;
+  o->v    = calloc((size_t)o->np, sizeof(*o->v));
+  o->vp   = calloc((size_t)o->np, sizeof(*o->vp));
+  o->vm   = calloc((size_t)o->np, sizeof(*o->vm));
+  o->dv   = calloc((size_t)o->np, sizeof(*o->dv));
+  o->flux = calloc((size_t)o->np, sizeof(*o->flux));
+  o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
+  /* shift pencil arrays so that index -2 is addressable */
+  o->v += 4; o->vp += 4; o->vm += 4; o->dv += 4; o->flux += 4;
+  o->press += 4; o->cmax += 4; o->bn += 4;
+  return o;
+}
+
+void oracle_destroy (Oracle *o)
+{
+  int d, nv;
+  if (!o) return;
+  for (nv = 0; nv < NV; nv++){ free(o->Vc[nv]); free(o->Uc[nv]); free(o->U0[nv]); }
+  for (d = 0; d < 3; d++){ free(o->Vs[d]); free(o->Bs0[d]); }
+  free(o->exj); free(o->exk); free(o->eyi); free(o->eyk); free(o->ezi); free(o->ezj);
+  free(o->ex); free(o->ey); free(o->ez); free(o->Ex1); free(o->Ex2); free(o->Ex3);
+  free(o->svx); free(o->svy); free(o->svz); free(o->C_dt);
+  free(o->v - 4); free(o->vp - 4); free(o->vm - 4); free(o->dv - 4); free(o->flux - 4);
+  free(o->press - 4); free(o->cmax - 4); free(o->bn - 4);
+  free(o);
+}
+
+/* ********************************************************************* */
+void oracle_set_interior (Oracle *o, const double *vc, const double *bx1s,
+                          const double *bx2s, const double *bx3s)
+{
+  int i, j, k, nv;
+  int n1 = o->c.n[0], n2 = o->c.n[1], n3 = (o->c.dims == 3 ? o->c.n[2] : 1);
+  int ib = o->beg[0], jb = o->beg[1], kb = o->beg[2];
+  for (nv = 0; nv < NV; nv++)
+  for (k = 0; k < n3; k++) for (j = 0; j < n2; j++) for (i = 0; i < n1; i++)
+    o->Vc[nv][IDX(o,k+kb,j+jb,i+ib)] = vc[((size_t)(nv*n3 + k)*n2 + j)*n1 + i];
+  for (k = 0; k < n3; k++) for (j = 0; j < n2; j++) for (i = 0; i <= n1; i++)
+    o->Vs[0][IDX(o,k+kb,j+jb,i+ib-1)] = bx1s[((size_t)k*n2 + j)*(n1+1) + i];
+  for (k = 0; k < n3; k++) for (j = 0; j <= n2; j++) for (i = 0; i < n1; i++)
+    o->Vs[1][IDX(o,k+kb,j+jb-1,i+ib)] = bx2s[((size_t)k*(n2+1) + j)*n1 + i];
+  if (o->c.dims == 3)
+  for (k = 0; k <= n3; k++) for (j = 0; j < n2; j++) for (i = 0; i < n1; i++)
+    o->Vs[2][IDX(o,k+kb-1,j+jb,i+ib)] = bx3s[((size_t)k*n2 + j)*n1 + i];
+}
+
+void oracle_get_interior (const Oracle *o, double *vc, double *bx1s,
+                          double *bx2s, double *bx3s)
+{
+  int i, j, k, nv;
+  int n1 = o->c.n[0], n2 = o->c.n[1], n3 = (o->c.dims == 3 ? o->c.n[2] : 1);
+  int ib = o->beg[0], jb = o->beg[1], kb = o->beg[2];
+  for (nv = 0; nv < NV; nv++)
+  for (k = 0; k < n3; k++) for (j = 0; j < n2; j++) for (i = 0; i < n1; i++)
+    vc[((size_t)(nv*n3 + k)*n2 + j)*n1 + i] = o->Vc[nv][IDX(o,k+kb,j+jb,i+ib)];
+  for (k = 0; k < n3; k++) for (j = 0; j < n2; j++) for (i = 0; i <= n1; i++)
+    bx1s[((size_t)k*n2 + j)*(n1+1) + i] = o->Vs[0][IDX(o,k+kb,j+jb,i+ib-1)];
+  for (k = 0; k < n3; k++) for (j = 0; j <= n2; j++) for (i = 0; i < n1; i++)
+    bx2s[((size_t)k*(n2+1) + j)*n1 + i] = o->Vs[1][IDX(o,k+kb,j+jb-1,i+ib)];
+  if (o->c.dims == 3 && bx3s)
+  for (k = 0; k <= n3; k++) for (j = 0; j < n2; j++) for (i = 0; i < n1; i++)
+    bx3s[((size_t)k*n2 + j)*n1 + i] = o->Vs[2][IDX(o,k+kb-1,j+jb,i+ib)];
+}
+
+/* =====================================================================
+   Boundary conditions  (reference boundary.c:41-315, 439-564;
+   MHD/CT/ct_fill_mag_field.c:38-179; MHD/CT/ct_field_average.c:134-272)
+   ===================================================================== */
+
+typedef struct { int ib, ie, jb, je, kb, ke; } Box;   /* may run backwards */
+
+#define BOXLOOP(b,k,j,i) \
+  for (dk_ = ((k = (b).kb) <= (b).ke ? 1:-1); k != (b).ke + dk_; k += dk_) \
+  for (dj_ = ((j = (b).jb) <= (b).je ? 1:-1); j != (b).je + dj_; j += dj_) \
+  for (di_ = ((i = (b).ib) <= (b).ie ? 1:-1); i != (b).ie + di_; i += di_)
+
+static void outflow_bound (Oracle *o, double *q, Box b, int side)
+/* boundary.c:439-477 */
+{
+  int i, j, k, di_, dj_, dk_;
+  BOXLOOP(b,k,j,i){
+    int ks = k, js = j, is = i;
+    switch (side){
+      case 0: is = o->beg[0]; break;  case 1: is = o->end[0]; break;
+      case 2: js = o->beg[1]; break;  case 3: js = o->end[1]; break;
+      case 4: ks = o->beg[2]; break;  case 5: ks = o->end[2]; break;
+    }
+    q[IDX(o,k,j,i)] = q[IDX(o,ks,js,is)];
+  }
+}
+
+static void periodic_bound (Oracle *o, double *q, Box b, int side)
+/* boundary.c:480-518 */
+{
+  int i, j, k, di_, dj_, dk_;
+  int n1 = o->c.n[0], n2 = o->c.n[1], n3 = o->c.n[2];
+  BOXLOOP(b,k,j,i){
+    int ks = k, js = j, is = i;
+    switch (side){
+      case 0: is = i + n1; break;  case 1: is = i - n1; break;
+      case 2: js = j + n2; break;  case 3: js = j - n2; break;
+      case 4: ks = k + n3; break;  case 5: ks = k - n3; break;
+    }
+    q[IDX(o,k,j,i)] = q[IDX(o,ks,js,is)];
+  }
+}
+
+static void reflective_bound (Oracle *o, double *q, int s, Box b, int side)
+/* boundary.c:521-564 */
+{
+  int i, j, k, di_, dj_, dk_;
+  BOXLOOP(b,k,j,i){
+    int ks = k, js = j, is = i;
+    switch (side){
+      case 0: is = 2*o->beg[0]-i-1; break;  case 1: is = 2*o->end[0]-i+1; break;
+      case 2: js = 2*o->beg[1]-j-1; break;  case 3: js = 2*o->end[1]-j+1; break;
+      case 4: ks = 2*o->beg[2]-k-1; break;  case 5: ks = 2*o->end[2]-k+1; break;
+    }
+    q[IDX(o,k,j,i)] = s*q[IDX(o,ks,js,is)];
+  }
+}
+
+static void fill_magnetic_field (Oracle *o, int side)
+/* ct_fill_mag_field.c:38-179.  Cartesian areas (set_geometry.c:149,180,202):
+   Ax1 = 1.0*dx2*dx3, Ax2 = dx1*1.0*dx3, Ax3 = dx1*dx2*1.0 (2-D: dx3 dropped). */
+{
+  int ibeg, iend, jbeg, jend, kbeg, kend, di = 1, dj = 1, dk = 1, i, j, k;
+  int dims = o->c.dims;
+  double *bx = o->Vs[0], *by = o->Vs[1], *bz = o->Vs[2];
+  double dx1 = o->c.dx[0], dx2 = o->c.dx[1], dx3 = o->c.dx[2];
+  double Ax, Ay, Az;
+  if (dims == 3){ Ax = 1.0*dx2*dx3; Ay = dx1*1.0*dx3; Az = dx1*dx2*1.0; }
+  else          { Ax = 1.0*dx2;     Ay = dx1*1.0;     Az = 0.0; }
+
+  ibeg = 0; iend = o->T[0]-1;
+  jbeg = 0; jend = o->T[1]-1;
+  if (dims == 3){ kbeg = 0; kend = o->T[2]-1; } else { kbeg = kend = 0; }
+  if (side == 0){ ibeg = o->beg[0]-1; iend = 0; di = -1; }
+  if (side == 1)  ibeg = o->end[0]+1;
+  if (side == 2){ jbeg = o->beg[1]-1; jend = 0; dj = -1; }
+  if (side == 3)  jbeg = o->end[1]+1;
+  if (side == 4){ kbeg = o->beg[2]-1; kend = 0; dk = -1; }
+  if (side == 5)  kbeg = o->end[2]+1;
+
+  for (k = kbeg; dk*k <= dk*kend; k += dk){
+  for (j = jbeg; dj*j <= dj*jend; j += dj){
+  for (i = ibeg; di*i <= di*iend; i += di){
+    double bxp = bx[IDX(o,k,j,i)], bxm = bx[IDX(o,k,j,i-1)];
+    double byp = by[IDX(o,k,j,i)], bym = by[IDX(o,k,j-1,i)];
+    double bzp = 0.0, bzm = 0.0, dBx, dBy, dBz = 0.0;
+    if (dims == 3){ bzp = bz[IDX(o,k,j,i)]; bzm = bz[IDX(o,k-1,j,i)]; }
+    dBx = (Ax*bxp - Ax*bxm);
+    dBy = (Ay*byp - Ay*bym);
+    if (dims == 3) dBz = (Az*bzp - Az*bzm);
+    if      (side == 0) bx[IDX(o,k,j,i-1)] = (Ax*bxp + dBy + dBz)/Ax;
+    else if (side == 1) bx[IDX(o,k,j,i)]   = (Ax*bxm - (dBy + dBz))/Ax;
+    else if (side == 2) by[IDX(o,k,j-1,i)] = (Ay*byp + dBx + dBz)/Ay;
+    else if (side == 3) by[IDX(o,k,j,i)]   = (Ay*bym - (dBx + dBz))/Ay;
+    else if (side == 4) bz[IDX(o,k-1,j,i)] = (Az*bzp + dBx + dBy)/Az;
+    else if (side == 5) bz[IDX(o,k,j,i)]   = (Az*bzm - (dBx + dBy))/Az;
+  }}}
+}
+
+static void average_normal_mag_field (Oracle *o, int side)
+/* ct_field_average.c:134-272 (Cartesian) */
+{
+  int i, j, k, d = side/2;
+  int lo[3] = {0,0,0}, hi[3];
+  double *B = o->Vc[BX1+d], *b = o->Vs[d];
+  hi[0] = o->T[0]-1; hi[1] = o->T[1]-1; hi[2] = o->T[2]-1;
+  if (side & 1) lo[d] = o->end[d]+1; else hi[d] = o->beg[d]-1;
+  for (k = lo[2]; k <= hi[2]; k++) for (j = lo[1]; j <= hi[1]; j++)
+  for (i = lo[0]; i <= hi[0]; i++){
+    int im = IDX(o, k - (d==2), j - (d==1), i - (d==0));
+    B[IDX(o,k,j,i)] = 0.5*(b[IDX(o,k,j,i)] + b[im]);
+  }
+}
+
+static void boundary (Oracle *o)
+/* boundary.c:41-315, serial (no AL_Exchange), ALL_DIR */
+{
+  int is, nv, d, dims = o->c.dims;
+  for (is = 0; is < 2*dims; is++){
+    int type = o->c.bc[is];
+    Box cb, fb[3];
+    cb.ib = 0; cb.ie = o->T[0]-1; cb.jb = 0; cb.je = o->T[1]-1; cb.kb = 0; cb.ke = o->T[2]-1;
+    if      (is == 0){ cb.ib = o->beg[0]-1; cb.ie = 0; }
+    else if (is == 1){ cb.ib = o->end[0]+1; cb.ie = o->T[0]-1; }
+    else if (is == 2){ cb.jb = o->beg[1]-1; cb.je = 0; }
+    else if (is == 3){ cb.jb = o->end[1]+1; cb.je = o->T[1]-1; }
+    else if (is == 4){ cb.kb = o->beg[2]-1; cb.ke = 0; }
+    else if (is == 5){ cb.kb = o->end[2]+1; cb.ke = o->T[2]-1; }
+    /* staggered boxes, boundary.c:157-164 */
+    fb[0] = fb[1] = fb[2] = cb;
+    if (cb.ib < cb.ie) fb[0].ib = cb.ib-1; else fb[0].ie = cb.ie-1;
+    if (cb.jb < cb.je) fb[1].jb = cb.jb-1; else fb[1].je = cb.je-1;
+    if (cb.kb < cb.ke) fb[2].kb = cb.kb-1; else fb[2].ke = cb.ke-1;
+    /* NB: in 2-D kb == ke == 0 -> "kb < ke" false -> ke-1 = -1: the x3 face
+       box is never used in 2-D (D_EXPAND drops it). */
+
+    if (type == ORC_BC_OUTFLOW){
+      for (nv = 0; nv < NV; nv++) outflow_bound (o, o->Vc[nv], cb, is);
+      for (d = 0; d < dims; d++) if (d != is/2) outflow_bound (o, o->Vs[d], fb[d], is);
+      fill_magnetic_field (o, is);
+      average_normal_mag_field (o, is);
+    }else if (type == ORC_BC_REFLECTIVE){
+      /* FlipSign, boundary.c:318-436: normal v and normal B change sign */
+      for (nv = 0; nv < NV; nv++){
+        int s = 1;
+        if (nv == VX1 + is/2 || nv == BX1 + is/2) s = -1;
+        reflective_bound (o, o->Vc[nv], s, cb, is);
+      }
+      for (d = 0; d < dims; d++) if (d != is/2) reflective_bound (o, o->Vs[d], 1, fb[d], is);
+      fill_magnetic_field (o, is);
+    }else if (type == ORC_BC_PERIODIC){
+      for (nv = 0; nv < NV; nv++) periodic_bound (o, o->Vc[nv], cb, is);
+      for (d = 0; d < dims; d++) periodic_bound (o, o->Vs[d], fb[d], is);
+    }
+  }
+}
+
+/* =====================================================================
+   Mappers (reference MHD/mappers.c:25-86, 88-254)
+   ===================================================================== */
+
+static void prim_to_cons (const Oracle *o, const double *v, double *u)
+{
+  double gmm1 = o->c.gamma - 1.0, kinb2;
+  u[RHO] = v[RHO];
+  u[MX1]   = v[RHO]*v[VX1];
+  u[MX1+1] = v[RHO]*v[VX2];
+  u[MX1+2] = v[RHO]*v[VX3];
+  u[BX1] = v[BX1]; u[BX2] = v[BX2]; u[BX3] = v[BX3];
+  kinb2  = v[VX1]*v[VX1] + v[VX2]*v[VX2] + v[VX3]*v[VX3];
+  kinb2  = v[RHO]*kinb2 + v[BX1]*v[BX1] + v[BX2]*v[BX2] + v[BX3]*v[BX3];  /* left-assoc: EXPAND has no parens */
+  kinb2 *= 0.5;
+  u[ENG] = kinb2 + v[PRS]/gmm1;
+}
+
+static int cons_to_prim (const Oracle *o, double *u, double *v)
+/* returns 1 when a floor was applied (FLAG_CONS2PRIM_FAIL) */
+{
+  double gmm1 = o->c.gamma - 1.0, m2, b2, tau, kinb2;
+  int fail = 0;
+  m2 = u[MX1]*u[MX1] + u[MX1+1]*u[MX1+1] + u[MX1+2]*u[MX1+2];
+  b2 = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
+  if (u[RHO] < 0.0){ u[RHO] = o->c.small_dn; fail = 1; }
+  v[RHO] = u[RHO];
+  tau = 1.0/u[RHO];
+  v[VX1] = u[MX1]*tau; v[VX2] = u[MX1+1]*tau; v[VX3] = u[MX1+2]*tau;
+  v[BX1] = u[BX1]; v[BX2] = u[BX2]; v[BX3] = u[BX3];
+  kinb2 = 0.5*(m2*tau + b2);
+  if (u[ENG] < 0.0){ u[ENG] = o->c.small_pr/gmm1 + kinb2; fail = 1; }
+  v[PRS] = gmm1*(u[ENG] - kinb2);
+  if (v[PRS] < 0.0){
+    v[PRS] = o->c.small_pr;
+    u[ENG] = v[PRS]/gmm1 + kinb2;
+    fail = 1;
+  }
+  return fail;
+}
+
+/* =====================================================================
+   Reconstruction
+   ===================================================================== */
+
+static void states_plm (Oracle *o, int beg, int end, int bxn)
+/* plm_states.c:80-312, CHAR_LIMITING NO, LIMITER DEFAULT,
+   UNIFORM_CARTESIAN_GRID YES (cp=cm=2, wp=wm=1, dp=dm=0.5).
+   Limiter macros: plm_coeffs.h:72-123.                                  */
+{
+  int i, nv;
+  double (*v)[NV] = o->v, (*vp)[NV] = o->vp, (*vm)[NV] = o->vm, (*dv)[NV] = o->dv;
+  for (i = beg-1; i <= end; i++)
+    for (nv = 0; nv < NV; nv++) dv[i][nv] = v[i+1][nv] - v[i][nv];
+
+  for (i = beg; i <= end; i++){
+    double dvl[NV];
+    for (nv = 0; nv < NV; nv++){
+      double dvp = dv[i][nv], dvm = dv[i-1][nv], lim;
+      if (nv == RHO){                         /* MC */
+        if (dvp*dvm > 0.0){
+          double qc = 0.5*(dvm + dvp), scrh = 2.0*ABS_MIN(dvp, dvm);
+          lim = ABS_MIN(qc, scrh);
+        }else lim = 0.0;
+      }else if (nv == PRS){                   /* minmod */
+        lim = (dvp*dvm > 0.0 ? ABS_MIN(dvp, dvm) : 0.0);
+      }else{                                  /* van Leer */
+        lim = (dvp*dvm > 0.0 ? 2.0*dvp*dvm/(dvp + dvm) : 0.0);
+      }
+      dvl[nv] = lim;
+    }
+    for (nv = 0; nv < NV; nv++){
+      vp[i][nv] = v[i][nv] + dvl[nv]*0.5;
+      vm[i][nv] = v[i][nv] - dvl[nv]*0.5;
+    }
+  }
+  for (i = beg-1; i <= end; i++) vp[i][bxn] = vm[i+1][bxn] = o->bn[i];
+}
+
+static void states_ppm (Oracle *o, int beg, int end, int bxn);   /* below */
+
+/* =====================================================================
+   Physics kernels shared by the Riemann solvers
+   ===================================================================== */
+
+typedef struct { int vn, vt, vb, bn, bt, bb; } Dirs;
+
+static Dirs set_vector_indices (int dir)       /* set_indexes.c:49-123 */
+{
+  Dirs q;
+  if (dir == 0){ q.vn = VX1; q.vt = VX2; q.vb = VX3; q.bn = BX1; q.bt = BX2; q.bb = BX3; }
+  else if (dir == 1){ q.vn = VX2; q.vt = VX1; q.vb = VX3; q.bn = BX2; q.bt = BX1; q.bb = BX3; }
+  else { q.vn = VX3; q.vt = VX1; q.vb = VX2; q.bn = BX3; q.bt = BX1; q.bb = BX2; }
+  return q;
+}
+
+static void mhd_flux (const double *v, const double *u, Dirs q, double *fx, double *prs)
+/* MHD/fluxes.c:159-215 */
+{
+  double Bmag2, ptot, vB;
+  Bmag2 = v[BX1]*v[BX1] + v[BX2]*v[BX2] + v[BX3]*v[BX3];
+  ptot  = v[PRS] + 0.5*Bmag2;
+  vB    = v[VX1]*v[BX1] + v[VX2]*v[BX2] + v[VX3]*v[BX3];
+  fx[RHO]   = u[q.vn];
+  fx[MX1]   = v[q.vn]*u[MX1]   - v[q.bn]*v[BX1];
+  fx[MX1+1] = v[q.vn]*u[MX1+1] - v[q.bn]*v[BX2];
+  fx[MX1+2] = v[q.vn]*u[MX1+2] - v[q.bn]*v[BX3];
+  fx[q.bn] = 0.0;
+  fx[q.bt] = v[q.vn]*v[q.bt] - v[q.bn]*v[q.vt];
+  fx[q.bb] = v[q.vn]*v[q.bb] - v[q.bn]*v[q.vb];
+  fx[ENG]  = (u[ENG] + ptot)*v[q.vn] - v[q.bn]*vB;
+  *prs = ptot;
+}
+
+static void max_signal_speed (const Oracle *o, const double *v, Dirs q,
+                              double *cmin, double *cmax)
+/* MHD/eigenv.c:35-104 (EOS IDEAL: gpr = g_gamma*p) */
+{
+  double gpr, b1, b2, b3, Btmag2, Bmag2, cf;
+  gpr = o->c.gamma*v[PRS];
+  b1 = v[q.bn]; b2 = v[q.bt]; b3 = v[q.bb];
+  Btmag2 = b2*b2 + b3*b3;
+  Bmag2  = b1*b1 + Btmag2;
+  cf = gpr - Bmag2;
+  cf = gpr + Bmag2 + sqrt(cf*cf + 4.0*gpr*Btmag2);
+  cf = sqrt(0.5*cf/v[RHO]);
+  *cmin = v[q.vn] - cf;
+  *cmax = v[q.vn] + cf;
+}
+
+static void hll_speed (Oracle *o, const double *vL, const double *vR, Dirs q,
+                       double a2L, double a2R, double *SL, double *SR)
+/* MHD/hll_speed.c:76-107 (DAVIS_ESTIMATE) */
+{
+  double slmin, slmax, srmin, srmax, scrh;
+  max_signal_speed (o, vL, q, &slmin, &slmax);
+  max_signal_speed (o, vR, q, &srmin, &srmax);
+  *SL = MINV(slmin, srmin);
+  *SR = MAXV(slmax, srmax);
+  scrh  = fabs(vL[q.vn]) + fabs(vR[q.vn]);
+  scrh /= sqrt(a2L) + sqrt(a2R);
+  o->max_mach = MAXV(scrh, o->max_mach);
+}
+
+/* =====================================================================
+   Riemann solvers: one interface at a time.
+   in: vL,vR,uL,uR; out: flux[NV], press, cmax
+   ===================================================================== */
+
+static void riemann_hll (Oracle *o, const double *vL, const double *vR,
+                         const double *uL, const double *uR, Dirs q,
+                         double *flux, double *press, double *cmax)
+/* MHD/hll.c:30-135 */
+{
+  double fL[NV], fR[NV], pL, pR, a2L, a2R, SL, SR, scrh;
+  int nv;
+  a2L = o->c.gamma*vL[PRS]/vL[RHO];                 /* EOS/Ideal/eos.c:33 */
+  a2R = o->c.gamma*vR[PRS]/vR[RHO];
+  mhd_flux (vL, uL, q, fL, &pL);
+  mhd_flux (vR, uR, q, fR, &pR);
+  hll_speed (o, vL, vR, q, a2L, a2R, &SL, &SR);
+  scrh = MAXV(fabs(SL), fabs(SR));
+  *cmax = scrh;
+  if (SL > 0.0){
+    for (nv = 0; nv < NV; nv++) flux[nv] = fL[nv];
+    *press = pL;
+  }else if (SR < 0.0){
+    for (nv = 0; nv < NV; nv++) flux[nv] = fR[nv];
+    *press = pR;
+  }else{
+    scrh = 1.0/(SR - SL);
+    for (nv = 0; nv < NV; nv++){
+      flux[nv]  = SL*SR*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
+      flux[nv] *= scrh;
+    }
+    *press = (SR*pL - SL*pR)*scrh;
+  }
+}
+
+static void riemann_hlld (Oracle *o, const double *vL, const double *vR,
+                          const double *uL, const double *uR, Dirs q,
+                          double *flux, double *press, double *cmax)
+/* MHD/hlld.c:44-452 (EOS IDEAL, no background field) */
+{
+  double fL[NV], fR[NV], ptL, ptR, a2L, a2R, SL, SR, scrh;
+  double usL[NV], usR[NV], ussl[NV], ussr[NV], Uhll[NV];
+  double vsL, wsL, scrhL, S1L, sqrL, duL;
+  double vsR, wsR, scrhR, S1R, sqrR, duR;
+  double Bx, Bx1, SM, sBx, pts, vss, wss;
+  int nv, revert_to_hllc;
+  int VXn = q.vn, VXt = q.vt, VXb = q.vb, BXn = q.bn, BXt = q.bt, BXb = q.bb;
+  int MXn = VXn, MXt = VXt, MXb = VXb;
+
+  a2L = o->c.gamma*vL[PRS]/vL[RHO];
+  a2R = o->c.gamma*vR[PRS]/vR[RHO];
+  mhd_flux (vL, uL, q, fL, &ptL);
+  mhd_flux (vR, uR, q, fR, &ptR);
+  hll_speed (o, vL, vR, q, a2L, a2R, &SL, &SR);
+
+  scrh  = MAXV(fabs(SL), fabs(SR));
+  *cmax = scrh;
+
+  if (SL >= 0.0){
+    for (nv = 0; nv < NV; nv++) flux[nv] = fL[nv];
+    *press = ptL;
+    return;
+  }else if (SR <= 0.0){
+    for (nv = 0; nv < NV; nv++) flux[nv] = fR[nv];
+    *press = ptR;
+    return;
+  }
+
+  for (nv = 0; nv < NV; nv++) usL[nv] = usR[nv] = 0.0;
+
+  scrh = 1.0/(SR - SL);
+  Bx1  = Bx = (SR*vR[BXn] - SL*vL[BXn])*scrh;
+  sBx  = (Bx > 0.0 ? 1.0 : -1.0);
+
+  duL = SL - vL[VXn];
+  duR = SR - vR[VXn];
+
+  scrh = 1.0/(duR*uR[RHO] - duL*uL[RHO]);
+  SM   = (duR*uR[MXn] - duL*uL[MXn] - ptR + ptL)*scrh;
+
+  pts  = duR*uR[RHO]*ptL - duL*uL[RHO]*ptR +
+         vL[RHO]*vR[RHO]*duR*duL*(vR[VXn] - vL[VXn]);
+  pts *= scrh;
+
+  usL[RHO] = uL[RHO]*duL/(SL - SM);
+  usR[RHO] = uR[RHO]*duR/(SR - SM);
+
+  sqrL = sqrt(usL[RHO]);
+  sqrR = sqrt(usR[RHO]);
+
+  S1L = SM - fabs(Bx)/sqrL;
+  S1R = SM + fabs(Bx)/sqrR;
+
+  revert_to_hllc = 0;
+  if ( (S1L - SL) <  1.e-4*(SM - SL) ) revert_to_hllc = 1;
+  if ( (S1R - SR) > -1.e-4*(SR - SM) ) revert_to_hllc = 1;
+
+  if (revert_to_hllc){
+    scrh = 1.0/(SR - SL);
+    for (nv = 0; nv < NV; nv++){
+      Uhll[nv]  = SR*uR[nv] - SL*uL[nv] + fL[nv] - fR[nv];
+      Uhll[nv] *= scrh;
+    }
+    usL[BXn] = usR[BXn] = Uhll[BXn];
+    usL[BXt] = usR[BXt] = Uhll[BXt];
+    usL[BXb] = usR[BXb] = Uhll[BXb];
+    S1L = S1R = SM;
+  }else{
+    scrhL = (uL[RHO]*duL*duL - Bx*Bx)/(uL[RHO]*duL*(SL - SM) - Bx*Bx);
+    scrhR = (uR[RHO]*duR*duR - Bx*Bx)/(uR[RHO]*duR*(SR - SM) - Bx*Bx);
+    usL[BXn] = Bx1;
+    usL[BXt] = uL[BXt]*scrhL;
+    usL[BXb] = uL[BXb]*scrhL;
+    usR[BXn] = Bx1;
+    usR[BXt] = uR[BXt]*scrhR;
+    usR[BXb] = uR[BXb]*scrhR;
+  }
+
+  scrhL = Bx/(uL[RHO]*duL);
+  scrhR = Bx/(uR[RHO]*duR);
+
+  vsL = vL[VXt] - scrhL*(usL[BXt] - uL[BXt]);
+  vsR = vR[VXt] - scrhR*(usR[BXt] - uR[BXt]);
+  wsL = vL[VXb] - scrhL*(usL[BXb] - uL[BXb]);
+  wsR = vR[VXb] - scrhR*(usR[BXb] - uR[BXb]);
+
+  usL[MXn] = usL[RHO]*SM;
+  usR[MXn] = usR[RHO]*SM;
+  usL[MXt] = usL[RHO]*vsL;
+  usR[MXt] = usR[RHO]*vsR;
+  usL[MXb] = usL[RHO]*wsL;
+  usR[MXb] = usR[RHO]*wsR;
+
+  scrhL  = vL[VXn]*Bx1 + vL[VXt]*uL[BXt] + vL[VXb]*uL[BXb];
+  scrhL -=      SM*Bx1 +    vsL*usL[BXt] +    wsL*usL[BXb];
+  usL[ENG]  = duL*uL[ENG] - ptL*vL[VXn] + pts*SM + Bx*scrhL;
+  usL[ENG] /= SL - SM;
+
+  scrhR  = vR[VXn]*Bx1 + vR[VXt]*uR[BXt] + vR[VXb]*uR[BXb];
+  scrhR -=      SM*Bx1 +    vsR*usR[BXt] +    wsR*usR[BXb];
+  usR[ENG]  = duR*uR[ENG] - ptR*vR[VXn] + pts*SM + Bx*scrhR;
+  usR[ENG] /= SR - SM;
+
+  if (S1L >= 0.0){
+    for (nv = 0; nv < NV; nv++) flux[nv] = fL[nv] + SL*(usL[nv] - uL[nv]);
+    *press = ptL;
+  }else if (S1R <= 0.0){
+    for (nv = 0; nv < NV; nv++) flux[nv] = fR[nv] + SR*(usR[nv] - uR[nv]);
+    *press = ptR;
+  }else{
+    ussl[RHO] = usL[RHO];
+    ussr[RHO] = usR[RHO];
+
+    vss  = sqrL*vsL + sqrR*vsR + (usR[BXt] - usL[BXt])*sBx;
+    vss /= sqrL + sqrR;
+    wss  = sqrL*wsL + sqrR*wsR + (usR[BXb] - usL[BXb])*sBx;
+    wss /= sqrL + sqrR;
+
+    ussl[MXn] = ussl[RHO]*SM;
+    ussr[MXn] = ussr[RHO]*SM;
+    ussl[MXt] = ussl[RHO]*vss;
+    ussr[MXt] = ussr[RHO]*vss;
+    ussl[MXb] = ussl[RHO]*wss;
+    ussr[MXb] = ussr[RHO]*wss;
+
+    ussl[BXn] = ussr[BXn] = Bx1;
+    ussl[BXt]  = sqrL*usR[BXt] + sqrR*usL[BXt] + sqrL*sqrR*(vsR - vsL)*sBx;
+    ussl[BXt] /= sqrL + sqrR;
+    ussr[BXt]  = ussl[BXt];
+    ussl[BXb]  = sqrL*usR[BXb] + sqrR*usL[BXb] + sqrL*sqrR*(wsR - wsL)*sBx;
+    ussl[BXb] /= sqrL + sqrR;
+    ussr[BXb]  = ussl[BXb];
+
+    scrhL  = SM*Bx1 + vsL*usL [BXt] + wsL*usL [BXb];
+    scrhL -= SM*Bx1 + vss*ussl[BXt] + wss*ussl[BXb];
+    scrhR  = SM*Bx1 + vsR*usR [BXt] + wsR*usR [BXb];
+    scrhR -= SM*Bx1 + vss*ussr[BXt] + wss*ussr[BXb];
+
+    ussl[ENG] = usL[ENG] - sqrL*scrhL*sBx;
+    ussr[ENG] = usR[ENG] + sqrR*scrhR*sBx;
+
+    if (SM >= 0.0){
+      for (nv = 0; nv < NV; nv++)
+        flux[nv] = fL[nv] + S1L*(ussl[nv] - usL[nv]) + SL*(usL[nv] - uL[nv]);
+      *press = ptL;
+    }else{
+      for (nv = 0; nv < NV; nv++)
+        flux[nv] = fR[nv] + S1R*(ussr[nv] - usR[nv]) + SR*(usR[nv] - uR[nv]);
+      *press = ptR;
+    }
+  }
+}
+
+static void riemann_roe (Oracle *o, const double *vL, const double *vR,
+                         const double *uL, const double *uR, Dirs q,
+                         double *flux, double *press, double *cmax);  /* below */
+
+/* =====================================================================
+   UpdateStage  (reference Time_Stepping/update_stage.c:37-314)
+   ===================================================================== */
+
+#define EPS_UCT_CONTACT 1.e-6      /* MHD/CT/ct_emf.c:102 */
+
+static void ct_compute_emf (Oracle *o);
+static void ct_update (Oracle *o, double dt);
+
+static void update_stage (Oracle *o, double dt)
+{
+  int dir, dims = o->c.dims, nv;
+  int i, j, k;
+
+  if (o->stage == 1) memset (o->C_dt, 0, sizeof(double)*(size_t)o->tot);  /* :86-90 */
+
+  for (dir = 0; dir < dims; dir++){
+    Dirs q = set_vector_indices (dir);
+    int lo[3], hi[3], t1, t2, tb, te, bb, be, a, b, n;
+    int nbeg = o->beg[dir], nend = o->end[dir], ntot = o->T[dir];
+    double dtdx   = dt/o->c.dx[dir];              /* rhs.c:195  scrh = dt/dx[i] */
+    double inv_dl = 1.0/o->c.dx[dir];             /* set_geometry.c: inv_dx     */
+    for (a = 0; a < 3; a++){ lo[a] = o->beg[a]; hi[a] = o->end[a]; }
+    /* transverse extension by one zone for CT, update_stage.c:144-148 */
+    for (a = 0; a < dims; a++) if (a != dir){ lo[a]--; hi[a]++; }
+    /* transverse loop order: BOX_TRANSVERSE_LOOP (macros.h:107-112):
+       IDIR: t=j,b=k ; JDIR: t=i,b=k ; KDIR: t=i,b=j  (b outer, t inner) */
+    if (dir == 0){ t1 = 1; t2 = 2; } else if (dir == 1){ t1 = 0; t2 = 2; } else { t1 = 0; t2 = 1; }
+    tb = lo[t1]; te = hi[t1]; bb = lo[t2]; be = hi[t2];
+
+    for (b = bb; b <= be; b++) for (a = tb; a <= te; a++){
+      int idx3[3];
+      idx3[t1] = a; idx3[t2] = b;
+      /* gather pencil, update_stage.c:158-164 */
+      for (n = 0; n < ntot; n++){
+        int id;
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++) o->v[n][nv] = o->Vc[nv][id];
+        o->bn[n] = o->Vs[dir][id];
+      }
+      /* States (nbeg-1 .. nend+1), :193 */
+      if (o->c.recon == ORC_RECON_PLM) states_plm (o, nbeg-1, nend+1, q.bn);
+      else                             states_ppm (o, nbeg-1, nend+1, q.bn);
+
+      /* Riemann (nbeg-1 .. nend), :194 ; stateL = vp[n], stateR = vm[n+1] */
+      for (n = nbeg-1; n <= nend; n++){
+        double uL[NV], uR[NV];
+        prim_to_cons (o, o->vp[n],   uL);          /* plm_states.c:310-311 */
+        prim_to_cons (o, o->vm[n+1], uR);
+        if      (o->c.solver == ORC_SOLVER_HLLD)
+          riemann_hlld (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
+        else if (o->c.solver == ORC_SOLVER_HLL)
+          riemann_hll  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
+        else
+          riemann_roe  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
+      }
+
+      /* CT_StoreUpwindEMF (nbeg-1 .. nend), ct_emf.c:104-190 */
+      for (n = nbeg-1; n <= nend; n++){
+        int id; signed char s;
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        if      (o->flux[n][RHO] >  EPS_UCT_CONTACT) s = 1;
+        else if (o->flux[n][RHO] < -EPS_UCT_CONTACT) s = -1;
+        else s = 0;
+        if (dir == 0){
+          o->ezi[id] = -o->flux[n][BX2];
+          if (dims == 3) o->eyi[id] = o->flux[n][BX3];
+          o->svx[id] = s;
+        }else if (dir == 1){
+          o->ezj[id] = o->flux[n][BX1];
+          if (dims == 3) o->exj[id] = -o->flux[n][BX3];
+          o->svy[id] = s;
+        }else{
+          o->eyk[id] = -o->flux[n][BX1];
+          o->exk[id] =  o->flux[n][BX2];
+          o->svz[id] = s;
+        }
+      }
+
+      /* RightHandSide + update (nbeg .. nend), rhs.c:193-201,
+         update_stage.c:214-216, 229-235 */
+      for (n = nbeg; n <= nend; n++){
+        int id;
+        double rhs[NV];
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
+        rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
+        for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
+        if (o->stage == 1)
+          o->C_dt[id] += 0.5*(o->cmax[n-1] + o->cmax[n])*inv_dl;
+      }
+    }
+  }
+  /* emf index ranges as left by the last sweeps, ct_emf.c:130,152,173 */
+  o->emf_ibeg = o->beg[0]-1; o->emf_iend = o->end[0];
+  o->emf_jbeg = o->beg[1]-1; o->emf_jend = o->end[1];
+  if (dims == 3){ o->emf_kbeg = o->beg[2]-1; o->emf_kend = o->end[2]; }
+  else          { o->emf_kbeg = o->emf_kend = 0; }
+
+  ct_compute_emf (o);                                   /* :250 */
+  ct_update (o, dt);                                    /* :284 */
+
+  if (o->stage == 1){                                   /* :308-312 */
+    for (k = o->beg[2]; k <= o->end[2]; k++)
+    for (j = o->beg[1]; j <= o->end[1]; j++)
+    for (i = o->beg[0]; i <= o->end[0]; i++)
+      o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->C_dt[IDX(o,k,j,i)]);
+    o->inv_dt_hyp /= (double)dims;
+  }
+}
+
+/* =====================================================================
+   Constrained transport
+   ===================================================================== */
+
+static void ct_compute_emf (Oracle *o)
+/* MHD/CT/ct_emf.c:210-254 (UCT_CONTACT): CT_ComputeCenterEMF (:348-388),
+   CT_EMF_ArithmeticAverage(w = 1) (ct_emf_average.c:13-49),
+   CT_EMF_IntegrateToCorner (ct_emf_average.c:52-164, scatter form as in
+   the reference, loop order k,j,i), then x0.25.                          */
+{
+  int i, j, k, dims = o->c.dims;
+  int koff = (dims == 3 ? 1 : 0);
+  int ibeg = o->emf_ibeg, iend = o->emf_iend, jbeg = o->emf_jbeg, jend = o->emf_jend;
+  int kbeg = o->emf_kbeg, kend = o->emf_kend;
+  double *exj = o->exj, *exk = o->exk, *eyi = o->eyi, *eyk = o->eyk, *ezi = o->ezi, *ezj = o->ezj;
+  double *ex = o->ex, *ey = o->ey, *ez = o->ez, *Ex1 = o->Ex1, *Ex2 = o->Ex2, *Ex3 = o->Ex3;
+
+  for (k = 0; k < o->T[2]; k++) for (j = 0; j < o->T[1]; j++) for (i = 0; i < o->T[0]; i++){
+    int id = IDX(o,k,j,i);
+    double vx1 = o->Vc[VX1][id], vx2 = o->Vc[VX2][id], vx3 = o->Vc[VX3][id];
+    double Bx1 = o->Vc[BX1][id], Bx2 = o->Vc[BX2][id], Bx3 = o->Vc[BX3][id];
+    Ex1[id] = (vx3*Bx2 - vx2*Bx3);
+    Ex2[id] = (vx1*Bx3 - vx3*Bx1);
+    Ex3[id] = (vx2*Bx1 - vx1*Bx2);
+  }
+
+#define I3(k,j,i) IDX(o,k,j,i)
+  for (k = kbeg; k <= kend; k++) for (j = jbeg; j <= jend; j++) for (i = ibeg; i <= iend; i++){
+    if (dims == 3){
+      ex[I3(k,j,i)] = 1.0*(  exk[I3(k,j,i)] + exk[I3(k,j+1,i)]
+                           + exj[I3(k,j,i)] + exj[I3(k+1,j,i)]);
+      ey[I3(k,j,i)] = 1.0*(  eyi[I3(k,j,i)] + eyi[I3(k+1,j,i)]
+                           + eyk[I3(k,j,i)] + eyk[I3(k,j,i+1)]);
+    }
+    ez[I3(k,j,i)] = 1.0*(  ezi[I3(k,j,i)] + ezi[I3(k,j+1,i)]
+                         + ezj[I3(k,j,i)] + ezj[I3(k,j,i+1)]);
+  }
+
+#define DEX_DYP(k,j,i) (exj[I3(k,j,i)] - Ex1[I3(k,j,i)])
+#define DEX_DZP(k,j,i) (exk[I3(k,j,i)] - Ex1[I3(k,j,i)])
+#define DEY_DXP(k,j,i) (eyi[I3(k,j,i)] - Ex2[I3(k,j,i)])
+#define DEY_DZP(k,j,i) (eyk[I3(k,j,i)] - Ex2[I3(k,j,i)])
+#define DEZ_DXP(k,j,i) (ezi[I3(k,j,i)] - Ex3[I3(k,j,i)])
+#define DEZ_DYP(k,j,i) (ezj[I3(k,j,i)] - Ex3[I3(k,j,i)])
+#define DEX_DYM(k,j,i) (Ex1[I3(k,j,i)] - exj[I3(k,j-1,i)])
+#define DEX_DZM(k,j,i) (Ex1[I3(k,j,i)] - exk[I3(k-1,j,i)])
+#define DEY_DXM(k,j,i) (Ex2[I3(k,j,i)] - eyi[I3(k,j,i-1)])
+#define DEY_DZM(k,j,i) (Ex2[I3(k,j,i)] - eyk[I3(k-1,j,i)])
+#define DEZ_DXM(k,j,i) (Ex3[I3(k,j,i)] - ezi[I3(k,j,i-1)])
+#define DEZ_DYM(k,j,i) (Ex3[I3(k,j,i)] - ezj[I3(k,j-1,i)])
+
+  for (k = kbeg; k <= kend + koff; k++)
+  for (j = jbeg; j <= jend + 1; j++)
+  for (i = ibeg; i <= iend + 1; i++){
+    signed char sx = o->svx[I3(k,j,i)], sy = o->svy[I3(k,j,i)], sz = 0;
+    int iu, ju, ku = k;
+    if (dims == 3) sz = o->svz[I3(k,j,i)];
+    iu = sx > 0 ? i : i+1;
+    ju = sy > 0 ? j : j+1;
+    if (dims == 3) ku = sz > 0 ? k : k+1;
+
+    if (sx == 0){
+      ez[I3(k,j,i)]   += 0.5*(DEZ_DYP(k,j,i) + DEZ_DYP(k,j,i+1));
+      ez[I3(k,j-1,i)] -= 0.5*(DEZ_DYM(k,j,i) + DEZ_DYM(k,j,i+1));
+      if (dims == 3){
+        ey[I3(k,j,i)]   += 0.5*(DEY_DZP(k,j,i) + DEY_DZP(k,j,i+1));
+        ey[I3(k-1,j,i)] -= 0.5*(DEY_DZM(k,j,i) + DEY_DZM(k,j,i+1));
+      }
+    }else{
+      ez[I3(k,j,i)]   += DEZ_DYP(k,j,iu);
+      ez[I3(k,j-1,i)] -= DEZ_DYM(k,j,iu);
+      if (dims == 3){
+        ey[I3(k,j,i)]   += DEY_DZP(k,j,iu);
+        ey[I3(k-1,j,i)] -= DEY_DZM(k,j,iu);
+      }
+    }
+
+    if (sy == 0){
+      ez[I3(k,j,i)]   += 0.5*(DEZ_DXP(k,j,i) + DEZ_DXP(k,j+1,i));
+      ez[I3(k,j,i-1)] -= 0.5*(DEZ_DXM(k,j,i) + DEZ_DXM(k,j+1,i));
+      if (dims == 3){
+        ex[I3(k,j,i)]   += 0.5*(DEX_DZP(k,j,i) + DEX_DZP(k,j+1,i));
+        ex[I3(k-1,j,i)] -= 0.5*(DEX_DZM(k,j,i) + DEX_DZM(k,j+1,i));
+      }
+    }else{
+      ez[I3(k,j,i)]   += DEZ_DXP(k,ju,i);
+      ez[I3(k,j,i-1)] -= DEZ_DXM(k,ju,i);
+      if (dims == 3){
+        ex[I3(k,j,i)]   += DEX_DZP(k,ju,i);
+        ex[I3(k-1,j,i)] -= DEX_DZM(k,ju,i);
+      }
+    }
+
+    if (dims == 3){
+      if (sz == 0){
+        ex[I3(k,j,i)]   += 0.5*(DEX_DYP(k,j,i) + DEX_DYP(k+1,j,i));
+        ex[I3(k,j-1,i)] -= 0.5*(DEX_DYM(k,j,i) + DEX_DYM(k+1,j,i));
+        ey[I3(k,j,i)]   += 0.5*(DEY_DXP(k,j,i) + DEY_DXP(k+1,j,i));
+        ey[I3(k,j,i-1)] -= 0.5*(DEY_DXM(k,j,i) + DEY_DXM(k+1,j,i));
+      }else{
+        ex[I3(k,j,i)]   += DEX_DYP(ku,j,i);
+        ex[I3(k,j-1,i)] -= DEX_DYM(ku,j,i);
+        ey[I3(k,j,i)]   += DEY_DXP(ku,j,i);
+        ey[I3(k,j,i-1)] -= DEY_DXM(ku,j,i);
+      }
+    }
+  }
+
+  for (k = kbeg; k <= kend; k++) for (j = jbeg; j <= jend; j++) for (i = ibeg; i <= iend; i++){
+    if (dims == 3){ ex[I3(k,j,i)] *= 0.25; ey[I3(k,j,i)] *= 0.25; }
+    ez[I3(k,j,i)] *= 0.25;
+  }
+}
+
+static void ct_update (Oracle *o, double dt)
+/* MHD/CT/ct_update.c:79-218 (Cartesian), in place on Vs */
+{
+  int i, j, k, dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
+  int ibeg = o->emf_ibeg, iend = o->emf_iend, jbeg = o->emf_jbeg, jend = o->emf_jend;
+  int kbeg = o->emf_kbeg, kend = o->emf_kend;
+  double dx1 = o->c.dx[0], dx2 = o->c.dx[1], dx3 = o->c.dx[2];
+  double *Ex1 = o->ex, *Ex2 = o->ey, *Ex3 = o->ez;
+  double rhs;
+
+  for (k = kbeg + koff; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
+  for (i = ibeg; i <= iend; i++){
+    if (dims == 3)
+      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)])
+                + dt/dx3*(Ex2[I3(k,j,i)] - Ex2[I3(k-1,j,i)]);
+    else
+      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)]);
+    o->Vs[0][I3(k,j,i)] = o->Vs[0][I3(k,j,i)] + rhs;
+  }
+  for (k = kbeg + koff; k <= kend; k++) for (j = jbeg; j <= jend; j++)
+  for (i = ibeg + 1; i <= iend; i++){
+    if (dims == 3)
+      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)])
+            - dt/dx3*(Ex1[I3(k,j,i)] - Ex1[I3(k-1,j,i)]);
+    else
+      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)]);
+    o->Vs[1][I3(k,j,i)] = o->Vs[1][I3(k,j,i)] + rhs;
+  }
+  if (dims == 3)
+  for (k = kbeg; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
+  for (i = ibeg + 1; i <= iend; i++){
+    rhs = - dt/dx1*(Ex2[I3(k,j,i)] - Ex2[I3(k,j,i-1)])
+          + dt/dx2*(Ex1[I3(k,j,i)] - Ex1[I3(k,j-1,i)]);
+    o->Vs[2][I3(k,j,i)] = o->Vs[2][I3(k,j,i)] + rhs;
+  }
+}
+
+static void ct_average_magnetic_field (Oracle *o)
+/* MHD/CT/ct_field_average.c:58-124 (Cartesian, CT_EN_CORRECTION NO):
+   DOM +/- 1 in every active direction, writes into Uc */
+{
+  int i, j, k, dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
+  for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)
+  for (j = o->beg[1]-1; j <= o->end[1]+1; j++)
+  for (i = o->beg[0]-1; i <= o->end[0]+1; i++){
+    o->Uc[BX1][I3(k,j,i)] = 0.5*(o->Vs[0][I3(k,j,i)] + o->Vs[0][I3(k,j,i-1)]);
+    o->Uc[BX2][I3(k,j,i)] = 0.5*(o->Vs[1][I3(k,j,i)] + o->Vs[1][I3(k,j-1,i)]);
+    if (dims == 3)
+      o->Uc[BX3][I3(k,j,i)] = 0.5*(o->Vs[2][I3(k,j,i)] + o->Vs[2][I3(k-1,j,i)]);
+  }
+}
+
+/* =====================================================================
+   AdvanceStep  (reference Time_Stepping/rk_step.c:27-254)
+   ===================================================================== */
+
+static void prim_to_cons_3d (Oracle *o)      /* mappers3D.c:74-119, DOM box */
+{
+  int i, j, k, nv;
+  for (k = o->beg[2]; k <= o->end[2]; k++) for (j = o->beg[1]; j <= o->end[1]; j++)
+  for (i = o->beg[0]; i <= o->end[0]; i++){
+    double v[NV], u[NV]; int id = I3(k,j,i);
+    for (nv = 0; nv < NV; nv++) v[nv] = o->Vc[nv][id];
+    prim_to_cons (o, v, u);
+    for (nv = 0; nv < NV; nv++) o->Uc[nv][id] = u[nv];
+  }
+}
+
+static void cons_to_prim_3d (Oracle *o)      /* mappers3D.c:16-72, DOM box */
+{
+  int i, j, k, nv;
+  for (k = o->beg[2]; k <= o->end[2]; k++) for (j = o->beg[1]; j <= o->end[1]; j++)
+  for (i = o->beg[0]; i <= o->end[0]; i++){
+    double v[NV], u[NV]; int id = I3(k,j,i);
+    for (nv = 0; nv < NV; nv++) u[nv] = o->Uc[nv][id];
+    o->floor_events += cons_to_prim (o, u, v);
+    for (nv = 0; nv < NV; nv++){ o->Uc[nv][id] = u[nv]; o->Vc[nv][id] = v[nv]; }
+  }
+}
+
+int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
+{
+  int i, j, k, nv, d, id, dims = o->c.dims;
+  double w0, wc;
+  o->max_mach = 0.0;                     /* main.c:304 */
+  o->inv_dt_hyp = 0.0;                   /* main.c:569 (reset by NextTimeStep) */
+  o->floor_events = 0;
+
+  /* ---- stage 1 (rk_step.c:85-139) ---- */
+  o->stage = 1;
+  boundary (o);
+  prim_to_cons_3d (o);
+  for (nv = 0; nv < NV; nv++)
+    for (k = o->beg[2]; k <= o->end[2]; k++) for (j = o->beg[1]; j <= o->end[1]; j++)
+    for (i = o->beg[0]; i <= o->end[0]; i++) o->U0[nv][I3(k,j,i)] = o->Uc[nv][I3(k,j,i)];
+  for (d = 0; d < dims; d++) memcpy (o->Bs0[d], o->Vs[d], sizeof(double)*(size_t)o->tot);
+  update_stage (o, dt);
+  ct_average_magnetic_field (o);
+  cons_to_prim_3d (o);
+
+  /* ---- stage 2 (rk_step.c:149-186) ---- */
+  if (o->c.rk_order == 3){ w0 = 0.75; wc = 0.25; } else { w0 = 0.5; wc = 0.5; }
+  o->stage = 2;
+  boundary (o);
+  update_stage (o, dt);
+  for (k = o->beg[2]; k <= o->end[2]; k++) for (j = o->beg[1]; j <= o->end[1]; j++)
+  for (i = o->beg[0]; i <= o->end[0]; i++){
+    id = I3(k,j,i);
+    for (nv = 0; nv < NV; nv++) o->Uc[nv][id] = w0*o->U0[nv][id] + wc*o->Uc[nv][id];
+  }
+  for (d = 0; d < dims; d++)
+    for (id = 0; id < o->tot; id++) o->Vs[d][id] = w0*o->Bs0[d][id] + wc*o->Vs[d][id];
+  ct_average_magnetic_field (o);
+  cons_to_prim_3d (o);
+
+  /* ---- stage 3 (rk_step.c:204-243) ---- */
+  if (o->c.rk_order == 3){
+    double one_third = 1.0/3.0;
+    o->stage = 3;
+    boundary (o);
+    update_stage (o, dt);
+    for (k = o->beg[2]; k <= o->end[2]; k++) for (j = o->beg[1]; j <= o->end[1]; j++)
+    for (i = o->beg[0]; i <= o->end[0]; i++){
+      id = I3(k,j,i);
+      for (nv = 0; nv < NV; nv++)
+        o->Uc[nv][id] = one_third*(o->U0[nv][id] + 2.0*o->Uc[nv][id]);
+    }
+    for (d = 0; d < dims; d++)
+      for (id = 0; id < o->tot; id++)
+        o->Vs[d][id] = (o->Bs0[d][id] + 2.0*o->Vs[d][id])/3.0;
+    ct_average_magnetic_field (o);
+    cons_to_prim_3d (o);
+  }
+
+  if (inv_dt_hyp) *inv_dt_hyp = o->inv_dt_hyp;
+  if (max_mach)   *max_mach   = o->max_mach;
+  return o->floor_events;
+}
+
+double oracle_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt)
+/* main.c:462-465, 532 */
+{
+  double dt_hyp = 1.0/inv_dt_hyp, dtnext;
+  dt_hyp *= cfl;
+  dtnext  = dt_hyp;
+  dtnext  = MINV(dtnext, cfl_max_var*dt);
+  return dtnext;
+}
+
+/* =====================================================================
+   PPM reconstruction and Roe solver
+   ===================================================================== */
+#include "mhd_oracle_ppm_roe.inc"
+
+/* ---- taps ---- */
+const double *oracle_tap (const Oracle *o, const char *name)
+{
+  static const char *vn[NV] = {"rho","vx1","vx2","vx3","bx1","bx2","bx3","prs"};
+  static const char *un[NV] = {"u_rho","u_mx1","u_mx2","u_mx3","u_bx1","u_bx2","u_bx3","u_eng"};
+  int nv;
+  for (nv = 0; nv < NV; nv++){
+    if (!strcmp(name, vn[nv])) return o->Vc[nv];
+    if (!strcmp(name, un[nv])) return o->Uc[nv];
+  }
+  if (!strcmp(name,"bx1s")) return o->Vs[0];
+  if (!strcmp(name,"bx2s")) return o->Vs[1];
+  if (!strcmp(name,"bx3s")) return o->Vs[2];
+  if (!strcmp(name,"exj")) return o->exj;  if (!strcmp(name,"exk")) return o->exk;
+  if (!strcmp(name,"eyi")) return o->eyi;  if (!strcmp(name,"eyk")) return o->eyk;
+  if (!strcmp(name,"ezi")) return o->ezi;  if (!strcmp(name,"ezj")) return o->ezj;
+  if (!strcmp(name,"ex")) return o->ex;  if (!strcmp(name,"ey")) return o->ey;
+  if (!strcmp(name,"ez")) return o->ez;
+  if (!strcmp(name,"C_dt")) return o->C_dt;
+  return NULL;
+}
+
+void oracle_tap_shape (const Oracle *o, int *s3, int *s2, int *s1, int *tot)
+{
+  *s3 = o->S3; *s2 = o->S2; *s1 = o->S1; *tot = o->tot;
+}

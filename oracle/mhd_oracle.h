@@ -1,0 +1,76 @@
+/*
+ * mhd_oracle.h -- CPU restatement of the PLUTO 4.3 unsplit RK2/RK3 + CT
+ * ideal-MHD step.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * load this library; the product (pluto_b200/) never links or calls it.
+ *
+ * Parity status: PINNED.  The reference ships no golden vectors for this
+ * path; the restatement is pinned by bit-comparison against
+ * the compiled, unmodified reference (oracle/_ref/pluto_*, built by
+ * oracle/ref_build/build_ref.sh) in tests/test_oracle_vs_ref.py and against
+ * the fixtures under tests/golden/ that the same binaries generated
+ * (tools/make_golden.py).
+ */
+#ifndef MHD_ORACLE_H
+#define MHD_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_RECON_PLM = 0, ORC_RECON_PPM = 1 };
+enum { ORC_SOLVER_HLLD = 0, ORC_SOLVER_HLL = 1, ORC_SOLVER_ROE = 2 };
+enum { ORC_BC_PERIODIC = 0, ORC_BC_OUTFLOW = 1, ORC_BC_REFLECTIVE = 2 };
+
+/* Variable order of the 8-slot state vector used by the oracle.  2-D
+   (COMPONENTS = 2) runs carry vx3 = Bx3 = 0 in the unused slots, which is
+   bit-identical to the reference's 6-variable arithmetic (every extra term
+   is an exact +0). */
+enum { ORC_RHO = 0, ORC_VX1, ORC_VX2, ORC_VX3, ORC_BX1, ORC_BX2, ORC_BX3, ORC_PRS, ORC_NV };
+
+typedef struct {
+  int    dims;          /* 2 or 3  (DIMENSIONS = COMPONENTS)               */
+  int    n[3];          /* interior zones NX1, NX2, NX3 (NX3 = 1 in 2-D)   */
+  int    recon;         /* ORC_RECON_*                                     */
+  int    solver;        /* ORC_SOLVER_*                                    */
+  int    rk_order;      /* 2 (RK2) or 3 (RK3)                              */
+  int    bc[6];         /* X1_BEG, X1_END, X2_BEG, X2_END, X3_BEG, X3_END  */
+  double gamma;         /* g_gamma                                         */
+  double dx[3];         /* uniform cell sizes                              */
+  double small_dn;      /* g_smallDensity  (1e-12)                         */
+  double small_pr;      /* g_smallPressure (1e-12)                         */
+} OracleConfig;
+
+typedef struct Oracle Oracle;
+
+Oracle *oracle_create (const OracleConfig *cfg);
+void    oracle_destroy (Oracle *o);
+int     oracle_nghost (const Oracle *o);
+
+/* Interior state in the reference's .dbl layout:
+   vc[nv][k][j][i]  (nv in oracle order, always 8 slots; n3*n2*n1 each)
+   bx1s[k][j][i] with n1+1 faces, bx2s with n2+1, bx3s with n3+1 (3-D). */
+void oracle_set_interior (Oracle *o, const double *vc, const double *bx1s,
+                          const double *bx2s, const double *bx3s);
+void oracle_get_interior (const Oracle *o, double *vc, double *bx1s,
+                          double *bx2s, double *bx3s);
+
+/* One AdvanceStep (reference Src/Time_Stepping/rk_step.c:27).  Returns the
+   number of ConsToPrim floor events; *inv_dt_hyp is Dts->invDt_hyp as left
+   by UpdateStage at stage 1 (update_stage.c:308-312), *max_mach is
+   g_maxMach after the step. */
+int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach);
+
+/* NextTimeStep restatement (reference Src/main.c:389-575, hyperbolic part). */
+double oracle_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt);
+
+/* Debug taps: raw pointers into the padded internal arrays, plus the
+   padded extents so tests can index them ((k+1)*S2*S1 + (j+1)*S1 + (i+1)). */
+const double *oracle_tap (const Oracle *o, const char *name);
+void oracle_tap_shape (const Oracle *o, int *s3, int *s2, int *s1, int *tot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

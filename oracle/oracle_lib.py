@@ -1,0 +1,151 @@
+"""ctypes wrapper of oracle/liboracle_mhd.so (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+import this module.  The product package (pluto_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle_mhd.so")
+
+RECON = {"plm": 0, "ppm": 1}
+SOLVER = {"hlld": 0, "hll": 1, "roe": 2}
+BC = {"periodic": 0, "outflow": 1, "reflective": 2}
+
+
+class OracleConfig(C.Structure):
+    _fields_ = [("dims", C.c_int), ("n", C.c_int * 3), ("recon", C.c_int),
+                ("solver", C.c_int), ("rk_order", C.c_int), ("bc", C.c_int * 6),
+                ("gamma", C.c_double), ("dx", C.c_double * 3),
+                ("small_dn", C.c_double), ("small_pr", C.c_double)]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle_mhd.so"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.POINTER(OracleConfig)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_nghost.argtypes = [C.c_void_p]
+        dp = C.POINTER(C.c_double)
+        L.oracle_set_interior.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.oracle_get_interior.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.oracle_advance.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.oracle_advance.restype = C.c_int
+        L.oracle_next_dt.argtypes = [C.c_double] * 4
+        L.oracle_next_dt.restype = C.c_double
+        L.oracle_tap.argtypes = [C.c_void_p, C.c_char_p]
+        L.oracle_tap.restype = dp
+        ip = C.POINTER(C.c_int)
+        L.oracle_tap_shape.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+VC_NAMES_3D = ["rho", "vx1", "vx2", "vx3", "Bx1", "Bx2", "Bx3", "prs"]
+
+
+class Oracle:
+    """State container + stepper.  Arrays use the .dbl interior layout."""
+
+    def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
+                 bc=("periodic",) * 6, gamma=5.0 / 3.0):
+        c = OracleConfig()
+        c.dims = dims
+        n = list(n) + [1] * (3 - len(n))
+        if dims == 2:
+            n[2] = 1
+        for d in range(3):
+            c.n[d] = n[d]
+            c.dx[d] = dx[d] if d < len(dx) else 1.0
+        c.recon = RECON[recon]
+        c.solver = SOLVER[solver]
+        c.rk_order = rk_order
+        for s in range(6):
+            c.bc[s] = BC[bc[s]]
+        c.gamma = gamma
+        c.small_dn = 1e-12
+        c.small_pr = 1e-12
+        self.cfg = c
+        self.dims = dims
+        self.n = tuple(n)
+        self._h = lib().oracle_create(C.byref(c))
+        self.ng = lib().oracle_nghost(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().oracle_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- state I/O in "dump dict" form (names as in dbl.out) ----
+    def set_state(self, dump: dict):
+        n1, n2, n3 = self.n
+        vc = np.zeros((8, n3, n2, n1))
+        for iv, nm in enumerate(VC_NAMES_3D):
+            if nm in dump:
+                vc[iv] = dump[nm]
+        b1 = np.ascontiguousarray(dump["Bx1s"], dtype=np.float64)
+        b2 = np.ascontiguousarray(dump["Bx2s"], dtype=np.float64)
+        b3 = np.ascontiguousarray(dump["Bx3s"], dtype=np.float64) if self.dims == 3 else None
+        self._keep = (vc, b1, b2, b3)
+        lib().oracle_set_interior(self._h, _dp(vc), _dp(b1), _dp(b2), _dp(b3))
+
+    def get_state(self) -> dict:
+        n1, n2, n3 = self.n
+        vc = np.zeros((8, n3, n2, n1))
+        b1 = np.zeros((n3, n2, n1 + 1))
+        b2 = np.zeros((n3, n2 + 1, n1))
+        b3 = np.zeros((n3 + 1, n2, n1)) if self.dims == 3 else None
+        lib().oracle_get_interior(self._h, _dp(vc), _dp(b1), _dp(b2), _dp(b3))
+        out = {}
+        for iv, nm in enumerate(VC_NAMES_3D):
+            if self.dims == 2 and nm in ("vx3", "Bx3"):
+                continue
+            out[nm] = vc[iv].copy()
+        out["Bx1s"] = b1
+        out["Bx2s"] = b2
+        if self.dims == 3:
+            out["Bx3s"] = b3
+        return out
+
+    def advance(self, dt: float):
+        inv = C.c_double(0.0)
+        mach = C.c_double(0.0)
+        nfloor = lib().oracle_advance(self._h, dt, C.byref(inv), C.byref(mach))
+        return inv.value, mach.value, nfloor
+
+    def tap(self, name: str) -> np.ndarray:
+        """Padded internal array [k+1][j+1][i+1] (copy)."""
+        s3, s2, s1, tot = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        lib().oracle_tap_shape(self._h, C.byref(s3), C.byref(s2), C.byref(s1), C.byref(tot))
+        p = lib().oracle_tap(self._h, name.encode())
+        if not p:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(s3.value, s2.value, s1.value)).copy()
+
+
+def next_dt(inv_dt_hyp, cfl, cfl_max_var, dt):
+    return lib().oracle_next_dt(inv_dt_hyp, cfl, cfl_max_var, dt)
