@@ -1,0 +1,42 @@
+"""The CPU restatement against the compiled reference run live
+(oracle/_ref/pluto_*), at sizes/configs beyond the committed fixtures.
+Skipped when the binaries are absent (they are git-ignored build products;
+`python -c 'import __graft_entry__ as g; g.build()'` creates them when
+/root/reference is present)."""
+import numpy as np
+import pytest
+
+from oracle.oracle_lib import Oracle, next_dt
+from oracle.refrun import RefConfig, have_ref, run_reference
+
+CASES = [
+    ("ot2d_hlld", RefConfig(problem="ot", dims=2, n=(48, 40, 1), first_dt=1.5e-2), 12),
+    ("ot3d_hll", RefConfig(problem="ot", dims=3, n=(12, 16, 10), first_dt=3e-2, cfl=0.3, solver="hll"), 6),
+    ("blast3d_roe", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, solver="roe"), 6),
+    ("rotor2d_ppm_hlld", RefConfig(problem="rotor", dims=2, n=(40, 36, 1), recon="ppm", first_dt=2e-3), 10),
+    ("turb2d_hlld", RefConfig(problem="turb", dims=2, n=(24, 20, 1), first_dt=2e-2), 8),
+]
+
+
+@pytest.mark.parametrize("label,cfg,nsteps", CASES, ids=[c[0] for c in CASES])
+def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
+    if not have_ref(cfg):
+        pytest.skip("oracle/_ref binary not built")
+    r = run_reference(cfg, maxsteps=nsteps + 1, dump_every=1)
+    n = list(cfg.n)
+    if cfg.dims == 2:
+        n[2] = 1
+    dom = cfg.resolved_domain()
+    dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
+    o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
+               gamma=cfg.resolved_gamma())
+    o.set_state(r.dumps[0])
+    tap = {int(a): c for a, b, c in r.dt_tap}
+    dt = cfg.first_dt
+    for s in range(1, nsteps + 1):
+        inv, mach, _ = o.advance(dt)
+        dt = next_dt(inv, cfg.cfl, cfg.cfl_max_var, dt)
+        assert dt == tap[s], f"dt after step {s}"
+        st = o.get_state()
+        for k, ref in r.dumps[s].items():
+            assert np.array_equal(st[k], ref), f"{label}: {k} differs after {s} steps"

@@ -1,0 +1,72 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import glob
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# BASELINE.json tolerances: per-variable relative L1 error vs the reference
+TOL_ONE_STEP = 1e-12
+TOL_100_STEPS = 1e-9
+TOL_DT = 1e-12
+
+
+def golden_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.problem = str(d["cfg_problem"])
+        self.dims = int(d["cfg_dims"])
+        n = [int(x) for x in d["cfg_n"]]
+        if self.dims == 2:
+            n[2] = 1
+        self.n = tuple(n)
+        self.recon = str(d["cfg_recon"])
+        self.solver = str(d["cfg_solver"])
+        self.tstep = str(d["cfg_tstep"])
+        self.cfl = float(d["cfg_cfl"])
+        self.cfl_max_var = float(d["cfg_cfl_max_var"])
+        self.first_dt = float(d["cfg_first_dt"])
+        self.gamma = float(d["cfg_gamma"])
+        self.domain = [tuple(float(x) for x in row) for row in d["cfg_domain"]]
+        self.bc = tuple(str(x) for x in d["cfg_bc"])
+        self.nsteps = int(d["cfg_nsteps"])
+        self.dt = d["dt"]
+        self.states = {}
+        for key in d.files:
+            if key.startswith("s") and "_" in key and key[1].isdigit():
+                s, nm = key.split("_", 1)
+                self.states.setdefault(int(s[1:]), {})[nm] = d[key]
+        # uniform cell size exactly as the reference computes it
+        # (Src/set_grid.c:400  dx = (xR - xL)/npoint)
+        self.dx = [(self.domain[a][1] - self.domain[a][0]) / self.n[a] for a in range(self.dims)]
+        self.rk_order = 3 if self.tstep == "rk3" else 2
+
+
+def rel_l1(a, b):
+    """Per-variable relative L1 error  sum|a-b| / sum|b|  (0 if both vanish)."""
+    num = np.abs(a - b).sum()
+    den = np.abs(b).sum()
+    if den == 0.0:
+        return 0.0 if num == 0.0 else np.inf
+    return num / den
+
+
+def max_rel_l1(state, ref):
+    return max(rel_l1(state[k], ref[k]) for k in ref)
+
+
+def divb_max(state, dims, dx):
+    """max |sum of face fluxes| / cell volume, from the staggered fields."""
+    bx, by = state["Bx1s"], state["Bx2s"]
+    div = (bx[:, :, 1:] - bx[:, :, :-1]) / dx[0] + (by[:, 1:, :] - by[:, :-1, :]) / dx[1]
+    if dims == 3:
+        bz = state["Bx3s"]
+        div = div + (bz[1:, :, :] - bz[:-1, :, :]) / dx[2]
+    return np.abs(div).max()

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the compiled, unmodified reference
+(oracle/_ref/pluto_*, built from /root/reference by
+oracle/ref_build/build_ref.sh: gcc -O3, serial, no FMA).
+
+Each fixture holds, for one small configuration:
+  cfg_*            the run parameters (problem, grid, solver, CFL, ...)
+  s0_<name>        the initial interior state as dumped in data.0000.dbl
+  s<K>_<name>      the state after K steps (K = 1 and K = nsteps)
+  dt               dt[s] used for step s (dt[0] = first_dt), full precision
+                   from the Analysis() tap in oracle/ref_build/problem/init.c
+
+Run here (container with /root/reference); the fixtures are committed so
+that the GPU box, which has no /root/reference, can check against them.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.refrun import RefConfig, run_reference  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (RefConfig, nsteps)
+    "ot2d_plm_hlld": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4), 20),
+    "ot2d_plm_hll": (RefConfig(problem="ot", dims=2, n=(24, 32, 1), first_dt=2.5e-2, cfl=0.4, solver="hll"), 10),
+    "ot2d_plm_roe": (RefConfig(problem="ot", dims=2, n=(24, 32, 1), first_dt=2.5e-2, cfl=0.4, solver="roe"), 10),
+    "ot3d_plm_hlld": (RefConfig(problem="ot", dims=3, n=(16, 12, 8), first_dt=3e-2, cfl=0.3), 10),
+    "blast3d_plm_hlld": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3), 12),
+    "blast2d_plm_hlld": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4), 20),
+    "rotor2d_ppm_roe": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), recon="ppm", solver="roe",
+                                  first_dt=2.5e-3, cfl=0.4), 20),
+    "turb3d_plm_hlld": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3), 10),
+    "ot3d_ppm_roe": (RefConfig(problem="ot", dims=3, n=(12, 8, 16), recon="ppm", solver="roe",
+                               first_dt=4.5e-2, cfl=0.3), 8),
+}
+
+
+def make(name):
+    cfg, nsteps = CASES[name]
+    r = run_reference(cfg, maxsteps=nsteps + 1, dump_every=1)
+    out = {
+        "cfg_problem": cfg.problem, "cfg_dims": cfg.dims, "cfg_n": np.array(cfg.n),
+        "cfg_recon": cfg.recon, "cfg_solver": cfg.solver, "cfg_tstep": cfg.tstep,
+        "cfg_cfl": cfg.cfl, "cfg_cfl_max_var": cfg.cfl_max_var,
+        "cfg_first_dt": cfg.first_dt, "cfg_gamma": cfg.resolved_gamma(),
+        "cfg_domain": np.array(cfg.resolved_domain()),
+        "cfg_bc": np.array(cfg.resolved_bc()), "cfg_nsteps": nsteps,
+    }
+    for s in (0, 1, nsteps):
+        for k, v in r.dumps[s].items():
+            out[f"s{s}_{k}"] = v
+    dt = np.zeros(nsteps + 1)
+    dt[0] = cfg.first_dt
+    tap = {int(a): c for a, b, c in r.dt_tap}
+    for s in range(1, nsteps + 1):
+        dt[s] = tap[s]
+    out["dt"] = dt
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path)/1024:.0f} KiB, dt[-1]/dt[-2] = {dt[-1]/dt[-2]:.4f}")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        make(nm)
