@@ -1,0 +1,158 @@
+/*
+ * pluto_gpu.h -- C ABI of the B200-native unsplit Godunov MHD step.
+ *
+ * This is the drop-in boundary for ONE path of PLUTO 4.3: the body of
+ *
+ *     int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
+ *
+ * (reference Src/prototypes.h:4, Src/Time_Stepping/rk_step.c:27-254, called
+ * only from Integrate(), Src/main.c:339-355) together with everything it
+ * calls per step: Boundary (Src/boundary.c:41), UpdateStage
+ * (Src/Time_Stepping/update_stage.c:37), States (Src/States/plm_states.c:80,
+ * ppm_states.c:68), the Riemann solvers (Src/MHD/hlld.c:44, hll.c:30,
+ * roe.c:53), RightHandSide (Src/MHD/rhs.c:84), the constrained-transport
+ * routines (Src/MHD/CT/ct_emf.c, ct_emf_average.c, ct_update.c,
+ * ct_field_average.c, ct_fill_mag_field.c), the mappers
+ * (Src/MHD/mappers.c, Src/mappers3D.c) and the CFL reduction feeding
+ * NextTimeStep (Src/main.c:389).
+ *
+ * Plain C types only.  Every function returns 0 on success and a non-zero
+ * code on failure (pluto_gpu_last_error() gives the text); the reference's
+ * convention for fatal errors is print + QUIT_PLUTO (Src/macros.h:161-170),
+ * which the reference-side shim maps these codes to.
+ *
+ * There is no CPU fallback: without a CUDA device pluto_gpu_create fails.
+ */
+#ifndef PLUTO_GPU_H
+#define PLUTO_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* RECONSTRUCTION in definitions.h (Src/pluto.h:305-435): LINEAR / PARABOLIC */
+enum { PLUTO_GPU_RECON_LINEAR = 0, PLUTO_GPU_RECON_PARABOLIC = 1 };
+/* [Solver] in pluto.ini -> SetSolver (Src/MHD/set_solver.c:40-47) */
+enum { PLUTO_GPU_SOLVER_HLLD = 0, PLUTO_GPU_SOLVER_HLL = 1, PLUTO_GPU_SOLVER_ROE = 2 };
+/* [Boundary] in pluto.ini (Src/boundary.c:171-218).  SHARED marks a side
+   that abuts another rank's block: it is filled by the halo exchange
+   (reference: AL_Exchange_dim, Src/Parallel/al_exchange_dim.c:25) instead
+   of a physical condition, exactly as boundary.c:139 skips it. */
+enum { PLUTO_GPU_BC_PERIODIC = 0, PLUTO_GPU_BC_OUTFLOW = 1, PLUTO_GPU_BC_REFLECTIVE = 2,
+       PLUTO_GPU_BC_SHARED = 3 };
+/* arithmetic mode.  EXACT: no FMA contraction, IEEE div/sqrt in the
+   reference's operation order (bit-identical to the gcc -O3 x86-64 build
+   of the reference).  FAST: same algorithm with FMA contraction and shared
+   reciprocals; within the BASELINE.json tolerances, not bit-identical. */
+enum { PLUTO_GPU_ARITH_EXACT = 0, PLUTO_GPU_ARITH_FAST = 1 };
+
+typedef struct {
+  int    dims;         /* DIMENSIONS = COMPONENTS: 2 or 3                     */
+  int    n[3];         /* interior zones of THIS block (NX1,NX2,NX3; n[2]=1 in 2-D) */
+  int    recon;        /* PLUTO_GPU_RECON_*                                   */
+  int    solver;       /* PLUTO_GPU_SOLVER_*                                  */
+  int    rk_order;     /* TIME_STEPPING: 2 = RK2, 3 = RK3                     */
+  int    bc[6];        /* X1_BEG, X1_END, X2_BEG, X2_END, X3_BEG, X3_END      */
+  int    arith;        /* PLUTO_GPU_ARITH_*                                   */
+  int    device;       /* CUDA device ordinal                                 */
+  double gamma;        /* g_gamma          (Src/globals.h:116)                */
+  double dx[3];        /* uniform cell sizes grid[d].dx[i]                    */
+  double small_dn;     /* g_smallDensity   (Src/globals.h:113)                */
+  double small_pr;     /* g_smallPressure                                     */
+} PlutoGpuConfig;
+
+typedef struct PlutoGpu PlutoGpu;
+
+/* per-step scalars the host needs (reference: Dts->invDt_hyp set at
+   update_stage.c:308-312, g_maxMach at hll_speed.c:105) */
+typedef struct {
+  double inv_dt_hyp;
+  double max_mach;
+  int    floor_events;     /* ConsToPrim repairs (Src/MHD/mappers.c:130-200)  */
+  int    nan_events;       /* zones whose updated state is not finite
+                              (reference: CheckNaN, update_stage.c:192)       */
+} PlutoGpuStepInfo;
+
+int  pluto_gpu_create   (const PlutoGpuConfig *cfg, PlutoGpu **out);
+void pluto_gpu_destroy  (PlutoGpu *h);
+const char *pluto_gpu_last_error (void);
+int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
+
+/* ---- state transfer ---------------------------------------------------
+   "interior" layout = the reference's .dbl dump layout (Src/bin_io.c:216):
+   vc[nv][k][j][i] with nv = rho,vx1,vx2,vx3,Bx1,Bx2,Bx3,prs (always 8
+   slots; vx3/Bx3 ignored in 2-D), n3*n2*n1 each; bx1s[k][j][i] with n1+1
+   faces, bx2s with n2+1, bx3s with n3+1 (NULL in 2-D).
+   "data" layout = the reference's Data arrays including ghost zones
+   (Src/structs.h:29-88, Src/arrays.c:222-330): Vc is one block
+   [NVAR][T3][T2][T1] (NVAR = 8 in 3-D, 6 in 2-D: rho,vx1,vx2,Bx1,Bx2,prs);
+   Vs[d] is the block whose base is &Vs[d][0][0][-1] etc.
+   (Src/initialize.c:448-453): T3 x T2 x (T1+1), T3 x (T2+1) x T1,
+   (T3+1) x T2 x T1.  Host pointers. */
+int pluto_gpu_upload_interior   (PlutoGpu *h, const double *vc, const double *bx1s,
+                                 const double *bx2s, const double *bx3s);
+int pluto_gpu_download_interior (PlutoGpu *h, double *vc, double *bx1s,
+                                 double *bx2s, double *bx3s);
+int pluto_gpu_upload_data       (PlutoGpu *h, const double *Vc, const double *Vs1,
+                                 const double *Vs2, const double *Vs3);
+int pluto_gpu_download_data     (PlutoGpu *h, double *Vc, double *Vs1,
+                                 double *Vs2, double *Vs3);
+
+/* ---- the step ---------------------------------------------------------
+   pluto_gpu_advance: one AdvanceStep on the device-resident state.
+   pluto_gpu_advance_data: the literal AdvanceStep contract on HOST Data
+   arrays: upload, step, download (ghost zones come back filled as the
+   reference leaves them after the last Boundary call is NOT guaranteed;
+   interior zones and interior faces are). */
+int pluto_gpu_advance      (PlutoGpu *h, double dt, PlutoGpuStepInfo *info);
+int pluto_gpu_advance_data (PlutoGpu *h, double dt, double *Vc, double *Vs1,
+                            double *Vs2, double *Vs3, PlutoGpuStepInfo *info);
+
+/* Boundary(d, ALL_DIR, grid) on the current state (reference
+   Src/startup.c:286 calls it once before the first output). */
+int pluto_gpu_boundary (PlutoGpu *h);
+
+/* NextTimeStep, hyperbolic part (Src/main.c:462-465, 532). Host only. */
+double pluto_gpu_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt);
+
+/* ---- multi-GPU halo exchange (replaces AL_Exchange_dim) ----------------
+   Sides flagged PLUTO_GPU_BC_SHARED abut another rank's block and are filled
+   by the caller: the step is split so that the host language can drive the
+   exchange (NCCL send/recv, peer copies) dimension by dimension:
+       pluto_gpu_step_begin (h)
+       for stage in 1..rk_order:
+         for dim in 0..dims-1:
+            pluto_gpu_halo_pack   (h, stage, dim, send_lo, send_hi)
+            <send_lo -> low neighbour, send_hi -> high neighbour along dim>
+            pluto_gpu_halo_unpack (h, stage, dim, recv_lo, recv_hi)
+            pluto_gpu_boundary_dim (h, stage, dim)     physical sides of dim
+         pluto_gpu_stage (h, stage, dt)
+       pluto_gpu_step_end (h, &info)     then max-reduce info over the ranks
+   Buffers are DEVICE pointers of pluto_gpu_halo_doubles(h, dim) doubles;
+   a NULL buffer skips that side.  recv_lo is what the low neighbour packed
+   as its send_hi, and vice versa.  All work is enqueued on
+   pluto_gpu_stream(h).  The sequential x1 -> x2 -> x3 order fills edges and
+   corners exactly as the reference's AL_Exchange_dim loop does
+   (Src/Parallel/al_exchange_dim.c:58-88, al_decompose.c:218-229). */
+long long pluto_gpu_halo_doubles (const PlutoGpu *h, int dim);
+int pluto_gpu_halo_pack    (PlutoGpu *h, int stage, int dim, double *send_lo, double *send_hi);
+int pluto_gpu_halo_unpack  (PlutoGpu *h, int stage, int dim, const double *recv_lo, const double *recv_hi);
+int pluto_gpu_boundary_dim (PlutoGpu *h, int stage, int dim);
+int pluto_gpu_step_begin   (PlutoGpu *h);
+int pluto_gpu_stage        (PlutoGpu *h, int stage, double dt);
+int pluto_gpu_step_end     (PlutoGpu *h, PlutoGpuStepInfo *info);
+
+/* ---- introspection (tests, bench, profiling) -------------------------- */
+void     *pluto_gpu_stream        (PlutoGpu *h);   /* cudaStream_t of all launches */
+long long pluto_gpu_launch_count  (const PlutoGpu *h);  /* kernels launched so far */
+long long pluto_gpu_device_bytes  (const PlutoGpu *h);
+/* raw DEVICE pointer + padded shape of an internal field, for debugging:
+   names rho vx1 vx2 vx3 bx1 bx2 bx3 prs bx1s bx2s bx3s.  Element (k,j,i),
+   valid from -1, lives at ((k+off[2])*shape[1] + (j+off[1]))*shape[0] + (i+off[0]). */
+int pluto_gpu_field (PlutoGpu *h, const char *name, double **dev_ptr,
+                     long long shape[3], int off[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,92 @@
+"""ctypes binding of include/pluto_gpu.h (the C ABI is the drop-in boundary)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libpluto_gpu.so")
+
+RECON = {"plm": 0, "linear": 0, "ppm": 1, "parabolic": 1}
+SOLVER = {"hlld": 0, "hll": 1, "roe": 2}
+BC = {"periodic": 0, "outflow": 1, "reflective": 2, "shared": 3}
+ARITH = {"exact": 0, "fast": 1}
+
+# every symbol include/pluto_gpu.h declares (checked by tests/test_cabi.py)
+SYMBOLS = [
+    "pluto_gpu_create", "pluto_gpu_destroy", "pluto_gpu_last_error", "pluto_gpu_nghost",
+    "pluto_gpu_upload_interior", "pluto_gpu_download_interior", "pluto_gpu_upload_data",
+    "pluto_gpu_download_data", "pluto_gpu_advance", "pluto_gpu_advance_data",
+    "pluto_gpu_boundary", "pluto_gpu_next_dt", "pluto_gpu_halo_doubles", "pluto_gpu_halo_pack",
+    "pluto_gpu_halo_unpack", "pluto_gpu_boundary_dim", "pluto_gpu_step_begin", "pluto_gpu_stage",
+    "pluto_gpu_step_end", "pluto_gpu_stream", "pluto_gpu_launch_count", "pluto_gpu_device_bytes",
+    "pluto_gpu_field",
+]
+
+
+class PlutoGpuConfig(C.Structure):
+    _fields_ = [("dims", C.c_int), ("n", C.c_int * 3), ("recon", C.c_int), ("solver", C.c_int),
+                ("rk_order", C.c_int), ("bc", C.c_int * 6), ("arith", C.c_int), ("device", C.c_int),
+                ("gamma", C.c_double), ("dx", C.c_double * 3), ("small_dn", C.c_double),
+                ("small_pr", C.c_double)]
+
+
+class PlutoGpuStepInfo(C.Structure):
+    _fields_ = [("inv_dt_hyp", C.c_double), ("max_mach", C.c_double),
+                ("floor_events", C.c_int), ("nan_events", C.c_int)]
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Load libpluto_gpu.so and declare the prototypes.  Fails loudly."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C pluto_b200/csrc).  pluto_b200 has no CPU fallback.")
+    L = C.CDLL(p)
+    dp = C.POINTER(C.c_double)
+    vp = C.c_void_p
+    L.pluto_gpu_create.argtypes = [C.POINTER(PlutoGpuConfig), C.POINTER(vp)]
+    L.pluto_gpu_create.restype = C.c_int
+    L.pluto_gpu_destroy.argtypes = [vp]
+    L.pluto_gpu_destroy.restype = None
+    L.pluto_gpu_last_error.restype = C.c_char_p
+    L.pluto_gpu_nghost.argtypes = [vp]
+    for nm in ("pluto_gpu_upload_interior", "pluto_gpu_download_interior",
+               "pluto_gpu_upload_data", "pluto_gpu_download_data"):
+        getattr(L, nm).argtypes = [vp, vp, vp, vp, vp]
+        getattr(L, nm).restype = C.c_int
+    L.pluto_gpu_advance.argtypes = [vp, C.c_double, C.POINTER(PlutoGpuStepInfo)]
+    L.pluto_gpu_advance_data.argtypes = [vp, C.c_double, vp, vp, vp, vp, C.POINTER(PlutoGpuStepInfo)]
+    L.pluto_gpu_boundary.argtypes = [vp]
+    L.pluto_gpu_next_dt.argtypes = [C.c_double] * 4
+    L.pluto_gpu_next_dt.restype = C.c_double
+    L.pluto_gpu_halo_doubles.argtypes = [vp, C.c_int]
+    L.pluto_gpu_halo_doubles.restype = C.c_longlong
+    L.pluto_gpu_halo_pack.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.pluto_gpu_halo_unpack.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.pluto_gpu_boundary_dim.argtypes = [vp, C.c_int, C.c_int]
+    L.pluto_gpu_step_begin.argtypes = [vp]
+    L.pluto_gpu_stage.argtypes = [vp, C.c_int, C.c_double]
+    L.pluto_gpu_step_end.argtypes = [vp, C.POINTER(PlutoGpuStepInfo)]
+    L.pluto_gpu_stream.argtypes = [vp]
+    L.pluto_gpu_stream.restype = vp
+    L.pluto_gpu_launch_count.argtypes = [vp]
+    L.pluto_gpu_launch_count.restype = C.c_longlong
+    L.pluto_gpu_device_bytes.argtypes = [vp]
+    L.pluto_gpu_device_bytes.restype = C.c_longlong
+    L.pluto_gpu_field.argtypes = [vp, C.c_char_p, C.POINTER(dp), C.POINTER(C.c_longlong * 3),
+                                  C.POINTER(C.c_int * 3)]
+    if path is None:
+        _lib = L
+    return L
+
+
+def last_error(L) -> str:
+    return (L.pluto_gpu_last_error() or b"").decode()

@@ -1,0 +1,380 @@
+// ct_kernels.cu -- constrained transport, stage completion, boundary fills and
+// halo pack/unpack.  Compiled once per arithmetic namespace (PG_NS).
+//
+//   ct_emf_kernel     CT_ComputeCenterEMF + CT_EMF_ArithmeticAverage +
+//                     CT_EMF_IntegrateToCorner + x0.25 in GATHER form: one
+//                     thread per edge, no scatter-add, no cell-centred EMF
+//                     array (reference Src/MHD/CT/ct_emf.c:210-254, 348-388,
+//                     ct_emf_average.c:13-49, 52-164).  The additions are
+//                     issued in the order the reference's (k,j,i) scatter
+//                     loop applies them to each edge, so the result is
+//                     bit-identical.
+//   ct_update_kernel  CT_Update (ct_update.c:79-218) fused with the RK stage
+//                     average of the staggered field (rk_step.c:172-174,
+//                     231-233).
+//   final_kernel      CT_AverageMagneticField (ct_field_average.c:58-124),
+//                     RK stage average of U (rk_step.c:168-171, 226-229),
+//                     ConsToPrim (mappers.c:88-254) and the floor/NaN counts.
+//   bc_kernel / bc_fill_kernel
+//                     Boundary (boundary.c:137-293), FillMagneticField
+//                     (ct_fill_mag_field.c:38-179), CT_AverageNormalMagField
+//                     (ct_field_average.c:134-272).
+#include "kernels_common.cuh"
+#include "mhd_device.cuh"
+
+namespace PG_NS {
+
+// ---------------------------------------------------------------------------
+//  edge EMFs
+// ---------------------------------------------------------------------------
+struct CellE { double e1, e2, e3; };
+
+template <int NC>
+__device__ __forceinline__ double cell_e3 (const CtArgs &a, long long id)
+{
+  return a.V[VX2][id]*a.V[BX1][id] - a.V[VX1][id]*a.V[BX2][id];
+}
+__device__ __forceinline__ double cell_e1 (const CtArgs &a, long long id)
+{
+  return a.V[VX3][id]*a.V[BX2][id] - a.V[VX2][id]*a.V[BX3][id];
+}
+__device__ __forceinline__ double cell_e2 (const CtArgs &a, long long id)
+{
+  return a.V[VX1][id]*a.V[BX3][id] - a.V[VX3][id]*a.V[BX1][id];
+}
+
+// upwind selection of a (face - centre) difference pair: s > 0 -> first,
+// s < 0 -> second, s == 0 -> mean (ct_emf_average.c:110-162)
+__device__ __forceinline__ double upw (signed char s, double d0, double d1)
+{
+  if (s == 0) return 0.5*(d0 + d1);
+  return s > 0 ? d0 : d1;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128)
+ct_emf_kernel (const __grid_constant__ CtArgs a)
+{
+  const Geom &g = a.g;
+  // edges (k,j,i) with i in [IBEG-1,IEND], j in [JBEG-1,JEND], k in [KBEG-1,KEND]
+  const int ni = g.n[0] + 1, nj = g.n[1] + 1, nk = (NC == 3 ? g.n[2] + 1 : 1);
+  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long long)ni*nj*nk) return;
+  const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
+  const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
+  const long long id = gidx (g, k, j, i);
+  const long long sx = 1, sy = g.S1, sz = g.S12;
+
+  {   // ---- ez at (i+1/2, j+1/2) ----
+    const double ezi0 = a.ezi[id], ezi1 = a.ezi[id + sy];
+    const double ezj0 = a.ezj[id], ezj1 = a.ezj[id + sx];
+    const double E00 = cell_e3<NC>(a, id),      E10 = cell_e3<NC>(a, id + sx);
+    const double E01 = cell_e3<NC>(a, id + sy), E11 = cell_e3<NC>(a, id + sx + sy);
+    double e = ezi0 + ezi1 + ezj0 + ezj1;
+    e += upw (a.svx[id],      ezj0 - E00, ezj1 - E10);          // DEZ_DYP(j, i | i+1)
+    e += upw (a.svy[id],      ezi0 - E00, ezi1 - E01);          // DEZ_DXP(j | j+1, i)
+    e -= upw (a.svy[id + sx], E10 - ezi0, E11 - ezi1);          // DEZ_DXM(j | j+1, i+1)
+    e -= upw (a.svx[id + sy], E01 - ezj0, E11 - ezj1);          // DEZ_DYM(j+1, i | i+1)
+    a.ez[id] = e*0.25;
+  }
+  if (NC == 3){
+    {   // ---- ex at (j+1/2, k+1/2) ----
+      const double exk0 = a.exk[id], exk1 = a.exk[id + sy];
+      const double exj0 = a.exj[id], exj1 = a.exj[id + sz];
+      const double E00 = cell_e1 (a, id),      E10 = cell_e1 (a, id + sy);
+      const double E01 = cell_e1 (a, id + sz), E11 = cell_e1 (a, id + sy + sz);
+      double e = exk0 + exk1 + exj0 + exj1;
+      e += upw (a.svy[id],      exk0 - E00, exk1 - E10);        // DEX_DZP(k, j | j+1)
+      e += upw (a.svz[id],      exj0 - E00, exj1 - E01);        // DEX_DYP(k | k+1, j)
+      e -= upw (a.svz[id + sy], E10 - exj0, E11 - exj1);        // DEX_DYM(k | k+1, j+1)
+      e -= upw (a.svy[id + sz], E01 - exk0, E11 - exk1);        // DEX_DZM(k+1, j | j+1)
+      a.ex[id] = e*0.25;
+    }
+    {   // ---- ey at (i+1/2, k+1/2) ----
+      const double eyi0 = a.eyi[id], eyi1 = a.eyi[id + sz];
+      const double eyk0 = a.eyk[id], eyk1 = a.eyk[id + sx];
+      const double E00 = cell_e2 (a, id),      E10 = cell_e2 (a, id + sx);
+      const double E01 = cell_e2 (a, id + sz), E11 = cell_e2 (a, id + sx + sz);
+      double e = eyi0 + eyi1 + eyk0 + eyk1;
+      e += upw (a.svx[id],      eyk0 - E00, eyk1 - E10);        // DEY_DZP(k, i | i+1)
+      e += upw (a.svz[id],      eyi0 - E00, eyi1 - E01);        // DEY_DXP(k | k+1, i)
+      e -= upw (a.svz[id + sx], E10 - eyi0, E11 - eyi1);        // DEY_DXM(k | k+1, i+1)
+      e -= upw (a.svx[id + sz], E01 - eyk0, E11 - eyk1);        // DEY_DZM(k+1, i | i+1)
+      a.ey[id] = e*0.25;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  staggered update + RK average
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double stage_mix (int combine, double w0, double wc, double b0, double b)
+{
+  if (combine == 1) return w0*b0 + wc*b;
+  if (combine == 2) return (b0 + 2.0*b)/3.0;
+  return b;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128)
+ct_update_kernel (const __grid_constant__ CtArgs a)
+{
+  const Geom &g = a.g;
+  const int ni = g.n[0] + 1, nj = g.n[1] + 1, nk = (NC == 3 ? g.n[2] + 1 : 1);
+  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long long)ni*nj*nk) return;
+  const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
+  const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
+  const long long id = gidx (g, k, j, i);
+  const long long sy = g.S1, sz = g.S12;
+  const bool in_i = i >= g.beg[0], in_j = j >= g.beg[1], in_k = (NC == 3 ? k >= g.beg[2] : true);
+
+  if (in_j && in_k){        // Bx1 at (i+1/2, j, k), i in [IBEG-1, IEND]
+    double rhs;
+    if (NC == 3) rhs = 0.0 - a.dtdx[1]*(a.ez[id] - a.ez[id - sy]) + a.dtdx[2]*(a.ey[id] - a.ey[id - sz]);
+    else         rhs = 0.0 - a.dtdx[1]*(a.ez[id] - a.ez[id - sy]);
+    double b = a.Bs_in[0][id] + rhs;
+    if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[0][id], b);
+    a.Bs_out[0][id] = b;
+  }
+  if (in_i && in_k){        // Bx2 at (i, j+1/2, k)
+    double rhs;
+    if (NC == 3) rhs = a.dtdx[0]*(a.ez[id] - a.ez[id - 1]) - a.dtdx[2]*(a.ex[id] - a.ex[id - sz]);
+    else         rhs = a.dtdx[0]*(a.ez[id] - a.ez[id - 1]);
+    double b = a.Bs_in[1][id] + rhs;
+    if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[1][id], b);
+    a.Bs_out[1][id] = b;
+  }
+  if (NC == 3 && in_i && in_j){   // Bx3 at (i, j, k+1/2)
+    double rhs = - a.dtdx[0]*(a.ey[id] - a.ey[id - 1]) + a.dtdx[1]*(a.ex[id] - a.ex[id - sy]);
+    double b = a.Bs_in[2][id] + rhs;
+    if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[2][id], b);
+    a.Bs_out[2][id] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  stage completion: face -> centre average, RK average, cons -> prim
+// ---------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128)
+final_kernel (const __grid_constant__ FinalArgs a)
+{
+  const Geom &g = a.g;
+  Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr;
+  const int ni = g.n[0], nj = g.n[1], nk = (NC == 3 ? g.n[2] : 1);
+  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  int fl = 0, bad = 0;
+  if (t < (long long)ni*nj*nk){
+    const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
+    const int i = g.beg[0] + ti, j = g.beg[1] + tj, k = (NC == 3 ? g.beg[2] + tk : 0);
+    const long long id = gidx (g, k, j, i);
+    double u[NV], v[NV];
+    u[RHO] = a.U[RHO][id]; u[MX1] = a.U[MX1][id]; u[MX2] = a.U[MX2][id];
+    if (NC == 3) u[MX3] = a.U[MX3][id];
+    u[ENG] = a.U[ENG][id];
+    if (a.combine){
+      double v0[NV], u0[NV];
+      PG_FOR_NV(nv) v0[nv] = a.V0[nv][id];
+      prim_to_cons<NC>(ph, v0, u0);
+      if (a.combine == 1){
+        u[RHO] = a.w0*u0[RHO] + a.wc*u[RHO];
+        u[MX1] = a.w0*u0[MX1] + a.wc*u[MX1];
+        u[MX2] = a.w0*u0[MX2] + a.wc*u[MX2];
+        if (NC == 3) u[MX3] = a.w0*u0[MX3] + a.wc*u[MX3];
+        u[ENG] = a.w0*u0[ENG] + a.wc*u[ENG];
+      }else{
+        const double one_third = 1.0/3.0;
+        u[RHO] = one_third*(u0[RHO] + 2.0*u[RHO]);
+        u[MX1] = one_third*(u0[MX1] + 2.0*u[MX1]);
+        u[MX2] = one_third*(u0[MX2] + 2.0*u[MX2]);
+        if (NC == 3) u[MX3] = one_third*(u0[MX3] + 2.0*u[MX3]);
+        u[ENG] = one_third*(u0[ENG] + 2.0*u[ENG]);
+      }
+    }
+    u[BX1] = 0.5*(a.Bs[0][id] + a.Bs[0][id - 1]);
+    u[BX2] = 0.5*(a.Bs[1][id] + a.Bs[1][id - g.S1]);
+    if (NC == 3) u[BX3] = 0.5*(a.Bs[2][id] + a.Bs[2][id - g.S12]);
+    fl = cons_to_prim<NC>(ph, u, v);
+    PG_FOR_NV(nv){
+      a.Vout[nv][id] = v[nv];
+      if (!(fabs(v[nv]) <= 1.7976931348623157e308)) bad = 1;
+    }
+  }
+  // block-level counts
+  unsigned mfl = __ballot_sync (0xffffffffu, fl), mbad = __ballot_sync (0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0){
+    if (mfl)  atomicAdd (a.red + RED_FLOOR, (unsigned long long)__popc (mfl));
+    if (mbad) atomicAdd (a.red + RED_NAN,   (unsigned long long)__popc (mbad));
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  boundary fills
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bc_kernel (const __grid_constant__ BcArgs a)
+{
+  const Geom &g = a.g;
+  const BcField &f = a.f[blockIdx.y];
+  const int ni = f.hi[0] - f.lo[0] + 1, nj = f.hi[1] - f.lo[1] + 1, nk = f.hi[2] - f.lo[2] + 1;
+  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long long)ni*nj*nk) return;
+  const int i = f.lo[0] + (int)(t % ni), j = f.lo[1] + (int)((t/ni) % nj), k = f.lo[2] + (int)(t/((long long)ni*nj));
+  int c[3] = {i, j, k};
+  const int d = a.side >> 1, hi_side = a.side & 1;
+  double s = 1.0;
+  if (a.type == 0){                 // periodic (boundary.c:480-518)
+    c[d] += hi_side ? -g.n[d] : g.n[d];
+  }else if (a.type == 1){           // outflow  (boundary.c:439-477)
+    c[d] = hi_side ? g.end[d] : g.beg[d];
+  }else{                            // reflective (boundary.c:521-564)
+    c[d] = hi_side ? 2*g.end[d] - c[d] + 1 : 2*g.beg[d] - c[d] - 1;
+    s = (double)f.sign;
+  }
+  const double x = f.q[gidx (g, c[2], c[1], c[0])];
+  f.q[gidx (g, k, j, i)] = (a.type == 2 ? s*x : x);
+}
+
+// normal staggered component in the ghost zones from div B = 0, marching
+// outwards (sequential along the normal), then the cell-centred normal
+// component as the face average.  One thread per transverse position.
+__global__ void __launch_bounds__(128)
+bc_fill_kernel (const __grid_constant__ BcFillArgs a)
+{
+  const Geom &g = a.g;
+  const int d = a.side >> 1, hi_side = a.side & 1;
+  const int d1 = (d == 0 ? 1 : 0), d2 = (d == 2 ? 1 : 2);     // transverse dims, d1 faster
+  const int n1 = g.T[d1], n2 = g.T[d2];
+  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long long)n1*n2) return;
+  int c[3];
+  c[d1] = (int)(t % n1); c[d2] = (int)(t / n1);
+  const double dx1 = g.dx[0], dx2 = g.dx[1], dx3 = g.dx[2];
+  double A[3];
+  if (g.dims == 3){ A[0] = 1.0*dx2*dx3; A[1] = dx1*1.0*dx3; A[2] = dx1*dx2*1.0; }
+  else            { A[0] = 1.0*dx2;     A[1] = dx1*1.0;     A[2] = 0.0; }
+  const long long st[3] = {1, g.S1, g.S12};
+  const int nbeg = hi_side ? g.end[d] + 1 : g.beg[d] - 1;
+  const int nend = hi_side ? g.T[d] - 1 : 0;
+  const int dn = hi_side ? 1 : -1;
+  for (int n = nbeg; dn*n <= dn*nend; n += dn){
+    c[d] = n;
+    const long long id = gidx (g, c[2], c[1], c[0]);
+    double dB[3] = {0.0, 0.0, 0.0};
+    double bp[3] = {0.0, 0.0, 0.0}, bm[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < g.dims; q++){
+      bp[q] = a.Bs[q][id]; bm[q] = a.Bs[q][id - st[q]];
+      dB[q] = (A[q]*bp[q] - A[q]*bm[q]);
+    }
+    // sum of the two transverse flux differences in the reference's order
+    // (ct_fill_mag_field.c:84-140): x: dBy + dBz, y: dBx + dBz, z: dBx + dBy
+    const int qa = (d == 0 ? 1 : 0), qb = (d == 2 ? 1 : 2);
+    // low side: (A*b+ + dB_a + dB_b)/A, left-associated; high side: (A*b- - (dB_a + dB_b))/A
+    if (!hi_side) a.Bs[d][id - st[d]] = (A[d]*bp[d] + dB[qa] + dB[qb])/A[d];
+    else          a.Bs[d][id]         = (A[d]*bm[d] - (dB[qa] + dB[qb]))/A[d];
+  }
+  if (a.Bc){
+    const int lo = hi_side ? g.end[d] + 1 : 0, hi = hi_side ? g.T[d] - 1 : g.beg[d] - 1;
+    for (int n = lo; n <= hi; n++){
+      c[d] = n;
+      const long long id = gidx (g, c[2], c[1], c[0]);
+      a.Bc[id] = 0.5*(a.Bs[d][id] + a.Bs[d][id - st[d]]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  halo pack / unpack (contiguous buffers for the inter-GPU exchange)
+// ---------------------------------------------------------------------------
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+halo_kernel (const __grid_constant__ HaloArgs a)
+{
+  const Geom &g = a.g;
+  const int f = blockIdx.y;
+  const int ni = a.hi[f][0] - a.lo[f][0] + 1, nj = a.hi[f][1] - a.lo[f][1] + 1, nk = a.hi[f][2] - a.lo[f][2] + 1;
+  const long long cnt = (long long)ni*nj*nk;
+  for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < cnt; t += (long long)gridDim.x*blockDim.x){
+    const int i = a.lo[f][0] + (int)(t % ni), j = a.lo[f][1] + (int)((t/ni) % nj), k = a.lo[f][2] + (int)(t/((long long)ni*nj));
+    const long long id = gidx (g, k, j, i);
+    if (PACK) a.buf[a.offset[f] + t] = a.q[f][id];
+    else      a.q[f][id] = a.buf[a.offset[f] + t];
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  launchers
+// ---------------------------------------------------------------------------
+static inline unsigned nblocks (long long n, int tpb) { return (unsigned)((n + tpb - 1)/tpb); }
+
+int launch_ct_emf (const CtArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const long long n = (long long)(g.n[0] + 1)*(g.n[1] + 1)*(g.dims == 3 ? g.n[2] + 1 : 1);
+  if (g.dims == 3) ct_emf_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
+  else             ct_emf_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+int launch_ct_update (const CtArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const long long n = (long long)(g.n[0] + 1)*(g.n[1] + 1)*(g.dims == 3 ? g.n[2] + 1 : 1);
+  if (g.dims == 3) ct_update_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
+  else             ct_update_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+int launch_final (const FinalArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const long long n = (long long)g.n[0]*g.n[1]*(g.dims == 3 ? g.n[2] : 1);
+  if (g.dims == 3) final_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
+  else             final_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+int launch_bc (const BcArgs &a, cudaStream_t s)
+{
+  long long nmax = 0;
+  for (int f = 0; f < a.nf; f++){
+    long long n = 1;
+    for (int d = 0; d < 3; d++) n *= (a.f[f].hi[d] - a.f[f].lo[d] + 1);
+    if (n > nmax) nmax = n;
+  }
+  if (nmax <= 0 || a.nf <= 0) return 0;
+  dim3 grid (nblocks (nmax, 128), a.nf);
+  bc_kernel<<<grid, 128, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+int launch_bc_fill (const BcFillArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const int d = a.side >> 1;
+  const int d1 = (d == 0 ? 1 : 0), d2 = (d == 2 ? 1 : 2);
+  const long long n = (long long)g.T[d1]*g.T[d2];
+  bc_fill_kernel<<<nblocks (n, 128), 128, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+static int launch_halo (const HaloArgs &a, cudaStream_t s, bool pack)
+{
+  long long nmax = 0;
+  for (int f = 0; f < a.nf; f++){
+    long long n = 1;
+    for (int d = 0; d < 3; d++) n *= (a.hi[f][d] - a.lo[f][d] + 1);
+    if (n > nmax) nmax = n;
+  }
+  if (nmax <= 0 || a.nf <= 0) return 0;
+  unsigned nb = nblocks (nmax, 256); if (nb > 4096) nb = 4096;
+  dim3 grid (nb, a.nf);
+  if (pack) halo_kernel<true><<<grid, 256, 0, s>>>(a);
+  else      halo_kernel<false><<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+int launch_halo_pack   (const HaloArgs &a, cudaStream_t s) { return launch_halo (a, s, true); }
+int launch_halo_unpack (const HaloArgs &a, cudaStream_t s) { return launch_halo (a, s, false); }
+
+} // namespace PG_NS

@@ -1,0 +1,122 @@
+// kernels_common.cuh -- geometry of one block in HBM, kernel argument structs
+// and the launch interface between the C-ABI host (pluto_gpu.cu) and the
+// kernel translation units.
+//
+// HBM layout.  Every scalar field (8 primitives, 5 conservative
+// accumulators, 3 staggered components, 6 face EMFs, 3 edge EMFs, C_dt) is
+// a separate array with the SAME padded shape: logical index -1 .. T in
+// every active dimension,
+//       idx(k,j,i) = (k + off3)*S12 + (j + off2)*S1 + (i + off1),
+// S1 = T1 + 2, S12 = S1*(T2 + 2); off = 1 in active dimensions (0 for x3 in
+// 2-D).  i is fastest, so warps always run along x1 whatever the sweep
+// direction (coalesced 256-byte rows).  Staggered component d at index i
+// is the face i+1/2 in direction d (valid from -1), the reference's
+// convention (Src/initialize.c:448-453).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct Geom {
+  int dims, ng;
+  int n[3], T[3], beg[3], end[3], off[3];
+  long long S1, S12, tot;
+  double dx[3];
+};
+
+__host__ __device__ __forceinline__ long long gidx (const Geom &g, int k, int j, int i)
+{
+  return (long long)(k + g.off[2])*g.S12 + (long long)(j + g.off[1])*g.S1 + (i + g.off[0]);
+}
+
+struct PhysPar { double gamma, gmm1, small_dn, small_pr; };
+
+// reduction slots (device, unsigned long long each)
+enum { RED_CDT = 0, RED_MACH = 1, RED_FLOOR = 2, RED_NAN = 3, RED_ROEFAIL = 4, RED_N = 8 };
+
+struct SweepArgs {
+  const double *V[8];        // primitives of the current stage (ghosts filled)
+  const double *Bn;          // staggered component normal to the sweep
+  double       *U[8];        // conservative accumulators (B slots unused)
+  double       *e1, *e2;     // face EMFs of this direction (see sweep_kernels.cuh)
+  signed char  *sv;          // sign of the mass flux (UCT_CONTACT upwinding)
+  double       *cdt;         // per-zone sum of directional inverse time steps
+  unsigned long long *red;   // reduction slots
+  Geom    g;
+  PhysPar ph;
+  double  dtdx, inv_dl;
+  int     stage1;            // accumulate C_dt / CFL (g_intStage == 1)
+  int     last_dir;          // this sweep completes C_dt -> reduce instead of store
+  int     chunk_len;         // marching kernels: zones per thread along the sweep
+  int     nchunk;
+};
+
+struct CtArgs {
+  const double *V[8];                        // current-stage primitives (cell-centre EMF)
+  const double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
+  const signed char *svx, *svy, *svz;
+  double *ex, *ey, *ez;                      // edge EMFs
+  const double *Bs_in[3];                    // staggered field of the current stage
+  const double *Bs0[3];                      // staggered field at t^n (stages >= 2)
+  double *Bs_out[3];
+  Geom   g;
+  double dtdx[3];
+  double w0, wc;                             // stage weights
+  int    combine;                            // 0: none, 1: w0*B0 + wc*B, 2: (B0 + 2 B)/3
+};
+
+struct FinalArgs {
+  const double *U[8];
+  const double *Bs[3];
+  const double *V0[8];                       // primitives at t^n (stages >= 2)
+  double *Vout[8];
+  unsigned long long *red;
+  Geom    g;
+  PhysPar ph;
+  double  w0, wc;
+  int     combine;                           // 0 none, 1 w0*U0 + wc*U, 2 (U0 + 2U)/3
+};
+
+// one boundary fill: up to 11 fields with their own boxes
+struct BcField {
+  double *q;
+  int lo[3], hi[3];          // inclusive destination box
+  int sign;                  // reflective: +1 / -1
+};
+struct BcArgs {
+  BcField f[11];
+  int nf;
+  int side, type;            // side 0..5, type PLUTO_GPU_BC_*
+  Geom g;
+};
+struct BcFillArgs {            // FillMagneticField + CT_AverageNormalMagField
+  double *Bs[3];
+  double *Bc;                // cell-centred normal component (NULL: no averaging)
+  int side;
+  Geom g;
+};
+
+struct HaloArgs {
+  double *q[11];
+  int lo[11][3], hi[11][3];  // inclusive box per field
+  long long offset[11];      // start of each field inside the buffer
+  int nf;
+  double *buf;
+  Geom g;
+};
+
+// ---- launch interface, one set per arithmetic namespace ----------------------
+#define PG_DECLARE_LAUNCHERS(NS)                                                         \
+namespace NS {                                                                           \
+  int launch_sweep_hlld (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
+  int launch_sweep_hll  (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
+  int launch_sweep_roe  (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
+  int launch_ct_emf     (const CtArgs &a, cudaStream_t s);                               \
+  int launch_ct_update  (const CtArgs &a, cudaStream_t s);                               \
+  int launch_final      (const FinalArgs &a, cudaStream_t s);                            \
+  int launch_bc         (const BcArgs &a, cudaStream_t s);                               \
+  int launch_bc_fill    (const BcFillArgs &a, cudaStream_t s);                           \
+  int launch_halo_pack  (const HaloArgs &a, cudaStream_t s);                             \
+  int launch_halo_unpack(const HaloArgs &a, cudaStream_t s);                             \
+}
+PG_DECLARE_LAUNCHERS(pg_exact)
+PG_DECLARE_LAUNCHERS(pg_fast)

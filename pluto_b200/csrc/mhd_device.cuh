@@ -1,0 +1,723 @@
+// mhd_device.cuh -- per-interface / per-zone device arithmetic of the ideal-MHD
+// Godunov step: limiters, PLM / PPM interface states, prim<->cons mappers,
+// flux, wave speeds, HLLD / HLL / Roe.  Everything is FP64 and lives in
+// registers: the `double q[8]` arrays are indexed by compile-time constants
+// only (DIR and NC are template parameters, loops are fully unrolled).
+//
+// The operation order follows the reference so that the EXACT build
+// (-fmad=false) reproduces its IEEE results bit for bit:
+//   limiters        Src/States/plm_coeffs.h:72-123, Src/macros.h:140-151
+//   PLM             Src/States/plm_states.c:134-275 (uniform Cartesian path)
+//   PPM             Src/States/ppm_states.c:146-207, ppm_coeffs.c:500-547
+//   mappers         Src/MHD/mappers.c:25-86, 88-254
+//   flux            Src/MHD/fluxes.c:159-215
+//   fast speed      Src/MHD/eigenv.c:35-104
+//   Davis speeds    Src/MHD/hll_speed.c:76-107
+//   HLLD            Src/MHD/hlld.c:98-427
+//   HLL             Src/MHD/hll.c:101-135
+//   Roe             Src/MHD/roe.c:98-700
+#pragma once
+#include <math.h>
+
+namespace PG_NS {
+
+enum { RHO = 0, VX1 = 1, VX2 = 2, VX3 = 3, BX1 = 4, BX2 = 5, BX3 = 6, PRS = 7, NV = 8 };
+enum { MX1 = VX1, MX2 = VX2, MX3 = VX3, ENG = PRS };
+enum { RECON_PLM = 0, RECON_PPM = 1 };
+enum { SOLVER_HLLD = 0, SOLVER_HLL = 1, SOLVER_ROE = 2 };
+
+struct Phys {
+  double gamma, gmm1, small_dn, small_pr;
+};
+
+// direction bookkeeping (reference Src/set_indexes.c:49-123)
+template <int DIR> struct Dirs;
+template <> struct Dirs<0> { enum { vn = VX1, vt = VX2, vb = VX3, bn = BX1, bt = BX2, bb = BX3 }; };
+template <> struct Dirs<1> { enum { vn = VX2, vt = VX1, vb = VX3, bn = BX2, bt = BX1, bb = BX3 }; };
+template <> struct Dirs<2> { enum { vn = VX3, vt = VX1, vb = VX2, bn = BX3, bt = BX1, bb = BX2 }; };
+
+// a variable slot is carried when NC == 3 or it is not a third component
+template <int NC> __device__ __forceinline__ constexpr bool live (int nv)
+{ return NC == 3 || (nv != VX3 && nv != BX3); }
+
+#define PG_UNROLL _Pragma("unroll")
+#define PG_FOR_NV(nv) PG_UNROLL for (int nv = 0; nv < NV; nv++) if (live<NC>(nv))
+
+__device__ __forceinline__ double maxv (double a, double b) { return a >= b ? a : b; }
+__device__ __forceinline__ double minv (double a, double b) { return a <= b ? a : b; }
+__device__ __forceinline__ double abs_min (double a, double b) { return fabs(a) < fabs(b) ? a : b; }
+__device__ __forceinline__ double minmod (double a, double b)
+{ return a*b > 0.0 ? (fabs(a) < fabs(b) ? a : b) : 0.0; }
+
+// ---------------------------------------------------------------------------
+//  limited slope, LIMITER DEFAULT: MC on density, minmod on pressure, van Leer
+//  on velocity and field (plm_states.c:192-227)
+// ---------------------------------------------------------------------------
+template <int NV_ID> __device__ __forceinline__ double plm_slope (double dvp, double dvm)
+{
+  if (NV_ID == RHO){
+    if (dvp*dvm > 0.0){
+      double qc = 0.5*(dvm + dvp), scrh = 2.0*abs_min(dvp, dvm);
+      return abs_min(qc, scrh);
+    }
+    return 0.0;
+  }else if (NV_ID == PRS){
+    return dvp*dvm > 0.0 ? abs_min(dvp, dvm) : 0.0;
+  }else{
+    return dvp*dvm > 0.0 ? 2.0*dvp*dvm/(dvp + dvm) : 0.0;
+  }
+}
+
+// vp = v + dvl/2, vm = v - dvl/2 for one zone from its two one-sided differences
+template <int NC>
+__device__ __forceinline__ void plm_zone (const double *v, const double *dvm, const double *dvp,
+                                          double *vp, double *vm)
+{
+  double dvl[NV];
+  dvl[RHO] = plm_slope<RHO>(dvp[RHO], dvm[RHO]);
+  dvl[VX1] = plm_slope<VX1>(dvp[VX1], dvm[VX1]);
+  dvl[VX2] = plm_slope<VX1>(dvp[VX2], dvm[VX2]);
+  if (NC == 3) dvl[VX3] = plm_slope<VX1>(dvp[VX3], dvm[VX3]);
+  dvl[BX1] = plm_slope<VX1>(dvp[BX1], dvm[BX1]);
+  dvl[BX2] = plm_slope<VX1>(dvp[BX2], dvm[BX2]);
+  if (NC == 3) dvl[BX3] = plm_slope<VX1>(dvp[BX3], dvm[BX3]);
+  dvl[PRS] = plm_slope<PRS>(dvp[PRS], dvm[PRS]);
+  PG_FOR_NV(nv){
+    vp[nv] = v[nv] + dvl[nv]*0.5;
+    vm[nv] = v[nv] - dvl[nv]*0.5;
+  }
+}
+
+// PPM 4th-order interface value at i+1/2, bounded (ppm_states.c:146-157):
+// W = v0 + MINMOD(P - v0, v1 - v0), P = -1/12 vm1 + 7/12 v0 + 7/12 v1 - 1/12 v2
+template <int NC>
+__device__ __forceinline__ void ppm_interface (const double *vm1, const double *v0,
+                                               const double *v1, const double *v2, double *W)
+{
+  const double wm1 = -1.0/12.0, w0 = 7.0/12.0, w1 = 7.0/12.0, w2 = -1.0/12.0;
+  PG_FOR_NV(nv){
+    double p = wm1*vm1[nv] + w0*v0[nv] + w1*v1[nv] + w2*v2[nv];
+    double dv = v1[nv] - v0[nv];
+    double dvp = p - v0[nv];
+    W[nv] = v0[nv] + minmod(dvp, dv);
+  }
+}
+
+// parabolic limiter on one zone (ppm_states.c:185-207, cm = cp = 2 on a
+// uniform Cartesian grid: (hm+1)/(hp-1) with hp = hm = 3)
+template <int NC>
+__device__ __forceinline__ void ppm_zone (const double *v, const double *Wm, const double *Wp,
+                                          double *vp, double *vm)
+{
+  const double hp = 3.0, hm = 3.0;
+  const double cm = (hm + 1.0)/(hp - 1.0), cp = (hp + 1.0)/(hm - 1.0);
+  PG_FOR_NV(nv){
+    double dvp = Wp[nv] - v[nv];
+    double dvm = Wm[nv] - v[nv];
+    if (dvp*dvm >= 0.0) dvp = dvm = 0.0;
+    else{
+      if      (fabs(dvp) >= cm*fabs(dvm)) dvp = -cm*dvm;
+      else if (fabs(dvm) >= cp*fabs(dvp)) dvm = -cp*dvp;
+    }
+    vp[nv] = v[nv] + dvp;
+    vm[nv] = v[nv] + dvm;
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  mappers
+// ---------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void prim_to_cons (const Phys &ph, const double *v, double *u)
+{
+  double kinb2;
+  u[RHO] = v[RHO];
+  u[MX1] = v[RHO]*v[VX1];
+  u[MX2] = v[RHO]*v[VX2];
+  if (NC == 3) u[MX3] = v[RHO]*v[VX3];
+  u[BX1] = v[BX1]; u[BX2] = v[BX2];
+  if (NC == 3) u[BX3] = v[BX3];
+  if (NC == 3){
+    kinb2 = v[VX1]*v[VX1] + v[VX2]*v[VX2] + v[VX3]*v[VX3];
+    kinb2 = v[RHO]*kinb2 + v[BX1]*v[BX1] + v[BX2]*v[BX2] + v[BX3]*v[BX3];
+  }else{
+    kinb2 = v[VX1]*v[VX1] + v[VX2]*v[VX2];
+    kinb2 = v[RHO]*kinb2 + v[BX1]*v[BX1] + v[BX2]*v[BX2];
+  }
+  kinb2 *= 0.5;
+  u[ENG] = kinb2 + v[PRS]/ph.gmm1;
+}
+
+// returns 1 when a floor was applied; u is repaired in place as the reference does
+template <int NC>
+__device__ __forceinline__ int cons_to_prim (const Phys &ph, double *u, double *v)
+{
+  double m2, b2, tau, kinb2;
+  int fail = 0;
+  if (NC == 3){
+    m2 = u[MX1]*u[MX1] + u[MX2]*u[MX2] + u[MX3]*u[MX3];
+    b2 = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
+  }else{
+    m2 = u[MX1]*u[MX1] + u[MX2]*u[MX2];
+    b2 = u[BX1]*u[BX1] + u[BX2]*u[BX2];
+  }
+  if (u[RHO] < 0.0){ u[RHO] = ph.small_dn; fail = 1; }
+  v[RHO] = u[RHO];
+  tau = 1.0/u[RHO];
+  v[VX1] = u[MX1]*tau; v[VX2] = u[MX2]*tau;
+  if (NC == 3) v[VX3] = u[MX3]*tau;
+  v[BX1] = u[BX1]; v[BX2] = u[BX2];
+  if (NC == 3) v[BX3] = u[BX3];
+  kinb2 = 0.5*(m2*tau + b2);
+  if (u[ENG] < 0.0){ u[ENG] = ph.small_pr/ph.gmm1 + kinb2; fail = 1; }
+  v[PRS] = ph.gmm1*(u[ENG] - kinb2);
+  if (v[PRS] < 0.0){
+    v[PRS] = ph.small_pr;
+    u[ENG] = v[PRS]/ph.gmm1 + kinb2;
+    fail = 1;
+  }
+  return fail;
+}
+
+// ---------------------------------------------------------------------------
+//  flux and speeds
+// ---------------------------------------------------------------------------
+template <int DIR, int NC>
+__device__ __forceinline__ void mhd_flux (const double *v, const double *u, double *fx, double &prs)
+{
+  typedef Dirs<DIR> D;
+  double Bmag2, ptot, vB;
+  if (NC == 3){
+    Bmag2 = v[BX1]*v[BX1] + v[BX2]*v[BX2] + v[BX3]*v[BX3];
+    vB    = v[VX1]*v[BX1] + v[VX2]*v[BX2] + v[VX3]*v[BX3];
+  }else{
+    Bmag2 = v[BX1]*v[BX1] + v[BX2]*v[BX2];
+    vB    = v[VX1]*v[BX1] + v[VX2]*v[BX2];
+  }
+  ptot = v[PRS] + 0.5*Bmag2;
+  fx[RHO] = u[D::vn];
+  fx[MX1] = v[D::vn]*u[MX1] - v[D::bn]*v[BX1];
+  fx[MX2] = v[D::vn]*u[MX2] - v[D::bn]*v[BX2];
+  if (NC == 3) fx[MX3] = v[D::vn]*u[MX3] - v[D::bn]*v[BX3];
+  fx[D::bn] = 0.0;
+  fx[D::bt] = v[D::vn]*v[D::bt] - v[D::bn]*v[D::vt];
+  if (NC == 3) fx[D::bb] = v[D::vn]*v[D::bb] - v[D::bn]*v[D::vb];
+  fx[ENG] = (u[ENG] + ptot)*v[D::vn] - v[D::bn]*vB;
+  prs = ptot;
+}
+
+template <int DIR, int NC>
+__device__ __forceinline__ void max_signal_speed (const Phys &ph, const double *v,
+                                                  double &cmin, double &cmax)
+{
+  typedef Dirs<DIR> D;
+  double gpr, b1, b2, b3, Btmag2, Bmag2, cf;
+  gpr = ph.gamma*v[PRS];
+  b1 = v[D::bn]; b2 = v[D::bt];
+  if (NC == 3){ b3 = v[D::bb]; Btmag2 = b2*b2 + b3*b3; }
+  else        { Btmag2 = b2*b2; }
+  Bmag2 = b1*b1 + Btmag2;
+  cf = gpr - Bmag2;
+  cf = gpr + Bmag2 + sqrt(cf*cf + 4.0*gpr*Btmag2);
+  cf = sqrt(0.5*cf/v[RHO]);
+  cmin = v[D::vn] - cf;
+  cmax = v[D::vn] + cf;
+}
+
+template <int DIR, int NC>
+__device__ __forceinline__ void hll_speed (const Phys &ph, const double *vL, const double *vR,
+                                           double a2L, double a2R, double &SL, double &SR,
+                                           double &mach)
+{
+  typedef Dirs<DIR> D;
+  double slmin, slmax, srmin, srmax, scrh;
+  max_signal_speed<DIR, NC>(ph, vL, slmin, slmax);
+  max_signal_speed<DIR, NC>(ph, vR, srmin, srmax);
+  SL = minv(slmin, srmin);
+  SR = maxv(slmax, srmax);
+  scrh  = fabs(vL[D::vn]) + fabs(vR[D::vn]);
+  scrh /= sqrt(a2L) + sqrt(a2R);
+  mach = scrh;
+}
+
+// ---------------------------------------------------------------------------
+//  Riemann solvers.  in: vL, vR (interface states), uL, uR; out: flux[NV]
+//  (slot bn is not meaningful), press, cmax, mach (candidate for g_maxMach).
+// ---------------------------------------------------------------------------
+template <int DIR, int NC>
+__device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, const double *vR,
+                                             const double *uL, const double *uR,
+                                             double *flux, double &press, double &cmax, double &mach)
+{
+  double fL[NV], fR[NV], pL, pR, a2L, a2R, SL, SR, scrh;
+  a2L = ph.gamma*vL[PRS]/vL[RHO];
+  a2R = ph.gamma*vR[PRS]/vR[RHO];
+  mhd_flux<DIR, NC>(vL, uL, fL, pL);
+  mhd_flux<DIR, NC>(vR, uR, fR, pR);
+  hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
+  scrh = maxv(fabs(SL), fabs(SR));
+  cmax = scrh;
+  if (SL > 0.0){
+    PG_FOR_NV(nv) flux[nv] = fL[nv];
+    press = pL;
+  }else if (SR < 0.0){
+    PG_FOR_NV(nv) flux[nv] = fR[nv];
+    press = pR;
+  }else{
+    scrh = 1.0/(SR - SL);
+    PG_FOR_NV(nv){
+      flux[nv]  = SL*SR*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
+      flux[nv] *= scrh;
+    }
+    press = (SR*pL - SL*pR)*scrh;
+  }
+}
+
+template <int DIR, int NC>
+__device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, const double *vR,
+                                              const double *uL, const double *uR,
+                                              double *flux, double &press, double &cmax, double &mach)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
+  const int MXn = VXn, MXt = VXt, MXb = VXb;
+  double fL[NV], fR[NV], ptL, ptR, a2L, a2R, SL, SR, scrh;
+  double usL[NV], usR[NV];
+  double vsL, wsL = 0.0, scrhL, S1L, sqrL, duL;
+  double vsR, wsR = 0.0, scrhR, S1R, sqrR, duR;
+  double Bx, Bx1, SM, sBx, pts;
+
+  a2L = ph.gamma*vL[PRS]/vL[RHO];
+  a2R = ph.gamma*vR[PRS]/vR[RHO];
+  mhd_flux<DIR, NC>(vL, uL, fL, ptL);
+  mhd_flux<DIR, NC>(vR, uR, fR, ptR);
+  hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
+
+  scrh = maxv(fabs(SL), fabs(SR));
+  cmax = scrh;
+
+  if (SL >= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fL[nv];
+    press = ptL;
+    return;
+  }else if (SR <= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fR[nv];
+    press = ptR;
+    return;
+  }
+
+  scrh = 1.0/(SR - SL);
+  Bx1  = Bx = (SR*vR[BXn] - SL*vL[BXn])*scrh;
+  sBx  = (Bx > 0.0 ? 1.0 : -1.0);
+
+  duL = SL - vL[VXn];
+  duR = SR - vR[VXn];
+
+  scrh = 1.0/(duR*uR[RHO] - duL*uL[RHO]);
+  SM   = (duR*uR[MXn] - duL*uL[MXn] - ptR + ptL)*scrh;
+
+  pts  = duR*uR[RHO]*ptL - duL*uL[RHO]*ptR +
+         vL[RHO]*vR[RHO]*duR*duL*(vR[VXn] - vL[VXn]);
+  pts *= scrh;
+
+  usL[RHO] = uL[RHO]*duL/(SL - SM);
+  usR[RHO] = uR[RHO]*duR/(SR - SM);
+
+  sqrL = sqrt(usL[RHO]);
+  sqrR = sqrt(usR[RHO]);
+
+  S1L = SM - fabs(Bx)/sqrL;
+  S1R = SM + fabs(Bx)/sqrR;
+
+  bool revert_to_hllc = false;
+  if ( (S1L - SL) <  1.e-4*(SM - SL) ) revert_to_hllc = true;
+  if ( (S1R - SR) > -1.e-4*(SR - SM) ) revert_to_hllc = true;
+
+  if (revert_to_hllc){
+    scrh = 1.0/(SR - SL);
+    double hn = (SR*uR[BXn] - SL*uL[BXn] + fL[BXn] - fR[BXn])*scrh;
+    double ht = (SR*uR[BXt] - SL*uL[BXt] + fL[BXt] - fR[BXt])*scrh;
+    usL[BXn] = usR[BXn] = hn;
+    usL[BXt] = usR[BXt] = ht;
+    if (NC == 3){
+      double hb = (SR*uR[BXb] - SL*uL[BXb] + fL[BXb] - fR[BXb])*scrh;
+      usL[BXb] = usR[BXb] = hb;
+    }
+    S1L = S1R = SM;
+  }else{
+    scrhL = (uL[RHO]*duL*duL - Bx*Bx)/(uL[RHO]*duL*(SL - SM) - Bx*Bx);
+    scrhR = (uR[RHO]*duR*duR - Bx*Bx)/(uR[RHO]*duR*(SR - SM) - Bx*Bx);
+    usL[BXn] = Bx1;
+    usL[BXt] = uL[BXt]*scrhL;
+    usR[BXn] = Bx1;
+    usR[BXt] = uR[BXt]*scrhR;
+    if (NC == 3){
+      usL[BXb] = uL[BXb]*scrhL;
+      usR[BXb] = uR[BXb]*scrhR;
+    }
+  }
+
+  scrhL = Bx/(uL[RHO]*duL);
+  scrhR = Bx/(uR[RHO]*duR);
+
+  vsL = vL[VXt] - scrhL*(usL[BXt] - uL[BXt]);
+  vsR = vR[VXt] - scrhR*(usR[BXt] - uR[BXt]);
+  if (NC == 3){
+    wsL = vL[VXb] - scrhL*(usL[BXb] - uL[BXb]);
+    wsR = vR[VXb] - scrhR*(usR[BXb] - uR[BXb]);
+  }
+
+  usL[MXn] = usL[RHO]*SM;
+  usR[MXn] = usR[RHO]*SM;
+  usL[MXt] = usL[RHO]*vsL;
+  usR[MXt] = usR[RHO]*vsR;
+  if (NC == 3){
+    usL[MXb] = usL[RHO]*wsL;
+    usR[MXb] = usR[RHO]*wsR;
+  }
+
+  if (NC == 3){
+    scrhL  = vL[VXn]*Bx1 + vL[VXt]*uL[BXt] + vL[VXb]*uL[BXb];
+    scrhL -=      SM*Bx1 +    vsL*usL[BXt] +    wsL*usL[BXb];
+  }else{
+    scrhL  = vL[VXn]*Bx1 + vL[VXt]*uL[BXt];
+    scrhL -=      SM*Bx1 +    vsL*usL[BXt];
+  }
+  usL[ENG]  = duL*uL[ENG] - ptL*vL[VXn] + pts*SM + Bx*scrhL;
+  usL[ENG] /= SL - SM;
+
+  if (NC == 3){
+    scrhR  = vR[VXn]*Bx1 + vR[VXt]*uR[BXt] + vR[VXb]*uR[BXb];
+    scrhR -=      SM*Bx1 +    vsR*usR[BXt] +    wsR*usR[BXb];
+  }else{
+    scrhR  = vR[VXn]*Bx1 + vR[VXt]*uR[BXt];
+    scrhR -=      SM*Bx1 +    vsR*usR[BXt];
+  }
+  usR[ENG]  = duR*uR[ENG] - ptR*vR[VXn] + pts*SM + Bx*scrhR;
+  usR[ENG] /= SR - SM;
+
+  if (S1L >= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fL[nv] + SL*(usL[nv] - uL[nv]);
+    press = ptL;
+  }else if (S1R <= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fR[nv] + SR*(usR[nv] - uR[nv]);
+    press = ptR;
+  }else{
+    double ussl[NV], ussr[NV], vss, wss = 0.0;
+    ussl[RHO] = usL[RHO];
+    ussr[RHO] = usR[RHO];
+
+    vss  = sqrL*vsL + sqrR*vsR + (usR[BXt] - usL[BXt])*sBx;
+    vss /= sqrL + sqrR;
+    if (NC == 3){
+      wss  = sqrL*wsL + sqrR*wsR + (usR[BXb] - usL[BXb])*sBx;
+      wss /= sqrL + sqrR;
+    }
+
+    ussl[MXn] = ussl[RHO]*SM;
+    ussr[MXn] = ussr[RHO]*SM;
+    ussl[MXt] = ussl[RHO]*vss;
+    ussr[MXt] = ussr[RHO]*vss;
+    if (NC == 3){
+      ussl[MXb] = ussl[RHO]*wss;
+      ussr[MXb] = ussr[RHO]*wss;
+    }
+
+    ussl[BXn] = ussr[BXn] = Bx1;
+    ussl[BXt]  = sqrL*usR[BXt] + sqrR*usL[BXt] + sqrL*sqrR*(vsR - vsL)*sBx;
+    ussl[BXt] /= sqrL + sqrR;
+    ussr[BXt]  = ussl[BXt];
+    if (NC == 3){
+      ussl[BXb]  = sqrL*usR[BXb] + sqrR*usL[BXb] + sqrL*sqrR*(wsR - wsL)*sBx;
+      ussl[BXb] /= sqrL + sqrR;
+      ussr[BXb]  = ussl[BXb];
+    }
+
+    if (NC == 3){
+      scrhL  = SM*Bx1 + vsL*usL [BXt] + wsL*usL [BXb];
+      scrhL -= SM*Bx1 + vss*ussl[BXt] + wss*ussl[BXb];
+      scrhR  = SM*Bx1 + vsR*usR [BXt] + wsR*usR [BXb];
+      scrhR -= SM*Bx1 + vss*ussr[BXt] + wss*ussr[BXb];
+    }else{
+      scrhL  = SM*Bx1 + vsL*usL [BXt];
+      scrhL -= SM*Bx1 + vss*ussl[BXt];
+      scrhR  = SM*Bx1 + vsR*usR [BXt];
+      scrhR -= SM*Bx1 + vss*ussr[BXt];
+    }
+
+    ussl[ENG] = usL[ENG] - sqrL*scrhL*sBx;
+    ussr[ENG] = usR[ENG] + sqrR*scrhR*sBx;
+
+    if (SM >= 0.0){
+      PG_FOR_NV(nv) flux[nv] = fL[nv] + S1L*(ussl[nv] - usL[nv]) + SL*(usL[nv] - uL[nv]);
+      press = ptL;
+    }else{
+      PG_FOR_NV(nv) flux[nv] = fR[nv] + S1R*(ussr[nv] - usR[nv]) + SR*(usR[nv] - uR[nv]);
+      press = ptR;
+    }
+  }
+}
+
+// Roe: returns false when a2 < 0 (the reference aborts, roe.c:300-306)
+template <int DIR, int NC>
+__device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, const double *vR,
+                                             const double *uL, const double *uR,
+                                             double *flux, double &press, double &cmax, double &mach)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
+  const int MXn = VXn, MXt = VXt, MXb = VXb;
+  enum { KFASTM, KFASTP, KENTRP, KDIVB, KSLOWM, KSLOWP, KALFVM, KALFVP, NW };
+  const double sqrt_1_2 = 0.70710678118654752440;
+  double fL[NV], fR[NV], pL, pR;
+  double rho, u, v, w = 0.0, vel2, bx, by, bz = 0.0;
+  double a2, a, ca2, cf2, cs2, cs, ca, cf, b2;
+  double alpha_f, alpha_s, beta_y, beta_z = 0.0, beta_v, scrh, sBx;
+  double dV[NV], dU[NV];
+  double Rc[NV][NW], eta[NW], lambda[NW], alambda[NW];
+  double sqrt_rho, delta = 1.e-6;
+  double g1 = ph.gmm1, sl, sr, H, Hgas, HL, HR, Bx, By, Bz = 0.0, X;
+  double vdm, BdB, beta_dv, beta_dB, bt2, Btmag, sqr_rho_L, sqr_rho_R;
+
+  mhd_flux<DIR, NC>(vL, uL, fL, pL);
+  mhd_flux<DIR, NC>(vR, uR, fR, pR);
+
+  PG_UNROLL for (int nv = 0; nv < NV; nv++){
+    PG_UNROLL for (int k = 0; k < NW; k++) Rc[nv][k] = 0.0;
+  }
+  PG_UNROLL for (int k = 0; k < NW; k++) eta[k] = lambda[k] = 0.0;
+
+  PG_UNROLL for (int nv = 0; nv < NV; nv++){ dV[nv] = 0.0; dU[nv] = 0.0; }
+  PG_FOR_NV(nv){
+    dV[nv] = vR[nv] - vL[nv];
+    dU[nv] = uR[nv] - uL[nv];
+  }
+
+  sqr_rho_L = sqrt(vL[RHO]);
+  sqr_rho_R = sqrt(vR[RHO]);
+  sl = sqr_rho_L/(sqr_rho_L + sqr_rho_R);
+  sr = sqr_rho_R/(sqr_rho_L + sqr_rho_R);
+  rho = sr*vL[RHO] + sl*vR[RHO];
+  sqrt_rho = sqrt(rho);
+
+  u = sl*vL[VXn] + sr*vR[VXn];
+  v = sl*vL[VXt] + sr*vR[VXt];
+  if (NC == 3) w = sl*vL[VXb] + sr*vR[VXb];
+  Bx = sr*vL[BXn] + sl*vR[BXn];
+  By = sr*vL[BXt] + sl*vR[BXt];
+  if (NC == 3) Bz = sr*vL[BXb] + sl*vR[BXb];
+
+  sBx = (Bx >= 0.0 ? 1.0 : -1.0);
+  bx = Bx/sqrt_rho;
+  by = By/sqrt_rho;
+  if (NC == 3) bz = Bz/sqrt_rho;
+
+  if (NC == 3) bt2 = 0.0 + by*by + bz*bz; else bt2 = 0.0 + by*by;
+  b2    = bx*bx + bt2;
+  Btmag = sqrt(bt2*rho);
+
+  if (NC == 3) X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt] + dV[BXb]*dV[BXb];
+  else         X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt];
+  X /= (sqr_rho_L + sqr_rho_R)*(sqr_rho_L + sqr_rho_R)*2.0;
+
+  if (NC == 3){
+    vdm = u*dU[MXn] + v*dU[MXt] + w*dU[MXb];
+    BdB = Bx*dU[BXn] + By*dU[BXt] + Bz*dU[BXb];
+    vel2 = u*u + v*v + w*w;
+  }else{
+    vdm = u*dU[MXn] + v*dU[MXt];
+    BdB = Bx*dU[BXn] + By*dU[BXt];
+    vel2 = u*u + v*v;
+  }
+  dV[PRS] = g1*((0.5*vel2 - X)*dV[RHO] - vdm + dU[ENG] - BdB);
+
+  HL   = (uL[ENG] + pL)/vL[RHO];
+  HR   = (uR[ENG] + pR)/vR[RHO];
+  H    = sl*HL + sr*HR;
+  Hgas = H - b2;
+
+  a2 = (2.0 - ph.gamma)*X + g1*(Hgas - 0.5*vel2);
+  bool ok = !(a2 < 0.0);
+
+  scrh = a2 - b2;
+  ca2  = bx*bx;
+  scrh = scrh*scrh + 4.0*bt2*a2;
+  scrh = sqrt(scrh);
+
+  cf2 = 0.5*(a2 + b2 + scrh);
+  cs2 = a2*ca2/cf2;
+
+  cf = sqrt(cf2);
+  cs = sqrt(cs2);
+  ca = sqrt(ca2);
+  a  = sqrt(a2);
+
+  if (cf == cs){
+    alpha_f = 1.0; alpha_s = 0.0;
+  }else if (a <= cs){
+    alpha_f = 0.0; alpha_s = 1.0;
+  }else if (cf <= a){
+    alpha_f = 1.0; alpha_s = 0.0;
+  }else{
+    scrh    = 1.0/(cf2 - cs2);
+    alpha_f = (a2  - cs2)*scrh;
+    alpha_s = (cf2 -  a2)*scrh;
+    alpha_f = maxv(0.0, alpha_f);
+    alpha_s = maxv(0.0, alpha_s);
+    alpha_f = sqrt(alpha_f);
+    alpha_s = sqrt(alpha_s);
+  }
+
+  if (Btmag > 1.e-9){
+    if (NC == 3){ beta_y = By/Btmag; beta_z = Bz/Btmag; }
+    else          beta_y = (By >= 0.0 ? 1.0 : -1.0);
+  }else{
+    if (NC == 3) beta_z = beta_y = sqrt_1_2;
+    else         beta_y = 1.0;
+  }
+
+  int k;
+  // ---- fast wave u - cf ----
+  k = KFASTM;
+  lambda[k] = u - cf;
+  scrh = alpha_s*cs*sBx;
+  if (NC == 3){
+    beta_dv = 0.0 + beta_y*dV[VXt] + beta_z*dV[VXb];
+    beta_dB = 0.0 + beta_y*dV[BXt] + beta_z*dV[BXb];
+    beta_v  = 0.0 + beta_y*v       + beta_z*w;
+  }else{
+    beta_dv = 0.0 + beta_y*dV[VXt];
+    beta_dB = 0.0 + beta_y*dV[BXt];
+    beta_v  = 0.0 + beta_y*v;
+  }
+  Rc[RHO][k] = alpha_f;
+  Rc[MXn][k] = alpha_f*lambda[k];
+  Rc[MXt][k] = alpha_f*v + scrh*beta_y;
+  if (NC == 3) Rc[MXb][k] = alpha_f*w + scrh*beta_z;
+  Rc[BXt][k] = alpha_s*a*beta_y/sqrt_rho;
+  if (NC == 3) Rc[BXb][k] = alpha_s*a*beta_z/sqrt_rho;
+  Rc[ENG][k] =   alpha_f*(Hgas - u*cf) + scrh*beta_v
+               + alpha_s*a*Btmag/sqrt_rho;
+  eta[k] =   alpha_f*(X*dV[RHO] + dV[PRS]) + rho*scrh*beta_dv
+           - rho*alpha_f*cf*dV[VXn]        + sqrt_rho*alpha_s*a*beta_dB;
+  eta[k] *= 0.5/a2;
+
+  // ---- fast wave u + cf ----
+  k = KFASTP;
+  lambda[k] = u + cf;
+  Rc[RHO][k] = alpha_f;
+  Rc[MXn][k] = alpha_f*lambda[k];
+  Rc[MXt][k] = alpha_f*v - scrh*beta_y;
+  if (NC == 3) Rc[MXb][k] = alpha_f*w - scrh*beta_z;
+  Rc[BXt][k] = Rc[BXt][KFASTM];
+  if (NC == 3) Rc[BXb][k] = Rc[BXb][KFASTM];
+  Rc[ENG][k] =   alpha_f*(Hgas + u*cf) - scrh*beta_v
+               + alpha_s*a*Btmag/sqrt_rho;
+  eta[k] =   alpha_f*(X*dV[RHO] + dV[PRS]) - rho*scrh*beta_dv
+           + rho*alpha_f*cf*dV[VXn]        + sqrt_rho*alpha_s*a*beta_dB;
+  eta[k] *= 0.5/a2;
+
+  // ---- entropy wave ----
+  k = KENTRP;
+  lambda[k] = u;
+  Rc[RHO][k] = 1.0;
+  Rc[MXn][k] = u;
+  Rc[MXt][k] = v;
+  if (NC == 3) Rc[MXb][k] = w;
+  Rc[ENG][k] = 0.5*vel2 + (ph.gamma - 2.0)/g1*X;
+  eta[k] = ((a2 - X)*dV[RHO] - dV[PRS])/a2;
+
+  // ---- div.B wave: no jump with CT ----
+  k = KDIVB;
+  lambda[k] = u;
+  Rc[BXn][k] = eta[k] = 0.0;
+
+  // ---- slow wave u - cs ----
+  scrh = alpha_f*cf*sBx;
+  k = KSLOWM;
+  lambda[k] = u - cs;
+  Rc[RHO][k] = alpha_s;
+  Rc[MXn][k] = alpha_s*lambda[k];
+  Rc[MXt][k] = alpha_s*v - scrh*beta_y;
+  if (NC == 3) Rc[MXb][k] = alpha_s*w - scrh*beta_z;
+  Rc[BXt][k] = - alpha_f*a*beta_y/sqrt_rho;
+  if (NC == 3) Rc[BXb][k] = - alpha_f*a*beta_z/sqrt_rho;
+  Rc[ENG][k] =   alpha_s*(Hgas - u*cs) - scrh*beta_v
+               - alpha_f*a*Btmag/sqrt_rho;
+  eta[k] =   alpha_s*(X*dV[RHO] + dV[PRS]) - rho*scrh*beta_dv
+           - rho*alpha_s*cs*dV[VXn]        - sqrt_rho*alpha_f*a*beta_dB;
+  eta[k] *= 0.5/a2;
+
+  // ---- slow wave u + cs ----
+  k = KSLOWP;
+  lambda[k] = u + cs;
+  Rc[RHO][k] = alpha_s;
+  Rc[MXn][k] = alpha_s*lambda[k];
+  Rc[MXt][k] = alpha_s*v + scrh*beta_y;
+  if (NC == 3) Rc[MXb][k] = alpha_s*w + scrh*beta_z;
+  Rc[BXt][k] = Rc[BXt][KSLOWM];
+  if (NC == 3) Rc[BXb][k] = Rc[BXb][KSLOWM];
+  Rc[ENG][k] =   alpha_s*(Hgas + u*cs) + scrh*beta_v
+               - alpha_f*a*Btmag/sqrt_rho;
+  eta[k] =   alpha_s*(X*dV[RHO] + dV[PRS]) + rho*scrh*beta_dv
+           + rho*alpha_s*cs*dV[VXn]        - sqrt_rho*alpha_f*a*beta_dB;
+  eta[k] *= 0.5/a2;
+
+  if (NC == 3){
+    // ---- Alfven wave u - ca ----
+    k = KALFVM;
+    lambda[k] = u - ca;
+    Rc[MXt][k] = - rho*beta_z;
+    Rc[MXb][k] = + rho*beta_y;
+    Rc[BXt][k] = - sBx*sqrt_rho*beta_z;
+    Rc[BXb][k] =   sBx*sqrt_rho*beta_y;
+    Rc[ENG][k] = - rho*(v*beta_z - w*beta_y);
+    eta[k] = + beta_y*dV[VXb]               - beta_z*dV[VXt]
+             + sBx/sqrt_rho*(beta_y*dV[BXb] - beta_z*dV[BXt]);
+    eta[k] *= 0.5;
+
+    // ---- Alfven wave u + ca ----
+    k = KALFVP;
+    lambda[k] = u + ca;
+    Rc[MXt][k] = - Rc[MXt][KALFVM];
+    Rc[MXb][k] = - Rc[MXb][KALFVM];
+    Rc[BXt][k] =   Rc[BXt][KALFVM];
+    Rc[BXb][k] =   Rc[BXb][KALFVM];
+    Rc[ENG][k] = - Rc[ENG][KALFVM];
+    eta[k] = - beta_y*dV[VXb]               + beta_z*dV[VXt]
+             + sBx/sqrt_rho*(beta_y*dV[BXb] - beta_z*dV[BXt]);
+    eta[k] *= 0.5;
+  }
+
+  cmax = fabs(u) + cf;
+  mach = fabs(u/a);
+  const int nw = (NC == 3 ? 8 : 6);
+  PG_UNROLL for (int kk = 0; kk < NW; kk++) alambda[kk] = fabs(lambda[kk]);
+
+  // entropy fix (roe.c:623-640)
+  if (alambda[KFASTM] < 0.5*delta) alambda[KFASTM] = lambda[KFASTM]*lambda[KFASTM]/delta + 0.25*delta;
+  if (alambda[KFASTP] < 0.5*delta) alambda[KFASTP] = lambda[KFASTP]*lambda[KFASTP]/delta + 0.25*delta;
+  if (alambda[KSLOWM] < 0.5*delta) alambda[KSLOWM] = lambda[KSLOWM]*lambda[KSLOWM]/delta + 0.25*delta;
+  if (alambda[KSLOWP] < 0.5*delta) alambda[KSLOWP] = lambda[KSLOWP]*lambda[KSLOWP]/delta + 0.25*delta;
+
+  PG_FOR_NV(nv){
+    scrh = 0.0;
+    PG_UNROLL for (int kk = 0; kk < NW; kk++) if (kk < nw) scrh += alambda[kk]*eta[kk]*Rc[nv][kk];
+    flux[nv] = 0.5*(fL[nv] + fR[nv] - scrh);
+  }
+  press = 0.5*(pL + pR);
+  return ok;
+}
+
+// solver dispatch on a compile-time constant
+template <int SOLVER, int DIR, int NC>
+__device__ __forceinline__ bool riemann (const Phys &ph, const double *vL, const double *vR,
+                                         const double *uL, const double *uR,
+                                         double *flux, double &press, double &cmax, double &mach)
+{
+  if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach); return true; }
+  else if (SOLVER == SOLVER_HLL){ riemann_hll<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach); return true; }
+  else return riemann_roe<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach);
+}
+
+} // namespace PG_NS

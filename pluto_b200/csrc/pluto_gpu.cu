@@ -1,0 +1,513 @@
+// pluto_gpu.cu -- host side of the C ABI declared in include/pluto_gpu.h:
+// device-resident state, the RK stage pipeline (the body of the reference's
+// AdvanceStep, Src/Time_Stepping/rk_step.c:27-254), boundary orchestration
+// (Src/boundary.c:41-315) and host<->device transfer in the reference's own
+// array layouts.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/pluto_gpu.h"
+#include "kernels_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int fail (const char *fmt, ...)
+{
+  va_list ap;
+  va_start (ap, fmt);
+  vsnprintf (g_err, sizeof (g_err), fmt, ap);
+  va_end (ap);
+  return 1;
+}
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+  return fail ("%s:%d: %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString (e_)); } while (0)
+
+enum { NVS = 8 };
+static const int kCons[5] = {0, 1, 2, 3, 7};       // RHO, MX1, MX2, MX3, ENG
+
+struct PlutoGpu {
+  PlutoGpuConfig cfg;
+  Geom    g;
+  PhysPar ph;
+  int     nbuf;                    // state buffers: 2 (RK2) or 3 (RK3)
+  cudaStream_t stream;
+  void   *pool;
+  size_t  pool_bytes;
+  double *V[3][NVS];
+  double *Bs[3][3];
+  double *U[NVS];
+  double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
+  double *ex, *ey, *ez;
+  double *cdt;
+  double *scratch;                 // = first array after the state buffers
+  size_t  scratch_doubles;
+  signed char *sv[3];
+  unsigned long long *red;         // device reduction slots
+  unsigned long long *red_host;    // pinned mirror
+  long long launches;
+  int     march_chunk;             // zones per thread along a marching sweep
+};
+
+const char *pluto_gpu_last_error (void) { return g_err; }
+
+int pluto_gpu_nghost (const PlutoGpu *h) { return h->g.ng; }
+
+static bool live_var (const PlutoGpu *h, int nv) { return h->g.dims == 3 || (nv != 3 && nv != 6); }
+
+#define DISPATCH(h, call) ((h)->cfg.arith == PLUTO_GPU_ARITH_FAST ? pg_fast::call : pg_exact::call)
+
+static int count (PlutoGpu *h, int r)
+{
+  if (r < 0) return fail ("kernel launch failed: %s", cudaGetErrorString (cudaGetLastError ()));
+  h->launches += r;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
+{
+  *out = NULL;
+  if (cfg->dims != 2 && cfg->dims != 3) return fail ("dims must be 2 or 3");
+  if (cfg->recon != PLUTO_GPU_RECON_LINEAR && cfg->recon != PLUTO_GPU_RECON_PARABOLIC) return fail ("bad recon");
+  if (cfg->solver < 0 || cfg->solver > 2) return fail ("bad solver");
+  if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount (&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail ("no CUDA device (%s): this library has no CPU path", cudaGetErrorString (e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail ("device %d out of range (%d devices)", cfg->device, ndev);
+  CU (cudaSetDevice (cfg->device));
+
+  PlutoGpu *h = (PlutoGpu *)calloc (1, sizeof (PlutoGpu));
+  h->cfg = *cfg;
+  Geom &g = h->g;
+  g.dims = cfg->dims;
+  g.ng = (cfg->recon == PLUTO_GPU_RECON_PARABOLIC ? 3 : 2);      // get_nghost.c:32-50
+  for (int d = 0; d < 3; d++){
+    if (d < g.dims){
+      if (cfg->n[d] < 2*g.ng){ free (h); return fail ("n[%d] = %d is smaller than 2*nghost", d, cfg->n[d]); }
+      g.n[d] = cfg->n[d]; g.T[d] = g.n[d] + 2*g.ng; g.beg[d] = g.ng; g.end[d] = g.ng + g.n[d] - 1; g.off[d] = 1;
+      g.dx[d] = cfg->dx[d];
+    }else{
+      g.n[d] = 1; g.T[d] = 1; g.beg[d] = g.end[d] = 0; g.off[d] = 0; g.dx[d] = 1.0;
+    }
+  }
+  g.S1  = g.T[0] + 2;
+  g.S12 = g.S1*(g.T[1] + 2);
+  g.tot = g.S12*(g.dims == 3 ? g.T[2] + 2 : 1);
+  h->ph.gamma = cfg->gamma; h->ph.gmm1 = cfg->gamma - 1.0;
+  h->ph.small_dn = cfg->small_dn; h->ph.small_pr = cfg->small_pr;
+  h->nbuf = (cfg->rk_order == 3 ? 3 : 2);
+  h->march_chunk = 64;
+
+  // one pool: [state buffers][U, face EMFs, edge EMFs, C_dt = scratch][sign bytes]
+  const size_t tot = (size_t)g.tot;
+  const size_t tot_al = (tot + 31) & ~(size_t)31;             // 256-byte aligned arrays
+  const int nstate = h->nbuf*(NVS + 3);
+  const int nwork = 5 + 6 + 3 + 1;
+  h->pool_bytes = (size_t)(nstate + nwork)*tot_al*sizeof (double) + 3*tot_al;
+  if (cudaMalloc (&h->pool, h->pool_bytes) != cudaSuccess){
+    size_t need = h->pool_bytes; free (h);
+    return fail ("cudaMalloc of %zu bytes failed", need);
+  }
+  CU (cudaMemset (h->pool, 0, h->pool_bytes));
+  double *p = (double *)h->pool;
+  for (int b = 0; b < h->nbuf; b++){
+    for (int nv = 0; nv < NVS; nv++){ h->V[b][nv] = p; p += tot_al; }
+    for (int d = 0; d < 3; d++){ h->Bs[b][d] = p; p += tot_al; }
+  }
+  h->scratch = p;
+  h->scratch_doubles = (size_t)nwork*tot_al;
+  for (int q = 0; q < 5; q++){ h->U[kCons[q]] = p; p += tot_al; }
+  h->exj = p; p += tot_al; h->exk = p; p += tot_al; h->eyi = p; p += tot_al;
+  h->eyk = p; p += tot_al; h->ezi = p; p += tot_al; h->ezj = p; p += tot_al;
+  h->ex = p; p += tot_al; h->ey = p; p += tot_al; h->ez = p; p += tot_al;
+  h->cdt = p; p += tot_al;
+  signed char *c = (signed char *)p;
+  for (int d = 0; d < 3; d++){ h->sv[d] = c; c += tot_al; }
+
+  CU (cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking));
+  CU (cudaMalloc ((void **)&h->red, RED_N*sizeof (unsigned long long)));
+  CU (cudaMemset (h->red, 0, RED_N*sizeof (unsigned long long)));
+  CU (cudaMallocHost ((void **)&h->red_host, RED_N*sizeof (unsigned long long)));
+  *out = h;
+  return 0;
+}
+
+void pluto_gpu_destroy (PlutoGpu *h)
+{
+  if (!h) return;
+  cudaSetDevice (h->cfg.device);
+  cudaStreamSynchronize (h->stream);
+  cudaFree (h->pool);
+  cudaFree (h->red);
+  cudaFreeHost (h->red_host);
+  cudaStreamDestroy (h->stream);
+  free (h);
+}
+
+void *pluto_gpu_stream (PlutoGpu *h) { return (void *)h->stream; }
+long long pluto_gpu_launch_count (const PlutoGpu *h) { return h->launches; }
+long long pluto_gpu_device_bytes (const PlutoGpu *h) { return (long long)h->pool_bytes; }
+
+int pluto_gpu_field (PlutoGpu *h, const char *name, double **dev_ptr, long long shape[3], int off[3])
+{
+  static const char *vn[NVS] = {"rho", "vx1", "vx2", "vx3", "bx1", "bx2", "bx3", "prs"};
+  static const char *sn[3] = {"bx1s", "bx2s", "bx3s"};
+  *dev_ptr = NULL;
+  for (int nv = 0; nv < NVS; nv++) if (!strcmp (name, vn[nv])) *dev_ptr = h->V[0][nv];
+  for (int d = 0; d < 3; d++) if (!strcmp (name, sn[d])) *dev_ptr = h->Bs[0][d];
+  if (!strcmp (name, "ex")) *dev_ptr = h->ex;
+  if (!strcmp (name, "ey")) *dev_ptr = h->ey;
+  if (!strcmp (name, "ez")) *dev_ptr = h->ez;
+  if (!strcmp (name, "cdt")) *dev_ptr = h->cdt;
+  if (!*dev_ptr) return fail ("unknown field '%s'", name);
+  shape[0] = h->g.S1; shape[1] = h->g.T[1] + 2; shape[2] = (h->g.dims == 3 ? h->g.T[2] + 2 : 1);
+  for (int d = 0; d < 3; d++) off[d] = h->g.off[d];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+//  host <-> device transfer through the scratch region + pack/unpack kernels
+// ---------------------------------------------------------------------------
+static void box_set (int lo[3], int hi[3], int l0, int h0, int l1, int h1, int l2, int h2)
+{ lo[0] = l0; hi[0] = h0; lo[1] = l1; hi[1] = h1; lo[2] = l2; hi[2] = h2; }
+
+static long long box_count (const int lo[3], const int hi[3])
+{ return (long long)(hi[0] - lo[0] + 1)*(hi[1] - lo[1] + 1)*(hi[2] - lo[2] + 1); }
+
+// describe the 11 (3-D) or 8 (2-D) fields of one host layout; returns nf
+//   layout 0: interior (.dbl): vc in 8 slots (dead slots skipped but their
+//             space kept), staggered with +1 face
+//   layout 1: reference Data arrays with ghosts: NVAR live slots only
+static int describe_layout (PlutoGpu *h, int layout, int buf, HaloArgs &a,
+                            long long seg_off[4], long long seg_len[4])
+{
+  const Geom &g = h->g;
+  const int d3 = (g.dims == 3);
+  int nf = 0;
+  long long off = 0;
+  int lo[3], hi[3];
+  if (layout == 0) box_set (lo, hi, g.beg[0], g.end[0], g.beg[1], g.end[1], g.beg[2], g.end[2]);
+  else             box_set (lo, hi, 0, g.T[0] - 1, 0, g.T[1] - 1, 0, g.T[2] - 1);
+  const long long ncell = box_count (lo, hi);
+  seg_off[0] = 0;
+  for (int nv = 0; nv < NVS; nv++){
+    if (!live_var (h, nv)){ if (layout == 0) off += ncell; continue; }
+    a.q[nf] = h->V[buf][nv];
+    for (int d = 0; d < 3; d++){ a.lo[nf][d] = lo[d]; a.hi[nf][d] = hi[d]; }
+    a.offset[nf] = off; off += ncell; nf++;
+  }
+  seg_len[0] = off;
+  for (int s = 0; s < 3; s++){
+    seg_off[1 + s] = off; seg_len[1 + s] = 0;
+    if (s == 2 && !d3) continue;
+    a.q[nf] = h->Bs[buf][s];
+    for (int d = 0; d < 3; d++){ a.lo[nf][d] = lo[d]; a.hi[nf][d] = hi[d]; }
+    a.lo[nf][s] -= 1;
+    a.offset[nf] = off;
+    seg_len[1 + s] = box_count (a.lo[nf], a.hi[nf]);
+    off += seg_len[1 + s]; nf++;
+  }
+  a.nf = nf; a.buf = h->scratch; a.g = g;
+  return nf;
+}
+
+static int transfer (PlutoGpu *h, int layout, bool upload, double *p0, double *p1, double *p2, double *p3)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  HaloArgs a; memset (&a, 0, sizeof (a));
+  long long so[4], sl[4];
+  describe_layout (h, layout, 0, a, so, sl);
+  double *hp[4] = {p0, p1, p2, p3};
+  if ((size_t)(so[3] + sl[3]) > h->scratch_doubles) return fail ("internal: scratch too small");
+  if (upload){
+    for (int s = 0; s < 4; s++) if (sl[s] > 0){
+      if (!hp[s]) return fail ("NULL host pointer for segment %d", s);
+      CU (cudaMemcpyAsync (h->scratch + so[s], hp[s], sl[s]*sizeof (double), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1;
+    CU (cudaStreamSynchronize (h->stream));
+  }else{
+    if (count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))) return 1;
+    for (int s = 0; s < 4; s++) if (sl[s] > 0){
+      if (!hp[s]) return fail ("NULL host pointer for segment %d", s);
+      CU (cudaMemcpyAsync (hp[s], h->scratch + so[s], sl[s]*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU (cudaStreamSynchronize (h->stream));
+  }
+  return 0;
+}
+
+int pluto_gpu_upload_interior (PlutoGpu *h, const double *vc, const double *b1, const double *b2, const double *b3)
+{ return transfer (h, 0, true, (double *)vc, (double *)b1, (double *)b2, (double *)b3); }
+int pluto_gpu_download_interior (PlutoGpu *h, double *vc, double *b1, double *b2, double *b3)
+{ return transfer (h, 0, false, vc, b1, b2, b3); }
+int pluto_gpu_upload_data (PlutoGpu *h, const double *Vc, const double *s1, const double *s2, const double *s3)
+{ return transfer (h, 1, true, (double *)Vc, (double *)s1, (double *)s2, (double *)s3); }
+int pluto_gpu_download_data (PlutoGpu *h, double *Vc, double *s1, double *s2, double *s3)
+{ return transfer (h, 1, false, Vc, s1, s2, s3); }
+
+// ---------------------------------------------------------------------------
+//  Boundary (boundary.c:137-293) on state buffer `buf`, one dimension
+// ---------------------------------------------------------------------------
+static int boundary_dim (PlutoGpu *h, int buf, int dim)
+{
+  const Geom &g = h->g;
+  for (int hs = 0; hs < 2; hs++){
+    const int side = 2*dim + hs;
+    const int type = h->cfg.bc[side];
+    if (type == PLUTO_GPU_BC_SHARED) continue;                 // boundary.c:139
+    // cell box of this side: ghost layers in `dim`, full extent elsewhere
+    int lo[3] = {0, 0, 0}, hi[3] = {g.T[0] - 1, g.T[1] - 1, g.T[2] - 1};
+    if (hs == 0) hi[dim] = g.beg[dim] - 1; else lo[dim] = g.end[dim] + 1;
+    BcArgs a; memset (&a, 0, sizeof (a));
+    a.side = side; a.type = type; a.g = g;
+    int nf = 0;
+    for (int nv = 0; nv < NVS; nv++){
+      if (!live_var (h, nv)) continue;
+      a.f[nf].q = h->V[buf][nv];
+      for (int d = 0; d < 3; d++){ a.f[nf].lo[d] = lo[d]; a.f[nf].hi[d] = hi[d]; }
+      a.f[nf].sign = (nv == 1 + dim || nv == 4 + dim) ? -1 : 1;   // FlipSign, boundary.c:318-436
+      nf++;
+    }
+    for (int s = 0; s < g.dims; s++){
+      // staggered boxes (boundary.c:157-164): one more face on the low end of
+      // their own direction; the normal component is skipped by outflow and
+      // reflective conditions (:175-180, 199-204) and rebuilt from div B = 0
+      if (s == dim && type != PLUTO_GPU_BC_PERIODIC) continue;
+      a.f[nf].q = h->Bs[buf][s];
+      for (int d = 0; d < 3; d++){ a.f[nf].lo[d] = lo[d]; a.f[nf].hi[d] = hi[d]; }
+      a.f[nf].lo[s] -= 1;
+      a.f[nf].sign = 1;
+      nf++;
+    }
+    a.nf = nf;
+    if (count (h, DISPATCH (h, launch_bc) (a, h->stream))) return 1;
+    if (type == PLUTO_GPU_BC_OUTFLOW || type == PLUTO_GPU_BC_REFLECTIVE){
+      BcFillArgs b; memset (&b, 0, sizeof (b));
+      for (int s = 0; s < 3; s++) b.Bs[s] = h->Bs[buf][s];
+      b.Bc = (type == PLUTO_GPU_BC_OUTFLOW ? h->V[buf][4 + dim] : NULL);
+      b.side = side; b.g = g;
+      if (count (h, DISPATCH (h, launch_bc_fill) (b, h->stream))) return 1;
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+//  one RK stage without its Boundary call: UpdateStage + CT + stage average +
+//  ConsToPrim.  in = buffer holding the stage's input state.
+// ---------------------------------------------------------------------------
+struct StagePlan { int in, out, combine; double w0, wc; };
+
+static StagePlan stage_plan (const PlutoGpu *h, int stage)
+{
+  StagePlan p; p.w0 = p.wc = 0.0; p.combine = 0; p.in = 0; p.out = 1;
+  if (h->cfg.rk_order == 2){
+    if (stage == 1){ p.in = 0; p.out = 1; }
+    else           { p.in = 1; p.out = 0; p.combine = 1; p.w0 = 0.5; p.wc = 0.5; }     // rk_step.c:18-20
+  }else{
+    if (stage == 1){ p.in = 0; p.out = 1; }
+    else if (stage == 2){ p.in = 1; p.out = 2; p.combine = 1; p.w0 = 0.75; p.wc = 0.25; } // rk_step.c:21-23
+    else { p.in = 2; p.out = 0; p.combine = 2; }                                         // rk_step.c:226-233
+  }
+  return p;
+}
+
+static int run_stage (PlutoGpu *h, int stage, double dt)
+{
+  const Geom &g = h->g;
+  const StagePlan sp = stage_plan (h, stage);
+  SweepArgs s; memset (&s, 0, sizeof (s));
+  for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
+  s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph;
+  s.stage1 = (stage == 1);
+  for (int dir = 0; dir < g.dims; dir++){
+    s.Bn = h->Bs[sp.in][dir];
+    s.dtdx = dt/g.dx[dir];                 // rhs.c:195
+    s.inv_dl = 1.0/g.dx[dir];              // set_geometry.c (inv_dx)
+    s.last_dir = (dir == g.dims - 1);
+    s.sv = h->sv[dir];
+    if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
+    else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
+    else { s.e1 = h->eyk; s.e2 = h->exk; }
+    s.chunk_len = h->march_chunk;
+    if (s.chunk_len > g.n[dir]) s.chunk_len = g.n[dir];
+    s.nchunk = (g.n[dir] + s.chunk_len - 1)/s.chunk_len;
+    int r;
+    const int recon = h->cfg.recon;
+    if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_sweep_hlld) (dir, recon, s, h->stream);
+    else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_sweep_hll)  (dir, recon, s, h->stream);
+    else                                             r = DISPATCH (h, launch_sweep_roe)  (dir, recon, s, h->stream);
+    if (count (h, r)) return 1;
+  }
+
+  CtArgs c; memset (&c, 0, sizeof (c));
+  for (int nv = 0; nv < NVS; nv++) c.V[nv] = h->V[sp.in][nv];
+  c.exj = h->exj; c.exk = h->exk; c.eyi = h->eyi; c.eyk = h->eyk; c.ezi = h->ezi; c.ezj = h->ezj;
+  c.svx = h->sv[0]; c.svy = h->sv[1]; c.svz = h->sv[2];
+  c.ex = h->ex; c.ey = h->ey; c.ez = h->ez;
+  for (int d = 0; d < 3; d++){
+    c.Bs_in[d] = h->Bs[sp.in][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[sp.out][d];
+    c.dtdx[d] = dt/g.dx[d];                // ct_update.c:87-89
+  }
+  c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine;
+  if (count (h, DISPATCH (h, launch_ct_emf) (c, h->stream))) return 1;
+  if (count (h, DISPATCH (h, launch_ct_update) (c, h->stream))) return 1;
+
+  FinalArgs f; memset (&f, 0, sizeof (f));
+  for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[sp.out][nv]; }
+  for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[sp.out][d];
+  f.red = h->red; f.g = g; f.ph = h->ph; f.w0 = sp.w0; f.wc = sp.wc; f.combine = sp.combine;
+  if (count (h, DISPATCH (h, launch_final) (f, h->stream))) return 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int pluto_gpu_step_begin (PlutoGpu *h)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  CU (cudaMemsetAsync (h->red, 0, RED_N*sizeof (unsigned long long), h->stream));
+  return 0;
+}
+
+static int stage_in_buf (const PlutoGpu *h, int stage) { return stage_plan (h, stage).in; }
+
+int pluto_gpu_boundary_dim (PlutoGpu *h, int stage, int dim)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  return boundary_dim (h, stage_in_buf (h, stage), dim);
+}
+
+int pluto_gpu_stage (PlutoGpu *h, int stage, double dt)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  return run_stage (h, stage, dt);
+}
+
+int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  CU (cudaMemcpyAsync (h->red_host, h->red, RED_N*sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CU (cudaStreamSynchronize (h->stream));
+  double cd, mach;
+  memcpy (&cd, &h->red_host[RED_CDT], sizeof (double));
+  memcpy (&mach, &h->red_host[RED_MACH], sizeof (double));
+  if (info){
+    info->inv_dt_hyp = cd/(double)h->g.dims;                   // update_stage.c:308-312
+    info->max_mach = mach;
+    info->floor_events = (int)h->red_host[RED_FLOOR];
+    info->nan_events = (int)h->red_host[RED_NAN];
+  }
+  if (h->red_host[RED_ROEFAIL])
+    return fail ("Roe_Solver: a2 < 0 at %llu interfaces (the reference aborts, roe.c:300-306)",
+                 h->red_host[RED_ROEFAIL]);
+  return 0;
+}
+
+int pluto_gpu_advance (PlutoGpu *h, double dt, PlutoGpuStepInfo *info)
+{
+  if (pluto_gpu_step_begin (h)) return 1;
+  for (int stage = 1; stage <= h->cfg.rk_order; stage++){
+    const int in = stage_in_buf (h, stage);
+    for (int d = 0; d < h->g.dims; d++) if (boundary_dim (h, in, d)) return 1;
+    if (run_stage (h, stage, dt)) return 1;
+  }
+  return pluto_gpu_step_end (h, info);
+}
+
+int pluto_gpu_boundary (PlutoGpu *h)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  for (int d = 0; d < h->g.dims; d++) if (boundary_dim (h, 0, d)) return 1;
+  CU (cudaStreamSynchronize (h->stream));
+  return 0;
+}
+
+int pluto_gpu_advance_data (PlutoGpu *h, double dt, double *Vc, double *s1, double *s2, double *s3,
+                            PlutoGpuStepInfo *info)
+{
+  if (pluto_gpu_upload_data (h, Vc, s1, s2, s3)) return 1;
+  if (pluto_gpu_advance (h, dt, info)) return 1;
+  return pluto_gpu_download_data (h, Vc, s1, s2, s3);
+}
+
+double pluto_gpu_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt)
+{
+  double dt_hyp = 1.0/inv_dt_hyp, dtnext;                      // main.c:462-465
+  dt_hyp *= cfl;
+  dtnext  = dt_hyp;
+  if (!(dtnext <= cfl_max_var*dt)) dtnext = cfl_max_var*dt;    // main.c:532 (MIN)
+  return dtnext;
+}
+
+// ---------------------------------------------------------------------------
+//  halo exchange support.  For dimension `dim` every field's box spans the
+//  FULL extent (ghosts included) of the other dimensions, so the sequential
+//  x1 -> x2 -> x3 exchange fills edges and corners (al_decompose.c:218-229).
+//  Cell-centred fields move ng layers; the staggered component normal to
+//  `dim` moves ng+1 layers towards the high neighbour (the shared face is
+//  owned by the low block, al_decompose.c:243-252) and ng the other way.
+// ---------------------------------------------------------------------------
+static void halo_describe (PlutoGpu *h, int buf, int dim, int hs, bool send, HaloArgs &a)
+{
+  const Geom &g = h->g;
+  memset (&a, 0, sizeof (a));
+  int nf = 0; long long off = 0;
+  for (int fidx = 0; fidx < NVS + 3; fidx++){
+    const bool stag = fidx >= NVS;
+    const int s = fidx - NVS;
+    if (!stag && !live_var (h, fidx)) continue;
+    if (stag && s >= g.dims) continue;
+    int lo[3] = {0, 0, 0}, hi[3] = {g.T[0] - 1, g.T[1] - 1, g.T[2] - 1};
+    if (stag) lo[s] = -1;
+    const bool normal = stag && s == dim;
+    if (send){
+      if (hs == 0){ lo[dim] = g.beg[dim]; hi[dim] = g.beg[dim] + g.ng - 1; }          // to the low neighbour
+      else        { lo[dim] = g.end[dim] - g.ng + 1 - (normal ? 1 : 0); hi[dim] = g.end[dim]; }
+    }else{
+      if (hs == 0){ lo[dim] = (normal ? -1 : 0); hi[dim] = g.beg[dim] - 1; }           // my low ghosts
+      else        { lo[dim] = g.end[dim] + 1; hi[dim] = g.T[dim] - 1; }
+    }
+    a.q[nf] = stag ? h->Bs[buf][s] : h->V[buf][fidx];
+    for (int d = 0; d < 3; d++){ a.lo[nf][d] = lo[d]; a.hi[nf][d] = hi[d]; }
+    a.offset[nf] = off; off += box_count (lo, hi); nf++;
+  }
+  a.nf = nf; a.g = g;
+}
+
+long long pluto_gpu_halo_doubles (const PlutoGpu *h, int dim)
+{
+  HaloArgs a;
+  halo_describe ((PlutoGpu *)h, 0, dim, 1, true, a);          // the larger of the two directions
+  return a.offset[a.nf - 1] + box_count (a.lo[a.nf - 1], a.hi[a.nf - 1]);
+}
+
+int pluto_gpu_halo_pack (PlutoGpu *h, int stage, int dim, double *send_lo, double *send_hi)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const int buf = stage_in_buf (h, stage);
+  HaloArgs a;
+  if (send_lo){ halo_describe (h, buf, dim, 0, true, a); a.buf = send_lo; if (count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))) return 1; }
+  if (send_hi){ halo_describe (h, buf, dim, 1, true, a); a.buf = send_hi; if (count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))) return 1; }
+  return 0;
+}
+
+int pluto_gpu_halo_unpack (PlutoGpu *h, int stage, int dim, const double *recv_lo, const double *recv_hi)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const int buf = stage_in_buf (h, stage);
+  HaloArgs a;
+  if (recv_lo){ halo_describe (h, buf, dim, 0, false, a); a.buf = (double *)recv_lo; if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1; }
+  if (recv_hi){ halo_describe (h, buf, dim, 1, false, a); a.buf = (double *)recv_hi; if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1; }
+  return 0;
+}
+

@@ -1,0 +1,245 @@
+"""Host-side mirror of the reference's step interface.
+
+``GpuStepper.advance(dt)`` is AdvanceStep (reference Src/Time_Stepping/
+rk_step.c:27) on device-resident state; ``Integrator`` is the time loop of
+main() (Src/main.c:133-243): clip dt to tstop, Integrate, g_time += g_dt,
+g_dt = NextTimeStep.  State dictionaries use the reference's dbl.out names
+(rho vx1 vx2 [vx3] Bx1 Bx2 [Bx3] prs Bx1s Bx2s [Bx3s]) and interior shapes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+VC_NAMES = ["rho", "vx1", "vx2", "vx3", "Bx1", "Bx2", "Bx3", "prs"]
+
+
+@dataclass
+class StepInfo:
+    inv_dt_hyp: float
+    max_mach: float
+    floor_events: int
+    nan_events: int
+
+
+class PlutoGpuError(RuntimeError):
+    pass
+
+
+class GpuStepper:
+    """One block of the domain resident on one GPU."""
+
+    def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
+                 bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0,
+                 small_dn=1e-12, small_pr=1e-12, lib_path=None):
+        self.L = _lib.load_library(lib_path)
+        c = _lib.PlutoGpuConfig()
+        n = list(n) + [1] * (3 - len(n))
+        if dims == 2:
+            n[2] = 1
+        c.dims = dims
+        for d in range(3):
+            c.n[d] = int(n[d])
+            c.dx[d] = float(dx[d]) if d < len(dx) else 1.0
+        c.recon = _lib.RECON[recon]
+        c.solver = _lib.SOLVER[solver]
+        c.rk_order = rk_order
+        for s in range(6):
+            c.bc[s] = _lib.BC[bc[s]]
+        c.arith = _lib.ARITH[arith]
+        c.device = device
+        c.gamma = gamma
+        c.small_dn = small_dn
+        c.small_pr = small_pr
+        self.cfg = c
+        self.dims = dims
+        self.n = tuple(n)
+        self.rk_order = rk_order
+        self._h = C.c_void_p()
+        if self.L.pluto_gpu_create(C.byref(c), C.byref(self._h)) != 0:
+            self._h = None
+            raise PlutoGpuError(_lib.last_error(self.L))
+        self.ng = self.L.pluto_gpu_nghost(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.pluto_gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PlutoGpuError(_lib.last_error(self.L))
+
+    # ---- interior (.dbl) layout -------------------------------------------
+    def interior_buffers(self, pinned=False):
+        """Host arrays in the interior layout: (vc[8,n3,n2,n1], bx1s, bx2s, bx3s|None)."""
+        n1, n2, n3 = self.n
+        shapes = [(8, n3, n2, n1), (n3, n2, n1 + 1), (n3, n2 + 1, n1)]
+        if self.dims == 3:
+            shapes.append((n3 + 1, n2, n1))
+        if pinned:
+            import torch
+            bufs = [torch.zeros(s, dtype=torch.float64).pin_memory().numpy() for s in shapes]
+        else:
+            bufs = [np.zeros(s) for s in shapes]
+        if self.dims == 2:
+            bufs.append(None)
+        return bufs
+
+    def upload_interior(self, vc, b1, b2, b3=None):
+        p = lambda a: a.ctypes.data if a is not None else None
+        for a in (vc, b1, b2, b3):
+            assert a is None or (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"])
+        self._check(self.L.pluto_gpu_upload_interior(self._h, p(vc), p(b1), p(b2), p(b3)))
+
+    def download_interior(self, vc, b1, b2, b3=None):
+        p = lambda a: a.ctypes.data if a is not None else None
+        self._check(self.L.pluto_gpu_download_interior(self._h, p(vc), p(b1), p(b2), p(b3)))
+
+    def set_state(self, dump: dict):
+        vc, b1, b2, b3 = self.interior_buffers()
+        for iv, nm in enumerate(VC_NAMES):
+            if nm in dump:
+                vc[iv] = dump[nm]
+        b1[...] = dump["Bx1s"]
+        b2[...] = dump["Bx2s"]
+        if self.dims == 3:
+            b3[...] = dump["Bx3s"]
+        self.upload_interior(vc, b1, b2, b3)
+
+    def get_state(self) -> dict:
+        vc, b1, b2, b3 = self.interior_buffers()
+        self.download_interior(vc, b1, b2, b3)
+        out = {}
+        for iv, nm in enumerate(VC_NAMES):
+            if self.dims == 2 and nm in ("vx3", "Bx3"):
+                continue
+            out[nm] = vc[iv].copy()
+        out["Bx1s"], out["Bx2s"] = b1, b2
+        if self.dims == 3:
+            out["Bx3s"] = b3
+        return out
+
+    # ---- reference Data layout (with ghost zones) --------------------------
+    def data_buffers(self, pinned=False):
+        n1, n2, n3 = self.n
+        g = self.ng
+        T1, T2 = n1 + 2 * g, n2 + 2 * g
+        T3 = n3 + 2 * g if self.dims == 3 else 1
+        nvar = 8 if self.dims == 3 else 6
+        shapes = [(nvar, T3, T2, T1), (T3, T2, T1 + 1), (T3, T2 + 1, T1)]
+        if self.dims == 3:
+            shapes.append((T3 + 1, T2, T1))
+        if pinned:
+            import torch
+            bufs = [torch.zeros(s, dtype=torch.float64).pin_memory().numpy() for s in shapes]
+        else:
+            bufs = [np.zeros(s) for s in shapes]
+        if self.dims == 2:
+            bufs.append(None)
+        return bufs
+
+    def upload_data(self, Vc, s1, s2, s3=None):
+        p = lambda a: a.ctypes.data if a is not None else None
+        self._check(self.L.pluto_gpu_upload_data(self._h, p(Vc), p(s1), p(s2), p(s3)))
+
+    def download_data(self, Vc, s1, s2, s3=None):
+        p = lambda a: a.ctypes.data if a is not None else None
+        self._check(self.L.pluto_gpu_download_data(self._h, p(Vc), p(s1), p(s2), p(s3)))
+
+    def advance_data(self, dt, Vc, s1, s2, s3=None) -> StepInfo:
+        """AdvanceStep on HOST Data arrays: upload, step, download."""
+        p = lambda a: a.ctypes.data if a is not None else None
+        info = _lib.PlutoGpuStepInfo()
+        self._check(self.L.pluto_gpu_advance_data(self._h, dt, p(Vc), p(s1), p(s2), p(s3), C.byref(info)))
+        return StepInfo(info.inv_dt_hyp, info.max_mach, info.floor_events, info.nan_events)
+
+    # ---- the step -----------------------------------------------------------
+    def advance(self, dt: float) -> StepInfo:
+        info = _lib.PlutoGpuStepInfo()
+        self._check(self.L.pluto_gpu_advance(self._h, dt, C.byref(info)))
+        return StepInfo(info.inv_dt_hyp, info.max_mach, info.floor_events, info.nan_events)
+
+    def boundary(self):
+        self._check(self.L.pluto_gpu_boundary(self._h))
+
+    def step_begin(self):
+        self._check(self.L.pluto_gpu_step_begin(self._h))
+
+    def stage(self, stage, dt):
+        self._check(self.L.pluto_gpu_stage(self._h, stage, dt))
+
+    def boundary_dim(self, stage, dim):
+        self._check(self.L.pluto_gpu_boundary_dim(self._h, stage, dim))
+
+    def step_end(self) -> StepInfo:
+        info = _lib.PlutoGpuStepInfo()
+        self._check(self.L.pluto_gpu_step_end(self._h, C.byref(info)))
+        return StepInfo(info.inv_dt_hyp, info.max_mach, info.floor_events, info.nan_events)
+
+    def halo_doubles(self, dim) -> int:
+        return int(self.L.pluto_gpu_halo_doubles(self._h, dim))
+
+    def halo_pack(self, stage, dim, send_lo_ptr, send_hi_ptr):
+        self._check(self.L.pluto_gpu_halo_pack(self._h, stage, dim, send_lo_ptr, send_hi_ptr))
+
+    def halo_unpack(self, stage, dim, recv_lo_ptr, recv_hi_ptr):
+        self._check(self.L.pluto_gpu_halo_unpack(self._h, stage, dim, recv_lo_ptr, recv_hi_ptr))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.pluto_gpu_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.pluto_gpu_launch_count(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.L.pluto_gpu_device_bytes(self._h))
+
+    def next_dt(self, inv_dt_hyp, cfl, cfl_max_var, dt) -> float:
+        return float(self.L.pluto_gpu_next_dt(inv_dt_hyp, cfl, cfl_max_var, dt))
+
+
+class Integrator:
+    """The reference's main loop around AdvanceStep (Src/main.c:133-243)."""
+
+    def __init__(self, stepper: GpuStepper, cfl: float, cfl_max_var: float = 1.1,
+                 first_dt: float = 1e-4, tstop: float = 1e30):
+        self.s = stepper
+        self.cfl, self.cfl_max_var = cfl, cfl_max_var
+        self.dt = first_dt
+        self.t = 0.0
+        self.tstop = tstop
+        self.nstep = 0
+        self.max_mach = 0.0
+        self.dt_history = [first_dt]
+
+    def step(self) -> StepInfo:
+        if self.t + self.dt >= self.tstop * (1.0 - 1e-8):      # main.c:145-148
+            self.dt = self.tstop - self.t
+        info = self.s.advance(self.dt)
+        if info.nan_events:
+            raise PlutoGpuError(f"step {self.nstep}: {info.nan_events} zones are not finite")
+        self.t += self.dt                                       # main.c:215
+        self.dt = self.s.next_dt(info.inv_dt_hyp, self.cfl, self.cfl_max_var, self.dt)  # main.c:236
+        self.max_mach = info.max_mach
+        self.nstep += 1
+        self.dt_history.append(self.dt)
+        return info
+
+    def run(self, nsteps: int):
+        for _ in range(nsteps):
+            self.step()
+        return self
