@@ -145,12 +145,21 @@ int pluto_gpu_step_end     (PlutoGpu *h, PlutoGpuStepInfo *info);
 /* ---- introspection (tests, bench, profiling) -------------------------- */
 void     *pluto_gpu_stream        (PlutoGpu *h);   /* cudaStream_t of all launches */
 long long pluto_gpu_launch_count  (const PlutoGpu *h);  /* kernels launched so far */
+/* per-kernel-class device time: CUDA events recorded on pluto_gpu_stream(h)
+   around every launch while enabled; accumulated at pluto_gpu_step_end.
+   Classes 0..7: sweep_x1 sweep_x2 sweep_x3 ct_emf ct_update final boundary halo. */
+int pluto_gpu_timing     (PlutoGpu *h, int enable);      /* (re)starts the accumulation */
+int pluto_gpu_timing_get (PlutoGpu *h, int cls, const char **name, double *ms, long long *launches);
 long long pluto_gpu_device_bytes  (const PlutoGpu *h);
 /* raw DEVICE pointer + padded shape of an internal field, for debugging:
    names rho vx1 vx2 vx3 bx1 bx2 bx3 prs bx1s bx2s bx3s.  Element (k,j,i),
    valid from -1, lives at ((k+off[2])*shape[1] + (j+off[1]))*shape[0] + (i+off[0]). */
 int pluto_gpu_field (PlutoGpu *h, const char *name, double **dev_ptr,
                      long long shape[3], int off[3]);
+/* copy the whole padded array of a field to host memory (shape[0]*shape[1]*shape[2]
+   doubles).  Further names: u_rho u_mx1 u_mx2 u_mx3 u_eng, exj exk eyi eyk ezi ezj,
+   ex ey ez, cdt; a "1:" / "2:" prefix selects the stage buffers. */
+int pluto_gpu_read_field (PlutoGpu *h, const char *name, double *host);
 
 #ifdef __cplusplus
 }

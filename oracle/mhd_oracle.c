@@ -55,6 +55,7 @@ struct Oracle {
   double max_mach, inv_dt_hyp;
   int    stage, floor_events;
   int    emf_ibeg, emf_iend, emf_jbeg, emf_jend, emf_kbeg, emf_kend;
+  int    debug_stop_after;   /* tests only: leave oracle_advance after this stage */
 };
 
 #define IDX(o,k,j,i) ((((k)+1)*(o)->S2 + ((j)+1))*(o)->S1 + ((i)+1))
@@ -988,6 +989,8 @@ int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
   ct_average_magnetic_field (o);
   cons_to_prim_3d (o);
 
+  if (o->debug_stop_after == 1) goto done;
+
   /* ---- stage 2 (rk_step.c:149-186) ---- */
   if (o->c.rk_order == 3){ w0 = 0.75; wc = 0.25; } else { w0 = 0.5; wc = 0.5; }
   o->stage = 2;
@@ -1022,10 +1025,13 @@ int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
     cons_to_prim_3d (o);
   }
 
+done:
   if (inv_dt_hyp) *inv_dt_hyp = o->inv_dt_hyp;
   if (max_mach)   *max_mach   = o->max_mach;
   return o->floor_events;
 }
+
+void oracle_debug_stop_after (Oracle *o, int stage) { o->debug_stop_after = stage; }
 
 double oracle_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt)
 /* main.c:462-465, 532 */

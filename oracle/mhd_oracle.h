@@ -65,6 +65,9 @@ int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach);
 /* NextTimeStep restatement (reference Src/main.c:389-575, hyperbolic part). */
 double oracle_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt);
 
+/* Debug: make oracle_advance return after the given stage (0 = whole step). */
+void oracle_debug_stop_after (Oracle *o, int stage);
+
 /* Debug taps: raw pointers into the padded internal arrays, plus the
    padded extents so tests can index them ((k+1)*S2*S1 + (j+1)*S1 + (i+1)). */
 const double *oracle_tap (const Oracle *o, const char *name);

@@ -50,6 +50,7 @@ def lib():
         L.oracle_advance.restype = C.c_int
         L.oracle_next_dt.argtypes = [C.c_double] * 4
         L.oracle_next_dt.restype = C.c_double
+        L.oracle_debug_stop_after.argtypes = [C.c_void_p, C.c_int]
         L.oracle_tap.argtypes = [C.c_void_p, C.c_char_p]
         L.oracle_tap.restype = dp
         ip = C.POINTER(C.c_int)
@@ -136,6 +137,9 @@ class Oracle:
         mach = C.c_double(0.0)
         nfloor = lib().oracle_advance(self._h, dt, C.byref(inv), C.byref(mach))
         return inv.value, mach.value, nfloor
+
+    def debug_stop_after(self, stage: int):
+        lib().oracle_debug_stop_after(self._h, stage)
 
     def tap(self, name: str) -> np.ndarray:
         """Padded internal array [k+1][j+1][i+1] (copy)."""

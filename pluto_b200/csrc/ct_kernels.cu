@@ -196,6 +196,12 @@ final_kernel (const __grid_constant__ FinalArgs a)
     u[BX2] = 0.5*(a.Bs[1][id] + a.Bs[1][id - g.S1]);
     if (NC == 3) u[BX3] = 0.5*(a.Bs[2][id] + a.Bs[2][id - g.S12]);
     fl = cons_to_prim<NC>(ph, u, v);
+    if (a.write_u == 1 || (a.write_u == 2 && fl)){
+      // the reference keeps Uc across stages (rk_step.c:149-186 has no PrimToCons3D)
+      a.Uw[RHO][id] = u[RHO]; a.Uw[MX1][id] = u[MX1]; a.Uw[MX2][id] = u[MX2];
+      if (NC == 3) a.Uw[MX3][id] = u[MX3];
+      a.Uw[ENG][id] = u[ENG];
+    }
     PG_FOR_NV(nv){
       a.Vout[nv][id] = v[nv];
       if (!(fabs(v[nv]) <= 1.7976931348623157e308)) bad = 1;

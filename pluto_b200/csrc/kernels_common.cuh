@@ -46,6 +46,8 @@ struct SweepArgs {
   double  dtdx, inv_dl;
   int     stage1;            // accumulate C_dt / CFL (g_intStage == 1)
   int     last_dir;          // this sweep completes C_dt -> reduce instead of store
+  int     u_from_v;          // x1 sweep: start from U = PrimToCons(V) (rk_step.c:93) instead of
+                             // continuing with the U left by the previous stage
   int     chunk_len;         // marching kernels: zones per thread along the sweep
   int     nchunk;
 };
@@ -74,6 +76,10 @@ struct FinalArgs {
   PhysPar ph;
   double  w0, wc;
   int     combine;                           // 0 none, 1 w0*U0 + wc*U, 2 (U0 + 2U)/3
+  int     write_u;                           // 0: U is dead after this stage; 1: store the stage
+                                             // result (a later stage continues from it);
+                                             // 2: store only ConsToPrim repairs
+  double *Uw[8];
 };
 
 // one boundary fill: up to 11 fields with their own boxes

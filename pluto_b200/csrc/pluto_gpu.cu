@@ -28,6 +28,10 @@ static int fail (const char *fmt, ...)
   return fail ("%s:%d: %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString (e_)); } while (0)
 
 enum { NVS = 8 };
+enum { PG_MAX_EV = 96, PG_NCLASS = 8 };
+enum { KC_SWEEP_X = 0, KC_SWEEP_Y, KC_SWEEP_Z, KC_CT_EMF, KC_CT_UPDATE, KC_FINAL, KC_BC, KC_HALO };
+static const char *kClassName[PG_NCLASS] = {"sweep_x1", "sweep_x2", "sweep_x3", "ct_emf", "ct_update",
+                                            "final", "boundary", "halo"};
 static const int kCons[5] = {0, 1, 2, 3, 7};       // RHO, MX1, MX2, MX3, ENG
 
 struct PlutoGpu {
@@ -51,6 +55,13 @@ struct PlutoGpu {
   unsigned long long *red_host;    // pinned mirror
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
+  // optional per-kernel-class device timing (CUDA events on `stream`)
+  int     timing;
+  int     nev;                                 // event pairs used in the current step
+  cudaEvent_t ev0[PG_MAX_EV], ev1[PG_MAX_EV];
+  int     ev_class[PG_MAX_EV];
+  double  class_ms[PG_NCLASS];
+  long long class_count[PG_NCLASS];
 };
 
 const char *pluto_gpu_last_error (void) { return g_err; }
@@ -67,6 +78,29 @@ static int count (PlutoGpu *h, int r)
   h->launches += r;
   return 0;
 }
+
+// bracket a launch with events when timing is on
+static int tbegin (PlutoGpu *h, int cls)
+{
+  if (!h->timing || h->nev >= PG_MAX_EV) return -1;
+  const int e = h->nev++;
+  if (!h->ev0[e]){ cudaEventCreate (&h->ev0[e]); cudaEventCreate (&h->ev1[e]); }
+  h->ev_class[e] = cls;
+  cudaEventRecord (h->ev0[e], h->stream);
+  return e;
+}
+static void tend (PlutoGpu *h, int e) { if (e >= 0) cudaEventRecord (h->ev1[e], h->stream); }
+static void tcollect (PlutoGpu *h)       // after a stream synchronise
+{
+  for (int e = 0; e < h->nev; e++){
+    float ms = 0.f;
+    if (cudaEventElapsedTime (&ms, h->ev0[e], h->ev1[e]) == cudaSuccess){
+      h->class_ms[h->ev_class[e]] += ms; h->class_count[h->ev_class[e]]++;
+    }
+  }
+  h->nev = 0;
+}
+#define TIMED(h, cls, expr) do { int te_ = tbegin (h, cls); int rc_ = (expr); tend (h, te_); if (rc_) return 1; } while (0)
 
 // ---------------------------------------------------------------------------
 int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
@@ -147,28 +181,66 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaFree (h->pool);
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
+  for (int e = 0; e < PG_MAX_EV; e++) if (h->ev0[e]){ cudaEventDestroy (h->ev0[e]); cudaEventDestroy (h->ev1[e]); }
   cudaStreamDestroy (h->stream);
   free (h);
 }
 
 void *pluto_gpu_stream (PlutoGpu *h) { return (void *)h->stream; }
+
+int pluto_gpu_timing (PlutoGpu *h, int enable)
+{
+  h->timing = enable; h->nev = 0;
+  for (int c = 0; c < PG_NCLASS; c++){ h->class_ms[c] = 0.0; h->class_count[c] = 0; }
+  return 0;
+}
+
+int pluto_gpu_timing_get (PlutoGpu *h, int cls, const char **name, double *ms, long long *launches)
+{
+  if (cls < 0 || cls >= PG_NCLASS) return 1;
+  *name = kClassName[cls]; *ms = h->class_ms[cls]; *launches = h->class_count[cls];
+  return 0;
+}
 long long pluto_gpu_launch_count (const PlutoGpu *h) { return h->launches; }
 long long pluto_gpu_device_bytes (const PlutoGpu *h) { return (long long)h->pool_bytes; }
 
 int pluto_gpu_field (PlutoGpu *h, const char *name, double **dev_ptr, long long shape[3], int off[3])
 {
   static const char *vn[NVS] = {"rho", "vx1", "vx2", "vx3", "bx1", "bx2", "bx3", "prs"};
+  static const char *un[NVS] = {"u_rho", "u_mx1", "u_mx2", "u_mx3", "", "", "", "u_eng"};
   static const char *sn[3] = {"bx1s", "bx2s", "bx3s"};
   *dev_ptr = NULL;
-  for (int nv = 0; nv < NVS; nv++) if (!strcmp (name, vn[nv])) *dev_ptr = h->V[0][nv];
-  for (int d = 0; d < 3; d++) if (!strcmp (name, sn[d])) *dev_ptr = h->Bs[0][d];
+  int buf = 0;                                  // "1:rho" selects state buffer 1
+  if (name[0] >= '0' && name[0] <= '2' && name[1] == ':'){ buf = name[0] - '0'; name += 2; }
+  if (buf >= h->nbuf) return fail ("state buffer %d does not exist", buf);
+  for (int nv = 0; nv < NVS; nv++){
+    if (!strcmp (name, vn[nv])) *dev_ptr = h->V[buf][nv];
+    if (un[nv][0] && !strcmp (name, un[nv])) *dev_ptr = h->U[nv];
+  }
+  for (int d = 0; d < 3; d++) if (!strcmp (name, sn[d])) *dev_ptr = h->Bs[buf][d];
   if (!strcmp (name, "ex")) *dev_ptr = h->ex;
   if (!strcmp (name, "ey")) *dev_ptr = h->ey;
   if (!strcmp (name, "ez")) *dev_ptr = h->ez;
+  if (!strcmp (name, "exj")) *dev_ptr = h->exj;
+  if (!strcmp (name, "exk")) *dev_ptr = h->exk;
+  if (!strcmp (name, "eyi")) *dev_ptr = h->eyi;
+  if (!strcmp (name, "eyk")) *dev_ptr = h->eyk;
+  if (!strcmp (name, "ezi")) *dev_ptr = h->ezi;
+  if (!strcmp (name, "ezj")) *dev_ptr = h->ezj;
   if (!strcmp (name, "cdt")) *dev_ptr = h->cdt;
   if (!*dev_ptr) return fail ("unknown field '%s'", name);
   shape[0] = h->g.S1; shape[1] = h->g.T[1] + 2; shape[2] = (h->g.dims == 3 ? h->g.T[2] + 2 : 1);
   for (int d = 0; d < 3; d++) off[d] = h->g.off[d];
+  return 0;
+}
+
+int pluto_gpu_read_field (PlutoGpu *h, const char *name, double *host)
+{
+  double *dev; long long shape[3]; int off[3];
+  if (pluto_gpu_field (h, name, &dev, shape, off)) return 1;
+  CU (cudaSetDevice (h->cfg.device));
+  CU (cudaStreamSynchronize (h->stream));
+  CU (cudaMemcpy (host, dev, (size_t)(shape[0]*shape[1]*shape[2])*sizeof (double), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -288,13 +360,13 @@ static int boundary_dim (PlutoGpu *h, int buf, int dim)
       nf++;
     }
     a.nf = nf;
-    if (count (h, DISPATCH (h, launch_bc) (a, h->stream))) return 1;
+    TIMED (h, KC_BC, count (h, DISPATCH (h, launch_bc) (a, h->stream)));
     if (type == PLUTO_GPU_BC_OUTFLOW || type == PLUTO_GPU_BC_REFLECTIVE){
       BcFillArgs b; memset (&b, 0, sizeof (b));
       for (int s = 0; s < 3; s++) b.Bs[s] = h->Bs[buf][s];
       b.Bc = (type == PLUTO_GPU_BC_OUTFLOW ? h->V[buf][4 + dim] : NULL);
       b.side = side; b.g = g;
-      if (count (h, DISPATCH (h, launch_bc_fill) (b, h->stream))) return 1;
+      TIMED (h, KC_BC, count (h, DISPATCH (h, launch_bc_fill) (b, h->stream)));
     }
   }
   return 0;
@@ -328,6 +400,10 @@ static int run_stage (PlutoGpu *h, int stage, double dt)
   for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph;
   s.stage1 = (stage == 1);
+  // EXACT: later stages continue from the conservative state the previous stage
+  // left (as the reference does); FAST: rebuild it from the primitives, which
+  // saves reading U in the x1 sweep and differs by round-off only
+  s.u_from_v = (stage == 1 || h->cfg.arith == PLUTO_GPU_ARITH_FAST);
   for (int dir = 0; dir < g.dims; dir++){
     s.Bn = h->Bs[sp.in][dir];
     s.dtdx = dt/g.dx[dir];                 // rhs.c:195
@@ -342,9 +418,11 @@ static int run_stage (PlutoGpu *h, int stage, double dt)
     s.nchunk = (g.n[dir] + s.chunk_len - 1)/s.chunk_len;
     int r;
     const int recon = h->cfg.recon;
+    const int te = tbegin (h, KC_SWEEP_X + dir);
     if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_sweep_hlld) (dir, recon, s, h->stream);
     else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_sweep_hll)  (dir, recon, s, h->stream);
     else                                             r = DISPATCH (h, launch_sweep_roe)  (dir, recon, s, h->stream);
+    tend (h, te);
     if (count (h, r)) return 1;
   }
 
@@ -358,14 +436,17 @@ static int run_stage (PlutoGpu *h, int stage, double dt)
     c.dtdx[d] = dt/g.dx[d];                // ct_update.c:87-89
   }
   c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine;
-  if (count (h, DISPATCH (h, launch_ct_emf) (c, h->stream))) return 1;
-  if (count (h, DISPATCH (h, launch_ct_update) (c, h->stream))) return 1;
+  TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
+  TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 
   FinalArgs f; memset (&f, 0, sizeof (f));
   for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[sp.out][nv]; }
   for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[sp.out][d];
   f.red = h->red; f.g = g; f.ph = h->ph; f.w0 = sp.w0; f.wc = sp.wc; f.combine = sp.combine;
-  if (count (h, DISPATCH (h, launch_final) (f, h->stream))) return 1;
+  for (int nv = 0; nv < NVS; nv++) f.Uw[nv] = h->U[nv];
+  f.write_u = 0;
+  if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine ? 1 : 2);
+  TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
   return 0;
 }
 
@@ -398,6 +479,7 @@ int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
   CU (cudaSetDevice (h->cfg.device));
   CU (cudaMemcpyAsync (h->red_host, h->red, RED_N*sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CU (cudaStreamSynchronize (h->stream));
+  if (h->timing) tcollect (h);
   double cd, mach;
   memcpy (&cd, &h->red_host[RED_CDT], sizeof (double));
   memcpy (&mach, &h->red_host[RED_MACH], sizeof (double));
@@ -496,8 +578,8 @@ int pluto_gpu_halo_pack (PlutoGpu *h, int stage, int dim, double *send_lo, doubl
   CU (cudaSetDevice (h->cfg.device));
   const int buf = stage_in_buf (h, stage);
   HaloArgs a;
-  if (send_lo){ halo_describe (h, buf, dim, 0, true, a); a.buf = send_lo; if (count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))) return 1; }
-  if (send_hi){ halo_describe (h, buf, dim, 1, true, a); a.buf = send_hi; if (count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))) return 1; }
+  if (send_lo){ halo_describe (h, buf, dim, 0, true, a); a.buf = send_lo; TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))); }
+  if (send_hi){ halo_describe (h, buf, dim, 1, true, a); a.buf = send_hi; TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_pack) (a, h->stream))); }
   return 0;
 }
 
@@ -506,8 +588,8 @@ int pluto_gpu_halo_unpack (PlutoGpu *h, int stage, int dim, const double *recv_l
   CU (cudaSetDevice (h->cfg.device));
   const int buf = stage_in_buf (h, stage);
   HaloArgs a;
-  if (recv_lo){ halo_describe (h, buf, dim, 0, false, a); a.buf = (double *)recv_lo; if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1; }
-  if (recv_hi){ halo_describe (h, buf, dim, 1, false, a); a.buf = (double *)recv_hi; if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1; }
+  if (recv_lo){ halo_describe (h, buf, dim, 0, false, a); a.buf = (double *)recv_lo; TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))); }
+  if (recv_hi){ halo_describe (h, buf, dim, 1, false, a); a.buf = (double *)recv_hi; TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))); }
   return 0;
 }
 

@@ -160,7 +160,12 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
   double cd = 0.0;
   if (upd){
     double u0[NV];
-    prim_to_cons<NC>(ph, v, u0);
+    if (a.u_from_v) prim_to_cons<NC>(ph, v, u0);
+    else{
+      u0[RHO] = a.U[RHO][id]; u0[MX1] = a.U[MX1][id]; u0[MX2] = a.U[MX2][id];
+      if (NC == 3) u0[MX3] = a.U[MX3][id];
+      u0[ENG] = a.U[ENG][id];
+    }
     const double dtdx = a.dtdx;
     double r;
     r = -dtdx*(F[RHO] - Fm[RHO]);                                 a.U[RHO][id] = u0[RHO] + r;

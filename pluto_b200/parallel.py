@@ -1,0 +1,290 @@
+"""Block domain decomposition and ghost-zone exchange across GPUs.
+
+Replaces the reference's ArrayLib layer for this path: the Cartesian process
+topology (Src/Parallel/al_decompose.c:125-137, Src/initialize.c:83-312), the
+per-dimension halo swap AL_Exchange_dim (Src/Parallel/al_exchange_dim.c:58-88)
+called at the top of Boundary (Src/boundary.c:98-110) and the MPI_Allreduce(MAX)
+of the inverse time step and Mach number (Src/main.c:195-199, 415).
+
+One process per GPU (torch.distributed, NCCL).  Per RK stage and per
+dimension, in the order x1 -> x2 -> x3 so that edges and corners are filled:
+pack the boundary layers of all cell-centred and staggered fields into two
+contiguous device buffers (CUDA kernels behind the C ABI), exchange them with
+the two neighbours (NCCL send/recv over NVLink), unpack into the ghost zones,
+then apply the physical conditions of that dimension.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .stepper import GpuStepper, StepInfo
+
+_GRIDS = {
+    3: {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2), 16: (2, 2, 4)},
+    2: {1: (1, 1, 1), 2: (1, 2, 1), 4: (2, 2, 1), 8: (2, 4, 1), 16: (4, 4, 1)},
+}
+
+
+@dataclass
+class BlockLayout:
+    """n1 x n2 x n3 rank grid over the global zones; rank = c1 + p1*(c2 + p2*c3)."""
+    dims: int
+    global_n: tuple
+    grid: tuple
+    periodic: tuple            # per dimension
+
+    @staticmethod
+    def pick_grid(dims, world):
+        if world not in _GRIDS[dims]:
+            raise ValueError(f"no rank grid for {world} ranks in {dims}-D")
+        return _GRIDS[dims][world]
+
+    @classmethod
+    def weak(cls, dims, n_per_rank, world, periodic=False):
+        grid = cls.pick_grid(dims, world)
+        n = list(n_per_rank) + [1] * (3 - len(n_per_rank))
+        gn = tuple(n[d] * grid[d] if d < dims else 1 for d in range(3))
+        per = (periodic,) * 3 if isinstance(periodic, bool) else tuple(periodic)
+        return cls(dims, gn, grid, per)
+
+    @classmethod
+    def strong(cls, dims, global_n, world, periodic=False):
+        grid = cls.pick_grid(dims, world)
+        gn = list(global_n) + [1] * (3 - len(global_n))
+        for d in range(dims):
+            if gn[d] % grid[d]:
+                raise ValueError(f"global zones {gn[d]} not divisible by {grid[d]} ranks in x{d+1}")
+        per = (periodic,) * 3 if isinstance(periodic, bool) else tuple(periodic)
+        return cls(dims, tuple(gn), grid, per)
+
+    @property
+    def world(self):
+        return self.grid[0] * self.grid[1] * self.grid[2]
+
+    def coords(self, rank):
+        p1, p2, _ = self.grid
+        return (rank % p1, (rank // p1) % p2, rank // (p1 * p2))
+
+    def rank_of(self, c):
+        p1, p2, _ = self.grid
+        return c[0] + p1 * (c[1] + p2 * c[2])
+
+    def local_n(self, rank=0):
+        return tuple(self.global_n[d] // self.grid[d] for d in range(3))
+
+    def offset(self, rank):
+        c, n = self.coords(rank), self.local_n(rank)
+        return tuple(c[d] * n[d] for d in range(3))
+
+    def neighbour(self, rank, dim, side):
+        """rank of the block abutting `side` (0 low, 1 high) along dim, or None."""
+        if self.grid[dim] == 1:
+            return None
+        c = list(self.coords(rank))
+        c[dim] += -1 if side == 0 else 1
+        if c[dim] < 0 or c[dim] >= self.grid[dim]:
+            if not self.periodic[dim]:
+                return None
+            c[dim] %= self.grid[dim]
+        return self.rank_of(c)
+
+    def block_bc(self, rank, physical_bc):
+        """bc names of one block: 'shared' where another block abuts (boundary.c:139)."""
+        bc = list(physical_bc)
+        for d in range(self.dims):
+            for side in range(2):
+                if self.neighbour(rank, d, side) is not None:
+                    bc[2 * d + side] = "shared"
+        return tuple(bc)
+
+
+def exchange_ops_order():
+    """Posting order of the four transfers of one dimension.  With two ranks in a
+    periodic dimension both neighbours are the SAME peer and NCCL/gloo match
+    messages per peer in posting order: my send_lo must meet the peer's recv_hi,
+    so sends go (lo, hi) and receives (hi, lo)."""
+    return (("send", 0), ("send", 1), ("recv", 1), ("recv", 0))
+
+
+class HaloExchanger:
+    """Per-dimension exchange of packed boundary layers between neighbouring ranks.
+
+    `pack(stage, dim, send_lo, send_hi)` / `unpack(stage, dim, recv_lo, recv_hi)`
+    take torch tensors (or None for a side without neighbour); the tensors live
+    on whatever device the process group moves (CUDA for NCCL, CPU for gloo)."""
+
+    def __init__(self, layout: BlockLayout, rank: int, halo_doubles, pack, unpack, device, group=None):
+        import torch
+        self.layout, self.rank, self.pack, self.unpack, self.group = layout, rank, pack, unpack, group
+        self.buf = {}
+        self.nbr = {}
+        for d in range(layout.dims):
+            lo, hi = layout.neighbour(rank, d, 0), layout.neighbour(rank, d, 1)
+            self.nbr[d] = (lo, hi)
+            if lo is None and hi is None:
+                continue
+            n = int(halo_doubles(d))
+            mk = lambda: torch.zeros(n, dtype=torch.float64, device=device)
+            self.buf[d] = {"send": [mk() if lo is not None else None, mk() if hi is not None else None],
+                           "recv": [mk() if lo is not None else None, mk() if hi is not None else None]}
+        self.bytes_per_exchange = sum(sum(t.numel() * 8 for t in b["send"] if t is not None) for b in self.buf.values())
+
+    def exchange_dim(self, stage, dim):
+        import torch.distributed as dist
+        if dim not in self.buf:
+            return
+        b, nbr = self.buf[dim], self.nbr[dim]
+        self.pack(stage, dim, b["send"][0], b["send"][1])
+        ops = []
+        for kind, side in exchange_ops_order():
+            if nbr[side] is None:
+                continue
+            if kind == "send":
+                ops.append(dist.P2POp(dist.isend, b["send"][side], nbr[side], group=self.group))
+            else:
+                ops.append(dist.P2POp(dist.irecv, b["recv"][side], nbr[side], group=self.group))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        self.unpack(stage, dim, b["recv"][0], b["recv"][1])
+
+
+class DistStepper:
+    """AdvanceStep on one block of a decomposed domain (one process per GPU)."""
+
+    def __init__(self, layout: BlockLayout, rank, dx, recon="plm", solver="hlld", rk_order=2,
+                 physical_bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0):
+        self.layout, self.rank = layout, rank
+        self.world = layout.world
+        n = layout.local_n(rank)
+        self.block = GpuStepper(layout.dims, n, dx, recon=recon, solver=solver, rk_order=rk_order,
+                                bc=layout.block_bc(rank, physical_bc), gamma=gamma, arith=arith, device=device)
+        self.rk_order = rk_order
+        self.dims = layout.dims
+        self.ex = None
+        if self.world > 1:
+            import torch
+            self._torch = torch
+            self._stream = torch.cuda.ExternalStream(self.block.stream, device=torch.device("cuda", device))
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            self.ex = HaloExchanger(
+                layout, rank, self.block.halo_doubles,
+                lambda st, d, lo, hi: self.block.halo_pack(st, d, ptr(lo), ptr(hi)),
+                lambda st, d, lo, hi: self.block.halo_unpack(st, d, ptr(lo), ptr(hi)),
+                device=torch.device("cuda", device))
+            self._red = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", device))
+
+    def set_state(self, dump):
+        self.block.set_state(dump)
+
+    def get_state(self):
+        return self.block.get_state()
+
+    def next_dt(self, *a):
+        return self.block.next_dt(*a)
+
+    def advance(self, dt) -> StepInfo:
+        if self.world == 1:
+            return self.block.advance(dt)
+        torch = self._torch
+        import torch.distributed as dist
+        b = self.block
+        with torch.cuda.stream(self._stream):
+            b.step_begin()
+            for stage in range(1, self.rk_order + 1):
+                for d in range(self.dims):
+                    self.ex.exchange_dim(stage, d)
+                    b.boundary_dim(stage, d)
+                b.stage(stage, dt)
+            info = b.step_end()
+            # MPI_Allreduce(MAX) of invDt_hyp and g_maxMach (main.c:195-199, 415)
+            self._red.copy_(torch.tensor([info.inv_dt_hyp, info.max_mach], dtype=torch.float64))
+            dist.all_reduce(self._red, op=dist.ReduceOp.MAX)
+            r = self._red.tolist()
+        return StepInfo(r[0], r[1], info.floor_events, info.nan_events)
+
+    def advance_data(self, dt, Vc, s1, s2, s3=None) -> StepInfo:
+        """AdvanceStep on this block's HOST Data arrays: upload, step, download."""
+        if self.world == 1:
+            return self.block.advance_data(dt, Vc, s1, s2, s3)
+        self.block.upload_data(Vc, s1, s2, s3)
+        info = self.advance(dt)
+        self.block.download_data(Vc, s1, s2, s3)
+        return info
+
+
+class LocalMultiBlock:
+    """Several blocks driven from ONE process (the reference's host is
+    single-threaded): the halo buffers of neighbouring blocks are
+    handed over directly (same device) -- used by the single-GPU test of the
+    decomposition and as the in-process alternative to one process per GPU."""
+
+    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, **kw):
+        import torch
+        self.layout = layout
+        self.blocks = [GpuStepper(layout.dims, layout.local_n(r), dx, bc=layout.block_bc(r, physical_bc),
+                                  device=device, **kw) for r in range(layout.world)]
+        self.rk_order = self.blocks[0].rk_order
+        dev = torch.device("cuda", device)
+        self.send = {}
+        for r, b in enumerate(self.blocks):
+            for d in range(layout.dims):
+                for side in range(2):
+                    if layout.neighbour(r, d, side) is not None:
+                        self.send[(r, d, side)] = torch.zeros(b.halo_doubles(d), dtype=torch.float64, device=dev)
+        self._torch = torch
+
+    def set_state(self, global_state):
+        lay = self.layout
+        for r, b in enumerate(self.blocks):
+            o, n = lay.offset(r), lay.local_n(r)
+            sl = lambda e1, e2, e3: (slice(o[2], o[2] + n[2] + e3), slice(o[1], o[1] + n[1] + e2), slice(o[0], o[0] + n[0] + e1))
+            sub = {}
+            for k, v in global_state.items():
+                ext = {"Bx1s": (1, 0, 0), "Bx2s": (0, 1, 0), "Bx3s": (0, 0, 1)}.get(k, (0, 0, 0))
+                sub[k] = np.ascontiguousarray(v[sl(*ext)])
+            b.set_state(sub)
+
+    def get_state(self):
+        lay = self.layout
+        gn = lay.global_n
+        out = None
+        for r, b in enumerate(self.blocks):
+            st = b.get_state()
+            if out is None:
+                out = {}
+                for k, v in st.items():
+                    ext = {"Bx1s": (1, 0, 0), "Bx2s": (0, 1, 0), "Bx3s": (0, 0, 1)}.get(k, (0, 0, 0))
+                    out[k] = np.zeros((gn[2] + ext[2], gn[1] + ext[1], gn[0] + ext[0]))
+            o, n = lay.offset(r), lay.local_n(r)
+            for k, v in st.items():
+                out[k][o[2]:o[2] + v.shape[0], o[1]:o[1] + v.shape[1], o[0]:o[0] + v.shape[2]] = v
+        return out
+
+    def advance(self, dt) -> StepInfo:
+        lay = self.layout
+        torch = self._torch
+        for b in self.blocks:
+            b.step_begin()
+        for stage in range(1, self.rk_order + 1):
+            for d in range(lay.dims):
+                for r, b in enumerate(self.blocks):
+                    lo, hi = self.send.get((r, d, 0)), self.send.get((r, d, 1))
+                    if lo is not None or hi is not None:
+                        b.halo_pack(stage, d, lo.data_ptr() if lo is not None else None,
+                                    hi.data_ptr() if hi is not None else None)
+                torch.cuda.synchronize()
+                for r, b in enumerate(self.blocks):
+                    nlo, nhi = lay.neighbour(r, d, 0), lay.neighbour(r, d, 1)
+                    rlo = self.send[(nlo, d, 1)].data_ptr() if nlo is not None else None
+                    rhi = self.send[(nhi, d, 0)].data_ptr() if nhi is not None else None
+                    if rlo is not None or rhi is not None:
+                        b.halo_unpack(stage, d, rlo, rhi)
+                    b.boundary_dim(stage, d)
+                torch.cuda.synchronize()
+            for b in self.blocks:
+                b.stage(stage, dt)
+        infos = [b.step_end() for b in self.blocks]
+        return StepInfo(max(i.inv_dt_hyp for i in infos), max(i.max_mach for i in infos),
+                        sum(i.floor_events for i in infos), sum(i.nan_events for i in infos))

@@ -196,6 +196,28 @@ class GpuStepper:
     def halo_unpack(self, stage, dim, recv_lo_ptr, recv_hi_ptr):
         self._check(self.L.pluto_gpu_halo_unpack(self._h, stage, dim, recv_lo_ptr, recv_hi_ptr))
 
+    def read_field(self, name: str) -> np.ndarray:
+        """Debug tap: the whole padded device array [k+off][j+1][i+1] of a field."""
+        dev = C.POINTER(C.c_double)()
+        shape = (C.c_longlong * 3)()
+        off = (C.c_int * 3)()
+        self._check(self.L.pluto_gpu_field(self._h, name.encode(), C.byref(dev), C.byref(shape), C.byref(off)))
+        out = np.zeros((shape[2], shape[1], shape[0]))
+        self._check(self.L.pluto_gpu_read_field(self._h, name.encode(), out.ctypes.data))
+        return out
+
+    def timing(self, enable: bool):
+        self.L.pluto_gpu_timing(self._h, 1 if enable else 0)
+
+    def timing_report(self) -> dict:
+        """{class name: (total ms, launches)} accumulated since timing(True)."""
+        out = {}
+        for c in range(8):
+            nm, ms, cnt = C.c_char_p(), C.c_double(), C.c_longlong()
+            if self.L.pluto_gpu_timing_get(self._h, c, C.byref(nm), C.byref(ms), C.byref(cnt)) == 0:
+                out[nm.value.decode()] = (ms.value, cnt.value)
+        return out
+
     @property
     def stream(self) -> int:
         return int(self.L.pluto_gpu_stream(self._h) or 0)

@@ -1,0 +1,93 @@
+"""numpy stand-in for one GPU block's ghost-zone layout (TEST DOUBLE): the same
+pack/unpack boxes as pluto_gpu_halo_pack/unpack (pluto_b200/csrc/pluto_gpu.cu,
+halo_describe), so that the rank-to-rank exchange logic of
+pluto_b200.parallel.HaloExchanger can be exercised on CPU with gloo."""
+import numpy as np
+
+
+class HostBlock:
+    def __init__(self, dims, n, ng=2):
+        self.dims, self.ng = dims, ng
+        self.n = tuple(n)
+        self.T = tuple(n[d] + 2 * ng if d < dims else 1 for d in range(3))
+        self.beg = tuple(ng if d < dims else 0 for d in range(3))
+        self.end = tuple(ng + n[d] - 1 if d < dims else 0 for d in range(3))
+        # arrays indexed [k+1][j+1][i+1] like the device layout (index -1 addressable)
+        shp = (self.T[2] + 2, self.T[1] + 2, self.T[0] + 2)
+        self.nf = (8 if dims == 3 else 6) + dims
+        self.f = [np.full(shp, np.nan) for _ in range(self.nf)]
+
+    def is_stag(self, q):
+        ncell = self.nf - self.dims
+        return q - ncell if q >= ncell else None
+
+    def box(self, q, dim, hs, send):
+        lo, hi = [0, 0, 0], [self.T[0] - 1, self.T[1] - 1, self.T[2] - 1]
+        s = self.is_stag(q)
+        if s is not None:
+            lo[s] = -1
+        normal = s is not None and s == dim
+        if send:
+            if hs == 0:
+                lo[dim], hi[dim] = self.beg[dim], self.beg[dim] + self.ng - 1
+            else:
+                lo[dim], hi[dim] = self.end[dim] - self.ng + 1 - (1 if normal else 0), self.end[dim]
+        else:
+            if hs == 0:
+                lo[dim], hi[dim] = (-1 if normal else 0), self.beg[dim] - 1
+            else:
+                lo[dim], hi[dim] = self.end[dim] + 1, self.T[dim] - 1
+        return lo, hi
+
+    def view(self, q, lo, hi):
+        return self.f[q][lo[2] + 1:hi[2] + 2, lo[1] + 1:hi[1] + 2, lo[0] + 1:hi[0] + 2]
+
+    def halo_doubles(self, dim):
+        tot = 0
+        for q in range(self.nf):
+            lo, hi = self.box(q, dim, 1, True)
+            tot += int(np.prod([hi[d] - lo[d] + 1 for d in range(3)]))
+        return tot
+
+    def pack(self, stage, dim, send_lo, send_hi):
+        for hs, buf in ((0, send_lo), (1, send_hi)):
+            if buf is None:
+                continue
+            off = 0
+            b = buf.numpy()
+            for q in range(self.nf):
+                lo, hi = self.box(q, dim, hs, True)
+                v = self.view(q, lo, hi)
+                b[off:off + v.size] = v.ravel()
+                off += v.size
+
+    def unpack(self, stage, dim, recv_lo, recv_hi):
+        for hs, buf in ((0, recv_lo), (1, recv_hi)):
+            if buf is None:
+                continue
+            off = 0
+            b = buf.numpy()
+            for q in range(self.nf):
+                lo, hi = self.box(q, dim, hs, False)
+                v = self.view(q, lo, hi)
+                v[...] = b[off:off + v.size].reshape(v.shape)
+                off += v.size
+
+    def periodic_local(self, dim):
+        """local periodic fill of one dimension (reference boundary.c:480-518)"""
+        for q in range(self.nf):
+            s = self.is_stag(q)
+            for hs in (0, 1):
+                lo, hi = [0, 0, 0], [self.T[0] - 1, self.T[1] - 1, self.T[2] - 1]
+                if s is not None:
+                    lo[s] = -1
+                if hs == 0:
+                    hi[dim] = self.beg[dim] - 1
+                else:
+                    lo[dim] = self.end[dim] + 1 - (1 if s == dim else 0)
+                    lo[dim] = self.end[dim] + 1 if s != dim else self.end[dim]
+                src_lo, src_hi = list(lo), list(hi)
+                sh = self.n[dim] if hs == 0 else -self.n[dim]
+                src_lo[dim] += sh
+                src_hi[dim] += sh
+                self.view(q, lo, hi)[...] = self.view(q, src_lo, src_hi)
