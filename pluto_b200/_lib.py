@@ -44,7 +44,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("PLUTO_GPU_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

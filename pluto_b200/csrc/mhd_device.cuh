@@ -50,6 +50,45 @@ __device__ __forceinline__ double minmod (double a, double b)
 { return a*b > 0.0 ? (fabs(a) < fabs(b) ? a : b) : 0.0; }
 
 // ---------------------------------------------------------------------------
+//  division and square root.  EXACT: IEEE (div.rn.f64 / sqrt.rn.f64), the
+//  reference's results bit for bit.  FAST (PG_FAST): branch-free MUFU seed
+//  (rcp/rsqrt.approx.ftz.f64, >= 20 good bits) + two Newton steps in FMA form,
+//  accurate to a few ulp, no slow-path branch -> the scheduler can interleave
+//  independent chains.  Arguments are physical magnitudes far from the
+//  subnormal / overflow range.
+// ---------------------------------------------------------------------------
+#ifdef PG_FAST
+__device__ __forceinline__ double pg_rcp (double b)
+{
+  double r;
+  asm ("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma (-b, r, 1.0);
+  r = fma (r, e, r);
+  e = fma (-b, r, 1.0);
+  r = fma (r, e, r);
+  return r;
+}
+__device__ __forceinline__ double pg_div (double a, double b) { return a*pg_rcp (b); }
+__device__ __forceinline__ double pg_sqrt (double x)
+{
+  double y;
+  asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma (-x*y, y, 1.0);
+  y = fma (0.5*y, e, y);
+  e = fma (-x*y, y, 1.0);
+  y = fma (0.5*y, e, y);
+  double s = x*y;
+  double r = fma (-s, s, x);
+  s = fma (r, 0.5*y, s);
+  return x > 0.0 ? s : 0.0;
+}
+#else
+__device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
+__device__ __forceinline__ double pg_div (double a, double b) { return a/b; }
+__device__ __forceinline__ double pg_sqrt (double x) { return sqrt (x); }
+#endif
+
+// ---------------------------------------------------------------------------
 //  limited slope, LIMITER DEFAULT: MC on density, minmod on pressure, van Leer
 //  on velocity and field (plm_states.c:192-227)
 // ---------------------------------------------------------------------------
@@ -64,7 +103,7 @@ template <int NV_ID> __device__ __forceinline__ double plm_slope (double dvp, do
   }else if (NV_ID == PRS){
     return dvp*dvm > 0.0 ? abs_min(dvp, dvm) : 0.0;
   }else{
-    return dvp*dvm > 0.0 ? 2.0*dvp*dvm/(dvp + dvm) : 0.0;
+    return dvp*dvm > 0.0 ? pg_div (2.0*dvp*dvm, dvp + dvm) : 0.0;
   }
 }
 
@@ -145,7 +184,7 @@ __device__ __forceinline__ void prim_to_cons (const Phys &ph, const double *v, d
     kinb2 = v[RHO]*kinb2 + v[BX1]*v[BX1] + v[BX2]*v[BX2];
   }
   kinb2 *= 0.5;
-  u[ENG] = kinb2 + v[PRS]/ph.gmm1;
+  u[ENG] = kinb2 + pg_div (v[PRS], ph.gmm1);
 }
 
 // returns 1 when a floor was applied; u is repaired in place as the reference does
@@ -163,17 +202,17 @@ __device__ __forceinline__ int cons_to_prim (const Phys &ph, double *u, double *
   }
   if (u[RHO] < 0.0){ u[RHO] = ph.small_dn; fail = 1; }
   v[RHO] = u[RHO];
-  tau = 1.0/u[RHO];
+  tau = pg_rcp (u[RHO]);
   v[VX1] = u[MX1]*tau; v[VX2] = u[MX2]*tau;
   if (NC == 3) v[VX3] = u[MX3]*tau;
   v[BX1] = u[BX1]; v[BX2] = u[BX2];
   if (NC == 3) v[BX3] = u[BX3];
   kinb2 = 0.5*(m2*tau + b2);
-  if (u[ENG] < 0.0){ u[ENG] = ph.small_pr/ph.gmm1 + kinb2; fail = 1; }
+  if (u[ENG] < 0.0){ u[ENG] = pg_div (ph.small_pr, ph.gmm1) + kinb2; fail = 1; }
   v[PRS] = ph.gmm1*(u[ENG] - kinb2);
   if (v[PRS] < 0.0){
     v[PRS] = ph.small_pr;
-    u[ENG] = v[PRS]/ph.gmm1 + kinb2;
+    u[ENG] = pg_div (v[PRS], ph.gmm1) + kinb2;
     fail = 1;
   }
   return fail;
@@ -218,8 +257,8 @@ __device__ __forceinline__ void max_signal_speed (const Phys &ph, const double *
   else        { Btmag2 = b2*b2; }
   Bmag2 = b1*b1 + Btmag2;
   cf = gpr - Bmag2;
-  cf = gpr + Bmag2 + sqrt(cf*cf + 4.0*gpr*Btmag2);
-  cf = sqrt(0.5*cf/v[RHO]);
+  cf = gpr + Bmag2 + pg_sqrt (cf*cf + 4.0*gpr*Btmag2);
+  cf = pg_sqrt (pg_div (0.5*cf, v[RHO]));
   cmin = v[D::vn] - cf;
   cmax = v[D::vn] + cf;
 }
@@ -236,7 +275,7 @@ __device__ __forceinline__ void hll_speed (const Phys &ph, const double *vL, con
   SL = minv(slmin, srmin);
   SR = maxv(slmax, srmax);
   scrh  = fabs(vL[D::vn]) + fabs(vR[D::vn]);
-  scrh /= sqrt(a2L) + sqrt(a2R);
+  scrh = pg_div (scrh, pg_sqrt (a2L) + pg_sqrt (a2R));
   mach = scrh;
 }
 
@@ -250,8 +289,8 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
                                              double *flux, double &press, double &cmax, double &mach)
 {
   double fL[NV], fR[NV], pL, pR, a2L, a2R, SL, SR, scrh;
-  a2L = ph.gamma*vL[PRS]/vL[RHO];
-  a2R = ph.gamma*vR[PRS]/vR[RHO];
+  a2L = pg_div (ph.gamma*vL[PRS], vL[RHO]);
+  a2R = pg_div (ph.gamma*vR[PRS], vR[RHO]);
   mhd_flux<DIR, NC>(vL, uL, fL, pL);
   mhd_flux<DIR, NC>(vR, uR, fR, pR);
   hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
@@ -264,7 +303,7 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
     PG_FOR_NV(nv) flux[nv] = fR[nv];
     press = pR;
   }else{
-    scrh = 1.0/(SR - SL);
+    scrh = pg_rcp (SR - SL);
     PG_FOR_NV(nv){
       flux[nv]  = SL*SR*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
       flux[nv] *= scrh;
@@ -287,8 +326,8 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
   double vsR, wsR = 0.0, scrhR, S1R, sqrR, duR;
   double Bx, Bx1, SM, sBx, pts;
 
-  a2L = ph.gamma*vL[PRS]/vL[RHO];
-  a2R = ph.gamma*vR[PRS]/vR[RHO];
+  a2L = pg_div (ph.gamma*vL[PRS], vL[RHO]);
+  a2R = pg_div (ph.gamma*vR[PRS], vR[RHO]);
   mhd_flux<DIR, NC>(vL, uL, fL, ptL);
   mhd_flux<DIR, NC>(vR, uR, fR, ptR);
   hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
@@ -306,35 +345,35 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     return;
   }
 
-  scrh = 1.0/(SR - SL);
+  scrh = pg_rcp (SR - SL);
   Bx1  = Bx = (SR*vR[BXn] - SL*vL[BXn])*scrh;
   sBx  = (Bx > 0.0 ? 1.0 : -1.0);
 
   duL = SL - vL[VXn];
   duR = SR - vR[VXn];
 
-  scrh = 1.0/(duR*uR[RHO] - duL*uL[RHO]);
+  scrh = pg_rcp (duR*uR[RHO] - duL*uL[RHO]);
   SM   = (duR*uR[MXn] - duL*uL[MXn] - ptR + ptL)*scrh;
 
   pts  = duR*uR[RHO]*ptL - duL*uL[RHO]*ptR +
          vL[RHO]*vR[RHO]*duR*duL*(vR[VXn] - vL[VXn]);
   pts *= scrh;
 
-  usL[RHO] = uL[RHO]*duL/(SL - SM);
-  usR[RHO] = uR[RHO]*duR/(SR - SM);
+  usL[RHO] = pg_div (uL[RHO]*duL, SL - SM);
+  usR[RHO] = pg_div (uR[RHO]*duR, SR - SM);
 
-  sqrL = sqrt(usL[RHO]);
-  sqrR = sqrt(usR[RHO]);
+  sqrL = pg_sqrt (usL[RHO]);
+  sqrR = pg_sqrt (usR[RHO]);
 
-  S1L = SM - fabs(Bx)/sqrL;
-  S1R = SM + fabs(Bx)/sqrR;
+  S1L = SM - pg_div (fabs(Bx), sqrL);
+  S1R = SM + pg_div (fabs(Bx), sqrR);
 
   bool revert_to_hllc = false;
   if ( (S1L - SL) <  1.e-4*(SM - SL) ) revert_to_hllc = true;
   if ( (S1R - SR) > -1.e-4*(SR - SM) ) revert_to_hllc = true;
 
   if (revert_to_hllc){
-    scrh = 1.0/(SR - SL);
+    scrh = pg_rcp (SR - SL);
     double hn = (SR*uR[BXn] - SL*uL[BXn] + fL[BXn] - fR[BXn])*scrh;
     double ht = (SR*uR[BXt] - SL*uL[BXt] + fL[BXt] - fR[BXt])*scrh;
     usL[BXn] = usR[BXn] = hn;
@@ -345,8 +384,8 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     }
     S1L = S1R = SM;
   }else{
-    scrhL = (uL[RHO]*duL*duL - Bx*Bx)/(uL[RHO]*duL*(SL - SM) - Bx*Bx);
-    scrhR = (uR[RHO]*duR*duR - Bx*Bx)/(uR[RHO]*duR*(SR - SM) - Bx*Bx);
+    scrhL = pg_div (uL[RHO]*duL*duL - Bx*Bx, uL[RHO]*duL*(SL - SM) - Bx*Bx);
+    scrhR = pg_div (uR[RHO]*duR*duR - Bx*Bx, uR[RHO]*duR*(SR - SM) - Bx*Bx);
     usL[BXn] = Bx1;
     usL[BXt] = uL[BXt]*scrhL;
     usR[BXn] = Bx1;
@@ -357,8 +396,8 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     }
   }
 
-  scrhL = Bx/(uL[RHO]*duL);
-  scrhR = Bx/(uR[RHO]*duR);
+  scrhL = pg_div (Bx, uL[RHO]*duL);
+  scrhR = pg_div (Bx, uR[RHO]*duR);
 
   vsL = vL[VXt] - scrhL*(usL[BXt] - uL[BXt]);
   vsR = vR[VXt] - scrhR*(usR[BXt] - uR[BXt]);
@@ -384,7 +423,7 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     scrhL -=      SM*Bx1 +    vsL*usL[BXt];
   }
   usL[ENG]  = duL*uL[ENG] - ptL*vL[VXn] + pts*SM + Bx*scrhL;
-  usL[ENG] /= SL - SM;
+  usL[ENG] = pg_div (usL[ENG], SL - SM);
 
   if (NC == 3){
     scrhR  = vR[VXn]*Bx1 + vR[VXt]*uR[BXt] + vR[VXb]*uR[BXb];
@@ -394,7 +433,7 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     scrhR -=      SM*Bx1 +    vsR*usR[BXt];
   }
   usR[ENG]  = duR*uR[ENG] - ptR*vR[VXn] + pts*SM + Bx*scrhR;
-  usR[ENG] /= SR - SM;
+  usR[ENG] = pg_div (usR[ENG], SR - SM);
 
   if (S1L >= 0.0){
     PG_FOR_NV(nv) flux[nv] = fL[nv] + SL*(usL[nv] - uL[nv]);
@@ -408,10 +447,10 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     ussr[RHO] = usR[RHO];
 
     vss  = sqrL*vsL + sqrR*vsR + (usR[BXt] - usL[BXt])*sBx;
-    vss /= sqrL + sqrR;
+    vss = pg_div (vss, sqrL + sqrR);
     if (NC == 3){
       wss  = sqrL*wsL + sqrR*wsR + (usR[BXb] - usL[BXb])*sBx;
-      wss /= sqrL + sqrR;
+      wss = pg_div (wss, sqrL + sqrR);
     }
 
     ussl[MXn] = ussl[RHO]*SM;
@@ -425,11 +464,11 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
 
     ussl[BXn] = ussr[BXn] = Bx1;
     ussl[BXt]  = sqrL*usR[BXt] + sqrR*usL[BXt] + sqrL*sqrR*(vsR - vsL)*sBx;
-    ussl[BXt] /= sqrL + sqrR;
+    ussl[BXt] = pg_div (ussl[BXt], sqrL + sqrR);
     ussr[BXt]  = ussl[BXt];
     if (NC == 3){
       ussl[BXb]  = sqrL*usR[BXb] + sqrR*usL[BXb] + sqrL*sqrR*(wsR - wsL)*sBx;
-      ussl[BXb] /= sqrL + sqrR;
+      ussl[BXb] = pg_div (ussl[BXb], sqrL + sqrR);
       ussr[BXb]  = ussl[BXb];
     }
 
@@ -493,12 +532,12 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     dU[nv] = uR[nv] - uL[nv];
   }
 
-  sqr_rho_L = sqrt(vL[RHO]);
-  sqr_rho_R = sqrt(vR[RHO]);
-  sl = sqr_rho_L/(sqr_rho_L + sqr_rho_R);
-  sr = sqr_rho_R/(sqr_rho_L + sqr_rho_R);
+  sqr_rho_L = pg_sqrt (vL[RHO]);
+  sqr_rho_R = pg_sqrt (vR[RHO]);
+  sl = pg_div (sqr_rho_L, sqr_rho_L + sqr_rho_R);
+  sr = pg_div (sqr_rho_R, sqr_rho_L + sqr_rho_R);
   rho = sr*vL[RHO] + sl*vR[RHO];
-  sqrt_rho = sqrt(rho);
+  sqrt_rho = pg_sqrt (rho);
 
   u = sl*vL[VXn] + sr*vR[VXn];
   v = sl*vL[VXt] + sr*vR[VXt];
@@ -508,17 +547,17 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   if (NC == 3) Bz = sr*vL[BXb] + sl*vR[BXb];
 
   sBx = (Bx >= 0.0 ? 1.0 : -1.0);
-  bx = Bx/sqrt_rho;
-  by = By/sqrt_rho;
-  if (NC == 3) bz = Bz/sqrt_rho;
+  bx = pg_div (Bx, sqrt_rho);
+  by = pg_div (By, sqrt_rho);
+  if (NC == 3) bz = pg_div (Bz, sqrt_rho);
 
   if (NC == 3) bt2 = 0.0 + by*by + bz*bz; else bt2 = 0.0 + by*by;
   b2    = bx*bx + bt2;
-  Btmag = sqrt(bt2*rho);
+  Btmag = pg_sqrt (bt2*rho);
 
   if (NC == 3) X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt] + dV[BXb]*dV[BXb];
   else         X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt];
-  X /= (sqr_rho_L + sqr_rho_R)*(sqr_rho_L + sqr_rho_R)*2.0;
+  X = pg_div (X, (sqr_rho_L + sqr_rho_R)*(sqr_rho_L + sqr_rho_R)*2.0);
 
   if (NC == 3){
     vdm = u*dU[MXn] + v*dU[MXt] + w*dU[MXb];
@@ -531,8 +570,8 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   }
   dV[PRS] = g1*((0.5*vel2 - X)*dV[RHO] - vdm + dU[ENG] - BdB);
 
-  HL   = (uL[ENG] + pL)/vL[RHO];
-  HR   = (uR[ENG] + pR)/vR[RHO];
+  HL   = pg_div (uL[ENG] + pL, vL[RHO]);
+  HR   = pg_div (uR[ENG] + pR, vR[RHO]);
   H    = sl*HL + sr*HR;
   Hgas = H - b2;
 
@@ -542,15 +581,15 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   scrh = a2 - b2;
   ca2  = bx*bx;
   scrh = scrh*scrh + 4.0*bt2*a2;
-  scrh = sqrt(scrh);
+  scrh = pg_sqrt (scrh);
 
   cf2 = 0.5*(a2 + b2 + scrh);
-  cs2 = a2*ca2/cf2;
+  cs2 = pg_div (a2*ca2, cf2);
 
-  cf = sqrt(cf2);
-  cs = sqrt(cs2);
-  ca = sqrt(ca2);
-  a  = sqrt(a2);
+  cf = pg_sqrt (cf2);
+  cs = pg_sqrt (cs2);
+  ca = pg_sqrt (ca2);
+  a  = pg_sqrt (a2);
 
   if (cf == cs){
     alpha_f = 1.0; alpha_s = 0.0;
@@ -559,17 +598,17 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   }else if (cf <= a){
     alpha_f = 1.0; alpha_s = 0.0;
   }else{
-    scrh    = 1.0/(cf2 - cs2);
+    scrh    = pg_rcp (cf2 - cs2);
     alpha_f = (a2  - cs2)*scrh;
     alpha_s = (cf2 -  a2)*scrh;
     alpha_f = maxv(0.0, alpha_f);
     alpha_s = maxv(0.0, alpha_s);
-    alpha_f = sqrt(alpha_f);
-    alpha_s = sqrt(alpha_s);
+    alpha_f = pg_sqrt (alpha_f);
+    alpha_s = pg_sqrt (alpha_s);
   }
 
   if (Btmag > 1.e-9){
-    if (NC == 3){ beta_y = By/Btmag; beta_z = Bz/Btmag; }
+    if (NC == 3){ beta_y = pg_div (By, Btmag); beta_z = pg_div (Bz, Btmag); }
     else          beta_y = (By >= 0.0 ? 1.0 : -1.0);
   }else{
     if (NC == 3) beta_z = beta_y = sqrt_1_2;
@@ -594,13 +633,13 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[MXn][k] = alpha_f*lambda[k];
   Rc[MXt][k] = alpha_f*v + scrh*beta_y;
   if (NC == 3) Rc[MXb][k] = alpha_f*w + scrh*beta_z;
-  Rc[BXt][k] = alpha_s*a*beta_y/sqrt_rho;
-  if (NC == 3) Rc[BXb][k] = alpha_s*a*beta_z/sqrt_rho;
+  Rc[BXt][k] = pg_div (alpha_s*a*beta_y, sqrt_rho);
+  if (NC == 3) Rc[BXb][k] = pg_div (alpha_s*a*beta_z, sqrt_rho);
   Rc[ENG][k] =   alpha_f*(Hgas - u*cf) + scrh*beta_v
-               + alpha_s*a*Btmag/sqrt_rho;
+               + pg_div (alpha_s*a*Btmag, sqrt_rho);
   eta[k] =   alpha_f*(X*dV[RHO] + dV[PRS]) + rho*scrh*beta_dv
            - rho*alpha_f*cf*dV[VXn]        + sqrt_rho*alpha_s*a*beta_dB;
-  eta[k] *= 0.5/a2;
+  eta[k] *= pg_div (0.5, a2);
 
   // ---- fast wave u + cf ----
   k = KFASTP;
@@ -612,10 +651,10 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[BXt][k] = Rc[BXt][KFASTM];
   if (NC == 3) Rc[BXb][k] = Rc[BXb][KFASTM];
   Rc[ENG][k] =   alpha_f*(Hgas + u*cf) - scrh*beta_v
-               + alpha_s*a*Btmag/sqrt_rho;
+               + pg_div (alpha_s*a*Btmag, sqrt_rho);
   eta[k] =   alpha_f*(X*dV[RHO] + dV[PRS]) - rho*scrh*beta_dv
            + rho*alpha_f*cf*dV[VXn]        + sqrt_rho*alpha_s*a*beta_dB;
-  eta[k] *= 0.5/a2;
+  eta[k] *= pg_div (0.5, a2);
 
   // ---- entropy wave ----
   k = KENTRP;
@@ -624,8 +663,8 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[MXn][k] = u;
   Rc[MXt][k] = v;
   if (NC == 3) Rc[MXb][k] = w;
-  Rc[ENG][k] = 0.5*vel2 + (ph.gamma - 2.0)/g1*X;
-  eta[k] = ((a2 - X)*dV[RHO] - dV[PRS])/a2;
+  Rc[ENG][k] = 0.5*vel2 + pg_div (ph.gamma - 2.0, g1)*X;
+  eta[k] = pg_div ((a2 - X)*dV[RHO] - dV[PRS], a2);
 
   // ---- div.B wave: no jump with CT ----
   k = KDIVB;
@@ -640,13 +679,13 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[MXn][k] = alpha_s*lambda[k];
   Rc[MXt][k] = alpha_s*v - scrh*beta_y;
   if (NC == 3) Rc[MXb][k] = alpha_s*w - scrh*beta_z;
-  Rc[BXt][k] = - alpha_f*a*beta_y/sqrt_rho;
-  if (NC == 3) Rc[BXb][k] = - alpha_f*a*beta_z/sqrt_rho;
+  Rc[BXt][k] = pg_div (- alpha_f*a*beta_y, sqrt_rho);
+  if (NC == 3) Rc[BXb][k] = pg_div (- alpha_f*a*beta_z, sqrt_rho);
   Rc[ENG][k] =   alpha_s*(Hgas - u*cs) - scrh*beta_v
-               - alpha_f*a*Btmag/sqrt_rho;
+               - pg_div (alpha_f*a*Btmag, sqrt_rho);
   eta[k] =   alpha_s*(X*dV[RHO] + dV[PRS]) - rho*scrh*beta_dv
            - rho*alpha_s*cs*dV[VXn]        - sqrt_rho*alpha_f*a*beta_dB;
-  eta[k] *= 0.5/a2;
+  eta[k] *= pg_div (0.5, a2);
 
   // ---- slow wave u + cs ----
   k = KSLOWP;
@@ -658,10 +697,10 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[BXt][k] = Rc[BXt][KSLOWM];
   if (NC == 3) Rc[BXb][k] = Rc[BXb][KSLOWM];
   Rc[ENG][k] =   alpha_s*(Hgas + u*cs) + scrh*beta_v
-               - alpha_f*a*Btmag/sqrt_rho;
+               - pg_div (alpha_f*a*Btmag, sqrt_rho);
   eta[k] =   alpha_s*(X*dV[RHO] + dV[PRS]) + rho*scrh*beta_dv
            + rho*alpha_s*cs*dV[VXn]        - sqrt_rho*alpha_f*a*beta_dB;
-  eta[k] *= 0.5/a2;
+  eta[k] *= pg_div (0.5, a2);
 
   if (NC == 3){
     // ---- Alfven wave u - ca ----
@@ -673,7 +712,7 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     Rc[BXb][k] =   sBx*sqrt_rho*beta_y;
     Rc[ENG][k] = - rho*(v*beta_z - w*beta_y);
     eta[k] = + beta_y*dV[VXb]               - beta_z*dV[VXt]
-             + sBx/sqrt_rho*(beta_y*dV[BXb] - beta_z*dV[BXt]);
+             + pg_div (sBx, sqrt_rho)*(beta_y*dV[BXb] - beta_z*dV[BXt]);
     eta[k] *= 0.5;
 
     // ---- Alfven wave u + ca ----
@@ -685,20 +724,20 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     Rc[BXb][k] =   Rc[BXb][KALFVM];
     Rc[ENG][k] = - Rc[ENG][KALFVM];
     eta[k] = - beta_y*dV[VXb]               + beta_z*dV[VXt]
-             + sBx/sqrt_rho*(beta_y*dV[BXb] - beta_z*dV[BXt]);
+             + pg_div (sBx, sqrt_rho)*(beta_y*dV[BXb] - beta_z*dV[BXt]);
     eta[k] *= 0.5;
   }
 
   cmax = fabs(u) + cf;
-  mach = fabs(u/a);
+  mach = fabs(pg_div (u, a));
   const int nw = (NC == 3 ? 8 : 6);
   PG_UNROLL for (int kk = 0; kk < NW; kk++) alambda[kk] = fabs(lambda[kk]);
 
   // entropy fix (roe.c:623-640)
-  if (alambda[KFASTM] < 0.5*delta) alambda[KFASTM] = lambda[KFASTM]*lambda[KFASTM]/delta + 0.25*delta;
-  if (alambda[KFASTP] < 0.5*delta) alambda[KFASTP] = lambda[KFASTP]*lambda[KFASTP]/delta + 0.25*delta;
-  if (alambda[KSLOWM] < 0.5*delta) alambda[KSLOWM] = lambda[KSLOWM]*lambda[KSLOWM]/delta + 0.25*delta;
-  if (alambda[KSLOWP] < 0.5*delta) alambda[KSLOWP] = lambda[KSLOWP]*lambda[KSLOWP]/delta + 0.25*delta;
+  if (alambda[KFASTM] < 0.5*delta) alambda[KFASTM] = pg_div (lambda[KFASTM]*lambda[KFASTM], delta) + 0.25*delta;
+  if (alambda[KFASTP] < 0.5*delta) alambda[KFASTP] = pg_div (lambda[KFASTP]*lambda[KFASTP], delta) + 0.25*delta;
+  if (alambda[KSLOWM] < 0.5*delta) alambda[KSLOWM] = pg_div (lambda[KSLOWM]*lambda[KSLOWM], delta) + 0.25*delta;
+  if (alambda[KSLOWP] < 0.5*delta) alambda[KSLOWP] = pg_div (lambda[KSLOWP]*lambda[KSLOWP], delta) + 0.25*delta;
 
   PG_FOR_NV(nv){
     scrh = 0.0;

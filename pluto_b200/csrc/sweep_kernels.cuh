@@ -25,6 +25,13 @@
 #include "kernels_common.cuh"
 #include "mhd_device.cuh"
 
+#ifndef PG_MINB_X
+#define PG_MINB_X 2
+#endif
+#ifndef PG_MINB_MARCH
+#define PG_MINB_MARCH 2
+#endif
+
 namespace PG_NS {
 
 __device__ __forceinline__ void atomic_max_pos (unsigned long long *slot, double x)
@@ -46,6 +53,18 @@ template <int NC>
 __device__ __forceinline__ void load_zone (const SweepArgs &a, long long id, double *v)
 {
   PG_FOR_NV(nv) v[nv] = __ldg (a.V[nv] + id);
+}
+
+#ifndef PG_PREFETCH
+#define PG_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l1 (const void *p)
+{
+#if PG_PREFETCH == 1
+  asm volatile ("prefetch.global.L1 [%0];" :: "l"(p));
+#elif PG_PREFETCH == 2
+  asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
 }
 
 // face EMFs from the induction flux (ct_emf.c:132-134,155-156,175-176) and
@@ -74,7 +93,7 @@ __device__ __forceinline__ void store_face_emf (const SweepArgs &a, long long id
 //  x1 sweep
 // ---------------------------------------------------------------------------
 template <int RECON, int SOLVER, int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PG_MINB_X)
 sweep_x_kernel (const __grid_constant__ SweepArgs a)
 {
   constexpr int DIR = 0;
@@ -190,7 +209,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
 //  x2 / x3 sweeps: marching pencils
 // ---------------------------------------------------------------------------
 template <int DIR, int RECON, int SOLVER, int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
   typedef Dirs<DIR> D;
@@ -251,6 +270,17 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   for (int f = c0 - 1; f <= c1; f++, id += sD){
     // id = zone f; interface f+1/2 lies between zone f (vb_) and zone f+1 (vc_)
     double vR[NV], vpn[NV];
+    if (f < c1){          // pull the next iteration's rows towards the SM while this face is solved
+      const long long ahead = id + (RECON == RECON_PLM ? 3 : 4)*sD;
+      PG_FOR_NV(nv) prefetch_l1 (a.V[nv] + ahead);
+      prefetch_l1 (a.Bn + id + sD);
+      if (upd){
+        prefetch_l1 (a.U[RHO] + id + sD); prefetch_l1 (a.U[MX1] + id + sD); prefetch_l1 (a.U[MX2] + id + sD);
+        if (NC == 3) prefetch_l1 (a.U[MX3] + id + sD);
+        prefetch_l1 (a.U[ENG] + id + sD);
+        if (a.stage1) prefetch_l1 (a.cdt + id + sD);
+      }
+    }
     if (RECON == RECON_PLM){
       double vnx[NV], dvm[NV], dvp[NV];
       load_zone<NC>(a, id + 2*sD, vnx);
