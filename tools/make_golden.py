@@ -37,6 +37,12 @@ CASES = {
     "turb3d_plm_hlld": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3), 10),
     "ot3d_ppm_roe": (RefConfig(problem="ot", dims=3, n=(12, 8, 16), recon="ppm", solver="roe",
                                first_dt=4.5e-2, cfl=0.3), 8),
+    # 100-step runs for the BASELINE.json "1e-9 after 100 steps" bar
+    "ot2d_plm_hlld_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4), 100),
+    "blast3d_plm_hlld_100": (RefConfig(problem="blast", dims=3, n=(24, 20, 16), first_dt=5e-4, cfl=0.3), 100),
+    "turb3d_plm_hlld_100": (RefConfig(problem="turb", dims=3, n=(16, 20, 24), first_dt=2e-2, cfl=0.3), 100),
+    "rotor2d_ppm_roe_100": (RefConfig(problem="rotor", dims=2, n=(48, 40, 1), recon="ppm", solver="roe",
+                                      first_dt=1e-3, cfl=0.4), 100),
 }
 
 
