@@ -1,0 +1,104 @@
+/* advance_step_gpu.c -- the reference-side binding of libpluto_gpu.so.
+ *
+ * Drop-in replacement for Src/Time_Stepping/rk_step.c + update_stage.c in a
+ * PLUTO 4.3 build: it defines the one symbol the driver calls,
+ *
+ *     int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
+ *
+ * (Src/prototypes.h:4, called from Integrate(), Src/main.c:339-355) and
+ * forwards the step to the C ABI of include/pluto_gpu.h.  Everything else of
+ * the reference (main loop, pluto.ini parser, Init(), output, restart) is
+ * untouched.  Compile it IN PLACE OF rk_step.o/update_stage.o, against the
+ * reference's own headers:
+ *
+ *     gcc -c -O3 -I. -I$PLUTO_DIR/Src -I<repo>/include advance_step_gpu.c
+ *     gcc $(OBJ) advance_step_gpu.o -L<repo>/pluto_b200/lib -lpluto_gpu -lm -o pluto
+ *
+ * Data ownership: the host owns d->Vc / d->Vs; this shim
+ * uploads them, steps on the GPU and downloads the result every call -- the
+ * literal AdvanceStep contract, so WriteData/Analysis/Restart keep working
+ * with no further hooks.  PLUTO_GPU_ARITH=fast|exact selects the arithmetic.
+ */
+#include "pluto.h"
+#include "pluto_gpu.h"
+
+static PlutoGpu *gpu = NULL;
+
+static int BoundaryCode (int type)
+{
+  if (type == PERIODIC)   return PLUTO_GPU_BC_PERIODIC;
+  if (type == OUTFLOW)    return PLUTO_GPU_BC_OUTFLOW;
+  if (type == REFLECTIVE) return PLUTO_GPU_BC_REFLECTIVE;
+  print ("! AdvanceStep(gpu): boundary type %d is not supported by libpluto_gpu\n", type);
+  QUIT_PLUTO(1);
+  return -1;
+}
+
+/* ********************************************************************* */
+int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
+/*
+ *********************************************************************** */
+{
+  PlutoGpuStepInfo info;
+  double *vs1, *vs2, *vs3 = NULL;
+
+#if PHYSICS != MHD || GEOMETRY != CARTESIAN || DIVB_CONTROL != CONSTRAINED_TRANSPORT \
+    || EOS != IDEAL || CT_EMF_AVERAGE != UCT_CONTACT || DIMENSIONS != COMPONENTS
+  #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT, DIMENSIONS == COMPONENTS"
+#endif
+
+  if (gpu == NULL){
+    PlutoGpuConfig c;
+    char *arith = getenv ("PLUTO_GPU_ARITH");
+    int idim;
+    memset (&c, 0, sizeof (c));
+    c.dims = DIMENSIONS;
+    c.n[0] = NX1; c.n[1] = NX2; c.n[2] = (DIMENSIONS == 3 ? NX3 : 1);
+    c.recon  = (RECONSTRUCTION == PARABOLIC ? PLUTO_GPU_RECON_PARABOLIC : PLUTO_GPU_RECON_LINEAR);
+    if      (Riemann == &HLLD_Solver) c.solver = PLUTO_GPU_SOLVER_HLLD;
+    else if (Riemann == &HLL_Solver)  c.solver = PLUTO_GPU_SOLVER_HLL;
+    else if (Riemann == &Roe_Solver)  c.solver = PLUTO_GPU_SOLVER_ROE;
+    else{
+      print ("! AdvanceStep(gpu): only hlld, hll and roe are available on the GPU\n");
+      QUIT_PLUTO(1);
+    }
+    c.rk_order = (TIME_STEPPING == RK3 ? 3 : 2);
+    for (idim = 0; idim < DIMENSIONS; idim++){
+      c.bc[2*idim]     = BoundaryCode (grid->lbound[idim]);      /* boundary.c:133-135 */
+      c.bc[2*idim + 1] = BoundaryCode (grid->rbound[idim]);
+      c.dx[idim] = grid->dx[idim][grid->lbeg[idim]];             /* uniform grid */
+    }
+    c.arith    = (arith != NULL && !strcmp (arith, "fast")) ? PLUTO_GPU_ARITH_FAST : PLUTO_GPU_ARITH_EXACT;
+    c.device   = 0;
+    c.gamma    = g_gamma;
+    c.small_dn = g_smallDensity;
+    c.small_pr = g_smallPressure;
+    if (pluto_gpu_create (&c, &gpu) != 0){
+      print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+      QUIT_PLUTO(1);
+    }
+    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones\n",
+           c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", pluto_gpu_nghost (gpu));
+  }
+
+/* -- contiguous blocks behind the pointer tables (Src/arrays.c:222-330,
+      Src/initialize.c:448-453) -- */
+
+  vs1 = &d->Vs[BX1s][0][0][-1];
+  vs2 = &d->Vs[BX2s][0][-1][0];
+#if DIMENSIONS == 3
+  vs3 = &d->Vs[BX3s][-1][0][0];
+#endif
+
+  if (pluto_gpu_advance_data (gpu, g_dt, d->Vc[0][0][0], vs1, vs2, vs3, &info) != 0){
+    print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+    QUIT_PLUTO(1);
+  }
+  if (info.nan_events > 0){
+    print ("! AdvanceStep(gpu): %d zones are not finite\n", info.nan_events);
+    QUIT_PLUTO(1);                       /* reference: CheckNaN, update_stage.c:192 */
+  }
+  Dts->invDt_hyp = MAX(Dts->invDt_hyp, info.inv_dt_hyp);   /* update_stage.c:308-312 */
+  g_maxMach      = MAX(g_maxMach, info.max_mach);          /* hll_speed.c:105 */
+  return 0;
+}

@@ -1,0 +1,30 @@
+#!/usr/bin/env bash
+# Build the UNMODIFIED reference driver (main loop, ini parser, Init, output)
+# with integration/advance_step_gpu.c in place of rk_step.o + update_stage.o,
+# linked against pluto_b200/lib/libpluto_gpu.so.  Output:
+# oracle/_ref/pluto_gpu_<variant> (git-ignored; travels to the GPU box).
+# Needs the reference sources (this container only) and a built libpluto_gpu.so.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/.." && pwd)"
+PLUTO_DIR="${PLUTO_DIR:-/root/reference}"
+[ -d "$PLUTO_DIR/Src" ] || { echo "build_shim.sh: no reference sources (skipping)" >&2; exit 0; }
+[ -f "$ROOT/pluto_b200/lib/libpluto_gpu.so" ] || { echo "build_shim.sh: build libpluto_gpu.so first" >&2; exit 1; }
+VARIANTS="${*:-2d_plm 3d_plm 2d_ppm 3d_ppm}"
+for VARIANT in $VARIANTS; do
+  B="$ROOT/oracle/_build/$VARIANT"
+  [ -f "$B/definitions.h" ] || "$ROOT/oracle/ref_build/build_ref.sh" "$VARIANT"
+  G="$ROOT/oracle/_build/gpu_$VARIANT"
+  mkdir -p "$G"
+  cp "$B/definitions.h" "$B/init.c" "$G/"
+  cp "$HERE/advance_step_gpu.c" "$G/"
+  # same makefile as the CPU reference build, with the two time-stepping objects
+  # replaced by the shim and the GPU library added to the link line
+  sed -e 's/rk_step.o update_stage.o/advance_step_gpu.o/' \
+      -e "s#^INCLUDE_DIRS = .*#INCLUDE_DIRS = -I. -I\$(SRC) -I$ROOT/include#" \
+      -e "s#^LDFLAGS = .*#LDFLAGS = -lm -L$ROOT/pluto_b200/lib -lpluto_gpu -Wl,-rpath,'\$\$ORIGIN/../../pluto_b200/lib'#" \
+      "$B/makefile" > "$G/makefile"
+  ( cd "$G" && make -j"$(nproc)" pluto >make.log 2>&1 ) || { tail -30 "$G/make.log"; exit 1; }
+  cp "$G/pluto" "$ROOT/oracle/_ref/pluto_gpu_$VARIANT"
+  echo "built oracle/_ref/pluto_gpu_$VARIANT"
+done

@@ -52,6 +52,7 @@ class RefConfig:
     blast: dict = field(default_factory=lambda: dict(
         P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.125))
     seed: int = 20240607
+    prefix: str = "pluto_"              # "pluto_gpu_" = reference driver + integration/advance_step_gpu.c
 
     def variant(self) -> str:
         v = f"{self.dims}d_{self.recon}"
@@ -60,7 +61,7 @@ class RefConfig:
         return v
 
     def binary(self) -> str:
-        return os.path.join(REF_DIR, "pluto_" + self.variant())
+        return os.path.join(REF_DIR, self.prefix + self.variant())
 
     def resolved_domain(self):
         if self.domain is not None:
@@ -173,7 +174,7 @@ class RefResult:
 
 def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
                   workdir: str | None = None, keep: bool = False,
-                  no_write: bool = False, timeout: float = 3600.0) -> RefResult:
+                  no_write: bool = False, timeout: float = 3600.0, env: dict | None = None) -> RefResult:
     """Run ``pluto -maxsteps M``.
 
     Reference main loop semantics (Src/main.c:133-243): ``-maxsteps M`` with
@@ -196,7 +197,8 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
         cmd.append("-no-write")
     t0 = time.perf_counter()
     p = subprocess.run(cmd, cwd=workdir, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, timeout=timeout)
+                       stderr=subprocess.STDOUT, timeout=timeout,
+                       env=(dict(os.environ, **env) if env else None))
     wall = time.perf_counter() - t0
     if p.returncode != 0:
         raise RuntimeError("reference run failed:\n" + p.stdout.decode()[-2000:])

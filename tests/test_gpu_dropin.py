@@ -1,0 +1,53 @@
+"""The drop-in proof: the reference's OWN driver (main loop, pluto.ini parser,
+Init(), .dbl writer -- compiled from the unmodified sources) linked with
+integration/advance_step_gpu.c + libpluto_gpu.so instead of rk_step.o /
+update_stage.o must reproduce the dumps of the all-CPU reference build:
+bit-identical states and dt sequence with EXACT arithmetic, within the
+BASELINE.json tolerances with FAST arithmetic.  The binaries are built in the
+development container (integration/build_shim.sh) and travel with the snapshot."""
+import numpy as np
+import pytest
+
+from oracle.refrun import RefConfig, have_ref, run_reference
+from tests.util import Golden, rel_l1, TOL_ONE_STEP, TOL_100_STEPS
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "ot2d_plm_hll", "turb3d_plm_hlld"]
+
+
+def _cfg(g):
+    return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
+                     cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
+                     prefix="pluto_gpu_")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_reference_driver_with_gpu_step_is_bit_identical(name):
+    g = Golden(name)
+    cfg = _cfg(g)
+    if not have_ref(cfg):
+        pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
+    r = run_reference(cfg, maxsteps=g.nsteps + 1, dump_every=1, env={"PLUTO_GPU_ARITH": "exact"})
+    tap = {int(a): c for a, b, c in r.dt_tap}
+    for s in range(1, g.nsteps + 1):
+        assert tap[s] == g.dt[s], f"dt after step {s}"
+    for s, ref in g.states.items():
+        for k, v in ref.items():
+            assert np.array_equal(r.dumps[s][k], v), f"{name}: {k} after {s} steps"
+
+
+@pytest.mark.parametrize("name", ["ot2d_plm_hlld_100", "blast3d_plm_hlld_100"])
+def test_reference_driver_with_gpu_step_fast_100_steps(name):
+    g = Golden(name)
+    cfg = _cfg(g)
+    if not have_ref(cfg):
+        pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
+    r = run_reference(cfg, maxsteps=g.nsteps + 1, dump_every=1, env={"PLUTO_GPU_ARITH": "fast"})
+    tap = {int(a): c for a, b, c in r.dt_tap}
+    for s in range(1, g.nsteps + 1):
+        assert abs(tap[s] - g.dt[s]) <= 1e-12 * g.dt[s], f"dt after step {s}"
+    for s, ref in g.states.items():
+        tol = TOL_ONE_STEP if s <= 1 else TOL_100_STEPS
+        for k, v in ref.items():
+            assert rel_l1(r.dumps[s][k], v) <= tol, f"{name}: {k} after {s} steps"
