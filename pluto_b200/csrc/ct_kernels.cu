@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128)
 final_kernel (const __grid_constant__ FinalArgs a)
 {
   const Geom &g = a.g;
-  Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr;
+  Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr; ph.igmm1 = a.ph.igmm1;
   const int ni = g.n[0], nj = g.n[1], nk = (NC == 3 ? g.n[2] : 1);
   long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
   int fl = 0, bad = 0;

@@ -28,7 +28,7 @@ __host__ __device__ __forceinline__ long long gidx (const Geom &g, int k, int j,
   return (long long)(k + g.off[2])*g.S12 + (long long)(j + g.off[1])*g.S1 + (i + g.off[0]);
 }
 
-struct PhysPar { double gamma, gmm1, small_dn, small_pr; };
+struct PhysPar { double gamma, gmm1, small_dn, small_pr, igmm1; };
 
 // reduction slots (device, unsigned long long each)
 enum { RED_CDT = 0, RED_MACH = 1, RED_FLOOR = 2, RED_NAN = 3, RED_ROEFAIL = 4, RED_N = 8 };

@@ -28,6 +28,7 @@ enum { SOLVER_HLLD = 0, SOLVER_HLL = 1, SOLVER_ROE = 2 };
 
 struct Phys {
   double gamma, gmm1, small_dn, small_pr;
+  double igmm1;                       // 1/(gamma - 1), FAST arithmetic only
 };
 
 // direction bookkeeping (reference Src/set_indexes.c:49-123)
@@ -81,6 +82,28 @@ __device__ __forceinline__ double pg_sqrt (double x)
   double r = fma (-s, s, x);
   s = fma (r, 0.5*y, s);
   return x > 0.0 ? s : 0.0;
+}
+// sqrt(x) and 1/sqrt(x) together (coupled Goldschmidt iteration, 7 FP64 ops)
+__device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs)
+{
+  double y;
+  asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x*y, h = 0.5*y;
+  double r = fma (-g, h, 0.5);
+  g = fma (g, r, g); h = fma (h, r, h);
+  r = fma (-g, h, 0.5);
+  g = fma (g, r, g); h = fma (h, r, h);
+  s = g; rs = h + h;
+}
+__device__ __forceinline__ double pg_sqrt_pos (double x)     // x > 0 guaranteed
+{
+  double y;
+  asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x*y, h = 0.5*y;
+  double r = fma (-g, h, 0.5);
+  g = fma (g, r, g); h = fma (h, r, h);
+  r = fma (-g, h, 0.5);
+  return fma (g, r, g);
 }
 #else
 __device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
@@ -184,7 +207,11 @@ __device__ __forceinline__ void prim_to_cons (const Phys &ph, const double *v, d
     kinb2 = v[RHO]*kinb2 + v[BX1]*v[BX1] + v[BX2]*v[BX2];
   }
   kinb2 *= 0.5;
+#ifdef PG_FAST
+  u[ENG] = kinb2 + v[PRS]*ph.igmm1;
+#else
   u[ENG] = kinb2 + pg_div (v[PRS], ph.gmm1);
+#endif
 }
 
 // returns 1 when a floor was applied; u is repaired in place as the reference does
@@ -312,6 +339,164 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
   }
 }
 
+#ifdef PG_FAST
+// FAST arithmetic: the same five-wave solver (same regions, same switches) with
+// shared reciprocals, sqrt/rsqrt pairs, 1/rho reused by both speed estimates and
+// the Mach-number diagnostic (g_maxMach, printed with 6 digits by the reference)
+// evaluated in single precision.
+template <int DIR, int NC>
+__device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, const double *vR,
+                                              const double *uL, const double *uR,
+                                              double *flux, double &press, double &cmax, double &mach)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
+  const int MXn = VXn, MXt = VXt, MXb = VXb;
+  double fL[NV], fR[NV], ptL, ptR, SL, SR;
+
+  mhd_flux<DIR, NC>(vL, uL, fL, ptL);
+  mhd_flux<DIR, NC>(vR, uR, fR, ptR);
+  {
+    // fast magnetosonic speeds (eigenv.c:87-101) and Davis estimate (hll_speed.c:76-107)
+    const double irL = pg_rcp (vL[RHO]), irR = pg_rcp (vR[RHO]);
+    const double gpL = ph.gamma*vL[PRS], gpR = ph.gamma*vR[PRS];
+    double bt2L = vL[BXt]*vL[BXt], bt2R = vR[BXt]*vR[BXt];
+    if (NC == 3){ bt2L = fma (vL[BXb], vL[BXb], bt2L); bt2R = fma (vR[BXb], vR[BXb], bt2R); }
+    const double b2L = fma (vL[BXn], vL[BXn], bt2L), b2R = fma (vR[BXn], vR[BXn], bt2R);
+    double dL = gpL - b2L, dR = gpR - b2R;
+    dL = gpL + b2L + pg_sqrt (fma (dL, dL, 4.0*gpL*bt2L));
+    dR = gpR + b2R + pg_sqrt (fma (dR, dR, 4.0*gpR*bt2R));
+    const double cfL = pg_sqrt_pos (0.5*dL*irL), cfR = pg_sqrt_pos (0.5*dR*irR);
+    SL = minv (vL[VXn] - cfL, vR[VXn] - cfR);
+    SR = maxv (vL[VXn] + cfL, vR[VXn] + cfR);
+    const float aL = sqrtf ((float)(gpL*irL)), aR = sqrtf ((float)(gpR*irR));
+    mach = (double)__fdividef ((float)(fabs (vL[VXn]) + fabs (vR[VXn])), aL + aR);
+  }
+  cmax = maxv (fabs (SL), fabs (SR));
+
+  if (SL >= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fL[nv];
+    press = ptL;
+    return;
+  }else if (SR <= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fR[nv];
+    press = ptR;
+    return;
+  }
+
+  const double iSRL = pg_rcp (SR - SL);
+  const double Bx = (SR*vR[BXn] - SL*vL[BXn])*iSRL;
+  const double sBx = (Bx > 0.0 ? 1.0 : -1.0);
+  const double duL = SL - vL[VXn], duR = SR - vR[VXn];
+  const double rduL = uL[RHO]*duL, rduR = uR[RHO]*duR;          // rho (S - vn)
+  const double idn = pg_rcp (rduR - rduL);
+  const double SM  = (duR*uR[MXn] - duL*uL[MXn] - ptR + ptL)*idn;
+  const double pts = (rduR*ptL - rduL*ptR + vL[RHO]*vR[RHO]*duR*duL*(vR[VXn] - vL[VXn]))*idn;
+
+  const double iSLM = pg_rcp (SL - SM), iSRM = pg_rcp (SR - SM);
+  const double rsL = rduL*iSLM, rsR = rduR*iSRM;                 // star densities
+  double sqrL, sqrR, isqL, isqR;
+  pg_sqrt_rsqrt (rsL, sqrL, isqL);
+  pg_sqrt_rsqrt (rsR, sqrR, isqR);
+  double S1L = SM - fabs (Bx)*isqL;
+  double S1R = SM + fabs (Bx)*isqR;
+
+  bool revert_to_hllc = false;
+  if ( (S1L - SL) <  1.e-4*(SM - SL) ) revert_to_hllc = true;
+  if ( (S1R - SR) > -1.e-4*(SR - SM) ) revert_to_hllc = true;
+
+  double BtsL, BtsR, BbsL = 0.0, BbsR = 0.0;                     // star transverse fields
+  const double Bx2 = Bx*Bx;
+  if (revert_to_hllc){
+    BtsL = BtsR = (SR*uR[BXt] - SL*uL[BXt] + fL[BXt] - fR[BXt])*iSRL;
+    if (NC == 3) BbsL = BbsR = (SR*uR[BXb] - SL*uL[BXb] + fL[BXb] - fR[BXb])*iSRL;
+    S1L = S1R = SM;
+  }else{
+    const double qL = (rduL*duL - Bx2)*pg_rcp (rduL*(SL - SM) - Bx2);
+    const double qR = (rduR*duR - Bx2)*pg_rcp (rduR*(SR - SM) - Bx2);
+    BtsL = uL[BXt]*qL; BtsR = uR[BXt]*qR;
+    if (NC == 3){ BbsL = uL[BXb]*qL; BbsR = uR[BXb]*qR; }
+  }
+  const double kL = Bx*pg_rcp (rduL), kR = Bx*pg_rcp (rduR);
+  const double vsL = vL[VXt] - kL*(BtsL - uL[BXt]);
+  const double vsR = vR[VXt] - kR*(BtsR - uR[BXt]);
+  double wsL = 0.0, wsR = 0.0;
+  if (NC == 3){
+    wsL = vL[VXb] - kL*(BbsL - uL[BXb]);
+    wsR = vR[VXb] - kR*(BbsR - uR[BXb]);
+  }
+  double vBL, vBsL, vBR, vBsR;                                   // v.B and its star value
+  if (NC == 3){
+    vBL  = vL[VXn]*Bx + vL[VXt]*uL[BXt] + vL[VXb]*uL[BXb];
+    vBsL = SM*Bx + vsL*BtsL + wsL*BbsL;
+    vBR  = vR[VXn]*Bx + vR[VXt]*uR[BXt] + vR[VXb]*uR[BXb];
+    vBsR = SM*Bx + vsR*BtsR + wsR*BbsR;
+  }else{
+    vBL  = vL[VXn]*Bx + vL[VXt]*uL[BXt];
+    vBsL = SM*Bx + vsL*BtsL;
+    vBR  = vR[VXn]*Bx + vR[VXt]*uR[BXt];
+    vBsR = SM*Bx + vsR*BtsR;
+  }
+  const double EsL = (duL*uL[ENG] - ptL*vL[VXn] + pts*SM + Bx*(vBL - vBsL))*iSLM;
+  const double EsR = (duR*uR[ENG] - ptR*vR[VXn] + pts*SM + Bx*(vBR - vBsR))*iSRM;
+
+  if (S1L >= 0.0){
+    flux[RHO] = fL[RHO] + SL*(rsL - uL[RHO]);
+    flux[MXn] = fL[MXn] + SL*(rsL*SM - uL[MXn]);
+    flux[MXt] = fL[MXt] + SL*(rsL*vsL - uL[MXt]);
+    if (NC == 3) flux[MXb] = fL[MXb] + SL*(rsL*wsL - uL[MXb]);
+    flux[BXn] = 0.0;
+    flux[BXt] = fL[BXt] + SL*(BtsL - uL[BXt]);
+    if (NC == 3) flux[BXb] = fL[BXb] + SL*(BbsL - uL[BXb]);
+    flux[ENG] = fL[ENG] + SL*(EsL - uL[ENG]);
+    press = ptL;
+  }else if (S1R <= 0.0){
+    flux[RHO] = fR[RHO] + SR*(rsR - uR[RHO]);
+    flux[MXn] = fR[MXn] + SR*(rsR*SM - uR[MXn]);
+    flux[MXt] = fR[MXt] + SR*(rsR*vsR - uR[MXt]);
+    if (NC == 3) flux[MXb] = fR[MXb] + SR*(rsR*wsR - uR[MXb]);
+    flux[BXn] = 0.0;
+    flux[BXt] = fR[BXt] + SR*(BtsR - uR[BXt]);
+    if (NC == 3) flux[BXb] = fR[BXb] + SR*(BbsR - uR[BXb]);
+    flux[ENG] = fR[ENG] + SR*(EsR - uR[ENG]);
+    press = ptR;
+  }else{
+    const double isum = pg_rcp (sqrL + sqrR);
+    const double vss = (sqrL*vsL + sqrR*vsR + (BtsR - BtsL)*sBx)*isum;
+    const double Btss = (sqrL*BtsR + sqrR*BtsL + sqrL*sqrR*(vsR - vsL)*sBx)*isum;
+    double wss = 0.0, Bbss = 0.0;
+    if (NC == 3){
+      wss  = (sqrL*wsL + sqrR*wsR + (BbsR - BbsL)*sBx)*isum;
+      Bbss = (sqrL*BbsR + sqrR*BbsL + sqrL*sqrR*(wsR - wsL)*sBx)*isum;
+    }
+    double vBss;
+    if (NC == 3) vBss = SM*Bx + vss*Btss + wss*Bbss; else vBss = SM*Bx + vss*Btss;
+    if (SM >= 0.0){
+      const double Ess = EsL - sqrL*(vBsL - vBss)*sBx;
+      flux[RHO] = fL[RHO] + SL*(rsL - uL[RHO]);
+      flux[MXn] = fL[MXn] + SL*(rsL*SM - uL[MXn]);
+      flux[MXt] = fL[MXt] + S1L*(rsL*vss - rsL*vsL) + SL*(rsL*vsL - uL[MXt]);
+      if (NC == 3) flux[MXb] = fL[MXb] + S1L*(rsL*wss - rsL*wsL) + SL*(rsL*wsL - uL[MXb]);
+      flux[BXn] = 0.0;
+      flux[BXt] = fL[BXt] + S1L*(Btss - BtsL) + SL*(BtsL - uL[BXt]);
+      if (NC == 3) flux[BXb] = fL[BXb] + S1L*(Bbss - BbsL) + SL*(BbsL - uL[BXb]);
+      flux[ENG] = fL[ENG] + S1L*(Ess - EsL) + SL*(EsL - uL[ENG]);
+      press = ptL;
+    }else{
+      const double Ess = EsR + sqrR*(vBsR - vBss)*sBx;
+      flux[RHO] = fR[RHO] + SR*(rsR - uR[RHO]);
+      flux[MXn] = fR[MXn] + SR*(rsR*SM - uR[MXn]);
+      flux[MXt] = fR[MXt] + S1R*(rsR*vss - rsR*vsR) + SR*(rsR*vsR - uR[MXt]);
+      if (NC == 3) flux[MXb] = fR[MXb] + S1R*(rsR*wss - rsR*wsR) + SR*(rsR*wsR - uR[MXb]);
+      flux[BXn] = 0.0;
+      flux[BXt] = fR[BXt] + S1R*(Btss - BtsR) + SR*(BtsR - uR[BXt]);
+      if (NC == 3) flux[BXb] = fR[BXb] + S1R*(Bbss - BbsR) + SR*(BbsR - uR[BXb]);
+      flux[ENG] = fR[ENG] + S1R*(Ess - EsR) + SR*(EsR - uR[ENG]);
+      press = ptR;
+    }
+  }
+}
+#else
 template <int DIR, int NC>
 __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, const double *vR,
                                               const double *uL, const double *uR,
@@ -496,6 +681,8 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     }
   }
 }
+
+#endif   // PG_FAST
 
 // Roe: returns false when a2 < 0 (the reference aborts, roe.c:300-306)
 template <int DIR, int NC>

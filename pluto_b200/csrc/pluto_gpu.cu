@@ -136,6 +136,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   g.tot = g.S12*(g.dims == 3 ? g.T[2] + 2 : 1);
   h->ph.gamma = cfg->gamma; h->ph.gmm1 = cfg->gamma - 1.0;
   h->ph.small_dn = cfg->small_dn; h->ph.small_pr = cfg->small_pr;
+  h->ph.igmm1 = 1.0/(cfg->gamma - 1.0);
   h->nbuf = (cfg->rk_order == 3 ? 3 : 2);
   h->march_chunk = 64;
 
