@@ -128,25 +128,26 @@ ct_update_kernel (const __grid_constant__ CtArgs a)
   const long long id = gidx (g, k, j, i);
   const long long sy = g.S1, sz = g.S12;
   const bool in_i = i >= g.beg[0], in_j = j >= g.beg[1], in_k = (NC == 3 ? k >= g.beg[2] : true);
+  const double dtdx0 = __ldg (a.dtp), dtdx1 = __ldg (a.dtp + 1), dtdx2 = (NC == 3 ? __ldg (a.dtp + 2) : 0.0);
 
   if (in_j && in_k){        // Bx1 at (i+1/2, j, k), i in [IBEG-1, IEND]
     double rhs;
-    if (NC == 3) rhs = 0.0 - a.dtdx[1]*(a.ez[id] - a.ez[id - sy]) + a.dtdx[2]*(a.ey[id] - a.ey[id - sz]);
-    else         rhs = 0.0 - a.dtdx[1]*(a.ez[id] - a.ez[id - sy]);
+    if (NC == 3) rhs = 0.0 - dtdx1*(a.ez[id] - a.ez[id - sy]) + dtdx2*(a.ey[id] - a.ey[id - sz]);
+    else         rhs = 0.0 - dtdx1*(a.ez[id] - a.ez[id - sy]);
     double b = a.Bs_in[0][id] + rhs;
     if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[0][id], b);
     a.Bs_out[0][id] = b;
   }
   if (in_i && in_k){        // Bx2 at (i, j+1/2, k)
     double rhs;
-    if (NC == 3) rhs = a.dtdx[0]*(a.ez[id] - a.ez[id - 1]) - a.dtdx[2]*(a.ex[id] - a.ex[id - sz]);
-    else         rhs = a.dtdx[0]*(a.ez[id] - a.ez[id - 1]);
+    if (NC == 3) rhs = dtdx0*(a.ez[id] - a.ez[id - 1]) - dtdx2*(a.ex[id] - a.ex[id - sz]);
+    else         rhs = dtdx0*(a.ez[id] - a.ez[id - 1]);
     double b = a.Bs_in[1][id] + rhs;
     if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[1][id], b);
     a.Bs_out[1][id] = b;
   }
   if (NC == 3 && in_i && in_j){   // Bx3 at (i, j, k+1/2)
-    double rhs = - a.dtdx[0]*(a.ey[id] - a.ey[id - 1]) + a.dtdx[1]*(a.ex[id] - a.ex[id - sy]);
+    double rhs = - dtdx0*(a.ey[id] - a.ey[id - 1]) + dtdx1*(a.ex[id] - a.ex[id - sy]);
     double b = a.Bs_in[2][id] + rhs;
     if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[2][id], b);
     a.Bs_out[2][id] = b;

@@ -43,7 +43,9 @@ struct SweepArgs {
   unsigned long long *red;   // reduction slots
   Geom    g;
   PhysPar ph;
-  double  dtdx, inv_dl;
+  const double *dtp;         // device: dt/dx1, dt/dx2, dt/dx3 (read at run time so that a
+                             // captured CUDA graph of the step can be replayed with a new dt)
+  double  inv_dl;
   int     stage1;            // accumulate C_dt / CFL (g_intStage == 1)
   int     last_dir;          // this sweep completes C_dt -> reduce instead of store
   int     u_from_v;          // x1 sweep: start from U = PrimToCons(V) (rk_step.c:93) instead of
@@ -61,7 +63,7 @@ struct CtArgs {
   const double *Bs0[3];                      // staggered field at t^n (stages >= 2)
   double *Bs_out[3];
   Geom   g;
-  double dtdx[3];
+  const double *dtp;                         // device: dt/dx1, dt/dx2, dt/dx3
   double w0, wc;                             // stage weights
   int    combine;                            // 0: none, 1: w0*B0 + wc*B, 2: (B0 + 2 B)/3
 };

@@ -53,6 +53,12 @@ struct PlutoGpu {
   signed char *sv[3];
   unsigned long long *red;         // device reduction slots
   unsigned long long *red_host;    // pinned mirror
+  double *dtdev;                   // device: dt/dx[0..2] of the current step
+  double *dthost;                  // pinned staging of the same
+  cudaGraphExec_t graph;           // captured single-GPU step (all stages), replayed with new dt
+  long long graph_launches;        // kernels inside the graph
+  int     use_graph;
+  long long steps_done;
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
   // optional per-kernel-class device timing (CUDA events on `stream`)
@@ -170,6 +176,9 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   CU (cudaMalloc ((void **)&h->red, RED_N*sizeof (unsigned long long)));
   CU (cudaMemset (h->red, 0, RED_N*sizeof (unsigned long long)));
   CU (cudaMallocHost ((void **)&h->red_host, RED_N*sizeof (unsigned long long)));
+  CU (cudaMalloc ((void **)&h->dtdev, 4*sizeof (double)));
+  CU (cudaMallocHost ((void **)&h->dthost, 4*sizeof (double)));
+  h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   *out = h;
   return 0;
 }
@@ -182,6 +191,8 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaFree (h->pool);
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
+  cudaFree (h->dtdev); cudaFreeHost (h->dthost);
+  if (h->graph) cudaGraphExecDestroy (h->graph);
   for (int e = 0; e < PG_MAX_EV; e++) if (h->ev0[e]){ cudaEventDestroy (h->ev0[e]); cudaEventDestroy (h->ev1[e]); }
   cudaStreamDestroy (h->stream);
   free (h);
@@ -393,13 +404,22 @@ static StagePlan stage_plan (const PlutoGpu *h, int stage)
   return p;
 }
 
-static int run_stage (PlutoGpu *h, int stage, double dt)
+// dt/dx (rhs.c:195, ct_update.c:87-89) goes to the device once per step
+static int set_dt (PlutoGpu *h, double dt)
+{
+  for (int d = 0; d < 3; d++) h->dthost[d] = dt/h->g.dx[d];
+  h->dthost[3] = dt;
+  CU (cudaMemcpyAsync (h->dtdev, h->dthost, 4*sizeof (double), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+static int run_stage (PlutoGpu *h, int stage)
 {
   const Geom &g = h->g;
   const StagePlan sp = stage_plan (h, stage);
   SweepArgs s; memset (&s, 0, sizeof (s));
   for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
-  s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph;
+  s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
   s.stage1 = (stage == 1);
   // EXACT: later stages continue from the conservative state the previous stage
   // left (as the reference does); FAST: rebuild it from the primitives, which
@@ -407,16 +427,26 @@ static int run_stage (PlutoGpu *h, int stage, double dt)
   s.u_from_v = (stage == 1 || h->cfg.arith == PLUTO_GPU_ARITH_FAST);
   for (int dir = 0; dir < g.dims; dir++){
     s.Bn = h->Bs[sp.in][dir];
-    s.dtdx = dt/g.dx[dir];                 // rhs.c:195
     s.inv_dl = 1.0/g.dx[dir];              // set_geometry.c (inv_dx)
     s.last_dir = (dir == g.dims - 1);
     s.sv = h->sv[dir];
     if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
-    s.chunk_len = h->march_chunk;
-    if (s.chunk_len > g.n[dir]) s.chunk_len = g.n[dir];
-    s.nchunk = (g.n[dir] + s.chunk_len - 1)/s.chunk_len;
+    if (dir > 0){
+      // zones per thread along a marching sweep: long enough to amortise the
+      // extra face per chunk, short enough to fill the 148 SMs (2-D grids have
+      // few pencils)
+      const int td = (dir == 1 ? 2 : 1);
+      const long long npen = (long long)(g.n[0] + 2)*(g.dims == 3 ? g.n[td] + 2 : 1);
+      const long long want = (228000 + npen - 1)/npen;               // chunks for ~4 waves of threads
+      long long len = (g.n[dir] + want - 1)/want;
+      if (len < 4) len = 4;
+      if (len > h->march_chunk) len = h->march_chunk;
+      if (len > g.n[dir]) len = g.n[dir];
+      s.chunk_len = (int)len;
+      s.nchunk = (g.n[dir] + s.chunk_len - 1)/s.chunk_len;
+    }
     int r;
     const int recon = h->cfg.recon;
     const int te = tbegin (h, KC_SWEEP_X + dir);
@@ -434,9 +464,8 @@ static int run_stage (PlutoGpu *h, int stage, double dt)
   c.ex = h->ex; c.ey = h->ey; c.ez = h->ez;
   for (int d = 0; d < 3; d++){
     c.Bs_in[d] = h->Bs[sp.in][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[sp.out][d];
-    c.dtdx[d] = dt/g.dx[d];                // ct_update.c:87-89
   }
-  c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine;
+  c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine; c.dtp = h->dtdev;
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 
@@ -472,7 +501,8 @@ int pluto_gpu_stage (PlutoGpu *h, int stage, double dt)
 {
   CU (cudaSetDevice (h->cfg.device));
   if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
-  return run_stage (h, stage, dt);
+  if (stage == 1 && set_dt (h, dt)) return 1;      // one dt per step
+  return run_stage (h, stage);
 }
 
 int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
@@ -496,14 +526,44 @@ int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
   return 0;
 }
 
-int pluto_gpu_advance (PlutoGpu *h, double dt, PlutoGpuStepInfo *info)
+static int enqueue_step (PlutoGpu *h)
 {
-  if (pluto_gpu_step_begin (h)) return 1;
+  CU (cudaMemsetAsync (h->red, 0, RED_N*sizeof (unsigned long long), h->stream));
   for (int stage = 1; stage <= h->cfg.rk_order; stage++){
     const int in = stage_in_buf (h, stage);
     for (int d = 0; d < h->g.dims; d++) if (boundary_dim (h, in, d)) return 1;
-    if (run_stage (h, stage, dt)) return 1;
+    if (run_stage (h, stage)) return 1;
   }
+  return 0;
+}
+
+int pluto_gpu_advance (PlutoGpu *h, double dt, PlutoGpuStepInfo *info)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (set_dt (h, dt)) return 1;
+  // The ~45-130 launches of a step are captured once into a CUDA graph (dt lives
+  // in device memory, so the graph is replayed unchanged); the first step and
+  // steps with per-kernel timing enabled are launched directly.
+  if (h->use_graph && !h->timing && h->steps_done >= 1){
+    if (!h->graph){
+      cudaGraph_t gr = NULL;
+      const long long l0 = h->launches;
+      CU (cudaStreamBeginCapture (h->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_step (h);
+      cudaError_t e = cudaStreamEndCapture (h->stream, &gr);
+      if (rc || e != cudaSuccess){ if (gr) cudaGraphDestroy (gr); return rc ? 1 : fail ("graph capture: %s", cudaGetErrorString (e)); }
+      h->graph_launches = h->launches - l0;
+      h->launches = l0;
+      e = cudaGraphInstantiate (&h->graph, gr, 0);
+      cudaGraphDestroy (gr);
+      if (e != cudaSuccess) return fail ("cudaGraphInstantiate: %s", cudaGetErrorString (e));
+    }
+    CU (cudaGraphLaunch (h->graph, h->stream));
+    h->launches += h->graph_launches;
+  }else{
+    if (enqueue_step (h)) return 1;
+  }
+  h->steps_done++;
   return pluto_gpu_step_end (h, info);
 }
 

@@ -232,7 +232,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
         if (NC == 3) u0[MX3] = a.U[MX3][id];
         u0[ENG] = a.U[ENG][id];
       }
-      const double dtdx = a.dtdx;
+      const double dtdx = __ldg (a.dtp + DIR);
       double rr;
       rr = -dtdx*(F[RHO] - Fm[RHO]);                                a.U[RHO][id] = u0[RHO] + rr;
       rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);       a.U[MX1][id] = u0[MX1] + rr;
@@ -395,7 +395,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     }
     const double pp = C_FP(5), cp = C_FP(6);
     if (upd && f >= c0){
-      const double dtdx = a.dtdx;
+      const double dtdx = __ldg (a.dtp + DIR);
       double r;
       r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = C_UA(cur, 0) + r;
       r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = C_UA(cur, 1) + r;
