@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="blast3d_256", choices=sorted(WORKLOADS))
-    ap.add_argument("--arith", default=os.environ.get("PLUTO_GPU_ARITH", "exact"), choices=["exact", "fast"])
+    ap.add_argument("--arith", default=os.environ.get("PLUTO_GPU_ARITH", "fast"), choices=["exact", "fast"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -316,6 +316,12 @@ def main():
     step_s = ms_max * 1e-3 / args.steps
     step_gbs = algo["bytes"] * zones_local / step_s / 1e9
     step_tf = algo["flops"] * zones_local / step_s / 1e12
+    import ctypes
+    from pluto_b200 import load_library
+    tf = ctypes.c_double(0.0)
+    fp64_measured = None
+    if load_library().pluto_gpu_measure_fp64(local, ctypes.byref(tf)) == 0 and tf.value > 0:
+        fp64_measured = tf.value
     bound_s = max(algo["bytes"] / (hbm_peak * 1e9), algo["flops"] / (FP64_PEAK_TFLOPS_NOMINAL * 1e12))
     traffic = None
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
@@ -332,6 +338,8 @@ def main():
                      "hbm_gbs": step_gbs, "hbm_frac": step_gbs / hbm_peak,
                      "fp64_tflops": step_tf, "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS_NOMINAL,
                      "fp64_frac": step_tf / FP64_PEAK_TFLOPS_NOMINAL,
+                     "fp64_peak_tflops_measured_dfma_chain": fp64_measured,
+                     "fp64_frac_of_measured": (step_tf / fp64_measured) if fp64_measured else None,
                      "stencil_roofline_zone_updates_per_sec_per_gpu": 1.0 / bound_s,
                      "stencil_roofline_frac": (value / world) * bound_s}
     kernels = {k: {"ms_per_step": v[0] / ksteps, "launches_per_step": v[1] / ksteps} for k, v in rep.items() if v[1]}

@@ -161,6 +161,10 @@ int pluto_gpu_field (PlutoGpu *h, const char *name, double **dev_ptr,
    ex ey ez, cdt; a "1:" / "2:" prefix selects the stage buffers. */
 int pluto_gpu_read_field (PlutoGpu *h, const char *name, double *host);
 
+/* FP64 pipe microbenchmark (independent DFMA chains on every SM): the measured
+   denominator of the FP64 roofline, in TFLOP/s (FMA = 2 flops). */
+int pluto_gpu_measure_fp64 (int device, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

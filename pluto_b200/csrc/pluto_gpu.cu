@@ -654,3 +654,45 @@ int pluto_gpu_halo_unpack (PlutoGpu *h, int stage, int dim, const double *recv_l
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+//  FP64 pipe microbenchmark: 8 independent DFMA chains per thread, enough warps
+//  to saturate the pipe.  Gives the MEASURED denominator of the FP64 roofline
+//  (SURVEY.md 8d asks for it instead of the nominal 37.2 TFLOP/s).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_chain_kernel (double *out, double a, double b, int iters)
+{
+  double x0 = threadIdx.x*1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+  double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; i++){
+    x0 = fma (x0, a, b); x1 = fma (x1, a, b); x2 = fma (x2, a, b); x3 = fma (x3, a, b);
+    x4 = fma (x4, a, b); x5 = fma (x5, a, b); x6 = fma (x6, a, b); x7 = fma (x7, a, b);
+  }
+  out[(size_t)blockIdx.x*blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int pluto_gpu_measure_fp64 (int device, double *tflops)
+{
+  CU (cudaSetDevice (device));
+  cudaDeviceProp prop;
+  CU (cudaGetDeviceProperties (&prop, device));
+  const int nb = prop.multiProcessorCount*8, tpb = 256, iters = 20000;
+  double *out;
+  CU (cudaMalloc ((void **)&out, (size_t)nb*tpb*sizeof (double)));
+  cudaEvent_t e0, e1;
+  CU (cudaEventCreate (&e0)); CU (cudaEventCreate (&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++){
+    CU (cudaEventRecord (e0, 0));
+    dfma_chain_kernel<<<nb, tpb>>>(out, 0.999999, 1e-7, iters);
+    CU (cudaEventRecord (e1, 0));
+    CU (cudaEventSynchronize (e1));
+    float ms = 0.f;
+    CU (cudaEventElapsedTime (&ms, e0, e1));
+    const double tf = 2.0*8.0*(double)iters*(double)nb*tpb/(ms*1e-3)/1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
+  *tflops = best;
+  return 0;
+}

@@ -303,7 +303,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   //   buffered: consumed at the END of an iteration, refilled at its top).
   extern __shared__ double carry_[];
   double *cs = carry_ + threadIdx.x;
-  const int CS = blockDim.x;
+  constexpr int CS = 128;                   // = blockDim.x (fixed by the launcher): immediate smem offsets
   constexpr int S_NX = (RECON == RECON_PLM ? 31 : 47), S_BN = S_NX + 8, S_UA = S_BN + 1;
   constexpr int LA = (RECON == RECON_PLM ? 2 : 3);      // look-ahead of the stencil
 #define C_VB(nv) cs[(0 + (nv))*CS]

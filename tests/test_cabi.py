@@ -11,7 +11,7 @@ from tests.util import ROOT
 def _declared():
     txt = open(os.path.join(ROOT, "include", "pluto_gpu.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(pluto_gpu_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(pluto_gpu_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_are_exported():
