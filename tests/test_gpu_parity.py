@@ -95,6 +95,14 @@ ORACLE_CASES = [
     ("turb", 3, (30, 28, 26), "plm", "hlld", 3, 5, 1e-2),
     ("ot", 2, (70, 64, 1), "ppm", "hll", 3, 8, 5e-3),
     ("turb", 2, (64, 72, 1), "plm", "roe", 2, 8, 8e-3),
+    # smallest legal blocks (n = 2*nghost), ragged extents, one-segment rows, chunk remainders
+    ("turb", 3, (4, 4, 4), "plm", "hlld", 2, 4, 2e-2),
+    ("turb", 3, (5, 4, 7), "plm", "hll", 2, 4, 2e-2),
+    ("turb", 3, (6, 7, 6), "ppm", "hlld", 2, 4, 2e-2),
+    ("ot", 2, (4, 5, 1), "plm", "hlld", 2, 4, 2e-2),
+    ("blast", 2, (31, 6, 1), "ppm", "roe", 3, 4, 2e-4),
+    ("ot", 2, (29, 300, 1), "plm", "hlld", 2, 3, 2e-3),
+    ("ot", 3, (61, 5, 130), "plm", "hlld", 2, 3, 2e-3),
 ]
 
 
