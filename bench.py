@@ -49,6 +49,9 @@ WORKLOADS = {
     "ot3d_256": ("ot", 3, (256, 256, 256), "plm", "hlld", 0.3, 1e-3),
     "ot2d_512": ("ot", 2, (512, 512, 1), "plm", "hlld", 0.4, 1e-3),
     "rotor2d_4096": ("rotor", 2, (4096, 4096, 1), "ppm", "roe", 0.4, 1e-5),
+    # strong scaling (BASELINE.json configs[2]): the GLOBAL grid is fixed and split over the ranks
+    "ot3d_1024_strong": ("ot", 3, (1024, 1024, 1024), "plm", "hlld", 0.3, 1e-3),
+    "ot3d_512_strong": ("ot", 3, (512, 512, 512), "plm", "hlld", 0.3, 1e-3),
 }
 # per-kernel algorithmic HBM bytes per zone and launch (DESIGN.md "Kernels"):
 # sweep: read 8 V + 1 Bn, U (x1: write 5; x2/x3: read 5 + write 5), write 2 face EMFs + 1 sign byte
@@ -220,8 +223,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # weak scaling: every rank owns one block of n zones of a larger domain
-    layout = BlockLayout.weak(dims, n, world, periodic=(problem in ("ot", "turb")))
+    strong = args.workload.endswith("_strong")
+    if strong:       # fixed global grid split over the ranks
+        layout = BlockLayout.strong(dims, n, world, periodic=(problem in ("ot", "turb")))
+        n = layout.local_n(rank)
+    else:            # weak scaling: every rank owns one block of n zones of a larger domain
+        layout = BlockLayout.weak(dims, n, world, periodic=(problem in ("ot", "turb")))
     off = layout.offset(rank)
     st0, meta = problems.make(problem, dims, layout.global_n, offset=off, count=n)
     s = DistStepper(layout, rank, meta["dx"], recon=recon, solver=solver, rk_order=2, physical_bc=meta["bc"],
@@ -356,7 +363,8 @@ def main():
     line = {
         "metric": "zone_updates_per_sec", "value": value, "unit": "zone-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": args.workload, "problem": problem, "zones_per_gpu": list(n[:dims]),
                    "global_zones": list(layout.global_n[:dims]), "rank_grid": list(layout.grid),
                    "scheme": f"{solver}+{recon}+ct_uct_contact+rk2", "arith": args.arith,

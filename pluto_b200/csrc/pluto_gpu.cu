@@ -53,6 +53,9 @@ struct PlutoGpu {
   signed char *sv[3];
   unsigned long long *red;         // device reduction slots
   unsigned long long *red_host;    // pinned mirror
+  const void *pinned[8];           // host blocks seen by pluto_gpu_advance_data
+  int     pinned_by_us[8];         // ... and page-locked here
+  int     npinned;
   double *dtdev;                   // device: dt/dx[0..2] of the current step
   double *dthost;                  // pinned staging of the same
   cudaGraphExec_t graph;           // captured single-GPU step (all stages), replayed with new dt
@@ -192,6 +195,8 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
   cudaFree (h->dtdev); cudaFreeHost (h->dthost);
+  for (int q = 0; q < h->npinned; q++)
+    if (h->pinned_by_us[q] && cudaHostUnregister ((void *)h->pinned[q]) != cudaSuccess) cudaGetLastError ();
   if (h->graph) cudaGraphExecDestroy (h->graph);
   for (int e = 0; e < PG_MAX_EV; e++) if (h->ev0[e]){ cudaEventDestroy (h->ev0[e]); cudaEventDestroy (h->ev1[e]); }
   cudaStreamDestroy (h->stream);
@@ -575,9 +580,33 @@ int pluto_gpu_boundary (PlutoGpu *h)
   return 0;
 }
 
+// The reference allocates Data once (Src/initialize.c:444-500) with malloc: page-lock
+// the four blocks the first time they are seen so that every later step moves them
+// by DMA at full PCIe rate instead of through the driver's pageable staging copy.
+static void pin_once (PlutoGpu *h, const void *p, size_t bytes)
+{
+  if (!p || h->npinned >= 8) return;
+  for (int q = 0; q < h->npinned; q++) if (h->pinned[q] == p) return;
+  cudaPointerAttributes at;
+  int ours = 0;
+  if (cudaPointerGetAttributes (&at, p) == cudaSuccess && at.type == cudaMemoryTypeUnregistered){
+    if (cudaHostRegister ((void *)p, bytes, cudaHostRegisterDefault) == cudaSuccess) ours = 1;
+    else cudaGetLastError ();
+  }
+  h->pinned[h->npinned] = p; h->pinned_by_us[h->npinned++] = ours;
+}
+
 int pluto_gpu_advance_data (PlutoGpu *h, double dt, double *Vc, double *s1, double *s2, double *s3,
                             PlutoGpuStepInfo *info)
 {
+  CU (cudaSetDevice (h->cfg.device));
+  {
+    HaloArgs a; memset (&a, 0, sizeof (a));
+    long long so[4], sl[4];
+    describe_layout (h, 1, 0, a, so, sl);
+    double *hp[4] = {Vc, s1, s2, s3};
+    for (int q = 0; q < 4; q++) if (sl[q] > 0) pin_once (h, hp[q], (size_t)sl[q]*sizeof (double));
+  }
   if (pluto_gpu_upload_data (h, Vc, s1, s2, s3)) return 1;
   if (pluto_gpu_advance (h, dt, info)) return 1;
   return pluto_gpu_download_data (h, Vc, s1, s2, s3);

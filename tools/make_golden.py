@@ -37,6 +37,13 @@ CASES = {
     "turb3d_plm_hlld": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3), 10),
     "ot3d_ppm_roe": (RefConfig(problem="ot", dims=3, n=(12, 8, 16), recon="ppm", solver="roe",
                                first_dt=4.5e-2, cfl=0.3), 8),
+    # reflective walls (FlipSign + FillMagneticField on reflective sides) and mixed conditions
+    "blast2d_reflective": (RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=4e-4, cfl=0.4,
+                                     bc=("reflective", "outflow", "reflective", "reflective", "outflow", "outflow"),
+                                     blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3)), 30),
+    "blast3d_reflective": (RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=6e-4, cfl=0.3,
+                                     bc=("reflective", "reflective", "outflow", "reflective", "reflective", "outflow"),
+                                     blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=30.0, RADIUS=0.35)), 25),
     # 100-step runs for the BASELINE.json "1e-9 after 100 steps" bar
     "ot2d_plm_hlld_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4), 100),
     "blast3d_plm_hlld_100": (RefConfig(problem="blast", dims=3, n=(24, 20, 16), first_dt=5e-4, cfl=0.3), 100),
