@@ -138,6 +138,18 @@ long long pluto_gpu_halo_doubles (const PlutoGpu *h, int dim);
 int pluto_gpu_halo_pack    (PlutoGpu *h, int stage, int dim, double *send_lo, double *send_hi);
 int pluto_gpu_halo_unpack  (PlutoGpu *h, int stage, int dim, const double *recv_lo, const double *recv_hi);
 int pluto_gpu_boundary_dim (PlutoGpu *h, int stage, int dim);
+/* All-neighbour variant (one pack launch, one communication group, one unpack
+   launch per stage): the caller lists its neighbours by block offset
+   (-1/0/+1 per dimension, up to 26 in 3-D; offsets = n_nbr x 3 ints) with one
+   send and one receive DEVICE buffer of pluto_gpu_halo_nbr_doubles() doubles
+   each.  What a block packs for offset o is what its neighbour unpacks for -o.
+   Per stage: pluto_gpu_halo_pack_all -> exchange -> pluto_gpu_halo_unpack_all ->
+   pluto_gpu_boundary_dim for every dimension -> pluto_gpu_stage. */
+long long pluto_gpu_halo_nbr_doubles (const PlutoGpu *h, const int off[3]);
+int pluto_gpu_halo_plan       (PlutoGpu *h, int n_nbr, const int *offsets,
+                               double *const *send_bufs, double *const *recv_bufs);
+int pluto_gpu_halo_pack_all   (PlutoGpu *h, int stage);
+int pluto_gpu_halo_unpack_all (PlutoGpu *h, int stage);
 int pluto_gpu_step_begin   (PlutoGpu *h);
 int pluto_gpu_stage        (PlutoGpu *h, int stage, double dt);
 int pluto_gpu_step_end     (PlutoGpu *h, PlutoGpuStepInfo *info);

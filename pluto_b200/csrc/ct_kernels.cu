@@ -310,6 +310,21 @@ halo_kernel (const __grid_constant__ HaloArgs a)
   }
 }
 
+// all boxes of all neighbours in ONE launch (blockIdx.y = table entry)
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+halo_table_kernel (const HaloEntry *__restrict__ tab, const Geom g)
+{
+  const HaloEntry e = tab[blockIdx.y];
+  const int ni = e.n[0], nj = e.n[1];
+  for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < e.count; t += (long long)gridDim.x*blockDim.x){
+    const int i = e.lo[0] + (int)(t % ni), j = e.lo[1] + (int)((t/ni) % nj), k = e.lo[2] + (int)(t/((long long)ni*nj));
+    const long long id = gidx (g, k, j, i);
+    if (PACK) e.buf[t] = e.field[id];
+    else      e.field[id] = e.buf[t];
+  }
+}
+
 // ---------------------------------------------------------------------------
 //  launchers
 // ---------------------------------------------------------------------------
@@ -379,6 +394,15 @@ static int launch_halo (const HaloArgs &a, cudaStream_t s, bool pack)
   dim3 grid (nb, a.nf);
   if (pack) halo_kernel<true><<<grid, 256, 0, s>>>(a);
   else      halo_kernel<false><<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s)
+{
+  if (n <= 0 || maxcount <= 0) return 0;
+  unsigned nb = nblocks (maxcount, 256); if (nb > 256) nb = 256;
+  dim3 grid (nb, n);
+  if (pack) halo_table_kernel<true><<<grid, 256, 0, s>>>(tab, g);
+  else      halo_table_kernel<false><<<grid, 256, 0, s>>>(tab, g);
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 int launch_halo_pack   (const HaloArgs &a, cudaStream_t s) { return launch_halo (a, s, true); }

@@ -112,6 +112,14 @@ struct HaloArgs {
   Geom g;
 };
 
+// all-neighbour halo exchange: one table entry per (neighbour, field), resident in device memory
+struct HaloEntry {
+  double *field;             // padded field array
+  double *buf;               // start of this field's segment inside the neighbour's buffer
+  int lo[3], n[3];           // box origin and extents
+  long long count;
+};
+
 // ---- launch interface, one set per arithmetic namespace ----------------------
 #define PG_DECLARE_LAUNCHERS(NS)                                                         \
 namespace NS {                                                                           \
@@ -125,6 +133,7 @@ namespace NS {                                                                  
   int launch_bc_fill    (const BcFillArgs &a, cudaStream_t s);                           \
   int launch_halo_pack  (const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_unpack(const HaloArgs &a, cudaStream_t s);                             \
+  int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s); \
 }
 PG_DECLARE_LAUNCHERS(pg_exact)
 PG_DECLARE_LAUNCHERS(pg_fast)

@@ -53,6 +53,10 @@ struct PlutoGpu {
   signed char *sv[3];
   unsigned long long *red;         // device reduction slots
   unsigned long long *red_host;    // pinned mirror
+  // all-neighbour halo plan: tables [state buffer][0 pack | 1 unpack] in device memory
+  HaloEntry *halo_tab[3][2];
+  int     halo_n[3][2];
+  long long halo_max[3][2];
   const void *pinned[8];           // host blocks seen by pluto_gpu_advance_data
   int     pinned_by_us[8];         // ... and page-locked here
   int     npinned;
@@ -195,6 +199,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
   cudaFree (h->dtdev); cudaFreeHost (h->dthost);
+  for (int b = 0; b < 3; b++) for (int q = 0; q < 2; q++) if (h->halo_tab[b][q]) cudaFree (h->halo_tab[b][q]);
   for (int q = 0; q < h->npinned; q++)
     if (h->pinned_by_us[q] && cudaHostUnregister ((void *)h->pinned[q]) != cudaSuccess) cudaGetLastError ();
   if (h->graph) cudaGraphExecDestroy (h->graph);
@@ -723,5 +728,101 @@ extern "C" int pluto_gpu_measure_fp64 (int device, double *tflops)
   }
   cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
   *tflops = best;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+//  All-neighbour exchange: instead of three sequential per-dimension swaps, every
+//  face, edge and corner neighbour (up to 26 in 3-D) gets its own buffer and all
+//  transfers of a stage are independent -> ONE pack launch, ONE communication
+//  group, ONE unpack launch per stage.  Boxes along a dimension with offset o:
+//    o = -1: send [beg, beg+ng-1]        receive [0 (-1 for the normal staggered comp), beg-1]
+//    o = +1: send [end-ng+1 (-1), end]   receive [end+1, T-1]
+//    o =  0: [beg (-1 for a component staggered in that dimension), end]
+//  i.e. the same layers AL_Exchange_dim moves (al_decompose.c:218-252), with the
+//  edge/corner pieces addressed directly instead of relayed through ghost zones.
+// ---------------------------------------------------------------------------
+static void nbr_box (const PlutoGpu *h, const int off[3], int stag, bool send, int lo[3], int hi[3])
+{
+  const Geom &g = h->g;
+  for (int d = 0; d < 3; d++){
+    const int st = (stag == d);
+    if (d >= g.dims){ lo[d] = hi[d] = 0; continue; }
+    if (off[d] == 0){ lo[d] = g.beg[d] - st; hi[d] = g.end[d]; }
+    else if (send){
+      if (off[d] < 0){ lo[d] = g.beg[d]; hi[d] = g.beg[d] + g.ng - 1; }
+      else           { lo[d] = g.end[d] - g.ng + 1 - st; hi[d] = g.end[d]; }
+    }else{
+      if (off[d] < 0){ lo[d] = -st; hi[d] = g.beg[d] - 1; }
+      else           { lo[d] = g.end[d] + 1; hi[d] = g.T[d] - 1; }
+    }
+  }
+}
+
+long long pluto_gpu_halo_nbr_doubles (const PlutoGpu *h, const int off[3])
+{
+  long long tot = 0, tot_r = 0;
+  for (int f = 0; f < NVS + 3; f++){
+    const int stag = f >= NVS ? f - NVS : -1;
+    if (stag < 0 && !live_var (h, f)) continue;
+    if (stag >= h->g.dims) continue;
+    int lo[3], hi[3];
+    nbr_box (h, off, stag, true, lo, hi);  tot   += box_count (lo, hi);
+    nbr_box (h, off, stag, false, lo, hi); tot_r += box_count (lo, hi);
+  }
+  return tot > tot_r ? tot : tot_r;
+}
+
+int pluto_gpu_halo_plan (PlutoGpu *h, int n_nbr, const int *offsets, double *const *send_bufs,
+                         double *const *recv_bufs)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  for (int b = 0; b < h->nbuf; b++) for (int dirn = 0; dirn < 2; dirn++){
+    HaloEntry *tab = (HaloEntry *)calloc ((size_t)n_nbr*(NVS + 3) + 1, sizeof (HaloEntry));
+    int ne = 0; long long mx = 0;
+    for (int q = 0; q < n_nbr; q++){
+      const int *off = offsets + 3*q;
+      double *buf = dirn == 0 ? send_bufs[q] : recv_bufs[q];
+      long long pos = 0;
+      for (int f = 0; f < NVS + 3; f++){
+        const int stag = f >= NVS ? f - NVS : -1;
+        if (stag < 0 && !live_var (h, f)) continue;
+        if (stag >= h->g.dims) continue;
+        int lo[3], hi[3];
+        nbr_box (h, off, stag, dirn == 0, lo, hi);
+        HaloEntry &e = tab[ne++];
+        e.field = stag >= 0 ? h->Bs[b][stag] : h->V[b][f];
+        e.buf = buf + pos;
+        for (int d = 0; d < 3; d++){ e.lo[d] = lo[d]; e.n[d] = hi[d] - lo[d] + 1; }
+        e.count = box_count (lo, hi);
+        pos += e.count;
+        if (e.count > mx) mx = e.count;
+      }
+    }
+    if (h->halo_tab[b][dirn]) cudaFree (h->halo_tab[b][dirn]);
+    h->halo_tab[b][dirn] = NULL;
+    if (ne > 0){
+      CU (cudaMalloc ((void **)&h->halo_tab[b][dirn], (size_t)ne*sizeof (HaloEntry)));
+      CU (cudaMemcpy (h->halo_tab[b][dirn], tab, (size_t)ne*sizeof (HaloEntry), cudaMemcpyHostToDevice));
+    }
+    h->halo_n[b][dirn] = ne; h->halo_max[b][dirn] = mx;
+    free (tab);
+  }
+  return 0;
+}
+
+int pluto_gpu_halo_pack_all (PlutoGpu *h, int stage)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const int b = stage_in_buf (h, stage);
+  TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_table) (h->halo_tab[b][0], h->halo_n[b][0], h->halo_max[b][0], h->g, true, h->stream)));
+  return 0;
+}
+
+int pluto_gpu_halo_unpack_all (PlutoGpu *h, int stage)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const int b = stage_in_buf (h, stage);
+  TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_table) (h->halo_tab[b][1], h->halo_n[b][1], h->halo_max[b][1], h->g, false, h->stream)));
   return 0;
 }

@@ -90,6 +90,27 @@ class BlockLayout:
             c[dim] %= self.grid[dim]
         return self.rank_of(c)
 
+    def neighbours(self, rank):
+        """[(offset, rank)] of every face / edge / corner neighbour block (up to 26)."""
+        import itertools
+        out = []
+        c0 = self.coords(rank)
+        rng = [(-1, 0, 1) if d < self.dims and self.grid[d] > 1 else (0,) for d in range(3)]
+        for o in itertools.product(*rng):
+            if o == (0, 0, 0):
+                continue
+            c, ok = list(c0), True
+            for d in range(3):
+                c[d] += o[d]
+                if c[d] < 0 or c[d] >= self.grid[d]:
+                    if not self.periodic[d]:
+                        ok = False
+                        break
+                    c[d] %= self.grid[d]
+            if ok:
+                out.append((o, self.rank_of(c)))
+        return out
+
     def block_bc(self, rank, physical_bc):
         """bc names of one block: 'shared' where another block abuts (boundary.c:139)."""
         bc = list(physical_bc)
@@ -150,12 +171,48 @@ class HaloExchanger:
         self.unpack(stage, dim, b["recv"][0], b["recv"][1])
 
 
+class NeighbourExchanger:
+    """All-neighbour exchange: every face, edge and corner neighbour has its own
+    send/receive buffer, so the transfers of a stage are independent and go out as
+    ONE communication group between one pack and one unpack launch.
+
+    Message matching: with 2 ranks in a periodic dimension several offsets map to
+    the same peer and the backends match messages per peer in posting order, so
+    sends are posted in ascending offset order and receives in ascending order of
+    the SENDER's offset (= minus mine)."""
+
+    def __init__(self, layout: BlockLayout, rank: int, nbr_doubles, plan, pack_all, unpack_all, device, group=None):
+        import torch
+        self.group = group
+        self.pack_all, self.unpack_all = pack_all, unpack_all
+        self.nbrs = layout.neighbours(rank)
+        mk = lambda o: torch.zeros(int(nbr_doubles(o)), dtype=torch.float64, device=device)
+        self.send = [mk(o) for o, _ in self.nbrs]
+        self.recv = [mk(o) for o, _ in self.nbrs]
+        plan([o for o, _ in self.nbrs], self.send, self.recv)
+        self.bytes_per_exchange = sum(t.numel() * 8 for t in self.send)
+        self._send_order = sorted(range(len(self.nbrs)), key=lambda q: self.nbrs[q][0])
+        self._recv_order = sorted(range(len(self.nbrs)), key=lambda q: tuple(-c for c in self.nbrs[q][0]))
+
+    def exchange(self, stage):
+        import torch.distributed as dist
+        if not self.nbrs:
+            return
+        self.pack_all(stage)
+        ops = [dist.P2POp(dist.isend, self.send[q], self.nbrs[q][1], group=self.group) for q in self._send_order]
+        ops += [dist.P2POp(dist.irecv, self.recv[q], self.nbrs[q][1], group=self.group) for q in self._recv_order]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        self.unpack_all(stage)
+
+
 class DistStepper:
     """AdvanceStep on one block of a decomposed domain (one process per GPU)."""
 
     def __init__(self, layout: BlockLayout, rank, dx, recon="plm", solver="hlld", rk_order=2,
-                 physical_bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0):
+                 physical_bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0, exchange="all"):
         self.layout, self.rank = layout, rank
+        self.exchange_mode = exchange       # "all": one 26-neighbour group per stage; "dims": x1->x2->x3 swaps
         self.world = layout.world
         n = layout.local_n(rank)
         self.block = GpuStepper(layout.dims, n, dx, recon=recon, solver=solver, rk_order=rk_order,
@@ -173,6 +230,13 @@ class DistStepper:
                 lambda st, d, lo, hi: self.block.halo_pack(st, d, ptr(lo), ptr(hi)),
                 lambda st, d, lo, hi: self.block.halo_unpack(st, d, ptr(lo), ptr(hi)),
                 device=torch.device("cuda", device))
+            self.nex = None
+            if exchange == "all":
+                b = self.block
+                self.nex = NeighbourExchanger(
+                    layout, rank, b.halo_nbr_doubles,
+                    lambda offs, sb, rb: b.halo_plan(offs, [t.data_ptr() for t in sb], [t.data_ptr() for t in rb]),
+                    b.halo_pack_all, b.halo_unpack_all, device=torch.device("cuda", device))
             self._red = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", device))
 
     def set_state(self, dump):
@@ -193,9 +257,14 @@ class DistStepper:
         with torch.cuda.stream(self._stream):
             b.step_begin()
             for stage in range(1, self.rk_order + 1):
-                for d in range(self.dims):
-                    self.ex.exchange_dim(stage, d)
-                    b.boundary_dim(stage, d)
+                if self.nex is not None:
+                    self.nex.exchange(stage)
+                    for d in range(self.dims):
+                        b.boundary_dim(stage, d)
+                else:
+                    for d in range(self.dims):
+                        self.ex.exchange_dim(stage, d)
+                        b.boundary_dim(stage, d)
                 b.stage(stage, dt)
             info = b.step_end()
             # MPI_Allreduce(MAX) of invDt_hyp and g_maxMach (main.c:195-199, 415)
@@ -220,9 +289,10 @@ class LocalMultiBlock:
     handed over directly (same device) -- used by the single-GPU test of the
     decomposition and as the in-process alternative to one process per GPU."""
 
-    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, **kw):
+    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, exchange="dims", **kw):
         import torch
         self.layout = layout
+        self.exchange_mode = exchange
         self.blocks = [GpuStepper(layout.dims, layout.local_n(r), dx, bc=layout.block_bc(r, physical_bc),
                                   device=device, **kw) for r in range(layout.world)]
         self.rk_order = self.blocks[0].rk_order
@@ -234,6 +304,17 @@ class LocalMultiBlock:
                     if layout.neighbour(r, d, side) is not None:
                         self.send[(r, d, side)] = torch.zeros(b.halo_doubles(d), dtype=torch.float64, device=dev)
         self._torch = torch
+        if exchange == "all":
+            # send buffer of (rank r, offset o) is the receive buffer of (neighbour, -o)
+            self.nsend = {}
+            for r, b in enumerate(self.blocks):
+                for o, nb in layout.neighbours(r):
+                    self.nsend[(r, o)] = torch.zeros(b.halo_nbr_doubles(o), dtype=torch.float64, device=dev)
+            for r, b in enumerate(self.blocks):
+                nbrs = layout.neighbours(r)
+                sp = [self.nsend[(r, o)].data_ptr() for o, _ in nbrs]
+                rp = [self.nsend[(nb, tuple(-c for c in o))].data_ptr() for o, nb in nbrs]
+                b.halo_plan([o for o, _ in nbrs], sp, rp)
 
     def set_state(self, global_state):
         lay = self.layout
@@ -268,7 +349,16 @@ class LocalMultiBlock:
         for b in self.blocks:
             b.step_begin()
         for stage in range(1, self.rk_order + 1):
-            for d in range(lay.dims):
+            if self.exchange_mode == "all":
+                for b in self.blocks:
+                    b.halo_pack_all(stage)
+                torch.cuda.synchronize()
+                for b in self.blocks:
+                    b.halo_unpack_all(stage)
+                    for d in range(lay.dims):
+                        b.boundary_dim(stage, d)
+                torch.cuda.synchronize()
+            for d in range(lay.dims if self.exchange_mode != "all" else 0):
                 for r, b in enumerate(self.blocks):
                     lo, hi = self.send.get((r, d, 0)), self.send.get((r, d, 1))
                     if lo is not None or hi is not None:

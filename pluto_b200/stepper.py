@@ -206,6 +206,24 @@ class GpuStepper:
         self._check(self.L.pluto_gpu_read_field(self._h, name.encode(), out.ctypes.data))
         return out
 
+    # ---- all-neighbour halo plan --------------------------------------------
+    def halo_nbr_doubles(self, off) -> int:
+        o = (C.c_int * 3)(*off)
+        return int(self.L.pluto_gpu_halo_nbr_doubles(self._h, C.byref(o)))
+
+    def halo_plan(self, offsets, send_ptrs, recv_ptrs):
+        n = len(offsets)
+        flat = (C.c_int * (3 * n))(*[c for o in offsets for c in o])
+        sp = (C.c_void_p * n)(*send_ptrs)
+        rp = (C.c_void_p * n)(*recv_ptrs)
+        self._check(self.L.pluto_gpu_halo_plan(self._h, n, flat, sp, rp))
+
+    def halo_pack_all(self, stage):
+        self._check(self.L.pluto_gpu_halo_pack_all(self._h, stage))
+
+    def halo_unpack_all(self, stage):
+        self._check(self.L.pluto_gpu_halo_unpack_all(self._h, stage))
+
     def timing(self, enable: bool):
         self.L.pluto_gpu_timing(self._h, 1 if enable else 0)
 

@@ -91,3 +91,59 @@ class HostBlock:
                 src_lo[dim] += sh
                 src_hi[dim] += sh
                 self.view(q, lo, hi)[...] = self.view(q, src_lo, src_hi)
+
+
+class HostBlockAll(HostBlock):
+    """all-neighbour plan (same boxes as nbr_box in pluto_b200/csrc/pluto_gpu.cu)"""
+
+    def nbr_box(self, q, off, send):
+        s = self.is_stag(q)
+        lo, hi = [0, 0, 0], [0, 0, 0]
+        for d in range(3):
+            st = 1 if s == d else 0
+            if d >= self.dims:
+                continue
+            if off[d] == 0:
+                lo[d], hi[d] = self.beg[d] - st, self.end[d]
+            elif send:
+                if off[d] < 0:
+                    lo[d], hi[d] = self.beg[d], self.beg[d] + self.ng - 1
+                else:
+                    lo[d], hi[d] = self.end[d] - self.ng + 1 - st, self.end[d]
+            else:
+                if off[d] < 0:
+                    lo[d], hi[d] = -st, self.beg[d] - 1
+                else:
+                    lo[d], hi[d] = self.end[d] + 1, self.T[d] - 1
+        return lo, hi
+
+    def nbr_doubles(self, off):
+        tot = [0, 0]
+        for q in range(self.nf):
+            for w, send in enumerate((True, False)):
+                lo, hi = self.nbr_box(q, off, send)
+                tot[w] += int(np.prod([hi[d] - lo[d] + 1 for d in range(3)]))
+        return max(tot)
+
+    def plan(self, offsets, send_bufs, recv_bufs):
+        self._plan = (list(offsets), send_bufs, recv_bufs)
+
+    def pack_all(self, stage):
+        offs, sb, _ = self._plan
+        for o, buf in zip(offs, sb):
+            pos, b = 0, buf.numpy()
+            for q in range(self.nf):
+                lo, hi = self.nbr_box(q, o, True)
+                v = self.view(q, lo, hi)
+                b[pos:pos + v.size] = v.ravel()
+                pos += v.size
+
+    def unpack_all(self, stage):
+        offs, _, rb = self._plan
+        for o, buf in zip(offs, rb):
+            pos, b = 0, buf.numpy()
+            for q in range(self.nf):
+                lo, hi = self.nbr_box(q, o, False)
+                v = self.view(q, lo, hi)
+                v[...] = b[pos:pos + v.size].reshape(v.shape)
+                pos += v.size

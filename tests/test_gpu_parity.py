@@ -226,14 +226,16 @@ def test_full_size_properties_blast_256():
     ("ot", 2, (48, 64, 1), 4, "plm", "hlld"),
     ("rotor", 2, (40, 48, 1), 2, "ppm", "roe"),
 ])
-def test_decomposed_blocks_match_single_block(problem, dims, gn, world, recon, solver):
+@pytest.mark.parametrize("exchange", ["dims", "all"])
+def test_decomposed_blocks_match_single_block(problem, dims, gn, world, recon, solver, exchange):
     from pluto_b200 import GpuStepper, problems
     from pluto_b200.parallel import BlockLayout, LocalMultiBlock
     st0, meta = problems.make(problem, dims, gn)
     periodic = meta["bc"][0] == "periodic"
     lay = BlockLayout.strong(dims, gn, world, periodic=periodic)
     one = GpuStepper(dims, gn, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"])
-    many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, gamma=meta["gamma"])
+    many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, gamma=meta["gamma"],
+                           exchange=exchange)
     one.set_state(st0)
     many.set_state(st0)
     dt = {"ot": 5e-3, "blast": 2e-4, "turb": 5e-3, "rotor": 1e-3}[problem]

@@ -10,8 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pluto_b200.parallel import BlockLayout, HaloExchanger, exchange_ops_order
-from tests.hostblock import HostBlock
+from pluto_b200.parallel import BlockLayout, HaloExchanger, NeighbourExchanger, exchange_ops_order
+from tests.hostblock import HostBlock, HostBlockAll
 
 
 def test_layout_grids_and_neighbours():
@@ -37,13 +37,13 @@ def _gfun(q, K, J, I, gn, stag):
     return q * 1e6 + (K % gn[2]) * 1e4 + (J % gn[1]) * 1e2 + (I % gn[0])
 
 
-def _worker(rank, world, port, dims, n, periodic, ret):
+def _worker(rank, world, port, dims, n, periodic, ret, mode="dims"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         lay = BlockLayout.weak(dims, n, world, periodic=periodic)
-        blk = HostBlock(dims, lay.local_n(rank))
+        blk = (HostBlockAll if mode == "all" else HostBlock)(dims, lay.local_n(rank))
         off = lay.offset(rank)
         gn = lay.global_n
         ng = blk.ng
@@ -58,11 +58,18 @@ def _worker(rank, world, port, dims, n, periodic, ret):
             if s is not None:
                 lo[s] -= 1
             blk.view(q, lo, hi)[...] = val[lo[2] + 1:hi[2] + 2, lo[1] + 1:hi[1] + 2, lo[0] + 1:hi[0] + 2]
-        ex = HaloExchanger(lay, rank, blk.halo_doubles, blk.pack, blk.unpack, device="cpu")
-        for d in range(dims):
-            ex.exchange_dim(1, d)
-            if lay.neighbour(rank, d, 0) is None and periodic:
-                blk.periodic_local(d)
+        if mode == "all":
+            ex = NeighbourExchanger(lay, rank, blk.nbr_doubles, blk.plan, blk.pack_all, blk.unpack_all, device="cpu")
+            ex.exchange(1)
+            for d in range(dims):
+                if lay.neighbour(rank, d, 0) is None and periodic:
+                    blk.periodic_local(d)
+        else:
+            ex = HaloExchanger(lay, rank, blk.halo_doubles, blk.pack, blk.unpack, device="cpu")
+            for d in range(dims):
+                ex.exchange_dim(1, d)
+                if lay.neighbour(rank, d, 0) is None and periodic:
+                    blk.periodic_local(d)
         # every zone (ghosts, edges, corners) must now equal the wrapped global function
         bad = 0
         for q in range(blk.nf):
@@ -92,11 +99,12 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("mode", ["dims", "all"])
 @pytest.mark.parametrize("world,dims,n", [(2, 3, (6, 5, 4)), (2, 2, (8, 6, 1)), (4, 3, (4, 6, 5)), (4, 2, (6, 8, 1))])
-def test_periodic_exchange_fills_all_ghosts(world, dims, n):
+def test_periodic_exchange_fills_all_ghosts(world, dims, n, mode):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), dims, n, True, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), dims, n, True, ret, mode), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         bad, red, nbytes = ret[r]
