@@ -58,16 +58,30 @@ __device__ __forceinline__ double minmod (double a, double b)
 //  independent chains.  Arguments are physical magnitudes far from the
 //  subnormal / overflow range.
 // ---------------------------------------------------------------------------
-#ifdef PG_FAST
+#if defined(PG_FAST) && defined(PG_HOST_EMU)
+// host build of the FAST algebra (tools/host_hlld_check.cpp): exact division and
+// sqrt stand in for the MUFU-seeded iterations
+__device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
+__device__ __forceinline__ double pg_div (double a, double b) { return a/b; }
+__device__ __forceinline__ double pg_sqrt (double x) { return x > 0.0 ? sqrt (x) : 0.0; }
+__device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs) { s = sqrt (x); rs = 1.0/s; }
+__device__ __forceinline__ double pg_sqrt_pos (double x) { return sqrt (x); }
+__device__ __forceinline__ float pg_sqrtf (float x) { return sqrtf (x); }
+#elif defined(PG_FAST)
+__device__ __forceinline__ float pg_sqrtf (float x)          // no slow-path call
+{
+  float y;
+  asm ("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ double pg_rcp (double b)
 {
+  // MUFU seed (>= 20 good bits), then ONE cubically convergent step:
+  // r (1 + e + e^2), e = 1 - b r  ->  relative error e^3 <= 2^-60
   double r;
   asm ("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  double e = fma (-b, r, 1.0);
-  r = fma (r, e, r);
-  e = fma (-b, r, 1.0);
-  r = fma (r, e, r);
-  return r;
+  const double e = fma (-b, r, 1.0);
+  return fma (r, fma (e, e, e), r);
 }
 __device__ __forceinline__ double pg_div (double a, double b) { return a*pg_rcp (b); }
 __device__ __forceinline__ double pg_sqrt (double x)
@@ -131,6 +145,42 @@ template <int NV_ID> __device__ __forceinline__ double plm_slope (double dvp, do
 }
 
 // vp = v + dvl/2, vm = v - dvl/2 for one zone from its two one-sided differences
+#ifdef PG_FAST
+// FAST: the HALF slope h = dvl/2 is formed directly (the factors 2 and 1/2 of the
+// van Leer and MC limiters cancel against it; scaling by powers of two is exact,
+// so h is the reference's dvl*0.5 up to the rounding of the division)
+template <int NV_ID> __device__ __forceinline__ void plm_half (double v, double dvp, double dvm, double &vp, double &vm)
+{
+  const double p = dvp*dvm, s = dvp + dvm;
+  if (NV_ID == RHO){          // MC: abs_min(0.5 (dvm+dvp), 2 abs_min(dvp, dvm))
+    const double q = 0.25*s, m = abs_min (dvp, dvm);
+    double h = abs_min (q, m);
+    h = p > 0.0 ? h : 0.0;
+    vp = v + h; vm = v - h;
+  }else if (NV_ID == PRS){    // minmod
+    double h = 0.5*abs_min (dvp, dvm);
+    h = p > 0.0 ? h : 0.0;
+    vp = v + h; vm = v - h;
+  }else{                      // van Leer: 2 dvp dvm/(dvp + dvm)
+    double r = pg_rcp (s);
+    r = p > 0.0 ? r : 0.0;
+    vp = fma (p, r, v); vm = fma (-p, r, v);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void plm_zone (const double *v, const double *dvm, const double *dvp,
+                                          double *vp, double *vm)
+{
+  plm_half<RHO>(v[RHO], dvp[RHO], dvm[RHO], vp[RHO], vm[RHO]);
+  plm_half<VX1>(v[VX1], dvp[VX1], dvm[VX1], vp[VX1], vm[VX1]);
+  plm_half<VX1>(v[VX2], dvp[VX2], dvm[VX2], vp[VX2], vm[VX2]);
+  if (NC == 3) plm_half<VX1>(v[VX3], dvp[VX3], dvm[VX3], vp[VX3], vm[VX3]);
+  plm_half<VX1>(v[BX1], dvp[BX1], dvm[BX1], vp[BX1], vm[BX1]);
+  plm_half<VX1>(v[BX2], dvp[BX2], dvm[BX2], vp[BX2], vm[BX2]);
+  if (NC == 3) plm_half<VX1>(v[BX3], dvp[BX3], dvm[BX3], vp[BX3], vm[BX3]);
+  plm_half<PRS>(v[PRS], dvp[PRS], dvm[PRS], vp[PRS], vm[PRS]);
+}
+#else
 template <int NC>
 __device__ __forceinline__ void plm_zone (const double *v, const double *dvm, const double *dvp,
                                           double *vp, double *vm)
@@ -149,6 +199,7 @@ __device__ __forceinline__ void plm_zone (const double *v, const double *dvm, co
     vm[nv] = v[nv] - dvl[nv]*0.5;
   }
 }
+#endif
 
 // PPM 4th-order interface value at i+1/2, bounded (ppm_states.c:146-157):
 // W = v0 + MINMOD(P - v0, v1 - v0), P = -1/12 vm1 + 7/12 v0 + 7/12 v1 - 1/12 v2
@@ -340,12 +391,171 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
 }
 
 #ifdef PG_FAST
-// FAST arithmetic: the same five-wave solver (same regions, same switches) with
-// shared reciprocals, sqrt/rsqrt pairs, 1/rho reused by both speed estimates and
-// the Mach-number diagnostic (g_maxMach, printed with 6 digits by the reference)
-// evaluated in single precision.
+// ---------------------------------------------------------------------------
+//  FAST HLLD.  Same five-wave solver, same wave-speed estimates, same region
+//  switches as hlld.c:98-427, evaluated in the form that needs the fewest FP64
+//  instructions and the fewest live registers:
+//   * every intermediate state of HLLD satisfies the jump conditions exactly, so
+//     the flux in a region is the ideal-MHD flux function applied to THAT state
+//     with its normal velocity and total pressure (Miyoshi & Kusano 2005,
+//     eqs 38-48, 59-63):  F = F(rho, un, vt, Bt, E; pT).  No F_L/F_R, no
+//     conservative input vectors, no differences U* - U are formed;
+//   * transverse star velocities use the same denominator as the star fields
+//     (M&K eq 44/46), which removes two divisions;
+//   * the normal field is the staggered one on both sides (plm_states.c:271-275),
+//     hence Bx = vL[BXn] = vR[BXn];
+//   * energies are evaluated on the side the flux is taken from only.
+//  The HLLC fallback of hlld.c:245-258 is not a consistent state: interfaces that
+//  need it (rare: Alfven speed within 1e-4 of the fast speed) take the cold path
+//  riemann_hlld_fallback, the previous formulation.
+//  Returns press = total pressure of the selected state and flux[MXn] without it,
+//  the split the callers expect (rhs.c:193-201 adds the two differences).
+// ---------------------------------------------------------------------------
+template <int DIR, int NC>
+__device__ __noinline__ void riemann_hlld_fallback (const Phys &ph, const double *vL, const double *vR,
+                                                    const double *uL, const double *uR,
+                                                    double *flux, double &press, double &cmax, double &mach);
+
+template <int DIR, int NC, bool LEFT>
+__device__ __forceinline__ void hlld_side_flux (const Phys &ph, const double *v, double b2, double pt,
+                                                double S, double S1, double SM, double pts, double Bx, double Bx2,
+                                                double rs, double sq_s, double iSM,
+                                                double vs, double ws, double Bts, double Bbs,
+                                                double vss, double wss, double Btss, double Bbss, double vBss,
+                                                double *flux, double &press)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXt = D::bt, BXb = D::bb;
+  double R, U, Vt, Vb = 0.0, BT, BB = 0.0, EE, PT, VB;
+  double v2 = v[VXn]*v[VXn] + v[VXt]*v[VXt];
+  if (NC == 3) v2 = fma (v[VXb], v[VXb], v2);
+  const double E = fma (v[PRS], ph.igmm1, 0.5*fma (v[RHO], v2, b2));
+  double vB = fma (v[VXt], v[BXt], v[VXn]*Bx);
+  if (NC == 3) vB = fma (v[VXb], v[BXb], vB);
+  if (LEFT ? S >= 0.0 : S <= 0.0){             // supersonic: the physical flux of this side
+    R = v[RHO]; U = v[VXn]; Vt = v[VXt]; BT = v[BXt]; EE = E; PT = pt; VB = vB;
+    if (NC == 3){ Vb = v[VXb]; BB = v[BXb]; }
+  }else{
+    double vBs = fma (vs, Bts, SM*Bx);
+    if (NC == 3) vBs = fma (ws, Bbs, vBs);
+    const double du = S - v[VXn];
+    const double Es = (fma (Bx, vB - vBs, fma (pts, SM, fma (du, E, -pt*v[VXn]))))*iSM;
+    // U** energy (hlld.c:396-411): E*L - sqrt(rho*L) (v*.B* - v**.B**) sBx, E*R + ...
+    const double Ess = LEFT ? fma (-sq_s, vBs - vBss, Es) : fma (sq_s, vBs - vBss, Es);
+    const bool star = LEFT ? S1 >= 0.0 : S1 <= 0.0;
+    R = rs; U = SM; PT = pts;
+    Vt = star ? vs : vss;  BT = star ? Bts : Btss;
+    EE = star ? Es : Ess;  VB = star ? vBs : vBss;
+    if (NC == 3){ Vb = star ? ws : wss; BB = star ? Bbs : Bbss; }
+  }
+  const double Fr = R*U;
+  flux[RHO]   = Fr;
+  flux[D::vn] = fma (Fr, U, -Bx2);
+  flux[D::vt] = fma (Fr, Vt, -Bx*BT);
+  flux[D::bn] = 0.0;
+  flux[D::bt] = fma (BT, U, -Bx*Vt);
+  if (NC == 3){
+    flux[D::vb] = fma (Fr, Vb, -Bx*BB);
+    flux[D::bb] = fma (BB, U, -Bx*Vb);
+  }
+  flux[ENG]   = fma (EE + PT, U, -Bx*VB);
+  press = PT;
+}
+
 template <int DIR, int NC>
 __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, const double *vR,
+                                              double *flux, double &press, double &cmax, double &mach)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
+  const double Bx = vL[BXn], Bx2 = Bx*Bx;
+  double SL, SR, b2L, b2R;
+  {
+    // fast magnetosonic speeds (eigenv.c:87-101) and Davis estimate (hll_speed.c:76-107)
+    const double irL = pg_rcp (vL[RHO]), irR = pg_rcp (vR[RHO]);
+    const double gpL = ph.gamma*vL[PRS], gpR = ph.gamma*vR[PRS];
+    double bt2L = vL[BXt]*vL[BXt], bt2R = vR[BXt]*vR[BXt];
+    if (NC == 3){ bt2L = fma (vL[BXb], vL[BXb], bt2L); bt2R = fma (vR[BXb], vR[BXb], bt2R); }
+    b2L = Bx2 + bt2L; b2R = Bx2 + bt2R;
+    double dL = gpL - b2L, dR = gpR - b2R;
+    dL = gpL + b2L + pg_sqrt (fma (dL, dL, 4.0*gpL*bt2L));
+    dR = gpR + b2R + pg_sqrt (fma (dR, dR, 4.0*gpR*bt2R));
+    const double cfL = pg_sqrt_pos (0.5*dL*irL), cfR = pg_sqrt_pos (0.5*dR*irR);
+    SL = minv (vL[VXn] - cfL, vR[VXn] - cfR);
+    SR = maxv (vL[VXn] + cfL, vR[VXn] + cfR);
+    // g_maxMach is a diagnostic the reference prints with 6 digits: single precision
+    const float aL = pg_sqrtf ((float)(gpL*irL)), aR = pg_sqrtf ((float)(gpR*irR));
+    mach = (double)__fdividef ((float)(fabs (vL[VXn]) + fabs (vR[VXn])), aL + aR);
+  }
+  cmax = maxv (fabs (SL), fabs (SR));
+  const double ptL = fma (0.5, b2L, vL[PRS]), ptR = fma (0.5, b2R, vR[PRS]);
+
+  const double duL = SL - vL[VXn], duR = SR - vR[VXn];
+  const double rduL = vL[RHO]*duL, rduR = vR[RHO]*duR;            // rho (S - vn)
+  const double idn = pg_rcp (rduR - rduL);
+  const double SM  = (fma (rduR, vR[VXn], -rduL*vL[VXn]) - ptR + ptL)*idn;
+  const double pts = (fma (rduR, ptL, -rduL*ptR) + rduL*rduR*(vR[VXn] - vL[VXn]))*idn;
+
+  const double dSL = SL - SM, dSR = SR - SM;
+  const double iSLM = pg_rcp (dSL), iSRM = pg_rcp (dSR);
+  const double rsL = rduL*iSLM, rsR = rduR*iSRM;                   // star densities
+  double sqrL, sqrR, isqL, isqR;
+  pg_sqrt_rsqrt (rsL, sqrL, isqL);
+  pg_sqrt_rsqrt (rsR, sqrR, isqR);
+  const double aBx = fabs (Bx);
+  const double S1L = fma (-aBx, isqL, SM), S1R = fma (aBx, isqR, SM);
+
+  // hlld.c:238-243
+  if ( (S1L - SL) < -1.e-4*dSL || (S1R - SR) > -1.e-4*dSR ){
+    // cold path: private copies, so that the caller's arrays never have their
+    // address taken (they stay in registers on the hot path)
+    double a[NV], b[NV], ua[NV], ub[NV], fl[NV], pr, cm, ma;
+    PG_UNROLL for (int nv = 0; nv < NV; nv++){ a[nv] = 0.0; b[nv] = 0.0; fl[nv] = 0.0; }
+    PG_FOR_NV(nv){ a[nv] = vL[nv]; b[nv] = vR[nv]; }
+    prim_to_cons<NC>(ph, a, ua);
+    prim_to_cons<NC>(ph, b, ub);
+    riemann_hlld_fallback<DIR, NC>(ph, a, b, ua, ub, fl, pr, cm, ma);
+    PG_FOR_NV(nv) flux[nv] = fl[nv];
+    press = pr;
+    return;
+  }
+
+  // star states (M&K eqs 44-47 with the common denominator rho (S-u)(S-SM) - Bx^2)
+  const double idL = pg_rcp (fma (rduL, dSL, -Bx2)), idR = pg_rcp (fma (rduR, dSR, -Bx2));
+  const double qL = fma (rduL, duL, -Bx2)*idL, qR = fma (rduR, duR, -Bx2)*idR;
+  const double tL = (SM - vL[VXn])*idL*Bx, tR = (SM - vR[VXn])*idR*Bx;
+  const double BtsL = vL[BXt]*qL, BtsR = vR[BXt]*qR;
+  const double vsL = fma (-tL, vL[BXt], vL[VXt]), vsR = fma (-tR, vR[BXt], vR[VXt]);
+  double BbsL = 0.0, BbsR = 0.0, wsL = 0.0, wsR = 0.0;
+  if (NC == 3){
+    BbsL = vL[BXb]*qL; BbsR = vR[BXb]*qR;
+    wsL = fma (-tL, vL[BXb], vL[VXb]); wsR = fma (-tR, vR[BXb], vR[VXb]);
+  }
+
+  // double-star state (hlld.c:349-394); sBx = sign(Bx) folded into the weights
+  const double isum = pg_rcp (sqrL + sqrR);
+  const double sgL = (Bx > 0.0 ? sqrL : -sqrL);                    // sBx sqrt(rho*L)
+  const double sI = (Bx > 0.0 ? isum : -isum);                      // sBx/(sqrt(rho*L) + sqrt(rho*R))
+  const double vss  = fma (BtsR - BtsL, sI, fma (sqrL, vsL, sqrR*vsR)*isum);
+  const double Btss = fma (sgL*sqrR, (vsR - vsL)*isum, fma (sqrL, BtsR, sqrR*BtsL)*isum);
+  double wss = 0.0, Bbss = 0.0;
+  if (NC == 3){
+    wss  = fma (BbsR - BbsL, sI, fma (sqrL, wsL, sqrR*wsR)*isum);
+    Bbss = fma (sgL*sqrR, (wsR - wsL)*isum, fma (sqrL, BbsR, sqrR*BbsL)*isum);
+  }
+  double vBss = fma (vss, Btss, SM*Bx);
+  if (NC == 3) vBss = fma (wss, Bbss, vBss);
+
+  if (SM >= 0.0)
+    hlld_side_flux<DIR, NC, true> (ph, vL, b2L, ptL, SL, S1L, SM, pts, Bx, Bx2, rsL, sgL, iSLM,
+                                   vsL, wsL, BtsL, BbsL, vss, wss, Btss, Bbss, vBss, flux, press);
+  else
+    hlld_side_flux<DIR, NC, false>(ph, vR, b2R, ptR, SR, S1R, SM, pts, Bx, Bx2, rsR, (Bx > 0.0 ? sqrR : -sqrR), iSRM,
+                                   vsR, wsR, BtsR, BbsR, vss, wss, Btss, Bbss, vBss, flux, press);
+}
+
+template <int DIR, int NC>
+__device__ __noinline__ void riemann_hlld_fallback (const Phys &ph, const double *vL, const double *vR,
                                               const double *uL, const double *uR,
                                               double *flux, double &press, double &cmax, double &mach)
 {
@@ -941,7 +1151,11 @@ __device__ __forceinline__ bool riemann (const Phys &ph, const double *vL, const
                                          const double *uL, const double *uR,
                                          double *flux, double &press, double &cmax, double &mach)
 {
+#ifdef PG_FAST
+  if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, flux, press, cmax, mach); return true; }
+#else
   if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach); return true; }
+#endif
   else if (SOLVER == SOLVER_HLL){ riemann_hll<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach); return true; }
   else return riemann_roe<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach);
 }
