@@ -147,6 +147,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   g.S1  = g.T[0] + 2;
   g.S12 = g.S1*(g.T[1] + 2);
   g.tot = g.S12*(g.dims == 3 ? g.T[2] + 2 : 1);
+  if (g.tot >= (1LL << 31)){ free (h); return fail ("block of %lld padded zones: the kernels index with 32 bits (< 2^31 zones per block)", g.tot); }
   h->ph.gamma = cfg->gamma; h->ph.gmm1 = cfg->gamma - 1.0;
   h->ph.small_dn = cfg->small_dn; h->ph.small_pr = cfg->small_pr;
   h->ph.igmm1 = 1.0/(cfg->gamma - 1.0);

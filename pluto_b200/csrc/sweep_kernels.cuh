@@ -22,11 +22,12 @@
 // Sweep box (update_stage.c:144-148): zones DOM along the sweep, DOM+-1 in
 // the transverse directions (the extra pencils only feed the face EMFs).
 #pragma once
+#include <stdlib.h>
 #include "kernels_common.cuh"
 #include "mhd_device.cuh"
 
 #ifndef PG_MINB_X
-#define PG_MINB_X 4
+#define PG_MINB_X 3
 #endif
 #ifndef PG_MINB_MARCH
 #define PG_MINB_MARCH 3
@@ -49,8 +50,15 @@ __device__ __forceinline__ double warp_max (double x)
   return x;
 }
 
+// Element indices inside the sweeps are 32-bit (pluto_gpu_create refuses blocks with
+// 2^31 or more padded zones): one IMAD.WIDE per address instead of 64-bit adds.
+__device__ __forceinline__ int gidx32 (const Geom &g, int k, int j, int i)
+{
+  return (k + g.off[2])*(int)g.S12 + (j + g.off[1])*(int)g.S1 + (i + g.off[0]);
+}
+
 template <int NC>
-__device__ __forceinline__ void load_zone (const SweepArgs &a, long long id, double *v)
+__device__ __forceinline__ void load_zone (const SweepArgs &a, int id, double *v)
 {
   PG_FOR_NV(nv) v[nv] = __ldg (a.V[nv] + id);
 }
@@ -62,9 +70,25 @@ __device__ __forceinline__ void cp_async8 (double *smem_dst, const double *gsrc)
   const unsigned sa = (unsigned)__cvta_generic_to_shared (smem_dst);
   asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc));
 }
+// same, as a compiler barrier: smem reads issued before it stay before it (the copy
+// overwrites a slot that has just been read)
+__device__ __forceinline__ void cp_async8_ordered (double *smem_dst, const double *gsrc)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared (smem_dst);
+  asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait ()     // all but the N most recent groups
+{ asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all () { asm volatile ("cp.async.wait_group 0;" ::: "memory"); }
 
+#ifndef PG_MARCH_L2PF
+#define PG_MARCH_L2PF 0
+#endif
+__device__ __forceinline__ void prefetch_l2 (const void *p)
+{
+  asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
+}
 #ifndef PG_PREFETCH
 #define PG_PREFETCH 0
 #endif
@@ -80,7 +104,7 @@ __device__ __forceinline__ void prefetch_l1 (const void *p)
 // face EMFs from the induction flux (ct_emf.c:132-134,155-156,175-176) and
 // the sign of the mass flux with the UCT_CONTACT dead band (:137-141)
 template <int DIR, int NC>
-__device__ __forceinline__ void store_face_emf (const SweepArgs &a, long long id, const double *F)
+__device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, const double *F)
 {
   const double eps = 1.e-6;
   signed char s = 0;
@@ -145,34 +169,35 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
   const bool emf_ok = face_ok && (lane >= HL || seg == 0);
   const bool upd_i = face_ok && lane >= HL && ii >= HL;
 
-  auto row_id = [&] (int r, int &j, int &k) -> long long {
-    const int jr = r % nrj, kr = r / nrj;
-    j = g.beg[1] - 1 + jr;
-    k = (NC == 3 ? g.beg[2] - 1 + kr : 0);
-    return gidx (g, k, j, i);
+  // rows are enumerated (k, j) with j fastest; (jr, kr) of the row being SOLVED and of
+  // the row being FETCHED advance incrementally (no division in the loop)
+  const int S1i = (int)g.S1, S12i = (int)g.S12;
+  int jr = r_beg % nrj, kr = r_beg / nrj;
+  int id = gidx32 (g, (NC == 3 ? g.beg[2] - 1 + kr : 0), g.beg[1] - 1 + jr, i);
+  int jr_n = jr, kr_n = kr, id_n = id;               // next row to fetch
+  auto advance = [&] (int &jq, int &kq, int &idq){
+    if (++jq == nrj){ jq = 0; kq++; idq += S12i - (nrj - 1)*S1i; }
+    else idq += S1i;
   };
-  auto issue = [&] (int r, int buf){
-    int j, k;
-    const long long id = row_id (r, j, k);
+  auto issue = [&] (int buf){
     double *dst = wb + buf*(9*W);
-    PG_FOR_NV(nv) cp_async8 (dst + nv*W + lane + 1, a.V[nv] + id);
-    cp_async8 (dst + 8*W + lane + 1, a.Bn + id);
+    PG_FOR_NV(nv) cp_async8 (dst + nv*W + lane + 1, a.V[nv] + id_n);
+    cp_async8 (dst + 8*W + lane + 1, a.Bn + id_n);
     if (lane < 4){                                   // stencil halo: entries -1, 32, 33, 34
       const int off = (lane == 0 ? -1 : 31 + lane);
-      PG_FOR_NV(nv) cp_async8 (dst + nv*W + off + 1, a.V[nv] + (id - lane) + off);
+      PG_FOR_NV(nv) cp_async8 (dst + nv*W + off + 1, a.V[nv] + (id_n - lane) + off);
     }
     cp_async_commit ();
+    advance (jr_n, kr_n, id_n);
   };
 
   double my_mach = 0.0, my_cdt = 0.0;
-  issue (r_beg, 0);
-  for (int r = r_beg; r < r_end; r++){
+  issue (0);
+  for (int r = r_beg; r < r_end; r++, advance (jr, kr, id)){
     const int buf = (r - r_beg) & 1;
     cp_async_wait_all ();
     __syncwarp ();                                   // the other lanes' copies are visible
-    if (r + 1 < r_end) issue (r + 1, buf ^ 1);
-    int j, k;
-    const long long id = row_id (r, j, k);
+    if (r + 1 < r_end) issue (buf ^ 1);
     const double *src = wb + buf*(9*W);
 
     double v[NV], vp[NV], vm[NV];
@@ -222,8 +247,9 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
     pm = __shfl_up_sync (0xffffffffu, press, 1);
     cm = __shfl_up_sync (0xffffffffu, cmax, 1);
 
-    bool upd = upd_i && j >= g.beg[1] && j <= g.end[1];
-    if (NC == 3) upd = upd && k >= g.beg[2] && k <= g.end[2];
+    // interior rows: jr, kr in [1, n] (row 0 and row n+1 are the transverse extension)
+    bool upd = upd_i && jr >= 1 && jr <= g.n[1];
+    if (NC == 3) upd = upd && kr >= 1 && kr <= g.n[2];
     if (upd){
       double u0[NV];
       if (a.u_from_v) prim_to_cons<NC>(ph, v, u0);
@@ -257,6 +283,21 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
 // ---------------------------------------------------------------------------
 //  x2 / x3 sweeps: marching pencils
 // ---------------------------------------------------------------------------
+#ifndef PG_MARCH_PF
+#define PG_MARCH_PF 1
+#endif
+// Faces of look-ahead of the asynchronous copies, and shared-memory slots (doubles per
+// thread).  Measured on B200 (256^3, HLLD+PLM): PF = 2 is 40 % SLOWER than PF = 1 --
+// cp.async.ca stages its lines in L1, and three blocks x 67 slots leave only 28 KB of
+// L1 next to 206 KB of shared memory (the same cliff appears with four blocks of 52
+// slots).  The second face of look-ahead is therefore an L2 prefetch (PG_MARCH_L2PF),
+// which needs no landing space.
+__host__ __device__ constexpr int march_prefetch (int recon) { return recon == RECON_PPM ? 1 : PG_MARCH_PF; }
+__host__ __device__ constexpr int march_slots (int recon)
+{
+  return 8*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + 8 + 7 + (recon == RECON_PPM ? 8 : 0)
+         + march_prefetch (recon) + 6*(march_prefetch (recon) + 1);
+}
 template <int DIR, int RECON, int SOLVER, int NC>
 __global__ void __launch_bounds__(128, PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
@@ -286,103 +327,139 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   bool upd = in_range && i >= g.beg[0] && i <= g.end[0];
   if (NC == 3) upd = upd && o2 >= g.beg[TD] && o2 <= g.end[TD];
 
-  const long long sD = (DIR == 1 ? g.S1 : g.S12);
+  const int sD = (DIR == 1 ? (int)g.S1 : (int)g.S12);
   // id of zone c0-1 along the pencil
-  long long id = (DIR == 1 ? gidx (g, o2, c0 - 1, i) : gidx (g, c0 - 1, o2, i));
+  int id = (DIR == 1 ? gidx32 (g, o2, c0 - 1, i) : gidx32 (g, c0 - 1, o2, i));
 
   // State carried from face to face lives in SHARED memory, one column per
   // thread (slot*blockDim.x + threadIdx.x: conflict-free), so that it does not
-  // occupy registers during the Riemann solve (the register allocator would
-  // otherwise spill it to local memory and thrash L1):
-  //   slots 0-7 zone f, 8-15 zone f+1, 16-23 plus state of zone f,
-  //   24-28 previous flux (rho, m1, m2, m3, E), 29 previous total pressure,
-  //   30 previous cmax, PPM only: 31-38 zone f+2, 39-46 interface value at f+1/2.
-  // Landing slots of the asynchronous copies (cp.async, issued one face ahead):
-  //   NX 8 slots: the zone entering the stencil, BN: the face field,
-  //   UA 2 x 6: conservative variables + C_dt of the zone to update (double
-  //   buffered: consumed at the END of an iteration, refilled at its top).
+  // occupy registers during the Riemann solve:
+  //   ring of zones (8 slots each): the stencil zones f .. f+LA plus the PF-1 zones
+  //     already in flight for the next faces.  cp.async lands every zone ONCE,
+  //     directly in its ring slot, PF faces ahead of its first use (PF = 2 covers the
+  //     HBM latency with one face of work per warp still to spare); the slot of zone
+  //     f is refilled as soon as zone f has been read (no copies between slots: the
+  //     slot pointers rotate instead);
+  //   VP 8 slots: plus state of zone f;  FP 7: previous flux (rho, m1, m2, m3, E),
+  //     total pressure and cmax;  PPM only, WF 8: interface value at f+1/2.
+  // Other landing slots: BN x PF the face field, UA (PF+1) x 6 conservative variables
+  //   + C_dt of the zones to update (consumed at the END of an iteration).
   extern __shared__ double carry_[];
   double *cs = carry_ + threadIdx.x;
   constexpr int CS = 128;                   // = blockDim.x (fixed by the launcher): immediate smem offsets
-  constexpr int S_NX = (RECON == RECON_PLM ? 31 : 47), S_BN = S_NX + 8, S_UA = S_BN + 1;
-  constexpr int LA = (RECON == RECON_PLM ? 2 : 3);      // look-ahead of the stencil
-#define C_VB(nv) cs[(0 + (nv))*CS]
-#define C_VC(nv) cs[(8 + (nv))*CS]
-#define C_VP(nv) cs[(16 + (nv))*CS]
-#define C_FP(q)  cs[(24 + (q))*CS]
-#define C_VD(nv) cs[(31 + (nv))*CS]
-#define C_WF(nv) cs[(39 + (nv))*CS]
-#define C_NX(nv) cs[(S_NX + (nv))*CS]
-#define C_BN     cs[S_BN*CS]
-#define C_UA(b, q) cs[(S_UA + 6*(b) + (q))*CS]
+  constexpr bool PPM = (RECON == RECON_PPM);
+  constexpr int LA = (PPM ? 3 : 2);         // look-ahead of the stencil
+  constexpr int PF = march_prefetch (RECON);
+  constexpr int NZ = LA + PF;               // ring slots
+  constexpr int S_VP = 8*NZ, S_FP = S_VP + 8, S_WF = S_FP + 7, S_BN = S_WF + (PPM ? 8 : 0), S_UA = S_BN + PF;
+  static_assert (S_UA + 6*(PF + 1) == march_slots (RECON), "shared-memory layout");
+#define C_VP(nv) cs[(S_VP + (nv))*CS]
+#define C_FP(q)  cs[(S_FP + (q))*CS]
+#define C_WF(nv) cs[(S_WF + (nv))*CS]
+  double *z[NZ], *bnp[PF], *uap[PF + 1];
+  PG_UNROLL for (int q = 0; q < NZ; q++) z[q] = cs + 8*q*CS;            // z[q]: zone f+q
+  PG_UNROLL for (int q = 0; q < PF; q++) bnp[q] = cs + (S_BN + q)*CS;   // bnp[q]: field of face f+q+1/2
+  PG_UNROLL for (int q = 0; q <= PF; q++) uap[q] = cs + (S_UA + 6*q)*CS; // uap[q]: zone f+q (uap[PF]: free)
+  auto fetch_ua = [&] (double *dst, int idz){
+    cp_async8 (dst, a.U[RHO] + idz); cp_async8 (dst + CS, a.U[MX1] + idz);
+    cp_async8 (dst + 2*CS, a.U[MX2] + idz);
+    if (NC == 3) cp_async8 (dst + 3*CS, a.U[MX3] + idz);
+    cp_async8 (dst + 4*CS, a.U[ENG] + idz);
+    if (a.stage1) cp_async8 (dst + 5*CS, a.cdt + idz);
+  };
   {
+    // group 0: what face c0-1/2 needs (zones c0-1 .. c0-1+LA, its field); groups
+    // 1 .. PF-1: the additional zone, field and U of the following faces
+    PG_UNROLL for (int q = 0; q <= LA; q++) PG_FOR_NV(nv) cp_async8 (z[q] + nv*CS, a.V[nv] + id + q*sD);
+    cp_async8 (bnp[0], a.Bn + id);
+    cp_async_commit ();
+    PG_UNROLL for (int q = 1; q < PF; q++){
+      PG_FOR_NV(nv) cp_async8 (z[LA + q] + nv*CS, a.V[nv] + id + (LA + q)*sD);
+      cp_async8 (bnp[q], a.Bn + id + q*sD);
+      if (upd) fetch_ua (uap[q], id + q*sD);
+      cp_async_commit ();
+    }
     double vb_[NV], vc_[NV], vpL[NV];
-    if (RECON == RECON_PLM){
+    if (!PPM){
       double va_[NV], dvm[NV], dvp[NV], vm_unused[NV];
       load_zone<NC>(a, id - sD, va_);
-      load_zone<NC>(a, id, vb_);
-      load_zone<NC>(a, id + sD, vc_);
+      cp_async_wait<PF - 1> ();
+      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
       plm_zone<NC>(vb_, dvm, dvp, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
       load_zone<NC>(a, id - sD, va_);
-      load_zone<NC>(a, id, vb_);
-      load_zone<NC>(a, id + sD, vc_);
-      load_zone<NC>(a, id + 2*sD, vd_);
+      cp_async_wait<PF - 1> ();
+      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vd_[nv] = z[2][nv*CS]; }
       ppm_interface<NC>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
       ppm_interface<NC>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
       ppm_zone<NC>(vb_, Wm, Wf, vpL, vm_unused);
-      PG_FOR_NV(nv){ C_VD(nv) = vd_[nv]; C_WF(nv) = Wf[nv]; }
+      PG_FOR_NV(nv) C_WF(nv) = Wf[nv];
     }
-    PG_FOR_NV(nv){ C_VB(nv) = vb_[nv]; C_VC(nv) = vc_[nv]; C_VP(nv) = vpL[nv]; }
+    PG_FOR_NV(nv) C_VP(nv) = vpL[nv];
     PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
   }
-  // first face: the entering zone and the face field
-  PG_FOR_NV(nv) cp_async8 (&C_NX(nv), a.V[nv] + id + LA*sD);
-  cp_async8 (&C_BN, a.Bn + id);
-  cp_async_commit ();
   double my_mach = 0.0, my_cdt = 0.0;
 
   for (int f = c0 - 1; f <= c1; f++, id += sD){
     // id = zone f; interface f+1/2 lies between zone f and zone f+1
     double vL[NV], vR[NV];
-    const int cur = (f - c0) & 1;            // UA buffer holding zone f (filled one iteration ago)
-    double vnx[NV];
-    cp_async_wait_all ();
-    PG_FOR_NV(nv) vnx[nv] = C_NX(nv);
-    const double bn = C_BN;
-    if (f < c1){          // start pulling everything the NEXT face needs
-      PG_FOR_NV(nv) cp_async8 (&C_NX(nv), a.V[nv] + id + (LA + 1)*sD);
-      cp_async8 (&C_BN, a.Bn + id + sD);
-      if (upd){
-        cp_async8 (&C_UA(cur ^ 1, 0), a.U[RHO] + id + sD); cp_async8 (&C_UA(cur ^ 1, 1), a.U[MX1] + id + sD);
-        cp_async8 (&C_UA(cur ^ 1, 2), a.U[MX2] + id + sD);
-        if (NC == 3) cp_async8 (&C_UA(cur ^ 1, 3), a.U[MX3] + id + sD);
-        cp_async8 (&C_UA(cur ^ 1, 4), a.U[ENG] + id + sD);
-        if (a.stage1) cp_async8 (&C_UA(cur ^ 1, 5), a.cdt + id + sD);
+    cp_async_wait<PF - 1> ();
+    const double bn = bnp[0][0];
+    const double *ua = uap[0];               // U and C_dt of zone f (landed at least one face ago)
+    {
+      double vb_[NV], vc_[NV], vd_[NV], vnx[NV], vpn[NV];
+      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vnx[nv] = z[LA][nv*CS]; }
+      if (PPM) PG_FOR_NV(nv) vd_[nv] = z[2][nv*CS];
+      // start pulling what face f+PF+1/2 needs; its new zone replaces zone f, its field
+      // the one just read.  Always commit (possibly empty) so that the group count holds.
+#if PG_MARCH_L2PF
+      if (f + PF + 1 <= c1){                 // one more face ahead: HBM -> L2 only
+        PG_FOR_NV(nv) prefetch_l2 (a.V[nv] + id + (LA + PF + 1)*sD);
+        prefetch_l2 (a.Bn + id + (PF + 1)*sD);
+        if (upd){
+          prefetch_l2 (a.U[RHO] + id + (PF + 1)*sD); prefetch_l2 (a.U[MX1] + id + (PF + 1)*sD);
+          prefetch_l2 (a.U[MX2] + id + (PF + 1)*sD);
+          if (NC == 3) prefetch_l2 (a.U[MX3] + id + (PF + 1)*sD);
+          prefetch_l2 (a.U[ENG] + id + (PF + 1)*sD);
+          if (a.stage1) prefetch_l2 (a.cdt + id + (PF + 1)*sD);
+        }
+      }
+#endif
+      if (f + PF <= c1){
+        cp_async8_ordered (z[0], a.V[0] + id + (LA + PF)*sD);
+        PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv)) cp_async8 (z[0] + nv*CS, a.V[nv] + id + (LA + PF)*sD);
+        cp_async8 (bnp[0], a.Bn + id + PF*sD);
+        if (upd) fetch_ua (uap[PF], id + PF*sD);
       }
       cp_async_commit ();
-    }
-    {
-      double vb_[NV], vc_[NV], vpn[NV];
-      PG_FOR_NV(nv){ vb_[nv] = C_VB(nv); vc_[nv] = C_VC(nv); }
-      if (RECON == RECON_PLM){
+      if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
         plm_zone<NC>(vc_, dvm, dvp, vpn, vR);
-        PG_FOR_NV(nv){ C_VB(nv) = vc_[nv]; C_VC(nv) = vnx[nv]; }
       }else{
-        double vd_[NV], Wf[NV], Wn[NV];
-        PG_FOR_NV(nv){ vd_[nv] = C_VD(nv); Wf[nv] = C_WF(nv); }
+        double Wf[NV], Wn[NV];
+        PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
         ppm_interface<NC>(vb_, vc_, vd_, vnx, Wn);    // W[f+1]
         ppm_zone<NC>(vc_, Wf, Wn, vpn, vR);
-        PG_FOR_NV(nv){ C_VB(nv) = vc_[nv]; C_VC(nv) = vd_[nv]; C_VD(nv) = vnx[nv]; C_WF(nv) = Wn[nv]; }
+        PG_FOR_NV(nv) C_WF(nv) = Wn[nv];
       }
       PG_FOR_NV(nv){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
     }
     vL[D::bn] = bn; vR[D::bn] = bn;
+    {                        // rotate: zone f+1 becomes zone f, the refilled slots go to the back
+      double *t0 = z[0];
+      PG_UNROLL for (int q = 0; q + 1 < NZ; q++) z[q] = z[q + 1];
+      z[NZ - 1] = t0;
+      t0 = bnp[0];
+      PG_UNROLL for (int q = 0; q + 1 < PF; q++) bnp[q] = bnp[q + 1];
+      bnp[PF - 1] = t0;
+      t0 = uap[0];
+      PG_UNROLL for (int q = 0; q < PF; q++) uap[q] = uap[q + 1];
+      uap[PF] = t0;
+    }
 
     double uL[NV], uR[NV], F[NV], press, cmax, mach;
     prim_to_cons<NC>(ph, vL, uL);
@@ -397,15 +474,15 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     if (upd && f >= c0){
       const double dtdx = __ldg (a.dtp + DIR);
       double r;
-      r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = C_UA(cur, 0) + r;
-      r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = C_UA(cur, 1) + r;
-      r = -dtdx*(F[MX2] - C_FP(2)); if (D::vn == MX2) r -= dtdx*(press - pp);   a.U[MX2][id] = C_UA(cur, 2) + r;
+      r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = ua[0] + r;
+      r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = ua[CS] + r;
+      r = -dtdx*(F[MX2] - C_FP(2)); if (D::vn == MX2) r -= dtdx*(press - pp);   a.U[MX2][id] = ua[2*CS] + r;
       if (NC == 3){
-        r = -dtdx*(F[MX3] - C_FP(3)); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][id] = C_UA(cur, 3) + r;
+        r = -dtdx*(F[MX3] - C_FP(3)); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][id] = ua[3*CS] + r;
       }
-      r = -dtdx*(F[ENG] - C_FP(4));                               a.U[ENG][id] = C_UA(cur, 4) + r;
+      r = -dtdx*(F[ENG] - C_FP(4));                               a.U[ENG][id] = ua[4*CS] + r;
       if (a.stage1){
-        double cd = C_UA(cur, 5) + 0.5*(cp + cmax)*a.inv_dl;
+        double cd = ua[5*CS] + 0.5*(cp + cmax)*a.inv_dl;
         if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
         else            a.cdt[id] = cd;
       }
@@ -414,15 +491,9 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     if (NC == 3) C_FP(3) = F[MX3];
     C_FP(4) = F[ENG]; C_FP(5) = press; C_FP(6) = cmax;
   }
-#undef C_VB
-#undef C_VC
 #undef C_VP
 #undef C_FP
-#undef C_VD
 #undef C_WF
-#undef C_NX
-#undef C_BN
-#undef C_UA
 
   my_mach = warp_max (my_mach);
   if (lane == 0) atomic_max_pos (a.red + RED_MACH, my_mach);
@@ -460,10 +531,12 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long npen = (long long)(g.n[0] + 2)*(nc == 3 ? g.n[td] + 2 : 1);
     const long long nthr = npen*a.nchunk;
     const unsigned nb = (unsigned)((nthr + TPB - 1)/TPB);
-    const size_t smem = (size_t)((recon == RECON_PPM ? 47 : 31) + 8 + 1 + 12)*TPB*sizeof (double);
+    const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
 #define PG_LM(DD, R, C) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C>;                       \
       static bool attr_set = false;                                                                   \
-      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8); attr_set = true; } \
+      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
+        if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
+        attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
     if (dir == 1){
       if      (recon == RECON_PLM && nc == 3) PG_LM(1, RECON_PLM, 3);
