@@ -52,6 +52,11 @@ struct SweepArgs {
                              // continuing with the U left by the previous stage
   int     chunk_len;         // marching kernels: zones per thread along the sweep
   int     nchunk;
+  // fused x1 + x2 sweep only: the x2 quantities next to the x1 ones above
+  const double *Bn2;         // Bx2s
+  double       *e3, *e4;     // ezj, exj
+  signed char  *sv2;         // svy
+  double  inv_dl2;
 };
 
 struct CtArgs {
@@ -126,6 +131,9 @@ namespace NS {                                                                  
   int launch_sweep_hlld (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
   int launch_sweep_hll  (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
   int launch_sweep_roe  (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
+  int launch_sweep_xy_hlld (int recon, const SweepArgs &a, cudaStream_t s);              \
+  int launch_sweep_xy_hll  (int recon, const SweepArgs &a, cudaStream_t s);              \
+  int launch_sweep_xy_roe  (int recon, const SweepArgs &a, cudaStream_t s);              \
   int launch_ct_emf     (const CtArgs &a, cudaStream_t s);                               \
   int launch_ct_update  (const CtArgs &a, cudaStream_t s);                               \
   int launch_final      (const FinalArgs &a, cudaStream_t s);                            \

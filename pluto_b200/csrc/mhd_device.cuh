@@ -26,7 +26,7 @@ enum { MX1 = VX1, MX2 = VX2, MX3 = VX3, ENG = PRS };
 enum { RECON_PLM = 0, RECON_PPM = 1 };
 enum { SOLVER_HLLD = 0, SOLVER_HLL = 1, SOLVER_ROE = 2 };
 
-struct Phys {
+struct Phys {                          // same layout as PhysPar (kernels_common.cuh)
   double gamma, gmm1, small_dn, small_pr;
   double igmm1;                       // 1/(gamma - 1), FAST arithmetic only
 };

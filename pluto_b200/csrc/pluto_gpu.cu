@@ -65,6 +65,7 @@ struct PlutoGpu {
   cudaGraphExec_t graph;           // captured single-GPU step (all stages), replayed with new dt
   long long graph_launches;        // kernels inside the graph
   int     use_graph;
+  int     fuse_xy;                 // FAST: fused x1+x2 sweep kernel (PLUTO_GPU_NO_FUSE_XY=1 disables)
   long long steps_done;
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
@@ -187,6 +188,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   CU (cudaMalloc ((void **)&h->dtdev, 4*sizeof (double)));
   CU (cudaMallocHost ((void **)&h->dthost, 4*sizeof (double)));
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
+  h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
   *out = h;
   return 0;
 }
@@ -436,6 +438,10 @@ static int run_stage (PlutoGpu *h, int stage)
   // left (as the reference does); FAST: rebuild it from the primitives, which
   // saves reading U in the x1 sweep and differs by round-off only
   s.u_from_v = (stage == 1 || h->cfg.arith == PLUTO_GPU_ARITH_FAST);
+  // FAST arithmetic: x1 and x2 are solved by ONE fused kernel (one pass over the
+  // primitives, U written once); EXACT keeps one kernel per direction, which continues
+  // from the conservative state of the previous stage as the reference does
+  const bool fuse_xy = h->fuse_xy && h->cfg.arith == PLUTO_GPU_ARITH_FAST;
   for (int dir = 0; dir < g.dims; dir++){
     s.Bn = h->Bs[sp.in][dir];
     s.inv_dl = 1.0/g.dx[dir];              // set_geometry.c (inv_dx)
@@ -444,22 +450,40 @@ static int run_stage (PlutoGpu *h, int stage)
     if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
-    if (dir > 0){
+    const int recon = h->cfg.recon;
+    if (dir > 0 || fuse_xy){
       // zones per thread along a marching sweep: long enough to amortise the
       // extra face per chunk, short enough to fill the 148 SMs (2-D grids have
       // few pencils)
-      const int td = (dir == 1 ? 2 : 1);
-      const long long npen = (long long)(g.n[0] + 2)*(g.dims == 3 ? g.n[td] + 2 : 1);
+      const int mdir = (dir == 0 ? 1 : dir);
+      const int td = (mdir == 1 ? 2 : 1);
+      long long npen = (long long)(g.n[0] + 2)*(g.dims == 3 ? g.n[td] + 2 : 1);
+      if (dir == 0){                       // fused: 32 lanes per x1 segment of (30 or 29) zones
+        const int stride = 32 - (recon == PLUTO_GPU_RECON_PARABOLIC ? 2 : 1) - 1;
+        npen = (long long)((g.n[0] + stride - 1)/stride)*32*(g.dims == 3 ? g.n[2] + 2 : 1);
+      }
       const long long want = (228000 + npen - 1)/npen;               // chunks for ~4 waves of threads
-      long long len = (g.n[dir] + want - 1)/want;
+      long long len = (g.n[mdir] + want - 1)/want;
       if (len < 4) len = 4;
       if (len > h->march_chunk) len = h->march_chunk;
-      if (len > g.n[dir]) len = g.n[dir];
+      if (len > g.n[mdir]) len = g.n[mdir];
       s.chunk_len = (int)len;
-      s.nchunk = (g.n[dir] + s.chunk_len - 1)/s.chunk_len;
+      s.nchunk = (g.n[mdir] + s.chunk_len - 1)/s.chunk_len;
     }
     int r;
-    const int recon = h->cfg.recon;
+    if (dir == 0 && fuse_xy){
+      s.Bn2 = h->Bs[sp.in][1]; s.e3 = h->ezj; s.e4 = h->exj; s.sv2 = h->sv[1];
+      s.inv_dl2 = 1.0/g.dx[1];
+      s.last_dir = (g.dims == 2);
+      const int te = tbegin (h, KC_SWEEP_X);
+      if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = pg_fast::launch_sweep_xy_hlld (recon, s, h->stream);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = pg_fast::launch_sweep_xy_hll  (recon, s, h->stream);
+      else                                             r = pg_fast::launch_sweep_xy_roe  (recon, s, h->stream);
+      tend (h, te);
+      if (count (h, r)) return 1;
+      dir = 1;                             // x2 is done
+      continue;
+    }
     const int te = tbegin (h, KC_SWEEP_X + dir);
     if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_sweep_hlld) (dir, recon, s, h->stream);
     else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_sweep_hll)  (dir, recon, s, h->stream);

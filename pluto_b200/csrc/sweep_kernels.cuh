@@ -104,24 +104,27 @@ __device__ __forceinline__ void prefetch_l1 (const void *p)
 // face EMFs from the induction flux (ct_emf.c:132-134,155-156,175-176) and
 // the sign of the mass flux with the UCT_CONTACT dead band (:137-141)
 template <int DIR, int NC>
-__device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, const double *F)
+__device__ __forceinline__ void store_face_emf_p (double *e1, double *e2, signed char *sv, int id, const double *F)
 {
   const double eps = 1.e-6;
   signed char s = 0;
   if      (F[RHO] >  eps) s = 1;
   else if (F[RHO] < -eps) s = -1;
   if (DIR == 0){            // e1 = ezi, e2 = eyi
-    a.e1[id] = -F[BX2];
-    if (NC == 3) a.e2[id] = F[BX3];
+    e1[id] = -F[BX2];
+    if (NC == 3) e2[id] = F[BX3];
   }else if (DIR == 1){      // e1 = ezj, e2 = exj
-    a.e1[id] = F[BX1];
-    if (NC == 3) a.e2[id] = -F[BX3];
+    e1[id] = F[BX1];
+    if (NC == 3) e2[id] = -F[BX3];
   }else{                    // e1 = eyk, e2 = exk
-    a.e1[id] = -F[BX1];
-    a.e2[id] =  F[BX2];
+    e1[id] = -F[BX1];
+    e2[id] =  F[BX2];
   }
-  a.sv[id] = s;
+  sv[id] = s;
 }
+template <int DIR, int NC>
+__device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, const double *F)
+{ store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F); }
 
 // ---------------------------------------------------------------------------
 //  x1 sweep
@@ -146,7 +149,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
   constexpr int STRIDE = 32 - HL - 1;
   constexpr int W = 36;                              // staged entries per array and row
   const Geom &g = a.g;
-  Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr; ph.igmm1 = a.ph.igmm1;
+  const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);     // stays in the kernel-parameter constant bank
 
   extern __shared__ double rowbuf_[];
   const int lane = threadIdx.x & 31;
@@ -304,7 +307,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
   typedef Dirs<DIR> D;
   const Geom &g = a.g;
-  Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr; ph.igmm1 = a.ph.igmm1;
+  const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);     // stays in the kernel-parameter constant bank
   const int lane = threadIdx.x & 31;
 
   // transverse enumeration: x1 (fastest) and the other transverse direction
@@ -501,6 +504,288 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     my_cdt = warp_max (my_cdt);
     if (lane == 0) atomic_max_pos (a.red + RED_CDT, my_cdt);
   }
+}
+
+// ---------------------------------------------------------------------------
+//  fused x1 + x2 sweep (FAST arithmetic): one pass over the primitives does both
+//  directions.  A warp owns a 32-entry segment of the x1 rows of one x3 plane and
+//  MARCHES along x2: the x2 faces are solved as in sweep_march_kernel (carried state
+//  in shared memory), and the x1 faces of the row the march is standing on are solved
+//  as in sweep_x_kernel, the neighbours in x1 being the adjacent columns of the SAME
+//  shared-memory ring of zone rows (plus four halo columns per warp).  The conservative
+//  update of a zone is written once, U = (PrimToCons(V) + rhs_x1) + rhs_x2 (the
+//  reference's order, update_stage.c:214-216): no U is read, the primitives and both
+//  face fields are read once, the four face EMFs of the two directions are written.
+//  HBM bytes per zone: read 8 V + Bx1s + Bx2s, write 5 U + 4 EMF (+ C_dt, 2 sign bytes)
+//  = 154 B (+8) instead of 129 + 169 for the two separate sweeps.
+// ---------------------------------------------------------------------------
+#ifndef PG_MINB_XY
+#define PG_MINB_XY 3
+#endif
+__host__ __device__ constexpr int xy_ring_cols () { return 4*36; }             // 4 warps x (32 + 4 halo columns)
+__host__ __device__ constexpr int xy_thread_slots (int recon) { return 8 + 7 + (recon == RECON_PPM ? 8 : 0) + 2; }
+// ring rows: the stencil rows f .. f+LA, plus (PLM) one free row for the copy in flight so
+// that nothing has to be read ahead of its use; with PPM that row would push three blocks
+// past the 164 KB carve-out (L1 cliff, see march_prefetch), so row f is read early instead
+__host__ __device__ constexpr int xy_ring_rows (int recon) { return recon == RECON_PPM ? 4 : 4; }
+__host__ __device__ constexpr size_t xy_smem_bytes (int recon)
+{
+  return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128)*sizeof (double);
+}
+
+template <int RECON, int SOLVER, int NC>
+__global__ void __launch_bounds__(128, PG_MINB_XY)
+sweep_xy_kernel (const __grid_constant__ SweepArgs a)
+{
+  typedef Dirs<0> DX;
+  typedef Dirs<1> DY;
+  constexpr bool PPM = (RECON == RECON_PPM);
+  constexpr int HL = (PPM ? 2 : 1);
+  constexpr int STRIDE = 32 - HL - 1;
+  constexpr int LA = (PPM ? 3 : 2);                  // look-ahead of the x2 stencil
+  constexpr int NZ = xy_ring_rows (RECON);           // ring rows: f .. f+LA (+ a free one)
+  constexpr int ZF = (NZ > LA + 1 ? NZ - 1 : 0);     // ring row the copy in flight lands in
+  constexpr int CW = xy_ring_cols ();                // ring columns per block
+  constexpr int CS = 128;
+  const Geom &g = a.g;
+  const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);     // stays in the kernel-parameter constant bank
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = g.n[0] + HL + 1;                     // zones IBEG-HL .. IEND+1 of one row
+  const int nseg = (g.n[0] + STRIDE - 1)/STRIDE;
+  const int np2 = (NC == 3 ? g.n[2] + 2 : 1);
+  const int gw = (int)(((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5);
+  const int seg = gw % nseg;
+  const int plane = (gw / nseg) % np2;
+  const int chunk = gw / (nseg*np2);
+  if (chunk >= a.nchunk) return;                     // whole warps leave together
+
+  const int ii = seg*STRIDE + lane;                  // entry within the row
+  const int i  = g.beg[0] - HL + ii;
+  const int k  = (NC == 3 ? g.beg[2] - 1 + plane : 0);
+  // x1 roles of the lanes (as in sweep_x_kernel)
+  bool zone_ok = ii < L;
+  if (PPM) zone_ok = zone_ok && lane >= 1 && ii >= 1;
+  const bool xface_ok = zone_ok && lane <= 30 && lane >= HL - 1 && ii >= HL - 1 && ii <= L - 2;
+  const bool xemf_ok = xface_ok && (lane >= HL || seg == 0);
+  const bool upd_i = xface_ok && lane >= HL && ii >= HL;
+  // x2 roles: columns IBEG-1 .. IEND+1; overlapping lanes of neighbouring segments are
+  // computed twice and stored once
+  const bool col_ok = ii < L && i >= g.beg[0] - 1;
+  const bool yemf_ok = col_ok && ((lane >= HL && lane <= 30) || (seg == 0 && lane < HL) || (lane == 31 && seg == nseg - 1));
+  bool upd = upd_i;
+  if (NC == 3) upd = upd && k >= g.beg[2] && k <= g.end[2];
+
+  const int c0 = g.beg[1] + chunk*a.chunk_len;
+  int c1 = c0 + a.chunk_len - 1; if (c1 > g.end[1]) c1 = g.end[1];
+  const bool last_chunk = (chunk == a.nchunk - 1);
+  const int f_end = c1 + (last_chunk ? 1 : 0);       // the last chunk also solves the x1 faces of row JEND+1
+  const int sD = (int)g.S1;
+  int id = gidx32 (g, k, c0 - 1, i);                 // zone (k, c0-1, i)
+
+  extern __shared__ double carry_[];
+  double *ring = carry_ + warp*36 + 1 + lane;        // own column; entries -1, 32, 33, 34 of the warp around it
+  double *cs = carry_ + 8*NZ*CW + threadIdx.x;
+  constexpr int S_VP = 0, S_FP = 8, S_WF = 15, S_BY = S_WF + (PPM ? 8 : 0), S_BX = S_BY + 1;
+  static_assert (S_BX + 1 == xy_thread_slots (RECON), "shared-memory layout");
+#define C_VP(nv) cs[(S_VP + (nv))*CS]
+#define C_FP(q)  cs[(S_FP + (q))*CS]
+#define C_WF(nv) cs[(S_WF + (nv))*CS]
+#define C_BY     cs[S_BY*CS]
+#define C_BX     cs[S_BX*CS]
+  double *z[NZ];
+  PG_UNROLL for (int q = 0; q < NZ; q++) z[q] = ring + 8*q*CW;           // z[q]: row f+q
+  auto fetch_row = [&] (double *dst, int idr, bool ordered){
+    if (ordered) cp_async8_ordered (dst, a.V[0] + idr); else cp_async8 (dst, a.V[0] + idr);
+    PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv)) cp_async8 (dst + nv*CW, a.V[nv] + idr);
+    if (lane < 4){                                   // stencil halo: entries -1, 32, 33, 34
+      const int off = (lane == 0 ? -1 : 31 + lane);
+      PG_FOR_NV(nv) cp_async8 (dst + nv*CW - lane + off, a.V[nv] + (idr - lane) + off);
+    }
+  };
+  {
+    PG_UNROLL for (int q = 0; q <= LA; q++) fetch_row (z[q], id + q*sD, false);
+    cp_async8 (&C_BY, a.Bn2 + id);
+    cp_async8 (&C_BX, a.Bn + id);
+    cp_async_commit ();
+    double vb_[NV], vc_[NV], vpL[NV];
+    if (!PPM){
+      double va_[NV], dvm[NV], dvp[NV], vm_unused[NV];
+      load_zone<NC>(a, id - sD, va_);
+      cp_async_wait_all ();
+      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
+      PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
+      plm_zone<NC>(vb_, dvm, dvp, vpL, vm_unused);
+    }else{
+      double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
+      load_zone<NC>(a, id - 2*sD, vz_);
+      load_zone<NC>(a, id - sD, va_);
+      cp_async_wait_all ();
+      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; vd_[nv] = z[2][nv*CW]; }
+      ppm_interface<NC>(vz_, va_, vb_, vc_, Wm);
+      ppm_interface<NC>(va_, vb_, vc_, vd_, Wf);
+      ppm_zone<NC>(vb_, Wm, Wf, vpL, vm_unused);
+      PG_FOR_NV(nv) C_WF(nv) = Wf[nv];
+    }
+    PG_FOR_NV(nv) C_VP(nv) = vpL[nv];
+    PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
+  }
+  double my_mach = 0.0, my_cdt = 0.0;
+  for (int f = c0 - 1; f <= f_end; f++, id += sD){
+    // id = zone (k, f, i).  x2 interface f+1/2 lies between rows f and f+1; the x1 faces
+    // solved here are those of row f.
+    const bool do_y = f <= c1;
+    const bool do_x = f >= c0 || chunk == 0;
+    cp_async_wait_all ();
+    __syncwarp ();                                   // the other lanes' copies are visible
+    const double bny = C_BY, bnx = C_BX;
+    double v[NV], rx[NV], cdx = 0.0;
+    double xvl[NV], xvr[NV], xvrr[NV];
+    PG_UNROLL for (int nv = 0; nv < NV; nv++) rx[nv] = 0.0;
+    auto read_row_f = [&] (){                        // zone (f, i) and its x1 neighbours
+      PG_FOR_NV(nv) v[nv] = z[0][nv*CW];
+      if (do_x){
+        PG_FOR_NV(nv){ xvl[nv] = z[0][nv*CW - 1]; xvr[nv] = z[0][nv*CW + 1]; }
+        if (PPM) PG_FOR_NV(nv) xvrr[nv] = z[0][nv*CW + 2];
+      }
+    };
+    // the copy of row f+LA+1 lands in the free ring row (PLM), or in the row of f itself
+    // (PPM), which must then be read first
+    if (ZF == 0) read_row_f ();
+    if (f + 1 <= c1) fetch_row (z[ZF], id + (LA + 1)*sD, true);
+    if (f + 1 <= c1) cp_async8 (&C_BY, a.Bn2 + id + sD);
+    if (f + 1 <= f_end) cp_async8_ordered (&C_BX, a.Bn + id + sD);
+    cp_async_commit ();
+    if (ZF != 0) read_row_f ();
+
+    if (do_x){
+      double vp[NV], vm[NV];
+      if (!PPM){
+        double dvm[NV], dvp[NV];
+        PG_FOR_NV(nv){ dvm[nv] = v[nv] - xvl[nv]; dvp[nv] = xvr[nv] - v[nv]; }
+        plm_zone<NC>(v, dvm, dvp, vp, vm);
+      }else{
+        double Wi[NV], Wm[NV];
+        ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
+        PG_FOR_NV(nv) Wm[nv] = __shfl_up_sync (0xffffffffu, Wi[nv], 1);
+        ppm_zone<NC>(v, Wm, Wi, vp, vm);
+      }
+      double vR[NV];
+      PG_FOR_NV(nv) vR[nv] = __shfl_down_sync (0xffffffffu, vm[nv], 1);
+      vp[DX::bn] = bnx; vR[DX::bn] = bnx;
+      double uL[NV], uR[NV], F[NV], press, cmax, mach;
+      prim_to_cons<NC>(ph, vp, uL);
+      prim_to_cons<NC>(ph, vR, uR);
+      bool ok = riemann<SOLVER, 0, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach);
+      if (xemf_ok) store_face_emf_p<0, NC>(a.e1, a.e2, a.sv, id, F);
+      if (xface_ok) my_mach = mach > my_mach ? mach : my_mach;
+      if (SOLVER == SOLVER_ROE && xface_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
+      double Fm[NV], pm, cm;
+      Fm[RHO] = __shfl_up_sync (0xffffffffu, F[RHO], 1);
+      Fm[MX1] = __shfl_up_sync (0xffffffffu, F[MX1], 1);
+      Fm[MX2] = __shfl_up_sync (0xffffffffu, F[MX2], 1);
+      if (NC == 3) Fm[MX3] = __shfl_up_sync (0xffffffffu, F[MX3], 1);
+      Fm[ENG] = __shfl_up_sync (0xffffffffu, F[ENG], 1);
+      pm = __shfl_up_sync (0xffffffffu, press, 1);
+      cm = __shfl_up_sync (0xffffffffu, cmax, 1);
+      const double dtdx0 = __ldg (a.dtp + 0);
+      rx[RHO] = -dtdx0*(F[RHO] - Fm[RHO]);
+      rx[MX1] = -dtdx0*(F[MX1] - Fm[MX1]); rx[MX1] -= dtdx0*(press - pm);
+      rx[MX2] = -dtdx0*(F[MX2] - Fm[MX2]);
+      if (NC == 3) rx[MX3] = -dtdx0*(F[MX3] - Fm[MX3]);
+      rx[ENG] = -dtdx0*(F[ENG] - Fm[ENG]);
+      cdx = 0.5*(cm + cmax)*a.inv_dl;
+    }
+
+    // ---------------- x2 face f+1/2 ----------------
+    if (do_y){
+      double vL[NV], vR[NV], vpn[NV], vc_[NV], vd_[NV], vnx[NV];
+      if (ZF != 0) PG_FOR_NV(nv) v[nv] = z[0][nv*CW];      // row f is still in the ring: not kept in registers
+      PG_FOR_NV(nv){ vc_[nv] = z[1][nv*CW]; vnx[nv] = z[LA][nv*CW]; }
+      if (PPM) PG_FOR_NV(nv) vd_[nv] = z[2][nv*CW];
+      if (!PPM){
+        double dvm[NV], dvp[NV];
+        PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
+        plm_zone<NC>(vc_, dvm, dvp, vpn, vR);
+      }else{
+        double Wf[NV], Wn[NV];
+        PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
+        ppm_interface<NC>(v, vc_, vd_, vnx, Wn);       // W[f+1]
+        ppm_zone<NC>(vc_, Wf, Wn, vpn, vR);
+        PG_FOR_NV(nv) C_WF(nv) = Wn[nv];
+      }
+      PG_FOR_NV(nv){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
+      vL[DY::bn] = bny; vR[DY::bn] = bny;
+      double uL[NV], uR[NV], F[NV], press, cmax, mach;
+      prim_to_cons<NC>(ph, vL, uL);
+      prim_to_cons<NC>(ph, vR, uR);
+      bool ok = riemann<SOLVER, 1, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach);
+      if (col_ok){
+        my_mach = mach > my_mach ? mach : my_mach;
+        if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
+      }
+      if (yemf_ok && (f >= c0 || chunk == 0)) store_face_emf_p<1, NC>(a.e3, a.e4, a.sv2, id, F);
+      const double pp = C_FP(5), cp = C_FP(6);
+      if (upd && f >= c0){
+        double u0[NV], r;
+        const double dtdx1 = __ldg (a.dtp + 1);
+        prim_to_cons<NC>(ph, v, u0);
+        r = -dtdx1*(F[RHO] - C_FP(0));                                   a.U[RHO][id] = (u0[RHO] + rx[RHO]) + r;
+        r = -dtdx1*(F[MX1] - C_FP(1));                                   a.U[MX1][id] = (u0[MX1] + rx[MX1]) + r;
+        r = -dtdx1*(F[MX2] - C_FP(2)); r -= dtdx1*(press - pp);          a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
+        if (NC == 3){ r = -dtdx1*(F[MX3] - C_FP(3));                     a.U[MX3][id] = (u0[MX3] + rx[MX3]) + r; }
+        r = -dtdx1*(F[ENG] - C_FP(4));                                   a.U[ENG][id] = (u0[ENG] + rx[ENG]) + r;
+        if (a.stage1){
+          const double cd = cdx + 0.5*(cp + cmax)*a.inv_dl2;
+          if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
+          else            a.cdt[id] = cd;
+        }
+      }
+      C_FP(0) = F[RHO]; C_FP(1) = F[MX1]; C_FP(2) = F[MX2];
+      if (NC == 3) C_FP(3) = F[MX3];
+      C_FP(4) = F[ENG]; C_FP(5) = press; C_FP(6) = cmax;
+    }
+    {                        // rotate the ring
+      double *t0 = z[0];
+      PG_UNROLL for (int q = 0; q + 1 < NZ; q++) z[q] = z[q + 1];
+      z[NZ - 1] = t0;
+    }
+  }
+#undef C_VP
+#undef C_FP
+#undef C_WF
+#undef C_BY
+#undef C_BX
+  my_mach = warp_max (my_mach);
+  if (lane == 0) atomic_max_pos (a.red + RED_MACH, my_mach);
+  if (a.stage1 && a.last_dir){
+    my_cdt = warp_max (my_cdt);
+    if (lane == 0) atomic_max_pos (a.red + RED_CDT, my_cdt);
+  }
+}
+
+template <int SOLVER>
+static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const int nc = g.dims;
+  const int TPB = 128;
+  const int HL = (recon == RECON_PPM ? 2 : 1);
+  const int stride = 32 - HL - 1;
+  const long long nseg = (g.n[0] + stride - 1)/stride;
+  const long long nwarp = nseg*(nc == 3 ? g.n[2] + 2 : 1)*a.nchunk;
+  const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
+  const size_t smem = xy_smem_bytes (recon);
+#define PG_LXY(R, C) do { auto kfn = sweep_xy_kernel<R, SOLVER, C>;                                   \
+      static bool attr_set = false;                                                                   \
+      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); attr_set = true; } \
+      kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+  if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
+  else if (recon == RECON_PLM && nc == 2) PG_LXY(RECON_PLM, 2);
+  else if (recon == RECON_PPM && nc == 3) PG_LXY(RECON_PPM, 3);
+  else                                    PG_LXY(RECON_PPM, 2);
+#undef PG_LXY
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 
 // ---------------------------------------------------------------------------
