@@ -217,45 +217,47 @@ final_kernel (const __grid_constant__ FinalArgs a)
 }
 
 // ---------------------------------------------------------------------------
-//  boundary fills
+//  boundary fills: one launch per dimension.  blockIdx.y < nf: copy job (one field,
+//  one side); otherwise the div B = 0 fill of one side.  A fill does not read the
+//  ghost values the copy jobs of the same launch write: it takes the tangential
+//  components through the same source mapping (bc_source), so the two are
+//  independent.
 // ---------------------------------------------------------------------------
+// source zone along d of ghost index n for a boundary of the given type
+__device__ __forceinline__ int bc_source (const Geom &g, int type, int d, int hi_side, int n)
+{
+  if (type == 0) return n + (hi_side ? -g.n[d] : g.n[d]);            // periodic  (boundary.c:480-518)
+  if (type == 1) return hi_side ? g.end[d] : g.beg[d];               // outflow   (boundary.c:439-477)
+  return hi_side ? 2*g.end[d] - n + 1 : 2*g.beg[d] - n - 1;          // reflective (boundary.c:521-564)
+}
+
 __global__ void __launch_bounds__(128)
 bc_kernel (const __grid_constant__ BcArgs a)
 {
   const Geom &g = a.g;
-  const BcField &f = a.f[blockIdx.y];
-  const int ni = f.hi[0] - f.lo[0] + 1, nj = f.hi[1] - f.lo[1] + 1, nk = f.hi[2] - f.lo[2] + 1;
-  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-  if (t >= (long long)ni*nj*nk) return;
-  const int i = f.lo[0] + (int)(t % ni), j = f.lo[1] + (int)((t/ni) % nj), k = f.lo[2] + (int)(t/((long long)ni*nj));
-  int c[3] = {i, j, k};
-  const int d = a.side >> 1, hi_side = a.side & 1;
-  double s = 1.0;
-  if (a.type == 0){                 // periodic (boundary.c:480-518)
-    c[d] += hi_side ? -g.n[d] : g.n[d];
-  }else if (a.type == 1){           // outflow  (boundary.c:439-477)
-    c[d] = hi_side ? g.end[d] : g.beg[d];
-  }else{                            // reflective (boundary.c:521-564)
-    c[d] = hi_side ? 2*g.end[d] - c[d] + 1 : 2*g.beg[d] - c[d] - 1;
-    s = (double)f.sign;
+  if ((int)blockIdx.y < a.nf){
+    const BcField &f = a.f[blockIdx.y];
+    const int ni = f.hi[0] - f.lo[0] + 1, nj = f.hi[1] - f.lo[1] + 1, nk = f.hi[2] - f.lo[2] + 1;
+    long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= (long long)ni*nj*nk) return;
+    const int i = f.lo[0] + (int)(t % ni), j = f.lo[1] + (int)((t/ni) % nj), k = f.lo[2] + (int)(t/((long long)ni*nj));
+    int c[3] = {i, j, k};
+    const int d = f.side >> 1, hi_side = f.side & 1;
+    c[d] = bc_source (g, f.type, d, hi_side, c[d]);
+    const double x = f.q[gidx (g, c[2], c[1], c[0])];
+    f.q[gidx (g, k, j, i)] = (f.type == 2 ? (double)f.sign*x : x);
+    return;
   }
-  const double x = f.q[gidx (g, c[2], c[1], c[0])];
-  f.q[gidx (g, k, j, i)] = (a.type == 2 ? s*x : x);
-}
-
-// normal staggered component in the ghost zones from div B = 0, marching
-// outwards (sequential along the normal), then the cell-centred normal
-// component as the face average.  One thread per transverse position.
-__global__ void __launch_bounds__(128)
-bc_fill_kernel (const __grid_constant__ BcFillArgs a)
-{
-  const Geom &g = a.g;
-  const int d = a.side >> 1, hi_side = a.side & 1;
+  // normal staggered component in the ghost zones from div B = 0, marching
+  // outwards (sequential along the normal), then the cell-centred normal
+  // component as the face average.  One thread per transverse position.
+  const BcFill &fl = a.fill[blockIdx.y - a.nf];
+  const int d = fl.side >> 1, hi_side = fl.side & 1;
   const int d1 = (d == 0 ? 1 : 0), d2 = (d == 2 ? 1 : 2);     // transverse dims, d1 faster
   const int n1 = g.T[d1], n2 = g.T[d2];
   long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
   if (t >= (long long)n1*n2) return;
-  int c[3];
+  int c[3], cs[3];
   c[d1] = (int)(t % n1); c[d2] = (int)(t / n1);
   const double dx1 = g.dx[0], dx2 = g.dx[1], dx3 = g.dx[2];
   double A[3];
@@ -268,10 +270,16 @@ bc_fill_kernel (const __grid_constant__ BcFillArgs a)
   for (int n = nbeg; dn*n <= dn*nend; n += dn){
     c[d] = n;
     const long long id = gidx (g, c[2], c[1], c[0]);
+    // tangential components of ghost zone n = those of its source zone (what the copy
+    // jobs of this side store there; reflective: tangential fields keep their sign)
+    cs[0] = c[0]; cs[1] = c[1]; cs[2] = c[2];
+    cs[d] = bc_source (g, fl.type, d, hi_side, n);
+    const long long ids = gidx (g, cs[2], cs[1], cs[0]);
     double dB[3] = {0.0, 0.0, 0.0};
     double bp[3] = {0.0, 0.0, 0.0}, bm[3] = {0.0, 0.0, 0.0};
     for (int q = 0; q < g.dims; q++){
-      bp[q] = a.Bs[q][id]; bm[q] = a.Bs[q][id - st[q]];
+      const long long idq = (q == d ? id : ids);
+      bp[q] = a.Bs[q][idq]; bm[q] = a.Bs[q][idq - st[q]];
       dB[q] = (A[q]*bp[q] - A[q]*bm[q]);
     }
     // sum of the two transverse flux differences in the reference's order
@@ -281,12 +289,12 @@ bc_fill_kernel (const __grid_constant__ BcFillArgs a)
     if (!hi_side) a.Bs[d][id - st[d]] = (A[d]*bp[d] + dB[qa] + dB[qb])/A[d];
     else          a.Bs[d][id]         = (A[d]*bm[d] - (dB[qa] + dB[qb]))/A[d];
   }
-  if (a.Bc){
+  if (fl.Bc){
     const int lo = hi_side ? g.end[d] + 1 : 0, hi = hi_side ? g.T[d] - 1 : g.beg[d] - 1;
     for (int n = lo; n <= hi; n++){
       c[d] = n;
       const long long id = gidx (g, c[2], c[1], c[0]);
-      a.Bc[id] = 0.5*(a.Bs[d][id] + a.Bs[d][id - st[d]]);
+      fl.Bc[id] = 0.5*(a.Bs[d][id] + a.Bs[d][id - st[d]]);
     }
   }
 }
@@ -359,25 +367,22 @@ int launch_final (const FinalArgs &a, cudaStream_t s)
 
 int launch_bc (const BcArgs &a, cudaStream_t s)
 {
+  const Geom &g = a.g;
   long long nmax = 0;
   for (int f = 0; f < a.nf; f++){
     long long n = 1;
     for (int d = 0; d < 3; d++) n *= (a.f[f].hi[d] - a.f[f].lo[d] + 1);
     if (n > nmax) nmax = n;
   }
-  if (nmax <= 0 || a.nf <= 0) return 0;
-  dim3 grid (nblocks (nmax, 128), a.nf);
+  for (int f = 0; f < a.nfill; f++){
+    const int d = a.fill[f].side >> 1;
+    const int d1 = (d == 0 ? 1 : 0), d2 = (d == 2 ? 1 : 2);
+    const long long n = (long long)g.T[d1]*g.T[d2];
+    if (n > nmax) nmax = n;
+  }
+  if (nmax <= 0 || a.nf + a.nfill <= 0) return 0;
+  dim3 grid (nblocks (nmax, 128), a.nf + a.nfill);
   bc_kernel<<<grid, 128, 0, s>>>(a);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
-}
-
-int launch_bc_fill (const BcFillArgs &a, cudaStream_t s)
-{
-  const Geom &g = a.g;
-  const int d = a.side >> 1;
-  const int d1 = (d == 0 ? 1 : 0), d2 = (d == 2 ? 1 : 2);
-  const long long n = (long long)g.T[d1]*g.T[d2];
-  bc_fill_kernel<<<nblocks (n, 128), 128, 0, s>>>(a);
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 

@@ -89,22 +89,23 @@ struct FinalArgs {
   double *Uw[8];
 };
 
-// one boundary fill: up to 11 fields with their own boxes
+// Boundary conditions of ONE dimension in one launch: the copy jobs (a field and
+// its ghost box on one side) and the div B = 0 fill jobs of both sides.
 struct BcField {
   double *q;
   int lo[3], hi[3];          // inclusive destination box
   int sign;                  // reflective: +1 / -1
+  int side, type;            // side 0..5, type PLUTO_GPU_BC_*
+};
+struct BcFill {              // FillMagneticField + CT_AverageNormalMagField
+  double *Bc;                // cell-centred normal component (NULL: no averaging)
+  int side, type;
 };
 struct BcArgs {
-  BcField f[11];
-  int nf;
-  int side, type;            // side 0..5, type PLUTO_GPU_BC_*
-  Geom g;
-};
-struct BcFillArgs {            // FillMagneticField + CT_AverageNormalMagField
+  BcField f[22];
+  BcFill  fill[2];
   double *Bs[3];
-  double *Bc;                // cell-centred normal component (NULL: no averaging)
-  int side;
+  int nf, nfill;
   Geom g;
 };
 
@@ -138,7 +139,6 @@ namespace NS {                                                                  
   int launch_ct_update  (const CtArgs &a, cudaStream_t s);                               \
   int launch_final      (const FinalArgs &a, cudaStream_t s);                            \
   int launch_bc         (const BcArgs &a, cudaStream_t s);                               \
-  int launch_bc_fill    (const BcFillArgs &a, cudaStream_t s);                           \
   int launch_halo_pack  (const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_unpack(const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s); \

@@ -356,44 +356,54 @@ int pluto_gpu_download_data (PlutoGpu *h, double *Vc, double *s1, double *s2, do
 static int boundary_dim (PlutoGpu *h, int buf, int dim)
 {
   const Geom &g = h->g;
+  BcArgs a; memset (&a, 0, sizeof (a));
+  a.g = g;
+  for (int s = 0; s < 3; s++) a.Bs[s] = h->Bs[buf][s];
+  int nf = 0, nfill = 0;
   for (int hs = 0; hs < 2; hs++){
     const int side = 2*dim + hs;
     const int type = h->cfg.bc[side];
     if (type == PLUTO_GPU_BC_SHARED) continue;                 // boundary.c:139
+    const bool fill = (type == PLUTO_GPU_BC_OUTFLOW || type == PLUTO_GPU_BC_REFLECTIVE);
     // cell box of this side: ghost layers in `dim`, full extent elsewhere
     int lo[3] = {0, 0, 0}, hi[3] = {g.T[0] - 1, g.T[1] - 1, g.T[2] - 1};
     if (hs == 0) hi[dim] = g.beg[dim] - 1; else lo[dim] = g.end[dim] + 1;
-    BcArgs a; memset (&a, 0, sizeof (a));
-    a.side = side; a.type = type; a.g = g;
-    int nf = 0;
     for (int nv = 0; nv < NVS; nv++){
       if (!live_var (h, nv)) continue;
-      a.f[nf].q = h->V[buf][nv];
-      for (int d = 0; d < 3; d++){ a.f[nf].lo[d] = lo[d]; a.f[nf].hi[d] = hi[d]; }
-      a.f[nf].sign = (nv == 1 + dim || nv == 4 + dim) ? -1 : 1;   // FlipSign, boundary.c:318-436
-      nf++;
+      // outflow: the cell-centred normal field of the ghost zones is the average of the
+      // filled faces (CT_AverageNormalMagField, boundary.c:188-189), written by the fill job
+      if (type == PLUTO_GPU_BC_OUTFLOW && nv == 4 + dim) continue;
+      BcField &f = a.f[nf++];
+      f.q = h->V[buf][nv];
+      for (int d = 0; d < 3; d++){ f.lo[d] = lo[d]; f.hi[d] = hi[d]; }
+      f.sign = (nv == 1 + dim || nv == 4 + dim) ? -1 : 1;     // FlipSign, boundary.c:318-436
+      f.side = side; f.type = type;
     }
     for (int s = 0; s < g.dims; s++){
       // staggered boxes (boundary.c:157-164): one more face on the low end of
       // their own direction; the normal component is skipped by outflow and
       // reflective conditions (:175-180, 199-204) and rebuilt from div B = 0
       if (s == dim && type != PLUTO_GPU_BC_PERIODIC) continue;
-      a.f[nf].q = h->Bs[buf][s];
-      for (int d = 0; d < 3; d++){ a.f[nf].lo[d] = lo[d]; a.f[nf].hi[d] = hi[d]; }
-      a.f[nf].lo[s] -= 1;
-      a.f[nf].sign = 1;
-      nf++;
+      BcField &f = a.f[nf++];
+      f.q = h->Bs[buf][s];
+      for (int d = 0; d < 3; d++){ f.lo[d] = lo[d]; f.hi[d] = hi[d]; }
+      // Periodic normal component: the reference fills the low side first, face IBEG-1 <-
+      // face IEND, and the high side would then copy it back onto face IEND unchanged
+      // (boundary.c:157-164 with the sides in sequence).  Both sides share a launch here,
+      // so the high-side box leaves that face out.
+      if (!(s == dim && hs == 1)) f.lo[s] -= 1;
+      f.sign = 1;
+      f.side = side; f.type = type;
     }
-    a.nf = nf;
-    TIMED (h, KC_BC, count (h, DISPATCH (h, launch_bc) (a, h->stream)));
-    if (type == PLUTO_GPU_BC_OUTFLOW || type == PLUTO_GPU_BC_REFLECTIVE){
-      BcFillArgs b; memset (&b, 0, sizeof (b));
-      for (int s = 0; s < 3; s++) b.Bs[s] = h->Bs[buf][s];
-      b.Bc = (type == PLUTO_GPU_BC_OUTFLOW ? h->V[buf][4 + dim] : NULL);
-      b.side = side; b.g = g;
-      TIMED (h, KC_BC, count (h, DISPATCH (h, launch_bc_fill) (b, h->stream)));
+    if (fill){
+      a.fill[nfill].Bc = (type == PLUTO_GPU_BC_OUTFLOW ? h->V[buf][4 + dim] : NULL);
+      a.fill[nfill].side = side; a.fill[nfill].type = type;
+      nfill++;
     }
   }
+  a.nf = nf; a.nfill = nfill;
+  if (nf + nfill == 0) return 0;
+  TIMED (h, KC_BC, count (h, DISPATCH (h, launch_bc) (a, h->stream)));
   return 0;
 }
 
