@@ -55,7 +55,13 @@ WORKLOADS = {
 }
 # per-kernel algorithmic HBM bytes per zone and launch (DESIGN.md "Kernels"):
 # sweep: read 8 V + 1 Bn, U (x1: write 5; x2/x3: read 5 + write 5), write 2 face EMFs + 1 sign byte
-SWEEP_BYTES_3D = {"sweep_x1": (9 + 5 + 2) * 8 + 1, "sweep_x2": (9 + 10 + 2) * 8 + 1, "sweep_x3": (9 + 10 + 2) * 8 + 1}
+# fused x1+x2 sweep (FAST): read 8 V + Bx1s + Bx2s, write 5 U + 4 face EMFs + 2 sign bytes (+ C_dt in stage 1)
+SWEEP_BYTES_3D = {"sweep_x1": (9 + 5 + 2) * 8 + 1, "sweep_x2": (9 + 10 + 2) * 8 + 1, "sweep_x3": (9 + 10 + 2) * 8 + 1,
+                  "sweep_x1x2": (10 + 5 + 4) * 8 + 2 + 4}
+SWEEP_BYTES_2D = {"sweep_x1": (7 + 4 + 1) * 8 + 1, "sweep_x2": (7 + 8 + 1) * 8 + 1, "sweep_x1x2": (8 + 4 + 2) * 8 + 2}
+# FP64 instructions per launch and zone of the sweep kernels (ncu smsp__sass_thread_inst_executed_op_d*,
+# profiles/): what the FP64 pipe, the binding unit of the sweeps, has to issue
+SWEEP_FP64_INSTR_3D = {"sweep_x1x2": 2 * 365, "sweep_x3": 365}
 
 
 def peaks():
@@ -74,11 +80,13 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.p, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start sampling (before the warm-up: nvidia-smi needs ~0.2 s to deliver its first line)."""
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "20"],
+                                       "--format=csv,noheader,nounits", "-lms", "10"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -87,7 +95,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Only samples that arrived inside [t0, t1] (the timed region) are reported."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.p:
@@ -97,16 +109,18 @@ class ClockSampler:
             self.p.wait(timeout=5)
         except Exception:
             pass
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 7 and (self.t0 is None or self.t0 <= t <= self.t1 + 0.02)]
+        if not rows:        # region shorter than the sampling period: fall back to the samples under load around it
+            rows = [r for t, r in self.rows if len(r) >= 7 and (self.t0 is None or self.t0 - 0.3 <= t <= self.t1 + 0.3)]
+        num = lambda v: v.replace(".", "").isdigit()
+        sm = [float(r[0]) for r in rows if num(r[0])]
+        mx = [float(r[1]) for r in rows if num(r[1])]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 7:
-                continue
+        for r in rows:
             for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if num(r[2])]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -191,7 +205,7 @@ def run_reference_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="blast3d_256", choices=sorted(WORKLOADS))
     ap.add_argument("--arith", default=os.environ.get("PLUTO_GPU_ARITH", "fast"), choices=["exact", "fast"])
@@ -245,16 +259,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     dt = first_dt
     for _ in range(args.warmup):
         info = s.advance(dt)
         dt = s.next_dt(info.inv_dt_hyp, cfl, 1.1, dt)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = s.block.launch_count
     barrier()
+    t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -262,6 +277,7 @@ def main():
         dt = s.next_dt(info.inv_dt_hyp, cfl, 1.1, dt)
     e1.record(stream)
     barrier()
+    sampler.window(t_wall0, time.time())
     ms = e0.elapsed_time(e1)
     launches = s.block.launch_count - launches0
     # per-kernel device times: a second, shorter pass with CUDA events around every
@@ -317,7 +333,7 @@ def main():
     top_ms, top_cnt = rep[top]
     kern_bytes = SWEEP_BYTES_3D.get(top, 0) if dims == 3 else 0
     if dims == 2:
-        kern_bytes = {"sweep_x1": (7 + 4 + 1) * 8 + 1, "sweep_x2": (7 + 8 + 1) * 8 + 1}.get(top, 0)
+        kern_bytes = SWEEP_BYTES_2D.get(top, 0)
     achieved = kern_bytes * zones_local / (top_ms / top_cnt * 1e-3) / 1e9 if kern_bytes else None
     algo = ALGO.get((solver, recon, dims), dict(bytes=440.0, flops=3300.0))
     step_s = ms_max * 1e-3 / args.steps
@@ -340,7 +356,20 @@ def main():
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": top_ms / top_cnt, "kernel_share_of_step": (top_ms / ksteps) / step_kernel_ms,
                 "algorithmic_bytes_per_zone": kern_bytes,
-                "note": "the sweeps are FP64-issue bound, see step_roofline and profiles/"}
+                "note": "the sweeps are bound by the FP64 pipe and instruction issue, not HBM: see roofline_fp64, "
+                        "step_roofline and profiles/"}
+    # the same kernel against the FP64 pipe, the unit that actually binds it: algorithmic flops per
+    # zone and launch from the SURVEY.md 8(d) hand count (PLM 115 + HLLD 360 + RHS 19 + update 8 + C_dt 4
+    # = 506 per direction and stage in 3-D; 370 in 2-D; the fused x1+x2 kernel does two directions)
+    ndir = 2 if top == "sweep_x1x2" else (1 if top.startswith("sweep") else 0)
+    kern_flops = ndir * (506.0 if dims == 3 else 370.0) if (solver, recon) == ("hlld", "plm") else None
+    fp64_peak = fp64_measured or FP64_PEAK_TFLOPS_NOMINAL
+    roofline_fp64 = None
+    if kern_flops:
+        ach_tf = kern_flops * zones_local / (top_ms / top_cnt * 1e-3) / 1e12
+        roofline_fp64 = {"bound": "fp64", "kernel": top, "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach_tf / fp64_peak, "algorithmic_flops_per_zone": kern_flops,
+                         "peak_source": "measured DFMA chain (pluto_gpu_measure_fp64)" if fp64_measured else "nominal"}
     step_roofline = {"algorithmic_bytes_per_zone_update": algo["bytes"], "flops_per_zone_update": algo["flops"],
                      "hbm_gbs": step_gbs, "hbm_frac": step_gbs / hbm_peak,
                      "fp64_tflops": step_tf, "fp64_peak_tflops_nominal": FP64_PEAK_TFLOPS_NOMINAL,
@@ -371,7 +400,8 @@ def main():
                    "l2": "inputs larger than L2 (state 1.5 GB/GPU at 256^3 vs 126 MB L2)",
                    "device_bytes_per_gpu": s.block.device_bytes},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "step_roofline": step_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "roofline_fp64": roofline_fp64, "step_roofline": step_roofline, "kernels": kernels,
+        "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

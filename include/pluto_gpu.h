@@ -159,7 +159,8 @@ void     *pluto_gpu_stream        (PlutoGpu *h);   /* cudaStream_t of all launch
 long long pluto_gpu_launch_count  (const PlutoGpu *h);  /* kernels launched so far */
 /* per-kernel-class device time: CUDA events recorded on pluto_gpu_stream(h)
    around every launch while enabled; accumulated at pluto_gpu_step_end.
-   Classes 0..7: sweep_x1 sweep_x2 sweep_x3 ct_emf ct_update final boundary halo. */
+   Classes 0..7: sweep_x1 sweep_x2 sweep_x3 ct_emf ct_update final boundary halo;
+   with FAST arithmetic class 0 is the fused x1+x2 sweep ("sweep_x1x2") and class 1 stays empty. */
 int pluto_gpu_timing     (PlutoGpu *h, int enable);      /* (re)starts the accumulation */
 int pluto_gpu_timing_get (PlutoGpu *h, int cls, const char **name, double *ms, long long *launches);
 long long pluto_gpu_device_bytes  (const PlutoGpu *h);

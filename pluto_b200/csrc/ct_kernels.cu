@@ -51,8 +51,11 @@ __device__ __forceinline__ double upw (signed char s, double d0, double d1)
   return s > 0 ? d0 : d1;
 }
 
+#ifndef PG_CT_MINB
+#define PG_CT_MINB 8
+#endif
 template <int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PG_CT_MINB)
 ct_emf_kernel (const __grid_constant__ CtArgs a)
 {
   const Geom &g = a.g;
@@ -116,7 +119,7 @@ __device__ __forceinline__ double stage_mix (int combine, double w0, double wc, 
 }
 
 template <int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 16)
 ct_update_kernel (const __grid_constant__ CtArgs a)
 {
   const Geom &g = a.g;

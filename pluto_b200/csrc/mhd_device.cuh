@@ -67,6 +67,7 @@ __device__ __forceinline__ double pg_sqrt (double x) { return x > 0.0 ? sqrt (x)
 __device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs) { s = sqrt (x); rs = 1.0/s; }
 __device__ __forceinline__ double pg_sqrt_pos (double x) { return sqrt (x); }
 __device__ __forceinline__ float pg_sqrtf (float x) { return sqrtf (x); }
+__device__ __forceinline__ double pg_sqrt_acc (double x) { return x > 0.0 ? sqrt (x) : 0.0; }
 #elif defined(PG_FAST)
 __device__ __forceinline__ float pg_sqrtf (float x)          // no slow-path call
 {
@@ -84,42 +85,39 @@ __device__ __forceinline__ double pg_rcp (double b)
   return fma (r, fma (e, e, e), r);
 }
 __device__ __forceinline__ double pg_div (double a, double b) { return a*pg_rcp (b); }
-__device__ __forceinline__ double pg_sqrt (double x)
+// 1/sqrt(x): MUFU seed, then one cubically convergent step
+// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2  ->  relative error ~ (5/16) e^3 <= 2^-60
+__device__ __forceinline__ double pg_rsqrt (double x)
 {
   double y;
   asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma (-x*y, y, 1.0);
-  y = fma (0.5*y, e, y);
-  e = fma (-x*y, y, 1.0);
-  y = fma (0.5*y, e, y);
+  const double e = fma (-x*y, y, 1.0);
+  return fma (y*e, fma (0.375, e, 0.5), y);
+}
+__device__ __forceinline__ double pg_sqrt_pos (double x) { return x*pg_rsqrt (x); }    // x > 0 guaranteed
+__device__ __forceinline__ double pg_sqrt (double x)
+{
+  const double s = x*pg_rsqrt (x);
+  return x > 0.0 ? s : 0.0;
+}
+// sqrt(x) and 1/sqrt(x) together
+__device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs)
+{
+  rs = pg_rsqrt (x);
+  s = x*rs;
+}
+// square root with a final correction step (correctly rounded but for rare ties): the Roe
+// solver compares square roots for equality (roe.c:336-364), which a 1-2 ulp result upsets
+__device__ __forceinline__ double pg_sqrt_acc (double x)
+{
+  const double y = pg_rsqrt (x);
   double s = x*y;
-  double r = fma (-s, s, x);
+  const double r = fma (-s, s, x);
   s = fma (r, 0.5*y, s);
   return x > 0.0 ? s : 0.0;
 }
-// sqrt(x) and 1/sqrt(x) together (coupled Goldschmidt iteration, 7 FP64 ops)
-__device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs)
-{
-  double y;
-  asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double g = x*y, h = 0.5*y;
-  double r = fma (-g, h, 0.5);
-  g = fma (g, r, g); h = fma (h, r, h);
-  r = fma (-g, h, 0.5);
-  g = fma (g, r, g); h = fma (h, r, h);
-  s = g; rs = h + h;
-}
-__device__ __forceinline__ double pg_sqrt_pos (double x)     // x > 0 guaranteed
-{
-  double y;
-  asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double g = x*y, h = 0.5*y;
-  double r = fma (-g, h, 0.5);
-  g = fma (g, r, g); h = fma (h, r, h);
-  r = fma (-g, h, 0.5);
-  return fma (g, r, g);
-}
 #else
+__device__ __forceinline__ double pg_sqrt_acc (double x) { return sqrt (x); }
 __device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
 __device__ __forceinline__ double pg_div (double a, double b) { return a/b; }
 __device__ __forceinline__ double pg_sqrt (double x) { return sqrt (x); }
@@ -929,12 +927,12 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     dU[nv] = uR[nv] - uL[nv];
   }
 
-  sqr_rho_L = pg_sqrt (vL[RHO]);
-  sqr_rho_R = pg_sqrt (vR[RHO]);
+  sqr_rho_L = pg_sqrt_acc (vL[RHO]);
+  sqr_rho_R = pg_sqrt_acc (vR[RHO]);
   sl = pg_div (sqr_rho_L, sqr_rho_L + sqr_rho_R);
   sr = pg_div (sqr_rho_R, sqr_rho_L + sqr_rho_R);
   rho = sr*vL[RHO] + sl*vR[RHO];
-  sqrt_rho = pg_sqrt (rho);
+  sqrt_rho = pg_sqrt_acc (rho);
 
   u = sl*vL[VXn] + sr*vR[VXn];
   v = sl*vL[VXt] + sr*vR[VXt];
@@ -950,7 +948,7 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
 
   if (NC == 3) bt2 = 0.0 + by*by + bz*bz; else bt2 = 0.0 + by*by;
   b2    = bx*bx + bt2;
-  Btmag = pg_sqrt (bt2*rho);
+  Btmag = pg_sqrt_acc (bt2*rho);
 
   if (NC == 3) X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt] + dV[BXb]*dV[BXb];
   else         X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt];
@@ -978,15 +976,15 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   scrh = a2 - b2;
   ca2  = bx*bx;
   scrh = scrh*scrh + 4.0*bt2*a2;
-  scrh = pg_sqrt (scrh);
+  scrh = pg_sqrt_acc (scrh);
 
   cf2 = 0.5*(a2 + b2 + scrh);
   cs2 = pg_div (a2*ca2, cf2);
 
-  cf = pg_sqrt (cf2);
-  cs = pg_sqrt (cs2);
-  ca = pg_sqrt (ca2);
-  a  = pg_sqrt (a2);
+  cf = pg_sqrt_acc (cf2);
+  cs = pg_sqrt_acc (cs2);
+  ca = pg_sqrt_acc (ca2);
+  a  = pg_sqrt_acc (a2);
 
   if (cf == cs){
     alpha_f = 1.0; alpha_s = 0.0;
@@ -1000,8 +998,8 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     alpha_s = (cf2 -  a2)*scrh;
     alpha_f = maxv(0.0, alpha_f);
     alpha_s = maxv(0.0, alpha_s);
-    alpha_f = pg_sqrt (alpha_f);
-    alpha_s = pg_sqrt (alpha_s);
+    alpha_f = pg_sqrt_acc (alpha_f);
+    alpha_s = pg_sqrt_acc (alpha_s);
   }
 
   if (Btmag > 1.e-9){
