@@ -150,6 +150,18 @@ int pluto_gpu_halo_plan       (PlutoGpu *h, int n_nbr, const int *offsets,
                                double *const *send_bufs, double *const *recv_bufs);
 int pluto_gpu_halo_pack_all   (PlutoGpu *h, int stage);
 int pluto_gpu_halo_unpack_all (PlutoGpu *h, int stage);
+/* Overlap of the exchange with computation: a stage can be issued in two parts,
+       pluto_gpu_stage_shell    (h, stage, dt)   sweeps, CT and the new state of the zones within
+                                                 nghost of a SHARED side (what the neighbours need)
+       <record an event on pluto_gpu_stream(h); on a second stream, after that event:
+        pluto_gpu_halo_pack_all_on (h, next_stage, stream2) and the exchange>
+       pluto_gpu_stage_interior (h, stage)       the new state of all other zones
+   so that the ghost zones of the NEXT stage travel (NVLink) while the interior of this one is
+   completed; the next stage then waits for the exchange, unpacks and carries on.
+   pluto_gpu_stage == shell followed by interior. */
+int pluto_gpu_stage_shell    (PlutoGpu *h, int stage, double dt);
+int pluto_gpu_stage_interior (PlutoGpu *h, int stage);
+int pluto_gpu_halo_pack_all_on (PlutoGpu *h, int stage, void *stream);
 int pluto_gpu_step_begin   (PlutoGpu *h);
 int pluto_gpu_stage        (PlutoGpu *h, int stage, double dt);
 int pluto_gpu_step_end     (PlutoGpu *h, PlutoGpuStepInfo *info);

@@ -21,7 +21,8 @@ SYMBOLS = [
     "pluto_gpu_halo_unpack", "pluto_gpu_boundary_dim", "pluto_gpu_step_begin", "pluto_gpu_stage",
     "pluto_gpu_step_end", "pluto_gpu_stream", "pluto_gpu_launch_count", "pluto_gpu_device_bytes",
     "pluto_gpu_field", "pluto_gpu_read_field", "pluto_gpu_timing", "pluto_gpu_timing_get", "pluto_gpu_measure_fp64", "pluto_gpu_halo_nbr_doubles", "pluto_gpu_halo_plan",
-    "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all",
+    "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on",
+    "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
 ]
 
 
@@ -91,6 +92,9 @@ def load_library(path: str | None = None):
     L.pluto_gpu_halo_plan.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp)]
     L.pluto_gpu_halo_pack_all.argtypes = [vp, C.c_int]
     L.pluto_gpu_halo_unpack_all.argtypes = [vp, C.c_int]
+    L.pluto_gpu_halo_pack_all_on.argtypes = [vp, C.c_int, vp]
+    L.pluto_gpu_stage_shell.argtypes = [vp, C.c_int, C.c_double]
+    L.pluto_gpu_stage_interior.argtypes = [vp, C.c_int]
     L.pluto_gpu_timing.argtypes = [vp, C.c_int]
     L.pluto_gpu_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_longlong)]
     if path is None:

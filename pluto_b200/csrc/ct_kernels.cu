@@ -166,12 +166,12 @@ final_kernel (const __grid_constant__ FinalArgs a)
 {
   const Geom &g = a.g;
   Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr; ph.igmm1 = a.ph.igmm1;
-  const int ni = g.n[0], nj = g.n[1], nk = (NC == 3 ? g.n[2] : 1);
+  const int ni = a.box_n[0], nj = a.box_n[1], nk = (NC == 3 ? a.box_n[2] : 1);
   long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
   int fl = 0, bad = 0;
   if (t < (long long)ni*nj*nk){
     const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
-    const int i = g.beg[0] + ti, j = g.beg[1] + tj, k = (NC == 3 ? g.beg[2] + tk : 0);
+    const int i = g.beg[0] + a.box_lo[0] + ti, j = g.beg[1] + a.box_lo[1] + tj, k = (NC == 3 ? g.beg[2] + a.box_lo[2] + tk : 0);
     const long long id = gidx (g, k, j, i);
     double u[NV], v[NV];
     u[RHO] = a.U[RHO][id]; u[MX1] = a.U[MX1][id]; u[MX2] = a.U[MX2][id];
@@ -362,7 +362,8 @@ int launch_ct_update (const CtArgs &a, cudaStream_t s)
 int launch_final (const FinalArgs &a, cudaStream_t s)
 {
   const Geom &g = a.g;
-  const long long n = (long long)g.n[0]*g.n[1]*(g.dims == 3 ? g.n[2] : 1);
+  const long long n = (long long)a.box_n[0]*a.box_n[1]*(g.dims == 3 ? a.box_n[2] : 1);
+  if (n <= 0) return 0;
   if (g.dims == 3) final_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
   else             final_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
   return cudaGetLastError () == cudaSuccess ? 1 : -1;

@@ -87,6 +87,7 @@ struct FinalArgs {
                                              // result (a later stage continues from it);
                                              // 2: store only ConsToPrim repairs
   double *Uw[8];
+  int     box_lo[3], box_n[3];               // zones of this launch, relative to the first interior zone
 };
 
 // Boundary conditions of ONE dimension in one launch: the copy jobs (a field and

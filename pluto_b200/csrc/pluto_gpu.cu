@@ -437,10 +437,62 @@ static int set_dt (PlutoGpu *h, double dt)
   return 0;
 }
 
-static int run_stage (PlutoGpu *h, int stage)
+// part: 0 = the whole stage; 1 = everything up to the stage completion of the SHELL (the
+// zones within nghost of a SHARED side, whose new values the neighbouring blocks need);
+// 2 = the stage completion of the remaining zones.  1 followed by 2 equals 0.
+enum { PART_ALL = 0, PART_SHELL = 1, PART_INTERIOR = 2 };
+
+static int launch_final_boxes (PlutoGpu *h, FinalArgs &f, int part)
+{
+  const Geom &g = h->g;
+  int mlo[3] = {0, 0, 0}, mhi[3] = {0, 0, 0};
+  bool split = (part != PART_ALL);
+  for (int d = 0; d < g.dims && split; d++){
+    if (h->cfg.bc[2*d] == PLUTO_GPU_BC_SHARED) mlo[d] = g.ng;
+    if (h->cfg.bc[2*d + 1] == PLUTO_GPU_BC_SHARED) mhi[d] = g.ng;
+    if (mlo[d] + mhi[d] >= g.n[d]) split = false;            // block too thin: no interior
+  }
+  if (!split){
+    if (part == PART_INTERIOR) return 0;
+    for (int d = 0; d < 3; d++){ f.box_lo[d] = 0; f.box_n[d] = g.n[d]; }
+    TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
+    return 0;
+  }
+  // inner box and the (up to six) disjoint slabs around it: x3 slabs span all of x1, x2;
+  // x2 slabs the inner x3 range; x1 slabs the inner x2 and x3 ranges
+  int ilo[3], in_[3];
+  for (int d = 0; d < 3; d++){ ilo[d] = mlo[d]; in_[d] = g.n[d] - mlo[d] - mhi[d]; }
+  if (part == PART_INTERIOR){
+    for (int d = 0; d < 3; d++){ f.box_lo[d] = ilo[d]; f.box_n[d] = in_[d]; }
+    TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
+    return 0;
+  }
+  for (int d = g.dims - 1; d >= 0; d--) for (int hs = 0; hs < 2; hs++){
+    const int w = hs ? mhi[d] : mlo[d];
+    if (w == 0) continue;
+    for (int q = 0; q < 3; q++){
+      if (q > d){ f.box_lo[q] = ilo[q]; f.box_n[q] = in_[q]; }      // already covered by the slabs of q
+      else      { f.box_lo[q] = 0;      f.box_n[q] = g.n[q]; }
+    }
+    f.box_lo[d] = hs ? g.n[d] - w : 0; f.box_n[d] = w;
+    TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
+  }
+  return 0;
+}
+
+static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
 {
   const Geom &g = h->g;
   const StagePlan sp = stage_plan (h, stage);
+  FinalArgs f; memset (&f, 0, sizeof (f));
+  for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[sp.out][nv]; }
+  for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[sp.out][d];
+  f.red = h->red; f.g = g; f.ph = h->ph; f.w0 = sp.w0; f.wc = sp.wc; f.combine = sp.combine;
+  for (int nv = 0; nv < NVS; nv++) f.Uw[nv] = h->U[nv];
+  f.write_u = 0;
+  if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine ? 1 : 2);
+  if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
+
   SweepArgs s; memset (&s, 0, sizeof (s));
   for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
@@ -515,15 +567,7 @@ static int run_stage (PlutoGpu *h, int stage)
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 
-  FinalArgs f; memset (&f, 0, sizeof (f));
-  for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[sp.out][nv]; }
-  for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[sp.out][d];
-  f.red = h->red; f.g = g; f.ph = h->ph; f.w0 = sp.w0; f.wc = sp.wc; f.combine = sp.combine;
-  for (int nv = 0; nv < NVS; nv++) f.Uw[nv] = h->U[nv];
-  f.write_u = 0;
-  if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine ? 1 : 2);
-  TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
-  return 0;
+  return launch_final_boxes (h, f, part);
 }
 
 // ---------------------------------------------------------------------------
@@ -549,6 +593,21 @@ int pluto_gpu_stage (PlutoGpu *h, int stage, double dt)
   if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
   if (stage == 1 && set_dt (h, dt)) return 1;      // one dt per step
   return run_stage (h, stage);
+}
+
+int pluto_gpu_stage_shell (PlutoGpu *h, int stage, double dt)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  if (stage == 1 && set_dt (h, dt)) return 1;
+  return run_stage (h, stage, PART_SHELL);
+}
+
+int pluto_gpu_stage_interior (PlutoGpu *h, int stage)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  return run_stage (h, stage, PART_INTERIOR);
 }
 
 int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
@@ -853,6 +912,13 @@ int pluto_gpu_halo_pack_all (PlutoGpu *h, int stage)
   const int b = stage_in_buf (h, stage);
   TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_table) (h->halo_tab[b][0], h->halo_n[b][0], h->halo_max[b][0], h->g, true, h->stream)));
   return 0;
+}
+
+int pluto_gpu_halo_pack_all_on (PlutoGpu *h, int stage, void *stream)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const int b = stage_in_buf (h, stage);
+  return count (h, DISPATCH (h, launch_halo_table) (h->halo_tab[b][0], h->halo_n[b][0], h->halo_max[b][0], h->g, true, (cudaStream_t)stream));
 }
 
 int pluto_gpu_halo_unpack_all (PlutoGpu *h, int stage)

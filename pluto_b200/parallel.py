@@ -15,6 +15,7 @@ then apply the physical conditions of that dimension.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -194,15 +195,22 @@ class NeighbourExchanger:
         self._send_order = sorted(range(len(self.nbrs)), key=lambda q: self.nbrs[q][0])
         self._recv_order = sorted(range(len(self.nbrs)), key=lambda q: tuple(-c for c in self.nbrs[q][0]))
 
-    def exchange(self, stage):
+    def post(self):
+        """Send the packed buffers / receive the neighbours' ones: one communication group,
+        ordered on the CURRENT stream (NCCL) -- nothing is packed or unpacked here."""
         import torch.distributed as dist
         if not self.nbrs:
             return
-        self.pack_all(stage)
         ops = [dist.P2POp(dist.isend, self.send[q], self.nbrs[q][1], group=self.group) for q in self._send_order]
         ops += [dist.P2POp(dist.irecv, self.recv[q], self.nbrs[q][1], group=self.group) for q in self._recv_order]
         for r in dist.batch_isend_irecv(ops):
             r.wait()
+
+    def exchange(self, stage):
+        if not self.nbrs:
+            return
+        self.pack_all(stage)
+        self.post()
         self.unpack_all(stage)
 
 
@@ -210,9 +218,16 @@ class DistStepper:
     """AdvanceStep on one block of a decomposed domain (one process per GPU)."""
 
     def __init__(self, layout: BlockLayout, rank, dx, recon="plm", solver="hlld", rk_order=2,
-                 physical_bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0, exchange="all"):
+                 physical_bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0, exchange="all",
+                 overlap=None):
         self.layout, self.rank = layout, rank
         self.exchange_mode = exchange       # "all": one 26-neighbour group per stage; "dims": x1->x2->x3 swaps
+        # overlap: the exchange of the NEXT stage travels on a second stream while the interior
+        # zones of the current stage are completed (all-neighbour exchange only)
+        if overlap is None:
+            overlap = os.environ.get("PLUTO_GPU_NO_OVERLAP") is None
+        self.overlap = bool(overlap) and exchange == "all"
+        self._prefetched = None             # stage whose ghost zones are already in flight / received
         self.world = layout.world
         n = layout.local_n(rank)
         self.block = GpuStepper(layout.dims, n, dx, recon=recon, solver=solver, rk_order=rk_order,
@@ -238,8 +253,19 @@ class DistStepper:
                     lambda offs, sb, rb: b.halo_plan(offs, [t.data_ptr() for t in sb], [t.data_ptr() for t in rb]),
                     b.halo_pack_all, b.halo_unpack_all, device=torch.device("cuda", device))
             self._red = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", device))
+            if self.overlap:
+                self._comm = torch.cuda.Stream(device=torch.device("cuda", device))
+                self._ev_shell = torch.cuda.Event()
+                self._ev_comm = torch.cuda.Event()
+
+    def _drain(self):
+        """The state is about to be replaced from outside: forget the exchange in flight."""
+        if self.world > 1 and self.overlap and self._prefetched is not None:
+            self._comm.synchronize()
+            self._prefetched = None
 
     def set_state(self, dump):
+        self._drain()
         self.block.set_state(dump)
 
     def get_state(self):
@@ -257,6 +283,29 @@ class DistStepper:
         with torch.cuda.stream(self._stream):
             b.step_begin()
             for stage in range(1, self.rk_order + 1):
+                if self.nex is not None and self.overlap:
+                    # ghost zones of this stage: already travelling (started while the previous
+                    # stage was completing its interior) or exchanged here, in line
+                    if self._prefetched == stage:
+                        self._stream.wait_event(self._ev_comm)
+                    else:
+                        b.halo_pack_all(stage)
+                        self.nex.post()
+                    self._prefetched = None
+                    b.halo_unpack_all(stage)
+                    for d in range(self.dims):
+                        b.boundary_dim(stage, d)
+                    b.stage_shell(stage, dt)
+                    self._ev_shell.record(self._stream)
+                    nxt = stage + 1 if stage < self.rk_order else 1
+                    with torch.cuda.stream(self._comm):
+                        self._comm.wait_event(self._ev_shell)
+                        b.halo_pack_all_on(nxt, self._comm.cuda_stream)
+                        self.nex.post()
+                        self._ev_comm.record(self._comm)
+                    b.stage_interior(stage)
+                    self._prefetched = nxt
+                    continue
                 if self.nex is not None:
                     self.nex.exchange(stage)
                     for d in range(self.dims):
@@ -277,6 +326,7 @@ class DistStepper:
         """AdvanceStep on this block's HOST Data arrays: upload, step, download."""
         if self.world == 1:
             return self.block.advance_data(dt, Vc, s1, s2, s3)
+        self._drain()
         self.block.upload_data(Vc, s1, s2, s3)
         info = self.advance(dt)
         self.block.download_data(Vc, s1, s2, s3)

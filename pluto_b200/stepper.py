@@ -179,6 +179,12 @@ class GpuStepper:
     def stage(self, stage, dt):
         self._check(self.L.pluto_gpu_stage(self._h, stage, dt))
 
+    def stage_shell(self, stage, dt):
+        self._check(self.L.pluto_gpu_stage_shell(self._h, stage, dt))
+
+    def stage_interior(self, stage):
+        self._check(self.L.pluto_gpu_stage_interior(self._h, stage))
+
     def boundary_dim(self, stage, dim):
         self._check(self.L.pluto_gpu_boundary_dim(self._h, stage, dim))
 
@@ -220,6 +226,9 @@ class GpuStepper:
 
     def halo_pack_all(self, stage):
         self._check(self.L.pluto_gpu_halo_pack_all(self._h, stage))
+
+    def halo_pack_all_on(self, stage, stream_ptr):
+        self._check(self.L.pluto_gpu_halo_pack_all_on(self._h, stage, stream_ptr))
 
     def halo_unpack_all(self, stage):
         self._check(self.L.pluto_gpu_halo_unpack_all(self._h, stage))
