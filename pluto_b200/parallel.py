@@ -339,10 +339,11 @@ class LocalMultiBlock:
     handed over directly (same device) -- used by the single-GPU test of the
     decomposition and as the in-process alternative to one process per GPU."""
 
-    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, exchange="dims", **kw):
+    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, exchange="dims", split=False, **kw):
         import torch
         self.layout = layout
         self.exchange_mode = exchange
+        self.split = split                  # issue every stage as shell + interior (the overlapped form)
         self.blocks = [GpuStepper(layout.dims, layout.local_n(r), dx, bc=layout.block_bc(r, physical_bc),
                                   device=device, **kw) for r in range(layout.world)]
         self.rk_order = self.blocks[0].rk_order
@@ -424,7 +425,11 @@ class LocalMultiBlock:
                     b.boundary_dim(stage, d)
                 torch.cuda.synchronize()
             for b in self.blocks:
-                b.stage(stage, dt)
+                if self.split:
+                    b.stage_shell(stage, dt)
+                    b.stage_interior(stage)
+                else:
+                    b.stage(stage, dt)
         infos = [b.step_end() for b in self.blocks]
         return StepInfo(max(i.inv_dt_hyp for i in infos), max(i.max_mach for i in infos),
                         sum(i.floor_events for i in infos), sum(i.nan_events for i in infos))

@@ -82,6 +82,25 @@ def test_fast_within_tolerance_of_reference_golden(name):
     s.close()
 
 
+def test_fast_unfused_sweeps_within_tolerance(monkeypatch):
+    """FAST with one kernel per direction (PLUTO_GPU_NO_FUSE_XY): the path EXACT uses, with FAST arithmetic."""
+    monkeypatch.setenv("PLUTO_GPU_NO_FUSE_XY", "1")
+    for name in ("blast3d_plm_hlld", "ot2d_plm_hlld", "ot3d_ppm_roe"):
+        g = Golden(name)
+        s = _stepper(g, "fast")
+        s.set_state(g.states[0])
+        dt = g.first_dt
+        for step in range(1, g.nsteps + 1):
+            info = s.advance(dt)
+            dt = s.next_dt(info.inv_dt_hyp, g.cfl, g.cfl_max_var, dt)
+            if step in g.states:
+                st = s.get_state()
+                tol = TOL_ONE_STEP if step == 1 else TOL_100_STEPS
+                for k, ref in g.states[step].items():
+                    assert rel_l1(st[k], ref) <= tol, f"{name}: {k} after {step} steps"
+        s.close()
+
+
 # ---- against the CPU restatement at sizes beyond the fixtures ------------------
 ORACLE_CASES = [
     # (problem, dims, n, recon, solver, rk_order, nsteps, first_dt)
@@ -226,7 +245,7 @@ def test_full_size_properties_blast_256():
     ("ot", 2, (48, 64, 1), 4, "plm", "hlld"),
     ("rotor", 2, (40, 48, 1), 2, "ppm", "roe"),
 ])
-@pytest.mark.parametrize("exchange", ["dims", "all"])
+@pytest.mark.parametrize("exchange", ["dims", "all", "all+split"])
 def test_decomposed_blocks_match_single_block(problem, dims, gn, world, recon, solver, exchange):
     from pluto_b200 import GpuStepper, problems
     from pluto_b200.parallel import BlockLayout, LocalMultiBlock
@@ -234,8 +253,9 @@ def test_decomposed_blocks_match_single_block(problem, dims, gn, world, recon, s
     periodic = meta["bc"][0] == "periodic"
     lay = BlockLayout.strong(dims, gn, world, periodic=periodic)
     one = GpuStepper(dims, gn, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"])
+    # "all+split": every stage issued as shell + interior, the form the overlapped NCCL exchange uses
     many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, gamma=meta["gamma"],
-                           exchange=exchange)
+                           exchange=exchange.split("+")[0], split=exchange.endswith("+split"))
     one.set_state(st0)
     many.set_state(st0)
     dt = {"ot": 5e-3, "blast": 2e-4, "turb": 5e-3, "rotor": 1e-3}[problem]
