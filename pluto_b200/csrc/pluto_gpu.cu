@@ -448,8 +448,11 @@ static int launch_final_boxes (PlutoGpu *h, FinalArgs &f, int part)
   int mlo[3] = {0, 0, 0}, mhi[3] = {0, 0, 0};
   bool split = (part != PART_ALL);
   for (int d = 0; d < g.dims && split; d++){
-    if (h->cfg.bc[2*d] == PLUTO_GPU_BC_SHARED) mlo[d] = g.ng;
-    if (h->cfg.bc[2*d + 1] == PLUTO_GPU_BC_SHARED) mhi[d] = g.ng;
+    // x1 slabs are a full warp wide when the block allows: an ng-wide slab would be read
+    // and written in 16-24 byte pieces per row
+    const int w = (d == 0 && g.n[0] >= 128 ? 32 : g.ng);
+    if (h->cfg.bc[2*d] == PLUTO_GPU_BC_SHARED) mlo[d] = w;
+    if (h->cfg.bc[2*d + 1] == PLUTO_GPU_BC_SHARED) mhi[d] = w;
     if (mlo[d] + mhi[d] >= g.n[d]) split = false;            // block too thin: no interior
   }
   if (!split){
