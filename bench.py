@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-dt", action="store_true", help="host-driven NextTimeStep (a device round trip per step)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -271,11 +272,22 @@ def main():
     barrier()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        info = s.advance(dt)
-        dt = s.next_dt(info.inv_dt_hyp, cfl, 1.1, dt)
-    e1.record(stream)
+    if args.host_dt:
+        # the reference's loop literally: the host waits for every step's CFL reduction (main.c:133-243)
+        e0.record(stream)
+        for _ in range(args.steps):
+            info = s.advance(dt)
+            dt = s.next_dt(info.inv_dt_hyp, cfl, 1.1, dt)
+        e1.record(stream)
+    else:
+        # same dt sequence, NextTimeStep evaluated on the device: the K steps are enqueued back to back
+        s.set_dt(dt)
+        e0.record(stream)
+        for _ in range(args.steps):
+            s.advance_async(cfl, 1.1)
+        e1.record(stream)
+        _, infos, dt = s.sync_results()
+        info = infos[-1]
     barrier()
     sampler.window(t_wall0, time.time())
     ms = e0.elapsed_time(e1)
@@ -397,6 +409,7 @@ def main():
         "config": {"workload": args.workload, "problem": problem, "zones_per_gpu": list(n[:dims]),
                    "global_zones": list(layout.global_n[:dims]), "rank_grid": list(layout.grid),
                    "scheme": f"{solver}+{recon}+ct_uct_contact+rk2", "arith": args.arith,
+                   "next_dt": "host" if args.host_dt else "device kernel, same dt sequence (tests/test_gpu_parity.py)",
                    "l2": "inputs larger than L2 (state 1.5 GB/GPU at 256^3 vs 126 MB L2)",
                    "device_bytes_per_gpu": s.block.device_bytes},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

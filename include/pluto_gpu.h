@@ -115,6 +115,26 @@ int pluto_gpu_boundary (PlutoGpu *h);
 /* NextTimeStep, hyperbolic part (Src/main.c:462-465, 532). Host only. */
 double pluto_gpu_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt);
 
+/* ---- NextTimeStep on the device ------------------------------------------
+   The same rule evaluated by a one-thread kernel at the end of every step, dt kept in device
+   memory: the host enqueues steps back to back and never waits for the CFL reduction (the
+   reference's loop main.c:133-243 with Integrate -> NextTimeStep, without the round trip).
+       pluto_gpu_set_dt (h, first_dt)
+       repeat:  pluto_gpu_advance_async (h, cfl, cfl_max_var)
+       pluto_gpu_sync_results (h, max, infos, dts, &n, &dt_next)   wait; dt used and StepInfo of every
+                                                                   step since the last call, the dt the
+                                                                   next step will use
+   Multi-GPU: per stage as above with pluto_gpu_stage (h, stage, -1.0) (a negative dt keeps the
+   device's), then all-reduce(MAX) the two doubles at pluto_gpu_reduction_slots (bit patterns of
+   non-negative doubles, so an integer or floating maximum both work) on pluto_gpu_stream(h) and call
+   pluto_gpu_next_dt_async.  At most 4096 steps between two synchronisations. */
+int pluto_gpu_set_dt          (PlutoGpu *h, double dt);
+int pluto_gpu_advance_async   (PlutoGpu *h, double cfl, double cfl_max_var);
+int pluto_gpu_next_dt_async   (PlutoGpu *h, double cfl, double cfl_max_var);
+int pluto_gpu_reduction_slots (PlutoGpu *h, void **dev_ptr);
+int pluto_gpu_sync_results    (PlutoGpu *h, int max_steps, PlutoGpuStepInfo *infos, double *dts,
+                               int *n_out, double *dt_next);
+
 /* ---- multi-GPU halo exchange (replaces AL_Exchange_dim) ----------------
    Sides flagged PLUTO_GPU_BC_SHARED abut another rank's block and are filled
    by the caller: the step is split so that the host language can drive the

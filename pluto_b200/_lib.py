@@ -23,6 +23,8 @@ SYMBOLS = [
     "pluto_gpu_field", "pluto_gpu_read_field", "pluto_gpu_timing", "pluto_gpu_timing_get", "pluto_gpu_measure_fp64", "pluto_gpu_halo_nbr_doubles", "pluto_gpu_halo_plan",
     "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on",
     "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
+    "pluto_gpu_set_dt", "pluto_gpu_advance_async", "pluto_gpu_next_dt_async", "pluto_gpu_reduction_slots",
+    "pluto_gpu_sync_results",
 ]
 
 
@@ -95,6 +97,11 @@ def load_library(path: str | None = None):
     L.pluto_gpu_halo_pack_all_on.argtypes = [vp, C.c_int, vp]
     L.pluto_gpu_stage_shell.argtypes = [vp, C.c_int, C.c_double]
     L.pluto_gpu_stage_interior.argtypes = [vp, C.c_int]
+    L.pluto_gpu_set_dt.argtypes = [vp, C.c_double]
+    L.pluto_gpu_advance_async.argtypes = [vp, C.c_double, C.c_double]
+    L.pluto_gpu_next_dt_async.argtypes = [vp, C.c_double, C.c_double]
+    L.pluto_gpu_reduction_slots.argtypes = [vp, C.POINTER(vp)]
+    L.pluto_gpu_sync_results.argtypes = [vp, C.c_int, C.POINTER(PlutoGpuStepInfo), dp, C.POINTER(C.c_int), dp]
     L.pluto_gpu_timing.argtypes = [vp, C.c_int]
     L.pluto_gpu_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_longlong)]
     if path is None:

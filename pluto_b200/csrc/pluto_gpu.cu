@@ -29,6 +29,7 @@ static int fail (const char *fmt, ...)
 
 enum { NVS = 8 };
 enum { PG_MAX_EV = 96, PG_NCLASS = 8 };
+enum { HIST_W = 6, HIST_N = 4096 };     // per step: dt used, inv_dt_hyp, max Mach, floors, NaNs, Roe failures
 enum { KC_SWEEP_X = 0, KC_SWEEP_Y, KC_SWEEP_Z, KC_CT_EMF, KC_CT_UPDATE, KC_FINAL, KC_BC, KC_HALO };
 static const char *kClassName[PG_NCLASS] = {"sweep_x1", "sweep_x2", "sweep_x3", "ct_emf", "ct_update",
                                             "final", "boundary", "halo"};
@@ -60,6 +61,12 @@ struct PlutoGpu {
   const void *pinned[8];           // host blocks seen by pluto_gpu_advance_data
   int     pinned_by_us[8];         // ... and page-locked here
   int     npinned;
+  // device-side NextTimeStep: results of the steps enqueued since the last synchronisation
+  double *hist;                    // device ring: HIST_W doubles per step
+  double *hist_host;               // pinned mirror
+  unsigned long long *hist_count;  // device: steps recorded so far
+  long long hist_read;             // steps already handed to the caller
+  long long hist_enq;              // steps enqueued so far
   double *dtdev;                   // device: dt/dx[0..2] of the current step
   double *dthost;                  // pinned staging of the same
   cudaGraphExec_t graph;           // captured single-GPU step (all stages), replayed with new dt
@@ -185,6 +192,10 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   CU (cudaMalloc ((void **)&h->red, RED_N*sizeof (unsigned long long)));
   CU (cudaMemset (h->red, 0, RED_N*sizeof (unsigned long long)));
   CU (cudaMallocHost ((void **)&h->red_host, RED_N*sizeof (unsigned long long)));
+  CU (cudaMalloc ((void **)&h->hist, (size_t)HIST_W*HIST_N*sizeof (double)));
+  CU (cudaMallocHost ((void **)&h->hist_host, (size_t)HIST_W*HIST_N*sizeof (double)));
+  CU (cudaMalloc ((void **)&h->hist_count, sizeof (unsigned long long)));
+  CU (cudaMemset (h->hist_count, 0, sizeof (unsigned long long)));
   CU (cudaMalloc ((void **)&h->dtdev, 4*sizeof (double)));
   CU (cudaMallocHost ((void **)&h->dthost, 4*sizeof (double)));
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
@@ -202,6 +213,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
   cudaFree (h->dtdev); cudaFreeHost (h->dthost);
+  cudaFree (h->hist); cudaFreeHost (h->hist_host); cudaFree (h->hist_count);
   for (int b = 0; b < 3; b++) for (int q = 0; q < 2; q++) if (h->halo_tab[b][q]) cudaFree (h->halo_tab[b][q]);
   for (int q = 0; q < h->npinned; q++)
     if (h->pinned_by_us[q] && cudaHostUnregister ((void *)h->pinned[q]) != cudaSuccess) cudaGetLastError ();
@@ -594,7 +606,7 @@ int pluto_gpu_stage (PlutoGpu *h, int stage, double dt)
 {
   CU (cudaSetDevice (h->cfg.device));
   if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
-  if (stage == 1 && set_dt (h, dt)) return 1;      // one dt per step
+  if (stage == 1 && dt >= 0.0 && set_dt (h, dt)) return 1;      // one dt per step (dt < 0: the device's own)
   return run_stage (h, stage);
 }
 
@@ -602,7 +614,7 @@ int pluto_gpu_stage_shell (PlutoGpu *h, int stage, double dt)
 {
   CU (cudaSetDevice (h->cfg.device));
   if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
-  if (stage == 1 && set_dt (h, dt)) return 1;
+  if (stage == 1 && dt >= 0.0 && set_dt (h, dt)) return 1;
   return run_stage (h, stage, PART_SHELL);
 }
 
@@ -713,6 +725,105 @@ int pluto_gpu_advance_data (PlutoGpu *h, double dt, double *Vc, double *s1, doub
   if (pluto_gpu_upload_data (h, Vc, s1, s2, s3)) return 1;
   if (pluto_gpu_advance (h, dt, info)) return 1;
   return pluto_gpu_download_data (h, Vc, s1, s2, s3);
+}
+
+// ---------------------------------------------------------------------------
+//  NextTimeStep on the device (Src/main.c:462-465, 532): one thread turns the CFL
+//  reduction of the step just enqueued into the next dt, in the arithmetic of
+//  pluto_gpu_next_dt, records the step in the history ring and stores dt/dx for the
+//  kernels of the next step.  The host never has to wait for a step to enqueue the next.
+// ---------------------------------------------------------------------------
+__global__ void next_dt_kernel (const unsigned long long *red, double *dtdev, double *hist,
+                                unsigned long long *hist_count, double dx0, double dx1, double dx2,
+                                int dims, double cfl, double cfl_max_var)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double dt = dtdev[3];
+  const double inv = __ddiv_rn (__longlong_as_double ((long long)red[RED_CDT]), (double)dims);   // update_stage.c:308-312
+  double dtnext = __dmul_rn (__ddiv_rn (1.0, inv), cfl);
+  const double cap = __dmul_rn (cfl_max_var, dt);
+  if (!(dtnext <= cap)) dtnext = cap;
+  const unsigned long long n = *hist_count;
+  double *hrow = hist + (n % HIST_N)*HIST_W;
+  hrow[0] = dt; hrow[1] = inv; hrow[2] = __longlong_as_double ((long long)red[RED_MACH]);
+  hrow[3] = (double)red[RED_FLOOR]; hrow[4] = (double)red[RED_NAN]; hrow[5] = (double)red[RED_ROEFAIL];
+  *hist_count = n + 1;
+  dtdev[0] = __ddiv_rn (dtnext, dx0); dtdev[1] = __ddiv_rn (dtnext, dx1); dtdev[2] = __ddiv_rn (dtnext, dx2);
+  dtdev[3] = dtnext;
+}
+
+int pluto_gpu_set_dt (PlutoGpu *h, double dt)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  return set_dt (h, dt);
+}
+
+int pluto_gpu_reduction_slots (PlutoGpu *h, void **dev_ptr)
+{
+  *dev_ptr = (void *)h->red;       // [RED_CDT], [RED_MACH]: bit patterns of non-negative doubles
+  return 0;
+}
+
+int pluto_gpu_next_dt_async (PlutoGpu *h, double cfl, double cfl_max_var)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (h->hist_enq - h->hist_read >= HIST_N) return fail ("more than %d steps enqueued without pluto_gpu_sync_results", HIST_N);
+  next_dt_kernel<<<1, 32, 0, h->stream>>>(h->red, h->dtdev, h->hist, h->hist_count, h->g.dx[0], h->g.dx[1], h->g.dx[2],
+                                          h->g.dims, cfl, cfl_max_var);
+  if (count (h, cudaGetLastError () == cudaSuccess ? 1 : -1)) return 1;
+  h->hist_enq++;
+  return 0;
+}
+
+int pluto_gpu_advance_async (PlutoGpu *h, double cfl, double cfl_max_var)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (h->use_graph && !h->timing && h->steps_done >= 1){
+    if (!h->graph){
+      cudaGraph_t gr = NULL;
+      const long long l0 = h->launches;
+      CU (cudaStreamBeginCapture (h->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_step (h);
+      cudaError_t e = cudaStreamEndCapture (h->stream, &gr);
+      if (rc || e != cudaSuccess){ if (gr) cudaGraphDestroy (gr); return rc ? 1 : fail ("graph capture: %s", cudaGetErrorString (e)); }
+      h->graph_launches = h->launches - l0;
+      h->launches = l0;
+      e = cudaGraphInstantiate (&h->graph, gr, 0);
+      cudaGraphDestroy (gr);
+      if (e != cudaSuccess) return fail ("cudaGraphInstantiate: %s", cudaGetErrorString (e));
+    }
+    CU (cudaGraphLaunch (h->graph, h->stream));
+    h->launches += h->graph_launches;
+  }else{
+    if (enqueue_step (h)) return 1;
+  }
+  h->steps_done++;
+  return pluto_gpu_next_dt_async (h, cfl, cfl_max_var);
+}
+
+int pluto_gpu_sync_results (PlutoGpu *h, int max_steps, PlutoGpuStepInfo *infos, double *dts, int *n_out, double *dt_next)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const long long n = h->hist_enq - h->hist_read;
+  if (n > 0) CU (cudaMemcpyAsync (h->hist_host, h->hist, (size_t)HIST_W*HIST_N*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
+  CU (cudaMemcpyAsync (h->dthost, h->dtdev, 4*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
+  CU (cudaStreamSynchronize (h->stream));
+  if (h->timing) tcollect (h);
+  if (dt_next) *dt_next = h->dthost[3];
+  int m = 0; unsigned long long roe = 0;
+  for (long long q = 0; q < n; q++){
+    const double *r = h->hist_host + ((h->hist_read + q) % HIST_N)*HIST_W;
+    roe += (unsigned long long)r[5];
+    if (m < max_steps){
+      if (dts) dts[m] = r[0];
+      if (infos){ infos[m].inv_dt_hyp = r[1]; infos[m].max_mach = r[2]; infos[m].floor_events = (int)r[3]; infos[m].nan_events = (int)r[4]; }
+      m++;
+    }
+  }
+  h->hist_read = h->hist_enq;
+  if (n_out) *n_out = m;
+  if (roe) return fail ("Roe_Solver: a2 < 0 at %llu interfaces (the reference aborts, roe.c:300-306)", roe);
+  return 0;
 }
 
 double pluto_gpu_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt)

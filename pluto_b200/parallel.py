@@ -274,11 +274,53 @@ class DistStepper:
     def next_dt(self, *a):
         return self.block.next_dt(*a)
 
+    def set_dt(self, dt):
+        self.block.set_dt(dt)
+
+    def advance_async(self, cfl, cfl_max_var=1.1):
+        """One step with NextTimeStep on the device: nothing here waits for the GPU, the
+        all-reduce(MAX) of the CFL reduction runs on the device slots in stream order."""
+        if self.world == 1:
+            return self.block.advance_async(cfl, cfl_max_var)
+        self._enqueue_step(-1.0)
+        import torch.distributed as dist
+        with self._torch.cuda.stream(self._stream):
+            dist.all_reduce(self._red_view(), op=dist.ReduceOp.MAX)
+            self.block.next_dt_async(cfl, cfl_max_var)
+
+    def sync_results(self, max_steps=4096):
+        return self.block.sync_results(max_steps)
+
+    def _red_view(self):
+        """torch view of the two device reduction slots (CFL, Mach: non-negative doubles)."""
+        if getattr(self, "_redv", None) is None:
+            class _Raw:
+                pass
+            raw = _Raw()
+            raw.__cuda_array_interface__ = {"shape": (2,), "typestr": "<f8", "data": (self.block.reduction_slots(), False),
+                                            "version": 3, "strides": None}
+            self._redv_owner = raw
+            self._redv = self._torch.as_tensor(raw, device=self._torch.device("cuda", self.block.cfg.device))
+        return self._redv
+
     def advance(self, dt) -> StepInfo:
         if self.world == 1:
             return self.block.advance(dt)
         torch = self._torch
         import torch.distributed as dist
+        b = self.block
+        self._enqueue_step(dt)
+        with torch.cuda.stream(self._stream):
+            info = b.step_end()
+            # MPI_Allreduce(MAX) of invDt_hyp and g_maxMach (main.c:195-199, 415)
+            self._red.copy_(torch.tensor([info.inv_dt_hyp, info.max_mach], dtype=torch.float64))
+            dist.all_reduce(self._red, op=dist.ReduceOp.MAX)
+            r = self._red.tolist()
+        return StepInfo(r[0], r[1], info.floor_events, info.nan_events)
+
+    def _enqueue_step(self, dt):
+        """All stages of one step with their exchanges (dt < 0: the device's own dt)."""
+        torch = self._torch
         b = self.block
         with torch.cuda.stream(self._stream):
             b.step_begin()
@@ -315,12 +357,6 @@ class DistStepper:
                         self.ex.exchange_dim(stage, d)
                         b.boundary_dim(stage, d)
                 b.stage(stage, dt)
-            info = b.step_end()
-            # MPI_Allreduce(MAX) of invDt_hyp and g_maxMach (main.c:195-199, 415)
-            self._red.copy_(torch.tensor([info.inv_dt_hyp, info.max_mach], dtype=torch.float64))
-            dist.all_reduce(self._red, op=dist.ReduceOp.MAX)
-            r = self._red.tolist()
-        return StepInfo(r[0], r[1], info.floor_events, info.nan_events)
 
     def advance_data(self, dt, Vc, s1, s2, s3=None) -> StepInfo:
         """AdvanceStep on this block's HOST Data arrays: upload, step, download."""

@@ -170,6 +170,32 @@ class GpuStepper:
         self._check(self.L.pluto_gpu_advance(self._h, dt, C.byref(info)))
         return StepInfo(info.inv_dt_hyp, info.max_mach, info.floor_events, info.nan_events)
 
+    # ---- NextTimeStep on the device: steps enqueued back to back ------------------
+    def set_dt(self, dt: float):
+        self._check(self.L.pluto_gpu_set_dt(self._h, dt))
+
+    def advance_async(self, cfl: float, cfl_max_var: float = 1.1):
+        """Enqueue one step with the device's dt; the next dt is computed on the device."""
+        self._check(self.L.pluto_gpu_advance_async(self._h, cfl, cfl_max_var))
+
+    def next_dt_async(self, cfl: float, cfl_max_var: float = 1.1):
+        self._check(self.L.pluto_gpu_next_dt_async(self._h, cfl, cfl_max_var))
+
+    def reduction_slots(self) -> int:
+        p = C.c_void_p()
+        self._check(self.L.pluto_gpu_reduction_slots(self._h, C.byref(p)))
+        return int(p.value)
+
+    def sync_results(self, max_steps: int = 4096):
+        """Wait for the enqueued steps: ([dt used], [StepInfo], dt of the next step)."""
+        infos = (_lib.PlutoGpuStepInfo * max_steps)()
+        dts = (C.c_double * max_steps)()
+        n, dtn = C.c_int(0), C.c_double(0.0)
+        self._check(self.L.pluto_gpu_sync_results(self._h, max_steps, infos, dts, C.byref(n), C.byref(dtn)))
+        out = [StepInfo(infos[q].inv_dt_hyp, infos[q].max_mach, infos[q].floor_events, infos[q].nan_events)
+               for q in range(n.value)]
+        return [dts[q] for q in range(n.value)], out, dtn.value
+
     def boundary(self):
         self._check(self.L.pluto_gpu_boundary(self._h))
 

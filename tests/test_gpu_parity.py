@@ -101,6 +101,42 @@ def test_fast_unfused_sweeps_within_tolerance(monkeypatch):
         s.close()
 
 
+@pytest.mark.parametrize("problem,dims,n,arith", [("blast", 3, (24, 20, 28), "exact"), ("ot", 2, (48, 40, 1), "exact"),
+                                                   ("turb", 3, (20, 24, 16), "fast")])
+def test_device_next_dt_matches_host_loop(problem, dims, n, arith):
+    """NextTimeStep evaluated on the device (steps enqueued back to back) gives the dt sequence,
+    the step scalars and the state of the host-driven loop, bit for bit."""
+    from pluto_b200 import GpuStepper, problems
+    st0, meta = problems.make(problem, dims, n)
+    mk = lambda: GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], arith=arith)
+    a, b = mk(), mk()
+    a.set_state(st0)
+    b.set_state(st0)
+    nsteps, dt0 = 12, 1e-4
+    dts, infos, dt = [], [], dt0
+    for _ in range(nsteps):
+        dts.append(dt)
+        info = a.advance(dt)
+        infos.append(info)
+        dt = a.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+    b.set_dt(dt0)
+    for _ in range(nsteps // 2):
+        b.advance_async(meta["cfl"], 1.1)
+    d1, i1, _ = b.sync_results()
+    for _ in range(nsteps - nsteps // 2):
+        b.advance_async(meta["cfl"], 1.1)
+    d2, i2, dt_next = b.sync_results()
+    assert d1 + d2 == dts
+    assert dt_next == dt
+    for x, y in zip(i1 + i2, infos):
+        assert (x.inv_dt_hyp, x.max_mach, x.floor_events, x.nan_events) == (y.inv_dt_hyp, y.max_mach, y.floor_events, y.nan_events)
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close()
+    b.close()
+
+
 # ---- against the CPU restatement at sizes beyond the fixtures ------------------
 ORACLE_CASES = [
     # (problem, dims, n, recon, solver, rk_order, nsteps, first_dt)

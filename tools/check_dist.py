@@ -34,6 +34,17 @@ for problem, dims, n, recon, solver in [("ot", 3, (16, 12, 16), "plm", "hlld"), 
         if a.inv_dt_hyp != b.inv_dt_hyp or a.max_mach != b.max_mach:
             ok = False; print(f"rank {rank} {problem}: step {step} scalars differ {a} {b}")
         dt = one.next_dt(a.inv_dt_hyp, meta["cfl"], 1.1, dt)
+    # the same with NextTimeStep on the device: steps enqueued back to back, all-reduce on the device slots
+    d.set_dt(dt)
+    dts = []
+    for step in range(4):
+        dts.append(dt)
+        a = one.advance(dt)
+        d.advance_async(meta["cfl"], 1.1)
+        dt = one.next_dt(a.inv_dt_hyp, meta["cfl"], 1.1, dt)
+    got, _, dtn = d.sync_results()
+    if got != dts or dtn != dt:
+        ok = False; print(f"rank {rank} {problem}: device dt sequence {got} {dtn} vs host {dts} {dt}")
     sa, sb = one.get_state(), d.get_state()
     for k, v in sb.items():
         e = {"Bx1s": (1, 0, 0), "Bx2s": (0, 1, 0), "Bx3s": (0, 0, 1)}.get(k, (0, 0, 0))
