@@ -45,6 +45,13 @@ enum { PLUTO_GPU_BC_PERIODIC = 0, PLUTO_GPU_BC_OUTFLOW = 1, PLUTO_GPU_BC_REFLECT
    of the reference).  FAST: same algorithm with FMA contraction and shared
    reciprocals; within the BASELINE.json tolerances, not bit-identical. */
 enum { PLUTO_GPU_ARITH_EXACT = 0, PLUTO_GPU_ARITH_FAST = 1 };
+/* LIMITER in definitions.h (Src/States/plm_states.c:192-236, plm_coeffs.h:72-123; LINEAR
+   reconstruction only).  DEFAULT: MC on density, van Leer on velocity and field, minmod on
+   pressure; any other value applies that limiter to every variable. */
+enum { PLUTO_GPU_LIM_DEFAULT = 0, PLUTO_GPU_LIM_FLAT, PLUTO_GPU_LIM_MINMOD, PLUTO_GPU_LIM_VANALBADA,
+       PLUTO_GPU_LIM_OSPRE, PLUTO_GPU_LIM_UMIST, PLUTO_GPU_LIM_VANLEER, PLUTO_GPU_LIM_MC };
+/* CT_EMF_AVERAGE in definitions.h (Src/MHD/CT/ct_emf.c:241-283) */
+enum { PLUTO_GPU_EMF_UCT_CONTACT = 0, PLUTO_GPU_EMF_ARITHMETIC = 1, PLUTO_GPU_EMF_UCT0 = 2 };
 
 typedef struct {
   int    dims;         /* DIMENSIONS = COMPONENTS: 2 or 3                     */
@@ -59,6 +66,8 @@ typedef struct {
   double dx[3];        /* uniform cell sizes grid[d].dx[i]                    */
   double small_dn;     /* g_smallDensity   (Src/globals.h:113)                */
   double small_pr;     /* g_smallPressure                                     */
+  int    limiter;      /* PLUTO_GPU_LIM_*  (0 = DEFAULT)                      */
+  int    emf_average;  /* PLUTO_GPU_EMF_*  (0 = UCT_CONTACT)                  */
 } PlutoGpuConfig;
 
 typedef struct PlutoGpu PlutoGpu;

@@ -43,8 +43,12 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
   double *vs1, *vs2, *vs3 = NULL;
 
 #if PHYSICS != MHD || GEOMETRY != CARTESIAN || DIVB_CONTROL != CONSTRAINED_TRANSPORT \
-    || EOS != IDEAL || CT_EMF_AVERAGE != UCT_CONTACT || DIMENSIONS != COMPONENTS
-  #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT, DIMENSIONS == COMPONENTS"
+    || EOS != IDEAL || DIMENSIONS != COMPONENTS \
+    || (CT_EMF_AVERAGE != UCT_CONTACT && CT_EMF_AVERAGE != ARITHMETIC && CT_EMF_AVERAGE != UCT0)
+  #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT / ARITHMETIC / UCT0, DIMENSIONS == COMPONENTS"
+#endif
+#if CHAR_LIMITING == YES || SHOCK_FLATTENING != NO || LIMITER == FOURTH_ORDER_LIM
+  #error "libpluto_gpu: CHAR_LIMITING, SHOCK_FLATTENING and FOURTH_ORDER_LIM are not available on the GPU"
 #endif
 
   if (gpu == NULL){
@@ -63,6 +67,13 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       QUIT_PLUTO(1);
     }
     c.rk_order = (TIME_STEPPING == RK3 ? 3 : 2);
+    /* LIMITER (plm_states.c:192-236) and CT_EMF_AVERAGE (ct_emf.c:241-283) of definitions.h */
+    c.limiter = (LIMITER == FLAT_LIM      ? PLUTO_GPU_LIM_FLAT      : LIMITER == MINMOD_LIM ? PLUTO_GPU_LIM_MINMOD :
+                 LIMITER == VANALBADA_LIM ? PLUTO_GPU_LIM_VANALBADA : LIMITER == OSPRE_LIM  ? PLUTO_GPU_LIM_OSPRE  :
+                 LIMITER == UMIST_LIM     ? PLUTO_GPU_LIM_UMIST     : LIMITER == VANLEER_LIM ? PLUTO_GPU_LIM_VANLEER :
+                 LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
+    c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
+                     CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 : PLUTO_GPU_EMF_UCT_CONTACT);
     for (idim = 0; idim < DIMENSIONS; idim++){
       c.bc[2*idim]     = BoundaryCode (grid->lbound[idim]);      /* boundary.c:133-135 */
       c.bc[2*idim + 1] = BoundaryCode (grid->rbound[idim]);

@@ -365,6 +365,40 @@ static int cons_to_prim (const Oracle *o, double *u, double *v)
    Reconstruction
    ===================================================================== */
 
+static double single_limiter (int lim, double dvp, double dvm)
+/* plm_coeffs.h:72-123, uniform Cartesian grid (cp = cm = 2) */
+{
+  double dv;
+  switch (lim){
+    case ORC_LIM_FLAT:   return 0.0;
+    case ORC_LIM_MINMOD: return (dvp*dvm > 0.0 ? ABS_MIN(dvp, dvm) : 0.0);
+    case ORC_LIM_VANALBADA:
+      if (dvp*dvm > 0.0){
+        double dpp = dvp*dvp, dmm = dvm*dvm;
+        dv = (dvp*(dmm + 1.e-18) + dvm*(dpp + 1.e-18))/(dpp + dmm + 1.e-18);
+      }else dv = 0.0;
+      return dv;
+    case ORC_LIM_OSPRE:
+      return (dvp*dvm > 0.0 ? 1.5*dvp*dvm*(dvm + dvp)/(dvp*dvp + dvm*dvm + dvp*dvm) : 0.0);
+    case ORC_LIM_UMIST:
+      if (dvp*dvm > 0.0){
+        double ddp = 0.25*(dvp + 3.0*dvm), ddm = 0.25*(dvm + 3.0*dvp);
+        double d2 = 2.0*ABS_MIN(dvp, dvm);
+        d2 = ABS_MIN(d2, ddp);
+        dv = ABS_MIN(d2, ddm);
+      }else dv = 0.0;
+      return dv;
+    case ORC_LIM_VANLEER:
+      return (dvp*dvm > 0.0 ? 2.0*dvp*dvm/(dvp + dvm) : 0.0);
+    default:             /* MC */
+      if (dvp*dvm > 0.0){
+        double qc = 0.5*(dvm + dvp), scrh = 2.0*ABS_MIN(dvp, dvm);
+        dv = ABS_MIN(qc, scrh);
+      }else dv = 0.0;
+      return dv;
+  }
+}
+
 static void states_plm (Oracle *o, int beg, int end, int bxn)
 /* plm_states.c:80-312, CHAR_LIMITING NO, LIMITER DEFAULT,
    UNIFORM_CARTESIAN_GRID YES (cp=cm=2, wp=wm=1, dp=dm=0.5).
@@ -379,7 +413,9 @@ static void states_plm (Oracle *o, int beg, int end, int bxn)
     double dvl[NV];
     for (nv = 0; nv < NV; nv++){
       double dvp = dv[i][nv], dvm = dv[i-1][nv], lim;
-      if (nv == RHO){                         /* MC */
+      if (o->c.limiter != ORC_LIM_DEFAULT){   /* same limiter for all variables, plm_states.c:234-236 */
+        lim = single_limiter (o->c.limiter, dvp, dvm);
+      }else if (nv == RHO){                   /* MC */
         if (dvp*dvm > 0.0){
           double qc = 0.5*(dvm + dvp), scrh = 2.0*ABS_MIN(dvp, dvm);
           lim = ABS_MIN(qc, scrh);
@@ -802,6 +838,36 @@ static void ct_compute_emf (Oracle *o)
   }
 
 #define I3(k,j,i) IDX(o,k,j,i)
+  if (o->c.emf_average != ORC_EMF_UCT_CONTACT){
+    /* ARITHMETIC: CT_EMF_ArithmeticAverage (emf, 0.25) (ct_emf.c:241-243);
+       UCT0: face EMFs <- 2 face - mean of the two adjacent cell-centred EMFs, over
+       k..kend+KOFFSET etc., then the same average (ct_emf.c:261-283) */
+    if (o->c.emf_average == ORC_EMF_UCT0){
+      for (k = kbeg; k <= kend + koff; k++) for (j = jbeg; j <= jend + 1; j++) for (i = ibeg; i <= iend + 1; i++){
+        if (dims == 3){
+          exj[I3(k,j,i)] *= 2.0; exk[I3(k,j,i)] *= 2.0; eyi[I3(k,j,i)] *= 2.0; eyk[I3(k,j,i)] *= 2.0;
+          exj[I3(k,j,i)] -= 0.5*(Ex1[I3(k,j,i)] + Ex1[I3(k,j+1,i)]);
+          exk[I3(k,j,i)] -= 0.5*(Ex1[I3(k,j,i)] + Ex1[I3(k+1,j,i)]);
+          eyi[I3(k,j,i)] -= 0.5*(Ex2[I3(k,j,i)] + Ex2[I3(k,j,i+1)]);
+          eyk[I3(k,j,i)] -= 0.5*(Ex2[I3(k,j,i)] + Ex2[I3(k+1,j,i)]);
+        }
+        ezi[I3(k,j,i)] *= 2.0; ezj[I3(k,j,i)] *= 2.0;
+        ezi[I3(k,j,i)] -= 0.5*(Ex3[I3(k,j,i)] + Ex3[I3(k,j,i+1)]);
+        ezj[I3(k,j,i)] -= 0.5*(Ex3[I3(k,j,i)] + Ex3[I3(k,j+1,i)]);
+      }
+    }
+    for (k = kbeg; k <= kend; k++) for (j = jbeg; j <= jend; j++) for (i = ibeg; i <= iend; i++){
+      if (dims == 3){
+        ex[I3(k,j,i)] = 0.25*(  exk[I3(k,j,i)] + exk[I3(k,j+1,i)]
+                              + exj[I3(k,j,i)] + exj[I3(k+1,j,i)]);
+        ey[I3(k,j,i)] = 0.25*(  eyi[I3(k,j,i)] + eyi[I3(k+1,j,i)]
+                              + eyk[I3(k,j,i)] + eyk[I3(k,j,i+1)]);
+      }
+      ez[I3(k,j,i)] = 0.25*(  ezi[I3(k,j,i)] + ezi[I3(k,j+1,i)]
+                            + ezj[I3(k,j,i)] + ezj[I3(k,j,i+1)]);
+    }
+    return;
+  }
   for (k = kbeg; k <= kend; k++) for (j = jbeg; j <= jend; j++) for (i = ibeg; i <= iend; i++){
     if (dims == 3){
       ex[I3(k,j,i)] = 1.0*(  exk[I3(k,j,i)] + exk[I3(k,j+1,i)]

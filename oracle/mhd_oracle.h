@@ -22,6 +22,11 @@ extern "C" {
 enum { ORC_RECON_PLM = 0, ORC_RECON_PPM = 1 };
 enum { ORC_SOLVER_HLLD = 0, ORC_SOLVER_HLL = 1, ORC_SOLVER_ROE = 2 };
 enum { ORC_BC_PERIODIC = 0, ORC_BC_OUTFLOW = 1, ORC_BC_REFLECTIVE = 2 };
+/* LIMITER (plm_states.c:192-236, plm_coeffs.h:72-123): DEFAULT mixes MC / van Leer / minmod */
+enum { ORC_LIM_DEFAULT = 0, ORC_LIM_FLAT, ORC_LIM_MINMOD, ORC_LIM_VANALBADA, ORC_LIM_OSPRE,
+       ORC_LIM_UMIST, ORC_LIM_VANLEER, ORC_LIM_MC };
+/* CT_EMF_AVERAGE (ct_emf.c:241-283) */
+enum { ORC_EMF_UCT_CONTACT = 0, ORC_EMF_ARITHMETIC = 1, ORC_EMF_UCT0 = 2 };
 
 /* Variable order of the 8-slot state vector used by the oracle.  2-D
    (COMPONENTS = 2) runs carry vx3 = Bx3 = 0 in the unused slots, which is
@@ -40,6 +45,8 @@ typedef struct {
   double dx[3];         /* uniform cell sizes                              */
   double small_dn;      /* g_smallDensity  (1e-12)                         */
   double small_pr;      /* g_smallPressure (1e-12)                         */
+  int    limiter;       /* ORC_LIM_*  (PLM only)                           */
+  int    emf_average;   /* ORC_EMF_*                                       */
 } OracleConfig;
 
 typedef struct Oracle Oracle;

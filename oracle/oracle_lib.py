@@ -17,13 +17,16 @@ LIB_PATH = os.path.join(ORACLE_DIR, "liboracle_mhd.so")
 RECON = {"plm": 0, "ppm": 1}
 SOLVER = {"hlld": 0, "hll": 1, "roe": 2}
 BC = {"periodic": 0, "outflow": 1, "reflective": 2}
+LIMITER = {"default": 0, "fl": 1, "mm": 2, "va": 3, "os": 4, "um": 5, "vl": 6, "mc": 7}
+EMF = {"uct_contact": 0, "arith": 1, "uct0": 2}
 
 
 class OracleConfig(C.Structure):
     _fields_ = [("dims", C.c_int), ("n", C.c_int * 3), ("recon", C.c_int),
                 ("solver", C.c_int), ("rk_order", C.c_int), ("bc", C.c_int * 6),
                 ("gamma", C.c_double), ("dx", C.c_double * 3),
-                ("small_dn", C.c_double), ("small_pr", C.c_double)]
+                ("small_dn", C.c_double), ("small_pr", C.c_double),
+                ("limiter", C.c_int), ("emf_average", C.c_int)]
 
 
 def build():
@@ -70,8 +73,10 @@ class Oracle:
     """State container + stepper.  Arrays use the .dbl interior layout."""
 
     def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
-                 bc=("periodic",) * 6, gamma=5.0 / 3.0):
+                 bc=("periodic",) * 6, gamma=5.0 / 3.0, limiter="default", emf="uct_contact"):
         c = OracleConfig()
+        c.limiter = LIMITER[limiter]
+        c.emf_average = EMF[emf]
         c.dims = dims
         n = list(n) + [1] * (3 - len(n))
         if dims == 2:

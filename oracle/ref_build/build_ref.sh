@@ -12,6 +12,9 @@
 #
 # usage: build_ref.sh <variant> [<variant> ...]
 #   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3
+#   optional suffixes:  _l{fl,mm,va,os,um,vl,mc}  single LIMITER for all variables
+#                                                 (Src/States/plm_coeffs.h:72-123)
+#                       _e{arith,uct0}            CT_EMF_AVERAGE (Src/MHD/CT/ct_emf.c:241-283)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ORACLE="$(cd "$HERE/.." && pwd)"
@@ -35,6 +38,14 @@ for VARIANT in "$@"; do
   case "$VARIANT" in
     *_rk3) TSTEP=RK3 ;;
     *)     TSTEP=RK2 ;;
+  esac
+  case "$VARIANT" in
+    *_lfl*) LIMITER=FLAT_LIM ;;  *_lmm*) LIMITER=MINMOD_LIM ;;  *_lva*) LIMITER=VANALBADA_LIM ;;
+    *_los*) LIMITER=OSPRE_LIM ;; *_lum*) LIMITER=UMIST_LIM ;;   *_lvl*) LIMITER=VANLEER_LIM ;;
+    *_lmc*) LIMITER=MC_LIM ;;    *)      LIMITER=DEFAULT ;;
+  esac
+  case "$VARIANT" in
+    *_earith*) EMFAVG=ARITHMETIC ;; *_euct0*) EMFAVG=UCT0 ;; *) EMFAVG=UCT_CONTACT ;;
   esac
   B="$ORACLE/_build/$VARIANT"
   mkdir -p "$B"
@@ -81,7 +92,8 @@ for VARIANT in "$@"; do
 
 /* [Beg] user-defined constants (do not change this line) */
 
-#define  CT_EMF_AVERAGE                 UCT_CONTACT
+#define  LIMITER                        $LIMITER
+#define  CT_EMF_AVERAGE                 $EMFAVG
 #define  CT_EN_CORRECTION               NO
 #define  ASSIGN_VECTOR_POTENTIAL        YES
 #define  CHECK_DIVB_CONDITION           NO

@@ -42,6 +42,8 @@ class RefConfig:
     recon: str = "plm"                  # plm (LINEAR) | ppm (PARABOLIC)
     solver: str = "hlld"                # hlld | hll | roe
     tstep: str = "rk2"                  # rk2 | rk3
+    limiter: str = "default"            # default | fl mm va os um vl mc  (LIMITER, plm only)
+    emf: str = "uct_contact"            # uct_contact | arith | uct0      (CT_EMF_AVERAGE)
     cfl: float = 0.4
     cfl_max_var: float = 1.1
     first_dt: float = 1.0e-3
@@ -58,6 +60,10 @@ class RefConfig:
         v = f"{self.dims}d_{self.recon}"
         if self.tstep == "rk3":
             v += "_rk3"
+        if self.limiter != "default":
+            v += "_l" + self.limiter
+        if self.emf != "uct_contact":
+            v += "_e" + self.emf
         return v
 
     def binary(self) -> str:

@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(PKG_DIR, "lib", "libpluto_gpu.so")
 RECON = {"plm": 0, "linear": 0, "ppm": 1, "parabolic": 1}
 SOLVER = {"hlld": 0, "hll": 1, "roe": 2}
 BC = {"periodic": 0, "outflow": 1, "reflective": 2, "shared": 3}
+LIMITER = {"default": 0, "fl": 1, "mm": 2, "va": 3, "os": 4, "um": 5, "vl": 6, "mc": 7}      # LIMITER
+EMF = {"uct_contact": 0, "arith": 1, "uct0": 2}                                                 # CT_EMF_AVERAGE
 ARITH = {"exact": 0, "fast": 1}
 
 # every symbol include/pluto_gpu.h declares (checked by tests/test_cabi.py)
@@ -32,7 +34,7 @@ class PlutoGpuConfig(C.Structure):
     _fields_ = [("dims", C.c_int), ("n", C.c_int * 3), ("recon", C.c_int), ("solver", C.c_int),
                 ("rk_order", C.c_int), ("bc", C.c_int * 6), ("arith", C.c_int), ("device", C.c_int),
                 ("gamma", C.c_double), ("dx", C.c_double * 3), ("small_dn", C.c_double),
-                ("small_pr", C.c_double)]
+                ("small_pr", C.c_double), ("limiter", C.c_int), ("emf_average", C.c_int)]
 
 
 class PlutoGpuStepInfo(C.Structure):

@@ -68,6 +68,25 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
   const long long id = gidx (g, k, j, i);
   const long long sx = 1, sy = g.S1, sz = g.S12;
 
+  if (a.avg != 0){
+    // ARITHMETIC: CT_EMF_ArithmeticAverage (emf, 0.25) (ct_emf.c:241-243).  UCT0: the face EMFs
+    // are first replaced by 2 face - mean of the two adjacent cell-centred EMFs (ct_emf.c:261-283);
+    // evaluated here per use instead of in place.
+    const bool u0 = (a.avg == 2);
+    auto fz_i = [&] (long long q){ double e = a.ezi[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e3<NC>(a, q) + cell_e3<NC>(a, q + sx)); } return e; };
+    auto fz_j = [&] (long long q){ double e = a.ezj[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e3<NC>(a, q) + cell_e3<NC>(a, q + sy)); } return e; };
+    a.ez[id] = 0.25*(fz_i (id) + fz_i (id + sy) + fz_j (id) + fz_j (id + sx));
+    if (NC == 3){
+      auto fx_j = [&] (long long q){ double e = a.exj[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e1 (a, q) + cell_e1 (a, q + sy)); } return e; };
+      auto fx_k = [&] (long long q){ double e = a.exk[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e1 (a, q) + cell_e1 (a, q + sz)); } return e; };
+      auto fy_i = [&] (long long q){ double e = a.eyi[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e2 (a, q) + cell_e2 (a, q + sx)); } return e; };
+      auto fy_k = [&] (long long q){ double e = a.eyk[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e2 (a, q) + cell_e2 (a, q + sz)); } return e; };
+      a.ex[id] = 0.25*(fx_k (id) + fx_k (id + sy) + fx_j (id) + fx_j (id + sz));
+      a.ey[id] = 0.25*(fy_i (id) + fy_i (id + sz) + fy_k (id) + fy_k (id + sx));
+    }
+    return;
+  }
+
   {   // ---- ez at (i+1/2, j+1/2) ----
     const double ezi0 = a.ezi[id], ezi1 = a.ezi[id + sy];
     const double ezj0 = a.ezj[id], ezj1 = a.ezj[id + sx];

@@ -52,6 +52,7 @@ struct SweepArgs {
                              // continuing with the U left by the previous stage
   int     chunk_len;         // marching kernels: zones per thread along the sweep
   int     nchunk;
+  int     limiter;           // PLUTO_GPU_LIM_* (PLM)
   // fused x1 + x2 sweep only: the x2 quantities next to the x1 ones above
   const double *Bn2;         // Bx2s
   double       *e3, *e4;     // ezj, exj
@@ -71,6 +72,7 @@ struct CtArgs {
   const double *dtp;                         // device: dt/dx1, dt/dx2, dt/dx3
   double w0, wc;                             // stage weights
   int    combine;                            // 0: none, 1: w0*B0 + wc*B, 2: (B0 + 2 B)/3
+  int    avg;                                // PLUTO_GPU_EMF_*
 };
 
 struct FinalArgs {

@@ -142,6 +142,39 @@ template <int NV_ID> __device__ __forceinline__ double plm_slope (double dvp, do
   }
 }
 
+// one limiter for every variable (LIMITER != DEFAULT, plm_states.c:234-236; macros of
+// plm_coeffs.h:72-123 on a uniform Cartesian grid), in the reference's operation order.
+// lim: 1 flat, 2 minmod, 3 van Albada, 4 OSPRE, 5 UMIST, 6 van Leer, 7 MC
+__device__ __forceinline__ double single_limiter (int lim, double dvp, double dvm)
+{
+  if (lim == 1 || !(dvp*dvm > 0.0)) return 0.0;
+  if (lim == 2) return abs_min (dvp, dvm);
+  if (lim == 3){
+    const double dpp = dvp*dvp, dmm = dvm*dvm;
+    return pg_div (dvp*(dmm + 1.e-18) + dvm*(dpp + 1.e-18), dpp + dmm + 1.e-18);
+  }
+  if (lim == 4) return pg_div (1.5*dvp*dvm*(dvm + dvp), dvp*dvp + dvm*dvm + dvp*dvm);
+  if (lim == 5){
+    const double ddp = 0.25*(dvp + 3.0*dvm), ddm = 0.25*(dvm + 3.0*dvp);
+    double d2 = 2.0*abs_min (dvp, dvm);
+    d2 = abs_min (d2, ddp);
+    return abs_min (d2, ddm);
+  }
+  if (lim == 6) return pg_div (2.0*dvp*dvm, dvp + dvm);
+  const double qc = 0.5*(dvm + dvp), scrh = 2.0*abs_min (dvp, dvm);
+  return abs_min (qc, scrh);
+}
+template <int NC>
+__device__ __forceinline__ void plm_zone_single (int lim, const double *v, const double *dvm, const double *dvp,
+                                                 double *vp, double *vm)
+{
+  PG_FOR_NV(nv){
+    const double dvl = single_limiter (lim, dvp[nv], dvm[nv]);
+    vp[nv] = v[nv] + dvl*0.5;
+    vm[nv] = v[nv] - dvl*0.5;
+  }
+}
+
 // vp = v + dvl/2, vm = v - dvl/2 for one zone from its two one-sided differences
 #ifdef PG_FAST
 // FAST: the HALF slope h = dvl/2 is formed directly (the factors 2 and 1/2 of the
@@ -166,8 +199,8 @@ template <int NV_ID> __device__ __forceinline__ void plm_half (double v, double 
   }
 }
 template <int NC>
-__device__ __forceinline__ void plm_zone (const double *v, const double *dvm, const double *dvp,
-                                          double *vp, double *vm)
+__device__ __forceinline__ void plm_zone_default (const double *v, const double *dvm, const double *dvp,
+                                                  double *vp, double *vm)
 {
   plm_half<RHO>(v[RHO], dvp[RHO], dvm[RHO], vp[RHO], vm[RHO]);
   plm_half<VX1>(v[VX1], dvp[VX1], dvm[VX1], vp[VX1], vm[VX1]);
@@ -180,8 +213,8 @@ __device__ __forceinline__ void plm_zone (const double *v, const double *dvm, co
 }
 #else
 template <int NC>
-__device__ __forceinline__ void plm_zone (const double *v, const double *dvm, const double *dvp,
-                                          double *vp, double *vm)
+__device__ __forceinline__ void plm_zone_default (const double *v, const double *dvm, const double *dvp,
+                                                  double *vp, double *vm)
 {
   double dvl[NV];
   dvl[RHO] = plm_slope<RHO>(dvp[RHO], dvm[RHO]);
@@ -198,6 +231,15 @@ __device__ __forceinline__ void plm_zone (const double *v, const double *dvm, co
   }
 }
 #endif
+
+// LIMITER DEFAULT (the fast path) or one limiter for all variables (uniform branch)
+template <int NC>
+__device__ __forceinline__ void plm_zone (int lim, const double *v, const double *dvm, const double *dvp,
+                                          double *vp, double *vm)
+{
+  if (lim == 0) plm_zone_default<NC>(v, dvm, dvp, vp, vm);
+  else          plm_zone_single<NC>(lim, v, dvm, dvp, vp, vm);
+}
 
 // PPM 4th-order interface value at i+1/2, bounded (ppm_states.c:146-157):
 // W = v0 + MINMOD(P - v0, v1 - v0), P = -1/12 vm1 + 7/12 v0 + 7/12 v1 - 1/12 v2

@@ -131,6 +131,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->recon != PLUTO_GPU_RECON_LINEAR && cfg->recon != PLUTO_GPU_RECON_PARABOLIC) return fail ("bad recon");
   if (cfg->solver < 0 || cfg->solver > 2) return fail ("bad solver");
   if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
+  if (cfg->limiter < 0 || cfg->limiter > PLUTO_GPU_LIM_MC) return fail ("bad limiter");
+  if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT0) return fail ("bad emf_average");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -512,6 +514,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
   s.stage1 = (stage == 1);
+  s.limiter = h->cfg.limiter;
   // EXACT: later stages continue from the conservative state the previous stage
   // left (as the reference does); FAST: rebuild it from the primitives, which
   // saves reading U in the x1 sweep and differs by round-off only
@@ -579,6 +582,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     c.Bs_in[d] = h->Bs[sp.in][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[sp.out][d];
   }
   c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine; c.dtp = h->dtdev;
+  c.avg = h->cfg.emf_average;
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 

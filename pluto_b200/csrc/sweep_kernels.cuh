@@ -212,7 +212,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
         dvm[nv] = v[nv] - vl;
         dvp[nv] = vr - v[nv];
       }
-      plm_zone<NC>(v, dvm, dvp, vp, vm);
+      plm_zone<NC>(a.limiter, v, dvm, dvp, vp, vm);
     }else{
       double vl[NV], vr[NV], vrr[NV], Wi[NV], Wm[NV];
       PG_FOR_NV(nv){
@@ -389,7 +389,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait<PF - 1> ();
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone<NC>(vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone<NC>(a.limiter, vb_, dvm, dvp, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
@@ -441,7 +441,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone<NC>(vc_, dvm, dvp, vpn, vR);
+        plm_zone<NC>(a.limiter, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
@@ -615,7 +615,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait_all ();
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone<NC>(vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone<NC>(a.limiter, vb_, dvm, dvp, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
@@ -663,7 +663,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = v[nv] - xvl[nv]; dvp[nv] = xvr[nv] - v[nv]; }
-        plm_zone<NC>(v, dvm, dvp, vp, vm);
+        plm_zone<NC>(a.limiter, v, dvm, dvp, vp, vm);
       }else{
         double Wi[NV], Wm[NV];
         ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
@@ -706,7 +706,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone<NC>(vc_, dvm, dvp, vpn, vR);
+        plm_zone<NC>(a.limiter, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV(nv) Wf[nv] = C_WF(nv);

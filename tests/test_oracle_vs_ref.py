@@ -15,6 +15,16 @@ CASES = [
     ("blast3d_roe", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, solver="roe"), 6),
     ("rotor2d_ppm_hlld", RefConfig(problem="rotor", dims=2, n=(40, 36, 1), recon="ppm", first_dt=2e-3), 10),
     ("turb2d_hlld", RefConfig(problem="turb", dims=2, n=(24, 20, 1), first_dt=2e-2), 8),
+    # single limiters (plm_coeffs.h:72-123) and the other EMF averages (ct_emf.c:241-283): the options the
+    # shipped Test_Problems/MHD configurations use (OT #03, Blast #02 #05, Rotor #01)
+    ("blast3d_vl_arith", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, limiter="vl", emf="arith"), 6),
+    ("ot2d_arith_roe", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, solver="roe", emf="arith"), 8),
+    ("rotor2d_mc_arith", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), first_dt=2e-3, limiter="mc", emf="arith"), 8),
+    ("blast3d_va_arith", RefConfig(problem="blast", dims=3, n=(10, 12, 14), first_dt=3e-4, cfl=0.3, limiter="va", emf="arith"), 6),
+    ("turb3d_uct0", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, emf="uct0"), 6),
+    ("ot2d_mm", RefConfig(problem="ot", dims=2, n=(28, 24, 1), first_dt=1.5e-2, limiter="mm"), 8),
+    ("turb3d_um", RefConfig(problem="turb", dims=3, n=(8, 10, 12), first_dt=2e-2, cfl=0.3, limiter="um"), 5),
+    ("blast2d_os", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, limiter="os"), 8),
 ]
 
 
@@ -29,7 +39,7 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dom = cfg.resolved_domain()
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
-               gamma=cfg.resolved_gamma())
+               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf)
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

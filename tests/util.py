@@ -37,6 +37,8 @@ class Golden:
         self.domain = [tuple(float(x) for x in row) for row in d["cfg_domain"]]
         self.bc = tuple(str(x) for x in d["cfg_bc"])
         self.nsteps = int(d["cfg_nsteps"])
+        self.limiter = str(d["cfg_limiter"]) if "cfg_limiter" in d.files else "default"
+        self.emf = str(d["cfg_emf"]) if "cfg_emf" in d.files else "uct_contact"
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:

@@ -50,6 +50,17 @@ CASES = {
     "turb3d_plm_hlld_100": (RefConfig(problem="turb", dims=3, n=(16, 20, 24), first_dt=2e-2, cfl=0.3), 100),
     "rotor2d_ppm_roe_100": (RefConfig(problem="rotor", dims=2, n=(48, 40, 1), recon="ppm", solver="roe",
                                       first_dt=1e-3, cfl=0.4), 100),
+    # the scheme options of the shipped Test_Problems/MHD configurations (single limiters, other EMF averages):
+    # Orszag_Tang #03 (ARITHMETIC, roe), Blast #02 (VANLEER_LIM, ARITHMETIC), Blast #05 (VANALBADA_LIM,
+    # ARITHMETIC), Rotor #01 (MC_LIM, ARITHMETIC), plus UCT0 and the remaining limiters
+    "ot2d_arith_roe": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, solver="roe", emf="arith"), 20),
+    "blast3d_vl_arith": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, limiter="vl", emf="arith"), 12),
+    "blast3d_va_arith": (RefConfig(problem="blast", dims=3, n=(12, 16, 8), first_dt=6e-4, cfl=0.3, limiter="va", emf="arith"), 12),
+    "rotor2d_mc_arith": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), first_dt=2.5e-3, cfl=0.4, limiter="mc", emf="arith"), 20),
+    "turb3d_uct0": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, emf="uct0"), 10),
+    "ot2d_mm": (RefConfig(problem="ot", dims=2, n=(24, 32, 1), first_dt=2.5e-2, cfl=0.4, limiter="mm"), 10),
+    "turb3d_um": (RefConfig(problem="turb", dims=3, n=(12, 8, 16), first_dt=3e-2, cfl=0.3, limiter="um"), 10),
+    "blast2d_os": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, limiter="os"), 20),
 }
 
 
@@ -63,6 +74,7 @@ def make(name):
         "cfg_first_dt": cfg.first_dt, "cfg_gamma": cfg.resolved_gamma(),
         "cfg_domain": np.array(cfg.resolved_domain()),
         "cfg_bc": np.array(cfg.resolved_bc()), "cfg_nsteps": nsteps,
+        "cfg_limiter": cfg.limiter, "cfg_emf": cfg.emf,
     }
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
