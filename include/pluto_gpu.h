@@ -51,7 +51,8 @@ enum { PLUTO_GPU_ARITH_EXACT = 0, PLUTO_GPU_ARITH_FAST = 1 };
 enum { PLUTO_GPU_LIM_DEFAULT = 0, PLUTO_GPU_LIM_FLAT, PLUTO_GPU_LIM_MINMOD, PLUTO_GPU_LIM_VANALBADA,
        PLUTO_GPU_LIM_OSPRE, PLUTO_GPU_LIM_UMIST, PLUTO_GPU_LIM_VANLEER, PLUTO_GPU_LIM_MC };
 /* CT_EMF_AVERAGE in definitions.h (Src/MHD/CT/ct_emf.c:241-283) */
-enum { PLUTO_GPU_EMF_UCT_CONTACT = 0, PLUTO_GPU_EMF_ARITHMETIC = 1, PLUTO_GPU_EMF_UCT0 = 2 };
+enum { PLUTO_GPU_EMF_UCT_CONTACT = 0, PLUTO_GPU_EMF_ARITHMETIC = 1, PLUTO_GPU_EMF_UCT0 = 2,
+       PLUTO_GPU_EMF_UCT_HLL = 3 /* the reference's default, Src/MHD/CT/ct.h:43-45 */ };
 
 typedef struct {
   int    dims;         /* DIMENSIONS = COMPONENTS: 2 or 3                     */

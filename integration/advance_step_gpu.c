@@ -44,8 +44,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
 
 #if PHYSICS != MHD || GEOMETRY != CARTESIAN || DIVB_CONTROL != CONSTRAINED_TRANSPORT \
     || EOS != IDEAL || DIMENSIONS != COMPONENTS \
-    || (CT_EMF_AVERAGE != UCT_CONTACT && CT_EMF_AVERAGE != ARITHMETIC && CT_EMF_AVERAGE != UCT0)
-  #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT / ARITHMETIC / UCT0, DIMENSIONS == COMPONENTS"
+    || (CT_EMF_AVERAGE != UCT_CONTACT && CT_EMF_AVERAGE != ARITHMETIC && CT_EMF_AVERAGE != UCT0 \
+        && CT_EMF_AVERAGE != UCT_HLL)
+  #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT / ARITHMETIC / UCT0 / UCT_HLL, DIMENSIONS == COMPONENTS"
 #endif
 #if CHAR_LIMITING == YES || SHOCK_FLATTENING != NO || LIMITER == FOURTH_ORDER_LIM
   #error "libpluto_gpu: CHAR_LIMITING, SHOCK_FLATTENING and FOURTH_ORDER_LIM are not available on the GPU"
@@ -73,7 +74,8 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
                  LIMITER == UMIST_LIM     ? PLUTO_GPU_LIM_UMIST     : LIMITER == VANLEER_LIM ? PLUTO_GPU_LIM_VANLEER :
                  LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
     c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
-                     CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 : PLUTO_GPU_EMF_UCT_CONTACT);
+                     CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 :
+                     CT_EMF_AVERAGE == UCT_HLL ? PLUTO_GPU_EMF_UCT_HLL : PLUTO_GPU_EMF_UCT_CONTACT);
     for (idim = 0; idim < DIMENSIONS; idim++){
       c.bc[2*idim]     = BoundaryCode (grid->lbound[idim]);      /* boundary.c:133-135 */
       c.bc[2*idim + 1] = BoundaryCode (grid->rbound[idim]);

@@ -47,11 +47,15 @@ struct Oracle {
   double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   double *ex, *ey, *ez, *Ex1, *Ex2, *Ex3;
   signed char *svx, *svy, *svz;
+  /* UCT_HLL (ct_emf.c:144-147,165-168,186-189, ct_stag_slopes.c:5-45): face speeds and velocity slopes */
+  double *SfL[3], *SfR[3];             /* max(0,-SL), max(0,SR) at the faces of each direction */
+  double *dvel[3][3];                  /* dvel[c][d] = d v_c / d x_d (limited slope vp - vm)   */
+  double cur_SL, cur_SR;               /* Riemann fan speeds of the interface just solved      */
   double *C_dt;
   /* pencil scratch */
   int np;
   double (*v)[NV], (*vp)[NV], (*vm)[NV], (*dv)[NV];
-  double (*flux)[NV], *press, *cmax, *bn;
+  double (*flux)[NV], *press, *cmax, *bn, *SLp, *SRp;
   double max_mach, inv_dt_hyp;
   int    stage, floor_events;
   int    emf_ibeg, emf_iend, emf_jbeg, emf_jend, emf_kbeg, emf_kend;
@@ -96,6 +100,13 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->svy = (signed char *)calloc((size_t)o->tot, 1);
   o->svz = (signed char *)calloc((size_t)o->tot, 1);
   o->C_dt = dalloc(o->tot);
+  if (cfg->emf_average == ORC_EMF_UCT_HLL){
+    int c;
+    for (d = 0; d < 3; d++){
+      o->SfL[d] = dalloc(o->tot); o->SfR[d] = dalloc(o->tot);
+      for (c = 0; c < 3; c++) o->dvel[c][d] = dalloc(o->tot);
+    }
+  }
   o->np = o->T[0];
   if (o->T[1] > o->np) o->np = o->T[1];
   if (o->T[2] > o->np) o->np = o->T[2];
@@ -106,6 +117,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->dv   = calloc((size_t)o->np, sizeof(*o->dv));
   o->flux = calloc((size_t)o->np, sizeof(*o->flux));
   o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
+  o->SLp = dalloc(o->np) + 4; o->SRp = dalloc(o->np) + 4;
   /* shift pencil arrays so that index -2 is addressable */
   o->v += 4; o->vp += 4; o->vm += 4; o->dv += 4; o->flux += 4;
   o->press += 4; o->cmax += 4; o->bn += 4;
@@ -495,6 +507,7 @@ static void hll_speed (Oracle *o, const double *vL, const double *vR, Dirs q,
   max_signal_speed (o, vR, q, &srmin, &srmax);
   *SL = MINV(slmin, srmin);
   *SR = MAXV(slmax, srmax);
+  o->cur_SL = *SL; o->cur_SR = *SR;      /* sweep->SL[i], SR[i] (hll_speed.c:92-93) */
   scrh  = fabs(vL[q.vn]) + fabs(vR[q.vn]);
   scrh /= sqrt(a2L) + sqrt(a2R);
   o->max_mach = MAXV(scrh, o->max_mach);
@@ -753,6 +766,7 @@ static void update_stage (Oracle *o, double dt)
           riemann_hll  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
         else
           riemann_roe  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
+        o->SLp[n] = o->cur_SL; o->SRp[n] = o->cur_SR;
       }
 
       /* CT_StoreUpwindEMF (nbeg-1 .. nend), ct_emf.c:104-190 */
@@ -760,6 +774,10 @@ static void update_stage (Oracle *o, double dt)
         int id; signed char s;
         idx3[dir] = n;
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        if (o->c.emf_average == ORC_EMF_UCT_HLL){
+          o->SfL[dir][id] = MAXV(0.0, -o->SLp[n]);
+          o->SfR[dir][id] = MAXV(0.0,  o->SRp[n]);
+        }
         if      (o->flux[n][RHO] >  EPS_UCT_CONTACT) s = 1;
         else if (o->flux[n][RHO] < -EPS_UCT_CONTACT) s = -1;
         else s = 0;
@@ -775,6 +793,16 @@ static void update_stage (Oracle *o, double dt)
           o->eyk[id] = -o->flux[n][BX1];
           o->exk[id] =  o->flux[n][BX2];
           o->svz[id] = s;
+        }
+      }
+
+      if (o->c.emf_average == ORC_EMF_UCT_HLL){
+        /* CT_StoreVelSlopes (beg = nbeg-1 .. end+1 = nend+1), ct_stag_slopes.c:5-45 */
+        for (n = nbeg-1; n <= nend+1; n++){
+          int id, c;
+          idx3[dir] = n;
+          id = IDX(o, idx3[2], idx3[1], idx3[0]);
+          for (c = 0; c < dims; c++) o->dvel[c][dir][id] = o->vp[n][VX1+c] - o->vm[n][VX1+c];
         }
       }
 
@@ -815,6 +843,93 @@ static void update_stage (Oracle *o, double dt)
    Constrained transport
    ===================================================================== */
 
+static double mc_lim2 (double dp, double dm)      /* ct_stag_slopes.c:97-108 */
+{
+  double dc, scrh;
+  if (dp*dm < 0.0) return 0.0;
+  dc   = 0.5*(dp + dm);
+  scrh = 2.0*(fabs(dp) < fabs(dm) ? dp : dm);
+  return (fabs(dc) < fabs(scrh) ? dc : scrh);
+}
+
+static void ct_emf_hll (Oracle *o)
+/* UCT_HLL: CT_GetStagSlopes (ct_stag_slopes.c:52-95) + CT_EMF_HLL_Solver
+   (ct_emf_average.c:180-359, Londrillo & Del Zanna 2004 eq. 56).  The staggered slopes
+   are evaluated where they are used instead of being stored.                       */
+{
+  int i, j, k, dims = o->c.dims;
+  int ibeg = o->emf_ibeg, iend = o->emf_iend, jbeg = o->emf_jbeg, jend = o->emf_jend;
+  int kbeg = o->emf_kbeg, kend = o->emf_kend;
+  const int st[3] = {1, o->S1, o->S1*o->S2};
+#define I3(k,j,i) IDX(o,k,j,i)
+  /* limited slope of staggered component c along direction d at zone id */
+#define DB(c, d, id) mc_lim2 (o->Vs[c][(id) + st[d]] - o->Vs[c][id], o->Vs[c][id] - o->Vs[c][(id) - st[d]])
+#define BP(c, d, id) (o->Vs[c][id] + 0.5*DB(c, d, id))
+#define BM(c, d, id) (o->Vs[c][id] - 0.5*DB(c, d, id))
+  /* velocity component c integrated from the centre of zone id to the edge, transverse
+     directions (x, y) of the edge: dPP, dPM, dMM, dMP of ct_emf_average.c:196-206 */
+#define VPP(c, x, y, id) (o->Vc[VX1+(c)][id] + 0.5*(o->dvel[c][x][id] + o->dvel[c][y][id]))
+#define VPM(c, x, y, id) (o->Vc[VX1+(c)][id] + 0.5*(o->dvel[c][x][id] - o->dvel[c][y][id]))
+#define VMM(c, x, y, id) (o->Vc[VX1+(c)][id] - 0.5*(o->dvel[c][x][id] + o->dvel[c][y][id]))
+#define VMP(c, x, y, id) (o->Vc[VX1+(c)][id] - 0.5*(o->dvel[c][x][id] - o->dvel[c][y][id]))
+  for (k = kbeg; k <= kend; k++) for (j = jbeg; j <= jend; j++) for (i = ibeg; i <= iend; i++){
+    int id = I3(k,j,i), ip = id + st[0], jp = id + st[1], kp = id + st[2];
+    double a_xp, a_xm, a_yp, a_ym, bS, bN, bW, bE, eSW, eSE, eNE, eNW, e;
+    /* ---- ez at (i+1/2, j+1/2, k) ---- */
+    a_xp = MAXV(o->SfR[0][id], o->SfR[0][jp]); a_xm = MAXV(o->SfL[0][id], o->SfL[0][jp]);
+    a_yp = MAXV(o->SfR[1][id], o->SfR[1][ip]); a_ym = MAXV(o->SfL[1][id], o->SfL[1][ip]);
+    bS = BP(0, 1, id); bW = BP(1, 0, id);
+    bN = BM(0, 1, jp); bE = BM(1, 0, ip);
+    eSW = VPP(1,0,1,id)*bS - VPP(0,0,1,id)*bW;
+    eSE = VMP(1,0,1,ip)*bS - VMP(0,0,1,ip)*bE;
+    eNE = VMM(1,0,1,ip + st[1])*bN - VMM(0,0,1,ip + st[1])*bE;
+    eNW = VPM(1,0,1,jp)*bN - VPM(0,0,1,jp)*bW;
+    e  = a_xp*a_yp*eSW + a_xm*a_yp*eSE + a_xm*a_ym*eNE + a_xp*a_ym*eNW;
+    e /= (a_xp + a_xm)*(a_yp + a_ym);
+    e -= a_yp*a_ym*(bN - bS)/(a_yp + a_ym);
+    e += a_xp*a_xm*(bE - bW)/(a_xp + a_xm);
+    o->ez[id] = e;
+    if (dims == 3){
+      /* ---- ex at (i, j+1/2, k+1/2) ---- */
+      a_xp = MAXV(o->SfR[1][id], o->SfR[1][kp]); a_xm = MAXV(o->SfL[1][id], o->SfL[1][kp]);
+      a_yp = MAXV(o->SfR[2][id], o->SfR[2][jp]); a_ym = MAXV(o->SfL[2][id], o->SfL[2][jp]);
+      bS = BP(1, 2, id); bW = BP(2, 1, id);
+      bN = BM(1, 2, kp); bE = BM(2, 1, jp);
+      eSW = VPP(2,1,2,id)*bS - VPP(1,1,2,id)*bW;
+      eSE = VMP(2,1,2,jp)*bS - VMP(1,1,2,jp)*bE;
+      eNE = VMM(2,1,2,jp + st[2])*bN - VMM(1,1,2,jp + st[2])*bE;
+      eNW = VPM(2,1,2,kp)*bN - VPM(1,1,2,kp)*bW;
+      e  = a_xp*a_yp*eSW + a_xm*a_yp*eSE + a_xm*a_ym*eNE + a_xp*a_ym*eNW;
+      e /= (a_xp + a_xm)*(a_yp + a_ym);
+      e -= a_yp*a_ym*(bN - bS)/(a_yp + a_ym);
+      e += a_xp*a_xm*(bE - bW)/(a_xp + a_xm);
+      o->ex[id] = e;
+      /* ---- ey at (i+1/2, j, k+1/2) ---- */
+      a_xp = MAXV(o->SfR[2][id], o->SfR[2][ip]); a_xm = MAXV(o->SfL[2][id], o->SfL[2][ip]);
+      a_yp = MAXV(o->SfR[0][id], o->SfR[0][kp]); a_ym = MAXV(o->SfL[0][id], o->SfL[0][kp]);
+      bS = BP(2, 0, id); bW = BP(0, 2, id);
+      bN = BM(2, 0, ip); bE = BM(0, 2, kp);
+      eSW = VPP(0,2,0,id)*bS - VPP(2,2,0,id)*bW;
+      eSE = VMP(0,2,0,kp)*bS - VMP(2,2,0,kp)*bE;
+      eNE = VMM(0,2,0,ip + st[2])*bN - VMM(2,2,0,ip + st[2])*bE;
+      eNW = VPM(0,2,0,ip)*bN - VPM(2,2,0,ip)*bW;
+      e  = a_xp*a_yp*eSW + a_xm*a_yp*eSE + a_xm*a_ym*eNE + a_xp*a_ym*eNW;
+      e /= (a_xp + a_xm)*(a_yp + a_ym);
+      e -= a_yp*a_ym*(bN - bS)/(a_yp + a_ym);
+      e += a_xp*a_xm*(bE - bW)/(a_xp + a_xm);
+      o->ey[id] = e;
+    }
+  }
+#undef I3
+#undef DB
+#undef BP
+#undef BM
+#undef VPP
+#undef VPM
+#undef VMM
+#undef VMP
+}
+
 static void ct_compute_emf (Oracle *o)
 /* MHD/CT/ct_emf.c:210-254 (UCT_CONTACT): CT_ComputeCenterEMF (:348-388),
    CT_EMF_ArithmeticAverage(w = 1) (ct_emf_average.c:13-49),
@@ -838,6 +953,7 @@ static void ct_compute_emf (Oracle *o)
   }
 
 #define I3(k,j,i) IDX(o,k,j,i)
+  if (o->c.emf_average == ORC_EMF_UCT_HLL){ ct_emf_hll (o); return; }
   if (o->c.emf_average != ORC_EMF_UCT_CONTACT){
     /* ARITHMETIC: CT_EMF_ArithmeticAverage (emf, 0.25) (ct_emf.c:241-243);
        UCT0: face EMFs <- 2 face - mean of the two adjacent cell-centred EMFs, over

@@ -26,7 +26,7 @@ enum { ORC_BC_PERIODIC = 0, ORC_BC_OUTFLOW = 1, ORC_BC_REFLECTIVE = 2 };
 enum { ORC_LIM_DEFAULT = 0, ORC_LIM_FLAT, ORC_LIM_MINMOD, ORC_LIM_VANALBADA, ORC_LIM_OSPRE,
        ORC_LIM_UMIST, ORC_LIM_VANLEER, ORC_LIM_MC };
 /* CT_EMF_AVERAGE (ct_emf.c:241-283) */
-enum { ORC_EMF_UCT_CONTACT = 0, ORC_EMF_ARITHMETIC = 1, ORC_EMF_UCT0 = 2 };
+enum { ORC_EMF_UCT_CONTACT = 0, ORC_EMF_ARITHMETIC = 1, ORC_EMF_UCT0 = 2, ORC_EMF_UCT_HLL = 3 };
 
 /* Variable order of the 8-slot state vector used by the oracle.  2-D
    (COMPONENTS = 2) runs carry vx3 = Bx3 = 0 in the unused slots, which is

@@ -14,7 +14,7 @@
 #   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3
 #   optional suffixes:  _l{fl,mm,va,os,um,vl,mc}  single LIMITER for all variables
 #                                                 (Src/States/plm_coeffs.h:72-123)
-#                       _e{arith,uct0}            CT_EMF_AVERAGE (Src/MHD/CT/ct_emf.c:241-283)
+#                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE (Src/MHD/CT/ct_emf.c:241-283)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ORACLE="$(cd "$HERE/.." && pwd)"
@@ -45,7 +45,7 @@ for VARIANT in "$@"; do
     *_lmc*) LIMITER=MC_LIM ;;    *)      LIMITER=DEFAULT ;;
   esac
   case "$VARIANT" in
-    *_earith*) EMFAVG=ARITHMETIC ;; *_euct0*) EMFAVG=UCT0 ;; *) EMFAVG=UCT_CONTACT ;;
+    *_earith*) EMFAVG=ARITHMETIC ;; *_euct0*) EMFAVG=UCT0 ;; *_euct_hll*) EMFAVG=UCT_HLL ;; *) EMFAVG=UCT_CONTACT ;;
   esac
   B="$ORACLE/_build/$VARIANT"
   mkdir -p "$B"

@@ -43,7 +43,7 @@ class RefConfig:
     solver: str = "hlld"                # hlld | hll | roe
     tstep: str = "rk2"                  # rk2 | rk3
     limiter: str = "default"            # default | fl mm va os um vl mc  (LIMITER, plm only)
-    emf: str = "uct_contact"            # uct_contact | arith | uct0      (CT_EMF_AVERAGE)
+    emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
     cfl: float = 0.4
     cfl_max_var: float = 1.1
     first_dt: float = 1.0e-3

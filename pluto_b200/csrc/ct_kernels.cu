@@ -68,6 +68,68 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
   const long long id = gidx (g, k, j, i);
   const long long sx = 1, sy = g.S1, sz = g.S12;
 
+  if (a.avg == 3){
+    // UCT_HLL: CT_GetStagSlopes (ct_stag_slopes.c:52-95) + CT_EMF_HLL_Solver (ct_emf_average.c:180-359,
+    // Londrillo & Del Zanna 2004, eq. 56) in the reference's operation order.  The face arrays hold
+    // the fan speeds max(0,-SL) [e1 of the direction] and max(0,SR) [e2]; the staggered slopes are
+    // evaluated where they are used.
+    const long long st[3] = {sx, sy, sz};
+    auto mc2 = [] (double dp, double dm){
+      if (dp*dm < 0.0) return 0.0;
+      const double dc = 0.5*(dp + dm), scrh = 2.0*(fabs (dp) < fabs (dm) ? dp : dm);
+      return fabs (dc) < fabs (scrh) ? dc : scrh;
+    };
+    auto DB = [&] (int c, int d, long long q){ return mc2 (a.Bs_in[c][q + st[d]] - a.Bs_in[c][q], a.Bs_in[c][q] - a.Bs_in[c][q - st[d]]); };
+    auto BP = [&] (int c, int d, long long q){ return a.Bs_in[c][q] + 0.5*DB (c, d, q); };
+    auto BM = [&] (int c, int d, long long q){ return a.Bs_in[c][q] - 0.5*DB (c, d, q); };
+    auto VPP = [&] (int c, int x, int y, long long q){ return a.V[VX1 + c][q] + 0.5*(a.dvel[c][x][q] + a.dvel[c][y][q]); };
+    auto VPM = [&] (int c, int x, int y, long long q){ return a.V[VX1 + c][q] + 0.5*(a.dvel[c][x][q] - a.dvel[c][y][q]); };
+    auto VMM = [&] (int c, int x, int y, long long q){ return a.V[VX1 + c][q] - 0.5*(a.dvel[c][x][q] + a.dvel[c][y][q]); };
+    auto VMP = [&] (int c, int x, int y, long long q){ return a.V[VX1 + c][q] - 0.5*(a.dvel[c][x][q] - a.dvel[c][y][q]); };
+    auto hll2d = [] (double a_xp, double a_xm, double a_yp, double a_ym, double eSW, double eSE, double eNE, double eNW,
+                     double bS, double bN, double bW, double bE){
+      double e = a_xp*a_yp*eSW + a_xm*a_yp*eSE + a_xm*a_ym*eNE + a_xp*a_ym*eNW;
+      e = pg_div (e, (a_xp + a_xm)*(a_yp + a_ym));
+      e -= pg_div (a_yp*a_ym*(bN - bS), a_yp + a_ym);
+      e += pg_div (a_xp*a_xm*(bE - bW), a_xp + a_xm);
+      return e;
+    };
+    const double *SL[3] = {a.ezi, a.ezj, a.eyk}, *SR[3] = {a.eyi, a.exj, a.exk};
+    const long long ip = id + sx, jp = id + sy, kp = id + sz;
+    {
+      const double a_xp = maxv (SR[0][id], SR[0][jp]), a_xm = maxv (SL[0][id], SL[0][jp]);
+      const double a_yp = maxv (SR[1][id], SR[1][ip]), a_ym = maxv (SL[1][id], SL[1][ip]);
+      const double bS = BP (0, 1, id), bW = BP (1, 0, id), bN = BM (0, 1, jp), bE = BM (1, 0, ip);
+      const double eSW = VPP (1, 0, 1, id)*bS - VPP (0, 0, 1, id)*bW;
+      const double eSE = VMP (1, 0, 1, ip)*bS - VMP (0, 0, 1, ip)*bE;
+      const double eNE = VMM (1, 0, 1, ip + sy)*bN - VMM (0, 0, 1, ip + sy)*bE;
+      const double eNW = VPM (1, 0, 1, jp)*bN - VPM (0, 0, 1, jp)*bW;
+      a.ez[id] = hll2d (a_xp, a_xm, a_yp, a_ym, eSW, eSE, eNE, eNW, bS, bN, bW, bE);
+    }
+    if (NC == 3){
+      {
+        const double a_xp = maxv (SR[1][id], SR[1][kp]), a_xm = maxv (SL[1][id], SL[1][kp]);
+        const double a_yp = maxv (SR[2][id], SR[2][jp]), a_ym = maxv (SL[2][id], SL[2][jp]);
+        const double bS = BP (1, 2, id), bW = BP (2, 1, id), bN = BM (1, 2, kp), bE = BM (2, 1, jp);
+        const double eSW = VPP (2, 1, 2, id)*bS - VPP (1, 1, 2, id)*bW;
+        const double eSE = VMP (2, 1, 2, jp)*bS - VMP (1, 1, 2, jp)*bE;
+        const double eNE = VMM (2, 1, 2, jp + sz)*bN - VMM (1, 1, 2, jp + sz)*bE;
+        const double eNW = VPM (2, 1, 2, kp)*bN - VPM (1, 1, 2, kp)*bW;
+        a.ex[id] = hll2d (a_xp, a_xm, a_yp, a_ym, eSW, eSE, eNE, eNW, bS, bN, bW, bE);
+      }
+      {
+        const double a_xp = maxv (SR[2][id], SR[2][ip]), a_xm = maxv (SL[2][id], SL[2][ip]);
+        const double a_yp = maxv (SR[0][id], SR[0][kp]), a_ym = maxv (SL[0][id], SL[0][kp]);
+        const double bS = BP (2, 0, id), bW = BP (0, 2, id), bN = BM (2, 0, ip), bE = BM (0, 2, kp);
+        const double eSW = VPP (0, 2, 0, id)*bS - VPP (2, 2, 0, id)*bW;
+        const double eSE = VMP (0, 2, 0, kp)*bS - VMP (2, 2, 0, kp)*bE;
+        const double eNE = VMM (0, 2, 0, ip + sz)*bN - VMM (2, 2, 0, ip + sz)*bE;
+        const double eNW = VPM (0, 2, 0, ip)*bN - VPM (2, 2, 0, ip)*bW;
+        a.ey[id] = hll2d (a_xp, a_xm, a_yp, a_ym, eSW, eSE, eNE, eNW, bS, bN, bW, bE);
+      }
+    }
+    return;
+  }
   if (a.avg != 0){
     // ARITHMETIC: CT_EMF_ArithmeticAverage (emf, 0.25) (ct_emf.c:241-243).  UCT0: the face EMFs
     // are first replaced by 2 face - mean of the two adjacent cell-centred EMFs (ct_emf.c:261-283);

@@ -53,6 +53,12 @@ struct SweepArgs {
   int     chunk_len;         // marching kernels: zones per thread along the sweep
   int     nchunk;
   int     limiter;           // PLUTO_GPU_LIM_* (PLM)
+  // UCT_HLL only (avg == 3): e1/e2 (e3/e4) receive the fan speeds max(0,-SL), max(0,SR) of the
+  // faces instead of the face EMFs, and the limited velocity slopes vp - vm of every
+  // reconstructed zone are kept (CT_StoreVelSlopes, ct_stag_slopes.c:5-45)
+  int     avg;               // PLUTO_GPU_EMF_*
+  double *dvel[3];           // d v_c / d x_dir of this sweep's direction, c = 0..2
+  double *dvel2[3];          // fused x1 + x2 sweep: the x2 slopes
   // fused x1 + x2 sweep only: the x2 quantities next to the x1 ones above
   const double *Bn2;         // Bx2s
   double       *e3, *e4;     // ezj, exj
@@ -73,6 +79,7 @@ struct CtArgs {
   double w0, wc;                             // stage weights
   int    combine;                            // 0: none, 1: w0*B0 + wc*B, 2: (B0 + 2 B)/3
   int    avg;                                // PLUTO_GPU_EMF_*
+  const double *dvel[3][3];                  // UCT_HLL: dvel[c][d] = d v_c / d x_d
 };
 
 struct FinalArgs {

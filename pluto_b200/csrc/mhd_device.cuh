@@ -397,6 +397,14 @@ __device__ __forceinline__ void hll_speed (const Phys &ph, const double *vL, con
   mach = scrh;
 }
 
+// UCT_HLL: the Riemann fan speeds of the face, as CT_StoreUpwindEMF keeps them
+// (ct_emf.c:144-147): max(0, -SL), max(0, SR).  Stored as soon as they are known so that
+// they do not stay in registers through the solve; null pointers = not wanted.
+__device__ __forceinline__ void store_fan_speeds (double *pSL, double *pSR, double SL, double SR)
+{
+  if (pSL){ *pSL = maxv (0.0, -SL); *pSR = maxv (0.0, SR); }
+}
+
 // ---------------------------------------------------------------------------
 //  Riemann solvers.  in: vL, vR (interface states), uL, uR; out: flux[NV]
 //  (slot bn is not meaningful), press, cmax, mach (candidate for g_maxMach).
@@ -404,7 +412,8 @@ __device__ __forceinline__ void hll_speed (const Phys &ph, const double *vL, con
 template <int DIR, int NC>
 __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, const double *vR,
                                              const double *uL, const double *uR,
-                                             double *flux, double &press, double &cmax, double &mach)
+                                             double *flux, double &press, double &cmax, double &mach,
+                                             double *pSL = nullptr, double *pSR = nullptr)
 {
   double fL[NV], fR[NV], pL, pR, a2L, a2R, SL, SR, scrh;
   a2L = pg_div (ph.gamma*vL[PRS], vL[RHO]);
@@ -412,6 +421,7 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
   mhd_flux<DIR, NC>(vL, uL, fL, pL);
   mhd_flux<DIR, NC>(vR, uR, fR, pR);
   hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
+  store_fan_speeds (pSL, pSR, SL, SR);
   scrh = maxv(fabs(SL), fabs(SR));
   cmax = scrh;
   if (SL > 0.0){
@@ -504,7 +514,8 @@ __device__ __forceinline__ void hlld_side_flux (const Phys &ph, const double *v,
 
 template <int DIR, int NC>
 __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, const double *vR,
-                                              double *flux, double &press, double &cmax, double &mach)
+                                              double *flux, double &press, double &cmax, double &mach,
+                                              double *pSL = nullptr, double *pSR = nullptr)
 {
   typedef Dirs<DIR> D;
   const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
@@ -527,6 +538,7 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
     const float aL = pg_sqrtf ((float)(gpL*irL)), aR = pg_sqrtf ((float)(gpR*irR));
     mach = (double)__fdividef ((float)(fabs (vL[VXn]) + fabs (vR[VXn])), aL + aR);
   }
+  store_fan_speeds (pSL, pSR, SL, SR);
   cmax = maxv (fabs (SL), fabs (SR));
   const double ptL = fma (0.5, b2L, vL[PRS]), ptR = fma (0.5, b2R, vR[PRS]);
 
@@ -750,7 +762,8 @@ __device__ __noinline__ void riemann_hlld_fallback (const Phys &ph, const double
 template <int DIR, int NC>
 __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, const double *vR,
                                               const double *uL, const double *uR,
-                                              double *flux, double &press, double &cmax, double &mach)
+                                              double *flux, double &press, double &cmax, double &mach,
+                                              double *pSL = nullptr, double *pSR = nullptr)
 {
   typedef Dirs<DIR> D;
   const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
@@ -766,6 +779,7 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
   mhd_flux<DIR, NC>(vL, uL, fL, ptL);
   mhd_flux<DIR, NC>(vR, uR, fR, ptR);
   hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
+  store_fan_speeds (pSL, pSR, SL, SR);
 
   scrh = maxv(fabs(SL), fabs(SR));
   cmax = scrh;
@@ -938,7 +952,8 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
 template <int DIR, int NC>
 __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, const double *vR,
                                              const double *uL, const double *uR,
-                                             double *flux, double &press, double &cmax, double &mach)
+                                             double *flux, double &press, double &cmax, double &mach,
+                                             double *pSL = nullptr, double *pSR = nullptr)
 {
   typedef Dirs<DIR> D;
   const int VXn = D::vn, VXt = D::vt, VXb = D::vb, BXn = D::bn, BXt = D::bt, BXb = D::bb;
@@ -1167,6 +1182,7 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
 
   cmax = fabs(u) + cf;
   mach = fabs(pg_div (u, a));
+  store_fan_speeds (pSL, pSR, lambda[KFASTM], lambda[KFASTP]);      // roe.c:681-682
   const int nw = (NC == 3 ? 8 : 6);
   PG_UNROLL for (int kk = 0; kk < NW; kk++) alambda[kk] = fabs(lambda[kk]);
 
@@ -1189,15 +1205,16 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
 template <int SOLVER, int DIR, int NC>
 __device__ __forceinline__ bool riemann (const Phys &ph, const double *vL, const double *vR,
                                          const double *uL, const double *uR,
-                                         double *flux, double &press, double &cmax, double &mach)
+                                         double *flux, double &press, double &cmax, double &mach,
+                                         double *pSL = nullptr, double *pSR = nullptr)
 {
 #ifdef PG_FAST
-  if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, flux, press, cmax, mach); return true; }
+  if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, flux, press, cmax, mach, pSL, pSR); return true; }
 #else
-  if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach); return true; }
+  if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }
 #endif
-  else if (SOLVER == SOLVER_HLL){ riemann_hll<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach); return true; }
-  else return riemann_roe<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach);
+  else if (SOLVER == SOLVER_HLL){ riemann_hll<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }
+  else return riemann_roe<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
 }
 
 } // namespace PG_NS

@@ -49,6 +49,8 @@ struct PlutoGpu {
   double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   double *ex, *ey, *ez;
   double *cdt;
+  double *dvel[3][3];              // UCT_HLL only: limited velocity slopes d v_c / d x_d (own allocation)
+  void   *dvel_pool;
   double *scratch;                 // = first array after the state buffers
   size_t  scratch_doubles;
   signed char *sv[3];
@@ -132,7 +134,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->solver < 0 || cfg->solver > 2) return fail ("bad solver");
   if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
   if (cfg->limiter < 0 || cfg->limiter > PLUTO_GPU_LIM_MC) return fail ("bad limiter");
-  if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT0) return fail ("bad emf_average");
+  if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -190,6 +192,14 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   signed char *c = (signed char *)p;
   for (int d = 0; d < 3; d++){ h->sv[d] = c; c += tot_al; }
 
+  if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL){
+    const size_t nb = (size_t)g.dims*g.dims*tot_al*sizeof (double);
+    if (cudaMalloc (&h->dvel_pool, nb) != cudaSuccess) return fail ("cudaMalloc of %zu bytes (UCT_HLL slopes) failed", nb);
+    CU (cudaMemset (h->dvel_pool, 0, nb));
+    double *q = (double *)h->dvel_pool;
+    for (int c = 0; c < g.dims; c++) for (int d = 0; d < g.dims; d++){ h->dvel[c][d] = q; q += tot_al; }
+    h->pool_bytes += nb;
+  }
   CU (cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking));
   CU (cudaMalloc ((void **)&h->red, RED_N*sizeof (unsigned long long)));
   CU (cudaMemset (h->red, 0, RED_N*sizeof (unsigned long long)));
@@ -212,6 +222,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaSetDevice (h->cfg.device);
   cudaStreamSynchronize (h->stream);
   cudaFree (h->pool);
+  if (h->dvel_pool) cudaFree (h->dvel_pool);
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
   cudaFree (h->dtdev); cudaFreeHost (h->dthost);
@@ -515,6 +526,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
   s.stage1 = (stage == 1);
   s.limiter = h->cfg.limiter;
+  s.avg = h->cfg.emf_average;
   // EXACT: later stages continue from the conservative state the previous stage
   // left (as the reference does); FAST: rebuild it from the primitives, which
   // saves reading U in the x1 sweep and differs by round-off only
@@ -531,6 +543,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
+    for (int c = 0; c < 3; c++) s.dvel[c] = h->dvel[c][dir];
     const int recon = h->cfg.recon;
     if (dir > 0 || fuse_xy){
       // zones per thread along a marching sweep: long enough to amortise the
@@ -554,6 +567,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     int r;
     if (dir == 0 && fuse_xy){
       s.Bn2 = h->Bs[sp.in][1]; s.e3 = h->ezj; s.e4 = h->exj; s.sv2 = h->sv[1];
+      for (int c = 0; c < 3; c++) s.dvel2[c] = h->dvel[c][1];
       s.inv_dl2 = 1.0/g.dx[1];
       s.last_dir = (g.dims == 2);
       const int te = tbegin (h, KC_SWEEP_X);
@@ -583,6 +597,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   }
   c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine; c.dtp = h->dtdev;
   c.avg = h->cfg.emf_average;
+  for (int q = 0; q < 3; q++) for (int d = 0; d < 3; d++) c.dvel[q][d] = h->dvel[q][d];
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 

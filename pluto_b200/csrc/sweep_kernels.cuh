@@ -122,6 +122,15 @@ __device__ __forceinline__ void store_face_emf_p (double *e1, double *e2, signed
   }
   sv[id] = s;
 }
+// UCT_HLL: limited velocity slopes of a reconstructed zone (ct_stag_slopes.c:16-44)
+template <int NC>
+__device__ __forceinline__ void store_vel_slopes (double *const *dv, int id, const double *vp, const double *vm)
+{
+  dv[0][id] = vp[VX1] - vm[VX1];
+  dv[1][id] = vp[VX2] - vm[VX2];
+  if (NC == 3) dv[2][id] = vp[VX3] - vm[VX3];
+}
+
 template <int DIR, int NC>
 __device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, const double *F)
 { store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F); }
@@ -133,7 +142,7 @@ __device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, cons
 #define PG_XROWS 16          // rows a warp walks through (software-pipelined)
 #endif
 
-template <int RECON, int SOLVER, int NC>
+template <int RECON, int SOLVER, int NC, bool HLL>      // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds + velocity slopes)
 __global__ void __launch_bounds__(128, PG_MINB_X)
 sweep_x_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -234,9 +243,12 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
     double uL[NV], uR[NV], F[NV], press, cmax, mach;
     prim_to_cons<NC>(ph, vp, uL);
     prim_to_cons<NC>(ph, vR, uR);
-    bool ok = riemann<SOLVER, DIR, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach);
+    constexpr bool hll = HLL;
+    if (hll && zone_ok && i >= g.beg[0] - 1) store_vel_slopes<NC>(a.dvel, id, vp, vm);
+    bool ok = riemann<SOLVER, DIR, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach,
+                                       hll && emf_ok ? a.e1 + id : nullptr, hll && emf_ok ? a.e2 + id : nullptr);
 
-    if (emf_ok) store_face_emf<DIR, NC>(a, id, F);
+    if (emf_ok && !hll) store_face_emf<DIR, NC>(a, id, F);
     if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
     if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
 
@@ -301,7 +313,7 @@ __host__ __device__ constexpr int march_slots (int recon)
   return 8*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + 8 + 7 + (recon == RECON_PPM ? 8 : 0)
          + march_prefetch (recon) + 6*(march_prefetch (recon) + 1);
 }
-template <int DIR, int RECON, int SOLVER, int NC>
+template <int DIR, int RECON, int SOLVER, int NC, bool HLL>
 __global__ void __launch_bounds__(128, PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -390,6 +402,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
       plm_zone<NC>(a.limiter, vb_, dvm, dvp, vpL, vm_unused);
+      if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
@@ -399,12 +412,14 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       ppm_interface<NC>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
       ppm_interface<NC>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
       ppm_zone<NC>(vb_, Wm, Wf, vpL, vm_unused);
+      if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
       PG_FOR_NV(nv) C_WF(nv) = Wf[nv];
     }
     PG_FOR_NV(nv) C_VP(nv) = vpL[nv];
     PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
   }
   double my_mach = 0.0, my_cdt = 0.0;
+  constexpr bool hll = HLL;
 
   for (int f = c0 - 1; f <= c1; f++, id += sD){
     // id = zone f; interface f+1/2 lies between zone f and zone f+1
@@ -449,6 +464,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
         ppm_zone<NC>(vc_, Wf, Wn, vpn, vR);
         PG_FOR_NV(nv) C_WF(nv) = Wn[nv];
       }
+      if (hll && in_range) store_vel_slopes<NC>(a.dvel, id + sD, vpn, vR);      // zone f+1
       PG_FOR_NV(nv){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
     }
     vL[D::bn] = bn; vR[D::bn] = bn;
@@ -467,11 +483,13 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     double uL[NV], uR[NV], F[NV], press, cmax, mach;
     prim_to_cons<NC>(ph, vL, uL);
     prim_to_cons<NC>(ph, vR, uR);
-    bool ok = riemann<SOLVER, DIR, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach);
+    const bool sf = hll && in_range && (f >= c0 || chunk == 0);
+    bool ok = riemann<SOLVER, DIR, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach,
+                                       sf ? a.e1 + id : nullptr, sf ? a.e2 + id : nullptr);
     if (in_range){
       my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
-      if (f >= c0 || chunk == 0) store_face_emf<DIR, NC>(a, id, F);
+      if (!hll && (f >= c0 || chunk == 0)) store_face_emf<DIR, NC>(a, id, F);
     }
     const double pp = C_FP(5), cp = C_FP(6);
     if (upd && f >= c0){
@@ -533,7 +551,7 @@ __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
   return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128)*sizeof (double);
 }
 
-template <int RECON, int SOLVER, int NC>
+template <int RECON, int SOLVER, int NC, bool HLL>
 __global__ void __launch_bounds__(128, PG_MINB_XY)
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -616,6 +634,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
       plm_zone<NC>(a.limiter, vb_, dvm, dvp, vpL, vm_unused);
+      if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
@@ -625,12 +644,14 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       ppm_interface<NC>(vz_, va_, vb_, vc_, Wm);
       ppm_interface<NC>(va_, vb_, vc_, vd_, Wf);
       ppm_zone<NC>(vb_, Wm, Wf, vpL, vm_unused);
+      if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
       PG_FOR_NV(nv) C_WF(nv) = Wf[nv];
     }
     PG_FOR_NV(nv) C_VP(nv) = vpL[nv];
     PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
   }
   double my_mach = 0.0, my_cdt = 0.0;
+  constexpr bool hll = HLL;
   for (int f = c0 - 1; f <= f_end; f++, id += sD){
     // id = zone (k, f, i).  x2 interface f+1/2 lies between rows f and f+1; the x1 faces
     // solved here are those of row f.
@@ -676,8 +697,10 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       double uL[NV], uR[NV], F[NV], press, cmax, mach;
       prim_to_cons<NC>(ph, vp, uL);
       prim_to_cons<NC>(ph, vR, uR);
-      bool ok = riemann<SOLVER, 0, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach);
-      if (xemf_ok) store_face_emf_p<0, NC>(a.e1, a.e2, a.sv, id, F);
+      if (hll && zone_ok && i >= g.beg[0] - 1) store_vel_slopes<NC>(a.dvel, id, vp, vm);
+      bool ok = riemann<SOLVER, 0, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach,
+                                       hll && xemf_ok ? a.e1 + id : nullptr, hll && xemf_ok ? a.e2 + id : nullptr);
+      if (xemf_ok && !hll) store_face_emf_p<0, NC>(a.e1, a.e2, a.sv, id, F);
       if (xface_ok) my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && xface_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
       double Fm[NV], pm, cm;
@@ -714,17 +737,20 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         ppm_zone<NC>(vc_, Wf, Wn, vpn, vR);
         PG_FOR_NV(nv) C_WF(nv) = Wn[nv];
       }
+      if (hll && col_ok) store_vel_slopes<NC>(a.dvel2, id + sD, vpn, vR);       // row f+1
       PG_FOR_NV(nv){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
       vL[DY::bn] = bny; vR[DY::bn] = bny;
       double uL[NV], uR[NV], F[NV], press, cmax, mach;
       prim_to_cons<NC>(ph, vL, uL);
       prim_to_cons<NC>(ph, vR, uR);
-      bool ok = riemann<SOLVER, 1, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach);
+      const bool sfy = hll && yemf_ok && (f >= c0 || chunk == 0);
+      bool ok = riemann<SOLVER, 1, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach,
+                                       sfy ? a.e3 + id : nullptr, sfy ? a.e4 + id : nullptr);
       if (col_ok){
         my_mach = mach > my_mach ? mach : my_mach;
         if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
       }
-      if (yemf_ok && (f >= c0 || chunk == 0)) store_face_emf_p<1, NC>(a.e3, a.e4, a.sv2, id, F);
+      if (!hll && yemf_ok && (f >= c0 || chunk == 0)) store_face_emf_p<1, NC>(a.e3, a.e4, a.sv2, id, F);
       const double pp = C_FP(5), cp = C_FP(6);
       if (upd && f >= c0){
         double u0[NV], r;
@@ -776,15 +802,17 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
   const long long nwarp = nseg*(nc == 3 ? g.n[2] + 2 : 1)*a.nchunk;
   const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
   const size_t smem = xy_smem_bytes (recon);
-#define PG_LXY(R, C) do { auto kfn = sweep_xy_kernel<R, SOLVER, C>;                                   \
+#define PG_LXY1(R, C, H) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H>;                            \
       static bool attr_set = false;                                                                   \
       if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+#define PG_LXY(R, C) do { if (a.avg == 3) PG_LXY1(R, C, true); else PG_LXY1(R, C, false); } while (0)
   if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
   else if (recon == RECON_PLM && nc == 2) PG_LXY(RECON_PLM, 2);
   else if (recon == RECON_PPM && nc == 3) PG_LXY(RECON_PPM, 3);
   else                                    PG_LXY(RECON_PPM, 2);
 #undef PG_LXY
+#undef PG_LXY1
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 
@@ -805,7 +833,8 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long nwarp = nseg*((nrows + PG_XROWS - 1)/PG_XROWS);
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
     const size_t xsmem = (size_t)(TPB/32)*2*9*36*sizeof (double);
-#define PG_LX(R, C) sweep_x_kernel<R, SOLVER, C><<<nb, TPB, xsmem, s>>>(a)
+#define PG_LX(R, C) do { if (a.avg == 3) sweep_x_kernel<R, SOLVER, C, true><<<nb, TPB, xsmem, s>>>(a); \
+                         else            sweep_x_kernel<R, SOLVER, C, false><<<nb, TPB, xsmem, s>>>(a); } while (0)
     if      (recon == RECON_PLM && nc == 3) PG_LX(RECON_PLM, 3);
     else if (recon == RECON_PLM && nc == 2) PG_LX(RECON_PLM, 2);
     else if (recon == RECON_PPM && nc == 3) PG_LX(RECON_PPM, 3);
@@ -817,12 +846,13 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long nthr = npen*a.nchunk;
     const unsigned nb = (unsigned)((nthr + TPB - 1)/TPB);
     const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
-#define PG_LM(DD, R, C) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C>;                       \
+#define PG_LM1(DD, R, C, H) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H>;                \
       static bool attr_set = false;                                                                   \
       if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
         attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+#define PG_LM(DD, R, C) do { if (a.avg == 3) PG_LM1(DD, R, C, true); else PG_LM1(DD, R, C, false); } while (0)
     if (dir == 1){
       if      (recon == RECON_PLM && nc == 3) PG_LM(1, RECON_PLM, 3);
       else if (recon == RECON_PLM && nc == 2) PG_LM(1, RECON_PLM, 2);
@@ -833,6 +863,7 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       else                    PG_LM(2, RECON_PPM, 3);
     }
 #undef PG_LM
+#undef PG_LM1
   }
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }

@@ -25,6 +25,11 @@ CASES = [
     ("ot2d_mm", RefConfig(problem="ot", dims=2, n=(28, 24, 1), first_dt=1.5e-2, limiter="mm"), 8),
     ("turb3d_um", RefConfig(problem="turb", dims=3, n=(8, 10, 12), first_dt=2e-2, cfl=0.3, limiter="um"), 5),
     ("blast2d_os", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, limiter="os"), 8),
+    # UCT_HLL, the reference's default average (ct.h:43-45): Blast #10 = MC_LIM + roe
+    ("blast3d_mc_uct_hll_roe", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, limiter="mc", emf="uct_hll", solver="roe"), 6),
+    ("ot2d_uct_hll", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, emf="uct_hll"), 8),
+    ("turb3d_uct_hll", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, emf="uct_hll"), 6),
+    ("rotor2d_ppm_uct_hll_hll", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), recon="ppm", first_dt=2e-3, emf="uct_hll", solver="hll"), 8),
 ]
 
 

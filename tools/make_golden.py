@@ -61,6 +61,13 @@ CASES = {
     "ot2d_mm": (RefConfig(problem="ot", dims=2, n=(24, 32, 1), first_dt=2.5e-2, cfl=0.4, limiter="mm"), 10),
     "turb3d_um": (RefConfig(problem="turb", dims=3, n=(12, 8, 16), first_dt=3e-2, cfl=0.3, limiter="um"), 10),
     "blast2d_os": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, limiter="os"), 20),
+    # UCT_HLL, the reference's default CT_EMF_AVERAGE (ct.h:43-45); Blast #10 = MC_LIM + roe + UCT_HLL
+    "blast3d_mc_uct_hll_roe": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, limiter="mc",
+                                         emf="uct_hll", solver="roe"), 12),
+    "ot2d_uct_hll": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, emf="uct_hll"), 20),
+    "turb3d_uct_hll": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, emf="uct_hll"), 10),
+    "rotor2d_ppm_uct_hll_hll": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), recon="ppm", solver="hll",
+                                          first_dt=2.5e-3, cfl=0.4, emf="uct_hll"), 20),
 }
 
 
