@@ -54,7 +54,7 @@ __device__ __forceinline__ double upw (signed char s, double d0, double d1)
 #ifndef PG_CT_MINB
 #define PG_CT_MINB 8
 #endif
-template <int NC>
+template <int NC, int AVG>          // AVG: PLUTO_GPU_EMF_* (compile time: the averages share no code)
 __global__ void __launch_bounds__(128, PG_CT_MINB)
 ct_emf_kernel (const __grid_constant__ CtArgs a)
 {
@@ -68,7 +68,7 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
   const long long id = gidx (g, k, j, i);
   const long long sx = 1, sy = g.S1, sz = g.S12;
 
-  if (a.avg == 3){
+  if (AVG == 3){
     // UCT_HLL: CT_GetStagSlopes (ct_stag_slopes.c:52-95) + CT_EMF_HLL_Solver (ct_emf_average.c:180-359,
     // Londrillo & Del Zanna 2004, eq. 56) in the reference's operation order.  The face arrays hold
     // the fan speeds max(0,-SL) [e1 of the direction] and max(0,SR) [e2]; the staggered slopes are
@@ -130,11 +130,11 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
     }
     return;
   }
-  if (a.avg != 0){
+  if (AVG != 0){
     // ARITHMETIC: CT_EMF_ArithmeticAverage (emf, 0.25) (ct_emf.c:241-243).  UCT0: the face EMFs
     // are first replaced by 2 face - mean of the two adjacent cell-centred EMFs (ct_emf.c:261-283);
     // evaluated here per use instead of in place.
-    const bool u0 = (a.avg == 2);
+    constexpr bool u0 = (AVG == 2);
     auto fz_i = [&] (long long q){ double e = a.ezi[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e3<NC>(a, q) + cell_e3<NC>(a, q + sx)); } return e; };
     auto fz_j = [&] (long long q){ double e = a.ezj[q]; if (u0){ e *= 2.0; e -= 0.5*(cell_e3<NC>(a, q) + cell_e3<NC>(a, q + sy)); } return e; };
     a.ez[id] = 0.25*(fz_i (id) + fz_i (id + sy) + fz_j (id) + fz_j (id + sx));
@@ -426,8 +426,13 @@ int launch_ct_emf (const CtArgs &a, cudaStream_t s)
 {
   const Geom &g = a.g;
   const long long n = (long long)(g.n[0] + 1)*(g.n[1] + 1)*(g.dims == 3 ? g.n[2] + 1 : 1);
-  if (g.dims == 3) ct_emf_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
-  else             ct_emf_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
+#define PG_LE(C) do { switch (a.avg){                                                   \
+      case 1:  ct_emf_kernel<C, 1><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
+      case 2:  ct_emf_kernel<C, 2><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
+      case 3:  ct_emf_kernel<C, 3><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
+      default: ct_emf_kernel<C, 0><<<nblocks (n, 128), 128, 0, s>>>(a); } } while (0)
+  if (g.dims == 3) PG_LE(3); else PG_LE(2);
+#undef PG_LE
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 
