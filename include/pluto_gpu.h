@@ -69,6 +69,8 @@ typedef struct {
   double small_pr;     /* g_smallPressure                                     */
   int    limiter;      /* PLUTO_GPU_LIM_*  (0 = DEFAULT)                      */
   int    emf_average;  /* PLUTO_GPU_EMF_*  (0 = UCT_CONTACT)                  */
+  int    shock_flattening; /* SHOCK_FLATTENING: 0 NO, 1 MULTID (Src/flag_shock.c:79-230;
+                              LINEAR reconstruction only)                      */
 } PlutoGpuConfig;
 
 typedef struct PlutoGpu PlutoGpu;

@@ -48,8 +48,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
         && CT_EMF_AVERAGE != UCT_HLL)
   #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT / ARITHMETIC / UCT0 / UCT_HLL, DIMENSIONS == COMPONENTS"
 #endif
-#if CHAR_LIMITING == YES || SHOCK_FLATTENING != NO || LIMITER == FOURTH_ORDER_LIM
-  #error "libpluto_gpu: CHAR_LIMITING, SHOCK_FLATTENING and FOURTH_ORDER_LIM are not available on the GPU"
+#if CHAR_LIMITING == YES || LIMITER == FOURTH_ORDER_LIM \
+    || (SHOCK_FLATTENING != NO && (SHOCK_FLATTENING != MULTID || RECONSTRUCTION != LINEAR))
+  #error "libpluto_gpu: CHAR_LIMITING, FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID with LINEAR are not available on the GPU"
 #endif
 
   if (gpu == NULL){
@@ -73,6 +74,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
                  LIMITER == VANALBADA_LIM ? PLUTO_GPU_LIM_VANALBADA : LIMITER == OSPRE_LIM  ? PLUTO_GPU_LIM_OSPRE  :
                  LIMITER == UMIST_LIM     ? PLUTO_GPU_LIM_UMIST     : LIMITER == VANLEER_LIM ? PLUTO_GPU_LIM_VANLEER :
                  LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
+    c.shock_flattening = (SHOCK_FLATTENING == MULTID);     /* flag_shock.c */
     c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
                      CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 :
                      CT_EMF_AVERAGE == UCT_HLL ? PLUTO_GPU_EMF_UCT_HLL : PLUTO_GPU_EMF_UCT_CONTACT);
@@ -88,6 +90,11 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     c.small_pr = g_smallPressure;
     if (pluto_gpu_create (&c, &gpu) != 0){
       print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+      QUIT_PLUTO(1);
+    }
+    if (pluto_gpu_nghost (gpu) != grid->nghost[IDIR]){      /* the host arrays are read with this padding */
+      print ("! AdvanceStep(gpu): the library expects %d ghost zones, the grid has %d (Src/get_nghost.c)\n",
+             pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
       QUIT_PLUTO(1);
     }
     print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones\n",

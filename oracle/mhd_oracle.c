@@ -51,6 +51,9 @@ struct Oracle {
   double *SfL[3], *SfR[3];             /* max(0,-SL), max(0,SR) at the faces of each direction */
   double *dvel[3][3];                  /* dvel[c][d] = d v_c / d x_d (limited slope vp - vm)   */
   double cur_SL, cur_SR;               /* Riemann fan speeds of the interface just solved      */
+  unsigned char *flag;                 /* SHOCK_FLATTENING MULTID: FLAG_MINMOD 1, FLAG_HLL 4 (pluto.h:192-194) */
+  unsigned char *pflag;                /* ... of the current pencil                            */
+  int use_hll;                         /* the interface being solved takes the HLL flux        */
   double *C_dt;
   /* pencil scratch */
   int np;
@@ -77,6 +80,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   Oracle *o = (Oracle *)calloc(1, sizeof(Oracle));
   o->c  = *cfg;
   o->ng = (cfg->recon == ORC_RECON_PPM ? 3 : 2);
+  if (cfg->shock_flattening && o->ng < 3) o->ng = 3;       /* get_nghost.c:67-77 */
   for (d = 0; d < 3; d++){
     if (d < cfg->dims){
       o->T[d]   = cfg->n[d] + 2*o->ng;
@@ -100,6 +104,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->svy = (signed char *)calloc((size_t)o->tot, 1);
   o->svz = (signed char *)calloc((size_t)o->tot, 1);
   o->C_dt = dalloc(o->tot);
+  o->flag = (unsigned char *)calloc((size_t)o->tot, 1);
   if (cfg->emf_average == ORC_EMF_UCT_HLL){
     int c;
     for (d = 0; d < 3; d++){
@@ -118,6 +123,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->flux = calloc((size_t)o->np, sizeof(*o->flux));
   o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
   o->SLp = dalloc(o->np) + 4; o->SRp = dalloc(o->np) + 4;
+  o->pflag = (unsigned char *)calloc((size_t)o->np, 1) + 4;
   /* shift pencil arrays so that index -2 is addressable */
   o->v += 4; o->vp += 4; o->vm += 4; o->dv += 4; o->flux += 4;
   o->press += 4; o->cmax += 4; o->bn += 4;
@@ -425,7 +431,9 @@ static void states_plm (Oracle *o, int beg, int end, int bxn)
     double dvl[NV];
     for (nv = 0; nv < NV; nv++){
       double dvp = dv[i][nv], dvm = dv[i-1][nv], lim;
-      if (o->c.limiter != ORC_LIM_DEFAULT){   /* same limiter for all variables, plm_states.c:234-236 */
+      if (o->pflag[i] & 1){                   /* FLAG_MINMOD, plm_states.c:174-180 */
+        lim = (dvp*dvm > 0.0 ? ABS_MIN(dvp, dvm) : 0.0);
+      }else if (o->c.limiter != ORC_LIM_DEFAULT){   /* same limiter for all variables, plm_states.c:234-236 */
         lim = single_limiter (o->c.limiter, dvp, dvm);
       }else if (nv == RHO){                   /* MC */
         if (dvp*dvm > 0.0){
@@ -578,6 +586,16 @@ static void riemann_hlld (Oracle *o, const double *vL, const double *vR,
   }else if (SR <= 0.0){
     for (nv = 0; nv < NV; nv++) flux[nv] = fR[nv];
     *press = ptR;
+    return;
+  }
+
+  if (o->use_hll){                       /* hlld.c:149-160 */
+    scrh = 1.0/(SR - SL);
+    for (nv = 0; nv < NV; nv++){
+      flux[nv]  = SR*SL*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
+      flux[nv] *= scrh;
+    }
+    *press = (SR*ptL - SL*ptR)*scrh;
     return;
   }
 
@@ -750,6 +768,7 @@ static void update_stage (Oracle *o, double dt)
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
         for (nv = 0; nv < NV; nv++) o->v[n][nv] = o->Vc[nv][id];
         o->bn[n] = o->Vs[dir][id];
+        o->pflag[n] = o->flag[id];
       }
       /* States (nbeg-1 .. nend+1), :193 */
       if (o->c.recon == ORC_RECON_PLM) states_plm (o, nbeg-1, nend+1, q.bn);
@@ -760,9 +779,11 @@ static void update_stage (Oracle *o, double dt)
         double uL[NV], uR[NV];
         prim_to_cons (o, o->vp[n],   uL);          /* plm_states.c:310-311 */
         prim_to_cons (o, o->vm[n+1], uR);
+        /* SHOCK_FLATTENING MULTID: HLL flux where either zone lies in a shock (hlld.c:149-160, roe.c:165-189) */
+        o->use_hll = ((o->pflag[n] & 4) || (o->pflag[n+1] & 4));
         if      (o->c.solver == ORC_SOLVER_HLLD)
           riemann_hlld (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
-        else if (o->c.solver == ORC_SOLVER_HLL)
+        else if (o->c.solver == ORC_SOLVER_HLL || o->use_hll)
           riemann_hll  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
         else
           riemann_roe  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
@@ -1151,6 +1172,48 @@ static void cons_to_prim_3d (Oracle *o)      /* mappers3D.c:16-72, DOM box */
   }
 }
 
+static void flag_shock (Oracle *o)
+/* flag_shock.c:79-230, SHOCK_FLATTENING MULTID, Cartesian, ideal EOS; flags zeroed every
+   step (main.c:329), evaluated once per step after the first Boundary call (rk_step.c:86-88) */
+{
+  int i, j, k, dims = o->c.dims;
+  int koff = (dims == 3 ? 1 : 0);
+  const double *vx1 = o->Vc[VX1], *vx2 = o->Vc[VX2], *vx3 = o->Vc[VX3], *pt = o->Vc[PRS];
+  memset (o->flag, 0, (size_t)o->tot);
+  for (k = koff; k < o->T[2] - koff; k++)
+  for (j = 1; j < o->T[1] - 1; j++)
+  for (i = 1; i < o->T[0] - 1; i++){
+    double dvx1, dvx2, dvx3 = 0.0, divv, gradp, pt_min, pt_min1, pt_min2, pt_min3, dpx1, dpx2, dpx3;
+    dvx1 = (vx1[I3(k,j,i+1)] - vx1[I3(k,j,i-1)])/o->c.dx[0];
+    dvx2 = (vx2[I3(k,j+1,i)] - vx2[I3(k,j-1,i)])/o->c.dx[1];
+    if (dims == 3){
+      dvx3 = (vx3[I3(k+1,j,i)] - vx3[I3(k-1,j,i)])/o->c.dx[2];
+      divv = dvx1 + dvx2 + dvx3;
+    }else divv = dvx1 + dvx2;
+    if (divv < 0.0){
+      pt_min  = pt[I3(k,j,i)];
+      pt_min1 = MINV(pt[I3(k,j,i+1)], pt[I3(k,j,i-1)]);
+      pt_min2 = MINV(pt[I3(k,j+1,i)], pt[I3(k,j-1,i)]);
+      pt_min  = MINV(pt_min, pt_min1);
+      pt_min  = MINV(pt_min, pt_min2);
+      dpx1 = fabs(pt[I3(k,j,i+1)] - pt[I3(k,j,i-1)]);
+      dpx2 = fabs(pt[I3(k,j+1,i)] - pt[I3(k,j-1,i)]);
+      if (dims == 3){
+        pt_min3 = MINV(pt[I3(k+1,j,i)], pt[I3(k-1,j,i)]);
+        pt_min  = MINV(pt_min, pt_min3);
+        dpx3 = fabs(pt[I3(k+1,j,i)] - pt[I3(k-1,j,i)]);
+        gradp = dpx1 + dpx2 + dpx3;
+      }else gradp = dpx1 + dpx2;
+      if (gradp > 5.0*pt_min){                 /* EPS_PSHOCK_FLATTEN, flag_shock.c:69-71 */
+        o->flag[I3(k,j,i)] |= 4 | 1;
+        o->flag[I3(k,j,i+1)] |= 1; o->flag[I3(k,j,i-1)] |= 1;
+        o->flag[I3(k,j-1,i)] |= 1; o->flag[I3(k,j+1,i)] |= 1;
+        if (dims == 3){ o->flag[I3(k-1,j,i)] |= 1; o->flag[I3(k+1,j,i)] |= 1; }
+      }
+    }
+  }
+}
+
 int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
 {
   int i, j, k, nv, d, id, dims = o->c.dims;
@@ -1162,6 +1225,7 @@ int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
   /* ---- stage 1 (rk_step.c:85-139) ---- */
   o->stage = 1;
   boundary (o);
+  if (o->c.shock_flattening) flag_shock (o);
   prim_to_cons_3d (o);
   for (nv = 0; nv < NV; nv++)
     for (k = o->beg[2]; k <= o->end[2]; k++) for (j = o->beg[1]; j <= o->end[1]; j++)

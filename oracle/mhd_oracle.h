@@ -47,6 +47,7 @@ typedef struct {
   double small_pr;      /* g_smallPressure (1e-12)                         */
   int    limiter;       /* ORC_LIM_*  (PLM only)                           */
   int    emf_average;   /* ORC_EMF_*                                       */
+  int    shock_flattening; /* 0 NO, 1 MULTID (flag_shock.c:79-230)            */
 } OracleConfig;
 
 typedef struct Oracle Oracle;

@@ -14,7 +14,8 @@
 #   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3
 #   optional suffixes:  _l{fl,mm,va,os,um,vl,mc}  single LIMITER for all variables
 #                                                 (Src/States/plm_coeffs.h:72-123)
-#                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE (Src/MHD/CT/ct_emf.c:241-283)
+#                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE
+#                       _sfl                      SHOCK_FLATTENING MULTID (Src/flag_shock.c) (Src/MHD/CT/ct_emf.c:241-283)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ORACLE="$(cd "$HERE/.." && pwd)"
@@ -46,6 +47,9 @@ for VARIANT in "$@"; do
   esac
   case "$VARIANT" in
     *_earith*) EMFAVG=ARITHMETIC ;; *_euct0*) EMFAVG=UCT0 ;; *_euct_hll*) EMFAVG=UCT_HLL ;; *) EMFAVG=UCT_CONTACT ;;
+  esac
+  case "$VARIANT" in
+    *_sfl*) SHOCKFLAT=MULTID ;; *) SHOCKFLAT=NO ;;
   esac
   B="$ORACLE/_build/$VARIANT"
   mkdir -p "$B"
@@ -93,6 +97,7 @@ for VARIANT in "$@"; do
 /* [Beg] user-defined constants (do not change this line) */
 
 #define  LIMITER                        $LIMITER
+#define  SHOCK_FLATTENING               $SHOCKFLAT
 #define  CT_EMF_AVERAGE                 $EMFAVG
 #define  CT_EN_CORRECTION               NO
 #define  ASSIGN_VECTOR_POTENTIAL        YES

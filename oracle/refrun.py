@@ -43,6 +43,7 @@ class RefConfig:
     solver: str = "hlld"                # hlld | hll | roe
     tstep: str = "rk2"                  # rk2 | rk3
     limiter: str = "default"            # default | fl mm va os um vl mc  (LIMITER, plm only)
+    flatten: bool = False               # SHOCK_FLATTENING MULTID
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
     cfl: float = 0.4
     cfl_max_var: float = 1.1
@@ -64,6 +65,8 @@ class RefConfig:
             v += "_l" + self.limiter
         if self.emf != "uct_contact":
             v += "_e" + self.emf
+        if self.flatten:
+            v += "_sfl"
         return v
 
     def binary(self) -> str:

@@ -34,7 +34,8 @@ class PlutoGpuConfig(C.Structure):
     _fields_ = [("dims", C.c_int), ("n", C.c_int * 3), ("recon", C.c_int), ("solver", C.c_int),
                 ("rk_order", C.c_int), ("bc", C.c_int * 6), ("arith", C.c_int), ("device", C.c_int),
                 ("gamma", C.c_double), ("dx", C.c_double * 3), ("small_dn", C.c_double),
-                ("small_pr", C.c_double), ("limiter", C.c_int), ("emf_average", C.c_int)]
+                ("small_pr", C.c_double), ("limiter", C.c_int), ("emf_average", C.c_int),
+                ("shock_flattening", C.c_int)]
 
 
 class PlutoGpuStepInfo(C.Structure):

@@ -24,6 +24,8 @@
 
 namespace PG_NS {
 
+static inline unsigned nblocks (long long n, int tpb) { return (unsigned)((n + tpb - 1)/tpb); }
+
 // ---------------------------------------------------------------------------
 //  edge EMFs
 // ---------------------------------------------------------------------------
@@ -384,6 +386,70 @@ bc_kernel (const __grid_constant__ BcArgs a)
 }
 
 // ---------------------------------------------------------------------------
+//  SHOCK_FLATTENING MULTID: FlagShock (flag_shock.c:79-230, Cartesian, ideal EOS).
+//  Pass 1: a zone with div v < 0 and |grad p| > 5 min(p) lies in a shock; pass 2 (gather
+//  form of the reference's scatter): the zone takes FLAG_HLL | FLAG_MINMOD, its six
+//  neighbours FLAG_MINMOD.  Evaluated once per step on the stage-1 state (rk_step.c:86-88).
+// ---------------------------------------------------------------------------
+template <int NC, int PASS>
+__global__ void __launch_bounds__(256)
+flag_shock_kernel (const __grid_constant__ FlagArgs a)
+{
+  const Geom &g = a.g;
+  const int ni = g.T[0], nj = g.T[1], nk = (NC == 3 ? g.T[2] : 1);
+  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long long)ni*nj*nk) return;
+  const int i = (int)(t % ni), j = (int)((t/ni) % nj), k = (int)(t/((long long)ni*nj));
+  const long long id = gidx (g, k, j, i);
+  const long long sx = 1, sy = g.S1, sz = g.S12;
+  const bool inner = i >= 1 && i < ni - 1 && j >= 1 && j < nj - 1 && (NC == 2 || (k >= 1 && k < nk - 1));
+  if (PASS == 1){
+    unsigned char sh = 0;
+    if (inner){
+      const double dvx1 = pg_div (a.vx[0][id + sx] - a.vx[0][id - sx], g.dx[0]);
+      const double dvx2 = pg_div (a.vx[1][id + sy] - a.vx[1][id - sy], g.dx[1]);
+      double divv = dvx1 + dvx2;
+      if (NC == 3) divv = dvx1 + dvx2 + pg_div (a.vx[2][id + sz] - a.vx[2][id - sz], g.dx[2]);
+      if (divv < 0.0){
+        double pt_min = a.prs[id];
+        const double p1 = minv (a.prs[id + sx], a.prs[id - sx]), p2 = minv (a.prs[id + sy], a.prs[id - sy]);
+        pt_min = minv (pt_min, p1);
+        pt_min = minv (pt_min, p2);
+        double gradp = fabs (a.prs[id + sx] - a.prs[id - sx]) + fabs (a.prs[id + sy] - a.prs[id - sy]);
+        if (NC == 3){
+          pt_min = minv (pt_min, minv (a.prs[id + sz], a.prs[id - sz]));
+          gradp = fabs (a.prs[id + sx] - a.prs[id - sx]) + fabs (a.prs[id + sy] - a.prs[id - sy])
+                + fabs (a.prs[id + sz] - a.prs[id - sz]);
+        }
+        if (gradp > 5.0*pt_min) sh = 1;                       // EPS_PSHOCK_FLATTEN
+      }
+    }
+    a.shock[id] = sh;
+  }else{
+    // neighbours outside the array never lie in a shock (pass 1 wrote 0 on the outermost layer)
+    unsigned char f = a.shock[id] ? (4 | 1) : 0;
+    if ((i > 0 && a.shock[id - sx]) || (i < ni - 1 && a.shock[id + sx]) ||
+        (j > 0 && a.shock[id - sy]) || (j < nj - 1 && a.shock[id + sy])) f |= 1;
+    if (NC == 3 && ((k > 0 && a.shock[id - sz]) || (k < nk - 1 && a.shock[id + sz]))) f |= 1;
+    a.flag[id] = f;
+  }
+}
+
+int launch_flag_shock (const FlagArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const long long n = (long long)g.T[0]*g.T[1]*(g.dims == 3 ? g.T[2] : 1);
+  if (g.dims == 3){
+    flag_shock_kernel<3, 1><<<nblocks (n, 256), 256, 0, s>>>(a);
+    flag_shock_kernel<3, 2><<<nblocks (n, 256), 256, 0, s>>>(a);
+  }else{
+    flag_shock_kernel<2, 1><<<nblocks (n, 256), 256, 0, s>>>(a);
+    flag_shock_kernel<2, 2><<<nblocks (n, 256), 256, 0, s>>>(a);
+  }
+  return cudaGetLastError () == cudaSuccess ? 2 : -1;
+}
+
+// ---------------------------------------------------------------------------
 //  halo pack / unpack (contiguous buffers for the inter-GPU exchange)
 // ---------------------------------------------------------------------------
 template <bool PACK>
@@ -420,7 +486,6 @@ halo_table_kernel (const HaloEntry *__restrict__ tab, const Geom g)
 // ---------------------------------------------------------------------------
 //  launchers
 // ---------------------------------------------------------------------------
-static inline unsigned nblocks (long long n, int tpb) { return (unsigned)((n + tpb - 1)/tpb); }
 
 int launch_ct_emf (const CtArgs &a, cudaStream_t s)
 {

@@ -59,6 +59,7 @@ struct SweepArgs {
   int     avg;               // PLUTO_GPU_EMF_*
   double *dvel[3];           // d v_c / d x_dir of this sweep's direction, c = 0..2
   double *dvel2[3];          // fused x1 + x2 sweep: the x2 slopes
+  const unsigned char *flag; // SHOCK_FLATTENING MULTID: FLAG_MINMOD 1 | FLAG_HLL 4 per zone (pluto.h:192-194)
   // fused x1 + x2 sweep only: the x2 quantities next to the x1 ones above
   const double *Bn2;         // Bx2s
   double       *e3, *e4;     // ezj, exj
@@ -119,6 +120,13 @@ struct BcArgs {
   Geom g;
 };
 
+struct FlagArgs {              // FlagShock (flag_shock.c:79-230)
+  const double *vx[3], *prs;
+  unsigned char *shock;      // pass 1: zone lies in a shock
+  unsigned char *flag;       // pass 2: FLAG_HLL | FLAG_MINMOD of the zone itself, FLAG_MINMOD of its neighbours
+  Geom g;
+};
+
 struct HaloArgs {
   double *q[11];
   int lo[11][3], hi[11][3];  // inclusive box per field
@@ -149,6 +157,7 @@ namespace NS {                                                                  
   int launch_ct_update  (const CtArgs &a, cudaStream_t s);                               \
   int launch_final      (const FinalArgs &a, cudaStream_t s);                            \
   int launch_bc         (const BcArgs &a, cudaStream_t s);                               \
+  int launch_flag_shock (const FlagArgs &a, cudaStream_t s);                             \
   int launch_halo_pack  (const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_unpack(const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s); \

@@ -409,7 +409,9 @@ __device__ __forceinline__ void store_fan_speeds (double *pSL, double *pSR, doub
 //  Riemann solvers.  in: vL, vR (interface states), uL, uR; out: flux[NV]
 //  (slot bn is not meaningful), press, cmax, mach (candidate for g_maxMach).
 // ---------------------------------------------------------------------------
-template <int DIR, int NC>
+// STRICT: hll.c's own tests SL > 0 / SR < 0 (:106,113); !STRICT: the HLL flux that HLLD
+// substitutes in flagged zones, after ITS tests SL >= 0 / SR <= 0 (hlld.c:131-160)
+template <int DIR, int NC, bool STRICT = true>
 __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, const double *vR,
                                              const double *uL, const double *uR,
                                              double *flux, double &press, double &cmax, double &mach,
@@ -424,10 +426,10 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
   store_fan_speeds (pSL, pSR, SL, SR);
   scrh = maxv(fabs(SL), fabs(SR));
   cmax = scrh;
-  if (SL > 0.0){
+  if (STRICT ? SL > 0.0 : SL >= 0.0){
     PG_FOR_NV(nv) flux[nv] = fL[nv];
     press = pL;
-  }else if (SR < 0.0){
+  }else if (STRICT ? SR < 0.0 : SR <= 0.0){
     PG_FOR_NV(nv) flux[nv] = fR[nv];
     press = pR;
   }else{
@@ -1199,6 +1201,18 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   }
   press = 0.5*(pL + pR);
   return ok;
+}
+
+// SHOCK_FLATTENING MULTID: the flux of an interface with a shocked zone on either side
+// (hlld.c:149-160, roe.c:165-189; hll.c is unchanged)
+template <int SOLVER, int DIR, int NC>
+__device__ __forceinline__ void riemann_flagged (const Phys &ph, const double *vL, const double *vR,
+                                                 const double *uL, const double *uR,
+                                                 double *flux, double &press, double &cmax, double &mach,
+                                                 double *pSL, double *pSR)
+{
+  if (SOLVER == SOLVER_HLLD) riemann_hll<DIR, NC, false>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
+  else                       riemann_hll<DIR, NC, true> (ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
 }
 
 // solver dispatch on a compile-time constant

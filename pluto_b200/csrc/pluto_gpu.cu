@@ -49,6 +49,7 @@ struct PlutoGpu {
   double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   double *ex, *ey, *ez;
   double *cdt;
+  unsigned char *flag, *shock;     // SHOCK_FLATTENING MULTID only: zone flags and the pass-1 shock marks
   double *dvel[3][3];              // UCT_HLL only: limited velocity slopes d v_c / d x_d (own allocation)
   void   *dvel_pool;
   double *scratch;                 // = first array after the state buffers
@@ -134,6 +135,10 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->solver < 0 || cfg->solver > 2) return fail ("bad solver");
   if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
   if (cfg->limiter < 0 || cfg->limiter > PLUTO_GPU_LIM_MC) return fail ("bad limiter");
+  if (cfg->shock_flattening != 0 && cfg->shock_flattening != 1) return fail ("bad shock_flattening");
+  if (cfg->shock_flattening && cfg->recon == PLUTO_GPU_RECON_PARABOLIC)
+    return fail ("SHOCK_FLATTENING MULTID is available with LINEAR reconstruction only (the reference's PARABOLIC "
+                 "fallback takes its weights from PLM_CoefficientsGet, ppm_states.c:167-181)");
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
@@ -147,6 +152,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   Geom &g = h->g;
   g.dims = cfg->dims;
   g.ng = (cfg->recon == PLUTO_GPU_RECON_PARABOLIC ? 3 : 2);      // get_nghost.c:32-50
+  if (cfg->shock_flattening && g.ng < 3) g.ng = 3;               // get_nghost.c:67-77
   for (int d = 0; d < 3; d++){
     if (d < g.dims){
       if (cfg->n[d] < 2*g.ng){ free (h); return fail ("n[%d] = %d is smaller than 2*nghost", d, cfg->n[d]); }
@@ -192,6 +198,12 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   signed char *c = (signed char *)p;
   for (int d = 0; d < 3; d++){ h->sv[d] = c; c += tot_al; }
 
+  if (cfg->shock_flattening){
+    CU (cudaMalloc ((void **)&h->flag, 2*(tot_al + 256)));
+    CU (cudaMemset (h->flag, 0, 2*(tot_al + 256)));
+    h->shock = h->flag + tot_al + 256;
+    h->pool_bytes += 2*(tot_al + 256);
+  }
   if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL){
     const size_t nb = (size_t)g.dims*g.dims*tot_al*sizeof (double);
     if (cudaMalloc (&h->dvel_pool, nb) != cudaSuccess) return fail ("cudaMalloc of %zu bytes (UCT_HLL slopes) failed", nb);
@@ -223,6 +235,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaStreamSynchronize (h->stream);
   cudaFree (h->pool);
   if (h->dvel_pool) cudaFree (h->dvel_pool);
+  if (h->flag) cudaFree (h->flag);
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
   cudaFree (h->dtdev); cudaFreeHost (h->dthost);
@@ -521,7 +534,15 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine ? 1 : 2);
   if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
 
+  if (h->flag && stage == 1){
+    // FlagShock on the stage-1 state, ghost zones filled (rk_step.c:85-88); the flags hold for the whole step
+    FlagArgs fa; memset (&fa, 0, sizeof (fa));
+    for (int d = 0; d < 3; d++) fa.vx[d] = h->V[sp.in][1 + d];
+    fa.prs = h->V[sp.in][7]; fa.shock = h->shock; fa.flag = h->flag; fa.g = g;
+    TIMED (h, KC_BC, count (h, DISPATCH (h, launch_flag_shock) (fa, h->stream)));
+  }
   SweepArgs s; memset (&s, 0, sizeof (s));
+  s.flag = h->flag;
   for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
   s.stage1 = (stage == 1);

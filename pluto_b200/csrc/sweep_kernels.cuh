@@ -131,6 +131,27 @@ __device__ __forceinline__ void store_vel_slopes (double *const *dv, int id, con
   if (NC == 3) dv[2][id] = vp[VX3] - vm[VX3];
 }
 
+// SHOCK_FLATTENING MULTID: minmod for every variable in a zone flagged FLAG_MINMOD
+// (plm_states.c:174-180), the HLL flux at an interface next to a zone flagged FLAG_HLL
+template <int NC, bool FLAT>
+__device__ __forceinline__ void plm_zone_f (const SweepArgs &a, unsigned fl, const double *v, const double *dvm,
+                                            const double *dvp, double *vp, double *vm)
+{
+  if (FLAT && (fl & 1u)) plm_zone_single<NC>(2, v, dvm, dvp, vp, vm);
+  else                   plm_zone<NC>(a.limiter, v, dvm, dvp, vp, vm);
+}
+template <int SOLVER, int DIR, int NC, bool FLAT>
+__device__ __forceinline__ bool riemann_f (const Phys &ph, unsigned fl2, const double *vL, const double *vR,
+                                           const double *uL, const double *uR, double *F, double &press,
+                                           double &cmax, double &mach, double *pSL, double *pSR)
+{
+  if (FLAT && (fl2 & 4u) && SOLVER != SOLVER_HLL){
+    riemann_flagged<SOLVER, DIR, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach, pSL, pSR);
+    return true;
+  }
+  return riemann<SOLVER, DIR, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach, pSL, pSR);
+}
+
 template <int DIR, int NC>
 __device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, const double *F)
 { store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F); }
@@ -142,7 +163,8 @@ __device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, cons
 #define PG_XROWS 16          // rows a warp walks through (software-pipelined)
 #endif
 
-template <int RECON, int SOLVER, int NC, bool HLL>      // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds + velocity slopes)
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT>   // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds + velocity
+                                                                 // slopes); FLAT: SHOCK_FLATTENING MULTID (zone flags)
 __global__ void __launch_bounds__(128, PG_MINB_X)
 sweep_x_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -214,6 +236,8 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
 
     double v[NV], vp[NV], vm[NV];
     PG_FOR_NV(nv) v[nv] = src[nv*W + lane + 1];
+    unsigned fl = 0;
+    if (FLAT) fl = a.flag[id];
     if (RECON == RECON_PLM){
       double dvm[NV], dvp[NV];
       PG_FOR_NV(nv){
@@ -221,7 +245,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
         dvm[nv] = v[nv] - vl;
         dvp[nv] = vr - v[nv];
       }
-      plm_zone<NC>(a.limiter, v, dvm, dvp, vp, vm);
+      plm_zone_f<NC, FLAT>(a, fl, v, dvm, dvp, vp, vm);
     }else{
       double vl[NV], vr[NV], vrr[NV], Wi[NV], Wm[NV];
       PG_FOR_NV(nv){
@@ -245,8 +269,9 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
     prim_to_cons<NC>(ph, vR, uR);
     constexpr bool hll = HLL;
     if (hll && zone_ok && i >= g.beg[0] - 1) store_vel_slopes<NC>(a.dvel, id, vp, vm);
-    bool ok = riemann<SOLVER, DIR, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach,
-                                       hll && emf_ok ? a.e1 + id : nullptr, hll && emf_ok ? a.e2 + id : nullptr);
+    const unsigned fl2 = FLAT ? (fl | __shfl_down_sync (0xffffffffu, fl, 1)) : 0u;
+    bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, fl2, vp, vR, uL, uR, F, press, cmax, mach,
+                                               hll && emf_ok ? a.e1 + id : nullptr, hll && emf_ok ? a.e2 + id : nullptr);
 
     if (emf_ok && !hll) store_face_emf<DIR, NC>(a, id, F);
     if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
@@ -313,7 +338,7 @@ __host__ __device__ constexpr int march_slots (int recon)
   return 8*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + 8 + 7 + (recon == RECON_PPM ? 8 : 0)
          + march_prefetch (recon) + 6*(march_prefetch (recon) + 1);
 }
-template <int DIR, int RECON, int SOLVER, int NC, bool HLL>
+template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT>
 __global__ void __launch_bounds__(128, PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -401,7 +426,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait<PF - 1> ();
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone<NC>(a.limiter, vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone_f<NC, FLAT>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
@@ -420,10 +445,14 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   }
   double my_mach = 0.0, my_cdt = 0.0;
   constexpr bool hll = HLL;
+  unsigned flb = 0;                          // flag of zone f
+  if (FLAT) flb = a.flag[id];
 
   for (int f = c0 - 1; f <= c1; f++, id += sD){
     // id = zone f; interface f+1/2 lies between zone f and zone f+1
     double vL[NV], vR[NV];
+    unsigned flc = 0;                        // flag of zone f+1
+    if (FLAT) flc = a.flag[id + sD];
     cp_async_wait<PF - 1> ();
     const double bn = bnp[0][0];
     const double *ua = uap[0];               // U and C_dt of zone f (landed at least one face ago)
@@ -456,7 +485,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone<NC>(a.limiter, vc_, dvm, dvp, vpn, vR);
+        plm_zone_f<NC, FLAT>(a, flc, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
@@ -484,8 +513,9 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     prim_to_cons<NC>(ph, vL, uL);
     prim_to_cons<NC>(ph, vR, uR);
     const bool sf = hll && in_range && (f >= c0 || chunk == 0);
-    bool ok = riemann<SOLVER, DIR, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach,
-                                       sf ? a.e1 + id : nullptr, sf ? a.e2 + id : nullptr);
+    bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, flb | flc, vL, vR, uL, uR, F, press, cmax, mach,
+                                               sf ? a.e1 + id : nullptr, sf ? a.e2 + id : nullptr);
+    flb = flc;
     if (in_range){
       my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
@@ -551,7 +581,7 @@ __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
   return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128)*sizeof (double);
 }
 
-template <int RECON, int SOLVER, int NC, bool HLL>
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT>
 __global__ void __launch_bounds__(128, PG_MINB_XY)
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -633,7 +663,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait_all ();
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
       PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone<NC>(a.limiter, vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone_f<NC, FLAT>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
@@ -660,6 +690,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     cp_async_wait_all ();
     __syncwarp ();                                   // the other lanes' copies are visible
     const double bny = C_BY, bnx = C_BX;
+    unsigned flz = 0, fln = 0;               // flags of zone (f, i) and of zone (f+1, i)
+    if (FLAT){ flz = a.flag[id]; fln = a.flag[id + sD]; }
     double v[NV], rx[NV], cdx = 0.0;
     double xvl[NV], xvr[NV], xvrr[NV];
     PG_UNROLL for (int nv = 0; nv < NV; nv++) rx[nv] = 0.0;
@@ -684,7 +716,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = v[nv] - xvl[nv]; dvp[nv] = xvr[nv] - v[nv]; }
-        plm_zone<NC>(a.limiter, v, dvm, dvp, vp, vm);
+        plm_zone_f<NC, FLAT>(a, flz, v, dvm, dvp, vp, vm);
       }else{
         double Wi[NV], Wm[NV];
         ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
@@ -698,8 +730,9 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       prim_to_cons<NC>(ph, vp, uL);
       prim_to_cons<NC>(ph, vR, uR);
       if (hll && zone_ok && i >= g.beg[0] - 1) store_vel_slopes<NC>(a.dvel, id, vp, vm);
-      bool ok = riemann<SOLVER, 0, NC>(ph, vp, vR, uL, uR, F, press, cmax, mach,
-                                       hll && xemf_ok ? a.e1 + id : nullptr, hll && xemf_ok ? a.e2 + id : nullptr);
+      const unsigned flx2 = FLAT ? (flz | __shfl_down_sync (0xffffffffu, flz, 1)) : 0u;
+      bool ok = riemann_f<SOLVER, 0, NC, FLAT>(ph, flx2, vp, vR, uL, uR, F, press, cmax, mach,
+                                               hll && xemf_ok ? a.e1 + id : nullptr, hll && xemf_ok ? a.e2 + id : nullptr);
       if (xemf_ok && !hll) store_face_emf_p<0, NC>(a.e1, a.e2, a.sv, id, F);
       if (xface_ok) my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && xface_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
@@ -729,7 +762,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone<NC>(a.limiter, vc_, dvm, dvp, vpn, vR);
+        plm_zone_f<NC, FLAT>(a, fln, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
@@ -744,8 +777,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       prim_to_cons<NC>(ph, vL, uL);
       prim_to_cons<NC>(ph, vR, uR);
       const bool sfy = hll && yemf_ok && (f >= c0 || chunk == 0);
-      bool ok = riemann<SOLVER, 1, NC>(ph, vL, vR, uL, uR, F, press, cmax, mach,
-                                       sfy ? a.e3 + id : nullptr, sfy ? a.e4 + id : nullptr);
+      bool ok = riemann_f<SOLVER, 1, NC, FLAT>(ph, flz | fln, vL, vR, uL, uR, F, press, cmax, mach,
+                                               sfy ? a.e3 + id : nullptr, sfy ? a.e4 + id : nullptr);
       if (col_ok){
         my_mach = mach > my_mach ? mach : my_mach;
         if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
@@ -802,11 +835,13 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
   const long long nwarp = nseg*(nc == 3 ? g.n[2] + 2 : 1)*a.nchunk;
   const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
   const size_t smem = xy_smem_bytes (recon);
-#define PG_LXY1(R, C, H) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H>;                            \
+#define PG_LXY1(R, C, H, F) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H, F>;                            \
       static bool attr_set = false;                                                                   \
       if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
-#define PG_LXY(R, C) do { if (a.avg == 3) PG_LXY1(R, C, true); else PG_LXY1(R, C, false); } while (0)
+#define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
+      if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                            \
+      else           { if (fl) PG_LXY1(R, C, false, P); else PG_LXY1(R, C, false, false); } } while (0)
   if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
   else if (recon == RECON_PLM && nc == 2) PG_LXY(RECON_PLM, 2);
   else if (recon == RECON_PPM && nc == 3) PG_LXY(RECON_PPM, 3);
@@ -833,8 +868,11 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long nwarp = nseg*((nrows + PG_XROWS - 1)/PG_XROWS);
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
     const size_t xsmem = (size_t)(TPB/32)*2*9*36*sizeof (double);
-#define PG_LX(R, C) do { if (a.avg == 3) sweep_x_kernel<R, SOLVER, C, true><<<nb, TPB, xsmem, s>>>(a); \
-                         else            sweep_x_kernel<R, SOLVER, C, false><<<nb, TPB, xsmem, s>>>(a); } while (0)
+#define PG_LX(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
+      if (a.avg == 3){ if (fl) sweep_x_kernel<R, SOLVER, C, true, P><<<nb, TPB, xsmem, s>>>(a);                     \
+                       else    sweep_x_kernel<R, SOLVER, C, true, false><<<nb, TPB, xsmem, s>>>(a); }               \
+      else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, P><<<nb, TPB, xsmem, s>>>(a);                    \
+                       else    sweep_x_kernel<R, SOLVER, C, false, false><<<nb, TPB, xsmem, s>>>(a); } } while (0)
     if      (recon == RECON_PLM && nc == 3) PG_LX(RECON_PLM, 3);
     else if (recon == RECON_PLM && nc == 2) PG_LX(RECON_PLM, 2);
     else if (recon == RECON_PPM && nc == 3) PG_LX(RECON_PPM, 3);
@@ -846,13 +884,15 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long nthr = npen*a.nchunk;
     const unsigned nb = (unsigned)((nthr + TPB - 1)/TPB);
     const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
-#define PG_LM1(DD, R, C, H) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H>;                \
+#define PG_LM1(DD, R, C, H, F) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H, F>;                \
       static bool attr_set = false;                                                                   \
       if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
         attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
-#define PG_LM(DD, R, C) do { if (a.avg == 3) PG_LM1(DD, R, C, true); else PG_LM1(DD, R, C, false); } while (0)
+#define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;          \
+      if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                      \
+      else           { if (fl) PG_LM1(DD, R, C, false, P); else PG_LM1(DD, R, C, false, false); } } while (0)
     if (dir == 1){
       if      (recon == RECON_PLM && nc == 3) PG_LM(1, RECON_PLM, 3);
       else if (recon == RECON_PLM && nc == 2) PG_LM(1, RECON_PLM, 2);

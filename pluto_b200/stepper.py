@@ -35,7 +35,8 @@ class GpuStepper:
 
     def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
                  bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0,
-                 small_dn=1e-12, small_pr=1e-12, lib_path=None, limiter="default", emf="uct_contact"):
+                 small_dn=1e-12, small_pr=1e-12, lib_path=None, limiter="default", emf="uct_contact",
+                 flatten=False):
         self.L = _lib.load_library(lib_path)
         c = _lib.PlutoGpuConfig()
         n = list(n) + [1] * (3 - len(n))
@@ -56,7 +57,8 @@ class GpuStepper:
         c.small_dn = small_dn
         c.small_pr = small_pr
         c.limiter = _lib.LIMITER[limiter]           # LIMITER (plm only): default | fl mm va os um vl mc
-        c.emf_average = _lib.EMF[emf]               # CT_EMF_AVERAGE: uct_contact | arith | uct0
+        c.emf_average = _lib.EMF[emf]               # CT_EMF_AVERAGE: uct_contact | arith | uct0 | uct_hll
+        c.shock_flattening = 1 if flatten else 0    # SHOCK_FLATTENING MULTID (plm only)
         self.cfg = c
         self.dims = dims
         self.n = tuple(n)

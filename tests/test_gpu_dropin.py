@@ -15,13 +15,13 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "ot2d_plm_hll", "turb3d_plm_hlld",
          # LIMITER / CT_EMF_AVERAGE read from definitions.h by the shim (Blast #02's and Rotor #01's scheme options)
-         "blast3d_vl_arith", "rotor2d_mc_arith", "blast3d_mc_uct_hll_roe"]
+         "blast3d_vl_arith", "rotor2d_mc_arith", "blast3d_mc_uct_hll_roe", "blast3d_sfl"]
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
-                     limiter=g.limiter, emf=g.emf, prefix="pluto_gpu_")
+                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
     return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf)
+                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten)
 
 
 @pytest.mark.parametrize("name", golden_names())

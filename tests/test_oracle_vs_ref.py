@@ -30,6 +30,10 @@ CASES = [
     ("ot2d_uct_hll", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, emf="uct_hll"), 8),
     ("turb3d_uct_hll", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, emf="uct_hll"), 6),
     ("rotor2d_ppm_uct_hll_hll", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), recon="ppm", first_dt=2e-3, emf="uct_hll", solver="hll"), 8),
+    # SHOCK_FLATTENING MULTID (flag_shock.c): minmod + HLL in shocked zones
+    ("blast3d_sfl", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, flatten=True), 10),
+    ("blast2d_sfl_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), first_dt=3e-4, solver="roe", flatten=True), 12),
+    ("blast3d_sfl_uct_hll", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, emf="uct_hll", flatten=True), 8),
 ]
 
 
@@ -44,7 +48,7 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dom = cfg.resolved_domain()
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
-               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf)
+               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten)
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

@@ -39,6 +39,7 @@ class Golden:
         self.nsteps = int(d["cfg_nsteps"])
         self.limiter = str(d["cfg_limiter"]) if "cfg_limiter" in d.files else "default"
         self.emf = str(d["cfg_emf"]) if "cfg_emf" in d.files else "uct_contact"
+        self.flatten = bool(int(d["cfg_flatten"])) if "cfg_flatten" in d.files else False
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:

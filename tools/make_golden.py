@@ -68,6 +68,11 @@ CASES = {
     "turb3d_uct_hll": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, emf="uct_hll"), 10),
     "rotor2d_ppm_uct_hll_hll": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), recon="ppm", solver="hll",
                                           first_dt=2.5e-3, cfl=0.4, emf="uct_hll"), 20),
+    # SHOCK_FLATTENING MULTID (flag_shock.c): minmod + HLL in shocked zones (Blast #07-#09's option)
+    "blast3d_sfl": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, flatten=True), 15),
+    "blast2d_sfl_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, solver="roe", flatten=True), 25),
+    "blast3d_sfl_uct_hll": (RefConfig(problem="blast", dims=3, n=(12, 16, 12), first_dt=6e-4, cfl=0.3, emf="uct_hll",
+                                      flatten=True), 15),
 }
 
 
@@ -81,7 +86,7 @@ def make(name):
         "cfg_first_dt": cfg.first_dt, "cfg_gamma": cfg.resolved_gamma(),
         "cfg_domain": np.array(cfg.resolved_domain()),
         "cfg_bc": np.array(cfg.resolved_bc()), "cfg_nsteps": nsteps,
-        "cfg_limiter": cfg.limiter, "cfg_emf": cfg.emf,
+        "cfg_limiter": cfg.limiter, "cfg_emf": cfg.emf, "cfg_flatten": int(cfg.flatten),
     }
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
