@@ -198,6 +198,21 @@ int pluto_gpu_step_begin   (PlutoGpu *h);
 int pluto_gpu_stage        (PlutoGpu *h, int stage, double dt);
 int pluto_gpu_step_end     (PlutoGpu *h, PlutoGpuStepInfo *info);
 
+/* ---- output, restart and run-time diagnostics from the device state -----
+   pluto_gpu_write_dbl: data.NNNN.dbl of the reference's "dbl ... single_file" output
+   (Src/write_data.c:92-205, Src/bin_io.c:216): for each of rho vx1 vx2 [vx3] Bx1 Bx2 [Bx3]
+   prs the interior zones [k][j][i], then Bx1s, Bx2s, [Bx3s] with their extra face, little
+   endian doubles; the matching line "nfile t dt nstep single_file little names..." is
+   appended to (nfile == 0: starts) <dir>/dbl.out (write_data.c:365-395), so the
+   reference's own tools (pyPLUTO, restart) read the files.
+   pluto_gpu_read_dbl: the inverse (what RestartFromFile does for d->Vc, d->Vs).
+   pluto_gpu_analysis: volume integrals of the state for Analysis()-type diagnostics, summed
+   on the device in a fixed order (deterministic): out[0] mass, [1] kinetic, [2] magnetic,
+   [3] thermal energy (p/(gamma-1)), [4..6] momentum, [7] max |div B| (staggered field). */
+int pluto_gpu_write_dbl (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep);
+int pluto_gpu_read_dbl  (PlutoGpu *h, const char *path);
+int pluto_gpu_analysis  (PlutoGpu *h, double out[8]);
+
 /* ---- introspection (tests, bench, profiling) -------------------------- */
 void     *pluto_gpu_stream        (PlutoGpu *h);   /* cudaStream_t of all launches */
 long long pluto_gpu_launch_count  (const PlutoGpu *h);  /* kernels launched so far */

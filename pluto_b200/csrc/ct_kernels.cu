@@ -450,6 +450,51 @@ int launch_flag_shock (const FlagArgs &a, cudaStream_t s)
 }
 
 // ---------------------------------------------------------------------------
+//  run-time diagnostics: per-block partial sums over a grid-stride loop (fixed order
+//  within a block: strided thread sums, then a shared-memory tree), summed on the host
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+analysis_kernel (const __grid_constant__ AnalysisArgs a)
+{
+  const Geom &g = a.g;
+  const bool d3 = (g.dims == 3);
+  const long long n = (long long)g.n[0]*g.n[1]*(d3 ? g.n[2] : 1);
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x*blockDim.x){
+    const int i = g.beg[0] + (int)(t % g.n[0]), j = g.beg[1] + (int)((t/g.n[0]) % g.n[1]);
+    const int k = d3 ? g.beg[2] + (int)(t/((long long)g.n[0]*g.n[1])) : 0;
+    const long long id = gidx (g, k, j, i);
+    const double rho = a.V[RHO][id], vx = a.V[VX1][id], vy = a.V[VX2][id], vz = d3 ? a.V[VX3][id] : 0.0;
+    const double bx = a.V[BX1][id], by = a.V[BX2][id], bz = d3 ? a.V[BX3][id] : 0.0;
+    s[0] += rho;
+    s[1] += 0.5*rho*(vx*vx + vy*vy + vz*vz);
+    s[2] += 0.5*(bx*bx + by*by + bz*bz);
+    s[3] += a.V[PRS][id]*a.igmm1;
+    s[4] += rho*vx; s[5] += rho*vy; s[6] += rho*vz;
+    double div = (a.Bs[0][id] - a.Bs[0][id - 1])/g.dx[0] + (a.Bs[1][id] - a.Bs[1][id - g.S1])/g.dx[1];
+    if (d3) div += (a.Bs[2][id] - a.Bs[2][id - g.S12])/g.dx[2];
+    s[7] = maxv (s[7], fabs (div));
+  }
+  __shared__ double sh[8][256];
+  for (int q = 0; q < 8; q++) sh[q][threadIdx.x] = s[q];
+  __syncthreads ();
+  for (int w = 128; w > 0; w >>= 1){
+    if ((int)threadIdx.x < w){
+      for (int q = 0; q < 7; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + w];
+      sh[7][threadIdx.x] = maxv (sh[7][threadIdx.x], sh[7][threadIdx.x + w]);
+    }
+    __syncthreads ();
+  }
+  if (threadIdx.x < 8) a.partial[(size_t)blockIdx.x*8 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+int launch_analysis (const AnalysisArgs &a, int nb, cudaStream_t s)
+{
+  analysis_kernel<<<nb, 256, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+// ---------------------------------------------------------------------------
 //  halo pack / unpack (contiguous buffers for the inter-GPU exchange)
 // ---------------------------------------------------------------------------
 template <bool PACK>

@@ -127,6 +127,14 @@ struct FlagArgs {              // FlagShock (flag_shock.c:79-230)
   Geom g;
 };
 
+struct AnalysisArgs {          // volume integrals of the interior state
+  const double *V[8];
+  const double *Bs[3];
+  double *partial;           // [gridDim.x][8] block partial sums (8th: max |div B|)
+  Geom g;
+  double igmm1;
+};
+
 struct HaloArgs {
   double *q[11];
   int lo[11][3], hi[11][3];  // inclusive box per field
@@ -158,6 +166,7 @@ namespace NS {                                                                  
   int launch_final      (const FinalArgs &a, cudaStream_t s);                            \
   int launch_bc         (const BcArgs &a, cudaStream_t s);                               \
   int launch_flag_shock (const FlagArgs &a, cudaStream_t s);                             \
+  int launch_analysis   (const AnalysisArgs &a, int nblocks, cudaStream_t s);            \
   int launch_halo_pack  (const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_unpack(const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s); \

@@ -866,6 +866,101 @@ int pluto_gpu_sync_results (PlutoGpu *h, int max_steps, PlutoGpuStepInfo *infos,
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+//  output / restart in the reference's .dbl format, diagnostics
+// ---------------------------------------------------------------------------
+static size_t interior_doubles (const PlutoGpu *h, size_t seg[4])
+{
+  const Geom &g = h->g;
+  const size_t n1 = g.n[0], n2 = g.n[1], n3 = (g.dims == 3 ? g.n[2] : 1);
+  seg[0] = (size_t)NVS*n1*n2*n3;                      // 8 slots (dead ones keep their space)
+  seg[1] = (n1 + 1)*n2*n3; seg[2] = n1*(n2 + 1)*n3; seg[3] = (g.dims == 3 ? n1*n2*(n3 + 1) : 0);
+  return seg[0] + seg[1] + seg[2] + seg[3];
+}
+
+int pluto_gpu_write_dbl (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep)
+{
+  size_t seg[4];
+  const size_t tot = interior_doubles (h, seg);
+  double *buf = NULL;
+  if (cudaMallocHost ((void **)&buf, tot*sizeof (double)) != cudaSuccess) return fail ("pinned staging of %zu bytes failed", tot*sizeof (double));
+  double *p[4] = {buf, buf + seg[0], buf + seg[0] + seg[1], seg[3] ? buf + seg[0] + seg[1] + seg[2] : NULL};
+  if (pluto_gpu_download_interior (h, p[0], p[1], p[2], p[3])){ cudaFreeHost (buf); return 1; }
+  char path[1024];
+  snprintf (path, sizeof (path), "%s/data.%04d.dbl", dir, nfile);
+  FILE *f = fopen (path, "wb");
+  if (!f){ cudaFreeHost (buf); return fail ("cannot open %s", path); }
+  const size_t ncell = seg[0]/NVS;
+  size_t nw = 0, want = 0;
+  for (int nv = 0; nv < NVS; nv++){
+    if (!live_var (h, nv)) continue;
+    nw += fwrite (buf + (size_t)nv*ncell, sizeof (double), ncell, f); want += ncell;
+  }
+  for (int s = 1; s < 4; s++) if (seg[s]){ nw += fwrite (p[s], sizeof (double), seg[s], f); want += seg[s]; }
+  fclose (f);
+  cudaFreeHost (buf);
+  if (nw != want) return fail ("short write to %s", path);
+  // dbl.out (write_data.c:365-395)
+  snprintf (path, sizeof (path), "%s/dbl.out", dir);
+  f = fopen (path, nfile == 0 ? "w" : "a");
+  if (!f) return fail ("cannot open %s", path);
+  fprintf (f, "%d %12.6e %12.6e %ld single_file little ", nfile, t, dt, nstep);
+  fprintf (f, h->g.dims == 3 ? "rho vx1 vx2 vx3 Bx1 Bx2 Bx3 prs Bx1s Bx2s Bx3s \n" : "rho vx1 vx2 Bx1 Bx2 prs Bx1s Bx2s \n");
+  fclose (f);
+  return 0;
+}
+
+int pluto_gpu_read_dbl (PlutoGpu *h, const char *path)
+{
+  size_t seg[4];
+  const size_t tot = interior_doubles (h, seg);
+  double *buf = (double *)calloc (tot, sizeof (double));
+  if (!buf) return fail ("out of host memory");
+  double *p[4] = {buf, buf + seg[0], buf + seg[0] + seg[1], seg[3] ? buf + seg[0] + seg[1] + seg[2] : NULL};
+  FILE *f = fopen (path, "rb");
+  if (!f){ free (buf); return fail ("cannot open %s", path); }
+  const size_t ncell = seg[0]/NVS;
+  size_t nr = 0, want = 0;
+  for (int nv = 0; nv < NVS; nv++){
+    if (!live_var (h, nv)) continue;
+    nr += fread (buf + (size_t)nv*ncell, sizeof (double), ncell, f); want += ncell;
+  }
+  for (int s = 1; s < 4; s++) if (seg[s]){ nr += fread (p[s], sizeof (double), seg[s], f); want += seg[s]; }
+  fclose (f);
+  int rc = 0;
+  if (nr != want) rc = fail ("%s: expected %zu doubles, read %zu (grid or dimensions differ)", path, want, nr);
+  else rc = pluto_gpu_upload_interior (h, p[0], p[1], p[2], p[3]);
+  free (buf);
+  return rc;
+}
+
+int pluto_gpu_analysis (PlutoGpu *h, double out[8])
+{
+  CU (cudaSetDevice (h->cfg.device));
+  int nb = 592;                                         // 148 SMs x 4 blocks
+  if ((size_t)nb*8 > h->scratch_doubles) nb = (int)(h->scratch_doubles/8);
+  if (nb < 1) return fail ("internal: scratch too small");
+  AnalysisArgs a; memset (&a, 0, sizeof (a));
+  for (int nv = 0; nv < NVS; nv++) a.V[nv] = h->V[0][nv];
+  for (int d = 0; d < 3; d++) a.Bs[d] = h->Bs[0][d];
+  a.partial = h->scratch;                               // the work arrays are free between steps
+  a.g = h->g; a.igmm1 = h->ph.igmm1;
+  if (count (h, pg_exact::launch_analysis (a, nb, h->stream))) return 1;
+  double *host = (double *)malloc ((size_t)nb*8*sizeof (double));
+  CU (cudaMemcpyAsync (host, a.partial, (size_t)nb*8*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
+  CU (cudaStreamSynchronize (h->stream));
+  double vol = 1.0;
+  for (int d = 0; d < h->g.dims; d++) vol *= h->g.dx[d];
+  for (int q = 0; q < 8; q++) out[q] = 0.0;
+  for (int b = 0; b < nb; b++){
+    for (int q = 0; q < 7; q++) out[q] += host[(size_t)b*8 + q];
+    if (host[(size_t)b*8 + 7] > out[7]) out[7] = host[(size_t)b*8 + 7];
+  }
+  for (int q = 0; q < 7; q++) out[q] *= vol;
+  free (host);
+  return 0;
+}
+
 double pluto_gpu_next_dt (double inv_dt_hyp, double cfl, double cfl_max_var, double dt)
 {
   double dt_hyp = 1.0/inv_dt_hyp, dtnext;                      // main.c:462-465

@@ -200,6 +200,20 @@ class GpuStepper:
                for q in range(n.value)]
         return [dts[q] for q in range(n.value)], out, dtn.value
 
+    # ---- output / restart / diagnostics from the device state ---------------------
+    def write_dbl(self, directory: str, nfile: int, t: float, dt: float, nstep: int):
+        """data.NNNN.dbl + dbl.out line in the reference's single_file format (Src/write_data.c)."""
+        self._check(self.L.pluto_gpu_write_dbl(self._h, directory.encode(), nfile, t, dt, nstep))
+
+    def read_dbl(self, path: str):
+        self._check(self.L.pluto_gpu_read_dbl(self._h, path.encode()))
+
+    def analysis(self) -> dict:
+        out = (C.c_double * 8)()
+        self._check(self.L.pluto_gpu_analysis(self._h, out))
+        return dict(mass=out[0], e_kin=out[1], e_mag=out[2], e_th=out[3],
+                    mom=(out[4], out[5], out[6]), max_divb=out[7])
+
     def boundary(self):
         self._check(self.L.pluto_gpu_boundary(self._h))
 

@@ -306,3 +306,44 @@ def test_decomposed_blocks_match_single_block(problem, dims, gn, world, recon, s
     one.close()
     for blk in many.blocks:
         blk.close()
+
+
+def test_dbl_output_restart_and_analysis(tmp_path):
+    """Device-side output in the reference's .dbl format (read back with the reader used for the reference's
+    own dumps), restart from it, and the diagnostics reductions against numpy."""
+    from oracle.refrun import read_dbl
+    from pluto_b200 import GpuStepper, problems
+    for dims, n in ((3, (20, 16, 12)), (2, (24, 20, 1))):
+        st0, meta = problems.make("ot", dims, n)
+        s = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"])
+        s.set_state(st0)
+        for _ in range(3):
+            s.advance(5e-3)
+        st = s.get_state()
+        s.write_dbl(str(tmp_path), 0, 0.015, 5e-3, 3)
+        s.write_dbl(str(tmp_path), 1, 0.015, 5e-3, 3)
+        back = read_dbl(str(tmp_path / "data.0001.dbl"), dims, n)
+        for k, v in st.items():
+            assert np.array_equal(back[k], v), k
+        lines = open(tmp_path / "dbl.out").read().splitlines()
+        assert len(lines) == 2 and lines[1].split()[0] == "1" and lines[1].split()[4:6] == ["single_file", "little"]
+        assert lines[1].split()[6:] == (["rho", "vx1", "vx2", "vx3", "Bx1", "Bx2", "Bx3", "prs", "Bx1s", "Bx2s", "Bx3s"]
+                                        if dims == 3 else ["rho", "vx1", "vx2", "Bx1", "Bx2", "prs", "Bx1s", "Bx2s"])
+        r = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"])
+        r.read_dbl(str(tmp_path / "data.0000.dbl"))
+        a, b = s.advance(5e-3), r.advance(5e-3)
+        assert (a.inv_dt_hyp, a.max_mach) == (b.inv_dt_hyp, b.max_mach)
+        sa, sb = s.get_state(), r.get_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), k
+        an = s.analysis()
+        vol = float(np.prod(meta["dx"][:dims]))
+        v2 = sa["vx1"]**2 + sa["vx2"]**2 + (sa["vx3"]**2 if dims == 3 else 0.0)
+        b2 = sa["Bx1"]**2 + sa["Bx2"]**2 + (sa["Bx3"]**2 if dims == 3 else 0.0)
+        assert abs(an["mass"] - sa["rho"].sum()*vol) <= 1e-12*abs(an["mass"])
+        assert abs(an["e_kin"] - (0.5*sa["rho"]*v2).sum()*vol) <= 1e-12*abs(an["e_kin"])
+        assert abs(an["e_mag"] - (0.5*b2).sum()*vol) <= 1e-12*abs(an["e_mag"])
+        assert abs(an["e_th"] - (sa["prs"]/(meta["gamma"] - 1.0)).sum()*vol) <= 1e-12*abs(an["e_th"])
+        assert an["max_divb"] <= 1.01*divb_max(sa, dims, meta["dx"]) + 1e-300 and an["max_divb"] < 1e-10
+        s.close()
+        r.close()
