@@ -63,9 +63,10 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
   const Geom &g = a.g;
   // edges (k,j,i) with i in [IBEG-1,IEND], j in [JBEG-1,JEND], k in [KBEG-1,KEND]
   const int ni = g.n[0] + 1, nj = g.n[1] + 1, nk = (NC == 3 ? g.n[2] + 1 : 1);
-  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-  if (t >= (long long)ni*nj*nk) return;
-  const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
+  const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;          // 32-bit: < 2^31 zones per block
+  if (t >= (unsigned)(ni*nj*nk)) return;
+  const unsigned tq = t/(unsigned)ni;
+  const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
   const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
   const long long id = gidx (g, k, j, i);
   const long long sx = 1, sy = g.S1, sz = g.S12;
@@ -207,9 +208,10 @@ ct_update_kernel (const __grid_constant__ CtArgs a)
 {
   const Geom &g = a.g;
   const int ni = g.n[0] + 1, nj = g.n[1] + 1, nk = (NC == 3 ? g.n[2] + 1 : 1);
-  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-  if (t >= (long long)ni*nj*nk) return;
-  const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
+  const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;          // 32-bit: < 2^31 zones per block
+  if (t >= (unsigned)(ni*nj*nk)) return;
+  const unsigned tq = t/(unsigned)ni;
+  const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
   const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
   const long long id = gidx (g, k, j, i);
   const long long sy = g.S1, sz = g.S12;
@@ -250,10 +252,11 @@ final_kernel (const __grid_constant__ FinalArgs a)
   const Geom &g = a.g;
   Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr; ph.igmm1 = a.ph.igmm1;
   const int ni = a.box_n[0], nj = a.box_n[1], nk = (NC == 3 ? a.box_n[2] : 1);
-  long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;
   int fl = 0, bad = 0;
-  if (t < (long long)ni*nj*nk){
-    const int ti = (int)(t % ni), tj = (int)((t/ni) % nj), tk = (int)(t/((long long)ni*nj));
+  if (t < (unsigned)(ni*nj*nk)){
+    const unsigned tq = t/(unsigned)ni;
+    const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
     const int i = g.beg[0] + a.box_lo[0] + ti, j = g.beg[1] + a.box_lo[1] + tj, k = (NC == 3 ? g.beg[2] + a.box_lo[2] + tk : 0);
     const long long id = gidx (g, k, j, i);
     double u[NV], v[NV];
@@ -323,10 +326,13 @@ bc_kernel (const __grid_constant__ BcArgs a)
   const Geom &g = a.g;
   if ((int)blockIdx.y < a.nf){
     const BcField &f = a.f[blockIdx.y];
+    // 32-bit index arithmetic (a ghost slab has far fewer than 2^31 zones): the three divisions
+    // per thread dominate this kernel otherwise
     const int ni = f.hi[0] - f.lo[0] + 1, nj = f.hi[1] - f.lo[1] + 1, nk = f.hi[2] - f.lo[2] + 1;
-    long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    if (t >= (long long)ni*nj*nk) return;
-    const int i = f.lo[0] + (int)(t % ni), j = f.lo[1] + (int)((t/ni) % nj), k = f.lo[2] + (int)(t/((long long)ni*nj));
+    const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= (unsigned)(ni*nj*nk)) return;
+    const unsigned tj = t/(unsigned)ni;
+    const int i = f.lo[0] + (int)(t - tj*(unsigned)ni), j = f.lo[1] + (int)(tj % (unsigned)nj), k = f.lo[2] + (int)(tj/(unsigned)nj);
     int c[3] = {i, j, k};
     const int d = f.side >> 1, hi_side = f.side & 1;
     c[d] = bc_source (g, f.type, d, hi_side, c[d]);
