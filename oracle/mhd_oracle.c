@@ -54,6 +54,9 @@ struct Oracle {
   unsigned char *flag;                 /* SHOCK_FLATTENING MULTID: FLAG_MINMOD 1, FLAG_HLL 4 (pluto.h:192-194) */
   unsigned char *pflag;                /* ... of the current pencil                            */
   int use_hll;                         /* the interface being solved takes the HLL flux        */
+  /* CTU (ctu_step.c:214-224): L/R conservative states and half-step rhs of every direction, half-step U */
+  double *Up[3][NV], *Um[3][NV], *rhs3[3][NV], *Uh[NV];
+  double (*up)[NV], (*um)[NV], (*vn)[NV];   /* pencil: conservative L/R states, t^n zone values */
   double *C_dt;
   /* pencil scratch */
   int np;
@@ -81,6 +84,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->c  = *cfg;
   o->ng = (cfg->recon == ORC_RECON_PPM ? 3 : 2);
   if (cfg->shock_flattening && o->ng < 3) o->ng = 3;       /* get_nghost.c:67-77 */
+  if (cfg->ctu) o->ng++;                                   /* CTU + CT, get_nghost.c:86-90 */
   for (d = 0; d < 3; d++){
     if (d < cfg->dims){
       o->T[d]   = cfg->n[d] + 2*o->ng;
@@ -123,6 +127,16 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->flux = calloc((size_t)o->np, sizeof(*o->flux));
   o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
   o->SLp = dalloc(o->np) + 4; o->SRp = dalloc(o->np) + 4;
+  if (cfg->ctu){
+    int c;
+    for (d = 0; d < 3; d++) for (c = 0; c < NV; c++){
+      o->Up[d][c] = dalloc(o->tot); o->Um[d][c] = dalloc(o->tot); o->rhs3[d][c] = dalloc(o->tot);
+    }
+    for (c = 0; c < NV; c++) o->Uh[c] = dalloc(o->tot);
+    o->up = calloc((size_t)o->np, sizeof(*o->up)); o->up += 4;
+    o->um = calloc((size_t)o->np, sizeof(*o->um)); o->um += 4;
+    o->vn = calloc((size_t)o->np, sizeof(*o->vn)); o->vn += 4;
+  }
   o->pflag = (unsigned char *)calloc((size_t)o->np, 1) + 4;
   /* shift pencil arrays so that index -2 is addressable */
   o->v += 4; o->vp += 4; o->vm += 4; o->dv += 4; o->flux += 4;
@@ -736,6 +750,10 @@ static void riemann_roe (Oracle *o, const double *vL, const double *vR,
 
 static void ct_compute_emf (Oracle *o);
 static void ct_update (Oracle *o, double dt);
+static void ct_update_from (Oracle *o, double *const *Bs, double dt);
+static void ct_average_magnetic_field (Oracle *o);
+static void cons_to_prim_3d (Oracle *o);
+static void flag_shock (Oracle *o);
 
 static void update_stage (Oracle *o, double dt)
 {
@@ -1029,7 +1047,8 @@ static void ct_compute_emf (Oracle *o)
 #define DEZ_DXM(k,j,i) (Ex3[I3(k,j,i)] - ezi[I3(k,j,i-1)])
 #define DEZ_DYM(k,j,i) (Ex3[I3(k,j,i)] - ezj[I3(k,j-1,i)])
 
-  for (k = kbeg; k <= kend + koff; k++)
+  /* CT_EMF_IntegrateToCorner returns at once in the CTU predictor (ct_emf_average.c:90-92) */
+  for (k = kbeg; k <= (o->c.ctu && o->stage == 1 ? kbeg - 1 : kend + koff); k++)
   for (j = jbeg; j <= jend + 1; j++)
   for (i = ibeg; i <= iend + 1; i++){
     signed char sx = o->svx[I3(k,j,i)], sy = o->svy[I3(k,j,i)], sz = 0;
@@ -1129,6 +1148,42 @@ static void ct_update (Oracle *o, double dt)
   }
 }
 
+static void ct_update_from (Oracle *o, double *const *Bs, double dt)
+/* CT_Update (d, Bs, dt): d->Vs = Bs + dt curl E on the faces of the emf ranges (ct_update.c:79-218) */
+{
+  int i, j, k, dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
+  int ibeg = o->emf_ibeg, iend = o->emf_iend, jbeg = o->emf_jbeg, jend = o->emf_jend;
+  int kbeg = o->emf_kbeg, kend = o->emf_kend;
+  double dx1 = o->c.dx[0], dx2 = o->c.dx[1], dx3 = o->c.dx[2];
+  double *Ex1 = o->ex, *Ex2 = o->ey, *Ex3 = o->ez;
+  double rhs;
+  for (k = kbeg + koff; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
+  for (i = ibeg; i <= iend; i++){
+    if (dims == 3)
+      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)])
+                + dt/dx3*(Ex2[I3(k,j,i)] - Ex2[I3(k-1,j,i)]);
+    else
+      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)]);
+    o->Vs[0][I3(k,j,i)] = Bs[0][I3(k,j,i)] + rhs;
+  }
+  for (k = kbeg + koff; k <= kend; k++) for (j = jbeg; j <= jend; j++)
+  for (i = ibeg + 1; i <= iend; i++){
+    if (dims == 3)
+      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)])
+            - dt/dx3*(Ex1[I3(k,j,i)] - Ex1[I3(k-1,j,i)]);
+    else
+      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)]);
+    o->Vs[1][I3(k,j,i)] = Bs[1][I3(k,j,i)] + rhs;
+  }
+  if (dims == 3)
+  for (k = kbeg; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
+  for (i = ibeg + 1; i <= iend; i++){
+    rhs = - dt/dx1*(Ex2[I3(k,j,i)] - Ex2[I3(k,j,i-1)])
+          + dt/dx2*(Ex1[I3(k,j,i)] - Ex1[I3(k,j-1,i)]);
+    o->Vs[2][I3(k,j,i)] = Bs[2][I3(k,j,i)] + rhs;
+  }
+}
+
 static void ct_average_magnetic_field (Oracle *o)
 /* MHD/CT/ct_field_average.c:58-124 (Cartesian, CT_EN_CORRECTION NO):
    DOM +/- 1 in every active direction, writes into Uc */
@@ -1214,6 +1269,284 @@ static void flag_shock (Oracle *o)
   }
 }
 
+/* =====================================================================
+   AdvanceStep, corner-transport upwind (Time_Stepping/ctu_step.c:142-727) with
+   the primitive MUSCL-Hancock predictor (States/hancock.c:33-142, MHD/prim_eqn.c:26-89;
+   PrimSource vanishes for Cartesian CT) and CTU_CT_Source (ctu_step.c:731-816)
+   ===================================================================== */
+static void prim_rhs (const Oracle *o, const double *v, const double *dv, Dirs q, double *Adv)
+{
+  int dims = o->c.dims;
+  double tau = 1.0/v[RHO], scrh;
+  int nv;
+  for (nv = 0; nv < NV; nv++) Adv[nv] = 0.0;
+  Adv[RHO] = v[q.vn]*dv[RHO] + v[RHO]*dv[q.vn];
+  if (dims == 3) scrh = 0.0 + v[q.bt]*dv[q.bt] + v[q.bb]*dv[q.bb];
+  else           scrh = 0.0 + v[q.bt]*dv[q.bt];
+  Adv[q.vn] = v[q.vn]*dv[q.vn] + tau*(dv[PRS] + scrh);
+  Adv[q.vt] = v[q.vn]*dv[q.vt] - tau*v[q.bn]*dv[q.bt];
+  if (dims == 3) Adv[q.vb] = v[q.vn]*dv[q.vb] - tau*v[q.bn]*dv[q.bb];
+  Adv[q.bn] = 0.0;
+  Adv[q.bt] = v[q.bt]*dv[q.vn] - v[q.bn]*dv[q.vt] + v[q.vn]*dv[q.bt];
+  if (dims == 3) Adv[q.bb] = v[q.bb]*dv[q.vn] - v[q.bn]*dv[q.vb] + v[q.vn]*dv[q.bb];
+  Adv[PRS] = o->c.gamma*v[PRS]*dv[q.vn] + v[q.vn]*dv[PRS];
+}
+
+static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, double dx)
+{
+  int i, nv, dims = o->c.dims;
+  double dt_2 = 0.5*dt, d_dl = 1.0/dx;
+  for (i = beg; i <= end; i++){
+    double dv[NV], Adv[NV];
+    for (nv = 0; nv < NV; nv++) dv[nv] = o->vp[i][nv] - o->vm[i][nv];
+    prim_rhs (o, o->v[i], dv, q, Adv);
+    for (nv = 0; nv < NV; nv++){
+      double scrh;
+      if (dims == 2 && (nv == VX3 || nv == BX3)) continue;
+      scrh = dt_2*(d_dl*Adv[nv] - 0.0);
+      o->vp[i][nv] -= scrh;
+      o->vm[i][nv] -= scrh;
+    }
+  }
+  /* CheckPrimStates (check_states.c:18-72): first order where p or rho turned negative */
+  for (i = beg; i <= end; i++){
+    double *ap = o->vp[i], *am = o->vm[i], *ac = o->v[i];
+    int sw = (ap[PRS] < 0.0) || (am[PRS] < 0.0);
+    sw = sw || (ap[RHO] < 0.0) || (am[RHO] < 0.0);
+    if (sw){
+      double bp = ap[q.bn], bm = am[q.bn];
+      for (nv = 0; nv < NV; nv++) am[nv] = ap[nv] = ac[nv];
+      ap[q.bn] = bp; am[q.bn] = bm;
+    }
+  }
+  for (i = beg; i <= end; i++)
+    for (nv = 0; nv < NV; nv++) o->v[i][nv] = 0.5*(o->vp[i][nv] + o->vm[i][nv]);
+}
+
+static void ctu_store_emf (Oracle *o, int dir, int nbeg, int nend, int *idx3)
+/* CT_StoreUpwindEMF (ct_emf.c:104-190) for faces nbeg-1 .. nend of the current pencil */
+{
+  int n, dims = o->c.dims;
+  for (n = nbeg-1; n <= nend; n++){
+    int id; signed char s;
+    idx3[dir] = n;
+    id = IDX(o, idx3[2], idx3[1], idx3[0]);
+    if      (o->flux[n][RHO] >  EPS_UCT_CONTACT) s = 1;
+    else if (o->flux[n][RHO] < -EPS_UCT_CONTACT) s = -1;
+    else s = 0;
+    if (dir == 0){
+      o->ezi[id] = -o->flux[n][BX2];
+      if (dims == 3) o->eyi[id] = o->flux[n][BX3];
+      o->svx[id] = s;
+    }else if (dir == 1){
+      o->ezj[id] = o->flux[n][BX1];
+      if (dims == 3) o->exj[id] = -o->flux[n][BX3];
+      o->svy[id] = s;
+    }else{
+      o->eyk[id] = -o->flux[n][BX1];
+      o->exk[id] =  o->flux[n][BX2];
+      o->svz[id] = s;
+    }
+  }
+}
+
+static void ctu_riemann (Oracle *o, Dirs q, int nbeg, int nend)
+/* Riemann (nbeg-1 .. nend): stateL = (vp[n], up[n]), stateR = (vm[n+1], um[n+1]) */
+{
+  int n;
+  for (n = nbeg-1; n <= nend; n++){
+    o->use_hll = ((o->pflag[n] & 4) || (o->pflag[n+1] & 4));
+    if      (o->c.solver == ORC_SOLVER_HLLD)
+      riemann_hlld (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
+    else if (o->c.solver == ORC_SOLVER_HLL || o->use_hll)
+      riemann_hll  (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
+    else
+      riemann_roe  (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
+  }
+}
+
+static void ctu_advance (Oracle *o, double dt)
+{
+  int dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
+  int dir, nv, i, j, k, d, id;
+  double dt2 = 0.5*dt;
+
+  /* 2. boundary conditions, shock flags (ctu_step.c:236-244) */
+  o->stage = 1;
+  boundary (o);
+  if (o->c.shock_flattening) flag_shock (o);
+  /* 3. Bs0 = Vs, Uc = PrimToCons (Vc) over TOT (:249-262) */
+  for (d = 0; d < dims; d++) memcpy (o->Bs0[d], o->Vs[d], sizeof(double)*(size_t)o->tot);
+  for (k = 0; k < o->T[2]; k++) for (j = 0; j < o->T[1]; j++) for (i = 0; i < o->T[0]; i++){
+    double v[NV], u[NV];
+    id = I3(k,j,i);
+    for (nv = 0; nv < NV; nv++) v[nv] = o->Vc[nv][id];
+    prim_to_cons (o, v, u);
+    for (nv = 0; nv < NV; nv++) o->Uc[nv][id] = u[nv];
+  }
+
+  /* 4. predictor: normal predictors and normal Riemann problems (:283-420) */
+  for (dir = 0; dir < dims; dir++){
+    Dirs q = set_vector_indices (dir);
+    int lo[3], hi[3], t1, t2, a, b, n, nbeg, nend, ntot = o->T[dir];
+    double dt2_dx = dt2/o->c.dx[dir], inv_dl = 1.0/o->c.dx[dir];
+    for (a = 0; a < 3; a++){ lo[a] = o->beg[a]; hi[a] = o->end[a]; }
+    /* transverse +-1 (:290-292), then with CT normal +-1 and transverse +-1 again (:293-297) */
+    for (a = 0; a < dims; a++){ if (a != dir){ lo[a] -= 2; hi[a] += 2; } else { lo[a]--; hi[a]++; } }
+    nbeg = lo[dir]; nend = hi[dir];
+    if (dir == 0){ t1 = 1; t2 = 2; } else if (dir == 1){ t1 = 0; t2 = 2; } else { t1 = 0; t2 = 1; }
+    for (b = lo[t2]; b <= hi[t2]; b++) for (a = lo[t1]; a <= hi[t1]; a++){
+      int idx3[3];
+      idx3[t1] = a; idx3[t2] = b;
+      for (n = 0; n < ntot; n++){
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++) o->vn[n][nv] = o->v[n][nv] = o->Vc[nv][id];
+        o->bn[n] = o->Vs[dir][id];
+        o->pflag[n] = o->flag[id];
+      }
+      /* 4d. States (nbeg-1 .. nend+1): PLM (incl. face field), Hancock, PrimToCons (plm_states.c:80-312) */
+      states_plm (o, nbeg-1, nend+1, q.bn);
+      hancock_step (o, nbeg-1, nend+1, q, dt, o->c.dx[dir]);
+      for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vp[n], o->up[n]); }
+      for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vm[n], o->um[n]); }
+      /* 4f. Riemann, EMF, rhs with dt/2 */
+      ctu_riemann (o, q, nbeg, nend);
+      ctu_store_emf (o, dir, nbeg, nend, idx3);
+      /* CTU_CT_Source (nbeg-1 .. nend+1), ctu_step.c:731-816 */
+      for (n = nbeg-1; n <= nend+1; n++){
+        double db = dt2_dx*(o->up[n][q.bn] - o->um[n][q.bn]), scrh;
+        const double *v = o->vn[n];
+        o->up[n][VX1] += v[BX1]*db; o->um[n][VX1] += v[BX1]*db;
+        o->up[n][VX2] += v[BX2]*db; o->um[n][VX2] += v[BX2]*db;
+        if (dims == 3){ o->up[n][VX3] += v[BX3]*db; o->um[n][VX3] += v[BX3]*db; }
+        o->up[n][q.bt] += v[q.vt]*db; o->um[n][q.bt] += v[q.vt]*db;
+        if (dims == 3){ o->up[n][q.bb] += v[q.vb]*db; o->um[n][q.bb] += v[q.vb]*db; }
+        if (dims == 3) scrh = v[VX1]*v[BX1] + v[VX2]*v[BX2] + v[VX3]*v[BX3];
+        else           scrh = v[VX1]*v[BX1] + v[VX2]*v[BX2];
+        o->up[n][ENG] += scrh*db; o->um[n][ENG] += scrh*db;
+      }
+      for (n = nbeg-1; n <= nend+1; n++){
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++){ o->Up[dir][nv][id] = o->up[n][nv]; o->Um[dir][nv][id] = o->um[n][nv]; }
+      }
+      /* RightHandSide (nbeg .. nend, dt/2), rhs.c:193-201; 4g. store */
+      for (n = nbeg; n <= nend; n++){
+        double rhs[NV];
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++) rhs[nv] = -dt2_dx*(o->flux[n][nv] - o->flux[n-1][nv]);
+        rhs[q.vn] -= dt2_dx*(o->press[n] - o->press[n-1]);
+        for (nv = 0; nv < NV; nv++) o->rhs3[dir][nv][id] = rhs[nv];
+        o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);       /* :416-419 */
+      }
+    }
+  }
+  /* emf ranges as left by the predictor sweeps (ct_emf.c:130,152,173 with beg = nbeg-1, end = nend) */
+  o->emf_ibeg = o->beg[0]-2; o->emf_iend = o->end[0]+1;
+  o->emf_jbeg = o->beg[1]-2; o->emf_jend = o->end[1]+1;
+  if (dims == 3){ o->emf_kbeg = o->beg[2]-2; o->emf_kend = o->end[2]+1; }
+  else          { o->emf_kbeg = o->emf_kend = 0; }
+
+  /* 5a. Uh = U^n + sum of the half-step rhs over DOM +- 1 (:427-441) */
+  for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)
+  for (j = o->beg[1]-1; j <= o->end[1]+1; j++)
+  for (i = o->beg[0]-1; i <= o->end[0]+1; i++){
+    id = I3(k,j,i);
+    for (nv = 0; nv < NV; nv++){
+      double dU;
+      if (dims == 3) dU = o->rhs3[0][nv][id] + o->rhs3[1][nv][id] + o->rhs3[2][nv][id];
+      else           dU = o->rhs3[0][nv][id] + o->rhs3[1][nv][id];
+      o->Uh[nv][id] = o->Uc[nv][id] + dU;
+    }
+  }
+  /* 5b. emf; 5d. half-step staggered field and its cell average into Uh (:447-470) */
+  ct_compute_emf (o);
+  ct_update (o, 0.5*dt);
+  for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)
+  for (j = o->beg[1]-1; j <= o->end[1]+1; j++)
+  for (i = o->beg[0]-1; i <= o->end[0]+1; i++){
+    o->Uh[BX1][I3(k,j,i)] = 0.5*(o->Vs[0][I3(k,j,i)] + o->Vs[0][I3(k,j,i-1)]);
+    o->Uh[BX2][I3(k,j,i)] = 0.5*(o->Vs[1][I3(k,j,i)] + o->Vs[1][I3(k,j-1,i)]);
+    if (dims == 3) o->Uh[BX3][I3(k,j,i)] = 0.5*(o->Vs[2][I3(k,j,i)] + o->Vs[2][I3(k-1,j,i)]);
+  }
+  /* 5f. Vc = ConsToPrim (Uh) over DOM +- 1: V^{n+1/2} (:486-497) */
+  for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)
+  for (j = o->beg[1]-1; j <= o->end[1]+1; j++)
+  for (i = o->beg[0]-1; i <= o->end[0]+1; i++){
+    double v[NV], u[NV];
+    id = I3(k,j,i);
+    for (nv = 0; nv < NV; nv++) u[nv] = o->Uh[nv][id];
+    o->floor_events += cons_to_prim (o, u, v);
+    for (nv = 0; nv < NV; nv++){ o->Uh[nv][id] = u[nv]; o->Vc[nv][id] = v[nv]; }
+  }
+
+  /* 6. corrector (:517-640) */
+  o->stage = 2;
+  for (dir = 0; dir < dims; dir++){
+    Dirs q = set_vector_indices (dir);
+    int lo[3], hi[3], t1, t2, a, b, n, nbeg = o->beg[dir], nend = o->end[dir];
+    double dtdx = dt/o->c.dx[dir], inv_dl = 1.0/o->c.dx[dir];
+    for (a = 0; a < 3; a++){ lo[a] = o->beg[a]; hi[a] = o->end[a]; }
+    for (a = 0; a < dims; a++) if (a != dir){ lo[a]--; hi[a]++; }
+    if (dir == 0){ t1 = 1; t2 = 2; } else if (dir == 1){ t1 = 0; t2 = 2; } else { t1 = 0; t2 = 1; }
+    for (b = lo[t2]; b <= hi[t2]; b++) for (a = lo[t1]; a <= hi[t1]; a++){
+      int idx3[3];
+      idx3[t1] = a; idx3[t2] = b;
+      for (n = nbeg-1; n <= nend+1; n++){
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++){
+          double dU;
+          if (dims == 3){
+            if      (dir == 0) dU = 0.0 + o->rhs3[1][nv][id] + o->rhs3[2][nv][id];
+            else if (dir == 1) dU = o->rhs3[0][nv][id] + 0.0 + o->rhs3[2][nv][id];
+            else               dU = o->rhs3[0][nv][id] + o->rhs3[1][nv][id];
+          }else{
+            if (dir == 0) dU = 0.0 + o->rhs3[1][nv][id];
+            else          dU = o->rhs3[0][nv][id] + 0.0;
+          }
+          o->up[n][nv] = o->Up[dir][nv][id] + dU;
+          o->um[n][nv] = o->Um[dir][nv][id] + dU;
+          o->v[n][nv]  = o->Vc[nv][id];
+        }
+        o->pflag[n] = o->flag[id];
+      }
+      /* normal field: the half-step staggered one (:583-587) */
+      for (n = nbeg-2; n <= nend+1; n++){
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        o->bn[n] = o->Vs[dir][id];
+        o->up[n][q.bn] = o->bn[n];
+        o->um[n+1][q.bn] = o->bn[n];
+      }
+      for (n = nbeg-1; n <= nend+1; n++) o->floor_events += cons_to_prim (o, o->um[n], o->vm[n]);
+      for (n = nbeg-1; n <= nend+1; n++) o->floor_events += cons_to_prim (o, o->up[n], o->vp[n]);
+      ctu_riemann (o, q, nbeg, nend);
+      ctu_store_emf (o, dir, nbeg, nend, idx3);
+      for (n = nbeg; n <= nend; n++){
+        double rhs[NV];
+        idx3[dir] = n;
+        id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
+        rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
+        for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
+        o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);
+      }
+    }
+  }
+  o->emf_ibeg = o->beg[0]-1; o->emf_iend = o->end[0];
+  o->emf_jbeg = o->beg[1]-1; o->emf_jend = o->end[1];
+  if (dims == 3){ o->emf_kbeg = o->beg[2]-1; o->emf_kend = o->end[2]; }
+  else          { o->emf_kbeg = o->emf_kend = 0; }
+  /* 8. emf; 11. Vs = Bs0 + dt curl E, cell average; 14. ConsToPrim over DOM (:646-700) */
+  ct_compute_emf (o);
+  ct_update_from (o, o->Bs0, dt);      /* faces outside the emf ranges keep their half-step values, as in the reference */
+  ct_average_magnetic_field (o);
+  cons_to_prim_3d (o);
+}
+
 int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
 {
   int i, j, k, nv, d, id, dims = o->c.dims;
@@ -1221,6 +1554,7 @@ int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
   o->max_mach = 0.0;                     /* main.c:304 */
   o->inv_dt_hyp = 0.0;                   /* main.c:569 (reset by NextTimeStep) */
   o->floor_events = 0;
+  if (o->c.ctu){ ctu_advance (o, dt); goto done; }
 
   /* ---- stage 1 (rk_step.c:85-139) ---- */
   o->stage = 1;

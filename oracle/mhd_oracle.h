@@ -48,6 +48,9 @@ typedef struct {
   int    limiter;       /* ORC_LIM_*  (PLM only)                           */
   int    emf_average;   /* ORC_EMF_*                                       */
   int    shock_flattening; /* 0 NO, 1 MULTID (flag_shock.c:79-230)            */
+  int    ctu;           /* 0: RK2/RK3 (rk_order); 1: corner-transport upwind with the
+                           primitive MUSCL-Hancock predictor (TIME_STEPPING HANCOCK,
+                           Time_Stepping/ctu_step.c, States/hancock.c)          */
 } OracleConfig;
 
 typedef struct Oracle Oracle;

@@ -11,7 +11,7 @@
 # reference: the makefile VPATHs into it.
 #
 # usage: build_ref.sh <variant> [<variant> ...]
-#   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3
+#   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3 2d_plm_hancock 3d_plm_hancock (CTU)
 #   optional suffixes:  _l{fl,mm,va,os,um,vl,mc}  single LIMITER for all variables
 #                                                 (Src/States/plm_coeffs.h:72-123)
 #                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE
@@ -37,8 +37,9 @@ for VARIANT in "$@"; do
     *)      RECON=LINEAR;    STATES_OBJ="plm_states.o";               EXTRA_HDR="" ;;
   esac
   case "$VARIANT" in
-    *_rk3) TSTEP=RK3 ;;
-    *)     TSTEP=RK2 ;;
+    *_rk3*)     TSTEP=RK3;     STEP_OBJ="rk_step.o update_stage.o" ;;
+    *_hancock*) TSTEP=HANCOCK; STEP_OBJ="ctu_step.o hancock.o" ;;     # define_problem.py:542-553
+    *)          TSTEP=RK2;     STEP_OBJ="rk_step.o update_stage.o" ;;
   esac
   case "$VARIANT" in
     *_lfl*) LIMITER=FLAT_LIM ;;  *_lmm*) LIMITER=MINMOD_LIM ;;  *_lva*) LIMITER=VANALBADA_LIM ;;
@@ -125,7 +126,7 @@ OBJ += bin_io.o colortable.o initialize.o jet_domain.o main.o output_log.o resta
        runtime_setup.o set_image.o show_config.o set_grid.o startup.o split_source.o \\
        userdef_output.o write_data.o write_tab.o write_img.o write_vtk.o write_vtk_proc.o
 include \$(SRC)/Math_Tools/makefile
-OBJ += $STATES_OBJ vec_pot_diff.o vec_pot_update.o rk_step.o update_stage.o
+OBJ += $STATES_OBJ vec_pot_diff.o vec_pot_update.o $STEP_OBJ
 include \$(SRC)/MHD/makefile
 include \$(SRC)/MHD/CT/makefile
 include \$(SRC)/EOS/Ideal/makefile

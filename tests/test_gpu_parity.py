@@ -21,7 +21,7 @@ def _stepper(g, arith):
                       bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten)
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names(ctu=False))
 def test_exact_bit_identical_to_reference_golden(name):
     g = Golden(name)
     s = _stepper(g, "exact")
@@ -55,7 +55,7 @@ def test_exact_bit_identical_to_reference_golden(name):
 DEGENERATE_ROE = {"rotor2d_ppm_roe": (1e-9, 1e-8), "rotor2d_ppm_roe_100": (1e-9, 1e-8)}
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", golden_names(ctu=False))
 def test_fast_within_tolerance_of_reference_golden(name):
     g = Golden(name)
     s = _stepper(g, "fast")

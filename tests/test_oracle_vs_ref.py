@@ -34,6 +34,17 @@ CASES = [
     ("blast3d_sfl", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, flatten=True), 10),
     ("blast2d_sfl_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), first_dt=3e-4, solver="roe", flatten=True), 12),
     ("blast3d_sfl_uct_hll", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, emf="uct_hll", flatten=True), 8),
+    # corner-transport upwind with the MUSCL-Hancock predictor (ctu_step.c, hancock.c): SURVEY 8f row 1
+    ("ot2d_ctu", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, tstep="hancock", cfl=0.4), 8),
+    ("blast3d_ctu", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, tstep="hancock"), 6),
+    ("turb3d_ctu_roe", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, tstep="hancock", solver="roe"), 6),
+    ("blast2d_ctu_hll_arith_vl", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="hancock", solver="hll",
+                                           emf="arith", limiter="vl"), 10),
+    ("blast3d_ctu_sfl_uct0", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, tstep="hancock",
+                                       emf="uct0", flatten=True), 8),
+    ("blast2d_ctu_reflective", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock",
+                                         bc=("reflective", "outflow", "reflective", "reflective", "outflow", "outflow"),
+                                         blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3)), 12),
 ]
 
 
@@ -48,7 +59,7 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dom = cfg.resolved_domain()
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
-               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten)
+               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"))
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

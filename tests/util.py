@@ -13,8 +13,12 @@ TOL_100_STEPS = 1e-9
 TOL_DT = 1e-12
 
 
-def golden_names():
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def golden_names(ctu=None):
+    """All fixtures, or only those with (ctu=True) / without (ctu=False) corner-transport-upwind time stepping."""
+    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    if ctu is None:
+        return names
+    return [n for n in names if ("_ctu" in n) == ctu]
 
 
 class Golden:
@@ -50,6 +54,7 @@ class Golden:
         # (Src/set_grid.c:400  dx = (xR - xL)/npoint)
         self.dx = [(self.domain[a][1] - self.domain[a][0]) / self.n[a] for a in range(self.dims)]
         self.rk_order = 3 if self.tstep == "rk3" else 2
+        self.ctu = self.tstep == "hancock"
 
 
 def rel_l1(a, b):

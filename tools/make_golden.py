@@ -73,6 +73,13 @@ CASES = {
     "blast2d_sfl_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, solver="roe", flatten=True), 25),
     "blast3d_sfl_uct_hll": (RefConfig(problem="blast", dims=3, n=(12, 16, 12), first_dt=6e-4, cfl=0.3, emf="uct_hll",
                                       flatten=True), 15),
+    # corner-transport upwind, MUSCL-Hancock predictor (TIME_STEPPING HANCOCK: ctu_step.c, hancock.c)
+    "ot2d_ctu": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, tstep="hancock"), 20),
+    "blast3d_ctu": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, tstep="hancock"), 12),
+    "turb3d_ctu_roe": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, tstep="hancock", solver="roe"), 10),
+    "blast3d_ctu_sfl_uct0": (RefConfig(problem="blast", dims=3, n=(12, 16, 12), first_dt=6e-4, cfl=0.3, tstep="hancock",
+                                       emf="uct0", flatten=True), 15),
+    "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
 
