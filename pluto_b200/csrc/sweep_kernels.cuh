@@ -65,6 +65,15 @@ __device__ __forceinline__ void load_zone (const SweepArgs &a, int id, double *v
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): no destination register,
 // so a thread can pull the rows of its NEXT face while the current one is solved
+#ifdef PG_EMU
+// host interpreter of the kernels (tests/emu, test infrastructure): the copies of a thread land
+// when it waits for them
+__device__ __forceinline__ void cp_async8 (double *smem_dst, const double *gsrc) { pg_emu::async_copy8 (smem_dst, gsrc); }
+__device__ __forceinline__ void cp_async8_ordered (double *smem_dst, const double *gsrc) { pg_emu::async_copy8 (smem_dst, gsrc); }
+__device__ __forceinline__ void cp_async_commit () { pg_emu::async_commit (); }
+template <int N> __device__ __forceinline__ void cp_async_wait () { pg_emu::async_wait (N); }
+__device__ __forceinline__ void cp_async_wait_all () { pg_emu::async_wait (0); }
+#else
 __device__ __forceinline__ void cp_async8 (double *smem_dst, const double *gsrc)
 {
   const unsigned sa = (unsigned)__cvta_generic_to_shared (smem_dst);
@@ -81,20 +90,25 @@ __device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.com
 template <int N> __device__ __forceinline__ void cp_async_wait ()     // all but the N most recent groups
 { asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all () { asm volatile ("cp.async.wait_group 0;" ::: "memory"); }
+#endif
 
 #ifndef PG_MARCH_L2PF
 #define PG_MARCH_L2PF 0
 #endif
 __device__ __forceinline__ void prefetch_l2 (const void *p)
 {
+#ifndef PG_EMU
   asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
 }
 #ifndef PG_PREFETCH
 #define PG_PREFETCH 0
 #endif
 __device__ __forceinline__ void prefetch_l1 (const void *p)
 {
-#if PG_PREFETCH == 1
+#if defined(PG_EMU)
+  (void)p;
+#elif PG_PREFETCH == 1
   asm volatile ("prefetch.global.L1 [%0];" :: "l"(p));
 #elif PG_PREFETCH == 2
   asm volatile ("prefetch.global.L2 [%0];" :: "l"(p));
