@@ -53,6 +53,12 @@ enum { PLUTO_GPU_LIM_DEFAULT = 0, PLUTO_GPU_LIM_FLAT, PLUTO_GPU_LIM_MINMOD, PLUT
 /* CT_EMF_AVERAGE in definitions.h (Src/MHD/CT/ct_emf.c:241-283) */
 enum { PLUTO_GPU_EMF_UCT_CONTACT = 0, PLUTO_GPU_EMF_ARITHMETIC = 1, PLUTO_GPU_EMF_UCT0 = 2,
        PLUTO_GPU_EMF_UCT_HLL = 3 /* the reference's default, Src/MHD/CT/ct.h:43-45 */ };
+/* TIME_STEPPING in definitions.h.  RK: rk_step.c (RK2 / RK3 by rk_order).  HANCOCK: the unsplit
+   corner-transport-upwind step of Src/Time_Stepping/ctu_step.c:142-727 with the primitive
+   MUSCL-Hancock predictor (Src/States/hancock.c:33-142) and CTU_CT_Source (ctu_step.c:731-816);
+   LINEAR reconstruction, one more ghost zone (Src/get_nghost.c:86-90), one Boundary call per
+   step; CT_EMF_AVERAGE UCT_CONTACT, ARITHMETIC or UCT0. */
+enum { PLUTO_GPU_TS_RK = 0, PLUTO_GPU_TS_HANCOCK = 1 };
 
 typedef struct {
   int    dims;         /* DIMENSIONS = COMPONENTS: 2 or 3                     */
@@ -71,6 +77,7 @@ typedef struct {
   int    emf_average;  /* PLUTO_GPU_EMF_*  (0 = UCT_CONTACT)                  */
   int    shock_flattening; /* SHOCK_FLATTENING: 0 NO, 1 MULTID (Src/flag_shock.c:79-230;
                               LINEAR reconstruction only)                      */
+  int    time_stepping;    /* PLUTO_GPU_TS_* (0 = RK2 / RK3 by rk_order)       */
 } PlutoGpuConfig;
 
 typedef struct PlutoGpu PlutoGpu;
@@ -89,6 +96,7 @@ int  pluto_gpu_create   (const PlutoGpuConfig *cfg, PlutoGpu **out);
 void pluto_gpu_destroy  (PlutoGpu *h);
 const char *pluto_gpu_last_error (void);
 int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
+int  pluto_gpu_nstages  (const PlutoGpu *h);     /* Boundary calls (= halo exchanges) per step: rk_order, 1 with HANCOCK */
 
 /* ---- state transfer ---------------------------------------------------
    "interior" layout = the reference's .dbl dump layout (Src/bin_io.c:216):

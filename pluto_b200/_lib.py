@@ -13,10 +13,11 @@ BC = {"periodic": 0, "outflow": 1, "reflective": 2, "shared": 3}
 LIMITER = {"default": 0, "fl": 1, "mm": 2, "va": 3, "os": 4, "um": 5, "vl": 6, "mc": 7}      # LIMITER
 EMF = {"uct_contact": 0, "arith": 1, "uct0": 2, "uct_hll": 3}                                                 # CT_EMF_AVERAGE
 ARITH = {"exact": 0, "fast": 1}
+TIME_STEPPING = {"rk": 0, "hancock": 1}                                                                       # TIME_STEPPING
 
 # every symbol include/pluto_gpu.h declares (checked by tests/test_cabi.py)
 SYMBOLS = [
-    "pluto_gpu_create", "pluto_gpu_destroy", "pluto_gpu_last_error", "pluto_gpu_nghost",
+    "pluto_gpu_create", "pluto_gpu_destroy", "pluto_gpu_last_error", "pluto_gpu_nghost", "pluto_gpu_nstages",
     "pluto_gpu_upload_interior", "pluto_gpu_download_interior", "pluto_gpu_upload_data",
     "pluto_gpu_download_data", "pluto_gpu_advance", "pluto_gpu_advance_data",
     "pluto_gpu_boundary", "pluto_gpu_next_dt", "pluto_gpu_halo_doubles", "pluto_gpu_halo_pack",
@@ -35,7 +36,7 @@ class PlutoGpuConfig(C.Structure):
                 ("rk_order", C.c_int), ("bc", C.c_int * 6), ("arith", C.c_int), ("device", C.c_int),
                 ("gamma", C.c_double), ("dx", C.c_double * 3), ("small_dn", C.c_double),
                 ("small_pr", C.c_double), ("limiter", C.c_int), ("emf_average", C.c_int),
-                ("shock_flattening", C.c_int)]
+                ("shock_flattening", C.c_int), ("time_stepping", C.c_int)]
 
 
 class PlutoGpuStepInfo(C.Structure):
@@ -65,6 +66,7 @@ def load_library(path: str | None = None):
     L.pluto_gpu_destroy.restype = None
     L.pluto_gpu_last_error.restype = C.c_char_p
     L.pluto_gpu_nghost.argtypes = [vp]
+    L.pluto_gpu_nstages.argtypes = [vp]
     for nm in ("pluto_gpu_upload_interior", "pluto_gpu_download_interior",
                "pluto_gpu_upload_data", "pluto_gpu_download_data"):
         getattr(L, nm).argtypes = [vp, vp, vp, vp, vp]

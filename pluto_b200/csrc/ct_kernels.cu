@@ -62,12 +62,13 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
 {
   const Geom &g = a.g;
   // edges (k,j,i) with i in [IBEG-1,IEND], j in [JBEG-1,JEND], k in [KBEG-1,KEND]
-  const int ni = g.n[0] + 1, nj = g.n[1] + 1, nk = (NC == 3 ? g.n[2] + 1 : 1);
+  const int ext = a.ext;
+  const int ni = g.n[0] + 1 + 2*ext, nj = g.n[1] + 1 + 2*ext, nk = (NC == 3 ? g.n[2] + 1 + 2*ext : 1);
   const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;          // 32-bit: < 2^31 zones per block
   if (t >= (unsigned)(ni*nj*nk)) return;
   const unsigned tq = t/(unsigned)ni;
   const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
-  const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
+  const int i = g.beg[0] - 1 - ext + ti, j = g.beg[1] - 1 - ext + tj, k = (NC == 3 ? g.beg[2] - 1 - ext + tk : 0);
   const long long id = gidx (g, k, j, i);
   const long long sx = 1, sy = g.S1, sz = g.S12;
 
@@ -207,15 +208,16 @@ __global__ void __launch_bounds__(128, 16)
 ct_update_kernel (const __grid_constant__ CtArgs a)
 {
   const Geom &g = a.g;
-  const int ni = g.n[0] + 1, nj = g.n[1] + 1, nk = (NC == 3 ? g.n[2] + 1 : 1);
+  const int ext = a.ext;
+  const int ni = g.n[0] + 1 + 2*ext, nj = g.n[1] + 1 + 2*ext, nk = (NC == 3 ? g.n[2] + 1 + 2*ext : 1);
   const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;          // 32-bit: < 2^31 zones per block
   if (t >= (unsigned)(ni*nj*nk)) return;
   const unsigned tq = t/(unsigned)ni;
   const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
-  const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
+  const int i = g.beg[0] - 1 - ext + ti, j = g.beg[1] - 1 - ext + tj, k = (NC == 3 ? g.beg[2] - 1 - ext + tk : 0);
   const long long id = gidx (g, k, j, i);
   const long long sy = g.S1, sz = g.S12;
-  const bool in_i = i >= g.beg[0], in_j = j >= g.beg[1], in_k = (NC == 3 ? k >= g.beg[2] : true);
+  const bool in_i = i >= g.beg[0] - ext, in_j = j >= g.beg[1] - ext, in_k = (NC == 3 ? k >= g.beg[2] - ext : true);
   const double dtdx0 = __ldg (a.dtp), dtdx1 = __ldg (a.dtp + 1), dtdx2 = (NC == 3 ? __ldg (a.dtp + 2) : 0.0);
 
   if (in_j && in_k){        // Bx1 at (i+1/2, j, k), i in [IBEG-1, IEND]
@@ -541,7 +543,7 @@ halo_table_kernel (const HaloEntry *__restrict__ tab, const Geom g)
 int launch_ct_emf (const CtArgs &a, cudaStream_t s)
 {
   const Geom &g = a.g;
-  const long long n = (long long)(g.n[0] + 1)*(g.n[1] + 1)*(g.dims == 3 ? g.n[2] + 1 : 1);
+  const long long n = (long long)(g.n[0] + 1 + 2*a.ext)*(g.n[1] + 1 + 2*a.ext)*(g.dims == 3 ? g.n[2] + 1 + 2*a.ext : 1);
 #define PG_LE(C) do { switch (a.avg){                                                   \
       case 1:  ct_emf_kernel<C, 1><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
       case 2:  ct_emf_kernel<C, 2><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
@@ -555,7 +557,7 @@ int launch_ct_emf (const CtArgs &a, cudaStream_t s)
 int launch_ct_update (const CtArgs &a, cudaStream_t s)
 {
   const Geom &g = a.g;
-  const long long n = (long long)(g.n[0] + 1)*(g.n[1] + 1)*(g.dims == 3 ? g.n[2] + 1 : 1);
+  const long long n = (long long)(g.n[0] + 1 + 2*a.ext)*(g.n[1] + 1 + 2*a.ext)*(g.dims == 3 ? g.n[2] + 1 + 2*a.ext : 1);
   if (g.dims == 3) ct_update_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
   else             ct_update_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
   return cudaGetLastError () == cudaSuccess ? 1 : -1;

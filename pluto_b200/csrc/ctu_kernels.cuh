@@ -1,0 +1,415 @@
+// ctu_kernels.cuh -- corner-transport-upwind time stepping (TIME_STEPPING HANCOCK with
+// CONSTRAINED_TRANSPORT): the reference's AdvanceStep of Src/Time_Stepping/ctu_step.c:142-727
+// with the primitive MUSCL-Hancock predictor (Src/States/hancock.c:33-142,
+// Src/MHD/prim_eqn.c:26-89), CheckPrimStates (Src/check_states.c:18-72) and CTU_CT_Source
+// (ctu_step.c:731-816).
+//
+// Two sweeps per direction and step, both fused like the RK sweeps (reconstruct -> Riemann ->
+// face-EMF store -> flux difference, nothing but the result in HBM):
+//   PHASE 0, predictor  (ctu_step.c:283-420): normal predictor states from V^n, Riemann problem,
+//            face EMFs, half-step right-hand side rhs[dir] (dt/2) of zones DOM+-1, on the pencils
+//            of DOM+-2.
+//   PHASE 1, corrector  (ctu_step.c:517-640): the normal predictor states are RECOMPUTED from V^n
+//            (PLM + Hancock + PrimToCons + CT source: ~250 flops per zone and direction) instead of
+//            being stored and read back as the reference's Up/Um arrays are (16 doubles written and
+//            read per zone and direction = 256 B: the recomputation is ~6 times cheaper on a B200
+//            and saves 48 arrays of HBM), corrected with the transverse half-step right-hand sides,
+//            given the half-step staggered normal field, mapped to primitives; Riemann problem, face
+//            EMFs, U += rhs (dt).
+// Thread mapping as in sweep_kernels.cuh: lanes always run along x1.  x1 sweep: a lane owns a zone
+// and its right face, the neighbour's minus state and the left face's flux travel by warp shuffles
+// (30 updated zones per warp).  x2 / x3 sweeps: a thread marches along the sweep with the stencil
+// window, the previous zone's plus state and the previous face's flux in registers.
+// In between, ctu_half_kernel forms U^n + sum of the half-step right-hand sides with the half-step
+// face-averaged field and maps it to V^{n+1/2} on DOM+-1 (ctu_step.c:427-497).
+#pragma once
+#include "sweep_kernels.cuh"
+
+namespace PG_NS {
+
+// A dV/dx of the primitive MHD equations along DIR (prim_eqn.c:26-89; the Powell term is absent with CT)
+template <int DIR, int NC>
+__device__ __forceinline__ void prim_rhs (const Phys &ph, const double *v, const double *dv, double *Adv)
+{
+  typedef Dirs<DIR> D;
+  const double tau = pg_rcp (v[RHO]);
+  double scrh;
+  PG_FOR_NV(nv) Adv[nv] = 0.0;
+  Adv[RHO] = v[D::vn]*dv[RHO] + v[RHO]*dv[D::vn];
+  if (NC == 3) scrh = 0.0 + v[D::bt]*dv[D::bt] + v[D::bb]*dv[D::bb];
+  else         scrh = 0.0 + v[D::bt]*dv[D::bt];
+  Adv[D::vn] = v[D::vn]*dv[D::vn] + tau*(dv[PRS] + scrh);
+  Adv[D::vt] = v[D::vn]*dv[D::vt] - tau*v[D::bn]*dv[D::bt];
+  if (NC == 3) Adv[D::vb] = v[D::vn]*dv[D::vb] - tau*v[D::bn]*dv[D::bb];
+  Adv[D::bn] = 0.0;
+  Adv[D::bt] = v[D::bt]*dv[D::vn] - v[D::bn]*dv[D::vt] + v[D::vn]*dv[D::bt];
+  if (NC == 3) Adv[D::bb] = v[D::bb]*dv[D::vn] - v[D::bn]*dv[D::vb] + v[D::vn]*dv[D::bb];
+  Adv[PRS] = ph.gamma*v[PRS]*dv[D::vn] + v[D::vn]*dv[PRS];
+}
+
+// normal predictor of one zone: PLM states (plm_states.c:134-275, the normal component takes the
+// staggered field of the zone's two faces), evolved by dt/2 with the primitive equations
+// (hancock.c:96-124), first order where density or pressure turned negative (check_states.c:35-66)
+template <int DIR, int NC, bool FLAT>
+__device__ __forceinline__ void ctu_states (const Phys &ph, int limiter, unsigned fl, const double *vl, const double *v,
+                                            const double *vr, double bsm, double bsp, double dt_2, double d_dl,
+                                            double *vp, double *vm)
+{
+  typedef Dirs<DIR> D;
+  double dvm[NV], dvp[NV], dv[NV], Adv[NV];
+  PG_FOR_NV(nv){ dvm[nv] = v[nv] - vl[nv]; dvp[nv] = vr[nv] - v[nv]; }
+  if (FLAT && (fl & 1u)) plm_zone_single<NC>(2, v, dvm, dvp, vp, vm);
+  else                   plm_zone<NC>(limiter, v, dvm, dvp, vp, vm);
+  vp[D::bn] = bsp; vm[D::bn] = bsm;
+  PG_FOR_NV(nv) dv[nv] = vp[nv] - vm[nv];
+  prim_rhs<DIR, NC>(ph, v, dv, Adv);
+  PG_FOR_NV(nv){
+    const double scrh = dt_2*(d_dl*Adv[nv] - 0.0);
+    vp[nv] -= scrh;
+    vm[nv] -= scrh;
+  }
+  bool sw = (vp[PRS] < 0.0) || (vm[PRS] < 0.0);
+  sw = sw || (vp[RHO] < 0.0) || (vm[RHO] < 0.0);
+  if (sw){
+    const double bp = vp[D::bn], bm = vm[D::bn];
+    PG_FOR_NV(nv) vm[nv] = vp[nv] = v[nv];
+    vp[D::bn] = bp; vm[D::bn] = bm;
+  }
+}
+
+// corrector states of one zone: conservative predictor states + CT source (ctu_step.c:731-816) +
+// transverse half-step right-hand sides, half-step staggered normal field, ConsToPrim
+// (ctu_step.c:545-603).  Returns the number of ConsToPrim repairs.
+template <int DIR, int NC>
+__device__ __forceinline__ int ctu_correct (const Phys &ph, const double *vc, const double *dU, double dt2_dx,
+                                            double bhm, double bhp, double *vp, double *vm, double *up, double *um)
+{
+  typedef Dirs<DIR> D;
+  prim_to_cons<NC>(ph, vp, up);
+  prim_to_cons<NC>(ph, vm, um);
+  const double db = dt2_dx*(up[D::bn] - um[D::bn]);
+  up[MX1] += vc[BX1]*db; um[MX1] += vc[BX1]*db;
+  up[MX2] += vc[BX2]*db; um[MX2] += vc[BX2]*db;
+  if (NC == 3){ up[MX3] += vc[BX3]*db; um[MX3] += vc[BX3]*db; }
+  up[D::bt] += vc[D::vt]*db; um[D::bt] += vc[D::vt]*db;
+  if (NC == 3){ up[D::bb] += vc[D::vb]*db; um[D::bb] += vc[D::vb]*db; }
+  double scrh;
+  if (NC == 3) scrh = vc[VX1]*vc[BX1] + vc[VX2]*vc[BX2] + vc[VX3]*vc[BX3];
+  else         scrh = vc[VX1]*vc[BX1] + vc[VX2]*vc[BX2];
+  up[ENG] += scrh*db; um[ENG] += scrh*db;
+  PG_FOR_NV(nv){ up[nv] = up[nv] + dU[nv]; um[nv] = um[nv] + dU[nv]; }
+  up[D::bn] = bhp; um[D::bn] = bhm;
+  int nfl = cons_to_prim<NC>(ph, um, vm);
+  nfl += cons_to_prim<NC>(ph, up, vp);
+  return nfl;
+}
+
+// sum of the transverse half-step right-hand sides of a zone, in the reference's order (ctu_step.c:551-562)
+template <int DIR, int NC>
+__device__ __forceinline__ void ctu_transverse (const CtuArgs &a, int id, double *dU)
+{
+  PG_FOR_NV(nv){
+    if (NC == 3){
+      if      (DIR == 0) dU[nv] = 0.0 + a.rhs[1][nv][id] + a.rhs[2][nv][id];
+      else if (DIR == 1) dU[nv] = a.rhs[0][nv][id] + 0.0 + a.rhs[2][nv][id];
+      else               dU[nv] = a.rhs[0][nv][id] + a.rhs[1][nv][id];
+    }else{
+      if (DIR == 0) dU[nv] = 0.0 + a.rhs[1][nv][id];
+      else          dU[nv] = a.rhs[0][nv][id] + 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  x1 sweep
+// ---------------------------------------------------------------------------
+template <int PHASE, int SOLVER, int NC, bool FLAT>
+__global__ void __launch_bounds__(128, 2)
+ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
+{
+  constexpr int DIR = 0;
+  typedef Dirs<DIR> D;
+  constexpr int E = (PHASE == 0 ? 2 : 1);            // transverse extension of the pencils, states of zones DOM+-E
+  constexpr int STRIDE = 30;
+  const Geom &g = a.g;
+  const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);
+  const int lane = threadIdx.x & 31;
+  const int gw = (int)(((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5);
+  const int L = g.n[0] + 2*E;                        // zones with states in one row
+  const int nseg = (L - 2 + STRIDE - 1)/STRIDE;
+  const int nrj = g.n[1] + 2*E;
+  const int nrows = nrj*(NC == 3 ? g.n[2] + 2*E : 1);
+  if (gw >= nseg*nrows) return;                      // whole warps leave together
+  const int seg = gw % nseg, row = gw / nseg;
+  const int jr = row % nrj, kr = row / nrj;
+  const int j = g.beg[1] - E + jr, k = (NC == 3 ? g.beg[2] - E + kr : 0);
+  const int ii = seg*STRIDE + lane;
+  const bool zone_ok = ii < L;
+  const bool face_ok = zone_ok && lane <= 30 && ii <= L - 2;
+  const bool emf_ok = face_ok && (lane >= 1 || seg == 0);
+  const bool rhs_ok = face_ok && lane >= 1;
+  const int i = g.beg[0] - E + (zone_ok ? ii : L - 1);
+  const int id = gidx32 (g, k, j, i);
+
+  const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
+  double vl[NV], v[NV], vr[NV], vp[NV], vm[NV], up[NV], um[NV];
+  PG_FOR_NV(nv){ vl[nv] = __ldg (a.V0[nv] + id - 1); v[nv] = __ldg (a.V0[nv] + id); vr[nv] = __ldg (a.V0[nv] + id + 1); }
+  const double bsm = __ldg (a.Bs0[DIR] + id - 1), bsp = __ldg (a.Bs0[DIR] + id);
+  unsigned fl = 0;
+  if (FLAT) fl = a.flag[id];
+  ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, vp, vm);
+  int nfl = 0;
+  if (PHASE == 0){
+    prim_to_cons<NC>(ph, vp, up);
+    prim_to_cons<NC>(ph, vm, um);
+  }else{
+    double dU[NV];
+    ctu_transverse<DIR, NC>(a, id, dU);
+    nfl = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, __ldg (a.Bsh[DIR] + id - 1), __ldg (a.Bsh[DIR] + id), vp, vm, up, um);
+    if (!(zone_ok && (lane >= 1 || seg == 0))) nfl = 0;      // zones shared by two segments count once
+  }
+
+  double vR[NV], uR[NV];
+  PG_FOR_NV(nv){ vR[nv] = __shfl_down_sync (0xffffffffu, vm[nv], 1); uR[nv] = __shfl_down_sync (0xffffffffu, um[nv], 1); }
+  const unsigned fl2 = FLAT ? (fl | __shfl_down_sync (0xffffffffu, fl, 1)) : 0u;
+  double F[NV], press, cmax, mach;
+  const bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, fl2, vp, vR, up, uR, F, press, cmax, mach, nullptr, nullptr);
+  if (emf_ok) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F);
+  double my_mach = 0.0, my_cdt = 0.0;
+  if (face_ok) my_mach = mach;
+  if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
+
+  double Fm[NV];
+  PG_FOR_NV(nv) Fm[nv] = __shfl_up_sync (0xffffffffu, F[nv], 1);
+  const double pm = __shfl_up_sync (0xffffffffu, press, 1);
+  if (rhs_ok){
+    my_cdt = cmax*a.inv_dl;                                    // ctu_step.c:416-419, 634-637
+    if (PHASE == 0){
+      PG_FOR_NV(nv){
+        double r = -dt2_dx*(F[nv] - Fm[nv]);
+        if (nv == D::vn) r -= dt2_dx*(press - pm);
+        a.rhs[DIR][nv][id] = r;
+      }
+    }else{
+      bool upd = jr >= 1 && jr <= g.n[1];
+      if (NC == 3) upd = upd && kr >= 1 && kr <= g.n[2];
+      if (upd){
+        const double dtdx = __ldg (a.dtp + DIR);
+        double u0[NV], r;
+        prim_to_cons<NC>(ph, v, u0);                           // Uc = PrimToCons (V^n), ctu_step.c:257-262
+        r = -dtdx*(F[RHO] - Fm[RHO]);                              a.U[RHO][id] = u0[RHO] + r;
+        r = -dtdx*(F[MX1] - Fm[MX1]); r -= dtdx*(press - pm);      a.U[MX1][id] = u0[MX1] + r;
+        r = -dtdx*(F[MX2] - Fm[MX2]);                              a.U[MX2][id] = u0[MX2] + r;
+        if (NC == 3){ r = -dtdx*(F[MX3] - Fm[MX3]);                a.U[MX3][id] = u0[MX3] + r; }
+        r = -dtdx*(F[ENG] - Fm[ENG]);                              a.U[ENG][id] = u0[ENG] + r;
+      }
+    }
+  }
+  my_cdt = warp_max (my_cdt);
+  my_mach = warp_max (my_mach);
+  const unsigned mfl = __ballot_sync (0xffffffffu, nfl > 0);
+  int tot_fl = nfl;
+  if (mfl) PG_UNROLL for (int o = 16; o > 0; o >>= 1) tot_fl += __shfl_xor_sync (0xffffffffu, tot_fl, o);
+  if (lane == 0){
+    atomic_max_pos (a.red + RED_CDT, my_cdt);
+    atomic_max_pos (a.red + RED_MACH, my_mach);
+    if (mfl) atomicAdd (a.red + RED_FLOOR, (unsigned long long)tot_fl);
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  x2 / x3 sweeps: marching pencils
+// ---------------------------------------------------------------------------
+template <int DIR, int PHASE, int SOLVER, int NC, bool FLAT>
+__global__ void __launch_bounds__(128, 2)
+ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
+{
+  typedef Dirs<DIR> D;
+  constexpr int E = (PHASE == 0 ? 2 : 1);
+  constexpr int TD = (DIR == 1 ? 2 : 1);               // second transverse dimension
+  const Geom &g = a.g;
+  const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);
+  const int lane = threadIdx.x & 31;
+  const int np1 = g.n[0] + 2*E;
+  const int np2 = (NC == 3 ? g.n[TD] + 2*E : 1);
+  const long long npen = (long long)np1*np2;
+  const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  double my_mach = 0.0, my_cdt = 0.0;
+  int nfl = 0;
+  if (t < npen*a.nchunk){
+    const int chunk = (int)(t/npen);
+    const long long p = t - (long long)chunk*npen;
+    const int t2 = (int)(p/np1), t1 = (int)(p - (long long)t2*np1);
+    const int i  = g.beg[0] - E + t1;
+    const int o2 = (NC == 3 ? g.beg[TD] - E + t2 : 0);
+    // zones that receive a right-hand side: DOM+-1 along the sweep in the predictor, DOM in the corrector
+    const int R0 = g.beg[DIR] - (PHASE == 0 ? 1 : 0), R1 = g.end[DIR] + (PHASE == 0 ? 1 : 0);
+    const int c0 = R0 + chunk*a.chunk_len;
+    int c1 = c0 + a.chunk_len - 1; if (c1 > R1) c1 = R1;
+    bool upd = i >= g.beg[0] && i <= g.end[0];
+    if (NC == 3) upd = upd && o2 >= g.beg[TD] && o2 <= g.end[TD];
+    const int sD = (DIR == 1 ? (int)g.S1 : (int)g.S12);
+    int id = (DIR == 1 ? gidx32 (g, o2, c0 - 1, i) : gidx32 (g, c0 - 1, o2, i));      // zone c0-1
+
+    const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
+    const double dtdx = __ldg (a.dtp + DIR);
+    double vl[NV], v[NV], vr[NV];
+    PG_FOR_NV(nv){ v[nv] = __ldg (a.V0[nv] + id - sD); vr[nv] = __ldg (a.V0[nv] + id); }
+    double bsp = __ldg (a.Bs0[DIR] + id - sD), bhp = 0.0;
+    if (PHASE == 1) bhp = __ldg (a.Bsh[DIR] + id - sD);
+    double vpL[NV], upL[NV], Fp[NV], pp = 0.0;
+    PG_FOR_NV(nv){ vpL[nv] = 0.0; upL[nv] = 0.0; Fp[nv] = 0.0; }
+    unsigned flb = 0;
+
+    for (int z = c0 - 1; z <= c1 + 1; z++, id += sD){
+      // id = zone z
+      PG_FOR_NV(nv){ vl[nv] = v[nv]; v[nv] = vr[nv]; vr[nv] = __ldg (a.V0[nv] + id + sD); }
+      const double bsm = bsp;
+      bsp = __ldg (a.Bs0[DIR] + id);
+      unsigned flz = 0;
+      if (FLAT) flz = a.flag[id];
+      double vp[NV], vm[NV], up[NV], um[NV];
+      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, vp, vm);
+      if (PHASE == 0){
+        prim_to_cons<NC>(ph, vp, up);
+        prim_to_cons<NC>(ph, vm, um);
+      }else{
+        double dU[NV];
+        ctu_transverse<DIR, NC>(a, id, dU);
+        const double bhm = bhp;
+        bhp = __ldg (a.Bsh[DIR] + id);
+        const int n = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, bhm, bhp, vp, vm, up, um);
+        if (z <= c1 || chunk == a.nchunk - 1) nfl += n;          // zones shared by two chunks count once
+      }
+      if (z >= c0){
+        // face z-1/2, stored with the index of zone z-1
+        const int idf = id - sD;
+        double F[NV], press, cmax, mach;
+        const bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, flb | flz, vpL, vm, upL, um, F, press, cmax, mach, nullptr, nullptr);
+        my_mach = mach > my_mach ? mach : my_mach;
+        if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
+        if (z - 1 >= c0 || chunk == 0) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, idf, F);
+        if (z - 1 >= c0){
+          // zone z-1: faces z-3/2 (Fp) and z-1/2 (F)
+          const double cd = cmax*a.inv_dl;
+          my_cdt = cd > my_cdt ? cd : my_cdt;
+          if (PHASE == 0){
+            PG_FOR_NV(nv){
+              double r = -dt2_dx*(F[nv] - Fp[nv]);
+              if (nv == D::vn) r -= dt2_dx*(press - pp);
+              a.rhs[DIR][nv][idf] = r;
+            }
+          }else if (upd){
+            double r;
+            r = -dtdx*(F[RHO] - Fp[RHO]);                                           a.U[RHO][idf] += r;
+            r = -dtdx*(F[MX1] - Fp[MX1]); if (D::vn == MX1) r -= dtdx*(press - pp); a.U[MX1][idf] += r;
+            r = -dtdx*(F[MX2] - Fp[MX2]); if (D::vn == MX2) r -= dtdx*(press - pp); a.U[MX2][idf] += r;
+            if (NC == 3){
+              r = -dtdx*(F[MX3] - Fp[MX3]); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][idf] += r;
+            }
+            r = -dtdx*(F[ENG] - Fp[ENG]);                                           a.U[ENG][idf] += r;
+          }
+        }
+        PG_FOR_NV(nv) Fp[nv] = F[nv];
+        pp = press;
+      }
+      PG_FOR_NV(nv){ vpL[nv] = vp[nv]; upL[nv] = up[nv]; }
+      flb = flz;
+    }
+  }
+  my_cdt = warp_max (my_cdt);
+  my_mach = warp_max (my_mach);
+  const unsigned mfl = __ballot_sync (0xffffffffu, nfl > 0);
+  int tot_fl = nfl;
+  if (mfl) PG_UNROLL for (int o = 16; o > 0; o >>= 1) tot_fl += __shfl_xor_sync (0xffffffffu, tot_fl, o);
+  if (lane == 0){
+    atomic_max_pos (a.red + RED_CDT, my_cdt);
+    atomic_max_pos (a.red + RED_MACH, my_mach);
+    if (mfl) atomicAdd (a.red + RED_FLOOR, (unsigned long long)tot_fl);
+  }
+}
+
+// ---------------------------------------------------------------------------
+//  V^{n+1/2} on DOM+-1: U^n + sum of the half-step right-hand sides, the cell average of the
+//  half-step staggered field, ConsToPrim (ctu_step.c:427-497)
+// ---------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128)
+ctu_half_kernel (const __grid_constant__ CtuArgs a)
+{
+  const Geom &g = a.g;
+  const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);
+  const int ni = g.n[0] + 2, nj = g.n[1] + 2, nk = (NC == 3 ? g.n[2] + 2 : 1);
+  const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;
+  int fl = 0;
+  if (t < (unsigned)(ni*nj*nk)){
+    const unsigned tq = t/(unsigned)ni;
+    const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
+    const int i = g.beg[0] - 1 + ti, j = g.beg[1] - 1 + tj, k = (NC == 3 ? g.beg[2] - 1 + tk : 0);
+    const int id = gidx32 (g, k, j, i);
+    double v0[NV], u[NV], v[NV];
+    PG_FOR_NV(nv) v0[nv] = __ldg (a.V0[nv] + id);
+    prim_to_cons<NC>(ph, v0, u);
+    PG_FOR_NV(nv){
+      double dU;
+      if (NC == 3) dU = a.rhs[0][nv][id] + a.rhs[1][nv][id] + a.rhs[2][nv][id];
+      else         dU = a.rhs[0][nv][id] + a.rhs[1][nv][id];
+      u[nv] = u[nv] + dU;
+    }
+    u[BX1] = 0.5*(a.Bsh[0][id] + a.Bsh[0][id - 1]);
+    u[BX2] = 0.5*(a.Bsh[1][id] + a.Bsh[1][id - (int)g.S1]);
+    if (NC == 3) u[BX3] = 0.5*(a.Bsh[2][id] + a.Bsh[2][id - (int)g.S12]);
+    fl = cons_to_prim<NC>(ph, u, v);
+    PG_FOR_NV(nv) a.Vh[nv][id] = v[nv];
+  }
+  const unsigned mfl = __ballot_sync (0xffffffffu, fl);
+  if ((threadIdx.x & 31) == 0 && mfl) atomicAdd (a.red + RED_FLOOR, (unsigned long long)__popc (mfl));
+}
+
+// ---------------------------------------------------------------------------
+//  launchers
+// ---------------------------------------------------------------------------
+template <int SOLVER>
+static int launch_ctu_sweep_t (int dir, int phase, const CtuArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const int nc = g.dims, TPB = 128;
+  const int E = (phase == 0 ? 2 : 1);
+  const bool fl = a.flag != nullptr;
+  if (dir == 0){
+    const long long nseg = (g.n[0] + 2*E - 2 + 29)/30;
+    const long long nrows = (long long)(g.n[1] + 2*E)*(nc == 3 ? g.n[2] + 2*E : 1);
+    const unsigned nb = (unsigned)((nseg*nrows*32 + TPB - 1)/TPB);
+#define PG_CX(P, C) do { if (fl) ctu_sweep_x_kernel<P, SOLVER, C, true><<<nb, TPB, 0, s>>>(a);             \
+                         else    ctu_sweep_x_kernel<P, SOLVER, C, false><<<nb, TPB, 0, s>>>(a); } while (0)
+    if (phase == 0){ if (nc == 3) PG_CX(0, 3); else PG_CX(0, 2); }
+    else           { if (nc == 3) PG_CX(1, 3); else PG_CX(1, 2); }
+#undef PG_CX
+  }else{
+    const int td = (dir == 1 ? 2 : 1);
+    const long long npen = (long long)(g.n[0] + 2*E)*(nc == 3 ? g.n[td] + 2*E : 1);
+    const unsigned nb = (unsigned)((npen*a.nchunk + TPB - 1)/TPB);
+#define PG_CM(DD, P, C) do { if (fl) ctu_sweep_march_kernel<DD, P, SOLVER, C, true><<<nb, TPB, 0, s>>>(a);  \
+                             else    ctu_sweep_march_kernel<DD, P, SOLVER, C, false><<<nb, TPB, 0, s>>>(a); } while (0)
+    if (dir == 1){
+      if (phase == 0){ if (nc == 3) PG_CM(1, 0, 3); else PG_CM(1, 0, 2); }
+      else           { if (nc == 3) PG_CM(1, 1, 3); else PG_CM(1, 1, 2); }
+    }else{
+      if (phase == 0) PG_CM(2, 0, 3); else PG_CM(2, 1, 3);
+    }
+#undef PG_CM
+  }
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+static int launch_ctu_half_t (const CtuArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const long long n = (long long)(g.n[0] + 2)*(g.n[1] + 2)*(g.dims == 3 ? g.n[2] + 2 : 1);
+  const unsigned nb = (unsigned)((n + 127)/128);
+  if (g.dims == 3) ctu_half_kernel<3><<<nb, 128, 0, s>>>(a);
+  else             ctu_half_kernel<2><<<nb, 128, 0, s>>>(a);
+  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+}
+
+} // namespace PG_NS

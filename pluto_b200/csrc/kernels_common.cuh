@@ -81,6 +81,28 @@ struct CtArgs {
   int    combine;                            // 0: none, 1: w0*B0 + wc*B, 2: (B0 + 2 B)/3
   int    avg;                                // PLUTO_GPU_EMF_*
   const double *dvel[3][3];                  // UCT_HLL: dvel[c][d] = d v_c / d x_d
+  int    ext;                                // edges / faces of [beg-1-ext, end+ext]: 0 (RK, CTU corrector) or
+                                             // 1 (CTU predictor, emf ranges of ctu_step.c:290-297)
+};
+
+// corner-transport-upwind step (TIME_STEPPING HANCOCK, Src/Time_Stepping/ctu_step.c:142-727)
+struct CtuArgs {
+  const double *V0[8];       // primitives at t^n, ghost zones filled
+  const double *Bs0[3];      // staggered field at t^n
+  const double *Bsh[3];      // staggered field at t^n + dt/2 (corrector, half-step kernel)
+  double       *rhs[3][8];   // half-step right-hand sides of the three normal predictors (ctu_step.c:221)
+  double       *U[8];        // conservative accumulators (corrector)
+  double       *Vh[8];       // half-step kernel: primitives at t^n + dt/2
+  double       *e1, *e2;     // face EMFs of this direction
+  signed char  *sv;
+  unsigned long long *red;
+  const unsigned char *flag;
+  Geom    g;
+  PhysPar ph;
+  const double *dtp;         // device: dt/dx1..3, dt, (dt/2)/dx1..3, dt/2
+  double  inv_dl;            // 1/dx of the sweep direction
+  int     limiter;
+  int     chunk_len, nchunk; // marching sweeps (x2, x3)
 };
 
 struct FinalArgs {
@@ -161,6 +183,10 @@ namespace NS {                                                                  
   int launch_sweep_xy_hlld (int recon, const SweepArgs &a, cudaStream_t s);              \
   int launch_sweep_xy_hll  (int recon, const SweepArgs &a, cudaStream_t s);              \
   int launch_sweep_xy_roe  (int recon, const SweepArgs &a, cudaStream_t s);              \
+  int launch_ctu_sweep_hlld (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
+  int launch_ctu_sweep_hll  (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
+  int launch_ctu_sweep_roe  (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
+  int launch_ctu_half   (const CtuArgs &a, cudaStream_t s);                              \
   int launch_ct_emf     (const CtArgs &a, cudaStream_t s);                               \
   int launch_ct_update  (const CtArgs &a, cudaStream_t s);                               \
   int launch_final      (const FinalArgs &a, cudaStream_t s);                            \

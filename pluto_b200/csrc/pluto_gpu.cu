@@ -79,6 +79,10 @@ struct PlutoGpu {
   long long steps_done;
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
+  int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
+  int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
+  double *rhs3[3][NVS];            // CTU: half-step right-hand sides of the normal predictors (own allocation)
+  void   *ctu_pool;
   // optional per-kernel-class device timing (CUDA events on `stream`)
   int     timing;
   int     nev;                                 // event pairs used in the current step
@@ -91,6 +95,7 @@ struct PlutoGpu {
 const char *pluto_gpu_last_error (void) { return g_err; }
 
 int pluto_gpu_nghost (const PlutoGpu *h) { return h->g.ng; }
+int pluto_gpu_nstages (const PlutoGpu *h) { return h->nstages; }
 
 static bool live_var (const PlutoGpu *h, int nv) { return h->g.dims == 3 || (nv != 3 && nv != 6); }
 
@@ -140,6 +145,11 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     return fail ("SHOCK_FLATTENING MULTID is available with LINEAR reconstruction only (the reference's PARABOLIC "
                  "fallback takes its weights from PLM_CoefficientsGet, ppm_states.c:167-181)");
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
+  if (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->time_stepping != PLUTO_GPU_TS_HANCOCK) return fail ("bad time_stepping");
+  if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
+    if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
+    if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL) return fail ("TIME_STEPPING HANCOCK: CT_EMF_AVERAGE UCT_HLL is not available (use UCT_CONTACT, ARITHMETIC or UCT0)");
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -153,6 +163,9 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   g.dims = cfg->dims;
   g.ng = (cfg->recon == PLUTO_GPU_RECON_PARABOLIC ? 3 : 2);      // get_nghost.c:32-50
   if (cfg->shock_flattening && g.ng < 3) g.ng = 3;               // get_nghost.c:67-77
+  h->ctu = (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK);
+  if (h->ctu) g.ng++;                                            // CTU + CT, get_nghost.c:86-90
+  h->nstages = h->ctu ? 1 : cfg->rk_order;
   for (int d = 0; d < 3; d++){
     if (d < g.dims){
       if (cfg->n[d] < 2*g.ng){ free (h); return fail ("n[%d] = %d is smaller than 2*nghost", d, cfg->n[d]); }
@@ -169,7 +182,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   h->ph.gamma = cfg->gamma; h->ph.gmm1 = cfg->gamma - 1.0;
   h->ph.small_dn = cfg->small_dn; h->ph.small_pr = cfg->small_pr;
   h->ph.igmm1 = 1.0/(cfg->gamma - 1.0);
-  h->nbuf = (cfg->rk_order == 3 ? 3 : 2);
+  h->nbuf = (cfg->rk_order == 3 && !h->ctu ? 3 : 2);
   h->march_chunk = 64;
 
   // one pool: [state buffers][U, face EMFs, edge EMFs, C_dt = scratch][sign bytes]
@@ -212,6 +225,16 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     for (int c = 0; c < g.dims; c++) for (int d = 0; d < g.dims; d++){ h->dvel[c][d] = q; q += tot_al; }
     h->pool_bytes += nb;
   }
+  if (h->ctu){
+    int nlive = 0;
+    for (int nv = 0; nv < NVS; nv++) nlive += live_var (h, nv);
+    const size_t nb = (size_t)g.dims*nlive*tot_al*sizeof (double);
+    if (cudaMalloc (&h->ctu_pool, nb) != cudaSuccess) return fail ("cudaMalloc of %zu bytes (CTU right-hand sides) failed", nb);
+    CU (cudaMemset (h->ctu_pool, 0, nb));
+    double *q = (double *)h->ctu_pool;
+    for (int d = 0; d < g.dims; d++) for (int nv = 0; nv < NVS; nv++) if (live_var (h, nv)){ h->rhs3[d][nv] = q; q += tot_al; }
+    h->pool_bytes += nb;
+  }
   CU (cudaStreamCreateWithFlags (&h->stream, cudaStreamNonBlocking));
   CU (cudaMalloc ((void **)&h->red, RED_N*sizeof (unsigned long long)));
   CU (cudaMemset (h->red, 0, RED_N*sizeof (unsigned long long)));
@@ -220,8 +243,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   CU (cudaMallocHost ((void **)&h->hist_host, (size_t)HIST_W*HIST_N*sizeof (double)));
   CU (cudaMalloc ((void **)&h->hist_count, sizeof (unsigned long long)));
   CU (cudaMemset (h->hist_count, 0, sizeof (unsigned long long)));
-  CU (cudaMalloc ((void **)&h->dtdev, 4*sizeof (double)));
-  CU (cudaMallocHost ((void **)&h->dthost, 4*sizeof (double)));
+  CU (cudaMalloc ((void **)&h->dtdev, 8*sizeof (double)));
+  CU (cudaMallocHost ((void **)&h->dthost, 8*sizeof (double)));
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
   *out = h;
@@ -235,6 +258,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaStreamSynchronize (h->stream);
   cudaFree (h->pool);
   if (h->dvel_pool) cudaFree (h->dvel_pool);
+  if (h->ctu_pool) cudaFree (h->ctu_pool);
   if (h->flag) cudaFree (h->flag);
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
@@ -455,7 +479,8 @@ struct StagePlan { int in, out, combine; double w0, wc; };
 static StagePlan stage_plan (const PlutoGpu *h, int stage)
 {
   StagePlan p; p.w0 = p.wc = 0.0; p.combine = 0; p.in = 0; p.out = 1;
-  if (h->cfg.rk_order == 2){
+  if (h->ctu){ p.in = 0; p.out = 0; }           // one Boundary call per step, the new state replaces the old one
+  else if (h->cfg.rk_order == 2){
     if (stage == 1){ p.in = 0; p.out = 1; }
     else           { p.in = 1; p.out = 0; p.combine = 1; p.w0 = 0.5; p.wc = 0.5; }     // rk_step.c:18-20
   }else{
@@ -471,7 +496,9 @@ static int set_dt (PlutoGpu *h, double dt)
 {
   for (int d = 0; d < 3; d++) h->dthost[d] = dt/h->g.dx[d];
   h->dthost[3] = dt;
-  CU (cudaMemcpyAsync (h->dtdev, h->dthost, 4*sizeof (double), cudaMemcpyHostToDevice, h->stream));
+  for (int d = 0; d < 3; d++) h->dthost[4 + d] = (0.5*dt)/h->g.dx[d];      // CTU half step (ctu_step.c:447-455)
+  h->dthost[7] = 0.5*dt;
+  CU (cudaMemcpyAsync (h->dtdev, h->dthost, 8*sizeof (double), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 
@@ -521,9 +548,13 @@ static int launch_final_boxes (PlutoGpu *h, FinalArgs &f, int part)
   return 0;
 }
 
+static int run_ctu (PlutoGpu *h);
+
 static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
 {
   const Geom &g = h->g;
+  // CTU: the whole step is one "stage" (one Boundary call); all of it belongs to the shell part
+  if (h->ctu) return part == PART_INTERIOR ? 0 : run_ctu (h);
   const StagePlan sp = stage_plan (h, stage);
   FinalArgs f; memset (&f, 0, sizeof (f));
   for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[sp.out][nv]; }
@@ -626,6 +657,91 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
 }
 
 // ---------------------------------------------------------------------------
+//  corner transport upwind: the body of AdvanceStep in ctu_step.c:142-727 after its Boundary
+//  call.  Buffer 0 holds t^n (and receives t^n + dt), buffer 1 the half-step state.
+// ---------------------------------------------------------------------------
+static int march_chunks (const PlutoGpu *h, int dir, int nzones, int ext, int *chunk_len)
+{
+  const Geom &g = h->g;
+  const int td = (dir == 1 ? 2 : 1);
+  const long long npen = (long long)(g.n[0] + 2*ext)*(g.dims == 3 ? g.n[td] + 2*ext : 1);
+  const long long want = (228000 + npen - 1)/npen;               // chunks for ~4 waves of threads
+  long long len = (nzones + want - 1)/want;
+  if (len < 4) len = 4;
+  if (len > h->march_chunk) len = h->march_chunk;
+  if (len > nzones) len = nzones;
+  *chunk_len = (int)len;
+  return (nzones + (int)len - 1)/(int)len;
+}
+
+static int run_ctu (PlutoGpu *h)
+{
+  const Geom &g = h->g;
+  if (h->flag){                          // FlagShock on V^n (ctu_step.c:240-244)
+    FlagArgs fa; memset (&fa, 0, sizeof (fa));
+    for (int d = 0; d < 3; d++) fa.vx[d] = h->V[0][1 + d];
+    fa.prs = h->V[0][7]; fa.shock = h->shock; fa.flag = h->flag; fa.g = g;
+    TIMED (h, KC_BC, count (h, DISPATCH (h, launch_flag_shock) (fa, h->stream)));
+  }
+  CtuArgs s; memset (&s, 0, sizeof (s));
+  for (int nv = 0; nv < NVS; nv++){ s.V0[nv] = h->V[0][nv]; s.U[nv] = h->U[nv]; s.Vh[nv] = h->V[1][nv]; }
+  for (int d = 0; d < 3; d++){
+    s.Bs0[d] = h->Bs[0][d]; s.Bsh[d] = h->Bs[1][d];
+    for (int nv = 0; nv < NVS; nv++) s.rhs[d][nv] = h->rhs3[d][nv];
+  }
+  s.red = h->red; s.flag = h->flag; s.g = g; s.ph = h->ph; s.dtp = h->dtdev; s.limiter = h->cfg.limiter;
+
+  CtArgs c; memset (&c, 0, sizeof (c));
+  c.exj = h->exj; c.exk = h->exk; c.eyi = h->eyi; c.eyk = h->eyk; c.ezi = h->ezi; c.ezj = h->ezj;
+  c.svx = h->sv[0]; c.svy = h->sv[1]; c.svz = h->sv[2];
+  c.ex = h->ex; c.ey = h->ey; c.ez = h->ez;
+  c.g = g;
+
+  for (int phase = 0; phase < 2; phase++){
+    for (int dir = 0; dir < g.dims; dir++){
+      s.inv_dl = 1.0/g.dx[dir];
+      s.sv = h->sv[dir];
+      if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
+      else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
+      else { s.e1 = h->eyk; s.e2 = h->exk; }
+      if (dir > 0) s.nchunk = march_chunks (h, dir, g.n[dir] + (phase == 0 ? 2 : 0), phase == 0 ? 2 : 1, &s.chunk_len);
+      int r;
+      const int te = tbegin (h, KC_SWEEP_X + dir);
+      if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_ctu_sweep_hlld) (dir, phase, s, h->stream);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_ctu_sweep_hll)  (dir, phase, s, h->stream);
+      else                                             r = DISPATCH (h, launch_ctu_sweep_roe)  (dir, phase, s, h->stream);
+      tend (h, te);
+      if (count (h, r)) return 1;
+    }
+    if (phase == 0){
+      // emf of the predictor fluxes on the extended ranges (CT_EMF_IntegrateToCorner returns at once in the
+      // predictor, ct_emf_average.c:90-92: UCT_CONTACT reduces to the arithmetic average), B^{n+1/2} on the
+      // faces of DOM+-1, V^{n+1/2} on DOM+-1 (ctu_step.c:447-497)
+      for (int nv = 0; nv < NVS; nv++) c.V[nv] = h->V[0][nv];
+      for (int d = 0; d < 3; d++){ c.Bs_in[d] = h->Bs[0][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[1][d]; }
+      c.avg = (h->cfg.emf_average == PLUTO_GPU_EMF_UCT_CONTACT ? PLUTO_GPU_EMF_ARITHMETIC : h->cfg.emf_average);
+      c.ext = 1; c.combine = 0; c.dtp = h->dtdev + 4;
+      TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
+      TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
+      TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_ctu_half) (s, h->stream)));
+    }
+  }
+  // emf of the corrector fluxes (cell-centred part from V^{n+1/2}), B^{n+1} = B^n + dt curl E, cell average,
+  // ConsToPrim (ctu_step.c:646-700)
+  for (int nv = 0; nv < NVS; nv++) c.V[nv] = h->V[1][nv];
+  for (int d = 0; d < 3; d++){ c.Bs_in[d] = h->Bs[0][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[0][d]; }
+  c.avg = h->cfg.emf_average; c.ext = 0; c.combine = 0; c.dtp = h->dtdev;
+  TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
+  TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
+
+  FinalArgs f; memset (&f, 0, sizeof (f));
+  for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[0][nv]; f.Uw[nv] = h->U[nv]; }
+  for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[0][d];
+  f.red = h->red; f.g = g; f.ph = h->ph; f.combine = 0; f.write_u = 0;
+  return launch_final_boxes (h, f, PART_ALL);
+}
+
+// ---------------------------------------------------------------------------
 int pluto_gpu_step_begin (PlutoGpu *h)
 {
   CU (cudaSetDevice (h->cfg.device));
@@ -638,14 +754,14 @@ static int stage_in_buf (const PlutoGpu *h, int stage) { return stage_plan (h, s
 int pluto_gpu_boundary_dim (PlutoGpu *h, int stage, int dim)
 {
   CU (cudaSetDevice (h->cfg.device));
-  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  if (stage < 1 || stage > h->nstages) return fail ("stage %d out of range", stage);
   return boundary_dim (h, stage_in_buf (h, stage), dim);
 }
 
 int pluto_gpu_stage (PlutoGpu *h, int stage, double dt)
 {
   CU (cudaSetDevice (h->cfg.device));
-  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  if (stage < 1 || stage > h->nstages) return fail ("stage %d out of range", stage);
   if (stage == 1 && dt >= 0.0 && set_dt (h, dt)) return 1;      // one dt per step (dt < 0: the device's own)
   return run_stage (h, stage);
 }
@@ -653,7 +769,7 @@ int pluto_gpu_stage (PlutoGpu *h, int stage, double dt)
 int pluto_gpu_stage_shell (PlutoGpu *h, int stage, double dt)
 {
   CU (cudaSetDevice (h->cfg.device));
-  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  if (stage < 1 || stage > h->nstages) return fail ("stage %d out of range", stage);
   if (stage == 1 && dt >= 0.0 && set_dt (h, dt)) return 1;
   return run_stage (h, stage, PART_SHELL);
 }
@@ -661,7 +777,7 @@ int pluto_gpu_stage_shell (PlutoGpu *h, int stage, double dt)
 int pluto_gpu_stage_interior (PlutoGpu *h, int stage)
 {
   CU (cudaSetDevice (h->cfg.device));
-  if (stage < 1 || stage > h->cfg.rk_order) return fail ("stage %d out of range", stage);
+  if (stage < 1 || stage > h->nstages) return fail ("stage %d out of range", stage);
   return run_stage (h, stage, PART_INTERIOR);
 }
 
@@ -675,7 +791,7 @@ int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
   memcpy (&cd, &h->red_host[RED_CDT], sizeof (double));
   memcpy (&mach, &h->red_host[RED_MACH], sizeof (double));
   if (info){
-    info->inv_dt_hyp = cd/(double)h->g.dims;                   // update_stage.c:308-312
+    info->inv_dt_hyp = h->ctu ? cd : cd/(double)h->g.dims;     // update_stage.c:308-312; ctu_step.c:416-419
     info->max_mach = mach;
     info->floor_events = (int)h->red_host[RED_FLOOR];
     info->nan_events = (int)h->red_host[RED_NAN];
@@ -689,7 +805,7 @@ int pluto_gpu_step_end (PlutoGpu *h, PlutoGpuStepInfo *info)
 static int enqueue_step (PlutoGpu *h)
 {
   CU (cudaMemsetAsync (h->red, 0, RED_N*sizeof (unsigned long long), h->stream));
-  for (int stage = 1; stage <= h->cfg.rk_order; stage++){
+  for (int stage = 1; stage <= h->nstages; stage++){
     const int in = stage_in_buf (h, stage);
     for (int d = 0; d < h->g.dims; d++) if (boundary_dim (h, in, d)) return 1;
     if (run_stage (h, stage)) return 1;
@@ -790,6 +906,9 @@ __global__ void next_dt_kernel (const unsigned long long *red, double *dtdev, do
   *hist_count = n + 1;
   dtdev[0] = __ddiv_rn (dtnext, dx0); dtdev[1] = __ddiv_rn (dtnext, dx1); dtdev[2] = __ddiv_rn (dtnext, dx2);
   dtdev[3] = dtnext;
+  const double dth = __dmul_rn (0.5, dtnext);
+  dtdev[4] = __ddiv_rn (dth, dx0); dtdev[5] = __ddiv_rn (dth, dx1); dtdev[6] = __ddiv_rn (dth, dx2);
+  dtdev[7] = dth;
 }
 
 int pluto_gpu_set_dt (PlutoGpu *h, double dt)
@@ -809,7 +928,7 @@ int pluto_gpu_next_dt_async (PlutoGpu *h, double cfl, double cfl_max_var)
   CU (cudaSetDevice (h->cfg.device));
   if (h->hist_enq - h->hist_read >= HIST_N) return fail ("more than %d steps enqueued without pluto_gpu_sync_results", HIST_N);
   next_dt_kernel<<<1, 32, 0, h->stream>>>(h->red, h->dtdev, h->hist, h->hist_count, h->g.dx[0], h->g.dx[1], h->g.dx[2],
-                                          h->g.dims, cfl, cfl_max_var);
+                                          h->ctu ? 1 : h->g.dims, cfl, cfl_max_var);
   if (count (h, cudaGetLastError () == cudaSuccess ? 1 : -1)) return 1;
   h->hist_enq++;
   return 0;
@@ -846,7 +965,7 @@ int pluto_gpu_sync_results (PlutoGpu *h, int max_steps, PlutoGpuStepInfo *infos,
   CU (cudaSetDevice (h->cfg.device));
   const long long n = h->hist_enq - h->hist_read;
   if (n > 0) CU (cudaMemcpyAsync (h->hist_host, h->hist, (size_t)HIST_W*HIST_N*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
-  CU (cudaMemcpyAsync (h->dthost, h->dtdev, 4*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
+  CU (cudaMemcpyAsync (h->dthost, h->dtdev, 8*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
   CU (cudaStreamSynchronize (h->stream));
   if (h->timing) tcollect (h);
   if (dt_next) *dt_next = h->dthost[3];

@@ -36,7 +36,7 @@ class GpuStepper:
     def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
                  bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0,
                  small_dn=1e-12, small_pr=1e-12, lib_path=None, limiter="default", emf="uct_contact",
-                 flatten=False):
+                 flatten=False, ctu=False):
         self.L = _lib.load_library(lib_path)
         c = _lib.PlutoGpuConfig()
         n = list(n) + [1] * (3 - len(n))
@@ -59,6 +59,7 @@ class GpuStepper:
         c.limiter = _lib.LIMITER[limiter]           # LIMITER (plm only): default | fl mm va os um vl mc
         c.emf_average = _lib.EMF[emf]               # CT_EMF_AVERAGE: uct_contact | arith | uct0 | uct_hll
         c.shock_flattening = 1 if flatten else 0    # SHOCK_FLATTENING MULTID (plm only)
+        c.time_stepping = 1 if ctu else 0           # TIME_STEPPING: RK2/RK3 (rk_order) | HANCOCK (corner transport upwind)
         self.cfg = c
         self.dims = dims
         self.n = tuple(n)
@@ -68,6 +69,7 @@ class GpuStepper:
             self._h = None
             raise PlutoGpuError(_lib.last_error(self.L))
         self.ng = self.L.pluto_gpu_nghost(self._h)
+        self.nstages = self.L.pluto_gpu_nstages(self._h)    # Boundary calls (halo exchanges) per step
 
     def close(self):
         if getattr(self, "_h", None):
