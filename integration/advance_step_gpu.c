@@ -1,6 +1,7 @@
 /* advance_step_gpu.c -- the reference-side binding of libpluto_gpu.so.
  *
- * Drop-in replacement for Src/Time_Stepping/rk_step.c + update_stage.c in a
+ * Drop-in replacement for Src/Time_Stepping/rk_step.c + update_stage.c (TIME_STEPPING RK2 /
+ * RK3) or ctu_step.c (TIME_STEPPING HANCOCK; hancock.o stays on the link line, plm_states.o refers to it) in a
  * PLUTO 4.3 build: it defines the one symbol the driver calls,
  *
  *     int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
@@ -69,6 +70,14 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       QUIT_PLUTO(1);
     }
     c.rk_order = (TIME_STEPPING == RK3 ? 3 : 2);
+#if TIME_STEPPING == HANCOCK
+  #if DIMENSIONAL_SPLITTING == YES || PRIMITIVE_HANCOCK != YES || CT_EMF_AVERAGE == UCT_HLL || RECONSTRUCTION != LINEAR
+    #error "libpluto_gpu, TIME_STEPPING HANCOCK: unsplit, primitive predictor, LINEAR, CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0"
+  #endif
+    c.time_stepping = PLUTO_GPU_TS_HANCOCK;                /* ctu_step.c */
+#elif TIME_STEPPING == CHARACTERISTIC_TRACING
+  #error "libpluto_gpu: TIME_STEPPING CHARACTERISTIC_TRACING is not available on the GPU"
+#endif
     /* LIMITER (plm_states.c:192-236) and CT_EMF_AVERAGE (ct_emf.c:241-283) of definitions.h */
     c.limiter = (LIMITER == FLAT_LIM      ? PLUTO_GPU_LIM_FLAT      : LIMITER == MINMOD_LIM ? PLUTO_GPU_LIM_MINMOD :
                  LIMITER == VANALBADA_LIM ? PLUTO_GPU_LIM_VANALBADA : LIMITER == OSPRE_LIM  ? PLUTO_GPU_LIM_OSPRE  :

@@ -279,7 +279,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         const double bhm = bhp;
         bhp = __ldg (a.Bsh[DIR] + id);
         const int n = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, bhm, bhp, vp, vm, up, um);
-        if (z <= c1 || chunk == a.nchunk - 1) nfl += n;          // zones shared by two chunks count once
+        if ((z >= c0 || chunk == 0) && (z <= c1 || chunk == a.nchunk - 1)) nfl += n;   // zones shared by two chunks count once
       }
       if (z >= c0){
         // face z-1/2, stored with the index of zone z-1

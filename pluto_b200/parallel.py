@@ -219,7 +219,7 @@ class DistStepper:
 
     def __init__(self, layout: BlockLayout, rank, dx, recon="plm", solver="hlld", rk_order=2,
                  physical_bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0, exchange="all",
-                 overlap=None):
+                 overlap=None, **scheme):
         self.layout, self.rank = layout, rank
         self.exchange_mode = exchange       # "all": one 26-neighbour group per stage; "dims": x1->x2->x3 swaps
         # overlap: the exchange of the NEXT stage travels on a second stream while the interior
@@ -231,8 +231,10 @@ class DistStepper:
         self.world = layout.world
         n = layout.local_n(rank)
         self.block = GpuStepper(layout.dims, n, dx, recon=recon, solver=solver, rk_order=rk_order,
-                                bc=layout.block_bc(rank, physical_bc), gamma=gamma, arith=arith, device=device)
+                                bc=layout.block_bc(rank, physical_bc), gamma=gamma, arith=arith, device=device,
+                                **scheme)          # limiter, emf, flatten, ctu
         self.rk_order = rk_order
+        self.nstages = self.block.nstages       # Boundary calls = exchanges per step (1 with TIME_STEPPING HANCOCK)
         self.dims = layout.dims
         self.ex = None
         if self.world > 1:
@@ -324,7 +326,7 @@ class DistStepper:
         b = self.block
         with torch.cuda.stream(self._stream):
             b.step_begin()
-            for stage in range(1, self.rk_order + 1):
+            for stage in range(1, self.nstages + 1):
                 if self.nex is not None and self.overlap:
                     # ghost zones of this stage: already travelling (started while the previous
                     # stage was completing its interior) or exchanged here, in line
@@ -339,7 +341,7 @@ class DistStepper:
                         b.boundary_dim(stage, d)
                     b.stage_shell(stage, dt)
                     self._ev_shell.record(self._stream)
-                    nxt = stage + 1 if stage < self.rk_order else 1
+                    nxt = stage + 1 if stage < self.nstages else 1
                     with torch.cuda.stream(self._comm):
                         self._comm.wait_event(self._ev_shell)
                         b.halo_pack_all_on(nxt, self._comm.cuda_stream)
@@ -375,15 +377,20 @@ class LocalMultiBlock:
     handed over directly (same device) -- used by the single-GPU test of the
     decomposition and as the in-process alternative to one process per GPU."""
 
-    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, exchange="dims", split=False, **kw):
+    def __init__(self, layout: BlockLayout, dx, physical_bc, device=0, exchange="dims", split=False,
+                 host_buffers=False, **kw):
         import torch
         self.layout = layout
+        # host_buffers: the exchange buffers live in host memory -- only meaningful with the kernel
+        # interpreter of tests/emu (lib_path=...), whose "device" pointers are host pointers
+        self._sync = (lambda: None) if host_buffers else torch.cuda.synchronize
         self.exchange_mode = exchange
         self.split = split                  # issue every stage as shell + interior (the overlapped form)
         self.blocks = [GpuStepper(layout.dims, layout.local_n(r), dx, bc=layout.block_bc(r, physical_bc),
                                   device=device, **kw) for r in range(layout.world)]
         self.rk_order = self.blocks[0].rk_order
-        dev = torch.device("cuda", device)
+        self.nstages = self.blocks[0].nstages
+        dev = torch.device("cpu") if host_buffers else torch.device("cuda", device)
         self.send = {}
         for r, b in enumerate(self.blocks):
             for d in range(layout.dims):
@@ -435,23 +442,23 @@ class LocalMultiBlock:
         torch = self._torch
         for b in self.blocks:
             b.step_begin()
-        for stage in range(1, self.rk_order + 1):
+        for stage in range(1, self.nstages + 1):
             if self.exchange_mode == "all":
                 for b in self.blocks:
                     b.halo_pack_all(stage)
-                torch.cuda.synchronize()
+                self._sync()
                 for b in self.blocks:
                     b.halo_unpack_all(stage)
                     for d in range(lay.dims):
                         b.boundary_dim(stage, d)
-                torch.cuda.synchronize()
+                self._sync()
             for d in range(lay.dims if self.exchange_mode != "all" else 0):
                 for r, b in enumerate(self.blocks):
                     lo, hi = self.send.get((r, d, 0)), self.send.get((r, d, 1))
                     if lo is not None or hi is not None:
                         b.halo_pack(stage, d, lo.data_ptr() if lo is not None else None,
                                     hi.data_ptr() if hi is not None else None)
-                torch.cuda.synchronize()
+                self._sync()
                 for r, b in enumerate(self.blocks):
                     nlo, nhi = lay.neighbour(r, d, 0), lay.neighbour(r, d, 1)
                     rlo = self.send[(nlo, d, 1)].data_ptr() if nlo is not None else None
@@ -459,7 +466,7 @@ class LocalMultiBlock:
                     if rlo is not None or rhi is not None:
                         b.halo_unpack(stage, d, rlo, rhi)
                     b.boundary_dim(stage, d)
-                torch.cuda.synchronize()
+                self._sync()
             for b in self.blocks:
                 if self.split:
                     b.stage_shell(stage, dt)

@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "ot2d_plm_hll", "turb3d_plm_hlld",
          # LIMITER / CT_EMF_AVERAGE read from definitions.h by the shim (Blast #02's and Rotor #01's scheme options)
-         "blast3d_vl_arith", "rotor2d_mc_arith", "blast3d_mc_uct_hll_roe", "blast3d_sfl"]
+         "blast3d_vl_arith", "rotor2d_mc_arith", "blast3d_mc_uct_hll_roe", "blast3d_sfl",
+         # TIME_STEPPING HANCOCK: the shim replaces ctu_step.o
+         "ot2d_ctu", "blast3d_ctu", "turb3d_ctu_roe"]
 
 
 def _cfg(g):

@@ -18,10 +18,10 @@ pytestmark = pytest.mark.gpu
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
     return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten)
+                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu)
 
 
-@pytest.mark.parametrize("name", golden_names(ctu=False))
+@pytest.mark.parametrize("name", golden_names())
 def test_exact_bit_identical_to_reference_golden(name):
     g = Golden(name)
     s = _stepper(g, "exact")
@@ -55,7 +55,7 @@ def test_exact_bit_identical_to_reference_golden(name):
 DEGENERATE_ROE = {"rotor2d_ppm_roe": (1e-9, 1e-8), "rotor2d_ppm_roe_100": (1e-9, 1e-8)}
 
 
-@pytest.mark.parametrize("name", golden_names(ctu=False))
+@pytest.mark.parametrize("name", golden_names())
 def test_fast_within_tolerance_of_reference_golden(name):
     g = Golden(name)
     s = _stepper(g, "fast")
@@ -188,6 +188,77 @@ def test_exact_bit_identical_to_oracle(case):
     s.close()
 
 
+# corner transport upwind (TIME_STEPPING HANCOCK): ctu_kernels.cuh against the restatement of
+# ctu_step.c / hancock.c, which is itself pinned bit for bit by the compiled reference (tests/test_oracle_vs_ref.py)
+CTU_ORACLE_CASES = [
+    # (problem, dims, n, solver, nsteps, first_dt, scheme options)
+    ("ot", 2, (70, 64, 1), "hlld", 10, 5e-3, {}),
+    ("blast", 3, (33, 28, 24), "hlld", 6, 2e-4, {}),
+    ("turb", 3, (24, 20, 28), "roe", 5, 1e-2, {}),
+    ("blast", 3, (20, 24, 16), "hll", 5, 2e-4, {"limiter": "vl", "emf": "arith"}),
+    ("blast", 3, (18, 16, 20), "hlld", 6, 2e-4, {"flatten": True, "emf": "uct0"}),
+    # smallest legal blocks (n = 2*nghost), ragged segments, chunk remainders
+    ("turb", 3, (6, 6, 6), "hlld", 4, 2e-2, {}),
+    ("ot", 2, (6, 7, 1), "hlld", 4, 2e-2, {}),
+    ("ot", 2, (31, 200, 1), "hlld", 3, 2e-3, {}),
+    ("ot", 3, (61, 7, 70), "hlld", 3, 2e-3, {}),
+]
+
+
+@pytest.mark.parametrize("case", CTU_ORACLE_CASES, ids=lambda c: f"ctu_{c[0]}{c[1]}d_{c[3]}_{'x'.join(map(str, c[2]))}")
+def test_ctu_exact_bit_identical_to_oracle(case):
+    from oracle.oracle_lib import Oracle, next_dt
+    from pluto_b200 import GpuStepper, problems
+    problem, dims, n, solver, nsteps, first_dt, opt = case
+    st0, meta = problems.make(problem, dims, n)
+    o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], ctu=True, **opt)
+    s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith="exact", ctu=True, **opt)
+    assert s.nstages == 1 and s.ng == (4 if opt.get("flatten") else 3)
+    o.set_state(st0)
+    s.set_state(st0)
+    dt_o = dt_g = first_dt
+    for step in range(nsteps):
+        inv, mach, nfl = o.advance(dt_o)
+        info = s.advance(dt_g)
+        assert info.inv_dt_hyp == inv, f"step {step}: inv_dt_hyp {info.inv_dt_hyp!r} vs {inv!r}"
+        assert info.max_mach == mach, f"step {step}: max_mach {info.max_mach!r} vs {mach!r}"
+        assert info.floor_events == nfl
+        dt_o = next_dt(inv, meta["cfl"], 1.1, dt_o)
+        dt_g = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt_g)
+        assert dt_o == dt_g
+    a, b = s.get_state(), o.get_state()
+    for k in b:
+        assert np.array_equal(a[k], b[k]), f"{k}: max abs diff {np.abs(a[k]-b[k]).max():.3e}"
+    s.close()
+
+
+def test_ctu_fast_within_tolerance_of_oracle_and_device_next_dt():
+    """FAST arithmetic on a seeded 3-D case beyond the fixtures, stepped with NextTimeStep on the device."""
+    from oracle.oracle_lib import Oracle, next_dt
+    from pluto_b200 import GpuStepper, problems
+    n = (28, 24, 20)
+    st0, meta = problems.make("turb", 3, n)
+    o = Oracle(3, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], ctu=True)
+    s = GpuStepper(3, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], arith="fast", ctu=True)
+    o.set_state(st0)
+    s.set_state(st0)
+    dt, dts = 1e-2, []
+    s.set_dt(dt)
+    for _ in range(8):
+        dts.append(dt)
+        inv, _, _ = o.advance(dt)
+        dt = next_dt(inv, meta["cfl"], 1.1, dt)
+        s.advance_async(meta["cfl"], 1.1)
+    d, infos, dt_next = s.sync_results()
+    assert len(d) == 8 and all(abs(x - y) <= TOL_DT*y for x, y in zip(d, dts)) and abs(dt_next - dt) <= TOL_DT*dt
+    a, b = s.get_state(), o.get_state()
+    for k in b:
+        assert rel_l1(a[k], b[k]) <= TOL_100_STEPS, k
+    bscale = max(np.abs(a["Bx1s"]).max(), 1e-30) / min(meta["dx"])
+    assert divb_max(a, 3, meta["dx"]) < 1e-12 * bscale
+    s.close()
+
+
 def test_reflective_boundaries_match_oracle():
     from oracle.oracle_lib import Oracle
     from pluto_b200 import GpuStepper, problems
@@ -280,18 +351,26 @@ def test_full_size_properties_blast_256():
     ("turb", 3, (16, 24, 32), 2, "ppm", "roe"),
     ("ot", 2, (48, 64, 1), 4, "plm", "hlld"),
     ("rotor", 2, (40, 48, 1), 2, "ppm", "roe"),
+    # corner transport upwind: ONE exchange per step, three ghost layers
+    ("ot", 3, (24, 32, 24), 8, "ctu", "hlld"),
+    ("blast", 3, (24, 16, 32), 4, "ctu", "roe"),
+    ("ot", 2, (48, 64, 1), 4, "ctu", "hlld"),
 ])
 @pytest.mark.parametrize("exchange", ["dims", "all", "all+split"])
 def test_decomposed_blocks_match_single_block(problem, dims, gn, world, recon, solver, exchange):
+    import os
     from pluto_b200 import GpuStepper, problems
     from pluto_b200.parallel import BlockLayout, LocalMultiBlock
     st0, meta = problems.make(problem, dims, gn)
     periodic = meta["bc"][0] == "periodic"
     lay = BlockLayout.strong(dims, gn, world, periodic=periodic)
-    one = GpuStepper(dims, gn, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"])
+    ctu = recon == "ctu"
+    recon = "plm" if ctu else recon
+    one = GpuStepper(dims, gn, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"], ctu=ctu)
     # "all+split": every stage issued as shell + interior, the form the overlapped NCCL exchange uses
-    many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, gamma=meta["gamma"],
-                           exchange=exchange.split("+")[0], split=exchange.endswith("+split"))
+    many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, gamma=meta["gamma"], ctu=ctu,
+                           exchange=exchange.split("+")[0], split=exchange.endswith("+split"),
+                           host_buffers=os.environ.get("PLUTO_GPU_LIB", "").endswith("_emu.so"))
     one.set_state(st0)
     many.set_state(st0)
     dt = {"ot": 5e-3, "blast": 2e-4, "turb": 5e-3, "rotor": 1e-3}[problem]
