@@ -62,6 +62,12 @@ SWEEP_BYTES_2D = {"sweep_x1": (7 + 4 + 1) * 8 + 1, "sweep_x2": (7 + 8 + 1) * 8 +
 # FP64 instructions per launch and zone of the sweep kernels (ncu smsp__sass_thread_inst_executed_op_d*,
 # profiles/): what the FP64 pipe, the binding unit of the sweeps, has to issue
 SWEEP_FP64_INSTR_3D = {"sweep_x1x2": 2 * 365, "sweep_x3": 365}
+# TIME_STEPPING HANCOCK (ctu_kernels.cuh), average of the predictor and the corrector launch of a direction:
+# predictor: read 8 V + Bn, write 8 rhs + 2 face EMFs + sign; corrector: read 8 V + Bn + Bn(half) + 16 transverse rhs
+# (+ 5 U for x2, x3), write 5 U + 2 face EMFs + sign
+CTU_SWEEP_BYTES_3D = {"sweep_x1": ((9 + 8 + 2) * 8 + 1 + (10 + 16 + 5 + 2) * 8 + 1) / 2,
+                      "sweep_x2": ((9 + 8 + 2) * 8 + 1 + (10 + 16 + 10 + 2) * 8 + 1) / 2,
+                      "sweep_x3": ((9 + 8 + 2) * 8 + 1 + (10 + 16 + 10 + 2) * 8 + 1) / 2}
 
 
 def peaks():
@@ -213,6 +219,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--host-dt", action="store_true", help="host-driven NextTimeStep (a device round trip per step)")
+    ap.add_argument("--time-stepping", default="rk2", choices=["rk2", "hancock"],
+                    help="hancock: the corner-transport-upwind step (ctu_step.c) instead of RK2")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -247,7 +255,7 @@ def main():
     off = layout.offset(rank)
     st0, meta = problems.make(problem, dims, layout.global_n, offset=off, count=n)
     s = DistStepper(layout, rank, meta["dx"], recon=recon, solver=solver, rk_order=2, physical_bc=meta["bc"],
-                    gamma=meta["gamma"], arith=args.arith, device=local)
+                    gamma=meta["gamma"], arith=args.arith, device=local, ctu=(args.time_stepping == "hancock"))
     s.set_state(st0)
     del st0
     zones_local = int(np.prod(n[:dims]))
@@ -346,6 +354,8 @@ def main():
     kern_bytes = SWEEP_BYTES_3D.get(top, 0) if dims == 3 else 0
     if dims == 2:
         kern_bytes = SWEEP_BYTES_2D.get(top, 0)
+    if args.time_stepping == "hancock":
+        kern_bytes = CTU_SWEEP_BYTES_3D.get(top, 0) if dims == 3 else 0
     achieved = kern_bytes * zones_local / (top_ms / top_cnt * 1e-3) / 1e9 if kern_bytes else None
     algo = ALGO.get((solver, recon, dims), dict(bytes=440.0, flops=3300.0))
     step_s = ms_max * 1e-3 / args.steps
@@ -375,6 +385,8 @@ def main():
     # = 506 per direction and stage in 3-D; 370 in 2-D; the fused x1+x2 kernel does two directions)
     ndir = 2 if top == "sweep_x1x2" else (1 if top.startswith("sweep") else 0)
     kern_flops = ndir * (506.0 if dims == 3 else 370.0) if (solver, recon) == ("hlld", "plm") else None
+    if args.time_stepping == "hancock":
+        kern_flops = None          # no SURVEY 8(d) contract figure for the CTU sweeps
     fp64_peak = fp64_measured or FP64_PEAK_TFLOPS_NOMINAL
     roofline_fp64 = None
     if kern_flops:
@@ -408,7 +420,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": args.workload, "problem": problem, "zones_per_gpu": list(n[:dims]),
                    "global_zones": list(layout.global_n[:dims]), "rank_grid": list(layout.grid),
-                   "scheme": f"{solver}+{recon}+ct_uct_contact+rk2", "arith": args.arith,
+                   "scheme": f"{solver}+{recon}+ct_uct_contact+" + ("ctu_hancock" if args.time_stepping == "hancock" else "rk2"),
+                   "arith": args.arith,
                    "next_dt": "host" if args.host_dt else "device kernel, same dt sequence (tests/test_gpu_parity.py)",
                    "l2": "inputs larger than L2 (state 1.5 GB/GPU at 256^3 vs 126 MB L2)",
                    "device_bytes_per_gpu": s.block.device_bytes},

@@ -25,6 +25,13 @@
 #pragma once
 #include "sweep_kernels.cuh"
 
+#ifndef PG_CTU_MINB_X
+#define PG_CTU_MINB_X 2
+#endif
+#ifndef PG_CTU_MINB_M
+#define PG_CTU_MINB_M 2
+#endif
+
 namespace PG_NS {
 
 // A dV/dx of the primitive MHD equations along DIR (prim_eqn.c:26-89; the Powell term is absent with CT)
@@ -124,7 +131,7 @@ __device__ __forceinline__ void ctu_transverse (const CtuArgs &a, int id, double
 //  x1 sweep
 // ---------------------------------------------------------------------------
 template <int PHASE, int SOLVER, int NC, bool FLAT>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, PG_CTU_MINB_X)
 ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
 {
   constexpr int DIR = 0;
@@ -221,7 +228,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
 //  x2 / x3 sweeps: marching pencils
 // ---------------------------------------------------------------------------
 template <int DIR, int PHASE, int SOLVER, int NC, bool FLAT>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, PG_CTU_MINB_M)
 ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
 {
   typedef Dirs<DIR> D;

@@ -8,6 +8,8 @@ division and square root stand in for the MUFU-seeded iterations) within the BAS
 tolerances.  The GPU parity tests (tests/test_gpu_parity.py) remain the parity gate.
 """
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -51,7 +53,11 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
     s.close()
 
 
-@pytest.mark.parametrize("name", SHORT)
+FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
+               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe"]
+
+
+@pytest.mark.parametrize("name", FAST_SUBSET)
 def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
     g = Golden(name)
     s = _stepper(g, "fast", emu_lib)
@@ -69,3 +75,45 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
     bscale = max(np.abs(st["Bx1s"]).max(), 1e-30) / min(g.dx)
     assert divb_max(st, g.dims, g.dx) < 1e-12 * bscale
     s.close()
+
+
+# A slice of the GPU test files themselves (same test code, same Python host) run against the interpreted
+# kernels: smallest and ragged blocks, multi-block decomposition with the halo pack/unpack kernels
+# (RK and corner transport upwind), NextTimeStep on the device, reflective walls, the reference Data layout.
+GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or ctu_blast3d_hll_20x24x16 or (decomposed and gn7) or (decomposed and gn4 and all) "
+                   "or (decomposed and gn2 and dims) or (device_next_dt and ot-2) or reflective or data_layout "
+                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3")
+
+
+def test_gpu_test_files_through_the_interpreter(emu_lib):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PLUTO_GPU_LIB=emu_lib, PLUTO_GPU_NO_GRAPH="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        "tests/test_gpu_parity.py", "-k", GPU_SUITE_SLICE], cwd=root, env=env, capture_output=True, text=True)
+    tail = r.stdout[-1500:] + r.stderr[-500:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
+    """The drop-in path of tests/test_gpu_dropin.py on the CPU: the reference's unmodified driver + the shim
+    (integration/advance_step_gpu.c), with the interpreted kernel library found first on the library path."""
+    from oracle.refrun import RefConfig, have_ref, run_reference
+    libdir = tmp_path / "lib"
+    libdir.mkdir()
+    os.symlink(emu_lib, libdir / "libpluto_gpu.so")
+    for name in ("ot2d_plm_hlld", "ot2d_ctu"):
+        g = Golden(name)
+        cfg = RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep, cfl=g.cfl,
+                        cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma, limiter=g.limiter, emf=g.emf,
+                        flatten=g.flatten, prefix="pluto_gpu_")
+        if not have_ref(cfg):
+            pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
+        r = run_reference(cfg, maxsteps=g.nsteps + 1, dump_every=1,
+                          env={"PLUTO_GPU_ARITH": "exact", "PLUTO_GPU_NO_GRAPH": "1", "LD_LIBRARY_PATH": str(libdir)})
+        tap = {int(a): c for a, b, c in r.dt_tap}
+        for s in range(1, g.nsteps + 1):
+            assert tap[s] == g.dt[s], f"{name}: dt after step {s}"
+        for s, ref in g.states.items():
+            for k, v in ref.items():
+                assert np.array_equal(r.dumps[s][k], v), f"{name}: {k} after {s} steps"
