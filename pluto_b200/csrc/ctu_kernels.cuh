@@ -26,7 +26,7 @@
 #include "sweep_kernels.cuh"
 
 #ifndef PG_CTU_MINB_X
-#define PG_CTU_MINB_X 2
+#define PG_CTU_MINB_X 3
 #endif
 #ifndef PG_CTU_MINB_M
 #define PG_CTU_MINB_M 2
@@ -128,8 +128,15 @@ __device__ __forceinline__ void ctu_transverse (const CtuArgs &a, int id, double
 }
 
 // ---------------------------------------------------------------------------
-//  x1 sweep
+//  x1 sweep.  A warp owns one 32-entry segment of the rows (30 updated zones) and walks through
+//  PG_CTU_XROWS consecutive rows; while it solves row r, what row r+1 needs streams into the warp's
+//  shared-memory buffer by cp.async (primitives with a two-entry halo, face fields, and in the
+//  corrector the transverse right-hand sides), so the ~30 loads per zone are never waited for.
 // ---------------------------------------------------------------------------
+#ifndef PG_CTU_XROWS
+#define PG_CTU_XROWS 8
+#endif
+__host__ __device__ constexpr int ctu_x_slot (int phase) { return 9*36 + (phase == 0 ? 0 : 36 + 16*32); }   // doubles per warp and row
 template <int PHASE, int SOLVER, int NC, bool FLAT>
 __global__ void __launch_bounds__(128, PG_CTU_MINB_X)
 ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
@@ -137,85 +144,133 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
   constexpr int DIR = 0;
   typedef Dirs<DIR> D;
   constexpr int E = (PHASE == 0 ? 2 : 1);            // transverse extension of the pencils, states of zones DOM+-E
-  constexpr int STRIDE = 30;
+  constexpr int STRIDE = 30, W = 36;
+  constexpr int NQ = ctu_x_slot (PHASE);
+  constexpr int Q_BS = 8*W, Q_BH = 9*W, Q_RA = 10*W, Q_RB = 10*W + 8*32;
   const Geom &g = a.g;
   const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);
+  extern __shared__ double xbuf_[];
   const int lane = threadIdx.x & 31;
+  double *wb = xbuf_ + (threadIdx.x >> 5)*(2*NQ);
   const int gw = (int)(((long long)blockIdx.x*blockDim.x + threadIdx.x) >> 5);
   const int L = g.n[0] + 2*E;                        // zones with states in one row
   const int nseg = (L - 2 + STRIDE - 1)/STRIDE;
   const int nrj = g.n[1] + 2*E;
   const int nrows = nrj*(NC == 3 ? g.n[2] + 2*E : 1);
-  if (gw >= nseg*nrows) return;                      // whole warps leave together
-  const int seg = gw % nseg, row = gw / nseg;
-  const int jr = row % nrj, kr = row / nrj;
-  const int j = g.beg[1] - E + jr, k = (NC == 3 ? g.beg[2] - E + kr : 0);
+  const int seg = gw % nseg;
+  const int r_beg = (gw / nseg)*PG_CTU_XROWS;
+  if (r_beg >= nrows) return;                        // whole warps leave together
+  const int r_end = (r_beg + PG_CTU_XROWS < nrows ? r_beg + PG_CTU_XROWS : nrows);
   const int ii = seg*STRIDE + lane;
   const bool zone_ok = ii < L;
   const bool face_ok = zone_ok && lane <= 30 && ii <= L - 2;
   const bool emf_ok = face_ok && (lane >= 1 || seg == 0);
   const bool rhs_ok = face_ok && lane >= 1;
-  const int i = g.beg[0] - E + (zone_ok ? ii : L - 1);
-  const int id = gidx32 (g, k, j, i);
+  // zone L (one past the last zone with a state) is the last one read; entries beyond it are clamped
+  const int iic = ii < L ? ii : L;
+  const int ih = (lane == 0 ? seg*STRIDE - 1 : (seg*STRIDE + 32 < L ? seg*STRIDE + 32 : L));   // halo entries 0 and 33
+
+  // rows are enumerated (k, j) with j fastest; idr = index of zone IBEG-E of the row
+  const int S1i = (int)g.S1, S12i = (int)g.S12;
+  int jr = r_beg % nrj, kr = r_beg / nrj;
+  int idr = gidx32 (g, (NC == 3 ? g.beg[2] - E + kr : 0), g.beg[1] - E + jr, g.beg[0] - E);
+  int jr_n = jr, kr_n = kr, idr_n = idr;
+  auto advance = [&] (int &jq, int &kq, int &idq){
+    if (++jq == nrj){ jq = 0; kq++; idq += S12i - (nrj - 1)*S1i; }
+    else idq += S1i;
+  };
+  auto issue = [&] (int buf){
+    double *dst = wb + buf*NQ;
+    const int ido = idr_n + iic;
+    PG_FOR_NV(nv) cp_async8 (dst + nv*W + lane + 1, a.V0[nv] + ido);
+    cp_async8 (dst + Q_BS + lane + 1, a.Bs0[DIR] + ido);
+    if (lane < 2){
+      const int e = (lane == 0 ? 0 : 33);
+      PG_FOR_NV(nv) cp_async8 (dst + nv*W + e, a.V0[nv] + idr_n + ih);
+    }
+    if (lane == 0) cp_async8 (dst + Q_BS, a.Bs0[DIR] + idr_n + ih);
+    if (PHASE == 1){
+      cp_async8 (dst + Q_BH + lane + 1, a.Bsh[DIR] + ido);
+      if (lane == 0) cp_async8 (dst + Q_BH, a.Bsh[DIR] + idr_n + ih);
+      PG_FOR_NV(nv) cp_async8 (dst + Q_RA + nv*32 + lane, a.rhs[1][nv] + ido);
+      if (NC == 3) PG_FOR_NV(nv) cp_async8 (dst + Q_RB + nv*32 + lane, a.rhs[2][nv] + ido);
+    }
+    cp_async_commit ();
+    advance (jr_n, kr_n, idr_n);
+  };
 
   const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
-  double vl[NV], v[NV], vr[NV], vp[NV], vm[NV], up[NV], um[NV];
-  PG_FOR_NV(nv){ vl[nv] = __ldg (a.V0[nv] + id - 1); v[nv] = __ldg (a.V0[nv] + id); vr[nv] = __ldg (a.V0[nv] + id + 1); }
-  const double bsm = __ldg (a.Bs0[DIR] + id - 1), bsp = __ldg (a.Bs0[DIR] + id);
-  unsigned fl = 0;
-  if (FLAT) fl = a.flag[id];
-  ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, vp, vm);
-  int nfl = 0;
-  if (PHASE == 0){
-    prim_to_cons<NC>(ph, vp, up);
-    prim_to_cons<NC>(ph, vm, um);
-  }else{
-    double dU[NV];
-    ctu_transverse<DIR, NC>(a, id, dU);
-    nfl = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, __ldg (a.Bsh[DIR] + id - 1), __ldg (a.Bsh[DIR] + id), vp, vm, up, um);
-    if (!(zone_ok && (lane >= 1 || seg == 0))) nfl = 0;      // zones shared by two segments count once
-  }
-
-  double vR[NV], uR[NV];
-  PG_FOR_NV(nv){ vR[nv] = __shfl_down_sync (0xffffffffu, vm[nv], 1); uR[nv] = __shfl_down_sync (0xffffffffu, um[nv], 1); }
-  const unsigned fl2 = FLAT ? (fl | __shfl_down_sync (0xffffffffu, fl, 1)) : 0u;
-  double F[NV], press, cmax, mach;
-  const bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, fl2, vp, vR, up, uR, F, press, cmax, mach, nullptr, nullptr);
-  if (emf_ok) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F);
+  const double dtdx = __ldg (a.dtp + DIR);
   double my_mach = 0.0, my_cdt = 0.0;
-  if (face_ok) my_mach = mach;
-  if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
+  int nfl_tot = 0;
+  issue (0);
+  for (int r = r_beg; r < r_end; r++, advance (jr, kr, idr)){
+    const int buf = (r - r_beg) & 1;
+    cp_async_wait_all ();
+    __syncwarp ();                                   // the other lanes' copies are visible, row r-1 has been read
+    if (r + 1 < r_end) issue (buf ^ 1);
+    const double *src = wb + buf*NQ;
+    const int id = idr + iic;
 
-  double Fm[NV];
-  PG_FOR_NV(nv) Fm[nv] = __shfl_up_sync (0xffffffffu, F[nv], 1);
-  const double pm = __shfl_up_sync (0xffffffffu, press, 1);
-  if (rhs_ok){
-    my_cdt = cmax*a.inv_dl;                                    // ctu_step.c:416-419, 634-637
+    double vl[NV], v[NV], vr[NV], vp[NV], vm[NV], up[NV], um[NV];
+    PG_FOR_NV(nv){ vl[nv] = src[nv*W + lane]; v[nv] = src[nv*W + lane + 1]; vr[nv] = src[nv*W + lane + 2]; }
+    const double bsm = src[Q_BS + lane], bsp = src[Q_BS + lane + 1];
+    unsigned fl = 0;
+    if (FLAT) fl = a.flag[id];
+    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, vp, vm);
     if (PHASE == 0){
-      PG_FOR_NV(nv){
-        double r = -dt2_dx*(F[nv] - Fm[nv]);
-        if (nv == D::vn) r -= dt2_dx*(press - pm);
-        a.rhs[DIR][nv][id] = r;
-      }
+      prim_to_cons<NC>(ph, vp, up);
+      prim_to_cons<NC>(ph, vm, um);
     }else{
-      bool upd = jr >= 1 && jr <= g.n[1];
-      if (NC == 3) upd = upd && kr >= 1 && kr <= g.n[2];
-      if (upd){
-        const double dtdx = __ldg (a.dtp + DIR);
-        double u0[NV], r;
-        prim_to_cons<NC>(ph, v, u0);                           // Uc = PrimToCons (V^n), ctu_step.c:257-262
-        r = -dtdx*(F[RHO] - Fm[RHO]);                              a.U[RHO][id] = u0[RHO] + r;
-        r = -dtdx*(F[MX1] - Fm[MX1]); r -= dtdx*(press - pm);      a.U[MX1][id] = u0[MX1] + r;
-        r = -dtdx*(F[MX2] - Fm[MX2]);                              a.U[MX2][id] = u0[MX2] + r;
-        if (NC == 3){ r = -dtdx*(F[MX3] - Fm[MX3]);                a.U[MX3][id] = u0[MX3] + r; }
-        r = -dtdx*(F[ENG] - Fm[ENG]);                              a.U[ENG][id] = u0[ENG] + r;
+      double dU[NV];
+      PG_FOR_NV(nv){                                 // ctu_step.c:551-562, the reference's order
+        if (NC == 3) dU[nv] = 0.0 + src[Q_RA + nv*32 + lane] + src[Q_RB + nv*32 + lane];
+        else         dU[nv] = 0.0 + src[Q_RA + nv*32 + lane];
+      }
+      const int n = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, src[Q_BH + lane], src[Q_BH + lane + 1], vp, vm, up, um);
+      if (zone_ok && (lane >= 1 || seg == 0)) nfl_tot += n;    // zones shared by two segments count once
+    }
+
+    double vR[NV], uR[NV];
+    PG_FOR_NV(nv){ vR[nv] = __shfl_down_sync (0xffffffffu, vm[nv], 1); uR[nv] = __shfl_down_sync (0xffffffffu, um[nv], 1); }
+    const unsigned fl2 = FLAT ? (fl | __shfl_down_sync (0xffffffffu, fl, 1)) : 0u;
+    double F[NV], press, cmax, mach;
+    const bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, fl2, vp, vR, up, uR, F, press, cmax, mach, nullptr, nullptr);
+    if (emf_ok) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F);
+    if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
+    if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
+
+    double Fm[NV];
+    PG_FOR_NV(nv) Fm[nv] = __shfl_up_sync (0xffffffffu, F[nv], 1);
+    const double pm = __shfl_up_sync (0xffffffffu, press, 1);
+    if (rhs_ok){
+      const double cd = cmax*a.inv_dl;                         // ctu_step.c:416-419, 634-637
+      my_cdt = cd > my_cdt ? cd : my_cdt;
+      if (PHASE == 0){
+        PG_FOR_NV(nv){
+          double rr = -dt2_dx*(F[nv] - Fm[nv]);
+          if (nv == D::vn) rr -= dt2_dx*(press - pm);
+          a.rhs[DIR][nv][id] = rr;
+        }
+      }else{
+        bool upd = jr >= 1 && jr <= g.n[1];
+        if (NC == 3) upd = upd && kr >= 1 && kr <= g.n[2];
+        if (upd){
+          double u0[NV], rr;
+          prim_to_cons<NC>(ph, v, u0);                           // Uc = PrimToCons (V^n), ctu_step.c:257-262
+          rr = -dtdx*(F[RHO] - Fm[RHO]);                              a.U[RHO][id] = u0[RHO] + rr;
+          rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);     a.U[MX1][id] = u0[MX1] + rr;
+          rr = -dtdx*(F[MX2] - Fm[MX2]);                              a.U[MX2][id] = u0[MX2] + rr;
+          if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                a.U[MX3][id] = u0[MX3] + rr; }
+          rr = -dtdx*(F[ENG] - Fm[ENG]);                              a.U[ENG][id] = u0[ENG] + rr;
+        }
       }
     }
   }
   my_cdt = warp_max (my_cdt);
   my_mach = warp_max (my_mach);
-  const unsigned mfl = __ballot_sync (0xffffffffu, nfl > 0);
-  int tot_fl = nfl;
+  const unsigned mfl = __ballot_sync (0xffffffffu, nfl_tot > 0);
+  int tot_fl = nfl_tot;
   if (mfl) PG_UNROLL for (int o = 16; o > 0; o >>= 1) tot_fl += __shfl_xor_sync (0xffffffffu, tot_fl, o);
   if (lane == 0){
     atomic_max_pos (a.red + RED_CDT, my_cdt);
@@ -225,8 +280,13 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
 }
 
 // ---------------------------------------------------------------------------
-//  x2 / x3 sweeps: marching pencils
+//  x2 / x3 sweeps: marching pencils.  What the iteration of zone z consumes -- V(z+1), the face
+//  field(s) of z, and in the corrector the 2 x 8 transverse right-hand sides of z and U(z-1) --
+//  is pulled ONE zone ahead by cp.async into the thread's own shared-memory column (two slots,
+//  conflict-free, no destination registers): with ~25 global loads per zone consumed at once the
+//  kernel otherwise waits on memory (ncu: long_scoreboard 8.6 stalls per issue at 12 % occupancy).
 // ---------------------------------------------------------------------------
+__host__ __device__ constexpr int ctu_march_slot (int phase) { return phase == 0 ? 9 : 8 + 2 + 16 + 5; }   // doubles per zone
 template <int DIR, int PHASE, int SOLVER, int NC, bool FLAT>
 __global__ void __launch_bounds__(128, PG_CTU_MINB_M)
 ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
@@ -234,6 +294,10 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
   typedef Dirs<DIR> D;
   constexpr int E = (PHASE == 0 ? 2 : 1);
   constexpr int TD = (DIR == 1 ? 2 : 1);               // second transverse dimension
+  constexpr int CS = 128;                              // = blockDim.x
+  constexpr int NQ = ctu_march_slot (PHASE);
+  constexpr int Q_BS = 8, Q_BH = 9, Q_RA = 10, Q_RB = 18, Q_U = 26;
+  constexpr int DA = 0, DB = (DIR == 1 ? 2 : 1);       // the two transverse directions (2-D: only DA)
   const Geom &g = a.g;
   const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);
   const int lane = threadIdx.x & 31;
@@ -241,6 +305,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
   const int np2 = (NC == 3 ? g.n[TD] + 2*E : 1);
   const long long npen = (long long)np1*np2;
   const long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  extern __shared__ double ring_[];
   double my_mach = 0.0, my_cdt = 0.0;
   int nfl = 0;
   if (t < npen*a.nchunk){
@@ -253,10 +318,30 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
     const int R0 = g.beg[DIR] - (PHASE == 0 ? 1 : 0), R1 = g.end[DIR] + (PHASE == 0 ? 1 : 0);
     const int c0 = R0 + chunk*a.chunk_len;
     int c1 = c0 + a.chunk_len - 1; if (c1 > R1) c1 = R1;
-    bool upd = i >= g.beg[0] && i <= g.end[0];
+    bool upd = PHASE == 1 && i >= g.beg[0] && i <= g.end[0];
     if (NC == 3) upd = upd && o2 >= g.beg[TD] && o2 <= g.end[TD];
     const int sD = (DIR == 1 ? (int)g.S1 : (int)g.S12);
     int id = (DIR == 1 ? gidx32 (g, o2, c0 - 1, i) : gidx32 (g, c0 - 1, o2, i));      // zone c0-1
+
+    double *cur = ring_ + threadIdx.x, *nxt = cur + NQ*CS;
+    // everything the iteration of zone z (index idz) reads from HBM
+    auto fetch = [&] (double *dst, int idz, bool first){
+      cp_async8_ordered (dst + Q_BS*CS, a.Bs0[DIR] + idz);          // compiler barrier: the slot has just been read
+      PG_FOR_NV(nv) cp_async8 (dst + nv*CS, a.V0[nv] + idz + sD);
+      if (PHASE == 1){
+        cp_async8 (dst + Q_BH*CS, a.Bsh[DIR] + idz);
+        PG_FOR_NV(nv) cp_async8 (dst + (Q_RA + nv)*CS, a.rhs[DA][nv] + idz);
+        if (NC == 3) PG_FOR_NV(nv) cp_async8 (dst + (Q_RB + nv)*CS, a.rhs[DB][nv] + idz);
+        if (upd && !first){                            // U of zone z-1, updated at the end of the iteration
+          cp_async8 (dst + (Q_U + 0)*CS, a.U[RHO] + idz - sD); cp_async8 (dst + (Q_U + 1)*CS, a.U[MX1] + idz - sD);
+          cp_async8 (dst + (Q_U + 2)*CS, a.U[MX2] + idz - sD);
+          if (NC == 3) cp_async8 (dst + (Q_U + 3)*CS, a.U[MX3] + idz - sD);
+          cp_async8 (dst + (Q_U + 4)*CS, a.U[ENG] + idz - sD);
+        }
+      }
+    };
+    fetch (cur, id, true);
+    cp_async_commit ();
 
     const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
     const double dtdx = __ldg (a.dtp + DIR);
@@ -269,10 +354,13 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
     unsigned flb = 0;
 
     for (int z = c0 - 1; z <= c1 + 1; z++, id += sD){
-      // id = zone z
-      PG_FOR_NV(nv){ vl[nv] = v[nv]; v[nv] = vr[nv]; vr[nv] = __ldg (a.V0[nv] + id + sD); }
+      // id = zone z; its data were requested one iteration ago
+      if (z + 1 <= c1 + 1) fetch (nxt, id + sD, false);
+      cp_async_commit ();
+      cp_async_wait<1> ();
+      PG_FOR_NV(nv){ vl[nv] = v[nv]; v[nv] = vr[nv]; vr[nv] = cur[nv*CS]; }
       const double bsm = bsp;
-      bsp = __ldg (a.Bs0[DIR] + id);
+      bsp = cur[Q_BS*CS];
       unsigned flz = 0;
       if (FLAT) flz = a.flag[id];
       double vp[NV], vm[NV], up[NV], um[NV];
@@ -282,9 +370,16 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         prim_to_cons<NC>(ph, vm, um);
       }else{
         double dU[NV];
-        ctu_transverse<DIR, NC>(a, id, dU);
+        PG_FOR_NV(nv){                                   // ctu_step.c:551-562, the reference's order
+          const double ra = cur[(Q_RA + nv)*CS];
+          if (NC == 3){
+            const double rb = cur[(Q_RB + nv)*CS];
+            if (DIR == 1) dU[nv] = ra + 0.0 + rb;
+            else          dU[nv] = ra + rb;
+          }else dU[nv] = ra + 0.0;
+        }
         const double bhm = bhp;
-        bhp = __ldg (a.Bsh[DIR] + id);
+        bhp = cur[Q_BH*CS];
         const int n = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, bhm, bhp, vp, vm, up, um);
         if ((z >= c0 || chunk == 0) && (z <= c1 || chunk == a.nchunk - 1)) nfl += n;   // zones shared by two chunks count once
       }
@@ -307,14 +402,15 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
               a.rhs[DIR][nv][idf] = r;
             }
           }else if (upd){
+            const double *ua = cur + Q_U*CS;
             double r;
-            r = -dtdx*(F[RHO] - Fp[RHO]);                                           a.U[RHO][idf] += r;
-            r = -dtdx*(F[MX1] - Fp[MX1]); if (D::vn == MX1) r -= dtdx*(press - pp); a.U[MX1][idf] += r;
-            r = -dtdx*(F[MX2] - Fp[MX2]); if (D::vn == MX2) r -= dtdx*(press - pp); a.U[MX2][idf] += r;
+            r = -dtdx*(F[RHO] - Fp[RHO]);                                           a.U[RHO][idf] = ua[0] + r;
+            r = -dtdx*(F[MX1] - Fp[MX1]); if (D::vn == MX1) r -= dtdx*(press - pp); a.U[MX1][idf] = ua[CS] + r;
+            r = -dtdx*(F[MX2] - Fp[MX2]); if (D::vn == MX2) r -= dtdx*(press - pp); a.U[MX2][idf] = ua[2*CS] + r;
             if (NC == 3){
-              r = -dtdx*(F[MX3] - Fp[MX3]); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][idf] += r;
+              r = -dtdx*(F[MX3] - Fp[MX3]); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][idf] = ua[3*CS] + r;
             }
-            r = -dtdx*(F[ENG] - Fp[ENG]);                                           a.U[ENG][idf] += r;
+            r = -dtdx*(F[ENG] - Fp[ENG]);                                           a.U[ENG][idf] = ua[4*CS] + r;
           }
         }
         PG_FOR_NV(nv) Fp[nv] = F[nv];
@@ -322,7 +418,9 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       }
       PG_FOR_NV(nv){ vpL[nv] = vp[nv]; upL[nv] = up[nv]; }
       flb = flz;
+      double *tmp = cur; cur = nxt; nxt = tmp;
     }
+    cp_async_wait_all ();
   }
   my_cdt = warp_max (my_cdt);
   my_mach = warp_max (my_mach);
@@ -386,18 +484,28 @@ static int launch_ctu_sweep_t (int dir, int phase, const CtuArgs &a, cudaStream_
   if (dir == 0){
     const long long nseg = (g.n[0] + 2*E - 2 + 29)/30;
     const long long nrows = (long long)(g.n[1] + 2*E)*(nc == 3 ? g.n[2] + 2*E : 1);
-    const unsigned nb = (unsigned)((nseg*nrows*32 + TPB - 1)/TPB);
-#define PG_CX(P, C) do { if (fl) ctu_sweep_x_kernel<P, SOLVER, C, true><<<nb, TPB, 0, s>>>(a);             \
-                         else    ctu_sweep_x_kernel<P, SOLVER, C, false><<<nb, TPB, 0, s>>>(a); } while (0)
+    const long long nwarp = nseg*((nrows + PG_CTU_XROWS - 1)/PG_CTU_XROWS);
+    const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
+#define PG_CX1(P, C, F) do { auto kfn = ctu_sweep_x_kernel<P, SOLVER, C, F>;                                  \
+      const size_t smem = (size_t)(TPB/32)*2*ctu_x_slot (P)*sizeof (double);                                  \
+      static bool attr_set = false;                                                                          \
+      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
+      kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+#define PG_CX(P, C) do { if (fl) PG_CX1(P, C, true); else PG_CX1(P, C, false); } while (0)
     if (phase == 0){ if (nc == 3) PG_CX(0, 3); else PG_CX(0, 2); }
     else           { if (nc == 3) PG_CX(1, 3); else PG_CX(1, 2); }
 #undef PG_CX
+#undef PG_CX1
   }else{
     const int td = (dir == 1 ? 2 : 1);
     const long long npen = (long long)(g.n[0] + 2*E)*(nc == 3 ? g.n[td] + 2*E : 1);
     const unsigned nb = (unsigned)((npen*a.nchunk + TPB - 1)/TPB);
-#define PG_CM(DD, P, C) do { if (fl) ctu_sweep_march_kernel<DD, P, SOLVER, C, true><<<nb, TPB, 0, s>>>(a);  \
-                             else    ctu_sweep_march_kernel<DD, P, SOLVER, C, false><<<nb, TPB, 0, s>>>(a); } while (0)
+#define PG_CM1(DD, P, C, F) do { auto kfn = ctu_sweep_march_kernel<DD, P, SOLVER, C, F>;                    \
+      const size_t smem = (size_t)2*ctu_march_slot (P)*TPB*sizeof (double);                                  \
+      static bool attr_set = false;                                                                          \
+      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
+      kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+#define PG_CM(DD, P, C) do { if (fl) PG_CM1(DD, P, C, true); else PG_CM1(DD, P, C, false); } while (0)
     if (dir == 1){
       if (phase == 0){ if (nc == 3) PG_CM(1, 0, 3); else PG_CM(1, 0, 2); }
       else           { if (nc == 3) PG_CM(1, 1, 3); else PG_CM(1, 1, 2); }
@@ -405,6 +513,7 @@ static int launch_ctu_sweep_t (int dir, int phase, const CtuArgs &a, cudaStream_
       if (phase == 0) PG_CM(2, 0, 3); else PG_CM(2, 1, 3);
     }
 #undef PG_CM
+#undef PG_CM1
   }
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
