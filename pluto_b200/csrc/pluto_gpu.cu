@@ -286,7 +286,7 @@ int pluto_gpu_timing_get (PlutoGpu *h, int cls, const char **name, double *ms, l
 {
   if (cls < 0 || cls >= PG_NCLASS) return 1;
   *name = kClassName[cls]; *ms = h->class_ms[cls]; *launches = h->class_count[cls];
-  if (cls == KC_SWEEP_X && h->fuse_xy && h->cfg.arith == PLUTO_GPU_ARITH_FAST) *name = "sweep_x1x2";
+  if (cls == KC_SWEEP_X && h->fuse_xy && h->cfg.arith == PLUTO_GPU_ARITH_FAST && !h->ctu) *name = "sweep_x1x2";
   return 0;
 }
 long long pluto_gpu_launch_count (const PlutoGpu *h) { return h->launches; }

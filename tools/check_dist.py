@@ -14,14 +14,20 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 for problem, dims, n, recon, solver in [("ot", 3, (16, 12, 16), "plm", "hlld"), ("blast", 3, (12, 16, 12), "plm", "hlld"),
-                                        ("rotor", 2, (24, 20, 1), "ppm", "roe")]:
+                                        ("rotor", 2, (24, 20, 1), "ppm", "roe"),
+                                        # corner transport upwind: ONE exchange per step, three ghost layers
+                                        ("ot", 3, (12, 16, 12), "ctu", "hlld"), ("blast", 2, (24, 20, 1), "ctu", "roe")]:
     periodic = problem in ("ot", "turb")
+    ctu = recon == "ctu"
+    recon = "plm" if ctu else recon
     lay = BlockLayout.weak(dims, n, world, periodic=periodic)
     gst, meta = problems.make(problem, dims, lay.global_n)
     off, ln = lay.offset(rank), lay.local_n(rank)
     sub, _ = problems.make(problem, dims, lay.global_n, offset=off, count=ln)
-    d = DistStepper(lay, rank, meta["dx"], recon=recon, solver=solver, physical_bc=meta["bc"], gamma=meta["gamma"], device=local)
-    one = GpuStepper(dims, lay.global_n, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"], device=local)
+    d = DistStepper(lay, rank, meta["dx"], recon=recon, solver=solver, physical_bc=meta["bc"], gamma=meta["gamma"], device=local,
+                    ctu=ctu)
+    one = GpuStepper(dims, lay.global_n, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"], device=local,
+                     ctu=ctu)
     # identical inputs: cut the block out of the global arrays (sub-block generation may differ by an ulp)
     cut = {}
     for k, v in gst.items():
