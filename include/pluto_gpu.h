@@ -78,6 +78,9 @@ typedef struct {
   int    shock_flattening; /* SHOCK_FLATTENING: 0 NO, 1 MULTID (Src/flag_shock.c:79-230;
                               LINEAR reconstruction only)                      */
   int    time_stepping;    /* PLUTO_GPU_TS_* (0 = RK2 / RK3 by rk_order)       */
+  int    en_correction;    /* CT_EN_CORRECTION YES: total energy redefined with the face-averaged field
+                              (Src/MHD/CT/ct_field_average.c:116-129); RK time stepping,
+                              CT_EMF_AVERAGE other than UCT_HLL                */
 } PlutoGpuConfig;
 
 typedef struct PlutoGpu PlutoGpu;

@@ -84,6 +84,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
                  LIMITER == UMIST_LIM     ? PLUTO_GPU_LIM_UMIST     : LIMITER == VANLEER_LIM ? PLUTO_GPU_LIM_VANLEER :
                  LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
     c.shock_flattening = (SHOCK_FLATTENING == MULTID);     /* flag_shock.c */
+    c.en_correction = (CT_EN_CORRECTION == YES);           /* ct_field_average.c:116-129 */
     c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
                      CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 :
                      CT_EMF_AVERAGE == UCT_HLL ? PLUTO_GPU_EMF_UCT_HLL : PLUTO_GPU_EMF_UCT_CONTACT);

@@ -1185,17 +1185,30 @@ static void ct_update_from (Oracle *o, double *const *Bs, double dt)
 }
 
 static void ct_average_magnetic_field (Oracle *o)
-/* MHD/CT/ct_field_average.c:58-124 (Cartesian, CT_EN_CORRECTION NO):
-   DOM +/- 1 in every active direction, writes into Uc */
+/* MHD/CT/ct_field_average.c:58-124 (Cartesian): DOM +/- 1 in every active direction, writes into Uc;
+   with CT_EN_CORRECTION YES the energy is redefined with the averaged field (:116-129) */
 {
   int i, j, k, dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
   for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)
   for (j = o->beg[1]-1; j <= o->end[1]+1; j++)
   for (i = o->beg[0]-1; i <= o->end[0]+1; i++){
-    o->Uc[BX1][I3(k,j,i)] = 0.5*(o->Vs[0][I3(k,j,i)] + o->Vs[0][I3(k,j,i-1)]);
-    o->Uc[BX2][I3(k,j,i)] = 0.5*(o->Vs[1][I3(k,j,i)] + o->Vs[1][I3(k,j-1,i)]);
-    if (dims == 3)
-      o->Uc[BX3][I3(k,j,i)] = 0.5*(o->Vs[2][I3(k,j,i)] + o->Vs[2][I3(k-1,j,i)]);
+    double bx_ave, by_ave, bz_ave = 0.0, b2_old = 0.0, b2_new;
+    bx_ave = 0.5*(o->Vs[0][I3(k,j,i)] + o->Vs[0][I3(k,j,i-1)]);
+    by_ave = 0.5*(o->Vs[1][I3(k,j,i)] + o->Vs[1][I3(k,j-1,i)]);
+    if (dims == 3) bz_ave = 0.5*(o->Vs[2][I3(k,j,i)] + o->Vs[2][I3(k-1,j,i)]);
+    if (o->c.en_correction){
+      if (dims == 3) b2_old = o->Uc[BX1][I3(k,j,i)]*o->Uc[BX1][I3(k,j,i)] + o->Uc[BX2][I3(k,j,i)]*o->Uc[BX2][I3(k,j,i)]
+                            + o->Uc[BX3][I3(k,j,i)]*o->Uc[BX3][I3(k,j,i)];
+      else           b2_old = o->Uc[BX1][I3(k,j,i)]*o->Uc[BX1][I3(k,j,i)] + o->Uc[BX2][I3(k,j,i)]*o->Uc[BX2][I3(k,j,i)];
+    }
+    o->Uc[BX1][I3(k,j,i)] = bx_ave;
+    o->Uc[BX2][I3(k,j,i)] = by_ave;
+    if (dims == 3) o->Uc[BX3][I3(k,j,i)] = bz_ave;
+    if (o->c.en_correction){
+      if (dims == 3) b2_new = bx_ave*bx_ave + by_ave*by_ave + bz_ave*bz_ave;
+      else           b2_new = bx_ave*bx_ave + by_ave*by_ave;
+      o->Uc[ENG][I3(k,j,i)] += 0.5*(b2_new - b2_old);
+    }
   }
 }
 

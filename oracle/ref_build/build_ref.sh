@@ -15,6 +15,7 @@
 #   optional suffixes:  _l{fl,mm,va,os,um,vl,mc}  single LIMITER for all variables
 #                                                 (Src/States/plm_coeffs.h:72-123)
 #                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE
+#                       _en                       CT_EN_CORRECTION YES
 #                       _sfl                      SHOCK_FLATTENING MULTID (Src/flag_shock.c) (Src/MHD/CT/ct_emf.c:241-283)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -51,6 +52,9 @@ for VARIANT in "$@"; do
   esac
   case "$VARIANT" in
     *_sfl*) SHOCKFLAT=MULTID ;; *) SHOCKFLAT=NO ;;
+  esac
+  case "$VARIANT" in
+    *_en*) ENCORR=YES ;; *) ENCORR=NO ;;         # CT_EN_CORRECTION (ct_field_average.c:116-129)
   esac
   B="$ORACLE/_build/$VARIANT"
   mkdir -p "$B"
@@ -100,7 +104,7 @@ for VARIANT in "$@"; do
 #define  LIMITER                        $LIMITER
 #define  SHOCK_FLATTENING               $SHOCKFLAT
 #define  CT_EMF_AVERAGE                 $EMFAVG
-#define  CT_EN_CORRECTION               NO
+#define  CT_EN_CORRECTION               $ENCORR
 #define  ASSIGN_VECTOR_POTENTIAL        YES
 #define  CHECK_DIVB_CONDITION           NO
 #define  WARNING_MESSAGES               NO

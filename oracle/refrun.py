@@ -45,6 +45,7 @@ class RefConfig:
     limiter: str = "default"            # default | fl mm va os um vl mc  (LIMITER, plm only)
     flatten: bool = False               # SHOCK_FLATTENING MULTID
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
+    en_corr: bool = False               # CT_EN_CORRECTION YES
     cfl: float = 0.4
     cfl_max_var: float = 1.1
     first_dt: float = 1.0e-3
@@ -69,6 +70,8 @@ class RefConfig:
             v += "_e" + self.emf
         if self.flatten:
             v += "_sfl"
+        if self.en_corr:
+            v += "_en"
         return v
 
     def binary(self) -> str:

@@ -284,9 +284,46 @@ final_kernel (const __grid_constant__ FinalArgs a)
         u[ENG] = one_third*(u0[ENG] + 2.0*u[ENG]);
       }
     }
+    double b2_old = 0.0;
+    if (a.en_corr){
+      // Uc[B] as the reference's sweeps leave it: U = ((U_in + rhs_x1) + rhs_x2) + rhs_x3, rhs = -dt/dx (F_i - F_{i-1})
+      // (update_stage.c:214-216, rhs.c:193-201) with the induction fluxes F of the stored face EMFs
+      // (ct_emf.c:132-176: x1 faces F[BX2] = -ezi, F[BX3] = eyi; x2: F[BX1] = ezj, F[BX3] = -exj; x3: F[BX1] = -eyk,
+      // F[BX2] = exk; the flux of the normal component is zero), then the RK average with U0[B] = V0[B]
+      const long long sy = g.S1, sz = g.S12;
+      const double dtdx0 = __ldg (a.dtp), dtdx1 = __ldg (a.dtp + 1), dtdx2 = (NC == 3 ? __ldg (a.dtp + 2) : 0.0);
+      double b1 = a.Vin[BX1][id], b2 = a.Vin[BX2][id], b3 = (NC == 3 ? a.Vin[BX3][id] : 0.0);
+      b1 = b1 + -dtdx0*(a.fbn[0] ? a.fbn[0][id] - a.fbn[0][id - 1] : 0.0 - 0.0);
+      b2 = b2 + -dtdx0*((-a.ezi[id]) - (-a.ezi[id - 1]));
+      if (NC == 3) b3 = b3 + -dtdx0*(a.eyi[id] - a.eyi[id - 1]);
+      b1 = b1 + -dtdx1*(a.ezj[id] - a.ezj[id - sy]);
+      b2 = b2 + -dtdx1*(a.fbn[1] ? a.fbn[1][id] - a.fbn[1][id - sy] : 0.0 - 0.0);
+      if (NC == 3) b3 = b3 + -dtdx1*((-a.exj[id]) - (-a.exj[id - sy]));
+      if (NC == 3){
+        b1 = b1 + -dtdx2*((-a.eyk[id]) - (-a.eyk[id - sz]));
+        b2 = b2 + -dtdx2*(a.exk[id] - a.exk[id - sz]);
+        b3 = b3 + -dtdx2*(a.fbn[2] ? a.fbn[2][id] - a.fbn[2][id - sz] : 0.0 - 0.0);
+      }
+      if (a.combine == 1){
+        b1 = a.w0*a.V0[BX1][id] + a.wc*b1; b2 = a.w0*a.V0[BX2][id] + a.wc*b2;
+        if (NC == 3) b3 = a.w0*a.V0[BX3][id] + a.wc*b3;
+      }else if (a.combine == 2){
+        const double one_third = 1.0/3.0;
+        b1 = one_third*(a.V0[BX1][id] + 2.0*b1); b2 = one_third*(a.V0[BX2][id] + 2.0*b2);
+        if (NC == 3) b3 = one_third*(a.V0[BX3][id] + 2.0*b3);
+      }
+      if (NC == 3) b2_old = b1*b1 + b2*b2 + b3*b3;
+      else         b2_old = b1*b1 + b2*b2;
+    }
     u[BX1] = 0.5*(a.Bs[0][id] + a.Bs[0][id - 1]);
     u[BX2] = 0.5*(a.Bs[1][id] + a.Bs[1][id - g.S1]);
     if (NC == 3) u[BX3] = 0.5*(a.Bs[2][id] + a.Bs[2][id - g.S12]);
+    if (a.en_corr){
+      double b2_new;
+      if (NC == 3) b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
+      else         b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2];
+      u[ENG] += 0.5*(b2_new - b2_old);
+    }
     fl = cons_to_prim<NC>(ph, u, v);
     if (a.write_u == 1 || (a.write_u == 2 && fl)){
       // the reference keeps Uc across stages (rk_step.c:149-186 has no PrimToCons3D)

@@ -65,6 +65,10 @@ struct SweepArgs {
   double       *e3, *e4;     // ezj, exj
   signed char  *sv2;         // svy
   double  inv_dl2;
+  // CT_EN_CORRECTION with EXACT arithmetic: the flux of the NORMAL field component of every face.  It is zero
+  // analytically, but hlld.c:200-330 forms it as SL*(Bx* - Bn) with Bx* = (SR Bn - SL Bn)/(SR - SL), a round-off
+  // residue that the reference adds to Uc[BXn] and that enters b2_old of ct_field_average.c:116-129
+  double *fbn;
 };
 
 struct CtArgs {
@@ -120,6 +124,13 @@ struct FinalArgs {
                                              // 2: store only ConsToPrim repairs
   double *Uw[8];
   int     box_lo[3], box_n[3];               // zones of this launch, relative to the first interior zone
+  // CT_EN_CORRECTION YES (ct_field_average.c:116-129): the cell-centred conservative field the sweeps WOULD have
+  // produced is rebuilt from the face EMFs (= the induction fluxes the sweeps stored) and the stage's input field
+  int     en_corr;
+  const double *Vin[8];                      // primitives the stage started from (B slots used)
+  const double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
+  const double *fbn[3];                      // normal-component flux of the x1, x2, x3 faces (EXACT; NULL: zero)
+  const double *dtp;                         // device: dt/dx1..3
 };
 
 // Boundary conditions of ONE dimension in one launch: the copy jobs (a field and

@@ -81,6 +81,8 @@ struct PlutoGpu {
   int     march_chunk;             // zones per thread along a marching sweep
   int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
   int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
+  double *fbn[3];                  // CT_EN_CORRECTION + EXACT: normal-field flux of the faces (own allocation)
+  void   *fbn_pool;
   double *rhs3[3][NVS];            // CTU: half-step right-hand sides of the normal predictors (own allocation)
   void   *ctu_pool;
   // optional per-kernel-class device timing (CUDA events on `stream`)
@@ -146,6 +148,10 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
                  "fallback takes its weights from PLM_CoefficientsGet, ppm_states.c:167-181)");
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
   if (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->time_stepping != PLUTO_GPU_TS_HANCOCK) return fail ("bad time_stepping");
+  if (cfg->en_correction != 0 && cfg->en_correction != 1) return fail ("bad en_correction");
+  if (cfg->en_correction && (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL))
+    return fail ("CT_EN_CORRECTION YES is available with RK time stepping and CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
+                 "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
   if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
     if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL) return fail ("TIME_STEPPING HANCOCK: CT_EMF_AVERAGE UCT_HLL is not available (use UCT_CONTACT, ARITHMETIC or UCT0)");
@@ -225,6 +231,13 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     for (int c = 0; c < g.dims; c++) for (int d = 0; d < g.dims; d++){ h->dvel[c][d] = q; q += tot_al; }
     h->pool_bytes += nb;
   }
+  if (cfg->en_correction && cfg->arith == PLUTO_GPU_ARITH_EXACT){
+    const size_t nb = (size_t)g.dims*tot_al*sizeof (double);
+    if (cudaMalloc (&h->fbn_pool, nb) != cudaSuccess) return fail ("cudaMalloc of %zu bytes (normal-field fluxes) failed", nb);
+    CU (cudaMemset (h->fbn_pool, 0, nb));
+    for (int d = 0; d < g.dims; d++) h->fbn[d] = (double *)h->fbn_pool + (size_t)d*tot_al;
+    h->pool_bytes += nb;
+  }
   if (h->ctu){
     int nlive = 0;
     for (int nv = 0; nv < NVS; nv++) nlive += live_var (h, nv);
@@ -259,6 +272,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   cudaFree (h->pool);
   if (h->dvel_pool) cudaFree (h->dvel_pool);
   if (h->ctu_pool) cudaFree (h->ctu_pool);
+  if (h->fbn_pool) cudaFree (h->fbn_pool);
   if (h->flag) cudaFree (h->flag);
   cudaFree (h->red);
   cudaFreeHost (h->red_host);
@@ -561,8 +575,12 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[sp.out][d];
   f.red = h->red; f.g = g; f.ph = h->ph; f.w0 = sp.w0; f.wc = sp.wc; f.combine = sp.combine;
   for (int nv = 0; nv < NVS; nv++) f.Uw[nv] = h->U[nv];
+  f.en_corr = h->cfg.en_correction; f.dtp = h->dtdev;
+  for (int nv = 0; nv < NVS; nv++) f.Vin[nv] = h->V[sp.in][nv];
+  f.exj = h->exj; f.exk = h->exk; f.eyi = h->eyi; f.eyk = h->eyk; f.ezi = h->ezi; f.ezj = h->ezj;
+  for (int d = 0; d < 3; d++) f.fbn[d] = h->fbn[d];
   f.write_u = 0;
-  if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine ? 1 : 2);
+  if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine || f.en_corr ? 1 : 2);   // the energy correction stays in Uc
   if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
 
   if (h->flag && stage == 1){
@@ -592,6 +610,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     s.inv_dl = 1.0/g.dx[dir];              // set_geometry.c (inv_dx)
     s.last_dir = (dir == g.dims - 1);
     s.sv = h->sv[dir];
+    s.fbn = h->fbn[dir];
     if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
@@ -1201,7 +1220,7 @@ extern "C" int pluto_gpu_measure_fp64 (int device, double *tflops)
 //  group, ONE unpack launch per stage.  Boxes along a dimension with offset o:
 //    o = -1: send [beg, beg+ng-1]        receive [0 (-1 for the normal staggered comp), beg-1]
 //    o = +1: send [end-ng+1 (-1), end]   receive [end+1, T-1]
-//    o =  0: [beg (-1 for a component staggered in that dimension), end]
+//    o =  0: [beg (-1 for a component staggered in that dimension whose low side is a physical boundary), end]
 //  i.e. the same layers AL_Exchange_dim moves (al_decompose.c:218-252), with the
 //  edge/corner pieces addressed directly instead of relayed through ghost zones.
 // ---------------------------------------------------------------------------
@@ -1211,7 +1230,11 @@ static void nbr_box (const PlutoGpu *h, const int off[3], int stag, bool send, i
   for (int d = 0; d < 3; d++){
     const int st = (stag == d);
     if (d >= g.dims){ lo[d] = hi[d] = 0; continue; }
-    if (off[d] == 0){ lo[d] = g.beg[d] - st; hi[d] = g.end[d]; }
+    // o = 0: the face beg-1 of a component staggered in d belongs to the low neighbour when that side is SHARED;
+    // it then arrives with the o[d] = -1 piece of the diagonal neighbour (the owner's value), not with this one --
+    // two senders would otherwise write it, with different bits wherever the blocks' own copies of a shared face
+    // are not identical (initial conditions evaluated at y = 0 and y = 2 pi)
+    if (off[d] == 0){ lo[d] = g.beg[d] - (st && h->cfg.bc[2*d] != PLUTO_GPU_BC_SHARED ? 1 : 0); hi[d] = g.end[d]; }
     else if (send){
       if (off[d] < 0){ lo[d] = g.beg[d]; hi[d] = g.beg[d] + g.ng - 1; }
       else           { lo[d] = g.end[d] - g.ng + 1 - st; hi[d] = g.end[d]; }

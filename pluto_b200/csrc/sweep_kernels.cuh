@@ -288,6 +288,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
                                                hll && emf_ok ? a.e1 + id : nullptr, hll && emf_ok ? a.e2 + id : nullptr);
 
     if (emf_ok && !hll) store_face_emf<DIR, NC>(a, id, F);
+    if (emf_ok && a.fbn) a.fbn[id] = F[D::bn];
     if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
     if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
 
@@ -534,6 +535,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
       if (!hll && (f >= c0 || chunk == 0)) store_face_emf<DIR, NC>(a, id, F);
+      if (a.fbn && (f >= c0 || chunk == 0)) a.fbn[id] = F[D::bn];
     }
     const double pp = C_FP(5), cp = C_FP(6);
     if (upd && f >= c0){

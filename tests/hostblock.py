@@ -16,6 +16,7 @@ class HostBlock:
         shp = (self.T[2] + 2, self.T[1] + 2, self.T[0] + 2)
         self.nf = (8 if dims == 3 else 6) + dims
         self.f = [np.full(shp, np.nan) for _ in range(self.nf)]
+        self.shared_lo = [False, False, False]      # low side of dimension d abuts another block (set by the caller)
 
     def is_stag(self, q):
         ncell = self.nf - self.dims
@@ -103,8 +104,8 @@ class HostBlockAll(HostBlock):
             st = 1 if s == d else 0
             if d >= self.dims:
                 continue
-            if off[d] == 0:
-                lo[d], hi[d] = self.beg[d] - st, self.end[d]
+            if off[d] == 0:        # a shared low face belongs to the low neighbour: it comes with the o[d] = -1 piece
+                lo[d], hi[d] = self.beg[d] - (st if not self.shared_lo[d] else 0), self.end[d]
             elif send:
                 if off[d] < 0:
                     lo[d], hi[d] = self.beg[d], self.beg[d] + self.ng - 1

@@ -29,7 +29,7 @@ def emu_lib():
 
 def _stepper(g, arith, lib):
     from pluto_b200 import GpuStepper
-    kw = dict(ctu=True) if g.ctu else {}
+    kw = dict(ctu=g.ctu, en_corr=g.en_corr)
     return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order, bc=g.bc, gamma=g.gamma,
                       arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, lib_path=lib, **kw)
 
@@ -54,7 +54,7 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
-               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe"]
+               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)
@@ -82,7 +82,7 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
 # (RK and corner transport upwind), NextTimeStep on the device, reflective walls, the reference Data layout.
 GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or ctu_blast3d_hll_20x24x16 or (decomposed and gn7) or (decomposed and gn4 and all) "
                    "or (decomposed and gn2 and dims) or (device_next_dt and ot-2) or reflective or data_layout "
-                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3")
+                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2))
 
 
 def test_gpu_test_files_through_the_interpreter(emu_lib):

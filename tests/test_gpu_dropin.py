@@ -17,13 +17,15 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # LIMITER / CT_EMF_AVERAGE read from definitions.h by the shim (Blast #02's and Rotor #01's scheme options)
          "blast3d_vl_arith", "rotor2d_mc_arith", "blast3d_mc_uct_hll_roe", "blast3d_sfl",
          # TIME_STEPPING HANCOCK: the shim replaces ctu_step.o
-         "ot2d_ctu", "blast3d_ctu", "turb3d_ctu_roe"]
+         "ot2d_ctu", "blast3d_ctu", "turb3d_ctu_roe",
+         # CT_EN_CORRECTION YES: the complete scheme of the shipped Blast #02 (definitions_02.h, pluto_02.ini)
+         "blast3d_blast02_en", "blast2d_en"]
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
-                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, prefix="pluto_gpu_")
+                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

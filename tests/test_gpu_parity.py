@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
     return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu)
+                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -257,6 +257,42 @@ def test_ctu_fast_within_tolerance_of_oracle_and_device_next_dt():
     bscale = max(np.abs(a["Bx1s"]).max(), 1e-30) / min(meta["dx"])
     assert divb_max(a, 3, meta["dx"]) < 1e-12 * bscale
     s.close()
+
+
+@pytest.mark.parametrize("problem,dims,n,recon,solver,rk,emf", [
+    ("turb", 3, (20, 24, 16), "ppm", "hlld", 2, "uct_contact"), ("blast", 3, (24, 20, 28), "plm", "roe", 3, "uct0"),
+    ("ot", 2, (70, 64, 1), "plm", "hll", 2, "arith"), ("blast", 2, (40, 36, 1), "plm", "hlld", 2, "uct_contact")])
+def test_en_correction_bit_identical_to_oracle(problem, dims, n, recon, solver, rk, emf):
+    """CT_EN_CORRECTION YES (ct_field_average.c:116-129): the energy correction needs the cell-centred field the
+    reference's sweeps carry in Uc; final_kernel rebuilds it from the face EMFs (+ the round-off residue of the
+    normal-component flux), bit for bit.  Single block and four blocks."""
+    import os
+    from oracle.oracle_lib import Oracle, next_dt
+    from pluto_b200 import GpuStepper, problems
+    from pluto_b200.parallel import BlockLayout, LocalMultiBlock
+    st0, meta = problems.make(problem, dims, n)
+    o = Oracle(dims, n, meta["dx"], recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], emf=emf, en_corr=True)
+    s = GpuStepper(dims, n, meta["dx"], recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], emf=emf,
+                   arith="exact", en_corr=True)
+    lay = BlockLayout.strong(dims, n, 4 if dims == 3 else 2, periodic=meta["bc"][0] == "periodic")
+    many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, rk_order=rk, gamma=meta["gamma"], emf=emf,
+                           en_corr=True, exchange="all", split=True,
+                           host_buffers=os.environ.get("PLUTO_GPU_LIB", "").endswith("_emu.so"))
+    o.set_state(st0); s.set_state(st0); many.set_state(st0)
+    dt = {"ot": 5e-3, "blast": 2e-4, "turb": 1e-2}[problem]
+    for step in range(5):
+        inv, mach, nfl = o.advance(dt)
+        info = s.advance(dt)
+        many.advance(dt)
+        assert (info.inv_dt_hyp, info.max_mach, info.floor_events) == (inv, mach, nfl), step
+        dt = next_dt(inv, meta["cfl"], 1.1, dt)
+    a, b, c = s.get_state(), o.get_state(), many.get_state()
+    for k in b:
+        assert np.array_equal(a[k], b[k]), f"{k}: max abs diff {np.abs(a[k]-b[k]).max():.3e}"
+        assert np.array_equal(c[k], b[k]), f"{k} (4 blocks): max abs diff {np.abs(c[k]-b[k]).max():.3e}"
+    s.close()
+    for blk in many.blocks:
+        blk.close()
 
 
 def test_reflective_boundaries_match_oracle():

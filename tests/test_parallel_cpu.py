@@ -44,6 +44,7 @@ def _worker(rank, world, port, dims, n, periodic, ret, mode="dims"):
     try:
         lay = BlockLayout.weak(dims, n, world, periodic=periodic)
         blk = (HostBlockAll if mode == "all" else HostBlock)(dims, lay.local_n(rank))
+        blk.shared_lo = [lay.block_bc(rank, ("periodic",) * 6)[2 * d] == "shared" for d in range(3)]
         off = lay.offset(rank)
         gn = lay.global_n
         ng = blk.ng

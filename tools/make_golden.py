@@ -79,6 +79,13 @@ CASES = {
     "turb3d_ctu_roe": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, tstep="hancock", solver="roe"), 10),
     "blast3d_ctu_sfl_uct0": (RefConfig(problem="blast", dims=3, n=(12, 16, 12), first_dt=6e-4, cfl=0.3, tstep="hancock",
                                        emf="uct0", flatten=True), 15),
+    # CT_EN_CORRECTION YES (ct_field_average.c:116-129); blast3d_blast02 = the scheme of the shipped Blast #02
+    # (LINEAR, RK2, VANLEER_LIM, ARITHMETIC, CT_EN_CORRECTION YES, roe, CFL 0.2)
+    "blast3d_blast02_en": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.2, limiter="vl", emf="arith",
+                                     solver="roe", en_corr=True), 12),
+    "blast2d_en": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, en_corr=True), 20),
+    "turb3d_rk3_uct0_en": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, tstep="rk3", emf="uct0",
+                                     en_corr=True), 10),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
@@ -94,6 +101,7 @@ def make(name):
         "cfg_domain": np.array(cfg.resolved_domain()),
         "cfg_bc": np.array(cfg.resolved_bc()), "cfg_nsteps": nsteps,
         "cfg_limiter": cfg.limiter, "cfg_emf": cfg.emf, "cfg_flatten": int(cfg.flatten),
+        "cfg_en_corr": int(cfg.en_corr),
     }
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
