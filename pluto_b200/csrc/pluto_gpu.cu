@@ -562,13 +562,13 @@ static int launch_final_boxes (PlutoGpu *h, FinalArgs &f, int part)
   return 0;
 }
 
-static int run_ctu (PlutoGpu *h);
+static int run_ctu (PlutoGpu *h, int part);
 
 static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
 {
   const Geom &g = h->g;
-  // CTU: the whole step is one "stage" (one Boundary call); all of it belongs to the shell part
-  if (h->ctu) return part == PART_INTERIOR ? 0 : run_ctu (h);
+  // CTU: the whole step is one "stage" (one Boundary call); shell / interior split the last kernel only
+  if (h->ctu) return run_ctu (h, part);
   const StagePlan sp = stage_plan (h, stage);
   FinalArgs f; memset (&f, 0, sizeof (f));
   for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[sp.out][nv]; }
@@ -693,9 +693,16 @@ static int march_chunks (const PlutoGpu *h, int dir, int nzones, int ext, int *c
   return (nzones + (int)len - 1)/(int)len;
 }
 
-static int run_ctu (PlutoGpu *h)
+static int run_ctu (PlutoGpu *h, int part)
 {
   const Geom &g = h->g;
+  FinalArgs f; memset (&f, 0, sizeof (f));
+  for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[0][nv]; f.Uw[nv] = h->U[nv]; }
+  for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[0][d];
+  f.red = h->red; f.g = g; f.ph = h->ph; f.combine = 0; f.write_u = 0;
+  // multi-GPU overlap: the new state of the zones next to SHARED sides first (PART_SHELL), so that the ONE
+  // exchange of the next step travels while the remaining zones are mapped to primitives (PART_INTERIOR)
+  if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
   if (h->flag){                          // FlagShock on V^n (ctu_step.c:240-244)
     FlagArgs fa; memset (&fa, 0, sizeof (fa));
     for (int d = 0; d < 3; d++) fa.vx[d] = h->V[0][1 + d];
@@ -753,11 +760,7 @@ static int run_ctu (PlutoGpu *h)
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 
-  FinalArgs f; memset (&f, 0, sizeof (f));
-  for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[0][nv]; f.Uw[nv] = h->U[nv]; }
-  for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[0][d];
-  f.red = h->red; f.g = g; f.ph = h->ph; f.combine = 0; f.write_u = 0;
-  return launch_final_boxes (h, f, PART_ALL);
+  return launch_final_boxes (h, f, part);
 }
 
 // ---------------------------------------------------------------------------
