@@ -79,7 +79,7 @@ typedef struct {
                               LINEAR reconstruction only)                      */
   int    time_stepping;    /* PLUTO_GPU_TS_* (0 = RK2 / RK3 by rk_order)       */
   int    en_correction;    /* CT_EN_CORRECTION YES: total energy redefined with the face-averaged field
-                              (Src/MHD/CT/ct_field_average.c:116-129); RK time stepping,
+                              (Src/MHD/CT/ct_field_average.c:116-129);
                               CT_EMF_AVERAGE other than UCT_HLL                */
 } PlutoGpuConfig;
 

@@ -1480,9 +1480,21 @@ static void ctu_advance (Oracle *o, double dt)
   for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)
   for (j = o->beg[1]-1; j <= o->end[1]+1; j++)
   for (i = o->beg[0]-1; i <= o->end[0]+1; i++){
+    double b2_old = 0.0, b2_new;          /* CT_AverageMagneticField (d->Vs, Uh), CT_EN_CORRECTION: ct_field_average.c:116-129 */
+    if (o->c.en_correction){
+      if (dims == 3) b2_old = o->Uh[BX1][I3(k,j,i)]*o->Uh[BX1][I3(k,j,i)] + o->Uh[BX2][I3(k,j,i)]*o->Uh[BX2][I3(k,j,i)]
+                            + o->Uh[BX3][I3(k,j,i)]*o->Uh[BX3][I3(k,j,i)];
+      else           b2_old = o->Uh[BX1][I3(k,j,i)]*o->Uh[BX1][I3(k,j,i)] + o->Uh[BX2][I3(k,j,i)]*o->Uh[BX2][I3(k,j,i)];
+    }
     o->Uh[BX1][I3(k,j,i)] = 0.5*(o->Vs[0][I3(k,j,i)] + o->Vs[0][I3(k,j,i-1)]);
     o->Uh[BX2][I3(k,j,i)] = 0.5*(o->Vs[1][I3(k,j,i)] + o->Vs[1][I3(k,j-1,i)]);
     if (dims == 3) o->Uh[BX3][I3(k,j,i)] = 0.5*(o->Vs[2][I3(k,j,i)] + o->Vs[2][I3(k-1,j,i)]);
+    if (o->c.en_correction){
+      if (dims == 3) b2_new = o->Uh[BX1][I3(k,j,i)]*o->Uh[BX1][I3(k,j,i)] + o->Uh[BX2][I3(k,j,i)]*o->Uh[BX2][I3(k,j,i)]
+                            + o->Uh[BX3][I3(k,j,i)]*o->Uh[BX3][I3(k,j,i)];
+      else           b2_new = o->Uh[BX1][I3(k,j,i)]*o->Uh[BX1][I3(k,j,i)] + o->Uh[BX2][I3(k,j,i)]*o->Uh[BX2][I3(k,j,i)];
+      o->Uh[ENG][I3(k,j,i)] += 0.5*(b2_new - b2_old);
+    }
   }
   /* 5f. Vc = ConsToPrim (Uh) over DOM +- 1: V^{n+1/2} (:486-497) */
   for (k = o->beg[2]-koff; k <= o->end[2]+koff; k++)

@@ -51,7 +51,7 @@ typedef struct {
   int    ctu;           /* 0: RK2/RK3 (rk_order); 1: corner-transport upwind with the
                            primitive MUSCL-Hancock predictor (TIME_STEPPING HANCOCK,
                            Time_Stepping/ctu_step.c, States/hancock.c)          */
-  int    en_correction; /* CT_EN_CORRECTION YES (MHD/CT/ct_field_average.c:116-129); RK only   */
+  int    en_correction; /* CT_EN_CORRECTION YES (MHD/CT/ct_field_average.c:116-129)            */
 } OracleConfig;
 
 typedef struct Oracle Oracle;

@@ -237,6 +237,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     double F[NV], press, cmax, mach;
     const bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, fl2, vp, vR, up, uR, F, press, cmax, mach, nullptr, nullptr);
     if (emf_ok) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F);
+    if (PHASE == 1 && emf_ok && a.fbn) a.fbn[id] = F[D::bn];
     if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
     if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
 
@@ -391,6 +392,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         my_mach = mach > my_mach ? mach : my_mach;
         if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
         if (z - 1 >= c0 || chunk == 0) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, idf, F);
+        if (PHASE == 1 && a.fbn && (z - 1 >= c0 || chunk == 0)) a.fbn[idf] = F[D::bn];
         if (z - 1 >= c0){
           // zone z-1: faces z-3/2 (Fp) and z-1/2 (F)
           const double cd = cmax*a.inv_dl;
@@ -461,9 +463,18 @@ ctu_half_kernel (const __grid_constant__ CtuArgs a)
       else         dU = a.rhs[0][nv][id] + a.rhs[1][nv][id];
       u[nv] = u[nv] + dU;
     }
+    double b2_old;                      // of Uh[B] = U^n[B] + sum of the half-step induction right-hand sides
+    if (NC == 3) b2_old = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
+    else         b2_old = u[BX1]*u[BX1] + u[BX2]*u[BX2];
     u[BX1] = 0.5*(a.Bsh[0][id] + a.Bsh[0][id - 1]);
     u[BX2] = 0.5*(a.Bsh[1][id] + a.Bsh[1][id - (int)g.S1]);
     if (NC == 3) u[BX3] = 0.5*(a.Bsh[2][id] + a.Bsh[2][id - (int)g.S12]);
+    if (a.en_corr){                     // CT_EN_CORRECTION YES (ct_field_average.c:116-129)
+      double b2_new;
+      if (NC == 3) b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
+      else         b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2];
+      u[ENG] += 0.5*(b2_new - b2_old);
+    }
     fl = cons_to_prim<NC>(ph, u, v);
     PG_FOR_NV(nv) a.Vh[nv][id] = v[nv];
   }

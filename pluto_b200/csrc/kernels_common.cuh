@@ -107,6 +107,8 @@ struct CtuArgs {
   double  inv_dl;            // 1/dx of the sweep direction
   int     limiter;
   int     chunk_len, nchunk; // marching sweeps (x2, x3)
+  int     en_corr;           // CT_EN_CORRECTION YES: half-step kernel (ct_field_average.c:116-129 on Uh)
+  double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
 };
 
 struct FinalArgs {

@@ -149,8 +149,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
   if (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->time_stepping != PLUTO_GPU_TS_HANCOCK) return fail ("bad time_stepping");
   if (cfg->en_correction != 0 && cfg->en_correction != 1) return fail ("bad en_correction");
-  if (cfg->en_correction && (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL))
-    return fail ("CT_EN_CORRECTION YES is available with RK time stepping and CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
+  if (cfg->en_correction && cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
+    return fail ("CT_EN_CORRECTION YES is available with CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
                  "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
   if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
@@ -700,6 +700,10 @@ static int run_ctu (PlutoGpu *h, int part)
   for (int nv = 0; nv < NVS; nv++){ f.U[nv] = h->U[nv]; f.V0[nv] = h->V[0][nv]; f.Vout[nv] = h->V[0][nv]; f.Uw[nv] = h->U[nv]; }
   for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[0][d];
   f.red = h->red; f.g = g; f.ph = h->ph; f.combine = 0; f.write_u = 0;
+  f.en_corr = h->cfg.en_correction; f.dtp = h->dtdev;           // Uc[B] = U^n[B] + the corrector's induction right-hand sides
+  for (int nv = 0; nv < NVS; nv++) f.Vin[nv] = h->V[0][nv];
+  f.exj = h->exj; f.exk = h->exk; f.eyi = h->eyi; f.eyk = h->eyk; f.ezi = h->ezi; f.ezj = h->ezj;
+  for (int d = 0; d < 3; d++) f.fbn[d] = h->fbn[d];
   // multi-GPU overlap: the new state of the zones next to SHARED sides first (PART_SHELL), so that the ONE
   // exchange of the next step travels while the remaining zones are mapped to primitives (PART_INTERIOR)
   if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
@@ -716,6 +720,7 @@ static int run_ctu (PlutoGpu *h, int part)
     for (int nv = 0; nv < NVS; nv++) s.rhs[d][nv] = h->rhs3[d][nv];
   }
   s.red = h->red; s.flag = h->flag; s.g = g; s.ph = h->ph; s.dtp = h->dtdev; s.limiter = h->cfg.limiter;
+  s.en_corr = h->cfg.en_correction;
 
   CtArgs c; memset (&c, 0, sizeof (c));
   c.exj = h->exj; c.exk = h->exk; c.eyi = h->eyi; c.eyk = h->eyk; c.ezi = h->ezi; c.ezj = h->ezj;
@@ -727,6 +732,7 @@ static int run_ctu (PlutoGpu *h, int part)
     for (int dir = 0; dir < g.dims; dir++){
       s.inv_dl = 1.0/g.dx[dir];
       s.sv = h->sv[dir];
+      s.fbn = h->fbn[dir];
       if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
       else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
       else { s.e1 = h->eyk; s.e2 = h->exk; }

@@ -117,3 +117,19 @@ def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
         for s, ref in g.states.items():
             for k, v in ref.items():
                 assert np.array_equal(r.dumps[s][k], v), f"{name}: {k} after {s} steps"
+
+
+def test_create_refuses_unsupported_combinations(emu_lib):
+    """pluto_gpu_create validates the scheme options (same code in the GPU library) and reports why."""
+    from pluto_b200 import GpuStepper
+    from pluto_b200.stepper import PlutoGpuError
+    ok = dict(dims=3, n=(8, 8, 8), dx=(0.1, 0.1, 0.1), lib_path=emu_lib)
+    for bad, msg in [(dict(recon="ppm", ctu=True), "LINEAR"), (dict(emf="uct_hll", ctu=True), "UCT_HLL"),
+                     (dict(emf="uct_hll", en_corr=True), "CT_EN_CORRECTION"), (dict(recon="ppm", flatten=True), "SHOCK_FLATTENING"),
+                     (dict(rk_order=4), "rk_order"), (dict(n=(8, 3, 8)), "nghost")]:
+        kw = dict(ok); kw.update(bad)
+        with pytest.raises(PlutoGpuError, match=msg):
+            GpuStepper(kw.pop("dims"), kw.pop("n"), kw.pop("dx"), **kw)
+    s = GpuStepper(3, (8, 8, 8), (0.1, 0.1, 0.1), lib_path=emu_lib, ctu=True, flatten=True)
+    assert (s.ng, s.nstages) == (4, 1)
+    s.close()

@@ -19,7 +19,7 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # TIME_STEPPING HANCOCK: the shim replaces ctu_step.o
          "ot2d_ctu", "blast3d_ctu", "turb3d_ctu_roe",
          # CT_EN_CORRECTION YES: the complete scheme of the shipped Blast #02 (definitions_02.h, pluto_02.ini)
-         "blast3d_blast02_en", "blast2d_en"]
+         "blast3d_blast02_en", "blast2d_en", "blast3d_ctu_en"]
 
 
 def _cfg(g):

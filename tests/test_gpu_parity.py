@@ -197,6 +197,8 @@ CTU_ORACLE_CASES = [
     ("turb", 3, (24, 20, 28), "roe", 5, 1e-2, {}),
     ("blast", 3, (20, 24, 16), "hll", 5, 2e-4, {"limiter": "vl", "emf": "arith"}),
     ("blast", 3, (18, 16, 20), "hlld", 6, 2e-4, {"flatten": True, "emf": "uct0"}),
+    ("turb", 3, (14, 12, 16), "hlld", 5, 1e-2, {"en_corr": True}),                 # CT_EN_CORRECTION on Uh and Uc
+    ("blast", 2, (36, 30, 1), "roe", 6, 2e-4, {"en_corr": True, "emf": "uct0"}),
     # smallest legal blocks (n = 2*nghost), ragged segments, chunk remainders
     ("turb", 3, (6, 6, 6), "hlld", 4, 2e-2, {}),
     ("ot", 2, (6, 7, 1), "hlld", 4, 2e-2, {}),
@@ -205,7 +207,7 @@ CTU_ORACLE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CTU_ORACLE_CASES, ids=lambda c: f"ctu_{c[0]}{c[1]}d_{c[3]}_{'x'.join(map(str, c[2]))}")
+@pytest.mark.parametrize("case", CTU_ORACLE_CASES, ids=lambda c: f"ctu_{c[0]}{c[1]}d_{c[3]}_{'x'.join(map(str, c[2]))}" + ("_en" if c[6].get("en_corr") else ""))
 def test_ctu_exact_bit_identical_to_oracle(case):
     from oracle.oracle_lib import Oracle, next_dt
     from pluto_b200 import GpuStepper, problems
@@ -214,6 +216,7 @@ def test_ctu_exact_bit_identical_to_oracle(case):
     o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], ctu=True, **opt)
     s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith="exact", ctu=True, **opt)
     assert s.nstages == 1 and s.ng == (4 if opt.get("flatten") else 3)
+    
     o.set_state(st0)
     s.set_state(st0)
     dt_o = dt_g = first_dt

@@ -86,6 +86,9 @@ CASES = {
     "blast2d_en": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, en_corr=True), 20),
     "turb3d_rk3_uct0_en": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, tstep="rk3", emf="uct0",
                                      en_corr=True), 10),
+    "blast3d_ctu_en": (RefConfig(problem="blast", dims=3, n=(12, 16, 8), first_dt=6e-4, cfl=0.3, tstep="hancock", en_corr=True), 12),
+    "ot2d_ctu_arith_en_roe": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, tstep="hancock", emf="arith",
+                                        solver="roe", en_corr=True), 20),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
