@@ -154,7 +154,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
                  "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
   if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
-    if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL) return fail ("TIME_STEPPING HANCOCK: CT_EMF_AVERAGE UCT_HLL is not available (use UCT_CONTACT, ARITHMETIC or UCT0)");
+    if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)      // the reference refuses the same combination (MHD/CT/ct_emf.c:196-200)
+      return fail ("UCT_HLL average not compatible with CTU schemes (stencil too small): use UCT_CONTACT, ARITHMETIC or UCT0");
   }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);

@@ -99,12 +99,19 @@ static void run_block (int nthr)
     makecontext (&f.ctx, fibre_entry, 0);
     f.state = RUN; f.ncoll = 0; f.groups.clear (); f.open.clear ();
   }
+  // PG_EMU_REVERSE=1 schedules the runnable threads (and the blocks) in descending order: a kernel whose result
+  // depends on the order in which the lanes of a warp run between two collectives has a race
+  static const bool reverse = getenv ("PG_EMU_REVERSE") != nullptr && getenv ("PG_EMU_REVERSE")[0] == '1';
   for (;;){
     bool progressed = false;
-    for (int t = 0; t < nthr; t++) if (g_fib[t].state == RUN){
+    for (int q = 0; q < nthr; q++){
+      const int t = reverse ? nthr - 1 - q : q;
+      if (g_fib[t].state != RUN) continue;
+      {
       g_cur = t; threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;
       swapcontext (&g_main, &g_fib[t].ctx);
       progressed = true;
+      }
     }
     int ndone = 0, nblock = 0;
     for (int t = 0; t < nthr; t++){ ndone += g_fib[t].state == DONE; nblock += g_fib[t].state == WAIT_BLOCK; }
@@ -140,7 +147,9 @@ void launch_impl (dim3 grid, dim3 block, size_t smem, const std::function<void (
   if (block.y != 1 || block.z != 1){ fprintf (stderr, "pg_emu: one-dimensional blocks only\n"); abort (); }
   gridDim = grid; blockDim = block;
   g_body = &body;
-  for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++){
+  const bool reverse = getenv ("PG_EMU_REVERSE") != nullptr && getenv ("PG_EMU_REVERSE")[0] == '1';
+  for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned qx = 0; qx < grid.x; qx++){
+    const unsigned bx = reverse ? grid.x - 1 - qx : qx;
     blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
     g_smem.assign (smem + 64, 0);
     run_block ((int)block.x);

@@ -133,3 +133,16 @@ def test_create_refuses_unsupported_combinations(emu_lib):
     s = GpuStepper(3, (8, 8, 8), (0.1, 0.1, 0.1), lib_path=emu_lib, ctu=True, flatten=True)
     assert (s.ng, s.nstages) == (4, 1)
     s.close()
+
+
+def test_results_do_not_depend_on_lane_or_block_order(emu_lib):
+    """PG_EMU_REVERSE=1 runs the lanes of every warp (between two collectives) and the blocks of every launch in
+    descending order.  Bit-identical goldens under both schedules: no kernel relies on an execution order that the
+    CUDA model does not promise (a missing __syncwarp / cp.async wait shows up here as a wrong result)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PG_EMU_REVERSE="1")
+    sel = ("(exact or fast) and (blast3d_plm_hlld or ot3d_ppm_roe or rotor2d_ppm_uct_hll_hll or blast3d_sfl_uct_hll "
+           "or blast3d_ctu_sfl_uct0 or ot2d_ctu_arith_en_roe or blast3d_ctu\\])")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", "tests/test_emu_kernels.py", "-k", sel],
+                       cwd=root, env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
