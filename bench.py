@@ -134,12 +134,12 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 #  reference CPU arm / cpu_baseline
 # ---------------------------------------------------------------------------
-def cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, steps, copies):
+def cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, steps, copies, tstep="rk2"):
     """Time `copies` concurrent runs of the compiled reference (oracle/_ref) on a
     bounded sample grid.  Returns (zone-updates/s aggregate, wall seconds, kind)."""
     from oracle.refrun import RefConfig, have_ref, run_reference
     cfg = RefConfig(problem=problem, dims=dims, n=tuple(n_sample), recon=recon, solver=solver,
-                    cfl=cfl, first_dt=first_dt)
+                    cfl=cfl, first_dt=first_dt, tstep=tstep)
     zones = int(np.prod(n_sample[:dims]))
     if have_ref(cfg):
         res = [None] * copies
@@ -157,7 +157,8 @@ def cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, ste
     from oracle.oracle_lib import Oracle, next_dt
     from pluto_b200 import problems
     st0, meta = problems.make(problem, dims, n_sample)
-    o = Oracle(dims, n_sample, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"])
+    o = Oracle(dims, n_sample, meta["dx"], recon=recon, solver=solver, bc=meta["bc"], gamma=meta["gamma"],
+               ctu=(tstep == "hancock"))
     o.set_state(st0)
     dt = first_dt
     t0 = time.perf_counter()
@@ -186,10 +187,11 @@ def run_reference_arm(args, wl):
     vals = []
     total = max(1, min(args.steps, 3))
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, 2, copies)
+        cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, 2, copies, args.time_stepping)
     t0 = time.perf_counter()
     for _ in range(total):
-        v, wall, kind = cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, steps_per, copies)
+        v, wall, kind = cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, steps_per, copies,
+                                          args.time_stepping)
         vals.append(v)
     value = float(np.mean(vals))
     sample = (f"{copies} concurrent serial copies of the compiled reference, {problem} {dims}-D "
@@ -199,7 +201,9 @@ def run_reference_arm(args, wl):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (time.perf_counter() - t0) / total, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "scheme": f"{solver}+{recon}+ct_uct_contact+rk2", "sample": sample},
+        "config": {"workload": args.workload,
+                   "scheme": f"{solver}+{recon}+ct_uct_contact+" + ("ctu_hancock" if args.time_stepping == "hancock" else "rk2"),
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "zone-updates/s", "cores": copies, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "zone-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -408,7 +412,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         n_sample, steps_per = sample_plan(dims)
         copies = os.cpu_count() or 1
-        v, wall, kind = cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, steps_per, copies)
+        v, wall, kind = cpu_reference_run(problem, dims, recon, solver, cfl, first_dt, n_sample, steps_per, copies,
+                                          args.time_stepping)
         cpu_baseline = {"value": v, "unit": "zone-updates/s", "cores": copies, "kind": kind,
                         "sample": f"{copies} concurrent serial copies, {problem} {dims}-D "
                                   f"{'x'.join(str(q) for q in n_sample[:dims])}, {steps_per} steps each, {wall:.1f} s wall"}
