@@ -37,13 +37,13 @@ def _gfun(q, K, J, I, gn, stag):
     return q * 1e6 + (K % gn[2]) * 1e4 + (J % gn[1]) * 1e2 + (I % gn[0])
 
 
-def _worker(rank, world, port, dims, n, periodic, ret, mode="dims"):
+def _worker(rank, world, port, dims, n, periodic, ret, mode="dims", ng=2):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         lay = BlockLayout.weak(dims, n, world, periodic=periodic)
-        blk = (HostBlockAll if mode == "all" else HostBlock)(dims, lay.local_n(rank))
+        blk = (HostBlockAll if mode == "all" else HostBlock)(dims, lay.local_n(rank), ng=ng)
         blk.shared_lo = [lay.block_bc(rank, ("periodic",) * 6)[2 * d] == "shared" for d in range(3)]
         off = lay.offset(rank)
         gn = lay.global_n
@@ -101,11 +101,13 @@ def _free_port():
 
 
 @pytest.mark.parametrize("mode", ["dims", "all"])
-@pytest.mark.parametrize("world,dims,n", [(2, 3, (6, 5, 4)), (2, 2, (8, 6, 1)), (4, 3, (4, 6, 5)), (4, 2, (6, 8, 1))])
-def test_periodic_exchange_fills_all_ghosts(world, dims, n, mode):
+@pytest.mark.parametrize("world,dims,n,ng", [(2, 3, (6, 5, 4), 2), (2, 2, (8, 6, 1), 2), (4, 3, (4, 6, 5), 2), (4, 2, (6, 8, 1), 2),
+                                             # three ghost layers: PARABOLIC, SHOCK_FLATTENING and the corner-transport-upwind step
+                                             (2, 3, (6, 7, 6), 3), (4, 2, (7, 6, 1), 3)])
+def test_periodic_exchange_fills_all_ghosts(world, dims, n, ng, mode):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), dims, n, True, ret, mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), dims, n, True, ret, mode, ng), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         bad, red, nbytes = ret[r]
