@@ -134,6 +134,8 @@ static void tcollect (PlutoGpu *h)       // after a stream synchronise
 #define TIMED(h, cls, expr) do { int te_ = tbegin (h, cls); int rc_ = (expr); tend (h, te_); if (rc_) return 1; } while (0)
 
 // ---------------------------------------------------------------------------
+static int create_resources (PlutoGpu *h);
+
 int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
 {
   *out = NULL;
@@ -165,7 +167,22 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   CU (cudaSetDevice (cfg->device));
 
   PlutoGpu *h = (PlutoGpu *)calloc (1, sizeof (PlutoGpu));
+  if (!h) return fail ("out of host memory");
   h->cfg = *cfg;
+  if (create_resources (h)){                   // nothing is leaked on a failed allocation
+    char msg[sizeof (g_err)];
+    snprintf (msg, sizeof (msg), "%s", g_err);
+    pluto_gpu_destroy (h);
+    snprintf (g_err, sizeof (g_err), "%s", msg);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+static int create_resources (PlutoGpu *h)
+{
+  const PlutoGpuConfig *cfg = &h->cfg;
   Geom &g = h->g;
   g.dims = cfg->dims;
   g.ng = (cfg->recon == PLUTO_GPU_RECON_PARABOLIC ? 3 : 2);      // get_nghost.c:32-50
@@ -175,7 +192,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   h->nstages = h->ctu ? 1 : cfg->rk_order;
   for (int d = 0; d < 3; d++){
     if (d < g.dims){
-      if (cfg->n[d] < 2*g.ng){ free (h); return fail ("n[%d] = %d is smaller than 2*nghost", d, cfg->n[d]); }
+      if (cfg->n[d] < 2*g.ng) return fail ("n[%d] = %d is smaller than 2*nghost", d, cfg->n[d]);
       g.n[d] = cfg->n[d]; g.T[d] = g.n[d] + 2*g.ng; g.beg[d] = g.ng; g.end[d] = g.ng + g.n[d] - 1; g.off[d] = 1;
       g.dx[d] = cfg->dx[d];
     }else{
@@ -185,7 +202,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   g.S1  = g.T[0] + 2;
   g.S12 = g.S1*(g.T[1] + 2);
   g.tot = g.S12*(g.dims == 3 ? g.T[2] + 2 : 1);
-  if (g.tot >= (1LL << 31)){ free (h); return fail ("block of %lld padded zones: the kernels index with 32 bits (< 2^31 zones per block)", g.tot); }
+  if (g.tot >= (1LL << 31)) return fail ("block of %lld padded zones: the kernels index with 32 bits (< 2^31 zones per block)", g.tot);
   h->ph.gamma = cfg->gamma; h->ph.gmm1 = cfg->gamma - 1.0;
   h->ph.small_dn = cfg->small_dn; h->ph.small_pr = cfg->small_pr;
   h->ph.igmm1 = 1.0/(cfg->gamma - 1.0);
@@ -198,10 +215,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   const int nstate = h->nbuf*(NVS + 3);
   const int nwork = 5 + 6 + 3 + 1;
   h->pool_bytes = (size_t)(nstate + nwork)*tot_al*sizeof (double) + 3*tot_al;
-  if (cudaMalloc (&h->pool, h->pool_bytes) != cudaSuccess){
-    size_t need = h->pool_bytes; free (h);
-    return fail ("cudaMalloc of %zu bytes failed", need);
-  }
+  if (cudaMalloc (&h->pool, h->pool_bytes) != cudaSuccess){ h->pool = NULL; return fail ("cudaMalloc of %zu bytes failed", h->pool_bytes); }
   CU (cudaMemset (h->pool, 0, h->pool_bytes));
   double *p = (double *)h->pool;
   for (int b = 0; b < h->nbuf; b++){
@@ -261,7 +275,6 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   CU (cudaMallocHost ((void **)&h->dthost, 8*sizeof (double)));
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
-  *out = h;
   return 0;
 }
 
@@ -269,22 +282,25 @@ void pluto_gpu_destroy (PlutoGpu *h)
 {
   if (!h) return;
   cudaSetDevice (h->cfg.device);
-  cudaStreamSynchronize (h->stream);
-  cudaFree (h->pool);
+  if (h->stream) cudaStreamSynchronize (h->stream);
+  if (h->pool) cudaFree (h->pool);
   if (h->dvel_pool) cudaFree (h->dvel_pool);
   if (h->ctu_pool) cudaFree (h->ctu_pool);
   if (h->fbn_pool) cudaFree (h->fbn_pool);
   if (h->flag) cudaFree (h->flag);
-  cudaFree (h->red);
-  cudaFreeHost (h->red_host);
-  cudaFree (h->dtdev); cudaFreeHost (h->dthost);
-  cudaFree (h->hist); cudaFreeHost (h->hist_host); cudaFree (h->hist_count);
+  if (h->red) cudaFree (h->red);
+  if (h->red_host) cudaFreeHost (h->red_host);
+  if (h->dtdev) cudaFree (h->dtdev);
+  if (h->dthost) cudaFreeHost (h->dthost);
+  if (h->hist) cudaFree (h->hist);
+  if (h->hist_host) cudaFreeHost (h->hist_host);
+  if (h->hist_count) cudaFree (h->hist_count);
   for (int b = 0; b < 3; b++) for (int q = 0; q < 2; q++) if (h->halo_tab[b][q]) cudaFree (h->halo_tab[b][q]);
   for (int q = 0; q < h->npinned; q++)
     if (h->pinned_by_us[q] && cudaHostUnregister ((void *)h->pinned[q]) != cudaSuccess) cudaGetLastError ();
   if (h->graph) cudaGraphExecDestroy (h->graph);
   for (int e = 0; e < PG_MAX_EV; e++) if (h->ev0[e]){ cudaEventDestroy (h->ev0[e]); cudaEventDestroy (h->ev1[e]); }
-  cudaStreamDestroy (h->stream);
+  if (h->stream) cudaStreamDestroy (h->stream);
   free (h);
 }
 
