@@ -45,6 +45,15 @@ CASES = [
     ("blast2d_ctu_reflective", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock",
                                          bc=("reflective", "outflow", "reflective", "reflective", "outflow", "outflow"),
                                          blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3)), 12),
+    # CT_EN_CORRECTION YES (ct_field_average.c:116-129): RK2 (the scheme of the shipped Blast #02), RK3 + UCT0, CTU
+    ("blast3d_blast02_en", RefConfig(problem="blast", dims=3, n=(14, 10, 12), first_dt=3e-4, cfl=0.2, limiter="vl", emf="arith",
+                                     solver="roe", en_corr=True), 8),
+    ("blast2d_en", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, en_corr=True), 10),
+    ("turb3d_rk3_uct0_en", RefConfig(problem="turb", dims=3, n=(10, 8, 12), first_dt=2e-2, cfl=0.3, tstep="rk3", emf="uct0",
+                                     en_corr=True), 5),
+    ("blast3d_ctu_en", RefConfig(problem="blast", dims=3, n=(10, 14, 12), first_dt=3e-4, cfl=0.3, tstep="hancock", en_corr=True), 8),
+    ("ot2d_ctu_arith_en_roe", RefConfig(problem="ot", dims=2, n=(28, 32, 1), first_dt=1.5e-2, tstep="hancock", emf="arith",
+                                        solver="roe", en_corr=True), 8),
 ]
 
 
@@ -59,7 +68,8 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dom = cfg.resolved_domain()
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
-               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"))
+               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"),
+               rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr)
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt
