@@ -854,6 +854,10 @@ static void update_stage (Oracle *o, double dt)
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
+        if (o->c.body_force){          /* RightHandSideSource, rhs_source.c:214-217 (x1), :277-280 (x2), :342-345 (x3) */
+          rhs[q.vn] += dt*o->v[n][RHO]*o->c.grav[dir];
+          rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*o->c.grav[dir];
+        }
         for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
         if (o->stage == 1)
           o->C_dt[id] += 0.5*(o->cmax[n-1] + o->cmax[n])*inv_dl;
@@ -1316,7 +1320,7 @@ static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, double
     for (nv = 0; nv < NV; nv++){
       double scrh;
       if (dims == 2 && (nv == VX3 || nv == BX3)) continue;
-      scrh = dt_2*(d_dl*Adv[nv] - 0.0);
+      scrh = dt_2*(d_dl*Adv[nv] - (o->c.body_force && nv == q.vn ? 0.0 + o->c.grav[q.vn - VX1] : 0.0));   /* PrimSource, prim_eqn.c:289-360 */
       o->vp[i][nv] -= scrh;
       o->vm[i][nv] -= scrh;
     }
@@ -1451,6 +1455,10 @@ static void ctu_advance (Oracle *o, double dt)
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dt2_dx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dt2_dx*(o->press[n] - o->press[n-1]);
+        if (o->c.body_force){          /* stateC->v is the half-step zone average left by HancockStep (hancock.c:136-141) */
+          rhs[q.vn] += dt2*o->v[n][RHO]*o->c.grav[dir];
+          rhs[ENG]  += dt2*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*o->c.grav[dir];
+        }
         for (nv = 0; nv < NV; nv++) o->rhs3[dir][nv][id] = rhs[nv];
         o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);       /* :416-419 */
       }
@@ -1556,6 +1564,10 @@ static void ctu_advance (Oracle *o, double dt)
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
+        if (o->c.body_force){          /* stateC->v = V^{n+1/2} (ctu_step.c:566-570) */
+          rhs[q.vn] += dt*o->v[n][RHO]*o->c.grav[dir];
+          rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*o->c.grav[dir];
+        }
         for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
         o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);
       }

@@ -52,6 +52,9 @@ typedef struct {
                            primitive MUSCL-Hancock predictor (TIME_STEPPING HANCOCK,
                            Time_Stepping/ctu_step.c, States/hancock.c)          */
   int    en_correction; /* CT_EN_CORRECTION YES (MHD/CT/ct_field_average.c:116-129)            */
+  int    body_force;    /* BODY_FORCE VECTOR with a uniform acceleration grav[] (MHD/rhs_source.c:214-217,
+                           277-280, 342-345; MHD/prim_eqn.c:289-360 in the Hancock predictor)     */
+  double grav[3];
 } OracleConfig;
 
 typedef struct Oracle Oracle;

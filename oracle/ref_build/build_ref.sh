@@ -16,6 +16,7 @@
 #                                                 (Src/States/plm_coeffs.h:72-123)
 #                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE
 #                       _en                       CT_EN_CORRECTION YES
+#                       _bf                       BODY_FORCE VECTOR (uniform acceleration)
 #                       _sfl                      SHOCK_FLATTENING MULTID (Src/flag_shock.c) (Src/MHD/CT/ct_emf.c:241-283)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -56,6 +57,9 @@ for VARIANT in "$@"; do
   case "$VARIANT" in
     *_en*) ENCORR=YES ;; *) ENCORR=NO ;;         # CT_EN_CORRECTION (ct_field_average.c:116-129)
   esac
+  case "$VARIANT" in
+    *_bf*) BODYF=VECTOR ;; *) BODYF=NO ;;        # BODY_FORCE VECTOR: uniform acceleration GRAV1..3 (init.c BodyForceVector)
+  esac
   B="$ORACLE/_build/$VARIANT"
   mkdir -p "$B"
   cp "$HERE/problem/init.c" "$B/init.c"
@@ -65,14 +69,14 @@ for VARIANT in "$@"; do
 #define  DIMENSIONS                     $DIMS
 #define  COMPONENTS                     $DIMS
 #define  GEOMETRY                       CARTESIAN
-#define  BODY_FORCE                     NO
+#define  BODY_FORCE                     $BODYF
 #define  FORCED_TURB                    NO
 #define  COOLING                        NO
 #define  RECONSTRUCTION                 $RECON
 #define  TIME_STEPPING                  $TSTEP
 #define  DIMENSIONAL_SPLITTING          NO
 #define  NTRACER                        0
-#define  USER_DEF_PARAMETERS            9
+#define  USER_DEF_PARAMETERS            12
 
 /* -- physics dependent declarations -- */
 
@@ -98,6 +102,9 @@ for VARIANT in "$@"; do
 #define  PHI                            6
 #define  RADIUS                         7
 #define  SEED                           8
+#define  GRAV1                          9
+#define  GRAV2                          10
+#define  GRAV3                          11
 
 /* [Beg] user-defined constants (do not change this line) */
 

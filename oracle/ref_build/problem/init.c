@@ -240,3 +240,23 @@ void UserDefBoundary (const Data *d, RBox *box, int side, Grid *grid)
  *********************************************************************** */
 {
 }
+
+#if BODY_FORCE != NO
+/* ********************************************************************* */
+void BodyForceVector(double *v, double *g, double x1, double x2, double x3)
+/*
+ * Uniform acceleration (the gravity of Rayleigh-Taylor-type set-ups).
+ *********************************************************************** */
+{
+  g[IDIR] = g_inputParam[GRAV1];
+  g[JDIR] = g_inputParam[GRAV2];
+  g[KDIR] = g_inputParam[GRAV3];
+}
+/* ********************************************************************* */
+double BodyForcePotential(double x1, double x2, double x3)
+/*
+ *********************************************************************** */
+{
+  return 0.0;
+}
+#endif

@@ -46,6 +46,7 @@ class RefConfig:
     flatten: bool = False               # SHOCK_FLATTENING MULTID
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
     en_corr: bool = False               # CT_EN_CORRECTION YES
+    grav: tuple = None                  # BODY_FORCE VECTOR with the uniform acceleration (g1, g2, g3)
     cfl: float = 0.4
     cfl_max_var: float = 1.1
     first_dt: float = 1.0e-3
@@ -72,6 +73,8 @@ class RefConfig:
             v += "_sfl"
         if self.en_corr:
             v += "_en"
+        if self.grav is not None:
+            v += "_bf"
         return v
 
     def binary(self) -> str:
@@ -143,6 +146,8 @@ def write_ini(cfg: RefConfig, path: str, dbl_dn: int = -1, analysis_dn: int = 1)
               ("P_IN", b["P_IN"]), ("P_OUT", b["P_OUT"]), ("BMAG", b["BMAG"]),
               ("THETA", b["THETA"]), ("PHI", b["PHI"]), ("RADIUS", b["RADIUS"]),
               ("SEED", cfg.seed)]
+    gr = cfg.grav if cfg.grav is not None else (0.0, 0.0, 0.0)
+    params += [("GRAV1", gr[0]), ("GRAV2", gr[1]), ("GRAV3", gr[2])]
     for k, v in params:
         lines.append(f"{k:<26s}  {float(v)!r}  ")
     with open(path, "w") as f:

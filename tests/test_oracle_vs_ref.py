@@ -54,6 +54,13 @@ CASES = [
     ("blast3d_ctu_en", RefConfig(problem="blast", dims=3, n=(10, 14, 12), first_dt=3e-4, cfl=0.3, tstep="hancock", en_corr=True), 8),
     ("ot2d_ctu_arith_en_roe", RefConfig(problem="ot", dims=2, n=(28, 32, 1), first_dt=1.5e-2, tstep="hancock", emf="arith",
                                         solver="roe", en_corr=True), 8),
+    # BODY_FORCE VECTOR, uniform acceleration (rhs_source.c:214-217, 277-280, 342-345; prim_eqn.c:289-360 in the Hancock predictor)
+    ("blast3d_bf", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(0.3, -1.0, 0.5)), 8),
+    ("ot2d_bf_roe", RefConfig(problem="ot", dims=2, n=(28, 24, 1), first_dt=1.5e-2, solver="roe", grav=(0.0, -0.8, 0.0)), 8),
+    ("rotor2d_ppm_rk3_bf", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", tstep="rk3", first_dt=2e-3, grav=(0.5, 0.25, 0.0)), 6),
+    ("turb3d_ctu_bf", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, tstep="hancock", grav=(0.3, -1.0, 0.5)), 6),
+    ("blast2d_ctu_bf_hll", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="hancock", solver="hll",
+                                     grav=(-2.0, 1.0, 0.0)), 10),
 ]
 
 
@@ -69,7 +76,7 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
                gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"),
-               rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr)
+               rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr, grav=cfg.grav)
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

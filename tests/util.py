@@ -45,6 +45,7 @@ class Golden:
         self.emf = str(d["cfg_emf"]) if "cfg_emf" in d.files else "uct_contact"
         self.flatten = bool(int(d["cfg_flatten"])) if "cfg_flatten" in d.files else False
         self.en_corr = bool(int(d["cfg_en_corr"])) if "cfg_en_corr" in d.files else False
+        self.grav = tuple(float(x) for x in d["cfg_grav"]) if "cfg_grav" in d.files else None
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:

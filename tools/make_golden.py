@@ -89,6 +89,11 @@ CASES = {
     "blast3d_ctu_en": (RefConfig(problem="blast", dims=3, n=(12, 16, 8), first_dt=6e-4, cfl=0.3, tstep="hancock", en_corr=True), 12),
     "ot2d_ctu_arith_en_roe": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, tstep="hancock", emf="arith",
                                         solver="roe", en_corr=True), 20),
+    # BODY_FORCE VECTOR with a uniform acceleration (first slice)
+    "blast3d_bf": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, grav=(0.3, -1.0, 0.5)), 12),
+    "rotor2d_ppm_rk3_bf": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), recon="ppm", tstep="rk3", first_dt=2.5e-3, cfl=0.4,
+                                     grav=(0.5, 0.25, 0.0)), 15),
+    "turb3d_ctu_bf": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, tstep="hancock", grav=(0.3, -1.0, 0.5)), 10),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
@@ -106,6 +111,8 @@ def make(name):
         "cfg_limiter": cfg.limiter, "cfg_emf": cfg.emf, "cfg_flatten": int(cfg.flatten),
         "cfg_en_corr": int(cfg.en_corr),
     }
+    if cfg.grav is not None:
+        out["cfg_grav"] = np.array(cfg.grav, dtype=float)
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
             out[f"s{s}_{k}"] = v
