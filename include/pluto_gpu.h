@@ -81,6 +81,12 @@ typedef struct {
   int    en_correction;    /* CT_EN_CORRECTION YES: total energy redefined with the face-averaged field
                               (Src/MHD/CT/ct_field_average.c:116-129);
                               CT_EMF_AVERAGE other than UCT_HLL                */
+  int    body_force;       /* BODY_FORCE VECTOR with a UNIFORM acceleration grav[] (what BodyForceVector of
+                              init.c returns everywhere): momentum and energy sources of
+                              Src/MHD/rhs_source.c:214-217, 277-280, 342-345 and, with HANCOCK, the
+                              predictor source of Src/MHD/prim_eqn.c:289-360.  Not with UCT_HLL or
+                              SHOCK_FLATTENING                                 */
+  double grav[3];
 } PlutoGpuConfig;
 
 typedef struct PlutoGpu PlutoGpu;

@@ -85,6 +85,35 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
                  LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
     c.shock_flattening = (SHOCK_FLATTENING == MULTID);     /* flag_shock.c */
     c.en_correction = (CT_EN_CORRECTION == YES);           /* ct_field_average.c:116-129 */
+#if BODY_FORCE != NO
+  #if BODY_FORCE != VECTOR
+    #error "libpluto_gpu: BODY_FORCE POTENTIAL is not available on the GPU"
+  #endif
+    {
+      /* the library takes a UNIFORM acceleration: BodyForceVector (init.c) is sampled at the corners and the centre
+         of the block with the first zone's state and must return the same vector everywhere */
+      double g0[3] = {0.0, 0.0, 0.0}, g1[3], *v0;
+      int q, kk, jj, ii, ks[3], js[3], is[3], bad = 0;
+      is[0] = IBEG; is[1] = (IBEG + IEND)/2; is[2] = IEND;
+      js[0] = JBEG; js[1] = (JBEG + JEND)/2; js[2] = JEND;
+      ks[0] = KBEG; ks[1] = (KBEG + KEND)/2; ks[2] = KEND;
+      v0 = (double *)malloc (NVAR*sizeof(double));
+      for (q = 0; q < NVAR; q++) v0[q] = d->Vc[q][KBEG][JBEG][IBEG];
+      BodyForceVector (v0, g0, grid->x[IDIR][IBEG], grid->x[JDIR][JBEG], grid->x[KDIR][KBEG]);
+      for (kk = 0; kk < 3; kk++) for (jj = 0; jj < 3; jj++) for (ii = 0; ii < 3; ii++){
+        g1[0] = g1[1] = g1[2] = 0.0;
+        BodyForceVector (v0, g1, grid->x[IDIR][is[ii]], grid->x[JDIR][js[jj]], grid->x[KDIR][ks[kk]]);
+        for (q = 0; q < DIMENSIONS; q++) bad |= (g1[q] != g0[q]);
+      }
+      free (v0);
+      if (bad){
+        print ("! AdvanceStep(gpu): BodyForceVector is not uniform; libpluto_gpu takes a constant acceleration only\n");
+        QUIT_PLUTO(1);
+      }
+      c.body_force = 1;
+      c.grav[0] = g0[0]; c.grav[1] = g0[1]; c.grav[2] = g0[2];
+    }
+#endif
     c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
                      CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 :
                      CT_EMF_AVERAGE == UCT_HLL ? PLUTO_GPU_EMF_UCT_HLL : PLUTO_GPU_EMF_UCT_CONTACT);

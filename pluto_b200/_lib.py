@@ -36,7 +36,8 @@ class PlutoGpuConfig(C.Structure):
                 ("rk_order", C.c_int), ("bc", C.c_int * 6), ("arith", C.c_int), ("device", C.c_int),
                 ("gamma", C.c_double), ("dx", C.c_double * 3), ("small_dn", C.c_double),
                 ("small_pr", C.c_double), ("limiter", C.c_int), ("emf_average", C.c_int),
-                ("shock_flattening", C.c_int), ("time_stepping", C.c_int), ("en_correction", C.c_int)]
+                ("shock_flattening", C.c_int), ("time_stepping", C.c_int), ("en_correction", C.c_int), ("body_force", C.c_int),
+                ("grav", C.c_double * 3)]
 
 
 class PlutoGpuStepInfo(C.Structure):

@@ -60,7 +60,7 @@ __device__ __forceinline__ void prim_rhs (const Phys &ph, const double *v, const
 template <int DIR, int NC, bool FLAT>
 __device__ __forceinline__ void ctu_states (const Phys &ph, int limiter, unsigned fl, const double *vl, const double *v,
                                             const double *vr, double bsm, double bsp, double dt_2, double d_dl,
-                                            double *vp, double *vm)
+                                            double src_n, double *vp, double *vm)
 {
   typedef Dirs<DIR> D;
   double dvm[NV], dvp[NV], dv[NV], Adv[NV];
@@ -70,8 +70,8 @@ __device__ __forceinline__ void ctu_states (const Phys &ph, int limiter, unsigne
   vp[D::bn] = bsp; vm[D::bn] = bsm;
   PG_FOR_NV(nv) dv[nv] = vp[nv] - vm[nv];
   prim_rhs<DIR, NC>(ph, v, dv, Adv);
-  PG_FOR_NV(nv){
-    const double scrh = dt_2*(d_dl*Adv[nv] - 0.0);
+  PG_FOR_NV(nv){                                     // src_n: PrimSource of the normal velocity (body force, prim_eqn.c:289-360)
+    const double scrh = dt_2*(d_dl*Adv[nv] - (nv == D::vn ? src_n : 0.0));
     vp[nv] -= scrh;
     vm[nv] -= scrh;
   }
@@ -201,6 +201,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
 
   const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
   const double dtdx = __ldg (a.dtp + DIR);
+  const double src_n = a.bf ? 0.0 + a.grav[DIR] : 0.0;
   double my_mach = 0.0, my_cdt = 0.0;
   int nfl_tot = 0;
   issue (0);
@@ -217,7 +218,11 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     const double bsm = src[Q_BS + lane], bsp = src[Q_BS + lane + 1];
     unsigned fl = 0;
     if (FLAT) fl = a.flag[id];
-    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, vp, vm);
+    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
+    // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
+    // V^{n+1/2} (ctu_step.c:566-570) in the corrector
+    double rho_c = 0.0;
+    if (a.bf) rho_c = (PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : __ldg (a.Vh[RHO] + id));
     if (PHASE == 0){
       prim_to_cons<NC>(ph, vp, up);
       prim_to_cons<NC>(ph, vm, um);
@@ -250,7 +255,8 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
       if (PHASE == 0){
         PG_FOR_NV(nv){
           double rr = -dt2_dx*(F[nv] - Fm[nv]);
-          if (nv == D::vn) rr -= dt2_dx*(press - pm);
+          if (nv == D::vn){ rr -= dt2_dx*(press - pm); if (a.bf) rr += dt_2*rho_c*a.grav[DIR]; }
+          if (nv == ENG && a.bf) rr += dt_2*0.5*(F[RHO] + Fm[RHO])*a.grav[DIR];
           a.rhs[DIR][nv][id] = rr;
         }
       }else{
@@ -260,10 +266,14 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
           double u0[NV], rr;
           prim_to_cons<NC>(ph, v, u0);                           // Uc = PrimToCons (V^n), ctu_step.c:257-262
           rr = -dtdx*(F[RHO] - Fm[RHO]);                              a.U[RHO][id] = u0[RHO] + rr;
-          rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);     a.U[MX1][id] = u0[MX1] + rr;
+          const double dtf = 2.0*dt_2;                                // = dt
+          rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);
+          if (a.bf) rr += dtf*rho_c*a.grav[DIR];                      a.U[MX1][id] = u0[MX1] + rr;
           rr = -dtdx*(F[MX2] - Fm[MX2]);                              a.U[MX2][id] = u0[MX2] + rr;
           if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                a.U[MX3][id] = u0[MX3] + rr; }
-          rr = -dtdx*(F[ENG] - Fm[ENG]);                              a.U[ENG][id] = u0[ENG] + rr;
+          rr = -dtdx*(F[ENG] - Fm[ENG]);
+          if (a.bf) rr += dtf*0.5*(F[RHO] + Fm[RHO])*a.grav[DIR];
+          a.U[ENG][id] = u0[ENG] + rr;
         }
       }
     }
@@ -346,6 +356,8 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
 
     const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
     const double dtdx = __ldg (a.dtp + DIR);
+    const double src_n = a.bf ? 0.0 + a.grav[DIR] : 0.0;
+    double rhoL = 0.0;                               // body force: stateC density of zone z-1 (predictor)
     double vl[NV], v[NV], vr[NV];
     PG_FOR_NV(nv){ v[nv] = __ldg (a.V0[nv] + id - sD); vr[nv] = __ldg (a.V0[nv] + id); }
     double bsp = __ldg (a.Bs0[DIR] + id - sD), bhp = 0.0;
@@ -365,7 +377,8 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       unsigned flz = 0;
       if (FLAT) flz = a.flag[id];
       double vp[NV], vm[NV], up[NV], um[NV];
-      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, vp, vm);
+      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
+      const double rho_z = (a.bf && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
       if (PHASE == 0){
         prim_to_cons<NC>(ph, vp, up);
         prim_to_cons<NC>(ph, vm, um);
@@ -400,25 +413,35 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
           if (PHASE == 0){
             PG_FOR_NV(nv){
               double r = -dt2_dx*(F[nv] - Fp[nv]);
-              if (nv == D::vn) r -= dt2_dx*(press - pp);
+              if (nv == D::vn){ r -= dt2_dx*(press - pp); if (a.bf) r += dt_2*rhoL*a.grav[DIR]; }
+              if (nv == ENG && a.bf) r += dt_2*0.5*(F[RHO] + Fp[RHO])*a.grav[DIR];
               a.rhs[DIR][nv][idf] = r;
             }
           }else if (upd){
             const double *ua = cur + Q_U*CS;
+            const double dtf = 2.0*dt_2;                                        // = dt
+            const double rho_h = a.bf ? __ldg (a.Vh[RHO] + idf) : 0.0;          // V^{n+1/2} (ctu_step.c:566-570)
             double r;
             r = -dtdx*(F[RHO] - Fp[RHO]);                                           a.U[RHO][idf] = ua[0] + r;
             r = -dtdx*(F[MX1] - Fp[MX1]); if (D::vn == MX1) r -= dtdx*(press - pp); a.U[MX1][idf] = ua[CS] + r;
-            r = -dtdx*(F[MX2] - Fp[MX2]); if (D::vn == MX2) r -= dtdx*(press - pp); a.U[MX2][idf] = ua[2*CS] + r;
+            r = -dtdx*(F[MX2] - Fp[MX2]);
+            if (D::vn == MX2){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*a.grav[DIR]; }
+            a.U[MX2][idf] = ua[2*CS] + r;
             if (NC == 3){
-              r = -dtdx*(F[MX3] - Fp[MX3]); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][idf] = ua[3*CS] + r;
+              r = -dtdx*(F[MX3] - Fp[MX3]);
+              if (D::vn == MX3){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*a.grav[DIR]; }
+              a.U[MX3][idf] = ua[3*CS] + r;
             }
-            r = -dtdx*(F[ENG] - Fp[ENG]);                                           a.U[ENG][idf] = ua[4*CS] + r;
+            r = -dtdx*(F[ENG] - Fp[ENG]);
+            if (a.bf) r += dtf*0.5*(F[RHO] + Fp[RHO])*a.grav[DIR];
+            a.U[ENG][idf] = ua[4*CS] + r;
           }
         }
         PG_FOR_NV(nv) Fp[nv] = F[nv];
         pp = press;
       }
       PG_FOR_NV(nv){ vpL[nv] = vp[nv]; upL[nv] = up[nv]; }
+      rhoL = rho_z;
       flb = flz;
       double *tmp = cur; cur = nxt; nxt = tmp;
     }

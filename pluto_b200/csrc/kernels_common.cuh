@@ -69,6 +69,8 @@ struct SweepArgs {
   // analytically, but hlld.c:200-330 forms it as SL*(Bx* - Bn) with Bx* = (SR Bn - SL Bn)/(SR - SL), a round-off
   // residue that the reference adds to Uc[BXn] and that enters b2_old of ct_field_average.c:116-129
   double *fbn;
+  // BODY_FORCE VECTOR with a uniform acceleration (rhs_source.c:214-217, 277-280, 342-345): template flag BF of the sweeps
+  double  grav[3];
 };
 
 struct CtArgs {
@@ -108,6 +110,8 @@ struct CtuArgs {
   int     limiter;
   int     chunk_len, nchunk; // marching sweeps (x2, x3)
   int     en_corr;           // CT_EN_CORRECTION YES: half-step kernel (ct_field_average.c:116-129 on Uh)
+  int     bf;                // BODY_FORCE VECTOR, uniform acceleration grav[] (rhs_source.c:214-345, prim_eqn.c:289-360)
+  double  grav[3];
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
 };
 
@@ -190,12 +194,12 @@ struct HaloEntry {
 // ---- launch interface, one set per arithmetic namespace ----------------------
 #define PG_DECLARE_LAUNCHERS(NS)                                                         \
 namespace NS {                                                                           \
-  int launch_sweep_hlld (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
-  int launch_sweep_hll  (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
-  int launch_sweep_roe  (int dir, int recon, const SweepArgs &a, cudaStream_t s);        \
-  int launch_sweep_xy_hlld (int recon, const SweepArgs &a, cudaStream_t s);              \
-  int launch_sweep_xy_hll  (int recon, const SweepArgs &a, cudaStream_t s);              \
-  int launch_sweep_xy_roe  (int recon, const SweepArgs &a, cudaStream_t s);              \
+  int launch_sweep_hlld (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
+  int launch_sweep_hll  (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
+  int launch_sweep_roe  (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
+  int launch_sweep_xy_hlld (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
+  int launch_sweep_xy_hll  (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
+  int launch_sweep_xy_roe  (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
   int launch_ctu_sweep_hlld (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
   int launch_ctu_sweep_hll  (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
   int launch_ctu_sweep_roe  (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \

@@ -154,6 +154,9 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->en_correction && cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
     return fail ("CT_EN_CORRECTION YES is available with CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
                  "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
+  if (cfg->body_force != 0 && cfg->body_force != 1) return fail ("bad body_force");
+  if (cfg->body_force && (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL || cfg->shock_flattening))
+    return fail ("BODY_FORCE is not available together with CT_EMF_AVERAGE UCT_HLL or SHOCK_FLATTENING");
   if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
     if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)      // the reference refuses the same combination (MHD/CT/ct_emf.c:196-200)
@@ -614,6 +617,8 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   s.stage1 = (stage == 1);
   s.limiter = h->cfg.limiter;
   s.avg = h->cfg.emf_average;
+  const bool bf = h->cfg.body_force != 0;
+  for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];
   // EXACT: later stages continue from the conservative state the previous stage
   // left (as the reference does); FAST: rebuild it from the primitives, which
   // saves reading U in the x1 sweep and differs by round-off only
@@ -659,18 +664,18 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       s.inv_dl2 = 1.0/g.dx[1];
       s.last_dir = (g.dims == 2);
       const int te = tbegin (h, KC_SWEEP_X);
-      if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = pg_fast::launch_sweep_xy_hlld (recon, s, h->stream);
-      else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = pg_fast::launch_sweep_xy_hll  (recon, s, h->stream);
-      else                                             r = pg_fast::launch_sweep_xy_roe  (recon, s, h->stream);
+      if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = pg_fast::launch_sweep_xy_hlld (recon, s, h->stream, bf);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = pg_fast::launch_sweep_xy_hll  (recon, s, h->stream, bf);
+      else                                             r = pg_fast::launch_sweep_xy_roe  (recon, s, h->stream, bf);
       tend (h, te);
       if (count (h, r)) return 1;
       dir = 1;                             // x2 is done
       continue;
     }
     const int te = tbegin (h, KC_SWEEP_X + dir);
-    if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_sweep_hlld) (dir, recon, s, h->stream);
-    else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_sweep_hll)  (dir, recon, s, h->stream);
-    else                                             r = DISPATCH (h, launch_sweep_roe)  (dir, recon, s, h->stream);
+    if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_sweep_hlld) (dir, recon, s, h->stream, bf);
+    else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_sweep_hll)  (dir, recon, s, h->stream, bf);
+    else                                             r = DISPATCH (h, launch_sweep_roe)  (dir, recon, s, h->stream, bf);
     tend (h, te);
     if (count (h, r)) return 1;
   }
@@ -738,6 +743,8 @@ static int run_ctu (PlutoGpu *h, int part)
   }
   s.red = h->red; s.flag = h->flag; s.g = g; s.ph = h->ph; s.dtp = h->dtdev; s.limiter = h->cfg.limiter;
   s.en_corr = h->cfg.en_correction;
+  s.bf = h->cfg.body_force;
+  for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];
 
   CtArgs c; memset (&c, 0, sizeof (c));
   c.exj = h->exj; c.exk = h->exk; c.eyi = h->eyi; c.eyk = h->eyk; c.ezi = h->ezi; c.ezj = h->ezj;

@@ -177,8 +177,8 @@ __device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, cons
 #define PG_XROWS 16          // rows a warp walks through (software-pipelined)
 #endif
 
-template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT>   // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds + velocity
-                                                                 // slopes); FLAT: SHOCK_FLATTENING MULTID (zone flags)
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false>   // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds +
+                                                  // velocity slopes); FLAT: SHOCK_FLATTENING MULTID (zone flags); BF: body force
 __global__ void __launch_bounds__(128, PG_MINB_X)
 sweep_x_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -316,10 +316,13 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
       const double dtdx = __ldg (a.dtp + DIR);
       double rr;
       rr = -dtdx*(F[RHO] - Fm[RHO]);                                a.U[RHO][id] = u0[RHO] + rr;
-      rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);       a.U[MX1][id] = u0[MX1] + rr;
+      rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);
+      if (BF) rr += __ldg (a.dtp + 3)*v[RHO]*a.grav[DIR];           a.U[MX1][id] = u0[MX1] + rr;
       rr = -dtdx*(F[MX2] - Fm[MX2]);                                a.U[MX2][id] = u0[MX2] + rr;
       if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                  a.U[MX3][id] = u0[MX3] + rr; }
-      rr = -dtdx*(F[ENG] - Fm[ENG]);                                a.U[ENG][id] = u0[ENG] + rr;
+      rr = -dtdx*(F[ENG] - Fm[ENG]);
+      if (BF) rr += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*a.grav[DIR];
+      a.U[ENG][id] = u0[ENG] + rr;
       if (a.stage1){
         const double cd = 0.5*(cm + cmax)*a.inv_dl;
         if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
@@ -353,7 +356,7 @@ __host__ __device__ constexpr int march_slots (int recon)
   return 8*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + 8 + 7 + (recon == RECON_PPM ? 8 : 0)
          + march_prefetch (recon) + 6*(march_prefetch (recon) + 1);
 }
-template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT>
+template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false>
 __global__ void __launch_bounds__(128, PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -471,9 +474,11 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     cp_async_wait<PF - 1> ();
     const double bn = bnp[0][0];
     const double *ua = uap[0];               // U and C_dt of zone f (landed at least one face ago)
+    double rho_f = 0.0;                      // density of zone f (body force)
     {
       double vb_[NV], vc_[NV], vd_[NV], vnx[NV], vpn[NV];
       PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vnx[nv] = z[LA][nv*CS]; }
+      if (BF) rho_f = vb_[RHO];
       if (PPM) PG_FOR_NV(nv) vd_[nv] = z[2][nv*CS];
       // start pulling what face f+PF+1/2 needs; its new zone replaces zone f, its field
       // the one just read.  Always commit (possibly empty) so that the group count holds.
@@ -542,12 +547,19 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       const double dtdx = __ldg (a.dtp + DIR);
       double r;
       r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = ua[0] + r;
+      const double dtg = BF ? __ldg (a.dtp + 3) : 0.0;
       r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = ua[CS] + r;
-      r = -dtdx*(F[MX2] - C_FP(2)); if (D::vn == MX2) r -= dtdx*(press - pp);   a.U[MX2][id] = ua[2*CS] + r;
+      r = -dtdx*(F[MX2] - C_FP(2));
+      if (D::vn == MX2){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*a.grav[DIR]; }
+      a.U[MX2][id] = ua[2*CS] + r;
       if (NC == 3){
-        r = -dtdx*(F[MX3] - C_FP(3)); if (D::vn == MX3) r -= dtdx*(press - pp); a.U[MX3][id] = ua[3*CS] + r;
+        r = -dtdx*(F[MX3] - C_FP(3));
+        if (D::vn == MX3){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*a.grav[DIR]; }
+        a.U[MX3][id] = ua[3*CS] + r;
       }
-      r = -dtdx*(F[ENG] - C_FP(4));                               a.U[ENG][id] = ua[4*CS] + r;
+      r = -dtdx*(F[ENG] - C_FP(4));
+      if (BF) r += dtg*0.5*(F[RHO] + C_FP(0))*a.grav[DIR];
+      a.U[ENG][id] = ua[4*CS] + r;
       if (a.stage1){
         double cd = ua[5*CS] + 0.5*(cp + cmax)*a.inv_dl;
         if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
@@ -597,7 +609,7 @@ __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
   return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128)*sizeof (double);
 }
 
-template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT>
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false>
 __global__ void __launch_bounds__(128, PG_MINB_XY)
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -766,6 +778,10 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       rx[MX2] = -dtdx0*(F[MX2] - Fm[MX2]);
       if (NC == 3) rx[MX3] = -dtdx0*(F[MX3] - Fm[MX3]);
       rx[ENG] = -dtdx0*(F[ENG] - Fm[ENG]);
+      if (BF){
+        rx[MX1] += __ldg (a.dtp + 3)*v[RHO]*a.grav[0];
+        rx[ENG] += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*a.grav[0];
+      }
       cdx = 0.5*(cm + cmax)*a.inv_dl;
     }
 
@@ -807,9 +823,12 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         prim_to_cons<NC>(ph, v, u0);
         r = -dtdx1*(F[RHO] - C_FP(0));                                   a.U[RHO][id] = (u0[RHO] + rx[RHO]) + r;
         r = -dtdx1*(F[MX1] - C_FP(1));                                   a.U[MX1][id] = (u0[MX1] + rx[MX1]) + r;
-        r = -dtdx1*(F[MX2] - C_FP(2)); r -= dtdx1*(press - pp);          a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
+        r = -dtdx1*(F[MX2] - C_FP(2)); r -= dtdx1*(press - pp);
+        if (BF) r += __ldg (a.dtp + 3)*v[RHO]*a.grav[1];                 a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
         if (NC == 3){ r = -dtdx1*(F[MX3] - C_FP(3));                     a.U[MX3][id] = (u0[MX3] + rx[MX3]) + r; }
-        r = -dtdx1*(F[ENG] - C_FP(4));                                   a.U[ENG][id] = (u0[ENG] + rx[ENG]) + r;
+        r = -dtdx1*(F[ENG] - C_FP(4));
+        if (BF) r += __ldg (a.dtp + 3)*0.5*(F[RHO] + C_FP(0))*a.grav[1];
+        a.U[ENG][id] = (u0[ENG] + rx[ENG]) + r;
         if (a.stage1){
           const double cd = cdx + 0.5*(cp + cmax)*a.inv_dl2;
           if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
@@ -840,7 +859,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 }
 
 template <int SOLVER>
-static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
+static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, bool bf)
 {
   const Geom &g = a.g;
   const int nc = g.dims;
@@ -851,12 +870,14 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
   const long long nwarp = nseg*(nc == 3 ? g.n[2] + 2 : 1)*a.nchunk;
   const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
   const size_t smem = xy_smem_bytes (recon);
-#define PG_LXY1(R, C, H, F) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H, F>;                            \
+#define PG_LXY1(R, C, H, F) PG_LXY2(R, C, H, F, false)
+#define PG_LXY2(R, C, H, F, B) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H, F, B>;                          \
       static bool attr_set = false;                                                                   \
       if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
 #define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
-      if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                            \
+      if (bf)             PG_LXY2(R, C, false, false, true);          /* refused with UCT_HLL / flattening at create */ \
+      else if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                       \
       else           { if (fl) PG_LXY1(R, C, false, P); else PG_LXY1(R, C, false, false); } } while (0)
   if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
   else if (recon == RECON_PLM && nc == 2) PG_LXY(RECON_PLM, 2);
@@ -864,6 +885,7 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
   else                                    PG_LXY(RECON_PPM, 2);
 #undef PG_LXY
 #undef PG_LXY1
+#undef PG_LXY2
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 
@@ -871,7 +893,7 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s)
 //  launcher for one solver (one translation unit per solver and arithmetic)
 // ---------------------------------------------------------------------------
 template <int SOLVER>
-static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t s)
+static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf)
 {
   const Geom &g = a.g;
   const int nc = g.dims;
@@ -885,7 +907,8 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
     const size_t xsmem = (size_t)(TPB/32)*2*9*36*sizeof (double);
 #define PG_LX(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
-      if (a.avg == 3){ if (fl) sweep_x_kernel<R, SOLVER, C, true, P><<<nb, TPB, xsmem, s>>>(a);                     \
+      if (bf) sweep_x_kernel<R, SOLVER, C, false, false, true><<<nb, TPB, xsmem, s>>>(a);                            \
+      else if (a.avg == 3){ if (fl) sweep_x_kernel<R, SOLVER, C, true, P><<<nb, TPB, xsmem, s>>>(a);                     \
                        else    sweep_x_kernel<R, SOLVER, C, true, false><<<nb, TPB, xsmem, s>>>(a); }               \
       else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, P><<<nb, TPB, xsmem, s>>>(a);                    \
                        else    sweep_x_kernel<R, SOLVER, C, false, false><<<nb, TPB, xsmem, s>>>(a); } } while (0)
@@ -900,14 +923,16 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long nthr = npen*a.nchunk;
     const unsigned nb = (unsigned)((nthr + TPB - 1)/TPB);
     const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
-#define PG_LM1(DD, R, C, H, F) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H, F>;                \
+#define PG_LM1(DD, R, C, H, F) PG_LM2(DD, R, C, H, F, false)
+#define PG_LM2(DD, R, C, H, F, B) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H, F, B>;             \
       static bool attr_set = false;                                                                   \
       if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
         attr_set = true; } \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
 #define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;          \
-      if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                      \
+      if (bf)             PG_LM2(DD, R, C, false, false, true);                                                      \
+      else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                    \
       else           { if (fl) PG_LM1(DD, R, C, false, P); else PG_LM1(DD, R, C, false, false); } } while (0)
     if (dir == 1){
       if      (recon == RECON_PLM && nc == 3) PG_LM(1, RECON_PLM, 3);
@@ -920,6 +945,7 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     }
 #undef PG_LM
 #undef PG_LM1
+#undef PG_LM2
   }
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }

@@ -29,7 +29,7 @@ def emu_lib():
 
 def _stepper(g, arith, lib):
     from pluto_b200 import GpuStepper
-    kw = dict(ctu=g.ctu, en_corr=g.en_corr)
+    kw = dict(ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
     return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order, bc=g.bc, gamma=g.gamma,
                       arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, lib_path=lib, **kw)
 
@@ -54,7 +54,7 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
-               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en"]
+               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)
@@ -82,7 +82,7 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
 # (RK and corner transport upwind), NextTimeStep on the device, reflective walls, the reference Data layout.
 GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or ctu_blast3d_hll_20x24x16 or (decomposed and gn7) or (decomposed and gn4 and all) "
                    "or (decomposed and gn2 and dims) or (device_next_dt and ot-2) or reflective or data_layout "
-                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2)")
+                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2) or (body_force and rotor)")
 
 
 def test_gpu_test_files_through_the_interpreter(emu_lib):
@@ -102,11 +102,11 @@ def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
     libdir = tmp_path / "lib"
     libdir.mkdir()
     os.symlink(emu_lib, libdir / "libpluto_gpu.so")
-    for name in ("ot2d_plm_hlld", "ot2d_ctu"):
+    for name in ("ot2d_plm_hlld", "ot2d_ctu", "rotor2d_ppm_rk3_bf"):
         g = Golden(name)
         cfg = RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep, cfl=g.cfl,
                         cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma, limiter=g.limiter, emf=g.emf,
-                        flatten=g.flatten, prefix="pluto_gpu_")
+                        flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, prefix="pluto_gpu_")
         if not have_ref(cfg):
             pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
         r = run_reference(cfg, maxsteps=g.nsteps + 1, dump_every=1,

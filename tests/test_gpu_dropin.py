@@ -19,13 +19,15 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # TIME_STEPPING HANCOCK: the shim replaces ctu_step.o
          "ot2d_ctu", "blast3d_ctu", "turb3d_ctu_roe",
          # CT_EN_CORRECTION YES: the complete scheme of the shipped Blast #02 (definitions_02.h, pluto_02.ini)
-         "blast3d_blast02_en", "blast2d_en", "blast3d_ctu_en"]
+         "blast3d_blast02_en", "blast2d_en", "blast3d_ctu_en",
+         # BODY_FORCE VECTOR: the shim samples init.c's BodyForceVector and passes the uniform acceleration
+         "blast3d_bf", "rotor2d_ppm_rk3_bf", "turb3d_ctu_bf"]
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
-                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, prefix="pluto_gpu_")
+                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

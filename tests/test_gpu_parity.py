@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
     return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr)
+                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -199,6 +199,8 @@ CTU_ORACLE_CASES = [
     ("blast", 3, (18, 16, 20), "hlld", 6, 2e-4, {"flatten": True, "emf": "uct0"}),
     ("turb", 3, (14, 12, 16), "hlld", 5, 1e-2, {"en_corr": True}),                 # CT_EN_CORRECTION on Uh and Uc
     ("blast", 2, (36, 30, 1), "roe", 6, 2e-4, {"en_corr": True, "emf": "uct0"}),
+    ("blast", 3, (20, 14, 18), "hlld", 6, 2e-4, {"grav": (0.3, -1.0, 0.5)}),         # BODY_FORCE VECTOR, uniform acceleration
+    ("ot", 2, (40, 33, 1), "hll", 6, 5e-3, {"grav": (-0.5, 2.0, 0.0), "en_corr": True, "emf": "arith"}),
     # smallest legal blocks (n = 2*nghost), ragged segments, chunk remainders
     ("turb", 3, (6, 6, 6), "hlld", 4, 2e-2, {}),
     ("ot", 2, (6, 7, 1), "hlld", 4, 2e-2, {}),
@@ -207,7 +209,7 @@ CTU_ORACLE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CTU_ORACLE_CASES, ids=lambda c: f"ctu_{c[0]}{c[1]}d_{c[3]}_{'x'.join(map(str, c[2]))}" + ("_en" if c[6].get("en_corr") else ""))
+@pytest.mark.parametrize("case", CTU_ORACLE_CASES, ids=lambda c: f"ctu_{c[0]}{c[1]}d_{c[3]}_{'x'.join(map(str, c[2]))}" + ("_en" if c[6].get("en_corr") else "") + ("_bf" if c[6].get("grav") else ""))
 def test_ctu_exact_bit_identical_to_oracle(case):
     from oracle.oracle_lib import Oracle, next_dt
     from pluto_b200 import GpuStepper, problems
@@ -296,6 +298,53 @@ def test_en_correction_bit_identical_to_oracle(problem, dims, n, recon, solver, 
     s.close()
     for blk in many.blocks:
         blk.close()
+
+
+@pytest.mark.parametrize("problem,dims,n,recon,solver,rk", [
+    ("blast", 3, (24, 20, 28), "plm", "hlld", 2), ("turb", 3, (16, 20, 12), "ppm", "roe", 3), ("rotor", 2, (50, 44, 1), "ppm", "hll", 2),
+    ("ot", 2, (61, 40, 1), "plm", "roe", 3)])
+def test_body_force_bit_identical_to_oracle(problem, dims, n, recon, solver, rk):
+    """BODY_FORCE VECTOR with a uniform acceleration (rhs_source.c:214-217, 277-280, 342-345), RK2 / RK3, single
+    block and decomposed (every exchange mode of the decomposition test is covered by the goldens' schemes)."""
+    import os
+    from oracle.oracle_lib import Oracle, next_dt
+    from pluto_b200 import GpuStepper, problems
+    from pluto_b200.parallel import BlockLayout, LocalMultiBlock
+    grav = (0.7, -1.3, 0.4) if dims == 3 else (0.7, -1.3, 0.0)
+    st0, meta = problems.make(problem, dims, n)
+    o = Oracle(dims, n, meta["dx"], recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], grav=grav)
+    s = GpuStepper(dims, n, meta["dx"], recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], arith="exact",
+                   grav=grav)
+    lay = BlockLayout.strong(dims, n, 4 if dims == 3 else 2, periodic=meta["bc"][0] == "periodic")
+    many = LocalMultiBlock(lay, meta["dx"], meta["bc"], recon=recon, solver=solver, rk_order=rk, gamma=meta["gamma"], grav=grav,
+                           exchange="all", split=True, host_buffers=os.environ.get("PLUTO_GPU_LIB", "").endswith("_emu.so"))
+    o.set_state(st0); s.set_state(st0); many.set_state(st0)
+    dt = {"ot": 5e-3, "blast": 2e-4, "turb": 1e-2, "rotor": 1e-3}[problem]
+    for step in range(5):
+        inv, mach, nfl = o.advance(dt)
+        info = s.advance(dt)
+        many.advance(dt)
+        assert (info.inv_dt_hyp, info.max_mach, info.floor_events) == (inv, mach, nfl), step
+        dt = next_dt(inv, meta["cfl"], 1.1, dt)
+    a, b, c = s.get_state(), o.get_state(), many.get_state()
+    for k in b:
+        assert np.array_equal(a[k], b[k]), f"{k}: max abs diff {np.abs(a[k]-b[k]).max():.3e}"
+        assert np.array_equal(c[k], b[k]), f"{k} (blocks): max abs diff {np.abs(c[k]-b[k]).max():.3e}"
+    s.close()
+    for blk in many.blocks:
+        blk.close()
+    # FAST arithmetic (the fused x1+x2 sweep carries the source as well) within the one-step tolerance
+    f = GpuStepper(dims, n, meta["dx"], recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], arith="fast",
+                   grav=grav)
+    o2 = Oracle(dims, n, meta["dx"], recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], grav=grav)
+    f.set_state(st0); o2.set_state(st0)
+    dt = {"ot": 5e-3, "blast": 2e-4, "turb": 1e-2, "rotor": 1e-3}[problem]
+    f.advance(dt); o2.advance(dt)
+    a, b = f.get_state(), o2.get_state()
+    tol = 1e-9 if (problem, solver) == ("rotor", "roe") else TOL_ONE_STEP
+    for k in b:
+        assert rel_l1(a[k], b[k]) <= tol, k
+    f.close()
 
 
 def test_reflective_boundaries_match_oracle():
