@@ -111,22 +111,6 @@ __device__ __forceinline__ int ctu_correct (const Phys &ph, const double *vc, co
   return nfl;
 }
 
-// sum of the transverse half-step right-hand sides of a zone, in the reference's order (ctu_step.c:551-562)
-template <int DIR, int NC>
-__device__ __forceinline__ void ctu_transverse (const CtuArgs &a, int id, double *dU)
-{
-  PG_FOR_NV(nv){
-    if (NC == 3){
-      if      (DIR == 0) dU[nv] = 0.0 + a.rhs[1][nv][id] + a.rhs[2][nv][id];
-      else if (DIR == 1) dU[nv] = a.rhs[0][nv][id] + 0.0 + a.rhs[2][nv][id];
-      else               dU[nv] = a.rhs[0][nv][id] + a.rhs[1][nv][id];
-    }else{
-      if (DIR == 0) dU[nv] = 0.0 + a.rhs[1][nv][id];
-      else          dU[nv] = a.rhs[0][nv][id] + 0.0;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
 //  x1 sweep.  A warp owns one 32-entry segment of the rows (30 updated zones) and walks through
 //  PG_CTU_XROWS consecutive rows; while it solves row r, what row r+1 needs streams into the warp's
