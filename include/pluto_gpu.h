@@ -85,7 +85,8 @@ typedef struct {
                               init.c returns everywhere): momentum and energy sources of
                               Src/MHD/rhs_source.c:214-217, 277-280, 342-345 and, with HANCOCK, the
                               predictor source of Src/MHD/prim_eqn.c:289-360.  Not with UCT_HLL or
-                              SHOCK_FLATTENING                                 */
+                              SHOCK_FLATTENING.  A static position-dependent force:
+                              pluto_gpu_set_body_force                         */
   double grav[3];
 } PlutoGpuConfig;
 
@@ -105,6 +106,10 @@ int  pluto_gpu_create   (const PlutoGpuConfig *cfg, PlutoGpu **out);
 void pluto_gpu_destroy  (PlutoGpu *h);
 const char *pluto_gpu_last_error (void);
 int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
+/* BODY_FORCE VECTOR with a STATIC position-dependent force instead of the uniform grav[] of the configuration (which must
+   have body_force = 1): component d of BodyForceVector (init.c) at every zone centre, ghost zones included, HOST arrays
+   g_d[k][j][i] with the extents T3 x T2 x T1 of the reference's Data arrays (g3 NULL in 2-D). */
+int  pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3);
 int  pluto_gpu_nstages  (const PlutoGpu *h);     /* Boundary calls (= halo exchanges) per step: rk_order, 1 with HANCOCK */
 
 /* ---- state transfer ---------------------------------------------------

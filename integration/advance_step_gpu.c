@@ -24,6 +24,10 @@
 #include "pluto_gpu.h"
 
 static PlutoGpu *gpu = NULL;
+#if BODY_FORCE != NO
+static double gpu_g0[3];
+static int    gpu_g_field = 0;       /* BodyForceVector depends on the position */
+#endif
 
 static int BoundaryCode (int type)
 {
@@ -90,28 +94,26 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     #error "libpluto_gpu: BODY_FORCE POTENTIAL is not available on the GPU"
   #endif
     {
-      /* the library takes a UNIFORM acceleration: BodyForceVector (init.c) is sampled at the corners and the centre
-         of the block with the first zone's state and must return the same vector everywhere */
-      double g0[3] = {0.0, 0.0, 0.0}, g1[3], *v0;
-      int q, kk, jj, ii, ks[3], js[3], is[3], bad = 0;
+      /* BodyForceVector (init.c) is sampled at the corners and the centre of the block: the same vector everywhere is
+         passed as the uniform acceleration of the configuration; otherwise it is tabulated per zone after the creation
+         (pluto_gpu_set_body_force).  The force must be static and must not depend on the state. */
+      double g1[3], *v0;
+      int q, kk, jj, ii, ks[3], js[3], is[3];
       is[0] = IBEG; is[1] = (IBEG + IEND)/2; is[2] = IEND;
       js[0] = JBEG; js[1] = (JBEG + JEND)/2; js[2] = JEND;
       ks[0] = KBEG; ks[1] = (KBEG + KEND)/2; ks[2] = KEND;
       v0 = (double *)malloc (NVAR*sizeof(double));
       for (q = 0; q < NVAR; q++) v0[q] = d->Vc[q][KBEG][JBEG][IBEG];
-      BodyForceVector (v0, g0, grid->x[IDIR][IBEG], grid->x[JDIR][JBEG], grid->x[KDIR][KBEG]);
+      gpu_g0[0] = gpu_g0[1] = gpu_g0[2] = 0.0;
+      BodyForceVector (v0, gpu_g0, grid->x[IDIR][IBEG], grid->x[JDIR][JBEG], grid->x[KDIR][KBEG]);
       for (kk = 0; kk < 3; kk++) for (jj = 0; jj < 3; jj++) for (ii = 0; ii < 3; ii++){
         g1[0] = g1[1] = g1[2] = 0.0;
         BodyForceVector (v0, g1, grid->x[IDIR][is[ii]], grid->x[JDIR][js[jj]], grid->x[KDIR][ks[kk]]);
-        for (q = 0; q < DIMENSIONS; q++) bad |= (g1[q] != g0[q]);
+        for (q = 0; q < DIMENSIONS; q++) gpu_g_field |= (g1[q] != gpu_g0[q]);
       }
       free (v0);
-      if (bad){
-        print ("! AdvanceStep(gpu): BodyForceVector is not uniform; libpluto_gpu takes a constant acceleration only\n");
-        QUIT_PLUTO(1);
-      }
       c.body_force = 1;
-      c.grav[0] = g0[0]; c.grav[1] = g0[1]; c.grav[2] = g0[2];
+      c.grav[0] = gpu_g0[0]; c.grav[1] = gpu_g0[1]; c.grav[2] = gpu_g0[2];
     }
 #endif
     c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
@@ -136,6 +138,25 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
              pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
       QUIT_PLUTO(1);
     }
+#if BODY_FORCE != NO
+    if (gpu_g_field){                 /* tabulate BodyForceVector at every zone centre, ghost zones included */
+      size_t nz = (size_t)NX1_TOT*NX2_TOT*NX3_TOT, id = 0;
+      double *gt = (double *)malloc (3*nz*sizeof(double)), g1[3], v1[NVAR];
+      int kk, jj, ii, q;
+      for (kk = 0; kk < NX3_TOT; kk++) for (jj = 0; jj < NX2_TOT; jj++) for (ii = 0; ii < NX1_TOT; ii++){
+        for (q = 0; q < NVAR; q++) v1[q] = d->Vc[q][kk][jj][ii];
+        g1[0] = g1[1] = g1[2] = 0.0;
+        BodyForceVector (v1, g1, grid->x[IDIR][ii], grid->x[JDIR][jj], grid->x[KDIR][kk]);
+        gt[id] = g1[0]; gt[nz + id] = g1[1]; gt[2*nz + id] = g1[2];
+        id++;
+      }
+      if (pluto_gpu_set_body_force (gpu, gt, gt + nz, DIMENSIONS == 3 ? gt + 2*nz : NULL) != 0){
+        print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+        QUIT_PLUTO(1);
+      }
+      free (gt);
+    }
+#endif
     print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones\n",
            c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", pluto_gpu_nghost (gpu));
   }

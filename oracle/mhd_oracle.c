@@ -44,6 +44,7 @@ struct Oracle {
   int beg[3], end[3];                  /* IBEG..KEND */
   double *Vc[NV], *Uc[NV], *U0[NV];
   double *Vs[3], *Bs0[3];
+  double *gf[3];                       /* per-zone body force (oracle_set_body_force), else NULL */
   double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   double *ex, *ey, *ez, *Ex1, *Ex2, *Ex3;
   signed char *svx, *svy, *svz;
@@ -51,6 +52,7 @@ struct Oracle {
   double *SfL[3], *SfR[3];             /* max(0,-SL), max(0,SR) at the faces of each direction */
   double *dvel[3][3];                  /* dvel[c][d] = d v_c / d x_d (limited slope vp - vm)   */
   double cur_SL, cur_SR;               /* Riemann fan speeds of the interface just solved      */
+  double *gpen;                        /* body force of the current pencil, sweep direction (PrimSource) */
   unsigned char *flag;                 /* SHOCK_FLATTENING MULTID: FLAG_MINMOD 1, FLAG_HLL 4 (pluto.h:192-194) */
   unsigned char *pflag;                /* ... of the current pencil                            */
   int use_hll;                         /* the interface being solved takes the HLL flux        */
@@ -126,6 +128,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->dv   = calloc((size_t)o->np, sizeof(*o->dv));
   o->flux = calloc((size_t)o->np, sizeof(*o->flux));
   o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
+  o->gpen = dalloc(o->np) + 4;
   o->SLp = dalloc(o->np) + 4; o->SRp = dalloc(o->np) + 4;
   if (cfg->ctu){
     int c;
@@ -159,6 +162,18 @@ void oracle_destroy (Oracle *o)
 }
 
 /* ********************************************************************* */
+void oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const double *g3)
+{
+  const double *src[3] = {g1, g2, g3};
+  int d, i, j, k;
+  for (d = 0; d < o->c.dims; d++){
+    if (!o->gf[d]) o->gf[d] = dalloc (o->tot);
+    for (k = 0; k < o->T[2]; k++) for (j = 0; j < o->T[1]; j++) for (i = 0; i < o->T[0]; i++)
+      o->gf[d][IDX(o,k,j,i)] = src[d][((size_t)k*o->T[1] + j)*o->T[0] + i];
+  }
+  o->c.body_force = 1;
+}
+
 void oracle_set_interior (Oracle *o, const double *vc, const double *bx1s,
                           const double *bx2s, const double *bx3s)
 {
@@ -855,8 +870,9 @@ static void update_stage (Oracle *o, double dt)
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
         if (o->c.body_force){          /* RightHandSideSource, rhs_source.c:214-217 (x1), :277-280 (x2), :342-345 (x3) */
-          rhs[q.vn] += dt*o->v[n][RHO]*o->c.grav[dir];
-          rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*o->c.grav[dir];
+          const double g = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
+          rhs[q.vn] += dt*o->v[n][RHO]*g;
+          rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*g;
         }
         for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
         if (o->stage == 1)
@@ -1320,7 +1336,7 @@ static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, double
     for (nv = 0; nv < NV; nv++){
       double scrh;
       if (dims == 2 && (nv == VX3 || nv == BX3)) continue;
-      scrh = dt_2*(d_dl*Adv[nv] - (o->c.body_force && nv == q.vn ? 0.0 + o->c.grav[q.vn - VX1] : 0.0));   /* PrimSource, prim_eqn.c:289-360 */
+      scrh = dt_2*(d_dl*Adv[nv] - (o->c.body_force && nv == q.vn ? 0.0 + o->gpen[i] : 0.0));   /* PrimSource, prim_eqn.c:289-360 */
       o->vp[i][nv] -= scrh;
       o->vm[i][nv] -= scrh;
     }
@@ -1419,6 +1435,7 @@ static void ctu_advance (Oracle *o, double dt)
         idx3[dir] = n;
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
         for (nv = 0; nv < NV; nv++) o->vn[n][nv] = o->v[n][nv] = o->Vc[nv][id];
+        o->gpen[n] = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
         o->bn[n] = o->Vs[dir][id];
         o->pflag[n] = o->flag[id];
       }
@@ -1456,8 +1473,9 @@ static void ctu_advance (Oracle *o, double dt)
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dt2_dx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dt2_dx*(o->press[n] - o->press[n-1]);
         if (o->c.body_force){          /* stateC->v is the half-step zone average left by HancockStep (hancock.c:136-141) */
-          rhs[q.vn] += dt2*o->v[n][RHO]*o->c.grav[dir];
-          rhs[ENG]  += dt2*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*o->c.grav[dir];
+          const double g = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
+          rhs[q.vn] += dt2*o->v[n][RHO]*g;
+          rhs[ENG]  += dt2*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*g;
         }
         for (nv = 0; nv < NV; nv++) o->rhs3[dir][nv][id] = rhs[nv];
         o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);       /* :416-419 */
@@ -1565,8 +1583,9 @@ static void ctu_advance (Oracle *o, double dt)
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
         if (o->c.body_force){          /* stateC->v = V^{n+1/2} (ctu_step.c:566-570) */
-          rhs[q.vn] += dt*o->v[n][RHO]*o->c.grav[dir];
-          rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*o->c.grav[dir];
+          const double g = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
+          rhs[q.vn] += dt*o->v[n][RHO]*g;
+          rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*g;
         }
         for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
         o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);

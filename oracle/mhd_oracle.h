@@ -60,6 +60,10 @@ typedef struct {
 typedef struct Oracle Oracle;
 
 Oracle *oracle_create (const OracleConfig *cfg);
+/* static, position-dependent body force: component d of BodyForceVector at every zone centre, ghost zones included,
+   g[d][k][j][i] with the extents T3 x T2 x T1 of the reference's Data arrays (NULL for the third component in 2-D).
+   Replaces the uniform grav[] of the configuration. */
+void    oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const double *g3);
 void    oracle_destroy (Oracle *o);
 int     oracle_nghost (const Oracle *o);
 

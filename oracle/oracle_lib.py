@@ -46,6 +46,7 @@ def lib():
         L.oracle_create.restype = C.c_void_p
         L.oracle_create.argtypes = [C.POINTER(OracleConfig)]
         L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_set_body_force.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_nghost.argtypes = [C.c_void_p]
         dp = C.POINTER(C.c_double)
         L.oracle_set_interior.argtypes = [C.c_void_p, dp, dp, dp, dp]
@@ -112,6 +113,12 @@ class Oracle:
                 self._h = None
         except Exception:
             pass
+
+    def set_body_force(self, g1, g2, g3=None):
+        """Static per-zone force: arrays [T3][T2][T1] (ghost zones included) of every component."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (g1, g2, g3)]
+        self._gkeep = arrs
+        lib().oracle_set_body_force(self._h, *[a.ctypes.data if a is not None else None for a in arrs])
 
     # ---- state I/O in "dump dict" form (names as in dbl.out) ----
     def set_state(self, dump: dict):

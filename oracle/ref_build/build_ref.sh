@@ -76,7 +76,7 @@ for VARIANT in "$@"; do
 #define  TIME_STEPPING                  $TSTEP
 #define  DIMENSIONAL_SPLITTING          NO
 #define  NTRACER                        0
-#define  USER_DEF_PARAMETERS            12
+#define  USER_DEF_PARAMETERS            13
 
 /* -- physics dependent declarations -- */
 
@@ -105,6 +105,7 @@ for VARIANT in "$@"; do
 #define  GRAV1                          9
 #define  GRAV2                          10
 #define  GRAV3                          11
+#define  GRAV_MODE                      12
 
 /* [Beg] user-defined constants (do not change this line) */
 

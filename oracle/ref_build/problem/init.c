@@ -245,12 +245,19 @@ void UserDefBoundary (const Data *d, RBox *box, int side, Grid *grid)
 /* ********************************************************************* */
 void BodyForceVector(double *v, double *g, double x1, double x2, double x3)
 /*
- * Uniform acceleration (the gravity of Rayleigh-Taylor-type set-ups).
+ * GRAV_MODE 0: uniform acceleration (the gravity of Rayleigh-Taylor-type set-ups).
+ * GRAV_MODE 1: static, position-dependent: every component points towards (GRAV > 0: away
+ *              from) the coordinate plane x_d = 0, with constant magnitude on either side.
  *********************************************************************** */
 {
   g[IDIR] = g_inputParam[GRAV1];
   g[JDIR] = g_inputParam[GRAV2];
   g[KDIR] = g_inputParam[GRAV3];
+  if ((int)(g_inputParam[GRAV_MODE] + 0.5) == 1){
+    if (x1 < 0.0) g[IDIR] = -g[IDIR];
+    if (x2 < 0.0) g[JDIR] = -g[JDIR];
+    if (x3 < 0.0) g[KDIR] = -g[KDIR];
+  }
 }
 /* ********************************************************************* */
 double BodyForcePotential(double x1, double x2, double x3)

@@ -47,6 +47,7 @@ class RefConfig:
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
     en_corr: bool = False               # CT_EN_CORRECTION YES
     grav: tuple = None                  # BODY_FORCE VECTOR with the uniform acceleration (g1, g2, g3)
+    grav_mode: int = 0                  # 1: static position-dependent force, component d = grav[d]*sign(x_d)
     cfl: float = 0.4
     cfl_max_var: float = 1.1
     first_dt: float = 1.0e-3
@@ -147,7 +148,7 @@ def write_ini(cfg: RefConfig, path: str, dbl_dn: int = -1, analysis_dn: int = 1)
               ("THETA", b["THETA"]), ("PHI", b["PHI"]), ("RADIUS", b["RADIUS"]),
               ("SEED", cfg.seed)]
     gr = cfg.grav if cfg.grav is not None else (0.0, 0.0, 0.0)
-    params += [("GRAV1", gr[0]), ("GRAV2", gr[1]), ("GRAV3", gr[2])]
+    params += [("GRAV1", gr[0]), ("GRAV2", gr[1]), ("GRAV3", gr[2]), ("GRAV_MODE", cfg.grav_mode)]
     for k, v in params:
         lines.append(f"{k:<26s}  {float(v)!r}  ")
     with open(path, "w") as f:

@@ -185,7 +185,6 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
 
   const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
   const double dtdx = __ldg (a.dtp + DIR);
-  const double src_n = a.bf ? 0.0 + a.grav[DIR] : 0.0;
   double my_mach = 0.0, my_cdt = 0.0;
   int nfl_tot = 0;
   issue (0);
@@ -202,6 +201,8 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     const double bsm = src[Q_BS + lane], bsp = src[Q_BS + lane + 1];
     unsigned fl = 0;
     if (FLAT) fl = a.flag[id];
+    const double gz = a.bf ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;      // body force at the zone centre
+    const double src_n = a.bf ? 0.0 + gz : 0.0;
     ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
     // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
     // V^{n+1/2} (ctu_step.c:566-570) in the corrector
@@ -239,8 +240,8 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
       if (PHASE == 0){
         PG_FOR_NV(nv){
           double rr = -dt2_dx*(F[nv] - Fm[nv]);
-          if (nv == D::vn){ rr -= dt2_dx*(press - pm); if (a.bf) rr += dt_2*rho_c*a.grav[DIR]; }
-          if (nv == ENG && a.bf) rr += dt_2*0.5*(F[RHO] + Fm[RHO])*a.grav[DIR];
+          if (nv == D::vn){ rr -= dt2_dx*(press - pm); if (a.bf) rr += dt_2*rho_c*gz; }
+          if (nv == ENG && a.bf) rr += dt_2*0.5*(F[RHO] + Fm[RHO])*gz;
           a.rhs[DIR][nv][id] = rr;
         }
       }else{
@@ -252,11 +253,11 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
           rr = -dtdx*(F[RHO] - Fm[RHO]);                              a.U[RHO][id] = u0[RHO] + rr;
           const double dtf = 2.0*dt_2;                                // = dt
           rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);
-          if (a.bf) rr += dtf*rho_c*a.grav[DIR];                      a.U[MX1][id] = u0[MX1] + rr;
+          if (a.bf) rr += dtf*rho_c*gz;                               a.U[MX1][id] = u0[MX1] + rr;
           rr = -dtdx*(F[MX2] - Fm[MX2]);                              a.U[MX2][id] = u0[MX2] + rr;
           if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                a.U[MX3][id] = u0[MX3] + rr; }
           rr = -dtdx*(F[ENG] - Fm[ENG]);
-          if (a.bf) rr += dtf*0.5*(F[RHO] + Fm[RHO])*a.grav[DIR];
+          if (a.bf) rr += dtf*0.5*(F[RHO] + Fm[RHO])*gz;
           a.U[ENG][id] = u0[ENG] + rr;
         }
       }
@@ -340,8 +341,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
 
     const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
     const double dtdx = __ldg (a.dtp + DIR);
-    const double src_n = a.bf ? 0.0 + a.grav[DIR] : 0.0;
-    double rhoL = 0.0;                               // body force: stateC density of zone z-1 (predictor)
+    double rhoL = 0.0, gL = 0.0;                     // body force: stateC density (predictor) and force of zone z-1
     double vl[NV], v[NV], vr[NV];
     PG_FOR_NV(nv){ v[nv] = __ldg (a.V0[nv] + id - sD); vr[nv] = __ldg (a.V0[nv] + id); }
     double bsp = __ldg (a.Bs0[DIR] + id - sD), bhp = 0.0;
@@ -361,6 +361,8 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       unsigned flz = 0;
       if (FLAT) flz = a.flag[id];
       double vp[NV], vm[NV], up[NV], um[NV];
+      const double gz = a.bf ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;    // body force at the centre of zone z
+      const double src_n = a.bf ? 0.0 + gz : 0.0;
       ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
       const double rho_z = (a.bf && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
       if (PHASE == 0){
@@ -397,8 +399,8 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
           if (PHASE == 0){
             PG_FOR_NV(nv){
               double r = -dt2_dx*(F[nv] - Fp[nv]);
-              if (nv == D::vn){ r -= dt2_dx*(press - pp); if (a.bf) r += dt_2*rhoL*a.grav[DIR]; }
-              if (nv == ENG && a.bf) r += dt_2*0.5*(F[RHO] + Fp[RHO])*a.grav[DIR];
+              if (nv == D::vn){ r -= dt2_dx*(press - pp); if (a.bf) r += dt_2*rhoL*gL; }
+              if (nv == ENG && a.bf) r += dt_2*0.5*(F[RHO] + Fp[RHO])*gL;
               a.rhs[DIR][nv][idf] = r;
             }
           }else if (upd){
@@ -409,15 +411,15 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
             r = -dtdx*(F[RHO] - Fp[RHO]);                                           a.U[RHO][idf] = ua[0] + r;
             r = -dtdx*(F[MX1] - Fp[MX1]); if (D::vn == MX1) r -= dtdx*(press - pp); a.U[MX1][idf] = ua[CS] + r;
             r = -dtdx*(F[MX2] - Fp[MX2]);
-            if (D::vn == MX2){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*a.grav[DIR]; }
+            if (D::vn == MX2){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*gL; }
             a.U[MX2][idf] = ua[2*CS] + r;
             if (NC == 3){
               r = -dtdx*(F[MX3] - Fp[MX3]);
-              if (D::vn == MX3){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*a.grav[DIR]; }
+              if (D::vn == MX3){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*gL; }
               a.U[MX3][idf] = ua[3*CS] + r;
             }
             r = -dtdx*(F[ENG] - Fp[ENG]);
-            if (a.bf) r += dtf*0.5*(F[RHO] + Fp[RHO])*a.grav[DIR];
+            if (a.bf) r += dtf*0.5*(F[RHO] + Fp[RHO])*gL;
             a.U[ENG][idf] = ua[4*CS] + r;
           }
         }
@@ -425,7 +427,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         pp = press;
       }
       PG_FOR_NV(nv){ vpL[nv] = vp[nv]; upL[nv] = up[nv]; }
-      rhoL = rho_z;
+      rhoL = rho_z; gL = gz;
       flb = flz;
       double *tmp = cur; cur = nxt; nxt = tmp;
     }

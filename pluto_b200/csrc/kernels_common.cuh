@@ -69,8 +69,10 @@ struct SweepArgs {
   // analytically, but hlld.c:200-330 forms it as SL*(Bx* - Bn) with Bx* = (SR Bn - SL Bn)/(SR - SL), a round-off
   // residue that the reference adds to Uc[BXn] and that enters b2_old of ct_field_average.c:116-129
   double *fbn;
-  // BODY_FORCE VECTOR with a uniform acceleration (rhs_source.c:214-217, 277-280, 342-345): template flag BF of the sweeps
+  // BODY_FORCE VECTOR (rhs_source.c:214-217, 277-280, 342-345): template flag BF of the sweeps.  Uniform acceleration
+  // grav[], or a static per-zone field gf (this sweep's component; gf2: the x2 component of the fused x1+x2 sweep)
   double  grav[3];
+  const double *gf, *gf2;
 };
 
 struct CtArgs {
@@ -110,8 +112,9 @@ struct CtuArgs {
   int     limiter;
   int     chunk_len, nchunk; // marching sweeps (x2, x3)
   int     en_corr;           // CT_EN_CORRECTION YES: half-step kernel (ct_field_average.c:116-129 on Uh)
-  int     bf;                // BODY_FORCE VECTOR, uniform acceleration grav[] (rhs_source.c:214-345, prim_eqn.c:289-360)
-  double  grav[3];
+  int     bf;                // BODY_FORCE VECTOR: uniform grav[] or per-zone gf of this direction (rhs_source.c:214-345,
+  double  grav[3];           // prim_eqn.c:289-360)
+  const double *gf;
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
 };
 

@@ -81,6 +81,8 @@ struct PlutoGpu {
   int     march_chunk;             // zones per thread along a marching sweep
   int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
   int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
+  double *gfield[3];               // static per-zone body force (pluto_gpu_set_body_force), else NULL
+  void   *gfield_pool;
   double *fbn[3];                  // CT_EN_CORRECTION + EXACT: normal-field flux of the faces (own allocation)
   void   *fbn_pool;
   double *rhs3[3][NVS];            // CTU: half-step right-hand sides of the normal predictors (own allocation)
@@ -290,6 +292,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->dvel_pool) cudaFree (h->dvel_pool);
   if (h->ctu_pool) cudaFree (h->ctu_pool);
   if (h->fbn_pool) cudaFree (h->fbn_pool);
+  if (h->gfield_pool) cudaFree (h->gfield_pool);
   if (h->flag) cudaFree (h->flag);
   if (h->red) cudaFree (h->red);
   if (h->red_host) cudaFreeHost (h->red_host);
@@ -446,6 +449,37 @@ int pluto_gpu_upload_data (PlutoGpu *h, const double *Vc, const double *s1, cons
 { return transfer (h, 1, true, (double *)Vc, (double *)s1, (double *)s2, (double *)s3); }
 int pluto_gpu_download_data (PlutoGpu *h, double *Vc, double *s1, double *s2, double *s3)
 { return transfer (h, 1, false, Vc, s1, s2, s3); }
+
+int pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (!h->cfg.body_force) return fail ("pluto_gpu_set_body_force: the configuration has body_force = 0");
+  const Geom &g = h->g;
+  const size_t tot_al = ((size_t)g.tot + 31) & ~(size_t)31;
+  if (!h->gfield_pool){
+    const size_t nb = (size_t)g.dims*tot_al*sizeof (double);
+    if (cudaMalloc (&h->gfield_pool, nb) != cudaSuccess){ h->gfield_pool = NULL; return fail ("cudaMalloc of %zu bytes (body force) failed", nb); }
+    CU (cudaMemset (h->gfield_pool, 0, nb));
+    h->pool_bytes += nb;
+  }
+  const double *src[3] = {g1, g2, g3};
+  const long long ncell = (long long)g.T[0]*g.T[1]*g.T[2];
+  if ((size_t)ncell > h->scratch_doubles) return fail ("internal: scratch too small");
+  for (int d = 0; d < g.dims; d++){
+    if (!src[d]) return fail ("pluto_gpu_set_body_force: NULL array for component %d", d + 1);
+    double *dev = (double *)h->gfield_pool + (size_t)d*tot_al;
+    HaloArgs a; memset (&a, 0, sizeof (a));
+    a.q[0] = dev; a.nf = 1; a.offset[0] = 0; a.buf = h->scratch; a.g = g;
+    a.lo[0][0] = a.lo[0][1] = a.lo[0][2] = 0;
+    a.hi[0][0] = g.T[0] - 1; a.hi[0][1] = g.T[1] - 1; a.hi[0][2] = g.T[2] - 1;
+    CU (cudaMemcpyAsync (h->scratch, src[d], (size_t)ncell*sizeof (double), cudaMemcpyHostToDevice, h->stream));
+    if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1;
+    CU (cudaStreamSynchronize (h->stream));
+    h->gfield[d] = dev;
+  }
+  if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }      // the captured step holds the old arguments
+  return 0;
+}
 
 // ---------------------------------------------------------------------------
 //  Boundary (boundary.c:137-293) on state buffer `buf`, one dimension
@@ -619,6 +653,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   s.avg = h->cfg.emf_average;
   const bool bf = h->cfg.body_force != 0;
   for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];
+  s.gf2 = h->gfield[1];
   // EXACT: later stages continue from the conservative state the previous stage
   // left (as the reference does); FAST: rebuild it from the primitives, which
   // saves reading U in the x1 sweep and differs by round-off only
@@ -633,6 +668,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     s.last_dir = (dir == g.dims - 1);
     s.sv = h->sv[dir];
     s.fbn = h->fbn[dir];
+    s.gf = h->gfield[dir];
     if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
@@ -757,6 +793,7 @@ static int run_ctu (PlutoGpu *h, int part)
       s.inv_dl = 1.0/g.dx[dir];
       s.sv = h->sv[dir];
       s.fbn = h->fbn[dir];
+      s.gf = h->gfield[dir];
       if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
       else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
       else { s.e1 = h->eyk; s.e2 = h->exk; }

@@ -317,11 +317,12 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
       double rr;
       rr = -dtdx*(F[RHO] - Fm[RHO]);                                a.U[RHO][id] = u0[RHO] + rr;
       rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);
-      if (BF) rr += __ldg (a.dtp + 3)*v[RHO]*a.grav[DIR];           a.U[MX1][id] = u0[MX1] + rr;
+      const double gx = BF ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;
+      if (BF) rr += __ldg (a.dtp + 3)*v[RHO]*gx;                    a.U[MX1][id] = u0[MX1] + rr;
       rr = -dtdx*(F[MX2] - Fm[MX2]);                                a.U[MX2][id] = u0[MX2] + rr;
       if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                  a.U[MX3][id] = u0[MX3] + rr; }
       rr = -dtdx*(F[ENG] - Fm[ENG]);
-      if (BF) rr += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*a.grav[DIR];
+      if (BF) rr += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*gx;
       a.U[ENG][id] = u0[ENG] + rr;
       if (a.stage1){
         const double cd = 0.5*(cm + cmax)*a.inv_dl;
@@ -548,17 +549,18 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       double r;
       r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = ua[0] + r;
       const double dtg = BF ? __ldg (a.dtp + 3) : 0.0;
+      const double gd = BF ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;
       r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = ua[CS] + r;
       r = -dtdx*(F[MX2] - C_FP(2));
-      if (D::vn == MX2){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*a.grav[DIR]; }
+      if (D::vn == MX2){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*gd; }
       a.U[MX2][id] = ua[2*CS] + r;
       if (NC == 3){
         r = -dtdx*(F[MX3] - C_FP(3));
-        if (D::vn == MX3){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*a.grav[DIR]; }
+        if (D::vn == MX3){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*gd; }
         a.U[MX3][id] = ua[3*CS] + r;
       }
       r = -dtdx*(F[ENG] - C_FP(4));
-      if (BF) r += dtg*0.5*(F[RHO] + C_FP(0))*a.grav[DIR];
+      if (BF) r += dtg*0.5*(F[RHO] + C_FP(0))*gd;
       a.U[ENG][id] = ua[4*CS] + r;
       if (a.stage1){
         double cd = ua[5*CS] + 0.5*(cp + cmax)*a.inv_dl;
@@ -779,8 +781,9 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (NC == 3) rx[MX3] = -dtdx0*(F[MX3] - Fm[MX3]);
       rx[ENG] = -dtdx0*(F[ENG] - Fm[ENG]);
       if (BF){
-        rx[MX1] += __ldg (a.dtp + 3)*v[RHO]*a.grav[0];
-        rx[ENG] += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*a.grav[0];
+        const double gx = (a.gf ? __ldg (a.gf + id) : a.grav[0]);
+        rx[MX1] += __ldg (a.dtp + 3)*v[RHO]*gx;
+        rx[ENG] += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*gx;
       }
       cdx = 0.5*(cm + cmax)*a.inv_dl;
     }
@@ -824,10 +827,11 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         r = -dtdx1*(F[RHO] - C_FP(0));                                   a.U[RHO][id] = (u0[RHO] + rx[RHO]) + r;
         r = -dtdx1*(F[MX1] - C_FP(1));                                   a.U[MX1][id] = (u0[MX1] + rx[MX1]) + r;
         r = -dtdx1*(F[MX2] - C_FP(2)); r -= dtdx1*(press - pp);
-        if (BF) r += __ldg (a.dtp + 3)*v[RHO]*a.grav[1];                 a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
+        const double gy = BF ? (a.gf2 ? __ldg (a.gf2 + id) : a.grav[1]) : 0.0;
+        if (BF) r += __ldg (a.dtp + 3)*v[RHO]*gy;                        a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
         if (NC == 3){ r = -dtdx1*(F[MX3] - C_FP(3));                     a.U[MX3][id] = (u0[MX3] + rx[MX3]) + r; }
         r = -dtdx1*(F[ENG] - C_FP(4));
-        if (BF) r += __ldg (a.dtp + 3)*0.5*(F[RHO] + C_FP(0))*a.grav[1];
+        if (BF) r += __ldg (a.dtp + 3)*0.5*(F[RHO] + C_FP(0))*gy;
         a.U[ENG][id] = (u0[ENG] + rx[ENG]) + r;
         if (a.stage1){
           const double cd = cdx + 0.5*(cp + cmax)*a.inv_dl2;

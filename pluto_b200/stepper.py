@@ -90,6 +90,12 @@ class GpuStepper:
         if rc != 0:
             raise PlutoGpuError(_lib.last_error(self.L))
 
+    def set_body_force(self, g1, g2, g3=None):
+        """Static position-dependent force (BodyForceVector at the zone centres): arrays [T3][T2][T1] incl. ghost zones.
+        The stepper must have been created with grav=... (BODY_FORCE VECTOR)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (g1, g2, g3)]
+        self._check(self.L.pluto_gpu_set_body_force(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
     # ---- interior (.dbl) layout -------------------------------------------
     def interior_buffers(self, pinned=False):
         """Host arrays in the interior layout: (vc[8,n3,n2,n1], bx1s, bx2s, bx3s|None)."""

@@ -21,13 +21,15 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # CT_EN_CORRECTION YES: the complete scheme of the shipped Blast #02 (definitions_02.h, pluto_02.ini)
          "blast3d_blast02_en", "blast2d_en", "blast3d_ctu_en",
          # BODY_FORCE VECTOR: the shim samples init.c's BodyForceVector and passes the uniform acceleration
-         "blast3d_bf", "rotor2d_ppm_rk3_bf", "turb3d_ctu_bf"]
+         "blast3d_bf", "rotor2d_ppm_rk3_bf", "turb3d_ctu_bf",
+         # position-dependent force: tabulated per zone by the shim (pluto_gpu_set_body_force)
+         "blast3d_bfx", "blast2d_ctu_bfx_roe"]
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
-                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, prefix="pluto_gpu_")
+                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

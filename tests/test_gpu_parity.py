@@ -10,15 +10,17 @@ Bars:  EXACT arithmetic  -> bit-identical states, dt sequence and max Mach.
 import numpy as np
 import pytest
 
-from tests.util import (Golden, golden_names, divb_max, rel_l1, TOL_ONE_STEP, TOL_100_STEPS, TOL_DT)
+from tests.util import (Golden, golden_names, divb_max, rel_l1, apply_force_field, TOL_ONE_STEP, TOL_100_STEPS, TOL_DT)
 
 pytestmark = pytest.mark.gpu
 
 
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
-    return GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                      bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
+    s = GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
+                   bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
+    apply_force_field(s, g)
+    return s
 
 
 @pytest.mark.parametrize("name", golden_names())

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle_lib import Oracle, next_dt
-from tests.util import Golden, golden_names, divb_max
+from tests.util import Golden, golden_names, divb_max, apply_force_field
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -14,6 +14,7 @@ def test_oracle_bit_exact_vs_reference_golden(name):
     g = Golden(name)
     o = Oracle(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
                bc=g.bc, gamma=g.gamma, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
+    apply_force_field(o, g)
     o.set_state(g.states[0])
     dt = g.first_dt
     for s in range(1, g.nsteps + 1):

@@ -61,6 +61,11 @@ CASES = [
     ("turb3d_ctu_bf", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, tstep="hancock", grav=(0.3, -1.0, 0.5)), 6),
     ("blast2d_ctu_bf_hll", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="hancock", solver="hll",
                                      grav=(-2.0, 1.0, 0.0)), 10),
+    # static position-dependent force (GRAV_MODE 1 of the problem file: component d = grav[d]*sign(x_d))
+    ("blast3d_bfx", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(-3.0, -1.0, 2.0), grav_mode=1), 8),
+    ("rotor2d_ppm_bfx", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", first_dt=2e-3, grav=(-1.5, -2.5, 0.0), grav_mode=1), 6),
+    ("blast3d_ctu_bfx", RefConfig(problem="blast", dims=3, n=(10, 12, 8), first_dt=3e-4, cfl=0.3, tstep="hancock",
+                                  grav=(-3.0, -1.0, 2.0), grav_mode=1), 6),
 ]
 
 
@@ -77,6 +82,9 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
                gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"),
                rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr, grav=cfg.grav)
+    if cfg.grav_mode == 1:
+        from tests.util import sign_force_arrays
+        o.set_body_force(*sign_force_arrays(cfg.dims, n, o.ng, dom, cfg.grav))
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

@@ -46,6 +46,7 @@ class Golden:
         self.flatten = bool(int(d["cfg_flatten"])) if "cfg_flatten" in d.files else False
         self.en_corr = bool(int(d["cfg_en_corr"])) if "cfg_en_corr" in d.files else False
         self.grav = tuple(float(x) for x in d["cfg_grav"]) if "cfg_grav" in d.files else None
+        self.grav_mode = int(d["cfg_grav_mode"]) if "cfg_grav_mode" in d.files else 0
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:
@@ -57,6 +58,12 @@ class Golden:
         self.dx = [(self.domain[a][1] - self.domain[a][0]) / self.n[a] for a in range(self.dims)]
         self.rk_order = 3 if self.tstep == "rk3" else 2
         self.ctu = self.tstep == "hancock"
+
+
+def apply_force_field(stepper, g):
+    """Golden fixtures with the static test force (GRAV_MODE 1): hand the per-zone arrays to an Oracle or a GpuStepper."""
+    if g.grav_mode == 1:
+        stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
 
 
 def rel_l1(a, b):
@@ -80,3 +87,26 @@ def divb_max(state, dims, dx):
         bz = state["Bx3s"]
         div = div + (bz[1:, :, :] - bz[:-1, :, :]) / dx[2]
     return np.abs(div).max()
+
+
+def sign_force_arrays(dims, n, ng, domain, grav):
+    """The static test force of oracle/ref_build/problem/init.c (GRAV_MODE 1): component d = grav[d]*sign(x_d), constant on
+    either side of the plane x_d = 0, as arrays [T3][T2][T1] with ghost zones.  Use even n on symmetric domains (no zone
+    centre on a plane)."""
+    T = [n[d] + 2 * ng if d < dims else 1 for d in range(3)]
+    x = []
+    for d in range(3):
+        if d < dims:
+            dx = (domain[d][1] - domain[d][0]) / n[d]
+            x.append(domain[d][0] + (np.arange(T[d]) - ng + 0.5) * dx)
+        else:
+            x.append(np.zeros(1))
+    out = []
+    for d in range(dims):
+        sgn = np.where(x[d] < 0.0, -1.0, 1.0)
+        shape = [1, 1, 1]
+        shape[2 - d] = T[d]
+        out.append(np.ascontiguousarray(np.broadcast_to((grav[d] * sgn).reshape(shape), (T[2], T[1], T[0]))))
+    while len(out) < 3:
+        out.append(None)
+    return out

@@ -94,6 +94,10 @@ CASES = {
     "rotor2d_ppm_rk3_bf": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), recon="ppm", tstep="rk3", first_dt=2.5e-3, cfl=0.4,
                                      grav=(0.5, 0.25, 0.0)), 15),
     "turb3d_ctu_bf": (RefConfig(problem="turb", dims=3, n=(8, 12, 16), first_dt=3e-2, cfl=0.3, tstep="hancock", grav=(0.3, -1.0, 0.5)), 10),
+    # static position-dependent force (GRAV_MODE 1: component d = grav[d]*sign(x_d)) through pluto_gpu_set_body_force
+    "blast3d_bfx": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, grav=(-3.0, -1.0, 2.0), grav_mode=1), 12),
+    "blast2d_ctu_bfx_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="hancock", solver="roe",
+                                      grav=(-3.0, -1.0, 0.0), grav_mode=1), 20),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
@@ -113,6 +117,7 @@ def make(name):
     }
     if cfg.grav is not None:
         out["cfg_grav"] = np.array(cfg.grav, dtype=float)
+        out["cfg_grav_mode"] = int(cfg.grav_mode)
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
             out[f"s{s}_{k}"] = v
