@@ -81,7 +81,8 @@ typedef struct {
   int    en_correction;    /* CT_EN_CORRECTION YES: total energy redefined with the face-averaged field
                               (Src/MHD/CT/ct_field_average.c:116-129);
                               CT_EMF_AVERAGE other than UCT_HLL                */
-  int    body_force;       /* BODY_FORCE VECTOR with a UNIFORM acceleration grav[] (what BodyForceVector of
+  int    body_force;       /* BODY_FORCE: bit 0 VECTOR, bit 1 POTENTIAL (pluto_gpu_set_body_potential).
+                              VECTOR with a UNIFORM acceleration grav[] (what BodyForceVector of
                               init.c returns everywhere): momentum and energy sources of
                               Src/MHD/rhs_source.c:214-217, 277-280, 342-345 and, with HANCOCK, the
                               predictor source of Src/MHD/prim_eqn.c:289-360.  Not with UCT_HLL or
@@ -110,6 +111,11 @@ int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
    have body_force = 1): component d of BodyForceVector (init.c) at every zone centre, ghost zones included, HOST arrays
    g_d[k][j][i] with the extents T3 x T2 x T1 of the reference's Data arrays (g3 NULL in 2-D). */
 int  pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3);
+/* BODY_FORCE POTENTIAL (body_force & 2; Src/MHD/rhs.c:162-187, 388-392, rhs_source.c:233-237, 316-320, 358-362,
+   prim_eqn.c:304-307): BodyForcePotential (init.c) at the zone centres, phic[k][j][i] (T3 x T2 x T1), and at the faces of
+   every direction in the layout of the staggered Data arrays (pf1: T3 x T2 x (T1+1) starting with face -1/2, pf2:
+   T3 x (T2+1) x T1, pf3: (T3+1) x T2 x T1, NULL in 2-D).  HOST arrays; must be called before the first step. */
+int  pluto_gpu_set_body_potential (PlutoGpu *h, const double *phic, const double *pf1, const double *pf2, const double *pf3);
 int  pluto_gpu_nstages  (const PlutoGpu *h);     /* Boundary calls (= halo exchanges) per step: rk_order, 1 with HANCOCK */
 
 /* ---- state transfer ---------------------------------------------------

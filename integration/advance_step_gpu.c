@@ -24,7 +24,7 @@
 #include "pluto_gpu.h"
 
 static PlutoGpu *gpu = NULL;
-#if BODY_FORCE != NO
+#if BODY_FORCE & VECTOR
 static double gpu_g0[3];
 static int    gpu_g_field = 0;       /* BodyForceVector depends on the position */
 #endif
@@ -89,10 +89,10 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
                  LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
     c.shock_flattening = (SHOCK_FLATTENING == MULTID);     /* flag_shock.c */
     c.en_correction = (CT_EN_CORRECTION == YES);           /* ct_field_average.c:116-129 */
-#if BODY_FORCE != NO
-  #if BODY_FORCE != VECTOR
-    #error "libpluto_gpu: BODY_FORCE POTENTIAL is not available on the GPU"
-  #endif
+#if BODY_FORCE & POTENTIAL
+    c.body_force |= 2;                                     /* tabulated after the creation */
+#endif
+#if BODY_FORCE & VECTOR
     {
       /* BodyForceVector (init.c) is sampled at the corners and the centre of the block: the same vector everywhere is
          passed as the uniform acceleration of the configuration; otherwise it is tabulated per zone after the creation
@@ -112,7 +112,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
         for (q = 0; q < DIMENSIONS; q++) gpu_g_field |= (g1[q] != gpu_g0[q]);
       }
       free (v0);
-      c.body_force = 1;
+      c.body_force |= 1;
       c.grav[0] = gpu_g0[0]; c.grav[1] = gpu_g0[1]; c.grav[2] = gpu_g0[2];
     }
 #endif
@@ -138,7 +138,36 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
              pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
       QUIT_PLUTO(1);
     }
-#if BODY_FORCE != NO
+#if BODY_FORCE & POTENTIAL
+    {                                 /* BodyForcePotential at the zone centres and at the faces of every direction
+                                         (rhs.c:162-187), in the layouts of Vc and of the staggered arrays */
+      size_t n1 = NX1_TOT, n2 = NX2_TOT, n3 = NX3_TOT, sz[4], off[4], q4;
+      double *pt;
+      int kk, jj, ii;
+      sz[0] = n1*n2*n3; sz[1] = (n1 + 1)*n2*n3; sz[2] = n1*(n2 + 1)*n3; sz[3] = (DIMENSIONS == 3 ? n1*n2*(n3 + 1) : 0);
+      off[0] = 0; for (q4 = 1; q4 < 4; q4++) off[q4] = off[q4 - 1] + sz[q4 - 1];
+      pt = (double *)malloc ((off[3] + sz[3] + 1)*sizeof(double));
+      for (kk = 0; kk < NX3_TOT; kk++) for (jj = 0; jj < NX2_TOT; jj++) for (ii = 0; ii < NX1_TOT; ii++)
+        pt[off[0] + ((size_t)kk*n2 + jj)*n1 + ii] = BodyForcePotential (grid->x[IDIR][ii], grid->x[JDIR][jj], grid->x[KDIR][kk]);
+      for (kk = 0; kk < NX3_TOT; kk++) for (jj = 0; jj < NX2_TOT; jj++) for (ii = -1; ii < NX1_TOT; ii++)
+        pt[off[1] + ((size_t)kk*n2 + jj)*(n1 + 1) + (ii + 1)] =
+          BodyForcePotential (ii < 0 ? grid->xl[IDIR][0] : grid->xr[IDIR][ii], grid->x[JDIR][jj], grid->x[KDIR][kk]);
+      for (kk = 0; kk < NX3_TOT; kk++) for (jj = -1; jj < NX2_TOT; jj++) for (ii = 0; ii < NX1_TOT; ii++)
+        pt[off[2] + ((size_t)kk*(n2 + 1) + (jj + 1))*n1 + ii] =
+          BodyForcePotential (grid->x[IDIR][ii], jj < 0 ? grid->xl[JDIR][0] : grid->xr[JDIR][jj], grid->x[KDIR][kk]);
+  #if DIMENSIONS == 3
+      for (kk = -1; kk < NX3_TOT; kk++) for (jj = 0; jj < NX2_TOT; jj++) for (ii = 0; ii < NX1_TOT; ii++)
+        pt[off[3] + ((size_t)(kk + 1)*n2 + jj)*n1 + ii] =
+          BodyForcePotential (grid->x[IDIR][ii], grid->x[JDIR][jj], kk < 0 ? grid->xl[KDIR][0] : grid->xr[KDIR][kk]);
+  #endif
+      if (pluto_gpu_set_body_potential (gpu, pt + off[0], pt + off[1], pt + off[2], DIMENSIONS == 3 ? pt + off[3] : NULL) != 0){
+        print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+        QUIT_PLUTO(1);
+      }
+      free (pt);
+    }
+#endif
+#if BODY_FORCE & VECTOR
     if (gpu_g_field){                 /* tabulate BodyForceVector at every zone centre, ghost zones included */
       size_t nz = (size_t)NX1_TOT*NX2_TOT*NX3_TOT, id = 0;
       double *gt = (double *)malloc (3*nz*sizeof(double)), g1[3], v1[NVAR];

@@ -45,6 +45,8 @@ struct Oracle {
   double *Vc[NV], *Uc[NV], *U0[NV];
   double *Vs[3], *Bs0[3];
   double *gf[3];                       /* per-zone body force (oracle_set_body_force), else NULL */
+  double *phic, *phif[3];              /* body-force potential at centres and faces (oracle_set_body_potential), else NULL */
+  double *ppen;                        /* face potential of the current pencil */
   double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   double *ex, *ey, *ez, *Ex1, *Ex2, *Ex3;
   signed char *svx, *svy, *svz;
@@ -129,6 +131,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->flux = calloc((size_t)o->np, sizeof(*o->flux));
   o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
   o->gpen = dalloc(o->np) + 4;
+  o->ppen = dalloc(o->np) + 4;
   o->SLp = dalloc(o->np) + 4; o->SRp = dalloc(o->np) + 4;
   if (cfg->ctu){
     int c;
@@ -172,6 +175,23 @@ void oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const
       o->gf[d][IDX(o,k,j,i)] = src[d][((size_t)k*o->T[1] + j)*o->T[0] + i];
   }
   o->c.body_force = 1;
+}
+
+void oracle_set_body_potential (Oracle *o, const double *phic, const double *pf1, const double *pf2, const double *pf3)
+{
+  const double *src[3] = {pf1, pf2, pf3};
+  int d, i, j, k;
+  if (!o->phic) o->phic = dalloc (o->tot);
+  for (k = 0; k < o->T[2]; k++) for (j = 0; j < o->T[1]; j++) for (i = 0; i < o->T[0]; i++)
+    o->phic[IDX(o,k,j,i)] = phic[((size_t)k*o->T[1] + j)*o->T[0] + i];
+  for (d = 0; d < o->c.dims; d++){
+    int e[3] = {0, 0, 0}, n1, n2;
+    e[d] = 1;
+    n1 = o->T[0] + e[0]; n2 = o->T[1] + e[1];
+    if (!o->phif[d]) o->phif[d] = dalloc (o->tot);
+    for (k = -e[2]; k < o->T[2]; k++) for (j = -e[1]; j < o->T[1]; j++) for (i = -e[0]; i < o->T[0]; i++)
+      o->phif[d][IDX(o,k,j,i)] = src[d][((size_t)(k + e[2])*n2 + (j + e[1]))*n1 + (i + e[0])];
+  }
 }
 
 void oracle_set_interior (Oracle *o, const double *vc, const double *bx1s,
@@ -860,6 +880,13 @@ static void update_stage (Oracle *o, double dt)
         }
       }
 
+      if (o->phic){                    /* TotalFlux, rhs.c:388-392: gravitational energy flux */
+        for (n = nbeg-1; n <= nend; n++){
+          idx3[dir] = n;
+          o->ppen[n] = o->phif[dir][IDX(o, idx3[2], idx3[1], idx3[0])];
+          o->flux[n][ENG] += o->flux[n][RHO]*o->ppen[n];
+        }
+      }
       /* RightHandSide + update (nbeg .. nend), rhs.c:193-201,
          update_stage.c:214-216, 229-235 */
       for (n = nbeg; n <= nend; n++){
@@ -873,6 +900,10 @@ static void update_stage (Oracle *o, double dt)
           const double g = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
           rhs[q.vn] += dt*o->v[n][RHO]*g;
           rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*g;
+        }
+        if (o->phic){                  /* rhs_source.c:233-237, 316-320, 358-362 */
+          rhs[q.vn] -= dtdx*o->v[n][RHO]*(o->ppen[n] - o->ppen[n-1]);
+          rhs[ENG]  -= o->phic[id]*rhs[RHO];
         }
         for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
         if (o->stage == 1)
@@ -1336,7 +1367,12 @@ static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, double
     for (nv = 0; nv < NV; nv++){
       double scrh;
       if (dims == 2 && (nv == VX3 || nv == BX3)) continue;
-      scrh = dt_2*(d_dl*Adv[nv] - (o->c.body_force && nv == q.vn ? 0.0 + o->gpen[i] : 0.0));   /* PrimSource, prim_eqn.c:289-360 */
+      double src = 0.0;                /* PrimSource, prim_eqn.c:289-360 */
+      if (nv == q.vn){
+        if (o->c.body_force) src += o->gpen[i];
+        if (o->phic) src -= (o->ppen[i] - o->ppen[i-1])/(1.0*dx);
+      }
+      scrh = dt_2*(d_dl*Adv[nv] - src);
       o->vp[i][nv] -= scrh;
       o->vm[i][nv] -= scrh;
     }
@@ -1436,6 +1472,7 @@ static void ctu_advance (Oracle *o, double dt)
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
         for (nv = 0; nv < NV; nv++) o->vn[n][nv] = o->v[n][nv] = o->Vc[nv][id];
         o->gpen[n] = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
+        if (o->phic) o->ppen[n] = o->phif[dir][id];
         o->bn[n] = o->Vs[dir][id];
         o->pflag[n] = o->flag[id];
       }
@@ -1447,6 +1484,7 @@ static void ctu_advance (Oracle *o, double dt)
       /* 4f. Riemann, EMF, rhs with dt/2 */
       ctu_riemann (o, q, nbeg, nend);
       ctu_store_emf (o, dir, nbeg, nend, idx3);
+      if (o->phic) for (n = nbeg-1; n <= nend; n++) o->flux[n][ENG] += o->flux[n][RHO]*o->ppen[n];   /* TotalFlux */
       /* CTU_CT_Source (nbeg-1 .. nend+1), ctu_step.c:731-816 */
       for (n = nbeg-1; n <= nend+1; n++){
         double db = dt2_dx*(o->up[n][q.bn] - o->um[n][q.bn]), scrh;
@@ -1476,6 +1514,10 @@ static void ctu_advance (Oracle *o, double dt)
           const double g = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
           rhs[q.vn] += dt2*o->v[n][RHO]*g;
           rhs[ENG]  += dt2*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*g;
+        }
+        if (o->phic){
+          rhs[q.vn] -= dt2_dx*o->v[n][RHO]*(o->ppen[n] - o->ppen[n-1]);
+          rhs[ENG]  -= o->phic[id]*rhs[RHO];
         }
         for (nv = 0; nv < NV; nv++) o->rhs3[dir][nv][id] = rhs[nv];
         o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);       /* :416-419 */
@@ -1576,6 +1618,11 @@ static void ctu_advance (Oracle *o, double dt)
       for (n = nbeg-1; n <= nend+1; n++) o->floor_events += cons_to_prim (o, o->up[n], o->vp[n]);
       ctu_riemann (o, q, nbeg, nend);
       ctu_store_emf (o, dir, nbeg, nend, idx3);
+      if (o->phic) for (n = nbeg-1; n <= nend; n++){
+        idx3[dir] = n;
+        o->ppen[n] = o->phif[dir][IDX(o, idx3[2], idx3[1], idx3[0])];
+        o->flux[n][ENG] += o->flux[n][RHO]*o->ppen[n];
+      }
       for (n = nbeg; n <= nend; n++){
         double rhs[NV];
         idx3[dir] = n;
@@ -1586,6 +1633,10 @@ static void ctu_advance (Oracle *o, double dt)
           const double g = (o->gf[dir] ? o->gf[dir][id] : o->c.grav[dir]);
           rhs[q.vn] += dt*o->v[n][RHO]*g;
           rhs[ENG]  += dt*0.5*(o->flux[n][RHO] + o->flux[n-1][RHO])*g;
+        }
+        if (o->phic){
+          rhs[q.vn] -= dtdx*o->v[n][RHO]*(o->ppen[n] - o->ppen[n-1]);
+          rhs[ENG]  -= o->phic[id]*rhs[RHO];
         }
         for (nv = 0; nv < NV; nv++) o->Uc[nv][id] += rhs[nv];
         o->inv_dt_hyp = MAXV(o->inv_dt_hyp, o->cmax[n]*inv_dl);

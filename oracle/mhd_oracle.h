@@ -64,6 +64,10 @@ Oracle *oracle_create (const OracleConfig *cfg);
    g[d][k][j][i] with the extents T3 x T2 x T1 of the reference's Data arrays (NULL for the third component in 2-D).
    Replaces the uniform grav[] of the configuration. */
 void    oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const double *g3);
+/* BODY_FORCE POTENTIAL (rhs.c:162-187, 388-392; rhs_source.c:233-237, 316-320, 358-362; prim_eqn.c:304-307): the potential
+   at the zone centres, phic[k][j][i] (T3 x T2 x T1), and at the faces of every direction in the layout of the staggered
+   Data arrays (pf1: T3 x T2 x (T1+1) from face -1/2, pf2: T3 x (T2+1) x T1, pf3: (T3+1) x T2 x T1; NULL in 2-D). */
+void    oracle_set_body_potential (Oracle *o, const double *phic, const double *pf1, const double *pf2, const double *pf3);
 void    oracle_destroy (Oracle *o);
 int     oracle_nghost (const Oracle *o);
 

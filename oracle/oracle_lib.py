@@ -47,6 +47,7 @@ def lib():
         L.oracle_create.argtypes = [C.POINTER(OracleConfig)]
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_body_force.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_set_body_potential.argtypes = [C.c_void_p] * 5
         L.oracle_nghost.argtypes = [C.c_void_p]
         dp = C.POINTER(C.c_double)
         L.oracle_set_interior.argtypes = [C.c_void_p, dp, dp, dp, dp]
@@ -119,6 +120,12 @@ class Oracle:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (g1, g2, g3)]
         self._gkeep = arrs
         lib().oracle_set_body_force(self._h, *[a.ctypes.data if a is not None else None for a in arrs])
+
+    def set_body_potential(self, phic, pf1, pf2, pf3=None):
+        """BODY_FORCE POTENTIAL: potential at the zone centres [T3][T2][T1] and at the faces (staggered Data layouts)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (phic, pf1, pf2, pf3)]
+        self._pkeep = arrs
+        lib().oracle_set_body_potential(self._h, *[a.ctypes.data if a is not None else None for a in arrs])
 
     # ---- state I/O in "dump dict" form (names as in dbl.out) ----
     def set_state(self, dump: dict):

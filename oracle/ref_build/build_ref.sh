@@ -58,7 +58,10 @@ for VARIANT in "$@"; do
     *_en*) ENCORR=YES ;; *) ENCORR=NO ;;         # CT_EN_CORRECTION (ct_field_average.c:116-129)
   esac
   case "$VARIANT" in
-    *_bf*) BODYF=VECTOR ;; *) BODYF=NO ;;        # BODY_FORCE VECTOR: uniform acceleration GRAV1..3 (init.c BodyForceVector)
+    *_bfp*) BODYF="(VECTOR+POTENTIAL)" ;;        # both (uniform acceleration and step potential from the same GRAV1..3)
+    *_bf*) BODYF=VECTOR ;;                       # BODY_FORCE VECTOR: acceleration GRAV1..3 (init.c BodyForceVector)
+    *_bp*) BODYF=POTENTIAL ;;                    # BODY_FORCE POTENTIAL: step potential of init.c BodyForcePotential
+    *) BODYF=NO ;;
   esac
   B="$ORACLE/_build/$VARIANT"
   mkdir -p "$B"

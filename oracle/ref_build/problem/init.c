@@ -262,8 +262,14 @@ void BodyForceVector(double *v, double *g, double x1, double x2, double x3)
 /* ********************************************************************* */
 double BodyForcePotential(double x1, double x2, double x3)
 /*
+ * Test potential (BODY_FORCE POTENTIAL): a step of height GRAV_d across the plane x_d = 0.013
+ * (off every face and zone centre of the test grids), summed over the directions.
  *********************************************************************** */
 {
-  return 0.0;
+  double phi = 0.0;
+  if (x1 < 0.013) phi += g_inputParam[GRAV1];
+  if (x2 < 0.013) phi += g_inputParam[GRAV2];
+  if (x3 < 0.013) phi += g_inputParam[GRAV3];
+  return phi;
 }
 #endif

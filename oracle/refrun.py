@@ -48,6 +48,8 @@ class RefConfig:
     en_corr: bool = False               # CT_EN_CORRECTION YES
     grav: tuple = None                  # BODY_FORCE VECTOR with the uniform acceleration (g1, g2, g3)
     grav_mode: int = 0                  # 1: static position-dependent force, component d = grav[d]*sign(x_d)
+    potential: bool = False             # BODY_FORCE POTENTIAL: step potential of height grav[d] across x_d = 0.013
+    vector_too: bool = False            # with potential: BODY_FORCE (VECTOR+POTENTIAL), the uniform acceleration grav as well
     cfl: float = 0.4
     cfl_max_var: float = 1.1
     first_dt: float = 1.0e-3
@@ -75,7 +77,7 @@ class RefConfig:
         if self.en_corr:
             v += "_en"
         if self.grav is not None:
-            v += "_bf"
+            v += ("_bfp" if self.vector_too else "_bp") if self.potential else "_bf"
         return v
 
     def binary(self) -> str:

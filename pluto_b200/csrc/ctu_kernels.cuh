@@ -202,12 +202,14 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     unsigned fl = 0;
     if (FLAT) fl = a.flag[id];
     const double gz = a.bf ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;      // body force at the zone centre
-    const double src_n = a.bf ? 0.0 + gz : 0.0;
+    double src_n = 0.0, dphi = 0.0;                    // PrimSource of the normal velocity (prim_eqn.c:289-307)
+    if (a.bf) src_n += gz;
+    if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - 1); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
     ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
     // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
     // V^{n+1/2} (ctu_step.c:566-570) in the corrector
     double rho_c = 0.0;
-    if (a.bf) rho_c = (PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : __ldg (a.Vh[RHO] + id));
+    if (a.bf || a.phif) rho_c = (PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : __ldg (a.Vh[RHO] + id));
     if (PHASE == 0){
       prim_to_cons<NC>(ph, vp, up);
       prim_to_cons<NC>(ph, vm, um);
@@ -228,6 +230,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     const bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, fl2, vp, vR, up, uR, F, press, cmax, mach, nullptr, nullptr);
     if (emf_ok) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, id, F);
     if (PHASE == 1 && emf_ok && a.fbn) a.fbn[id] = F[D::bn];
+    if (a.phif && zone_ok) F[ENG] += F[RHO]*__ldg (a.phif + id);      // TotalFlux, rhs.c:388-392
     if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
     if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
 
@@ -240,8 +243,13 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
       if (PHASE == 0){
         PG_FOR_NV(nv){
           double rr = -dt2_dx*(F[nv] - Fm[nv]);
-          if (nv == D::vn){ rr -= dt2_dx*(press - pm); if (a.bf) rr += dt_2*rho_c*gz; }
+          if (nv == D::vn){
+            rr -= dt2_dx*(press - pm);
+            if (a.bf) rr += dt_2*rho_c*gz;
+            if (a.phif) rr -= dt2_dx*rho_c*dphi;
+          }
           if (nv == ENG && a.bf) rr += dt_2*0.5*(F[RHO] + Fm[RHO])*gz;
+          if (nv == ENG && a.phic) rr -= __ldg (a.phic + id)*(-dt2_dx*(F[RHO] - Fm[RHO]));
           a.rhs[DIR][nv][id] = rr;
         }
       }else{
@@ -253,11 +261,14 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
           rr = -dtdx*(F[RHO] - Fm[RHO]);                              a.U[RHO][id] = u0[RHO] + rr;
           const double dtf = 2.0*dt_2;                                // = dt
           rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);
-          if (a.bf) rr += dtf*rho_c*gz;                               a.U[MX1][id] = u0[MX1] + rr;
+          if (a.bf) rr += dtf*rho_c*gz;
+          if (a.phif) rr -= dtdx*rho_c*dphi;
+          a.U[MX1][id] = u0[MX1] + rr;
           rr = -dtdx*(F[MX2] - Fm[MX2]);                              a.U[MX2][id] = u0[MX2] + rr;
           if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                a.U[MX3][id] = u0[MX3] + rr; }
           rr = -dtdx*(F[ENG] - Fm[ENG]);
           if (a.bf) rr += dtf*0.5*(F[RHO] + Fm[RHO])*gz;
+          if (a.phic) rr -= __ldg (a.phic + id)*(-dtdx*(F[RHO] - Fm[RHO]));
           a.U[ENG][id] = u0[ENG] + rr;
         }
       }
@@ -341,7 +352,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
 
     const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
     const double dtdx = __ldg (a.dtp + DIR);
-    double rhoL = 0.0, gL = 0.0;                     // body force: stateC density (predictor) and force of zone z-1
+    double rhoL = 0.0, gL = 0.0, dphiL = 0.0;        // body force: stateC density (predictor), force, potential step of zone z-1
     double vl[NV], v[NV], vr[NV];
     PG_FOR_NV(nv){ v[nv] = __ldg (a.V0[nv] + id - sD); vr[nv] = __ldg (a.V0[nv] + id); }
     double bsp = __ldg (a.Bs0[DIR] + id - sD), bhp = 0.0;
@@ -362,9 +373,11 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       if (FLAT) flz = a.flag[id];
       double vp[NV], vm[NV], up[NV], um[NV];
       const double gz = a.bf ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;    // body force at the centre of zone z
-      const double src_n = a.bf ? 0.0 + gz : 0.0;
+      double src_n = 0.0, dphi = 0.0;                  // PrimSource of the normal velocity (prim_eqn.c:289-307)
+      if (a.bf) src_n += gz;
+      if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - sD); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
       ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
-      const double rho_z = (a.bf && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
+      const double rho_z = ((a.bf || a.phif) && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
       if (PHASE == 0){
         prim_to_cons<NC>(ph, vp, up);
         prim_to_cons<NC>(ph, vm, um);
@@ -391,6 +404,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         my_mach = mach > my_mach ? mach : my_mach;
         if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
         if (z - 1 >= c0 || chunk == 0) store_face_emf_p<DIR, NC>(a.e1, a.e2, a.sv, idf, F);
+        if (a.phif) F[ENG] += F[RHO]*__ldg (a.phif + idf);              // TotalFlux, rhs.c:388-392
         if (PHASE == 1 && a.fbn && (z - 1 >= c0 || chunk == 0)) a.fbn[idf] = F[D::bn];
         if (z - 1 >= c0){
           // zone z-1: faces z-3/2 (Fp) and z-1/2 (F)
@@ -399,27 +413,33 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
           if (PHASE == 0){
             PG_FOR_NV(nv){
               double r = -dt2_dx*(F[nv] - Fp[nv]);
-              if (nv == D::vn){ r -= dt2_dx*(press - pp); if (a.bf) r += dt_2*rhoL*gL; }
+              if (nv == D::vn){
+                r -= dt2_dx*(press - pp);
+                if (a.bf) r += dt_2*rhoL*gL;
+                if (a.phif) r -= dt2_dx*rhoL*dphiL;
+              }
               if (nv == ENG && a.bf) r += dt_2*0.5*(F[RHO] + Fp[RHO])*gL;
+              if (nv == ENG && a.phic) r -= __ldg (a.phic + idf)*(-dt2_dx*(F[RHO] - Fp[RHO]));
               a.rhs[DIR][nv][idf] = r;
             }
           }else if (upd){
             const double *ua = cur + Q_U*CS;
             const double dtf = 2.0*dt_2;                                        // = dt
-            const double rho_h = a.bf ? __ldg (a.Vh[RHO] + idf) : 0.0;          // V^{n+1/2} (ctu_step.c:566-570)
+            const double rho_h = (a.bf || a.phif) ? __ldg (a.Vh[RHO] + idf) : 0.0;   // V^{n+1/2} (ctu_step.c:566-570)
             double r;
             r = -dtdx*(F[RHO] - Fp[RHO]);                                           a.U[RHO][idf] = ua[0] + r;
             r = -dtdx*(F[MX1] - Fp[MX1]); if (D::vn == MX1) r -= dtdx*(press - pp); a.U[MX1][idf] = ua[CS] + r;
             r = -dtdx*(F[MX2] - Fp[MX2]);
-            if (D::vn == MX2){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*gL; }
+            if (D::vn == MX2){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*gL; if (a.phif) r -= dtdx*rho_h*dphiL; }
             a.U[MX2][idf] = ua[2*CS] + r;
             if (NC == 3){
               r = -dtdx*(F[MX3] - Fp[MX3]);
-              if (D::vn == MX3){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*gL; }
+              if (D::vn == MX3){ r -= dtdx*(press - pp); if (a.bf) r += dtf*rho_h*gL; if (a.phif) r -= dtdx*rho_h*dphiL; }
               a.U[MX3][idf] = ua[3*CS] + r;
             }
             r = -dtdx*(F[ENG] - Fp[ENG]);
             if (a.bf) r += dtf*0.5*(F[RHO] + Fp[RHO])*gL;
+            if (a.phic) r -= __ldg (a.phic + idf)*(-dtdx*(F[RHO] - Fp[RHO]));
             a.U[ENG][idf] = ua[4*CS] + r;
           }
         }
@@ -427,7 +447,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         pp = press;
       }
       PG_FOR_NV(nv){ vpL[nv] = vp[nv]; upL[nv] = up[nv]; }
-      rhoL = rho_z; gL = gz;
+      rhoL = rho_z; gL = gz; dphiL = dphi;
       flb = flz;
       double *tmp = cur; cur = nxt; nxt = tmp;
     }

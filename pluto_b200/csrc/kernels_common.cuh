@@ -73,6 +73,10 @@ struct SweepArgs {
   // grav[], or a static per-zone field gf (this sweep's component; gf2: the x2 component of the fused x1+x2 sweep)
   double  grav[3];
   const double *gf, *gf2;
+  int     bfv;               // vector part present (BODY_FORCE & VECTOR)
+  // BODY_FORCE & POTENTIAL (rhs.c:388-392, rhs_source.c:233-237, 316-320, 358-362): potential at the zone centres and at
+  // the faces of this sweep's direction (phif2: x2 faces, fused x1+x2 sweep); NULL without a potential
+  const double *phic, *phif, *phif2;
 };
 
 struct CtArgs {
@@ -115,6 +119,7 @@ struct CtuArgs {
   int     bf;                // BODY_FORCE VECTOR: uniform grav[] or per-zone gf of this direction (rhs_source.c:214-345,
   double  grav[3];           // prim_eqn.c:289-360)
   const double *gf;
+  const double *phic, *phif; // BODY_FORCE & POTENTIAL: potential at the centres / the faces of this direction (else NULL)
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
 };
 

@@ -83,6 +83,8 @@ struct PlutoGpu {
   int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
   double *gfield[3];               // static per-zone body force (pluto_gpu_set_body_force), else NULL
   void   *gfield_pool;
+  double *phic, *phif[3];          // body-force potential at centres and faces (pluto_gpu_set_body_potential), else NULL
+  void   *phi_pool;
   double *fbn[3];                  // CT_EN_CORRECTION + EXACT: normal-field flux of the faces (own allocation)
   void   *fbn_pool;
   double *rhs3[3][NVS];            // CTU: half-step right-hand sides of the normal predictors (own allocation)
@@ -156,7 +158,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->en_correction && cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
     return fail ("CT_EN_CORRECTION YES is available with CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
                  "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
-  if (cfg->body_force != 0 && cfg->body_force != 1) return fail ("bad body_force");
+  if (cfg->body_force < 0 || cfg->body_force > 3) return fail ("bad body_force");
   if (cfg->body_force && (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL || cfg->shock_flattening))
     return fail ("BODY_FORCE is not available together with CT_EMF_AVERAGE UCT_HLL or SHOCK_FLATTENING");
   if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
@@ -293,6 +295,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->ctu_pool) cudaFree (h->ctu_pool);
   if (h->fbn_pool) cudaFree (h->fbn_pool);
   if (h->gfield_pool) cudaFree (h->gfield_pool);
+  if (h->phi_pool) cudaFree (h->phi_pool);
   if (h->flag) cudaFree (h->flag);
   if (h->red) cudaFree (h->red);
   if (h->red_host) cudaFreeHost (h->red_host);
@@ -453,7 +456,7 @@ int pluto_gpu_download_data (PlutoGpu *h, double *Vc, double *s1, double *s2, do
 int pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3)
 {
   CU (cudaSetDevice (h->cfg.device));
-  if (!h->cfg.body_force) return fail ("pluto_gpu_set_body_force: the configuration has body_force = 0");
+  if (!(h->cfg.body_force & 1)) return fail ("pluto_gpu_set_body_force: the configuration has no BODY_FORCE VECTOR (body_force & 1)");
   const Geom &g = h->g;
   const size_t tot_al = ((size_t)g.tot + 31) & ~(size_t)31;
   if (!h->gfield_pool){
@@ -478,6 +481,38 @@ int pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, c
     h->gfield[d] = dev;
   }
   if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }      // the captured step holds the old arguments
+  return 0;
+}
+
+int pluto_gpu_set_body_potential (PlutoGpu *h, const double *phic, const double *pf1, const double *pf2, const double *pf3)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  if (!(h->cfg.body_force & 2)) return fail ("pluto_gpu_set_body_potential: the configuration has no BODY_FORCE POTENTIAL (body_force & 2)");
+  const Geom &g = h->g;
+  const size_t tot_al = ((size_t)g.tot + 31) & ~(size_t)31;
+  if (!h->phi_pool){
+    const size_t nb = (size_t)(1 + g.dims)*tot_al*sizeof (double);
+    if (cudaMalloc (&h->phi_pool, nb) != cudaSuccess){ h->phi_pool = NULL; return fail ("cudaMalloc of %zu bytes (potential) failed", nb); }
+    CU (cudaMemset (h->phi_pool, 0, nb));
+    h->pool_bytes += nb;
+  }
+  const double *src[4] = {phic, pf1, pf2, pf3};
+  for (int q = 0; q < 1 + g.dims; q++){
+    if (!src[q]) return fail ("pluto_gpu_set_body_potential: NULL array %d", q);
+    double *dev = (double *)h->phi_pool + (size_t)q*tot_al;
+    HaloArgs a; memset (&a, 0, sizeof (a));
+    a.q[0] = dev; a.nf = 1; a.offset[0] = 0; a.buf = h->scratch; a.g = g;
+    a.lo[0][0] = a.lo[0][1] = a.lo[0][2] = 0;
+    a.hi[0][0] = g.T[0] - 1; a.hi[0][1] = g.T[1] - 1; a.hi[0][2] = g.T[2] - 1;
+    if (q > 0) a.lo[0][q - 1] = -1;                      // faces of direction q-1: one more, starting at -1/2
+    const long long cnt = box_count (a.lo[0], a.hi[0]);
+    if ((size_t)cnt > h->scratch_doubles) return fail ("internal: scratch too small");
+    CU (cudaMemcpyAsync (h->scratch, src[q], (size_t)cnt*sizeof (double), cudaMemcpyHostToDevice, h->stream));
+    if (count (h, DISPATCH (h, launch_halo_unpack) (a, h->stream))) return 1;
+    CU (cudaStreamSynchronize (h->stream));
+    if (q == 0) h->phic = dev; else h->phif[q - 1] = dev;
+  }
+  if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }
   return 0;
 }
 
@@ -654,6 +689,9 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   const bool bf = h->cfg.body_force != 0;
   for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];
   s.gf2 = h->gfield[1];
+  s.bfv = h->cfg.body_force & 1;
+  s.phic = h->phic; s.phif2 = h->phif[1];
+  if ((h->cfg.body_force & 2) && !h->phic) return fail ("BODY_FORCE POTENTIAL: call pluto_gpu_set_body_potential before the first step");
   // EXACT: later stages continue from the conservative state the previous stage
   // left (as the reference does); FAST: rebuild it from the primitives, which
   // saves reading U in the x1 sweep and differs by round-off only
@@ -669,6 +707,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     s.sv = h->sv[dir];
     s.fbn = h->fbn[dir];
     s.gf = h->gfield[dir];
+    s.phif = h->phif[dir];
     if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
@@ -779,8 +818,10 @@ static int run_ctu (PlutoGpu *h, int part)
   }
   s.red = h->red; s.flag = h->flag; s.g = g; s.ph = h->ph; s.dtp = h->dtdev; s.limiter = h->cfg.limiter;
   s.en_corr = h->cfg.en_correction;
-  s.bf = h->cfg.body_force;
+  s.bf = h->cfg.body_force & 1;
   for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];
+  s.phic = h->phic;
+  if ((h->cfg.body_force & 2) && !h->phic) return fail ("BODY_FORCE POTENTIAL: call pluto_gpu_set_body_potential before the first step");
 
   CtArgs c; memset (&c, 0, sizeof (c));
   c.exj = h->exj; c.exk = h->exk; c.eyi = h->eyi; c.eyk = h->eyk; c.ezi = h->ezi; c.ezj = h->ezj;
@@ -794,6 +835,7 @@ static int run_ctu (PlutoGpu *h, int part)
       s.sv = h->sv[dir];
       s.fbn = h->fbn[dir];
       s.gf = h->gfield[dir];
+      s.phif = h->phif[dir];
       if (dir == 0){ s.e1 = h->ezi; s.e2 = h->eyi; }
       else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
       else { s.e1 = h->eyk; s.e2 = h->exk; }

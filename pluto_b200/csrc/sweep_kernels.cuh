@@ -289,6 +289,8 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
 
     if (emf_ok && !hll) store_face_emf<DIR, NC>(a, id, F);
     if (emf_ok && a.fbn) a.fbn[id] = F[D::bn];
+    double pfx = 0.0;                                  // potential of the face i+1/2: gravitational energy flux (rhs.c:388-392)
+    if (BF && a.phif && zone_ok){ pfx = __ldg (a.phif + id); F[ENG] += F[RHO]*pfx; }
     if (face_ok) my_mach = mach > my_mach ? mach : my_mach;
     if (SOLVER == SOLVER_ROE && face_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
 
@@ -316,13 +318,17 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
       const double dtdx = __ldg (a.dtp + DIR);
       double rr;
       rr = -dtdx*(F[RHO] - Fm[RHO]);                                a.U[RHO][id] = u0[RHO] + rr;
+      const double r_rho = rr;
       rr = -dtdx*(F[MX1] - Fm[MX1]); rr -= dtdx*(press - pm);
       const double gx = BF ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;
-      if (BF) rr += __ldg (a.dtp + 3)*v[RHO]*gx;                    a.U[MX1][id] = u0[MX1] + rr;
+      if (BF && a.bfv) rr += __ldg (a.dtp + 3)*v[RHO]*gx;
+      if (BF && a.phif) rr -= dtdx*v[RHO]*(pfx - __ldg (a.phif + id - 1));
+      a.U[MX1][id] = u0[MX1] + rr;
       rr = -dtdx*(F[MX2] - Fm[MX2]);                                a.U[MX2][id] = u0[MX2] + rr;
       if (NC == 3){ rr = -dtdx*(F[MX3] - Fm[MX3]);                  a.U[MX3][id] = u0[MX3] + rr; }
       rr = -dtdx*(F[ENG] - Fm[ENG]);
-      if (BF) rr += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*gx;
+      if (BF && a.bfv) rr += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*gx;
+      if (BF && a.phic) rr -= __ldg (a.phic + id)*r_rho;
       a.U[ENG][id] = u0[ENG] + rr;
       if (a.stage1){
         const double cd = 0.5*(cm + cmax)*a.inv_dl;
@@ -537,6 +543,8 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     bool ok = riemann_f<SOLVER, DIR, NC, FLAT>(ph, flb | flc, vL, vR, uL, uR, F, press, cmax, mach,
                                                sf ? a.e1 + id : nullptr, sf ? a.e2 + id : nullptr);
     flb = flc;
+    double pfd = 0.0;                                  // potential of the face f+1/2
+    if (BF && a.phif){ pfd = __ldg (a.phif + id); F[ENG] += F[RHO]*pfd; }
     if (in_range){
       my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
@@ -548,19 +556,22 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       const double dtdx = __ldg (a.dtp + DIR);
       double r;
       r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = ua[0] + r;
+      const double r_rho = r;
+      const double dphi = (BF && a.phif) ? pfd - __ldg (a.phif + id - sD) : 0.0;
       const double dtg = BF ? __ldg (a.dtp + 3) : 0.0;
       const double gd = BF ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;
       r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = ua[CS] + r;
       r = -dtdx*(F[MX2] - C_FP(2));
-      if (D::vn == MX2){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*gd; }
+      if (D::vn == MX2){ r -= dtdx*(press - pp); if (BF && a.bfv) r += dtg*rho_f*gd; if (BF && a.phif) r -= dtdx*rho_f*dphi; }
       a.U[MX2][id] = ua[2*CS] + r;
       if (NC == 3){
         r = -dtdx*(F[MX3] - C_FP(3));
-        if (D::vn == MX3){ r -= dtdx*(press - pp); if (BF) r += dtg*rho_f*gd; }
+        if (D::vn == MX3){ r -= dtdx*(press - pp); if (BF && a.bfv) r += dtg*rho_f*gd; if (BF && a.phif) r -= dtdx*rho_f*dphi; }
         a.U[MX3][id] = ua[3*CS] + r;
       }
       r = -dtdx*(F[ENG] - C_FP(4));
-      if (BF) r += dtg*0.5*(F[RHO] + C_FP(0))*gd;
+      if (BF && a.bfv) r += dtg*0.5*(F[RHO] + C_FP(0))*gd;
+      if (BF && a.phic) r -= __ldg (a.phic + id)*r_rho;
       a.U[ENG][id] = ua[4*CS] + r;
       if (a.stage1){
         double cd = ua[5*CS] + 0.5*(cp + cmax)*a.inv_dl;
@@ -764,6 +775,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       bool ok = riemann_f<SOLVER, 0, NC, FLAT>(ph, flx2, vp, vR, uL, uR, F, press, cmax, mach,
                                                hll && xemf_ok ? a.e1 + id : nullptr, hll && xemf_ok ? a.e2 + id : nullptr);
       if (xemf_ok && !hll) store_face_emf_p<0, NC>(a.e1, a.e2, a.sv, id, F);
+      double pfx = 0.0;
+      if (BF && a.phif && zone_ok){ pfx = __ldg (a.phif + id); F[ENG] += F[RHO]*pfx; }
       if (xface_ok) my_mach = mach > my_mach ? mach : my_mach;
       if (SOLVER == SOLVER_ROE && xface_ok && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
       double Fm[NV], pm, cm;
@@ -780,10 +793,14 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       rx[MX2] = -dtdx0*(F[MX2] - Fm[MX2]);
       if (NC == 3) rx[MX3] = -dtdx0*(F[MX3] - Fm[MX3]);
       rx[ENG] = -dtdx0*(F[ENG] - Fm[ENG]);
-      if (BF){
+      if (BF && a.bfv){
         const double gx = (a.gf ? __ldg (a.gf + id) : a.grav[0]);
         rx[MX1] += __ldg (a.dtp + 3)*v[RHO]*gx;
         rx[ENG] += __ldg (a.dtp + 3)*0.5*(F[RHO] + Fm[RHO])*gx;
+      }
+      if (BF && a.phif && upd_i){
+        rx[MX1] -= dtdx0*v[RHO]*(pfx - __ldg (a.phif + id - 1));
+        rx[ENG] -= __ldg (a.phic + id)*rx[RHO];
       }
       cdx = 0.5*(cm + cmax)*a.inv_dl;
     }
@@ -814,6 +831,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       const bool sfy = hll && yemf_ok && (f >= c0 || chunk == 0);
       bool ok = riemann_f<SOLVER, 1, NC, FLAT>(ph, flz | fln, vL, vR, uL, uR, F, press, cmax, mach,
                                                sfy ? a.e3 + id : nullptr, sfy ? a.e4 + id : nullptr);
+      double pfy = 0.0;
+      if (BF && a.phif2 && col_ok){ pfy = __ldg (a.phif2 + id); F[ENG] += F[RHO]*pfy; }
       if (col_ok){
         my_mach = mach > my_mach ? mach : my_mach;
         if (SOLVER == SOLVER_ROE && !ok) atomicAdd (a.red + RED_ROEFAIL, 1ull);
@@ -825,13 +844,17 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         const double dtdx1 = __ldg (a.dtp + 1);
         prim_to_cons<NC>(ph, v, u0);
         r = -dtdx1*(F[RHO] - C_FP(0));                                   a.U[RHO][id] = (u0[RHO] + rx[RHO]) + r;
+        const double r_rho = r;
         r = -dtdx1*(F[MX1] - C_FP(1));                                   a.U[MX1][id] = (u0[MX1] + rx[MX1]) + r;
         r = -dtdx1*(F[MX2] - C_FP(2)); r -= dtdx1*(press - pp);
         const double gy = BF ? (a.gf2 ? __ldg (a.gf2 + id) : a.grav[1]) : 0.0;
-        if (BF) r += __ldg (a.dtp + 3)*v[RHO]*gy;                        a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
+        if (BF && a.bfv) r += __ldg (a.dtp + 3)*v[RHO]*gy;
+        if (BF && a.phif2) r -= dtdx1*v[RHO]*(pfy - __ldg (a.phif2 + id - sD));
+        a.U[MX2][id] = (u0[MX2] + rx[MX2]) + r;
         if (NC == 3){ r = -dtdx1*(F[MX3] - C_FP(3));                     a.U[MX3][id] = (u0[MX3] + rx[MX3]) + r; }
         r = -dtdx1*(F[ENG] - C_FP(4));
-        if (BF) r += __ldg (a.dtp + 3)*0.5*(F[RHO] + C_FP(0))*gy;
+        if (BF && a.bfv) r += __ldg (a.dtp + 3)*0.5*(F[RHO] + C_FP(0))*gy;
+        if (BF && a.phic) r -= __ldg (a.phic + id)*r_rho;
         a.U[ENG][id] = (u0[ENG] + rx[ENG]) + r;
         if (a.stage1){
           const double cd = cdx + 0.5*(cp + cmax)*a.inv_dl2;

@@ -36,7 +36,7 @@ class GpuStepper:
     def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
                  bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0,
                  small_dn=1e-12, small_pr=1e-12, lib_path=None, limiter="default", emf="uct_contact",
-                 flatten=False, ctu=False, en_corr=False, grav=None):
+                 flatten=False, ctu=False, en_corr=False, grav=None, potential=False):
         self.L = _lib.load_library(lib_path)
         c = _lib.PlutoGpuConfig()
         n = list(n) + [1] * (3 - len(n))
@@ -61,7 +61,8 @@ class GpuStepper:
         c.shock_flattening = 1 if flatten else 0    # SHOCK_FLATTENING MULTID (plm only)
         c.time_stepping = 1 if ctu else 0           # TIME_STEPPING: RK2/RK3 (rk_order) | HANCOCK (corner transport upwind)
         c.en_correction = 1 if en_corr else 0       # CT_EN_CORRECTION YES
-        c.body_force = 0 if grav is None else 1     # BODY_FORCE VECTOR with the uniform acceleration grav
+        # BODY_FORCE: VECTOR (bit 0) with the uniform acceleration grav, POTENTIAL (bit 1, set_body_potential)
+        c.body_force = (0 if grav is None else 1) | (2 if potential else 0)
         for d in range(3):
             c.grav[d] = 0.0 if grav is None else float(grav[d])
         self.cfg = c
@@ -95,6 +96,12 @@ class GpuStepper:
         The stepper must have been created with grav=... (BODY_FORCE VECTOR)."""
         arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (g1, g2, g3)]
         self._check(self.L.pluto_gpu_set_body_force(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
+    def set_body_potential(self, phic, pf1, pf2, pf3=None):
+        """BODY_FORCE POTENTIAL: BodyForcePotential at the zone centres [T3][T2][T1] and at the faces of every direction
+        (staggered Data layouts, one more face starting at -1/2).  Create the stepper with potential=True."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (phic, pf1, pf2, pf3)]
+        self._check(self.L.pluto_gpu_set_body_potential(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
 
     # ---- interior (.dbl) layout -------------------------------------------
     def interior_buffers(self, pinned=False):

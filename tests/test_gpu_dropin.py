@@ -23,13 +23,15 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # BODY_FORCE VECTOR: the shim samples init.c's BodyForceVector and passes the uniform acceleration
          "blast3d_bf", "rotor2d_ppm_rk3_bf", "turb3d_ctu_bf",
          # position-dependent force: tabulated per zone by the shim (pluto_gpu_set_body_force)
-         "blast3d_bfx", "blast2d_ctu_bfx_roe"]
+         "blast3d_bfx", "blast2d_ctu_bfx_roe",
+         # BODY_FORCE POTENTIAL: the shim tabulates BodyForcePotential at the zone centres and faces
+         "blast3d_bp", "blast2d_ctu_bp"]
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
-                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, prefix="pluto_gpu_")
+                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential, prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
     s = GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                   bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
+                   bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.force, potential=g.potential)
     apply_force_field(s, g)
     return s
 
@@ -346,6 +346,49 @@ def test_body_force_bit_identical_to_oracle(problem, dims, n, recon, solver, rk)
     tol = 1e-9 if (problem, solver) == ("rotor", "roe") else TOL_ONE_STEP
     for k in b:
         assert rel_l1(a[k], b[k]) <= tol, k
+    f.close()
+
+
+@pytest.mark.parametrize("problem,dims,n,recon,solver,rk,ctu,vector", [
+    ("blast", 3, (20, 16, 24), "plm", "hlld", 2, False, False), ("rotor", 2, (44, 40, 1), "ppm", "hll", 3, False, True),
+    ("blast", 3, (16, 20, 12), "plm", "roe", 2, True, True), ("blast", 2, (40, 30, 1), "plm", "hlld", 2, True, False)])
+def test_body_potential_bit_identical_to_oracle(problem, dims, n, recon, solver, rk, ctu, vector):
+    """BODY_FORCE POTENTIAL (gravitational energy flux rhs.c:388-392, sources rhs_source.c:233-237, 316-320, 358-362, predictor
+    source prim_eqn.c:304-307), alone and together with a uniform VECTOR force; RK2 / RK3 / CTU; one block and decomposed."""
+    import os
+    from oracle.oracle_lib import Oracle, next_dt
+    from pluto_b200 import GpuStepper, problems
+    from pluto_b200.parallel import BlockLayout, LocalMultiBlock
+    from tests.util import step_potential_arrays
+    st0, meta = problems.make(problem, dims, n)
+    dom = ((-0.5, 0.5),) * 3
+    steps = (0.05, -0.03, 0.04 if dims == 3 else 0.0)
+    grav = ((0.4, -0.9, 0.3) if dims == 3 else (0.4, -0.9, 0.0)) if vector else None
+    kw = dict(recon=recon, solver=solver, rk_order=rk, gamma=meta["gamma"], ctu=ctu, grav=grav)
+    o = Oracle(dims, n, meta["dx"], bc=meta["bc"], **kw)
+    o.set_body_potential(*step_potential_arrays(dims, n, o.ng, dom, steps))
+    s = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], arith="exact", potential=True, **kw)
+    s.set_body_potential(*step_potential_arrays(dims, n, s.ng, dom, steps))
+    o.set_state(st0); s.set_state(st0)
+    dt = {"blast": 2e-4, "rotor": 1e-3}[problem]
+    for step in range(5):
+        inv, mach, nfl = o.advance(dt)
+        info = s.advance(dt)
+        assert (info.inv_dt_hyp, info.max_mach, info.floor_events) == (inv, mach, nfl), step
+        dt = next_dt(inv, meta["cfl"], 1.1, dt)
+    a, b = s.get_state(), o.get_state()
+    for k in b:
+        assert np.array_equal(a[k], b[k]), f"{k}: max abs diff {np.abs(a[k]-b[k]).max():.3e}"
+    s.close()
+    f = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], arith="fast", potential=True, **kw)
+    f.set_body_potential(*step_potential_arrays(dims, n, f.ng, dom, steps))
+    o2 = Oracle(dims, n, meta["dx"], bc=meta["bc"], **kw)
+    o2.set_body_potential(*step_potential_arrays(dims, n, o2.ng, dom, steps))
+    f.set_state(st0); o2.set_state(st0)
+    f.advance(dt); o2.advance(dt)
+    a, b = f.get_state(), o2.get_state()
+    for k in b:
+        assert rel_l1(a[k], b[k]) <= TOL_ONE_STEP, k
     f.close()
 
 

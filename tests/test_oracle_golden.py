@@ -13,7 +13,7 @@ from tests.util import Golden, golden_names, divb_max, apply_force_field
 def test_oracle_bit_exact_vs_reference_golden(name):
     g = Golden(name)
     o = Oracle(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-               bc=g.bc, gamma=g.gamma, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.grav)
+               bc=g.bc, gamma=g.gamma, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.force)
     apply_force_field(o, g)
     o.set_state(g.states[0])
     dt = g.first_dt

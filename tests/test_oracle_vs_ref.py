@@ -66,6 +66,16 @@ CASES = [
     ("rotor2d_ppm_bfx", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", first_dt=2e-3, grav=(-1.5, -2.5, 0.0), grav_mode=1), 6),
     ("blast3d_ctu_bfx", RefConfig(problem="blast", dims=3, n=(10, 12, 8), first_dt=3e-4, cfl=0.3, tstep="hancock",
                                   grav=(-3.0, -1.0, 2.0), grav_mode=1), 6),
+    # BODY_FORCE POTENTIAL (rhs.c:388-392, rhs_source.c:233-237, prim_eqn.c:304-307): step potential of the problem file
+    ("blast3d_bp", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(0.05, -0.03, 0.04), potential=True), 8),
+    ("rotor2d_ppm_rk3_bp", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", tstep="rk3", first_dt=2e-3,
+                                     grav=(0.02, -0.03, 0.0), potential=True), 6),
+    ("blast3d_ctu_bp", RefConfig(problem="blast", dims=3, n=(10, 12, 8), first_dt=3e-4, cfl=0.3, tstep="hancock",
+                                 grav=(0.05, -0.03, 0.04), potential=True), 6),
+    ("blast3d_bfp", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(0.05, -0.03, 0.04), potential=True,
+                              vector_too=True), 6),
+    ("blast2d_ctu_bfp", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock", grav=(0.05, -0.03, 0.0),
+                                  potential=True, vector_too=True), 8),
 ]
 
 
@@ -81,7 +91,10 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
                gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"),
-               rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr, grav=cfg.grav)
+               rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr, grav=(None if cfg.potential and not cfg.vector_too else cfg.grav))
+    if cfg.potential:
+        from tests.util import step_potential_arrays
+        o.set_body_potential(*step_potential_arrays(cfg.dims, n, o.ng, dom, cfg.grav))
     if cfg.grav_mode == 1:
         from tests.util import sign_force_arrays
         o.set_body_force(*sign_force_arrays(cfg.dims, n, o.ng, dom, cfg.grav))

@@ -47,6 +47,8 @@ class Golden:
         self.en_corr = bool(int(d["cfg_en_corr"])) if "cfg_en_corr" in d.files else False
         self.grav = tuple(float(x) for x in d["cfg_grav"]) if "cfg_grav" in d.files else None
         self.grav_mode = int(d["cfg_grav_mode"]) if "cfg_grav_mode" in d.files else 0
+        self.potential = bool(int(d["cfg_potential"])) if "cfg_potential" in d.files else False
+        self.force = None if self.potential else self.grav      # the `grav=` argument of Oracle / GpuStepper
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:
@@ -64,6 +66,8 @@ def apply_force_field(stepper, g):
     """Golden fixtures with the static test force (GRAV_MODE 1): hand the per-zone arrays to an Oracle or a GpuStepper."""
     if g.grav_mode == 1:
         stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
+    if g.potential:
+        stepper.set_body_potential(*step_potential_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
 
 
 def rel_l1(a, b):
@@ -108,5 +112,37 @@ def sign_force_arrays(dims, n, ng, domain, grav):
         shape[2 - d] = T[d]
         out.append(np.ascontiguousarray(np.broadcast_to((grav[d] * sgn).reshape(shape), (T[2], T[1], T[0]))))
     while len(out) < 3:
+        out.append(None)
+    return out
+
+
+def step_potential_arrays(dims, n, ng, domain, grav, x0=0.013):
+    """The test potential of oracle/ref_build/problem/init.c (BODY_FORCE POTENTIAL): steps of height grav[d] across the
+    planes x_d = x0, at the zone centres [T3][T2][T1] and at the faces of every direction (staggered Data layouts)."""
+    T = [n[d] + 2 * ng if d < dims else 1 for d in range(3)]
+    xc, xf = [], []
+    for d in range(3):
+        if d < dims:
+            dx = (domain[d][1] - domain[d][0]) / n[d]
+            xc.append(domain[d][0] + (np.arange(T[d]) - ng + 0.5) * dx)
+            xf.append(domain[d][0] + (np.arange(-1, T[d]) - ng + 1.0) * dx)          # faces -1/2 .. T-1/2
+        else:
+            xc.append(np.array([0.5 * (domain[d][0] + domain[d][1])]))
+            xf.append(None)
+
+    def phi(x1, x2, x3):
+        X3, X2, X1 = np.meshgrid(x3, x2, x1, indexing="ij")
+        p = np.zeros(X1.shape)
+        p = p + np.where(X1 < x0, grav[0], 0.0)
+        p = p + np.where(X2 < x0, grav[1], 0.0)
+        p = p + np.where(X3 < x0, grav[2], 0.0)
+        return np.ascontiguousarray(p)
+
+    out = [phi(xc[0], xc[1], xc[2])]
+    for d in range(dims):
+        xs = list(xc)
+        xs[d] = xf[d]
+        out.append(phi(xs[0], xs[1], xs[2]))
+    while len(out) < 4:
         out.append(None)
     return out

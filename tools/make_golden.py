@@ -98,6 +98,10 @@ CASES = {
     "blast3d_bfx": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, grav=(-3.0, -1.0, 2.0), grav_mode=1), 12),
     "blast2d_ctu_bfx_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="hancock", solver="roe",
                                       grav=(-3.0, -1.0, 0.0), grav_mode=1), 20),
+    # BODY_FORCE POTENTIAL: step potential of the problem file (pluto_gpu_set_body_potential)
+    "blast3d_bp": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, grav=(0.05, -0.03, 0.04), potential=True), 12),
+    "blast2d_ctu_bp": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="hancock",
+                                 grav=(0.05, -0.03, 0.0), potential=True), 20),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
@@ -118,6 +122,7 @@ def make(name):
     if cfg.grav is not None:
         out["cfg_grav"] = np.array(cfg.grav, dtype=float)
         out["cfg_grav_mode"] = int(cfg.grav_mode)
+        out["cfg_potential"] = int(cfg.potential)
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
             out[f"s{s}_{k}"] = v
