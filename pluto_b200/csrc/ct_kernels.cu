@@ -247,7 +247,7 @@ ct_update_kernel (const __grid_constant__ CtArgs a)
 // ---------------------------------------------------------------------------
 //  stage completion: face -> centre average, RK average, cons -> prim
 // ---------------------------------------------------------------------------
-template <int NC>
+template <int NC, bool EN>        // EN: CT_EN_CORRECTION YES (compile time: the default instantiation keeps its 32 registers)
 __global__ void __launch_bounds__(128)
 final_kernel (const __grid_constant__ FinalArgs a)
 {
@@ -285,7 +285,7 @@ final_kernel (const __grid_constant__ FinalArgs a)
       }
     }
     double b2_old = 0.0;
-    if (a.en_corr){
+    if (EN){
       // Uc[B] as the reference's sweeps leave it: U = ((U_in + rhs_x1) + rhs_x2) + rhs_x3, rhs = -dt/dx (F_i - F_{i-1})
       // (update_stage.c:214-216, rhs.c:193-201) with the induction fluxes F of the stored face EMFs
       // (ct_emf.c:132-176: x1 faces F[BX2] = -ezi, F[BX3] = eyi; x2: F[BX1] = ezj, F[BX3] = -exj; x3: F[BX1] = -eyk,
@@ -318,7 +318,7 @@ final_kernel (const __grid_constant__ FinalArgs a)
     u[BX1] = 0.5*(a.Bs[0][id] + a.Bs[0][id - 1]);
     u[BX2] = 0.5*(a.Bs[1][id] + a.Bs[1][id - g.S1]);
     if (NC == 3) u[BX3] = 0.5*(a.Bs[2][id] + a.Bs[2][id - g.S12]);
-    if (a.en_corr){
+    if (EN){
       double b2_new;
       if (NC == 3) b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
       else         b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2];
@@ -605,8 +605,13 @@ int launch_final (const FinalArgs &a, cudaStream_t s)
   const Geom &g = a.g;
   const long long n = (long long)a.box_n[0]*a.box_n[1]*(g.dims == 3 ? a.box_n[2] : 1);
   if (n <= 0) return 0;
-  if (g.dims == 3) final_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
-  else             final_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
+  if (a.en_corr){
+    if (g.dims == 3) final_kernel<3, true><<<nblocks (n, 128), 128, 0, s>>>(a);
+    else             final_kernel<2, true><<<nblocks (n, 128), 128, 0, s>>>(a);
+  }else{
+    if (g.dims == 3) final_kernel<3, false><<<nblocks (n, 128), 128, 0, s>>>(a);
+    else             final_kernel<2, false><<<nblocks (n, 128), 128, 0, s>>>(a);
+  }
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 

@@ -82,7 +82,7 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
 # A slice of the GPU test files themselves (same test code, same Python host) run against the interpreted
 # kernels: smallest and ragged blocks, multi-block decomposition with the halo pack/unpack kernels
 # (RK and corner transport upwind), NextTimeStep on the device, reflective walls, the reference Data layout.
-GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or ctu_blast3d_hll_20x24x16 or (decomposed and gn7) or (decomposed and gn4 and all) "
+GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or (decomposed and gn7 and split) or (decomposed and gn4 and all) "
                    "or (decomposed and gn2 and dims) or (device_next_dt and ot-2) or reflective or data_layout "
                    "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2) or (body_force and rotor)")
 
@@ -143,7 +143,7 @@ def test_results_do_not_depend_on_lane_or_block_order(emu_lib):
     CUDA model does not promise (a missing __syncwarp / cp.async wait shows up here as a wrong result)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, PG_EMU_REVERSE="1")
-    sel = ("(exact or fast) and (blast3d_plm_hlld or ot3d_ppm_roe or rotor2d_ppm_uct_hll_hll or blast3d_sfl_uct_hll "
+    sel = ("(exact or fast) and (blast3d_plm_hlld or ot3d_ppm_roe or rotor2d_ppm_uct_hll_hll "
            "or blast3d_ctu_sfl_uct0 or ot2d_ctu_arith_en_roe or blast3d_ctu\\])")
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", "tests/test_emu_kernels.py", "-k", sel],
                        cwd=root, env=env, capture_output=True, text=True)

@@ -103,7 +103,7 @@ def _free_port():
 @pytest.mark.parametrize("mode", ["dims", "all"])
 @pytest.mark.parametrize("world,dims,n,ng", [(2, 3, (6, 5, 4), 2), (2, 2, (8, 6, 1), 2), (4, 3, (4, 6, 5), 2), (4, 2, (6, 8, 1), 2),
                                              # three ghost layers: PARABOLIC, SHOCK_FLATTENING and the corner-transport-upwind step
-                                             (2, 3, (6, 7, 6), 3), (4, 2, (7, 6, 1), 3)])
+                                             (2, 3, (6, 7, 6), 3)])
 def test_periodic_exchange_fills_all_ghosts(world, dims, n, ng, mode):
     mgr = mp.Manager()
     ret = mgr.dict()

@@ -19,7 +19,7 @@ from oracle.refrun import read_dbl
 from tests.util import ROOT
 
 SHIPPED = os.path.join(ROOT, "oracle", "_ref", "shipped")
-CASES = [("orszag_tang_03", 4), ("rotor_01", 3)]
+CASES = [("orszag_tang_03", 3), ("rotor_01", 2)]
 
 
 def _grid(ini):
