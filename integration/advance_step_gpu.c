@@ -53,6 +53,11 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
         && CT_EMF_AVERAGE != UCT_HLL)
   #error "libpluto_gpu covers ideal MHD, Cartesian, CT with UCT_CONTACT / ARITHMETIC / UCT0 / UCT_HLL, DIMENSIONS == COMPONENTS"
 #endif
+#if BACKGROUND_FIELD == YES || ENTROPY_SWITCH != NO || RESISTIVITY != NO || VISCOSITY != NO || THERMAL_CONDUCTION != NO \
+    || HALL_MHD != NO || AMBIPOLAR_DIFFUSION != NO || ROTATING_FRAME != NO || COOLING != NO || FORCED_TURB != NO || NTRACER != 0 \
+    || DIMENSIONAL_SPLITTING != NO || (defined SHEARINGBOX) || (defined FARGO) || (defined PARTICLES)
+  #error "libpluto_gpu covers the ideal-MHD step only: no background field, entropy switch, diffusion terms, Hall / ambipolar, rotating frame, cooling, forced turbulence, tracers, dimensional splitting, shearing box, FARGO, particles"
+#endif
 #if CHAR_LIMITING == YES || LIMITER == FOURTH_ORDER_LIM \
     || (SHOCK_FLATTENING != NO && (SHOCK_FLATTENING != MULTID || RECONSTRUCTION != LINEAR))
   #error "libpluto_gpu: CHAR_LIMITING, FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID with LINEAR are not available on the GPU"
