@@ -39,7 +39,9 @@ enum { PLUTO_GPU_SOLVER_HLLD = 0, PLUTO_GPU_SOLVER_HLL = 1, PLUTO_GPU_SOLVER_ROE
    (reference: AL_Exchange_dim, Src/Parallel/al_exchange_dim.c:25) instead
    of a physical condition, exactly as boundary.c:139 skips it. */
 enum { PLUTO_GPU_BC_PERIODIC = 0, PLUTO_GPU_BC_OUTFLOW = 1, PLUTO_GPU_BC_REFLECTIVE = 2,
-       PLUTO_GPU_BC_SHARED = 3 };
+       PLUTO_GPU_BC_SHARED = 3,
+       PLUTO_GPU_BC_EQTSYMMETRIC = 4 /* reflective, with the sign table of Src/boundary.c:333-336, 423-427: the normal
+                                        velocity and the TRANSVERSE field components change sign */ };
 /* arithmetic mode.  EXACT: no FMA contraction, IEEE div/sqrt in the
    reference's operation order (bit-identical to the gcc -O3 x86-64 build
    of the reference).  FAST: same algorithm with FMA contraction and shared

@@ -34,6 +34,7 @@ static int BoundaryCode (int type)
   if (type == PERIODIC)   return PLUTO_GPU_BC_PERIODIC;
   if (type == OUTFLOW)    return PLUTO_GPU_BC_OUTFLOW;
   if (type == REFLECTIVE) return PLUTO_GPU_BC_REFLECTIVE;
+  if (type == EQTSYMMETRIC) return PLUTO_GPU_BC_EQTSYMMETRIC;
   print ("! AdvanceStep(gpu): boundary type %d is not supported by libpluto_gpu\n", type);
   QUIT_PLUTO(1);
   return -1;

@@ -371,14 +371,17 @@ static void boundary (Oracle *o)
       for (d = 0; d < dims; d++) if (d != is/2) outflow_bound (o, o->Vs[d], fb[d], is);
       fill_magnetic_field (o, is);
       average_normal_mag_field (o, is);
-    }else if (type == ORC_BC_REFLECTIVE){
-      /* FlipSign, boundary.c:318-436: normal v and normal B change sign */
+    }else if (type == ORC_BC_REFLECTIVE || type == ORC_BC_EQTSYMMETRIC){
+      /* FlipSign, boundary.c:318-436.  REFLECTIVE: normal v and normal B change sign; EQTSYMMETRIC (:423-427): normal v
+         and the two TRANSVERSE field components do */
+      const int eqt = (type == ORC_BC_EQTSYMMETRIC);
       for (nv = 0; nv < NV; nv++){
         int s = 1;
-        if (nv == VX1 + is/2 || nv == BX1 + is/2) s = -1;
+        if (nv == VX1 + is/2) s = -1;
+        if (nv >= BX1 && nv <= BX1 + 2) s = ((nv == BX1 + is/2) != eqt) ? -1 : 1;
         reflective_bound (o, o->Vc[nv], s, cb, is);
       }
-      for (d = 0; d < dims; d++) if (d != is/2) reflective_bound (o, o->Vs[d], 1, fb[d], is);
+      for (d = 0; d < dims; d++) if (d != is/2) reflective_bound (o, o->Vs[d], eqt ? -1 : 1, fb[d], is);
       fill_magnetic_field (o, is);
     }else if (type == ORC_BC_PERIODIC){
       for (nv = 0; nv < NV; nv++) periodic_bound (o, o->Vc[nv], cb, is);

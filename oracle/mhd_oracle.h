@@ -21,7 +21,7 @@ extern "C" {
 
 enum { ORC_RECON_PLM = 0, ORC_RECON_PPM = 1 };
 enum { ORC_SOLVER_HLLD = 0, ORC_SOLVER_HLL = 1, ORC_SOLVER_ROE = 2 };
-enum { ORC_BC_PERIODIC = 0, ORC_BC_OUTFLOW = 1, ORC_BC_REFLECTIVE = 2 };
+enum { ORC_BC_PERIODIC = 0, ORC_BC_OUTFLOW = 1, ORC_BC_REFLECTIVE = 2, ORC_BC_EQTSYMMETRIC = 3 };
 /* LIMITER (plm_states.c:192-236, plm_coeffs.h:72-123): DEFAULT mixes MC / van Leer / minmod */
 enum { ORC_LIM_DEFAULT = 0, ORC_LIM_FLAT, ORC_LIM_MINMOD, ORC_LIM_VANALBADA, ORC_LIM_OSPRE,
        ORC_LIM_UMIST, ORC_LIM_VANLEER, ORC_LIM_MC };

@@ -356,7 +356,7 @@ __device__ __forceinline__ int bc_source (const Geom &g, int type, int d, int hi
 {
   if (type == 0) return n + (hi_side ? -g.n[d] : g.n[d]);            // periodic  (boundary.c:480-518)
   if (type == 1) return hi_side ? g.end[d] : g.beg[d];               // outflow   (boundary.c:439-477)
-  return hi_side ? 2*g.end[d] - n + 1 : 2*g.beg[d] - n - 1;          // reflective (boundary.c:521-564)
+  return hi_side ? 2*g.end[d] - n + 1 : 2*g.beg[d] - n - 1;          // reflective / eqtsymmetric (boundary.c:521-564)
 }
 
 __global__ void __launch_bounds__(128)
@@ -376,7 +376,7 @@ bc_kernel (const __grid_constant__ BcArgs a)
     const int d = f.side >> 1, hi_side = f.side & 1;
     c[d] = bc_source (g, f.type, d, hi_side, c[d]);
     const double x = f.q[gidx (g, c[2], c[1], c[0])];
-    f.q[gidx (g, k, j, i)] = (f.type == 2 ? (double)f.sign*x : x);
+    f.q[gidx (g, k, j, i)] = (f.type == 2 || f.type == 4 ? (double)f.sign*x : x);
     return;
   }
   // normal staggered component in the ghost zones from div B = 0, marching
@@ -408,9 +408,11 @@ bc_kernel (const __grid_constant__ BcArgs a)
     const long long ids = gidx (g, cs[2], cs[1], cs[0]);
     double dB[3] = {0.0, 0.0, 0.0};
     double bp[3] = {0.0, 0.0, 0.0}, bm[3] = {0.0, 0.0, 0.0};
+    const double tsign = (fl.type == 4 ? -1.0 : 1.0);        // EQTSYMMETRIC: the tangential components change sign
     for (int q = 0; q < g.dims; q++){
       const long long idq = (q == d ? id : ids);
       bp[q] = a.Bs[q][idq]; bm[q] = a.Bs[q][idq - st[q]];
+      if (q != d){ bp[q] *= tsign; bm[q] *= tsign; }
       dB[q] = (A[q]*bp[q] - A[q]*bm[q]);
     }
     // sum of the two transverse flux differences in the reference's order

@@ -530,7 +530,8 @@ static int boundary_dim (PlutoGpu *h, int buf, int dim)
     const int side = 2*dim + hs;
     const int type = h->cfg.bc[side];
     if (type == PLUTO_GPU_BC_SHARED) continue;                 // boundary.c:139
-    const bool fill = (type == PLUTO_GPU_BC_OUTFLOW || type == PLUTO_GPU_BC_REFLECTIVE);
+    const bool eqt = (type == PLUTO_GPU_BC_EQTSYMMETRIC);
+    const bool fill = (type == PLUTO_GPU_BC_OUTFLOW || type == PLUTO_GPU_BC_REFLECTIVE || eqt);
     // cell box of this side: ghost layers in `dim`, full extent elsewhere
     int lo[3] = {0, 0, 0}, hi[3] = {g.T[0] - 1, g.T[1] - 1, g.T[2] - 1};
     if (hs == 0) hi[dim] = g.beg[dim] - 1; else lo[dim] = g.end[dim] + 1;
@@ -543,6 +544,7 @@ static int boundary_dim (PlutoGpu *h, int buf, int dim)
       f.q = h->V[buf][nv];
       for (int d = 0; d < 3; d++){ f.lo[d] = lo[d]; f.hi[d] = hi[d]; }
       f.sign = (nv == 1 + dim || nv == 4 + dim) ? -1 : 1;     // FlipSign, boundary.c:318-436
+      if (eqt && nv >= 4 && nv <= 6) f.sign = (nv == 4 + dim) ? 1 : -1;        // EQTSYMMETRIC: Bn -> Bn, Bt -> -Bt (:423-427)
       f.side = side; f.type = type;
     }
     for (int s = 0; s < g.dims; s++){
@@ -558,7 +560,7 @@ static int boundary_dim (PlutoGpu *h, int buf, int dim)
       // (boundary.c:157-164 with the sides in sequence).  Both sides share a launch here,
       // so the high-side box leaves that face out.
       if (!(s == dim && hs == 1)) f.lo[s] -= 1;
-      f.sign = 1;
+      f.sign = eqt ? -1 : 1;                                  // tangential staggered components
       f.side = side; f.type = type;
     }
     if (fill){

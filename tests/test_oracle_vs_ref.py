@@ -72,6 +72,13 @@ CASES = [
                                      grav=(0.02, -0.03, 0.0), potential=True), 6),
     ("blast3d_ctu_bp", RefConfig(problem="blast", dims=3, n=(10, 12, 8), first_dt=3e-4, cfl=0.3, tstep="hancock",
                                  grav=(0.05, -0.03, 0.04), potential=True), 6),
+    # EQTSYMMETRIC boundaries (boundary.c:333-336, 423-427), the condition of the shipped Blast #02
+    ("blast3d_eqtsym", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3,
+                                 bc=("reflective", "outflow", "eqtsymmetric", "outflow", "eqtsymmetric", "reflective"),
+                                 blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=30.0, RADIUS=0.3)), 10),
+    ("blast2d_ctu_eqtsym", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock",
+                                     bc=("eqtsymmetric", "eqtsymmetric", "outflow", "eqtsymmetric", "outflow", "outflow"),
+                                     blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3)), 12),
     ("blast3d_bfp", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(0.05, -0.03, 0.04), potential=True,
                               vector_too=True), 6),
     ("blast2d_ctu_bfp", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock", grav=(0.05, -0.03, 0.0),

@@ -102,6 +102,13 @@ CASES = {
     "blast3d_bp": (RefConfig(problem="blast", dims=3, n=(16, 12, 8), first_dt=6e-4, cfl=0.3, grav=(0.05, -0.03, 0.04), potential=True), 12),
     "blast2d_ctu_bp": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="hancock",
                                  grav=(0.05, -0.03, 0.0), potential=True), 20),
+    # EQTSYMMETRIC boundaries (the condition of the shipped Blast #02), mixed with reflective and outflow sides
+    "blast3d_eqtsym": (RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=6e-4, cfl=0.3,
+                                 bc=("reflective", "outflow", "eqtsymmetric", "outflow", "eqtsymmetric", "reflective"),
+                                 blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=30.0, RADIUS=0.3)), 25),
+    "blast2d_ctu_eqtsym": (RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=4e-4, cfl=0.4, tstep="hancock",
+                                     bc=("eqtsymmetric", "eqtsymmetric", "outflow", "eqtsymmetric", "outflow", "outflow"),
+                                     blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3)), 30),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
