@@ -19,6 +19,16 @@
 #pragma once
 #include <math.h>
 
+// PG_FAST selects the FAST kernel STRUCTURE (fused x1+x2 sweep, stage-2 U rebuilt from V);
+// PG_FAST_MATH the FAST ARITHMETIC of this file (MUFU-seeded division / square root, FMA forms,
+// the flux-form HLLD).  The Roe translation units (PG_SOLVER == 2) keep the reference's IEEE
+// arithmetic: Roe's eigenvector normalisation switches on comparisons that round-off decides
+// where the transverse field vanishes exactly (roe.c:336-364, see riemann_roe), so the states
+// and averages that feed them must be the reference's own, bit for bit.
+#if defined(PG_FAST) && !(defined(PG_SOLVER) && PG_SOLVER == 2)
+#define PG_FAST_MATH 1
+#endif
+
 namespace PG_NS {
 
 enum { RHO = 0, VX1 = 1, VX2 = 2, VX3 = 3, BX1 = 4, BX2 = 5, BX3 = 6, PRS = 7, NV = 8 };
@@ -52,22 +62,22 @@ __device__ __forceinline__ double minmod (double a, double b)
 
 // ---------------------------------------------------------------------------
 //  division and square root.  EXACT: IEEE (div.rn.f64 / sqrt.rn.f64), the
-//  reference's results bit for bit.  FAST (PG_FAST): branch-free MUFU seed
-//  (rcp/rsqrt.approx.ftz.f64, >= 20 good bits) + two Newton steps in FMA form,
-//  accurate to a few ulp, no slow-path branch -> the scheduler can interleave
+//  reference's results bit for bit.  FAST: branch-free MUFU seed
+//  (rcp/rsqrt.approx.ftz.f64, >= 20 good bits) + one cubically convergent step in
+//  FMA form, accurate to 1-2 ulp, no slow-path branch -> the scheduler can interleave
 //  independent chains.  Arguments are physical magnitudes far from the
 //  subnormal / overflow range.
+//    fq_*  the FAST family itself (exists in every PG_FAST unit),
+//    pg_*  what the kernels call: fq_* with PG_FAST_MATH, IEEE otherwise,
+//    pq_*  fq_* in every PG_FAST unit, IEEE otherwise: the part of the Roe solver
+//          downstream of its eigenvector switches.
 // ---------------------------------------------------------------------------
 #if defined(PG_FAST) && defined(PG_HOST_EMU)
-// host build of the FAST algebra (tools/host_hlld_check.cpp): exact division and
-// sqrt stand in for the MUFU-seeded iterations
-__device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
-__device__ __forceinline__ double pg_div (double a, double b) { return a/b; }
-__device__ __forceinline__ double pg_sqrt (double x) { return x > 0.0 ? sqrt (x) : 0.0; }
-__device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs) { s = sqrt (x); rs = 1.0/s; }
-__device__ __forceinline__ double pg_sqrt_pos (double x) { return sqrt (x); }
+// host build of the FAST algebra (tools/host_hlld_check.cpp, tests/emu): the quotient is formed
+// as a*(1/b) and the root as x*(1/sqrt(x)) -- two roundings, the 1-2 ulp of the device iterations
+__device__ __forceinline__ double fq_rcp (double b) { return 1.0/b; }
+__device__ __forceinline__ double fq_rsqrt (double x) { return 1.0/sqrt (x); }
 __device__ __forceinline__ float pg_sqrtf (float x) { return sqrtf (x); }
-__device__ __forceinline__ double pg_sqrt_acc (double x) { return x > 0.0 ? sqrt (x) : 0.0; }
 #elif defined(PG_FAST)
 __device__ __forceinline__ float pg_sqrtf (float x)          // no slow-path call
 {
@@ -75,7 +85,7 @@ __device__ __forceinline__ float pg_sqrtf (float x)          // no slow-path cal
   asm ("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ double pg_rcp (double b)
+__device__ __forceinline__ double fq_rcp (double b)
 {
   // MUFU seed (>= 20 good bits), then ONE cubically convergent step:
   // r (1 + e + e^2), e = 1 - b r  ->  relative error e^3 <= 2^-60
@@ -84,40 +94,44 @@ __device__ __forceinline__ double pg_rcp (double b)
   const double e = fma (-b, r, 1.0);
   return fma (r, fma (e, e, e), r);
 }
-__device__ __forceinline__ double pg_div (double a, double b) { return a*pg_rcp (b); }
 // 1/sqrt(x): MUFU seed, then one cubically convergent step
 // y (1 + e/2 + 3 e^2/8), e = 1 - x y^2  ->  relative error ~ (5/16) e^3 <= 2^-60
-__device__ __forceinline__ double pg_rsqrt (double x)
+__device__ __forceinline__ double fq_rsqrt (double x)
 {
   double y;
   asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double e = fma (-x*y, y, 1.0);
   return fma (y*e, fma (0.375, e, 0.5), y);
 }
-__device__ __forceinline__ double pg_sqrt_pos (double x) { return x*pg_rsqrt (x); }    // x > 0 guaranteed
-__device__ __forceinline__ double pg_sqrt (double x)
+#endif
+#ifdef PG_FAST
+__device__ __forceinline__ double fq_div (double a, double b) { return a*fq_rcp (b); }
+__device__ __forceinline__ double fq_sqrt (double x)
 {
-  const double s = x*pg_rsqrt (x);
+  const double s = x*fq_rsqrt (x);
   return x > 0.0 ? s : 0.0;
 }
+__device__ __forceinline__ double pq_rcp (double b) { return fq_rcp (b); }
+__device__ __forceinline__ double pq_div (double a, double b) { return fq_div (a, b); }
+__device__ __forceinline__ double pq_sqrt (double x) { return fq_sqrt (x); }
+#else
+__device__ __forceinline__ double pq_rcp (double b) { return 1.0/b; }
+__device__ __forceinline__ double pq_div (double a, double b) { return a/b; }
+__device__ __forceinline__ double pq_sqrt (double x) { return sqrt (x); }
+#endif
+#ifdef PG_FAST_MATH
+__device__ __forceinline__ double pg_rcp (double b) { return fq_rcp (b); }
+__device__ __forceinline__ double pg_div (double a, double b) { return fq_div (a, b); }
+__device__ __forceinline__ double pg_rsqrt (double x) { return fq_rsqrt (x); }
+__device__ __forceinline__ double pg_sqrt (double x) { return fq_sqrt (x); }
+__device__ __forceinline__ double pg_sqrt_pos (double x) { return x*fq_rsqrt (x); }    // x > 0 guaranteed
 // sqrt(x) and 1/sqrt(x) together
 __device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs)
 {
-  rs = pg_rsqrt (x);
+  rs = fq_rsqrt (x);
   s = x*rs;
 }
-// square root with a final correction step (correctly rounded but for rare ties): the Roe
-// solver compares square roots for equality (roe.c:336-364), which a 1-2 ulp result upsets
-__device__ __forceinline__ double pg_sqrt_acc (double x)
-{
-  const double y = pg_rsqrt (x);
-  double s = x*y;
-  const double r = fma (-s, s, x);
-  s = fma (r, 0.5*y, s);
-  return x > 0.0 ? s : 0.0;
-}
 #else
-__device__ __forceinline__ double pg_sqrt_acc (double x) { return sqrt (x); }
 __device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
 __device__ __forceinline__ double pg_div (double a, double b) { return a/b; }
 __device__ __forceinline__ double pg_sqrt (double x) { return sqrt (x); }
@@ -176,7 +190,7 @@ __device__ __forceinline__ void plm_zone_single (int lim, const double *v, const
 }
 
 // vp = v + dvl/2, vm = v - dvl/2 for one zone from its two one-sided differences
-#ifdef PG_FAST
+#ifdef PG_FAST_MATH
 // FAST: the HALF slope h = dvl/2 is formed directly (the factors 2 and 1/2 of the
 // van Leer and MC limiters cancel against it; scaling by powers of two is exact,
 // so h is the reference's dvl*0.5 up to the rounding of the division)
@@ -298,7 +312,7 @@ __device__ __forceinline__ void prim_to_cons (const Phys &ph, const double *v, d
     kinb2 = v[RHO]*kinb2 + v[BX1]*v[BX1] + v[BX2]*v[BX2];
   }
   kinb2 *= 0.5;
-#ifdef PG_FAST
+#ifdef PG_FAST_MATH
   u[ENG] = kinb2 + v[PRS]*ph.igmm1;
 #else
   u[ENG] = kinb2 + pg_div (v[PRS], ph.gmm1);
@@ -442,7 +456,7 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
   }
 }
 
-#ifdef PG_FAST
+#ifdef PG_FAST_MATH
 // ---------------------------------------------------------------------------
 //  FAST HLLD.  Same five-wave solver, same wave-speed estimates, same region
 //  switches as hlld.c:98-427, evaluated in the form that needs the fewest FP64
@@ -948,9 +962,15 @@ __device__ __forceinline__ void riemann_hlld (const Phys &ph, const double *vL, 
   }
 }
 
-#endif   // PG_FAST
+#endif   // PG_FAST_MATH
 
-// Roe: returns false when a2 < 0 (the reference aborts, roe.c:300-306)
+// Roe: returns false when a2 < 0 (the reference aborts, roe.c:300-306).
+// The eigenvector normalisation switches on `cf == cs`, `a <= cs`, `cf <= a` (roe.c:336-364).  Where the transverse
+// field vanishes exactly (a rotor or blast at t = 0) cf2 equals a2 or b2 up to the last rounding, round-off decides the
+// branch and the branches differ by sqrt(ulp) ~ 1e-8 in alpha_s / alpha_f: everything UPSTREAM of the switches (the
+// interface states, the Roe averages, a2, cf2, cs2 and their roots) is therefore evaluated in the reference's IEEE
+// arithmetic and operation order in every build (pg_* are IEEE in the Roe units, -fmad=false); what follows the
+// switches is smooth in its inputs and uses the FAST division / square root / FMA (pq_*) in the FAST build.
 template <int DIR, int NC>
 __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, const double *vR,
                                              const double *uL, const double *uR,
@@ -986,12 +1006,12 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     dU[nv] = uR[nv] - uL[nv];
   }
 
-  sqr_rho_L = pg_sqrt_acc (vL[RHO]);
-  sqr_rho_R = pg_sqrt_acc (vR[RHO]);
+  sqr_rho_L = pg_sqrt (vL[RHO]);
+  sqr_rho_R = pg_sqrt (vR[RHO]);
   sl = pg_div (sqr_rho_L, sqr_rho_L + sqr_rho_R);
   sr = pg_div (sqr_rho_R, sqr_rho_L + sqr_rho_R);
   rho = sr*vL[RHO] + sl*vR[RHO];
-  sqrt_rho = pg_sqrt_acc (rho);
+  sqrt_rho = pg_sqrt (rho);
 
   u = sl*vL[VXn] + sr*vR[VXn];
   v = sl*vL[VXt] + sr*vR[VXt];
@@ -1007,7 +1027,7 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
 
   if (NC == 3) bt2 = 0.0 + by*by + bz*bz; else bt2 = 0.0 + by*by;
   b2    = bx*bx + bt2;
-  Btmag = pg_sqrt_acc (bt2*rho);
+  Btmag = pg_sqrt (bt2*rho);
 
   if (NC == 3) X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt] + dV[BXb]*dV[BXb];
   else         X = dV[BXn]*dV[BXn] + dV[BXt]*dV[BXt];
@@ -1035,15 +1055,15 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   scrh = a2 - b2;
   ca2  = bx*bx;
   scrh = scrh*scrh + 4.0*bt2*a2;
-  scrh = pg_sqrt_acc (scrh);
+  scrh = pg_sqrt (scrh);
 
   cf2 = 0.5*(a2 + b2 + scrh);
   cs2 = pg_div (a2*ca2, cf2);
 
-  cf = pg_sqrt_acc (cf2);
-  cs = pg_sqrt_acc (cs2);
-  ca = pg_sqrt_acc (ca2);
-  a  = pg_sqrt_acc (a2);
+  cf = pg_sqrt (cf2);
+  cs = pg_sqrt (cs2);
+  ca = pg_sqrt (ca2);
+  a  = pg_sqrt (a2);
 
   if (cf == cs){
     alpha_f = 1.0; alpha_s = 0.0;
@@ -1052,17 +1072,17 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   }else if (cf <= a){
     alpha_f = 1.0; alpha_s = 0.0;
   }else{
-    scrh    = pg_rcp (cf2 - cs2);
+    scrh    = pq_rcp (cf2 - cs2);
     alpha_f = (a2  - cs2)*scrh;
     alpha_s = (cf2 -  a2)*scrh;
     alpha_f = maxv(0.0, alpha_f);
     alpha_s = maxv(0.0, alpha_s);
-    alpha_f = pg_sqrt_acc (alpha_f);
-    alpha_s = pg_sqrt_acc (alpha_s);
+    alpha_f = pq_sqrt (alpha_f);
+    alpha_s = pq_sqrt (alpha_s);
   }
 
   if (Btmag > 1.e-9){
-    if (NC == 3){ beta_y = pg_div (By, Btmag); beta_z = pg_div (Bz, Btmag); }
+    if (NC == 3){ beta_y = pq_div (By, Btmag); beta_z = pq_div (Bz, Btmag); }
     else          beta_y = (By >= 0.0 ? 1.0 : -1.0);
   }else{
     if (NC == 3) beta_z = beta_y = sqrt_1_2;
@@ -1087,13 +1107,13 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[MXn][k] = alpha_f*lambda[k];
   Rc[MXt][k] = alpha_f*v + scrh*beta_y;
   if (NC == 3) Rc[MXb][k] = alpha_f*w + scrh*beta_z;
-  Rc[BXt][k] = pg_div (alpha_s*a*beta_y, sqrt_rho);
-  if (NC == 3) Rc[BXb][k] = pg_div (alpha_s*a*beta_z, sqrt_rho);
+  Rc[BXt][k] = pq_div (alpha_s*a*beta_y, sqrt_rho);
+  if (NC == 3) Rc[BXb][k] = pq_div (alpha_s*a*beta_z, sqrt_rho);
   Rc[ENG][k] =   alpha_f*(Hgas - u*cf) + scrh*beta_v
-               + pg_div (alpha_s*a*Btmag, sqrt_rho);
+               + pq_div (alpha_s*a*Btmag, sqrt_rho);
   eta[k] =   alpha_f*(X*dV[RHO] + dV[PRS]) + rho*scrh*beta_dv
            - rho*alpha_f*cf*dV[VXn]        + sqrt_rho*alpha_s*a*beta_dB;
-  eta[k] *= pg_div (0.5, a2);
+  eta[k] *= pq_div (0.5, a2);
 
   // ---- fast wave u + cf ----
   k = KFASTP;
@@ -1105,10 +1125,10 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[BXt][k] = Rc[BXt][KFASTM];
   if (NC == 3) Rc[BXb][k] = Rc[BXb][KFASTM];
   Rc[ENG][k] =   alpha_f*(Hgas + u*cf) - scrh*beta_v
-               + pg_div (alpha_s*a*Btmag, sqrt_rho);
+               + pq_div (alpha_s*a*Btmag, sqrt_rho);
   eta[k] =   alpha_f*(X*dV[RHO] + dV[PRS]) - rho*scrh*beta_dv
            + rho*alpha_f*cf*dV[VXn]        + sqrt_rho*alpha_s*a*beta_dB;
-  eta[k] *= pg_div (0.5, a2);
+  eta[k] *= pq_div (0.5, a2);
 
   // ---- entropy wave ----
   k = KENTRP;
@@ -1117,8 +1137,8 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[MXn][k] = u;
   Rc[MXt][k] = v;
   if (NC == 3) Rc[MXb][k] = w;
-  Rc[ENG][k] = 0.5*vel2 + pg_div (ph.gamma - 2.0, g1)*X;
-  eta[k] = pg_div ((a2 - X)*dV[RHO] - dV[PRS], a2);
+  Rc[ENG][k] = 0.5*vel2 + pq_div (ph.gamma - 2.0, g1)*X;
+  eta[k] = pq_div ((a2 - X)*dV[RHO] - dV[PRS], a2);
 
   // ---- div.B wave: no jump with CT ----
   k = KDIVB;
@@ -1133,13 +1153,13 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[MXn][k] = alpha_s*lambda[k];
   Rc[MXt][k] = alpha_s*v - scrh*beta_y;
   if (NC == 3) Rc[MXb][k] = alpha_s*w - scrh*beta_z;
-  Rc[BXt][k] = pg_div (- alpha_f*a*beta_y, sqrt_rho);
-  if (NC == 3) Rc[BXb][k] = pg_div (- alpha_f*a*beta_z, sqrt_rho);
+  Rc[BXt][k] = pq_div (- alpha_f*a*beta_y, sqrt_rho);
+  if (NC == 3) Rc[BXb][k] = pq_div (- alpha_f*a*beta_z, sqrt_rho);
   Rc[ENG][k] =   alpha_s*(Hgas - u*cs) - scrh*beta_v
-               - pg_div (alpha_f*a*Btmag, sqrt_rho);
+               - pq_div (alpha_f*a*Btmag, sqrt_rho);
   eta[k] =   alpha_s*(X*dV[RHO] + dV[PRS]) - rho*scrh*beta_dv
            - rho*alpha_s*cs*dV[VXn]        - sqrt_rho*alpha_f*a*beta_dB;
-  eta[k] *= pg_div (0.5, a2);
+  eta[k] *= pq_div (0.5, a2);
 
   // ---- slow wave u + cs ----
   k = KSLOWP;
@@ -1151,10 +1171,10 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
   Rc[BXt][k] = Rc[BXt][KSLOWM];
   if (NC == 3) Rc[BXb][k] = Rc[BXb][KSLOWM];
   Rc[ENG][k] =   alpha_s*(Hgas + u*cs) + scrh*beta_v
-               - pg_div (alpha_f*a*Btmag, sqrt_rho);
+               - pq_div (alpha_f*a*Btmag, sqrt_rho);
   eta[k] =   alpha_s*(X*dV[RHO] + dV[PRS]) + rho*scrh*beta_dv
            + rho*alpha_s*cs*dV[VXn]        - sqrt_rho*alpha_f*a*beta_dB;
-  eta[k] *= pg_div (0.5, a2);
+  eta[k] *= pq_div (0.5, a2);
 
   if (NC == 3){
     // ---- Alfven wave u - ca ----
@@ -1166,7 +1186,7 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     Rc[BXb][k] =   sBx*sqrt_rho*beta_y;
     Rc[ENG][k] = - rho*(v*beta_z - w*beta_y);
     eta[k] = + beta_y*dV[VXb]               - beta_z*dV[VXt]
-             + pg_div (sBx, sqrt_rho)*(beta_y*dV[BXb] - beta_z*dV[BXt]);
+             + pq_div (sBx, sqrt_rho)*(beta_y*dV[BXb] - beta_z*dV[BXt]);
     eta[k] *= 0.5;
 
     // ---- Alfven wave u + ca ----
@@ -1178,27 +1198,36 @@ __device__ __forceinline__ bool riemann_roe (const Phys &ph, const double *vL, c
     Rc[BXb][k] =   Rc[BXb][KALFVM];
     Rc[ENG][k] = - Rc[ENG][KALFVM];
     eta[k] = - beta_y*dV[VXb]               + beta_z*dV[VXt]
-             + pg_div (sBx, sqrt_rho)*(beta_y*dV[BXb] - beta_z*dV[BXt]);
+             + pq_div (sBx, sqrt_rho)*(beta_y*dV[BXb] - beta_z*dV[BXt]);
     eta[k] *= 0.5;
   }
 
   cmax = fabs(u) + cf;
-  mach = fabs(pg_div (u, a));
+  mach = fabs(pq_div (u, a));
   store_fan_speeds (pSL, pSR, lambda[KFASTM], lambda[KFASTP]);      // roe.c:681-682
   const int nw = (NC == 3 ? 8 : 6);
   PG_UNROLL for (int kk = 0; kk < NW; kk++) alambda[kk] = fabs(lambda[kk]);
 
   // entropy fix (roe.c:623-640)
-  if (alambda[KFASTM] < 0.5*delta) alambda[KFASTM] = pg_div (lambda[KFASTM]*lambda[KFASTM], delta) + 0.25*delta;
-  if (alambda[KFASTP] < 0.5*delta) alambda[KFASTP] = pg_div (lambda[KFASTP]*lambda[KFASTP], delta) + 0.25*delta;
-  if (alambda[KSLOWM] < 0.5*delta) alambda[KSLOWM] = pg_div (lambda[KSLOWM]*lambda[KSLOWM], delta) + 0.25*delta;
-  if (alambda[KSLOWP] < 0.5*delta) alambda[KSLOWP] = pg_div (lambda[KSLOWP]*lambda[KSLOWP], delta) + 0.25*delta;
+  if (alambda[KFASTM] < 0.5*delta) alambda[KFASTM] = pq_div (lambda[KFASTM]*lambda[KFASTM], delta) + 0.25*delta;
+  if (alambda[KFASTP] < 0.5*delta) alambda[KFASTP] = pq_div (lambda[KFASTP]*lambda[KFASTP], delta) + 0.25*delta;
+  if (alambda[KSLOWM] < 0.5*delta) alambda[KSLOWM] = pq_div (lambda[KSLOWM]*lambda[KSLOWM], delta) + 0.25*delta;
+  if (alambda[KSLOWP] < 0.5*delta) alambda[KSLOWP] = pq_div (lambda[KSLOWP]*lambda[KSLOWP], delta) + 0.25*delta;
 
+#ifdef PG_FAST
+  PG_UNROLL for (int kk = 0; kk < NW; kk++) alambda[kk] *= eta[kk];
+  PG_FOR_NV(nv){
+    scrh = 0.0;
+    PG_UNROLL for (int kk = 0; kk < NW; kk++) if (kk < nw) scrh = fma (alambda[kk], Rc[nv][kk], scrh);
+    flux[nv] = 0.5*(fL[nv] + fR[nv] - scrh);
+  }
+#else
   PG_FOR_NV(nv){
     scrh = 0.0;
     PG_UNROLL for (int kk = 0; kk < NW; kk++) if (kk < nw) scrh += alambda[kk]*eta[kk]*Rc[nv][kk];
     flux[nv] = 0.5*(fL[nv] + fR[nv] - scrh);
   }
+#endif
   press = 0.5*(pL + pR);
   return ok;
 }
@@ -1222,7 +1251,7 @@ __device__ __forceinline__ bool riemann (const Phys &ph, const double *vL, const
                                          double *flux, double &press, double &cmax, double &mach,
                                          double *pSL = nullptr, double *pSR = nullptr)
 {
-#ifdef PG_FAST
+#ifdef PG_FAST_MATH
   if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, flux, press, cmax, mach, pSL, pSR); return true; }
 #else
   if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }

@@ -69,12 +69,15 @@ def build(verbose: bool = False) -> str:
     fast = common + ["-mfma", "-ffp-contract=fast", "-DPG_NS=pg_fast", "-DPG_FAST=1", "-DPG_HOST_EMU=1"]
     jobs = [(common + ["-ffp-contract=off"], "pluto_gpu.cu", "pluto_gpu.o"),
             (exact, "ct_kernels.cu", "ct_exact.o"), (fast, "ct_kernels.cu", "ct_fast.o")]
+    # the Roe units (solver 2) of the FAST library keep IEEE arithmetic (pluto_b200/csrc/Makefile: -fmad=false)
+    fast_roe = common + ["-ffp-contract=off", "-DPG_NS=pg_fast", "-DPG_FAST=1", "-DPG_HOST_EMU=1"]
     for s in range(3):
+        fs = fast_roe if s == 2 else fast
         jobs.append((exact + [f"-DPG_SOLVER={s}"], "sweep_inst.cu", f"sweep_exact_{s}.o"))
-        jobs.append((fast + [f"-DPG_SOLVER={s}"], "sweep_inst.cu", f"sweep_fast_{s}.o"))
+        jobs.append((fs + [f"-DPG_SOLVER={s}"], "sweep_inst.cu", f"sweep_fast_{s}.o"))
         if os.path.exists(os.path.join(CSRC, "ctu_inst.cu")):
             jobs.append((exact + [f"-DPG_SOLVER={s}"], "ctu_inst.cu", f"ctu_exact_{s}.o"))
-            jobs.append((fast + [f"-DPG_SOLVER={s}"], "ctu_inst.cu", f"ctu_fast_{s}.o"))
+            jobs.append((fs + [f"-DPG_SOLVER={s}"], "ctu_inst.cu", f"ctu_fast_{s}.o"))
     objs = []
 
     def cc(job):

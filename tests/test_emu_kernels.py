@@ -17,7 +17,6 @@ import pytest
 from tests.util import Golden, golden_names, divb_max, rel_l1, apply_force_field, TOL_ONE_STEP, TOL_100_STEPS
 
 SHORT = [n for n in golden_names() if not n.endswith("_100")]
-DEGENERATE_ROE = {"rotor2d_ppm_roe": (1e-9, 1e-8)}        # see tests/test_gpu_parity.py
 
 
 @pytest.fixture(scope="module")
@@ -56,7 +55,7 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
-               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf"]
+               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf", "blast2d_ctu_bfx_roe"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)
@@ -65,7 +64,7 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
     s = _stepper(g, "fast", emu_lib)
     s.set_state(g.states[0])
     dt = g.first_dt
-    tol1, tolN = DEGENERATE_ROE.get(name, (TOL_ONE_STEP, TOL_100_STEPS))
+    tol1, tolN = TOL_ONE_STEP, TOL_100_STEPS
     for step in range(1, g.nsteps + 1):
         info = s.advance(dt)
         dt = s.next_dt(info.inv_dt_hyp, g.cfl, g.cfl_max_var, dt)

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Small cases of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
+
+    compute-sanitizer --tool racecheck python tools/sanitize_cases.py [family ...]
+
+families: rk (fused x1+x2 sweep, x3 march, CT, final, bc), exact (one kernel per direction), ppm_roe, hll_uct_hll,
+ctu, bc (outflow / reflective / eqtsymmetric fills incl. div B), halo (two blocks in one process: pack / unpack tables),
+io (dbl writer / analysis).  Launches run without graph capture so that a report names the kernel.
+"""
+import os
+import sys
+
+os.environ["PLUTO_GPU_NO_GRAPH"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np                                   # noqa: E402
+from pluto_b200 import GpuStepper, problems          # noqa: E402
+
+
+def run(problem, dims, n, steps=2, dt=1e-4, **kw):
+    st0, meta = problems.make(problem, dims, n)
+    bc = kw.pop("bc", meta["bc"])
+    s = GpuStepper(dims, n, meta["dx"], bc=bc, gamma=meta["gamma"], **kw)
+    s.set_state(st0)
+    for _ in range(steps):
+        info = s.advance(dt)
+        dt = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+    st = s.get_state()
+    assert all(np.isfinite(v).all() for v in st.values())
+    s.close()
+
+
+def fam_rk():
+    run("blast", 3, (40, 24, 20), arith="fast")
+    run("ot", 2, (48, 40, 1), arith="fast", dt=1e-3)
+    run("turb", 3, (24, 24, 24), arith="fast", rk_order=3, dt=1e-3)
+
+
+def fam_exact():
+    run("blast", 3, (40, 24, 20), arith="exact")
+    run("ot", 2, (48, 40, 1), arith="exact", dt=1e-3)
+
+
+def fam_ppm_roe():
+    run("rotor", 2, (48, 40, 1), arith="fast", recon="ppm", solver="roe", dt=1e-4)
+    run("ot", 3, (24, 20, 16), arith="fast", recon="ppm", solver="roe", dt=1e-3)
+    run("ot", 3, (24, 20, 16), arith="exact", recon="ppm", solver="roe", dt=1e-3)
+
+
+def fam_hll_uct_hll():
+    run("turb", 3, (24, 20, 16), arith="fast", solver="hll", emf="uct_hll", dt=1e-3)
+    run("blast", 3, (24, 20, 16), arith="fast", flatten=True, emf="uct0")
+    run("blast", 3, (24, 20, 16), arith="fast", en_corr=True, emf="arith", limiter="vl")
+
+
+def fam_ctu():
+    run("blast", 3, (24, 20, 16), arith="fast", ctu=True)
+    run("blast", 3, (24, 20, 16), arith="exact", ctu=True)
+    run("ot", 2, (48, 40, 1), arith="fast", ctu=True, dt=1e-3)
+
+
+def fam_bc():
+    for b in ("outflow", "reflective", "eqtsymmetric"):
+        run("blast", 3, (20, 16, 24), arith="fast", bc=(b,) * 6)
+        run("blast", 2, (32, 24, 1), arith="exact", bc=(b,) * 4 + ("outflow",) * 2)
+
+
+def fam_halo():
+    from pluto_b200.parallel import BlockLayout, LocalMultiBlock
+    for problem, dims, n in (("turb", 3, (24, 20, 16)), ("blast", 3, (24, 20, 16))):
+        st0, meta = problems.make(problem, dims, n)
+        lay = BlockLayout.strong(dims, n, 4, periodic=meta["bc"][0] == "periodic")
+        for split in (False, True):
+            many = LocalMultiBlock(lay, meta["dx"], meta["bc"], gamma=meta["gamma"], arith="fast", exchange="all", split=split)
+            many.set_state(st0)
+            many.advance(1e-4)
+            many.advance(1e-4)
+            many.get_state()
+            for blk in many.blocks:
+                blk.close()
+
+
+def fam_io():
+    import tempfile
+    st0, meta = problems.make("ot", 3, (24, 20, 16))
+    s = GpuStepper(3, (24, 20, 16), meta["dx"], bc=meta["bc"], gamma=meta["gamma"], arith="fast")
+    s.set_state(st0)
+    s.advance(1e-3)
+    with tempfile.TemporaryDirectory() as d:
+        if hasattr(s, "write_dbl"):
+            s.write_dbl(d, 0, 0.0, 1e-3, 1)
+            s.read_dbl(os.path.join(d, "data.0000.dbl"))
+    if hasattr(s, "analysis"):
+        s.analysis()
+    s.close()
+
+
+FAMILIES = {"rk": fam_rk, "exact": fam_exact, "ppm_roe": fam_ppm_roe, "hll_uct_hll": fam_hll_uct_hll, "ctu": fam_ctu,
+            "bc": fam_bc, "halo": fam_halo, "io": fam_io}
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(FAMILIES)):
+        FAMILIES[name]()
+        print("family", name, "done", flush=True)
