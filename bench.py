@@ -225,7 +225,13 @@ def main():
     ap.add_argument("--host-dt", action="store_true", help="host-driven NextTimeStep (a device round trip per step)")
     ap.add_argument("--time-stepping", default="rk2", choices=["rk2", "hancock"],
                     help="hancock: the corner-transport-upwind step (ctu_step.c) instead of RK2")
+    ap.add_argument("--dev-lib", default=None, help="development only: time a variant build of libpluto_gpu.so; the line "
+                    "carries \"dev_lib\" and is not a bench value")
     args = ap.parse_args()
+    if os.environ.get("PLUTO_GPU_LIB"):
+        # the test suite may point the loader at the kernel interpreter (tests/emu); a measurement never does
+        print("bench.py: PLUTO_GPU_LIB is set -- refusing to time anything but pluto_b200/lib/libpluto_gpu.so", file=sys.stderr)
+        sys.exit(2)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)
@@ -237,6 +243,9 @@ def main():
     import torch.distributed as dist
     from pluto_b200 import problems
     from pluto_b200.parallel import BlockLayout, DistStepper
+    if args.dev_lib:
+        from pluto_b200 import _lib as _pl
+        _pl._lib = _pl.load_library(os.path.abspath(args.dev_lib))
 
     problem, dims, n, recon, solver, cfl, first_dt = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -434,6 +443,8 @@ def main():
         "roofline": roofline, "roofline_fp64": roofline_fp64, "step_roofline": step_roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
+    if args.dev_lib:
+        line["dev_lib"] = args.dev_lib
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

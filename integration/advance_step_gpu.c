@@ -15,19 +15,51 @@
  *     gcc -c -O3 -I. -I$PLUTO_DIR/Src -I<repo>/include advance_step_gpu.c
  *     gcc $(OBJ) advance_step_gpu.o -L<repo>/pluto_b200/lib -lpluto_gpu -lm -o pluto
  *
- * Data ownership: the host owns d->Vc / d->Vs; this shim
- * uploads them, steps on the GPU and downloads the result every call -- the
- * literal AdvanceStep contract, so WriteData/Analysis/Restart keep working
- * with no further hooks.  PLUTO_GPU_ARITH=fast|exact selects the arithmetic.
+ * Data ownership: the host owns d->Vc / d->Vs.  Two modes:
+ *   default             the literal AdvanceStep contract: upload d->Vc, d->Vs, step on the GPU, download the
+ *                       result, every call (PCIe-bound) -- WriteData / Analysis / Restart work with no hooks;
+ *   PLUTO_GPU_RESIDENT=1  the state stays in HBM: uploaded at the first call (after Startup / RestartFromFile),
+ *                       advanced in place by pluto_gpu_advance, and copied back to d->Vc, d->Vs only when the
+ *                       host reads it: PlutoGpuSyncHost(d), called from the two one-line hooks of INTEGRATION.md
+ *                       (WriteData, Src/write_data.c:92, and CheckForAnalysis, Src/main.c:706).  A hook call is a
+ *                       no-op when the host copy is current or the mode is off.
+ * PLUTO_GPU_ARITH=fast|exact selects the arithmetic, PLUTO_GPU_DEVICE=<n> the device ordinal (default 0).
  */
 #include "pluto.h"
 #include "pluto_gpu.h"
 
 static PlutoGpu *gpu = NULL;
-#if BODY_FORCE & VECTOR
-static double gpu_g0[3];
-static int    gpu_g_field = 0;       /* BodyForceVector depends on the position */
+static int gpu_resident = 0;         /* PLUTO_GPU_RESIDENT: the state lives in HBM between calls */
+static int gpu_host_stale = 0;       /* resident mode: d->Vc, d->Vs are older than the device state */
+
+static void StaggeredBase (const Data *d, double **vs1, double **vs2, double **vs3)
+/* contiguous blocks behind the pointer tables (Src/arrays.c:222-330, Src/initialize.c:448-453) */
+{
+  *vs1 = &d->Vs[BX1s][0][0][-1];
+  *vs2 = &d->Vs[BX2s][0][-1][0];
+  *vs3 = NULL;
+#if DIMENSIONS == 3
+  *vs3 = &d->Vs[BX3s][-1][0][0];
 #endif
+}
+
+/* ********************************************************************* */
+void PlutoGpuSyncHost (Data *d)
+/*
+ * Resident mode: bring d->Vc, d->Vs up to date with the device state (interior and ghost zones) if they are
+ * not.  Called by the host wherever it reads the arrays (WriteData, Analysis).
+ *********************************************************************** */
+{
+  double *vs1, *vs2, *vs3;
+  if (gpu == NULL || !gpu_resident || !gpu_host_stale) return;
+  StaggeredBase (d, &vs1, &vs2, &vs3);
+  if (pluto_gpu_download_data (gpu, d->Vc[0][0][0], vs1, vs2, vs3) != 0){
+    print ("! PlutoGpuSyncHost: %s\n", pluto_gpu_last_error());
+    QUIT_PLUTO(1);
+  }
+  gpu_host_stale = 0;
+  print ("> PlutoGpuSyncHost: state copied from the device at step %ld\n", g_stepNumber);
+}
 
 static int BoundaryCode (int type)
 {
@@ -58,6 +90,15 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     || HALL_MHD != NO || AMBIPOLAR_DIFFUSION != NO || ROTATING_FRAME != NO || COOLING != NO || FORCED_TURB != NO || NTRACER != 0 \
     || DIMENSIONAL_SPLITTING != NO || (defined SHEARINGBOX) || (defined FARGO) || (defined PARTICLES)
   #error "libpluto_gpu covers the ideal-MHD step only: no background field, entropy switch, diffusion terms, Hall / ambipolar, rotating frame, cooling, forced turbulence, tracers, dimensional splitting, shearing box, FARGO, particles"
+#endif
+#if TIME_STEPPING != RK2 && TIME_STEPPING != RK3 && TIME_STEPPING != HANCOCK
+  #error "libpluto_gpu: TIME_STEPPING must be RK2, RK3 or HANCOCK (EULER and CHARACTERISTIC_TRACING are not available on the GPU)"
+#endif
+#if INTERNAL_BOUNDARY == YES
+  #error "libpluto_gpu: INTERNAL_BOUNDARY YES is not available (UserDefBoundary(d, NULL, 0, grid) / InternalBoundaryReset are not called on the GPU)"
+#endif
+#if UPDATE_VECTOR_POTENTIAL == YES
+  #error "libpluto_gpu: UPDATE_VECTOR_POTENTIAL YES is not available (d->Ax1..3 are not advanced on the GPU)"
 #endif
 #if CHAR_LIMITING == YES || LIMITER == FOURTH_ORDER_LIM \
     || (SHOCK_FLATTENING != NO && (SHOCK_FLATTENING != MULTID || RECONSTRUCTION != LINEAR))
@@ -99,28 +140,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     c.body_force |= 2;                                     /* tabulated after the creation */
 #endif
 #if BODY_FORCE & VECTOR
-    {
-      /* BodyForceVector (init.c) is sampled at the corners and the centre of the block: the same vector everywhere is
-         passed as the uniform acceleration of the configuration; otherwise it is tabulated per zone after the creation
-         (pluto_gpu_set_body_force).  The force must be static and must not depend on the state. */
-      double g1[3], *v0;
-      int q, kk, jj, ii, ks[3], js[3], is[3];
-      is[0] = IBEG; is[1] = (IBEG + IEND)/2; is[2] = IEND;
-      js[0] = JBEG; js[1] = (JBEG + JEND)/2; js[2] = JEND;
-      ks[0] = KBEG; ks[1] = (KBEG + KEND)/2; ks[2] = KEND;
-      v0 = (double *)malloc (NVAR*sizeof(double));
-      for (q = 0; q < NVAR; q++) v0[q] = d->Vc[q][KBEG][JBEG][IBEG];
-      gpu_g0[0] = gpu_g0[1] = gpu_g0[2] = 0.0;
-      BodyForceVector (v0, gpu_g0, grid->x[IDIR][IBEG], grid->x[JDIR][JBEG], grid->x[KDIR][KBEG]);
-      for (kk = 0; kk < 3; kk++) for (jj = 0; jj < 3; jj++) for (ii = 0; ii < 3; ii++){
-        g1[0] = g1[1] = g1[2] = 0.0;
-        BodyForceVector (v0, g1, grid->x[IDIR][is[ii]], grid->x[JDIR][js[jj]], grid->x[KDIR][ks[kk]]);
-        for (q = 0; q < DIMENSIONS; q++) gpu_g_field |= (g1[q] != gpu_g0[q]);
-      }
-      free (v0);
-      c.body_force |= 1;
-      c.grav[0] = gpu_g0[0]; c.grav[1] = gpu_g0[1]; c.grav[2] = gpu_g0[2];
-    }
+    c.body_force |= 1;                                     /* tabulated per zone after the creation */
 #endif
     c.emf_average = (CT_EMF_AVERAGE == ARITHMETIC ? PLUTO_GPU_EMF_ARITHMETIC :
                      CT_EMF_AVERAGE == UCT0 ? PLUTO_GPU_EMF_UCT0 :
@@ -128,10 +148,20 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     for (idim = 0; idim < DIMENSIONS; idim++){
       c.bc[2*idim]     = BoundaryCode (grid->lbound[idim]);      /* boundary.c:133-135 */
       c.bc[2*idim + 1] = BoundaryCode (grid->rbound[idim]);
-      c.dx[idim] = grid->dx[idim][grid->lbeg[idim]];             /* uniform grid */
+      c.dx[idim] = grid->dx[idim][grid->lbeg[idim]];             /* uniform grid: set_grid.c:400 gives every zone */
+      {                                                          /* of a uniform patch the same dx, bit for bit    */
+        int ii;
+        for (ii = 0; ii < grid->np_tot[idim]; ii++) if (grid->dx[idim][ii] != c.dx[idim]){
+          print ("! AdvanceStep(gpu): the grid is not uniform in direction %d (dx[%d] = %12.6e, dx[%d] = %12.6e);\n"
+                 "  stretched, logarithmic and multi-patch grids are not available on the GPU\n",
+                 idim, grid->lbeg[idim], c.dx[idim], ii, grid->dx[idim][ii]);
+          QUIT_PLUTO(1);
+        }
+      }
     }
     c.arith    = (arith != NULL && !strcmp (arith, "fast")) ? PLUTO_GPU_ARITH_FAST : PLUTO_GPU_ARITH_EXACT;
-    c.device   = 0;
+    c.device   = getenv ("PLUTO_GPU_DEVICE") ? atoi (getenv ("PLUTO_GPU_DEVICE")) : 0;
+    gpu_resident = getenv ("PLUTO_GPU_RESIDENT") != NULL && atoi (getenv ("PLUTO_GPU_RESIDENT")) != 0;
     c.gamma    = g_gamma;
     c.small_dn = g_smallDensity;
     c.small_pr = g_smallPressure;
@@ -174,14 +204,22 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     }
 #endif
 #if BODY_FORCE & VECTOR
-    if (gpu_g_field){                 /* tabulate BodyForceVector at every zone centre, ghost zones included */
+    {                                 /* BodyForceVector (init.c) tabulated at every zone centre, ghost zones included.
+                                         The force must be static and must not depend on the state: every zone is probed
+                                         with its own state and with a different one, and a force that answers differently
+                                         is refused (rhs_source.c:214-345 would evaluate it with the stage's state) */
       size_t nz = (size_t)NX1_TOT*NX2_TOT*NX3_TOT, id = 0;
-      double *gt = (double *)malloc (3*nz*sizeof(double)), g1[3], v1[NVAR];
+      double *gt = (double *)malloc (3*nz*sizeof(double)), g1[3], g2[3], v1[NVAR], v2[NVAR];
       int kk, jj, ii, q;
       for (kk = 0; kk < NX3_TOT; kk++) for (jj = 0; jj < NX2_TOT; jj++) for (ii = 0; ii < NX1_TOT; ii++){
-        for (q = 0; q < NVAR; q++) v1[q] = d->Vc[q][kk][jj][ii];
-        g1[0] = g1[1] = g1[2] = 0.0;
+        for (q = 0; q < NVAR; q++){ v1[q] = d->Vc[q][kk][jj][ii]; v2[q] = 1.75*v1[q] + 0.375; }
+        g1[0] = g1[1] = g1[2] = 0.0; g2[0] = g2[1] = g2[2] = 0.0;
         BodyForceVector (v1, g1, grid->x[IDIR][ii], grid->x[JDIR][jj], grid->x[KDIR][kk]);
+        BodyForceVector (v2, g2, grid->x[IDIR][ii], grid->x[JDIR][jj], grid->x[KDIR][kk]);
+        if (g1[0] != g2[0] || g1[1] != g2[1] || g1[2] != g2[2]){
+          print ("! AdvanceStep(gpu): BodyForceVector depends on the state (zone %d %d %d); only static forces are available on the GPU\n", ii, jj, kk);
+          QUIT_PLUTO(1);
+        }
         gt[id] = g1[0]; gt[nz + id] = g1[1]; gt[2*nz + id] = g1[2];
         id++;
       }
@@ -192,20 +230,26 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       free (gt);
     }
 #endif
-    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones\n",
-           c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", pluto_gpu_nghost (gpu));
+    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones, device %d, state %s\n",
+           c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", pluto_gpu_nghost (gpu), c.device,
+           gpu_resident ? "resident in HBM" : "on the host (upload + download per step)");
+    if (gpu_resident){              /* the state the driver prepared (Startup or RestartFromFile) goes up once */
+      StaggeredBase (d, &vs1, &vs2, &vs3);
+      if (pluto_gpu_upload_data (gpu, d->Vc[0][0][0], vs1, vs2, vs3) != 0){
+        print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+        QUIT_PLUTO(1);
+      }
+    }
   }
 
-/* -- contiguous blocks behind the pointer tables (Src/arrays.c:222-330,
-      Src/initialize.c:448-453) -- */
-
-  vs1 = &d->Vs[BX1s][0][0][-1];
-  vs2 = &d->Vs[BX2s][0][-1][0];
-#if DIMENSIONS == 3
-  vs3 = &d->Vs[BX3s][-1][0][0];
-#endif
-
-  if (pluto_gpu_advance_data (gpu, g_dt, d->Vc[0][0][0], vs1, vs2, vs3, &info) != 0){
+  StaggeredBase (d, &vs1, &vs2, &vs3);
+  if (gpu_resident){
+    if (pluto_gpu_advance (gpu, g_dt, &info) != 0){
+      print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+      QUIT_PLUTO(1);
+    }
+    gpu_host_stale = 1;
+  }else if (pluto_gpu_advance_data (gpu, g_dt, d->Vc[0][0][0], vs1, vs2, vs3, &info) != 0){
     print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
     QUIT_PLUTO(1);
   }

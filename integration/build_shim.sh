@@ -18,6 +18,13 @@ for VARIANT in $VARIANTS; do
   mkdir -p "$G"
   cp "$B/definitions.h" "$B/init.c" "$G/"
   cp "$HERE/advance_step_gpu.c" "$G/"
+  # the two one-line hooks of INTEGRATION.md ("Keeping the state on the device"): patched copies of the reference's
+  # write_data.c and main.c in the (git-ignored) build directory, found first through the makefile's VPATH = ./:...
+  sed -e 's|^  output->nfile++;|  { void PlutoGpuSyncHost (Data *); PlutoGpuSyncHost ((Data *)d); }   /* libpluto_gpu: resident state */\n  output->nfile++;|' \
+      "$PLUTO_DIR/Src/write_data.c" > "$G/write_data.c"
+  sed -e 's|^  if (check_dt \|\| check_dn) Analysis (d, grid);|  if (check_dt \|\| check_dn){ void PlutoGpuSyncHost (Data *); PlutoGpuSyncHost (d); Analysis (d, grid); }|' \
+      "$PLUTO_DIR/Src/main.c" > "$G/main.c"
+  grep -q PlutoGpuSyncHost "$G/write_data.c" && grep -q PlutoGpuSyncHost "$G/main.c" || { echo "build_shim.sh: hook patch did not apply" >&2; exit 1; }
   # same makefile as the CPU reference build, with the two time-stepping objects
   # replaced by the shim and the GPU library added to the link line
   sed -e 's/rk_step.o update_stage.o/advance_step_gpu.o/' -e 's/ctu_step.o hancock.o/advance_step_gpu.o hancock.o/' \

@@ -192,11 +192,13 @@ class RefResult:
     wall_s: float
     steps_run: int
     workdir: str
+    stdout: str = ""       # the driver's log (serial build: print() goes to stdout)
 
 
 def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
                   workdir: str | None = None, keep: bool = False,
-                  no_write: bool = False, timeout: float = 3600.0, env: dict | None = None) -> RefResult:
+                  no_write: bool = False, timeout: float = 3600.0, env: dict | None = None,
+                  analysis_every: int = 1) -> RefResult:
     """Run ``pluto -maxsteps M``.
 
     Reference main loop semantics (Src/main.c:133-243): ``-maxsteps M`` with
@@ -213,7 +215,7 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
         workdir = tempfile.mkdtemp(prefix="plutoref_")
     os.makedirs(workdir, exist_ok=True)
     write_ini(cfg, os.path.join(workdir, "pluto.ini"), dbl_dn=dump_every,
-              analysis_dn=1)
+              analysis_dn=analysis_every)
     cmd = [cfg.binary(), "-maxsteps", str(maxsteps)]
     if no_write:
         cmd.append("-no-write")
@@ -241,7 +243,7 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
     tap = (np.fromfile(tap_path, dtype="<f8").reshape(-1, 3)
            if os.path.exists(tap_path) else np.zeros((0, 3)))
     res = RefResult(dumps=dumps, dt_tap=tap, wall_s=wall, steps_run=steps_run,
-                    workdir=workdir)
+                    workdir=workdir, stdout=p.stdout.decode(errors="replace"))
     if own and not keep:
         shutil.rmtree(workdir, ignore_errors=True)
     return res

@@ -53,6 +53,9 @@ template <int NC> __device__ __forceinline__ constexpr bool live (int nv)
 
 #define PG_UNROLL _Pragma("unroll")
 #define PG_FOR_NV(nv) PG_UNROLL for (int nv = 0; nv < NV; nv++) if (live<NC>(nv))
+// the same without slot SKIP: the reconstructed cell-centred field component NORMAL to a sweep is never used (the
+// interface states take the staggered field, plm_states.c:271-275), so the marching sweeps leave it out (SKIP = -1: none)
+#define PG_FOR_NV_SKIP(nv, SKIP) PG_UNROLL for (int nv = 0; nv < NV; nv++) if (live<NC>(nv) && nv != (SKIP))
 
 __device__ __forceinline__ double maxv (double a, double b) { return a >= b ? a : b; }
 __device__ __forceinline__ double minv (double a, double b) { return a <= b ? a : b; }
@@ -178,11 +181,11 @@ __device__ __forceinline__ double single_limiter (int lim, double dvp, double dv
   const double qc = 0.5*(dvm + dvp), scrh = 2.0*abs_min (dvp, dvm);
   return abs_min (qc, scrh);
 }
-template <int NC>
+template <int NC, int SKIP = -1>
 __device__ __forceinline__ void plm_zone_single (int lim, const double *v, const double *dvm, const double *dvp,
                                                  double *vp, double *vm)
 {
-  PG_FOR_NV(nv){
+  PG_FOR_NV_SKIP(nv, SKIP){
     const double dvl = single_limiter (lim, dvp[nv], dvm[nv]);
     vp[nv] = v[nv] + dvl*0.5;
     vm[nv] = v[nv] - dvl*0.5;
@@ -212,7 +215,7 @@ template <int NV_ID> __device__ __forceinline__ void plm_half (double v, double 
     vp = fma (p, r, v); vm = fma (-p, r, v);
   }
 }
-template <int NC>
+template <int NC, int SKIP = -1>
 __device__ __forceinline__ void plm_zone_default (const double *v, const double *dvm, const double *dvp,
                                                   double *vp, double *vm)
 {
@@ -220,13 +223,13 @@ __device__ __forceinline__ void plm_zone_default (const double *v, const double 
   plm_half<VX1>(v[VX1], dvp[VX1], dvm[VX1], vp[VX1], vm[VX1]);
   plm_half<VX1>(v[VX2], dvp[VX2], dvm[VX2], vp[VX2], vm[VX2]);
   if (NC == 3) plm_half<VX1>(v[VX3], dvp[VX3], dvm[VX3], vp[VX3], vm[VX3]);
-  plm_half<VX1>(v[BX1], dvp[BX1], dvm[BX1], vp[BX1], vm[BX1]);
-  plm_half<VX1>(v[BX2], dvp[BX2], dvm[BX2], vp[BX2], vm[BX2]);
-  if (NC == 3) plm_half<VX1>(v[BX3], dvp[BX3], dvm[BX3], vp[BX3], vm[BX3]);
+  if (SKIP != BX1) plm_half<VX1>(v[BX1], dvp[BX1], dvm[BX1], vp[BX1], vm[BX1]);
+  if (SKIP != BX2) plm_half<VX1>(v[BX2], dvp[BX2], dvm[BX2], vp[BX2], vm[BX2]);
+  if (NC == 3 && SKIP != BX3) plm_half<VX1>(v[BX3], dvp[BX3], dvm[BX3], vp[BX3], vm[BX3]);
   plm_half<PRS>(v[PRS], dvp[PRS], dvm[PRS], vp[PRS], vm[PRS]);
 }
 #else
-template <int NC>
+template <int NC, int SKIP = -1>
 __device__ __forceinline__ void plm_zone_default (const double *v, const double *dvm, const double *dvp,
                                                   double *vp, double *vm)
 {
@@ -235,11 +238,11 @@ __device__ __forceinline__ void plm_zone_default (const double *v, const double 
   dvl[VX1] = plm_slope<VX1>(dvp[VX1], dvm[VX1]);
   dvl[VX2] = plm_slope<VX1>(dvp[VX2], dvm[VX2]);
   if (NC == 3) dvl[VX3] = plm_slope<VX1>(dvp[VX3], dvm[VX3]);
-  dvl[BX1] = plm_slope<VX1>(dvp[BX1], dvm[BX1]);
-  dvl[BX2] = plm_slope<VX1>(dvp[BX2], dvm[BX2]);
-  if (NC == 3) dvl[BX3] = plm_slope<VX1>(dvp[BX3], dvm[BX3]);
+  if (SKIP != BX1) dvl[BX1] = plm_slope<VX1>(dvp[BX1], dvm[BX1]);
+  if (SKIP != BX2) dvl[BX2] = plm_slope<VX1>(dvp[BX2], dvm[BX2]);
+  if (NC == 3 && SKIP != BX3) dvl[BX3] = plm_slope<VX1>(dvp[BX3], dvm[BX3]);
   dvl[PRS] = plm_slope<PRS>(dvp[PRS], dvm[PRS]);
-  PG_FOR_NV(nv){
+  PG_FOR_NV_SKIP(nv, SKIP){
     vp[nv] = v[nv] + dvl[nv]*0.5;
     vm[nv] = v[nv] - dvl[nv]*0.5;
   }
@@ -247,22 +250,22 @@ __device__ __forceinline__ void plm_zone_default (const double *v, const double 
 #endif
 
 // LIMITER DEFAULT (the fast path) or one limiter for all variables (uniform branch)
-template <int NC>
+template <int NC, int SKIP = -1>
 __device__ __forceinline__ void plm_zone (int lim, const double *v, const double *dvm, const double *dvp,
                                           double *vp, double *vm)
 {
-  if (lim == 0) plm_zone_default<NC>(v, dvm, dvp, vp, vm);
-  else          plm_zone_single<NC>(lim, v, dvm, dvp, vp, vm);
+  if (lim == 0) plm_zone_default<NC, SKIP>(v, dvm, dvp, vp, vm);
+  else          plm_zone_single<NC, SKIP>(lim, v, dvm, dvp, vp, vm);
 }
 
 // PPM 4th-order interface value at i+1/2, bounded (ppm_states.c:146-157):
 // W = v0 + MINMOD(P - v0, v1 - v0), P = -1/12 vm1 + 7/12 v0 + 7/12 v1 - 1/12 v2
-template <int NC>
+template <int NC, int SKIP = -1>
 __device__ __forceinline__ void ppm_interface (const double *vm1, const double *v0,
                                                const double *v1, const double *v2, double *W)
 {
   const double wm1 = -1.0/12.0, w0 = 7.0/12.0, w1 = 7.0/12.0, w2 = -1.0/12.0;
-  PG_FOR_NV(nv){
+  PG_FOR_NV_SKIP(nv, SKIP){
     double p = wm1*vm1[nv] + w0*v0[nv] + w1*v1[nv] + w2*v2[nv];
     double dv = v1[nv] - v0[nv];
     double dvp = p - v0[nv];
@@ -272,13 +275,13 @@ __device__ __forceinline__ void ppm_interface (const double *vm1, const double *
 
 // parabolic limiter on one zone (ppm_states.c:185-207, cm = cp = 2 on a
 // uniform Cartesian grid: (hm+1)/(hp-1) with hp = hm = 3)
-template <int NC>
+template <int NC, int SKIP = -1>
 __device__ __forceinline__ void ppm_zone (const double *v, const double *Wm, const double *Wp,
                                           double *vp, double *vm)
 {
   const double hp = 3.0, hm = 3.0;
   const double cm = (hm + 1.0)/(hp - 1.0), cp = (hp + 1.0)/(hm - 1.0);
-  PG_FOR_NV(nv){
+  PG_FOR_NV_SKIP(nv, SKIP){
     double dvp = Wp[nv] - v[nv];
     double dvm = Wm[nv] - v[nv];
     if (dvp*dvm >= 0.0) dvp = dvm = 0.0;

@@ -79,6 +79,7 @@ struct PlutoGpu {
   long long steps_done;
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
+  int     plan;                    // the sweep launchers choose the chunk count (PLUTO_GPU_NO_PLAN=1 disables)
   int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
   int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
   double *gfield[3];               // static per-zone body force (pluto_gpu_set_body_force), else NULL
@@ -282,6 +283,7 @@ static int create_resources (PlutoGpu *h)
   CU (cudaMallocHost ((void **)&h->dthost, 8*sizeof (double)));
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
+  h->plan = (getenv ("PLUTO_GPU_NO_PLAN") == NULL);
   return 0;
 }
 
@@ -733,6 +735,10 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       if (len > g.n[mdir]) len = g.n[mdir];
       s.chunk_len = (int)len;
       s.nchunk = (g.n[mdir] + s.chunk_len - 1)/s.chunk_len;
+      // default: the launcher chooses the chunk count that fills the SMs in whole rounds (plan_chunks,
+      // sweep_kernels.cuh); the figures above are what PLUTO_GPU_NO_PLAN=1 falls back to
+      s.plan = h->plan;
+      if (s.plan){ s.chunk_len = (g.n[mdir] < 128 ? g.n[mdir] : 128); s.nchunk = (g.n[mdir] + s.chunk_len - 1)/s.chunk_len; }
     }
     int r;
     if (dir == 0 && fuse_xy){

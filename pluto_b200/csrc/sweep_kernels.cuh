@@ -147,12 +147,12 @@ __device__ __forceinline__ void store_vel_slopes (double *const *dv, int id, con
 
 // SHOCK_FLATTENING MULTID: minmod for every variable in a zone flagged FLAG_MINMOD
 // (plm_states.c:174-180), the HLL flux at an interface next to a zone flagged FLAG_HLL
-template <int NC, bool FLAT>
+template <int NC, bool FLAT, int SKIP = -1>
 __device__ __forceinline__ void plm_zone_f (const SweepArgs &a, unsigned fl, const double *v, const double *dvm,
                                             const double *dvp, double *vp, double *vm)
 {
-  if (FLAT && (fl & 1u)) plm_zone_single<NC>(2, v, dvm, dvp, vp, vm);
-  else                   plm_zone<NC>(a.limiter, v, dvm, dvp, vp, vm);
+  if (FLAT && (fl & 1u)) plm_zone_single<NC, SKIP>(2, v, dvm, dvp, vp, vm);
+  else                   plm_zone<NC, SKIP>(a.limiter, v, dvm, dvp, vp, vm);
 }
 template <int SOLVER, int DIR, int NC, bool FLAT>
 __device__ __forceinline__ bool riemann_f (const Phys &ph, unsigned fl2, const double *vL, const double *vR,
@@ -413,6 +413,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   double *cs = carry_ + threadIdx.x;
   constexpr int CS = 128;                   // = blockDim.x (fixed by the launcher): immediate smem offsets
   constexpr bool PPM = (RECON == RECON_PPM);
+  constexpr int SK = D::bn;                 // the cell-centred normal field is neither staged nor reconstructed (PG_FOR_NV_SKIP)
   constexpr int LA = (PPM ? 3 : 2);         // look-ahead of the stencil
   constexpr int PF = march_prefetch (RECON);
   constexpr int NZ = LA + PF;               // ring slots
@@ -435,11 +436,11 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   {
     // group 0: what face c0-1/2 needs (zones c0-1 .. c0-1+LA, its field); groups
     // 1 .. PF-1: the additional zone, field and U of the following faces
-    PG_UNROLL for (int q = 0; q <= LA; q++) PG_FOR_NV(nv) cp_async8 (z[q] + nv*CS, a.V[nv] + id + q*sD);
+    PG_UNROLL for (int q = 0; q <= LA; q++) PG_FOR_NV_SKIP(nv, SK) cp_async8 (z[q] + nv*CS, a.V[nv] + id + q*sD);
     cp_async8 (bnp[0], a.Bn + id);
     cp_async_commit ();
     PG_UNROLL for (int q = 1; q < PF; q++){
-      PG_FOR_NV(nv) cp_async8 (z[LA + q] + nv*CS, a.V[nv] + id + (LA + q)*sD);
+      PG_FOR_NV_SKIP(nv, SK) cp_async8 (z[LA + q] + nv*CS, a.V[nv] + id + (LA + q)*sD);
       cp_async8 (bnp[q], a.Bn + id + q*sD);
       if (upd) fetch_ua (uap[q], id + q*sD);
       cp_async_commit ();
@@ -449,23 +450,23 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       double va_[NV], dvm[NV], dvp[NV], vm_unused[NV];
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait<PF - 1> ();
-      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
-      PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone_f<NC, FLAT>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
+      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
+      PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
+      plm_zone_f<NC, FLAT, SK>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait<PF - 1> ();
-      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vd_[nv] = z[2][nv*CS]; }
-      ppm_interface<NC>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
-      ppm_interface<NC>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
-      ppm_zone<NC>(vb_, Wm, Wf, vpL, vm_unused);
+      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vd_[nv] = z[2][nv*CS]; }
+      ppm_interface<NC, SK>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
+      ppm_interface<NC, SK>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
+      ppm_zone<NC, SK>(vb_, Wm, Wf, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
-      PG_FOR_NV(nv) C_WF(nv) = Wf[nv];
+      PG_FOR_NV_SKIP(nv, SK) C_WF(nv) = Wf[nv];
     }
-    PG_FOR_NV(nv) C_VP(nv) = vpL[nv];
+    PG_FOR_NV_SKIP(nv, SK) C_VP(nv) = vpL[nv];
     PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
   }
   double my_mach = 0.0, my_cdt = 0.0;
@@ -484,9 +485,9 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     double rho_f = 0.0;                      // density of zone f (body force)
     {
       double vb_[NV], vc_[NV], vd_[NV], vnx[NV], vpn[NV];
-      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vnx[nv] = z[LA][nv*CS]; }
+      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vnx[nv] = z[LA][nv*CS]; }
       if (BF) rho_f = vb_[RHO];
-      if (PPM) PG_FOR_NV(nv) vd_[nv] = z[2][nv*CS];
+      if (PPM) PG_FOR_NV_SKIP(nv, SK) vd_[nv] = z[2][nv*CS];
       // start pulling what face f+PF+1/2 needs; its new zone replaces zone f, its field
       // the one just read.  Always commit (possibly empty) so that the group count holds.
 #if PG_MARCH_L2PF
@@ -504,24 +505,24 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 #endif
       if (f + PF <= c1){
         cp_async8_ordered (z[0], a.V[0] + id + (LA + PF)*sD);
-        PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv)) cp_async8 (z[0] + nv*CS, a.V[nv] + id + (LA + PF)*sD);
+        PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv) && nv != SK) cp_async8 (z[0] + nv*CS, a.V[nv] + id + (LA + PF)*sD);
         cp_async8 (bnp[0], a.Bn + id + PF*sD);
         if (upd) fetch_ua (uap[PF], id + PF*sD);
       }
       cp_async_commit ();
       if (!PPM){
         double dvm[NV], dvp[NV];
-        PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone_f<NC, FLAT>(a, flc, vc_, dvm, dvp, vpn, vR);
+        PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
+        plm_zone_f<NC, FLAT, SK>(a, flc, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
-        PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
-        ppm_interface<NC>(vb_, vc_, vd_, vnx, Wn);    // W[f+1]
-        ppm_zone<NC>(vc_, Wf, Wn, vpn, vR);
-        PG_FOR_NV(nv) C_WF(nv) = Wn[nv];
+        PG_FOR_NV_SKIP(nv, SK) Wf[nv] = C_WF(nv);
+        ppm_interface<NC, SK>(vb_, vc_, vd_, vnx, Wn);    // W[f+1]
+        ppm_zone<NC, SK>(vc_, Wf, Wn, vpn, vR);
+        PG_FOR_NV_SKIP(nv, SK) C_WF(nv) = Wn[nv];
       }
       if (hll && in_range) store_vel_slopes<NC>(a.dvel, id + sD, vpn, vR);      // zone f+1
-      PG_FOR_NV(nv){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
+      PG_FOR_NV_SKIP(nv, SK){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
     }
     vL[D::bn] = bn; vR[D::bn] = bn;
     {                        // rotate: zone f+1 becomes zone f, the refilled slots go to the back
@@ -702,23 +703,23 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       double va_[NV], dvm[NV], dvp[NV], vm_unused[NV];
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait_all ();
-      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
-      PG_FOR_NV(nv){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone_f<NC, FLAT>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
+      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
+      PG_FOR_NV_SKIP(nv, DY::bn){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
+      plm_zone_f<NC, FLAT, DY::bn>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
       load_zone<NC>(a, id - 2*sD, vz_);
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait_all ();
-      PG_FOR_NV(nv){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; vd_[nv] = z[2][nv*CW]; }
-      ppm_interface<NC>(vz_, va_, vb_, vc_, Wm);
-      ppm_interface<NC>(va_, vb_, vc_, vd_, Wf);
-      ppm_zone<NC>(vb_, Wm, Wf, vpL, vm_unused);
+      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; vd_[nv] = z[2][nv*CW]; }
+      ppm_interface<NC, DY::bn>(vz_, va_, vb_, vc_, Wm);
+      ppm_interface<NC, DY::bn>(va_, vb_, vc_, vd_, Wf);
+      ppm_zone<NC, DY::bn>(vb_, Wm, Wf, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
-      PG_FOR_NV(nv) C_WF(nv) = Wf[nv];
+      PG_FOR_NV_SKIP(nv, DY::bn) C_WF(nv) = Wf[nv];
     }
-    PG_FOR_NV(nv) C_VP(nv) = vpL[nv];
+    PG_FOR_NV_SKIP(nv, DY::bn) C_VP(nv) = vpL[nv];
     PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
   }
   double my_mach = 0.0, my_cdt = 0.0;
@@ -745,7 +746,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     };
     // the copy of row f+LA+1 lands in the free ring row (PLM), or in the row of f itself
     // (PPM), which must then be read first
-    if (ZF == 0) read_row_f ();
+    if (ZF == 0){ read_row_f (); __syncwarp (); }     // every lane has read its neighbours' columns of row f before they are refilled
     if (f + 1 <= c1) fetch_row (z[ZF], id + (LA + 1)*sD, true);
     if (f + 1 <= c1) cp_async8 (&C_BY, a.Bn2 + id + sD);
     if (f + 1 <= f_end) cp_async8_ordered (&C_BX, a.Bn + id + sD);
@@ -809,21 +810,22 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     if (do_y){
       double vL[NV], vR[NV], vpn[NV], vc_[NV], vd_[NV], vnx[NV];
       if (ZF != 0) PG_FOR_NV(nv) v[nv] = z[0][nv*CW];      // row f is still in the ring: not kept in registers
-      PG_FOR_NV(nv){ vc_[nv] = z[1][nv*CW]; vnx[nv] = z[LA][nv*CW]; }
-      if (PPM) PG_FOR_NV(nv) vd_[nv] = z[2][nv*CW];
+      constexpr int SKY = DY::bn;            // the cell-centred BX2 is not reconstructed along x2 (PG_FOR_NV_SKIP)
+      PG_FOR_NV_SKIP(nv, SKY){ vc_[nv] = z[1][nv*CW]; vnx[nv] = z[LA][nv*CW]; }
+      if (PPM) PG_FOR_NV_SKIP(nv, SKY) vd_[nv] = z[2][nv*CW];
       if (!PPM){
         double dvm[NV], dvp[NV];
-        PG_FOR_NV(nv){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone_f<NC, FLAT>(a, fln, vc_, dvm, dvp, vpn, vR);
+        PG_FOR_NV_SKIP(nv, SKY){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
+        plm_zone_f<NC, FLAT, SKY>(a, fln, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
-        PG_FOR_NV(nv) Wf[nv] = C_WF(nv);
-        ppm_interface<NC>(v, vc_, vd_, vnx, Wn);       // W[f+1]
-        ppm_zone<NC>(vc_, Wf, Wn, vpn, vR);
-        PG_FOR_NV(nv) C_WF(nv) = Wn[nv];
+        PG_FOR_NV_SKIP(nv, SKY) Wf[nv] = C_WF(nv);
+        ppm_interface<NC, SKY>(v, vc_, vd_, vnx, Wn);       // W[f+1]
+        ppm_zone<NC, SKY>(vc_, Wf, Wn, vpn, vR);
+        PG_FOR_NV_SKIP(nv, SKY) C_WF(nv) = Wn[nv];
       }
       if (hll && col_ok) store_vel_slopes<NC>(a.dvel2, id + sD, vpn, vR);       // row f+1
-      PG_FOR_NV(nv){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
+      PG_FOR_NV_SKIP(nv, SKY){ vL[nv] = C_VP(nv); C_VP(nv) = vpn[nv]; }
       vL[DY::bn] = bny; vR[DY::bn] = bny;
       double uL[NV], uR[NV], F[NV], press, cmax, mach;
       prim_to_cons<NC>(ph, vL, uL);
@@ -885,6 +887,43 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------
+//  Chunks of a marching sweep.  A thread (fused sweep: a warp) marches chunk_len zones along the sweep and pays one
+//  extra face for its first left state, so long chunks are cheap -- but the blocks of a launch run in rounds of
+//  (SMs x resident blocks per SM), and a last round that is nearly empty costs a whole chunk: at 256^3 the fused
+//  sweep with 4 chunks of 64 rows is 2322 blocks = 5.2 rounds of 444, i.e. 6 rounds; 3 chunks of 86 rows are 3.9.
+//  plan_chunks picks the chunk count with the smallest  rounds x (chunk_len + extra face + set-up)  among those the
+//  host allows (a.chunk_len = the longest chunk wanted, a.nchunk = the fewest chunks wanted).
+// ---------------------------------------------------------------------------
+static int sm_count ()
+{
+  static int n = 0;
+  if (!n){
+    int dev = 0; cudaDeviceProp prop;
+    cudaGetDevice (&dev);
+    n = (cudaGetDeviceProperties (&prop, dev) == cudaSuccess && prop.multiProcessorCount > 0) ? prop.multiProcessorCount : 148;
+  }
+  return n;
+}
+static void plan_chunks (SweepArgs &b, int nzones, long long blocks_per_chunk_x1000, int blocks_per_sm)
+{
+  const long long slots = (long long)sm_count ()*(blocks_per_sm > 0 ? blocks_per_sm : 1);
+  const int max_len = b.chunk_len > 0 ? b.chunk_len : nzones;
+  int best_n = 0; double best_cost = 0.0;
+  for (int nc = 1; nc <= nzones; nc++){
+    const int len = (nzones + nc - 1)/nc;
+    if (len > max_len) continue;
+    if (len < 4 && nc > 1) break;
+    const int nce = (nzones + len - 1)/len;               // chunks actually launched with this length
+    const long long blocks = (blocks_per_chunk_x1000*nce + 999)/1000;
+    const long long rounds = (blocks + slots - 1)/slots;
+    // a partly filled last round still costs most of a chunk (the SMs it uses run fewer blocks each, not faster ones)
+    const double cost = (double)rounds*(len + 2.0);
+    if (best_n == 0 || cost < best_cost*0.995){ best_n = nce; best_cost = cost; b.chunk_len = len; }
+  }
+  b.nchunk = (nzones + b.chunk_len - 1)/b.chunk_len;
+}
+
 template <int SOLVER>
 static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, bool bf)
 {
@@ -894,14 +933,17 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
   const int HL = (recon == RECON_PPM ? 2 : 1);
   const int stride = 32 - HL - 1;
   const long long nseg = (g.n[0] + stride - 1)/stride;
-  const long long nwarp = nseg*(nc == 3 ? g.n[2] + 2 : 1)*a.nchunk;
-  const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
+  const long long nwarp1 = nseg*(nc == 3 ? g.n[2] + 2 : 1);             // warps of one chunk
   const size_t smem = xy_smem_bytes (recon);
+  SweepArgs b = a;
 #define PG_LXY1(R, C, H, F) PG_LXY2(R, C, H, F, false)
 #define PG_LXY2(R, C, H, F, B) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H, F, B>;                          \
-      static bool attr_set = false;                                                                   \
-      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); attr_set = true; } \
-      kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+      static int bps = 0;                                                                             \
+      if (!bps){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_XY; } \
+      if (a.plan) plan_chunks (b, g.n[1], nwarp1*32*1000/TPB, bps);                                   \
+      const unsigned nb = (unsigned)((nwarp1*b.nchunk*32 + TPB - 1)/TPB);                             \
+      kfn<<<nb, TPB, smem, s>>>(b); } while (0)
 #define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
       if (bf)             PG_LXY2(R, C, false, false, true);          /* refused with UCT_HLL / flattening at create */ \
       else if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                       \
@@ -947,16 +989,17 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
   }else{
     const int td = (dir == 1 ? 2 : 1);
     const long long npen = (long long)(g.n[0] + 2)*(nc == 3 ? g.n[td] + 2 : 1);
-    const long long nthr = npen*a.nchunk;
-    const unsigned nb = (unsigned)((nthr + TPB - 1)/TPB);
     const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
+    SweepArgs b = a;
 #define PG_LM1(DD, R, C, H, F) PG_LM2(DD, R, C, H, F, false)
 #define PG_LM2(DD, R, C, H, F, B) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H, F, B>;             \
-      static bool attr_set = false;                                                                   \
-      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
+      static int bps = 0;                                                                             \
+      if (!bps){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
-        attr_set = true; } \
-      kfn<<<nb, TPB, smem, s>>>(a); } while (0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_MARCH; } \
+      if (a.plan) plan_chunks (b, g.n[dir], npen*1000/TPB, bps);                                      \
+      const unsigned nb = (unsigned)((npen*b.nchunk + TPB - 1)/TPB);                                  \
+      kfn<<<nb, TPB, smem, s>>>(b); } while (0)
 #define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;          \
       if (bf)             PG_LM2(DD, R, C, false, false, true);                                                      \
       else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                    \

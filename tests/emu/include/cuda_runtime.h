@@ -53,6 +53,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFu
 inline const char *cudaGetErrorString (cudaError_t e) { return e == cudaSuccess ? "no error" : "emulation: unsupported call"; }
 inline cudaError_t cudaGetLastError () { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount (int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDevice (int *d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice (int) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc (T **p, size_t n) { *p = (T *)calloc (n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
 template <class T> inline cudaError_t cudaMallocHost (T **p, size_t n) { *p = (T *)calloc (n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
@@ -83,6 +84,7 @@ inline cudaError_t cudaHostRegister (void *, size_t, unsigned) { return cudaSucc
 inline cudaError_t cudaHostUnregister (void *) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties (cudaDeviceProp *p, int) { p->multiProcessorCount = 2; return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute (F, int, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor (int *n, F, int, size_t) { *n = 3; return cudaSuccess; }
 
 // ---- the interpreter ---------------------------------------------------------------------
 namespace pg_emu {

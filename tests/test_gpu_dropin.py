@@ -63,3 +63,35 @@ def test_reference_driver_with_gpu_step_fast_100_steps(name):
         tol = TOL_ONE_STEP if s <= 1 else TOL_100_STEPS
         for k, v in ref.items():
             assert rel_l1(r.dumps[s][k], v) <= tol, f"{name}: {k} after {s} steps"
+
+
+@pytest.mark.parametrize("name,arith", [("blast3d_plm_hlld_100", "exact"), ("ot2d_ctu_100", "exact"), ("rotor2d_ppm_roe_100", "exact"),
+                                        ("turb3d_plm_hlld_100", "fast")])
+def test_resident_state_drop_in(name, arith):
+    """PLUTO_GPU_RESIDENT=1: the state is uploaded once, advanced in HBM by pluto_gpu_advance and copied back only where
+    the driver reads it (the two one-line hooks of INTEGRATION.md in WriteData and CheckForAnalysis).  With a dump and an
+    analysis call every 25 steps the host arrays are refreshed 5 times in 100 steps, and every dump is the all-CPU
+    reference's, bit for bit (EXACT) / within tolerance (FAST)."""
+    g = Golden(name)
+    cfg = _cfg(g)
+    if not have_ref(cfg):
+        pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
+    every = 25
+    r = run_reference(cfg, maxsteps=g.nsteps - 1, dump_every=every, analysis_every=every,
+                      env={"PLUTO_GPU_ARITH": arith, "PLUTO_GPU_RESIDENT": "1"})
+    assert "resident in HBM" in r.stdout
+    syncs = r.stdout.count("PlutoGpuSyncHost: state copied")
+    assert 1 <= syncs <= g.nsteps // every + 1, r.stdout[-2000:]      # not once per step
+    cpu = run_reference(RefConfig(**{**cfg.__dict__, "prefix": "pluto_"}), maxsteps=g.nsteps - 1, dump_every=every,
+                        analysis_every=every)
+    assert sorted(r.dumps) == sorted(cpu.dumps) and max(r.dumps) == g.nsteps
+    for s in sorted(cpu.dumps):
+        for k, v in cpu.dumps[s].items():
+            if arith == "exact":
+                assert np.array_equal(r.dumps[s][k], v), f"{name}: {k} after {s} steps"
+            else:
+                assert rel_l1(r.dumps[s][k], v) <= (TOL_ONE_STEP if s <= 1 else TOL_100_STEPS), f"{name}: {k} after {s} steps"
+    # the final dump is also the golden fixture's last state
+    for k, v in g.states[g.nsteps].items():
+        if arith == "exact":
+            assert np.array_equal(r.dumps[g.nsteps][k], v), f"{name}: {k} (golden)"
