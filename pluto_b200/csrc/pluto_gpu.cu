@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1160,11 +1161,25 @@ int pluto_gpu_write_dbl (PlutoGpu *h, const char *dir, int nfile, double t, doub
   if (nw != want) return fail ("short write to %s", path);
   // dbl.out (write_data.c:365-395)
   snprintf (path, sizeof (path), "%s/dbl.out", dir);
-  f = fopen (path, nfile == 0 ? "w" : "a");
+  // as the reference does: file 0 starts the list; file n goes on line n, after skipping the n lines before it, and
+  // whatever followed (a run restarted from an earlier file, a re-run into the same directory) is overwritten -- the
+  // reference's restart and pyPLUTO read line n as file n
+  if (nfile == 0) f = fopen (path, "w");
+  else{
+    f = fopen (path, "r+");
+    if (!f) f = fopen (path, "w");                    // no list yet (the reference would fail here)
+    else{
+      char sline[512];
+      for (int q = 0; q < nfile; q++) if (!fgets (sline, sizeof (sline), f)) break;
+      fseek (f, ftell (f), SEEK_SET);
+    }
+  }
   if (!f) return fail ("cannot open %s", path);
   fprintf (f, "%d %12.6e %12.6e %ld single_file little ", nfile, t, dt, nstep);
   fprintf (f, h->g.dims == 3 ? "rho vx1 vx2 vx3 Bx1 Bx2 Bx3 prs Bx1s Bx2s Bx3s \n" : "rho vx1 vx2 Bx1 Bx2 prs Bx1s Bx2s \n");
+  const long end = ftell (f);
   fclose (f);
+  if (end > 0 && truncate (path, end) != 0) return fail ("cannot truncate %s", path);   // drop the stale lines of an earlier run
   return 0;
 }
 
@@ -1205,8 +1220,10 @@ int pluto_gpu_analysis (PlutoGpu *h, double out[8])
   a.g = h->g; a.igmm1 = h->ph.igmm1;
   if (count (h, pg_exact::launch_analysis (a, nb, h->stream))) return 1;
   double *host = (double *)malloc ((size_t)nb*8*sizeof (double));
-  CU (cudaMemcpyAsync (host, a.partial, (size_t)nb*8*sizeof (double), cudaMemcpyDeviceToHost, h->stream));
-  CU (cudaStreamSynchronize (h->stream));
+  if (!host) return fail ("out of host memory");
+  cudaError_t ce = cudaMemcpyAsync (host, a.partial, (size_t)nb*8*sizeof (double), cudaMemcpyDeviceToHost, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize (h->stream);
+  if (ce != cudaSuccess){ free (host); return fail ("pluto_gpu_analysis: %s", cudaGetErrorString (ce)); }
   double vol = 1.0;
   for (int d = 0; d < h->g.dims; d++) vol *= h->g.dx[d];
   for (int q = 0; q < 8; q++) out[q] = 0.0;
@@ -1408,8 +1425,9 @@ int pluto_gpu_halo_plan (PlutoGpu *h, int n_nbr, const int *offsets, double *con
     if (h->halo_tab[b][dirn]) cudaFree (h->halo_tab[b][dirn]);
     h->halo_tab[b][dirn] = NULL;
     if (ne > 0){
-      CU (cudaMalloc ((void **)&h->halo_tab[b][dirn], (size_t)ne*sizeof (HaloEntry)));
-      CU (cudaMemcpy (h->halo_tab[b][dirn], tab, (size_t)ne*sizeof (HaloEntry), cudaMemcpyHostToDevice));
+      cudaError_t ce = cudaMalloc ((void **)&h->halo_tab[b][dirn], (size_t)ne*sizeof (HaloEntry));
+      if (ce == cudaSuccess) ce = cudaMemcpy (h->halo_tab[b][dirn], tab, (size_t)ne*sizeof (HaloEntry), cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess){ free (tab); return fail ("pluto_gpu_halo_plan: %s", cudaGetErrorString (ce)); }
     }
     h->halo_n[b][dirn] = ne; h->halo_max[b][dirn] = mx;
     free (tab);

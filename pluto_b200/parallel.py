@@ -214,6 +214,29 @@ class NeighbourExchanger:
         self.unpack_all(stage)
 
 
+def agree_step_results(err, out, device, group=None):
+    """SUM over the ranks of (failed, floor events per step..., NaN events per step...): every rank raises when any rank
+    failed, and every rank returns the global event counts.  `out` = ([dt], [StepInfo], dt_next) of this rank or None."""
+    import torch
+    import torch.distributed as dist
+    from .stepper import PlutoGpuError
+    infos = out[1] if out is not None else []
+    n = torch.tensor([len(infos)], dtype=torch.int64, device=device)
+    dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
+    nmax = int(n.item())
+    v = torch.zeros(1 + 2 * nmax, dtype=torch.float64)
+    v[0] = 0.0 if err is None else 1.0
+    for q, i in enumerate(infos):
+        v[1 + q], v[1 + nmax + q] = i.floor_events, i.nan_events
+    v = v.to(device)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+    v = v.tolist()
+    if v[0] > 0:
+        raise PlutoGpuError(str(err) if err is not None else f"the step failed on {int(v[0])} other rank(s)")
+    infos = [StepInfo(i.inv_dt_hyp, i.max_mach, int(v[1 + q]), int(v[1 + nmax + q])) for q, i in enumerate(infos)]
+    return out[0], infos, out[2]
+
+
 class DistStepper:
     """AdvanceStep on one block of a decomposed domain (one process per GPU)."""
 
@@ -291,7 +314,22 @@ class DistStepper:
             self.block.next_dt_async(cfl, cfl_max_var)
 
     def sync_results(self, max_steps=4096):
-        return self.block.sync_results(max_steps)
+        """Wait for the enqueued steps.  A failure on ONE rank (Roe solver abort, CUDA error) or its event counts must
+        reach every rank -- a rank that raised alone would leave the others waiting in the next exchange -- so the
+        failure flag and the floor / NaN counts are summed over the ranks before anything is raised or returned."""
+        if self.world == 1:
+            return self.block.sync_results(max_steps)
+        from .stepper import PlutoGpuError
+        err, out = None, None
+        try:
+            out = self.block.sync_results(max_steps)
+        except PlutoGpuError as e:
+            err = e
+        out = self._agree(err, out)
+        return out
+
+    def _agree(self, err, out):
+        return agree_step_results(err, out, self._red.device)
 
     def _red_view(self):
         """torch view of the two device reduction slots (CFL, Mach: non-negative doubles)."""
@@ -312,13 +350,19 @@ class DistStepper:
         import torch.distributed as dist
         b = self.block
         self._enqueue_step(dt)
+        from .stepper import PlutoGpuError
         with torch.cuda.stream(self._stream):
-            info = b.step_end()
+            err, info = None, StepInfo(0.0, 0.0, 0, 0)
+            try:
+                info = b.step_end()
+            except PlutoGpuError as e:       # e.g. the Roe solver's abort (roe.c:300-306) on this rank only: every rank
+                err = e                      # must still enter the collectives below, then all of them raise
             # MPI_Allreduce(MAX) of invDt_hyp and g_maxMach (main.c:195-199, 415)
             self._red.copy_(torch.tensor([info.inv_dt_hyp, info.max_mach], dtype=torch.float64))
             dist.all_reduce(self._red, op=dist.ReduceOp.MAX)
             r = self._red.tolist()
-        return StepInfo(r[0], r[1], info.floor_events, info.nan_events)
+            _, infos, _ = self._agree(err, ([], [StepInfo(r[0], r[1], info.floor_events, info.nan_events)], 0.0))
+        return infos[0]
 
     def _enqueue_step(self, dt):
         """All stages of one step with their exchanges (dt < 0: the device's own dt)."""

@@ -538,6 +538,12 @@ def test_dbl_output_restart_and_analysis(tmp_path):
         assert len(lines) == 2 and lines[1].split()[0] == "1" and lines[1].split()[4:6] == ["single_file", "little"]
         assert lines[1].split()[6:] == (["rho", "vx1", "vx2", "vx3", "Bx1", "Bx2", "Bx3", "prs", "Bx1s", "Bx2s", "Bx3s"]
                                         if dims == 3 else ["rho", "vx1", "vx2", "Bx1", "Bx2", "prs", "Bx1s", "Bx2s"])
+        # a run restarted from file 0 writes file 1 again: its line REPLACES line 1 and drops what followed
+        # (write_data.c:369-376 opens r+ and skips nfile lines), it is not appended
+        s.write_dbl(str(tmp_path), 2, 0.020, 5e-3, 4)
+        s.write_dbl(str(tmp_path), 1, 0.017, 5e-3, 7)
+        lines = open(tmp_path / "dbl.out").read().splitlines()
+        assert [l.split()[0] for l in lines] == ["0", "1"] and lines[1].split()[3] == "7"
         r = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"])
         r.read_dbl(str(tmp_path / "data.0000.dbl"))
         a, b = s.advance(5e-3), r.advance(5e-3)

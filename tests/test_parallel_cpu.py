@@ -114,3 +114,36 @@ def test_periodic_exchange_fills_all_ghosts(world, dims, n, ng, mode):
         assert bad == 0, f"rank {r}: {bad} ghost values wrong"
         assert red == [float(world), 10.0]
         assert nbytes > 0
+
+
+def _agree_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pluto_b200.parallel import agree_step_results
+        from pluto_b200.stepper import StepInfo, PlutoGpuError
+        # (a) nobody failed: the event counts are summed over the ranks, the scalars stay the rank's own (already reduced)
+        out = ([1e-3, 2e-3], [StepInfo(5.0, 0.5, rank + 1, 0), StepInfo(6.0, 0.6, 0, 2 * rank)], 3e-3)
+        dts, infos, dtn = agree_step_results(None, out, torch.device("cpu"))
+        a = (dts, [(i.inv_dt_hyp, i.max_mach, i.floor_events, i.nan_events) for i in infos], dtn)
+        # (b) rank 1 alone failed (no results): EVERY rank raises instead of waiting in the next exchange
+        raised = False
+        try:
+            agree_step_results(PlutoGpuError("Roe_Solver: a2 < 0") if rank == 1 else None, None if rank == 1 else out,
+                               torch.device("cpu"))
+        except PlutoGpuError:
+            raised = True
+        ret[rank] = (a, raised)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_step_failure_and_event_counts_reach_every_rank():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_agree_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        a, raised = ret[r]
+        assert a == ([1e-3, 2e-3], [(5.0, 0.5, 3, 0), (6.0, 0.6, 0, 2)], 3e-3)
+        assert raised

@@ -12,7 +12,7 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'sm__warps_act
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
         'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum',
         'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum', 'sm__cycles_elapsed.max',
-        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum']
+        'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum']
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     print('==', d['Kernel Name'], 'grid', d.get('launch__grid_size'), 'block', d.get('launch__block_size'))
