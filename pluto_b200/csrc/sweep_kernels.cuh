@@ -92,6 +92,56 @@ template <int N> __device__ __forceinline__ void cp_async_wait ()     // all but
 __device__ __forceinline__ void cp_async_wait_all () { asm volatile ("cp.async.wait_group 0;" ::: "memory"); }
 #endif
 
+// ---------------------------------------------------------------------------
+//  TMA staging (fused x1+x2 sweep, SweepArgs.tma): ONE lane of a warp issues ONE cp.async.bulk.tensor.4d per ring row
+//  -- box {36 entries along x1, 1 row, 1 plane, 8 variables} of the tensor map over the primitives -- and the arrival
+//  is counted in bytes on the warp's own mbarrier; the other lanes only wait on its phase.  Replaces 8 (+8 for the four
+//  halo lanes) 8-byte cp.async per lane and row together with their address arithmetic.
+// ---------------------------------------------------------------------------
+#ifdef PG_EMU
+__device__ __forceinline__ void mbar_init (unsigned long long *bar) { *bar = 0; }
+__device__ __forceinline__ void tma_load_row (double *dst, const PgTensorMap *map, unsigned long long *bar, int x, int y, int z, unsigned)
+{
+  const PgTensorMapEmu *m = reinterpret_cast<const PgTensorMapEmu *>(map);
+  int n = 0;                                           // lands at once; out-of-range entries are zero
+  for (int v = 0; v < m->box[3]; v++) for (int i = 0; i < m->box[0]; i++, n++){
+    const long long xi = x + i;
+    const bool in = xi >= 0 && xi < m->dim[0] && y >= 0 && y < m->dim[1] && z >= 0 && z < m->dim[2] && v < m->dim[3];
+    dst[n] = in ? m->base[xi*m->stride[0] + (long long)y*m->stride[1] + (long long)z*m->stride[2] + (long long)v*m->stride[3]] : 0.0;
+  }
+  (void)bar;
+}
+__device__ __forceinline__ void mbar_expect (unsigned long long *, unsigned) {}
+__device__ __forceinline__ void mbar_wait (unsigned long long *, unsigned) {}
+__device__ __forceinline__ void fence_proxy_async () {}
+#else
+__device__ __forceinline__ void mbar_init (unsigned long long *bar)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared (bar);
+  asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(sa) : "memory");
+  asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect (unsigned long long *bar, unsigned bytes)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared (bar);
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_row (double *dst, const PgTensorMap *map, unsigned long long *bar, int x, int y, int z, unsigned)
+{
+  const unsigned sd = (unsigned)__cvta_generic_to_shared (dst), sb = (unsigned)__cvta_generic_to_shared (bar);
+  asm volatile ("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                :: "r"(sd), "l"(map), "r"(sb), "r"(x), "r"(y), "r"(z), "r"(0) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (unsigned long long *bar, unsigned phase)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared (bar);
+  asm volatile ("{\n .reg .pred p;\n W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra D_%=;\n bra W_%=;\n D_%=:\n}"
+                :: "r"(sa), "r"(phase) : "memory");
+}
+// generic-proxy reads of a ring row come before the async-proxy write that refills it
+__device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 #ifndef PG_MARCH_L2PF
 #define PG_MARCH_L2PF 0
 #endif
@@ -620,10 +670,10 @@ __host__ __device__ constexpr int xy_thread_slots (int recon) { return 8 + 7 + (
 __host__ __device__ constexpr int xy_ring_rows (int recon) { return recon == RECON_PPM ? 4 : 4; }
 __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
 {
-  return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128)*sizeof (double);
+  return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128 + 4)*sizeof (double);   // + 4 mbarriers (TMA)
 }
 
-template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false>
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool TMA = false>
 __global__ void __launch_bounds__(128, PG_MINB_XY)
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -636,6 +686,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
   constexpr int NZ = xy_ring_rows (RECON);           // ring rows: f .. f+LA (+ a free one)
   constexpr int ZF = (NZ > LA + 1 ? NZ - 1 : 0);     // ring row the copy in flight lands in
   constexpr int CW = xy_ring_cols ();                // ring columns per block
+  constexpr int VS = 36;                             // ring layout [row][warp][variable][36 entries]: the TMA box of a warp
+                                                     // ({36, 1, 1, 8}) lands contiguously, 2304 bytes, 128-byte aligned
   constexpr int CS = 128;
   const Geom &g = a.g;
   const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);     // stays in the kernel-parameter constant bank
@@ -673,9 +725,17 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
   const int sD = (int)g.S1;
   int id = gidx32 (g, k, c0 - 1, i);                 // zone (k, c0-1, i)
 
-  extern __shared__ double carry_[];
-  double *ring = carry_ + warp*36 + 1 + lane;        // own column; entries -1, 32, 33, 34 of the warp around it
+  extern __shared__ __align__(128) double carry_[];
+  double *ring = carry_ + warp*(8*VS) + 1 + lane;    // own column; entries -1, 32, 33, 34 of the warp around it
   double *cs = carry_ + 8*NZ*CW + threadIdx.x;
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(carry_ + 8*NZ*CW + xy_thread_slots (RECON)*CS) + warp;
+  unsigned tphase = 0;                               // TMA: parity of the warp's mbarrier
+  const int tx0 = g.beg[0] - HL + seg*STRIDE + g.off[0] - 1;        // tensor coordinates of ring entry -1 of this warp
+  const int tz0 = k + g.off[2];
+  if (TMA){
+    if (lane == 0) mbar_init (mbar);
+    __syncwarp ();
+  }
   constexpr int S_VP = 0, S_FP = 8, S_WF = 15, S_BY = S_WF + (PPM ? 8 : 0), S_BX = S_BY + 1;
   static_assert (S_BX + 1 == xy_thread_slots (RECON), "shared-memory layout");
 #define C_VP(nv) cs[(S_VP + (nv))*CS]
@@ -685,16 +745,26 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 #define C_BX     cs[S_BX*CS]
   double *z[NZ];
   PG_UNROLL for (int q = 0; q < NZ; q++) z[q] = ring + 8*q*CW;           // z[q]: row f+q
+  // TMA: rows [jrow, jrow + nrows) of the plane -> ring rows dst, dst + 8*CW, ...; one elected lane, bytes counted on mbar
+  auto fetch_rows_tma = [&] (double *dst, int jrow, int nrows){
+    if (lane == 0){
+      fence_proxy_async ();
+      mbar_expect (mbar, (unsigned)(nrows*8*VS*sizeof (double)));
+      for (int q = 0; q < nrows; q++)
+        tma_load_row (dst - 1 - lane + q*(8*CW), &a.vmap, mbar, tx0, jrow + q + g.off[1], tz0, 0u);
+    }
+  };
   auto fetch_row = [&] (double *dst, int idr, bool ordered){
     if (ordered) cp_async8_ordered (dst, a.V[0] + idr); else cp_async8 (dst, a.V[0] + idr);
-    PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv)) cp_async8 (dst + nv*CW, a.V[nv] + idr);
+    PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv)) cp_async8 (dst + nv*VS, a.V[nv] + idr);
     if (lane < 4){                                   // stencil halo: entries -1, 32, 33, 34
       const int off = (lane == 0 ? -1 : 31 + lane);
-      PG_FOR_NV(nv) cp_async8 (dst + nv*CW - lane + off, a.V[nv] + (idr - lane) + off);
+      PG_FOR_NV(nv) cp_async8 (dst + nv*VS - lane + off, a.V[nv] + (idr - lane) + off);
     }
   };
   {
-    PG_UNROLL for (int q = 0; q <= LA; q++) fetch_row (z[q], id + q*sD, false);
+    if (TMA) fetch_rows_tma (z[0], c0 - 1, LA + 1);
+    else PG_UNROLL for (int q = 0; q <= LA; q++) fetch_row (z[q], id + q*sD, false);
     cp_async8 (&C_BY, a.Bn2 + id);
     cp_async8 (&C_BX, a.Bn + id);
     cp_async_commit ();
@@ -703,7 +773,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       double va_[NV], dvm[NV], dvp[NV], vm_unused[NV];
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait_all ();
-      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; }
+      if (TMA){ mbar_wait (mbar, tphase); tphase ^= 1u; }
+      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; }
       PG_FOR_NV_SKIP(nv, DY::bn){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
       plm_zone_f<NC, FLAT, DY::bn>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
@@ -712,7 +783,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       load_zone<NC>(a, id - 2*sD, vz_);
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait_all ();
-      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*CW]; vc_[nv] = z[1][nv*CW]; vd_[nv] = z[2][nv*CW]; }
+      if (TMA){ mbar_wait (mbar, tphase); tphase ^= 1u; }
+      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; vd_[nv] = z[2][nv*VS]; }
       ppm_interface<NC, DY::bn>(vz_, va_, vb_, vc_, Wm);
       ppm_interface<NC, DY::bn>(va_, vb_, vc_, vd_, Wf);
       ppm_zone<NC, DY::bn>(vb_, Wm, Wf, vpL, vm_unused);
@@ -724,12 +796,14 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
   }
   double my_mach = 0.0, my_cdt = 0.0;
   constexpr bool hll = HLL;
+  bool tpending = false;                             // TMA: a ring row is in flight
   for (int f = c0 - 1; f <= f_end; f++, id += sD){
     // id = zone (k, f, i).  x2 interface f+1/2 lies between rows f and f+1; the x1 faces
     // solved here are those of row f.
     const bool do_y = f <= c1;
     const bool do_x = f >= c0 || chunk == 0;
     cp_async_wait_all ();
+    if (TMA && tpending){ mbar_wait (mbar, tphase); tphase ^= 1u; }
     __syncwarp ();                                   // the other lanes' copies are visible
     const double bny = C_BY, bnx = C_BX;
     unsigned flz = 0, fln = 0;               // flags of zone (f, i) and of zone (f+1, i)
@@ -738,16 +812,17 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     double xvl[NV], xvr[NV], xvrr[NV];
     PG_UNROLL for (int nv = 0; nv < NV; nv++) rx[nv] = 0.0;
     auto read_row_f = [&] (){                        // zone (f, i) and its x1 neighbours
-      PG_FOR_NV(nv) v[nv] = z[0][nv*CW];
+      PG_FOR_NV(nv) v[nv] = z[0][nv*VS];
       if (do_x){
-        PG_FOR_NV(nv){ xvl[nv] = z[0][nv*CW - 1]; xvr[nv] = z[0][nv*CW + 1]; }
-        if (PPM) PG_FOR_NV(nv) xvrr[nv] = z[0][nv*CW + 2];
+        PG_FOR_NV(nv){ xvl[nv] = z[0][nv*VS - 1]; xvr[nv] = z[0][nv*VS + 1]; }
+        if (PPM) PG_FOR_NV(nv) xvrr[nv] = z[0][nv*VS + 2];
       }
     };
     // the copy of row f+LA+1 lands in the free ring row (PLM), or in the row of f itself
     // (PPM), which must then be read first
     if (ZF == 0){ read_row_f (); __syncwarp (); }     // every lane has read its neighbours' columns of row f before they are refilled
-    if (f + 1 <= c1) fetch_row (z[ZF], id + (LA + 1)*sD, true);
+    tpending = (f + 1 <= c1);
+    if (f + 1 <= c1){ if (TMA) fetch_rows_tma (z[ZF], f + LA + 1, 1); else fetch_row (z[ZF], id + (LA + 1)*sD, true); }
     if (f + 1 <= c1) cp_async8 (&C_BY, a.Bn2 + id + sD);
     if (f + 1 <= f_end) cp_async8_ordered (&C_BX, a.Bn + id + sD);
     cp_async_commit ();
@@ -809,10 +884,10 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     // ---------------- x2 face f+1/2 ----------------
     if (do_y){
       double vL[NV], vR[NV], vpn[NV], vc_[NV], vd_[NV], vnx[NV];
-      if (ZF != 0) PG_FOR_NV(nv) v[nv] = z[0][nv*CW];      // row f is still in the ring: not kept in registers
+      if (ZF != 0) PG_FOR_NV(nv) v[nv] = z[0][nv*VS];      // row f is still in the ring: not kept in registers
       constexpr int SKY = DY::bn;            // the cell-centred BX2 is not reconstructed along x2 (PG_FOR_NV_SKIP)
-      PG_FOR_NV_SKIP(nv, SKY){ vc_[nv] = z[1][nv*CW]; vnx[nv] = z[LA][nv*CW]; }
-      if (PPM) PG_FOR_NV_SKIP(nv, SKY) vd_[nv] = z[2][nv*CW];
+      PG_FOR_NV_SKIP(nv, SKY){ vc_[nv] = z[1][nv*VS]; vnx[nv] = z[LA][nv*VS]; }
+      if (PPM) PG_FOR_NV_SKIP(nv, SKY) vd_[nv] = z[2][nv*VS];
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV_SKIP(nv, SKY){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
@@ -937,7 +1012,9 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
   const size_t smem = xy_smem_bytes (recon);
   SweepArgs b = a;
 #define PG_LXY1(R, C, H, F) PG_LXY2(R, C, H, F, false)
-#define PG_LXY2(R, C, H, F, B) do { auto kfn = sweep_xy_kernel<R, SOLVER, C, H, F, B>;                          \
+#define PG_LXY3(R, C) PG_LXYK((sweep_xy_kernel<R, SOLVER, C, false, false, false, true>))
+#define PG_LXY2(R, C, H, F, B) PG_LXYK((sweep_xy_kernel<R, SOLVER, C, H, F, B>))
+#define PG_LXYK(KF) do { auto kfn = KF;                          \
       static int bps = 0;                                                                             \
       if (!bps){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); \
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_XY; } \
@@ -947,7 +1024,9 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
 #define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
       if (bf)             PG_LXY2(R, C, false, false, true);          /* refused with UCT_HLL / flattening at create */ \
       else if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                       \
-      else           { if (fl) PG_LXY1(R, C, false, P); else PG_LXY1(R, C, false, false); } } while (0)
+      else if (fl)        PG_LXY1(R, C, false, P);                                                                     \
+      else if (a.tma)     PG_LXY3(R, C);                               /* TMA staging of the ring rows */              \
+      else                PG_LXY1(R, C, false, false); } while (0)
   if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
   else if (recon == RECON_PLM && nc == 2) PG_LXY(RECON_PLM, 2);
   else if (recon == RECON_PPM && nc == 3) PG_LXY(RECON_PPM, 3);
@@ -955,6 +1034,8 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
 #undef PG_LXY
 #undef PG_LXY1
 #undef PG_LXY2
+#undef PG_LXY3
+#undef PG_LXYK
   return cudaGetLastError () == cudaSuccess ? 1 : -1;
 }
 

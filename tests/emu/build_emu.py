@@ -27,7 +27,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libpluto_gpu_emu.so")
 
 LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;{}]*?>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
-DYN_SMEM = re.compile(r"extern\s+__shared__\s+(\w+)\s+(\w+)\s*\[\s*\]\s*;")
+DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\s*\(\s*\d+\s*\)\s+)?(\w+)\s+(\w+)\s*\[\s*\]\s*;")
 
 
 def transform(text: str) -> str:
