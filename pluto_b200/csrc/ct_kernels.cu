@@ -493,7 +493,7 @@ int launch_flag_shock (const FlagArgs &a, cudaStream_t s)
     flag_shock_kernel<2, 1><<<nblocks (n, 256), 256, 0, s>>>(a);
     flag_shock_kernel<2, 2><<<nblocks (n, 256), 256, 0, s>>>(a);
   }
-  return cudaGetLastError () == cudaSuccess ? 2 : -1;
+  return pg_launch_status (2);
 }
 
 // ---------------------------------------------------------------------------
@@ -538,7 +538,7 @@ analysis_kernel (const __grid_constant__ AnalysisArgs a)
 int launch_analysis (const AnalysisArgs &a, int nb, cudaStream_t s)
 {
   analysis_kernel<<<nb, 256, 0, s>>>(a);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 // ---------------------------------------------------------------------------
@@ -590,7 +590,7 @@ int launch_ct_emf (const CtArgs &a, cudaStream_t s)
       default: ct_emf_kernel<C, 0><<<nblocks (n, 128), 128, 0, s>>>(a); } } while (0)
   if (g.dims == 3) PG_LE(3); else PG_LE(2);
 #undef PG_LE
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 int launch_ct_update (const CtArgs &a, cudaStream_t s)
@@ -599,7 +599,7 @@ int launch_ct_update (const CtArgs &a, cudaStream_t s)
   const long long n = (long long)(g.n[0] + 1 + 2*a.ext)*(g.n[1] + 1 + 2*a.ext)*(g.dims == 3 ? g.n[2] + 1 + 2*a.ext : 1);
   if (g.dims == 3) ct_update_kernel<3><<<nblocks (n, 128), 128, 0, s>>>(a);
   else             ct_update_kernel<2><<<nblocks (n, 128), 128, 0, s>>>(a);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 int launch_final (const FinalArgs &a, cudaStream_t s)
@@ -614,7 +614,7 @@ int launch_final (const FinalArgs &a, cudaStream_t s)
     if (g.dims == 3) final_kernel<3, false><<<nblocks (n, 128), 128, 0, s>>>(a);
     else             final_kernel<2, false><<<nblocks (n, 128), 128, 0, s>>>(a);
   }
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 int launch_bc (const BcArgs &a, cudaStream_t s)
@@ -635,7 +635,7 @@ int launch_bc (const BcArgs &a, cudaStream_t s)
   if (nmax <= 0 || a.nf + a.nfill <= 0) return 0;
   dim3 grid (nblocks (nmax, 128), a.nf + a.nfill);
   bc_kernel<<<grid, 128, 0, s>>>(a);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 static int launch_halo (const HaloArgs &a, cudaStream_t s, bool pack)
@@ -651,7 +651,7 @@ static int launch_halo (const HaloArgs &a, cudaStream_t s, bool pack)
   dim3 grid (nb, a.nf);
   if (pack) halo_kernel<true><<<grid, 256, 0, s>>>(a);
   else      halo_kernel<false><<<grid, 256, 0, s>>>(a);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s)
 {
@@ -660,7 +660,7 @@ int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Ge
   dim3 grid (nb, n);
   if (pack) halo_table_kernel<true><<<grid, 256, 0, s>>>(tab, g);
   else      halo_table_kernel<false><<<grid, 256, 0, s>>>(tab, g);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 int launch_halo_pack   (const HaloArgs &a, cudaStream_t s) { return launch_halo (a, s, true); }
 int launch_halo_unpack (const HaloArgs &a, cudaStream_t s) { return launch_halo (a, s, false); }

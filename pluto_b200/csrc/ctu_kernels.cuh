@@ -555,7 +555,7 @@ static int launch_ctu_sweep_t (int dir, int phase, const CtuArgs &a, cudaStream_
 #undef PG_CM
 #undef PG_CM1
   }
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 static int launch_ctu_half_t (const CtuArgs &a, cudaStream_t s)
@@ -565,7 +565,7 @@ static int launch_ctu_half_t (const CtuArgs &a, cudaStream_t s)
   const unsigned nb = (unsigned)((n + 127)/128);
   if (g.dims == 3) ctu_half_kernel<3><<<nb, 128, 0, s>>>(a);
   else             ctu_half_kernel<2><<<nb, 128, 0, s>>>(a);
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 } // namespace PG_NS

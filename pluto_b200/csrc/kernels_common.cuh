@@ -30,13 +30,6 @@ __host__ __device__ __forceinline__ long long gidx (const Geom &g, int k, int j,
 
 struct PhysPar { double gamma, gmm1, small_dn, small_pr, igmm1; };
 
-// A TMA descriptor (CUtensorMap: 128 opaque bytes, 64-byte aligned) of the 8 primitive arrays of one state buffer seen as
-// ONE 4-D tensor [variable][x3][x2][x1]: a single cp.async.bulk.tensor instruction, issued by one lane, lands the 36-entry row
-// segments of all 8 variables of a warp in shared memory.  Under the kernel interpreter (tests/emu) the same bytes hold a
-// plain description that the interpreted copy reads.
-struct alignas(64) PgTensorMap { unsigned long long opaque[16]; };
-struct PgTensorMapEmu { const double *base; long long dim[4]; long long stride[4]; int box[4]; };   // stride in elements
-
 // reduction slots (device, unsigned long long each)
 enum { RED_CDT = 0, RED_MACH = 1, RED_FLOOR = 2, RED_NAN = 3, RED_ROEFAIL = 4, RED_N = 8 };
 
@@ -59,7 +52,8 @@ struct SweepArgs {
                              // continuing with the U left by the previous stage
   int     chunk_len;         // marching kernels: zones per thread along the sweep
   int     nchunk;
-  int     tma;               // fused x1+x2 sweep: stage the ring rows with TMA (vmap) instead of per-lane cp.async
+  int     tma;               // fused x1+x2 sweep: stage the ring rows with bulk asynchronous copies (TMA engine, one elected
+                             // lane + mbarrier) instead of per-lane cp.async; needs rows of an even number of doubles
   int     plan;              // 1: the launcher picks the chunk count that fills the SMs in whole rounds (plan_chunks),
                              //    chunk_len = the longest chunk the host wants; 0: use chunk_len / nchunk as given
   int     limiter;           // PLUTO_GPU_LIM_* (PLM)
@@ -87,7 +81,6 @@ struct SweepArgs {
   // BODY_FORCE & POTENTIAL (rhs.c:388-392, rhs_source.c:233-237, 316-320, 358-362): potential at the zone centres and at
   // the faces of this sweep's direction (phif2: x2 faces, fused x1+x2 sweep); NULL without a potential
   const double *phic, *phif, *phif2;
-  PgTensorMap vmap;          // tma: the primitives of this stage's input buffer (see PgTensorMap)
 };
 
 struct CtArgs {
@@ -209,6 +202,13 @@ struct HaloEntry {
   int lo[3], n[3];           // box origin and extents
   long long count;
 };
+
+// launchers return the number of kernels launched, or -1 - cudaError of a failed launch (count() in pluto_gpu.cu reports it)
+static inline int pg_launch_status (int n = 1)
+{
+  const cudaError_t e = cudaGetLastError ();
+  return e == cudaSuccess ? n : -1 - (int)e;
+}
 
 // ---- launch interface, one set per arithmetic namespace ----------------------
 #define PG_DECLARE_LAUNCHERS(NS)                                                         \

@@ -81,8 +81,7 @@ struct PlutoGpu {
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
   int     plan;                    // the sweep launchers choose the chunk count (PLUTO_GPU_NO_PLAN=1 disables)
-  int     tma;                     // fused sweep: ring rows staged by TMA (PLUTO_GPU_TMA=1; the strides must be multiples of 16 bytes)
-  PgTensorMap vmap[3];             // tensor map over V[b][0..7] of every state buffer (see kernels_common.cuh)
+  int     tma;                     // fused sweep: ring rows staged by bulk asynchronous copies (PLUTO_GPU_TMA=1)
   int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
   int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
   double *gfield[3];               // static per-zone body force (pluto_gpu_set_body_force), else NULL
@@ -113,7 +112,7 @@ static bool live_var (const PlutoGpu *h, int nv) { return h->g.dims == 3 || (nv 
 
 static int count (PlutoGpu *h, int r)
 {
-  if (r < 0) return fail ("kernel launch failed: %s", cudaGetErrorString (cudaGetLastError ()));
+  if (r < 0) return fail ("kernel launch failed: %s", cudaGetErrorString ((cudaError_t)(-1 - r)));
   h->launches += r;
   return 0;
 }
@@ -189,54 +188,6 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   }
   *out = h;
   return 0;
-}
-
-// ---------------------------------------------------------------------------
-//  TMA descriptors of the primitives: V[b][0..7] are 8 equally spaced arrays (tot_al doubles apart) of the padded shape
-//  [T3+2][T2+2][S1], i.e. one 4-D tensor {S1, T2+2, T3+2 | 1, 8}; box {36, 1, 1, 8} = the ring-row block of one warp of the
-//  fused x1+x2 sweep.  The driver entry point is taken through the runtime (no link against libcuda).
-// ---------------------------------------------------------------------------
-#ifndef PG_EMU
-#include <cuda.h>
-#endif
-static int make_tensor_maps (PlutoGpu *h, size_t tot_al)
-{
-  const Geom &g = h->g;
-  const unsigned long long dim[4] = {(unsigned long long)g.S1, (unsigned long long)(g.T[1] + 2),
-                                     (unsigned long long)(g.dims == 3 ? g.T[2] + 2 : 1), (unsigned long long)NVS};
-  const unsigned long long str[3] = {(unsigned long long)g.S1*8ull, (unsigned long long)g.S12*8ull, (unsigned long long)tot_al*8ull};
-  const unsigned box[4] = {36u, 1u, 1u, (unsigned)NVS};
-#ifdef PG_EMU
-  for (int b = 0; b < h->nbuf; b++){
-    PgTensorMapEmu m; memset (&m, 0, sizeof (m));
-    m.base = h->V[b][0];
-    for (int q = 0; q < 4; q++){ m.dim[q] = (long long)dim[q]; m.box[q] = (int)box[q]; }
-    m.stride[0] = 1; for (int q = 0; q < 3; q++) m.stride[q + 1] = (long long)(str[q]/8);
-    static_assert (sizeof (PgTensorMapEmu) <= sizeof (PgTensorMap), "emulated tensor map");
-    memset (&h->vmap[b], 0, sizeof (PgTensorMap));
-    memcpy (&h->vmap[b], &m, sizeof (m));
-  }
-  return 0;
-#else
-  typedef CUresult (*EncodeFn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  void *fn = NULL;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return 1;
-  static_assert (sizeof (CUtensorMap) == sizeof (PgTensorMap), "CUtensorMap is 128 bytes");
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  for (int b = 0; b < h->nbuf; b++){
-    CUtensorMap m;
-    const CUresult r = ((EncodeFn)fn) (&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)h->V[b][0], (const cuuint64_t *)dim,
-                                        (const cuuint64_t *)str, (const cuuint32_t *)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 1;
-    memcpy (&h->vmap[b], &m, sizeof (m));
-  }
-  return 0;
-#endif
 }
 
 static int create_resources (PlutoGpu *h)
@@ -335,11 +286,8 @@ static int create_resources (PlutoGpu *h)
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
   h->plan = (getenv ("PLUTO_GPU_NO_PLAN") == NULL);
-  h->tma = 0;
-  if (getenv ("PLUTO_GPU_TMA") && atoi (getenv ("PLUTO_GPU_TMA")) != 0){
-    // cuTensorMapEncodeTiled wants strides that are multiples of 16 bytes: rows of an even number of doubles
-    if (g.S1 % 2 == 0 && make_tensor_maps (h, tot_al) == 0) h->tma = 1;
-  }
+  // bulk copies need 16-byte aligned rows: an even number of doubles per row (arrays are 256-byte aligned)
+  h->tma = (getenv ("PLUTO_GPU_TMA") && atoi (getenv ("PLUTO_GPU_TMA")) != 0 && g.S1 % 2 == 0);
   return 0;
 }
 
@@ -803,7 +751,6 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       s.inv_dl2 = 1.0/g.dx[1];
       s.last_dir = (g.dims == 2);
       s.tma = h->tma;
-      if (s.tma) s.vmap = h->vmap[sp.in];
       const int te = tbegin (h, KC_SWEEP_X);
       if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = pg_fast::launch_sweep_xy_hlld (recon, s, h->stream, bf);
       else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = pg_fast::launch_sweep_xy_hll  (recon, s, h->stream, bf);
@@ -1126,7 +1073,7 @@ int pluto_gpu_next_dt_async (PlutoGpu *h, double cfl, double cfl_max_var)
   if (h->hist_enq - h->hist_read >= HIST_N) return fail ("more than %d steps enqueued without pluto_gpu_sync_results", HIST_N);
   next_dt_kernel<<<1, 32, 0, h->stream>>>(h->red, h->dtdev, h->hist, h->hist_count, h->g.dx[0], h->g.dx[1], h->g.dx[2],
                                           h->ctu ? 1 : h->g.dims, cfl, cfl_max_var);
-  if (count (h, cudaGetLastError () == cudaSuccess ? 1 : -1)) return 1;
+  if (count (h, pg_launch_status ())) return 1;
   h->hist_enq++;
   return 0;
 }

@@ -93,24 +93,18 @@ __device__ __forceinline__ void cp_async_wait_all () { asm volatile ("cp.async.w
 #endif
 
 // ---------------------------------------------------------------------------
-//  TMA staging (fused x1+x2 sweep, SweepArgs.tma): ONE lane of a warp issues ONE cp.async.bulk.tensor.4d per ring row
-//  -- box {36 entries along x1, 1 row, 1 plane, 8 variables} of the tensor map over the primitives -- and the arrival
-//  is counted in bytes on the warp's own mbarrier; the other lanes only wait on its phase.  Replaces 8 (+8 for the four
-//  halo lanes) 8-byte cp.async per lane and row together with their address arithmetic.
+//  TMA staging (fused x1+x2 sweep, SweepArgs.tma): ONE lane of a warp issues one bulk asynchronous copy
+//  (cp.async.bulk.shared.global, the TMA engine's 1-D form) per variable and ring row -- 38 consecutive entries of the row,
+//  starting at an even index so that source and destination are 16-byte aligned -- and the arrival is counted in bytes on the
+//  warp's own mbarrier; the other lanes only wait on its phase.  Replaces 8 (+8 for the four halo lanes) 8-byte cp.async per
+//  lane and row together with their address arithmetic.  (A 4-D tensor map over the 8 primitive arrays, one
+//  cp.async.bulk.tensor per row, was tried first: cuTensorMapEncodeTiled accepted it, the B200 raised "illegal instruction" on
+//  the first UTMALDG with the descriptor in the kernel parameters and in global memory alike -- profiles/r2_tma_ab.txt.)
 // ---------------------------------------------------------------------------
 #ifdef PG_EMU
 __device__ __forceinline__ void mbar_init (unsigned long long *bar) { *bar = 0; }
-__device__ __forceinline__ void tma_load_row (double *dst, const PgTensorMap *map, unsigned long long *bar, int x, int y, int z, unsigned)
-{
-  const PgTensorMapEmu *m = reinterpret_cast<const PgTensorMapEmu *>(map);
-  int n = 0;                                           // lands at once; out-of-range entries are zero
-  for (int v = 0; v < m->box[3]; v++) for (int i = 0; i < m->box[0]; i++, n++){
-    const long long xi = x + i;
-    const bool in = xi >= 0 && xi < m->dim[0] && y >= 0 && y < m->dim[1] && z >= 0 && z < m->dim[2] && v < m->dim[3];
-    dst[n] = in ? m->base[xi*m->stride[0] + (long long)y*m->stride[1] + (long long)z*m->stride[2] + (long long)v*m->stride[3]] : 0.0;
-  }
-  (void)bar;
-}
+__device__ __forceinline__ void bulk_copy (double *dst, const double *src, unsigned bytes, unsigned long long *)
+{ for (unsigned q = 0; q < bytes/8; q++) dst[q] = src[q]; }             // lands at once
 __device__ __forceinline__ void mbar_expect (unsigned long long *, unsigned) {}
 __device__ __forceinline__ void mbar_wait (unsigned long long *, unsigned) {}
 __device__ __forceinline__ void fence_proxy_async () {}
@@ -126,11 +120,11 @@ __device__ __forceinline__ void mbar_expect (unsigned long long *bar, unsigned b
   const unsigned sa = (unsigned)__cvta_generic_to_shared (bar);
   asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sa), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_row (double *dst, const PgTensorMap *map, unsigned long long *bar, int x, int y, int z, unsigned)
+__device__ __forceinline__ void bulk_copy (double *dst, const double *src, unsigned bytes, unsigned long long *bar)
 {
   const unsigned sd = (unsigned)__cvta_generic_to_shared (dst), sb = (unsigned)__cvta_generic_to_shared (bar);
-  asm volatile ("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                :: "r"(sd), "l"(map), "r"(sb), "r"(x), "r"(y), "r"(z), "r"(0) : "memory");
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"(sd), "l"(src), "r"(bytes), "r"(sb) : "memory");
 }
 __device__ __forceinline__ void mbar_wait (unsigned long long *bar, unsigned phase)
 {
@@ -662,7 +656,8 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 #ifndef PG_MINB_XY
 #define PG_MINB_XY 3
 #endif
-__host__ __device__ constexpr int xy_ring_cols () { return 4*36; }             // 4 warps x (32 + 4 halo columns)
+__host__ __device__ constexpr int xy_ring_cols () { return 4*38; }             // 4 warps x (32 + 4 halo columns + 2: the bulk copies
+                                                                               // of the TMA variant start at an even entry)
 __host__ __device__ constexpr int xy_thread_slots (int recon) { return 8 + 7 + (recon == RECON_PPM ? 8 : 0) + 2; }
 // ring rows: the stencil rows f .. f+LA, plus (PLM) one free row for the copy in flight so
 // that nothing has to be read ahead of its use; with PPM that row would push three blocks
@@ -686,8 +681,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
   constexpr int NZ = xy_ring_rows (RECON);           // ring rows: f .. f+LA (+ a free one)
   constexpr int ZF = (NZ > LA + 1 ? NZ - 1 : 0);     // ring row the copy in flight lands in
   constexpr int CW = xy_ring_cols ();                // ring columns per block
-  constexpr int VS = 36;                             // ring layout [row][warp][variable][36 entries]: the TMA box of a warp
-                                                     // ({36, 1, 1, 8}) lands contiguously, 2304 bytes, 128-byte aligned
+  constexpr int VS = 38;                             // ring layout [row][warp][variable][38 entries] (36 used by cp.async)
   constexpr int CS = 128;
   const Geom &g = a.g;
   const Phys &ph = *reinterpret_cast<const Phys *>(&a.ph);     // stays in the kernel-parameter constant bank
@@ -726,12 +720,12 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
   int id = gidx32 (g, k, c0 - 1, i);                 // zone (k, c0-1, i)
 
   extern __shared__ __align__(128) double carry_[];
-  double *ring = carry_ + warp*(8*VS) + 1 + lane;    // own column; entries -1, 32, 33, 34 of the warp around it
+  // TMA: the 38-entry window of a row starts at the even entry at or below the warp's entry -1
+  const int tpar = TMA ? ((id - lane - 1) & 1) : 0;
+  double *ring = carry_ + warp*(8*VS) + 1 + lane + tpar;   // own column; entries -1, 32, 33, 34 of the warp around it
   double *cs = carry_ + 8*NZ*CW + threadIdx.x;
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(carry_ + 8*NZ*CW + xy_thread_slots (RECON)*CS) + warp;
   unsigned tphase = 0;                               // TMA: parity of the warp's mbarrier
-  const int tx0 = g.beg[0] - HL + seg*STRIDE + g.off[0] - 1;        // tensor coordinates of ring entry -1 of this warp
-  const int tz0 = k + g.off[2];
   if (TMA){
     if (lane == 0) mbar_init (mbar);
     __syncwarp ();
@@ -745,13 +739,15 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 #define C_BX     cs[S_BX*CS]
   double *z[NZ];
   PG_UNROLL for (int q = 0; q < NZ; q++) z[q] = ring + 8*q*CW;           // z[q]: row f+q
-  // TMA: rows [jrow, jrow + nrows) of the plane -> ring rows dst, dst + 8*CW, ...; one elected lane, bytes counted on mbar
-  auto fetch_rows_tma = [&] (double *dst, int jrow, int nrows){
+  // TMA: `nrows` consecutive rows starting with the row of zone idr -> ring rows dst, dst + 8*CW, ...; one elected lane,
+  // bytes counted on mbar
+  constexpr int NLIVE = (NC == 3 ? 8 : 6);
+  auto fetch_rows_tma = [&] (double *dst, int idr, int nrows){
     if (lane == 0){
       fence_proxy_async ();
-      mbar_expect (mbar, (unsigned)(nrows*8*VS*sizeof (double)));
+      mbar_expect (mbar, (unsigned)(nrows*NLIVE*VS*sizeof (double)));
       for (int q = 0; q < nrows; q++)
-        tma_load_row (dst - 1 - lane + q*(8*CW), &a.vmap, mbar, tx0, jrow + q + g.off[1], tz0, 0u);
+        PG_FOR_NV(nv) bulk_copy (dst - 1 - tpar + q*(8*CW) + nv*VS, a.V[nv] + (idr - 1 - tpar) + q*sD, (unsigned)(VS*sizeof (double)), mbar);
     }
   };
   auto fetch_row = [&] (double *dst, int idr, bool ordered){
@@ -763,7 +759,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     }
   };
   {
-    if (TMA) fetch_rows_tma (z[0], c0 - 1, LA + 1);
+    if (TMA) fetch_rows_tma (z[0], id, LA + 1);
     else PG_UNROLL for (int q = 0; q <= LA; q++) fetch_row (z[q], id + q*sD, false);
     cp_async8 (&C_BY, a.Bn2 + id);
     cp_async8 (&C_BX, a.Bn + id);
@@ -822,7 +818,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     // (PPM), which must then be read first
     if (ZF == 0){ read_row_f (); __syncwarp (); }     // every lane has read its neighbours' columns of row f before they are refilled
     tpending = (f + 1 <= c1);
-    if (f + 1 <= c1){ if (TMA) fetch_rows_tma (z[ZF], f + LA + 1, 1); else fetch_row (z[ZF], id + (LA + 1)*sD, true); }
+    if (f + 1 <= c1){ if (TMA) fetch_rows_tma (z[ZF], id + (LA + 1)*sD, 1); else fetch_row (z[ZF], id + (LA + 1)*sD, true); }
     if (f + 1 <= c1) cp_async8 (&C_BY, a.Bn2 + id + sD);
     if (f + 1 <= f_end) cp_async8_ordered (&C_BX, a.Bn + id + sD);
     cp_async_commit ();
@@ -1036,7 +1032,7 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
 #undef PG_LXY2
 #undef PG_LXY3
 #undef PG_LXYK
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 // ---------------------------------------------------------------------------
@@ -1098,7 +1094,7 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
 #undef PG_LM1
 #undef PG_LM2
   }
-  return cudaGetLastError () == cudaSuccess ? 1 : -1;
+  return pg_launch_status ();
 }
 
 } // namespace PG_NS
