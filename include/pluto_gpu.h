@@ -266,6 +266,10 @@ int pluto_gpu_read_field (PlutoGpu *h, const char *name, double *host);
 /* FP64 pipe microbenchmark (independent DFMA chains on every SM): the measured
    denominator of the FP64 roofline, in TFLOP/s (FMA = 2 flops). */
 int pluto_gpu_measure_fp64 (int device, double *tflops);
+/* Self-test of the arithmetic of the FAST Roe kernels: their branch-free division, reciprocal and square root must be the
+ * IEEE results (the Roe solver compares square roots, Src/MHD/roe.c:336-364).  `samples` random and adversarial operand pairs
+ * are compared bit for bit with div.rn.f64 / sqrt.rn.f64 on the device; mismatches[0..2] = quotient, reciprocal, root. */
+int pluto_gpu_selftest_arith (int device, long long samples, unsigned long long seed, unsigned long long mismatches[3]);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ SYMBOLS = [
     "pluto_gpu_boundary", "pluto_gpu_next_dt", "pluto_gpu_halo_doubles", "pluto_gpu_halo_pack",
     "pluto_gpu_halo_unpack", "pluto_gpu_boundary_dim", "pluto_gpu_step_begin", "pluto_gpu_stage",
     "pluto_gpu_step_end", "pluto_gpu_stream", "pluto_gpu_launch_count", "pluto_gpu_device_bytes",
-    "pluto_gpu_field", "pluto_gpu_read_field", "pluto_gpu_timing", "pluto_gpu_timing_get", "pluto_gpu_measure_fp64", "pluto_gpu_halo_nbr_doubles", "pluto_gpu_halo_plan",
+    "pluto_gpu_field", "pluto_gpu_read_field", "pluto_gpu_timing", "pluto_gpu_timing_get", "pluto_gpu_measure_fp64", "pluto_gpu_selftest_arith", "pluto_gpu_halo_nbr_doubles", "pluto_gpu_halo_plan",
     "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on",
     "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
     "pluto_gpu_set_dt", "pluto_gpu_advance_async", "pluto_gpu_next_dt_async", "pluto_gpu_reduction_slots",
@@ -97,6 +97,7 @@ def load_library(path: str | None = None):
                                   C.POINTER(C.c_int * 3)]
     L.pluto_gpu_read_field.argtypes = [vp, C.c_char_p, vp]
     L.pluto_gpu_measure_fp64.argtypes = [C.c_int, dp]
+    L.pluto_gpu_selftest_arith.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_ulonglong * 3)]
     L.pluto_gpu_halo_nbr_doubles.argtypes = [vp, C.POINTER(C.c_int * 3)]
     L.pluto_gpu_halo_nbr_doubles.restype = C.c_longlong
     L.pluto_gpu_halo_plan.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp)]

@@ -253,13 +253,14 @@ final_kernel (const __grid_constant__ FinalArgs a)
 {
   const Geom &g = a.g;
   Phys ph; ph.gamma = a.ph.gamma; ph.gmm1 = a.ph.gmm1; ph.small_dn = a.ph.small_dn; ph.small_pr = a.ph.small_pr; ph.igmm1 = a.ph.igmm1;
-  const int ni = a.box_n[0], nj = a.box_n[1], nk = (NC == 3 ? a.box_n[2] : 1);
+  const int *blo = a.nbox ? a.boxes_lo[blockIdx.y] : a.box_lo, *bn = a.nbox ? a.boxes_n[blockIdx.y] : a.box_n;
+  const int ni = bn[0], nj = bn[1], nk = (NC == 3 ? bn[2] : 1);
   const unsigned t = blockIdx.x*blockDim.x + threadIdx.x;
   int fl = 0, bad = 0;
   if (t < (unsigned)(ni*nj*nk)){
     const unsigned tq = t/(unsigned)ni;
     const int ti = (int)(t - tq*(unsigned)ni), tj = (int)(tq % (unsigned)nj), tk = (int)(tq/(unsigned)nj);
-    const int i = g.beg[0] + a.box_lo[0] + ti, j = g.beg[1] + a.box_lo[1] + tj, k = (NC == 3 ? g.beg[2] + a.box_lo[2] + tk : 0);
+    const int i = g.beg[0] + blo[0] + ti, j = g.beg[1] + blo[1] + tj, k = (NC == 3 ? g.beg[2] + blo[2] + tk : 0);
     const long long id = gidx (g, k, j, i);
     double u[NV], v[NV];
     u[RHO] = a.U[RHO][id]; u[MX1] = a.U[MX1][id]; u[MX2] = a.U[MX2][id];
@@ -605,14 +606,19 @@ int launch_ct_update (const CtArgs &a, cudaStream_t s)
 int launch_final (const FinalArgs &a, cudaStream_t s)
 {
   const Geom &g = a.g;
-  const long long n = (long long)a.box_n[0]*a.box_n[1]*(g.dims == 3 ? a.box_n[2] : 1);
+  long long n = (long long)a.box_n[0]*a.box_n[1]*(g.dims == 3 ? a.box_n[2] : 1);
+  for (int b = 0; b < a.nbox; b++){           // several boxes: the grid covers the largest, blockIdx.y = box
+    const long long nb = (long long)a.boxes_n[b][0]*a.boxes_n[b][1]*(g.dims == 3 ? a.boxes_n[b][2] : 1);
+    if (b == 0 || nb > n) n = nb;
+  }
   if (n <= 0) return 0;
+  const dim3 grid (nblocks (n, 128), a.nbox ? a.nbox : 1);
   if (a.en_corr){
-    if (g.dims == 3) final_kernel<3, true><<<nblocks (n, 128), 128, 0, s>>>(a);
-    else             final_kernel<2, true><<<nblocks (n, 128), 128, 0, s>>>(a);
+    if (g.dims == 3) final_kernel<3, true><<<grid, 128, 0, s>>>(a);
+    else             final_kernel<2, true><<<grid, 128, 0, s>>>(a);
   }else{
-    if (g.dims == 3) final_kernel<3, false><<<nblocks (n, 128), 128, 0, s>>>(a);
-    else             final_kernel<2, false><<<nblocks (n, 128), 128, 0, s>>>(a);
+    if (g.dims == 3) final_kernel<3, false><<<grid, 128, 0, s>>>(a);
+    else             final_kernel<2, false><<<grid, 128, 0, s>>>(a);
   }
   return pg_launch_status ();
 }

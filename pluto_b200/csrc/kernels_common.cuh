@@ -142,6 +142,9 @@ struct FinalArgs {
                                              // 2: store only ConsToPrim repairs
   double *Uw[8];
   int     box_lo[3], box_n[3];               // zones of this launch, relative to the first interior zone
+  // several boxes in ONE launch (the up to six shell slabs of a decomposed block): blockIdx.y selects the box
+  int     nbox;                              // 0: the single box above
+  int     boxes_lo[6][3], boxes_n[6][3];
   // CT_EN_CORRECTION YES (ct_field_average.c:116-129): the cell-centred conservative field the sweeps WOULD have
   // produced is rebuilt from the face EMFs (= the induction fluxes the sweeps stored) and the stage's input field
   int     en_corr;

@@ -134,6 +134,41 @@ __device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs)
   rs = fq_rsqrt (x);
   s = x*rs;
 }
+#elif defined(PG_FAST) && !defined(PG_HOST_EMU)
+// The Roe units of the FAST library: IEEE results (correctly rounded quotient / root, what div.rn.f64 / sqrt.rn.f64 give),
+// but branch-free -- no exponent-range test, no slow-path call, so the surrounding code keeps its registers and schedule.
+// MUFU seed -> one cubic step (2^-60) -> one Markstein step: the reciprocal is then correctly rounded (b's mantissa not all
+// ones); quotient q = a y, exact residual r = a - b q (FMA), q' = RN(q + r y) = RN(a/b) (Markstein 1990; the sequence
+// div.rn.f64 itself runs on its fast path).  Root: s = x y, r = x - s^2 exact, s' = RN(s + r y/2).  Arguments are physical
+// magnitudes far from the subnormal / overflow range.  pluto_gpu_selftest_arith compares both with div.rn / sqrt.rn on the
+// device over random and adversarial mantissas (tests/test_gpu_parity.py).
+__device__ __forceinline__ double pg_rcp (double b)
+{
+  double y;
+  asm ("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+  double e = fma (-b, y, 1.0);
+  y = fma (y, fma (e, e, e), y);
+  e = fma (-b, y, 1.0);
+  return fma (y, e, y);
+}
+__device__ __forceinline__ double pg_div (double a, double b)
+{
+  const double y = pg_rcp (b);
+  const double q = a*y;
+  const double r = fma (-b, q, a);
+  return fma (r, y, q);
+}
+__device__ __forceinline__ double pg_sqrt (double x)
+{
+  double y;
+  asm ("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma (-x*y, y, 1.0);
+  y = fma (y*e, fma (0.375, e, 0.5), y);
+  double s = x*y;
+  const double r = fma (-s, s, x);
+  s = fma (r, 0.5*y, s);
+  return x > 0.0 ? s : (x < 0.0 ? __longlong_as_double (0x7ff8000000000000LL) : x);     // sqrt(+-0) = +-0, sqrt(< 0) = NaN
+}
 #else
 __device__ __forceinline__ double pg_rcp (double b) { return 1.0/b; }
 __device__ __forceinline__ double pg_div (double a, double b) { return a/b; }

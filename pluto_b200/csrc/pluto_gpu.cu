@@ -646,15 +646,22 @@ static int launch_final_boxes (PlutoGpu *h, FinalArgs &f, int part)
     TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
     return 0;
   }
+  // all shell slabs in ONE launch (blockIdx.y = slab)
+  f.nbox = 0;
   for (int d = g.dims - 1; d >= 0; d--) for (int hs = 0; hs < 2; hs++){
     const int w = hs ? mhi[d] : mlo[d];
     if (w == 0) continue;
+    int *lo = f.boxes_lo[f.nbox], *nn = f.boxes_n[f.nbox];
     for (int q = 0; q < 3; q++){
-      if (q > d){ f.box_lo[q] = ilo[q]; f.box_n[q] = in_[q]; }      // already covered by the slabs of q
-      else      { f.box_lo[q] = 0;      f.box_n[q] = g.n[q]; }
+      if (q > d){ lo[q] = ilo[q]; nn[q] = in_[q]; }      // already covered by the slabs of q
+      else      { lo[q] = 0;      nn[q] = g.n[q]; }
     }
-    f.box_lo[d] = hs ? g.n[d] - w : 0; f.box_n[d] = w;
+    lo[d] = hs ? g.n[d] - w : 0; nn[d] = w;
+    f.nbox++;
+  }
+  if (f.nbox){
     TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_final) (f, h->stream)));
+    f.nbox = 0;
   }
   return 0;
 }
@@ -1351,6 +1358,24 @@ extern "C" int pluto_gpu_measure_fp64 (int device, double *tflops)
   }
   cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
   *tflops = best;
+  return 0;
+}
+
+namespace pg_fast { int launch_arith_selftest (unsigned long long seed, int nblocks, int n, unsigned long long *bad, cudaStream_t s); }
+
+// The FAST Roe kernels use a branch-free correctly rounded division / reciprocal / square root (mhd_device.cuh): compare them
+// with div.rn.f64 / sqrt.rn.f64 on `samples` operand pairs; mismatches[0..2] = quotient, reciprocal, root.
+extern "C" int pluto_gpu_selftest_arith (int device, long long samples, unsigned long long seed, unsigned long long mismatches[3])
+{
+  CU (cudaSetDevice (device));
+  unsigned long long *bad;
+  CU (cudaMalloc ((void **)&bad, 3*sizeof (unsigned long long)));
+  CU (cudaMemset (bad, 0, 3*sizeof (unsigned long long)));
+  const int nblocks = 148*8, per = (int)((samples + (long long)nblocks*256 - 1)/((long long)nblocks*256));
+  if (pg_fast::launch_arith_selftest (seed, nblocks, per < 1 ? 1 : per, bad, 0) < 0){ cudaFree (bad); return fail ("selftest launch failed"); }
+  cudaError_t ce = cudaMemcpy (mismatches, bad, 3*sizeof (unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree (bad);
+  if (ce != cudaSuccess) return fail ("pluto_gpu_selftest_arith: %s", cudaGetErrorString (ce));
   return 0;
 }
 

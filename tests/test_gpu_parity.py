@@ -106,6 +106,18 @@ def test_tma_staging_bit_identical_to_cp_async(monkeypatch, problem, dims, n, re
         assert np.array_equal(v, out[1][0][k]), k
 
 
+def test_fast_roe_division_and_square_root_are_ieee():
+    """The FAST Roe kernels keep IEEE arithmetic upstream of the solver's eigenvector switches (mhd_device.cuh) with a
+    branch-free correctly rounded division / reciprocal / square root.  2e9 operand pairs (random and adversarial
+    mantissas, 2^-40 .. 2^40) against div.rn.f64 / sqrt.rn.f64 on the device: no mismatch."""
+    import ctypes as C
+    from pluto_b200 import load_library
+    bad = (C.c_ulonglong * 3)()
+    for seed in (1, 20240607):
+        assert load_library().pluto_gpu_selftest_arith(0, 1_000_000_000, seed, C.byref(bad)) == 0
+        assert list(bad) == [0, 0, 0], f"quotient / reciprocal / root mismatches: {list(bad)}"
+
+
 def test_fast_unfused_sweeps_within_tolerance(monkeypatch):
     """FAST with one kernel per direction (PLUTO_GPU_NO_FUSE_XY): the path EXACT uses, with FAST arithmetic."""
     monkeypatch.setenv("PLUTO_GPU_NO_FUSE_XY", "1")
