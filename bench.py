@@ -327,6 +327,7 @@ def run_workload(cx, name, steps, warmup, arith, tstep, host_dt=False, want_e2e=
            "ms_per_step": ms_max / steps, "launches": launches, "window": (t_wall0, t_wall1),
            "zones_local": zones_local, "zones_total": zones_total, "layout": layout, "n": n, "dims": dims,
            "device_bytes": s.block.device_bytes, "strong": strong, "nan": info.nan_events,
+           "halo": (getattr(s, "halo", None) if world > 1 else None),
            "l2_flush": bool(small)}
 
     rep, ksteps = None, 0
@@ -637,7 +638,7 @@ def main():
         "higher_is_better": True, "scaling": "strong" if res["strong"] else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": cfg,
         "run": {"zones_per_gpu": list(res["n"][:dims]), "global_zones": list(lay.global_n[:dims]), "rank_grid": list(lay.grid),
-                "arith": args.arith,
+                "arith": args.arith, "halo": res.get("halo"),
                 "next_dt": "host" if args.host_dt else "device kernel, same dt sequence (tests/test_gpu_parity.py)",
                 "device_bytes_per_gpu": res["device_bytes"], "timed_region_s": res["ms"] * 1e-3,
                 "l2_flush_between_repetitions": res["l2_flush"]},

@@ -211,6 +211,22 @@ long long pluto_gpu_halo_nbr_doubles (const PlutoGpu *h, const int off[3]);
 int pluto_gpu_halo_plan       (PlutoGpu *h, int n_nbr, const int *offsets,
                                double *const *send_bufs, double *const *recv_bufs);
 int pluto_gpu_halo_pack_all   (PlutoGpu *h, int stage);
+/* The plan of ONE stage (its state buffer) only: a host may give every stage its own send / receive buffers. */
+int pluto_gpu_halo_plan_stage (PlutoGpu *h, int stage, int n_nbr, const int *offsets,
+                               double *const *send_bufs, double *const *recv_bufs);
+/* Ghost zones stored directly into the neighbour GPU's memory over NVLink (replaces the MPI_Sendrecv of
+ * Src/Parallel/al_exchange_dim.c:58-88 for ranks on one node): a rank allocates its receive arena with pluto_gpu_ipc_alloc
+ * and publishes the 64-byte handle; a neighbouring process maps it (pluto_gpu_ipc_open) and passes the mapped addresses as
+ * SEND buffers of pluto_gpu_halo_plan_stage, so the pack launch is the transfer.  pluto_gpu_halo_signal (after the pack
+ * launch, same stream) stores the exchange number into one 64-bit counter per peer (addresses inside the peers' arenas);
+ * pluto_gpu_halo_wait (before the unpack launch) spins on the device until the `n` counters of this rank, consecutive at
+ * `counters`, have reached it.  stream == NULL: the block's own stream. */
+int pluto_gpu_ipc_alloc   (int device, size_t bytes, void **ptr, unsigned char handle[64]);
+int pluto_gpu_ipc_open    (int device, const unsigned char handle[64], void **ptr);
+int pluto_gpu_ipc_close   (void *ptr);
+int pluto_gpu_ipc_free    (void *ptr);
+int pluto_gpu_halo_signal (PlutoGpu *h, void *stream, int n, unsigned long long *const *peer_counters, unsigned long long value);
+int pluto_gpu_halo_wait   (PlutoGpu *h, void *stream, int n, const unsigned long long *counters, unsigned long long value);
 int pluto_gpu_halo_unpack_all (PlutoGpu *h, int stage);
 /* Overlap of the exchange with computation: a stage can be issued in two parts,
        pluto_gpu_stage_shell    (h, stage, dt)   sweeps, CT and the new state of the zones within

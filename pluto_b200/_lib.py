@@ -24,7 +24,8 @@ SYMBOLS = [
     "pluto_gpu_halo_unpack", "pluto_gpu_boundary_dim", "pluto_gpu_step_begin", "pluto_gpu_stage",
     "pluto_gpu_step_end", "pluto_gpu_stream", "pluto_gpu_launch_count", "pluto_gpu_device_bytes",
     "pluto_gpu_field", "pluto_gpu_read_field", "pluto_gpu_timing", "pluto_gpu_timing_get", "pluto_gpu_measure_fp64", "pluto_gpu_selftest_arith", "pluto_gpu_halo_nbr_doubles", "pluto_gpu_halo_plan",
-    "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on",
+    "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on", "pluto_gpu_halo_plan_stage",
+    "pluto_gpu_ipc_alloc", "pluto_gpu_ipc_open", "pluto_gpu_ipc_close", "pluto_gpu_ipc_free", "pluto_gpu_halo_signal", "pluto_gpu_halo_wait",
     "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
     "pluto_gpu_set_dt", "pluto_gpu_advance_async", "pluto_gpu_next_dt_async", "pluto_gpu_reduction_slots",
     "pluto_gpu_sync_results", "pluto_gpu_write_dbl", "pluto_gpu_read_dbl", "pluto_gpu_analysis",
@@ -101,6 +102,13 @@ def load_library(path: str | None = None):
     L.pluto_gpu_halo_nbr_doubles.argtypes = [vp, C.POINTER(C.c_int * 3)]
     L.pluto_gpu_halo_nbr_doubles.restype = C.c_longlong
     L.pluto_gpu_halo_plan.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp)]
+    L.pluto_gpu_halo_plan_stage.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp)]
+    L.pluto_gpu_ipc_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.pluto_gpu_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.pluto_gpu_ipc_close.argtypes = [vp]
+    L.pluto_gpu_ipc_free.argtypes = [vp]
+    L.pluto_gpu_halo_signal.argtypes = [vp, vp, C.c_int, C.POINTER(vp), C.c_ulonglong]
+    L.pluto_gpu_halo_wait.argtypes = [vp, vp, C.c_int, vp, C.c_ulonglong]
     L.pluto_gpu_halo_pack_all.argtypes = [vp, C.c_int]
     L.pluto_gpu_halo_unpack_all.argtypes = [vp, C.c_int]
     L.pluto_gpu_halo_pack_all_on.argtypes = [vp, C.c_int, vp]

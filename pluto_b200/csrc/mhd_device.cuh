@@ -137,11 +137,13 @@ __device__ __forceinline__ void pg_sqrt_rsqrt (double x, double &s, double &rs)
 #elif defined(PG_FAST) && !defined(PG_HOST_EMU)
 // The Roe units of the FAST library: IEEE results (correctly rounded quotient / root, what div.rn.f64 / sqrt.rn.f64 give),
 // but branch-free -- no exponent-range test, no slow-path call, so the surrounding code keeps its registers and schedule.
-// MUFU seed -> one cubic step (2^-60) -> one Markstein step: the reciprocal is then correctly rounded (b's mantissa not all
-// ones); quotient q = a y, exact residual r = a - b q (FMA), q' = RN(q + r y) = RN(a/b) (Markstein 1990; the sequence
-// div.rn.f64 itself runs on its fast path).  Root: s = x y, r = x - s^2 exact, s' = RN(s + r y/2).  Arguments are physical
-// magnitudes far from the subnormal / overflow range.  pluto_gpu_selftest_arith compares both with div.rn / sqrt.rn on the
-// device over random and adversarial mantissas (tests/test_gpu_parity.py).
+// Reciprocal: MUFU seed -> one cubic step (2^-60) -> one Markstein step y + y (1 - b y): correctly rounded except when b's
+// mantissa is all ones (1/b then lies just above a rounding tie that the iteration resolves downwards): that one pattern is
+// patched by an integer increment.  Quotient: q = a y, then twice  r = a - b q (exact, FMA), q <- RN(q + r y): the first pass
+// makes q faithful, the second correctly rounded (Markstein 1990; Muller et al., Handbook of Floating-Point Arithmetic, 4.7).
+// Root: s = x y, r = x - s^2 exact, s' = RN(s + r y/2).  Arguments are physical magnitudes far from the subnormal / overflow
+// range.  pluto_gpu_selftest_arith compares all three with div.rn / sqrt.rn on the device over random and adversarial
+// mantissas (tests/test_gpu_parity.py).
 __device__ __forceinline__ double pg_rcp (double b)
 {
   double y;
@@ -149,13 +151,18 @@ __device__ __forceinline__ double pg_rcp (double b)
   double e = fma (-b, y, 1.0);
   y = fma (y, fma (e, e, e), y);
   e = fma (-b, y, 1.0);
-  return fma (y, e, y);
+  y = fma (y, e, y);
+  const long long ones = 0x000FFFFFFFFFFFFFLL;
+  if ((__double_as_longlong (b) & ones) == ones) y = __longlong_as_double (__double_as_longlong (y) + 1);
+  return y;
 }
 __device__ __forceinline__ double pg_div (double a, double b)
 {
   const double y = pg_rcp (b);
-  const double q = a*y;
-  const double r = fma (-b, q, a);
+  double q = a*y;
+  double r = fma (-b, q, a);
+  q = fma (r, y, q);
+  r = fma (-b, q, a);
   return fma (r, y, q);
 }
 __device__ __forceinline__ double pg_sqrt (double x)

@@ -1425,11 +1425,27 @@ long long pluto_gpu_halo_nbr_doubles (const PlutoGpu *h, const int off[3])
   return tot > tot_r ? tot : tot_r;
 }
 
+static int halo_plan_buffers (PlutoGpu *h, int b0, int b1, int n_nbr, const int *offsets, double *const *send_bufs,
+                              double *const *recv_bufs);
+
 int pluto_gpu_halo_plan (PlutoGpu *h, int n_nbr, const int *offsets, double *const *send_bufs,
                          double *const *recv_bufs)
+{ return halo_plan_buffers (h, 0, h->nbuf, n_nbr, offsets, send_bufs, recv_bufs); }
+
+// the same for ONE state buffer (= one stage of the step): lets a host give every stage its own buffers, e.g. receive
+// areas in a peer GPU's memory that alternate from stage to stage (pluto_gpu_ipc_*, pluto_b200/parallel.py PeerExchanger)
+int pluto_gpu_halo_plan_stage (PlutoGpu *h, int stage, int n_nbr, const int *offsets, double *const *send_bufs,
+                               double *const *recv_bufs)
+{
+  const int b = stage_in_buf (h, stage);
+  return halo_plan_buffers (h, b, b + 1, n_nbr, offsets, send_bufs, recv_bufs);
+}
+
+static int halo_plan_buffers (PlutoGpu *h, int b0, int b1, int n_nbr, const int *offsets, double *const *send_bufs,
+                              double *const *recv_bufs)
 {
   CU (cudaSetDevice (h->cfg.device));
-  for (int b = 0; b < h->nbuf; b++) for (int dirn = 0; dirn < 2; dirn++){
+  for (int b = b0; b < b1; b++) for (int dirn = 0; dirn < 2; dirn++){
     HaloEntry *tab = (HaloEntry *)calloc ((size_t)n_nbr*(NVS + 3) + 1, sizeof (HaloEntry));
     int ne = 0; long long mx = 0;
     for (int q = 0; q < n_nbr; q++){
@@ -1485,4 +1501,106 @@ int pluto_gpu_halo_unpack_all (PlutoGpu *h, int stage)
   const int b = stage_in_buf (h, stage);
   TIMED (h, KC_HALO, count (h, DISPATCH (h, launch_halo_table) (h->halo_tab[b][1], h->halo_n[b][1], h->halo_max[b][1], h->g, false, h->stream)));
   return 0;
+}
+
+// ---------------------------------------------------------------------------
+//  Ghost zones written straight into the neighbour GPU's memory (NVLink peer stores), no communication library on the data
+//  path: a rank allocates its receive arena with pluto_gpu_ipc_alloc and publishes the 64-byte IPC handle; a neighbour
+//  (another process on the same node) maps it with pluto_gpu_ipc_open and hands the mapped addresses to
+//  pluto_gpu_halo_plan_stage as its SEND buffers -- the pack launch then IS the transfer.  Arrival is signalled by a counter
+//  per (receiver, sender) pair in the same arena: pluto_gpu_halo_signal (after the pack launch, same stream) stores the
+//  exchange number into the peers' counters, pluto_gpu_halo_wait (before the unpack launch) spins until every counter of
+//  this rank has reached it.  All of it is stream-ordered device work: nothing waits on the host.
+//  Replaces AL_Exchange_dim's MPI_Sendrecv (Src/Parallel/al_exchange_dim.c:58-88).
+// ---------------------------------------------------------------------------
+struct PeerFlags { unsigned long long *p[32]; };
+
+__global__ void halo_signal_kernel (PeerFlags f, int n, unsigned long long value)
+{
+  const int q = threadIdx.x;
+  if (q < n){
+    __threadfence_system ();                      // the pack launch before this one has completed; order the counter after it
+    *(volatile unsigned long long *)f.p[q] = value;
+    __threadfence_system ();
+  }
+}
+
+__global__ void halo_wait_kernel (const unsigned long long *flags, int n, unsigned long long value, unsigned long long *red)
+{
+  const int q = threadIdx.x;
+  if (q < n){
+    const volatile unsigned long long *p = flags + q;
+    const long long t0 = clock64 ();
+    while (*p < value){
+      if (clock64 () - t0 > 20000000000LL){       // ~10 s: a neighbour died -- report instead of hanging the GPU
+        atomicAdd (red + RED_NAN, 1ull);
+        break;
+      }
+    }
+    __threadfence_system ();
+  }
+}
+
+int pluto_gpu_ipc_alloc (int device, size_t bytes, void **ptr, unsigned char handle[64])
+{
+#ifdef PG_EMU
+  (void)device; (void)bytes; (void)ptr; (void)handle;
+  return fail ("pluto_gpu_ipc_alloc: not available under the kernel interpreter");
+#else
+  CU (cudaSetDevice (device));
+  static_assert (sizeof (cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU (cudaMalloc (ptr, bytes));
+  CU (cudaMemset (*ptr, 0, bytes));
+  cudaIpcMemHandle_t hd;
+  CU (cudaIpcGetMemHandle (&hd, *ptr));
+  memcpy (handle, &hd, 64);
+  return 0;
+#endif
+}
+
+int pluto_gpu_ipc_open (int device, const unsigned char handle[64], void **ptr)
+{
+#ifdef PG_EMU
+  (void)device; (void)handle; (void)ptr;
+  return fail ("pluto_gpu_ipc_open: not available under the kernel interpreter");
+#else
+  CU (cudaSetDevice (device));
+  cudaIpcMemHandle_t hd;
+  memcpy (&hd, handle, 64);
+  CU (cudaIpcOpenMemHandle (ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+#endif
+}
+
+int pluto_gpu_ipc_close (void *ptr)
+{
+#ifndef PG_EMU
+  if (ptr) CU (cudaIpcCloseMemHandle (ptr));
+#endif
+  return 0;
+}
+
+int pluto_gpu_ipc_free (void *ptr)
+{
+  if (ptr) CU (cudaFree (ptr));
+  return 0;
+}
+
+int pluto_gpu_halo_signal (PlutoGpu *h, void *stream, int n, unsigned long long *const *peer_counters, unsigned long long value)
+{
+  if (n < 0 || n > 32) return fail ("pluto_gpu_halo_signal: %d neighbours", n);
+  if (n == 0) return 0;
+  CU (cudaSetDevice (h->cfg.device));
+  PeerFlags f; memset (&f, 0, sizeof (f));
+  for (int q = 0; q < n; q++) f.p[q] = peer_counters[q];
+  halo_signal_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : h->stream>>>(f, n, value);
+  return count (h, pg_launch_status ());
+}
+
+int pluto_gpu_halo_wait (PlutoGpu *h, void *stream, int n, const unsigned long long *counters, unsigned long long value)
+{
+  if (n <= 0) return 0;
+  CU (cudaSetDevice (h->cfg.device));
+  halo_wait_kernel<<<1, 32, 0, stream ? (cudaStream_t)stream : h->stream>>>(counters, n, value, h->red);
+  return count (h, pg_launch_status ());
 }

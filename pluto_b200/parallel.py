@@ -214,6 +214,97 @@ class NeighbourExchanger:
         self.unpack_all(stage)
 
 
+class PeerExchanger:
+    """All-neighbour exchange by PEER STORES over NVLink, no communication library on the data path (ranks of one node).
+
+    Every rank owns a receive arena in its HBM: per stage and per neighbour one buffer, plus one 64-bit arrival counter per
+    neighbour.  The arenas are exchanged once as CUDA IPC handles; a rank maps its neighbours' arenas and plans its pack
+    launch to write THERE (pluto_gpu_halo_plan_stage with the mapped addresses as send buffers): packing is sending.  After the
+    pack launch a one-warp kernel stores the exchange number into the neighbours' counters; before the unpack launch a
+    one-warp kernel spins until all of this rank's counters have reached it.  The buffer of a stage is reused one step
+    later: by then the neighbour has unpacked it (it signalled the exchange in between only after that unpack, in stream
+    order), so no acknowledgement travels back.  Steps with a single stage (TIME_STEPPING HANCOCK) would need one: they
+    stay with the NCCL exchanger."""
+
+    def __init__(self, layout: BlockLayout, rank: int, block, device: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        if block.nstages < 2:
+            raise RuntimeError("peer exchange needs >= 2 stages per step (buffers alternate)")
+        self.block, self.L, self.device = block, block.L, device
+        self.nbrs = layout.neighbours(rank)
+        n = len(self.nbrs)
+        self.n = n
+        al = lambda b: (b + 255) & ~255
+        sizes = [8 * int(block.halo_nbr_doubles(o)) for o, _ in self.nbrs]
+        off, self.recv_off = 0, []
+        for _ in range(block.nstages):
+            row = []
+            for q in range(n):
+                row.append(off)
+                off += al(sizes[q])
+            self.recv_off.append(row)
+        self.cnt_off = off
+        off += al(8 * max(n, 1))
+        self.arena = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        block._check(self.L.pluto_gpu_ipc_alloc(device, max(off, 256), C.byref(self.arena), handle))
+        torch.cuda.synchronize()
+        mine = dict(handle=handle.raw, recv_off=self.recv_off, cnt_off=self.cnt_off, offsets=[tuple(o) for o, _ in self.nbrs])
+        info = [None] * layout.world
+        dist.all_gather_object(info, mine, group=group)
+        self.mapped = {}
+        for _, p in self.nbrs:
+            if p not in self.mapped:
+                ptr = C.c_void_p()
+                block._check(self.L.pluto_gpu_ipc_open(device, info[p]["handle"], C.byref(ptr)))
+                self.mapped[p] = ptr.value
+        self.peer_cnt = []
+        send = [[] for _ in range(block.nstages)]
+        for o, p in self.nbrs:
+            qp = info[p]["offsets"].index(tuple(-c for c in o))          # my slot in the neighbour's tables
+            self.peer_cnt.append(self.mapped[p] + info[p]["cnt_off"] + 8 * qp)
+            for st in range(block.nstages):
+                send[st].append(self.mapped[p] + info[p]["recv_off"][st][qp])
+        for st in range(block.nstages):
+            recv = [self.arena.value + self.recv_off[st][q] for q in range(n)]
+            block.halo_plan_stage(st + 1, [o for o, _ in self.nbrs], send[st], recv)
+        self.bytes_per_exchange = sum(sizes)
+        self.seq_push = self.seq_wait = 0
+        dist.barrier(group=group)                                        # every arena is mapped before anyone stores into it
+
+    def push(self, stage, stream_ptr=None):
+        """Pack = store into the neighbours' arenas, then signal (both on `stream_ptr` or the block's stream)."""
+        if not self.n:
+            return
+        self.seq_push += 1
+        if stream_ptr is None:
+            self.block.halo_pack_all(stage)
+        else:
+            self.block.halo_pack_all_on(stage, stream_ptr)
+        self.block.halo_signal(stream_ptr, self.peer_cnt, self.seq_push)
+
+    def wait_unpack(self, stage):
+        if not self.n:
+            return
+        self.seq_wait += 1
+        self.block.halo_wait(None, self.n, self.arena.value + self.cnt_off, self.seq_wait)
+        self.block.halo_unpack_all(stage)
+
+    def forget_in_flight(self):
+        """The state was replaced from outside: an exchange already pushed will never be unpacked."""
+        self.seq_wait = self.seq_push
+
+    def close(self):
+        for p in self.mapped.values():
+            self.L.pluto_gpu_ipc_close(p)
+        self.mapped = {}
+        if self.arena:
+            self.L.pluto_gpu_ipc_free(self.arena)
+            self.arena = None
+
+
 def agree_step_results(err, out, device, group=None):
     """SUM over the ranks of (failed, floor events per step..., NaN events per step...): every rank raises when any rank
     failed, and every rank returns the global event counts.  `out` = ([dt], [StepInfo], dt_next) of this rank or None."""
@@ -277,6 +368,12 @@ class DistStepper:
                     layout, rank, b.halo_nbr_doubles,
                     lambda offs, sb, rb: b.halo_plan(offs, [t.data_ptr() for t in sb], [t.data_ptr() for t in rb]),
                     b.halo_pack_all, b.halo_unpack_all, device=torch.device("cuda", device))
+            # ghost zones by peer stores over NVLink (PLUTO_GPU_HALO=peer; all ranks on one node) instead of NCCL send/recv
+            self.pex = None
+            self.halo = "nccl"
+            if exchange == "all" and os.environ.get("PLUTO_GPU_HALO", "nccl") == "peer" and self.block.nstages >= 2:
+                self.pex = PeerExchanger(layout, rank, self.block, device)
+                self.halo = "peer"
             self._red = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", device))
             if self.overlap:
                 self._comm = torch.cuda.Stream(device=torch.device("cuda", device))
@@ -288,6 +385,8 @@ class DistStepper:
         if self.world > 1 and self.overlap and self._prefetched is not None:
             self._comm.synchronize()
             self._prefetched = None
+            if self.pex is not None:
+                self.pex.forget_in_flight()
 
     def set_state(self, dump):
         self._drain()
@@ -376,11 +475,16 @@ class DistStepper:
                     # stage was completing its interior) or exchanged here, in line
                     if self._prefetched == stage:
                         self._stream.wait_event(self._ev_comm)
+                    elif self.pex is not None:
+                        self.pex.push(stage)
                     else:
                         b.halo_pack_all(stage)
                         self.nex.post()
                     self._prefetched = None
-                    b.halo_unpack_all(stage)
+                    if self.pex is not None:
+                        self.pex.wait_unpack(stage)
+                    else:
+                        b.halo_unpack_all(stage)
                     for d in range(self.dims):
                         b.boundary_dim(stage, d)
                     b.stage_shell(stage, dt)
@@ -388,13 +492,21 @@ class DistStepper:
                     nxt = stage + 1 if stage < self.nstages else 1
                     with torch.cuda.stream(self._comm):
                         self._comm.wait_event(self._ev_shell)
-                        b.halo_pack_all_on(nxt, self._comm.cuda_stream)
-                        self.nex.post()
+                        if self.pex is not None:
+                            self.pex.push(nxt, self._comm.cuda_stream)
+                        else:
+                            b.halo_pack_all_on(nxt, self._comm.cuda_stream)
+                            self.nex.post()
                         self._ev_comm.record(self._comm)
                     b.stage_interior(stage)
                     self._prefetched = nxt
                     continue
-                if self.nex is not None:
+                if self.pex is not None:
+                    self.pex.push(stage)
+                    self.pex.wait_unpack(stage)
+                    for d in range(self.dims):
+                        b.boundary_dim(stage, d)
+                elif self.nex is not None:
                     self.nex.exchange(stage)
                     for d in range(self.dims):
                         b.boundary_dim(stage, d)

@@ -287,6 +287,21 @@ class GpuStepper:
         rp = (C.c_void_p * n)(*recv_ptrs)
         self._check(self.L.pluto_gpu_halo_plan(self._h, n, flat, sp, rp))
 
+    def halo_plan_stage(self, stage, offsets, send_ptrs, recv_ptrs):
+        n = len(offsets)
+        flat = (C.c_int * (3 * n))(*[c for o in offsets for c in o])
+        sp = (C.c_void_p * n)(*send_ptrs)
+        rp = (C.c_void_p * n)(*recv_ptrs)
+        self._check(self.L.pluto_gpu_halo_plan_stage(self._h, stage, n, flat, sp, rp))
+
+    def halo_signal(self, stream_ptr, peer_counter_ptrs, value):
+        n = len(peer_counter_ptrs)
+        pp = (C.c_void_p * max(n, 1))(*peer_counter_ptrs)
+        self._check(self.L.pluto_gpu_halo_signal(self._h, stream_ptr, n, pp, value))
+
+    def halo_wait(self, stream_ptr, n, counters_ptr, value):
+        self._check(self.L.pluto_gpu_halo_wait(self._h, stream_ptr, n, counters_ptr, value))
+
     def halo_pack_all(self, stage):
         self._check(self.L.pluto_gpu_halo_pack_all(self._h, stage))
 

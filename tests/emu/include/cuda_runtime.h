@@ -128,6 +128,8 @@ inline long long __double_as_longlong (double x) { long long r; memcpy (&r, &x, 
 inline double __longlong_as_double (long long x) { double r; memcpy (&r, &x, 8); return r; }
 inline double __ddiv_rn (double a, double b) { return a/b; }
 inline double __dsqrt_rn (double a) { return sqrt (a); }
+inline void __threadfence_system () {}
+inline long long clock64 () { return 0; }
 inline double __dmul_rn (double a, double b) { return a*b; }
 inline double __dadd_rn (double a, double b) { return a + b; }
 inline float __fdividef (float a, float b) { return a/b; }

@@ -8,7 +8,7 @@ import sys, json
 for line in sys.stdin:
     if line.startswith('{'):
         d = json.loads(line)
-        print('  value %.3e  ms/step %.3f  e2e %.3e  launches %d  roofline_frac %.3f' % (d['value'], d['ms_per_step'], (d["e2e"] or {}).get("value", 0), d['gpu_launches'], d['step_roofline']['stencil_roofline_frac']), {k: round(v['ms_per_step'], 3) for k, v in d['kernels'].items()})
+        print('  value %.3e  ms/step %.3f  e2e %.3e  launches %d  roofline_frac %.3f' % (d['value'], d['ms_per_step'], (d['e2e'] or {}).get('value', 0), d['gpu_launches'], d['step_roofline']['stencil_roofline_frac']), {k: round(v['ms_per_step'], 3) for k, v in d['kernels'].items()})
     else:
         print(line.rstrip()[:300])
 "
