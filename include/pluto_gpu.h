@@ -257,6 +257,14 @@ int pluto_gpu_step_end     (PlutoGpu *h, PlutoGpuStepInfo *info);
    [3] thermal energy (p/(gamma-1)), [4..6] momentum, [7] max |div B| (staggered field). */
 int pluto_gpu_write_dbl (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep);
 int pluto_gpu_read_dbl  (PlutoGpu *h, const char *path);
+/* Single-precision output of the cell-centred variables from the device state, in the reference's formats and file lists:
+ * data.NNNN.flt + flt.out (Src/write_data.c:178-206, Convert_dbl2flt Src/bin_io.c:51) and the legacy-VTK rectilinear-grid
+ * file data.NNNN.vtk + vtk.out (Src/write_vtk.c:92-351: header, big-endian node coordinates xl1/xl2/xl3 with n+1 entries
+ * each -- grid->xl_glob of the interior, x3 NULL in 2-D -- and one SCALARS block per variable; VTK_VECTOR_DUMP NO,
+ * VTK_TIME_INFO NO).  The conversion (and the byte swap) runs on the device; floats cross PCIe. */
+int pluto_gpu_write_flt (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep);
+int pluto_gpu_write_vtk (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep,
+                         const double *xl1, const double *xl2, const double *xl3);
 int pluto_gpu_analysis  (PlutoGpu *h, double out[8]);
 
 /* ---- introspection (tests, bench, profiling) -------------------------- */

@@ -108,7 +108,7 @@ def have_ref(cfg: RefConfig) -> bool:
     return os.path.isfile(cfg.binary()) and os.access(cfg.binary(), os.X_OK)
 
 
-def write_ini(cfg: RefConfig, path: str, dbl_dn: int = -1, analysis_dn: int = 1):
+def write_ini(cfg: RefConfig, path: str, dbl_dn: int = -1, analysis_dn: int = 1, flt_dn: int = -1, vtk_dn: int = -1):
     dom = cfg.resolved_domain()
     bc = cfg.resolved_bc()
     n = list(cfg.n)
@@ -136,8 +136,8 @@ def write_ini(cfg: RefConfig, path: str, dbl_dn: int = -1, analysis_dn: int = 1)
         lines.append(f"{nm}        {b}")
     lines += ["", "[Static Grid Output]", "", "uservar    0",
               f"dbl       -1.0  {dbl_dn}   single_file",
-              "flt       -1.0  -1   single_file",
-              "vtk       -1.0  -1   single_file",
+              f"flt       -1.0  {flt_dn}   single_file",
+              f"vtk       -1.0  {vtk_dn}   single_file",
               "tab       -1.0  -1   ", "ppm       -1.0  -1   ",
               "png       -1.0  -1   ", "log        100000 ",
               f"analysis  -1.0  {analysis_dn} ", "",
@@ -198,7 +198,7 @@ class RefResult:
 def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
                   workdir: str | None = None, keep: bool = False,
                   no_write: bool = False, timeout: float = 3600.0, env: dict | None = None,
-                  analysis_every: int = 1) -> RefResult:
+                  analysis_every: int = 1, flt_every: int = -1, vtk_every: int = -1) -> RefResult:
     """Run ``pluto -maxsteps M``.
 
     Reference main loop semantics (Src/main.c:133-243): ``-maxsteps M`` with
@@ -215,7 +215,7 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
         workdir = tempfile.mkdtemp(prefix="plutoref_")
     os.makedirs(workdir, exist_ok=True)
     write_ini(cfg, os.path.join(workdir, "pluto.ini"), dbl_dn=dump_every,
-              analysis_dn=analysis_every)
+              analysis_dn=analysis_every, flt_dn=flt_every, vtk_dn=vtk_every)
     cmd = [cfg.binary(), "-maxsteps", str(maxsteps)]
     if no_write:
         cmd.append("-no-write")

@@ -28,7 +28,7 @@ SYMBOLS = [
     "pluto_gpu_ipc_alloc", "pluto_gpu_ipc_open", "pluto_gpu_ipc_close", "pluto_gpu_ipc_free", "pluto_gpu_halo_signal", "pluto_gpu_halo_wait",
     "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
     "pluto_gpu_set_dt", "pluto_gpu_advance_async", "pluto_gpu_next_dt_async", "pluto_gpu_reduction_slots",
-    "pluto_gpu_sync_results", "pluto_gpu_write_dbl", "pluto_gpu_read_dbl", "pluto_gpu_analysis",
+    "pluto_gpu_sync_results", "pluto_gpu_write_dbl", "pluto_gpu_read_dbl", "pluto_gpu_analysis", "pluto_gpu_write_flt", "pluto_gpu_write_vtk",
 ]
 
 
@@ -116,6 +116,8 @@ def load_library(path: str | None = None):
     L.pluto_gpu_stage_interior.argtypes = [vp, C.c_int]
     L.pluto_gpu_write_dbl.argtypes = [vp, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_long]
     L.pluto_gpu_read_dbl.argtypes = [vp, C.c_char_p]
+    L.pluto_gpu_write_flt.argtypes = [vp, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_long]
+    L.pluto_gpu_write_vtk.argtypes = [vp, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_long, vp, vp, vp]
     L.pluto_gpu_analysis.argtypes = [vp, dp]
     L.pluto_gpu_set_dt.argtypes = [vp, C.c_double]
     L.pluto_gpu_advance_async.argtypes = [vp, C.c_double, C.c_double]

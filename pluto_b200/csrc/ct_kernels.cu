@@ -536,6 +536,32 @@ analysis_kernel (const __grid_constant__ AnalysisArgs a)
   if (threadIdx.x < 8) a.partial[(size_t)blockIdx.x*8 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// double -> float of the interior zones (Convert_dbl2flt, Src/bin_io.c:51-83: (float)(V*unit), unit = 1), optionally
+// byte-swapped as write_vtk.c stores it
+__global__ void __launch_bounds__(256)
+cvt_float_kernel (const __grid_constant__ CvtArgs a)
+{
+  const Geom &g = a.g;
+  const long long n1 = g.n[0], n2 = g.n[1], n3 = (g.dims == 3 ? g.n[2] : 1), nz = n1*n2*n3;
+  const int nv = blockIdx.y;
+  if (a.live[nv] < 0) return;
+  for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < nz; t += (long long)gridDim.x*blockDim.x){
+    const int i = (int)(t % n1), j = (int)((t/n1) % n2), k = (int)(t/(n1*n2));
+    const float f = (float)a.V[nv][gidx (g, g.beg[2] + k, g.beg[1] + j, g.beg[0] + i)];
+    unsigned u = __float_as_uint (f);
+    if (a.swap) u = __byte_perm (u, 0u, 0x0123);
+    reinterpret_cast<unsigned *>(a.out)[(long long)a.live[nv]*nz + t] = u;
+  }
+}
+int launch_cvt_float (const CvtArgs &a, cudaStream_t s)
+{
+  const Geom &g = a.g;
+  const long long nz = (long long)g.n[0]*g.n[1]*(g.dims == 3 ? g.n[2] : 1);
+  unsigned nb = nblocks (nz, 256); if (nb > 4096) nb = 4096;
+  cvt_float_kernel<<<dim3 (nb, 8), 256, 0, s>>>(a);
+  return pg_launch_status ();
+}
+
 int launch_analysis (const AnalysisArgs &a, int nb, cudaStream_t s)
 {
   analysis_kernel<<<nb, 256, 0, s>>>(a);

@@ -189,6 +189,14 @@ struct AnalysisArgs {          // volume integrals of the interior state
   double igmm1;
 };
 
+struct CvtArgs {               // interior zones of the 8 primitives as single-precision values, variable after variable
+  const double *V[8];
+  float *out;                // [live variable][n3][n2][n1]
+  Geom g;
+  int live[8];               // slot of each variable in `out` (-1: not written)
+  int swap;                  // byte-swapped (the big-endian floats of a .vtk file)
+};
+
 struct HaloArgs {
   double *q[11];
   int lo[11][3], hi[11][3];  // inclusive box per field
@@ -232,6 +240,7 @@ namespace NS {                                                                  
   int launch_bc         (const BcArgs &a, cudaStream_t s);                               \
   int launch_flag_shock (const FlagArgs &a, cudaStream_t s);                             \
   int launch_analysis   (const AnalysisArgs &a, int nblocks, cudaStream_t s);            \
+  int launch_cvt_float  (const CvtArgs &a, cudaStream_t s);                              \
   int launch_halo_pack  (const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_unpack(const HaloArgs &a, cudaStream_t s);                             \
   int launch_halo_table (const HaloEntry *tab, int n, long long maxcount, const Geom &g, bool pack, cudaStream_t s); \

@@ -1194,6 +1194,112 @@ int pluto_gpu_write_dbl (PlutoGpu *h, const char *dir, int nfile, double t, doub
   return 0;
 }
 
+// one line of a "<ext>.out" list in the reference's format and position (write_data.c:365-395)
+static int write_out_line (PlutoGpu *h, const char *dir, const char *ext, int nfile, double t, double dt, long nstep, bool staggered)
+{
+  char path[1024];
+  snprintf (path, sizeof (path), "%s/%s.out", dir, ext);
+  FILE *f;
+  if (nfile == 0) f = fopen (path, "w");
+  else{
+    f = fopen (path, "r+");
+    if (!f) f = fopen (path, "w");
+    else{
+      char sline[512];
+      for (int q = 0; q < nfile; q++) if (!fgets (sline, sizeof (sline), f)) break;
+      fseek (f, ftell (f), SEEK_SET);
+    }
+  }
+  if (!f) return fail ("cannot open %s", path);
+  fprintf (f, "%d %12.6e %12.6e %ld single_file little ", nfile, t, dt, nstep);
+  fprintf (f, h->g.dims == 3 ? "rho vx1 vx2 vx3 Bx1 Bx2 Bx3 prs " : "rho vx1 vx2 Bx1 Bx2 prs ");
+  if (staggered) fprintf (f, h->g.dims == 3 ? "Bx1s Bx2s Bx3s " : "Bx1s Bx2s ");
+  fprintf (f, "\n");
+  const long end = ftell (f);
+  fclose (f);
+  if (end > 0 && truncate (path, end) != 0) return fail ("cannot truncate %s", path);
+  return 0;
+}
+
+// interior primitives as floats in pinned host memory: converted on the device (half the bytes cross PCIe)
+static int stage_floats (PlutoGpu *h, bool swap, float **host, size_t *nz_out, int *nlive_out)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const Geom &g = h->g;
+  const size_t nz = (size_t)g.n[0]*g.n[1]*(g.dims == 3 ? g.n[2] : 1);
+  CvtArgs a; memset (&a, 0, sizeof (a));
+  int nlive = 0;
+  for (int nv = 0; nv < NVS; nv++){ a.V[nv] = h->V[0][nv]; a.live[nv] = live_var (h, nv) ? nlive++ : -1; }
+  if ((size_t)nlive*nz*sizeof (float) > h->scratch_doubles*sizeof (double)) return fail ("internal: scratch too small");
+  a.out = (float *)h->scratch;                          // the work arrays are free between steps
+  a.g = g; a.swap = swap ? 1 : 0;
+  if (count (h, pg_exact::launch_cvt_float (a, h->stream))) return 1;
+  if (cudaMallocHost ((void **)host, (size_t)nlive*nz*sizeof (float)) != cudaSuccess) return fail ("pinned staging of %zu bytes failed", (size_t)nlive*nz*sizeof (float));
+  cudaError_t ce = cudaMemcpyAsync (*host, a.out, (size_t)nlive*nz*sizeof (float), cudaMemcpyDeviceToHost, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize (h->stream);
+  if (ce != cudaSuccess){ cudaFreeHost (*host); *host = NULL; return fail ("stage_floats: %s", cudaGetErrorString (ce)); }
+  *nz_out = nz; *nlive_out = nlive;
+  return 0;
+}
+
+// data.NNNN.flt + flt.out: single-precision cell-centred variables, single_file (write_data.c:178-206)
+int pluto_gpu_write_flt (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep)
+{
+  float *buf = NULL; size_t nz = 0; int nlive = 0;
+  if (stage_floats (h, false, &buf, &nz, &nlive)) return 1;
+  char path[1024];
+  snprintf (path, sizeof (path), "%s/data.%04d.flt", dir, nfile);
+  FILE *f = fopen (path, "wb");
+  if (!f){ cudaFreeHost (buf); return fail ("cannot open %s", path); }
+  const size_t nw = fwrite (buf, sizeof (float), (size_t)nlive*nz, f);
+  fclose (f);
+  cudaFreeHost (buf);
+  if (nw != (size_t)nlive*nz) return fail ("short write to %s", path);
+  return write_out_line (h, dir, "flt", nfile, t, dt, nstep, false);
+}
+
+// data.NNNN.vtk + vtk.out: legacy VTK, BINARY, RECTILINEAR_GRID with the node coordinates xl (n+1 per direction; x3 may be
+// NULL in 2-D), every cell-centred variable as a SCALARS block of big-endian floats (write_vtk.c:92-351, write_data.c:234-262;
+// VTK_VECTOR_DUMP NO and VTK_TIME_INFO NO, the reference's defaults)
+int pluto_gpu_write_vtk (PlutoGpu *h, const char *dir, int nfile, double t, double dt, long nstep,
+                         const double *xl1, const double *xl2, const double *xl3)
+{
+  const Geom &g = h->g;
+  float *buf = NULL; size_t nz = 0; int nlive = 0;
+  if (stage_floats (h, true, &buf, &nz, &nlive)) return 1;
+  char path[1024];
+  snprintf (path, sizeof (path), "%s/data.%04d.vtk", dir, nfile);
+  FILE *f = fopen (path, "wb");
+  if (!f){ cudaFreeHost (buf); return fail ("cannot open %s", path); }
+  const int np[3] = {g.n[0] + 1, g.n[1] + 1, g.dims == 3 ? g.n[2] + 1 : 1};
+  const double *xl[3] = {xl1, xl2, xl3};
+  fprintf (f, "# vtk DataFile Version 2.0\nPLUTO 4.3 VTK Data\nBINARY\nDATASET RECTILINEAR_GRID\n");
+  fprintf (f, "DIMENSIONS %d %d %d\n", np[0], np[1], np[2]);
+  const char *cname[3] = {"X_COORDINATES", "\nY_COORDINATES", "\nZ_COORDINATES"};
+  for (int d = 0; d < 3; d++){
+    fprintf (f, "%s %d float\n", cname[d], np[d]);
+    for (int i = 0; i < np[d]; i++){
+      const float x = (d < g.dims && xl[d]) ? (float)xl[d][i] : 0.0f;
+      unsigned u; memcpy (&u, &x, 4);
+      u = (u >> 24) | ((u >> 8) & 0xff00u) | ((u << 8) & 0xff0000u) | (u << 24);
+      fwrite (&u, 4, 1, f);
+    }
+  }
+  fprintf (f, "\nCELL_DATA %zu\n", nz);
+  static const char *names[NVS] = {"rho", "vx1", "vx2", "vx3", "Bx1", "Bx2", "Bx3", "prs"};
+  size_t nw = 0; int q = 0;
+  for (int nv = 0; nv < NVS; nv++){
+    if (!live_var (h, nv)) continue;
+    fprintf (f, "\nSCALARS %s float\nLOOKUP_TABLE default\n", names[nv]);
+    nw += fwrite (buf + (size_t)q*nz, sizeof (float), nz, f);
+    q++;
+  }
+  fclose (f);
+  cudaFreeHost (buf);
+  if (nw != (size_t)nlive*nz) return fail ("short write to %s", path);
+  return write_out_line (h, dir, "vtk", nfile, t, dt, nstep, false);
+}
+
 int pluto_gpu_read_dbl (PlutoGpu *h, const char *path)
 {
   size_t seg[4];

@@ -21,6 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .stepper import GpuStepper, StepInfo
+from ._lib import last_error as _last_error
 
 _GRIDS = {
     3: {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2), 16: (2, 2, 4)},
@@ -247,19 +248,30 @@ class PeerExchanger:
             self.recv_off.append(row)
         self.cnt_off = off
         off += al(8 * max(n, 1))
+        # every step below is collective: a rank that cannot allocate or map (ranks on different nodes, IPC disabled) must
+        # not leave the others waiting, so failures are agreed on before anyone raises
         self.arena = C.c_void_p()
+        self.mapped = {}
         handle = C.create_string_buffer(64)
-        block._check(self.L.pluto_gpu_ipc_alloc(device, max(off, 256), C.byref(self.arena), handle))
+        ok = self.L.pluto_gpu_ipc_alloc(device, max(off, 256), C.byref(self.arena), handle) == 0
         torch.cuda.synchronize()
-        mine = dict(handle=handle.raw, recv_off=self.recv_off, cnt_off=self.cnt_off, offsets=[tuple(o) for o, _ in self.nbrs])
+        mine = dict(ok=ok, handle=handle.raw, recv_off=self.recv_off, cnt_off=self.cnt_off, offsets=[tuple(o) for o, _ in self.nbrs])
         info = [None] * layout.world
         dist.all_gather_object(info, mine, group=group)
-        self.mapped = {}
-        for _, p in self.nbrs:
-            if p not in self.mapped:
-                ptr = C.c_void_p()
-                block._check(self.L.pluto_gpu_ipc_open(device, info[p]["handle"], C.byref(ptr)))
-                self.mapped[p] = ptr.value
+        ok = all(i["ok"] for i in info)
+        if ok:
+            for _, p in self.nbrs:
+                if p not in self.mapped:
+                    ptr = C.c_void_p()
+                    if self.L.pluto_gpu_ipc_open(device, info[p]["handle"], C.byref(ptr)) != 0:
+                        ok = False
+                        break
+                    self.mapped[p] = ptr.value
+        flag = torch.tensor([1.0 if ok else 0.0], device=torch.device("cuda", device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if flag.item() != 1.0:
+            self.close()
+            raise RuntimeError("peer exchange unavailable (CUDA IPC between the ranks): " + _last_error(self.L))
         self.peer_cnt = []
         send = [[] for _ in range(block.nstages)]
         for o, p in self.nbrs:
@@ -300,9 +312,9 @@ class PeerExchanger:
         for p in self.mapped.values():
             self.L.pluto_gpu_ipc_close(p)
         self.mapped = {}
-        if self.arena:
+        if self.arena is not None and self.arena.value:
             self.L.pluto_gpu_ipc_free(self.arena)
-            self.arena = None
+        self.arena = None
 
 
 def agree_step_results(err, out, device, group=None):
@@ -371,9 +383,19 @@ class DistStepper:
             # ghost zones by peer stores over NVLink (PLUTO_GPU_HALO=peer; all ranks on one node) instead of NCCL send/recv
             self.pex = None
             self.halo = "nccl"
-            if exchange == "all" and os.environ.get("PLUTO_GPU_HALO", "nccl") == "peer" and self.block.nstages >= 2:
-                self.pex = PeerExchanger(layout, rank, self.block, device)
-                self.halo = "peer"
+            want = os.environ.get("PLUTO_GPU_HALO", "auto")         # auto: peer stores when the ranks can map each other's memory
+            if exchange == "all" and want in ("auto", "peer") and self.block.nstages >= 2:
+                try:
+                    self.pex = PeerExchanger(layout, rank, self.block, device)
+                    self.halo = "peer"
+                    # the plan now points at the peers' arenas
+                except RuntimeError:
+                    if want == "peer":
+                        raise
+                    self.pex = None                                  # the NCCL plan has to be restored
+                    b = self.block
+                    b.halo_plan([o for o, _ in self.nex.nbrs], [t.data_ptr() for t in self.nex.send],
+                                [t.data_ptr() for t in self.nex.recv])
             self._red = torch.zeros(2, dtype=torch.float64, device=torch.device("cuda", device))
             if self.overlap:
                 self._comm = torch.cuda.Stream(device=torch.device("cuda", device))

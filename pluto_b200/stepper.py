@@ -224,6 +224,16 @@ class GpuStepper:
         """data.NNNN.dbl + dbl.out line in the reference's single_file format (Src/write_data.c)."""
         self._check(self.L.pluto_gpu_write_dbl(self._h, directory.encode(), nfile, t, dt, nstep))
 
+    def write_flt(self, directory: str, nfile: int, t: float, dt: float, nstep: int):
+        """data.NNNN.flt + flt.out: the cell-centred variables in single precision (Src/write_data.c:178-206)."""
+        self._check(self.L.pluto_gpu_write_flt(self._h, directory.encode(), nfile, t, dt, nstep))
+
+    def write_vtk(self, directory: str, nfile: int, t: float, dt: float, nstep: int, xl):
+        """data.NNNN.vtk + vtk.out (Src/write_vtk.c); xl = node coordinates per direction (n+1 values each)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (list(xl) + [None] * 3)[:3]]
+        self._check(self.L.pluto_gpu_write_vtk(self._h, directory.encode(), nfile, t, dt, nstep,
+                                               *[a.ctypes.data if a is not None else None for a in arrs]))
+
     def read_dbl(self, path: str):
         self._check(self.L.pluto_gpu_read_dbl(self._h, path.encode()))
 

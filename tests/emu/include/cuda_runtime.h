@@ -129,6 +129,14 @@ inline double __longlong_as_double (long long x) { double r; memcpy (&r, &x, 8);
 inline double __ddiv_rn (double a, double b) { return a/b; }
 inline double __dsqrt_rn (double a) { return sqrt (a); }
 inline void __threadfence_system () {}
+inline unsigned __float_as_uint (float f) { unsigned u; memcpy (&u, &f, 4); return u; }
+inline unsigned __byte_perm (unsigned x, unsigned y, unsigned s)
+{
+  const unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int q = 0; q < 4; q++) r |= (unsigned)((v >> (8*((s >> (4*q)) & 7))) & 0xff) << (8*q);
+  return r;
+}
 inline long long clock64 () { return 0; }
 inline double __dmul_rn (double a, double b) { return a*b; }
 inline double __dadd_rn (double a, double b) { return a + b; }

@@ -599,3 +599,43 @@ def test_dbl_output_restart_and_analysis(tmp_path):
         assert an["max_divb"] <= 1.01*divb_max(sa, dims, meta["dx"]) + 1e-300 and an["max_divb"] < 1e-10
         s.close()
         r.close()
+
+
+@pytest.mark.parametrize("dims,n", [(3, (12, 10, 8)), (2, (16, 12, 1))])
+def test_flt_and_vtk_output_match_the_reference_files(tmp_path, dims, n):
+    """Device-side single-precision output: data.NNNN.flt and the legacy-VTK file written from the device state are the
+    reference's own files BYTE FOR BYTE (header text, big-endian node coordinates, SCALARS blocks; flt.out / vtk.out
+    lines), for the state after 3 steps of the same run (EXACT arithmetic, the reference's dt sequence)."""
+    from oracle.refrun import RefConfig, have_ref, run_reference, read_dbl
+    from pluto_b200 import GpuStepper
+    cfg = RefConfig(problem="ot", dims=dims, n=n, first_dt=1e-3, cfl=0.3)
+    if not have_ref(cfg):
+        pytest.skip("oracle/_ref not built")
+    ref = run_reference(cfg, maxsteps=2, dump_every=1, flt_every=1, vtk_every=1, workdir=str(tmp_path / "ref"), keep=True)
+    dom = cfg.resolved_domain()
+    dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(dims)]
+    s = GpuStepper(dims, n, dx, bc=cfg.resolved_bc(), gamma=cfg.resolved_gamma(), arith="exact")
+    s.read_dbl(str(tmp_path / "ref" / "data.0000.dbl"))
+    dt = cfg.first_dt
+    for step in range(3):
+        info = s.advance(dt)
+        dt = s.next_dt(info.inv_dt_hyp, cfg.cfl, cfg.cfl_max_var, dt)
+    st, last = s.get_state(), read_dbl(str(tmp_path / "ref" / "data.0002.dbl"), dims, n)
+    for k, v in last.items():
+        assert np.array_equal(st[k], v), k          # same state as the reference's last dump, bit for bit
+    out = tmp_path / "gpu"
+    out.mkdir()
+    # node coordinates as the reference builds them (set_grid.c:400-402: xlft = xL + (i - iL)*dx)
+    xl = [dom[d][0] + np.arange(n[d] + 1) * dx[d] for d in range(dims)]
+    lines = {e: open(tmp_path / "ref" / f"{e}.out").read().splitlines() for e in ("flt", "vtk")}
+    for nfile in range(3):          # the .out lists grow line by line; only file 2 holds this state
+        w = lines["flt"][nfile].split()
+        s.write_flt(str(out), nfile, float(w[1]), float(w[2]), int(w[3]))
+        s.write_vtk(str(out), nfile, float(w[1]), float(w[2]), int(w[3]), xl)
+    for ext in ("flt", "vtk"):
+        a = open(out / f"data.0002.{ext}", "rb").read()
+        b = open(tmp_path / "ref" / f"data.0002.{ext}", "rb").read()
+        assert a == b, f"data.0002.{ext}: {len(a)} vs {len(b)} bytes, first difference at " \
+            f"{next((q for q in range(min(len(a), len(b))) if a[q] != b[q]), -1)}"
+        assert open(out / f"{ext}.out").read() == open(tmp_path / "ref" / f"{ext}.out").read()
+    s.close()
