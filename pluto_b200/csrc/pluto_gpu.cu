@@ -81,6 +81,7 @@ struct PlutoGpu {
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
   int     plan;                    // the sweep launchers choose the chunk count (PLUTO_GPU_NO_PLAN=1 disables)
+  int     shell_w;                 // width of the x1 slabs of the shell (stage completion next to shared sides)
   int     tma;                     // fused sweep: ring rows staged by bulk asynchronous copies (PLUTO_GPU_TMA=1)
   int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
   int     nstages;                 // Boundary calls per step: rk_order, or 1 with CTU
@@ -286,6 +287,12 @@ static int create_resources (PlutoGpu *h)
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
   h->plan = (getenv ("PLUTO_GPU_NO_PLAN") == NULL);
+  // x1 shell slabs: ng zones are needed; 4 zones = one 32-byte sector per row and array.  (Round 1 used a full warp, 32 zones:
+  // coalesced, but 8 x the zones of the slab at 256-byte pieces 4 KB apart -- at 512^3 on 8 GPUs the split stage completion
+  // took 8.2 ms per step against 6.7 ms unsplit.)
+  h->shell_w = g.ng > 4 ? g.ng : 4;
+  if (getenv ("PLUTO_GPU_SHELL_W") && atoi (getenv ("PLUTO_GPU_SHELL_W")) >= g.ng) h->shell_w = atoi (getenv ("PLUTO_GPU_SHELL_W"));
+  if (h->shell_w*2 >= g.n[0]) h->shell_w = g.ng;
   // bulk copies need 16-byte aligned rows: an even number of doubles per row (arrays are 256-byte aligned)
   h->tma = (getenv ("PLUTO_GPU_TMA") && atoi (getenv ("PLUTO_GPU_TMA")) != 0 && g.S1 % 2 == 0);
   return 0;
@@ -626,7 +633,7 @@ static int launch_final_boxes (PlutoGpu *h, FinalArgs &f, int part)
   for (int d = 0; d < g.dims && split; d++){
     // x1 slabs are a full warp wide when the block allows: an ng-wide slab would be read
     // and written in 16-24 byte pieces per row
-    const int w = (d == 0 && g.n[0] >= 128 ? 32 : g.ng);
+    const int w = (d == 0 ? h->shell_w : g.ng);
     if (h->cfg.bc[2*d] == PLUTO_GPU_BC_SHARED) mlo[d] = w;
     if (h->cfg.bc[2*d + 1] == PLUTO_GPU_BC_SHARED) mhi[d] = w;
     if (mlo[d] + mhi[d] >= g.n[d]) split = false;            // block too thin: no interior
