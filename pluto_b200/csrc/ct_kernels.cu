@@ -247,7 +247,28 @@ ct_update_kernel (const __grid_constant__ CtArgs a)
 // ---------------------------------------------------------------------------
 //  stage completion: face -> centre average, RK average, cons -> prim
 // ---------------------------------------------------------------------------
-template <int NC, bool EN>        // EN: CT_EN_CORRECTION YES (compile time: the default instantiation keeps its 32 registers)
+// the new staggered field of ONE face, exactly as ct_update_kernel forms it (ct_update.c:79-218 + rk_step.c:172-174)
+template <int NC, int D>
+__device__ __forceinline__ double face_update (const FinalArgs &a, long long id, long long sy, long long sz,
+                                               double dtdx0, double dtdx1, double dtdx2)
+{
+  double rhs;
+  if (D == 0){
+    if (NC == 3) rhs = 0.0 - dtdx1*(a.ez[id] - a.ez[id - sy]) + dtdx2*(a.ey[id] - a.ey[id - sz]);
+    else         rhs = 0.0 - dtdx1*(a.ez[id] - a.ez[id - sy]);
+  }else if (D == 1){
+    if (NC == 3) rhs = dtdx0*(a.ez[id] - a.ez[id - 1]) - dtdx2*(a.ex[id] - a.ex[id - sz]);
+    else         rhs = dtdx0*(a.ez[id] - a.ez[id - 1]);
+  }else{
+    rhs = - dtdx0*(a.ey[id] - a.ey[id - 1]) + dtdx1*(a.ex[id] - a.ex[id - sy]);
+  }
+  double b = a.Bs_in[D][id] + rhs;
+  if (a.combine) b = stage_mix (a.combine, a.w0, a.wc, a.Bs0[D][id], b);
+  return b;
+}
+
+template <int NC, bool EN, bool FUSE = false>   // EN: CT_EN_CORRECTION YES (compile time: the default instantiation keeps its 32
+                                                // registers); FUSE: CT_Update evaluated here (FinalArgs.fuse_ct)
 __global__ void __launch_bounds__(128)
 final_kernel (const __grid_constant__ FinalArgs a)
 {
@@ -316,9 +337,27 @@ final_kernel (const __grid_constant__ FinalArgs a)
       if (NC == 3) b2_old = b1*b1 + b2*b2 + b3*b3;
       else         b2_old = b1*b1 + b2*b2;
     }
-    u[BX1] = 0.5*(a.Bs[0][id] + a.Bs[0][id - 1]);
-    u[BX2] = 0.5*(a.Bs[1][id] + a.Bs[1][id - g.S1]);
-    if (NC == 3) u[BX3] = 0.5*(a.Bs[2][id] + a.Bs[2][id - g.S12]);
+    if (FUSE){
+      const long long sy = g.S1, sz = g.S12;
+      const double dtdx0 = __ldg (a.dtp), dtdx1 = __ldg (a.dtp + 1), dtdx2 = (NC == 3 ? __ldg (a.dtp + 2) : 0.0);
+      const double b1p = face_update<NC, 0>(a, id, sy, sz, dtdx0, dtdx1, dtdx2), b1m = face_update<NC, 0>(a, id - 1, sy, sz, dtdx0, dtdx1, dtdx2);
+      const double b2p = face_update<NC, 1>(a, id, sy, sz, dtdx0, dtdx1, dtdx2), b2m = face_update<NC, 1>(a, id - sy, sy, sz, dtdx0, dtdx1, dtdx2);
+      a.Bs_out[0][id] = b1p; a.Bs_out[1][id] = b2p;
+      if (i == g.beg[0]) a.Bs_out[0][id - 1] = b1m;          // the face beg-1 has no zone of its own
+      if (j == g.beg[1]) a.Bs_out[1][id - sy] = b2m;
+      u[BX1] = 0.5*(b1p + b1m);
+      u[BX2] = 0.5*(b2p + b2m);
+      if (NC == 3){
+        const double b3p = face_update<NC, 2>(a, id, sy, sz, dtdx0, dtdx1, dtdx2), b3m = face_update<NC, 2>(a, id - sz, sy, sz, dtdx0, dtdx1, dtdx2);
+        a.Bs_out[2][id] = b3p;
+        if (k == g.beg[2]) a.Bs_out[2][id - sz] = b3m;
+        u[BX3] = 0.5*(b3p + b3m);
+      }
+    }else{
+      u[BX1] = 0.5*(a.Bs[0][id] + a.Bs[0][id - 1]);
+      u[BX2] = 0.5*(a.Bs[1][id] + a.Bs[1][id - g.S1]);
+      if (NC == 3) u[BX3] = 0.5*(a.Bs[2][id] + a.Bs[2][id - g.S12]);
+    }
     if (EN){
       double b2_new;
       if (NC == 3) b2_new = u[BX1]*u[BX1] + u[BX2]*u[BX2] + u[BX3]*u[BX3];
@@ -639,7 +678,10 @@ int launch_final (const FinalArgs &a, cudaStream_t s)
   }
   if (n <= 0) return 0;
   const dim3 grid (nblocks (n, 128), a.nbox ? a.nbox : 1);
-  if (a.en_corr){
+  if (a.fuse_ct && !a.en_corr){
+    if (g.dims == 3) final_kernel<3, false, true><<<grid, 128, 0, s>>>(a);
+    else             final_kernel<2, false, true><<<grid, 128, 0, s>>>(a);
+  }else if (a.en_corr){
     if (g.dims == 3) final_kernel<3, true><<<grid, 128, 0, s>>>(a);
     else             final_kernel<2, true><<<grid, 128, 0, s>>>(a);
   }else{

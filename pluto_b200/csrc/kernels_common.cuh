@@ -152,6 +152,13 @@ struct FinalArgs {
   const double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   const double *fbn[3];                      // normal-component flux of the x1, x2, x3 faces (EXACT; NULL: zero)
   const double *dtp;                         // device: dt/dx1..3
+  // fuse_ct: CT_Update (+ the RK average of the staggered field) evaluated HERE instead of in ct_update_kernel: a zone
+  // computes the new field of its six faces from the edge EMFs (the three low ones a second time, bit-identical to the
+  // neighbour's), stores the three high ones (and a low one on the face beg-1) into Bs (= Bs_out) and averages them
+  int     fuse_ct;
+  const double *ex, *ey, *ez;                // edge EMFs
+  const double *Bs_in[3], *Bs0[3];           // staggered field of the stage's input and at t^n
+  double *Bs_out[3];
 };
 
 // Boundary conditions of ONE dimension in one launch: the copy jobs (a field and

@@ -81,6 +81,7 @@ struct PlutoGpu {
   long long launches;
   int     march_chunk;             // zones per thread along a marching sweep
   int     plan;                    // the sweep launchers choose the chunk count (PLUTO_GPU_NO_PLAN=1 disables)
+  int     fuse_ct;                 // RK stages: CT_Update inside final_kernel (PLUTO_GPU_FUSE_CT=1)
   int     shell_w;                 // width of the x1 slabs of the shell (stage completion next to shared sides)
   int     tma;                     // fused sweep: ring rows staged by bulk asynchronous copies (PLUTO_GPU_TMA=1)
   int     ctu;                     // TIME_STEPPING HANCOCK (corner transport upwind)
@@ -287,6 +288,7 @@ static int create_resources (PlutoGpu *h)
   h->use_graph = (getenv ("PLUTO_GPU_NO_GRAPH") == NULL);
   h->fuse_xy = (getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL);
   h->plan = (getenv ("PLUTO_GPU_NO_PLAN") == NULL);
+  h->fuse_ct = (getenv ("PLUTO_GPU_FUSE_CT") != NULL && atoi (getenv ("PLUTO_GPU_FUSE_CT")) != 0);
   // x1 shell slabs: ng zones are needed; 4 zones = one 32-byte sector per row and array.  (Round 1 used a full warp, 32 zones:
   // coalesced, but 8 x the zones of the slab at 256-byte pieces 4 KB apart -- at 512^3 on 8 GPUs the split stage completion
   // took 8.2 ms per step against 6.7 ms unsplit.)
@@ -692,6 +694,12 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   for (int d = 0; d < 3; d++) f.fbn[d] = h->fbn[d];
   f.write_u = 0;
   if (stage < h->cfg.rk_order && h->cfg.arith == PLUTO_GPU_ARITH_EXACT) f.write_u = (sp.combine || f.en_corr ? 1 : 2);   // the energy correction stays in Uc
+  // CT_Update inside the stage completion (one launch and one pass over the new field less); not with CT_EN_CORRECTION
+  // -- and not where the new field overwrites the t^n field it is averaged with (the last RK stage writes buffer 0 in place:
+  // a zone would read its low neighbour's face after that neighbour has replaced it)
+  f.fuse_ct = (h->fuse_ct && !f.en_corr && !(sp.combine && sp.out == 0));
+  f.ex = h->ex; f.ey = h->ey; f.ez = h->ez;
+  for (int d = 0; d < 3; d++){ f.Bs_in[d] = h->Bs[sp.in][d]; f.Bs0[d] = h->Bs[0][d]; f.Bs_out[d] = h->Bs[sp.out][d]; }
   if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
 
   if (h->flag && stage == 1){
@@ -794,7 +802,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   c.avg = h->cfg.emf_average;
   for (int q = 0; q < 3; q++) for (int d = 0; d < 3; d++) c.dvel[q][d] = h->dvel[q][d];
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
-  TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
+  if (!f.fuse_ct) TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 
   return launch_final_boxes (h, f, part);
 }
