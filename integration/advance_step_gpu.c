@@ -100,9 +100,13 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
 #if UPDATE_VECTOR_POTENTIAL == YES
   #error "libpluto_gpu: UPDATE_VECTOR_POTENTIAL YES is not available (d->Ax1..3 are not advanced on the GPU)"
 #endif
-#if CHAR_LIMITING == YES || LIMITER == FOURTH_ORDER_LIM \
+#if LIMITER == FOURTH_ORDER_LIM \
     || (SHOCK_FLATTENING != NO && (SHOCK_FLATTENING != MULTID || RECONSTRUCTION != LINEAR))
-  #error "libpluto_gpu: CHAR_LIMITING, FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID with LINEAR are not available on the GPU"
+  #error "libpluto_gpu: FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID with LINEAR are not available on the GPU"
+#endif
+#if CHAR_LIMITING == YES && (DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || (TIME_STEPPING != RK2 && TIME_STEPPING != RK3) \
+                             || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EMF_AVERAGE == UCT_HLL)
+  #error "libpluto_gpu: CHAR_LIMITING YES is available in 2-D with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
 #endif
 
   if (gpu == NULL){
@@ -136,6 +140,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
                  LIMITER == MC_LIM        ? PLUTO_GPU_LIM_MC        : PLUTO_GPU_LIM_DEFAULT);
     c.shock_flattening = (SHOCK_FLATTENING == MULTID);     /* flag_shock.c */
     c.en_correction = (CT_EN_CORRECTION == YES);           /* ct_field_average.c:116-129 */
+    c.char_limiting = (CHAR_LIMITING == YES);              /* plm_states.c:448-706 */
 #if BODY_FORCE & POTENTIAL
     c.body_force |= 2;                                     /* tabulated after the creation */
 #endif

@@ -65,6 +65,7 @@ struct Oracle {
   /* pencil scratch */
   int np;
   double (*v)[NV], (*vp)[NV], (*vm)[NV], (*dv)[NV];
+  double (*Rp)[NV][NV];                /* CHAR_LIMITING: right eigenvectors per pencil index, never cleared (as stateC->Rp) */
   double (*flux)[NV], *press, *cmax, *bn, *SLp, *SRp;
   double max_mach, inv_dt_hyp;
   int    stage, floor_events;
@@ -128,6 +129,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   o->vp   = calloc((size_t)o->np, sizeof(*o->vp));
   o->vm   = calloc((size_t)o->np, sizeof(*o->vm));
   o->dv   = calloc((size_t)o->np, sizeof(*o->dv));
+  o->Rp   = calloc((size_t)o->np, sizeof(*o->Rp));
   o->flux = calloc((size_t)o->np, sizeof(*o->flux));
   o->press = dalloc(o->np); o->cmax = dalloc(o->np); o->bn = dalloc(o->np);
   o->gpen = dalloc(o->np) + 4;
@@ -145,7 +147,7 @@ Oracle *oracle_create (const OracleConfig *cfg)
   }
   o->pflag = (unsigned char *)calloc((size_t)o->np, 1) + 4;
   /* shift pencil arrays so that index -2 is addressable */
-  o->v += 4; o->vp += 4; o->vm += 4; o->dv += 4; o->flux += 4;
+  o->v += 4; o->vp += 4; o->vm += 4; o->dv += 4; o->flux += 4; o->Rp += 4;
   o->press += 4; o->cmax += 4; o->bn += 4;
   return o;
 }
@@ -507,13 +509,218 @@ static void states_plm (Oracle *o, int beg, int end, int bxn)
   for (i = beg-1; i <= end; i++) vp[i][bxn] = vm[i+1][bxn] = o->bn[i];
 }
 
+typedef struct { int vn, vt, vb, bn, bt, bb; } Dirs;
+
+enum { KFASTM = 0, KFASTP, KENTRP, KDIVB, KSLOWM, KSLOWP, KALFVM, KALFVP, NWAVE };    /* MHD/mod_defs.h:54-74 */
+
+static void states_plm_char (Oracle *o, int beg, int end, Dirs q)
+/* plm_states.c:448-706 (CHAR_LIMITING YES, UNIFORM_CARTESIAN_GRID YES: cp = cm = 2, dp = dm = 0.5, cpk = cmk = kstp),
+   PrimEigenvectors eigenv.c:190-560 (ideal EOS, CT: no div.B wave), PrimToChar eigenv.c:1310-1400.
+   2 components (DIMENSIONS = COMPONENTS = 2): 6 waves, beta_y = sign(Bt); 3 components: 8 waves.
+   o->Rp[i] is persistent, like stateC->Rp of the reference: only the entries a sweep direction defines are written. */
+{
+  const int nc = o->c.dims, nw = (nc == 3 ? 8 : 6);
+  const double sqrt_1_2 = 0.70710678118654752440;
+  int i, nv, k;
+  double (*v)[NV] = o->v, (*vp)[NV] = o->vp, (*vm)[NV] = o->vm, (*dv)[NV] = o->dv;
+  double kstp[NWAVE];
+  for (i = beg-1; i <= end; i++)
+    for (nv = 0; nv < NV; nv++) dv[i][nv] = v[i+1][nv] - v[i][nv];
+  for (k = 0; k < NWAVE; k++) kstp[k] = 2.0;
+  kstp[KFASTP] = kstp[KFASTM] = 1.0;
+  kstp[KSLOWP] = kstp[KSLOWM] = 1.0;
+
+  for (i = beg; i <= end; i++){
+    const double *qv = v[i];
+    double (*RR)[NV] = o->Rp[i];           /* RR[nv][k] */
+    double LL[NWAVE][NV];
+    double a2 = o->c.gamma*qv[PRS]/qv[RHO];            /* SoundSpeed2, eos.c:16-42 */
+    double u, tau, sqrt_rho, scrh0, scrh1, scrh2, scrh3, scrh4, b2, ca2, A2, At2, cf2, cs2, cf, cs, ca, a;
+    double alpha_f, alpha_s, beta_y, beta_z = 0.0, S;
+    double dvp[NV], dvm[NV], dwp[NWAVE], dwm[NWAVE], dw_lim[NWAVE], dv_lim[NV];
+    memset (LL, 0, sizeof (LL));
+
+    u   = qv[q.vn];
+    tau = 1.0/qv[RHO];
+    sqrt_rho = sqrt(qv[RHO]);
+    scrh2 = qv[q.bn]*qv[q.bn];
+    if (nc == 3) scrh3 = 0.0 + qv[q.bt]*qv[q.bt] + qv[q.bb]*qv[q.bb];
+    else         scrh3 = 0.0 + qv[q.bt]*qv[q.bt];
+    b2  = scrh2 + scrh3;
+    ca2 = scrh2*tau;
+    A2  = b2*tau;
+    At2 = scrh3*tau;
+    scrh1 = a2 - A2;
+    scrh0 = sqrt(scrh1*scrh1 + 4.0*a2*At2);
+    cf2 = 0.5*(a2 + A2 + scrh0);
+    cs2 = a2*ca2/cf2;
+    cf = sqrt(cf2); cs = sqrt(cs2); ca = sqrt(ca2); a = sqrt(a2);
+    if (cf == cs){
+      alpha_f = 1.0; alpha_s = 0.0;
+    }else{
+      scrh0   = 1.0/scrh0;
+      alpha_f = (a2 - cs2)*scrh0;
+      alpha_s = (cf2 - a2)*scrh0;
+      alpha_f = MAXV(0.0, alpha_f);
+      alpha_s = MAXV(0.0, alpha_s);
+      alpha_f = sqrt(alpha_f);
+      alpha_s = sqrt(alpha_s);
+    }
+    scrh0 = sqrt(scrh3);
+    if (scrh0 > 1.e-9){
+      if (nc == 3){ beta_y = qv[q.bt]/scrh0; beta_z = qv[q.bb]/scrh0; }
+      else          beta_y = (qv[q.bt] >= 0.0 ? 1.0 : -1.0);
+    }else{
+      if (nc == 3) beta_z = beta_y = sqrt_1_2;
+      else         beta_y = 1.0;
+    }
+    S = (qv[q.bn] >= 0.0 ? 1.0 : -1.0);
+    (void)ca;
+
+    /* fast wave u - cf */
+    k = KFASTM;
+    scrh0 = alpha_s*cs*S;
+    scrh1 = alpha_s*sqrt_rho*a;
+    scrh2 = 0.5/a2;
+    scrh3 = scrh2*tau;
+    RR[RHO][k] = qv[RHO]*alpha_f;
+    RR[q.vn][k] = -cf*alpha_f;
+    RR[q.vt][k] = scrh0*beta_y;
+    if (nc == 3) RR[q.vb][k] = scrh0*beta_z;
+    RR[q.bt][k] = scrh1*beta_y;
+    if (nc == 3) RR[q.bb][k] = scrh1*beta_z;
+    scrh4 = alpha_f*a2*qv[RHO];
+    RR[PRS][k] = scrh4;
+    LL[k][q.vn] = RR[q.vn][k]*scrh2;
+    LL[k][q.vt] = RR[q.vt][k]*scrh2;
+    if (nc == 3) LL[k][q.vb] = RR[q.vb][k]*scrh2;
+    LL[k][q.bt] = RR[q.bt][k]*scrh3;
+    if (nc == 3) LL[k][q.bb] = RR[q.bb][k]*scrh3;
+    LL[k][PRS] = alpha_f*scrh3;
+    /* fast wave u + cf */
+    k = KFASTP;
+    RR[RHO][k] = RR[RHO][KFASTM];
+    RR[q.vn][k] = -RR[q.vn][KFASTM];
+    RR[q.vt][k] = -RR[q.vt][KFASTM];
+    if (nc == 3) RR[q.vb][k] = -RR[q.vb][KFASTM];
+    RR[q.bt][k] = RR[q.bt][KFASTM];
+    if (nc == 3) RR[q.bb][k] = RR[q.bb][KFASTM];
+    RR[PRS][k] = RR[PRS][KFASTM];
+    /* entropy wave */
+    k = KENTRP;
+    RR[RHO][k] = 1.0;
+    LL[k][RHO] = 1.0;
+    LL[k][PRS] = -1.0/a2;
+    /* slow wave u - cs */
+    k = KSLOWM;
+    scrh0 = alpha_f*cf*S;
+    scrh1 = alpha_f*sqrt_rho*a;
+    RR[RHO][k] = qv[RHO]*alpha_s;
+    RR[q.vn][k] = -cs*alpha_s;
+    RR[q.vt][k] = -scrh0*beta_y;
+    if (nc == 3) RR[q.vb][k] = -scrh0*beta_z;
+    RR[q.bt][k] = -scrh1*beta_y;
+    if (nc == 3) RR[q.bb][k] = -scrh1*beta_z;
+    scrh4 = alpha_s*a2*qv[RHO];
+    RR[PRS][k] = scrh4;
+    LL[k][q.vn] = RR[q.vn][k]*scrh2;
+    LL[k][q.vt] = RR[q.vt][k]*scrh2;
+    if (nc == 3) LL[k][q.vb] = RR[q.vb][k]*scrh2;
+    LL[k][q.bt] = RR[q.bt][k]*scrh3;
+    if (nc == 3) LL[k][q.bb] = RR[q.bb][k]*scrh3;
+    LL[k][PRS] = alpha_s*scrh3;
+    /* slow wave u + cs */
+    k = KSLOWP;
+    RR[RHO][k] = RR[RHO][KSLOWM];
+    RR[q.vn][k] = -RR[q.vn][KSLOWM];
+    RR[q.vt][k] = -RR[q.vt][KSLOWM];
+    if (nc == 3) RR[q.vb][k] = -RR[q.vb][KSLOWM];
+    RR[q.bt][k] = RR[q.bt][KSLOWM];
+    if (nc == 3) RR[q.bb][k] = RR[q.bb][KSLOWM];
+    RR[PRS][k] = scrh4;
+    if (nc == 3){
+      /* Alfven waves */
+      k = KALFVM;
+      scrh2 = beta_y*sqrt_1_2;
+      scrh3 = beta_z*sqrt_1_2;
+      RR[q.vt][k] = -scrh3;
+      RR[q.vb][k] =  scrh2;
+      RR[q.bt][k] = -scrh3*sqrt_rho*S;
+      RR[q.bb][k] =  scrh2*sqrt_rho*S;
+      LL[k][q.vt] = RR[q.vt][k];
+      LL[k][q.vb] = RR[q.vb][k];
+      LL[k][q.bt] = RR[q.bt][k]*tau;
+      LL[k][q.bb] = RR[q.bb][k]*tau;
+      k = KALFVP;
+      RR[q.vt][k] =   RR[q.vt][KALFVM];
+      RR[q.vb][k] =   RR[q.vb][KALFVM];
+      RR[q.bt][k] = - RR[q.bt][KALFVM];
+      RR[q.bb][k] = - RR[q.bb][KALFVM];
+    }
+
+    /* 2a. undivided differences projected on the characteristics (PrimToChar) */
+    for (nv = 0; nv < NV; nv++){ dvp[nv] = dv[i][nv]; dvm[nv] = dv[i-1][nv]; }
+    {
+      const double *pass[2] = {dvm, dvp};
+      double *out[2] = {dwm, dwp};
+      int s;
+      for (s = 0; s < 2; s++){
+        const double *d = pass[s]; double *w = out[s], wv, wB; const double *L;
+        for (k = 0; k < NWAVE; k++) w[k] = 0.0;
+        L = LL[KFASTM];
+        if (nc == 3){ wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt] + L[q.vb]*d[q.vb]; wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt] + L[q.bb]*d[q.bb]; }
+        else        { wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt];                   wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt]; }
+        w[KFASTM] =  wv + wB;
+        w[KFASTP] = -wv + wB;
+        L = LL[KENTRP];
+        w[KENTRP] = L[RHO]*d[RHO] + L[PRS]*d[PRS];
+        w[KDIVB] = 0.0;
+        L = LL[KSLOWM];
+        if (nc == 3){ wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt] + L[q.vb]*d[q.vb]; wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt] + L[q.bb]*d[q.bb]; }
+        else        { wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt];                   wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt]; }
+        w[KSLOWM] =  wv + wB;
+        w[KSLOWP] = -wv + wB;
+        if (nc == 3){
+          L = LL[KALFVM];
+          wv = L[q.vt]*d[q.vt] + L[q.vb]*d[q.vb];
+          wB = L[q.bt]*d[q.bt] + L[q.bb]*d[q.bb];
+          w[KALFVM] = wv + wB;
+          w[KALFVP] = wv - wB;
+        }
+      }
+    }
+    /* 2b. limiter on the characteristic differences */
+    for (k = nw; k--;   ){
+      if (o->c.limiter == ORC_LIM_DEFAULT){              /* SET_GM_LIMITER (plm_coeffs.h:96-100) with cpk = cmk = kstp[k] */
+        if (dwp[k]*dwm[k] > 0.0){
+          double qc = 0.5*(dwm[k] + dwp[k]), scrh = ABS_MIN(dwp[k]*kstp[k], dwm[k]*kstp[k]);
+          dw_lim[k] = ABS_MIN(qc, scrh);
+        }else dw_lim[k] = 0.0;
+      }else dw_lim[k] = single_limiter (o->c.limiter, dwp[k], dwm[k]);
+    }
+    /* 2c. back to primitive slopes, monotonicity in the primitive variables as well */
+    for (nv = NV; nv--;   ){
+      double dc = 0.0, d2v;
+      if (nc == 2 && (nv == VX3 || nv == BX3)){ dv_lim[nv] = 0.0; continue; }
+      for (k = 0; k < nw; k++) dc += dw_lim[k]*RR[nv][k];
+      if (dvp[nv]*dvm[nv] > 0.0){
+        d2v = ABS_MIN(2.0*dvp[nv], 2.0*dvm[nv]);
+        dv_lim[nv] = MINMOD(d2v, dc);
+      }else dv_lim[nv] = 0.0;
+    }
+    for (nv = NV; nv--;   ){
+      vp[i][nv] = v[i][nv] + dv_lim[nv]*0.5;
+      vm[i][nv] = v[i][nv] - dv_lim[nv]*0.5;
+    }
+  }
+  for (i = beg-1; i <= end; i++) vp[i][q.bn] = vm[i+1][q.bn] = o->bn[i];
+}
+
 static void states_ppm (Oracle *o, int beg, int end, int bxn);   /* below */
 
 /* =====================================================================
    Physics kernels shared by the Riemann solvers
    ===================================================================== */
-
-typedef struct { int vn, vt, vb, bn, bt, bb; } Dirs;
 
 static Dirs set_vector_indices (int dir)       /* set_indexes.c:49-123 */
 {
@@ -827,7 +1034,8 @@ static void update_stage (Oracle *o, double dt)
         o->pflag[n] = o->flag[id];
       }
       /* States (nbeg-1 .. nend+1), :193 */
-      if (o->c.recon == ORC_RECON_PLM) states_plm (o, nbeg-1, nend+1, q.bn);
+      if (o->c.recon == ORC_RECON_PLM && o->c.char_limiting) states_plm_char (o, nbeg-1, nend+1, q);
+      else if (o->c.recon == ORC_RECON_PLM) states_plm (o, nbeg-1, nend+1, q.bn);
       else                             states_ppm (o, nbeg-1, nend+1, q.bn);
 
       /* Riemann (nbeg-1 .. nend), :194 ; stateL = vp[n], stateR = vm[n+1] */

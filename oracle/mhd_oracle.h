@@ -55,6 +55,10 @@ typedef struct {
   int    body_force;    /* BODY_FORCE VECTOR with a uniform acceleration grav[] (MHD/rhs_source.c:214-217,
                            277-280, 342-345; MHD/prim_eqn.c:289-360 in the Hancock predictor)     */
   double grav[3];
+  int    char_limiting; /* CHAR_LIMITING YES (States/plm_states.c:448-706 with MHD/eigenv.c:190-560, LINEAR only): slopes limited
+                           on the characteristic variables.  PINNED IN 2-D ONLY: the reference's right-eigenvector scratch keeps
+                           the entries of the previous sweep direction (only non-zero entries are ever written); in 2-D no stale
+                           entry reaches a result, in 3-D the stale Alfven entries of the normal-velocity row do               */
 } OracleConfig;
 
 typedef struct Oracle Oracle;

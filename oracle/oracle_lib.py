@@ -27,7 +27,8 @@ class OracleConfig(C.Structure):
                 ("gamma", C.c_double), ("dx", C.c_double * 3),
                 ("small_dn", C.c_double), ("small_pr", C.c_double),
                 ("limiter", C.c_int), ("emf_average", C.c_int), ("shock_flattening", C.c_int),
-                ("ctu", C.c_int), ("en_correction", C.c_int), ("body_force", C.c_int), ("grav", C.c_double * 3)]
+                ("ctu", C.c_int), ("en_correction", C.c_int), ("body_force", C.c_int), ("grav", C.c_double * 3),
+                ("char_limiting", C.c_int)]
 
 
 def build():
@@ -76,13 +77,15 @@ class Oracle:
     """State container + stepper.  Arrays use the .dbl interior layout."""
 
     def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
-                 bc=("periodic",) * 6, gamma=5.0 / 3.0, limiter="default", emf="uct_contact", flatten=False, ctu=False, en_corr=False, grav=None):
+                 bc=("periodic",) * 6, gamma=5.0 / 3.0, limiter="default", emf="uct_contact", flatten=False, ctu=False, en_corr=False, grav=None,
+                 char_lim=False):
         c = OracleConfig()
         c.body_force = 0 if grav is None else 1
         for d in range(3):
             c.grav[d] = 0.0 if grav is None else float(grav[d])
         c.ctu = 1 if ctu else 0
         c.en_correction = 1 if en_corr else 0
+        c.char_limiting = 1 if char_lim else 0
         c.shock_flattening = 1 if flatten else 0
         c.limiter = LIMITER[limiter]
         c.emf_average = EMF[emf]

@@ -18,6 +18,7 @@
 #                       _en                       CT_EN_CORRECTION YES
 #                       _bf                       BODY_FORCE VECTOR (uniform acceleration)
 #                       _sfl                      SHOCK_FLATTENING MULTID (Src/flag_shock.c) (Src/MHD/CT/ct_emf.c:241-283)
+#                       _cl                       CHAR_LIMITING YES (Src/States/plm_states.c:448-706, Src/MHD/eigenv.c:190)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ORACLE="$(cd "$HERE/.." && pwd)"
@@ -56,6 +57,9 @@ for VARIANT in "$@"; do
   esac
   case "$VARIANT" in
     *_en*) ENCORR=YES ;; *) ENCORR=NO ;;         # CT_EN_CORRECTION (ct_field_average.c:116-129)
+  esac
+  case "$VARIANT" in
+    *_cl*) CHARLIM=YES ;; *) CHARLIM=NO ;;       # limiting on characteristic variables (plm_states.c:448-706)
   esac
   case "$VARIANT" in
     *_bfp*) BODYF="(VECTOR+POTENTIAL)" ;;        # both (uniform acceleration and step potential from the same GRAV1..3)
@@ -113,6 +117,7 @@ for VARIANT in "$@"; do
 /* [Beg] user-defined constants (do not change this line) */
 
 #define  LIMITER                        $LIMITER
+#define  CHAR_LIMITING                  $CHARLIM
 #define  SHOCK_FLATTENING               $SHOCKFLAT
 #define  CT_EMF_AVERAGE                 $EMFAVG
 #define  CT_EN_CORRECTION               $ENCORR

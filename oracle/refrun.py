@@ -45,6 +45,7 @@ class RefConfig:
     limiter: str = "default"            # default | fl mm va os um vl mc  (LIMITER, plm only)
     flatten: bool = False               # SHOCK_FLATTENING MULTID
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
+    char_lim: bool = False              # CHAR_LIMITING YES (plm only; pinned in 2-D, see oracle/mhd_oracle.c states_plm_char)
     en_corr: bool = False               # CT_EN_CORRECTION YES
     grav: tuple = None                  # BODY_FORCE VECTOR with the uniform acceleration (g1, g2, g3)
     grav_mode: int = 0                  # 1: static position-dependent force, component d = grav[d]*sign(x_d)
@@ -76,6 +77,8 @@ class RefConfig:
             v += "_sfl"
         if self.en_corr:
             v += "_en"
+        if self.char_lim:
+            v += "_cl"
         if self.grav is not None:
             v += ("_bfp" if self.vector_too else "_bp") if self.potential else "_bf"
         return v

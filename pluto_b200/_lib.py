@@ -38,7 +38,7 @@ class PlutoGpuConfig(C.Structure):
                 ("gamma", C.c_double), ("dx", C.c_double * 3), ("small_dn", C.c_double),
                 ("small_pr", C.c_double), ("limiter", C.c_int), ("emf_average", C.c_int),
                 ("shock_flattening", C.c_int), ("time_stepping", C.c_int), ("en_correction", C.c_int), ("body_force", C.c_int),
-                ("grav", C.c_double * 3)]
+                ("grav", C.c_double * 3), ("char_limiting", C.c_int)]
 
 
 class PlutoGpuStepInfo(C.Structure):

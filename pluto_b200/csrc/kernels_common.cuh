@@ -57,6 +57,7 @@ struct SweepArgs {
   int     plan;              // 1: the launcher picks the chunk count that fills the SMs in whole rounds (plan_chunks),
                              //    chunk_len = the longest chunk the host wants; 0: use chunk_len / nchunk as given
   int     limiter;           // PLUTO_GPU_LIM_* (PLM)
+  int     char_lim;          // CHAR_LIMITING YES (2-D, LINEAR): slopes limited on the characteristic variables
   // UCT_HLL only (avg == 3): e1/e2 (e3/e4) receive the fan speeds max(0,-SL), max(0,SR) of the
   // faces instead of the face EMFs, and the limited velocity slopes vp - vm of every
   // reconstructed zone are kept (CT_StoreVelSlopes, ct_stag_slopes.c:5-45)

@@ -291,6 +291,132 @@ __device__ __forceinline__ void plm_zone_default (const double *v, const double 
 }
 #endif
 
+// ---------------------------------------------------------------------------
+//  CHAR_LIMITING YES, 2 components (DIMENSIONS = COMPONENTS = 2): slopes limited on the characteristic variables
+//  (plm_states.c:448-706 on a uniform Cartesian grid: cp = cm = 2, dp = dm = 1/2, cpk = cmk = kstp; PrimEigenvectors
+//  eigenv.c:190-470 for the ideal EOS with CT -- six waves, no div.B jump; PrimToChar eigenv.c:1310-1375).
+//  The reference fills 6 x 6 matrices; only their non-zero entries are formed here, and the sums run in its order
+//  (waves: fast-, fast+, entropy, div.B, slow-, slow+).  The row of the normal field is never needed: the interface
+//  states take the staggered component.  (3 components are not offered: the reference's never-cleared eigenvector
+//  scratch makes its own 3-D result depend on the sweep order, see oracle/mhd_oracle.h.)
+//  alpha_s (alpha_f) is the square root of a difference that is pure round-off where the transverse field vanishes
+//  exactly -- the same sensitivity as Roe's switches -- so the chain up to the alphas keeps IEEE operations in every
+//  build (x_* below: no contraction, div.rn / sqrt.rn).
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double x_mul (double a, double b) { return __dmul_rn (a, b); }
+__device__ __forceinline__ double x_add (double a, double b) { return __dadd_rn (a, b); }
+__device__ __forceinline__ double x_div (double a, double b) { return __ddiv_rn (a, b); }
+__device__ __forceinline__ double x_sqrt (double a) { return __dsqrt_rn (a); }
+#else      // host builds (kernel interpreter): keep the compiler from contracting a product with a following sum
+__device__ __forceinline__ double x_mul (double a, double b) { double t = a*b; asm volatile ("" : "+x"(t)); return t; }
+__device__ __forceinline__ double x_add (double a, double b) { double t = a + b; asm volatile ("" : "+x"(t)); return t; }
+__device__ __forceinline__ double x_div (double a, double b) { double t = a/b; asm volatile ("" : "+x"(t)); return t; }
+__device__ __forceinline__ double x_sqrt (double a) { return sqrt (a); }
+#endif
+
+__device__ __forceinline__ double gm_limiter (double dwp, double dwm, double ck)
+{
+  if (dwp*dwm > 0.0){
+    const double qc = 0.5*(dwm + dwp), scrh = abs_min (dwp*ck, dwm*ck);
+    return abs_min (qc, scrh);
+  }
+  return 0.0;
+}
+
+template <int DIR>
+__device__ __forceinline__ void plm_zone_char2 (const Phys &ph, int lim, const double *v, const double *dvm, const double *dvp,
+                                                double *vp, double *vm)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, BXn = D::bn, BXt = D::bt;
+  // ---- PrimEigenvectors up to alpha_f, alpha_s: IEEE operations in the reference's order ----
+  const double a2   = x_div (x_mul (ph.gamma, v[PRS]), v[RHO]);           // SoundSpeed2
+  const double tau  = x_div (1.0, v[RHO]);
+  const double sqrt_rho = x_sqrt (v[RHO]);
+  const double bn2  = x_mul (v[BXn], v[BXn]);
+  const double bt2  = x_add (0.0, x_mul (v[BXt], v[BXt]));
+  const double b2   = x_add (bn2, bt2);
+  const double ca2  = x_mul (bn2, tau);
+  const double A2   = x_mul (b2, tau);
+  const double At2  = x_mul (bt2, tau);
+  const double d1   = x_add (a2, -A2);
+  const double disc = x_sqrt (x_add (x_mul (d1, d1), x_mul (x_mul (4.0, a2), At2)));
+  const double cf2  = x_mul (0.5, x_add (x_add (a2, A2), disc));
+  const double cs2  = x_div (x_mul (a2, ca2), cf2);
+  const double cf = x_sqrt (cf2), cs = x_sqrt (cs2), a = x_sqrt (a2);
+  double alpha_f, alpha_s;
+  if (cf == cs){
+    alpha_f = 1.0; alpha_s = 0.0;
+  }else{
+    const double id = x_div (1.0, disc);
+    alpha_f = x_mul (x_add (a2, -cs2), id);
+    alpha_s = x_mul (x_add (cf2, -a2), id);
+    alpha_f = maxv (0.0, alpha_f);
+    alpha_s = maxv (0.0, alpha_s);
+    alpha_f = x_sqrt (alpha_f);
+    alpha_s = x_sqrt (alpha_s);
+  }
+  double beta_y;
+  if (x_sqrt (bt2) > 1.e-9) beta_y = (v[BXt] >= 0.0 ? 1.0 : -1.0);
+  else                      beta_y = 1.0;
+  const double S = (v[BXn] >= 0.0 ? 1.0 : -1.0);
+
+  // ---- non-zero entries of the right and left eigenvectors ----
+  const double h2 = pg_div (0.5, a2), h3 = h2*tau;                          // scrh2, scrh3
+  // fast waves
+  const double f0 = alpha_s*cs*S, f1 = alpha_s*sqrt_rho*a;
+  const double Rf_rho = v[RHO]*alpha_f, Rf_vn = -cf*alpha_f, Rf_vt = f0*beta_y, Rf_bt = f1*beta_y, Rf_p = alpha_f*a2*v[RHO];
+  const double Lf_vn = Rf_vn*h2, Lf_vt = Rf_vt*h2, Lf_bt = Rf_bt*h3, Lf_p = alpha_f*h3;
+  // entropy wave
+  const double Le_p = -pg_div (1.0, a2);
+  // slow waves
+  const double s0 = alpha_f*cf*S, s1 = alpha_f*sqrt_rho*a;
+  const double Rs_rho = v[RHO]*alpha_s, Rs_vn = -cs*alpha_s, Rs_vt = -s0*beta_y, Rs_bt = -s1*beta_y, Rs_p = alpha_s*a2*v[RHO];
+  const double Ls_vn = Rs_vn*h2, Ls_vt = Rs_vt*h2, Ls_bt = Rs_bt*h3, Ls_p = alpha_s*h3;
+
+  // ---- PrimToChar of the backward and forward differences, limiter per wave ----
+  double wl[6];                                      // limited characteristic slopes (index 3, div.B: zero)
+  {
+    double wm_[6], wp_[6];
+    PG_UNROLL for (int s = 0; s < 2; s++){
+      const double *d = (s == 0 ? dvm : dvp);
+      double *w = (s == 0 ? wm_ : wp_);
+      double wv = Lf_vn*d[VXn] + Lf_vt*d[VXt];
+      double wB = Lf_p*d[PRS] + Lf_bt*d[BXt];
+      w[0] = wv + wB; w[1] = -wv + wB;
+      w[2] = 1.0*d[RHO] + Le_p*d[PRS];
+      w[3] = 0.0;
+      wv = Ls_vn*d[VXn] + Ls_vt*d[VXt];
+      wB = Ls_p*d[PRS] + Ls_bt*d[BXt];
+      w[4] = wv + wB; w[5] = -wv + wB;
+    }
+    PG_UNROLL for (int k = 0; k < 6; k++){
+      if (k == 3){ wl[k] = 0.0; continue; }
+      if (lim == 0) wl[k] = gm_limiter (wp_[k], wm_[k], k == 2 ? 2.0 : 1.0);        // kstp: 1 for the fast and slow families
+      else          wl[k] = single_limiter (lim, wp_[k], wm_[k]);
+    }
+  }
+  // ---- back to primitive slopes (sum over the waves in the reference's order), monotone in the primitive variables too ----
+  double dc[NV];
+  dc[RHO] = 0.0 + wl[0]*Rf_rho; dc[RHO] += wl[1]*Rf_rho; dc[RHO] += wl[2]*1.0; dc[RHO] += wl[4]*Rs_rho; dc[RHO] += wl[5]*Rs_rho;
+  dc[VXn] = 0.0 + wl[0]*Rf_vn;  dc[VXn] += wl[1]*(-Rf_vn);                      dc[VXn] += wl[4]*Rs_vn;  dc[VXn] += wl[5]*(-Rs_vn);
+  dc[VXt] = 0.0 + wl[0]*Rf_vt;  dc[VXt] += wl[1]*(-Rf_vt);                      dc[VXt] += wl[4]*Rs_vt;  dc[VXt] += wl[5]*(-Rs_vt);
+  dc[BXt] = 0.0 + wl[0]*Rf_bt;  dc[BXt] += wl[1]*Rf_bt;                         dc[BXt] += wl[4]*Rs_bt;  dc[BXt] += wl[5]*Rs_bt;
+  dc[PRS] = 0.0 + wl[0]*Rf_p;   dc[PRS] += wl[1]*Rf_p;                          dc[PRS] += wl[4]*Rs_p;   dc[PRS] += wl[5]*Rs_p;
+  vp[BXn] = vm[BXn] = v[BXn];                       // replaced by the staggered component (plm_states.c:663-667)
+  PG_UNROLL for (int nv = 0; nv < NV; nv++){
+    if (nv == VX3 || nv == BX3 || nv == BXn) continue;
+    double dvl = 0.0;
+    if (dvp[nv]*dvm[nv] > 0.0){
+      const double d2v = abs_min (2.0*dvp[nv], 2.0*dvm[nv]);
+      dvl = minmod (d2v, dc[nv]);
+    }
+    vp[nv] = v[nv] + dvl*0.5;
+    vm[nv] = v[nv] - dvl*0.5;
+  }
+}
+
 // LIMITER DEFAULT (the fast path) or one limiter for all variables (uniform branch)
 template <int NC, int SKIP = -1>
 __device__ __forceinline__ void plm_zone (int lim, const double *v, const double *dvm, const double *dvp,

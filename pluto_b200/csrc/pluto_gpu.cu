@@ -166,6 +166,15 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail ("bad body_force");
   if (cfg->body_force && (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL || cfg->shock_flattening))
     return fail ("BODY_FORCE is not available together with CT_EMF_AVERAGE UCT_HLL or SHOCK_FLATTENING");
+  if (cfg->char_limiting != 0 && cfg->char_limiting != 1) return fail ("bad char_limiting");
+  if (cfg->char_limiting){
+    if (cfg->dims != 2)
+      return fail ("CHAR_LIMITING YES is available in 2-D only (in 3-D the reference's eigenvector scratch, eigenv.c:190-560, keeps "
+                   "entries of the previous sweep direction: its result depends on the sweep order and cannot be reproduced)");
+    if (cfg->recon != PLUTO_GPU_RECON_LINEAR || cfg->time_stepping != PLUTO_GPU_TS_RK || cfg->shock_flattening || cfg->body_force
+        || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
+      return fail ("CHAR_LIMITING YES is available with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL");
+  }
   if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
     if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)      // the reference refuses the same combination (MHD/CT/ct_emf.c:196-200)
@@ -715,6 +724,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
   s.stage1 = (stage == 1);
   s.limiter = h->cfg.limiter;
+  s.char_lim = h->cfg.char_limiting;
   s.avg = h->cfg.emf_average;
   const bool bf = h->cfg.body_force != 0;
   for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];

@@ -191,12 +191,14 @@ __device__ __forceinline__ void store_vel_slopes (double *const *dv, int id, con
 
 // SHOCK_FLATTENING MULTID: minmod for every variable in a zone flagged FLAG_MINMOD
 // (plm_states.c:174-180), the HLL flux at an interface next to a zone flagged FLAG_HLL
-template <int NC, bool FLAT, int SKIP = -1>
+// CL: CHAR_LIMITING YES (2 components), the slopes of the sweep direction DIR limited on the characteristic variables
+template <int NC, bool FLAT, int SKIP = -1, bool CL = false, int DIR = 0>
 __device__ __forceinline__ void plm_zone_f (const SweepArgs &a, unsigned fl, const double *v, const double *dvm,
                                             const double *dvp, double *vp, double *vm)
 {
-  if (FLAT && (fl & 1u)) plm_zone_single<NC, SKIP>(2, v, dvm, dvp, vp, vm);
-  else                   plm_zone<NC, SKIP>(a.limiter, v, dvm, dvp, vp, vm);
+  if (CL && NC == 2) plm_zone_char2<DIR>(*reinterpret_cast<const Phys *>(&a.ph), a.limiter, v, dvm, dvp, vp, vm);
+  else if (FLAT && (fl & 1u)) plm_zone_single<NC, SKIP>(2, v, dvm, dvp, vp, vm);
+  else                        plm_zone<NC, SKIP>(a.limiter, v, dvm, dvp, vp, vm);
 }
 template <int SOLVER, int DIR, int NC, bool FLAT>
 __device__ __forceinline__ bool riemann_f (const Phys &ph, unsigned fl2, const double *vL, const double *vR,
@@ -221,8 +223,9 @@ __device__ __forceinline__ void store_face_emf (const SweepArgs &a, int id, cons
 #define PG_XROWS 16          // rows a warp walks through (software-pipelined)
 #endif
 
-template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false>   // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds +
-                                                  // velocity slopes); FLAT: SHOCK_FLATTENING MULTID (zone flags); BF: body force
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool CL = false>   // HLL: CT_EMF_AVERAGE == UCT_HLL (fan speeds +
+                                                  // velocity slopes); FLAT: SHOCK_FLATTENING MULTID (zone flags); BF: body force;
+                                                  // CL: CHAR_LIMITING YES (2 components)
 __global__ void __launch_bounds__(128, PG_MINB_X)
 sweep_x_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -303,7 +306,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
         dvm[nv] = v[nv] - vl;
         dvp[nv] = vr - v[nv];
       }
-      plm_zone_f<NC, FLAT>(a, fl, v, dvm, dvp, vp, vm);
+      plm_zone_f<NC, FLAT, -1, CL, 0>(a, fl, v, dvm, dvp, vp, vm);
     }else{
       double vl[NV], vr[NV], vrr[NV], Wi[NV], Wm[NV];
       PG_FOR_NV(nv){
@@ -407,7 +410,7 @@ __host__ __device__ constexpr int march_slots (int recon)
   return 8*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + 8 + 7 + (recon == RECON_PPM ? 8 : 0)
          + march_prefetch (recon) + 6*(march_prefetch (recon) + 1);
 }
-template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false>
+template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool CL = false>
 __global__ void __launch_bounds__(128, PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -457,7 +460,8 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   double *cs = carry_ + threadIdx.x;
   constexpr int CS = 128;                   // = blockDim.x (fixed by the launcher): immediate smem offsets
   constexpr bool PPM = (RECON == RECON_PPM);
-  constexpr int SK = D::bn;                 // the cell-centred normal field is neither staged nor reconstructed (PG_FOR_NV_SKIP)
+  constexpr int SK = CL ? -1 : (int)D::bn;  // the cell-centred normal field is neither staged nor reconstructed (PG_FOR_NV_SKIP),
+                                            // except with CHAR_LIMITING, whose eigenvectors are built from it
   constexpr int LA = (PPM ? 3 : 2);         // look-ahead of the stencil
   constexpr int PF = march_prefetch (RECON);
   constexpr int NZ = LA + PF;               // ring slots
@@ -496,7 +500,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait<PF - 1> ();
       PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
       PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone_f<NC, FLAT, SK>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone_f<NC, FLAT, SK, CL, DIR>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
@@ -557,7 +561,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone_f<NC, FLAT, SK>(a, flc, vc_, dvm, dvp, vpn, vR);
+        plm_zone_f<NC, FLAT, SK, CL, DIR>(a, flc, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV_SKIP(nv, SK) Wf[nv] = C_WF(nv);
@@ -668,7 +672,7 @@ __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
   return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128 + 4)*sizeof (double);   // + 4 mbarriers (TMA)
 }
 
-template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool TMA = false>
+template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool TMA = false, bool CL = false>
 __global__ void __launch_bounds__(128, PG_MINB_XY)
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
@@ -759,6 +763,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     }
   };
   {
+    constexpr int SKP = CL ? -1 : (int)DY::bn;
     if (TMA) fetch_rows_tma (z[0], id, LA + 1);
     else PG_UNROLL for (int q = 0; q <= LA; q++) fetch_row (z[q], id + q*sD, false);
     cp_async8 (&C_BY, a.Bn2 + id);
@@ -770,9 +775,9 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait_all ();
       if (TMA){ mbar_wait (mbar, tphase); tphase ^= 1u; }
-      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; }
-      PG_FOR_NV_SKIP(nv, DY::bn){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone_f<NC, FLAT, DY::bn>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
+      PG_FOR_NV_SKIP(nv, SKP){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; }
+      PG_FOR_NV_SKIP(nv, SKP){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
+      plm_zone_f<NC, FLAT, SKP, CL, 1>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
@@ -780,14 +785,14 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait_all ();
       if (TMA){ mbar_wait (mbar, tphase); tphase ^= 1u; }
-      PG_FOR_NV_SKIP(nv, DY::bn){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; vd_[nv] = z[2][nv*VS]; }
-      ppm_interface<NC, DY::bn>(vz_, va_, vb_, vc_, Wm);
-      ppm_interface<NC, DY::bn>(va_, vb_, vc_, vd_, Wf);
-      ppm_zone<NC, DY::bn>(vb_, Wm, Wf, vpL, vm_unused);
+      PG_FOR_NV_SKIP(nv, SKP){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; vd_[nv] = z[2][nv*VS]; }
+      ppm_interface<NC, SKP>(vz_, va_, vb_, vc_, Wm);
+      ppm_interface<NC, SKP>(va_, vb_, vc_, vd_, Wf);
+      ppm_zone<NC, SKP>(vb_, Wm, Wf, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
-      PG_FOR_NV_SKIP(nv, DY::bn) C_WF(nv) = Wf[nv];
+      PG_FOR_NV_SKIP(nv, SKP) C_WF(nv) = Wf[nv];
     }
-    PG_FOR_NV_SKIP(nv, DY::bn) C_VP(nv) = vpL[nv];
+    PG_FOR_NV_SKIP(nv, SKP) C_VP(nv) = vpL[nv];
     PG_UNROLL for (int q = 0; q < 7; q++) C_FP(q) = 0.0;
   }
   double my_mach = 0.0, my_cdt = 0.0;
@@ -829,7 +834,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = v[nv] - xvl[nv]; dvp[nv] = xvr[nv] - v[nv]; }
-        plm_zone_f<NC, FLAT>(a, flz, v, dvm, dvp, vp, vm);
+        plm_zone_f<NC, FLAT, -1, CL, 0>(a, flz, v, dvm, dvp, vp, vm);
       }else{
         double Wi[NV], Wm[NV];
         ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
@@ -881,13 +886,13 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     if (do_y){
       double vL[NV], vR[NV], vpn[NV], vc_[NV], vd_[NV], vnx[NV];
       if (ZF != 0) PG_FOR_NV(nv) v[nv] = z[0][nv*VS];      // row f is still in the ring: not kept in registers
-      constexpr int SKY = DY::bn;            // the cell-centred BX2 is not reconstructed along x2 (PG_FOR_NV_SKIP)
+      constexpr int SKY = CL ? -1 : (int)DY::bn;       // the cell-centred BX2 is not reconstructed along x2 (PG_FOR_NV_SKIP)
       PG_FOR_NV_SKIP(nv, SKY){ vc_[nv] = z[1][nv*VS]; vnx[nv] = z[LA][nv*VS]; }
       if (PPM) PG_FOR_NV_SKIP(nv, SKY) vd_[nv] = z[2][nv*VS];
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV_SKIP(nv, SKY){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone_f<NC, FLAT, SKY>(a, fln, vc_, dvm, dvp, vpn, vR);
+        plm_zone_f<NC, FLAT, SKY, CL, 1>(a, fln, vc_, dvm, dvp, vpn, vR);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV_SKIP(nv, SKY) Wf[nv] = C_WF(nv);
@@ -1021,6 +1026,7 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
       if (bf)             PG_LXY2(R, C, false, false, true);          /* refused with UCT_HLL / flattening at create */ \
       else if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                       \
       else if (fl)        PG_LXY1(R, C, false, P);                                                                     \
+      else if (a.char_lim && P && C == 2) PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, false, false, false, false, true>)); \
       else if (a.tma)     PG_LXY3(R, C);                               /* TMA staging of the ring rows */              \
       else                PG_LXY1(R, C, false, false); } while (0)
   if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
@@ -1053,7 +1059,8 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
     const size_t xsmem = (size_t)(TPB/32)*2*9*36*sizeof (double);
 #define PG_LX(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
-      if (bf) sweep_x_kernel<R, SOLVER, C, false, false, true><<<nb, TPB, xsmem, s>>>(a);                            \
+      if (a.char_lim && P && C == 2) sweep_x_kernel<RECON_PLM, SOLVER, 2, false, false, false, true><<<nb, TPB, xsmem, s>>>(a); \
+      else if (bf) sweep_x_kernel<R, SOLVER, C, false, false, true><<<nb, TPB, xsmem, s>>>(a);                            \
       else if (a.avg == 3){ if (fl) sweep_x_kernel<R, SOLVER, C, true, P><<<nb, TPB, xsmem, s>>>(a);                     \
                        else    sweep_x_kernel<R, SOLVER, C, true, false><<<nb, TPB, xsmem, s>>>(a); }               \
       else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, P><<<nb, TPB, xsmem, s>>>(a);                    \
@@ -1069,7 +1076,8 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
     SweepArgs b = a;
 #define PG_LM1(DD, R, C, H, F) PG_LM2(DD, R, C, H, F, false)
-#define PG_LM2(DD, R, C, H, F, B) do { auto kfn = sweep_march_kernel<DD, R, SOLVER, C, H, F, B>;             \
+#define PG_LM2(DD, R, C, H, F, B) PG_LMK((sweep_march_kernel<DD, R, SOLVER, C, H, F, B>))
+#define PG_LMK(KF) do { auto kfn = KF;             \
       static int bps = 0;                                                                             \
       if (!bps){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
@@ -1078,7 +1086,8 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       const unsigned nb = (unsigned)((npen*b.nchunk + TPB - 1)/TPB);                                  \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
 #define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;          \
-      if (bf)             PG_LM2(DD, R, C, false, false, true);                                                      \
+      if (a.char_lim && P && C == 2 && DD == 1) PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, false, true>)); \
+      else if (bf)        PG_LM2(DD, R, C, false, false, true);                                                      \
       else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                    \
       else           { if (fl) PG_LM1(DD, R, C, false, P); else PG_LM1(DD, R, C, false, false); } } while (0)
     if (dir == 1){
@@ -1093,6 +1102,7 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
 #undef PG_LM
 #undef PG_LM1
 #undef PG_LM2
+#undef PG_LMK
   }
   return pg_launch_status ();
 }

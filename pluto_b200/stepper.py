@@ -36,7 +36,7 @@ class GpuStepper:
     def __init__(self, dims, n, dx, recon="plm", solver="hlld", rk_order=2,
                  bc=("periodic",) * 6, gamma=5.0 / 3.0, arith="exact", device=0,
                  small_dn=1e-12, small_pr=1e-12, lib_path=None, limiter="default", emf="uct_contact",
-                 flatten=False, ctu=False, en_corr=False, grav=None, potential=False):
+                 flatten=False, ctu=False, en_corr=False, grav=None, potential=False, char_lim=False):
         self.L = _lib.load_library(lib_path)
         c = _lib.PlutoGpuConfig()
         n = list(n) + [1] * (3 - len(n))
@@ -61,6 +61,7 @@ class GpuStepper:
         c.shock_flattening = 1 if flatten else 0    # SHOCK_FLATTENING MULTID (plm only)
         c.time_stepping = 1 if ctu else 0           # TIME_STEPPING: RK2/RK3 (rk_order) | HANCOCK (corner transport upwind)
         c.en_correction = 1 if en_corr else 0       # CT_EN_CORRECTION YES
+        c.char_limiting = 1 if char_lim else 0      # CHAR_LIMITING YES (2-D, plm, RK)
         # BODY_FORCE: VECTOR (bit 0) with the uniform acceleration grav, POTENTIAL (bit 1, set_body_potential)
         c.body_force = (0 if grav is None else 1) | (2 if potential else 0)
         for d in range(3):

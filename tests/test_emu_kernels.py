@@ -28,7 +28,7 @@ def emu_lib():
 
 def _stepper(g, arith, lib):
     from pluto_b200 import GpuStepper
-    kw = dict(ctu=g.ctu, en_corr=g.en_corr, grav=g.force, potential=g.potential)
+    kw = dict(ctu=g.ctu, en_corr=g.en_corr, grav=g.force, potential=g.potential, char_lim=g.char_lim)
     s = GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order, bc=g.bc, gamma=g.gamma,
                    arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, lib_path=lib, **kw)
     apply_force_field(s, g)
@@ -55,7 +55,8 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
-               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf", "blast2d_ctu_bfx_roe"]
+               "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf", "blast2d_ctu_bfx_roe",
+               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)
@@ -103,11 +104,12 @@ def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
     libdir = tmp_path / "lib"
     libdir.mkdir()
     os.symlink(emu_lib, libdir / "libpluto_gpu.so")
-    for name in ("ot2d_plm_hlld", "ot2d_ctu", "rotor2d_ppm_rk3_bf", "blast2d_ctu_bfx_roe", "blast2d_ctu_bp"):
+    for name in ("ot2d_plm_hlld", "ot2d_ctu", "rotor2d_ppm_rk3_bf", "blast2d_ctu_bfx_roe", "blast2d_ctu_bp", "rotor2d_cl_vl_rk3"):
         g = Golden(name)
         cfg = RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep, cfl=g.cfl,
                         cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma, limiter=g.limiter, emf=g.emf,
-                        flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential, prefix="pluto_gpu_")
+                        flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential, char_lim=g.char_lim,
+                        prefix="pluto_gpu_")
         if not have_ref(cfg):
             pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
         r = run_reference(cfg, maxsteps=g.nsteps + 1, dump_every=1,

@@ -25,13 +25,16 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # position-dependent force: tabulated per zone by the shim (pluto_gpu_set_body_force)
          "blast3d_bfx", "blast2d_ctu_bfx_roe",
          # BODY_FORCE POTENTIAL: the shim tabulates BodyForcePotential at the zone centres and faces
-         "blast3d_bp", "blast2d_ctu_bp"]
+         "blast3d_bp", "blast2d_ctu_bp",
+         # CHAR_LIMITING YES (2-D): the shim reads it from definitions.h
+         "ot2d_cl", "rotor2d_cl_vl_rk3"]
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
-                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential, prefix="pluto_gpu_")
+                     limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential,
+                     char_lim=g.char_lim, prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

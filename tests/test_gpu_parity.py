@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def _stepper(g, arith):
     from pluto_b200 import GpuStepper
     s = GpuStepper(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-                   bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.force, potential=g.potential)
+                   bc=g.bc, gamma=g.gamma, arith=arith, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.force, potential=g.potential, char_lim=g.char_lim)
     apply_force_field(s, g)
     return s
 

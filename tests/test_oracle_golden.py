@@ -13,7 +13,8 @@ from tests.util import Golden, golden_names, divb_max, apply_force_field
 def test_oracle_bit_exact_vs_reference_golden(name):
     g = Golden(name)
     o = Oracle(g.dims, g.n, g.dx, recon=g.recon, solver=g.solver, rk_order=g.rk_order,
-               bc=g.bc, gamma=g.gamma, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.force)
+               bc=g.bc, gamma=g.gamma, limiter=g.limiter, emf=g.emf, flatten=g.flatten, ctu=g.ctu, en_corr=g.en_corr, grav=g.force,
+               char_lim=g.char_lim)
     apply_force_field(o, g)
     o.set_state(g.states[0])
     dt = g.first_dt

@@ -45,6 +45,7 @@ class Golden:
         self.emf = str(d["cfg_emf"]) if "cfg_emf" in d.files else "uct_contact"
         self.flatten = bool(int(d["cfg_flatten"])) if "cfg_flatten" in d.files else False
         self.en_corr = bool(int(d["cfg_en_corr"])) if "cfg_en_corr" in d.files else False
+        self.char_lim = bool(int(d["cfg_char_lim"])) if "cfg_char_lim" in d.files else False
         self.grav = tuple(float(x) for x in d["cfg_grav"]) if "cfg_grav" in d.files else None
         self.grav_mode = int(d["cfg_grav_mode"]) if "cfg_grav_mode" in d.files else 0
         self.potential = bool(int(d["cfg_potential"])) if "cfg_potential" in d.files else False

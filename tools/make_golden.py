@@ -109,6 +109,11 @@ CASES = {
     "blast2d_ctu_eqtsym": (RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=4e-4, cfl=0.4, tstep="hancock",
                                      bc=("eqtsymmetric", "eqtsymmetric", "outflow", "eqtsymmetric", "outflow", "outflow"),
                                      blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3)), 30),
+    # CHAR_LIMITING YES (plm_states.c:448-706): slopes limited on the characteristic variables, 2-D (see tests/test_oracle_vs_ref.py)
+    "ot2d_cl": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, char_lim=True), 20),
+    "blast2d_cl_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, solver="roe", char_lim=True), 20),
+    "rotor2d_cl_vl_rk3": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), first_dt=2.5e-3, cfl=0.4, limiter="vl", tstep="rk3",
+                                    char_lim=True), 15),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
 }
 
@@ -124,7 +129,7 @@ def make(name):
         "cfg_domain": np.array(cfg.resolved_domain()),
         "cfg_bc": np.array(cfg.resolved_bc()), "cfg_nsteps": nsteps,
         "cfg_limiter": cfg.limiter, "cfg_emf": cfg.emf, "cfg_flatten": int(cfg.flatten),
-        "cfg_en_corr": int(cfg.en_corr),
+        "cfg_en_corr": int(cfg.en_corr), "cfg_char_lim": int(cfg.char_lim),
     }
     if cfg.grav is not None:
         out["cfg_grav"] = np.array(cfg.grav, dtype=float)

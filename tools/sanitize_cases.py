@@ -34,6 +34,8 @@ def run(problem, dims, n, steps=2, dt=1e-4, **kw):
 def fam_rk():
     run("blast", 3, (40, 24, 20), arith="fast")
     run("ot", 2, (48, 40, 1), arith="fast", dt=1e-3)
+    run("ot", 2, (48, 40, 1), arith="fast", dt=1e-3, char_lim=True)
+    run("rotor", 2, (40, 32, 1), arith="exact", dt=1e-3, char_lim=True, solver="roe")
     run("turb", 3, (24, 24, 24), arith="fast", rk_order=3, dt=1e-3)
 
 
