@@ -292,6 +292,27 @@ int pluto_gpu_field (PlutoGpu *h, const char *name, double **dev_ptr,
    ex ey ez, cdt; a "1:" / "2:" prefix selects the stage buffers. */
 int pluto_gpu_read_field (PlutoGpu *h, const char *name, double *host);
 
+/* ---- several GPUs from ONE host thread ----------------------------------------------------------------------
+ * The reference's host is a single-threaded, non-re-entrant C program; without MPI it still gets the GPUs
+ * of a box: pluto_gpu_multi_create cuts the domain of cfg (n = zones of the WHOLE domain, bc = the physical conditions;
+ * cfg->device is ignored) into grid[0] x grid[1] x grid[2] blocks numbered as Src/Parallel/al_decompose.c does, block b on
+ * devices[b] (NULL: device b).  Ghost zones travel by peer stores between the devices inside the pack launch, ordered by
+ * events; one host thread issues everything.  The host arrays of upload / download / advance_data are the reference's
+ * Data arrays of the whole domain (layouts as pluto_gpu_upload_data); download refreshes the interior zones and faces.
+ * Replaces AL_Decompose / AL_Exchange_dim / MPI_Allreduce(MAX) (Src/Parallel/al_decompose.c, al_exchange_dim.c:25-96,
+ * Src/main.c:195-199, 415) for a host that is not an MPI program. */
+typedef struct PlutoGpuMulti PlutoGpuMulti;
+int  pluto_gpu_device_count (void);                          /* CUDA devices visible to this process */
+int  pluto_gpu_multi_create (const PlutoGpuConfig *cfg, const int grid[3], const int *devices, PlutoGpuMulti **out);
+void pluto_gpu_multi_destroy (PlutoGpuMulti *m);
+int  pluto_gpu_multi_nghost (const PlutoGpuMulti *m);
+int  pluto_gpu_multi_nblocks (const PlutoGpuMulti *m);
+int  pluto_gpu_multi_upload_data (PlutoGpuMulti *m, const double *Vc, const double *Vs1, const double *Vs2, const double *Vs3);
+int  pluto_gpu_multi_download_data (PlutoGpuMulti *m, double *Vc, double *Vs1, double *Vs2, double *Vs3);
+int  pluto_gpu_multi_advance (PlutoGpuMulti *m, double dt, PlutoGpuStepInfo *info);
+int  pluto_gpu_multi_advance_data (PlutoGpuMulti *m, double dt, double *Vc, double *Vs1, double *Vs2, double *Vs3,
+                                   PlutoGpuStepInfo *info);
+
 /* FP64 pipe microbenchmark (independent DFMA chains on every SM): the measured
    denominator of the FP64 roofline, in TFLOP/s (FMA = 2 flops). */
 int pluto_gpu_measure_fp64 (int device, double *tflops);

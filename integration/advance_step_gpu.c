@@ -23,12 +23,16 @@
  *                       host reads it: PlutoGpuSyncHost(d), called from the two one-line hooks of INTEGRATION.md
  *                       (WriteData, Src/write_data.c:92, and CheckForAnalysis, Src/main.c:706).  A hook call is a
  *                       no-op when the host copy is current or the mode is off.
- * PLUTO_GPU_ARITH=fast|exact selects the arithmetic, PLUTO_GPU_DEVICE=<n> the device ordinal (default 0).
+ * PLUTO_GPU_ARITH=fast|exact selects the arithmetic, PLUTO_GPU_DEVICE=<n> the (first) device ordinal (default 0).
+ * PLUTO_GPU_NDEV=2|4|8: the domain is cut into that many blocks, one per GPU (round robin over the visible devices), all
+ * driven from this single thread through pluto_gpu_multi_* -- the serial reference build uses the GPUs of a box with no MPI;
+ * the rank grids are those of Src/Parallel for these counts (slowest index split first).
  */
 #include "pluto.h"
 #include "pluto_gpu.h"
 
 static PlutoGpu *gpu = NULL;
+static PlutoGpuMulti *gpum = NULL;   /* PLUTO_GPU_NDEV > 1: blocks on several devices instead of `gpu` */
 static int gpu_resident = 0;         /* PLUTO_GPU_RESIDENT: the state lives in HBM between calls */
 static int gpu_host_stale = 0;       /* resident mode: d->Vc, d->Vs are older than the device state */
 
@@ -51,9 +55,10 @@ void PlutoGpuSyncHost (Data *d)
  *********************************************************************** */
 {
   double *vs1, *vs2, *vs3;
-  if (gpu == NULL || !gpu_resident || !gpu_host_stale) return;
+  if ((gpu == NULL && gpum == NULL) || !gpu_resident || !gpu_host_stale) return;
   StaggeredBase (d, &vs1, &vs2, &vs3);
-  if (pluto_gpu_download_data (gpu, d->Vc[0][0][0], vs1, vs2, vs3) != 0){
+  if ((gpum ? pluto_gpu_multi_download_data (gpum, d->Vc[0][0][0], vs1, vs2, vs3)
+            : pluto_gpu_download_data (gpu, d->Vc[0][0][0], vs1, vs2, vs3)) != 0){
     print ("! PlutoGpuSyncHost: %s\n", pluto_gpu_last_error());
     QUIT_PLUTO(1);
   }
@@ -109,8 +114,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
   #error "libpluto_gpu: CHAR_LIMITING YES is available in 2-D with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
 #endif
 
-  if (gpu == NULL){
+  if (gpu == NULL && gpum == NULL){
     PlutoGpuConfig c;
+    int ndev_blocks = getenv ("PLUTO_GPU_NDEV") ? atoi (getenv ("PLUTO_GPU_NDEV")) : 1;
     char *arith = getenv ("PLUTO_GPU_ARITH");
     int idim;
     memset (&c, 0, sizeof (c));
@@ -170,13 +176,27 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     c.gamma    = g_gamma;
     c.small_dn = g_smallDensity;
     c.small_pr = g_smallPressure;
-    if (pluto_gpu_create (&c, &gpu) != 0){
+    if (ndev_blocks > 1){
+      /* rank grids as Src/Parallel would choose them for 2 / 4 / 8 processes, slowest index first */
+      int g3[3] = {1, 1, 1}, devs[16], nvis = pluto_gpu_device_count (), b;
+      if (DIMENSIONS == 3){ if (ndev_blocks >= 2) g3[2] = 2; if (ndev_blocks >= 4) g3[1] = 2; if (ndev_blocks >= 8) g3[0] = 2; }
+      else                { if (ndev_blocks >= 2) g3[1] = 2; if (ndev_blocks >= 4) g3[0] = 2; if (ndev_blocks >= 8) g3[1] = 4; }
+      if (g3[0]*g3[1]*g3[2] != ndev_blocks || nvis < 1){
+        print ("! AdvanceStep(gpu): PLUTO_GPU_NDEV must be 2, 4 or 8 (and a CUDA device must be visible)\n");
+        QUIT_PLUTO(1);
+      }
+      for (b = 0; b < ndev_blocks; b++) devs[b] = (c.device + b) % nvis;
+      if (pluto_gpu_multi_create (&c, g3, devs, &gpum) != 0){
+        print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+        QUIT_PLUTO(1);
+      }
+    }else if (pluto_gpu_create (&c, &gpu) != 0){
       print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
       QUIT_PLUTO(1);
     }
-    if (pluto_gpu_nghost (gpu) != grid->nghost[IDIR]){      /* the host arrays are read with this padding */
+    if ((gpum ? pluto_gpu_multi_nghost (gpum) : pluto_gpu_nghost (gpu)) != grid->nghost[IDIR]){   /* the host arrays are read with this padding */
       print ("! AdvanceStep(gpu): the library expects %d ghost zones, the grid has %d (Src/get_nghost.c)\n",
-             pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
+             gpum ? pluto_gpu_multi_nghost (gpum) : pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
       QUIT_PLUTO(1);
     }
 #if BODY_FORCE & POTENTIAL
@@ -235,12 +255,13 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       free (gt);
     }
 #endif
-    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones, device %d, state %s\n",
-           c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", pluto_gpu_nghost (gpu), c.device,
+    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones, %d block(s) from device %d, state %s\n",
+           c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", grid->nghost[IDIR], ndev_blocks > 1 ? ndev_blocks : 1, c.device,
            gpu_resident ? "resident in HBM" : "on the host (upload + download per step)");
     if (gpu_resident){              /* the state the driver prepared (Startup or RestartFromFile) goes up once */
       StaggeredBase (d, &vs1, &vs2, &vs3);
-      if (pluto_gpu_upload_data (gpu, d->Vc[0][0][0], vs1, vs2, vs3) != 0){
+      if ((gpum ? pluto_gpu_multi_upload_data (gpum, d->Vc[0][0][0], vs1, vs2, vs3)
+                : pluto_gpu_upload_data (gpu, d->Vc[0][0][0], vs1, vs2, vs3)) != 0){
         print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
         QUIT_PLUTO(1);
       }
@@ -249,12 +270,13 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
 
   StaggeredBase (d, &vs1, &vs2, &vs3);
   if (gpu_resident){
-    if (pluto_gpu_advance (gpu, g_dt, &info) != 0){
+    if ((gpum ? pluto_gpu_multi_advance (gpum, g_dt, &info) : pluto_gpu_advance (gpu, g_dt, &info)) != 0){
       print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
       QUIT_PLUTO(1);
     }
     gpu_host_stale = 1;
-  }else if (pluto_gpu_advance_data (gpu, g_dt, d->Vc[0][0][0], vs1, vs2, vs3, &info) != 0){
+  }else if ((gpum ? pluto_gpu_multi_advance_data (gpum, g_dt, d->Vc[0][0][0], vs1, vs2, vs3, &info)
+                  : pluto_gpu_advance_data (gpu, g_dt, d->Vc[0][0][0], vs1, vs2, vs3, &info)) != 0){
     print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
     QUIT_PLUTO(1);
   }

@@ -11,4 +11,4 @@ There is no CPU path: importing works anywhere, but creating a stepper
 without the built library or without a CUDA device raises.
 """
 from ._lib import load_library, LIB_PATH, PlutoGpuConfig, PlutoGpuStepInfo  # noqa: F401
-from .stepper import GpuStepper, Integrator, StepInfo  # noqa: F401
+from .stepper import GpuStepper, MultiGpuStepper, Integrator, StepInfo  # noqa: F401

@@ -25,6 +25,8 @@ SYMBOLS = [
     "pluto_gpu_step_end", "pluto_gpu_stream", "pluto_gpu_launch_count", "pluto_gpu_device_bytes",
     "pluto_gpu_field", "pluto_gpu_read_field", "pluto_gpu_timing", "pluto_gpu_timing_get", "pluto_gpu_measure_fp64", "pluto_gpu_selftest_arith", "pluto_gpu_halo_nbr_doubles", "pluto_gpu_halo_plan",
     "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on", "pluto_gpu_halo_plan_stage",
+    "pluto_gpu_device_count", "pluto_gpu_multi_create", "pluto_gpu_multi_destroy", "pluto_gpu_multi_nghost", "pluto_gpu_multi_nblocks", "pluto_gpu_multi_upload_data",
+    "pluto_gpu_multi_download_data", "pluto_gpu_multi_advance", "pluto_gpu_multi_advance_data",
     "pluto_gpu_ipc_alloc", "pluto_gpu_ipc_open", "pluto_gpu_ipc_close", "pluto_gpu_ipc_free", "pluto_gpu_halo_signal", "pluto_gpu_halo_wait",
     "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
     "pluto_gpu_set_dt", "pluto_gpu_advance_async", "pluto_gpu_next_dt_async", "pluto_gpu_reduction_slots",
@@ -102,6 +104,15 @@ def load_library(path: str | None = None):
     L.pluto_gpu_halo_nbr_doubles.argtypes = [vp, C.POINTER(C.c_int * 3)]
     L.pluto_gpu_halo_nbr_doubles.restype = C.c_longlong
     L.pluto_gpu_halo_plan.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp)]
+    L.pluto_gpu_multi_create.argtypes = [C.POINTER(PlutoGpuConfig), C.POINTER(C.c_int * 3), C.POINTER(C.c_int), C.POINTER(vp)]
+    L.pluto_gpu_multi_destroy.argtypes = [vp]
+    L.pluto_gpu_multi_destroy.restype = None
+    L.pluto_gpu_multi_nghost.argtypes = [vp]
+    L.pluto_gpu_multi_nblocks.argtypes = [vp]
+    L.pluto_gpu_multi_upload_data.argtypes = [vp, vp, vp, vp, vp]
+    L.pluto_gpu_multi_download_data.argtypes = [vp, vp, vp, vp, vp]
+    L.pluto_gpu_multi_advance.argtypes = [vp, C.c_double, C.POINTER(PlutoGpuStepInfo)]
+    L.pluto_gpu_multi_advance_data.argtypes = [vp, C.c_double, vp, vp, vp, vp, C.POINTER(PlutoGpuStepInfo)]
     L.pluto_gpu_halo_plan_stage.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.POINTER(vp)]
     L.pluto_gpu_ipc_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
     L.pluto_gpu_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]

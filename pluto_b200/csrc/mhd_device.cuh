@@ -298,7 +298,7 @@ __device__ __forceinline__ void plm_zone_default (const double *v, const double 
 //  The reference fills 6 x 6 matrices; only their non-zero entries are formed here, and the sums run in its order
 //  (waves: fast-, fast+, entropy, div.B, slow-, slow+).  The row of the normal field is never needed: the interface
 //  states take the staggered component.  (3 components are not offered: the reference's never-cleared eigenvector
-//  scratch makes its own 3-D result depend on the sweep order, see oracle/mhd_oracle.h.)
+//  scratch makes its own 3-D result depend on the sweep order)
 //  alpha_s (alpha_f) is the square root of a difference that is pure round-off where the transverse field vanishes
 //  exactly -- the same sensitivity as Roe's switches -- so the chain up to the alphas keeps IEEE operations in every
 //  build (x_* below: no contraction, div.rn / sqrt.rn).

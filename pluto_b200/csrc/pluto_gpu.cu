@@ -1492,6 +1492,250 @@ extern "C" int pluto_gpu_measure_fp64 (int device, double *tflops)
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+//  Several blocks -- one per GPU -- driven from ONE host thread: what the reference's single-threaded, non-re-entrant C
+//  host needs to use the 8 GPUs of a box.  Replaces Src/Parallel for a host that is NOT an MPI program: the
+//  domain is cut into grid[0] x grid[1] x grid[2] blocks (rank = c1 + p1 (c2 + p2 c3), as al_decompose.c numbers them), every
+//  block lives on its own device and stream, and the ghost zones travel by peer stores: a block's pack launch writes into
+//  its neighbours' receive buffers (cudaDeviceEnablePeerAccess; same process, no IPC), an event per block and exchange orders
+//  pack -> unpack across the streams, a second one unpack -> next pack (the buffers are single).  The host arrays are the
+//  reference's Data arrays of the WHOLE domain.
+// ---------------------------------------------------------------------------
+enum { PGM_MAX_BLOCKS = 16, PGM_MAX_NBR = 26 };
+struct PlutoGpuMulti {
+  int nb, dims, ng, grid[3], gn[3], ln[3];
+  PlutoGpu *blk[PGM_MAX_BLOCKS];
+  int nnbr[PGM_MAX_BLOCKS], nbr[PGM_MAX_BLOCKS][PGM_MAX_NBR], noff[PGM_MAX_BLOCKS][PGM_MAX_NBR][3];
+  double *recv[PGM_MAX_BLOCKS][PGM_MAX_NBR];           // receive buffer of block b for its neighbour q (on b's device)
+  cudaEvent_t ev_pack[PGM_MAX_BLOCKS], ev_unpack[PGM_MAX_BLOCKS];
+  double *hV[PGM_MAX_BLOCKS], *hS[PGM_MAX_BLOCKS][3];  // pinned staging of a block's Data arrays
+};
+
+static void pgm_coords (const PlutoGpuMulti *m, int r, int c[3])
+{ c[0] = r % m->grid[0]; c[1] = (r/m->grid[0]) % m->grid[1]; c[2] = r/(m->grid[0]*m->grid[1]); }
+
+void pluto_gpu_multi_destroy (PlutoGpuMulti *m)
+{
+  if (!m) return;
+  for (int b = 0; b < m->nb; b++){
+    if (m->blk[b]) cudaSetDevice (m->blk[b]->cfg.device);
+    for (int q = 0; q < PGM_MAX_NBR; q++) if (m->recv[b][q]) cudaFree (m->recv[b][q]);
+    if (m->ev_pack[b]) cudaEventDestroy (m->ev_pack[b]);
+    if (m->ev_unpack[b]) cudaEventDestroy (m->ev_unpack[b]);
+    if (m->hV[b]) cudaFreeHost (m->hV[b]);
+    for (int d = 0; d < 3; d++) if (m->hS[b][d]) cudaFreeHost (m->hS[b][d]);
+    if (m->blk[b]) pluto_gpu_destroy (m->blk[b]);
+  }
+  free (m);
+}
+
+int pluto_gpu_multi_create (const PlutoGpuConfig *cfg, const int grid[3], const int *devices, PlutoGpuMulti **out)
+{
+  *out = NULL;
+  const int dims = cfg->dims;
+  const int nb = grid[0]*grid[1]*(dims == 3 ? grid[2] : 1);
+  if (nb < 1 || nb > PGM_MAX_BLOCKS) return fail ("pluto_gpu_multi_create: %d blocks (1 .. %d)", nb, PGM_MAX_BLOCKS);
+  if (dims == 2 && grid[2] != 1) return fail ("pluto_gpu_multi_create: grid[2] must be 1 in 2-D");
+  if (cfg->body_force) return fail ("pluto_gpu_multi_create: BODY_FORCE is not available with several blocks yet");
+  for (int d = 0; d < dims; d++) if (cfg->n[d] % grid[d]) return fail ("pluto_gpu_multi_create: n[%d] = %d is not divisible by %d blocks", d, cfg->n[d], grid[d]);
+  PlutoGpuMulti *m = (PlutoGpuMulti *)calloc (1, sizeof (PlutoGpuMulti));
+  if (!m) return fail ("out of host memory");
+  m->nb = nb; m->dims = dims;
+  for (int d = 0; d < 3; d++){ m->grid[d] = (d < dims ? grid[d] : 1); m->gn[d] = (d < dims ? cfg->n[d] : 1); m->ln[d] = m->gn[d]/m->grid[d]; }
+  int rc = 0;
+  for (int b = 0; b < nb && !rc; b++){
+    int c[3]; pgm_coords (m, b, c);
+    PlutoGpuConfig bc = *cfg;
+    bc.device = devices ? devices[b] : b;
+    for (int d = 0; d < 3; d++) bc.n[d] = m->ln[d];
+    // a side is SHARED where another block abuts (boundary.c:139), across a periodic boundary too
+    for (int d = 0; d < dims; d++) if (m->grid[d] > 1){
+      const bool per = cfg->bc[2*d] == PLUTO_GPU_BC_PERIODIC;
+      if (c[d] > 0 || per) bc.bc[2*d] = PLUTO_GPU_BC_SHARED;
+      if (c[d] < m->grid[d] - 1 || per) bc.bc[2*d + 1] = PLUTO_GPU_BC_SHARED;
+    }
+    rc = pluto_gpu_create (&bc, &m->blk[b]);
+  }
+  if (rc){ char msg[sizeof (g_err)]; snprintf (msg, sizeof (msg), "%s", g_err); pluto_gpu_multi_destroy (m); snprintf (g_err, sizeof (g_err), "%s", msg); return 1; }
+  m->ng = m->blk[0]->g.ng;
+  // peer access between every pair of distinct devices (stores into a neighbour's buffer, events across devices)
+  for (int a = 0; a < nb; a++) for (int b = 0; b < nb; b++){
+    const int da = m->blk[a]->cfg.device, db = m->blk[b]->cfg.device;
+    if (da == db) continue;
+#ifndef PG_EMU
+    int can = 0;
+    cudaDeviceCanAccessPeer (&can, da, db);
+    if (!can){ pluto_gpu_multi_destroy (m); return fail ("device %d cannot access device %d directly", da, db); }
+    cudaSetDevice (da);
+    const cudaError_t e = cudaDeviceEnablePeerAccess (db, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled){ pluto_gpu_multi_destroy (m); return fail ("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString (e)); }
+    cudaGetLastError ();
+#endif
+  }
+  // neighbours of every block (faces, edges, corners), their receive buffers, events, staging
+  for (int b = 0; b < nb; b++){
+    int c[3]; pgm_coords (m, b, c);
+    PlutoGpu *h = m->blk[b];
+    cudaSetDevice (h->cfg.device);
+    int n = 0;
+    for (int o2 = (dims == 3 && m->grid[2] > 1 ? -1 : 0); o2 <= (dims == 3 && m->grid[2] > 1 ? 1 : 0); o2++)
+    for (int o1 = (m->grid[1] > 1 ? -1 : 0); o1 <= (m->grid[1] > 1 ? 1 : 0); o1++)
+    for (int o0 = (m->grid[0] > 1 ? -1 : 0); o0 <= (m->grid[0] > 1 ? 1 : 0); o0++){
+      const int o[3] = {o0, o1, o2};
+      if (!o0 && !o1 && !o2) continue;
+      int cc[3]; bool ok = true;
+      for (int d = 0; d < 3; d++){
+        cc[d] = c[d] + o[d];
+        if (cc[d] < 0 || cc[d] >= m->grid[d]){
+          if (d < dims && cfg->bc[2*d] == PLUTO_GPU_BC_PERIODIC) cc[d] = (cc[d] + m->grid[d]) % m->grid[d];
+          else ok = false;
+        }
+      }
+      if (!ok) continue;
+      m->nbr[b][n] = cc[0] + m->grid[0]*(cc[1] + m->grid[1]*cc[2]);
+      for (int d = 0; d < 3; d++) m->noff[b][n][d] = o[d];
+      const long long cnt = pluto_gpu_halo_nbr_doubles (h, o);
+      if (cudaMalloc ((void **)&m->recv[b][n], (size_t)(cnt > 0 ? cnt : 1)*sizeof (double)) != cudaSuccess){ pluto_gpu_multi_destroy (m); return fail ("cudaMalloc of a halo buffer failed"); }
+      n++;
+    }
+    m->nnbr[b] = n;
+    cudaEventCreateWithFlags (&m->ev_pack[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags (&m->ev_unpack[b], cudaEventDisableTiming);
+    const Geom &g = h->g;
+    const size_t T1 = g.T[0], T2 = g.T[1], T3 = g.T[2];
+    const int nvar = (dims == 3 ? NVS : 6);
+    if (cudaMallocHost ((void **)&m->hV[b], nvar*T1*T2*T3*sizeof (double)) != cudaSuccess ||
+        cudaMallocHost ((void **)&m->hS[b][0], (T1 + 1)*T2*T3*sizeof (double)) != cudaSuccess ||
+        cudaMallocHost ((void **)&m->hS[b][1], T1*(T2 + 1)*T3*sizeof (double)) != cudaSuccess ||
+        (dims == 3 && cudaMallocHost ((void **)&m->hS[b][2], T1*T2*(T3 + 1)*sizeof (double)) != cudaSuccess)){
+      pluto_gpu_multi_destroy (m); return fail ("pinned staging for block %d failed", b);
+    }
+  }
+  // plans: block b sends to neighbour q by writing into q's receive buffer for the opposite offset
+  for (int b = 0; b < nb; b++){
+    double *send[PGM_MAX_NBR], *recv[PGM_MAX_NBR]; int offs[3*PGM_MAX_NBR];
+    for (int q = 0; q < m->nnbr[b]; q++){
+      const int p = m->nbr[b][q];
+      int qp = -1;
+      for (int t = 0; t < m->nnbr[p]; t++)
+        if (m->nbr[p][t] == b && m->noff[p][t][0] == -m->noff[b][q][0] && m->noff[p][t][1] == -m->noff[b][q][1] && m->noff[p][t][2] == -m->noff[b][q][2]) qp = t;
+      if (qp < 0){ pluto_gpu_multi_destroy (m); return fail ("internal: neighbour tables are not symmetric"); }
+      send[q] = m->recv[p][qp]; recv[q] = m->recv[b][q];
+      for (int d = 0; d < 3; d++) offs[3*q + d] = m->noff[b][q][d];
+    }
+    if (m->nnbr[b] && pluto_gpu_halo_plan (m->blk[b], m->nnbr[b], offs, send, recv)){ pluto_gpu_multi_destroy (m); return 1; }
+  }
+  *out = m;
+  return 0;
+}
+
+int pluto_gpu_device_count (void)
+{
+  int n = 0;
+  return cudaGetDeviceCount (&n) == cudaSuccess ? n : 0;
+}
+
+int pluto_gpu_multi_nghost (const PlutoGpuMulti *m) { return m->ng; }
+int pluto_gpu_multi_nblocks (const PlutoGpuMulti *m) { return m->nb; }
+
+// copy between the global Data arrays (host) and one block's staging arrays: rows along x1
+static void pgm_rows (const PlutoGpuMulti *m, int b, bool to_block, int stag, double *glob, double *loc, bool interior_only)
+{
+  int c[3]; pgm_coords (m, b, c);
+  const int ng = m->ng, dims = m->dims;
+  int Tg[3], Tl[3], off[3];
+  for (int d = 0; d < 3; d++){
+    Tg[d] = (d < dims ? m->gn[d] + 2*ng : 1); Tl[d] = (d < dims ? m->ln[d] + 2*ng : 1); off[d] = c[d]*m->ln[d];
+  }
+  const int eg[3] = {Tg[0] + (stag == 0), Tg[1] + (stag == 1), Tg[2] + (stag == 2)};
+  const int el[3] = {Tl[0] + (stag == 0), Tl[1] + (stag == 1), Tl[2] + (stag == 2)};
+  int lo[3] = {0, 0, 0}, hi[3] = {el[0] - 1, el[1] - 1, el[2] - 1};
+  if (interior_only) for (int d = 0; d < dims; d++){
+    // interior zones; a staggered component keeps the face below its first zone (array position = face index + 1)
+    lo[d] = ng; hi[d] = ng + m->ln[d] - 1 + (stag == d ? 1 : 0);
+  }
+  const size_t nrow = (size_t)(hi[0] - lo[0] + 1);
+  for (int k = lo[2]; k <= hi[2]; k++) for (int j = lo[1]; j <= hi[1]; j++){
+    double *pl = loc + ((size_t)k*el[1] + j)*el[0] + lo[0];
+    double *pg = glob + ((size_t)(k + off[2])*eg[1] + (j + off[1]))*eg[0] + lo[0] + off[0];
+    if (to_block) memcpy (pl, pg, nrow*sizeof (double)); else memcpy (pg, pl, nrow*sizeof (double));
+  }
+}
+
+int pluto_gpu_multi_upload_data (PlutoGpuMulti *m, const double *Vc, const double *s1, const double *s2, const double *s3)
+{
+  const int nvar = (m->dims == 3 ? NVS : 6), ng = m->ng;
+  size_t totg = 1, totl = 1;
+  for (int d = 0; d < m->dims; d++){ totg *= (size_t)(m->gn[d] + 2*ng); totl *= (size_t)(m->ln[d] + 2*ng); }
+  const double *S[3] = {s1, s2, s3};
+  for (int b = 0; b < m->nb; b++){
+    for (int nv = 0; nv < nvar; nv++) pgm_rows (m, b, true, -1, (double *)Vc + (size_t)nv*totg, m->hV[b] + (size_t)nv*totl, false);
+    for (int d = 0; d < m->dims; d++) pgm_rows (m, b, true, d, (double *)S[d], m->hS[b][d], false);
+    if (pluto_gpu_upload_data (m->blk[b], m->hV[b], m->hS[b][0], m->hS[b][1], m->dims == 3 ? m->hS[b][2] : NULL)) return 1;
+  }
+  return 0;
+}
+
+int pluto_gpu_multi_download_data (PlutoGpuMulti *m, double *Vc, double *s1, double *s2, double *s3)
+{
+  const int nvar = (m->dims == 3 ? NVS : 6), ng = m->ng;
+  size_t totg = 1, totl = 1;
+  for (int d = 0; d < m->dims; d++){ totg *= (size_t)(m->gn[d] + 2*ng); totl *= (size_t)(m->ln[d] + 2*ng); }
+  double *S[3] = {s1, s2, s3};
+  for (int b = 0; b < m->nb; b++){
+    if (pluto_gpu_download_data (m->blk[b], m->hV[b], m->hS[b][0], m->hS[b][1], m->dims == 3 ? m->hS[b][2] : NULL)) return 1;
+    for (int nv = 0; nv < nvar; nv++) pgm_rows (m, b, false, -1, Vc + (size_t)nv*totg, m->hV[b] + (size_t)nv*totl, true);
+    for (int d = 0; d < m->dims; d++) pgm_rows (m, b, false, d, S[d], m->hS[b][d], true);
+  }
+  return 0;
+}
+
+int pluto_gpu_multi_advance (PlutoGpuMulti *m, double dt, PlutoGpuStepInfo *info)
+{
+  const int nst = m->blk[0]->nstages;
+  for (int b = 0; b < m->nb; b++) if (pluto_gpu_step_begin (m->blk[b])) return 1;
+  for (int stage = 1; stage <= nst; stage++){
+    for (int b = 0; b < m->nb; b++){
+      PlutoGpu *h = m->blk[b];
+      if (!m->nnbr[b]) continue;
+      CU (cudaSetDevice (h->cfg.device));
+      // the neighbours have emptied the buffers this block is about to fill (previous exchange)
+      for (int q = 0; q < m->nnbr[b]; q++) CU (cudaStreamWaitEvent (h->stream, m->ev_unpack[m->nbr[b][q]], 0));
+      if (pluto_gpu_halo_pack_all (h, stage)) return 1;
+      CU (cudaEventRecord (m->ev_pack[b], h->stream));
+    }
+    for (int b = 0; b < m->nb; b++){
+      PlutoGpu *h = m->blk[b];
+      CU (cudaSetDevice (h->cfg.device));
+      if (m->nnbr[b]){
+        for (int q = 0; q < m->nnbr[b]; q++) CU (cudaStreamWaitEvent (h->stream, m->ev_pack[m->nbr[b][q]], 0));
+        if (pluto_gpu_halo_unpack_all (h, stage)) return 1;
+        CU (cudaEventRecord (m->ev_unpack[b], h->stream));
+      }
+      for (int d = 0; d < m->dims; d++) if (pluto_gpu_boundary_dim (h, stage, d)) return 1;
+      if (pluto_gpu_stage (h, stage, dt)) return 1;
+    }
+  }
+  PlutoGpuStepInfo tot; memset (&tot, 0, sizeof (tot));
+  int rc = 0;
+  for (int b = 0; b < m->nb; b++){            // MPI_Allreduce(MAX) of invDt_hyp and g_maxMach (main.c:195-199, 415)
+    PlutoGpuStepInfo i; memset (&i, 0, sizeof (i));
+    if (pluto_gpu_step_end (m->blk[b], &i)) rc = 1;
+    if (i.inv_dt_hyp > tot.inv_dt_hyp) tot.inv_dt_hyp = i.inv_dt_hyp;
+    if (i.max_mach > tot.max_mach) tot.max_mach = i.max_mach;
+    tot.floor_events += i.floor_events; tot.nan_events += i.nan_events;
+  }
+  if (info) *info = tot;
+  return rc;
+}
+
+int pluto_gpu_multi_advance_data (PlutoGpuMulti *m, double dt, double *Vc, double *s1, double *s2, double *s3, PlutoGpuStepInfo *info)
+{
+  if (pluto_gpu_multi_upload_data (m, Vc, s1, s2, s3)) return 1;
+  if (pluto_gpu_multi_advance (m, dt, info)) return 1;
+  return pluto_gpu_multi_download_data (m, Vc, s1, s2, s3);
+}
+
 namespace pg_fast { int launch_arith_selftest (unsigned long long seed, int nblocks, int n, unsigned long long *bad, cudaStream_t s); }
 
 // The FAST Roe kernels use a branch-free correctly rounded division / reciprocal / square root (mhd_device.cuh): compare them

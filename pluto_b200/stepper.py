@@ -350,6 +350,110 @@ class GpuStepper:
         return float(self.L.pluto_gpu_next_dt(inv_dt_hyp, cfl, cfl_max_var, dt))
 
 
+class MultiGpuStepper:
+    """AdvanceStep on a domain cut into blocks, one per GPU, driven from THIS thread through the C ABI alone
+    (pluto_gpu_multi_*): what a single-threaded C host uses to reach the GPUs of a box without MPI.  Host arrays are the
+    reference's Data arrays of the whole domain (ghost zones included)."""
+
+    def __init__(self, dims, n, dx, grid, devices=None, recon="plm", solver="hlld", rk_order=2, bc=("periodic",) * 6,
+                 gamma=5.0 / 3.0, arith="exact", lib_path=None, limiter="default", emf="uct_contact", flatten=False, ctu=False,
+                 en_corr=False, char_lim=False):
+        self.L = _lib.load_library(lib_path)
+        c = _lib.PlutoGpuConfig()
+        n = list(n) + [1] * (3 - len(n))
+        if dims == 2:
+            n[2] = 1
+        c.dims = dims
+        for d in range(3):
+            c.n[d] = int(n[d])
+            c.dx[d] = float(dx[d]) if d < len(dx) else 1.0
+        c.recon, c.solver, c.rk_order = _lib.RECON[recon], _lib.SOLVER[solver], rk_order
+        for s in range(6):
+            c.bc[s] = _lib.BC[bc[s]]
+        c.arith, c.gamma, c.small_dn, c.small_pr = _lib.ARITH[arith], gamma, 1e-12, 1e-12
+        c.limiter, c.emf_average = _lib.LIMITER[limiter], _lib.EMF[emf]
+        c.shock_flattening, c.time_stepping = (1 if flatten else 0), (1 if ctu else 0)
+        c.en_correction, c.char_limiting = (1 if en_corr else 0), (1 if char_lim else 0)
+        self.dims, self.n = dims, tuple(n)
+        g = (C.c_int * 3)(*(list(grid) + [1] * (3 - len(grid))))
+        nb = g[0] * g[1] * g[2]
+        dev = (C.c_int * nb)(*(devices if devices is not None else [0] * nb))
+        self._h = C.c_void_p()
+        if self.L.pluto_gpu_multi_create(C.byref(c), C.byref(g), dev, C.byref(self._h)) != 0:
+            self._h = None
+            raise PlutoGpuError(_lib.last_error(self.L))
+        self.ng = self.L.pluto_gpu_multi_nghost(self._h)
+        self.nblocks = self.L.pluto_gpu_multi_nblocks(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.pluto_gpu_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PlutoGpuError(_lib.last_error(self.L))
+
+    def data_buffers(self):
+        n1, n2, n3 = self.n
+        g = self.ng
+        T1, T2 = n1 + 2 * g, n2 + 2 * g
+        T3 = n3 + 2 * g if self.dims == 3 else 1
+        shapes = [(8 if self.dims == 3 else 6, T3, T2, T1), (T3, T2, T1 + 1), (T3, T2 + 1, T1)]
+        if self.dims == 3:
+            shapes.append((T3 + 1, T2, T1))
+        bufs = [np.zeros(s) for s in shapes]
+        if self.dims == 2:
+            bufs.append(None)
+        return bufs
+
+    def upload_data(self, Vc, s1, s2, s3=None):
+        p = lambda a: a.ctypes.data if a is not None else None
+        self._check(self.L.pluto_gpu_multi_upload_data(self._h, p(Vc), p(s1), p(s2), p(s3)))
+
+    def download_data(self, Vc, s1, s2, s3=None):
+        p = lambda a: a.ctypes.data if a is not None else None
+        self._check(self.L.pluto_gpu_multi_download_data(self._h, p(Vc), p(s1), p(s2), p(s3)))
+
+    def advance(self, dt: float) -> StepInfo:
+        info = _lib.PlutoGpuStepInfo()
+        self._check(self.L.pluto_gpu_multi_advance(self._h, dt, C.byref(info)))
+        return StepInfo(info.inv_dt_hyp, info.max_mach, info.floor_events, info.nan_events)
+
+    def set_state(self, dump: dict):
+        """Interior (.dbl) state -> the Data arrays of the whole domain (ghost zones left to the exchange / Boundary)."""
+        Vc, s1, s2, s3 = self.data_buffers()
+        g = self.ng
+        names = VC_NAMES if self.dims == 3 else ["rho", "vx1", "vx2", "Bx1", "Bx2", "prs"]
+        k = slice(g, -g) if self.dims == 3 else slice(None)
+        for iv, nm in enumerate(names):
+            Vc[iv][k, g:-g, g:-g] = dump[nm]
+        s1[k, g:-g, g:-g] = dump["Bx1s"]
+        s2[k, g:-g, g:-g] = dump["Bx2s"]
+        if self.dims == 3:
+            s3[g:-g, g:-g, g:-g] = dump["Bx3s"]
+        self.upload_data(Vc, s1, s2, s3)
+
+    def get_state(self) -> dict:
+        Vc, s1, s2, s3 = self.data_buffers()
+        self.download_data(Vc, s1, s2, s3)
+        g = self.ng
+        names = VC_NAMES if self.dims == 3 else ["rho", "vx1", "vx2", "Bx1", "Bx2", "prs"]
+        k = slice(g, -g) if self.dims == 3 else slice(None)
+        out = {nm: Vc[iv][k, g:-g, g:-g].copy() for iv, nm in enumerate(names)}
+        out["Bx1s"] = s1[k, g:-g, g:-g].copy()
+        out["Bx2s"] = s2[k, g:-g, g:-g].copy()
+        if self.dims == 3:
+            out["Bx3s"] = s3[g:-g, g:-g, g:-g].copy()
+        return out
+
+
 class Integrator:
     """The reference's main loop around AdvanceStep (Src/main.c:133-243)."""
 

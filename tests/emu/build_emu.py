@@ -43,6 +43,18 @@ def newer(src_files, target):
 
 
 def build(verbose: bool = False) -> str:
+    """Build (or reuse) the interpreter library; concurrent callers (pytest-xdist workers) take turns on a lock file."""
+    import fcntl
+    os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build(verbose: bool = False) -> str:
     src_dir = os.path.join(BUILD, "src")
     os.makedirs(src_dir, exist_ok=True)
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))

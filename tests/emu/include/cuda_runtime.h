@@ -67,6 +67,9 @@ inline cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) { *s = 
 inline cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate (cudaEvent_t *e) { *e = (void *)1; return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags (cudaEvent_t *e, unsigned) { *e = (void *)1; return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaEventDestroy (cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord (cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize (cudaEvent_t) { return cudaSuccess; }

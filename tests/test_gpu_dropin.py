@@ -98,3 +98,26 @@ def test_resident_state_drop_in(name, arith):
     for k, v in g.states[g.nsteps].items():
         if arith == "exact":
             assert np.array_equal(r.dumps[g.nsteps][k], v), f"{name}: {k} (golden)"
+
+
+@pytest.mark.parametrize("name,ndev,resident", [("turb3d_plm_hlld", 8, False), ("blast3d_plm_hlld_100", 4, True), ("rotor2d_ppm_roe", 2, False),
+                                                ("ot2d_ctu", 4, True), ("ot2d_cl", 2, False)])
+def test_reference_driver_on_several_blocks(name, ndev, resident):
+    """PLUTO_GPU_NDEV: the reference's serial, single-threaded driver with the domain cut into 2 / 4 / 8 blocks (one per GPU where
+    the box has them, round robin otherwise), driven through pluto_gpu_multi_* -- no MPI, no Python.  Dumps bit-identical to the
+    all-CPU reference (= the golden fixtures), also with the state resident on the devices."""
+    g = Golden(name)
+    cfg = _cfg(g)
+    if not have_ref(cfg):
+        pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
+    env = {"PLUTO_GPU_ARITH": "exact", "PLUTO_GPU_NDEV": str(ndev)}
+    if resident:
+        env["PLUTO_GPU_RESIDENT"] = "1"
+    every = 1 if g.nsteps <= 30 else 50
+    r = run_reference(cfg, maxsteps=g.nsteps - 1 if every > 1 else g.nsteps + 1, dump_every=every, analysis_every=every, env=env)
+    assert f"{ndev} block(s)" in r.stdout
+    for s_, ref in g.states.items():
+        if s_ in r.dumps:
+            for k, v in ref.items():
+                assert np.array_equal(r.dumps[s_][k], v), f"{name}: {k} after {s_} steps on {ndev} blocks"
+    assert g.nsteps in r.dumps

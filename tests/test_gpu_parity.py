@@ -639,3 +639,35 @@ def test_flt_and_vtk_output_match_the_reference_files(tmp_path, dims, n):
             f"{next((q for q in range(min(len(a), len(b))) if a[q] != b[q]), -1)}"
         assert open(out / f"{ext}.out").read() == open(tmp_path / "ref" / f"{ext}.out").read()
     s.close()
+
+
+@pytest.mark.parametrize("problem,dims,n,grid,recon,solver,rk,ctu", [
+    ("turb", 3, (16, 16, 16), (2, 2, 2), "plm", "hlld", 2, False), ("blast", 3, (16, 12, 24), (1, 2, 2), "plm", "hlld", 2, False),
+    ("ot", 2, (32, 24, 1), (2, 2, 1), "ppm", "roe", 3, False), ("rotor", 2, (32, 24, 1), (1, 2, 1), "plm", "hll", 2, False),
+    ("ot", 3, (16, 16, 12), (2, 1, 2), "plm", "hlld", 2, True)])
+def test_single_thread_multi_block_stepper_matches_single_block(problem, dims, n, grid, recon, solver, rk, ctu):
+    """pluto_gpu_multi_*: the domain cut into blocks that ONE host thread drives through the C ABI (peer stores between the
+    blocks inside the pack launch, events between the streams) reproduces the single-block run bit for bit, from the
+    reference's Data arrays of the whole domain and back.  On a one-GPU box all blocks share device 0; on several GPUs the
+    blocks are spread over them (tests/test_gpu_dist.py)."""
+    import torch
+    from pluto_b200 import GpuStepper, MultiGpuStepper, problems
+    st0, meta = problems.make(problem, dims, n)
+    kw = dict(recon=recon, solver=solver, rk_order=rk, bc=meta["bc"], gamma=meta["gamma"], arith="exact", ctu=ctu)
+    one = GpuStepper(dims, n, meta["dx"], **kw)
+    nb = grid[0] * grid[1] * grid[2]
+    ndev = torch.cuda.device_count() if torch.cuda.is_available() else 1
+    many = MultiGpuStepper(dims, n, meta["dx"], grid, devices=[b % max(ndev, 1) for b in range(nb)], **kw)
+    assert many.nblocks == nb
+    one.set_state(st0)
+    many.set_state(st0)
+    dt = {"ot": 5e-3, "blast": 2e-4, "turb": 5e-3, "rotor": 1e-3}[problem]
+    for step in range(4):
+        a, b = one.advance(dt), many.advance(dt)
+        assert (a.inv_dt_hyp, a.max_mach, a.floor_events) == (b.inv_dt_hyp, b.max_mach, b.floor_events), step
+        dt = one.next_dt(a.inv_dt_hyp, meta["cfl"], 1.1, dt)
+    sa, sb = one.get_state(), many.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), f"{k}: max abs diff {np.abs(sa[k] - sb[k]).max():.3e}"
+    one.close()
+    many.close()
