@@ -267,8 +267,9 @@ __device__ __forceinline__ double face_update (const FinalArgs &a, long long id,
   return b;
 }
 
-template <int NC, bool EN, bool FUSE = false>   // EN: CT_EN_CORRECTION YES (compile time: the default instantiation keeps its 32
-                                                // registers); FUSE: CT_Update evaluated here (FinalArgs.fuse_ct)
+template <int NC, bool EN, bool FUSE = false, bool R3 = false>   // EN: CT_EN_CORRECTION YES (compile time: the default instantiation
+                                                // keeps its 32 registers); FUSE: CT_Update evaluated here (FinalArgs.fuse_ct);
+                                                // R3: the x3 sweep kept its flux difference apart (FinalArgs.R3): u = U + R3
 __global__ void __launch_bounds__(128)
 final_kernel (const __grid_constant__ FinalArgs a)
 {
@@ -287,6 +288,11 @@ final_kernel (const __grid_constant__ FinalArgs a)
     u[RHO] = a.U[RHO][id]; u[MX1] = a.U[MX1][id]; u[MX2] = a.U[MX2][id];
     if (NC == 3) u[MX3] = a.U[MX3][id];
     u[ENG] = a.U[ENG][id];
+    if (R3){                 // U = ((U0 + rhs_x1) + rhs_x2) + rhs_x3, the sum of update_stage.c:214-216 completed here
+      u[RHO] = u[RHO] + a.R3[RHO][id]; u[MX1] = u[MX1] + a.R3[MX1][id]; u[MX2] = u[MX2] + a.R3[MX2][id];
+      if (NC == 3) u[MX3] = u[MX3] + a.R3[MX3][id];
+      u[ENG] = u[ENG] + a.R3[ENG][id];
+    }
     if (a.combine){
       double v0[NV], u0[NV];
       PG_FOR_NV(nv) v0[nv] = a.V0[nv][id];
@@ -684,6 +690,8 @@ int launch_final (const FinalArgs &a, cudaStream_t s)
   }else if (a.en_corr){
     if (g.dims == 3) final_kernel<3, true><<<grid, 128, 0, s>>>(a);
     else             final_kernel<2, true><<<grid, 128, 0, s>>>(a);
+  }else if (a.R3[RHO] && g.dims == 3){
+    final_kernel<3, false, false, true><<<grid, 128, 0, s>>>(a);
   }else{
     if (g.dims == 3) final_kernel<3, false><<<grid, 128, 0, s>>>(a);
     else             final_kernel<2, false><<<grid, 128, 0, s>>>(a);

@@ -528,8 +528,8 @@ static int launch_ctu_sweep_t (int dir, int phase, const CtuArgs &a, cudaStream_
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
 #define PG_CX1(P, C, F) do { auto kfn = ctu_sweep_x_kernel<P, SOLVER, C, F>;                                  \
       const size_t smem = (size_t)(TPB/32)*2*ctu_x_slot (P)*sizeof (double);                                  \
-      static bool attr_set = false;                                                                          \
-      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
+      static unsigned long long devs = 0;                                                                    \
+      if (pg_attr_needed (devs)) cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
 #define PG_CX(P, C) do { if (fl) PG_CX1(P, C, true); else PG_CX1(P, C, false); } while (0)
     if (phase == 0){ if (nc == 3) PG_CX(0, 3); else PG_CX(0, 2); }
@@ -542,8 +542,8 @@ static int launch_ctu_sweep_t (int dir, int phase, const CtuArgs &a, cudaStream_
     const unsigned nb = (unsigned)((npen*a.nchunk + TPB - 1)/TPB);
 #define PG_CM1(DD, P, C, F) do { auto kfn = ctu_sweep_march_kernel<DD, P, SOLVER, C, F>;                    \
       const size_t smem = (size_t)2*ctu_march_slot (P)*TPB*sizeof (double);                                  \
-      static bool attr_set = false;                                                                          \
-      if (!attr_set){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; } \
+      static unsigned long long devs = 0;                                                                    \
+      if (pg_attr_needed (devs)) cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       kfn<<<nb, TPB, smem, s>>>(a); } while (0)
 #define PG_CM(DD, P, C) do { if (fl) PG_CM1(DD, P, C, true); else PG_CM1(DD, P, C, false); } while (0)
     if (dir == 1){

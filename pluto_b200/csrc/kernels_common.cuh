@@ -82,6 +82,10 @@ struct SweepArgs {
   // BODY_FORCE & POTENTIAL (rhs.c:388-392, rhs_source.c:233-237, 316-320, 358-362): potential at the zone centres and at
   // the faces of this sweep's direction (phif2: x2 faces, fused x1+x2 sweep); NULL without a potential
   const double *phic, *phif, *phif2;
+  // x3 sweep of the bench configuration (FAST, 3-D, LINEAR, plain options): the flux difference of the sweep is STORED here
+  // (slots RHO, MX1..3, ENG) instead of being added to U -- the sweep then stages no U (38 instead of 48 shared-memory slots per
+  // thread: four blocks per SM) and does not depend on the fused x1+x2 sweep; the stage completion forms U + R3.  NULL: U += rhs.
+  double *R3[8];
 };
 
 struct CtArgs {
@@ -160,6 +164,7 @@ struct FinalArgs {
   const double *ex, *ey, *ez;                // edge EMFs
   const double *Bs_in[3], *Bs0[3];           // staggered field of the stage's input and at t^n
   double *Bs_out[3];
+  const double *R3[8];                       // flux difference of the x3 sweep kept apart (SweepArgs.R3): u = U + R3; NULL: u = U
 };
 
 // Boundary conditions of ONE dimension in one launch: the copy jobs (a field and
@@ -227,6 +232,18 @@ static inline int pg_launch_status (int n = 1)
 {
   const cudaError_t e = cudaGetLastError ();
   return e == cudaSuccess ? n : -1 - (int)e;
+}
+
+// Function attributes (dynamic shared-memory limit, carve-out) belong to the device the call was made on: a process that drives
+// several GPUs (pluto_gpu_multi_*) has to set them once PER DEVICE.  `mask` is the launch site's static record of the devices done.
+static inline bool pg_attr_needed (unsigned long long &mask)
+{
+  int dev = 0;
+  cudaGetDevice (&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
 }
 
 // ---- launch interface, one set per arithmetic namespace ----------------------

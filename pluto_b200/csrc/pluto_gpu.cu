@@ -92,6 +92,8 @@ struct PlutoGpu {
   void   *phi_pool;
   double *fbn[3];                  // CT_EN_CORRECTION + EXACT: normal-field flux of the faces (own allocation)
   void   *fbn_pool;
+  double *R3[NVS];                 // FAST, 3-D, LINEAR, plain options: flux difference of the x3 sweep (own allocation), else NULL
+  void   *r3_pool;
   double *rhs3[3][NVS];            // CTU: half-step right-hand sides of the normal predictors (own allocation)
   void   *ctu_pool;
   // optional per-kernel-class device timing (CUDA events on `stream`)
@@ -274,6 +276,18 @@ static int create_resources (PlutoGpu *h)
     for (int d = 0; d < g.dims; d++) h->fbn[d] = (double *)h->fbn_pool + (size_t)d*tot_al;
     h->pool_bytes += nb;
   }
+  // x3 sweep with its flux difference kept apart (SweepArgs.R3; PLUTO_GPU_R3=1): a measured opt-in.  The x3 sweep then stages no U,
+  // fits four blocks per SM and is 7.5 % faster, but the stage completion reads 40 B per zone more and loses twice that
+  // (profiles/r2r_*: 6.18 against 6.12 ms per step at 256^3)
+  if (getenv ("PLUTO_GPU_R3") && atoi (getenv ("PLUTO_GPU_R3")) != 0 && cfg->arith == PLUTO_GPU_ARITH_FAST && g.dims == 3 && cfg->recon == PLUTO_GPU_RECON_LINEAR && !h->ctu && !cfg->shock_flattening
+      && cfg->emf_average != PLUTO_GPU_EMF_UCT_HLL && !cfg->body_force && !cfg->en_correction && !cfg->char_limiting
+      && getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL){
+    const size_t nb = (size_t)5*tot_al*sizeof (double);
+    if (cudaMalloc (&h->r3_pool, nb) != cudaSuccess) return fail ("cudaMalloc of %zu bytes (x3 flux differences) failed", nb);
+    CU (cudaMemset (h->r3_pool, 0, nb));
+    for (int q = 0; q < 5; q++) h->R3[kCons[q]] = (double *)h->r3_pool + (size_t)q*tot_al;
+    h->pool_bytes += nb;
+  }
   if (h->ctu){
     int nlive = 0;
     for (int nv = 0; nv < NVS; nv++) nlive += live_var (h, nv);
@@ -318,6 +332,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->dvel_pool) cudaFree (h->dvel_pool);
   if (h->ctu_pool) cudaFree (h->ctu_pool);
   if (h->fbn_pool) cudaFree (h->fbn_pool);
+  if (h->r3_pool) cudaFree (h->r3_pool);
   if (h->gfield_pool) cudaFree (h->gfield_pool);
   if (h->phi_pool) cudaFree (h->phi_pool);
   if (h->flag) cudaFree (h->flag);
@@ -709,6 +724,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   f.fuse_ct = (h->fuse_ct && !f.en_corr && !(sp.combine && sp.out == 0));
   f.ex = h->ex; f.ey = h->ey; f.ez = h->ez;
   for (int d = 0; d < 3; d++){ f.Bs_in[d] = h->Bs[sp.in][d]; f.Bs0[d] = h->Bs[0][d]; f.Bs_out[d] = h->Bs[sp.out][d]; }
+  if (!f.fuse_ct) for (int nv = 0; nv < NVS; nv++) f.R3[nv] = h->R3[nv];
   if (part == PART_INTERIOR) return launch_final_boxes (h, f, part);
 
   if (h->flag && stage == 1){
@@ -722,6 +738,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   s.flag = h->flag;
   for (int nv = 0; nv < NVS; nv++){ s.V[nv] = h->V[sp.in][nv]; s.U[nv] = h->U[nv]; }
   s.cdt = h->cdt; s.red = h->red; s.g = g; s.ph = h->ph; s.dtp = h->dtdev;
+  if (!f.fuse_ct) for (int nv = 0; nv < NVS; nv++) s.R3[nv] = h->R3[nv];
   s.stage1 = (stage == 1);
   s.limiter = h->cfg.limiter;
   s.char_lim = h->cfg.char_limiting;

@@ -405,13 +405,22 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
 // slots).  The second face of look-ahead is therefore an L2 prefetch (PG_MARCH_L2PF),
 // which needs no landing space.
 __host__ __device__ constexpr int march_prefetch (int recon) { return recon == RECON_PPM ? 1 : PG_MARCH_PF; }
-__host__ __device__ constexpr int march_slots (int recon)
+// cl: CHAR_LIMITING (the ring then keeps all 8 primitives, otherwise the 7 without the cell-centred normal field);
+// r3: the flux difference goes to its own arrays (SweepArgs.R3) -- no U is staged, only C_dt
+__host__ __device__ constexpr int march_ring_vars (bool cl) { return cl ? 8 : 7; }
+__host__ __device__ constexpr int march_slots (int recon, bool cl = false, bool r3 = false)
 {
-  return 8*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + 8 + 7 + (recon == RECON_PPM ? 8 : 0)
-         + march_prefetch (recon) + 6*(march_prefetch (recon) + 1);
+  return march_ring_vars (cl)*((recon == RECON_PPM ? 3 : 2) + march_prefetch (recon)) + march_ring_vars (cl) + 7 + (recon == RECON_PPM ? 8 : 0)
+         + march_prefetch (recon) + (r3 ? 1 : 6)*(march_prefetch (recon) + 1);
 }
-template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool CL = false>
-__global__ void __launch_bounds__(128, PG_MINB_MARCH)
+// R3 (the bench configuration's x3 sweep): 38 slots = 38 KB per block and 128 registers -> FOUR blocks per SM (16 warps, 152 KB of
+// shared memory, below the L1 cliff) instead of three: the sweeps are bound by FP64 issue latency, a fourth warp per scheduler
+// is what hides it
+#ifndef PG_MINB_MARCH_R3
+#define PG_MINB_MARCH_R3 4
+#endif
+template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool CL = false, bool R3 = false>
+__global__ void __launch_bounds__(128, R3 ? PG_MINB_MARCH_R3 : PG_MINB_MARCH)
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
   typedef Dirs<DIR> D;
@@ -465,16 +474,20 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   constexpr int LA = (PPM ? 3 : 2);         // look-ahead of the stencil
   constexpr int PF = march_prefetch (RECON);
   constexpr int NZ = LA + PF;               // ring slots
-  constexpr int S_VP = 8*NZ, S_FP = S_VP + 8, S_WF = S_FP + 7, S_BN = S_WF + (PPM ? 8 : 0), S_UA = S_BN + PF;
-  static_assert (S_UA + 6*(PF + 1) == march_slots (RECON), "shared-memory layout");
-#define C_VP(nv) cs[(S_VP + (nv))*CS]
+  constexpr int NR = march_ring_vars (CL);  // variables per ring zone: slot ZS(nv) of variable nv (the skipped one has none)
+  constexpr int NUA = (R3 ? 1 : 6);         // staged per zone to update: 5 U + C_dt, or C_dt alone
+  constexpr int S_VP = NR*NZ, S_FP = S_VP + NR, S_WF = S_FP + 7, S_BN = S_WF + (PPM ? 8 : 0), S_UA = S_BN + PF;
+  static_assert (S_UA + NUA*(PF + 1) == march_slots (RECON, CL, R3), "shared-memory layout");
+#define ZS(nv)   ((SK >= 0 && (nv) > SK) ? (nv) - 1 : (nv))
+#define C_VP(nv) cs[(S_VP + ZS(nv))*CS]
 #define C_FP(q)  cs[(S_FP + (q))*CS]
 #define C_WF(nv) cs[(S_WF + (nv))*CS]
   double *z[NZ], *bnp[PF], *uap[PF + 1];
-  PG_UNROLL for (int q = 0; q < NZ; q++) z[q] = cs + 8*q*CS;            // z[q]: zone f+q
+  PG_UNROLL for (int q = 0; q < NZ; q++) z[q] = cs + NR*q*CS;           // z[q]: zone f+q
   PG_UNROLL for (int q = 0; q < PF; q++) bnp[q] = cs + (S_BN + q)*CS;   // bnp[q]: field of face f+q+1/2
-  PG_UNROLL for (int q = 0; q <= PF; q++) uap[q] = cs + (S_UA + 6*q)*CS; // uap[q]: zone f+q (uap[PF]: free)
+  PG_UNROLL for (int q = 0; q <= PF; q++) uap[q] = cs + (S_UA + NUA*q)*CS; // uap[q]: zone f+q (uap[PF]: free)
   auto fetch_ua = [&] (double *dst, int idz){
+    if (R3){ if (a.stage1) cp_async8 (dst, a.cdt + idz); return; }
     cp_async8 (dst, a.U[RHO] + idz); cp_async8 (dst + CS, a.U[MX1] + idz);
     cp_async8 (dst + 2*CS, a.U[MX2] + idz);
     if (NC == 3) cp_async8 (dst + 3*CS, a.U[MX3] + idz);
@@ -484,11 +497,11 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
   {
     // group 0: what face c0-1/2 needs (zones c0-1 .. c0-1+LA, its field); groups
     // 1 .. PF-1: the additional zone, field and U of the following faces
-    PG_UNROLL for (int q = 0; q <= LA; q++) PG_FOR_NV_SKIP(nv, SK) cp_async8 (z[q] + nv*CS, a.V[nv] + id + q*sD);
+    PG_UNROLL for (int q = 0; q <= LA; q++) PG_FOR_NV_SKIP(nv, SK) cp_async8 (z[q] + ZS(nv)*CS, a.V[nv] + id + q*sD);
     cp_async8 (bnp[0], a.Bn + id);
     cp_async_commit ();
     PG_UNROLL for (int q = 1; q < PF; q++){
-      PG_FOR_NV_SKIP(nv, SK) cp_async8 (z[LA + q] + nv*CS, a.V[nv] + id + (LA + q)*sD);
+      PG_FOR_NV_SKIP(nv, SK) cp_async8 (z[LA + q] + ZS(nv)*CS, a.V[nv] + id + (LA + q)*sD);
       cp_async8 (bnp[q], a.Bn + id + q*sD);
       if (upd) fetch_ua (uap[q], id + q*sD);
       cp_async_commit ();
@@ -498,7 +511,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       double va_[NV], dvm[NV], dvp[NV], vm_unused[NV];
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait<PF - 1> ();
-      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; }
+      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][ZS(nv)*CS]; vc_[nv] = z[1][ZS(nv)*CS]; }
       PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
       plm_zone_f<NC, FLAT, SK, CL, DIR>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
@@ -507,7 +520,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       load_zone<NC>(a, id - 2*sD, vz_);
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait<PF - 1> ();
-      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vd_[nv] = z[2][nv*CS]; }
+      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][ZS(nv)*CS]; vc_[nv] = z[1][ZS(nv)*CS]; vd_[nv] = z[2][ZS(nv)*CS]; }
       ppm_interface<NC, SK>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
       ppm_interface<NC, SK>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
       ppm_zone<NC, SK>(vb_, Wm, Wf, vpL, vm_unused);
@@ -533,9 +546,9 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     double rho_f = 0.0;                      // density of zone f (body force)
     {
       double vb_[NV], vc_[NV], vd_[NV], vnx[NV], vpn[NV];
-      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][nv*CS]; vc_[nv] = z[1][nv*CS]; vnx[nv] = z[LA][nv*CS]; }
+      PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][ZS(nv)*CS]; vc_[nv] = z[1][ZS(nv)*CS]; vnx[nv] = z[LA][ZS(nv)*CS]; }
       if (BF) rho_f = vb_[RHO];
-      if (PPM) PG_FOR_NV_SKIP(nv, SK) vd_[nv] = z[2][nv*CS];
+      if (PPM) PG_FOR_NV_SKIP(nv, SK) vd_[nv] = z[2][ZS(nv)*CS];
       // start pulling what face f+PF+1/2 needs; its new zone replaces zone f, its field
       // the one just read.  Always commit (possibly empty) so that the group count holds.
 #if PG_MARCH_L2PF
@@ -553,7 +566,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 #endif
       if (f + PF <= c1){
         cp_async8_ordered (z[0], a.V[0] + id + (LA + PF)*sD);
-        PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv) && nv != SK) cp_async8 (z[0] + nv*CS, a.V[nv] + id + (LA + PF)*sD);
+        PG_UNROLL for (int nv = 1; nv < NV; nv++) if (live<NC>(nv) && nv != SK) cp_async8 (z[0] + ZS(nv)*CS, a.V[nv] + id + (LA + PF)*sD);
         cp_async8 (bnp[0], a.Bn + id + PF*sD);
         if (upd) fetch_ua (uap[PF], id + PF*sD);
       }
@@ -604,26 +617,29 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     if (upd && f >= c0){
       const double dtdx = __ldg (a.dtp + DIR);
       double r;
-      r = -dtdx*(F[RHO] - C_FP(0));                               a.U[RHO][id] = ua[0] + r;
+      // R3: the flux difference alone is stored; the stage completion forms U + r, the same sum
+      double *const *Uo = R3 ? a.R3 : a.U;
+#define UPD_(q, r) (R3 ? (r) : ua[(q)*CS] + (r))
+      r = -dtdx*(F[RHO] - C_FP(0));                               Uo[RHO][id] = UPD_(0, r);
       const double r_rho = r;
       const double dphi = (BF && a.phif) ? pfd - __ldg (a.phif + id - sD) : 0.0;
       const double dtg = BF ? __ldg (a.dtp + 3) : 0.0;
       const double gd = BF ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;
-      r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   a.U[MX1][id] = ua[CS] + r;
+      r = -dtdx*(F[MX1] - C_FP(1)); if (D::vn == MX1) r -= dtdx*(press - pp);   Uo[MX1][id] = UPD_(1, r);
       r = -dtdx*(F[MX2] - C_FP(2));
       if (D::vn == MX2){ r -= dtdx*(press - pp); if (BF && a.bfv) r += dtg*rho_f*gd; if (BF && a.phif) r -= dtdx*rho_f*dphi; }
-      a.U[MX2][id] = ua[2*CS] + r;
+      Uo[MX2][id] = UPD_(2, r);
       if (NC == 3){
         r = -dtdx*(F[MX3] - C_FP(3));
         if (D::vn == MX3){ r -= dtdx*(press - pp); if (BF && a.bfv) r += dtg*rho_f*gd; if (BF && a.phif) r -= dtdx*rho_f*dphi; }
-        a.U[MX3][id] = ua[3*CS] + r;
+        Uo[MX3][id] = UPD_(3, r);
       }
       r = -dtdx*(F[ENG] - C_FP(4));
       if (BF && a.bfv) r += dtg*0.5*(F[RHO] + C_FP(0))*gd;
       if (BF && a.phic) r -= __ldg (a.phic + id)*r_rho;
-      a.U[ENG][id] = ua[4*CS] + r;
+      Uo[ENG][id] = UPD_(4, r);
       if (a.stage1){
-        double cd = ua[5*CS] + 0.5*(cp + cmax)*a.inv_dl;
+        double cd = ua[(NUA - 1)*CS] + 0.5*(cp + cmax)*a.inv_dl;
         if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
         else            a.cdt[id] = cd;
       }
@@ -635,6 +651,8 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 #undef C_VP
 #undef C_FP
 #undef C_WF
+#undef ZS
+#undef UPD_
 
   my_mach = warp_max (my_mach);
   if (lane == 0) atomic_max_pos (a.red + RED_MACH, my_mach);
@@ -666,7 +684,10 @@ __host__ __device__ constexpr int xy_thread_slots (int recon) { return 8 + 7 + (
 // ring rows: the stencil rows f .. f+LA, plus (PLM) one free row for the copy in flight so
 // that nothing has to be read ahead of its use; with PPM that row would push three blocks
 // past the 164 KB carve-out (L1 cliff, see march_prefetch), so row f is read early instead
-__host__ __device__ constexpr int xy_ring_rows (int recon) { return recon == RECON_PPM ? 4 : 4; }
+#ifndef PG_XY_ROWS
+#define PG_XY_ROWS 4
+#endif
+__host__ __device__ constexpr int xy_ring_rows (int recon) { return recon == RECON_PPM ? 4 : PG_XY_ROWS; }
 __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
 {
   return (size_t)(8*xy_ring_rows (recon)*xy_ring_cols () + xy_thread_slots (recon)*128 + 4)*sizeof (double);   // + 4 mbarriers (TMA)
@@ -1016,8 +1037,8 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
 #define PG_LXY3(R, C) PG_LXYK((sweep_xy_kernel<R, SOLVER, C, false, false, false, true>))
 #define PG_LXY2(R, C, H, F, B) PG_LXYK((sweep_xy_kernel<R, SOLVER, C, H, F, B>))
 #define PG_LXYK(KF) do { auto kfn = KF;                          \
-      static int bps = 0;                                                                             \
-      if (!bps){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); \
+      static int bps = 0; static unsigned long long devs = 0;                                         \
+      if (pg_attr_needed (devs)){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); \
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_XY; } \
       if (a.plan) plan_chunks (b, g.n[1], nwarp1*32*1000/TPB, bps);                                   \
       const unsigned nb = (unsigned)((nwarp1*b.nchunk*32 + TPB - 1)/TPB);                             \
@@ -1073,20 +1094,21 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
   }else{
     const int td = (dir == 1 ? 2 : 1);
     const long long npen = (long long)(g.n[0] + 2)*(nc == 3 ? g.n[td] + 2 : 1);
-    const size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
+    size_t smem = (size_t)march_slots (recon)*TPB*sizeof (double);
     SweepArgs b = a;
 #define PG_LM1(DD, R, C, H, F) PG_LM2(DD, R, C, H, F, false)
 #define PG_LM2(DD, R, C, H, F, B) PG_LMK((sweep_march_kernel<DD, R, SOLVER, C, H, F, B>))
 #define PG_LMK(KF) do { auto kfn = KF;             \
-      static int bps = 0;                                                                             \
-      if (!bps){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
+      static int bps = 0; static unsigned long long devs = 0;                                         \
+      if (pg_attr_needed (devs)){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_MARCH; } \
       if (a.plan) plan_chunks (b, g.n[dir], npen*1000/TPB, bps);                                      \
       const unsigned nb = (unsigned)((npen*b.nchunk + TPB - 1)/TPB);                                  \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
 #define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;          \
-      if (a.char_lim && P && C == 2 && DD == 1) PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, false, true>)); \
+      if (a.char_lim && P && C == 2 && DD == 1){ smem = (size_t)march_slots (RECON_PLM, true)*TPB*sizeof (double);            \
+                                                 PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, false, true>)); } \
       else if (bf)        PG_LM2(DD, R, C, false, false, true);                                                      \
       else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                    \
       else           { if (fl) PG_LM1(DD, R, C, false, P); else PG_LM1(DD, R, C, false, false); } } while (0)
@@ -1096,6 +1118,12 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       else if (recon == RECON_PPM && nc == 3) PG_LM(1, RECON_PPM, 3);
       else                                    PG_LM(1, RECON_PPM, 2);
     }else{
+#ifdef PG_FAST
+      if (recon == RECON_PLM && a.R3[RHO] && !bf && a.avg != 3 && !a.flag){     // flux difference kept apart, four blocks per SM
+        smem = (size_t)march_slots (RECON_PLM, false, true)*TPB*sizeof (double);
+        PG_LMK((sweep_march_kernel<2, RECON_PLM, SOLVER, 3, false, false, false, false, true>));
+      }else
+#endif
       if (recon == RECON_PLM) PG_LM(2, RECON_PLM, 3);
       else                    PG_LM(2, RECON_PPM, 3);
     }

@@ -106,6 +106,31 @@ def test_tma_staging_bit_identical_to_cp_async(monkeypatch, problem, dims, n, re
         assert np.array_equal(v, out[1][0][k]), k
 
 
+@pytest.mark.parametrize("problem,n,solver", [("blast", (40, 24, 20), "hlld"), ("turb", (31, 17, 70), "roe")])
+def test_x3_flux_difference_kept_apart(monkeypatch, problem, n, solver):
+    """PLUTO_GPU_R3=1 (measured opt-in): the x3 sweep stores its flux difference instead of adding it to U (no U staged: 38
+    shared-memory slots per thread, four blocks per SM) and the stage completion forms U + R3 -- the same sum up to the FMA
+    contraction of the last addition, so the results agree to round-off, the dt sequence included."""
+    from pluto_b200 import GpuStepper, problems
+    st0, meta = problems.make(problem, 3, n)
+    out = []
+    for r3 in ("0", "1"):
+        monkeypatch.setenv("PLUTO_GPU_R3", r3)
+        s = GpuStepper(3, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith="fast")
+        s.set_state(st0)
+        dt = 1e-3 if problem != "blast" else 1e-4
+        for _ in range(4):
+            info = s.advance(dt)
+            assert info.nan_events == 0
+            dt = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+        out.append((s.get_state(), dt, s.device_bytes))
+        s.close()
+    assert out[1][2] > out[0][2]                     # the five extra arrays: the path was taken
+    assert abs(out[0][1] - out[1][1]) <= 1e-12 * out[0][1]
+    for k, v in out[0][0].items():
+        assert rel_l1(out[1][0][k], v) <= TOL_ONE_STEP, k
+
+
 def test_fast_roe_division_and_square_root_are_ieee():
     """The FAST Roe kernels keep IEEE arithmetic upstream of the solver's eigenvector switches (mhd_device.cuh) with a
     branch-free correctly rounded division / reciprocal / square root.  2e9 operand pairs (random and adversarial

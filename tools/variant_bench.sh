@@ -3,7 +3,7 @@
 arith=$1; shift
 for lib in "$@"; do
   echo "== $lib ($arith)"
-  python bench.py --dev-lib $lib --steps ${STEPS:-10} --warmup 3 --no-e2e --no-cpu-baseline --arith $arith ${BENCH_ARGS:-} 2>&1 | python -c "
+  python bench.py --dev-lib $lib --steps ${STEPS:-10} --warmup 3 --no-e2e --no-cpu-baseline --no-extras --arith $arith ${BENCH_ARGS:-} 2>&1 | python -c "
 import sys, json
 for line in sys.stdin:
     if line.startswith('{'):
