@@ -117,6 +117,13 @@ int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
 /* BODY_FORCE VECTOR with a STATIC position-dependent force instead of the uniform grav[] of the configuration (which must
    have body_force = 1): component d of BodyForceVector (init.c) at every zone centre, ghost zones included, HOST arrays
    g_d[k][j][i] with the extents T3 x T2 x T1 of the reference's Data arrays (g3 NULL in 2-D). */
+/* Non-uniform Cartesian grid (uniform and stretched patches of pluto.ini's [Grid] block, Src/set_grid.c:330-560): the zone
+   widths of every direction, dx_d[0 .. T_d-1] = grid->dx[d] with the ghost zones (T_d = n[d] + 2 nghost).  The reference's
+   CARTESIAN builds keep the uniform reconstruction weights (UNIFORM_CARTESIAN_GRID YES, Src/States/plm_coeffs.h:23-29); the
+   widths enter Src/MHD/rhs.c:195, the inverse time step (Src/Time_Stepping/update_stage.c:229-235), Src/MHD/CT/ct_update.c:91-204
+   and the face areas of Src/MHD/CT/ct_fill_mag_field.c:108-114.  RK2 / RK3 with LINEAR reconstruction; dx3 may be NULL in 2-D.
+   PlutoGpuConfig.dx is then used by nothing on the path.  Call once after pluto_gpu_create. */
+int  pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const double *dx3);
 int  pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3);
 /* BODY_FORCE POTENTIAL (body_force & 2; Src/MHD/rhs.c:162-187, 388-392, rhs_source.c:233-237, 316-320, 358-362,
    prim_eqn.c:304-307): BodyForcePotential (init.c) at the zone centres, phic[k][j][i] (T3 x T2 x T1), and at the faces of

@@ -116,6 +116,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
 
   if (gpu == NULL && gpum == NULL){
     PlutoGpuConfig c;
+    int nonuniform = 0;
     int ndev_blocks = getenv ("PLUTO_GPU_NDEV") ? atoi (getenv ("PLUTO_GPU_NDEV")) : 1;
     char *arith = getenv ("PLUTO_GPU_ARITH");
     int idim;
@@ -162,12 +163,22 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       c.dx[idim] = grid->dx[idim][grid->lbeg[idim]];             /* uniform grid: set_grid.c:400 gives every zone */
       {                                                          /* of a uniform patch the same dx, bit for bit    */
         int ii;
-        for (ii = 0; ii < grid->np_tot[idim]; ii++) if (grid->dx[idim][ii] != c.dx[idim]){
-          print ("! AdvanceStep(gpu): the grid is not uniform in direction %d (dx[%d] = %12.6e, dx[%d] = %12.6e);\n"
-                 "  stretched, logarithmic and multi-patch grids are not available on the GPU\n",
-                 idim, grid->lbeg[idim], c.dx[idim], ii, grid->dx[idim][ii]);
-          QUIT_PLUTO(1);
-        }
+        for (ii = 0; ii < grid->np_tot[idim]; ii++) if (grid->dx[idim][ii] != c.dx[idim]) nonuniform = 1;
+      }
+    }
+    if (nonuniform){
+      /* stretched / logarithmic / multi-patch grids (set_grid.c:330-560): the zone widths go to the library after its creation */
+#if UNIFORM_CARTESIAN_GRID != YES
+  #error "libpluto_gpu: the grid-dependent reconstruction weights of UNIFORM_CARTESIAN_GRID NO (plm_coeffs.c) are not available on the GPU"
+#endif
+#if TIME_STEPPING == HANCOCK || RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES
+      print ("! AdvanceStep(gpu): a non-uniform grid needs RK2 / RK3 with LINEAR reconstruction, without SHOCK_FLATTENING,\n"
+             "  BODY_FORCE, CT_EN_CORRECTION and CHAR_LIMITING on the GPU\n");
+      QUIT_PLUTO(1);
+#endif
+      if (ndev_blocks > 1){
+        print ("! AdvanceStep(gpu): PLUTO_GPU_NDEV > 1 is not available on a non-uniform grid\n");
+        QUIT_PLUTO(1);
       }
     }
     c.arith    = (arith != NULL && !strcmp (arith, "fast")) ? PLUTO_GPU_ARITH_FAST : PLUTO_GPU_ARITH_EXACT;
@@ -197,6 +208,10 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     if ((gpum ? pluto_gpu_multi_nghost (gpum) : pluto_gpu_nghost (gpu)) != grid->nghost[IDIR]){   /* the host arrays are read with this padding */
       print ("! AdvanceStep(gpu): the library expects %d ghost zones, the grid has %d (Src/get_nghost.c)\n",
              gpum ? pluto_gpu_multi_nghost (gpum) : pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
+      QUIT_PLUTO(1);
+    }
+    if (nonuniform && pluto_gpu_set_grid (gpu, grid->dx[IDIR], grid->dx[JDIR], DIMENSIONS == 3 ? grid->dx[KDIR] : NULL) != 0){
+      print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
       QUIT_PLUTO(1);
     }
 #if BODY_FORCE & POTENTIAL
@@ -255,9 +270,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       free (gt);
     }
 #endif
-    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones, %d block(s) from device %d, state %s\n",
+    print ("> AdvanceStep: libpluto_gpu (%s arithmetic), %d ghost zones, %d block(s) from device %d, state %s%s\n",
            c.arith == PLUTO_GPU_ARITH_FAST ? "fast" : "exact", grid->nghost[IDIR], ndev_blocks > 1 ? ndev_blocks : 1, c.device,
-           gpu_resident ? "resident in HBM" : "on the host (upload + download per step)");
+           gpu_resident ? "resident in HBM" : "on the host (upload + download per step)", nonuniform ? ", non-uniform grid" : "");
     if (gpu_resident){              /* the state the driver prepared (Startup or RestartFromFile) goes up once */
       StaggeredBase (d, &vs1, &vs2, &vs3);
       if ((gpum ? pluto_gpu_multi_upload_data (gpum, d->Vc[0][0][0], vs1, vs2, vs3)

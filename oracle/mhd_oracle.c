@@ -44,6 +44,7 @@ struct Oracle {
   int beg[3], end[3];                  /* IBEG..KEND */
   double *Vc[NV], *Uc[NV], *U0[NV];
   double *Vs[3], *Bs0[3];
+  double *dxa[3];                      /* zone widths of a non-uniform grid (oracle_set_grid: grid->dx[d][0..T-1]), else NULL */
   double *gf[3];                       /* per-zone body force (oracle_set_body_force), else NULL */
   double *phic, *phif[3];              /* body-force potential at centres and faces (oracle_set_body_potential), else NULL */
   double *ppen;                        /* face potential of the current pencil */
@@ -74,6 +75,8 @@ struct Oracle {
 };
 
 #define IDX(o,k,j,i) ((((k)+1)*(o)->S2 + ((j)+1))*(o)->S1 + ((i)+1))
+/* width of zone n in direction d: grid->dx[d][n] (set_grid.c); a uniform grid has the same double in every zone */
+#define DXA(o,d,n)   ((o)->dxa[d] ? (o)->dxa[d][n] : (o)->c.dx[d])
 
 static double *dalloc (int n) { return (double *)calloc((size_t)n, sizeof(double)); }
 
@@ -161,12 +164,28 @@ void oracle_destroy (Oracle *o)
   free(o->exj); free(o->exk); free(o->eyi); free(o->eyk); free(o->ezi); free(o->ezj);
   free(o->ex); free(o->ey); free(o->ez); free(o->Ex1); free(o->Ex2); free(o->Ex3);
   free(o->svx); free(o->svy); free(o->svz); free(o->C_dt);
+  for (d = 0; d < 3; d++) free(o->dxa[d]);
   free(o->v - 4); free(o->vp - 4); free(o->vm - 4); free(o->dv - 4); free(o->flux - 4);
   free(o->press - 4); free(o->cmax - 4); free(o->bn - 4);
   free(o);
 }
 
 /* ********************************************************************* */
+void oracle_set_grid (Oracle *o, const double *dx1, const double *dx2, const double *dx3)
+/* Non-uniform Cartesian grid: dx_d[0 .. T_d-1] = the reference's grid->dx[d] (ghost zones included).  With the reference's
+   default UNIFORM_CARTESIAN_GRID YES (plm_coeffs.h:23-29: every CARTESIAN build) the reconstruction keeps its uniform
+   weights; the zone widths enter the flux difference (rhs.c:195), the inverse time step (update_stage.c:229-235 with
+   inv_dl = 1/dx, set_geometry.c), CT_Update (ct_update.c:79-218: dt/dx2[j], dt/dx3[k], ...) and the face areas of
+   FillMagneticField (ct_fill_mag_field.c:108-114, set_geometry.c:149,180,202). */
+{
+  const double *src[3] = {dx1, dx2, dx3};
+  int d;
+  for (d = 0; d < o->c.dims; d++){
+    if (!o->dxa[d]) o->dxa[d] = dalloc (o->T[d]);
+    memcpy (o->dxa[d], src[d], sizeof(double)*(size_t)o->T[d]);
+  }
+}
+
 void oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const double *g3)
 {
   const double *src[3] = {g1, g2, g3};
@@ -297,10 +316,7 @@ static void fill_magnetic_field (Oracle *o, int side)
   int ibeg, iend, jbeg, jend, kbeg, kend, di = 1, dj = 1, dk = 1, i, j, k;
   int dims = o->c.dims;
   double *bx = o->Vs[0], *by = o->Vs[1], *bz = o->Vs[2];
-  double dx1 = o->c.dx[0], dx2 = o->c.dx[1], dx3 = o->c.dx[2];
   double Ax, Ay, Az;
-  if (dims == 3){ Ax = 1.0*dx2*dx3; Ay = dx1*1.0*dx3; Az = dx1*dx2*1.0; }
-  else          { Ax = 1.0*dx2;     Ay = dx1*1.0;     Az = 0.0; }
 
   ibeg = 0; iend = o->T[0]-1;
   jbeg = 0; jend = o->T[1]-1;
@@ -318,6 +334,9 @@ static void fill_magnetic_field (Oracle *o, int side)
     double bxp = bx[IDX(o,k,j,i)], bxm = bx[IDX(o,k,j,i-1)];
     double byp = by[IDX(o,k,j,i)], bym = by[IDX(o,k,j-1,i)];
     double bzp = 0.0, bzm = 0.0, dBx, dBy, dBz = 0.0;
+    double dx1 = DXA(o,0,i), dx2 = DXA(o,1,j), dx3 = (dims == 3 ? DXA(o,2,k) : 1.0);
+    if (dims == 3){ Ax = 1.0*dx2*dx3; Ay = dx1*1.0*dx3; Az = dx1*dx2*1.0; }
+    else          { Ax = 1.0*dx2;     Ay = dx1*1.0;     Az = 0.0; }
     if (dims == 3){ bzp = bz[IDX(o,k,j,i)]; bzm = bz[IDX(o,k-1,j,i)]; }
     dBx = (Ax*bxp - Ax*bxm);
     dBy = (Ay*byp - Ay*bym);
@@ -1011,8 +1030,6 @@ static void update_stage (Oracle *o, double dt)
     Dirs q = set_vector_indices (dir);
     int lo[3], hi[3], t1, t2, tb, te, bb, be, a, b, n;
     int nbeg = o->beg[dir], nend = o->end[dir], ntot = o->T[dir];
-    double dtdx   = dt/o->c.dx[dir];              /* rhs.c:195  scrh = dt/dx[i] */
-    double inv_dl = 1.0/o->c.dx[dir];             /* set_geometry.c: inv_dx     */
     for (a = 0; a < 3; a++){ lo[a] = o->beg[a]; hi[a] = o->end[a]; }
     /* transverse extension by one zone for CT, update_stage.c:144-148 */
     for (a = 0; a < dims; a++) if (a != dir){ lo[a]--; hi[a]++; }
@@ -1105,6 +1122,8 @@ static void update_stage (Oracle *o, double dt)
         double rhs[NV];
         idx3[dir] = n;
         id = IDX(o, idx3[2], idx3[1], idx3[0]);
+        const double dtdx   = dt/DXA(o,dir,n);    /* rhs.c:195  scrh = dt/dx[i] */
+        const double inv_dl = 1.0/DXA(o,dir,n);   /* set_geometry.c: inv_dx     */
         for (nv = 0; nv < NV; nv++) rhs[nv] = -dtdx*(o->flux[n][nv] - o->flux[n-1][nv]);
         rhs[q.vn] -= dtdx*(o->press[n] - o->press[n-1]);
         if (o->c.body_force){          /* RightHandSideSource, rhs_source.c:214-217 (x1), :277-280 (x2), :342-345 (x3) */
@@ -1379,33 +1398,32 @@ static void ct_update (Oracle *o, double dt)
   int i, j, k, dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
   int ibeg = o->emf_ibeg, iend = o->emf_iend, jbeg = o->emf_jbeg, jend = o->emf_jend;
   int kbeg = o->emf_kbeg, kend = o->emf_kend;
-  double dx1 = o->c.dx[0], dx2 = o->c.dx[1], dx3 = o->c.dx[2];
   double *Ex1 = o->ex, *Ex2 = o->ey, *Ex3 = o->ez;
   double rhs;
 
   for (k = kbeg + koff; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
   for (i = ibeg; i <= iend; i++){
     if (dims == 3)
-      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)])
-                + dt/dx3*(Ex2[I3(k,j,i)] - Ex2[I3(k-1,j,i)]);
+      rhs = 0.0 - dt/DXA(o,1,j)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)])
+                + dt/DXA(o,2,k)*(Ex2[I3(k,j,i)] - Ex2[I3(k-1,j,i)]);
     else
-      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)]);
+      rhs = 0.0 - dt/DXA(o,1,j)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)]);
     o->Vs[0][I3(k,j,i)] = o->Vs[0][I3(k,j,i)] + rhs;
   }
   for (k = kbeg + koff; k <= kend; k++) for (j = jbeg; j <= jend; j++)
   for (i = ibeg + 1; i <= iend; i++){
     if (dims == 3)
-      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)])
-            - dt/dx3*(Ex1[I3(k,j,i)] - Ex1[I3(k-1,j,i)]);
+      rhs =   dt/DXA(o,0,i)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)])
+            - dt/DXA(o,2,k)*(Ex1[I3(k,j,i)] - Ex1[I3(k-1,j,i)]);
     else
-      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)]);
+      rhs =   dt/DXA(o,0,i)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)]);
     o->Vs[1][I3(k,j,i)] = o->Vs[1][I3(k,j,i)] + rhs;
   }
   if (dims == 3)
   for (k = kbeg; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
   for (i = ibeg + 1; i <= iend; i++){
-    rhs = - dt/dx1*(Ex2[I3(k,j,i)] - Ex2[I3(k,j,i-1)])
-          + dt/dx2*(Ex1[I3(k,j,i)] - Ex1[I3(k,j-1,i)]);
+    rhs = - dt/DXA(o,0,i)*(Ex2[I3(k,j,i)] - Ex2[I3(k,j,i-1)])
+          + dt/DXA(o,1,j)*(Ex1[I3(k,j,i)] - Ex1[I3(k,j-1,i)]);
     o->Vs[2][I3(k,j,i)] = o->Vs[2][I3(k,j,i)] + rhs;
   }
 }
@@ -1416,32 +1434,31 @@ static void ct_update_from (Oracle *o, double *const *Bs, double dt)
   int i, j, k, dims = o->c.dims, koff = (dims == 3 ? 1 : 0);
   int ibeg = o->emf_ibeg, iend = o->emf_iend, jbeg = o->emf_jbeg, jend = o->emf_jend;
   int kbeg = o->emf_kbeg, kend = o->emf_kend;
-  double dx1 = o->c.dx[0], dx2 = o->c.dx[1], dx3 = o->c.dx[2];
   double *Ex1 = o->ex, *Ex2 = o->ey, *Ex3 = o->ez;
   double rhs;
   for (k = kbeg + koff; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
   for (i = ibeg; i <= iend; i++){
     if (dims == 3)
-      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)])
-                + dt/dx3*(Ex2[I3(k,j,i)] - Ex2[I3(k-1,j,i)]);
+      rhs = 0.0 - dt/DXA(o,1,j)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)])
+                + dt/DXA(o,2,k)*(Ex2[I3(k,j,i)] - Ex2[I3(k-1,j,i)]);
     else
-      rhs = 0.0 - dt/dx2*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)]);
+      rhs = 0.0 - dt/DXA(o,1,j)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j-1,i)]);
     o->Vs[0][I3(k,j,i)] = Bs[0][I3(k,j,i)] + rhs;
   }
   for (k = kbeg + koff; k <= kend; k++) for (j = jbeg; j <= jend; j++)
   for (i = ibeg + 1; i <= iend; i++){
     if (dims == 3)
-      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)])
-            - dt/dx3*(Ex1[I3(k,j,i)] - Ex1[I3(k-1,j,i)]);
+      rhs =   dt/DXA(o,0,i)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)])
+            - dt/DXA(o,2,k)*(Ex1[I3(k,j,i)] - Ex1[I3(k-1,j,i)]);
     else
-      rhs =   dt/dx1*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)]);
+      rhs =   dt/DXA(o,0,i)*(Ex3[I3(k,j,i)] - Ex3[I3(k,j,i-1)]);
     o->Vs[1][I3(k,j,i)] = Bs[1][I3(k,j,i)] + rhs;
   }
   if (dims == 3)
   for (k = kbeg; k <= kend; k++) for (j = jbeg + 1; j <= jend; j++)
   for (i = ibeg + 1; i <= iend; i++){
-    rhs = - dt/dx1*(Ex2[I3(k,j,i)] - Ex2[I3(k,j,i-1)])
-          + dt/dx2*(Ex1[I3(k,j,i)] - Ex1[I3(k,j-1,i)]);
+    rhs = - dt/DXA(o,0,i)*(Ex2[I3(k,j,i)] - Ex2[I3(k,j,i-1)])
+          + dt/DXA(o,1,j)*(Ex1[I3(k,j,i)] - Ex1[I3(k,j-1,i)]);
     o->Vs[2][I3(k,j,i)] = Bs[2][I3(k,j,i)] + rhs;
   }
 }

@@ -48,6 +48,7 @@ def lib():
         L.oracle_create.argtypes = [C.POINTER(OracleConfig)]
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_body_force.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_set_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_set_body_potential.argtypes = [C.c_void_p] * 5
         L.oracle_nghost.argtypes = [C.c_void_p]
         dp = C.POINTER(C.c_double)
@@ -117,6 +118,11 @@ class Oracle:
                 self._h = None
         except Exception:
             pass
+
+    def set_grid(self, dx1, dx2, dx3=None):
+        """Non-uniform Cartesian grid: the zone widths grid->dx[d] of every direction, ghost zones included (T_d entries)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (dx1, dx2, dx3)]
+        lib().oracle_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs])
 
     def set_body_force(self, g1, g2, g3=None):
         """Static per-zone force: arrays [T3][T2][T1] (ghost zones included) of every component."""

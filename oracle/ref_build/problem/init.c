@@ -22,7 +22,9 @@
 
   Analysis() is the full-precision time-step tap of SURVEY.md 8c: the
   reference log prints dt with 5 digits only, so every call appends the
-  triple (step, t, dt) as raw doubles to "dt_tap.bin".
+  triple (step, t, dt) as raw doubles to "dt_tap.bin".  Its first call also
+  writes the zone widths grid->dx[d] of every direction to "grid_tap.bin"
+  (non-uniform grids: the patches of pluto.ini's [Grid] block).
 */
 /* ///////////////////////////////////////////////////////////////////// */
 #include "pluto.h"
@@ -232,6 +234,17 @@ void Analysis (const Data *d, Grid *grid)
   rec[2] = g_dt;
   fwrite (rec, sizeof(double), 3, fp);
   fclose (fp);
+  if (g_stepNumber <= 1){          /* zone widths of every direction, ghost zones included: grid->dx[d][0 .. np_tot-1] */
+    int dir;
+    fp = fopen("grid_tap.bin", "wb");
+    if (fp == NULL) return;
+    for (dir = 0; dir < DIMENSIONS; dir++){
+      rec[0] = (double)grid->np_tot[dir];
+      fwrite (rec, sizeof(double), 1, fp);
+      fwrite (grid->dx[dir], sizeof(double), grid->np_tot[dir], fp);
+    }
+    fclose (fp);
+  }
 }
 
 /* ********************************************************************* */

@@ -58,6 +58,8 @@ class RefConfig:
     gamma: float = 5.0 / 3.0
     domain: tuple = None                # ((x1b,x1e),(x2b,x2e),(x3b,x3e)); default per problem
     bc: tuple = None                    # 6 strings; default per problem
+    grid: tuple = None                  # non-uniform grid: per direction the text of the "Xd-grid" line after the keyword, e.g.
+                                        # "2  -0.5  12  u  0.0  20  s  0.5" (patches: set_grid.c:330-560), or None: one uniform patch
     blast: dict = field(default_factory=lambda: dict(
         P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.125))
     seed: int = 20240607
@@ -122,7 +124,10 @@ def write_ini(cfg: RefConfig, path: str, dbl_dn: int = -1, analysis_dn: int = 1,
         lo, hi = dom[d]
         if cfg.dims == 2 and d == 2:
             lo, hi = 0.0, 1.0
-        lines.append(f"X{d+1}-grid    1    {lo!r}    {n[d]}    u    {hi!r}")
+        if cfg.grid is not None and d < len(cfg.grid) and cfg.grid[d] and not (cfg.dims == 2 and d == 2):
+            lines.append(f"X{d+1}-grid    {cfg.grid[d]}")
+        else:
+            lines.append(f"X{d+1}-grid    1    {lo!r}    {n[d]}    u    {hi!r}")
     lines += ["", "[Chombo Refinement]", "", "Levels           4",
               "Ref_ratio        2 2 2 2 2", "Regrid_interval  2 2 2 2",
               "Refine_thresh    0.3", "Tag_buffer_size  3", "Block_factor     4",
@@ -196,6 +201,7 @@ class RefResult:
     steps_run: int
     workdir: str
     stdout: str = ""       # the driver's log (serial build: print() goes to stdout)
+    dx: list = None        # zone widths grid->dx[d] (ghost zones included) from grid_tap.bin, one array per direction
 
 
 def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
@@ -245,8 +251,17 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
     tap_path = os.path.join(workdir, "dt_tap.bin")
     tap = (np.fromfile(tap_path, dtype="<f8").reshape(-1, 3)
            if os.path.exists(tap_path) else np.zeros((0, 3)))
+    dx = None
+    gpath = os.path.join(workdir, "grid_tap.bin")
+    if os.path.exists(gpath):
+        raw = np.fromfile(gpath, dtype="<f8")
+        dx, off = [], 0
+        while off < raw.size:
+            m = int(raw[off])
+            dx.append(raw[off + 1:off + 1 + m].copy())
+            off += 1 + m
     res = RefResult(dumps=dumps, dt_tap=tap, wall_s=wall, steps_run=steps_run,
-                    workdir=workdir, stdout=p.stdout.decode(errors="replace"))
+                    workdir=workdir, stdout=p.stdout.decode(errors="replace"), dx=dx)
     if own and not keep:
         shutil.rmtree(workdir, ignore_errors=True)
     return res

@@ -218,7 +218,8 @@ ct_update_kernel (const __grid_constant__ CtArgs a)
   const long long id = gidx (g, k, j, i);
   const long long sy = g.S1, sz = g.S12;
   const bool in_i = i >= g.beg[0] - ext, in_j = j >= g.beg[1] - ext, in_k = (NC == 3 ? k >= g.beg[2] - ext : true);
-  const double dtdx0 = __ldg (a.dtp), dtdx1 = __ldg (a.dtp + 1), dtdx2 = (NC == 3 ? __ldg (a.dtp + 2) : 0.0);
+  // dt/dx2[j], dt/dx3[k], ... of the zone the face belongs to (ct_update.c:91-96, 147-152, 202-204); uniform grid: gs = 0
+  const double dtdx0 = __ldg (a.dtx[0] + i*a.gs), dtdx1 = __ldg (a.dtx[1] + j*a.gs), dtdx2 = (NC == 3 ? __ldg (a.dtx[2] + k*a.gs) : 0.0);
 
   if (in_j && in_k){        // Bx1 at (i+1/2, j, k), i in [IBEG-1, IEND]
     double rhs;
@@ -436,10 +437,7 @@ bc_kernel (const __grid_constant__ BcArgs a)
   if (t >= (long long)n1*n2) return;
   int c[3], cs[3];
   c[d1] = (int)(t % n1); c[d2] = (int)(t / n1);
-  const double dx1 = g.dx[0], dx2 = g.dx[1], dx3 = g.dx[2];
   double A[3];
-  if (g.dims == 3){ A[0] = 1.0*dx2*dx3; A[1] = dx1*1.0*dx3; A[2] = dx1*dx2*1.0; }
-  else            { A[0] = 1.0*dx2;     A[1] = dx1*1.0;     A[2] = 0.0; }
   const long long st[3] = {1, g.S1, g.S12};
   const int nbeg = hi_side ? g.end[d] + 1 : g.beg[d] - 1;
   const int nend = hi_side ? g.T[d] - 1 : 0;
@@ -447,6 +445,12 @@ bc_kernel (const __grid_constant__ BcArgs a)
   for (int n = nbeg; dn*n <= dn*nend; n += dn){
     c[d] = n;
     const long long id = gidx (g, c[2], c[1], c[0]);
+    {   // face areas of zone (c[2], c[1], c[0]) (set_geometry.c:149,180,202): on a non-uniform grid they change along the march
+      const double dx1 = a.dxa[0] ? a.dxa[0][c[0]] : g.dx[0], dx2 = a.dxa[1] ? a.dxa[1][c[1]] : g.dx[1];
+      const double dx3 = (g.dims == 3 ? (a.dxa[2] ? a.dxa[2][c[2]] : g.dx[2]) : 1.0);
+      if (g.dims == 3){ A[0] = 1.0*dx2*dx3; A[1] = dx1*1.0*dx3; A[2] = dx1*dx2*1.0; }
+      else            { A[0] = 1.0*dx2;     A[1] = dx1*1.0;     A[2] = 0.0; }
+    }
     // tangential components of ghost zone n = those of its source zone (what the copy
     // jobs of this side store there; reflective: tangential fields keep their sign)
     cs[0] = c[0]; cs[1] = c[1]; cs[2] = c[2];

@@ -86,6 +86,11 @@ struct SweepArgs {
   // (slots RHO, MX1..3, ENG) instead of being added to U -- the sweep then stages no U (38 instead of 48 shared-memory slots per
   // thread: four blocks per SM) and does not depend on the fused x1+x2 sweep; the stage completion forms U + R3.  NULL: U += rhs.
   double *R3[8];
+  // Non-uniform Cartesian grid (pluto_gpu_set_grid): gs = 1 and dtx / idl point at per-zone arrays along the sweep direction,
+  // dt/dx[n] (rhs.c:195) and 1/dx[n] (inv_dl of update_stage.c:229-235); uniform grid: gs = 0, dtx = dtp + direction (the scalar),
+  // idl unused (inv_dl above).  dtx2 / idl2: the x2 direction of the fused x1+x2 sweep.
+  const double *dtx, *idl, *dtx2, *idl2;
+  int     gs;
 };
 
 struct CtArgs {
@@ -104,6 +109,8 @@ struct CtArgs {
   const double *dvel[3][3];                  // UCT_HLL: dvel[c][d] = d v_c / d x_d
   int    ext;                                // edges / faces of [beg-1-ext, end+ext]: 0 (RK, CTU corrector) or
                                              // 1 (CTU predictor, emf ranges of ctu_step.c:290-297)
+  const double *dtx[3];                      // dt/dx of direction d: per zone (gs = 1, non-uniform grid: ct_update.c:91-96 takes
+  int    gs;                                 // dt/dx2[j], dt/dx3[k], ...) or the scalar dtp + d (gs = 0)
 };
 
 // corner-transport-upwind step (TIME_STEPPING HANCOCK, Src/Time_Stepping/ctu_step.c:142-727)
@@ -185,6 +192,7 @@ struct BcArgs {
   double *Bs[3];
   int nf, nfill;
   Geom g;
+  const double *dxa[3];      // zone widths of a non-uniform grid (face areas of FillMagneticField), else NULL: g.dx
 };
 
 struct FlagArgs {              // FlagShock (flag_shock.c:79-230)

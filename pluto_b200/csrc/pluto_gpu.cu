@@ -94,6 +94,11 @@ struct PlutoGpu {
   void   *fbn_pool;
   double *R3[NVS];                 // FAST, 3-D, LINEAR, plain options: flux difference of the x3 sweep (own allocation), else NULL
   void   *r3_pool;
+  // non-uniform Cartesian grid (pluto_gpu_set_grid): per direction the zone widths dx[n], 1/dx[n] and dt/dx[n] (refreshed with
+  // every new dt), n = 0 .. T-1 as in the reference's grid->dx[d]; nu = 0: uniform grid, the scalars of dtdev
+  int     nu;
+  double *dxa[3], *idxa[3], *dtxa[3];
+  void   *grid_pool;
   double *rhs3[3][NVS];            // CTU: half-step right-hand sides of the normal predictors (own allocation)
   void   *ctu_pool;
   // optional per-kernel-class device timing (CUDA events on `stream`)
@@ -333,6 +338,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->ctu_pool) cudaFree (h->ctu_pool);
   if (h->fbn_pool) cudaFree (h->fbn_pool);
   if (h->r3_pool) cudaFree (h->r3_pool);
+  if (h->grid_pool) cudaFree (h->grid_pool);
   if (h->gfield_pool) cudaFree (h->gfield_pool);
   if (h->phi_pool) cudaFree (h->phi_pool);
   if (h->flag) cudaFree (h->flag);
@@ -492,6 +498,56 @@ int pluto_gpu_upload_data (PlutoGpu *h, const double *Vc, const double *s1, cons
 int pluto_gpu_download_data (PlutoGpu *h, double *Vc, double *s1, double *s2, double *s3)
 { return transfer (h, 1, false, Vc, s1, s2, s3); }
 
+// Non-uniform Cartesian grid: the zone widths of every direction, dx_d[0 .. T_d-1] = the reference's grid->dx[d] (ghost zones
+// included; set_grid.c builds them from the patches of pluto.ini's [Grid] block).  What changes on the path, with the reference's
+// default UNIFORM_CARTESIAN_GRID YES (plm_coeffs.h:23-29: the reconstruction keeps its uniform weights in every CARTESIAN
+// build): scrh = dt/dx[i] of the flux difference (rhs.c:195), inv_dl = 1/dx[i] of the inverse time step (update_stage.c:229-235),
+// dt/dx2[j], dt/dx3[k], ... of CT_Update (ct_update.c:91-96, 147-152, 202-204) and the face areas of FillMagneticField
+// (ct_fill_mag_field.c:108-114).  RK time stepping with LINEAR reconstruction; call after pluto_gpu_create, before the first step.
+int pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const double *dx3)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const Geom &g = h->g;
+  if (h->ctu) return fail ("pluto_gpu_set_grid: non-uniform grids are not available with TIME_STEPPING HANCOCK");
+  if (h->cfg.recon != PLUTO_GPU_RECON_LINEAR)
+    return fail ("pluto_gpu_set_grid: non-uniform grids need LINEAR reconstruction (PARABOLIC takes its weights from the grid, ppm_coeffs.c)");
+  if (h->cfg.shock_flattening || h->cfg.body_force || h->cfg.en_correction || h->cfg.char_limiting)
+    return fail ("pluto_gpu_set_grid: non-uniform grids are not available with SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION or CHAR_LIMITING");
+  const double *src[3] = {dx1, dx2, dx3};
+  for (int d = 0; d < g.dims; d++){
+    if (!src[d]) return fail ("pluto_gpu_set_grid: NULL array for direction %d", d + 1);
+    for (int n = 0; n < g.T[d]; n++) if (!(src[d][n] > 0.0)) return fail ("pluto_gpu_set_grid: dx%d[%d] = %g", d + 1, n, src[d][n]);
+  }
+  // padded rows: the lanes of a sweep that lie beyond the last zone still form an address
+  size_t off[4] = {0, 0, 0, 0};
+  for (int d = 0; d < 3; d++) off[d + 1] = off[d] + (size_t)(((d < g.dims ? g.T[d] : 1) + 64 + 31) & ~31);
+  if (!h->grid_pool){
+    const size_t nb = 3*off[3]*sizeof (double);
+    if (cudaMalloc (&h->grid_pool, nb) != cudaSuccess){ h->grid_pool = NULL; return fail ("cudaMalloc of %zu bytes (grid) failed", nb); }
+    h->pool_bytes += nb;
+  }
+  double *host = (double *)malloc (3*off[3]*sizeof (double));
+  if (!host) return fail ("out of host memory");
+  for (size_t q = 0; q < 3*off[3]; q++) host[q] = 1.0;
+  for (int d = 0; d < 3; d++){
+    h->dxa[d] = (double *)h->grid_pool + off[d];
+    h->idxa[d] = (double *)h->grid_pool + off[3] + off[d];
+    h->dtxa[d] = (double *)h->grid_pool + 2*off[3] + off[d];
+    if (d >= g.dims) continue;
+    for (int n = 0; n < g.T[d]; n++){
+      host[off[d] + n] = src[d][n];
+      host[off[3] + off[d] + n] = 1.0/src[d][n];           // grid->inv_dx (set_geometry.c:244)
+    }
+  }
+  cudaError_t e = cudaMemcpyAsync (h->grid_pool, host, 3*off[3]*sizeof (double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (h->stream);
+  free (host);
+  if (e != cudaSuccess) return fail ("pluto_gpu_set_grid: %s", cudaGetErrorString (e));
+  h->nu = 1;
+  if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }      // the captured step holds the old arguments
+  return 0;
+}
+
 int pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3)
 {
   CU (cudaSetDevice (h->cfg.device));
@@ -609,6 +665,7 @@ static int boundary_dim (PlutoGpu *h, int buf, int dim)
     }
   }
   a.nf = nf; a.nfill = nfill;
+  for (int d = 0; d < 3; d++) a.dxa[d] = h->nu ? h->dxa[d] : NULL;
   if (nf + nfill == 0) return 0;
   TIMED (h, KC_BC, count (h, DISPATCH (h, launch_bc) (a, h->stream)));
   return 0;
@@ -635,6 +692,27 @@ static StagePlan stage_plan (const PlutoGpu *h, int stage)
   return p;
 }
 
+// Non-uniform grid: dt/dx[n] of every zone and direction from the dt in dtdev[3] (the host's, or the one next_dt_kernel
+// left there): the quotient the reference forms zone by zone (rhs.c:195 scrh = dt/dx[i]; ct_update.c:91-96), IEEE division.
+__global__ void dtx_fill_kernel (const double *dtdev, const double *dx0, const double *dx1, const double *dx2,
+                                 double *o0, double *o1, double *o2, int n0, int n1, int n2)
+{
+  const double dt = dtdev[3];
+  for (int n = blockIdx.x*blockDim.x + threadIdx.x; n < n0 + n1 + n2; n += gridDim.x*blockDim.x){
+    if      (n < n0)      o0[n] = __ddiv_rn (dt, dx0[n]);
+    else if (n < n0 + n1) o1[n - n0] = __ddiv_rn (dt, dx1[n - n0]);
+    else                  o2[n - n0 - n1] = __ddiv_rn (dt, dx2[n - n0 - n1]);
+  }
+}
+static int refresh_dtx (PlutoGpu *h)
+{
+  if (!h->nu) return 0;
+  const Geom &g = h->g;
+  dtx_fill_kernel<<<4, 256, 0, h->stream>>>(h->dtdev, h->dxa[0], h->dxa[1], h->dxa[2], h->dtxa[0], h->dtxa[1], h->dtxa[2],
+                                             g.T[0], g.T[1], g.dims == 3 ? g.T[2] : 0);
+  return count (h, pg_launch_status ());
+}
+
 // dt/dx (rhs.c:195, ct_update.c:87-89) goes to the device once per step
 static int set_dt (PlutoGpu *h, double dt)
 {
@@ -643,7 +721,7 @@ static int set_dt (PlutoGpu *h, double dt)
   for (int d = 0; d < 3; d++) h->dthost[4 + d] = (0.5*dt)/h->g.dx[d];      // CTU half step (ctu_step.c:447-455)
   h->dthost[7] = 0.5*dt;
   CU (cudaMemcpyAsync (h->dtdev, h->dthost, 8*sizeof (double), cudaMemcpyHostToDevice, h->stream));
-  return 0;
+  return refresh_dtx (h);
 }
 
 // part: 0 = the whole stage; 1 = everything up to the stage completion of the SHELL (the
@@ -721,7 +799,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   // CT_Update inside the stage completion (one launch and one pass over the new field less); not with CT_EN_CORRECTION
   // -- and not where the new field overwrites the t^n field it is averaged with (the last RK stage writes buffer 0 in place:
   // a zone would read its low neighbour's face after that neighbour has replaced it)
-  f.fuse_ct = (h->fuse_ct && !f.en_corr && !(sp.combine && sp.out == 0));
+  f.fuse_ct = (h->fuse_ct && !h->nu && !f.en_corr && !(sp.combine && sp.out == 0));
   f.ex = h->ex; f.ey = h->ey; f.ez = h->ez;
   for (int d = 0; d < 3; d++){ f.Bs_in[d] = h->Bs[sp.in][d]; f.Bs0[d] = h->Bs[0][d]; f.Bs_out[d] = h->Bs[sp.out][d]; }
   if (!f.fuse_ct) for (int nv = 0; nv < NVS; nv++) f.R3[nv] = h->R3[nv];
@@ -760,6 +838,9 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   for (int dir = 0; dir < g.dims; dir++){
     s.Bn = h->Bs[sp.in][dir];
     s.inv_dl = 1.0/g.dx[dir];              // set_geometry.c (inv_dx)
+    s.gs = h->nu;
+    s.dtx = h->nu ? h->dtxa[dir] : h->dtdev + dir;
+    s.idl = h->idxa[dir];
     s.last_dir = (dir == g.dims - 1);
     s.sv = h->sv[dir];
     s.fbn = h->fbn[dir];
@@ -798,6 +879,8 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       s.Bn2 = h->Bs[sp.in][1]; s.e3 = h->ezj; s.e4 = h->exj; s.sv2 = h->sv[1];
       for (int c = 0; c < 3; c++) s.dvel2[c] = h->dvel[c][1];
       s.inv_dl2 = 1.0/g.dx[1];
+      s.dtx2 = h->nu ? h->dtxa[1] : h->dtdev + 1;
+      s.idl2 = h->idxa[1];
       s.last_dir = (g.dims == 2);
       s.tma = h->tma;
       const int te = tbegin (h, KC_SWEEP_X);
@@ -826,6 +909,8 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     c.Bs_in[d] = h->Bs[sp.in][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[sp.out][d];
   }
   c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine; c.dtp = h->dtdev;
+  c.gs = h->nu;
+  for (int d = 0; d < 3; d++) c.dtx[d] = h->nu && d < g.dims ? h->dtxa[d] : h->dtdev + d;
   c.avg = h->cfg.emf_average;
   for (int q = 0; q < 3; q++) for (int d = 0; d < 3; d++) c.dvel[q][d] = h->dvel[q][d];
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
@@ -918,6 +1003,7 @@ static int run_ctu (PlutoGpu *h, int part)
       for (int d = 0; d < 3; d++){ c.Bs_in[d] = h->Bs[0][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[1][d]; }
       c.avg = (h->cfg.emf_average == PLUTO_GPU_EMF_UCT_CONTACT ? PLUTO_GPU_EMF_ARITHMETIC : h->cfg.emf_average);
       c.ext = 1; c.combine = 0; c.dtp = h->dtdev + 4;
+      for (int d = 0; d < 3; d++) c.dtx[d] = c.dtp + d;
       TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
       TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
       TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_ctu_half) (s, h->stream)));
@@ -928,6 +1014,7 @@ static int run_ctu (PlutoGpu *h, int part)
   for (int nv = 0; nv < NVS; nv++) c.V[nv] = h->V[1][nv];
   for (int d = 0; d < 3; d++){ c.Bs_in[d] = h->Bs[0][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[0][d]; }
   c.avg = h->cfg.emf_average; c.ext = 0; c.combine = 0; c.dtp = h->dtdev;
+  for (int d = 0; d < 3; d++) c.dtx[d] = c.dtp + d;
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 
@@ -1123,6 +1210,7 @@ int pluto_gpu_next_dt_async (PlutoGpu *h, double cfl, double cfl_max_var)
   next_dt_kernel<<<1, 32, 0, h->stream>>>(h->red, h->dtdev, h->hist, h->hist_count, h->g.dx[0], h->g.dx[1], h->g.dx[2],
                                           h->ctu ? 1 : h->g.dims, cfl, cfl_max_var);
   if (count (h, pg_launch_status ())) return 1;
+  if (refresh_dtx (h)) return 1;
   h->hist_enq++;
   return 0;
 }
@@ -1384,6 +1472,7 @@ int pluto_gpu_analysis (PlutoGpu *h, double out[8])
   if (ce == cudaSuccess) ce = cudaStreamSynchronize (h->stream);
   if (ce != cudaSuccess){ free (host); return fail ("pluto_gpu_analysis: %s", cudaGetErrorString (ce)); }
   double vol = 1.0;
+  if (h->nu){ free (host); return fail ("pluto_gpu_analysis: volume integrals on a non-uniform grid are not available"); }
   for (int d = 0; d < h->g.dims; d++) vol *= h->g.dx[d];
   for (int q = 0; q < 8; q++) out[q] = 0.0;
   for (int b = 0; b < nb; b++){

@@ -362,7 +362,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
         if (NC == 3) u0[MX3] = a.U[MX3][id];
         u0[ENG] = a.U[ENG][id];
       }
-      const double dtdx = __ldg (a.dtp + DIR);
+      const double dtdx = __ldg (a.dtx + i*a.gs);      // dt/dx[i] (rhs.c:195); a uniform grid has one value (gs = 0)
       double rr;
       rr = -dtdx*(F[RHO] - Fm[RHO]);                                a.U[RHO][id] = u0[RHO] + rr;
       const double r_rho = rr;
@@ -378,7 +378,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
       if (BF && a.phic) rr -= __ldg (a.phic + id)*r_rho;
       a.U[ENG][id] = u0[ENG] + rr;
       if (a.stage1){
-        const double cd = 0.5*(cm + cmax)*a.inv_dl;
+        const double cd = 0.5*(cm + cmax)*(a.gs ? __ldg (a.idl + i) : a.inv_dl);
         if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
         else            a.cdt[id] = cd;
       }
@@ -615,7 +615,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
     }
     const double pp = C_FP(5), cp = C_FP(6);
     if (upd && f >= c0){
-      const double dtdx = __ldg (a.dtp + DIR);
+      const double dtdx = __ldg (a.dtx + f*a.gs);      // dt/dx[f] of the zone being updated
       double r;
       // R3: the flux difference alone is stored; the stage completion forms U + r, the same sum
       double *const *Uo = R3 ? a.R3 : a.U;
@@ -639,7 +639,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       if (BF && a.phic) r -= __ldg (a.phic + id)*r_rho;
       Uo[ENG][id] = UPD_(4, r);
       if (a.stage1){
-        double cd = ua[(NUA - 1)*CS] + 0.5*(cp + cmax)*a.inv_dl;
+        double cd = ua[(NUA - 1)*CS] + 0.5*(cp + cmax)*(a.gs ? __ldg (a.idl + f) : a.inv_dl);
         if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
         else            a.cdt[id] = cd;
       }
@@ -885,7 +885,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       Fm[ENG] = __shfl_up_sync (0xffffffffu, F[ENG], 1);
       pm = __shfl_up_sync (0xffffffffu, press, 1);
       cm = __shfl_up_sync (0xffffffffu, cmax, 1);
-      const double dtdx0 = __ldg (a.dtp + 0);
+      const double dtdx0 = __ldg (a.dtx + i*a.gs);
       rx[RHO] = -dtdx0*(F[RHO] - Fm[RHO]);
       rx[MX1] = -dtdx0*(F[MX1] - Fm[MX1]); rx[MX1] -= dtdx0*(press - pm);
       rx[MX2] = -dtdx0*(F[MX2] - Fm[MX2]);
@@ -900,7 +900,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         rx[MX1] -= dtdx0*v[RHO]*(pfx - __ldg (a.phif + id - 1));
         rx[ENG] -= __ldg (a.phic + id)*rx[RHO];
       }
-      cdx = 0.5*(cm + cmax)*a.inv_dl;
+      cdx = 0.5*(cm + cmax)*(a.gs ? __ldg (a.idl + i) : a.inv_dl);
     }
 
     // ---------------- x2 face f+1/2 ----------------
@@ -940,7 +940,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       const double pp = C_FP(5), cp = C_FP(6);
       if (upd && f >= c0){
         double u0[NV], r;
-        const double dtdx1 = __ldg (a.dtp + 1);
+        const double dtdx1 = __ldg (a.dtx2 + f*a.gs);
         prim_to_cons<NC>(ph, v, u0);
         r = -dtdx1*(F[RHO] - C_FP(0));                                   a.U[RHO][id] = (u0[RHO] + rx[RHO]) + r;
         const double r_rho = r;
@@ -956,7 +956,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         if (BF && a.phic) r -= __ldg (a.phic + id)*r_rho;
         a.U[ENG][id] = (u0[ENG] + rx[ENG]) + r;
         if (a.stage1){
-          const double cd = cdx + 0.5*(cp + cmax)*a.inv_dl2;
+          const double cd = cdx + 0.5*(cp + cmax)*(a.gs ? __ldg (a.idl2 + f) : a.inv_dl2);
           if (a.last_dir) my_cdt = cd > my_cdt ? cd : my_cdt;
           else            a.cdt[id] = cd;
         }

@@ -92,6 +92,15 @@ class GpuStepper:
         if rc != 0:
             raise PlutoGpuError(_lib.last_error(self.L))
 
+    def set_grid(self, dx1, dx2, dx3=None):
+        """Non-uniform Cartesian grid: the zone widths grid->dx[d] of every direction, ghost zones included (n[d] + 2 nghost
+        entries).  RK2 / RK3 with LINEAR reconstruction; call before the first step."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (dx1, dx2, dx3)]
+        for d, a in enumerate(arrs[:self.dims]):
+            if a is None or a.size != self.n[d] + 2 * self.ng:
+                raise ValueError(f"set_grid: dx{d+1} needs {self.n[d] + 2 * self.ng} entries")
+        self._check(self.L.pluto_gpu_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
     def set_body_force(self, g1, g2, g3=None):
         """Static position-dependent force (BodyForceVector at the zone centres): arrays [T3][T2][T1] incl. ghost zones.
         The stepper must have been created with grav=... (BODY_FORCE VECTOR)."""

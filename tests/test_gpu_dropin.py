@@ -27,14 +27,24 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # BODY_FORCE POTENTIAL: the shim tabulates BodyForcePotential at the zone centres and faces
          "blast3d_bp", "blast2d_ctu_bp",
          # CHAR_LIMITING YES (2-D): the shim reads it from definitions.h
-         "ot2d_cl", "rotor2d_cl_vl_rk3"]
+         "ot2d_cl", "rotor2d_cl_vl_rk3",
+         # non-uniform grids (uniform + stretched patches in pluto.ini): the shim hands grid->dx to pluto_gpu_set_grid
+         "blast3d_nug", "rotor2d_nug_roe_rk3", "blast2d_nug_mc_arith_reflective"]
+
+
+def _blast_params(g):
+    """The blast fixtures on walls use a larger sphere (tools/make_golden.py); everything else the default parameters."""
+    b = dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.125)
+    if g.name == "blast2d_nug_mc_arith_reflective":
+        b["RADIUS"] = 0.3
+    return b
 
 
 def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
                      limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential,
-                     char_lim=g.char_lim, prefix="pluto_gpu_")
+                     char_lim=g.char_lim, grid=g.grid, bc=g.bc, blast=_blast_params(g), prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

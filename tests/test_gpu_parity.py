@@ -42,7 +42,7 @@ def test_exact_bit_identical_to_reference_golden(name):
     assert dt == g.dt[g.nsteps]
     st = s.get_state()
     bscale = max(np.abs(st["Bx1s"]).max(), 1e-30) / min(g.dx)
-    assert divb_max(st, g.dims, g.dx) < 1e-12 * bscale
+    assert divb_max(st, g.dims, g.dx_zones) < 1e-12 * bscale
     s.close()
 
 
@@ -77,7 +77,7 @@ def test_fast_within_tolerance_of_reference_golden(name):
     print(f"FAST {name}: worst rel L1 " + ", ".join(f"step {k}: {v:.2e}" for k, v in worst.items()))
     st = s.get_state()
     bscale = max(np.abs(st["Bx1s"]).max(), 1e-30) / min(g.dx)
-    assert divb_max(st, g.dims, g.dx) < 1e-12 * bscale
+    assert divb_max(st, g.dims, g.dx_zones) < 1e-12 * bscale
     s.close()
 
 
@@ -104,6 +104,71 @@ def test_tma_staging_bit_identical_to_cp_async(monkeypatch, problem, dims, n, re
     assert out[0][1] == out[1][1]
     for k, v in out[0][0].items():
         assert np.array_equal(v, out[1][0][k]), k
+
+
+@pytest.mark.parametrize("problem,dims,n,solver,rk", [("blast", 3, (37, 12, 10), "hlld", 2), ("rotor", 2, (33, 70, 1), "hlld", 3),
+                                                     ("turb", 3, (10, 9, 12), "hll", 2), ("ot", 2, (64, 31, 1), "roe", 2)])
+def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk):
+    """pluto_gpu_set_grid with zone widths drawn at random (0.7 .. 1.3 of the uniform one, every direction): dt/dx[i] of the
+    flux differences, 1/dx[i] of the inverse time step, dt/dx2[j] ... of CT_Update and the face areas of the div B fill all
+    differ from zone to zone.  EXACT: bit-identical to the oracle (pinned against the live reference on stretched grids,
+    tests/test_oracle_vs_ref.py) incl. the inverse time step; FAST: within the one-step tolerance; div B at round-off."""
+    from oracle.oracle_lib import Oracle, next_dt
+    from pluto_b200 import GpuStepper, problems
+    st0, meta = problems.make(problem, dims, n)
+    rng = np.random.default_rng(11)
+    ng = 2
+    dxs = [meta["dx"][d] * (0.7 + 0.6 * rng.random(n[d] + 2 * ng)) for d in range(dims)]
+    if meta["bc"][0] == "periodic":            # the ghost zones of a periodic side repeat the interior widths
+        for d in range(dims):
+            a = dxs[d]
+            a[:ng] = a[n[d]:n[d] + ng]
+            a[n[d] + ng:] = a[ng:2 * ng]
+    for arith in ("exact", "fast"):
+        o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], rk_order=rk)
+        s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith=arith, rk_order=rk)
+        o.set_grid(*dxs)
+        s.set_grid(*dxs)
+        o.set_state(st0)
+        s.set_state(st0)
+        dt = 1e-4 if problem == "blast" else 1e-3
+        for _ in range(3):
+            inv, mach, _ = o.advance(dt)
+            info = s.advance(dt)
+            assert info.nan_events == 0
+            if arith == "exact":
+                assert info.inv_dt_hyp == inv and info.max_mach == mach
+            else:
+                assert abs(info.inv_dt_hyp - inv) <= 1e-12 * inv
+            dt = next_dt(inv, meta["cfl"], 1.1, dt)
+        a, b = s.get_state(), o.get_state()
+        for k in b:
+            if arith == "exact":
+                assert np.array_equal(a[k], b[k]), k
+            else:
+                assert rel_l1(a[k], b[k]) <= TOL_ONE_STEP, k
+        # constrained transport keeps the divergence of THIS metric (the initial field was built on the uniform one, so
+        # it is the change that must vanish)
+        zones = [dxs[d][ng:ng + n[d]] for d in range(dims)]
+        bscale = max(np.abs(a["Bx1s"]).max(), 1e-30) / min(z.min() for z in zones)
+        assert divb_max({k: a[k] - st0[k] for k in ("Bx1s", "Bx2s", "Bx3s") if k in a}, dims, zones) < 1e-12 * bscale
+        s.close()
+
+
+def test_nonuniform_grid_is_refused_where_the_weights_would_change():
+    """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c), the corner-transport-upwind predictor, shock
+    flattening, body forces and the energy correction use the zone width elsewhere: pluto_gpu_set_grid says so."""
+    from pluto_b200 import GpuStepper
+    from pluto_b200.stepper import PlutoGpuError
+    for kw, ng in ((dict(recon="ppm"), 3), (dict(ctu=True), 3), (dict(flatten=True), 3), (dict(en_corr=True), 2), (dict(grav=(0.0, 1.0, 0.0)), 2)):
+        s = GpuStepper(2, (16, 16, 1), (0.1, 0.1), **kw)
+        with pytest.raises(PlutoGpuError, match="non-uniform"):
+            s.set_grid(np.full(16 + 2 * ng, 0.1), np.full(16 + 2 * ng, 0.1))
+        s.close()
+    s = GpuStepper(2, (16, 16, 1), (0.1, 0.1))
+    with pytest.raises(PlutoGpuError, match="dx1"):
+        s.set_grid(np.zeros(20), np.full(20, 0.1))
+    s.close()
 
 
 @pytest.mark.parametrize("problem,n,solver", [("blast", (40, 24, 20), "hlld"), ("turb", (31, 17, 70), "roe")])

@@ -30,7 +30,7 @@ def test_oracle_bit_exact_vs_reference_golden(name):
     # div B at round-off (reference check: CT_CheckDivB, ct_update.c:223)
     st = o.get_state()
     bscale = max(np.abs(st["Bx1s"]).max(), 1e-30) / min(g.dx)
-    assert divb_max(st, g.dims, g.dx) < 1e-12 * bscale
+    assert divb_max(st, g.dims, g.dx_zones) < 1e-12 * bscale
 
 
 def test_golden_fixtures_present():

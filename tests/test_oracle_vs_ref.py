@@ -91,6 +91,18 @@ CASES = [
                               vector_too=True), 6),
     ("blast2d_ctu_bfp", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock", grav=(0.05, -0.03, 0.0),
                                   potential=True, vector_too=True), 8),
+    # non-uniform Cartesian grids: uniform + stretched patches of pluto.ini's [Grid] block (set_grid.c:330-560).
+    # With the reference's default UNIFORM_CARTESIAN_GRID YES the reconstruction keeps its uniform weights; the zone widths
+    # enter rhs.c:195, the inverse time step, CT_Update and the face areas of FillMagneticField
+    ("blast3d_nug", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3,
+                              grid=("2  -0.5  8  u  0.1  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                    "3  -0.5  4  s  -0.2  8  u  0.2  4  s  0.5")), 10),
+    ("rotor2d_nug_roe", RefConfig(problem="rotor", dims=2, n=(36, 30, 1), first_dt=2e-3, solver="roe",
+                                  grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  10  s  0.5", None)), 10),
+    ("blast2d_nug_mc_arith_reflective", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, limiter="mc", emf="arith",
+                                                  bc=("reflective", "outflow", "outflow", "reflective", "outflow", "outflow"),
+                                                  blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3),
+                                                  grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 12),
 ]
 
 
@@ -114,6 +126,9 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     if cfg.grav_mode == 1:
         from tests.util import sign_force_arrays
         o.set_body_force(*sign_force_arrays(cfg.dims, n, o.ng, dom, cfg.grav))
+    if cfg.grid is not None:
+        assert r.dx is not None and len(r.dx) == cfg.dims and max(np.ptp(a) for a in r.dx) > 0.0
+        o.set_grid(*r.dx)
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

@@ -21,7 +21,7 @@ def test_ic_matches_reference_startup(name, problem):
         assert np.abs(st[k] - v).max() <= 2e-12 * scale, (name, k, np.abs(st[k] - v).max())
     assert np.allclose(meta["dx"], g.dx, rtol=1e-15)
     bscale = max(np.abs(st["Bx1s"]).max(), 1e-30) / min(g.dx)
-    assert divb_max(st, g.dims, g.dx) < 1e-12 * bscale
+    assert divb_max(st, g.dims, g.dx_zones) < 1e-12 * bscale
 
 
 def test_subblock_generation_is_consistent():

@@ -50,6 +50,9 @@ class Golden:
         self.grav_mode = int(d["cfg_grav_mode"]) if "cfg_grav_mode" in d.files else 0
         self.potential = bool(int(d["cfg_potential"])) if "cfg_potential" in d.files else False
         self.force = None if self.potential else self.grav      # the `grav=` argument of Oracle / GpuStepper
+        # non-uniform grid: the zone widths grid->dx[d] (ghost zones included) and the "Xd-grid" lines that produced them
+        self.grid_dx = [d[f"grid_dx{a+1}"] for a in range(self.dims)] if "grid_dx1" in d.files else None
+        self.grid = tuple((str(x) or None) for x in d["cfg_grid"]) if "cfg_grid" in d.files else None
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:
@@ -59,12 +62,23 @@ class Golden:
         # uniform cell size exactly as the reference computes it
         # (Src/set_grid.c:400  dx = (xR - xL)/npoint)
         self.dx = [(self.domain[a][1] - self.domain[a][0]) / self.n[a] for a in range(self.dims)]
+        # what divb_max divides by: the interior zone widths of a non-uniform grid, else the uniform ones
+        self.dx_zones = self.dx
+        if self.grid_dx is not None:
+            self.dx_zones = []
+            for a in range(self.dims):
+                ngz = (len(self.grid_dx[a]) - self.n[a]) // 2
+                self.dx_zones.append(self.grid_dx[a][ngz:ngz + self.n[a]])
+            self.dx = [float(np.min(z)) for z in self.dx_zones]      # scale of the smallest zone (tolerances, bscale)
         self.rk_order = 3 if self.tstep == "rk3" else 2
         self.ctu = self.tstep == "hancock"
 
 
 def apply_force_field(stepper, g):
-    """Golden fixtures with the static test force (GRAV_MODE 1): hand the per-zone arrays to an Oracle or a GpuStepper."""
+    """Golden fixtures with the static test force (GRAV_MODE 1): hand the per-zone arrays to an Oracle or a GpuStepper.
+    Fixtures on a non-uniform grid: hand over the zone widths."""
+    if g.grid_dx is not None:
+        stepper.set_grid(*g.grid_dx)
     if g.grav_mode == 1:
         stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
     if g.potential:
@@ -85,12 +99,17 @@ def max_rel_l1(state, ref):
 
 
 def divb_max(state, dims, dx):
-    """max |sum of face fluxes| / cell volume, from the staggered fields."""
+    """max |sum of face fluxes| / cell volume, from the staggered fields.  dx[d]: the zone width, or the widths of the interior
+    zones of a non-uniform grid (Golden.dx_zones)."""
     bx, by = state["Bx1s"], state["Bx2s"]
-    div = (bx[:, :, 1:] - bx[:, :, :-1]) / dx[0] + (by[:, 1:, :] - by[:, :-1, :]) / dx[1]
+    w = [np.asarray(dx[d], dtype=float) for d in range(dims)]
+    d1 = w[0].reshape(1, 1, -1) if w[0].ndim else w[0]
+    d2 = w[1].reshape(1, -1, 1) if w[1].ndim else w[1]
+    div = (bx[:, :, 1:] - bx[:, :, :-1]) / d1 + (by[:, 1:, :] - by[:, :-1, :]) / d2
     if dims == 3:
         bz = state["Bx3s"]
-        div = div + (bz[1:, :, :] - bz[:-1, :, :]) / dx[2]
+        d3 = w[2].reshape(-1, 1, 1) if w[2].ndim else w[2]
+        div = div + (bz[1:, :, :] - bz[:-1, :, :]) / d3
     return np.abs(div).max()
 
 

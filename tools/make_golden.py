@@ -115,6 +115,17 @@ CASES = {
     "rotor2d_cl_vl_rk3": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), first_dt=2.5e-3, cfl=0.4, limiter="vl", tstep="rk3",
                                     char_lim=True), 15),
     "ot2d_ctu_100": (RefConfig(problem="ot", dims=2, n=(64, 48, 1), first_dt=1e-2, cfl=0.4, tstep="hancock"), 100),
+    # non-uniform Cartesian grids: uniform + stretched patches (set_grid.c:330-560); the fixtures carry the zone
+    # widths grid->dx[d] the reference built (grid_tap.bin of the problem file's Analysis)
+    "blast3d_nug": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3,
+                              grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                    "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 15),
+    "rotor2d_nug_roe_rk3": (RefConfig(problem="rotor", dims=2, n=(36, 28, 1), first_dt=2.5e-3, cfl=0.4, solver="roe", tstep="rk3",
+                                      grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 15),
+    "blast2d_nug_mc_arith_reflective": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, limiter="mc", emf="arith",
+                                                  bc=("reflective", "outflow", "outflow", "reflective", "outflow", "outflow"),
+                                                  blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3),
+                                                  grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
 }
 
 
@@ -135,6 +146,10 @@ def make(name):
         out["cfg_grav"] = np.array(cfg.grav, dtype=float)
         out["cfg_grav_mode"] = int(cfg.grav_mode)
         out["cfg_potential"] = int(cfg.potential)
+    if cfg.grid is not None:
+        out["cfg_grid"] = np.array([g or "" for g in cfg.grid])
+        for d in range(cfg.dims):
+            out[f"grid_dx{d+1}"] = r.dx[d]
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
             out[f"s{s}_{k}"] = v
