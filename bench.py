@@ -55,10 +55,11 @@ WORKLOADS = {
 }
 # per-kernel algorithmic HBM bytes per zone and launch (DESIGN.md "Kernels"):
 # sweep: read 8 V + 1 Bn, U (x1: write 5; x2/x3: read 5 + write 5), write 2 face EMFs + 1 sign byte
-# fused x1+x2 sweep (FAST): read 8 V + Bx1s + Bx2s, write 5 U + 4 face EMFs + 2 sign bytes (+ C_dt in stage 1)
+# fused x1+x2 sweep (FAST): read 8 V + Bx1s + Bx2s, write 5 U + 4 face EMFs + 2 sign bytes (+ C_dt in stage 1) + the 3 (2-D: 1)
+# cell-centred EMFs it stores for ct_emf_kernel
 SWEEP_BYTES_3D = {"sweep_x1": (9 + 5 + 2) * 8 + 1, "sweep_x2": (9 + 10 + 2) * 8 + 1, "sweep_x3": (9 + 10 + 2) * 8 + 1,
-                  "sweep_x1x2": (10 + 5 + 4) * 8 + 2 + 4}
-SWEEP_BYTES_2D = {"sweep_x1": (7 + 4 + 1) * 8 + 1, "sweep_x2": (7 + 8 + 1) * 8 + 1, "sweep_x1x2": (8 + 4 + 2) * 8 + 2}
+                  "sweep_x1x2": (10 + 5 + 4 + 3) * 8 + 2 + 4}
+SWEEP_BYTES_2D = {"sweep_x1": (7 + 4 + 1) * 8 + 1, "sweep_x2": (7 + 8 + 1) * 8 + 1, "sweep_x1x2": (8 + 4 + 2 + 1) * 8 + 2}
 # FP64 instructions per launch and zone of the sweep kernels (ncu smsp__sass_thread_inst_executed_op_d*,
 # profiles/): what the FP64 pipe, the binding unit of the sweeps, has to issue
 SWEEP_FP64_INSTR_3D = {"sweep_x1x2": 2 * 365, "sweep_x3": 365}

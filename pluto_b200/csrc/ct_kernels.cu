@@ -56,7 +56,8 @@ __device__ __forceinline__ double upw (signed char s, double d0, double d1)
 #ifndef PG_CT_MINB
 #define PG_CT_MINB 8
 #endif
-template <int NC, int AVG>          // AVG: PLUTO_GPU_EMF_* (compile time: the averages share no code)
+template <int NC, int AVG, bool EC = false>   // AVG: PLUTO_GPU_EMF_* (compile time: the averages share no code); EC: the cell-centred
+                                              // EMFs come from the arrays the fused x1+x2 sweep stored (CtArgs.Ec)
 __global__ void __launch_bounds__(128, PG_CT_MINB)
 ct_emf_kernel (const __grid_constant__ CtArgs a)
 {
@@ -153,11 +154,14 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
     return;
   }
 
+#define CE1(q) (EC ? a.Ec[0][q] : cell_e1 (a, q))
+#define CE2(q) (EC ? a.Ec[1][q] : cell_e2 (a, q))
+#define CE3(q) (EC ? a.Ec[2][q] : cell_e3<NC>(a, q))
   {   // ---- ez at (i+1/2, j+1/2) ----
     const double ezi0 = a.ezi[id], ezi1 = a.ezi[id + sy];
     const double ezj0 = a.ezj[id], ezj1 = a.ezj[id + sx];
-    const double E00 = cell_e3<NC>(a, id),      E10 = cell_e3<NC>(a, id + sx);
-    const double E01 = cell_e3<NC>(a, id + sy), E11 = cell_e3<NC>(a, id + sx + sy);
+    const double E00 = CE3(id),      E10 = CE3(id + sx);
+    const double E01 = CE3(id + sy), E11 = CE3(id + sx + sy);
     double e = ezi0 + ezi1 + ezj0 + ezj1;
     e += upw (a.svx[id],      ezj0 - E00, ezj1 - E10);          // DEZ_DYP(j, i | i+1)
     e += upw (a.svy[id],      ezi0 - E00, ezi1 - E01);          // DEZ_DXP(j | j+1, i)
@@ -169,8 +173,8 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
     {   // ---- ex at (j+1/2, k+1/2) ----
       const double exk0 = a.exk[id], exk1 = a.exk[id + sy];
       const double exj0 = a.exj[id], exj1 = a.exj[id + sz];
-      const double E00 = cell_e1 (a, id),      E10 = cell_e1 (a, id + sy);
-      const double E01 = cell_e1 (a, id + sz), E11 = cell_e1 (a, id + sy + sz);
+      const double E00 = CE1(id),      E10 = CE1(id + sy);
+      const double E01 = CE1(id + sz), E11 = CE1(id + sy + sz);
       double e = exk0 + exk1 + exj0 + exj1;
       e += upw (a.svy[id],      exk0 - E00, exk1 - E10);        // DEX_DZP(k, j | j+1)
       e += upw (a.svz[id],      exj0 - E00, exj1 - E01);        // DEX_DYP(k | k+1, j)
@@ -181,8 +185,8 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
     {   // ---- ey at (i+1/2, k+1/2) ----
       const double eyi0 = a.eyi[id], eyi1 = a.eyi[id + sz];
       const double eyk0 = a.eyk[id], eyk1 = a.eyk[id + sx];
-      const double E00 = cell_e2 (a, id),      E10 = cell_e2 (a, id + sx);
-      const double E01 = cell_e2 (a, id + sz), E11 = cell_e2 (a, id + sx + sz);
+      const double E00 = CE2(id),      E10 = CE2(id + sx);
+      const double E01 = CE2(id + sz), E11 = CE2(id + sx + sz);
       double e = eyi0 + eyi1 + eyk0 + eyk1;
       e += upw (a.svx[id],      eyk0 - E00, eyk1 - E10);        // DEY_DZP(k, i | i+1)
       e += upw (a.svz[id],      eyi0 - E00, eyi1 - E01);        // DEY_DXP(k | k+1, i)
@@ -192,6 +196,9 @@ ct_emf_kernel (const __grid_constant__ CtArgs a)
     }
   }
 }
+#undef CE1
+#undef CE2
+#undef CE3
 
 // ---------------------------------------------------------------------------
 //  staggered update + RK average
@@ -663,7 +670,8 @@ int launch_ct_emf (const CtArgs &a, cudaStream_t s)
       case 1:  ct_emf_kernel<C, 1><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
       case 2:  ct_emf_kernel<C, 2><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
       case 3:  ct_emf_kernel<C, 3><<<nblocks (n, 128), 128, 0, s>>>(a); break;            \
-      default: ct_emf_kernel<C, 0><<<nblocks (n, 128), 128, 0, s>>>(a); } } while (0)
+      default: if (a.Ec[2]) ct_emf_kernel<C, 0, true><<<nblocks (n, 128), 128, 0, s>>>(a);  \
+               else         ct_emf_kernel<C, 0><<<nblocks (n, 128), 128, 0, s>>>(a); } } while (0)
   if (g.dims == 3) PG_LE(3); else PG_LE(2);
 #undef PG_LE
   return pg_launch_status ();

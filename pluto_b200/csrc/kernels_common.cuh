@@ -91,6 +91,10 @@ struct SweepArgs {
   // idl unused (inv_dl above).  dtx2 / idl2: the x2 direction of the fused x1+x2 sweep.
   const double *dtx, *idl, *dtx2, *idl2;
   int     gs;
+  // fused x1+x2 sweep: cell-centred EMFs of every zone it reads (CT_ComputeCenterEMF, ct_emf.c:348-388: Ex1 = vz By - vy Bz,
+  // Ex2 = vx Bz - vz Bx, Ex3 = vy Bx - vx By of the stage's input state), stored for ct_emf_kernel, which then loads 12 values
+  // per edge triple instead of the 36 primitives it would recompute them from.  NULL: not stored.
+  double *Ec[3];
 };
 
 struct CtArgs {
@@ -109,6 +113,7 @@ struct CtArgs {
   const double *dvel[3][3];                  // UCT_HLL: dvel[c][d] = d v_c / d x_d
   int    ext;                                // edges / faces of [beg-1-ext, end+ext]: 0 (RK, CTU corrector) or
                                              // 1 (CTU predictor, emf ranges of ctu_step.c:290-297)
+  const double *Ec[3];                       // cell-centred EMFs stored by the fused x1+x2 sweep (SweepArgs.Ec), else NULL
   const double *dtx[3];                      // dt/dx of direction d: per zone (gs = 1, non-uniform grid: ct_update.c:91-96 takes
   int    gs;                                 // dt/dx2[j], dt/dx3[k], ...) or the scalar dtp + d (gs = 0)
 };

@@ -94,6 +94,8 @@ struct PlutoGpu {
   void   *fbn_pool;
   double *R3[NVS];                 // FAST, 3-D, LINEAR, plain options: flux difference of the x3 sweep (own allocation), else NULL
   void   *r3_pool;
+  double *Ec[3];                   // FAST + fused x1+x2 sweep + UCT_CONTACT: cell-centred EMFs stored by the sweep (own allocation)
+  void   *ec_pool;
   // non-uniform Cartesian grid (pluto_gpu_set_grid): per direction the zone widths dx[n], 1/dx[n] and dt/dx[n] (refreshed with
   // every new dt), n = 0 .. T-1 as in the reference's grid->dx[d]; nu = 0: uniform grid, the scalars of dtdev
   int     nu;
@@ -293,6 +295,17 @@ static int create_resources (PlutoGpu *h)
     for (int q = 0; q < 5; q++) h->R3[kCons[q]] = (double *)h->r3_pool + (size_t)q*tot_al;
     h->pool_bytes += nb;
   }
+  // cell-centred EMFs written by the fused x1+x2 sweep for ct_emf_kernel (SweepArgs.Ec): 12 loads per edge triple instead of 36
+  if (cfg->arith == PLUTO_GPU_ARITH_FAST && !h->ctu && cfg->emf_average == PLUTO_GPU_EMF_UCT_CONTACT
+      && getenv ("PLUTO_GPU_NO_FUSE_XY") == NULL && getenv ("PLUTO_GPU_NO_EC") == NULL){
+    const int ne = (g.dims == 3 ? 3 : 1);
+    const size_t nb = (size_t)ne*tot_al*sizeof (double);
+    if (cudaMalloc (&h->ec_pool, nb) != cudaSuccess) return fail ("cudaMalloc of %zu bytes (cell-centred EMFs) failed", nb);
+    CU (cudaMemset (h->ec_pool, 0, nb));
+    if (g.dims == 3) for (int q = 0; q < 3; q++) h->Ec[q] = (double *)h->ec_pool + (size_t)q*tot_al;
+    else h->Ec[2] = (double *)h->ec_pool;
+    h->pool_bytes += nb;
+  }
   if (h->ctu){
     int nlive = 0;
     for (int nv = 0; nv < NVS; nv++) nlive += live_var (h, nv);
@@ -339,6 +352,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->fbn_pool) cudaFree (h->fbn_pool);
   if (h->r3_pool) cudaFree (h->r3_pool);
   if (h->grid_pool) cudaFree (h->grid_pool);
+  if (h->ec_pool) cudaFree (h->ec_pool);
   if (h->gfield_pool) cudaFree (h->gfield_pool);
   if (h->phi_pool) cudaFree (h->phi_pool);
   if (h->flag) cudaFree (h->flag);
@@ -881,6 +895,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       s.inv_dl2 = 1.0/g.dx[1];
       s.dtx2 = h->nu ? h->dtxa[1] : h->dtdev + 1;
       s.idl2 = h->idxa[1];
+      for (int q = 0; q < 3; q++) s.Ec[q] = h->Ec[q];
       s.last_dir = (g.dims == 2);
       s.tma = h->tma;
       const int te = tbegin (h, KC_SWEEP_X);
@@ -911,6 +926,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine; c.dtp = h->dtdev;
   c.gs = h->nu;
   for (int d = 0; d < 3; d++) c.dtx[d] = h->nu && d < g.dims ? h->dtxa[d] : h->dtdev + d;
+  if (fuse_xy) for (int q = 0; q < 3; q++) c.Ec[q] = h->Ec[q];
   c.avg = h->cfg.emf_average;
   for (int q = 0; q < 3; q++) for (int d = 0; d < 3; d++) c.dvel[q][d] = h->dvel[q][d];
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));

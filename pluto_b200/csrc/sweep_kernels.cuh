@@ -840,6 +840,16 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         if (PPM) PG_FOR_NV(nv) xvrr[nv] = z[0][nv*VS + 2];
       }
     };
+    if (a.Ec[2] && col_ok){                          // cell-centred EMFs of zone (f, i) for ct_emf_kernel (ct_emf.c:348-388),
+      const double *zr = z[0];                       // straight from the ring while few registers are live
+      const double ux = zr[VX1*VS], uy = zr[VX2*VS], bx = zr[BX1*VS], by = zr[BX2*VS];
+      a.Ec[2][id] = uy*bx - ux*by;
+      if (NC == 3){
+        const double uz = zr[VX3*VS], bz = zr[BX3*VS];
+        a.Ec[0][id] = uz*by - uy*bz;
+        a.Ec[1][id] = ux*bz - uz*bx;
+      }
+    }
     // the copy of row f+LA+1 lands in the free ring row (PLM), or in the row of f itself
     // (PPM), which must then be read first
     if (ZF == 0){ read_row_f (); __syncwarp (); }     // every lane has read its neighbours' columns of row f before they are refilled
@@ -849,7 +859,6 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
     if (f + 1 <= f_end) cp_async8_ordered (&C_BX, a.Bn + id + sD);
     cp_async_commit ();
     if (ZF != 0) read_row_f ();
-
     if (do_x){
       double vp[NV], vm[NV];
       if (!PPM){
