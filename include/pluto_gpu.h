@@ -124,6 +124,11 @@ int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
    and the face areas of Src/MHD/CT/ct_fill_mag_field.c:108-114.  RK2 / RK3 with LINEAR reconstruction; dx3 may be NULL in 2-D.
    PlutoGpuConfig.dx is then used by nothing on the path.  Call once after pluto_gpu_create. */
 int  pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const double *dx3);
+/* UNIFORM_CARTESIAN_GRID NO (Src/States/plm_coeffs.h:23-29): grid-dependent weights of the linear reconstruction.  Hand over, for
+   every direction, the six arrays of PLM_CoefficientsGet (Src/States/plm_coeffs.c:86-104: cp, cm, wp, wm, dp, dm; T_dir entries each)
+   after pluto_gpu_create (and pluto_gpu_set_grid on a non-uniform grid).  RK2 / RK3, LINEAR, plain scheme options. */
+int  pluto_gpu_set_plm_coeffs (PlutoGpu *h, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
+                               const double *dp, const double *dm);
 int  pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3);
 /* BODY_FORCE POTENTIAL (body_force & 2; Src/MHD/rhs.c:162-187, 388-392, rhs_source.c:233-237, 316-320, 358-362,
    prim_eqn.c:304-307): BodyForcePotential (init.c) at the zone centres, phic[k][j][i] (T3 x T2 x T1), and at the faces of

@@ -168,9 +168,6 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     }
     if (nonuniform){
       /* stretched / logarithmic / multi-patch grids (set_grid.c:330-560): the zone widths go to the library after its creation */
-#if UNIFORM_CARTESIAN_GRID != YES
-  #error "libpluto_gpu: the grid-dependent reconstruction weights of UNIFORM_CARTESIAN_GRID NO (plm_coeffs.c) are not available on the GPU"
-#endif
 #if TIME_STEPPING == HANCOCK || RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES
       print ("! AdvanceStep(gpu): a non-uniform grid needs RK2 / RK3 with LINEAR reconstruction, without SHOCK_FLATTENING,\n"
              "  BODY_FORCE, CT_EN_CORRECTION and CHAR_LIMITING on the GPU\n");
@@ -214,6 +211,23 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
       QUIT_PLUTO(1);
     }
+#if UNIFORM_CARTESIAN_GRID == NO && RECONSTRUCTION == LINEAR
+    /* grid-dependent reconstruction weights: the arrays PLM_CoefficientsSet built for this grid (plm_coeffs.c:30-104) */
+    if (ndev_blocks > 1){
+      print ("! AdvanceStep(gpu): PLUTO_GPU_NDEV > 1 is not available with UNIFORM_CARTESIAN_GRID NO\n");
+      QUIT_PLUTO(1);
+    }
+    for (idim = 0; idim < DIMENSIONS; idim++){
+      PLM_Coeffs pc;
+      PLM_CoefficientsGet (&pc, idim);
+      if (pluto_gpu_set_plm_coeffs (gpu, idim, pc.cp, pc.cm, pc.wp, pc.wm, pc.dp, pc.dm) != 0){
+        print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+        QUIT_PLUTO(1);
+      }
+    }
+#elif UNIFORM_CARTESIAN_GRID == NO
+  #error "libpluto_gpu: UNIFORM_CARTESIAN_GRID NO is available with LINEAR reconstruction only"
+#endif
 #if BODY_FORCE & POTENTIAL
     {                                 /* BodyForcePotential at the zone centres and at the faces of every direction
                                          (rhs.c:162-187), in the layouts of Vc and of the staggered arrays */

@@ -45,6 +45,7 @@ struct Oracle {
   double *Vc[NV], *Uc[NV], *U0[NV];
   double *Vs[3], *Bs0[3];
   double *dxa[3];                      /* zone widths of a non-uniform grid (oracle_set_grid: grid->dx[d][0..T-1]), else NULL */
+  double *plmc[3][6];                  /* UNIFORM_CARTESIAN_GRID NO: cp, cm, wp, wm, dp, dm of every direction (oracle_set_plm_coeffs) */
   double *gf[3];                       /* per-zone body force (oracle_set_body_force), else NULL */
   double *phic, *phif[3];              /* body-force potential at centres and faces (oracle_set_body_potential), else NULL */
   double *ppen;                        /* face potential of the current pencil */
@@ -164,7 +165,7 @@ void oracle_destroy (Oracle *o)
   free(o->exj); free(o->exk); free(o->eyi); free(o->eyk); free(o->ezi); free(o->ezj);
   free(o->ex); free(o->ey); free(o->ez); free(o->Ex1); free(o->Ex2); free(o->Ex3);
   free(o->svx); free(o->svy); free(o->svz); free(o->C_dt);
-  for (d = 0; d < 3; d++) free(o->dxa[d]);
+  for (d = 0; d < 3; d++){ int q; free(o->dxa[d]); for (q = 0; q < 6; q++) free(o->plmc[d][q]); }
   free(o->v - 4); free(o->vp - 4); free(o->vm - 4); free(o->dv - 4); free(o->flux - 4);
   free(o->press - 4); free(o->cmax - 4); free(o->bn - 4);
   free(o);
@@ -183,6 +184,21 @@ void oracle_set_grid (Oracle *o, const double *dx1, const double *dx2, const dou
   for (d = 0; d < o->c.dims; d++){
     if (!o->dxa[d]) o->dxa[d] = dalloc (o->T[d]);
     memcpy (o->dxa[d], src[d], sizeof(double)*(size_t)o->T[d]);
+  }
+}
+
+void oracle_set_plm_coeffs (Oracle *o, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
+                            const double *dp, const double *dm)
+/* UNIFORM_CARTESIAN_GRID NO (plm_coeffs.h:23-29): the grid-dependent weights of the linear reconstruction, as
+   PLM_CoefficientsGet returns them for direction dir (plm_coeffs.c:30-104; T entries each, first and last unused):
+   dvp = dv[i] wp, dvm = dv[i-1] wm (plm_states.c:157-164), the limiters of plm_coeffs.h:130-152 with cp, cm,
+   vp = v + dv_lim dp, vm = v - dv_lim dm (:240-241). */
+{
+  const double *src[6] = {cp, cm, wp, wm, dp, dm};
+  int q;
+  for (q = 0; q < 6; q++){
+    if (!o->plmc[dir][q]) o->plmc[dir][q] = dalloc (o->T[dir]);
+    memcpy (o->plmc[dir][q], src[q], sizeof(double)*(size_t)o->T[dir]);
   }
 }
 
@@ -490,6 +506,33 @@ static double single_limiter (int lim, double dvp, double dvm)
   }
 }
 
+static double general_limiter (int lim, int nv, double dvp, double dvm, double cp, double cm)
+/* plm_coeffs.h:72-152 with UNIFORM_CARTESIAN_GRID NO: the limiters "on irregular or non-Cartesian grids" (OS, VL, MC take the
+   weights cp, cm; FL, MM, VA, UM are the same on every grid).  lim == DEFAULT: MC on the density, minmod on the pressure,
+   van Leer on velocity and field (plm_states.c:192-227). */
+{
+  double dv;
+  if (lim == ORC_LIM_DEFAULT) lim = (nv == RHO ? ORC_LIM_MC : nv == PRS ? ORC_LIM_MINMOD : ORC_LIM_VANLEER);
+  switch (lim){
+    case ORC_LIM_OSPRE:
+      if (dvp*dvm > 0.0){
+        double den = 2.0*dvp*dvp + 2.0*dvm*dvm + (cp + cm - 2.0)*dvp*dvm;
+        dv = dvp*dvm*((1.0+cp)*dvm + (1.0+cm)*dvp)/den;
+      }else dv = 0.0;
+      return dv;
+    case ORC_LIM_VANLEER:
+      return (dvp*dvm > 0.0 ? dvp*dvm*(cp*dvm + cm*dvp)/(dvp*dvp + dvm*dvm + (cp + cm - 2.0)*dvp*dvm) : 0.0);
+    case ORC_LIM_MC:
+      if (dvp*dvm > 0.0){
+        double qc = 0.5*(dvm + dvp), scrh = ABS_MIN(dvp*cp, dvm*cm);
+        dv = ABS_MIN(qc, scrh);
+      }else dv = 0.0;
+      return dv;
+    default:
+      return single_limiter (lim, dvp, dvm);
+  }
+}
+
 static void states_plm (Oracle *o, int beg, int end, int bxn)
 /* plm_states.c:80-312, CHAR_LIMITING NO, LIMITER DEFAULT,
    UNIFORM_CARTESIAN_GRID YES (cp=cm=2, wp=wm=1, dp=dm=0.5).
@@ -500,6 +543,20 @@ static void states_plm (Oracle *o, int beg, int end, int bxn)
   for (i = beg-1; i <= end; i++)
     for (nv = 0; nv < NV; nv++) dv[i][nv] = v[i+1][nv] - v[i][nv];
 
+  if (o->plmc[bxn - BX1][0]){                 /* UNIFORM_CARTESIAN_GRID NO: grid-dependent weights (plm_states.c:122-124, 156-164) */
+    double *const *c = o->plmc[bxn - BX1];
+    for (i = beg; i <= end; i++){
+      const double cp = c[0][i], cm = c[1][i], wp = c[2][i], wm = c[3][i], dp = c[4][i], dm = c[5][i];
+      for (nv = 0; nv < NV; nv++){
+        const double dvp = dv[i][nv]*wp, dvm = dv[i-1][nv]*wm;
+        const double lim = general_limiter (o->c.limiter, nv, dvp, dvm, cp, cm);
+        vp[i][nv] = v[i][nv] + lim*dp;
+        vm[i][nv] = v[i][nv] - lim*dm;
+      }
+    }
+    for (i = beg-1; i <= end; i++) vp[i][bxn] = vm[i+1][bxn] = o->bn[i];
+    return;
+  }
   for (i = beg; i <= end; i++){
     double dvl[NV];
     for (nv = 0; nv < NV; nv++){

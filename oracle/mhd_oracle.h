@@ -69,6 +69,9 @@ Oracle *oracle_create (const OracleConfig *cfg);
    Replaces the uniform grav[] of the configuration. */
 /* non-uniform Cartesian grid: zone widths grid->dx[d][0 .. T_d-1], ghost zones included (RK path, LINEAR reconstruction) */
 void    oracle_set_grid (Oracle *o, const double *dx1, const double *dx2, const double *dx3);
+/* UNIFORM_CARTESIAN_GRID NO: the weights PLM_CoefficientsGet returns for direction dir (T entries each) */
+void    oracle_set_plm_coeffs (Oracle *o, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
+                               const double *dp, const double *dm);
 void    oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const double *g3);
 /* BODY_FORCE POTENTIAL (rhs.c:162-187, 388-392; rhs_source.c:233-237, 316-320, 358-362; prim_eqn.c:304-307): the potential
    at the zone centres, phic[k][j][i] (T3 x T2 x T1), and at the faces of every direction in the layout of the staggered

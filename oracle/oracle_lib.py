@@ -49,6 +49,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_body_force.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_set_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_set_plm_coeffs.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.oracle_set_body_potential.argtypes = [C.c_void_p] * 5
         L.oracle_nghost.argtypes = [C.c_void_p]
         dp = C.POINTER(C.c_double)
@@ -123,6 +124,12 @@ class Oracle:
         """Non-uniform Cartesian grid: the zone widths grid->dx[d] of every direction, ghost zones included (T_d entries)."""
         arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (dx1, dx2, dx3)]
         lib().oracle_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs])
+
+    def set_plm_coeffs(self, coeffs):
+        """UNIFORM_CARTESIAN_GRID NO: per direction the six arrays (cp, cm, wp, wm, dp, dm) of PLM_CoefficientsGet, T entries each."""
+        for d, six in enumerate(coeffs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in six]
+            lib().oracle_set_plm_coeffs(self._h, d, *[a.ctypes.data for a in arrs])
 
     def set_body_force(self, g1, g2, g3=None):
         """Static per-zone force: arrays [T3][T2][T1] (ghost zones included) of every component."""

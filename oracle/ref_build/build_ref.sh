@@ -19,6 +19,7 @@
 #                       _bf                       BODY_FORCE VECTOR (uniform acceleration)
 #                       _sfl                      SHOCK_FLATTENING MULTID (Src/flag_shock.c) (Src/MHD/CT/ct_emf.c:241-283)
 #                       _cl                       CHAR_LIMITING YES (Src/States/plm_states.c:448-706, Src/MHD/eigenv.c:190)
+#                       _nuw                      UNIFORM_CARTESIAN_GRID NO (Src/States/plm_coeffs.c: weights of a non-uniform grid)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 ORACLE="$(cd "$HERE/.." && pwd)"
@@ -60,6 +61,9 @@ for VARIANT in "$@"; do
   esac
   case "$VARIANT" in
     *_cl*) CHARLIM=YES ;; *) CHARLIM=NO ;;       # limiting on characteristic variables (plm_states.c:448-706)
+  esac
+  case "$VARIANT" in
+    *_nuw*) UCG=NO ;; *) UCG=YES ;;              # UNIFORM_CARTESIAN_GRID NO: grid-dependent reconstruction weights (plm_coeffs.c)
   esac
   case "$VARIANT" in
     *_bfp*) BODYF="(VECTOR+POTENTIAL)" ;;        # both (uniform acceleration and step potential from the same GRAV1..3)
@@ -118,6 +122,7 @@ for VARIANT in "$@"; do
 
 #define  LIMITER                        $LIMITER
 #define  CHAR_LIMITING                  $CHARLIM
+#define  UNIFORM_CARTESIAN_GRID         $UCG
 #define  SHOCK_FLATTENING               $SHOCKFLAT
 #define  CT_EMF_AVERAGE                 $EMFAVG
 #define  CT_EN_CORRECTION               $ENCORR

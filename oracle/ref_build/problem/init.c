@@ -243,6 +243,24 @@ void Analysis (const Data *d, Grid *grid)
       fwrite (rec, sizeof(double), 1, fp);
       fwrite (grid->dx[dir], sizeof(double), grid->np_tot[dir], fp);
     }
+#if UNIFORM_CARTESIAN_GRID == NO && RECONSTRUCTION == LINEAR
+    for (dir = 0; dir < DIMENSIONS; dir++){     /* reconstruction weights of every direction: cp, cm, wp, wm, dp, dm */
+      PLM_Coeffs c;
+      PLM_CoefficientsGet (&c, dir);
+      {                                         /* first and last zone are never set (plm_coeffs.c:62-64): written as 0 */
+        double *six[6], zero = 0.0;
+        int q, m = grid->np_tot[dir];
+        six[0] = c.cp; six[1] = c.cm; six[2] = c.wp; six[3] = c.wm; six[4] = c.dp; six[5] = c.dm;
+        rec[0] = -6.0;                          /* marker: six arrays of np_tot follow */
+        fwrite (rec, sizeof(double), 1, fp);
+        for (q = 0; q < 6; q++){
+          fwrite (&zero, sizeof(double), 1, fp);
+          fwrite (six[q] + 1, sizeof(double), m - 2, fp);
+          fwrite (&zero, sizeof(double), 1, fp);
+        }
+      }
+    }
+#endif
     fclose (fp);
   }
 }

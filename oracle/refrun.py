@@ -46,6 +46,7 @@ class RefConfig:
     flatten: bool = False               # SHOCK_FLATTENING MULTID
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
     char_lim: bool = False              # CHAR_LIMITING YES (plm only; pinned in 2-D, see oracle/mhd_oracle.c states_plm_char)
+    grid_weights: bool = False          # UNIFORM_CARTESIAN_GRID NO: reconstruction weights from the grid (plm_coeffs.c)
     en_corr: bool = False               # CT_EN_CORRECTION YES
     grav: tuple = None                  # BODY_FORCE VECTOR with the uniform acceleration (g1, g2, g3)
     grav_mode: int = 0                  # 1: static position-dependent force, component d = grav[d]*sign(x_d)
@@ -81,6 +82,8 @@ class RefConfig:
             v += "_en"
         if self.char_lim:
             v += "_cl"
+        if self.grid_weights:
+            v += "_nuw"
         if self.grav is not None:
             v += ("_bfp" if self.vector_too else "_bp") if self.potential else "_bf"
         return v
@@ -202,6 +205,7 @@ class RefResult:
     workdir: str
     stdout: str = ""       # the driver's log (serial build: print() goes to stdout)
     dx: list = None        # zone widths grid->dx[d] (ghost zones included) from grid_tap.bin, one array per direction
+    plm_coeffs: list = None  # UNIFORM_CARTESIAN_GRID NO builds: per direction [cp, cm, wp, wm, dp, dm] (PLM_CoefficientsGet)
 
 
 def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
@@ -251,17 +255,22 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
     tap_path = os.path.join(workdir, "dt_tap.bin")
     tap = (np.fromfile(tap_path, dtype="<f8").reshape(-1, 3)
            if os.path.exists(tap_path) else np.zeros((0, 3)))
-    dx = None
+    dx = plmc = None
     gpath = os.path.join(workdir, "grid_tap.bin")
     if os.path.exists(gpath):
         raw = np.fromfile(gpath, dtype="<f8")
-        dx, off = [], 0
+        dx, plmc, off = [], [], 0
         while off < raw.size:
             m = int(raw[off])
+            if m == -6:                # six reconstruction-weight arrays of the next direction (UNIFORM_CARTESIAN_GRID NO)
+                t = len(dx[len(plmc)])
+                plmc.append([raw[off + 1 + q * t:off + 1 + (q + 1) * t].copy() for q in range(6)])
+                off += 1 + 6 * t
+                continue
             dx.append(raw[off + 1:off + 1 + m].copy())
             off += 1 + m
     res = RefResult(dumps=dumps, dt_tap=tap, wall_s=wall, steps_run=steps_run,
-                    workdir=workdir, stdout=p.stdout.decode(errors="replace"), dx=dx)
+                    workdir=workdir, stdout=p.stdout.decode(errors="replace"), dx=dx, plm_coeffs=(plmc or None))
     if own and not keep:
         shutil.rmtree(workdir, ignore_errors=True)
     return res

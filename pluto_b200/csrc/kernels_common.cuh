@@ -95,6 +95,9 @@ struct SweepArgs {
   // Ex2 = vx Bz - vz Bx, Ex3 = vy Bx - vx By of the stage's input state), stored for ct_emf_kernel, which then loads 12 values
   // per edge triple instead of the 36 primitives it would recompute them from.  NULL: not stored.
   double *Ec[3];
+  // RECON_PLMW (UNIFORM_CARTESIAN_GRID NO): cp, cm, wp, wm, dp, dm of the sweep direction, one entry per zone along it
+  // (PLM_CoefficientsGet, plm_coeffs.c:86-104); pc2: the x2 direction of the fused x1+x2 sweep
+  const double *pc[6], *pc2[6];
 };
 
 struct CtArgs {

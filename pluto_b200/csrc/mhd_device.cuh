@@ -33,7 +33,7 @@ namespace PG_NS {
 
 enum { RHO = 0, VX1 = 1, VX2 = 2, VX3 = 3, BX1 = 4, BX2 = 5, BX3 = 6, PRS = 7, NV = 8 };
 enum { MX1 = VX1, MX2 = VX2, MX3 = VX3, ENG = PRS };
-enum { RECON_PLM = 0, RECON_PPM = 1 };
+enum { RECON_PLM = 0, RECON_PPM = 1, RECON_PLMW = 2 };      // PLMW: linear with the grid-dependent weights of UNIFORM_CARTESIAN_GRID NO
 enum { SOLVER_HLLD = 0, SOLVER_HLL = 1, SOLVER_ROE = 2 };
 
 struct Phys {                          // same layout as PhysPar (kernels_common.cuh)
@@ -414,6 +414,39 @@ __device__ __forceinline__ void plm_zone_char2 (const Phys &ph, int lim, const d
     }
     vp[nv] = v[nv] + dvl*0.5;
     vm[nv] = v[nv] - dvl*0.5;
+  }
+}
+
+// UNIFORM_CARTESIAN_GRID NO (plm_coeffs.h:23-29): the weights of PLM_CoefficientsGet (plm_coeffs.c:30-104) for this zone and
+// direction -- dvp = dv[i] wp, dvm = dv[i-1] wm (plm_states.c:157-164), the limiters "on irregular grids" with cp, cm
+// (plm_coeffs.h:130-152: OSPRE, van Leer, MC; flat, minmod, van Albada, UMIST are the same on every grid),
+// vp = v + dv_lim dp, vm = v - dv_lim dm (:240-241), in the reference's operation order.
+__device__ __forceinline__ double general_limiter (int lim, double dvp, double dvm, double cp, double cm)
+{
+  if (!(dvp*dvm > 0.0)) return 0.0;
+  if (lim == 4){
+    const double den = 2.0*dvp*dvp + 2.0*dvm*dvm + (cp + cm - 2.0)*dvp*dvm;
+    return pg_div (dvp*dvm*((1.0 + cp)*dvm + (1.0 + cm)*dvp), den);
+  }
+  if (lim == 6) return pg_div (dvp*dvm*(cp*dvm + cm*dvp), dvp*dvp + dvm*dvm + (cp + cm - 2.0)*dvp*dvm);
+  if (lim == 7){
+    const double qc = 0.5*(dvm + dvp), scrh = abs_min (dvp*cp, dvm*cm);
+    return abs_min (qc, scrh);
+  }
+  return single_limiter (lim, dvp, dvm);
+}
+template <int NC, int SKIP = -1>
+__device__ __forceinline__ void plm_zone_w (int lim, const double *const *pc, int n, const double *v, const double *dvm,
+                                            const double *dvp, double *vp, double *vm)
+{
+  const double cp = __ldg (pc[0] + n), cm = __ldg (pc[1] + n), wp = __ldg (pc[2] + n), wm = __ldg (pc[3] + n);
+  const double dp = __ldg (pc[4] + n), dm = __ldg (pc[5] + n);
+  PG_FOR_NV_SKIP(nv, SKIP){
+    // LIMITER DEFAULT: MC on the density, minmod on the pressure, van Leer on velocity and field (plm_states.c:192-227)
+    const int l = (lim != 0 ? lim : nv == RHO ? 7 : nv == PRS ? 2 : 6);
+    const double dvl = general_limiter (l, dvp[nv]*wp, dvm[nv]*wm, cp, cm);
+    vp[nv] = v[nv] + dvl*dp;
+    vm[nv] = v[nv] - dvl*dm;
   }
 }
 

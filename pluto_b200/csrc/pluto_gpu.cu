@@ -94,6 +94,9 @@ struct PlutoGpu {
   void   *fbn_pool;
   double *R3[NVS];                 // FAST, 3-D, LINEAR, plain options: flux difference of the x3 sweep (own allocation), else NULL
   void   *r3_pool;
+  double *plmc[3][6];              // UNIFORM_CARTESIAN_GRID NO: reconstruction weights cp, cm, wp, wm, dp, dm per direction
+  void   *plmc_pool;               // (pluto_gpu_set_plm_coeffs); plmw: all directions set -> the sweeps run their RECON_PLMW variants
+  int     plmw;
   double *Ec[3];                   // FAST + fused x1+x2 sweep + UCT_CONTACT: cell-centred EMFs stored by the sweep (own allocation)
   void   *ec_pool;
   // non-uniform Cartesian grid (pluto_gpu_set_grid): per direction the zone widths dx[n], 1/dx[n] and dt/dx[n] (refreshed with
@@ -353,6 +356,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->r3_pool) cudaFree (h->r3_pool);
   if (h->grid_pool) cudaFree (h->grid_pool);
   if (h->ec_pool) cudaFree (h->ec_pool);
+  if (h->plmc_pool) cudaFree (h->plmc_pool);
   if (h->gfield_pool) cudaFree (h->gfield_pool);
   if (h->phi_pool) cudaFree (h->phi_pool);
   if (h->flag) cudaFree (h->flag);
@@ -559,6 +563,43 @@ int pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const
   if (e != cudaSuccess) return fail ("pluto_gpu_set_grid: %s", cudaGetErrorString (e));
   h->nu = 1;
   if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }      // the captured step holds the old arguments
+  return 0;
+}
+
+// UNIFORM_CARTESIAN_GRID NO (Src/States/plm_coeffs.h:23-29): the linear reconstruction takes grid-dependent weights.  The six
+// arrays PLM_CoefficientsGet returns for direction dir (plm_coeffs.c:86-104; T_dir entries each, the first and last are never
+// used) are handed over as they are, so the host keeps computing them with the reference's own PLM_CoefficientsSet.  Once every
+// direction is set the sweeps run their RECON_PLMW variants: dvp = dv[i] wp, dvm = dv[i-1] wm, the limiters of
+// plm_coeffs.h:130-152 with cp, cm, vp = v + dv_lim dp, vm = v - dv_lim dm.  RK2 / RK3, LINEAR, plain scheme options.
+int pluto_gpu_set_plm_coeffs (PlutoGpu *h, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
+                              const double *dp, const double *dm)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const Geom &g = h->g;
+  if (dir < 0 || dir >= g.dims) return fail ("pluto_gpu_set_plm_coeffs: direction %d", dir);
+  if (h->ctu || h->cfg.recon != PLUTO_GPU_RECON_LINEAR || h->cfg.shock_flattening || h->cfg.body_force || h->cfg.en_correction
+      || h->cfg.char_limiting || h->cfg.emf_average == PLUTO_GPU_EMF_UCT_HLL)
+    return fail ("pluto_gpu_set_plm_coeffs: grid-dependent reconstruction weights need RK2 / RK3 with LINEAR reconstruction, without "
+                 "SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION, CHAR_LIMITING and UCT_HLL");
+  const double *src[6] = {cp, cm, wp, wm, dp, dm};
+  for (int q = 0; q < 6; q++) if (!src[q]) return fail ("pluto_gpu_set_plm_coeffs: NULL array");
+  int maxT = 1;
+  for (int d = 0; d < g.dims; d++) if (g.T[d] > maxT) maxT = g.T[d];
+  const size_t row = (size_t)((maxT + 64 + 31) & ~31);
+  if (!h->plmc_pool){
+    const size_t nb = 18*row*sizeof (double);
+    if (cudaMalloc (&h->plmc_pool, nb) != cudaSuccess){ h->plmc_pool = NULL; return fail ("cudaMalloc of %zu bytes (reconstruction weights) failed", nb); }
+    CU (cudaMemset (h->plmc_pool, 0, nb));
+    h->pool_bytes += nb;
+  }
+  for (int q = 0; q < 6; q++){
+    double *dev = (double *)h->plmc_pool + (size_t)(6*dir + q)*row;
+    CU (cudaMemcpy (dev, src[q], (size_t)g.T[dir]*sizeof (double), cudaMemcpyHostToDevice));
+    h->plmc[dir][q] = dev;
+  }
+  h->plmw = 1;
+  for (int d = 0; d < g.dims; d++) if (!h->plmc[d][0]) h->plmw = 0;
+  if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }
   return 0;
 }
 
@@ -864,7 +905,8 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     else if (dir == 1){ s.e1 = h->ezj; s.e2 = h->exj; }
     else { s.e1 = h->eyk; s.e2 = h->exk; }
     for (int c = 0; c < 3; c++) s.dvel[c] = h->dvel[c][dir];
-    const int recon = h->cfg.recon;
+    const int recon = h->plmw ? 2 /* RECON_PLMW */ : h->cfg.recon;
+    for (int q = 0; q < 6; q++){ s.pc[q] = h->plmc[dir][q]; s.pc2[q] = h->plmc[1][q]; }
     if (dir > 0 || fuse_xy){
       // zones per thread along a marching sweep: long enough to amortise the
       // extra face per chunk, short enough to fill the 148 SMs (2-D grids have

@@ -192,10 +192,12 @@ __device__ __forceinline__ void store_vel_slopes (double *const *dv, int id, con
 // SHOCK_FLATTENING MULTID: minmod for every variable in a zone flagged FLAG_MINMOD
 // (plm_states.c:174-180), the HLL flux at an interface next to a zone flagged FLAG_HLL
 // CL: CHAR_LIMITING YES (2 components), the slopes of the sweep direction DIR limited on the characteristic variables
-template <int NC, bool FLAT, int SKIP = -1, bool CL = false, int DIR = 0>
+// W: grid-dependent weights (RECON_PLMW); pc, n: the weight arrays of the direction and the zone's index along it
+template <int NC, bool FLAT, int SKIP = -1, bool CL = false, int DIR = 0, bool W = false>
 __device__ __forceinline__ void plm_zone_f (const SweepArgs &a, unsigned fl, const double *v, const double *dvm,
-                                            const double *dvp, double *vp, double *vm)
+                                            const double *dvp, double *vp, double *vm, const double *const *pc = nullptr, int n = 0)
 {
+  if (W){ plm_zone_w<NC, SKIP>(a.limiter, pc, n, v, dvm, dvp, vp, vm); return; }
   if (CL && NC == 2) plm_zone_char2<DIR>(*reinterpret_cast<const Phys *>(&a.ph), a.limiter, v, dvm, dvp, vp, vm);
   else if (FLAT && (fl & 1u)) plm_zone_single<NC, SKIP>(2, v, dvm, dvp, vp, vm);
   else                        plm_zone<NC, SKIP>(a.limiter, v, dvm, dvp, vp, vm);
@@ -299,14 +301,14 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
     PG_FOR_NV(nv) v[nv] = src[nv*W + lane + 1];
     unsigned fl = 0;
     if (FLAT) fl = a.flag[id];
-    if (RECON == RECON_PLM){
+    if (RECON != RECON_PPM){
       double dvm[NV], dvp[NV];
       PG_FOR_NV(nv){
         const double vl = src[nv*W + lane], vr = src[nv*W + lane + 2];
         dvm[nv] = v[nv] - vl;
         dvp[nv] = vr - v[nv];
       }
-      plm_zone_f<NC, FLAT, -1, CL, 0>(a, fl, v, dvm, dvp, vp, vm);
+      plm_zone_f<NC, FLAT, -1, CL, 0, RECON == RECON_PLMW>(a, fl, v, dvm, dvp, vp, vm, a.pc, i);
     }else{
       double vl[NV], vr[NV], vrr[NV], Wi[NV], Wm[NV];
       PG_FOR_NV(nv){
@@ -513,7 +515,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait<PF - 1> ();
       PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][ZS(nv)*CS]; vc_[nv] = z[1][ZS(nv)*CS]; }
       PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone_f<NC, FLAT, SK, CL, DIR>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone_f<NC, FLAT, SK, CL, DIR, RECON == RECON_PLMW>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused, a.pc, c0 - 1);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
@@ -574,7 +576,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV_SKIP(nv, SK){ dvm[nv] = vc_[nv] - vb_[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone_f<NC, FLAT, SK, CL, DIR>(a, flc, vc_, dvm, dvp, vpn, vR);
+        plm_zone_f<NC, FLAT, SK, CL, DIR, RECON == RECON_PLMW>(a, flc, vc_, dvm, dvp, vpn, vR, a.pc, f + 1);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV_SKIP(nv, SK) Wf[nv] = C_WF(nv);
@@ -798,7 +800,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (TMA){ mbar_wait (mbar, tphase); tphase ^= 1u; }
       PG_FOR_NV_SKIP(nv, SKP){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; }
       PG_FOR_NV_SKIP(nv, SKP){ dvm[nv] = vb_[nv] - va_[nv]; dvp[nv] = vc_[nv] - vb_[nv]; }
-      plm_zone_f<NC, FLAT, SKP, CL, 1>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused);
+      plm_zone_f<NC, FLAT, SKP, CL, 1, RECON == RECON_PLMW>(a, FLAT ? a.flag[id] : 0u, vb_, dvm, dvp, vpL, vm_unused, a.pc2, c0 - 1);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
     }else{
       double vz_[NV], va_[NV], vd_[NV], Wm[NV], Wf[NV], vm_unused[NV];
@@ -864,7 +866,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV(nv){ dvm[nv] = v[nv] - xvl[nv]; dvp[nv] = xvr[nv] - v[nv]; }
-        plm_zone_f<NC, FLAT, -1, CL, 0>(a, flz, v, dvm, dvp, vp, vm);
+        plm_zone_f<NC, FLAT, -1, CL, 0, RECON == RECON_PLMW>(a, flz, v, dvm, dvp, vp, vm, a.pc, i);
       }else{
         double Wi[NV], Wm[NV];
         ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
@@ -922,7 +924,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       if (!PPM){
         double dvm[NV], dvp[NV];
         PG_FOR_NV_SKIP(nv, SKY){ dvm[nv] = vc_[nv] - v[nv]; dvp[nv] = vnx[nv] - vc_[nv]; }
-        plm_zone_f<NC, FLAT, SKY, CL, 1>(a, fln, vc_, dvm, dvp, vpn, vR);
+        plm_zone_f<NC, FLAT, SKY, CL, 1, RECON == RECON_PLMW>(a, fln, vc_, dvm, dvp, vpn, vR, a.pc2, f + 1);
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV_SKIP(nv, SKY) Wf[nv] = C_WF(nv);
@@ -1059,7 +1061,9 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
       else if (a.char_lim && P && C == 2) PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, false, false, false, false, true>)); \
       else if (a.tma)     PG_LXY3(R, C);                               /* TMA staging of the ring rows */              \
       else                PG_LXY1(R, C, false, false); } while (0)
-  if      (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
+  if      (recon == RECON_PLMW && nc == 3) PG_LXY1(RECON_PLMW, 3, false, false);      // grid weights: plain options only (checked at create)
+  else if (recon == RECON_PLMW && nc == 2) PG_LXY1(RECON_PLMW, 2, false, false);
+  else if (recon == RECON_PLM && nc == 3) PG_LXY(RECON_PLM, 3);
   else if (recon == RECON_PLM && nc == 2) PG_LXY(RECON_PLM, 2);
   else if (recon == RECON_PPM && nc == 3) PG_LXY(RECON_PPM, 3);
   else                                    PG_LXY(RECON_PPM, 2);
@@ -1095,7 +1099,9 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
                        else    sweep_x_kernel<R, SOLVER, C, true, false><<<nb, TPB, xsmem, s>>>(a); }               \
       else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, P><<<nb, TPB, xsmem, s>>>(a);                    \
                        else    sweep_x_kernel<R, SOLVER, C, false, false><<<nb, TPB, xsmem, s>>>(a); } } while (0)
-    if      (recon == RECON_PLM && nc == 3) PG_LX(RECON_PLM, 3);
+    if      (recon == RECON_PLMW && nc == 3) sweep_x_kernel<RECON_PLMW, SOLVER, 3, false, false><<<nb, TPB, xsmem, s>>>(a);
+    else if (recon == RECON_PLMW && nc == 2) sweep_x_kernel<RECON_PLMW, SOLVER, 2, false, false><<<nb, TPB, xsmem, s>>>(a);
+    else if (recon == RECON_PLM && nc == 3) PG_LX(RECON_PLM, 3);
     else if (recon == RECON_PLM && nc == 2) PG_LX(RECON_PLM, 2);
     else if (recon == RECON_PPM && nc == 3) PG_LX(RECON_PPM, 3);
     else                                    PG_LX(RECON_PPM, 2);
@@ -1122,7 +1128,9 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                    \
       else           { if (fl) PG_LM1(DD, R, C, false, P); else PG_LM1(DD, R, C, false, false); } } while (0)
     if (dir == 1){
-      if      (recon == RECON_PLM && nc == 3) PG_LM(1, RECON_PLM, 3);
+      if      (recon == RECON_PLMW && nc == 3) PG_LM1(1, RECON_PLMW, 3, false, false);
+      else if (recon == RECON_PLMW && nc == 2) PG_LM1(1, RECON_PLMW, 2, false, false);
+      else if (recon == RECON_PLM && nc == 3) PG_LM(1, RECON_PLM, 3);
       else if (recon == RECON_PLM && nc == 2) PG_LM(1, RECON_PLM, 2);
       else if (recon == RECON_PPM && nc == 3) PG_LM(1, RECON_PPM, 3);
       else                                    PG_LM(1, RECON_PPM, 2);
@@ -1133,8 +1141,9 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
         PG_LMK((sweep_march_kernel<2, RECON_PLM, SOLVER, 3, false, false, false, false, true>));
       }else
 #endif
-      if (recon == RECON_PLM) PG_LM(2, RECON_PLM, 3);
-      else                    PG_LM(2, RECON_PPM, 3);
+      if      (recon == RECON_PLMW) PG_LM1(2, RECON_PLMW, 3, false, false);
+      else if (recon == RECON_PLM)  PG_LM(2, RECON_PLM, 3);
+      else                          PG_LM(2, RECON_PPM, 3);
     }
 #undef PG_LM
 #undef PG_LM1

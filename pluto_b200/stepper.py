@@ -101,6 +101,15 @@ class GpuStepper:
                 raise ValueError(f"set_grid: dx{d+1} needs {self.n[d] + 2 * self.ng} entries")
         self._check(self.L.pluto_gpu_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
 
+    def set_plm_coeffs(self, coeffs):
+        """UNIFORM_CARTESIAN_GRID NO: per direction the six arrays (cp, cm, wp, wm, dp, dm) PLM_CoefficientsGet returns
+        (n[d] + 2 nghost entries each)."""
+        for d, six in enumerate(coeffs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in six]
+            if len(arrs) != 6 or any(a.size != self.n[d] + 2 * self.ng for a in arrs):
+                raise ValueError(f"set_plm_coeffs: direction {d+1} needs six arrays of {self.n[d] + 2 * self.ng} entries")
+            self._check(self.L.pluto_gpu_set_plm_coeffs(self._h, d, *[a.ctypes.data for a in arrs]))
+
     def set_body_force(self, g1, g2, g3=None):
         """Static position-dependent force (BodyForceVector at the zone centres): arrays [T3][T2][T1] incl. ghost zones.
         The stepper must have been created with grav=... (BODY_FORCE VECTOR)."""

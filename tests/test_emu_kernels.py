@@ -105,12 +105,12 @@ def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
     libdir.mkdir()
     os.symlink(emu_lib, libdir / "libpluto_gpu.so")
     for name in ("ot2d_plm_hlld", "ot2d_ctu", "rotor2d_ppm_rk3_bf", "blast2d_ctu_bfx_roe", "blast2d_ctu_bp", "rotor2d_cl_vl_rk3",
-                 "rotor2d_nug_roe_rk3"):
+                 "rotor2d_nug_roe_rk3", "blast2d_nuw_mc_arith"):
         g = Golden(name)
         cfg = RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep, cfl=g.cfl,
                         cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma, limiter=g.limiter, emf=g.emf,
                         flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential, char_lim=g.char_lim,
-                        grid=g.grid, prefix="pluto_gpu_")
+                        grid=g.grid, grid_weights=g.grid_weights, prefix="pluto_gpu_")
         if not have_ref(cfg):
             pytest.skip("oracle/_ref/pluto_gpu_* not built (integration/build_shim.sh)")
         r = run_reference(cfg, maxsteps=g.nsteps + 1, dump_every=1,

@@ -29,7 +29,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # CHAR_LIMITING YES (2-D): the shim reads it from definitions.h
          "ot2d_cl", "rotor2d_cl_vl_rk3",
          # non-uniform grids (uniform + stretched patches in pluto.ini): the shim hands grid->dx to pluto_gpu_set_grid
-         "blast3d_nug", "rotor2d_nug_roe_rk3", "blast2d_nug_mc_arith_reflective"]
+         "blast3d_nug", "rotor2d_nug_roe_rk3", "blast2d_nug_mc_arith_reflective",
+         # UNIFORM_CARTESIAN_GRID NO: the shim hands the arrays of PLM_CoefficientsGet to pluto_gpu_set_plm_coeffs
+         "blast3d_nuw", "blast2d_nuw_mc_arith"]
 
 
 def _blast_params(g):
@@ -44,7 +46,7 @@ def _cfg(g):
     return RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep,
                      cfl=g.cfl, cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma,
                      limiter=g.limiter, emf=g.emf, flatten=g.flatten, en_corr=g.en_corr, grav=g.grav, grav_mode=g.grav_mode, potential=g.potential,
-                     char_lim=g.char_lim, grid=g.grid, bc=g.bc, blast=_blast_params(g), prefix="pluto_gpu_")
+                     char_lim=g.char_lim, grid=g.grid, grid_weights=g.grid_weights, bc=g.bc, blast=_blast_params(g), prefix="pluto_gpu_")
 
 
 @pytest.mark.parametrize("name", CASES)

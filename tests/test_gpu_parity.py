@@ -106,9 +106,28 @@ def test_tma_staging_bit_identical_to_cp_async(monkeypatch, problem, dims, n, re
         assert np.array_equal(v, out[1][0][k]), k
 
 
-@pytest.mark.parametrize("problem,dims,n,solver,rk", [("blast", 3, (37, 12, 10), "hlld", 2), ("rotor", 2, (33, 70, 1), "hlld", 3),
-                                                     ("turb", 3, (10, 9, 12), "hll", 2), ("ot", 2, (64, 31, 1), "roe", 2)])
-def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk):
+def _plm_weights(dx):
+    """PLM_CoefficientsSet (plm_coeffs.c:56-75) for a Cartesian direction with zone widths dx: xgc = zone centres."""
+    xl = np.concatenate([[0.0], np.cumsum(dx)[:-1]])
+    xr = xl + dx
+    x = 0.5 * (xl + xr)
+    six = [np.zeros(dx.size) for _ in range(6)]
+    for i in range(1, dx.size - 1):
+        six[0][i] = (x[i + 1] - x[i]) / (xr[i] - x[i])
+        six[1][i] = (x[i] - x[i - 1]) / (x[i] - xr[i - 1])
+        six[2][i] = dx[i] / (x[i + 1] - x[i])
+        six[3][i] = dx[i] / (x[i] - x[i - 1])
+        six[4][i] = (xr[i] - x[i]) / dx[i]
+        six[5][i] = (x[i] - xr[i - 1]) / dx[i]
+    return six
+
+
+@pytest.mark.parametrize("problem,dims,n,solver,rk,weights", [("blast", 3, (37, 12, 10), "hlld", 2, None), ("rotor", 2, (33, 70, 1), "hlld", 3, None),
+                                                             ("turb", 3, (10, 9, 12), "hll", 2, None), ("ot", 2, (64, 31, 1), "roe", 2, None),
+                                                             # UNIFORM_CARTESIAN_GRID NO: grid-dependent weights, LIMITER as named
+                                                             ("blast", 3, (33, 12, 10), "hlld", 2, "default"), ("rotor", 2, (33, 40, 1), "hlld", 3, "vl"),
+                                                             ("turb", 3, (10, 9, 12), "roe", 2, "mc"), ("ot", 2, (40, 31, 1), "hll", 2, "os")])
+def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk, weights):
     """pluto_gpu_set_grid with zone widths drawn at random (0.7 .. 1.3 of the uniform one, every direction): dt/dx[i] of the
     flux differences, 1/dx[i] of the inverse time step, dt/dx2[j] ... of CT_Update and the face areas of the div B fill all
     differ from zone to zone.  EXACT: bit-identical to the oracle (pinned against the live reference on stretched grids,
@@ -125,10 +144,14 @@ def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk):
             a[:ng] = a[n[d]:n[d] + ng]
             a[n[d] + ng:] = a[ng:2 * ng]
     for arith in ("exact", "fast"):
-        o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], rk_order=rk)
-        s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith=arith, rk_order=rk)
+        lim = weights or "default"
+        o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], rk_order=rk, limiter=lim)
+        s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith=arith, rk_order=rk, limiter=lim)
         o.set_grid(*dxs)
         s.set_grid(*dxs)
+        if weights:
+            o.set_plm_coeffs([_plm_weights(d) for d in dxs])
+            s.set_plm_coeffs([_plm_weights(d) for d in dxs])
         o.set_state(st0)
         s.set_state(st0)
         dt = 1e-4 if problem == "blast" else 1e-3

@@ -103,6 +103,16 @@ CASES = [
                                                   bc=("reflective", "outflow", "outflow", "reflective", "outflow", "outflow"),
                                                   blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3),
                                                   grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 12),
+    # UNIFORM_CARTESIAN_GRID NO: the reconstruction takes the grid-dependent weights of PLM_CoefficientsGet (plm_coeffs.c:30-104)
+    # and the limiters "on irregular grids" (plm_coeffs.h:130-152)
+    ("blast3d_nuw", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, grid_weights=True,
+                              grid=("2  -0.5  8  u  0.1  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                    "3  -0.5  4  s  -0.2  8  u  0.2  4  s  0.5")), 10),
+    ("rotor2d_nuw_roe", RefConfig(problem="rotor", dims=2, n=(36, 30, 1), first_dt=2e-3, solver="roe", grid_weights=True,
+                                  grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  10  s  0.5", None)), 10),
+    ("blast2d_nuw_mc_arith", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, limiter="mc", emf="arith", grid_weights=True,
+                                       grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 12),
+    ("ot2d_nuw_uniform", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, grid_weights=True), 8),
 ]
 
 
@@ -129,6 +139,9 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     if cfg.grid is not None:
         assert r.dx is not None and len(r.dx) == cfg.dims and max(np.ptp(a) for a in r.dx) > 0.0
         o.set_grid(*r.dx)
+    if cfg.grid_weights:
+        assert r.plm_coeffs is not None and len(r.plm_coeffs) == cfg.dims
+        o.set_plm_coeffs(r.plm_coeffs)
     o.set_state(r.dumps[0])
     tap = {int(a): c for a, b, c in r.dt_tap}
     dt = cfg.first_dt

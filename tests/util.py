@@ -53,6 +53,9 @@ class Golden:
         # non-uniform grid: the zone widths grid->dx[d] (ghost zones included) and the "Xd-grid" lines that produced them
         self.grid_dx = [d[f"grid_dx{a+1}"] for a in range(self.dims)] if "grid_dx1" in d.files else None
         self.grid = tuple((str(x) or None) for x in d["cfg_grid"]) if "cfg_grid" in d.files else None
+        # UNIFORM_CARTESIAN_GRID NO: per direction the six weight arrays of PLM_CoefficientsGet
+        self.grid_weights = "cfg_grid_weights" in d.files
+        self.plm_coeffs = [list(d[f"plm_coeffs{a+1}"]) for a in range(self.dims)] if self.grid_weights else None
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:
@@ -79,6 +82,8 @@ def apply_force_field(stepper, g):
     Fixtures on a non-uniform grid: hand over the zone widths."""
     if g.grid_dx is not None:
         stepper.set_grid(*g.grid_dx)
+    if g.plm_coeffs is not None:
+        stepper.set_plm_coeffs(g.plm_coeffs)
     if g.grav_mode == 1:
         stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
     if g.potential:

@@ -126,6 +126,13 @@ CASES = {
                                                   bc=("reflective", "outflow", "outflow", "reflective", "outflow", "outflow"),
                                                   blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3),
                                                   grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
+    # UNIFORM_CARTESIAN_GRID NO: grid-dependent reconstruction weights (plm_coeffs.c) -- the fixtures carry the arrays of PLM_CoefficientsGet
+    "blast3d_nuw": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grid_weights=True,
+                              grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                    "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 15),
+    "blast2d_nuw_mc_arith": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, limiter="mc", emf="arith",
+                                       grid_weights=True,
+                                       grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
 }
 
 
@@ -150,6 +157,10 @@ def make(name):
         out["cfg_grid"] = np.array([g or "" for g in cfg.grid])
         for d in range(cfg.dims):
             out[f"grid_dx{d+1}"] = r.dx[d]
+    if cfg.grid_weights:
+        out["cfg_grid_weights"] = 1
+        for d in range(cfg.dims):
+            out[f"plm_coeffs{d+1}"] = np.array(r.plm_coeffs[d])
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
             out[f"s{s}_{k}"] = v
