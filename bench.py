@@ -610,7 +610,7 @@ def main():
         except Exception as ex:
             strong = {"workload": "ot3d_1024_strong", "error": str(ex)[:300]}
     elif extras and world > 1:
-        strong = {"workload": "ot3d_1024_strong", "skipped": "1024^3 needs 161 GB per GPU on 2 GPUs (37.4 arrays): run on 4 or 8"}
+        strong = {"workload": "ot3d_1024_strong", "skipped": "1024^3 needs 174 GB per GPU on 2 GPUs (40.4 arrays): run on 4 or 8"}
 
     if cx.rank != 0:
         if world > 1:

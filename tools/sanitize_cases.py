@@ -5,7 +5,7 @@
 
 families: rk (fused x1+x2 sweep, x3 march, CT, final, bc), exact (one kernel per direction), ppm_roe, hll_uct_hll,
 ctu, bc (outflow / reflective / eqtsymmetric fills incl. div B), halo (two blocks in one process: pack / unpack tables),
-io (dbl writer / analysis).  Launches run without graph capture so that a report names the kernel.
+io (dbl writer / analysis), grid (non-uniform grids, grid-dependent weights, PLUTO_GPU_R3).  Launches run without graph capture so that a report names the kernel.
 """
 import os
 import sys
@@ -83,6 +83,39 @@ def fam_halo():
                 blk.close()
 
 
+def fam_grid():
+    """Non-uniform grids (pluto_gpu_set_grid), grid-dependent reconstruction weights (RECON_PLMW variants), and the x3 sweep with its
+    flux difference kept apart (PLUTO_GPU_R3=1); the cell-centred EMF arrays of the fused sweep are part of every FAST case."""
+    rng = np.random.default_rng(3)
+
+    def weights(dx):
+        xl = np.concatenate([[0.0], np.cumsum(dx)[:-1]]); xr = xl + dx; x = 0.5*(xl + xr)
+        six = [np.zeros(dx.size) for _ in range(6)]
+        for i in range(1, dx.size - 1):
+            six[0][i] = (x[i+1] - x[i])/(xr[i] - x[i]); six[1][i] = (x[i] - x[i-1])/(x[i] - xr[i-1])
+            six[2][i] = dx[i]/(x[i+1] - x[i]); six[3][i] = dx[i]/(x[i] - x[i-1])
+            six[4][i] = (xr[i] - x[i])/dx[i]; six[5][i] = (x[i] - xr[i-1])/dx[i]
+        return six
+    for dims, n, arith, w in ((3, (40, 24, 20), "fast", False), (3, (24, 20, 16), "fast", True), (2, (48, 40, 1), "exact", True),
+                              (3, (24, 20, 16), "exact", False)):
+        st0, meta = problems.make("blast", dims, n)
+        s = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], arith=arith)
+        dxs = [meta["dx"][d]*(0.7 + 0.6*rng.random(n[d] + 4)) for d in range(dims)]
+        s.set_grid(*dxs)
+        if w:
+            s.set_plm_coeffs([weights(d) for d in dxs])
+        s.set_state(st0)
+        dt = 1e-4
+        for _ in range(2):
+            info = s.advance(dt)
+            dt = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+        assert all(np.isfinite(v).all() for v in s.get_state().values())
+        s.close()
+    os.environ["PLUTO_GPU_R3"] = "1"
+    run("blast", 3, (40, 24, 20), arith="fast")
+    del os.environ["PLUTO_GPU_R3"]
+
+
 def fam_io():
     import tempfile
     st0, meta = problems.make("ot", 3, (24, 20, 16))
@@ -99,7 +132,7 @@ def fam_io():
 
 
 FAMILIES = {"rk": fam_rk, "exact": fam_exact, "ppm_roe": fam_ppm_roe, "hll_uct_hll": fam_hll_uct_hll, "ctu": fam_ctu,
-            "bc": fam_bc, "halo": fam_halo, "io": fam_io}
+            "bc": fam_bc, "halo": fam_halo, "io": fam_io, "grid": fam_grid}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(FAMILIES)):
