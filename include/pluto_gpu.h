@@ -60,7 +60,9 @@ enum { PLUTO_GPU_EMF_UCT_CONTACT = 0, PLUTO_GPU_EMF_ARITHMETIC = 1, PLUTO_GPU_EM
    MUSCL-Hancock predictor (Src/States/hancock.c:33-142) and CTU_CT_Source (ctu_step.c:731-816);
    LINEAR reconstruction, one more ghost zone (Src/get_nghost.c:86-90), one Boundary call per
    step; CT_EMF_AVERAGE UCT_CONTACT, ARITHMETIC or UCT0. */
-enum { PLUTO_GPU_TS_RK = 0, PLUTO_GPU_TS_HANCOCK = 1 };
+enum { PLUTO_GPU_TS_RK = 0, PLUTO_GPU_TS_HANCOCK = 1,
+       PLUTO_GPU_TS_CHAR_TRACING = 2 };  /* corner transport upwind with the characteristic-tracing predictor
+                                            (Src/States/char_tracing.c:278-560), 2-D, LINEAR */
 
 typedef struct {
   int    dims;         /* DIMENSIONS = COMPONENTS: 2 or 3                     */

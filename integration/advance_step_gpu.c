@@ -96,8 +96,8 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     || DIMENSIONAL_SPLITTING != NO || (defined SHEARINGBOX) || (defined FARGO) || (defined PARTICLES)
   #error "libpluto_gpu covers the ideal-MHD step only: no background field, entropy switch, diffusion terms, Hall / ambipolar, rotating frame, cooling, forced turbulence, tracers, dimensional splitting, shearing box, FARGO, particles"
 #endif
-#if TIME_STEPPING != RK2 && TIME_STEPPING != RK3 && TIME_STEPPING != HANCOCK
-  #error "libpluto_gpu: TIME_STEPPING must be RK2, RK3 or HANCOCK (EULER and CHARACTERISTIC_TRACING are not available on the GPU)"
+#if TIME_STEPPING != RK2 && TIME_STEPPING != RK3 && TIME_STEPPING != HANCOCK && TIME_STEPPING != CHARACTERISTIC_TRACING
+  #error "libpluto_gpu: TIME_STEPPING must be RK2, RK3, HANCOCK or CHARACTERISTIC_TRACING (EULER is not available on the GPU)"
 #endif
 #if INTERNAL_BOUNDARY == YES
   #error "libpluto_gpu: INTERNAL_BOUNDARY YES is not available (UserDefBoundary(d, NULL, 0, grid) / InternalBoundaryReset are not called on the GPU)"
@@ -138,7 +138,11 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
   #endif
     c.time_stepping = PLUTO_GPU_TS_HANCOCK;                /* ctu_step.c */
 #elif TIME_STEPPING == CHARACTERISTIC_TRACING
-  #error "libpluto_gpu: TIME_STEPPING CHARACTERISTIC_TRACING is not available on the GPU"
+  #if DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || CHAR_LIMITING == YES || SHOCK_FLATTENING != NO || BODY_FORCE != NO \
+      || CT_EN_CORRECTION == YES || CT_EMF_AVERAGE == UCT_HLL || (defined CHTR_REF_STATE && CHTR_REF_STATE != 3)
+    #error "libpluto_gpu, TIME_STEPPING CHARACTERISTIC_TRACING: 2-D, LINEAR, CHAR_LIMITING NO, no SHOCK_FLATTENING / BODY_FORCE / CT_EN_CORRECTION, CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
+  #endif
+    c.time_stepping = PLUTO_GPU_TS_CHAR_TRACING;           /* ctu_step.c with char_tracing.c:278-560 as the predictor */
 #endif
     /* LIMITER (plm_states.c:192-236) and CT_EMF_AVERAGE (ct_emf.c:241-283) of definitions.h */
     c.limiter = (LIMITER == FLAT_LIM      ? PLUTO_GPU_LIM_FLAT      : LIMITER == MINMOD_LIM ? PLUTO_GPU_LIM_MINMOD :
@@ -168,7 +172,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     }
     if (nonuniform){
       /* stretched / logarithmic / multi-patch grids (set_grid.c:330-560): the zone widths go to the library after its creation */
-#if TIME_STEPPING == HANCOCK || RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES
+#if TIME_STEPPING == HANCOCK || TIME_STEPPING == CHARACTERISTIC_TRACING || RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES
       print ("! AdvanceStep(gpu): a non-uniform grid needs RK2 / RK3 with LINEAR reconstruction, without SHOCK_FLATTENING,\n"
              "  BODY_FORCE, CT_EN_CORRECTION and CHAR_LIMITING on the GPU\n");
       QUIT_PLUTO(1);

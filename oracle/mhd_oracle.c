@@ -589,6 +589,144 @@ typedef struct { int vn, vt, vb, bn, bt, bb; } Dirs;
 
 enum { KFASTM = 0, KFASTP, KENTRP, KDIVB, KSLOWM, KSLOWP, KALFVM, KALFVP, NWAVE };    /* MHD/mod_defs.h:54-74 */
 
+static void prim_eigenvectors (const Oracle *o, const double *qv, Dirs q, double (*RR)[NV], double LL[NWAVE][NV], double *lambda)
+/* PrimEigenvectors (eigenv.c:190-560) for one zone, ideal EOS, CT (no div.B wave: lambda[KDIVB] = 0, eigenv.c:410-415).
+   Only the entries this sweep direction defines are written into RR (= stateC->Rp[i], persistent in the reference);
+   LL is cleared by the reference for every zone (eigenv.c:262-266 sets the left eigenvectors it uses). */
+{
+  const int nc = o->c.dims;
+  const double sqrt_1_2 = 0.70710678118654752440;
+  int k;
+  double a2 = o->c.gamma*qv[PRS]/qv[RHO];            /* SoundSpeed2, eos.c:16-42 */
+  double u, tau, sqrt_rho, scrh0, scrh1, scrh2, scrh3, scrh4, b2, ca2, A2, At2, cf2, cs2, cf, cs, ca, a;
+  double alpha_f, alpha_s, beta_y, beta_z = 0.0, S;
+  memset (LL, 0, sizeof (double)*NWAVE*NV);
+
+  u   = qv[q.vn];
+  tau = 1.0/qv[RHO];
+  sqrt_rho = sqrt(qv[RHO]);
+  scrh2 = qv[q.bn]*qv[q.bn];
+  if (nc == 3) scrh3 = 0.0 + qv[q.bt]*qv[q.bt] + qv[q.bb]*qv[q.bb];
+  else         scrh3 = 0.0 + qv[q.bt]*qv[q.bt];
+  b2  = scrh2 + scrh3;
+  ca2 = scrh2*tau;
+  A2  = b2*tau;
+  At2 = scrh3*tau;
+  scrh1 = a2 - A2;
+  scrh0 = sqrt(scrh1*scrh1 + 4.0*a2*At2);
+  cf2 = 0.5*(a2 + A2 + scrh0);
+  cs2 = a2*ca2/cf2;
+  cf = sqrt(cf2); cs = sqrt(cs2); ca = sqrt(ca2); a = sqrt(a2);
+  if (cf == cs){
+    alpha_f = 1.0; alpha_s = 0.0;
+  }else{
+    scrh0   = 1.0/scrh0;
+    alpha_f = (a2 - cs2)*scrh0;
+    alpha_s = (cf2 - a2)*scrh0;
+    alpha_f = MAXV(0.0, alpha_f);
+    alpha_s = MAXV(0.0, alpha_s);
+    alpha_f = sqrt(alpha_f);
+    alpha_s = sqrt(alpha_s);
+  }
+  scrh0 = sqrt(scrh3);
+  if (scrh0 > 1.e-9){
+    if (nc == 3){ beta_y = qv[q.bt]/scrh0; beta_z = qv[q.bb]/scrh0; }
+    else          beta_y = (qv[q.bt] >= 0.0 ? 1.0 : -1.0);
+  }else{
+    if (nc == 3) beta_z = beta_y = sqrt_1_2;
+    else         beta_y = 1.0;
+  }
+  S = (qv[q.bn] >= 0.0 ? 1.0 : -1.0);
+  (void)ca;
+
+  /* fast wave u - cf */
+  k = KFASTM;
+  scrh0 = alpha_s*cs*S;
+  scrh1 = alpha_s*sqrt_rho*a;
+  scrh2 = 0.5/a2;
+  scrh3 = scrh2*tau;
+  RR[RHO][k] = qv[RHO]*alpha_f;
+  RR[q.vn][k] = -cf*alpha_f;
+  RR[q.vt][k] = scrh0*beta_y;
+  if (nc == 3) RR[q.vb][k] = scrh0*beta_z;
+  RR[q.bt][k] = scrh1*beta_y;
+  if (nc == 3) RR[q.bb][k] = scrh1*beta_z;
+  scrh4 = alpha_f*a2*qv[RHO];
+  RR[PRS][k] = scrh4;
+  LL[k][q.vn] = RR[q.vn][k]*scrh2;
+  LL[k][q.vt] = RR[q.vt][k]*scrh2;
+  if (nc == 3) LL[k][q.vb] = RR[q.vb][k]*scrh2;
+  LL[k][q.bt] = RR[q.bt][k]*scrh3;
+  if (nc == 3) LL[k][q.bb] = RR[q.bb][k]*scrh3;
+  LL[k][PRS] = alpha_f*scrh3;
+  /* fast wave u + cf */
+  k = KFASTP;
+  RR[RHO][k] = RR[RHO][KFASTM];
+  RR[q.vn][k] = -RR[q.vn][KFASTM];
+  RR[q.vt][k] = -RR[q.vt][KFASTM];
+  if (nc == 3) RR[q.vb][k] = -RR[q.vb][KFASTM];
+  RR[q.bt][k] = RR[q.bt][KFASTM];
+  if (nc == 3) RR[q.bb][k] = RR[q.bb][KFASTM];
+  RR[PRS][k] = RR[PRS][KFASTM];
+  /* entropy wave */
+  k = KENTRP;
+  RR[RHO][k] = 1.0;
+  LL[k][RHO] = 1.0;
+  LL[k][PRS] = -1.0/a2;
+  /* slow wave u - cs */
+  k = KSLOWM;
+  scrh0 = alpha_f*cf*S;
+  scrh1 = alpha_f*sqrt_rho*a;
+  RR[RHO][k] = qv[RHO]*alpha_s;
+  RR[q.vn][k] = -cs*alpha_s;
+  RR[q.vt][k] = -scrh0*beta_y;
+  if (nc == 3) RR[q.vb][k] = -scrh0*beta_z;
+  RR[q.bt][k] = -scrh1*beta_y;
+  if (nc == 3) RR[q.bb][k] = -scrh1*beta_z;
+  scrh4 = alpha_s*a2*qv[RHO];
+  RR[PRS][k] = scrh4;
+  LL[k][q.vn] = RR[q.vn][k]*scrh2;
+  LL[k][q.vt] = RR[q.vt][k]*scrh2;
+  if (nc == 3) LL[k][q.vb] = RR[q.vb][k]*scrh2;
+  LL[k][q.bt] = RR[q.bt][k]*scrh3;
+  if (nc == 3) LL[k][q.bb] = RR[q.bb][k]*scrh3;
+  LL[k][PRS] = alpha_s*scrh3;
+  /* slow wave u + cs */
+  k = KSLOWP;
+  RR[RHO][k] = RR[RHO][KSLOWM];
+  RR[q.vn][k] = -RR[q.vn][KSLOWM];
+  RR[q.vt][k] = -RR[q.vt][KSLOWM];
+  if (nc == 3) RR[q.vb][k] = -RR[q.vb][KSLOWM];
+  RR[q.bt][k] = RR[q.bt][KSLOWM];
+  if (nc == 3) RR[q.bb][k] = RR[q.bb][KSLOWM];
+  RR[PRS][k] = scrh4;
+  if (nc == 3){
+    /* Alfven waves */
+    k = KALFVM;
+    scrh2 = beta_y*sqrt_1_2;
+    scrh3 = beta_z*sqrt_1_2;
+    RR[q.vt][k] = -scrh3;
+    RR[q.vb][k] =  scrh2;
+    RR[q.bt][k] = -scrh3*sqrt_rho*S;
+    RR[q.bb][k] =  scrh2*sqrt_rho*S;
+    LL[k][q.vt] = RR[q.vt][k];
+    LL[k][q.vb] = RR[q.vb][k];
+    LL[k][q.bt] = RR[q.bt][k]*tau;
+    LL[k][q.bb] = RR[q.bb][k]*tau;
+    k = KALFVP;
+    RR[q.vt][k] =   RR[q.vt][KALFVM];
+    RR[q.vb][k] =   RR[q.vb][KALFVM];
+    RR[q.bt][k] = - RR[q.bt][KALFVM];
+    RR[q.bb][k] = - RR[q.bb][KALFVM];
+  }
+
+  if (lambda){
+    lambda[KFASTM] = u - cf; lambda[KFASTP] = u + cf; lambda[KENTRP] = u; lambda[KDIVB] = 0.0;
+    lambda[KSLOWM] = u - cs; lambda[KSLOWP] = u + cs;
+    if (nc == 3){ lambda[KALFVM] = u - ca; lambda[KALFVP] = u + ca; }
+  }
+}
+
 static void states_plm_char (Oracle *o, int beg, int end, Dirs q)
 /* plm_states.c:448-706 (CHAR_LIMITING YES, UNIFORM_CARTESIAN_GRID YES: cp = cm = 2, dp = dm = 0.5, cpk = cmk = kstp),
    PrimEigenvectors eigenv.c:190-560 (ideal EOS, CT: no div.B wave), PrimToChar eigenv.c:1310-1400.
@@ -607,132 +745,10 @@ static void states_plm_char (Oracle *o, int beg, int end, Dirs q)
   kstp[KSLOWP] = kstp[KSLOWM] = 1.0;
 
   for (i = beg; i <= end; i++){
-    const double *qv = v[i];
     double (*RR)[NV] = o->Rp[i];           /* RR[nv][k] */
     double LL[NWAVE][NV];
-    double a2 = o->c.gamma*qv[PRS]/qv[RHO];            /* SoundSpeed2, eos.c:16-42 */
-    double u, tau, sqrt_rho, scrh0, scrh1, scrh2, scrh3, scrh4, b2, ca2, A2, At2, cf2, cs2, cf, cs, ca, a;
-    double alpha_f, alpha_s, beta_y, beta_z = 0.0, S;
     double dvp[NV], dvm[NV], dwp[NWAVE], dwm[NWAVE], dw_lim[NWAVE], dv_lim[NV];
-    memset (LL, 0, sizeof (LL));
-
-    u   = qv[q.vn];
-    tau = 1.0/qv[RHO];
-    sqrt_rho = sqrt(qv[RHO]);
-    scrh2 = qv[q.bn]*qv[q.bn];
-    if (nc == 3) scrh3 = 0.0 + qv[q.bt]*qv[q.bt] + qv[q.bb]*qv[q.bb];
-    else         scrh3 = 0.0 + qv[q.bt]*qv[q.bt];
-    b2  = scrh2 + scrh3;
-    ca2 = scrh2*tau;
-    A2  = b2*tau;
-    At2 = scrh3*tau;
-    scrh1 = a2 - A2;
-    scrh0 = sqrt(scrh1*scrh1 + 4.0*a2*At2);
-    cf2 = 0.5*(a2 + A2 + scrh0);
-    cs2 = a2*ca2/cf2;
-    cf = sqrt(cf2); cs = sqrt(cs2); ca = sqrt(ca2); a = sqrt(a2);
-    if (cf == cs){
-      alpha_f = 1.0; alpha_s = 0.0;
-    }else{
-      scrh0   = 1.0/scrh0;
-      alpha_f = (a2 - cs2)*scrh0;
-      alpha_s = (cf2 - a2)*scrh0;
-      alpha_f = MAXV(0.0, alpha_f);
-      alpha_s = MAXV(0.0, alpha_s);
-      alpha_f = sqrt(alpha_f);
-      alpha_s = sqrt(alpha_s);
-    }
-    scrh0 = sqrt(scrh3);
-    if (scrh0 > 1.e-9){
-      if (nc == 3){ beta_y = qv[q.bt]/scrh0; beta_z = qv[q.bb]/scrh0; }
-      else          beta_y = (qv[q.bt] >= 0.0 ? 1.0 : -1.0);
-    }else{
-      if (nc == 3) beta_z = beta_y = sqrt_1_2;
-      else         beta_y = 1.0;
-    }
-    S = (qv[q.bn] >= 0.0 ? 1.0 : -1.0);
-    (void)ca;
-
-    /* fast wave u - cf */
-    k = KFASTM;
-    scrh0 = alpha_s*cs*S;
-    scrh1 = alpha_s*sqrt_rho*a;
-    scrh2 = 0.5/a2;
-    scrh3 = scrh2*tau;
-    RR[RHO][k] = qv[RHO]*alpha_f;
-    RR[q.vn][k] = -cf*alpha_f;
-    RR[q.vt][k] = scrh0*beta_y;
-    if (nc == 3) RR[q.vb][k] = scrh0*beta_z;
-    RR[q.bt][k] = scrh1*beta_y;
-    if (nc == 3) RR[q.bb][k] = scrh1*beta_z;
-    scrh4 = alpha_f*a2*qv[RHO];
-    RR[PRS][k] = scrh4;
-    LL[k][q.vn] = RR[q.vn][k]*scrh2;
-    LL[k][q.vt] = RR[q.vt][k]*scrh2;
-    if (nc == 3) LL[k][q.vb] = RR[q.vb][k]*scrh2;
-    LL[k][q.bt] = RR[q.bt][k]*scrh3;
-    if (nc == 3) LL[k][q.bb] = RR[q.bb][k]*scrh3;
-    LL[k][PRS] = alpha_f*scrh3;
-    /* fast wave u + cf */
-    k = KFASTP;
-    RR[RHO][k] = RR[RHO][KFASTM];
-    RR[q.vn][k] = -RR[q.vn][KFASTM];
-    RR[q.vt][k] = -RR[q.vt][KFASTM];
-    if (nc == 3) RR[q.vb][k] = -RR[q.vb][KFASTM];
-    RR[q.bt][k] = RR[q.bt][KFASTM];
-    if (nc == 3) RR[q.bb][k] = RR[q.bb][KFASTM];
-    RR[PRS][k] = RR[PRS][KFASTM];
-    /* entropy wave */
-    k = KENTRP;
-    RR[RHO][k] = 1.0;
-    LL[k][RHO] = 1.0;
-    LL[k][PRS] = -1.0/a2;
-    /* slow wave u - cs */
-    k = KSLOWM;
-    scrh0 = alpha_f*cf*S;
-    scrh1 = alpha_f*sqrt_rho*a;
-    RR[RHO][k] = qv[RHO]*alpha_s;
-    RR[q.vn][k] = -cs*alpha_s;
-    RR[q.vt][k] = -scrh0*beta_y;
-    if (nc == 3) RR[q.vb][k] = -scrh0*beta_z;
-    RR[q.bt][k] = -scrh1*beta_y;
-    if (nc == 3) RR[q.bb][k] = -scrh1*beta_z;
-    scrh4 = alpha_s*a2*qv[RHO];
-    RR[PRS][k] = scrh4;
-    LL[k][q.vn] = RR[q.vn][k]*scrh2;
-    LL[k][q.vt] = RR[q.vt][k]*scrh2;
-    if (nc == 3) LL[k][q.vb] = RR[q.vb][k]*scrh2;
-    LL[k][q.bt] = RR[q.bt][k]*scrh3;
-    if (nc == 3) LL[k][q.bb] = RR[q.bb][k]*scrh3;
-    LL[k][PRS] = alpha_s*scrh3;
-    /* slow wave u + cs */
-    k = KSLOWP;
-    RR[RHO][k] = RR[RHO][KSLOWM];
-    RR[q.vn][k] = -RR[q.vn][KSLOWM];
-    RR[q.vt][k] = -RR[q.vt][KSLOWM];
-    if (nc == 3) RR[q.vb][k] = -RR[q.vb][KSLOWM];
-    RR[q.bt][k] = RR[q.bt][KSLOWM];
-    if (nc == 3) RR[q.bb][k] = RR[q.bb][KSLOWM];
-    RR[PRS][k] = scrh4;
-    if (nc == 3){
-      /* Alfven waves */
-      k = KALFVM;
-      scrh2 = beta_y*sqrt_1_2;
-      scrh3 = beta_z*sqrt_1_2;
-      RR[q.vt][k] = -scrh3;
-      RR[q.vb][k] =  scrh2;
-      RR[q.bt][k] = -scrh3*sqrt_rho*S;
-      RR[q.bb][k] =  scrh2*sqrt_rho*S;
-      LL[k][q.vt] = RR[q.vt][k];
-      LL[k][q.vb] = RR[q.vb][k];
-      LL[k][q.bt] = RR[q.bt][k]*tau;
-      LL[k][q.bb] = RR[q.bb][k]*tau;
-      k = KALFVP;
-      RR[q.vt][k] =   RR[q.vt][KALFVM];
-      RR[q.vb][k] =   RR[q.vb][KALFVM];
-      RR[q.bt][k] = - RR[q.bt][KALFVM];
-      RR[q.bb][k] = - RR[q.bb][KALFVM];
-    }
+    prim_eigenvectors (o, v[i], q, RR, LL, NULL);
 
     /* 2a. undivided differences projected on the characteristics (PrimToChar) */
     for (nv = 0; nv < NV; nv++){ dvp[nv] = dv[i][nv]; dvm[nv] = dv[i-1][nv]; }
@@ -1677,6 +1693,98 @@ static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, double
     for (nv = 0; nv < NV; nv++) o->v[i][nv] = 0.5*(o->vp[i][nv] + o->vm[i][nv]);
 }
 
+static void prim_to_char (const Oracle *o, double LL[NWAVE][NV], const double *d, double *w, Dirs q)
+/* PrimToChar (eigenv.c:1310-1400): only the non-zero entries of the left eigenvectors; CT: w[KDIVB] = 0 */
+{
+  const int nc = o->c.dims;
+  const double *L;
+  double wv, wB;
+  int k;
+  for (k = 0; k < NWAVE; k++) w[k] = 0.0;
+  L = LL[KFASTM];
+  if (nc == 3){ wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt] + L[q.vb]*d[q.vb]; wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt] + L[q.bb]*d[q.bb]; }
+  else        { wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt];                   wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt]; }
+  w[KFASTM] =  wv + wB;
+  w[KFASTP] = -wv + wB;
+  L = LL[KENTRP];
+  w[KENTRP] = L[RHO]*d[RHO] + L[PRS]*d[PRS];
+  w[KDIVB] = 0.0;
+  L = LL[KSLOWM];
+  if (nc == 3){ wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt] + L[q.vb]*d[q.vb]; wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt] + L[q.bb]*d[q.bb]; }
+  else        { wv = L[q.vn]*d[q.vn] + L[q.vt]*d[q.vt];                   wB = L[PRS]*d[PRS] + L[q.bt]*d[q.bt]; }
+  w[KSLOWM] =  wv + wB;
+  w[KSLOWP] = -wv + wB;
+  if (nc == 3){
+    L = LL[KALFVM];
+    wv = L[q.vt]*d[q.vt] + L[q.vb]*d[q.vb];
+    wB = L[q.bt]*d[q.bt] + L[q.bb]*d[q.bb];
+    w[KALFVM] = wv + wB;
+    w[KALFVP] = wv - wB;
+  }
+}
+
+static void char_tracing_step (Oracle *o, int beg, int end, Dirs q, double dt, int dir)
+/* CharTracingStep for LINEAR reconstruction (States/char_tracing.c:278-560), CARTESIAN, CHAR_LIMITING NO,
+   UNIFORM_CARTESIAN_GRID YES, CHTR_REF_STATE 3 (:268-270), no source terms (PrimSource vanishes with CT and without body
+   forces, prim_eqn.c:289-360).  Pinned with 2 components; with 3 the reference's right-eigenvector scratch keeps entries of
+   the previous sweep direction (see states_plm_char). */
+{
+  const int nc = o->c.dims, nw = (nc == 3 ? 8 : 6);
+  int i, nv, k;
+  for (i = beg; i <= end; i++){
+    double (*RR)[NV] = o->Rp[i];
+    double LL[NWAVE][NV], lambda[NWAVE], nu[NWAVE], dv[NV], dw[NWAVE];
+    double *vc = o->v[i], *vp = o->vp[i], *vm = o->vm[i];
+    double dx, dtdx, nu_max, nu_min;
+    prim_eigenvectors (o, vc, q, RR, LL, lambda);          /* SoundSpeed2 + PrimEigenvectors, :323-324 */
+    dx   = DXA(o,dir,i);                                    /* :346-347 */
+    dtdx = dt/dx;
+    for (k = 0; k < nw; k++) nu[k] = dtdx*lambda[k];        /* :361 */
+    nu_max = MAXV(nu[1], 0.0); nu_min = MINV(nu[0], 0.0);   /* :362 */
+    for (nv = NV; nv--;  ) dv[nv] = vp[nv] - vm[nv];        /* :388 */
+    prim_to_char (o, LL, dv, dw, q);                        /* :389 */
+    for (nv = NV; nv--;  ){                                 /* :409-417, CHTR_REF_STATE 3 */
+      if (nc == 2 && (nv == VX3 || nv == BX3)) continue;
+      vp[nv] = vc[nv] + 0.5*dv[nv]*(1.0 - nu_max);
+      vm[nv] = vc[nv] - 0.5*dv[nv]*(1.0 + nu_min);
+    }
+    for (k = 0; k < nw; k++){                               /* :441-471 */
+      if (nu[k] >= 0.0){
+        dw[k] *= 0.5*(nu_max - nu[k]);
+        for (nv = 0; nv < NV; nv++){
+          if (nc == 2 && (nv == VX3 || nv == BX3)) continue;
+          vp[nv] += dw[k]*RR[nv][k];
+        }
+      }else{
+        dw[k] *= 0.5*(nu_min - nu[k]);
+        for (nv = 0; nv < NV; nv++){
+          if (nc == 2 && (nv == VX3 || nv == BX3)) continue;
+          vm[nv] += dw[k]*RR[nv][k];
+        }
+      }
+    }
+    for (nv = NV; nv--;  ){                                 /* :477-480: src = 0 */
+      if (nc == 2 && (nv == VX3 || nv == BX3)) continue;
+      vp[nv] += 0.5*dt*0.0;
+      vm[nv] += 0.5*dt*0.0;
+    }
+  }
+  for (i = beg-1; i <= end; i++) o->vp[i][q.bn] = o->vm[i+1][q.bn] = o->bn[i];      /* :531-535 */
+  /* CheckPrimStates (check_states.c:18-72): first order where p or rho turned negative */
+  for (i = beg; i <= end; i++){
+    double *ap = o->vp[i], *am = o->vm[i], *ac = o->v[i];
+    int sw = (ap[PRS] < 0.0) || (am[PRS] < 0.0);
+    sw = sw || (ap[RHO] < 0.0) || (am[RHO] < 0.0);
+    if (sw){
+      double bp = ap[q.bn], bm = am[q.bn];
+      for (nv = 0; nv < NV; nv++) am[nv] = ap[nv] = ac[nv];
+      ap[q.bn] = bp; am[q.bn] = bm;
+    }
+  }
+  for (i = beg; i <= end; i++)                             /* :551-555 */
+    for (nv = 0; nv < NV; nv++) o->v[i][nv] = 0.5*(o->vp[i][nv] + o->vm[i][nv]);
+}
+
 static void ctu_store_emf (Oracle *o, int dir, int nbeg, int nend, int *idx3)
 /* CT_StoreUpwindEMF (ct_emf.c:104-190) for faces nbeg-1 .. nend of the current pencil */
 {
@@ -1763,7 +1871,8 @@ static void ctu_advance (Oracle *o, double dt)
       }
       /* 4d. States (nbeg-1 .. nend+1): PLM (incl. face field), Hancock, PrimToCons (plm_states.c:80-312) */
       states_plm (o, nbeg-1, nend+1, q.bn);
-      hancock_step (o, nbeg-1, nend+1, q, dt, o->c.dx[dir]);
+      if (o->c.ctu == 2) char_tracing_step (o, nbeg-1, nend+1, q, dt, dir);      /* TIME_STEPPING CHARACTERISTIC_TRACING */
+      else               hancock_step (o, nbeg-1, nend+1, q, dt, o->c.dx[dir]);
       for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vp[n], o->up[n]); }
       for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vm[n], o->um[n]); }
       /* 4f. Riemann, EMF, rhs with dt/2 */

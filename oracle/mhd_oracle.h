@@ -50,7 +50,9 @@ typedef struct {
   int    shock_flattening; /* 0 NO, 1 MULTID (flag_shock.c:79-230)            */
   int    ctu;           /* 0: RK2/RK3 (rk_order); 1: corner-transport upwind with the
                            primitive MUSCL-Hancock predictor (TIME_STEPPING HANCOCK,
-                           Time_Stepping/ctu_step.c, States/hancock.c)          */
+                           Time_Stepping/ctu_step.c, States/hancock.c); 2: the same step with
+                           the characteristic-tracing predictor (TIME_STEPPING CHARACTERISTIC_TRACING,
+                           States/char_tracing.c:278-560; 2 components)        */
   int    en_correction; /* CT_EN_CORRECTION YES (MHD/CT/ct_field_average.c:116-129)            */
   int    body_force;    /* BODY_FORCE VECTOR with a uniform acceleration grav[] (MHD/rhs_source.c:214-217,
                            277-280, 342-345; MHD/prim_eqn.c:289-360 in the Hancock predictor)     */

@@ -85,7 +85,7 @@ class Oracle:
         c.body_force = 0 if grav is None else 1
         for d in range(3):
             c.grav[d] = 0.0 if grav is None else float(grav[d])
-        c.ctu = 1 if ctu else 0
+        c.ctu = 2 if ctu == "chtr" else (1 if ctu else 0)      # "chtr": TIME_STEPPING CHARACTERISTIC_TRACING
         c.en_correction = 1 if en_corr else 0
         c.char_limiting = 1 if char_lim else 0
         c.shock_flattening = 1 if flatten else 0

@@ -11,7 +11,7 @@
 # reference: the makefile VPATHs into it.
 #
 # usage: build_ref.sh <variant> [<variant> ...]
-#   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3 2d_plm_hancock 3d_plm_hancock (CTU)
+#   variants:  2d_plm 3d_plm 2d_ppm 3d_ppm 2d_plm_rk3 3d_plm_rk3 2d_plm_hancock 3d_plm_hancock (CTU) 2d_plm_chtr (CTU, characteristic tracing)
 #   optional suffixes:  _l{fl,mm,va,os,um,vl,mc}  single LIMITER for all variables
 #                                                 (Src/States/plm_coeffs.h:72-123)
 #                       _e{arith,uct0,uct_hll}    CT_EMF_AVERAGE
@@ -43,6 +43,7 @@ for VARIANT in "$@"; do
   case "$VARIANT" in
     *_rk3*)     TSTEP=RK3;     STEP_OBJ="rk_step.o update_stage.o" ;;
     *_hancock*) TSTEP=HANCOCK; STEP_OBJ="ctu_step.o hancock.o" ;;     # define_problem.py:542-553
+    *_chtr*)    TSTEP=CHARACTERISTIC_TRACING; STEP_OBJ="ctu_step.o char_tracing.o" ;;   # define_problem.py:555-557
     *)          TSTEP=RK2;     STEP_OBJ="rk_step.o update_stage.o" ;;
   esac
   case "$VARIANT" in

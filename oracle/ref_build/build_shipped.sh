@@ -18,6 +18,11 @@ while [ $# -ge 2 ]; do
   PROB="$1"; NN="$2"; shift 2
   TP="$PLUTO_DIR/Test_Problems/MHD/$PROB"
   TAG="$(echo "$PROB" | tr 'A-Z' 'a-z')_$NN"
+  # base makefile by the configuration's time stepping: RK2 / RK3 (rk_step.o update_stage.o) or the corner-transport-upwind step
+  # with the characteristic-tracing predictor (ctu_step.o char_tracing.o; plm_states.o still calls CharTracingStep in the GPU build)
+  BASE=2d_plm
+  if grep -q "TIME_STEPPING *CHARACTERISTIC_TRACING" "$TP/definitions_$NN.h"; then BASE=2d_plm_chtr; fi
+  [ -f "$ORACLE/_build/$BASE/makefile" ] || "$HERE/build_ref.sh" "$BASE"
   for KIND in cpu gpu; do
     B="$ORACLE/_build/shipped_${TAG}_$KIND"
     mkdir -p "$B"
@@ -26,12 +31,12 @@ while [ $# -ge 2 ]; do
     [ "$KIND" = gpu ] && cp "$ROOT/integration/advance_step_gpu.c" "$B/"
     # the object lists of the LINEAR + RK2/RK3 build (oracle/_build/2d_plm/makefile = Src/Templates/makefile + module lists)
     if [ "$KIND" = gpu ]; then
-      sed -e 's/rk_step.o update_stage.o/advance_step_gpu.o/' \
+      sed -e 's/rk_step.o update_stage.o/advance_step_gpu.o/' -e 's/ctu_step.o char_tracing.o/advance_step_gpu.o char_tracing.o/' \
           -e "s#^INCLUDE_DIRS = .*#INCLUDE_DIRS = -I. -I\$(SRC) -I$ROOT/include#" \
           -e "s#^LDFLAGS = .*#LDFLAGS = -lm -L$ROOT/pluto_b200/lib -lpluto_gpu -Wl,-rpath,'\$\$ORIGIN/../../../pluto_b200/lib'#" \
-          "$ORACLE/_build/2d_plm/makefile" > "$B/makefile"
+          "$ORACLE/_build/$BASE/makefile" > "$B/makefile"
     else
-      cp "$ORACLE/_build/2d_plm/makefile" "$B/makefile"
+      cp "$ORACLE/_build/$BASE/makefile" "$B/makefile"
     fi
     ( cd "$B" && make -j"$(nproc)" pluto >make.log 2>&1 ) || { tail -30 "$B/make.log"; exit 1; }
     if [ "$KIND" = gpu ]; then cp "$B/pluto" "$ORACLE/_ref/shipped/${TAG}_gpu"; else cp "$B/pluto" "$ORACLE/_ref/shipped/$TAG"; fi

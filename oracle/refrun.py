@@ -41,7 +41,7 @@ class RefConfig:
     n: tuple = (64, 64, 1)              # NX1, NX2, NX3
     recon: str = "plm"                  # plm (LINEAR) | ppm (PARABOLIC)
     solver: str = "hlld"                # hlld | hll | roe
-    tstep: str = "rk2"                  # rk2 | rk3 | hancock (CTU)
+    tstep: str = "rk2"                  # rk2 | rk3 | hancock (CTU) | chtr (CTU with TIME_STEPPING CHARACTERISTIC_TRACING)
     limiter: str = "default"            # default | fl mm va os um vl mc  (LIMITER, plm only)
     flatten: bool = False               # SHOCK_FLATTENING MULTID
     emf: str = "uct_contact"            # uct_contact | arith | uct0 | uct_hll  (CT_EMF_AVERAGE)
@@ -72,6 +72,8 @@ class RefConfig:
             v += "_rk3"
         if self.tstep == "hancock":         # CTU with the MUSCL-Hancock predictor (ctu_step.c, hancock.c)
             v += "_hancock"
+        if self.tstep == "chtr":            # CTU with the characteristic-tracing predictor (ctu_step.c, char_tracing.c)
+            v += "_chtr"
         if self.limiter != "default":
             v += "_l" + self.limiter
         if self.emf != "uct_contact":

@@ -13,7 +13,7 @@ BC = {"periodic": 0, "outflow": 1, "reflective": 2, "shared": 3, "eqtsymmetric":
 LIMITER = {"default": 0, "fl": 1, "mm": 2, "va": 3, "os": 4, "um": 5, "vl": 6, "mc": 7}      # LIMITER
 EMF = {"uct_contact": 0, "arith": 1, "uct0": 2, "uct_hll": 3}                                                 # CT_EMF_AVERAGE
 ARITH = {"exact": 0, "fast": 1}
-TIME_STEPPING = {"rk": 0, "hancock": 1}                                                                       # TIME_STEPPING
+TIME_STEPPING = {"rk": 0, "hancock": 1, "chtr": 2}                                                                       # TIME_STEPPING
 
 # every symbol include/pluto_gpu.h declares (checked by tests/test_cabi.py)
 SYMBOLS = [

@@ -57,10 +57,12 @@ __device__ __forceinline__ void prim_rhs (const Phys &ph, const double *v, const
 // normal predictor of one zone: PLM states (plm_states.c:134-275, the normal component takes the
 // staggered field of the zone's two faces), evolved by dt/2 with the primitive equations
 // (hancock.c:96-124), first order where density or pressure turned negative (check_states.c:35-66)
+// chtr_dtdx > 0: TIME_STEPPING CHARACTERISTIC_TRACING (2 components), the states are traced along the characteristics with
+// dt/dx = chtr_dtdx (char_tracing2, mhd_device.cuh) instead of the Hancock half step
 template <int DIR, int NC, bool FLAT>
 __device__ __forceinline__ void ctu_states (const Phys &ph, int limiter, unsigned fl, const double *vl, const double *v,
                                             const double *vr, double bsm, double bsp, double dt_2, double d_dl,
-                                            double src_n, double *vp, double *vm)
+                                            double src_n, double *vp, double *vm, double chtr_dtdx = 0.0)
 {
   typedef Dirs<DIR> D;
   double dvm[NV], dvp[NV], dv[NV], Adv[NV];
@@ -68,12 +70,16 @@ __device__ __forceinline__ void ctu_states (const Phys &ph, int limiter, unsigne
   if (FLAT && (fl & 1u)) plm_zone_single<NC>(2, v, dvm, dvp, vp, vm);
   else                   plm_zone<NC>(limiter, v, dvm, dvp, vp, vm);
   vp[D::bn] = bsp; vm[D::bn] = bsm;
+  if (NC == 2 && DIR < 2 && chtr_dtdx > 0.0){
+    char_tracing2<DIR>(ph, v, chtr_dtdx, vp, vm);
+  }else{
   PG_FOR_NV(nv) dv[nv] = vp[nv] - vm[nv];
   prim_rhs<DIR, NC>(ph, v, dv, Adv);
   PG_FOR_NV(nv){                                     // src_n: PrimSource of the normal velocity (body force, prim_eqn.c:289-360)
     const double scrh = dt_2*(d_dl*Adv[nv] - (nv == D::vn ? src_n : 0.0));
     vp[nv] -= scrh;
     vm[nv] -= scrh;
+  }
   }
   bool sw = (vp[PRS] < 0.0) || (vm[PRS] < 0.0);
   sw = sw || (vp[RHO] < 0.0) || (vm[RHO] < 0.0);
@@ -205,7 +211,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     double src_n = 0.0, dphi = 0.0;                    // PrimSource of the normal velocity (prim_eqn.c:289-307)
     if (a.bf) src_n += gz;
     if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - 1); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
-    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
+    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0);
     // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
     // V^{n+1/2} (ctu_step.c:566-570) in the corrector
     double rho_c = 0.0;
@@ -376,7 +382,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       double src_n = 0.0, dphi = 0.0;                  // PrimSource of the normal velocity (prim_eqn.c:289-307)
       if (a.bf) src_n += gz;
       if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - sD); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
-      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm);
+      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0);
       const double rho_z = ((a.bf || a.phif) && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
       if (PHASE == 0){
         prim_to_cons<NC>(ph, vp, up);

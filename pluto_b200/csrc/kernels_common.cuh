@@ -145,6 +145,7 @@ struct CtuArgs {
   const double *gf;
   const double *phic, *phif; // BODY_FORCE & POTENTIAL: potential at the centres / the faces of this direction (else NULL)
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
+  int     chtr;              // TIME_STEPPING CHARACTERISTIC_TRACING: predictor by characteristic tracing (2 components)
 };
 
 struct FinalArgs {

@@ -450,6 +450,105 @@ __device__ __forceinline__ void plm_zone_w (int lim, const double *const *pc, in
   }
 }
 
+// ---------------------------------------------------------------------------
+//  TIME_STEPPING CHARACTERISTIC_TRACING, 2 components: the predictor of the corner-transport-upwind step by characteristic
+//  tracing (States/char_tracing.c:278-560: LINEAR reconstruction, CARTESIAN, CHAR_LIMITING NO, CHTR_REF_STATE 3, no source
+//  terms).  In: the limited interface states vp, vm of the zone (normal field = the staggered one of its two faces), the zone
+//  value vc, dt/dx.  The eigenvectors are those of plm_zone_char2 (PrimEigenvectors, eigenv.c:190-470: six waves, no div.B
+//  jump, lambda[KDIVB] = 0), the chain up to the alphas in IEEE operations for the same reason; only non-zero entries of
+//  the right eigenvectors are summed (the reference's scratch holds zeros elsewhere, and a stale row of the normal field
+//  that the staggered component overwrites).  Waves in the reference's order: fast-, fast+, entropy, div.B, slow-, slow+.
+// ---------------------------------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ void char_tracing2 (const Phys &ph, const double *v, double dtdx, double *vp, double *vm)
+{
+  typedef Dirs<DIR> D;
+  const int VXn = D::vn, VXt = D::vt, BXn = D::bn, BXt = D::bt;
+  const double a2   = x_div (x_mul (ph.gamma, v[PRS]), v[RHO]);           // SoundSpeed2
+  const double u    = v[VXn];
+  const double tau  = x_div (1.0, v[RHO]);
+  const double sqrt_rho = x_sqrt (v[RHO]);
+  const double bn2  = x_mul (v[BXn], v[BXn]);
+  const double bt2  = x_add (0.0, x_mul (v[BXt], v[BXt]));
+  const double b2   = x_add (bn2, bt2);
+  const double ca2  = x_mul (bn2, tau);
+  const double A2   = x_mul (b2, tau);
+  const double At2  = x_mul (bt2, tau);
+  const double d1   = x_add (a2, -A2);
+  const double disc = x_sqrt (x_add (x_mul (d1, d1), x_mul (x_mul (4.0, a2), At2)));
+  const double cf2  = x_mul (0.5, x_add (x_add (a2, A2), disc));
+  const double cs2  = x_div (x_mul (a2, ca2), cf2);
+  const double cf = x_sqrt (cf2), cs = x_sqrt (cs2), a = x_sqrt (a2);
+  double alpha_f, alpha_s;
+  if (cf == cs){
+    alpha_f = 1.0; alpha_s = 0.0;
+  }else{
+    const double id = x_div (1.0, disc);
+    alpha_f = x_mul (x_add (a2, -cs2), id);
+    alpha_s = x_mul (x_add (cf2, -a2), id);
+    alpha_f = maxv (0.0, alpha_f);
+    alpha_s = maxv (0.0, alpha_s);
+    alpha_f = x_sqrt (alpha_f);
+    alpha_s = x_sqrt (alpha_s);
+  }
+  double beta_y;
+  if (x_sqrt (bt2) > 1.e-9) beta_y = (v[BXt] >= 0.0 ? 1.0 : -1.0);
+  else                      beta_y = 1.0;
+  const double S = (v[BXn] >= 0.0 ? 1.0 : -1.0);
+  const double h2 = pg_div (0.5, a2), h3 = h2*tau;
+  const double f0 = alpha_s*cs*S, f1 = alpha_s*sqrt_rho*a;
+  const double Rf_rho = v[RHO]*alpha_f, Rf_vn = -cf*alpha_f, Rf_vt = f0*beta_y, Rf_bt = f1*beta_y, Rf_p = alpha_f*a2*v[RHO];
+  const double Lf_vn = Rf_vn*h2, Lf_vt = Rf_vt*h2, Lf_bt = Rf_bt*h3, Lf_p = alpha_f*h3;
+  const double Le_p = -pg_div (1.0, a2);
+  const double s0 = alpha_f*cf*S, s1 = alpha_f*sqrt_rho*a;
+  const double Rs_rho = v[RHO]*alpha_s, Rs_vn = -cs*alpha_s, Rs_vt = -s0*beta_y, Rs_bt = -s1*beta_y, Rs_p = alpha_s*a2*v[RHO];
+  const double Ls_vn = Rs_vn*h2, Ls_vt = Rs_vt*h2, Ls_bt = Rs_bt*h3, Ls_p = alpha_s*h3;
+
+  // characteristic Courant numbers (char_tracing.c:361-362)
+  double nu[6];
+  nu[0] = dtdx*(u - cf); nu[1] = dtdx*(u + cf); nu[2] = dtdx*u; nu[3] = dtdx*0.0; nu[4] = dtdx*(u - cs); nu[5] = dtdx*(u + cs);
+  const double nu_max = maxv (nu[1], 0.0), nu_min = minv (nu[0], 0.0);
+  // dv = vp - vm projected on the left eigenvectors (:388-389, PrimToChar eigenv.c:1310-1375)
+  const double d_rho = vp[RHO] - vm[RHO], d_vn = vp[VXn] - vm[VXn], d_vt = vp[VXt] - vm[VXt], d_bt = vp[BXt] - vm[BXt], d_p = vp[PRS] - vm[PRS];
+  double dw[6];
+  {
+    double wv = Lf_vn*d_vn + Lf_vt*d_vt;
+    double wB = Lf_p*d_p + Lf_bt*d_bt;
+    dw[0] = wv + wB; dw[1] = -wv + wB;
+    dw[2] = 1.0*d_rho + Le_p*d_p;
+    dw[3] = 0.0;
+    wv = Ls_vn*d_vn + Ls_vt*d_vt;
+    wB = Ls_p*d_p + Ls_bt*d_bt;
+    dw[4] = wv + wB; dw[5] = -wv + wB;
+  }
+  // reference state of the fastest waves (:409-417)
+  double qp[5], qm[5];                  // rho, vn, vt, bt, p
+  const double dq[5] = {d_rho, d_vn, d_vt, d_bt, d_p};
+  const double qc[5] = {v[RHO], v[VXn], v[VXt], v[BXt], v[PRS]};
+  PG_UNROLL for (int q = 0; q < 5; q++){
+    qp[q] = qc[q] + 0.5*dq[q]*(1.0 - nu_max);
+    qm[q] = qc[q] - 0.5*dq[q]*(1.0 + nu_min);
+  }
+  // right eigenvectors, rows rho, vn, vt, bt, p; columns = waves (zero entries left out)
+  const double R[5][6] = {{Rf_rho,  Rf_rho, 1.0, 0.0, Rs_rho,  Rs_rho},
+                          {Rf_vn,  -Rf_vn,  0.0, 0.0, Rs_vn,  -Rs_vn},
+                          {Rf_vt,  -Rf_vt,  0.0, 0.0, Rs_vt,  -Rs_vt},
+                          {Rf_bt,   Rf_bt,  0.0, 0.0, Rs_bt,   Rs_bt},
+                          {Rf_p,    Rf_p,   0.0, 0.0, Rs_p,    Rs_p}};
+  PG_UNROLL for (int k = 0; k < 6; k++){            // :441-471
+    if (k == 3) continue;                           // dw = 0: nothing is added
+    if (nu[k] >= 0.0){
+      const double w = dw[k]*(0.5*(nu_max - nu[k]));
+      PG_UNROLL for (int q = 0; q < 5; q++) if (!(k == 2 && q > 0)) qp[q] += w*R[q][k];
+    }else{
+      const double w = dw[k]*(0.5*(nu_min - nu[k]));
+      PG_UNROLL for (int q = 0; q < 5; q++) if (!(k == 2 && q > 0)) qm[q] += w*R[q][k];
+    }
+  }
+  vp[RHO] = qp[0]; vp[VXn] = qp[1]; vp[VXt] = qp[2]; vp[BXt] = qp[3]; vp[PRS] = qp[4];
+  vm[RHO] = qm[0]; vm[VXn] = qm[1]; vm[VXt] = qm[2]; vm[BXt] = qm[3]; vm[PRS] = qm[4];
+}
+
 // LIMITER DEFAULT (the fast path) or one limiter for all variables (uniform branch)
 template <int NC, int SKIP = -1>
 __device__ __forceinline__ void plm_zone (int lim, const double *v, const double *dvm, const double *dvp,

@@ -170,7 +170,14 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     return fail ("SHOCK_FLATTENING MULTID is available with LINEAR reconstruction only (the reference's PARABOLIC "
                  "fallback takes its weights from PLM_CoefficientsGet, ppm_states.c:167-181)");
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
-  if (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->time_stepping != PLUTO_GPU_TS_HANCOCK) return fail ("bad time_stepping");
+  if (cfg->time_stepping < PLUTO_GPU_TS_RK || cfg->time_stepping > PLUTO_GPU_TS_CHAR_TRACING) return fail ("bad time_stepping");
+  if (cfg->time_stepping == PLUTO_GPU_TS_CHAR_TRACING){
+    if (cfg->dims != 2)
+      return fail ("TIME_STEPPING CHARACTERISTIC_TRACING is available in 2-D only (in 3-D the reference's eigenvector scratch, eigenv.c:190-560, "
+                   "keeps entries of the previous sweep direction: its result depends on the sweep order and cannot be reproduced)");
+    if (cfg->shock_flattening || cfg->body_force || cfg->en_correction || cfg->char_limiting)
+      return fail ("TIME_STEPPING CHARACTERISTIC_TRACING is available without SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION and CHAR_LIMITING");
+  }
   if (cfg->en_correction != 0 && cfg->en_correction != 1) return fail ("bad en_correction");
   if (cfg->en_correction && cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
     return fail ("CT_EN_CORRECTION YES is available with CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
@@ -187,7 +194,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
         || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
       return fail ("CHAR_LIMITING YES is available with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL");
   }
-  if (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK){
+  if (cfg->time_stepping != PLUTO_GPU_TS_RK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
     if (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)      // the reference refuses the same combination (MHD/CT/ct_emf.c:196-200)
       return fail ("UCT_HLL average not compatible with CTU schemes (stencil too small): use UCT_CONTACT, ARITHMETIC or UCT0");
@@ -220,7 +227,7 @@ static int create_resources (PlutoGpu *h)
   g.dims = cfg->dims;
   g.ng = (cfg->recon == PLUTO_GPU_RECON_PARABOLIC ? 3 : 2);      // get_nghost.c:32-50
   if (cfg->shock_flattening && g.ng < 3) g.ng = 3;               // get_nghost.c:67-77
-  h->ctu = (cfg->time_stepping == PLUTO_GPU_TS_HANCOCK);
+  h->ctu = (cfg->time_stepping != PLUTO_GPU_TS_RK);
   if (h->ctu) g.ng++;                                            // CTU + CT, get_nghost.c:86-90
   h->nstages = h->ctu ? 1 : cfg->rk_order;
   for (int d = 0; d < 3; d++){
@@ -1022,6 +1029,7 @@ static int run_ctu (PlutoGpu *h, int part)
     for (int nv = 0; nv < NVS; nv++) s.rhs[d][nv] = h->rhs3[d][nv];
   }
   s.red = h->red; s.flag = h->flag; s.g = g; s.ph = h->ph; s.dtp = h->dtdev; s.limiter = h->cfg.limiter;
+  s.chtr = (h->cfg.time_stepping == PLUTO_GPU_TS_CHAR_TRACING);
   s.en_corr = h->cfg.en_correction;
   s.bf = h->cfg.body_force & 1;
   for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];

@@ -59,7 +59,7 @@ class GpuStepper:
         c.limiter = _lib.LIMITER[limiter]           # LIMITER (plm only): default | fl mm va os um vl mc
         c.emf_average = _lib.EMF[emf]               # CT_EMF_AVERAGE: uct_contact | arith | uct0 | uct_hll
         c.shock_flattening = 1 if flatten else 0    # SHOCK_FLATTENING MULTID (plm only)
-        c.time_stepping = 1 if ctu else 0           # TIME_STEPPING: RK2/RK3 (rk_order) | HANCOCK (corner transport upwind)
+        c.time_stepping = 2 if ctu == "chtr" else (1 if ctu else 0)   # TIME_STEPPING: RK2/RK3 (rk_order) | HANCOCK | CHARACTERISTIC_TRACING (ctu="chtr")
         c.en_correction = 1 if en_corr else 0       # CT_EN_CORRECTION YES
         c.char_limiting = 1 if char_lim else 0      # CHAR_LIMITING YES (2-D, plm, RK)
         # BODY_FORCE: VECTOR (bit 0) with the uniform acceleration grav, POTENTIAL (bit 1, set_body_potential)
@@ -390,7 +390,7 @@ class MultiGpuStepper:
             c.bc[s] = _lib.BC[bc[s]]
         c.arith, c.gamma, c.small_dn, c.small_pr = _lib.ARITH[arith], gamma, 1e-12, 1e-12
         c.limiter, c.emf_average = _lib.LIMITER[limiter], _lib.EMF[emf]
-        c.shock_flattening, c.time_stepping = (1 if flatten else 0), (1 if ctu else 0)
+        c.shock_flattening, c.time_stepping = (1 if flatten else 0), (2 if ctu == "chtr" else (1 if ctu else 0))
         c.en_correction, c.char_limiting = (1 if en_corr else 0), (1 if char_lim else 0)
         self.dims, self.n = dims, tuple(n)
         g = (C.c_int * 3)(*(list(grid) + [1] * (3 - len(grid))))

@@ -56,7 +56,7 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
                "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf", "blast2d_ctu_bfx_roe",
-               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3", "blast3d_nug", "blast2d_nug_mc_arith_reflective"]
+               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3", "blast3d_nug", "blast2d_nug_mc_arith_reflective", "ot2d_chtr"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)
@@ -84,7 +84,7 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
 # (RK and corner transport upwind), NextTimeStep on the device, reflective walls, the reference Data layout.
 GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or (decomposed and gn7 and split) or (decomposed and gn4 and all) "
                    "or (decomposed and gn2 and dims) or (device_next_dt and ot-2) or reflective or data_layout "
-                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2) or (body_force and rotor) or tma_staging or (flux_difference_kept_apart and blast) or (nonuniform_grid and (rotor or turb or refused))")
+                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2) or (body_force and rotor) or tma_staging or (flux_difference_kept_apart and blast) or (nonuniform_grid and (rotor or turb or refused)) or characteristic_tracing_is_2d")
 
 
 def test_gpu_test_files_through_the_interpreter(emu_lib):
@@ -105,7 +105,7 @@ def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
     libdir.mkdir()
     os.symlink(emu_lib, libdir / "libpluto_gpu.so")
     for name in ("ot2d_plm_hlld", "ot2d_ctu", "rotor2d_ppm_rk3_bf", "blast2d_ctu_bfx_roe", "blast2d_ctu_bp", "rotor2d_cl_vl_rk3",
-                 "rotor2d_nug_roe_rk3", "blast2d_nuw_mc_arith"):
+                 "rotor2d_nug_roe_rk3", "blast2d_nuw_mc_arith", "rotor2d_chtr_mc_uct0"):
         g = Golden(name)
         cfg = RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep, cfl=g.cfl,
                         cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma, limiter=g.limiter, emf=g.emf,

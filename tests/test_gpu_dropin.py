@@ -31,7 +31,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # non-uniform grids (uniform + stretched patches in pluto.ini): the shim hands grid->dx to pluto_gpu_set_grid
          "blast3d_nug", "rotor2d_nug_roe_rk3", "blast2d_nug_mc_arith_reflective",
          # UNIFORM_CARTESIAN_GRID NO: the shim hands the arrays of PLM_CoefficientsGet to pluto_gpu_set_plm_coeffs
-         "blast3d_nuw", "blast2d_nuw_mc_arith"]
+         "blast3d_nuw", "blast2d_nuw_mc_arith",
+         # TIME_STEPPING CHARACTERISTIC_TRACING (2-D): the shim replaces ctu_step.o, plm_states.o keeps char_tracing.o
+         "ot2d_chtr", "rotor2d_chtr_mc_uct0", "blast2d_chtr_mc_roe"]
 
 
 def _blast_params(g):

@@ -178,6 +178,19 @@ def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk, weights):
         s.close()
 
 
+def test_characteristic_tracing_is_2d_only():
+    """TIME_STEPPING CHARACTERISTIC_TRACING: in 3-D the reference's own result depends on never-cleared eigenvector scratch
+    (as with CHAR_LIMITING), so pluto_gpu_create refuses it with that reason; PARABOLIC and UCT_HLL as for the Hancock step."""
+    from pluto_b200 import GpuStepper
+    from pluto_b200.stepper import PlutoGpuError
+    with pytest.raises(PlutoGpuError, match="2-D only"):
+        GpuStepper(3, (8, 8, 8), (0.1, 0.1, 0.1), ctu="chtr")
+    with pytest.raises(PlutoGpuError, match="LINEAR"):
+        GpuStepper(2, (16, 16, 1), (0.1, 0.1), ctu="chtr", recon="ppm")
+    with pytest.raises(PlutoGpuError, match="SHOCK_FLATTENING"):
+        GpuStepper(2, (16, 16, 1), (0.1, 0.1), ctu="chtr", flatten=True)
+
+
 def test_nonuniform_grid_is_refused_where_the_weights_would_change():
     """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c), the corner-transport-upwind predictor, shock
     flattening, body forces and the energy correction use the zone width elsewhere: pluto_gpu_set_grid says so."""

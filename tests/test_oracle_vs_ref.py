@@ -113,6 +113,13 @@ CASES = [
     ("blast2d_nuw_mc_arith", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, limiter="mc", emf="arith", grid_weights=True,
                                        grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 12),
     ("ot2d_nuw_uniform", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, grid_weights=True), 8),
+    # TIME_STEPPING CHARACTERISTIC_TRACING (States/char_tracing.c:278-560): the corner-transport-upwind step with the
+    # characteristic-tracing predictor, the scheme of the shipped Field_Loop #01 / #02 (LINEAR, MC_LIM, UCT_CONTACT / UCT0).
+    # 2 components (3: the reference's eigenvector scratch keeps entries of the previous sweep direction, as with CHAR_LIMITING)
+    ("ot2d_chtr", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, tstep="chtr", cfl=0.4), 10),
+    ("blast2d_chtr_mc_roe", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="roe"), 12),
+    ("rotor2d_chtr_mc_uct0_hll", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), first_dt=2e-3, tstep="chtr", limiter="mc", emf="uct0",
+                                           solver="hll"), 10),
 ]
 
 
@@ -127,7 +134,7 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     dom = cfg.resolved_domain()
     dx = [(dom[d][1] - dom[d][0]) / n[d] for d in range(cfg.dims)]
     o = Oracle(cfg.dims, n, dx, recon=cfg.recon, solver=cfg.solver, bc=cfg.resolved_bc(),
-               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=(cfg.tstep == "hancock"),
+               gamma=cfg.resolved_gamma(), limiter=cfg.limiter, emf=cfg.emf, flatten=cfg.flatten, ctu=("chtr" if cfg.tstep == "chtr" else cfg.tstep == "hancock"),
                rk_order=(3 if cfg.tstep == "rk3" else 2), en_corr=cfg.en_corr, grav=(None if cfg.potential and not cfg.vector_too else cfg.grav),
                char_lim=cfg.char_lim)
     if cfg.potential:

@@ -7,6 +7,7 @@ The binaries are built in the development container by oracle/ref_build/build_sh
   Orszag_Tang #03  2-D 256^2, LINEAR, RK2, roe, CT_EMF_AVERAGE ARITHMETIC, periodic
   Rotor #01        2-D 400^2, LINEAR, RK2, hlld, ARITHMETIC, MC_LIM, outflow
   Blast #02        3-D 64^3, LINEAR, RK2, roe, VANLEER_LIM, ARITHMETIC, CT_EN_CORRECTION YES, reflective / eqtsymmetric / outflow
+  Field_Loop #01   2-D 128 x 64, LINEAR, CHARACTERISTIC_TRACING (corner transport upwind), roe, MC_LIM, UCT_CONTACT, periodic, CFL 0.8
 """
 import os
 import shutil
@@ -20,7 +21,7 @@ from oracle.refrun import read_dbl
 from tests.util import ROOT
 
 SHIPPED = os.path.join(ROOT, "oracle", "_ref", "shipped")
-CASES = [("orszag_tang_03", 3), ("rotor_01", 2), ("blast_02", 1)]
+CASES = [("orszag_tang_03", 3), ("rotor_01", 2), ("blast_02", 1), ("field_loop_01", 4)]
 
 
 def _grid(ini):

@@ -74,7 +74,7 @@ class Golden:
                 self.dx_zones.append(self.grid_dx[a][ngz:ngz + self.n[a]])
             self.dx = [float(np.min(z)) for z in self.dx_zones]      # scale of the smallest zone (tolerances, bscale)
         self.rk_order = 3 if self.tstep == "rk3" else 2
-        self.ctu = self.tstep == "hancock"
+        self.ctu = "chtr" if self.tstep == "chtr" else self.tstep == "hancock"     # the `ctu=` argument of Oracle / GpuStepper
 
 
 def apply_force_field(stepper, g):

@@ -130,6 +130,13 @@ CASES = {
     "blast3d_nuw": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grid_weights=True,
                               grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
                                     "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 15),
+    # TIME_STEPPING CHARACTERISTIC_TRACING (char_tracing.c): CTU with the characteristic-tracing predictor, 2 components;
+    # rotor2d_chtr_mc_uct0 = the scheme of the shipped Field_Loop #02 (LINEAR, MC_LIM, UCT0), ot2d_chtr_mc_roe #01's with roe
+    "ot2d_chtr": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, tstep="chtr"), 20),
+    "rotor2d_chtr_mc_uct0": (RefConfig(problem="rotor", dims=2, n=(32, 24, 1), first_dt=2.5e-3, cfl=0.4, tstep="chtr", limiter="mc",
+                                       emf="uct0"), 20),
+    "blast2d_chtr_mc_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="chtr", limiter="mc",
+                                      solver="roe"), 20),
     "blast2d_nuw_mc_arith": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, limiter="mc", emf="arith",
                                        grid_weights=True,
                                        grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
