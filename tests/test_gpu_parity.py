@@ -58,6 +58,8 @@ def test_exact_bit_identical_to_reference_golden(name):
 @pytest.mark.parametrize("name", golden_names())
 def test_fast_within_tolerance_of_reference_golden(name):
     g = Golden(name)
+    if g.ctu == "chtr":
+        pytest.skip("TIME_STEPPING CHARACTERISTIC_TRACING is offered with EXACT arithmetic only (test_characteristic_tracing_is_2d_only)")
     s = _stepper(g, "fast")
     s.set_state(g.states[0])
     dt = g.first_dt
@@ -189,6 +191,10 @@ def test_characteristic_tracing_is_2d_only():
         GpuStepper(2, (16, 16, 1), (0.1, 0.1), ctu="chtr", recon="ppm")
     with pytest.raises(PlutoGpuError, match="SHOCK_FLATTENING"):
         GpuStepper(2, (16, 16, 1), (0.1, 0.1), ctu="chtr", flatten=True)
+    # the predictor carries sqrt(cf^2 - a^2) at first order: round-off where the transverse field vanishes, so only the
+    # reference's operation order reproduces the reference -- FAST arithmetic is refused instead of missing the tolerance
+    with pytest.raises(PlutoGpuError, match="EXACT arithmetic only"):
+        GpuStepper(2, (16, 16, 1), (0.1, 0.1), ctu="chtr", arith="fast")
 
 
 def test_nonuniform_grid_is_refused_where_the_weights_would_change():
