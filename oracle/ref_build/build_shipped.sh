@@ -22,6 +22,7 @@ while [ $# -ge 2 ]; do
   # with the characteristic-tracing predictor (ctu_step.o char_tracing.o; plm_states.o still calls CharTracingStep in the GPU build)
   BASE=2d_plm
   if grep -q "TIME_STEPPING *CHARACTERISTIC_TRACING" "$TP/definitions_$NN.h"; then BASE=2d_plm_chtr; fi
+  if grep -q "TIME_STEPPING *HANCOCK" "$TP/definitions_$NN.h"; then BASE=2d_plm_hancock; fi      # ctu_step.o hancock.o
   [ -f "$ORACLE/_build/$BASE/makefile" ] || "$HERE/build_ref.sh" "$BASE"
   for KIND in cpu gpu; do
     B="$ORACLE/_build/shipped_${TAG}_$KIND"
@@ -32,6 +33,7 @@ while [ $# -ge 2 ]; do
     # the object lists of the LINEAR + RK2/RK3 build (oracle/_build/2d_plm/makefile = Src/Templates/makefile + module lists)
     if [ "$KIND" = gpu ]; then
       sed -e 's/rk_step.o update_stage.o/advance_step_gpu.o/' -e 's/ctu_step.o char_tracing.o/advance_step_gpu.o char_tracing.o/' \
+          -e 's/ctu_step.o hancock.o/advance_step_gpu.o hancock.o/' \
           -e "s#^INCLUDE_DIRS = .*#INCLUDE_DIRS = -I. -I\$(SRC) -I$ROOT/include#" \
           -e "s#^LDFLAGS = .*#LDFLAGS = -lm -L$ROOT/pluto_b200/lib -lpluto_gpu -Wl,-rpath,'\$\$ORIGIN/../../../pluto_b200/lib'#" \
           "$ORACLE/_build/$BASE/makefile" > "$B/makefile"

@@ -8,6 +8,11 @@ The binaries are built in the development container by oracle/ref_build/build_sh
   Rotor #01        2-D 400^2, LINEAR, RK2, hlld, ARITHMETIC, MC_LIM, outflow
   Blast #02        3-D 64^3, LINEAR, RK2, roe, VANLEER_LIM, ARITHMETIC, CT_EN_CORRECTION YES, reflective / eqtsymmetric / outflow
   Field_Loop #01   2-D 128 x 64, LINEAR, CHARACTERISTIC_TRACING (corner transport upwind), roe, MC_LIM, UCT_CONTACT, periodic, CFL 0.8
+  Field_Loop #02   the same with CT_EMF_AVERAGE UCT0
+  Blast #01        2-D 200^2, LINEAR, RK2, roe, VANLEER_LIM, ARITHMETIC, CT_EN_CORRECTION YES, outflow
+  Orszag_Tang #05  2-D 256^2, LINEAR, RK3, hlld, MC_LIM, ARITHMETIC, periodic
+  Rayleigh_Taylor #05  2-D 256 x 512, LINEAR, HANCOCK (corner transport upwind), roe, MC_LIM, ARITHMETIC, BODY_FORCE VECTOR,
+                   periodic / reflective
 """
 import os
 import shutil
@@ -21,7 +26,8 @@ from oracle.refrun import read_dbl
 from tests.util import ROOT
 
 SHIPPED = os.path.join(ROOT, "oracle", "_ref", "shipped")
-CASES = [("orszag_tang_03", 3), ("rotor_01", 2), ("blast_02", 1), ("field_loop_01", 4)]
+CASES = [("orszag_tang_03", 3), ("rotor_01", 2), ("blast_02", 1), ("field_loop_01", 4), ("field_loop_02", 3), ("blast_01", 2),
+         ("orszag_tang_05", 2), ("rayleigh_taylor_05", 1)]
 
 
 def _grid(ini):
