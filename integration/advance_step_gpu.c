@@ -109,7 +109,7 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     || (SHOCK_FLATTENING != NO && (SHOCK_FLATTENING != MULTID || RECONSTRUCTION != LINEAR))
   #error "libpluto_gpu: FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID with LINEAR are not available on the GPU"
 #endif
-#if CHAR_LIMITING == YES && (DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || (TIME_STEPPING != RK2 && TIME_STEPPING != RK3) \
+#if CHAR_LIMITING == YES && (DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || (TIME_STEPPING != RK2 && TIME_STEPPING != RK3 && CT_EN_CORRECTION == YES) \
                              || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EMF_AVERAGE == UCT_HLL)
   #error "libpluto_gpu: CHAR_LIMITING YES is available in 2-D with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
 #endif
@@ -138,9 +138,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
   #endif
     c.time_stepping = PLUTO_GPU_TS_HANCOCK;                /* ctu_step.c */
 #elif TIME_STEPPING == CHARACTERISTIC_TRACING
-  #if DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || CHAR_LIMITING == YES || SHOCK_FLATTENING != NO || BODY_FORCE != NO \
+  #if DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || BODY_FORCE != NO \
       || CT_EN_CORRECTION == YES || CT_EMF_AVERAGE == UCT_HLL || (defined CHTR_REF_STATE && CHTR_REF_STATE != 3)
-    #error "libpluto_gpu, TIME_STEPPING CHARACTERISTIC_TRACING: 2-D, LINEAR, CHAR_LIMITING NO, no SHOCK_FLATTENING / BODY_FORCE / CT_EN_CORRECTION, CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
+    #error "libpluto_gpu, TIME_STEPPING CHARACTERISTIC_TRACING: 2-D, LINEAR, no SHOCK_FLATTENING / BODY_FORCE / CT_EN_CORRECTION, CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
   #endif
     c.time_stepping = PLUTO_GPU_TS_CHAR_TRACING;           /* ctu_step.c with char_tracing.c:278-560 as the predictor */
 #endif

@@ -1870,7 +1870,8 @@ static void ctu_advance (Oracle *o, double dt)
         o->pflag[n] = o->flag[id];
       }
       /* 4d. States (nbeg-1 .. nend+1): PLM (incl. face field), Hancock, PrimToCons (plm_states.c:80-312) */
-      states_plm (o, nbeg-1, nend+1, q.bn);
+      if (o->c.char_limiting) states_plm_char (o, nbeg-1, nend+1, q);      /* CHAR_LIMITING YES (plm_states.c:448-706) */
+      else                    states_plm (o, nbeg-1, nend+1, q.bn);
       if (o->c.ctu == 2) char_tracing_step (o, nbeg-1, nend+1, q, dt, dir);      /* TIME_STEPPING CHARACTERISTIC_TRACING */
       else               hancock_step (o, nbeg-1, nend+1, q, dt, o->c.dx[dir]);
       for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vp[n], o->up[n]); }

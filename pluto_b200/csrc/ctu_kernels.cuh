@@ -62,12 +62,13 @@ __device__ __forceinline__ void prim_rhs (const Phys &ph, const double *v, const
 template <int DIR, int NC, bool FLAT>
 __device__ __forceinline__ void ctu_states (const Phys &ph, int limiter, unsigned fl, const double *vl, const double *v,
                                             const double *vr, double bsm, double bsp, double dt_2, double d_dl,
-                                            double src_n, double *vp, double *vm, double chtr_dtdx = 0.0)
+                                            double src_n, double *vp, double *vm, double chtr_dtdx = 0.0, int char_lim = 0)
 {
   typedef Dirs<DIR> D;
   double dvm[NV], dvp[NV], dv[NV], Adv[NV];
   PG_FOR_NV(nv){ dvm[nv] = v[nv] - vl[nv]; dvp[nv] = vr[nv] - v[nv]; }
   if (FLAT && (fl & 1u)) plm_zone_single<NC>(2, v, dvm, dvp, vp, vm);
+  else if (NC == 2 && DIR < 2 && char_lim) plm_zone_char2<DIR>(ph, limiter, v, dvm, dvp, vp, vm);     // CHAR_LIMITING YES
   else                   plm_zone<NC>(limiter, v, dvm, dvp, vp, vm);
   vp[D::bn] = bsp; vm[D::bn] = bsm;
   if (NC == 2 && DIR < 2 && chtr_dtdx > 0.0){
@@ -211,7 +212,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     double src_n = 0.0, dphi = 0.0;                    // PrimSource of the normal velocity (prim_eqn.c:289-307)
     if (a.bf) src_n += gz;
     if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - 1); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
-    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0);
+    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0, a.char_lim);
     // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
     // V^{n+1/2} (ctu_step.c:566-570) in the corrector
     double rho_c = 0.0;
@@ -382,7 +383,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       double src_n = 0.0, dphi = 0.0;                  // PrimSource of the normal velocity (prim_eqn.c:289-307)
       if (a.bf) src_n += gz;
       if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - sD); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
-      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0);
+      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0, a.char_lim);
       const double rho_z = ((a.bf || a.phif) && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
       if (PHASE == 0){
         prim_to_cons<NC>(ph, vp, up);

@@ -146,6 +146,7 @@ struct CtuArgs {
   const double *phic, *phif; // BODY_FORCE & POTENTIAL: potential at the centres / the faces of this direction (else NULL)
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
   int     chtr;              // TIME_STEPPING CHARACTERISTIC_TRACING: predictor by characteristic tracing (2 components)
+  int     char_lim;          // CHAR_LIMITING YES (2 components): slopes limited on the characteristic variables (plm_zone_char2)
 };
 
 struct FinalArgs {

@@ -175,8 +175,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     if (cfg->dims != 2)
       return fail ("TIME_STEPPING CHARACTERISTIC_TRACING is available in 2-D only (in 3-D the reference's eigenvector scratch, eigenv.c:190-560, "
                    "keeps entries of the previous sweep direction: its result depends on the sweep order and cannot be reproduced)");
-    if (cfg->shock_flattening || cfg->body_force || cfg->en_correction || cfg->char_limiting)
-      return fail ("TIME_STEPPING CHARACTERISTIC_TRACING is available without SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION and CHAR_LIMITING");
+    if (cfg->shock_flattening || cfg->body_force || cfg->en_correction)
+      return fail ("TIME_STEPPING CHARACTERISTIC_TRACING is available without SHOCK_FLATTENING, BODY_FORCE and CT_EN_CORRECTION");
     // The traced states contain alpha_s = sqrt((cf^2 - a^2)/...) at FIRST order (the fast and the slow family are weighted by their
     // own Courant numbers), and where the transverse field vanishes exactly that difference is pure round-off: the reference's own
     // result moves by 1e-9 with the last bit of the state.  Only its operation order reproduces it, so the re-associated FAST
@@ -197,9 +197,10 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     if (cfg->dims != 2)
       return fail ("CHAR_LIMITING YES is available in 2-D only (in 3-D the reference's eigenvector scratch, eigenv.c:190-560, keeps "
                    "entries of the previous sweep direction: its result depends on the sweep order and cannot be reproduced)");
-    if (cfg->recon != PLUTO_GPU_RECON_LINEAR || cfg->time_stepping != PLUTO_GPU_TS_RK || cfg->shock_flattening || cfg->body_force
-        || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
-      return fail ("CHAR_LIMITING YES is available with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL");
+    if (cfg->recon != PLUTO_GPU_RECON_LINEAR || cfg->shock_flattening || cfg->body_force || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL
+        || (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->en_correction))
+      return fail ("CHAR_LIMITING YES is available with LINEAR reconstruction (RK2 / RK3 / HANCOCK / CHARACTERISTIC_TRACING), without "
+                   "SHOCK_FLATTENING, BODY_FORCE and UCT_HLL");
   }
   if (cfg->time_stepping != PLUTO_GPU_TS_RK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");
@@ -1037,6 +1038,7 @@ static int run_ctu (PlutoGpu *h, int part)
   }
   s.red = h->red; s.flag = h->flag; s.g = g; s.ph = h->ph; s.dtp = h->dtdev; s.limiter = h->cfg.limiter;
   s.chtr = (h->cfg.time_stepping == PLUTO_GPU_TS_CHAR_TRACING);
+  s.char_lim = h->cfg.char_limiting;
   s.en_corr = h->cfg.en_correction;
   s.bf = h->cfg.body_force & 1;
   for (int d = 0; d < 3; d++) s.grav[d] = h->cfg.grav[d];

@@ -33,7 +33,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # UNIFORM_CARTESIAN_GRID NO: the shim hands the arrays of PLM_CoefficientsGet to pluto_gpu_set_plm_coeffs
          "blast3d_nuw", "blast2d_nuw_mc_arith",
          # TIME_STEPPING CHARACTERISTIC_TRACING (2-D): the shim replaces ctu_step.o, plm_states.o keeps char_tracing.o
-         "ot2d_chtr", "rotor2d_chtr_mc_uct0", "blast2d_chtr_mc_roe"]
+         "ot2d_chtr", "rotor2d_chtr_mc_uct0", "blast2d_chtr_mc_roe",
+         # CHAR_LIMITING YES with the corner-transport-upwind steps (Orszag_Tang #09's scheme; with characteristic tracing)
+         "ot2d_ctu_cl_mc_arith", "blast2d_chtr_cl"]
 
 
 def _blast_params(g):

@@ -118,6 +118,10 @@ CASES = [
     # 2 components (3: the reference's eigenvector scratch keeps entries of the previous sweep direction, as with CHAR_LIMITING)
     ("ot2d_chtr", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, tstep="chtr", cfl=0.4), 10),
     ("blast2d_chtr_mc_roe", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="roe"), 12),
+    # CHAR_LIMITING YES with the corner-transport-upwind steps: ot2d_ctu_cl_mc_arith = the scheme of the shipped Orszag_Tang #09
+    ("ot2d_ctu_cl_mc_arith", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, tstep="hancock", char_lim=True, limiter="mc",
+                                       emf="arith"), 10),
+    ("blast2d_chtr_cl", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", char_lim=True), 10),
     ("rotor2d_chtr_mc_uct0_hll", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), first_dt=2e-3, tstep="chtr", limiter="mc", emf="uct0",
                                            solver="hll"), 10),
 ]

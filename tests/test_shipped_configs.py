@@ -11,6 +11,7 @@ The binaries are built in the development container by oracle/ref_build/build_sh
   Field_Loop #02   the same with CT_EMF_AVERAGE UCT0
   Blast #01        2-D 200^2, LINEAR, RK2, roe, VANLEER_LIM, ARITHMETIC, CT_EN_CORRECTION YES, outflow
   Orszag_Tang #05  2-D 256^2, LINEAR, RK3, hlld, MC_LIM, ARITHMETIC, periodic
+  Orszag_Tang #09  2-D 512^2, LINEAR, HANCOCK (corner transport upwind), hlld, MC_LIM, ARITHMETIC, CHAR_LIMITING YES, periodic
   Rayleigh_Taylor #05  2-D 256 x 512, LINEAR, HANCOCK (corner transport upwind), roe, MC_LIM, ARITHMETIC, BODY_FORCE VECTOR,
                    periodic / reflective
 """
@@ -27,7 +28,7 @@ from tests.util import ROOT
 
 SHIPPED = os.path.join(ROOT, "oracle", "_ref", "shipped")
 CASES = [("orszag_tang_03", 3), ("rotor_01", 2), ("blast_02", 1), ("field_loop_01", 4), ("field_loop_02", 3), ("blast_01", 2),
-         ("orszag_tang_05", 2), ("rayleigh_taylor_05", 1)]
+         ("orszag_tang_05", 2), ("rayleigh_taylor_05", 1), ("orszag_tang_09", 1)]
 
 
 def _grid(ini):

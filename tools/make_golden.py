@@ -137,6 +137,10 @@ CASES = {
                                        emf="uct0"), 20),
     "blast2d_chtr_mc_roe": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="chtr", limiter="mc",
                                       solver="roe"), 20),
+    # CHAR_LIMITING YES with the corner-transport-upwind steps; ot2d_ctu_cl_mc_arith = the scheme of the shipped Orszag_Tang #09
+    "ot2d_ctu_cl_mc_arith": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, tstep="hancock", char_lim=True,
+                                       limiter="mc", emf="arith"), 20),
+    "blast2d_chtr_cl": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="chtr", char_lim=True), 20),
     "blast2d_nuw_mc_arith": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, limiter="mc", emf="arith",
                                        grid_weights=True,
                                        grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
