@@ -323,6 +323,10 @@ int  pluto_gpu_multi_nghost (const PlutoGpuMulti *m);
 int  pluto_gpu_multi_nblocks (const PlutoGpuMulti *m);
 int  pluto_gpu_multi_upload_data (PlutoGpuMulti *m, const double *Vc, const double *Vs1, const double *Vs2, const double *Vs3);
 int  pluto_gpu_multi_download_data (PlutoGpuMulti *m, double *Vc, double *Vs1, double *Vs2, double *Vs3);
+/* pluto_gpu_set_grid / pluto_gpu_set_plm_coeffs for the blocks: arrays of the WHOLE domain (gn[d] + 2 nghost entries), sliced per block */
+int  pluto_gpu_multi_set_grid (PlutoGpuMulti *m, const double *dx1, const double *dx2, const double *dx3);
+int  pluto_gpu_multi_set_plm_coeffs (PlutoGpuMulti *m, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
+                                     const double *dp, const double *dm);
 int  pluto_gpu_multi_advance (PlutoGpuMulti *m, double dt, PlutoGpuStepInfo *info);
 int  pluto_gpu_multi_advance_data (PlutoGpuMulti *m, double dt, double *Vc, double *Vs1, double *Vs2, double *Vs3,
                                    PlutoGpuStepInfo *info);

@@ -177,10 +177,6 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
              "  BODY_FORCE, CT_EN_CORRECTION and CHAR_LIMITING on the GPU\n");
       QUIT_PLUTO(1);
 #endif
-      if (ndev_blocks > 1){
-        print ("! AdvanceStep(gpu): PLUTO_GPU_NDEV > 1 is not available on a non-uniform grid\n");
-        QUIT_PLUTO(1);
-      }
     }
     c.arith    = (arith != NULL && !strcmp (arith, "fast")) ? PLUTO_GPU_ARITH_FAST : PLUTO_GPU_ARITH_EXACT;
     c.device   = getenv ("PLUTO_GPU_DEVICE") ? atoi (getenv ("PLUTO_GPU_DEVICE")) : 0;
@@ -211,20 +207,18 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
              gpum ? pluto_gpu_multi_nghost (gpum) : pluto_gpu_nghost (gpu), grid->nghost[IDIR]);
       QUIT_PLUTO(1);
     }
-    if (nonuniform && pluto_gpu_set_grid (gpu, grid->dx[IDIR], grid->dx[JDIR], DIMENSIONS == 3 ? grid->dx[KDIR] : NULL) != 0){
+    if (nonuniform && (gpum ? pluto_gpu_multi_set_grid (gpum, grid->dx[IDIR], grid->dx[JDIR], DIMENSIONS == 3 ? grid->dx[KDIR] : NULL)
+                            : pluto_gpu_set_grid (gpu, grid->dx[IDIR], grid->dx[JDIR], DIMENSIONS == 3 ? grid->dx[KDIR] : NULL)) != 0){
       print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
       QUIT_PLUTO(1);
     }
 #if UNIFORM_CARTESIAN_GRID == NO && RECONSTRUCTION == LINEAR
     /* grid-dependent reconstruction weights: the arrays PLM_CoefficientsSet built for this grid (plm_coeffs.c:30-104) */
-    if (ndev_blocks > 1){
-      print ("! AdvanceStep(gpu): PLUTO_GPU_NDEV > 1 is not available with UNIFORM_CARTESIAN_GRID NO\n");
-      QUIT_PLUTO(1);
-    }
     for (idim = 0; idim < DIMENSIONS; idim++){
       PLM_Coeffs pc;
       PLM_CoefficientsGet (&pc, idim);
-      if (pluto_gpu_set_plm_coeffs (gpu, idim, pc.cp, pc.cm, pc.wp, pc.wm, pc.dp, pc.dm) != 0){
+      if ((gpum ? pluto_gpu_multi_set_plm_coeffs (gpum, idim, pc.cp, pc.cm, pc.wp, pc.wm, pc.dp, pc.dm)
+                : pluto_gpu_set_plm_coeffs (gpu, idim, pc.cp, pc.cm, pc.wp, pc.wm, pc.dp, pc.dm)) != 0){
         print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
         QUIT_PLUTO(1);
       }

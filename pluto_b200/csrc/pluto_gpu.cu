@@ -1810,6 +1810,34 @@ int pluto_gpu_multi_create (const PlutoGpuConfig *cfg, const int grid[3], const 
   return 0;
 }
 
+// non-uniform grid / grid-dependent reconstruction weights of the WHOLE domain: every block takes its slice (its own zones and the
+// ghost entries on either side are contiguous in the global arrays)
+int pluto_gpu_multi_set_grid (PlutoGpuMulti *m, const double *dx1, const double *dx2, const double *dx3)
+{
+  const double *src[3] = {dx1, dx2, dx3};
+  for (int b = 0; b < m->nb; b++){
+    int c[3]; pgm_coords (m, b, c);
+    const double *p[3] = {NULL, NULL, NULL};
+    for (int d = 0; d < m->dims; d++){
+      if (!src[d]) return fail ("pluto_gpu_multi_set_grid: NULL array for direction %d", d + 1);
+      p[d] = src[d] + (size_t)c[d]*m->ln[d];
+    }
+    if (pluto_gpu_set_grid (m->blk[b], p[0], p[1], p[2])) return 1;
+  }
+  return 0;
+}
+int pluto_gpu_multi_set_plm_coeffs (PlutoGpuMulti *m, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
+                                    const double *dp, const double *dm)
+{
+  if (dir < 0 || dir >= m->dims) return fail ("pluto_gpu_multi_set_plm_coeffs: direction %d", dir);
+  for (int b = 0; b < m->nb; b++){
+    int c[3]; pgm_coords (m, b, c);
+    const size_t off = (size_t)c[dir]*m->ln[dir];
+    if (pluto_gpu_set_plm_coeffs (m->blk[b], dir, cp + off, cm + off, wp + off, wm + off, dp + off, dm + off)) return 1;
+  }
+  return 0;
+}
+
 int pluto_gpu_device_count (void)
 {
   int n = 0;

@@ -80,6 +80,12 @@ class BlockLayout:
         c, n = self.coords(rank), self.local_n(rank)
         return tuple(c[d] * n[d] for d in range(3))
 
+    def slice_1d(self, rank, dim, arr, ng):
+        """The block's part of a per-direction array of the WHOLE grid (zone widths, reconstruction weights; global_n[dim] + 2 ng
+        entries, ghost zones included): its own zones and ng ghost entries on either side."""
+        o, n = self.offset(rank)[dim], self.local_n(rank)[dim]
+        return np.ascontiguousarray(np.asarray(arr, dtype=np.float64)[o:o + n + 2 * ng])
+
     def neighbour(self, rank, dim, side):
         """rank of the block abutting `side` (0 low, 1 high) along dim, or None."""
         if self.grid[dim] == 1:
@@ -402,6 +408,16 @@ class DistStepper:
                 self._ev_shell = torch.cuda.Event()
                 self._ev_comm = torch.cuda.Event()
 
+    def set_grid(self, *global_dx):
+        """Non-uniform grid: the zone widths of the WHOLE grid per direction (ghost zones included); every rank takes its slice."""
+        ng = self.block.ng
+        self.block.set_grid(*[self.layout.slice_1d(self.rank, d, a, ng) for d, a in enumerate(global_dx[:self.dims])])
+
+    def set_plm_coeffs(self, global_coeffs):
+        """UNIFORM_CARTESIAN_GRID NO: the six weight arrays of the WHOLE grid per direction; every rank takes its slice."""
+        ng = self.block.ng
+        self.block.set_plm_coeffs([[self.layout.slice_1d(self.rank, d, a, ng) for a in six] for d, six in enumerate(global_coeffs)])
+
     def _drain(self):
         """The state is about to be replaced from outside: forget the exchange in flight."""
         if self.world > 1 and self.overlap and self._prefetched is not None:
@@ -587,6 +603,14 @@ class LocalMultiBlock:
                 sp = [self.nsend[(r, o)].data_ptr() for o, _ in nbrs]
                 rp = [self.nsend[(nb, tuple(-c for c in o))].data_ptr() for o, nb in nbrs]
                 b.halo_plan([o for o, _ in nbrs], sp, rp)
+
+    def set_grid(self, *global_dx):
+        for r, b in enumerate(self.blocks):
+            b.set_grid(*[self.layout.slice_1d(r, d, a, b.ng) for d, a in enumerate(global_dx[:self.layout.dims])])
+
+    def set_plm_coeffs(self, global_coeffs):
+        for r, b in enumerate(self.blocks):
+            b.set_plm_coeffs([[self.layout.slice_1d(r, d, a, b.ng) for a in six] for d, six in enumerate(global_coeffs)])
 
     def set_state(self, global_state):
         lay = self.layout

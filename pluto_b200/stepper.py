@@ -418,6 +418,17 @@ class MultiGpuStepper:
         if rc != 0:
             raise PlutoGpuError(_lib.last_error(self.L))
 
+    def set_grid(self, dx1, dx2, dx3=None):
+        """Zone widths of the WHOLE domain per direction (ghost zones included); every block takes its slice."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (dx1, dx2, dx3)]
+        self._check(self.L.pluto_gpu_multi_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
+    def set_plm_coeffs(self, coeffs):
+        """UNIFORM_CARTESIAN_GRID NO: per direction the six weight arrays of the WHOLE domain."""
+        for d, six in enumerate(coeffs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in six]
+            self._check(self.L.pluto_gpu_multi_set_plm_coeffs(self._h, d, *[a.ctypes.data for a in arrs]))
+
     def data_buffers(self):
         n1, n2, n3 = self.n
         g = self.ng

@@ -84,7 +84,7 @@ def test_emulated_fast_kernels_within_tolerance(name, emu_lib):
 # (RK and corner transport upwind), NextTimeStep on the device, reflective walls, the reference Data layout.
 GPU_SUITE_SLICE = ("6x6x6 or 6x7x1 or 31x200x1 or (decomposed and gn7 and split) or (decomposed and gn4 and all) "
                    "or (decomposed and gn2 and dims) or (device_next_dt and ot-2) or reflective or data_layout "
-                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2) or (body_force and rotor) or tma_staging or (flux_difference_kept_apart and blast) or (nonuniform_grid and (rotor or turb or refused)) or characteristic_tracing_is_2d")
+                   "or turb3d_plm_hll_rk2 or ot2d_plm_hlld_rk2_1 or blast2d_ppm_roe_rk3 or (en_correction and ot-2) or (body_force and rotor) or tma_staging or (flux_difference_kept_apart and blast) or (nonuniform_grid and (rotor or turb or refused)) or characteristic_tracing_is_2d or (decomposed_blocks_on_a_nonuniform and ot-2)")
 
 
 def test_gpu_test_files_through_the_interpreter(emu_lib):

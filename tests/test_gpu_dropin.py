@@ -117,7 +117,9 @@ def test_resident_state_drop_in(name, arith):
 
 
 @pytest.mark.parametrize("name,ndev,resident", [("turb3d_plm_hlld", 8, False), ("blast3d_plm_hlld_100", 4, True), ("rotor2d_ppm_roe", 2, False),
-                                                ("ot2d_ctu", 4, True), ("ot2d_cl", 2, False)])
+                                                ("ot2d_ctu", 4, True), ("ot2d_cl", 2, False),
+                                                # non-uniform grid / grid-dependent weights: every block takes its slice
+                                                ("blast3d_nug", 4, False), ("blast2d_nuw_mc_arith", 2, True)])
 def test_reference_driver_on_several_blocks(name, ndev, resident):
     """PLUTO_GPU_NDEV: the reference's serial, single-threaded driver with the domain cut into 2 / 4 / 8 blocks (one per GPU where
     the box has them, round robin otherwise), driven through pluto_gpu_multi_* -- no MPI, no Python.  Dumps bit-identical to the
