@@ -243,8 +243,9 @@ void Analysis (const Data *d, Grid *grid)
       fwrite (rec, sizeof(double), 1, fp);
       fwrite (grid->dx[dir], sizeof(double), grid->np_tot[dir], fp);
     }
-#if UNIFORM_CARTESIAN_GRID == NO && RECONSTRUCTION == LINEAR
-    for (dir = 0; dir < DIMENSIONS; dir++){     /* reconstruction weights of every direction: cp, cm, wp, wm, dp, dm */
+#if (UNIFORM_CARTESIAN_GRID == NO && RECONSTRUCTION == LINEAR) || (SHOCK_FLATTENING == MULTID && RECONSTRUCTION == PARABOLIC)
+    for (dir = 0; dir < DIMENSIONS; dir++){     /* reconstruction weights of every direction: cp, cm, wp, wm, dp, dm (PARABOLIC +
+                                                   MULTID: what the minmod fallback of flagged zones takes, ppm_states.c:167-181) */
       PLM_Coeffs c;
       PLM_CoefficientsGet (&c, dir);
       {                                         /* first and last zone are never set (plm_coeffs.c:62-64): written as 0 */

@@ -594,6 +594,23 @@ __device__ __forceinline__ void ppm_zone (const double *v, const double *Wm, con
   }
 }
 
+// SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: a zone flagged FLAG_MINMOD falls back to the minmod-limited linear
+// states with the weights of PLM_CoefficientsGet (ppm_states.c:167-181) -- wp, wm, dp, dm of the zone; on a uniform grid they are 1
+// and 1/2 only up to the round-off of the grid coordinates, so the host hands the reference's arrays over (pluto_gpu_set_plm_coeffs)
+template <int NC, int SKIP = -1>
+__device__ __forceinline__ void ppm_flat_zone (const double *const *pc, int n, const double *vl, const double *v, const double *vr,
+                                               double *vp, double *vm)
+{
+  const double wp = __ldg (pc[2] + n), wm = __ldg (pc[3] + n), dp = __ldg (pc[4] + n), dm = __ldg (pc[5] + n);
+  PG_FOR_NV_SKIP(nv, SKIP){
+    const double dvp = (vr[nv] - v[nv])*wp;
+    const double dvm = (v[nv] - vl[nv])*wm;
+    const double dv  = minmod (dvp, dvm);
+    vp[nv] = v[nv] + dv*dp;
+    vm[nv] = v[nv] - dv*dm;
+  }
+}
+
 // ---------------------------------------------------------------------------
 //  mappers
 // ---------------------------------------------------------------------------

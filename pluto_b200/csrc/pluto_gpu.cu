@@ -166,9 +166,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
   if (cfg->limiter < 0 || cfg->limiter > PLUTO_GPU_LIM_MC) return fail ("bad limiter");
   if (cfg->shock_flattening != 0 && cfg->shock_flattening != 1) return fail ("bad shock_flattening");
-  if (cfg->shock_flattening && cfg->recon == PLUTO_GPU_RECON_PARABOLIC)
-    return fail ("SHOCK_FLATTENING MULTID is available with LINEAR reconstruction only (the reference's PARABOLIC "
-                 "fallback takes its weights from PLM_CoefficientsGet, ppm_states.c:167-181)");
+  if (cfg->shock_flattening && cfg->recon == PLUTO_GPU_RECON_PARABOLIC && cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
+    return fail ("SHOCK_FLATTENING MULTID with PARABOLIC reconstruction is not available with CT_EMF_AVERAGE UCT_HLL");
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
   if (cfg->time_stepping < PLUTO_GPU_TS_RK || cfg->time_stepping > PLUTO_GPU_TS_CHAR_TRACING) return fail ("bad time_stepping");
   if (cfg->time_stepping == PLUTO_GPU_TS_CHAR_TRACING){
@@ -592,10 +591,12 @@ int pluto_gpu_set_plm_coeffs (PlutoGpu *h, int dir, const double *cp, const doub
   CU (cudaSetDevice (h->cfg.device));
   const Geom &g = h->g;
   if (dir < 0 || dir >= g.dims) return fail ("pluto_gpu_set_plm_coeffs: direction %d", dir);
-  if (h->ctu || h->cfg.recon != PLUTO_GPU_RECON_LINEAR || h->cfg.shock_flattening || h->cfg.body_force || h->cfg.en_correction
-      || h->cfg.char_limiting || h->cfg.emf_average == PLUTO_GPU_EMF_UCT_HLL)
+  // PARABOLIC + SHOCK_FLATTENING MULTID: the weights serve the minmod fallback of flagged zones (ppm_states.c:167-181) only
+  const bool ppm_flat = (h->cfg.recon == PLUTO_GPU_RECON_PARABOLIC && h->cfg.shock_flattening && !h->ctu);
+  if (!ppm_flat && (h->ctu || h->cfg.recon != PLUTO_GPU_RECON_LINEAR || h->cfg.shock_flattening || h->cfg.body_force || h->cfg.en_correction
+                    || h->cfg.char_limiting || h->cfg.emf_average == PLUTO_GPU_EMF_UCT_HLL))
     return fail ("pluto_gpu_set_plm_coeffs: grid-dependent reconstruction weights need RK2 / RK3 with LINEAR reconstruction, without "
-                 "SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION, CHAR_LIMITING and UCT_HLL");
+                 "SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION, CHAR_LIMITING and UCT_HLL (or PARABOLIC with SHOCK_FLATTENING MULTID)");
   const double *src[6] = {cp, cm, wp, wm, dp, dm};
   for (int q = 0; q < 6; q++) if (!src[q]) return fail ("pluto_gpu_set_plm_coeffs: NULL array");
   int maxT = 1;
@@ -612,7 +613,7 @@ int pluto_gpu_set_plm_coeffs (PlutoGpu *h, int dir, const double *cp, const doub
     CU (cudaMemcpy (dev, src[q], (size_t)g.T[dir]*sizeof (double), cudaMemcpyHostToDevice));
     h->plmc[dir][q] = dev;
   }
-  h->plmw = 1;
+  h->plmw = (h->cfg.recon == PLUTO_GPU_RECON_LINEAR);
   for (int d = 0; d < g.dims; d++) if (!h->plmc[d][0]) h->plmw = 0;
   if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }
   return 0;
@@ -921,6 +922,9 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     else { s.e1 = h->eyk; s.e2 = h->exk; }
     for (int c = 0; c < 3; c++) s.dvel[c] = h->dvel[c][dir];
     const int recon = h->plmw ? 2 /* RECON_PLMW */ : h->cfg.recon;
+    if (h->flag && h->cfg.recon == PLUTO_GPU_RECON_PARABOLIC && !h->plmc[dir][0])
+      return fail ("SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: hand over the weights of PLM_CoefficientsGet first "
+                   "(pluto_gpu_set_plm_coeffs; ppm_states.c:167-181 takes them for the zones it flattens)");
     for (int q = 0; q < 6; q++){ s.pc[q] = h->plmc[dir][q]; s.pc2[q] = h->plmc[1][q]; }
     if (dir > 0 || fuse_xy){
       // zones per thread along a marching sweep: long enough to amortise the

@@ -319,6 +319,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
       ppm_interface<NC>(vl, v, vr, vrr, Wi);
       PG_FOR_NV(nv) Wm[nv] = __shfl_up_sync (0xffffffffu, Wi[nv], 1);
       ppm_zone<NC>(v, Wm, Wi, vp, vm);
+      if (FLAT && (fl & 1u)) ppm_flat_zone<NC>(a.pc, i, vl, v, vr, vp, vm);         // FLAG_MINMOD, ppm_states.c:167-181
     }
 
     // right interface state of face i+1/2 = minus state of zone i+1
@@ -526,6 +527,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       ppm_interface<NC, SK>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
       ppm_interface<NC, SK>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
       ppm_zone<NC, SK>(vb_, Wm, Wf, vpL, vm_unused);
+      if (FLAT && (a.flag[id] & 1u)) ppm_flat_zone<NC, SK>(a.pc, c0 - 1, va_, vb_, vc_, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
       PG_FOR_NV_SKIP(nv, SK) C_WF(nv) = Wf[nv];
     }
@@ -582,6 +584,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
         PG_FOR_NV_SKIP(nv, SK) Wf[nv] = C_WF(nv);
         ppm_interface<NC, SK>(vb_, vc_, vd_, vnx, Wn);    // W[f+1]
         ppm_zone<NC, SK>(vc_, Wf, Wn, vpn, vR);
+        if (FLAT && (flc & 1u)) ppm_flat_zone<NC, SK>(a.pc, f + 1, vb_, vc_, vd_, vpn, vR);
         PG_FOR_NV_SKIP(nv, SK) C_WF(nv) = Wn[nv];
       }
       if (hll && in_range) store_vel_slopes<NC>(a.dvel, id + sD, vpn, vR);      // zone f+1
@@ -812,6 +815,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       ppm_interface<NC, SKP>(vz_, va_, vb_, vc_, Wm);
       ppm_interface<NC, SKP>(va_, vb_, vc_, vd_, Wf);
       ppm_zone<NC, SKP>(vb_, Wm, Wf, vpL, vm_unused);
+      if (FLAT && (a.flag[id] & 1u)) ppm_flat_zone<NC, SKP>(a.pc2, c0 - 1, va_, vb_, vc_, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
       PG_FOR_NV_SKIP(nv, SKP) C_WF(nv) = Wf[nv];
     }
@@ -872,6 +876,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
         PG_FOR_NV(nv) Wm[nv] = __shfl_up_sync (0xffffffffu, Wi[nv], 1);
         ppm_zone<NC>(v, Wm, Wi, vp, vm);
+        if (FLAT && (flz & 1u)) ppm_flat_zone<NC>(a.pc, i, xvl, v, xvr, vp, vm);
       }
       double vR[NV];
       PG_FOR_NV(nv) vR[nv] = __shfl_down_sync (0xffffffffu, vm[nv], 1);
@@ -930,6 +935,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         PG_FOR_NV_SKIP(nv, SKY) Wf[nv] = C_WF(nv);
         ppm_interface<NC, SKY>(v, vc_, vd_, vnx, Wn);       // W[f+1]
         ppm_zone<NC, SKY>(vc_, Wf, Wn, vpn, vR);
+        if (FLAT && (fln & 1u)) ppm_flat_zone<NC, SKY>(a.pc2, f + 1, v, vc_, vd_, vpn, vR);
         PG_FOR_NV_SKIP(nv, SKY) C_WF(nv) = Wn[nv];
       }
       if (hll && col_ok) store_vel_slopes<NC>(a.dvel2, id + sD, vpn, vR);       // row f+1
@@ -1054,10 +1060,10 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
       if (a.plan) plan_chunks (b, g.n[1], nwarp1*32*1000/TPB, bps);                                   \
       const unsigned nb = (unsigned)((nwarp1*b.nchunk*32 + TPB - 1)/TPB);                             \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
-#define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
+#define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = a.flag != nullptr;     /* PARABOLIC + MULTID: not with UCT_HLL (create) */ \
       if (bf)             PG_LXY2(R, C, false, false, true);          /* refused with UCT_HLL / flattening at create */ \
       else if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, P); else PG_LXY1(R, C, true, false); }                       \
-      else if (fl)        PG_LXY1(R, C, false, P);                                                                     \
+      else if (fl)        PG_LXY1(R, C, false, true);                                                                  \
       else if (a.char_lim && P && C == 2) PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, false, false, false, false, true>)); \
       else if (a.tma)     PG_LXY3(R, C);                               /* TMA staging of the ring rows */              \
       else                PG_LXY1(R, C, false, false); } while (0)
@@ -1092,12 +1098,12 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const long long nwarp = nseg*((nrows + PG_XROWS - 1)/PG_XROWS);
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
     const size_t xsmem = (size_t)(TPB/32)*2*9*36*sizeof (double);
-#define PG_LX(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;             \
+#define PG_LX(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = a.flag != nullptr;                  \
       if (a.char_lim && P && C == 2) sweep_x_kernel<RECON_PLM, SOLVER, 2, false, false, false, true><<<nb, TPB, xsmem, s>>>(a); \
       else if (bf) sweep_x_kernel<R, SOLVER, C, false, false, true><<<nb, TPB, xsmem, s>>>(a);                            \
       else if (a.avg == 3){ if (fl) sweep_x_kernel<R, SOLVER, C, true, P><<<nb, TPB, xsmem, s>>>(a);                     \
                        else    sweep_x_kernel<R, SOLVER, C, true, false><<<nb, TPB, xsmem, s>>>(a); }               \
-      else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, P><<<nb, TPB, xsmem, s>>>(a);                    \
+      else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, true><<<nb, TPB, xsmem, s>>>(a);                 \
                        else    sweep_x_kernel<R, SOLVER, C, false, false><<<nb, TPB, xsmem, s>>>(a); } } while (0)
     if      (recon == RECON_PLMW && nc == 3) sweep_x_kernel<RECON_PLMW, SOLVER, 3, false, false><<<nb, TPB, xsmem, s>>>(a);
     else if (recon == RECON_PLMW && nc == 2) sweep_x_kernel<RECON_PLMW, SOLVER, 2, false, false><<<nb, TPB, xsmem, s>>>(a);
@@ -1121,12 +1127,12 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       if (a.plan) plan_chunks (b, g.n[dir], npen*1000/TPB, bps);                                      \
       const unsigned nb = (unsigned)((npen*b.nchunk + TPB - 1)/TPB);                                  \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
-#define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = P && a.flag != nullptr;          \
+#define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = a.flag != nullptr;               \
       if (a.char_lim && P && C == 2 && DD == 1){ smem = (size_t)march_slots (RECON_PLM, true)*TPB*sizeof (double);            \
                                                  PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, false, true>)); } \
       else if (bf)        PG_LM2(DD, R, C, false, false, true);                                                      \
       else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, P); else PG_LM1(DD, R, C, true, false); }                    \
-      else           { if (fl) PG_LM1(DD, R, C, false, P); else PG_LM1(DD, R, C, false, false); } } while (0)
+      else           { if (fl) PG_LM1(DD, R, C, false, true); else PG_LM1(DD, R, C, false, false); } } while (0)
     if (dir == 1){
       if      (recon == RECON_PLMW && nc == 3) PG_LM1(1, RECON_PLMW, 3, false, false);
       else if (recon == RECON_PLMW && nc == 2) PG_LM1(1, RECON_PLMW, 2, false, false);

@@ -56,7 +56,7 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
                "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf", "blast2d_ctu_bfx_roe",
-               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3", "blast3d_nug", "blast2d_nug_mc_arith_reflective"]
+               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3", "blast3d_nug", "blast2d_nug_mc_arith_reflective", "blast3d_ppm_sfl"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)
@@ -105,7 +105,7 @@ def test_reference_driver_with_interpreted_kernels(emu_lib, tmp_path):
     libdir.mkdir()
     os.symlink(emu_lib, libdir / "libpluto_gpu.so")
     for name in ("ot2d_plm_hlld", "ot2d_ctu", "rotor2d_ppm_rk3_bf", "blast2d_ctu_bfx_roe", "blast2d_ctu_bp", "rotor2d_cl_vl_rk3",
-                 "rotor2d_nug_roe_rk3", "blast2d_nuw_mc_arith", "rotor2d_chtr_mc_uct0"):
+                 "rotor2d_nug_roe_rk3", "blast2d_nuw_mc_arith", "rotor2d_chtr_mc_uct0", "blast2d_ppm_sfl_roe"):
         g = Golden(name)
         cfg = RefConfig(problem=g.problem, dims=g.dims, n=g.n, recon=g.recon, solver=g.solver, tstep=g.tstep, cfl=g.cfl,
                         cfl_max_var=g.cfl_max_var, first_dt=g.first_dt, gamma=g.gamma, limiter=g.limiter, emf=g.emf,
@@ -129,13 +129,20 @@ def test_create_refuses_unsupported_combinations(emu_lib):
     from pluto_b200.stepper import PlutoGpuError
     ok = dict(dims=3, n=(8, 8, 8), dx=(0.1, 0.1, 0.1), lib_path=emu_lib)
     for bad, msg in [(dict(recon="ppm", ctu=True), "LINEAR"), (dict(emf="uct_hll", ctu=True), "UCT_HLL"),
-                     (dict(emf="uct_hll", en_corr=True), "CT_EN_CORRECTION"), (dict(recon="ppm", flatten=True), "SHOCK_FLATTENING"),
+                     (dict(emf="uct_hll", en_corr=True), "CT_EN_CORRECTION"), (dict(recon="ppm", flatten=True, emf="uct_hll"), "SHOCK_FLATTENING"),
                      (dict(rk_order=4), "rk_order"), (dict(n=(8, 3, 8)), "nghost")]:
         kw = dict(ok); kw.update(bad)
         with pytest.raises(PlutoGpuError, match=msg):
             GpuStepper(kw.pop("dims"), kw.pop("n"), kw.pop("dx"), **kw)
     s = GpuStepper(3, (8, 8, 8), (0.1, 0.1, 0.1), lib_path=emu_lib, ctu=True, flatten=True)
     assert (s.ng, s.nstages) == (4, 1)
+    s.close()
+    # PARABOLIC + MULTID: the minmod fallback of flagged zones takes the weights of PLM_CoefficientsGet -- a step without them says so
+    s = GpuStepper(3, (8, 8, 8), (0.1, 0.1, 0.1), lib_path=emu_lib, recon="ppm", flatten=True)
+    from pluto_b200 import problems
+    s.set_state(problems.make("blast", 3, (8, 8, 8))[0])
+    with pytest.raises(PlutoGpuError, match="pluto_gpu_set_plm_coeffs"):
+        s.advance(1e-4)
     s.close()
 
 

@@ -35,7 +35,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # TIME_STEPPING CHARACTERISTIC_TRACING (2-D): the shim replaces ctu_step.o, plm_states.o keeps char_tracing.o
          "ot2d_chtr", "rotor2d_chtr_mc_uct0", "blast2d_chtr_mc_roe",
          # CHAR_LIMITING YES with the corner-transport-upwind steps (Orszag_Tang #09's scheme; with characteristic tracing)
-         "ot2d_ctu_cl_mc_arith", "blast2d_chtr_cl"]
+         "ot2d_ctu_cl_mc_arith", "blast2d_chtr_cl",
+         # SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: the shim hands over the weights of PLM_CoefficientsGet
+         "blast2d_ppm_sfl_roe", "blast3d_ppm_sfl"]
 
 
 def _blast_params(g):

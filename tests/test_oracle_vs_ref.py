@@ -122,6 +122,10 @@ CASES = [
     ("ot2d_ctu_cl_mc_arith", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, tstep="hancock", char_lim=True, limiter="mc",
                                        emf="arith"), 10),
     ("blast2d_chtr_cl", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", char_lim=True), 10),
+    # SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: flagged zones fall back to minmod-limited linear states with the
+    # weights of PLM_CoefficientsGet (ppm_states.c:167-181), handed over as the reference built them
+    ("blast2d_ppm_sfl_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=3e-4, solver="roe", flatten=True), 12),
+    ("blast3d_ppm_sfl", RefConfig(problem="blast", dims=3, n=(14, 12, 16), recon="ppm", first_dt=3e-4, cfl=0.3, flatten=True), 10),
     ("rotor2d_chtr_mc_uct0_hll", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), first_dt=2e-3, tstep="chtr", limiter="mc", emf="uct0",
                                            solver="hll"), 10),
 ]
@@ -150,7 +154,7 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     if cfg.grid is not None:
         assert r.dx is not None and len(r.dx) == cfg.dims and max(np.ptp(a) for a in r.dx) > 0.0
         o.set_grid(*r.dx)
-    if cfg.grid_weights:
+    if cfg.grid_weights or (cfg.flatten and cfg.recon == "ppm"):
         assert r.plm_coeffs is not None and len(r.plm_coeffs) == cfg.dims
         o.set_plm_coeffs(r.plm_coeffs)
     o.set_state(r.dumps[0])

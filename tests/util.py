@@ -55,7 +55,7 @@ class Golden:
         self.grid = tuple((str(x) or None) for x in d["cfg_grid"]) if "cfg_grid" in d.files else None
         # UNIFORM_CARTESIAN_GRID NO: per direction the six weight arrays of PLM_CoefficientsGet
         self.grid_weights = "cfg_grid_weights" in d.files
-        self.plm_coeffs = [list(d[f"plm_coeffs{a+1}"]) for a in range(self.dims)] if self.grid_weights else None
+        self.plm_coeffs = [list(d[f"plm_coeffs{a+1}"]) for a in range(self.dims)] if "plm_coeffs1" in d.files else None
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:

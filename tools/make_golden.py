@@ -141,6 +141,10 @@ CASES = {
     "ot2d_ctu_cl_mc_arith": (RefConfig(problem="ot", dims=2, n=(32, 24, 1), first_dt=2e-2, cfl=0.4, tstep="hancock", char_lim=True,
                                        limiter="mc", emf="arith"), 20),
     "blast2d_chtr_cl": (RefConfig(problem="blast", dims=2, n=(32, 24, 1), first_dt=4e-4, cfl=0.4, tstep="chtr", char_lim=True), 20),
+    # SHOCK_FLATTENING MULTID with PARABOLIC reconstruction (ppm_states.c:167-181; fixtures carry the weights of PLM_CoefficientsGet)
+    "blast2d_ppm_sfl_roe": (RefConfig(problem="blast", dims=2, n=(36, 24, 1), recon="ppm", first_dt=4e-4, cfl=0.4, solver="roe",
+                                      flatten=True), 25),
+    "blast3d_ppm_sfl": (RefConfig(problem="blast", dims=3, n=(18, 12, 14), recon="ppm", first_dt=6e-4, cfl=0.3, flatten=True), 15),
     "blast2d_nuw_mc_arith": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, limiter="mc", emf="arith",
                                        grid_weights=True,
                                        grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
@@ -170,6 +174,7 @@ def make(name):
             out[f"grid_dx{d+1}"] = r.dx[d]
     if cfg.grid_weights:
         out["cfg_grid_weights"] = 1
+    if r.plm_coeffs is not None:           # UNIFORM_CARTESIAN_GRID NO, or PARABOLIC + MULTID (the minmod fallback's weights)
         for d in range(cfg.dims):
             out[f"plm_coeffs{d+1}"] = np.array(r.plm_coeffs[d])
     for s in (0, 1, nsteps):
