@@ -5,7 +5,7 @@
 
 families: rk (fused x1+x2 sweep, x3 march, CT, final, bc), exact (one kernel per direction), ppm_roe, hll_uct_hll,
 ctu, bc (outflow / reflective / eqtsymmetric fills incl. div B), halo (two blocks in one process: pack / unpack tables),
-io (dbl writer / analysis), grid (non-uniform grids, grid-dependent weights, PLUTO_GPU_R3).  Launches run without graph capture so that a report names the kernel.
+io (dbl writer / analysis), grid (non-uniform grids, grid-dependent weights, PLUTO_GPU_R3), schemes2 (CHARACTERISTIC_TRACING, CHAR_LIMITING + CTU, MULTID + PARABOLIC).  Launches run without graph capture so that a report names the kernel.
 """
 import os
 import sys
@@ -116,6 +116,25 @@ def fam_grid():
     del os.environ["PLUTO_GPU_R3"]
 
 
+def fam_schemes2():
+    """Scheme options added late in round 2: CHARACTERISTIC_TRACING (2-D), CHAR_LIMITING with the CTU steps, MULTID + PARABOLIC."""
+    run("ot", 2, (48, 40, 1), arith="exact", ctu="chtr", dt=1e-3)
+    run("rotor", 2, (40, 32, 1), arith="exact", ctu="chtr", dt=1e-3, solver="roe", limiter="mc", emf="uct0")
+    run("ot", 2, (48, 40, 1), arith="fast", ctu=True, char_lim=True, dt=1e-3, limiter="mc", emf="arith")
+    run("blast", 2, (40, 32, 1), arith="exact", ctu="chtr", char_lim=True)
+    for dims, n, arith in ((3, (24, 20, 16), "fast"), (2, (48, 40, 1), "exact")):
+        st0, meta = problems.make("blast", dims, n)
+        s = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], arith=arith, recon="ppm", flatten=True)
+        s.set_plm_coeffs([[np.full(n[d] + 6, c) for c in (2.0, 2.0, 1.0, 1.0, 0.5, 0.5)] for d in range(dims)])
+        s.set_state(st0)
+        dt = 1e-4
+        for _ in range(6):                  # the blast has to start moving before zones are flagged
+            info = s.advance(dt)
+            dt = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+        assert all(np.isfinite(v).all() for v in s.get_state().values())
+        s.close()
+
+
 def fam_io():
     import tempfile
     st0, meta = problems.make("ot", 3, (24, 20, 16))
@@ -132,7 +151,7 @@ def fam_io():
 
 
 FAMILIES = {"rk": fam_rk, "exact": fam_exact, "ppm_roe": fam_ppm_roe, "hll_uct_hll": fam_hll_uct_hll, "ctu": fam_ctu,
-            "bc": fam_bc, "halo": fam_halo, "io": fam_io, "grid": fam_grid}
+            "bc": fam_bc, "halo": fam_halo, "io": fam_io, "grid": fam_grid, "schemes2": fam_schemes2}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(FAMILIES)):
