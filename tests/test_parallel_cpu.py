@@ -32,6 +32,21 @@ def test_layout_grids_and_neighbours():
     assert [k for k, _ in exchange_ops_order()] == ["send", "send", "recv", "recv"]
 
 
+def test_blocks_take_their_slice_of_per_direction_arrays():
+    """Zone widths / reconstruction weights of a non-uniform grid are arrays of the whole domain (ghost zones included); a
+    block's array is its own zones with ng ghost entries on either side -- the neighbours' zones, or the domain's ghost entries."""
+    lay = BlockLayout.strong(3, (16, 12, 8), 8, periodic=False)
+    ng = 2
+    for d, gn in enumerate((16, 12, 8)):
+        arr = np.arange(gn + 2 * ng, dtype=float) + 100 * d
+        for rank in range(8):
+            o, n = lay.offset(rank)[d], lay.local_n(rank)[d]
+            sl = lay.slice_1d(rank, d, arr, ng)
+            assert sl.size == n + 2 * ng and sl.flags["C_CONTIGUOUS"]
+            assert np.array_equal(sl, arr[o:o + n + 2 * ng])
+            assert sl[ng] == arr[ng + o] and sl[-ng - 1] == arr[ng + o + n - 1]      # first / last own zone
+
+
 def _gfun(q, K, J, I, gn, stag):
     """unique value per (field, wrapped global index); staggered index = face"""
     return q * 1e6 + (K % gn[2]) * 1e4 + (J % gn[1]) * 1e2 + (I % gn[0])
