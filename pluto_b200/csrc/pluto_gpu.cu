@@ -543,8 +543,8 @@ int pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const
   if (h->ctu) return fail ("pluto_gpu_set_grid: non-uniform grids are not available with TIME_STEPPING HANCOCK");
   if (h->cfg.recon != PLUTO_GPU_RECON_LINEAR)
     return fail ("pluto_gpu_set_grid: non-uniform grids need LINEAR reconstruction (PARABOLIC takes its weights from the grid, ppm_coeffs.c)");
-  if (h->cfg.shock_flattening || h->cfg.body_force || h->cfg.en_correction || h->cfg.char_limiting)
-    return fail ("pluto_gpu_set_grid: non-uniform grids are not available with SHOCK_FLATTENING, BODY_FORCE, CT_EN_CORRECTION or CHAR_LIMITING");
+  if (h->cfg.shock_flattening || h->cfg.en_correction || h->cfg.char_limiting)
+    return fail ("pluto_gpu_set_grid: non-uniform grids are not available with SHOCK_FLATTENING, CT_EN_CORRECTION or CHAR_LIMITING");
   const double *src[3] = {dx1, dx2, dx3};
   for (int d = 0; d < g.dims; d++){
     if (!src[d]) return fail ("pluto_gpu_set_grid: NULL array for direction %d", d + 1);

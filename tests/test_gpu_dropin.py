@@ -37,7 +37,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # CHAR_LIMITING YES with the corner-transport-upwind steps (Orszag_Tang #09's scheme; with characteristic tracing)
          "ot2d_ctu_cl_mc_arith", "blast2d_chtr_cl",
          # SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: the shim hands over the weights of PLM_CoefficientsGet
-         "blast2d_ppm_sfl_roe", "blast3d_ppm_sfl"]
+         "blast2d_ppm_sfl_roe", "blast3d_ppm_sfl",
+         # body forces on non-uniform grids: potential and position-dependent force tabulated by the shim at grid->x / xr
+         "blast3d_nug_bp", "blast2d_nug_bfx_roe"]
 
 
 def _blast_params(g):

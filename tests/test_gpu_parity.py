@@ -199,10 +199,10 @@ def test_characteristic_tracing_is_2d_only():
 
 def test_nonuniform_grid_is_refused_where_the_weights_would_change():
     """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c), the corner-transport-upwind predictor, shock
-    flattening, body forces and the energy correction use the zone width elsewhere: pluto_gpu_set_grid says so."""
+    flattening and the energy correction use the zone width elsewhere: pluto_gpu_set_grid says so."""
     from pluto_b200 import GpuStepper
     from pluto_b200.stepper import PlutoGpuError
-    for kw, ng in ((dict(recon="ppm"), 3), (dict(ctu=True), 3), (dict(flatten=True), 3), (dict(en_corr=True), 2), (dict(grav=(0.0, 1.0, 0.0)), 2)):
+    for kw, ng in ((dict(recon="ppm"), 3), (dict(ctu=True), 3), (dict(flatten=True), 3), (dict(en_corr=True), 2)):
         s = GpuStepper(2, (16, 16, 1), (0.1, 0.1), **kw)
         with pytest.raises(PlutoGpuError, match="non-uniform"):
             s.set_grid(np.full(16 + 2 * ng, 0.1), np.full(16 + 2 * ng, 0.1))

@@ -103,6 +103,16 @@ CASES = [
                                                   bc=("reflective", "outflow", "outflow", "reflective", "outflow", "outflow"),
                                                   blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3),
                                                   grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 12),
+    # body forces on a non-uniform grid (stratified set-ups on stretched grids): uniform acceleration, position-dependent
+    # force, potential (its momentum source takes dt/dx[i] of the zone)
+    ("blast3d_nug_bf", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, grav=(0.3, -1.0, 0.5),
+                                 grid=("2  -0.5  8  u  0.1  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                       "3  -0.5  4  s  -0.2  8  u  0.2  4  s  0.5")), 8),
+    ("blast2d_nug_bp", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, grav=(0.05, -0.03, 0.0), potential=True,
+                                 grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 10),
+    ("blast3d_nug_bfx", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, grav=(-3.0, -1.0, 2.0), grav_mode=1,
+                                  grid=("2  -0.5  8  u  0.1  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                        "3  -0.5  4  s  -0.2  8  u  0.2  4  s  0.5")), 8),
     # UNIFORM_CARTESIAN_GRID NO: the reconstruction takes the grid-dependent weights of PLM_CoefficientsGet (plm_coeffs.c:30-104)
     # and the limiters "on irregular grids" (plm_coeffs.h:130-152)
     ("blast3d_nuw", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, grid_weights=True,
@@ -147,10 +157,10 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
                char_lim=cfg.char_lim)
     if cfg.potential:
         from tests.util import step_potential_arrays
-        o.set_body_potential(*step_potential_arrays(cfg.dims, n, o.ng, dom, cfg.grav))
+        o.set_body_potential(*step_potential_arrays(cfg.dims, n, o.ng, dom, cfg.grav, widths=(r.dx if cfg.grid is not None else None)))
     if cfg.grav_mode == 1:
         from tests.util import sign_force_arrays
-        o.set_body_force(*sign_force_arrays(cfg.dims, n, o.ng, dom, cfg.grav))
+        o.set_body_force(*sign_force_arrays(cfg.dims, n, o.ng, dom, cfg.grav, widths=(r.dx if cfg.grid is not None else None)))
     if cfg.grid is not None:
         assert r.dx is not None and len(r.dx) == cfg.dims and max(np.ptp(a) for a in r.dx) > 0.0
         o.set_grid(*r.dx)

@@ -85,9 +85,9 @@ def apply_force_field(stepper, g):
     if g.plm_coeffs is not None:
         stepper.set_plm_coeffs(g.plm_coeffs)
     if g.grav_mode == 1:
-        stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
+        stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav, widths=g.grid_dx))
     if g.potential:
-        stepper.set_body_potential(*step_potential_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav))
+        stepper.set_body_potential(*step_potential_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav, widths=g.grid_dx))
 
 
 def rel_l1(a, b):
@@ -118,7 +118,7 @@ def divb_max(state, dims, dx):
     return np.abs(div).max()
 
 
-def sign_force_arrays(dims, n, ng, domain, grav):
+def sign_force_arrays(dims, n, ng, domain, grav, widths=None):
     """The static test force of oracle/ref_build/problem/init.c (GRAV_MODE 1): component d = grav[d]*sign(x_d), constant on
     either side of the plane x_d = 0, as arrays [T3][T2][T1] with ghost zones.  Use even n on symmetric domains (no zone
     centre on a plane)."""
@@ -126,8 +126,7 @@ def sign_force_arrays(dims, n, ng, domain, grav):
     x = []
     for d in range(3):
         if d < dims:
-            dx = (domain[d][1] - domain[d][0]) / n[d]
-            x.append(domain[d][0] + (np.arange(T[d]) - ng + 0.5) * dx)
+            x.append(_coords(d, n, ng, domain, widths)[0])
         else:
             x.append(np.zeros(1))
     out = []
@@ -141,16 +140,29 @@ def sign_force_arrays(dims, n, ng, domain, grav):
     return out
 
 
-def step_potential_arrays(dims, n, ng, domain, grav, x0=0.013):
+def _coords(d, n, ng, domain, widths):
+    """Zone centres and faces (-1/2 .. T-1/2) of direction d: uniform, or from the zone widths of a non-uniform grid
+    (the first interior face lies at the domain's lower end)."""
+    T = n[d] + 2 * ng
+    if widths is None:
+        dx = (domain[d][1] - domain[d][0]) / n[d]
+        return domain[d][0] + (np.arange(T) - ng + 0.5) * dx, domain[d][0] + (np.arange(-1, T) - ng + 1.0) * dx
+    w = np.asarray(widths[d], dtype=float)
+    xf = np.concatenate([[0.0], np.cumsum(w)])
+    xf = xf - xf[ng] + domain[d][0]
+    return 0.5 * (xf[1:] + xf[:-1]), xf
+
+
+def step_potential_arrays(dims, n, ng, domain, grav, x0=0.013, widths=None):
     """The test potential of oracle/ref_build/problem/init.c (BODY_FORCE POTENTIAL): steps of height grav[d] across the
     planes x_d = x0, at the zone centres [T3][T2][T1] and at the faces of every direction (staggered Data layouts)."""
     T = [n[d] + 2 * ng if d < dims else 1 for d in range(3)]
     xc, xf = [], []
     for d in range(3):
         if d < dims:
-            dx = (domain[d][1] - domain[d][0]) / n[d]
-            xc.append(domain[d][0] + (np.arange(T[d]) - ng + 0.5) * dx)
-            xf.append(domain[d][0] + (np.arange(-1, T[d]) - ng + 1.0) * dx)          # faces -1/2 .. T-1/2
+            c_, f_ = _coords(d, n, ng, domain, widths)
+            xc.append(c_)
+            xf.append(f_)
         else:
             xc.append(np.array([0.5 * (domain[d][0] + domain[d][1])]))
             xf.append(None)

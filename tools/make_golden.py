@@ -126,6 +126,12 @@ CASES = {
                                                   bc=("reflective", "outflow", "outflow", "reflective", "outflow", "outflow"),
                                                   blast=dict(P_IN=100.0, P_OUT=1.0, BMAG=10.0, THETA=45.0, PHI=0.0, RADIUS=0.3),
                                                   grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 25),
+    # body forces on non-uniform grids: potential (momentum source with dt/dx[i]), position-dependent force
+    "blast3d_nug_bp": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grav=(0.05, -0.03, 0.04), potential=True,
+                                 grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                                         "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 12),
+    "blast2d_nug_bfx_roe": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, solver="roe", grav=(-3.0, -1.0, 0.0),
+                                      grav_mode=1, grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 20),
     # UNIFORM_CARTESIAN_GRID NO: grid-dependent reconstruction weights (plm_coeffs.c) -- the fixtures carry the arrays of PLM_CoefficientsGet
     "blast3d_nuw": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grid_weights=True,
                               grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
