@@ -123,7 +123,9 @@ int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
    widths of every direction, dx_d[0 .. T_d-1] = grid->dx[d] with the ghost zones (T_d = n[d] + 2 nghost).  The reference's
    CARTESIAN builds keep the uniform reconstruction weights (UNIFORM_CARTESIAN_GRID YES, Src/States/plm_coeffs.h:23-29); the
    widths enter Src/MHD/rhs.c:195, the inverse time step (Src/Time_Stepping/update_stage.c:229-235), Src/MHD/CT/ct_update.c:91-204
-   and the face areas of Src/MHD/CT/ct_fill_mag_field.c:108-114.  RK2 / RK3 with LINEAR reconstruction; dx3 may be NULL in 2-D.
+   and the face areas of Src/MHD/CT/ct_fill_mag_field.c:108-114; with the corner-transport-upwind steps also the predictors
+   (Src/States/hancock.c:245-296, char_tracing.c:347-362) and the transverse correction of ctu_step.c:310, 731-785.  LINEAR
+   reconstruction without SHOCK_FLATTENING / CT_EN_CORRECTION / CHAR_LIMITING (refused otherwise); dx3 may be NULL in 2-D.
    PlutoGpuConfig.dx is then used by nothing on the path.  Call once after pluto_gpu_create. */
 int  pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const double *dx3);
 /* UNIFORM_CARTESIAN_GRID NO (Src/States/plm_coeffs.h:23-29): grid-dependent weights of the linear reconstruction.  Hand over, for

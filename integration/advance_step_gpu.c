@@ -172,9 +172,10 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     }
     if (nonuniform){
       /* stretched / logarithmic / multi-patch grids (set_grid.c:330-560): the zone widths go to the library after its creation */
-#if TIME_STEPPING == HANCOCK || TIME_STEPPING == CHARACTERISTIC_TRACING || RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES
-      print ("! AdvanceStep(gpu): a non-uniform grid needs RK2 / RK3 with LINEAR reconstruction, without SHOCK_FLATTENING,\n"
-             "  CT_EN_CORRECTION and CHAR_LIMITING on the GPU\n");
+#if RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES \
+    || ((TIME_STEPPING == HANCOCK || TIME_STEPPING == CHARACTERISTIC_TRACING) && BODY_FORCE != NO)
+      print ("! AdvanceStep(gpu): a non-uniform grid needs LINEAR reconstruction, without SHOCK_FLATTENING, CT_EN_CORRECTION and\n"
+             "  CHAR_LIMITING (and without BODY_FORCE with the corner-transport-upwind steps) on the GPU\n");
       QUIT_PLUTO(1);
 #endif
     }

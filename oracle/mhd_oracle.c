@@ -1657,12 +1657,13 @@ static void prim_rhs (const Oracle *o, const double *v, const double *dv, Dirs q
   Adv[PRS] = o->c.gamma*v[PRS]*dv[q.vn] + v[q.vn]*dv[PRS];
 }
 
-static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, double dx)
+static void hancock_step (Oracle *o, int beg, int end, Dirs q, double dt, int dir)
 {
   int i, nv, dims = o->c.dims;
-  double dt_2 = 0.5*dt, d_dl = 1.0/dx;
+  double dt_2 = 0.5*dt;
   for (i = beg; i <= end; i++){
     double dv[NV], Adv[NV];
+    const double dx = DXA(o,dir,i), d_dl = 1.0/dx;          /* hancock.c:83: d_dl[i] = 1/dx[i] */
     for (nv = 0; nv < NV; nv++) dv[nv] = o->vp[i][nv] - o->vm[i][nv];
     prim_rhs (o, o->v[i], dv, q, Adv);
     for (nv = 0; nv < NV; nv++){
@@ -1851,7 +1852,8 @@ static void ctu_advance (Oracle *o, double dt)
   for (dir = 0; dir < dims; dir++){
     Dirs q = set_vector_indices (dir);
     int lo[3], hi[3], t1, t2, a, b, n, nbeg, nend, ntot = o->T[dir];
-    double dt2_dx = dt2/o->c.dx[dir], inv_dl = 1.0/o->c.dx[dir];
+#define dt2_dx (dt2/DXA(o,dir,n))                  /* ctu_step.c:310  dt2_dx[i] = dt2/dx[i]; inv_dl[i] = 1/dx[i] */
+#define inv_dl (1.0/DXA(o,dir,n))
     for (a = 0; a < 3; a++){ lo[a] = o->beg[a]; hi[a] = o->end[a]; }
     /* transverse +-1 (:290-292), then with CT normal +-1 and transverse +-1 again (:293-297) */
     for (a = 0; a < dims; a++){ if (a != dir){ lo[a] -= 2; hi[a] += 2; } else { lo[a]--; hi[a]++; } }
@@ -1873,7 +1875,7 @@ static void ctu_advance (Oracle *o, double dt)
       if (o->c.char_limiting) states_plm_char (o, nbeg-1, nend+1, q);      /* CHAR_LIMITING YES (plm_states.c:448-706) */
       else                    states_plm (o, nbeg-1, nend+1, q.bn);
       if (o->c.ctu == 2) char_tracing_step (o, nbeg-1, nend+1, q, dt, dir);      /* TIME_STEPPING CHARACTERISTIC_TRACING */
-      else               hancock_step (o, nbeg-1, nend+1, q, dt, o->c.dx[dir]);
+      else               hancock_step (o, nbeg-1, nend+1, q, dt, dir);
       for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vp[n], o->up[n]); }
       for (n = nbeg-1; n <= nend+1; n++){ prim_to_cons (o, o->vm[n], o->um[n]); }
       /* 4f. Riemann, EMF, rhs with dt/2 */
@@ -1975,7 +1977,8 @@ static void ctu_advance (Oracle *o, double dt)
   for (dir = 0; dir < dims; dir++){
     Dirs q = set_vector_indices (dir);
     int lo[3], hi[3], t1, t2, a, b, n, nbeg = o->beg[dir], nend = o->end[dir];
-    double dtdx = dt/o->c.dx[dir], inv_dl = 1.0/o->c.dx[dir];
+#undef dt2_dx
+#define dtdx (dt/DXA(o,dir,n))
     for (a = 0; a < 3; a++){ lo[a] = o->beg[a]; hi[a] = o->end[a]; }
     for (a = 0; a < dims; a++) if (a != dir){ lo[a]--; hi[a]++; }
     if (dir == 0){ t1 = 1; t2 = 2; } else if (dir == 1){ t1 = 0; t2 = 2; } else { t1 = 0; t2 = 1; }
@@ -2048,6 +2051,8 @@ static void ctu_advance (Oracle *o, double dt)
   ct_average_magnetic_field (o);
   cons_to_prim_3d (o);
 }
+#undef dtdx
+#undef inv_dl
 
 int oracle_advance (Oracle *o, double dt, double *inv_dt_hyp, double *max_mach)
 {

@@ -226,7 +226,8 @@ ct_update_kernel (const __grid_constant__ CtArgs a)
   const long long sy = g.S1, sz = g.S12;
   const bool in_i = i >= g.beg[0] - ext, in_j = j >= g.beg[1] - ext, in_k = (NC == 3 ? k >= g.beg[2] - ext : true);
   // dt/dx2[j], dt/dx3[k], ... of the zone the face belongs to (ct_update.c:91-96, 147-152, 202-204); uniform grid: gs = 0
-  const double dtdx0 = __ldg (a.dtx[0] + i*a.gs), dtdx1 = __ldg (a.dtx[1] + j*a.gs), dtdx2 = (NC == 3 ? __ldg (a.dtx[2] + k*a.gs) : 0.0);
+  const double dtdx0 = a.dts*__ldg (a.dtx[0] + i*a.gs), dtdx1 = a.dts*__ldg (a.dtx[1] + j*a.gs);
+  const double dtdx2 = (NC == 3 ? a.dts*__ldg (a.dtx[2] + k*a.gs) : 0.0);
 
   if (in_j && in_k){        // Bx1 at (i+1/2, j, k), i in [IBEG-1, IEND]
     double rhs;

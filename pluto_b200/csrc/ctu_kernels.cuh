@@ -190,8 +190,11 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     advance (jr_n, kr_n, idr_n);
   };
 
-  const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
-  const double dtdx = __ldg (a.dtp + DIR);
+  // dt/dx, (dt/2)/dx = half of it (exact) and 1/dx of the lane's zone: per-zone arrays on a non-uniform grid (gs = 1; rhs.c:195,
+  // ctu_step.c:310, hancock.c:83), the scalars otherwise
+  const int izn = g.beg[0] - E + iic;
+  const double dtdx = __ldg (a.dtx + izn*a.gs), dt2_dx = 0.5*dtdx, dt_2 = 0.5*__ldg (a.dtp + 3);
+  const double d_dl = a.gs ? __ldg (a.idl + izn) : a.inv_dl;
   double my_mach = 0.0, my_cdt = 0.0;
   int nfl_tot = 0;
   issue (0);
@@ -212,7 +215,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     double src_n = 0.0, dphi = 0.0;                    // PrimSource of the normal velocity (prim_eqn.c:289-307)
     if (a.bf) src_n += gz;
     if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - 1); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
-    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0, a.char_lim);
+    ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? dtdx : 0.0, a.char_lim);
     // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
     // V^{n+1/2} (ctu_step.c:566-570) in the corrector
     double rho_c = 0.0;
@@ -245,7 +248,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     PG_FOR_NV(nv) Fm[nv] = __shfl_up_sync (0xffffffffu, F[nv], 1);
     const double pm = __shfl_up_sync (0xffffffffu, press, 1);
     if (rhs_ok){
-      const double cd = cmax*a.inv_dl;                         // ctu_step.c:416-419, 634-637
+      const double cd = cmax*d_dl;                             // ctu_step.c:416-419, 634-637: cmax[i] inv_dl[i]
       my_cdt = cd > my_cdt ? cd : my_cdt;
       if (PHASE == 0){
         PG_FOR_NV(nv){
@@ -357,8 +360,8 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
     fetch (cur, id, true);
     cp_async_commit ();
 
-    const double dt2_dx = 0.5*__ldg (a.dtp + DIR), dt_2 = 0.5*__ldg (a.dtp + 3), d_dl = a.inv_dl;
-    const double dtdx = __ldg (a.dtp + DIR);
+    const double dt_2 = 0.5*__ldg (a.dtp + 3);
+    double dtdx = 0.0, dt2_dx = 0.0, d_dlL = 0.0;     // dt/dx, (dt/2)/dx, 1/dx of zone z-1 (the zone that receives the right-hand side)
     double rhoL = 0.0, gL = 0.0, dphiL = 0.0;        // body force: stateC density (predictor), force, potential step of zone z-1
     double vl[NV], v[NV], vr[NV];
     PG_FOR_NV(nv){ v[nv] = __ldg (a.V0[nv] + id - sD); vr[nv] = __ldg (a.V0[nv] + id); }
@@ -383,7 +386,8 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       double src_n = 0.0, dphi = 0.0;                  // PrimSource of the normal velocity (prim_eqn.c:289-307)
       if (a.bf) src_n += gz;
       if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - sD); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
-      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? __ldg (a.dtp + DIR) : 0.0, a.char_lim);
+      const double dtdx_z = __ldg (a.dtx + z*a.gs), d_dl = a.gs ? __ldg (a.idl + z) : a.inv_dl;       // of zone z
+      ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? dtdx_z : 0.0, a.char_lim);
       const double rho_z = ((a.bf || a.phif) && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141
       if (PHASE == 0){
         prim_to_cons<NC>(ph, vp, up);
@@ -400,7 +404,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         }
         const double bhm = bhp;
         bhp = cur[Q_BH*CS];
-        const int n = ctu_correct<DIR, NC>(ph, v, dU, dt2_dx, bhm, bhp, vp, vm, up, um);
+        const int n = ctu_correct<DIR, NC>(ph, v, dU, 0.5*dtdx_z, bhm, bhp, vp, vm, up, um);
         if ((z >= c0 || chunk == 0) && (z <= c1 || chunk == a.nchunk - 1)) nfl += n;   // zones shared by two chunks count once
       }
       if (z >= c0){
@@ -415,7 +419,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
         if (PHASE == 1 && a.fbn && (z - 1 >= c0 || chunk == 0)) a.fbn[idf] = F[D::bn];
         if (z - 1 >= c0){
           // zone z-1: faces z-3/2 (Fp) and z-1/2 (F)
-          const double cd = cmax*a.inv_dl;
+          const double cd = cmax*d_dlL;                          // cmax[z-1] inv_dl[z-1]
           my_cdt = cd > my_cdt ? cd : my_cdt;
           if (PHASE == 0){
             PG_FOR_NV(nv){
@@ -455,6 +459,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       }
       PG_FOR_NV(nv){ vpL[nv] = vp[nv]; upL[nv] = up[nv]; }
       rhoL = rho_z; gL = gz; dphiL = dphi;
+      dtdx = dtdx_z; dt2_dx = 0.5*dtdx_z; d_dlL = d_dl;
       flb = flz;
       double *tmp = cur; cur = nxt; nxt = tmp;
     }

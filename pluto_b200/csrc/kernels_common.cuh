@@ -119,6 +119,8 @@ struct CtArgs {
   const double *Ec[3];                       // cell-centred EMFs stored by the fused x1+x2 sweep (SweepArgs.Ec), else NULL
   const double *dtx[3];                      // dt/dx of direction d: per zone (gs = 1, non-uniform grid: ct_update.c:91-96 takes
   int    gs;                                 // dt/dx2[j], dt/dx3[k], ...) or the scalar dtp + d (gs = 0)
+  double dts;                                // factor on dt/dx: 1, or 1/2 for the half step of the CTU predictor on a non-uniform
+                                             // grid (halving is exact: (dt/2)/dx = (dt/dx)/2 bit for bit)
 };
 
 // corner-transport-upwind step (TIME_STEPPING HANCOCK, Src/Time_Stepping/ctu_step.c:142-727)
@@ -145,6 +147,8 @@ struct CtuArgs {
   const double *gf;
   const double *phic, *phif; // BODY_FORCE & POTENTIAL: potential at the centres / the faces of this direction (else NULL)
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
+  const double *dtx, *idl;   // dt/dx[n] and 1/dx[n] along the sweep on a non-uniform grid (gs = 1), else dtp + direction (gs = 0)
+  int     gs;
   int     chtr;              // TIME_STEPPING CHARACTERISTIC_TRACING: predictor by characteristic tracing (2 components)
   int     char_lim;          // CHAR_LIMITING YES (2 components): slopes limited on the characteristic variables (plm_zone_char2)
 };

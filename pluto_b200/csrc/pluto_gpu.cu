@@ -540,7 +540,8 @@ int pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const
 {
   CU (cudaSetDevice (h->cfg.device));
   const Geom &g = h->g;
-  if (h->ctu) return fail ("pluto_gpu_set_grid: non-uniform grids are not available with TIME_STEPPING HANCOCK");
+  if (h->ctu && h->cfg.body_force)
+    return fail ("pluto_gpu_set_grid: non-uniform grids are not available with the corner-transport-upwind steps AND BODY_FORCE");
   if (h->cfg.recon != PLUTO_GPU_RECON_LINEAR)
     return fail ("pluto_gpu_set_grid: non-uniform grids need LINEAR reconstruction (PARABOLIC takes its weights from the grid, ppm_coeffs.c)");
   if (h->cfg.shock_flattening || h->cfg.en_correction || h->cfg.char_limiting)
@@ -985,7 +986,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     c.Bs_in[d] = h->Bs[sp.in][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[sp.out][d];
   }
   c.g = g; c.w0 = sp.w0; c.wc = sp.wc; c.combine = sp.combine; c.dtp = h->dtdev;
-  c.gs = h->nu;
+  c.gs = h->nu; c.dts = 1.0;
   for (int d = 0; d < 3; d++) c.dtx[d] = h->nu && d < g.dims ? h->dtxa[d] : h->dtdev + d;
   if (fuse_xy) for (int q = 0; q < 3; q++) c.Ec[q] = h->Ec[q];
   c.avg = h->cfg.emf_average;
@@ -1058,6 +1059,7 @@ static int run_ctu (PlutoGpu *h, int part)
   for (int phase = 0; phase < 2; phase++){
     for (int dir = 0; dir < g.dims; dir++){
       s.inv_dl = 1.0/g.dx[dir];
+      s.gs = h->nu; s.dtx = h->nu ? h->dtxa[dir] : h->dtdev + dir; s.idl = h->idxa[dir];
       s.sv = h->sv[dir];
       s.fbn = h->fbn[dir];
       s.gf = h->gfield[dir];
@@ -1082,7 +1084,8 @@ static int run_ctu (PlutoGpu *h, int part)
       for (int d = 0; d < 3; d++){ c.Bs_in[d] = h->Bs[0][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[1][d]; }
       c.avg = (h->cfg.emf_average == PLUTO_GPU_EMF_UCT_CONTACT ? PLUTO_GPU_EMF_ARITHMETIC : h->cfg.emf_average);
       c.ext = 1; c.combine = 0; c.dtp = h->dtdev + 4;
-      for (int d = 0; d < 3; d++) c.dtx[d] = c.dtp + d;
+      c.gs = h->nu; c.dts = (h->nu ? 0.5 : 1.0);           // non-uniform grid: half of the per-zone dt/dx (exact)
+      for (int d = 0; d < 3; d++) c.dtx[d] = h->nu && d < g.dims ? h->dtxa[d] : c.dtp + d;
       TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
       TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
       TIMED (h, KC_FINAL, count (h, DISPATCH (h, launch_ctu_half) (s, h->stream)));
@@ -1093,7 +1096,8 @@ static int run_ctu (PlutoGpu *h, int part)
   for (int nv = 0; nv < NVS; nv++) c.V[nv] = h->V[1][nv];
   for (int d = 0; d < 3; d++){ c.Bs_in[d] = h->Bs[0][d]; c.Bs0[d] = h->Bs[0][d]; c.Bs_out[d] = h->Bs[0][d]; }
   c.avg = h->cfg.emf_average; c.ext = 0; c.combine = 0; c.dtp = h->dtdev;
-  for (int d = 0; d < 3; d++) c.dtx[d] = c.dtp + d;
+  c.gs = h->nu; c.dts = 1.0;
+  for (int d = 0; d < 3; d++) c.dtx[d] = h->nu && d < g.dims ? h->dtxa[d] : c.dtp + d;
   TIMED (h, KC_CT_EMF, count (h, DISPATCH (h, launch_ct_emf) (c, h->stream)));
   TIMED (h, KC_CT_UPDATE, count (h, DISPATCH (h, launch_ct_update) (c, h->stream)));
 

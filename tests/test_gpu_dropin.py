@@ -39,7 +39,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: the shim hands over the weights of PLM_CoefficientsGet
          "blast2d_ppm_sfl_roe", "blast3d_ppm_sfl",
          # body forces on non-uniform grids: potential and position-dependent force tabulated by the shim at grid->x / xr
-         "blast3d_nug_bp", "blast2d_nug_bfx_roe"]
+         "blast3d_nug_bp", "blast2d_nug_bfx_roe",
+         # the corner-transport-upwind steps on non-uniform grids
+         "blast3d_nug_ctu", "rotor2d_nug_chtr_mc"]
 
 
 def _blast_params(g):

@@ -128,7 +128,10 @@ def _plm_weights(dx):
                                                              ("turb", 3, (10, 9, 12), "hll", 2, None), ("ot", 2, (64, 31, 1), "roe", 2, None),
                                                              # UNIFORM_CARTESIAN_GRID NO: grid-dependent weights, LIMITER as named
                                                              ("blast", 3, (33, 12, 10), "hlld", 2, "default"), ("rotor", 2, (33, 40, 1), "hlld", 3, "vl"),
-                                                             ("turb", 3, (10, 9, 12), "roe", 2, "mc"), ("ot", 2, (40, 31, 1), "hll", 2, "os")])
+                                                             ("turb", 3, (10, 9, 12), "roe", 2, "mc"), ("ot", 2, (40, 31, 1), "hll", 2, "os"),
+                                                             # corner transport upwind (rk = 0: Hancock, -1: characteristic tracing)
+                                                             ("blast", 3, (33, 12, 10), "hlld", 0, None), ("rotor", 2, (33, 40, 1), "roe", 0, None),
+                                                             ("ot", 2, (40, 31, 1), "hlld", -1, None)])
 def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk, weights):
     """pluto_gpu_set_grid with zone widths drawn at random (0.7 .. 1.3 of the uniform one, every direction): dt/dx[i] of the
     flux differences, 1/dx[i] of the inverse time step, dt/dx2[j] ... of CT_Update and the face areas of the div B fill all
@@ -138,17 +141,19 @@ def test_nonuniform_grid_random_widths(problem, dims, n, solver, rk, weights):
     from pluto_b200 import GpuStepper, problems
     st0, meta = problems.make(problem, dims, n)
     rng = np.random.default_rng(11)
-    ng = 2
+    ctu = {0: True, -1: "chtr"}.get(rk, False)
+    rk = rk if rk > 0 else 2
+    ng = 3 if ctu else 2
     dxs = [meta["dx"][d] * (0.7 + 0.6 * rng.random(n[d] + 2 * ng)) for d in range(dims)]
     if meta["bc"][0] == "periodic":            # the ghost zones of a periodic side repeat the interior widths
         for d in range(dims):
             a = dxs[d]
             a[:ng] = a[n[d]:n[d] + ng]
             a[n[d] + ng:] = a[ng:2 * ng]
-    for arith in ("exact", "fast"):
+    for arith in (("exact",) if ctu == "chtr" else ("exact", "fast")):
         lim = weights or "default"
-        o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], rk_order=rk, limiter=lim)
-        s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith=arith, rk_order=rk, limiter=lim)
+        o = Oracle(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], rk_order=rk, limiter=lim, ctu=ctu)
+        s = GpuStepper(dims, n, meta["dx"], solver=solver, bc=meta["bc"], gamma=meta["gamma"], arith=arith, rk_order=rk, limiter=lim, ctu=ctu)
         o.set_grid(*dxs)
         s.set_grid(*dxs)
         if weights:
@@ -198,11 +203,11 @@ def test_characteristic_tracing_is_2d_only():
 
 
 def test_nonuniform_grid_is_refused_where_the_weights_would_change():
-    """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c), the corner-transport-upwind predictor, shock
-    flattening and the energy correction use the zone width elsewhere: pluto_gpu_set_grid says so."""
+    """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c); shock flattening, the energy correction and the
+    body-force source of the Hancock predictor use the zone width elsewhere: pluto_gpu_set_grid says so."""
     from pluto_b200 import GpuStepper
     from pluto_b200.stepper import PlutoGpuError
-    for kw, ng in ((dict(recon="ppm"), 3), (dict(ctu=True), 3), (dict(flatten=True), 3), (dict(en_corr=True), 2)):
+    for kw, ng in ((dict(recon="ppm"), 3), (dict(ctu=True, grav=(0.0, 1.0, 0.0)), 3), (dict(flatten=True), 3), (dict(en_corr=True), 2)):
         s = GpuStepper(2, (16, 16, 1), (0.1, 0.1), **kw)
         with pytest.raises(PlutoGpuError, match="non-uniform"):
             s.set_grid(np.full(16 + 2 * ng, 0.1), np.full(16 + 2 * ng, 0.1))

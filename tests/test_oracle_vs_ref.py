@@ -113,6 +113,15 @@ CASES = [
     ("blast3d_nug_bfx", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, grav=(-3.0, -1.0, 2.0), grav_mode=1,
                                   grid=("2  -0.5  8  u  0.1  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
                                         "3  -0.5  4  s  -0.2  8  u  0.2  4  s  0.5")), 8),
+    # the corner-transport-upwind steps on non-uniform grids: d_dl[i] of the Hancock predictor (hancock.c:83), dt/dx[i] of the
+    # characteristic tracing (char_tracing.c:346-347), dt2_dx[i] of CTU_CT_Source and of both right-hand sides (ctu_step.c:310)
+    ("blast3d_nug_ctu", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, tstep="hancock",
+                                  grid=("2  -0.5  8  u  0.1  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                        "3  -0.5  4  s  -0.2  8  u  0.2  4  s  0.5")), 8),
+    ("rotor2d_nug_ctu_roe", RefConfig(problem="rotor", dims=2, n=(36, 30, 1), first_dt=2e-3, solver="roe", tstep="hancock",
+                                      grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  10  s  0.5", None)), 10),
+    ("blast2d_nug_chtr_mc", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc",
+                                      grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 12),
     # UNIFORM_CARTESIAN_GRID NO: the reconstruction takes the grid-dependent weights of PLM_CoefficientsGet (plm_coeffs.c:30-104)
     # and the limiters "on irregular grids" (plm_coeffs.h:130-152)
     ("blast3d_nuw", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, grid_weights=True,

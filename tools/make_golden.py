@@ -132,6 +132,12 @@ CASES = {
                                                          "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 12),
     "blast2d_nug_bfx_roe": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, solver="roe", grav=(-3.0, -1.0, 0.0),
                                       grav_mode=1, grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 20),
+    # the corner-transport-upwind steps on non-uniform grids (Hancock 3-D; characteristic tracing 2-D, MC_LIM)
+    "blast3d_nug_ctu": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, tstep="hancock",
+                                  grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                        "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 12),
+    "rotor2d_nug_chtr_mc": (RefConfig(problem="rotor", dims=2, n=(36, 28, 1), first_dt=2.5e-3, cfl=0.4, tstep="chtr", limiter="mc",
+                                      grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 15),
     # UNIFORM_CARTESIAN_GRID NO: grid-dependent reconstruction weights (plm_coeffs.c) -- the fixtures carry the arrays of PLM_CoefficientsGet
     "blast3d_nuw": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grid_weights=True,
                               grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
