@@ -33,7 +33,9 @@ extern "C" {
 /* RECONSTRUCTION in definitions.h (Src/pluto.h:305-435): LINEAR / PARABOLIC */
 enum { PLUTO_GPU_RECON_LINEAR = 0, PLUTO_GPU_RECON_PARABOLIC = 1 };
 /* [Solver] in pluto.ini -> SetSolver (Src/MHD/set_solver.c:40-47) */
-enum { PLUTO_GPU_SOLVER_HLLD = 0, PLUTO_GPU_SOLVER_HLL = 1, PLUTO_GPU_SOLVER_ROE = 2 };
+enum { PLUTO_GPU_SOLVER_HLLD = 0, PLUTO_GPU_SOLVER_HLL = 1, PLUTO_GPU_SOLVER_ROE = 2,
+       PLUTO_GPU_SOLVER_HLLC = 3,      /* Src/MHD/hllc.c:42-236 */
+       PLUTO_GPU_SOLVER_TVDLF = 4 };   /* Src/MHD/tvdlf.c:51-135 (Lax-Friedrichs / Rusanov) */
 /* [Boundary] in pluto.ini (Src/boundary.c:171-218).  SHARED marks a side
    that abuts another rank's block: it is filled by the halo exchange
    (reference: AL_Exchange_dim, Src/Parallel/al_exchange_dim.c:25) instead

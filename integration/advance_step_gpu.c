@@ -127,8 +127,10 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     if      (Riemann == &HLLD_Solver) c.solver = PLUTO_GPU_SOLVER_HLLD;
     else if (Riemann == &HLL_Solver)  c.solver = PLUTO_GPU_SOLVER_HLL;
     else if (Riemann == &Roe_Solver)  c.solver = PLUTO_GPU_SOLVER_ROE;
+    else if (Riemann == &HLLC_Solver) c.solver = PLUTO_GPU_SOLVER_HLLC;
+    else if (Riemann == &LF_Solver)   c.solver = PLUTO_GPU_SOLVER_TVDLF;
     else{
-      print ("! AdvanceStep(gpu): only hlld, hll and roe are available on the GPU\n");
+      print ("! AdvanceStep(gpu): only hlld, hllc, hll, tvdlf and roe are available on the GPU\n");
       QUIT_PLUTO(1);
     }
     c.rk_order = (TIME_STEPPING == RK3 ? 3 : 2);

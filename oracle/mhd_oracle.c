@@ -907,6 +907,104 @@ static void riemann_hll (Oracle *o, const double *vL, const double *vR,
   }
 }
 
+static void riemann_tvdlf (Oracle *o, const double *vL, const double *vR,
+                           const double *uL, const double *uR, Dirs q,
+                           double *flux, double *press, double *cmax)
+/* MHD/tvdlf.c:51-135 (Lax-Friedrichs / Rusanov; EOS IDEAL) */
+{
+  double fL[NV], fR[NV], vRL[NV], pL, pR, cminRL, cmaxRL, cRL, scrh;
+  int nv;
+  mhd_flux (vL, uL, q, fL, &pL);
+  mhd_flux (vR, uR, q, fR, &pR);
+  for (nv = 0; nv < NV; nv++) vRL[nv] = 0.5*(vL[nv] + vR[nv]);                       /* :102 */
+  scrh = fabs(vRL[q.vn])/sqrt(o->c.gamma*vRL[PRS]/vRL[RHO]);                          /* :104-105 */
+  o->max_mach = MAXV(o->max_mach, scrh);
+  max_signal_speed (o, vRL, q, &cminRL, &cmaxRL);                                     /* :119 */
+  cRL = MAXV(fabs(cminRL), fabs(cmaxRL));
+  o->cur_SL = -cRL; o->cur_SR = cRL;                                                  /* :123-124 */
+  *cmax = cRL;
+  for (nv = 0; nv < NV; nv++) flux[nv] = 0.5*(fL[nv] + fR[nv] - cRL*(uR[nv] - uL[nv]));
+  *press = 0.5*(pL + pR);
+}
+
+static void riemann_hllc (Oracle *o, const double *vL, const double *vR,
+                          const double *uL, const double *uR, Dirs q,
+                          double *flux, double *press, double *cmax)
+/* MHD/hllc.c:42-236 (EOS IDEAL; Li 2005 / Gurski 2004) */
+{
+  double fL[NV], fR[NV], Uhll[NV], Fhll[NV], usl[NV], usr[NV];
+  double pL, pR, a2L, a2R, SL, SR, scrh;
+  double pl, pr, vBl, vBr, vxl, vxr, Bxs, Bys, Bzs, vxs, ps, vBs;
+  int nv, mxn = MX1 + (q.vn - VX1), mxt = MX1 + (q.vt - VX1), mxb = MX1 + (q.vb - VX1);
+  a2L = o->c.gamma*vL[PRS]/vL[RHO];
+  a2R = o->c.gamma*vR[PRS]/vR[RHO];
+  mhd_flux (vL, uL, q, fL, &pL);
+  mhd_flux (vR, uR, q, fR, &pR);
+  hll_speed (o, vL, vR, q, a2L, a2R, &SL, &SR);
+  scrh = MAXV(fabs(SL), fabs(SR));
+  *cmax = scrh;
+  if (SL >= 0.0){                                         /* :106-111 */
+    for (nv = 0; nv < NV; nv++) flux[nv] = fL[nv];
+    *press = pL;
+    return;
+  }
+  if (SR <= 0.0){                                         /* :113-118 */
+    for (nv = 0; nv < NV; nv++) flux[nv] = fR[nv];
+    *press = pR;
+    return;
+  }
+  scrh = 1.0/(SR - SL);                                   /* :127-138 */
+  for (nv = 0; nv < NV; nv++){
+    Uhll[nv]  = SR*uR[nv] - SL*uL[nv] + fL[nv] - fR[nv];
+    Uhll[nv] *= scrh;
+    Fhll[nv]  = SL*SR*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
+    Fhll[nv] *= scrh;
+  }
+  Uhll[mxn] += (pL - pR)*scrh;
+  Fhll[mxn] += (SR*pL - SL*pR)*scrh;
+  if (o->use_hll){                                        /* SHOCK_FLATTENING MULTID, :140-150 */
+    for (nv = 0; nv < NV; nv++){
+      flux[nv]  = SL*SR*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
+      flux[nv] *= scrh;
+    }
+    *press = (SR*pL - SL*pR)*scrh;
+    return;
+  }
+  pl = vL[BX1]*vL[BX1] + vL[BX2]*vL[BX2] + vL[BX3]*vL[BX3];       /* :154-164 */
+  pr = vR[BX1]*vR[BX1] + vR[BX2]*vR[BX2] + vR[BX3]*vR[BX3];
+  pl = vL[PRS] + 0.5*pl;
+  pr = vR[PRS] + 0.5*pr;
+  vBl = vL[VX1]*vL[BX1] + vL[VX2]*vL[BX2] + vL[VX3]*vL[BX3];
+  vBr = vR[VX1]*vR[BX1] + vR[VX2]*vR[BX2] + vR[VX3]*vR[BX3];
+  vxl = vL[q.vn];
+  vxr = vR[q.vn];
+  Bxs = Uhll[q.bn]; Bys = Uhll[q.bt]; Bzs = Uhll[q.bb];           /* :168-170 */
+  vxs = Uhll[mxn]/Uhll[RHO];                                       /* :174-175 */
+  ps  = Fhll[mxn] + Bxs*Bxs - Fhll[RHO]*vxs;
+  vBs = Uhll[BX1]*Uhll[MX1] + Uhll[BX2]*Uhll[MX1+1] + Uhll[BX3]*Uhll[MX1+2];   /* :179-183 */
+  vBs /= Uhll[RHO];
+  usl[RHO] = uL[RHO]*(SL - vxl)/(SL - vxs);                        /* :185-191 */
+  usr[RHO] = uR[RHO]*(SR - vxr)/(SR - vxs);
+  usl[ENG] = (uL[ENG]*(SL - vxl) + ps*vxs - pl*vxl - Bxs*vBs + vL[q.bn]*vBl)/(SL - vxs);
+  usr[ENG] = (uR[ENG]*(SR - vxr) + ps*vxs - pr*vxr - Bxs*vBs + vR[q.bn]*vBr)/(SR - vxs);
+  usl[mxn] = usl[RHO]*vxs;                                         /* :193-205 */
+  usr[mxn] = usr[RHO]*vxs;
+  usl[mxt] = (uL[mxt]*(SL - vxl) - (Bxs*Bys - vL[q.bn]*vL[q.bt]))/(SL - vxs);
+  usr[mxt] = (uR[mxt]*(SR - vxr) - (Bxs*Bys - vR[q.bn]*vR[q.bt]))/(SR - vxs);
+  usl[mxb] = (uL[mxb]*(SL - vxl) - (Bxs*Bzs - vL[q.bn]*vL[q.bb]))/(SL - vxs);
+  usr[mxb] = (uR[mxb]*(SR - vxr) - (Bxs*Bzs - vR[q.bn]*vR[q.bb]))/(SR - vxs);
+  usl[q.bn] = usr[q.bn] = Bxs;                                     /* :207-209 */
+  usl[q.bt] = usr[q.bt] = Bys;
+  usl[q.bb] = usr[q.bb] = Bzs;
+  if (vxs >= 0.0){                                                 /* :215-225 */
+    for (nv = 0; nv < NV; nv++) flux[nv] = fL[nv] + SL*(usl[nv] - uL[nv]);
+    *press = pL;
+  }else{
+    for (nv = 0; nv < NV; nv++) flux[nv] = fR[nv] + SR*(usr[nv] - uR[nv]);
+    *press = pR;
+  }
+}
+
 static void riemann_hlld (Oracle *o, const double *vL, const double *vR,
                           const double *uL, const double *uR, Dirs q,
                           double *flux, double *press, double *cmax)
@@ -1137,6 +1235,10 @@ static void update_stage (Oracle *o, double dt)
         o->use_hll = ((o->pflag[n] & 4) || (o->pflag[n+1] & 4));
         if      (o->c.solver == ORC_SOLVER_HLLD)
           riemann_hlld (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
+        else if (o->c.solver == ORC_SOLVER_HLLC)
+          riemann_hllc (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
+        else if (o->c.solver == ORC_SOLVER_TVDLF)
+          riemann_tvdlf (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
         else if (o->c.solver == ORC_SOLVER_HLL || o->use_hll)
           riemann_hll  (o, o->vp[n], o->vm[n+1], uL, uR, q, o->flux[n], &o->press[n], &o->cmax[n]);
         else
@@ -1821,6 +1923,10 @@ static void ctu_riemann (Oracle *o, Dirs q, int nbeg, int nend)
     o->use_hll = ((o->pflag[n] & 4) || (o->pflag[n+1] & 4));
     if      (o->c.solver == ORC_SOLVER_HLLD)
       riemann_hlld (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
+    else if (o->c.solver == ORC_SOLVER_HLLC)
+      riemann_hllc (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
+    else if (o->c.solver == ORC_SOLVER_TVDLF)
+      riemann_tvdlf (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
     else if (o->c.solver == ORC_SOLVER_HLL || o->use_hll)
       riemann_hll  (o, o->vp[n], o->vm[n+1], o->up[n], o->um[n+1], q, o->flux[n], &o->press[n], &o->cmax[n]);
     else

@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 enum { ORC_RECON_PLM = 0, ORC_RECON_PPM = 1 };
-enum { ORC_SOLVER_HLLD = 0, ORC_SOLVER_HLL = 1, ORC_SOLVER_ROE = 2 };
+enum { ORC_SOLVER_HLLD = 0, ORC_SOLVER_HLL = 1, ORC_SOLVER_ROE = 2, ORC_SOLVER_HLLC = 3, ORC_SOLVER_TVDLF = 4 };
 enum { ORC_BC_PERIODIC = 0, ORC_BC_OUTFLOW = 1, ORC_BC_REFLECTIVE = 2, ORC_BC_EQTSYMMETRIC = 3 };
 /* LIMITER (plm_states.c:192-236, plm_coeffs.h:72-123): DEFAULT mixes MC / van Leer / minmod */
 enum { ORC_LIM_DEFAULT = 0, ORC_LIM_FLAT, ORC_LIM_MINMOD, ORC_LIM_VANALBADA, ORC_LIM_OSPRE,

@@ -15,7 +15,7 @@ ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(ORACLE_DIR, "liboracle_mhd.so")
 
 RECON = {"plm": 0, "ppm": 1}
-SOLVER = {"hlld": 0, "hll": 1, "roe": 2}
+SOLVER = {"hlld": 0, "hll": 1, "roe": 2, "hllc": 3, "tvdlf": 4}
 BC = {"periodic": 0, "outflow": 1, "reflective": 2, "eqtsymmetric": 3}
 LIMITER = {"default": 0, "fl": 1, "mm": 2, "va": 3, "os": 4, "um": 5, "vl": 6, "mc": 7}
 EMF = {"uct_contact": 0, "arith": 1, "uct0": 2, "uct_hll": 3}

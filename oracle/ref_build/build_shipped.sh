@@ -21,6 +21,7 @@ while [ $# -ge 2 ]; do
   # base makefile by the configuration's time stepping: RK2 / RK3 (rk_step.o update_stage.o) or the corner-transport-upwind step
   # with the characteristic-tracing predictor (ctu_step.o char_tracing.o; plm_states.o still calls CharTracingStep in the GPU build)
   BASE=2d_plm
+  if grep -q "RECONSTRUCTION *PARABOLIC" "$TP/definitions_$NN.h"; then BASE=2d_ppm; fi            # ppm_states.o ppm_coeffs.o (RK2 / RK3)
   if grep -q "TIME_STEPPING *CHARACTERISTIC_TRACING" "$TP/definitions_$NN.h"; then BASE=2d_plm_chtr; fi
   if grep -q "TIME_STEPPING *HANCOCK" "$TP/definitions_$NN.h"; then BASE=2d_plm_hancock; fi      # ctu_step.o hancock.o
   [ -f "$ORACLE/_build/$BASE/makefile" ] || "$HERE/build_ref.sh" "$BASE"

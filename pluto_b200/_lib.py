@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libpluto_gpu.so")
 
 RECON = {"plm": 0, "linear": 0, "ppm": 1, "parabolic": 1}
-SOLVER = {"hlld": 0, "hll": 1, "roe": 2}
+SOLVER = {"hlld": 0, "hll": 1, "roe": 2, "hllc": 3, "tvdlf": 4}
 BC = {"periodic": 0, "outflow": 1, "reflective": 2, "shared": 3, "eqtsymmetric": 4}
 LIMITER = {"default": 0, "fl": 1, "mm": 2, "va": 3, "os": 4, "um": 5, "vl": 6, "mc": 7}      # LIMITER
 EMF = {"uct_contact": 0, "arith": 1, "uct0": 2, "uct_hll": 3}                                                 # CT_EMF_AVERAGE

@@ -10,6 +10,12 @@ int launch_ctu_half (const CtuArgs &a, cudaStream_t s) { return launch_ctu_half_
 #elif PG_SOLVER == 1
 int launch_ctu_sweep_hll (int dir, int phase, const CtuArgs &a, cudaStream_t s)
 { return launch_ctu_sweep_t<SOLVER_HLL>(dir, phase, a, s); }
+#elif PG_SOLVER == 3
+int launch_ctu_sweep_hllc (int dir, int phase, const CtuArgs &a, cudaStream_t s)
+{ return launch_ctu_sweep_t<SOLVER_HLLC>(dir, phase, a, s); }
+#elif PG_SOLVER == 4
+int launch_ctu_sweep_tvdlf (int dir, int phase, const CtuArgs &a, cudaStream_t s)
+{ return launch_ctu_sweep_t<SOLVER_TVDLF>(dir, phase, a, s); }
 #else
 int launch_ctu_sweep_roe (int dir, int phase, const CtuArgs &a, cudaStream_t s)
 { return launch_ctu_sweep_t<SOLVER_ROE>(dir, phase, a, s); }

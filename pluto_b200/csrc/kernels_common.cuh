@@ -274,12 +274,18 @@ namespace NS {                                                                  
   int launch_sweep_hlld (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
   int launch_sweep_hll  (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
   int launch_sweep_roe  (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
+  int launch_sweep_hllc (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf);  \
+  int launch_sweep_tvdlf (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf); \
   int launch_sweep_xy_hlld (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
   int launch_sweep_xy_hll  (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
   int launch_sweep_xy_roe  (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
+  int launch_sweep_xy_hllc (int recon, const SweepArgs &a, cudaStream_t s, bool bf);        \
+  int launch_sweep_xy_tvdlf (int recon, const SweepArgs &a, cudaStream_t s, bool bf);       \
   int launch_ctu_sweep_hlld (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
   int launch_ctu_sweep_hll  (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
   int launch_ctu_sweep_roe  (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
+  int launch_ctu_sweep_hllc (int dir, int phase, const CtuArgs &a, cudaStream_t s);      \
+  int launch_ctu_sweep_tvdlf (int dir, int phase, const CtuArgs &a, cudaStream_t s);     \
   int launch_ctu_half   (const CtuArgs &a, cudaStream_t s);                              \
   int launch_ct_emf     (const CtArgs &a, cudaStream_t s);                               \
   int launch_ct_update  (const CtArgs &a, cudaStream_t s);                               \

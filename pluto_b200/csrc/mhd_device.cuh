@@ -34,7 +34,7 @@ namespace PG_NS {
 enum { RHO = 0, VX1 = 1, VX2 = 2, VX3 = 3, BX1 = 4, BX2 = 5, BX3 = 6, PRS = 7, NV = 8 };
 enum { MX1 = VX1, MX2 = VX2, MX3 = VX3, ENG = PRS };
 enum { RECON_PLM = 0, RECON_PPM = 1, RECON_PLMW = 2 };      // PLMW: linear with the grid-dependent weights of UNIFORM_CARTESIAN_GRID NO
-enum { SOLVER_HLLD = 0, SOLVER_HLL = 1, SOLVER_ROE = 2 };
+enum { SOLVER_HLLD = 0, SOLVER_HLL = 1, SOLVER_ROE = 2, SOLVER_HLLC = 3, SOLVER_TVDLF = 4 };
 
 struct Phys {                          // same layout as PhysPar (kernels_common.cuh)
   double gamma, gmm1, small_dn, small_pr;
@@ -774,6 +774,130 @@ __device__ __forceinline__ void riemann_hll (const Phys &ph, const double *vL, c
     }
     press = (SR*pL - SL*pR)*scrh;
   }
+}
+
+// Lax-Friedrichs (Rusanov) flux, tvdlf.c:51-135: one speed from the arithmetic mean of the two states; the fan speeds that
+// UCT_HLL keeps are -cRL and +cRL (:123-124), the Mach number is that of the mean state (:104-105).
+template <int DIR, int NC>
+__device__ __forceinline__ void riemann_tvdlf (const Phys &ph, const double *vL, const double *vR,
+                                               const double *uL, const double *uR,
+                                               double *flux, double &press, double &cmax, double &mach,
+                                               double *pSL = nullptr, double *pSR = nullptr)
+{
+  typedef Dirs<DIR> D;
+  double fL[NV], fR[NV], vRL[NV], pL, pR, cminRL, cmaxRL;
+  mhd_flux<DIR, NC>(vL, uL, fL, pL);
+  mhd_flux<DIR, NC>(vR, uR, fR, pR);
+  PG_FOR_NV(nv) vRL[nv] = 0.5*(vL[nv] + vR[nv]);
+  mach = pg_div (fabs(vRL[D::vn]), pg_sqrt (pg_div (ph.gamma*vRL[PRS], vRL[RHO])));
+  max_signal_speed<DIR, NC>(ph, vRL, cminRL, cmaxRL);
+  const double cRL = maxv(fabs(cminRL), fabs(cmaxRL));
+  store_fan_speeds (pSL, pSR, -cRL, cRL);
+  cmax = cRL;
+  PG_FOR_NV(nv) flux[nv] = 0.5*(fL[nv] + fR[nv] - cRL*(uR[nv] - uL[nv]));
+  press = 0.5*(pL + pR);
+}
+
+// HLLC (Li 2005), hllc.c:42-236: the HLL average supplies the field and the contact speed of the two star states.  FLAGGED: the
+// interface touches a zone that SHOCK_FLATTENING MULTID marked FLAG_HLL -> the plain HLL flux inside the fan (:140-150).
+template <int DIR, int NC, bool FLAGGED = false>
+__device__ __forceinline__ void riemann_hllc (const Phys &ph, const double *vL, const double *vR,
+                                              const double *uL, const double *uR,
+                                              double *flux, double &press, double &cmax, double &mach,
+                                              double *pSL = nullptr, double *pSR = nullptr)
+{
+  typedef Dirs<DIR> D;
+  constexpr int mxn = D::vn, mxt = D::vt, mxb = D::vb;            // momentum slots = velocity slots
+  double fL[NV], fR[NV], pL, pR, a2L, a2R, SL, SR, scrh;
+  a2L = pg_div (ph.gamma*vL[PRS], vL[RHO]);
+  a2R = pg_div (ph.gamma*vR[PRS], vR[RHO]);
+  mhd_flux<DIR, NC>(vL, uL, fL, pL);
+  mhd_flux<DIR, NC>(vR, uR, fR, pR);
+  hll_speed<DIR, NC>(ph, vL, vR, a2L, a2R, SL, SR, mach);
+  store_fan_speeds (pSL, pSR, SL, SR);
+  cmax = maxv(fabs(SL), fabs(SR));
+  if (SL >= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fL[nv];
+    press = pL;
+    return;
+  }
+  if (SR <= 0.0){
+    PG_FOR_NV(nv) flux[nv] = fR[nv];
+    press = pR;
+    return;
+  }
+  scrh = pg_rcp (SR - SL);
+  if (FLAGGED){
+    PG_FOR_NV(nv){
+      flux[nv]  = SL*SR*(uR[nv] - uL[nv]) + SR*fL[nv] - SL*fR[nv];
+      flux[nv] *= scrh;
+    }
+    press = (SR*pL - SL*pR)*scrh;
+    return;
+  }
+  double Uhll[NV];
+  PG_FOR_NV(nv){
+    Uhll[nv]  = SR*uR[nv] - SL*uL[nv] + fL[nv] - fR[nv];
+    Uhll[nv] *= scrh;
+  }
+  Uhll[mxn] += (pL - pR)*scrh;
+  double Fn  = SL*SR*(uR[mxn] - uL[mxn]) + SR*fL[mxn] - SL*fR[mxn];      // Fhll[MXn], Fhll[RHO]: the only two in use
+  Fn *= scrh;
+  Fn += (SR*pL - SL*pR)*scrh;
+  double Fr  = SL*SR*(uR[RHO] - uL[RHO]) + SR*fL[RHO] - SL*fR[RHO];
+  Fr *= scrh;
+
+  double pl, pr, vBl, vBr, vBs;
+  if (NC == 3){
+    pl  = vL[BX1]*vL[BX1] + vL[BX2]*vL[BX2] + vL[BX3]*vL[BX3];
+    pr  = vR[BX1]*vR[BX1] + vR[BX2]*vR[BX2] + vR[BX3]*vR[BX3];
+    vBl = vL[VX1]*vL[BX1] + vL[VX2]*vL[BX2] + vL[VX3]*vL[BX3];
+    vBr = vR[VX1]*vR[BX1] + vR[VX2]*vR[BX2] + vR[VX3]*vR[BX3];
+    vBs = Uhll[BX1]*Uhll[MX1] + Uhll[BX2]*Uhll[MX2] + Uhll[BX3]*Uhll[MX3];
+  }else{
+    pl  = vL[BX1]*vL[BX1] + vL[BX2]*vL[BX2];
+    pr  = vR[BX1]*vR[BX1] + vR[BX2]*vR[BX2];
+    vBl = vL[VX1]*vL[BX1] + vL[VX2]*vL[BX2];
+    vBr = vR[VX1]*vR[BX1] + vR[VX2]*vR[BX2];
+    vBs = Uhll[BX1]*Uhll[MX1] + Uhll[BX2]*Uhll[MX2];
+  }
+  pl = vL[PRS] + 0.5*pl;
+  pr = vR[PRS] + 0.5*pr;
+  const double vxl = vL[D::vn], vxr = vR[D::vn];
+  const double Bxs = Uhll[D::bn], Bys = Uhll[D::bt];
+  const double vxs = pg_div (Uhll[mxn], Uhll[RHO]);
+  const double ps  = Fn + Bxs*Bxs - Fr*vxs;
+  vBs = pg_div (vBs, Uhll[RHO]);
+
+  // the state on the side of the contact the interface lies on (the reference builds both, :185-209); selects value by
+  // value, so that the state arrays stay in registers
+  const bool left = (vxs >= 0.0);
+  #define PG_SIDE(aL, aR) (left ? (aL) : (aR))
+  const double S = PG_SIDE (SL, SR), vx = PG_SIDE (vxl, vxr), pt = PG_SIDE (pl, pr), vB = PG_SIDE (vBl, vBr);
+  const double bn = PG_SIDE (vL[D::bn], vR[D::bn]);
+#ifdef PG_FAST_MATH
+  const double idn = pg_rcp (S - vxs);
+  #define PG_HLLC_DIV(x) ((x)*idn)
+#else
+  const double den = S - vxs;
+  #define PG_HLLC_DIV(x) pg_div ((x), den)
+#endif
+  double us[NV];
+  us[RHO] = PG_HLLC_DIV (PG_SIDE (uL[RHO], uR[RHO])*(S - vx));
+  us[ENG] = PG_HLLC_DIV (PG_SIDE (uL[ENG], uR[ENG])*(S - vx) + ps*vxs - pt*vx - Bxs*vBs + bn*vB);
+  us[mxn] = us[RHO]*vxs;
+  us[mxt] = PG_HLLC_DIV (PG_SIDE (uL[mxt], uR[mxt])*(S - vx) - (Bxs*Bys - bn*PG_SIDE (vL[D::bt], vR[D::bt])));
+  if (NC == 3){
+    const double Bzs = Uhll[D::bb];
+    us[mxb] = PG_HLLC_DIV (PG_SIDE (uL[mxb], uR[mxb])*(S - vx) - (Bxs*Bzs - bn*PG_SIDE (vL[D::bb], vR[D::bb])));
+    us[D::bb] = Bzs;
+  }
+  #undef PG_HLLC_DIV
+  us[D::bn] = Bxs;
+  us[D::bt] = Bys;
+  PG_FOR_NV(nv) flux[nv] = PG_SIDE (fL[nv], fR[nv]) + S*(us[nv] - PG_SIDE (uL[nv], uR[nv]));
+  press = PG_SIDE (pL, pR);
+  #undef PG_SIDE
 }
 
 #ifdef PG_FAST_MATH
@@ -1560,8 +1684,10 @@ __device__ __forceinline__ void riemann_flagged (const Phys &ph, const double *v
                                                  double *flux, double &press, double &cmax, double &mach,
                                                  double *pSL, double *pSR)
 {
-  if (SOLVER == SOLVER_HLLD) riemann_hll<DIR, NC, false>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
-  else                       riemann_hll<DIR, NC, true> (ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
+  if      (SOLVER == SOLVER_HLLD)  riemann_hll<DIR, NC, false>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
+  else if (SOLVER == SOLVER_HLLC)  riemann_hllc<DIR, NC, true>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);    // hllc.c:140-150
+  else if (SOLVER == SOLVER_TVDLF) riemann_tvdlf<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);         // tvdlf.c has no flagged branch
+  else                             riemann_hll<DIR, NC, true> (ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
 }
 
 // solver dispatch on a compile-time constant
@@ -1577,6 +1703,8 @@ __device__ __forceinline__ bool riemann (const Phys &ph, const double *vL, const
   if (SOLVER == SOLVER_HLLD){ riemann_hlld<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }
 #endif
   else if (SOLVER == SOLVER_HLL){ riemann_hll<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }
+  else if (SOLVER == SOLVER_HLLC){ riemann_hllc<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }
+  else if (SOLVER == SOLVER_TVDLF){ riemann_tvdlf<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR); return true; }
   else return riemann_roe<DIR, NC>(ph, vL, vR, uL, uR, flux, press, cmax, mach, pSL, pSR);
 }
 

@@ -162,7 +162,7 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   *out = NULL;
   if (cfg->dims != 2 && cfg->dims != 3) return fail ("dims must be 2 or 3");
   if (cfg->recon != PLUTO_GPU_RECON_LINEAR && cfg->recon != PLUTO_GPU_RECON_PARABOLIC) return fail ("bad recon");
-  if (cfg->solver < 0 || cfg->solver > 2) return fail ("bad solver");
+  if (cfg->solver < 0 || cfg->solver > 4) return fail ("bad solver");
   if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
   if (cfg->limiter < 0 || cfg->limiter > PLUTO_GPU_LIM_MC) return fail ("bad limiter");
   if (cfg->shock_flattening != 0 && cfg->shock_flattening != 1) return fail ("bad shock_flattening");
@@ -189,8 +189,8 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     return fail ("CT_EN_CORRECTION YES is available with CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
                  "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail ("bad body_force");
-  if (cfg->body_force && (cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL || cfg->shock_flattening))
-    return fail ("BODY_FORCE is not available together with CT_EMF_AVERAGE UCT_HLL or SHOCK_FLATTENING");
+  if (cfg->body_force && cfg->shock_flattening)
+    return fail ("BODY_FORCE is not available together with SHOCK_FLATTENING");
   if (cfg->char_limiting != 0 && cfg->char_limiting != 1) return fail ("bad char_limiting");
   if (cfg->char_limiting){
     if (cfg->dims != 2)
@@ -963,6 +963,8 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       const int te = tbegin (h, KC_SWEEP_X);
       if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = pg_fast::launch_sweep_xy_hlld (recon, s, h->stream, bf);
       else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = pg_fast::launch_sweep_xy_hll  (recon, s, h->stream, bf);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLLC)  r = pg_fast::launch_sweep_xy_hllc  (recon, s, h->stream, bf);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_TVDLF) r = pg_fast::launch_sweep_xy_tvdlf (recon, s, h->stream, bf);
       else                                             r = pg_fast::launch_sweep_xy_roe  (recon, s, h->stream, bf);
       tend (h, te);
       if (count (h, r)) return 1;
@@ -972,6 +974,8 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     const int te = tbegin (h, KC_SWEEP_X + dir);
     if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_sweep_hlld) (dir, recon, s, h->stream, bf);
     else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_sweep_hll)  (dir, recon, s, h->stream, bf);
+    else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLLC)  r = DISPATCH (h, launch_sweep_hllc)  (dir, recon, s, h->stream, bf);
+    else if (h->cfg.solver == PLUTO_GPU_SOLVER_TVDLF) r = DISPATCH (h, launch_sweep_tvdlf) (dir, recon, s, h->stream, bf);
     else                                             r = DISPATCH (h, launch_sweep_roe)  (dir, recon, s, h->stream, bf);
     tend (h, te);
     if (count (h, r)) return 1;
@@ -1072,6 +1076,8 @@ static int run_ctu (PlutoGpu *h, int part)
       const int te = tbegin (h, KC_SWEEP_X + dir);
       if      (h->cfg.solver == PLUTO_GPU_SOLVER_HLLD) r = DISPATCH (h, launch_ctu_sweep_hlld) (dir, phase, s, h->stream);
       else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLL)  r = DISPATCH (h, launch_ctu_sweep_hll)  (dir, phase, s, h->stream);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_HLLC)  r = DISPATCH (h, launch_ctu_sweep_hllc)  (dir, phase, s, h->stream);
+      else if (h->cfg.solver == PLUTO_GPU_SOLVER_TVDLF) r = DISPATCH (h, launch_ctu_sweep_tvdlf) (dir, phase, s, h->stream);
       else                                             r = DISPATCH (h, launch_ctu_sweep_roe)  (dir, phase, s, h->stream);
       tend (h, te);
       if (count (h, r)) return 1;

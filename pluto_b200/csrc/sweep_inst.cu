@@ -18,6 +18,20 @@ int launch_sweep_hll (int dir, int recon, const SweepArgs &a, cudaStream_t s, bo
 int launch_sweep_xy_hll (int recon, const SweepArgs &a, cudaStream_t s, bool bf)
 { return launch_sweep_xy_t<SOLVER_HLL>(recon, a, s, bf); }
 #endif
+#elif PG_SOLVER == 3
+int launch_sweep_hllc (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf)
+{ return launch_sweep_t<SOLVER_HLLC>(dir, recon, a, s, bf); }
+#ifdef PG_FAST
+int launch_sweep_xy_hllc (int recon, const SweepArgs &a, cudaStream_t s, bool bf)
+{ return launch_sweep_xy_t<SOLVER_HLLC>(recon, a, s, bf); }
+#endif
+#elif PG_SOLVER == 4
+int launch_sweep_tvdlf (int dir, int recon, const SweepArgs &a, cudaStream_t s, bool bf)
+{ return launch_sweep_t<SOLVER_TVDLF>(dir, recon, a, s, bf); }
+#ifdef PG_FAST
+int launch_sweep_xy_tvdlf (int recon, const SweepArgs &a, cudaStream_t s, bool bf)
+{ return launch_sweep_xy_t<SOLVER_TVDLF>(recon, a, s, bf); }
+#endif
 #else
 #ifdef PG_FAST
 // self-test of the branch-free IEEE division / square root of this unit (mhd_device.cuh) against div.rn.f64 / sqrt.rn.f64:

@@ -83,7 +83,7 @@ def _build(verbose: bool = False) -> str:
             (exact, "ct_kernels.cu", "ct_exact.o"), (fast, "ct_kernels.cu", "ct_fast.o")]
     # the Roe units (solver 2) of the FAST library keep IEEE arithmetic (pluto_b200/csrc/Makefile: -fmad=false)
     fast_roe = common + ["-ffp-contract=off", "-DPG_NS=pg_fast", "-DPG_FAST=1", "-DPG_HOST_EMU=1"]
-    for s in range(3):
+    for s in range(5):
         fs = fast_roe if s == 2 else fast
         jobs.append((exact + [f"-DPG_SOLVER={s}"], "sweep_inst.cu", f"sweep_exact_{s}.o"))
         jobs.append((fs + [f"-DPG_SOLVER={s}"], "sweep_inst.cu", f"sweep_fast_{s}.o"))

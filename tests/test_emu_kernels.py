@@ -56,7 +56,8 @@ def test_emulated_exact_kernels_bit_identical_to_golden(name, emu_lib):
 
 FAST_SUBSET = ["blast3d_plm_hlld", "ot2d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe", "turb3d_uct_hll", "blast3d_sfl",
                "blast3d_ctu", "ot2d_ctu", "turb3d_ctu_roe", "blast3d_blast02_en", "blast3d_bf", "turb3d_ctu_bf", "blast2d_ctu_bfx_roe",
-               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3", "blast3d_nug", "blast2d_nug_mc_arith_reflective", "blast3d_ppm_sfl"]
+               "ot2d_cl", "blast2d_cl_roe", "rotor2d_cl_vl_rk3", "blast3d_nug", "blast2d_nug_mc_arith_reflective", "blast3d_ppm_sfl",
+               "blast3d_hllc", "ot3d_ctu_um_uct0_tvdlf", "blast3d_nug_ctu"]
 
 
 @pytest.mark.parametrize("name", FAST_SUBSET)

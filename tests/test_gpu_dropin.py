@@ -41,7 +41,11 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # body forces on non-uniform grids: potential and position-dependent force tabulated by the shim at grid->x / xr
          "blast3d_nug_bp", "blast2d_nug_bfx_roe",
          # the corner-transport-upwind steps on non-uniform grids
-         "blast3d_nug_ctu", "rotor2d_nug_chtr_mc"]
+         "blast3d_nug_ctu", "rotor2d_nug_chtr_mc",
+         # [Solver] hllc / tvdlf
+         "blast3d_hllc", "rotor2d_ppm_rk3_hllc", "turb3d_ctu_hllc", "ot2d_tvdlf",
+         # BODY_FORCE with UCT_HLL
+         "blast3d_bf_uct_hll", "rotor2d_ppm_rk3_bp_uct_hll_roe"]
 
 
 def _blast_params(g):

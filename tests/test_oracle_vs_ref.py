@@ -147,6 +147,24 @@ CASES = [
     ("blast3d_ppm_sfl", RefConfig(problem="blast", dims=3, n=(14, 12, 16), recon="ppm", first_dt=3e-4, cfl=0.3, flatten=True), 10),
     ("rotor2d_chtr_mc_uct0_hll", RefConfig(problem="rotor", dims=2, n=(36, 32, 1), first_dt=2e-3, tstep="chtr", limiter="mc", emf="uct0",
                                            solver="hll"), 10),
+    # the HLLC (hllc.c) and Lax-Friedrichs (tvdlf.c) solvers: pluto.ini's [Solver] block picks them at run time
+    ("ot2d_hllc", RefConfig(problem="ot", dims=2, n=(48, 40, 1), first_dt=1.5e-2, solver="hllc"), 12),
+    ("blast3d_hllc", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, solver="hllc"), 8),
+    ("rotor2d_ppm_rk3_hllc", RefConfig(problem="rotor", dims=2, n=(40, 36, 1), recon="ppm", tstep="rk3", first_dt=2e-3, solver="hllc"), 8),
+    ("blast3d_sfl_uct_hll_hllc", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, emf="uct_hll", flatten=True,
+                                           solver="hllc"), 8),
+    ("turb3d_ctu_hllc", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, tstep="hancock", solver="hllc"), 6),
+    ("ot2d_tvdlf", RefConfig(problem="ot", dims=2, n=(48, 40, 1), first_dt=1.5e-2, solver="tvdlf"), 12),
+    ("blast3d_tvdlf_uct_hll", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, solver="tvdlf", emf="uct_hll"), 8),
+    ("ot3d_ctu_um_uct0_tvdlf", RefConfig(problem="ot", dims=3, n=(12, 16, 10), first_dt=3e-2, cfl=0.3, tstep="hancock", limiter="um",
+                                         emf="uct0", solver="tvdlf"), 6),
+    ("blast2d_sfl_tvdlf", RefConfig(problem="blast", dims=2, n=(36, 32, 1), first_dt=3e-4, solver="tvdlf", flatten=True), 10),
+    # BODY_FORCE with CT_EMF_AVERAGE UCT_HLL (the reference's DEFAULT average, CT/ct.h: what a configuration with gravity and no
+    # explicit CT_EMF_AVERAGE runs, e.g. the shipped Rayleigh_Taylor #07)
+    ("blast3d_bf_uct_hll", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(0.3, -1.0, 0.5), emf="uct_hll"), 8),
+    ("rotor2d_ppm_rk3_bp_uct_hll_roe", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", tstep="rk3", first_dt=2e-3,
+                                                 grav=(0.05, -0.03, 0.0), potential=True, emf="uct_hll", solver="roe"), 6),
+    ("blast2d_chtr_mc_hllc", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="hllc"), 10),
 ]
 
 

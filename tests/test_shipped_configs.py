@@ -14,6 +14,8 @@ The binaries are built in the development container by oracle/ref_build/build_sh
   Orszag_Tang #09  2-D 512^2, LINEAR, HANCOCK (corner transport upwind), hlld, MC_LIM, ARITHMETIC, CHAR_LIMITING YES, periodic
   Rayleigh_Taylor #05  2-D 256 x 512, LINEAR, HANCOCK (corner transport upwind), roe, MC_LIM, ARITHMETIC, BODY_FORCE VECTOR,
                    periodic / reflective
+  Orszag_Tang #07  3-D 64^3, LINEAR, HANCOCK (corner transport upwind), tvdlf, UMIST_LIM, UCT0, periodic
+  Rayleigh_Taylor #07  2-D 128 x 256, PARABOLIC, RK3, roe, UCT_CONTACT, BODY_FORCE POTENTIAL, periodic / reflective
 """
 import os
 import shutil
@@ -28,7 +30,7 @@ from tests.util import ROOT
 
 SHIPPED = os.path.join(ROOT, "oracle", "_ref", "shipped")
 CASES = [("orszag_tang_03", 3), ("rotor_01", 2), ("blast_02", 1), ("field_loop_01", 4), ("field_loop_02", 3), ("blast_01", 2),
-         ("orszag_tang_05", 2), ("rayleigh_taylor_05", 1), ("orszag_tang_09", 1)]
+         ("orszag_tang_05", 2), ("rayleigh_taylor_05", 1), ("orszag_tang_09", 1), ("orszag_tang_07", 1), ("rayleigh_taylor_07", 1)]
 
 
 def _grid(ini):

@@ -132,6 +132,19 @@ CASES = {
                                                          "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 12),
     "blast2d_nug_bfx_roe": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=4e-4, cfl=0.4, solver="roe", grav=(-3.0, -1.0, 0.0),
                                       grav_mode=1, grid=("2  -0.5  20  u  0.2  8  s  0.5", "2  -0.5  8  s  -0.1  16  u  0.5", None)), 20),
+    # the HLLC and Lax-Friedrichs solvers (hllc.c, tvdlf.c)
+    "blast3d_hllc": (RefConfig(problem="blast", dims=3, n=(20, 16, 12), first_dt=6e-4, cfl=0.3, solver="hllc"), 12),
+    "rotor2d_ppm_rk3_hllc": (RefConfig(problem="rotor", dims=2, n=(40, 36, 1), recon="ppm", tstep="rk3", first_dt=2.5e-3, solver="hllc"), 12),
+    "turb3d_ctu_hllc": (RefConfig(problem="turb", dims=3, n=(12, 14, 10), first_dt=2e-2, cfl=0.3, tstep="hancock", solver="hllc"), 10),
+    "ot2d_tvdlf": (RefConfig(problem="ot", dims=2, n=(48, 40, 1), first_dt=1.5e-2, solver="tvdlf"), 15),
+    "ot3d_ctu_um_uct0_tvdlf": (RefConfig(problem="ot", dims=3, n=(12, 16, 10), first_dt=3e-2, cfl=0.3, tstep="hancock", limiter="um",
+                                         emf="uct0", solver="tvdlf"), 10),
+    "blast3d_sfl_uct_hll_hllc": (RefConfig(problem="blast", dims=3, n=(14, 16, 12), first_dt=6e-4, cfl=0.3, emf="uct_hll", flatten=True,
+                                           solver="hllc"), 10),
+    # BODY_FORCE with the reference's default EMF average, UCT_HLL
+    "blast3d_bf_uct_hll": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grav=(0.3, -1.0, 0.5), emf="uct_hll"), 12),
+    "rotor2d_ppm_rk3_bp_uct_hll_roe": (RefConfig(problem="rotor", dims=2, n=(36, 28, 1), recon="ppm", tstep="rk3", first_dt=2.5e-3,
+                                                 grav=(0.05, -0.03, 0.0), potential=True, emf="uct_hll", solver="roe"), 10),
     # the corner-transport-upwind steps on non-uniform grids (Hancock 3-D; characteristic tracing 2-D, MC_LIM)
     "blast3d_nug_ctu": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, tstep="hancock",
                                   grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
