@@ -10,7 +10,7 @@
  * calls per step: Boundary (Src/boundary.c:41), UpdateStage
  * (Src/Time_Stepping/update_stage.c:37), States (Src/States/plm_states.c:80,
  * ppm_states.c:68), the Riemann solvers (Src/MHD/hlld.c:44, hll.c:30,
- * roe.c:53), RightHandSide (Src/MHD/rhs.c:84), the constrained-transport
+ * roe.c:53, hllc.c:42, tvdlf.c:51), RightHandSide (Src/MHD/rhs.c:84), the constrained-transport
  * routines (Src/MHD/CT/ct_emf.c, ct_emf_average.c, ct_update.c,
  * ct_field_average.c, ct_fill_mag_field.c), the mappers
  * (Src/MHD/mappers.c, Src/mappers3D.c) and the CFL reduction feeding
@@ -126,8 +126,9 @@ int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
    CARTESIAN builds keep the uniform reconstruction weights (UNIFORM_CARTESIAN_GRID YES, Src/States/plm_coeffs.h:23-29); the
    widths enter Src/MHD/rhs.c:195, the inverse time step (Src/Time_Stepping/update_stage.c:229-235), Src/MHD/CT/ct_update.c:91-204
    and the face areas of Src/MHD/CT/ct_fill_mag_field.c:108-114; with the corner-transport-upwind steps also the predictors
-   (Src/States/hancock.c:245-296, char_tracing.c:347-362) and the transverse correction of ctu_step.c:310, 731-785.  LINEAR
-   reconstruction without SHOCK_FLATTENING / CT_EN_CORRECTION / CHAR_LIMITING (refused otherwise); dx3 may be NULL in 2-D.
+   (Src/States/hancock.c:245-296, char_tracing.c:347-362), the transverse correction of ctu_step.c:310, 731-785 and the potential's
+   source of Src/MHD/prim_eqn.c:304-307; with SHOCK_FLATTENING MULTID Src/flag_shock.c:143-145.  LINEAR reconstruction (PARABOLIC
+   is refused: its weights come from ppm_coeffs.c); dx3 may be NULL in 2-D.
    PlutoGpuConfig.dx is then used by nothing on the path.  Call once after pluto_gpu_create. */
 int  pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const double *dx3);
 /* UNIFORM_CARTESIAN_GRID NO (Src/States/plm_coeffs.h:23-29): grid-dependent weights of the linear reconstruction.  Hand over, for
@@ -331,6 +332,10 @@ int  pluto_gpu_multi_download_data (PlutoGpuMulti *m, double *Vc, double *Vs1, d
 int  pluto_gpu_multi_set_grid (PlutoGpuMulti *m, const double *dx1, const double *dx2, const double *dx3);
 int  pluto_gpu_multi_set_plm_coeffs (PlutoGpuMulti *m, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
                                      const double *dp, const double *dm);
+/* pluto_gpu_set_body_force / pluto_gpu_set_body_potential for the blocks: HOST arrays of the WHOLE domain in the same layouts
+   (ghost zones included; the face arrays with one more entry along their direction), cut into the blocks' pieces */
+int  pluto_gpu_multi_set_body_force (PlutoGpuMulti *m, const double *g1, const double *g2, const double *g3);
+int  pluto_gpu_multi_set_body_potential (PlutoGpuMulti *m, const double *phic, const double *pf1, const double *pf2, const double *pf3);
 int  pluto_gpu_multi_advance (PlutoGpuMulti *m, double dt, PlutoGpuStepInfo *info);
 int  pluto_gpu_multi_advance_data (PlutoGpuMulti *m, double dt, double *Vc, double *Vs1, double *Vs2, double *Vs3,
                                    PlutoGpuStepInfo *info);

@@ -174,10 +174,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     }
     if (nonuniform){
       /* stretched / logarithmic / multi-patch grids (set_grid.c:330-560): the zone widths go to the library after its creation */
-#if RECONSTRUCTION != LINEAR || SHOCK_FLATTENING != NO || CT_EN_CORRECTION == YES || CHAR_LIMITING == YES \
-    || ((TIME_STEPPING == HANCOCK || TIME_STEPPING == CHARACTERISTIC_TRACING) && BODY_FORCE != NO)
-      print ("! AdvanceStep(gpu): a non-uniform grid needs LINEAR reconstruction, without SHOCK_FLATTENING, CT_EN_CORRECTION and\n"
-             "  CHAR_LIMITING (and without BODY_FORCE with the corner-transport-upwind steps) on the GPU\n");
+#if RECONSTRUCTION != LINEAR || (UNIFORM_CARTESIAN_GRID == NO && (SHOCK_FLATTENING != NO || CHAR_LIMITING == YES))
+      print ("! AdvanceStep(gpu): a non-uniform grid needs LINEAR reconstruction (UNIFORM_CARTESIAN_GRID NO: without SHOCK_FLATTENING\n"
+             "  and CHAR_LIMITING) on the GPU\n");
       QUIT_PLUTO(1);
 #endif
     }
@@ -252,7 +251,8 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
         pt[off[3] + ((size_t)(kk + 1)*n2 + jj)*n1 + ii] =
           BodyForcePotential (grid->x[IDIR][ii], grid->x[JDIR][jj], kk < 0 ? grid->xl[KDIR][0] : grid->xr[KDIR][kk]);
   #endif
-      if (pluto_gpu_set_body_potential (gpu, pt + off[0], pt + off[1], pt + off[2], DIMENSIONS == 3 ? pt + off[3] : NULL) != 0){
+      if ((gpum ? pluto_gpu_multi_set_body_potential (gpum, pt + off[0], pt + off[1], pt + off[2], DIMENSIONS == 3 ? pt + off[3] : NULL)
+                : pluto_gpu_set_body_potential (gpu, pt + off[0], pt + off[1], pt + off[2], DIMENSIONS == 3 ? pt + off[3] : NULL)) != 0){
         print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
         QUIT_PLUTO(1);
       }
@@ -279,7 +279,8 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
         gt[id] = g1[0]; gt[nz + id] = g1[1]; gt[2*nz + id] = g1[2];
         id++;
       }
-      if (pluto_gpu_set_body_force (gpu, gt, gt + nz, DIMENSIONS == 3 ? gt + 2*nz : NULL) != 0){
+      if ((gpum ? pluto_gpu_multi_set_body_force (gpum, gt, gt + nz, DIMENSIONS == 3 ? gt + 2*nz : NULL)
+                : pluto_gpu_set_body_force (gpu, gt, gt + nz, DIMENSIONS == 3 ? gt + 2*nz : NULL)) != 0){
         print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
         QUIT_PLUTO(1);
       }

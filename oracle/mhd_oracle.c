@@ -1706,10 +1706,10 @@ static void flag_shock (Oracle *o)
   for (j = 1; j < o->T[1] - 1; j++)
   for (i = 1; i < o->T[0] - 1; i++){
     double dvx1, dvx2, dvx3 = 0.0, divv, gradp, pt_min, pt_min1, pt_min2, pt_min3, dpx1, dpx2, dpx3;
-    dvx1 = (vx1[I3(k,j,i+1)] - vx1[I3(k,j,i-1)])/o->c.dx[0];
-    dvx2 = (vx2[I3(k,j+1,i)] - vx2[I3(k,j-1,i)])/o->c.dx[1];
+    dvx1 = (vx1[I3(k,j,i+1)] - vx1[I3(k,j,i-1)])/DXA(o,0,i);       /* dx1[i], dx2[j], dx3[k]: flag_shock.c:143-145 */
+    dvx2 = (vx2[I3(k,j+1,i)] - vx2[I3(k,j-1,i)])/DXA(o,1,j);
     if (dims == 3){
-      dvx3 = (vx3[I3(k+1,j,i)] - vx3[I3(k-1,j,i)])/o->c.dx[2];
+      dvx3 = (vx3[I3(k+1,j,i)] - vx3[I3(k-1,j,i)])/DXA(o,2,k);
       divv = dvx1 + dvx2 + dvx3;
     }else divv = dvx1 + dvx2;
     if (divv < 0.0){

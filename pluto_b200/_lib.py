@@ -27,6 +27,7 @@ SYMBOLS = [
     "pluto_gpu_halo_pack_all", "pluto_gpu_halo_unpack_all", "pluto_gpu_halo_pack_all_on", "pluto_gpu_halo_plan_stage",
     "pluto_gpu_device_count", "pluto_gpu_multi_create", "pluto_gpu_multi_destroy", "pluto_gpu_multi_nghost", "pluto_gpu_multi_nblocks", "pluto_gpu_multi_upload_data",
     "pluto_gpu_multi_download_data", "pluto_gpu_multi_advance", "pluto_gpu_multi_advance_data", "pluto_gpu_multi_set_grid", "pluto_gpu_multi_set_plm_coeffs",
+    "pluto_gpu_multi_set_body_force", "pluto_gpu_multi_set_body_potential",
     "pluto_gpu_ipc_alloc", "pluto_gpu_ipc_open", "pluto_gpu_ipc_close", "pluto_gpu_ipc_free", "pluto_gpu_halo_signal", "pluto_gpu_halo_wait",
     "pluto_gpu_stage_shell", "pluto_gpu_stage_interior",
     "pluto_gpu_set_dt", "pluto_gpu_advance_async", "pluto_gpu_next_dt_async", "pluto_gpu_reduction_slots",
@@ -76,6 +77,8 @@ def load_library(path: str | None = None):
     L.pluto_gpu_set_plm_coeffs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.pluto_gpu_multi_set_grid.argtypes = [vp, vp, vp, vp]
     L.pluto_gpu_multi_set_plm_coeffs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.pluto_gpu_multi_set_body_force.argtypes = [vp, vp, vp, vp]
+    L.pluto_gpu_multi_set_body_potential.argtypes = [vp, vp, vp, vp, vp]
     L.pluto_gpu_set_body_potential.argtypes = [vp, vp, vp, vp, vp]
     for nm in ("pluto_gpu_upload_interior", "pluto_gpu_download_interior",
                "pluto_gpu_upload_data", "pluto_gpu_download_data"):

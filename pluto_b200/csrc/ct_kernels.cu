@@ -328,7 +328,7 @@ final_kernel (const __grid_constant__ FinalArgs a)
       // (ct_emf.c:132-176: x1 faces F[BX2] = -ezi, F[BX3] = eyi; x2: F[BX1] = ezj, F[BX3] = -exj; x3: F[BX1] = -eyk,
       // F[BX2] = exk; the flux of the normal component is zero), then the RK average with U0[B] = V0[B]
       const long long sy = g.S1, sz = g.S12;
-      const double dtdx0 = __ldg (a.dtp), dtdx1 = __ldg (a.dtp + 1), dtdx2 = (NC == 3 ? __ldg (a.dtp + 2) : 0.0);
+      const double dtdx0 = __ldg (a.dtx[0] + i*a.gs), dtdx1 = __ldg (a.dtx[1] + j*a.gs), dtdx2 = (NC == 3 ? __ldg (a.dtx[2] + k*a.gs) : 0.0);
       double b1 = a.Vin[BX1][id], b2 = a.Vin[BX2][id], b3 = (NC == 3 ? a.Vin[BX3][id] : 0.0);
       b1 = b1 + -dtdx0*(a.fbn[0] ? a.fbn[0][id] - a.fbn[0][id - 1] : 0.0 - 0.0);
       b2 = b2 + -dtdx0*((-a.ezi[id]) - (-a.ezi[id - 1]));
@@ -511,10 +511,10 @@ flag_shock_kernel (const __grid_constant__ FlagArgs a)
   if (PASS == 1){
     unsigned char sh = 0;
     if (inner){
-      const double dvx1 = pg_div (a.vx[0][id + sx] - a.vx[0][id - sx], g.dx[0]);
-      const double dvx2 = pg_div (a.vx[1][id + sy] - a.vx[1][id - sy], g.dx[1]);
+      const double dvx1 = pg_div (a.vx[0][id + sx] - a.vx[0][id - sx], a.dxa[0] ? __ldg (a.dxa[0] + i) : g.dx[0]);
+      const double dvx2 = pg_div (a.vx[1][id + sy] - a.vx[1][id - sy], a.dxa[1] ? __ldg (a.dxa[1] + j) : g.dx[1]);
       double divv = dvx1 + dvx2;
-      if (NC == 3) divv = dvx1 + dvx2 + pg_div (a.vx[2][id + sz] - a.vx[2][id - sz], g.dx[2]);
+      if (NC == 3) divv = dvx1 + dvx2 + pg_div (a.vx[2][id + sz] - a.vx[2][id - sz], a.dxa[2] ? __ldg (a.dxa[2] + k) : g.dx[2]);
       if (divv < 0.0){
         double pt_min = a.prs[id];
         const double p1 = minv (a.prs[id + sx], a.prs[id - sx]), p2 = minv (a.prs[id + sy], a.prs[id - sy]);

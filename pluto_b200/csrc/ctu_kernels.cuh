@@ -214,7 +214,7 @@ ctu_sweep_x_kernel (const __grid_constant__ CtuArgs a)
     const double gz = a.bf ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;      // body force at the zone centre
     double src_n = 0.0, dphi = 0.0;                    // PrimSource of the normal velocity (prim_eqn.c:289-307)
     if (a.bf) src_n += gz;
-    if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - 1); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
+    if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - 1); src_n -= pg_div (dphi, 1.0*(a.dxz ? __ldg (a.dxz + izn) : g.dx[DIR])); }
     ctu_states<DIR, NC, FLAT>(ph, a.limiter, fl, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? dtdx : 0.0, a.char_lim);
     // body force: density of stateC -- the half-step zone average of hancock.c:136-141 in the predictor,
     // V^{n+1/2} (ctu_step.c:566-570) in the corrector
@@ -385,7 +385,7 @@ ctu_sweep_march_kernel (const __grid_constant__ CtuArgs a)
       const double gz = a.bf ? (a.gf ? __ldg (a.gf + id) : a.grav[DIR]) : 0.0;    // body force at the centre of zone z
       double src_n = 0.0, dphi = 0.0;                  // PrimSource of the normal velocity (prim_eqn.c:289-307)
       if (a.bf) src_n += gz;
-      if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - sD); src_n -= pg_div (dphi, 1.0*g.dx[DIR]); }
+      if (a.phif){ dphi = __ldg (a.phif + id) - __ldg (a.phif + id - sD); src_n -= pg_div (dphi, 1.0*(a.dxz ? __ldg (a.dxz + z) : g.dx[DIR])); }
       const double dtdx_z = __ldg (a.dtx + z*a.gs), d_dl = a.gs ? __ldg (a.idl + z) : a.inv_dl;       // of zone z
       ctu_states<DIR, NC, FLAT>(ph, a.limiter, flz, vl, v, vr, bsm, bsp, dt_2, d_dl, src_n, vp, vm, a.chtr ? dtdx_z : 0.0, a.char_lim);
       const double rho_z = ((a.bf || a.phif) && PHASE == 0 ? 0.5*(vp[RHO] + vm[RHO]) : 0.0);   // hancock.c:136-141

@@ -148,6 +148,7 @@ struct CtuArgs {
   const double *phic, *phif; // BODY_FORCE & POTENTIAL: potential at the centres / the faces of this direction (else NULL)
   double *fbn;               // corrector, EXACT + CT_EN_CORRECTION: normal-component flux of the faces (see SweepArgs)
   const double *dtx, *idl;   // dt/dx[n] and 1/dx[n] along the sweep on a non-uniform grid (gs = 1), else dtp + direction (gs = 0)
+  const double *dxz;         // ... and dx[n] itself (the potential's source of the predictor, prim_eqn.c:304-307), NULL on a uniform grid
   int     gs;
   int     chtr;              // TIME_STEPPING CHARACTERISTIC_TRACING: predictor by characteristic tracing (2 components)
   int     char_lim;          // CHAR_LIMITING YES (2 components): slopes limited on the characteristic variables (plm_zone_char2)
@@ -178,6 +179,7 @@ struct FinalArgs {
   const double *exj, *exk, *eyi, *eyk, *ezi, *ezj;
   const double *fbn[3];                      // normal-component flux of the x1, x2, x3 faces (EXACT; NULL: zero)
   const double *dtp;                         // device: dt/dx1..3
+  const double *dtx[3]; int gs;              // energy correction: dt/dx of the zone along each direction (gs = 1: per-zone arrays, 0: one value)
   // fuse_ct: CT_Update (+ the RK average of the staggered field) evaluated HERE instead of in ct_update_kernel: a zone
   // computes the new field of its six faces from the edge EMFs (the three low ones a second time, bit-identical to the
   // neighbour's), stores the three high ones (and a low one on the face beg-1) into Bs (= Bs_out) and averages them
@@ -213,6 +215,7 @@ struct FlagArgs {              // FlagShock (flag_shock.c:79-230)
   const double *vx[3], *prs;
   unsigned char *shock;      // pass 1: zone lies in a shock
   unsigned char *flag;       // pass 2: FLAG_HLL | FLAG_MINMOD of the zone itself, FLAG_MINMOD of its neighbours
+  const double *dxa[3];      // non-uniform grid: zone widths per direction (flag_shock.c:143-145), else NULL
   Geom g;
 };
 

@@ -189,8 +189,6 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     return fail ("CT_EN_CORRECTION YES is available with CT_EMF_AVERAGE UCT_CONTACT / ARITHMETIC / UCT0 "
                  "(the correction is rebuilt from the face EMFs, which UCT_HLL replaces by the fan speeds)");
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail ("bad body_force");
-  if (cfg->body_force && cfg->shock_flattening)
-    return fail ("BODY_FORCE is not available together with SHOCK_FLATTENING");
   if (cfg->char_limiting != 0 && cfg->char_limiting != 1) return fail ("bad char_limiting");
   if (cfg->char_limiting){
     if (cfg->dims != 2)
@@ -540,12 +538,8 @@ int pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const
 {
   CU (cudaSetDevice (h->cfg.device));
   const Geom &g = h->g;
-  if (h->ctu && h->cfg.body_force)
-    return fail ("pluto_gpu_set_grid: non-uniform grids are not available with the corner-transport-upwind steps AND BODY_FORCE");
   if (h->cfg.recon != PLUTO_GPU_RECON_LINEAR)
     return fail ("pluto_gpu_set_grid: non-uniform grids need LINEAR reconstruction (PARABOLIC takes its weights from the grid, ppm_coeffs.c)");
-  if (h->cfg.shock_flattening || h->cfg.en_correction || h->cfg.char_limiting)
-    return fail ("pluto_gpu_set_grid: non-uniform grids are not available with SHOCK_FLATTENING, CT_EN_CORRECTION or CHAR_LIMITING");
   const double *src[3] = {dx1, dx2, dx3};
   for (int d = 0; d < g.dims; d++){
     if (!src[d]) return fail ("pluto_gpu_set_grid: NULL array for direction %d", d + 1);
@@ -863,6 +857,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
   f.red = h->red; f.g = g; f.ph = h->ph; f.w0 = sp.w0; f.wc = sp.wc; f.combine = sp.combine;
   for (int nv = 0; nv < NVS; nv++) f.Uw[nv] = h->U[nv];
   f.en_corr = h->cfg.en_correction; f.dtp = h->dtdev;
+  f.gs = h->nu; for (int d = 0; d < 3; d++) f.dtx[d] = h->nu ? h->dtxa[d] : h->dtdev + d;
   for (int nv = 0; nv < NVS; nv++) f.Vin[nv] = h->V[sp.in][nv];
   f.exj = h->exj; f.exk = h->exk; f.eyi = h->eyi; f.eyk = h->eyk; f.ezi = h->ezi; f.ezj = h->ezj;
   for (int d = 0; d < 3; d++) f.fbn[d] = h->fbn[d];
@@ -882,6 +877,7 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
     FlagArgs fa; memset (&fa, 0, sizeof (fa));
     for (int d = 0; d < 3; d++) fa.vx[d] = h->V[sp.in][1 + d];
     fa.prs = h->V[sp.in][7]; fa.shock = h->shock; fa.flag = h->flag; fa.g = g;
+    for (int d = 0; d < 3; d++) fa.dxa[d] = h->nu ? h->dxa[d] : NULL;
     TIMED (h, KC_BC, count (h, DISPATCH (h, launch_flag_shock) (fa, h->stream)));
   }
   SweepArgs s; memset (&s, 0, sizeof (s));
@@ -1027,6 +1023,7 @@ static int run_ctu (PlutoGpu *h, int part)
   for (int d = 0; d < 3; d++) f.Bs[d] = h->Bs[0][d];
   f.red = h->red; f.g = g; f.ph = h->ph; f.combine = 0; f.write_u = 0;
   f.en_corr = h->cfg.en_correction; f.dtp = h->dtdev;           // Uc[B] = U^n[B] + the corrector's induction right-hand sides
+  f.gs = h->nu; for (int d = 0; d < 3; d++) f.dtx[d] = h->nu ? h->dtxa[d] : h->dtdev + d;
   for (int nv = 0; nv < NVS; nv++) f.Vin[nv] = h->V[0][nv];
   f.exj = h->exj; f.exk = h->exk; f.eyi = h->eyi; f.eyk = h->eyk; f.ezi = h->ezi; f.ezj = h->ezj;
   for (int d = 0; d < 3; d++) f.fbn[d] = h->fbn[d];
@@ -1037,6 +1034,7 @@ static int run_ctu (PlutoGpu *h, int part)
     FlagArgs fa; memset (&fa, 0, sizeof (fa));
     for (int d = 0; d < 3; d++) fa.vx[d] = h->V[0][1 + d];
     fa.prs = h->V[0][7]; fa.shock = h->shock; fa.flag = h->flag; fa.g = g;
+    for (int d = 0; d < 3; d++) fa.dxa[d] = h->nu ? h->dxa[d] : NULL;
     TIMED (h, KC_BC, count (h, DISPATCH (h, launch_flag_shock) (fa, h->stream)));
   }
   CtuArgs s; memset (&s, 0, sizeof (s));
@@ -1063,7 +1061,7 @@ static int run_ctu (PlutoGpu *h, int part)
   for (int phase = 0; phase < 2; phase++){
     for (int dir = 0; dir < g.dims; dir++){
       s.inv_dl = 1.0/g.dx[dir];
-      s.gs = h->nu; s.dtx = h->nu ? h->dtxa[dir] : h->dtdev + dir; s.idl = h->idxa[dir];
+      s.gs = h->nu; s.dtx = h->nu ? h->dtxa[dir] : h->dtdev + dir; s.idl = h->idxa[dir]; s.dxz = h->nu ? h->dxa[dir] : NULL;
       s.sv = h->sv[dir];
       s.fbn = h->fbn[dir];
       s.gf = h->gfield[dir];
@@ -1731,7 +1729,6 @@ int pluto_gpu_multi_create (const PlutoGpuConfig *cfg, const int grid[3], const 
   const int nb = grid[0]*grid[1]*(dims == 3 ? grid[2] : 1);
   if (nb < 1 || nb > PGM_MAX_BLOCKS) return fail ("pluto_gpu_multi_create: %d blocks (1 .. %d)", nb, PGM_MAX_BLOCKS);
   if (dims == 2 && grid[2] != 1) return fail ("pluto_gpu_multi_create: grid[2] must be 1 in 2-D");
-  if (cfg->body_force) return fail ("pluto_gpu_multi_create: BODY_FORCE is not available with several blocks yet");
   for (int d = 0; d < dims; d++) if (cfg->n[d] % grid[d]) return fail ("pluto_gpu_multi_create: n[%d] = %d is not divisible by %d blocks", d, cfg->n[d], grid[d]);
   PlutoGpuMulti *m = (PlutoGpuMulti *)calloc (1, sizeof (PlutoGpuMulti));
   if (!m) return fail ("out of host memory");
@@ -1883,6 +1880,43 @@ static void pgm_rows (const PlutoGpuMulti *m, int b, bool to_block, int stag, do
     double *pg = glob + ((size_t)(k + off[2])*eg[1] + (j + off[1]))*eg[0] + lo[0] + off[0];
     if (to_block) memcpy (pl, pg, nrow*sizeof (double)); else memcpy (pg, pl, nrow*sizeof (double));
   }
+}
+
+// BODY_FORCE with several blocks: the arrays of the whole domain (layouts of pluto_gpu_set_body_force / _potential), cut into
+// the blocks' pieces -- ghost zones included, which overlap the neighbours' interiors exactly as the state's do
+static int pgm_sliced (PlutoGpuMulti *m, int narr, const double *const *glob, const int *stag, const char *what,
+                       int (*set) (PlutoGpu *, const double *const *))
+{
+  size_t totl = 1;
+  for (int d = 0; d < m->dims; d++) totl *= (size_t)(m->ln[d] + 2*m->ng + 1);
+  double *tmp = (double *)malloc ((size_t)narr*totl*sizeof (double));
+  if (!tmp) return fail ("out of host memory");
+  int rc = 0;
+  for (int b = 0; b < m->nb && !rc; b++){
+    const double *loc[4] = {NULL, NULL, NULL, NULL};
+    for (int q = 0; q < narr && !rc; q++){
+      if (!glob[q]){ rc = fail ("%s: NULL array %d", what, q); break; }
+      pgm_rows (m, b, true, stag[q], (double *)glob[q], tmp + (size_t)q*totl, false);
+      loc[q] = tmp + (size_t)q*totl;
+    }
+    if (!rc) rc = set (m->blk[b], loc);
+  }
+  free (tmp);
+  return rc;
+}
+int pluto_gpu_multi_set_body_force (PlutoGpuMulti *m, const double *g1, const double *g2, const double *g3)
+{
+  const double *glob[3] = {g1, g2, g3};
+  const int stag[3] = {-1, -1, -1};
+  return pgm_sliced (m, m->dims, glob, stag, "pluto_gpu_multi_set_body_force",
+                     [] (PlutoGpu *h, const double *const *l){ return pluto_gpu_set_body_force (h, l[0], l[1], l[2]); });
+}
+int pluto_gpu_multi_set_body_potential (PlutoGpuMulti *m, const double *phic, const double *pf1, const double *pf2, const double *pf3)
+{
+  const double *glob[4] = {phic, pf1, pf2, pf3};
+  const int stag[4] = {-1, 0, 1, 2};
+  return pgm_sliced (m, 1 + m->dims, glob, stag, "pluto_gpu_multi_set_body_potential",
+                     [] (PlutoGpu *h, const double *const *l){ return pluto_gpu_set_body_potential (h, l[0], l[1], l[2], l[3]); });
 }
 
 int pluto_gpu_multi_upload_data (PlutoGpuMulti *m, const double *Vc, const double *s1, const double *s2, const double *s3)

@@ -423,6 +423,16 @@ class MultiGpuStepper:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (dx1, dx2, dx3)]
         self._check(self.L.pluto_gpu_multi_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
 
+    def set_body_force(self, g1, g2, g3=None):
+        """BodyForceVector at the zone centres of the WHOLE domain ([T3][T2][T1], ghost zones included); every block takes its piece."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (g1, g2, g3)]
+        self._check(self.L.pluto_gpu_multi_set_body_force(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
+    def set_body_potential(self, phic, pf1, pf2, pf3=None):
+        """BodyForcePotential of the WHOLE domain: zone centres and the faces of every direction (staggered Data layouts)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (phic, pf1, pf2, pf3)]
+        self._check(self.L.pluto_gpu_multi_set_body_potential(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
     def set_plm_coeffs(self, coeffs):
         """UNIFORM_CARTESIAN_GRID NO: per direction the six weight arrays of the WHOLE domain."""
         for d, six in enumerate(coeffs):

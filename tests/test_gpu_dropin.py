@@ -45,7 +45,11 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # [Solver] hllc / tvdlf
          "blast3d_hllc", "rotor2d_ppm_rk3_hllc", "turb3d_ctu_hllc", "ot2d_tvdlf",
          # BODY_FORCE with UCT_HLL
-         "blast3d_bf_uct_hll", "rotor2d_ppm_rk3_bp_uct_hll_roe"]
+         "blast3d_bf_uct_hll", "rotor2d_ppm_rk3_bp_uct_hll_roe",
+         # BODY_FORCE with SHOCK_FLATTENING MULTID
+         "blast3d_sfl_bf", "blast3d_ctu_sfl_bf", "blast2d_ppm_sfl_bp",
+         # non-uniform grids with SHOCK_FLATTENING, CHAR_LIMITING, CT_EN_CORRECTION, BODY_FORCE inside the corner-transport-upwind step
+         "blast3d_nug_sfl", "blast2d_nug_cl_roe", "blast2d_nug_en", "blast2d_nug_ctu_bp"]
 
 
 def _blast_params(g):
@@ -129,7 +133,10 @@ def test_resident_state_drop_in(name, arith):
 @pytest.mark.parametrize("name,ndev,resident", [("turb3d_plm_hlld", 8, False), ("blast3d_plm_hlld_100", 4, True), ("rotor2d_ppm_roe", 2, False),
                                                 ("ot2d_ctu", 4, True), ("ot2d_cl", 2, False),
                                                 # non-uniform grid / grid-dependent weights: every block takes its slice
-                                                ("blast3d_nug", 4, False), ("blast2d_nuw_mc_arith", 2, True)])
+                                                ("blast3d_nug", 4, False), ("blast2d_nuw_mc_arith", 2, True),
+                                                # BODY_FORCE: the force / potential arrays of the whole domain are cut into the blocks' pieces
+                                                ("blast3d_bfx", 4, False), ("blast3d_bp", 2, True), ("blast3d_nug_bp", 4, False),
+                                                ("blast2d_ctu_bfx_roe", 2, False)])
 def test_reference_driver_on_several_blocks(name, ndev, resident):
     """PLUTO_GPU_NDEV: the reference's serial, single-threaded driver with the domain cut into 2 / 4 / 8 blocks (one per GPU where
     the box has them, round robin otherwise), driven through pluto_gpu_multi_* -- no MPI, no Python.  Dumps bit-identical to the

@@ -164,6 +164,34 @@ CASES = [
     ("blast3d_bf_uct_hll", RefConfig(problem="blast", dims=3, n=(12, 10, 14), first_dt=3e-4, cfl=0.3, grav=(0.3, -1.0, 0.5), emf="uct_hll"), 8),
     ("rotor2d_ppm_rk3_bp_uct_hll_roe", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", tstep="rk3", first_dt=2e-3,
                                                  grav=(0.05, -0.03, 0.0), potential=True, emf="uct_hll", solver="roe"), 6),
+    # BODY_FORCE with SHOCK_FLATTENING MULTID
+    ("blast3d_sfl_bf", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, flatten=True, grav=(0.3, -1.0, 0.5)), 10),
+    ("blast3d_sfl_uct_hll_bf_roe", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, flatten=True, emf="uct_hll",
+                                             solver="roe", grav=(0.3, -1.0, 0.5)), 8),
+    ("blast3d_ctu_sfl_bf", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, tstep="hancock", flatten=True,
+                                     grav=(0.3, -1.0, 0.5)), 8),
+    ("blast2d_ppm_sfl_bp", RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=3e-4, flatten=True, grav=(0.05, -0.03, 0.0),
+                                     potential=True), 10),
+    # non-uniform grids with SHOCK_FLATTENING MULTID (flag_shock.c:143-145 divides by the zone's widths) and CHAR_LIMITING
+    ("blast3d_nug_sfl", RefConfig(problem="blast", dims=3, n=(14, 12, 16), first_dt=3e-4, cfl=0.3, flatten=True,
+                                  grid=("2  -0.5  8  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5", "3  -0.5  4  s  -0.3  8  u  0.3  4  s  0.5")), 10),
+    ("blast2d_nug_sfl_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), first_dt=3e-4, solver="roe", flatten=True,
+                                      grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  24  u  0.1  8  s  0.5", None)), 12),
+    ("blast3d_nug_ctu_sfl_uct0", RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=3e-4, cfl=0.3, tstep="hancock", flatten=True, emf="uct0",
+                                  grid=("2  -0.5  6  u  0.0  6  s  0.5", "2  -0.5  6  s  -0.2  8  u  0.5", "2  -0.5  4  s  -0.3  6  u  0.5")), 8),
+    ("blast2d_nug_cl_roe", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, solver="roe", char_lim=True,
+                                     grid=("2  -0.5  20  u  0.2  8  s  0.5", "3  -0.5  6  s  -0.3  12  u  0.3  6  s  0.5", None)), 10),
+    ("ot2d_nug_ctu_cl_mc_arith", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, tstep="hancock", char_lim=True, limiter="mc", emf="arith",
+                                           grid=("2  0.0  20  u  4.0  12  s  6.283185307179586", "2  0.0  8  s  1.5  20  u  6.283185307179586", None)), 8),
+    ("blast2d_nug_en", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, en_corr=True,
+                                 grid=("2  -0.5  20  u  0.2  8  s  0.5", "3  -0.5  6  s  -0.3  12  u  0.3  6  s  0.5", None)), 10),
+    ("blast3d_nug_ctu_en", RefConfig(problem="blast", dims=3, n=(10, 14, 12), first_dt=3e-4, cfl=0.3, tstep="hancock", en_corr=True,
+                                     grid=("2  -0.5  4  u  -0.1  6  s  0.5", "2  -0.5  6  s  -0.2  8  u  0.5", "2  -0.5  4  s  -0.3  8  u  0.5")), 8),
+    # corner transport upwind + BODY_FORCE on non-uniform grids (prim_eqn.c:304-307, 335-338 divide the potential difference by dx[i])
+    ("turb3d_nug_ctu_bf", RefConfig(problem="turb", dims=3, n=(10, 12, 8), first_dt=2e-2, cfl=0.3, tstep="hancock", grav=(0.3, -1.0, 0.5),
+                                    grid=("2  0.0  6  u  0.6  4  s  1.0", "2  0.0  4  s  0.3  8  u  1.0", "2  0.0  4  u  0.5  4  s  1.0")), 6),
+    ("blast2d_nug_ctu_bp", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock", grav=(0.05, -0.03, 0.0), potential=True,
+                                     grid=("2  -0.5  16  u  0.2  8  s  0.5", "3  -0.5  4  s  -0.3  12  u  0.3  4  s  0.5", None)), 8),
     ("blast2d_chtr_mc_hllc", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="hllc"), 10),
 ]
 

@@ -145,12 +145,28 @@ CASES = {
     "blast3d_bf_uct_hll": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grav=(0.3, -1.0, 0.5), emf="uct_hll"), 12),
     "rotor2d_ppm_rk3_bp_uct_hll_roe": (RefConfig(problem="rotor", dims=2, n=(36, 28, 1), recon="ppm", tstep="rk3", first_dt=2.5e-3,
                                                  grav=(0.05, -0.03, 0.0), potential=True, emf="uct_hll", solver="roe"), 10),
+    # BODY_FORCE with SHOCK_FLATTENING MULTID
+    "blast3d_sfl_bf": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, flatten=True, grav=(0.3, -1.0, 0.5)), 12),
+    "blast3d_ctu_sfl_bf": (RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=6e-4, cfl=0.3, tstep="hancock", flatten=True,
+                                     grav=(0.3, -1.0, 0.5)), 10),
+    "blast2d_ppm_sfl_bp": (RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=6e-4, flatten=True, grav=(0.05, -0.03, 0.0),
+                                     potential=True), 12),
     # the corner-transport-upwind steps on non-uniform grids (Hancock 3-D; characteristic tracing 2-D, MC_LIM)
     "blast3d_nug_ctu": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, tstep="hancock",
                                   grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
                                         "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 12),
     "rotor2d_nug_chtr_mc": (RefConfig(problem="rotor", dims=2, n=(36, 28, 1), first_dt=2.5e-3, cfl=0.4, tstep="chtr", limiter="mc",
                                       grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 15),
+    # ... with SHOCK_FLATTENING MULTID, CHAR_LIMITING, CT_EN_CORRECTION and BODY_FORCE inside the corner-transport-upwind step
+    "blast3d_nug_sfl": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, flatten=True,
+                                  grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                        "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 12),
+    "blast2d_nug_cl_roe": (RefConfig(problem="blast", dims=2, n=(36, 28, 1), first_dt=6e-4, solver="roe", char_lim=True,
+                                     grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 12),
+    "blast2d_nug_en": (RefConfig(problem="blast", dims=2, n=(36, 28, 1), first_dt=6e-4, en_corr=True,
+                                 grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 12),
+    "blast2d_nug_ctu_bp": (RefConfig(problem="blast", dims=2, n=(36, 28, 1), first_dt=6e-4, tstep="hancock", grav=(0.05, -0.03, 0.0), potential=True,
+                                     grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 12),
     # UNIFORM_CARTESIAN_GRID NO: grid-dependent reconstruction weights (plm_coeffs.c) -- the fixtures carry the arrays of PLM_CoefficientsGet
     "blast3d_nuw": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grid_weights=True,
                               grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
