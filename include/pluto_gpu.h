@@ -127,8 +127,8 @@ int  pluto_gpu_nghost   (const PlutoGpu *h);     /* Src/get_nghost.c:32-50 */
    widths enter Src/MHD/rhs.c:195, the inverse time step (Src/Time_Stepping/update_stage.c:229-235), Src/MHD/CT/ct_update.c:91-204
    and the face areas of Src/MHD/CT/ct_fill_mag_field.c:108-114; with the corner-transport-upwind steps also the predictors
    (Src/States/hancock.c:245-296, char_tracing.c:347-362), the transverse correction of ctu_step.c:310, 731-785 and the potential's
-   source of Src/MHD/prim_eqn.c:304-307; with SHOCK_FLATTENING MULTID Src/flag_shock.c:143-145.  LINEAR reconstruction (PARABOLIC
-   is refused: its weights come from ppm_coeffs.c); dx3 may be NULL in 2-D.
+   source of Src/MHD/prim_eqn.c:304-307; with SHOCK_FLATTENING MULTID Src/flag_shock.c:143-145.  PARABOLIC reconstruction
+   needs pluto_gpu_set_ppm_coeffs as well; dx3 may be NULL in 2-D.
    PlutoGpuConfig.dx is then used by nothing on the path.  Call once after pluto_gpu_create. */
 int  pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const double *dx3);
 /* UNIFORM_CARTESIAN_GRID NO (Src/States/plm_coeffs.h:23-29): grid-dependent weights of the linear reconstruction.  Hand over, for
@@ -136,6 +136,11 @@ int  pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, cons
    after pluto_gpu_create (and pluto_gpu_set_grid on a non-uniform grid).  RK2 / RK3, LINEAR, plain scheme options. */
 int  pluto_gpu_set_plm_coeffs (PlutoGpu *h, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
                                const double *dp, const double *dm);
+/* PARABOLIC reconstruction on a non-uniform grid: the interface weights of Src/States/ppm_states.c:146-150 as PPM_CoefficientsGet
+   returns them (Src/States/ppm_coeffs.c:586-609; PPM_FindWeights, :300-480, where a direction is not uniform) -- wp[i][-1], wp[i][0],
+   wp[i][1], wp[i][2] of every zone i of direction dir, T_dir entries each (set for 1 <= i <= T_dir - 3).  hp = hm = 3 on every
+   Cartesian grid (ppm_coeffs.c:544-547).  Required after pluto_gpu_set_grid with PARABOLIC; RK2 / RK3. */
+int  pluto_gpu_set_ppm_coeffs (PlutoGpu *h, int dir, const double *wm1, const double *w0, const double *w1, const double *w2);
 int  pluto_gpu_set_body_force (PlutoGpu *h, const double *g1, const double *g2, const double *g3);
 /* BODY_FORCE POTENTIAL (body_force & 2; Src/MHD/rhs.c:162-187, 388-392, rhs_source.c:233-237, 316-320, 358-362,
    prim_eqn.c:304-307): BodyForcePotential (init.c) at the zone centres, phic[k][j][i] (T3 x T2 x T1), and at the faces of
@@ -332,6 +337,7 @@ int  pluto_gpu_multi_download_data (PlutoGpuMulti *m, double *Vc, double *Vs1, d
 int  pluto_gpu_multi_set_grid (PlutoGpuMulti *m, const double *dx1, const double *dx2, const double *dx3);
 int  pluto_gpu_multi_set_plm_coeffs (PlutoGpuMulti *m, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
                                      const double *dp, const double *dm);
+int  pluto_gpu_multi_set_ppm_coeffs (PlutoGpuMulti *m, int dir, const double *wm1, const double *w0, const double *w1, const double *w2);
 /* pluto_gpu_set_body_force / pluto_gpu_set_body_potential for the blocks: HOST arrays of the WHOLE domain in the same layouts
    (ghost zones included; the face arrays with one more entry along their direction), cut into the blocks' pieces */
 int  pluto_gpu_multi_set_body_force (PlutoGpuMulti *m, const double *g1, const double *g2, const double *g3);

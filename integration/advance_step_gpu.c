@@ -174,9 +174,9 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
     }
     if (nonuniform){
       /* stretched / logarithmic / multi-patch grids (set_grid.c:330-560): the zone widths go to the library after its creation */
-#if RECONSTRUCTION != LINEAR || (UNIFORM_CARTESIAN_GRID == NO && (SHOCK_FLATTENING != NO || CHAR_LIMITING == YES))
-      print ("! AdvanceStep(gpu): a non-uniform grid needs LINEAR reconstruction (UNIFORM_CARTESIAN_GRID NO: without SHOCK_FLATTENING\n"
-             "  and CHAR_LIMITING) on the GPU\n");
+#if UNIFORM_CARTESIAN_GRID == NO && (SHOCK_FLATTENING != NO || CHAR_LIMITING == YES)
+      print ("! AdvanceStep(gpu): a non-uniform grid with UNIFORM_CARTESIAN_GRID NO is available without SHOCK_FLATTENING and\n"
+             "  CHAR_LIMITING on the GPU\n");
       QUIT_PLUTO(1);
 #endif
     }
@@ -214,6 +214,26 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
       print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
       QUIT_PLUTO(1);
     }
+#if RECONSTRUCTION == PARABOLIC
+    if (nonuniform){
+      /* interface weights of the parabolic reconstruction as PPM_CoefficientsSet found them for this grid (ppm_coeffs.c:122-139,
+         300-480): wp[i][-1 .. 2] of every zone, set for 1 <= i <= np_tot-3 */
+      for (idim = 0; idim < DIMENSIONS; idim++){
+        PPM_Coeffs qc;
+        int np = grid->np_tot[idim], q, ii, rc;
+        double *w4 = (double *)calloc ((size_t)4*np, sizeof(double));
+        PPM_CoefficientsGet (&qc, idim);
+        for (q = -1; q <= 2; q++) for (ii = 1; ii <= np - 3; ii++) w4[(q + 1)*np + ii] = qc.wp[ii][q];
+        rc = (gpum ? pluto_gpu_multi_set_ppm_coeffs (gpum, idim, w4, w4 + np, w4 + 2*np, w4 + 3*np)
+                   : pluto_gpu_set_ppm_coeffs (gpu, idim, w4, w4 + np, w4 + 2*np, w4 + 3*np));
+        free (w4);
+        if (rc != 0){
+          print ("! AdvanceStep(gpu): %s\n", pluto_gpu_last_error());
+          QUIT_PLUTO(1);
+        }
+      }
+    }
+#endif
 #if (UNIFORM_CARTESIAN_GRID == NO && RECONSTRUCTION == LINEAR) || (SHOCK_FLATTENING == MULTID && RECONSTRUCTION == PARABOLIC)
     /* grid-dependent reconstruction weights: the arrays PLM_CoefficientsSet built for this grid (plm_coeffs.c:30-104); with
        PARABOLIC + MULTID they serve the minmod fallback of the flagged zones (ppm_states.c:167-181) */

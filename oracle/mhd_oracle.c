@@ -46,6 +46,7 @@ struct Oracle {
   double *Vs[3], *Bs0[3];
   double *dxa[3];                      /* zone widths of a non-uniform grid (oracle_set_grid: grid->dx[d][0..T-1]), else NULL */
   double *plmc[3][6];                  /* UNIFORM_CARTESIAN_GRID NO: cp, cm, wp, wm, dp, dm of every direction (oracle_set_plm_coeffs) */
+  double *ppmc[3][4];                  /* PARABOLIC on a non-uniform grid: interface weights wp[i][-1 .. 2] of every direction (oracle_set_ppm_coeffs) */
   double *gf[3];                       /* per-zone body force (oracle_set_body_force), else NULL */
   double *phic, *phif[3];              /* body-force potential at centres and faces (oracle_set_body_potential), else NULL */
   double *ppen;                        /* face potential of the current pencil */
@@ -165,7 +166,7 @@ void oracle_destroy (Oracle *o)
   free(o->exj); free(o->exk); free(o->eyi); free(o->eyk); free(o->ezi); free(o->ezj);
   free(o->ex); free(o->ey); free(o->ez); free(o->Ex1); free(o->Ex2); free(o->Ex3);
   free(o->svx); free(o->svy); free(o->svz); free(o->C_dt);
-  for (d = 0; d < 3; d++){ int q; free(o->dxa[d]); for (q = 0; q < 6; q++) free(o->plmc[d][q]); }
+  for (d = 0; d < 3; d++){ int q; free(o->dxa[d]); for (q = 0; q < 6; q++) free(o->plmc[d][q]); for (q = 0; q < 4; q++) free(o->ppmc[d][q]); }
   free(o->v - 4); free(o->vp - 4); free(o->vm - 4); free(o->dv - 4); free(o->flux - 4);
   free(o->press - 4); free(o->cmax - 4); free(o->bn - 4);
   free(o);
@@ -184,6 +185,19 @@ void oracle_set_grid (Oracle *o, const double *dx1, const double *dx2, const dou
   for (d = 0; d < o->c.dims; d++){
     if (!o->dxa[d]) o->dxa[d] = dalloc (o->T[d]);
     memcpy (o->dxa[d], src[d], sizeof(double)*(size_t)o->T[d]);
+  }
+}
+
+void oracle_set_ppm_coeffs (Oracle *o, int dir, const double *wm1, const double *w0, const double *w1, const double *w2)
+/* PARABOLIC reconstruction on a non-uniform grid: the interface weights wp[i][-1], wp[i][0], wp[i][1], wp[i][2] of every zone as
+   PPM_CoefficientsGet returns them for direction dir (ppm_coeffs.c:586-609; found numerically by PPM_FindWeights, :300-480, where the
+   direction is not uniform; T entries each, set for 1 <= i <= T-3).  hp = hm = 3 on every Cartesian grid (ppm_coeffs.c:544-547). */
+{
+  const double *src[4] = {wm1, w0, w1, w2};
+  int q;
+  for (q = 0; q < 4; q++){
+    if (!o->ppmc[dir][q]) o->ppmc[dir][q] = dalloc (o->T[dir]);
+    memcpy (o->ppmc[dir][q], src[q], sizeof(double)*(size_t)o->T[dir]);
   }
 }
 

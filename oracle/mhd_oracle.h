@@ -72,6 +72,7 @@ Oracle *oracle_create (const OracleConfig *cfg);
 /* non-uniform Cartesian grid: zone widths grid->dx[d][0 .. T_d-1], ghost zones included (RK path, LINEAR reconstruction) */
 void    oracle_set_grid (Oracle *o, const double *dx1, const double *dx2, const double *dx3);
 /* UNIFORM_CARTESIAN_GRID NO: the weights PLM_CoefficientsGet returns for direction dir (T entries each) */
+void    oracle_set_ppm_coeffs (Oracle *o, int dir, const double *wm1, const double *w0, const double *w1, const double *w2);
 void    oracle_set_plm_coeffs (Oracle *o, int dir, const double *cp, const double *cm, const double *wp, const double *wm,
                                const double *dp, const double *dm);
 void    oracle_set_body_force (Oracle *o, const double *g1, const double *g2, const double *g3);

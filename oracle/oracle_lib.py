@@ -50,6 +50,7 @@ def lib():
         L.oracle_set_body_force.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_set_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_set_plm_coeffs.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.oracle_set_ppm_coeffs.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.oracle_set_body_potential.argtypes = [C.c_void_p] * 5
         L.oracle_nghost.argtypes = [C.c_void_p]
         dp = C.POINTER(C.c_double)
@@ -130,6 +131,12 @@ class Oracle:
         for d, six in enumerate(coeffs):
             arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in six]
             lib().oracle_set_plm_coeffs(self._h, d, *[a.ctypes.data for a in arrs])
+
+    def set_ppm_coeffs(self, coeffs):
+        """PARABOLIC on a non-uniform grid: per direction the four interface-weight arrays wp[i][-1 .. 2] of PPM_CoefficientsGet."""
+        for d, four in enumerate(coeffs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in four]
+            lib().oracle_set_ppm_coeffs(self._h, d, *[a.ctypes.data for a in arrs])
 
     def set_body_force(self, g1, g2, g3=None):
         """Static per-zone force: arrays [T3][T2][T1] (ghost zones included) of every component."""

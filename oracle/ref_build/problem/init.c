@@ -262,6 +262,21 @@ void Analysis (const Data *d, Grid *grid)
       }
     }
 #endif
+#if RECONSTRUCTION == PARABOLIC
+    for (dir = 0; dir < DIMENSIONS; dir++){     /* interface weights of the parabolic reconstruction, wp[i][-1 .. 2] of every zone
+                                                   (PPM_ORDER 4, ppm_states.c:146-150; set for 1 <= i <= np_tot-3, ppm_coeffs.c:348-349,
+                                                   analytic on a uniform direction): four arrays of np_tot, zeros where never set */
+      PPM_Coeffs c;
+      int q, i, m = grid->np_tot[dir];
+      PPM_CoefficientsGet (&c, dir);
+      rec[0] = -4.0;                            /* marker: four arrays of np_tot follow */
+      fwrite (rec, sizeof(double), 1, fp);
+      for (q = -1; q <= 2; q++) for (i = 0; i < m; i++){
+        double w = (i >= 1 && i <= m - 3 ? c.wp[i][q] : 0.0);
+        fwrite (&w, sizeof(double), 1, fp);
+      }
+    }
+#endif
     fclose (fp);
   }
 }

@@ -208,6 +208,7 @@ class RefResult:
     stdout: str = ""       # the driver's log (serial build: print() goes to stdout)
     dx: list = None        # zone widths grid->dx[d] (ghost zones included) from grid_tap.bin, one array per direction
     plm_coeffs: list = None  # UNIFORM_CARTESIAN_GRID NO builds: per direction [cp, cm, wp, wm, dp, dm] (PLM_CoefficientsGet)
+    ppm_coeffs: list = None  # PARABOLIC builds: per direction the interface weights [w(-1), w(0), w(1), w(2)] of every zone (PPM_CoefficientsGet)
 
 
 def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
@@ -257,13 +258,18 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
     tap_path = os.path.join(workdir, "dt_tap.bin")
     tap = (np.fromfile(tap_path, dtype="<f8").reshape(-1, 3)
            if os.path.exists(tap_path) else np.zeros((0, 3)))
-    dx = plmc = None
+    dx = plmc = ppmc = None
     gpath = os.path.join(workdir, "grid_tap.bin")
     if os.path.exists(gpath):
         raw = np.fromfile(gpath, dtype="<f8")
-        dx, plmc, off = [], [], 0
+        dx, plmc, ppmc, off = [], [], [], 0
         while off < raw.size:
             m = int(raw[off])
+            if m == -4:                # four interface-weight arrays of the next direction (PARABOLIC: wp[i][-1 .. 2])
+                t = len(dx[len(ppmc)])
+                ppmc.append([raw[off + 1 + q * t:off + 1 + (q + 1) * t].copy() for q in range(4)])
+                off += 1 + 4 * t
+                continue
             if m == -6:                # six reconstruction-weight arrays of the next direction (UNIFORM_CARTESIAN_GRID NO)
                 t = len(dx[len(plmc)])
                 plmc.append([raw[off + 1 + q * t:off + 1 + (q + 1) * t].copy() for q in range(6)])
@@ -272,7 +278,8 @@ def run_reference(cfg: RefConfig, maxsteps: int, dump_every: int = -1,
             dx.append(raw[off + 1:off + 1 + m].copy())
             off += 1 + m
     res = RefResult(dumps=dumps, dt_tap=tap, wall_s=wall, steps_run=steps_run,
-                    workdir=workdir, stdout=p.stdout.decode(errors="replace"), dx=dx, plm_coeffs=(plmc or None))
+                    workdir=workdir, stdout=p.stdout.decode(errors="replace"), dx=dx, plm_coeffs=(plmc or None),
+                    ppm_coeffs=(ppmc or None))
     if own and not keep:
         shutil.rmtree(workdir, ignore_errors=True)
     return res

@@ -17,7 +17,7 @@ TIME_STEPPING = {"rk": 0, "hancock": 1, "chtr": 2}                              
 
 # every symbol include/pluto_gpu.h declares (checked by tests/test_cabi.py)
 SYMBOLS = [
-    "pluto_gpu_create", "pluto_gpu_destroy", "pluto_gpu_last_error", "pluto_gpu_nghost", "pluto_gpu_nstages", "pluto_gpu_set_body_force", "pluto_gpu_set_body_potential", "pluto_gpu_set_grid", "pluto_gpu_set_plm_coeffs",
+    "pluto_gpu_create", "pluto_gpu_destroy", "pluto_gpu_last_error", "pluto_gpu_nghost", "pluto_gpu_nstages", "pluto_gpu_set_body_force", "pluto_gpu_set_body_potential", "pluto_gpu_set_grid", "pluto_gpu_set_plm_coeffs", "pluto_gpu_set_ppm_coeffs", "pluto_gpu_multi_set_ppm_coeffs",
     "pluto_gpu_upload_interior", "pluto_gpu_download_interior", "pluto_gpu_upload_data",
     "pluto_gpu_download_data", "pluto_gpu_advance", "pluto_gpu_advance_data",
     "pluto_gpu_boundary", "pluto_gpu_next_dt", "pluto_gpu_halo_doubles", "pluto_gpu_halo_pack",
@@ -75,6 +75,8 @@ def load_library(path: str | None = None):
     L.pluto_gpu_set_body_force.argtypes = [vp, vp, vp, vp]
     L.pluto_gpu_set_grid.argtypes = [vp, vp, vp, vp]
     L.pluto_gpu_set_plm_coeffs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.pluto_gpu_set_ppm_coeffs.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.pluto_gpu_multi_set_ppm_coeffs.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.pluto_gpu_multi_set_grid.argtypes = [vp, vp, vp, vp]
     L.pluto_gpu_multi_set_plm_coeffs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.pluto_gpu_multi_set_body_force.argtypes = [vp, vp, vp, vp]

@@ -98,6 +98,7 @@ struct SweepArgs {
   // RECON_PLMW (UNIFORM_CARTESIAN_GRID NO): cp, cm, wp, wm, dp, dm of the sweep direction, one entry per zone along it
   // (PLM_CoefficientsGet, plm_coeffs.c:86-104); pc2: the x2 direction of the fused x1+x2 sweep
   const double *pc[6], *pc2[6];
+  const double *qc, *qc2;            // PARABOLIC on a non-uniform grid: interface weights wp[n][-1 .. 2] along the sweep (qc2: along x2 in the fused sweep), else NULL
 };
 
 struct CtArgs {

@@ -560,11 +560,15 @@ __device__ __forceinline__ void plm_zone (int lim, const double *v, const double
 
 // PPM 4th-order interface value at i+1/2, bounded (ppm_states.c:146-157):
 // W = v0 + MINMOD(P - v0, v1 - v0), P = -1/12 vm1 + 7/12 v0 + 7/12 v1 - 1/12 v2
+// qc: non-uniform grid -- the weights wp[n][-1 .. 2] of zone n (ppm_states.c:147, found by PPM_FindWeights, ppm_coeffs.c:300-480),
+// four consecutive doubles per zone; NULL: the analytic ones of a uniform direction (ppm_coeffs.c:500-505)
 template <int NC, int SKIP = -1>
 __device__ __forceinline__ void ppm_interface (const double *vm1, const double *v0,
-                                               const double *v1, const double *v2, double *W)
+                                               const double *v1, const double *v2, double *W,
+                                               const double *qc = nullptr, int n = 0)
 {
-  const double wm1 = -1.0/12.0, w0 = 7.0/12.0, w1 = 7.0/12.0, w2 = -1.0/12.0;
+  double wm1 = -1.0/12.0, w0 = 7.0/12.0, w1 = 7.0/12.0, w2 = -1.0/12.0;
+  if (qc){ qc += 4*n; wm1 = __ldg (qc); w0 = __ldg (qc + 1); w1 = __ldg (qc + 2); w2 = __ldg (qc + 3); }
   PG_FOR_NV_SKIP(nv, SKIP){
     double p = wm1*vm1[nv] + w0*v0[nv] + w1*v1[nv] + w2*v2[nv];
     double dv = v1[nv] - v0[nv];

@@ -95,6 +95,7 @@ struct PlutoGpu {
   double *R3[NVS];                 // FAST, 3-D, LINEAR, plain options: flux difference of the x3 sweep (own allocation), else NULL
   void   *r3_pool;
   double *plmc[3][6];              // UNIFORM_CARTESIAN_GRID NO: reconstruction weights cp, cm, wp, wm, dp, dm per direction
+  double *ppmc[3]; void *ppmc_pool; // PARABOLIC on a non-uniform grid: interface weights wp[n][-1 .. 2] per direction (pluto_gpu_set_ppm_coeffs)
   void   *plmc_pool;               // (pluto_gpu_set_plm_coeffs); plmw: all directions set -> the sweeps run their RECON_PLMW variants
   int     plmw;
   double *Ec[3];                   // FAST + fused x1+x2 sweep + UCT_CONTACT: cell-centred EMFs stored by the sweep (own allocation)
@@ -369,6 +370,7 @@ void pluto_gpu_destroy (PlutoGpu *h)
   if (h->grid_pool) cudaFree (h->grid_pool);
   if (h->ec_pool) cudaFree (h->ec_pool);
   if (h->plmc_pool) cudaFree (h->plmc_pool);
+  if (h->ppmc_pool) cudaFree (h->ppmc_pool);
   if (h->gfield_pool) cudaFree (h->gfield_pool);
   if (h->phi_pool) cudaFree (h->phi_pool);
   if (h->flag) cudaFree (h->flag);
@@ -538,8 +540,6 @@ int pluto_gpu_set_grid (PlutoGpu *h, const double *dx1, const double *dx2, const
 {
   CU (cudaSetDevice (h->cfg.device));
   const Geom &g = h->g;
-  if (h->cfg.recon != PLUTO_GPU_RECON_LINEAR)
-    return fail ("pluto_gpu_set_grid: non-uniform grids need LINEAR reconstruction (PARABOLIC takes its weights from the grid, ppm_coeffs.c)");
   const double *src[3] = {dx1, dx2, dx3};
   for (int d = 0; d < g.dims; d++){
     if (!src[d]) return fail ("pluto_gpu_set_grid: NULL array for direction %d", d + 1);
@@ -610,6 +610,37 @@ int pluto_gpu_set_plm_coeffs (PlutoGpu *h, int dir, const double *cp, const doub
   }
   h->plmw = (h->cfg.recon == PLUTO_GPU_RECON_LINEAR);
   for (int d = 0; d < g.dims; d++) if (!h->plmc[d][0]) h->plmw = 0;
+  if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }
+  return 0;
+}
+
+// PARABOLIC reconstruction on a non-uniform grid (ppm_states.c:146-150 with the weights of PPM_CoefficientsGet, ppm_coeffs.c:586-609):
+// wp[n][-1], wp[n][0], wp[n][1], wp[n][2] of every zone n of direction dir, T_dir entries each.  On the device four consecutive
+// doubles per zone, with 32 zones of padding below (the lanes of a sweep that lie outside the row still form an address).
+int pluto_gpu_set_ppm_coeffs (PlutoGpu *h, int dir, const double *wm1, const double *w0, const double *w1, const double *w2)
+{
+  CU (cudaSetDevice (h->cfg.device));
+  const Geom &g = h->g;
+  if (dir < 0 || dir >= g.dims) return fail ("pluto_gpu_set_ppm_coeffs: direction %d", dir);
+  if (h->cfg.recon != PLUTO_GPU_RECON_PARABOLIC) return fail ("pluto_gpu_set_ppm_coeffs: the configuration has no PARABOLIC reconstruction");
+  if (!wm1 || !w0 || !w1 || !w2) return fail ("pluto_gpu_set_ppm_coeffs: NULL array");
+  int maxT = 1;
+  for (int d = 0; d < g.dims; d++) if (g.T[d] > maxT) maxT = g.T[d];
+  const size_t row = 4*(size_t)((maxT + 128 + 31) & ~31);
+  if (!h->ppmc_pool){
+    const size_t nb = 3*row*sizeof (double);
+    if (cudaMalloc (&h->ppmc_pool, nb) != cudaSuccess){ h->ppmc_pool = NULL; return fail ("cudaMalloc of %zu bytes (parabolic weights) failed", nb); }
+    CU (cudaMemset (h->ppmc_pool, 0, nb));
+    h->pool_bytes += nb;
+  }
+  double *host = (double *)malloc ((size_t)g.T[dir]*4*sizeof (double));
+  if (!host) return fail ("out of host memory");
+  for (int n = 0; n < g.T[dir]; n++){ host[4*n] = wm1[n]; host[4*n + 1] = w0[n]; host[4*n + 2] = w1[n]; host[4*n + 3] = w2[n]; }
+  double *dev = (double *)h->ppmc_pool + (size_t)dir*row + 4*32;
+  const cudaError_t e = cudaMemcpy (dev, host, (size_t)g.T[dir]*4*sizeof (double), cudaMemcpyHostToDevice);
+  free (host);
+  if (e != cudaSuccess) return fail ("cudaMemcpy (parabolic weights): %s", cudaGetErrorString (e));
+  h->ppmc[dir] = dev;
   if (h->graph){ cudaGraphExecDestroy (h->graph); h->graph = NULL; }
   return 0;
 }
@@ -923,6 +954,11 @@ static int run_stage (PlutoGpu *h, int stage, int part = PART_ALL)
       return fail ("SHOCK_FLATTENING MULTID with PARABOLIC reconstruction: hand over the weights of PLM_CoefficientsGet first "
                    "(pluto_gpu_set_plm_coeffs; ppm_states.c:167-181 takes them for the zones it flattens)");
     for (int q = 0; q < 6; q++){ s.pc[q] = h->plmc[dir][q]; s.pc2[q] = h->plmc[1][q]; }
+    if (h->nu && h->cfg.recon == PLUTO_GPU_RECON_PARABOLIC){
+      for (int d = 0; d < g.dims; d++) if (!h->ppmc[d])
+        return fail ("PARABOLIC reconstruction on a non-uniform grid: hand over the weights of PPM_CoefficientsGet first (pluto_gpu_set_ppm_coeffs)");
+    }
+    s.qc = h->ppmc[dir]; s.qc2 = h->ppmc[1];
     if (dir > 0 || fuse_xy){
       // zones per thread along a marching sweep: long enough to amortise the
       // extra face per chunk, short enough to fill the 148 SMs (2-D grids have
@@ -1845,6 +1881,17 @@ int pluto_gpu_multi_set_plm_coeffs (PlutoGpuMulti *m, int dir, const double *cp,
     int c[3]; pgm_coords (m, b, c);
     const size_t off = (size_t)c[dir]*m->ln[dir];
     if (pluto_gpu_set_plm_coeffs (m->blk[b], dir, cp + off, cm + off, wp + off, wm + off, dp + off, dm + off)) return 1;
+  }
+  return 0;
+}
+
+int pluto_gpu_multi_set_ppm_coeffs (PlutoGpuMulti *m, int dir, const double *wm1, const double *w0, const double *w1, const double *w2)
+{
+  if (dir < 0 || dir >= m->dims) return fail ("pluto_gpu_multi_set_ppm_coeffs: direction %d", dir);
+  for (int b = 0; b < m->nb; b++){
+    int c[3]; pgm_coords (m, b, c);
+    const size_t off = (size_t)c[dir]*m->ln[dir];
+    if (pluto_gpu_set_ppm_coeffs (m->blk[b], dir, wm1 + off, w0 + off, w1 + off, w2 + off)) return 1;
   }
   return 0;
 }

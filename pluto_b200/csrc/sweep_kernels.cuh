@@ -316,7 +316,7 @@ sweep_x_kernel (const __grid_constant__ SweepArgs a)
         vr[nv]  = src[nv*W + lane + 2];
         vrr[nv] = src[nv*W + lane + 3];
       }
-      ppm_interface<NC>(vl, v, vr, vrr, Wi);
+      ppm_interface<NC>(vl, v, vr, vrr, Wi, a.qc, i);
       PG_FOR_NV(nv) Wm[nv] = __shfl_up_sync (0xffffffffu, Wi[nv], 1);
       ppm_zone<NC>(v, Wm, Wi, vp, vm);
       if (FLAT && (fl & 1u)) ppm_flat_zone<NC>(a.pc, i, vl, v, vr, vp, vm);         // FLAG_MINMOD, ppm_states.c:167-181
@@ -524,8 +524,8 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       load_zone<NC>(a, id - sD, va_);
       cp_async_wait<PF - 1> ();
       PG_FOR_NV_SKIP(nv, SK){ vb_[nv] = z[0][ZS(nv)*CS]; vc_[nv] = z[1][ZS(nv)*CS]; vd_[nv] = z[2][ZS(nv)*CS]; }
-      ppm_interface<NC, SK>(vz_, va_, vb_, vc_, Wm);      // W[c0-2]
-      ppm_interface<NC, SK>(va_, vb_, vc_, vd_, Wf);      // W[c0-1]
+      ppm_interface<NC, SK>(vz_, va_, vb_, vc_, Wm, a.qc, c0 - 2);      // W[c0-2]
+      ppm_interface<NC, SK>(va_, vb_, vc_, vd_, Wf, a.qc, c0 - 1);      // W[c0-1]
       ppm_zone<NC, SK>(vb_, Wm, Wf, vpL, vm_unused);
       if (FLAT && (a.flag[id] & 1u)) ppm_flat_zone<NC, SK>(a.pc, c0 - 1, va_, vb_, vc_, vpL, vm_unused);
       if (HLL && chunk == 0 && in_range) store_vel_slopes<NC>(a.dvel, id, vpL, vm_unused);
@@ -582,7 +582,7 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV_SKIP(nv, SK) Wf[nv] = C_WF(nv);
-        ppm_interface<NC, SK>(vb_, vc_, vd_, vnx, Wn);    // W[f+1]
+        ppm_interface<NC, SK>(vb_, vc_, vd_, vnx, Wn, a.qc, f + 1);    // W[f+1]
         ppm_zone<NC, SK>(vc_, Wf, Wn, vpn, vR);
         if (FLAT && (flc & 1u)) ppm_flat_zone<NC, SK>(a.pc, f + 1, vb_, vc_, vd_, vpn, vR);
         PG_FOR_NV_SKIP(nv, SK) C_WF(nv) = Wn[nv];
@@ -812,8 +812,8 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       cp_async_wait_all ();
       if (TMA){ mbar_wait (mbar, tphase); tphase ^= 1u; }
       PG_FOR_NV_SKIP(nv, SKP){ vb_[nv] = z[0][nv*VS]; vc_[nv] = z[1][nv*VS]; vd_[nv] = z[2][nv*VS]; }
-      ppm_interface<NC, SKP>(vz_, va_, vb_, vc_, Wm);
-      ppm_interface<NC, SKP>(va_, vb_, vc_, vd_, Wf);
+      ppm_interface<NC, SKP>(vz_, va_, vb_, vc_, Wm, a.qc2, c0 - 2);
+      ppm_interface<NC, SKP>(va_, vb_, vc_, vd_, Wf, a.qc2, c0 - 1);
       ppm_zone<NC, SKP>(vb_, Wm, Wf, vpL, vm_unused);
       if (FLAT && (a.flag[id] & 1u)) ppm_flat_zone<NC, SKP>(a.pc2, c0 - 1, va_, vb_, vc_, vpL, vm_unused);
       if (HLL && chunk == 0 && col_ok) store_vel_slopes<NC>(a.dvel2, id, vpL, vm_unused);
@@ -873,7 +873,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
         plm_zone_f<NC, FLAT, -1, CL, 0, RECON == RECON_PLMW>(a, flz, v, dvm, dvp, vp, vm, a.pc, i);
       }else{
         double Wi[NV], Wm[NV];
-        ppm_interface<NC>(xvl, v, xvr, xvrr, Wi);
+        ppm_interface<NC>(xvl, v, xvr, xvrr, Wi, a.qc, i);
         PG_FOR_NV(nv) Wm[nv] = __shfl_up_sync (0xffffffffu, Wi[nv], 1);
         ppm_zone<NC>(v, Wm, Wi, vp, vm);
         if (FLAT && (flz & 1u)) ppm_flat_zone<NC>(a.pc, i, xvl, v, xvr, vp, vm);
@@ -933,7 +933,7 @@ sweep_xy_kernel (const __grid_constant__ SweepArgs a)
       }else{
         double Wf[NV], Wn[NV];
         PG_FOR_NV_SKIP(nv, SKY) Wf[nv] = C_WF(nv);
-        ppm_interface<NC, SKY>(v, vc_, vd_, vnx, Wn);       // W[f+1]
+        ppm_interface<NC, SKY>(v, vc_, vd_, vnx, Wn, a.qc2, f + 1);       // W[f+1]
         ppm_zone<NC, SKY>(vc_, Wf, Wn, vpn, vR);
         if (FLAT && (fln & 1u)) ppm_flat_zone<NC, SKY>(a.pc2, f + 1, v, vc_, vd_, vpn, vR);
         PG_FOR_NV_SKIP(nv, SKY) C_WF(nv) = Wn[nv];

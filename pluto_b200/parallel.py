@@ -418,6 +418,11 @@ class DistStepper:
         ng = self.block.ng
         self.block.set_plm_coeffs([[self.layout.slice_1d(self.rank, d, a, ng) for a in six] for d, six in enumerate(global_coeffs)])
 
+    def set_ppm_coeffs(self, global_coeffs):
+        """PARABOLIC on a non-uniform grid: the four interface-weight arrays of the WHOLE grid per direction; every rank takes its slice."""
+        ng = self.block.ng
+        self.block.set_ppm_coeffs([[self.layout.slice_1d(self.rank, d, a, ng) for a in four] for d, four in enumerate(global_coeffs)])
+
     def _drain(self):
         """The state is about to be replaced from outside: forget the exchange in flight."""
         if self.world > 1 and self.overlap and self._prefetched is not None:
@@ -611,6 +616,10 @@ class LocalMultiBlock:
     def set_plm_coeffs(self, global_coeffs):
         for r, b in enumerate(self.blocks):
             b.set_plm_coeffs([[self.layout.slice_1d(r, d, a, b.ng) for a in six] for d, six in enumerate(global_coeffs)])
+
+    def set_ppm_coeffs(self, global_coeffs):
+        for r, b in enumerate(self.blocks):
+            b.set_ppm_coeffs([[self.layout.slice_1d(r, d, a, b.ng) for a in four] for d, four in enumerate(global_coeffs)])
 
     def set_state(self, global_state):
         lay = self.layout

@@ -110,6 +110,15 @@ class GpuStepper:
                 raise ValueError(f"set_plm_coeffs: direction {d+1} needs six arrays of {self.n[d] + 2 * self.ng} entries")
             self._check(self.L.pluto_gpu_set_plm_coeffs(self._h, d, *[a.ctypes.data for a in arrs]))
 
+    def set_ppm_coeffs(self, coeffs):
+        """PARABOLIC on a non-uniform grid: per direction the four interface-weight arrays wp[i][-1 .. 2] PPM_CoefficientsGet returns
+        (n[d] + 2 nghost entries each)."""
+        for d, four in enumerate(coeffs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in four]
+            if len(arrs) != 4 or any(a.size != self.n[d] + 2 * self.ng for a in arrs):
+                raise ValueError(f"set_ppm_coeffs: direction {d+1} needs four arrays of {self.n[d] + 2 * self.ng} entries")
+            self._check(self.L.pluto_gpu_set_ppm_coeffs(self._h, d, *[a.ctypes.data for a in arrs]))
+
     def set_body_force(self, g1, g2, g3=None):
         """Static position-dependent force (BodyForceVector at the zone centres): arrays [T3][T2][T1] incl. ghost zones.
         The stepper must have been created with grav=... (BODY_FORCE VECTOR)."""
@@ -422,6 +431,12 @@ class MultiGpuStepper:
         """Zone widths of the WHOLE domain per direction (ghost zones included); every block takes its slice."""
         arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (dx1, dx2, dx3)]
         self._check(self.L.pluto_gpu_multi_set_grid(self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
+    def set_ppm_coeffs(self, coeffs):
+        """PARABOLIC on a non-uniform grid: per direction the four interface-weight arrays of the WHOLE domain."""
+        for d, four in enumerate(coeffs):
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in four]
+            self._check(self.L.pluto_gpu_multi_set_ppm_coeffs(self._h, d, *[a.ctypes.data for a in arrs]))
 
     def set_body_force(self, g1, g2, g3=None):
         """BodyForceVector at the zone centres of the WHOLE domain ([T3][T2][T1], ghost zones included); every block takes its piece."""

@@ -49,7 +49,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # BODY_FORCE with SHOCK_FLATTENING MULTID
          "blast3d_sfl_bf", "blast3d_ctu_sfl_bf", "blast2d_ppm_sfl_bp",
          # non-uniform grids with SHOCK_FLATTENING, CHAR_LIMITING, CT_EN_CORRECTION, BODY_FORCE inside the corner-transport-upwind step
-         "blast3d_nug_sfl", "blast2d_nug_cl_roe", "blast2d_nug_en", "blast2d_nug_ctu_bp"]
+         "blast3d_nug_sfl", "blast2d_nug_cl_roe", "blast2d_nug_en", "blast2d_nug_ctu_bp",
+         # PARABOLIC on non-uniform grids: the shim hands over the weights of PPM_CoefficientsGet
+         "rotor2d_nug_ppm", "blast3d_nug_ppm_roe", "blast2d_nug_ppm_sfl_rk3"]
 
 
 def _blast_params(g):
@@ -136,7 +138,9 @@ def test_resident_state_drop_in(name, arith):
                                                 ("blast3d_nug", 4, False), ("blast2d_nuw_mc_arith", 2, True),
                                                 # BODY_FORCE: the force / potential arrays of the whole domain are cut into the blocks' pieces
                                                 ("blast3d_bfx", 4, False), ("blast3d_bp", 2, True), ("blast3d_nug_bp", 4, False),
-                                                ("blast2d_ctu_bfx_roe", 2, False)])
+                                                ("blast2d_ctu_bfx_roe", 2, False),
+                                                # PARABOLIC on a non-uniform grid: slices of the interface weights
+                                                ("rotor2d_nug_ppm", 4, False)])
 def test_reference_driver_on_several_blocks(name, ndev, resident):
     """PLUTO_GPU_NDEV: the reference's serial, single-threaded driver with the domain cut into 2 / 4 / 8 blocks (one per GPU where
     the box has them, round robin otherwise), driven through pluto_gpu_multi_* -- no MPI, no Python.  Dumps bit-identical to the

@@ -208,7 +208,10 @@ def test_characteristic_tracing_is_2d_only():
     ("blast", 2, (28, 24, 1), "roe", dict(char_lim=True)), ("ot", 2, (32, 28, 1), "hlld", dict(char_lim=True, ctu=True, limiter="mc", emf="arith")),
     ("blast", 2, (28, 24, 1), "hlld", dict(en_corr=True)), ("blast", 3, (10, 14, 12), "hlld", dict(en_corr=True, ctu=True)),
     ("turb", 3, (10, 8, 12), "hll", dict(en_corr=True, rk_order=3, emf="uct0")),
-    ("turb", 3, (10, 12, 8), "hllc", dict(ctu=True, grav=(0.3, -1.0, 0.5))), ("blast", 2, (28, 24, 1), "roe", dict(ctu=True, grav=(0.5, 0.25, 0.0), flatten=True))])
+    ("turb", 3, (10, 12, 8), "hllc", dict(ctu=True, grav=(0.3, -1.0, 0.5))), ("blast", 2, (28, 24, 1), "roe", dict(ctu=True, grav=(0.5, 0.25, 0.0), flatten=True)),
+    # PARABOLIC: per-zone interface weights (any four numbers per zone serve the comparison; here the uniform ones +- 10 %)
+    ("rotor", 2, (33, 40, 1), "roe", dict(recon="ppm")), ("blast", 3, (33, 12, 10), "hlld", dict(recon="ppm", rk_order=3)),
+    ("turb", 3, (10, 9, 12), "hll", dict(recon="ppm", emf="uct_hll", grav=(0.3, -1.0, 0.5)))])
 def test_nonuniform_grid_with_scheme_options(problem, dims, n, solver, kw):
     """Random zone widths together with the options that read the grid elsewhere: SHOCK_FLATTENING MULTID (flag_shock.c:143-145 divides
     the velocity differences by dx1[i], dx2[j], dx3[k]), CT_EN_CORRECTION (the cell-centred field of the sweeps is rebuilt with dt/dx of
@@ -231,6 +234,12 @@ def test_nonuniform_grid_with_scheme_options(problem, dims, n, solver, kw):
                     a[n[d] + ng:] = a[ng:2 * ng]
         o.set_grid(*dxs)
         s.set_grid(*dxs)
+        if kw.get("recon") == "ppm":
+            if arith == "exact":
+                uni = (-1.0 / 12.0, 7.0 / 12.0, 7.0 / 12.0, -1.0 / 12.0)
+                qcs = [[w * (0.9 + 0.2 * rng.random(a.size)) for w in uni] for a in dxs]
+            o.set_ppm_coeffs(qcs)
+            s.set_ppm_coeffs(qcs)
         o.set_state(st0)
         s.set_state(st0)
         dt = 1e-4 if problem == "blast" else 1e-3
@@ -253,14 +262,16 @@ def test_nonuniform_grid_with_scheme_options(problem, dims, n, solver, kw):
 
 
 def test_nonuniform_grid_is_refused_where_the_weights_would_change():
-    """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c): pluto_gpu_set_grid says so."""
-    from pluto_b200 import GpuStepper
+    """PARABOLIC reconstruction takes its weights from the grid (ppm_coeffs.c): on a non-uniform grid the step asks for them."""
+    from pluto_b200 import GpuStepper, problems
     from pluto_b200.stepper import PlutoGpuError
-    for kw, ng in ((dict(recon="ppm"), 3),):
-        s = GpuStepper(2, (16, 16, 1), (0.1, 0.1), **kw)
-        with pytest.raises(PlutoGpuError, match="non-uniform"):
-            s.set_grid(np.full(16 + 2 * ng, 0.1), np.full(16 + 2 * ng, 0.1))
-        s.close()
+    st0, meta = problems.make("ot", 2, (16, 16, 1))
+    s = GpuStepper(2, (16, 16, 1), meta["dx"], recon="ppm", bc=meta["bc"], gamma=meta["gamma"])
+    s.set_grid(np.full(16 + 2 * s.ng, meta["dx"][0]), np.full(16 + 2 * s.ng, meta["dx"][1]))
+    s.set_state(st0)
+    with pytest.raises(PlutoGpuError, match="PPM_CoefficientsGet"):
+        s.advance(1e-3)
+    s.close()
     s = GpuStepper(2, (16, 16, 1), (0.1, 0.1))
     with pytest.raises(PlutoGpuError, match="dx1"):
         s.set_grid(np.zeros(20), np.full(20, 0.1))

@@ -192,6 +192,16 @@ CASES = [
                                     grid=("2  0.0  6  u  0.6  4  s  1.0", "2  0.0  4  s  0.3  8  u  1.0", "2  0.0  4  u  0.5  4  s  1.0")), 6),
     ("blast2d_nug_ctu_bp", RefConfig(problem="blast", dims=2, n=(24, 20, 1), first_dt=3e-4, tstep="hancock", grav=(0.05, -0.03, 0.0), potential=True,
                                      grid=("2  -0.5  16  u  0.2  8  s  0.5", "3  -0.5  4  s  -0.3  12  u  0.3  4  s  0.5", None)), 8),
+    # PARABOLIC on non-uniform grids: the interface weights of PPM_FindWeights (ppm_coeffs.c:300-480), handed over as the reference built them
+    ("rotor2d_nug_ppm", RefConfig(problem="rotor", dims=2, n=(40, 36, 1), recon="ppm", first_dt=2e-3,
+                                  grid=("3  -0.5  10  s  -0.2  20  u  0.2  10  s  0.5", "2  -0.5  24  u  0.1  12  s  0.5", None)), 10),
+    ("blast3d_nug_ppm_roe", RefConfig(problem="blast", dims=3, n=(14, 12, 16), recon="ppm", first_dt=3e-4, cfl=0.3, solver="roe",
+                                      grid=("2  -0.5  8  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5", "3  -0.5  4  s  -0.3  8  u  0.3  4  s  0.5")), 8),
+    ("rotor2d_nug_ppm_rk3_bp", RefConfig(problem="rotor", dims=2, n=(28, 24, 1), recon="ppm", tstep="rk3", first_dt=2e-3,
+                                         grav=(0.05, -0.03, 0.0), potential=True,
+                                         grid=("2  -0.5  20  u  0.2  8  s  0.5", "3  -0.5  6  s  -0.3  12  u  0.3  6  s  0.5", None)), 6),
+    ("blast2d_nug_ppm_sfl_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=3e-4, solver="roe", flatten=True,
+                                          grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  24  u  0.1  8  s  0.5", None)), 10),
     ("blast2d_chtr_mc_hllc", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="hllc"), 10),
 ]
 
@@ -219,6 +229,9 @@ def test_oracle_bit_exact_vs_live_reference(label, cfg, nsteps):
     if cfg.grid is not None:
         assert r.dx is not None and len(r.dx) == cfg.dims and max(np.ptp(a) for a in r.dx) > 0.0
         o.set_grid(*r.dx)
+    if cfg.grid is not None and cfg.recon == "ppm":
+        assert r.ppm_coeffs is not None and len(r.ppm_coeffs) == cfg.dims
+        o.set_ppm_coeffs(r.ppm_coeffs)
     if cfg.grid_weights or (cfg.flatten and cfg.recon == "ppm"):
         assert r.plm_coeffs is not None and len(r.plm_coeffs) == cfg.dims
         o.set_plm_coeffs(r.plm_coeffs)

@@ -56,6 +56,8 @@ class Golden:
         # UNIFORM_CARTESIAN_GRID NO: per direction the six weight arrays of PLM_CoefficientsGet
         self.grid_weights = "cfg_grid_weights" in d.files
         self.plm_coeffs = [list(d[f"plm_coeffs{a+1}"]) for a in range(self.dims)] if "plm_coeffs1" in d.files else None
+        # PARABOLIC on a non-uniform grid: per direction the four interface-weight arrays of PPM_CoefficientsGet
+        self.ppm_coeffs = [list(d[f"ppm_coeffs{a+1}"]) for a in range(self.dims)] if "ppm_coeffs1" in d.files else None
         self.dt = d["dt"]
         self.states = {}
         for key in d.files:
@@ -84,6 +86,8 @@ def apply_force_field(stepper, g):
         stepper.set_grid(*g.grid_dx)
     if g.plm_coeffs is not None:
         stepper.set_plm_coeffs(g.plm_coeffs)
+    if g.ppm_coeffs is not None:
+        stepper.set_ppm_coeffs(g.ppm_coeffs)
     if g.grav_mode == 1:
         stepper.set_body_force(*sign_force_arrays(g.dims, g.n, stepper.ng, g.domain, g.grav, widths=g.grid_dx))
     if g.potential:

@@ -167,6 +167,14 @@ CASES = {
                                  grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 12),
     "blast2d_nug_ctu_bp": (RefConfig(problem="blast", dims=2, n=(36, 28, 1), first_dt=6e-4, tstep="hancock", grav=(0.05, -0.03, 0.0), potential=True,
                                      grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  20  u  0.1  8  s  0.5", None)), 12),
+    # PARABOLIC on non-uniform grids (the fixtures carry the interface weights of PPM_CoefficientsGet)
+    "rotor2d_nug_ppm": (RefConfig(problem="rotor", dims=2, n=(40, 36, 1), recon="ppm", first_dt=2.5e-3,
+                                  grid=("3  -0.5  10  s  -0.2  20  u  0.2  10  s  0.5", "2  -0.5  24  u  0.1  12  s  0.5", None)), 12),
+    "blast3d_nug_ppm_roe": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), recon="ppm", first_dt=6e-4, cfl=0.3, solver="roe",
+                                      grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
+                                            "3  -0.5  3  s  -0.3  8  u  0.3  3  s  0.5")), 10),
+    "blast2d_nug_ppm_sfl_rk3": (RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", tstep="rk3", first_dt=6e-4, flatten=True,
+                                          grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  24  u  0.1  8  s  0.5", None)), 10),
     # UNIFORM_CARTESIAN_GRID NO: grid-dependent reconstruction weights (plm_coeffs.c) -- the fixtures carry the arrays of PLM_CoefficientsGet
     "blast3d_nuw": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grid_weights=True,
                               grid=("2  -0.5  10  u  0.0  6  s  0.5", "2  -0.5  4  s  -0.2  8  u  0.5",
@@ -218,6 +226,9 @@ def make(name):
     if r.plm_coeffs is not None:           # UNIFORM_CARTESIAN_GRID NO, or PARABOLIC + MULTID (the minmod fallback's weights)
         for d in range(cfg.dims):
             out[f"plm_coeffs{d+1}"] = np.array(r.plm_coeffs[d])
+    if r.ppm_coeffs is not None and cfg.grid is not None:       # PARABOLIC on a non-uniform grid: the interface weights of PPM_CoefficientsGet
+        for d in range(cfg.dims):
+            out[f"ppm_coeffs{d+1}"] = np.array(r.ppm_coeffs[d])
     for s in (0, 1, nsteps):
         for k, v in r.dumps[s].items():
             out[f"s{s}_{k}"] = v
