@@ -49,6 +49,11 @@ WORKLOADS = {
     "ot3d_256": ("ot", 3, (256, 256, 256), "plm", "hlld", 0.3, 1e-3),
     "ot2d_512": ("ot", 2, (512, 512, 1), "plm", "hlld", 0.4, 1e-3),
     "rotor2d_4096": ("rotor", 2, (4096, 4096, 1), "ppm", "roe", 0.4, 1e-5),
+    # development: the other reconstruction / solver pairs at the sizes above (launch-bound A/B, profiles/r2ad_*)
+    "blast3d_256_ppm": ("blast", 3, (256, 256, 256), "ppm", "hlld", 0.3, 1e-4),
+    "blast3d_256_hllc": ("blast", 3, (256, 256, 256), "plm", "hllc", 0.3, 1e-4),
+    "rotor2d_4096_plm_roe": ("rotor", 2, (4096, 4096, 1), "plm", "roe", 0.4, 1e-5),
+    "rotor2d_4096_ppm_hlld": ("rotor", 2, (4096, 4096, 1), "ppm", "hlld", 0.4, 1e-5),
     # strong scaling (BASELINE.json configs[2]): the GLOBAL grid is fixed and split over the ranks
     "ot3d_1024_strong": ("ot", 3, (1024, 1024, 1024), "plm", "hlld", 0.3, 1e-3),
     "ot3d_512_strong": ("ot", 3, (512, 512, 512), "plm", "hlld", 0.3, 1e-3),

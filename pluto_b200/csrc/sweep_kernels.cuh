@@ -683,6 +683,11 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 #ifndef PG_MINB_XY
 #define PG_MINB_XY 3
 #endif
+// Resident blocks per SM the fused sweep is compiled for.  LINEAR: three (168 registers, no spills; two blocks with 255 registers
+// lose 3 - 9 %).  PARABOLIC: two -- at 168 registers its variants spill 100 - 190 B per thread, with up to 255 they do not and the
+// sweep runs 11 - 17 % faster (profiles/r2ad_launch_bounds_ab.txt: rotor 4096^2 PARABOLIC + roe 5.26 -> 4.74 ms per step, + hlld
+// 4.85 -> 4.04, blast 256^3 PARABOLIC + hlld 4.20 -> 3.73)
+__host__ __device__ constexpr int xy_min_blocks (int recon) { return recon == RECON_PPM ? 2 : PG_MINB_XY; }
 __host__ __device__ constexpr int xy_ring_cols () { return 4*38; }             // 4 warps x (32 + 4 halo columns + 2: the bulk copies
                                                                                // of the TMA variant start at an even entry)
 __host__ __device__ constexpr int xy_thread_slots (int recon) { return 8 + 7 + (recon == RECON_PPM ? 8 : 0) + 2; }
@@ -699,7 +704,7 @@ __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
 }
 
 template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool TMA = false, bool CL = false>
-__global__ void __launch_bounds__(128, PG_MINB_XY)
+__global__ void __launch_bounds__(128, xy_min_blocks (RECON))
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
   typedef Dirs<0> DX;
@@ -1056,7 +1061,7 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
 #define PG_LXYK(KF) do { auto kfn = KF;                          \
       static int bps = 0; static unsigned long long devs = 0;                                         \
       if (pg_attr_needed (devs)){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_XY; } \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = xy_min_blocks (recon); } \
       if (a.plan) plan_chunks (b, g.n[1], nwarp1*32*1000/TPB, bps);                                   \
       const unsigned nb = (unsigned)((nwarp1*b.nchunk*32 + TPB - 1)/TPB);                             \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
