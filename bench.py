@@ -52,6 +52,8 @@ WORKLOADS = {
     # development: the other reconstruction / solver pairs at the sizes above (launch-bound A/B, profiles/r2ad_*)
     "blast3d_256_ppm": ("blast", 3, (256, 256, 256), "ppm", "hlld", 0.3, 1e-4),
     "blast3d_256_hllc": ("blast", 3, (256, 256, 256), "plm", "hllc", 0.3, 1e-4),
+    "ot3d_256_roe": ("ot", 3, (256, 256, 256), "plm", "roe", 0.3, 1e-3),
+    "ot3d_256_ppm_roe": ("ot", 3, (256, 256, 256), "ppm", "roe", 0.3, 1e-3),
     "rotor2d_4096_plm_roe": ("rotor", 2, (4096, 4096, 1), "plm", "roe", 0.4, 1e-5),
     "rotor2d_4096_ppm_hlld": ("rotor", 2, (4096, 4096, 1), "ppm", "hlld", 0.4, 1e-5),
     # strong scaling (BASELINE.json configs[2]): the GLOBAL grid is fixed and split over the ranks

@@ -35,6 +35,11 @@
 
 namespace PG_NS {
 
+// resident blocks per SM of a marching sweep: three, except PARABOLIC + roe (50 - 76 B spilled at 168 registers: x3 sweep of
+// ot 256^3 3.1 - 3.4 -> 2.56 ms per step with two; LINEAR + roe loses 7 % with two; profiles/r2ag_roe_march_ab.txt)
+__host__ __device__ constexpr int march_min_blocks (int recon, int solver)
+{ return (recon == 1 /* RECON_PPM */ && solver == 2 /* SOLVER_ROE */) ? 2 : PG_MINB_MARCH; }
+
 __device__ __forceinline__ void atomic_max_pos (unsigned long long *slot, double x)
 {
   // non-negative doubles order like their bit patterns
@@ -423,7 +428,7 @@ __host__ __device__ constexpr int march_slots (int recon, bool cl = false, bool 
 #define PG_MINB_MARCH_R3 4
 #endif
 template <int DIR, int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool CL = false, bool R3 = false>
-__global__ void __launch_bounds__(128, R3 ? PG_MINB_MARCH_R3 : PG_MINB_MARCH)
+__global__ void __launch_bounds__(128, R3 ? PG_MINB_MARCH_R3 : march_min_blocks (RECON, SOLVER))
 sweep_march_kernel (const __grid_constant__ SweepArgs a)
 {
   typedef Dirs<DIR> D;
@@ -687,7 +692,10 @@ sweep_march_kernel (const __grid_constant__ SweepArgs a)
 // lose 3 - 9 %).  PARABOLIC: two -- at 168 registers its variants spill 100 - 190 B per thread, with up to 255 they do not and the
 // sweep runs 11 - 17 % faster (profiles/r2ad_launch_bounds_ab.txt: rotor 4096^2 PARABOLIC + roe 5.26 -> 4.74 ms per step, + hlld
 // 4.85 -> 4.04, blast 256^3 PARABOLIC + hlld 4.20 -> 3.73)
-__host__ __device__ constexpr int xy_min_blocks (int recon) { return recon == RECON_PPM ? 2 : PG_MINB_XY; }
+// Roe in 3-D likewise (160 - 190 B spilled at 168 registers): LINEAR + roe 256^3 7.49 -> 6.20 ms per step (profiles/r2af_roe3d_ab.txt);
+// in 2-D the LINEAR Roe sweep fits and keeps three blocks (two: - 9 %).
+__host__ __device__ constexpr int xy_min_blocks (int recon, int solver, int nc)
+{ return (recon == RECON_PPM || (solver == SOLVER_ROE && nc == 3)) ? 2 : PG_MINB_XY; }
 __host__ __device__ constexpr int xy_ring_cols () { return 4*38; }             // 4 warps x (32 + 4 halo columns + 2: the bulk copies
                                                                                // of the TMA variant start at an even entry)
 __host__ __device__ constexpr int xy_thread_slots (int recon) { return 8 + 7 + (recon == RECON_PPM ? 8 : 0) + 2; }
@@ -704,7 +712,7 @@ __host__ __device__ constexpr size_t xy_smem_bytes (int recon)
 }
 
 template <int RECON, int SOLVER, int NC, bool HLL, bool FLAT, bool BF = false, bool TMA = false, bool CL = false>
-__global__ void __launch_bounds__(128, xy_min_blocks (RECON))
+__global__ void __launch_bounds__(128, xy_min_blocks (RECON, SOLVER, NC))
 sweep_xy_kernel (const __grid_constant__ SweepArgs a)
 {
   typedef Dirs<0> DX;
@@ -1061,7 +1069,7 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
 #define PG_LXYK(KF) do { auto kfn = KF;                          \
       static int bps = 0; static unsigned long long devs = 0;                                         \
       if (pg_attr_needed (devs)){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem_bytes (RECON_PPM)); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = xy_min_blocks (recon); } \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = xy_min_blocks (recon, SOLVER, nc); } \
       if (a.plan) plan_chunks (b, g.n[1], nwarp1*32*1000/TPB, bps);                                   \
       const unsigned nb = (unsigned)((nwarp1*b.nchunk*32 + TPB - 1)/TPB);                             \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
@@ -1132,7 +1140,7 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       static int bps = 0; static unsigned long long devs = 0;                                         \
       if (pg_attr_needed (devs)){ cudaFuncSetAttribute (kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 72*TPB*8);       \
         if (getenv ("PLUTO_GPU_CARVEOUT")) cudaFuncSetAttribute (kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PLUTO_GPU_CARVEOUT"))); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = PG_MINB_MARCH; } \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&bps, kfn, TPB, smem) != cudaSuccess || bps < 1) bps = march_min_blocks (recon, SOLVER); } \
       if (a.plan) plan_chunks (b, g.n[dir], npen*1000/TPB, bps);                                      \
       const unsigned nb = (unsigned)((npen*b.nchunk + TPB - 1)/TPB);                                  \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)

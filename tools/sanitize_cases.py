@@ -5,7 +5,7 @@
 
 families: rk (fused x1+x2 sweep, x3 march, CT, final, bc), exact (one kernel per direction), ppm_roe, hll_uct_hll,
 ctu, bc (outflow / reflective / eqtsymmetric fills incl. div B), halo (two blocks in one process: pack / unpack tables),
-io (dbl writer / analysis), grid (non-uniform grids, grid-dependent weights, PLUTO_GPU_R3), schemes2 (CHARACTERISTIC_TRACING, CHAR_LIMITING + CTU, MULTID + PARABOLIC).  Launches run without graph capture so that a report names the kernel.
+io (dbl writer / analysis), grid (non-uniform grids, grid-dependent weights, PLUTO_GPU_R3), schemes2 (CHARACTERISTIC_TRACING, CHAR_LIMITING + CTU, MULTID + PARABOLIC), schemes3 (hllc / tvdlf, BODY_FORCE combinations, scheme options and PARABOLIC on non-uniform grids).  Launches run without graph capture so that a report names the kernel.
 """
 import os
 import sys
@@ -135,6 +135,36 @@ def fam_schemes2():
         s.close()
 
 
+def fam_schemes3():
+    """Last part of round 2: hllc / tvdlf in every kernel family, BODY_FORCE with UCT_HLL and with flattening, non-uniform grids with
+    flattening / energy correction / body force inside the CTU step, PARABOLIC with per-zone interface weights."""
+    run("blast", 3, (40, 24, 20), arith="fast", solver="hllc")
+    run("blast", 3, (24, 20, 16), arith="exact", solver="hllc", recon="ppm", rk_order=3)
+    run("ot", 2, (48, 40, 1), arith="fast", solver="tvdlf", emf="uct_hll", dt=1e-3)
+    run("turb", 3, (24, 20, 16), arith="fast", solver="tvdlf", ctu=True, limiter="um", emf="uct0", dt=1e-3)
+    run("blast", 3, (24, 20, 16), arith="fast", solver="hllc", ctu=True)
+    run("blast", 3, (24, 20, 16), arith="fast", emf="uct_hll", grav=(0.3, -1.0, 0.5))
+    run("blast", 3, (24, 20, 16), arith="fast", flatten=True, grav=(0.3, -1.0, 0.5), steps=6)
+    run("blast", 3, (24, 20, 16), arith="fast", flatten=True, emf="uct_hll", grav=(0.3, -1.0, 0.5), steps=6)
+    rng = np.random.default_rng(5)
+    for dims, n, kw in ((3, (24, 20, 16), dict(arith="fast", flatten=True)), (2, (48, 40, 1), dict(arith="fast", en_corr=True)),
+                        (3, (24, 20, 16), dict(arith="fast", ctu=True, grav=(0.3, -1.0, 0.5))),
+                        (3, (24, 20, 16), dict(arith="fast", recon="ppm")), (2, (48, 40, 1), dict(arith="exact", recon="ppm", solver="roe"))):
+        st0, meta = problems.make("blast", dims, n)
+        s = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], **kw)
+        dxs = [meta["dx"][d]*(0.7 + 0.6*rng.random(n[d] + 2*s.ng)) for d in range(dims)]
+        s.set_grid(*dxs)
+        if kw.get("recon") == "ppm":
+            s.set_ppm_coeffs([[w*(0.9 + 0.2*rng.random(a.size)) for w in (-1/12, 7/12, 7/12, -1/12)] for a in dxs])
+        s.set_state(st0)
+        dt = 1e-4
+        for _ in range(6 if kw.get("flatten") else 2):
+            info = s.advance(dt)
+            dt = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+        assert all(np.isfinite(v).all() for v in s.get_state().values())
+        s.close()
+
+
 def fam_io():
     import tempfile
     st0, meta = problems.make("ot", 3, (24, 20, 16))
@@ -151,7 +181,7 @@ def fam_io():
 
 
 FAMILIES = {"rk": fam_rk, "exact": fam_exact, "ppm_roe": fam_ppm_roe, "hll_uct_hll": fam_hll_uct_hll, "ctu": fam_ctu,
-            "bc": fam_bc, "halo": fam_halo, "io": fam_io, "grid": fam_grid, "schemes2": fam_schemes2}
+            "bc": fam_bc, "halo": fam_halo, "io": fam_io, "grid": fam_grid, "schemes2": fam_schemes2, "schemes3": fam_schemes3}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(FAMILIES)):
