@@ -106,8 +106,8 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
   #error "libpluto_gpu: UPDATE_VECTOR_POTENTIAL YES is not available (d->Ax1..3 are not advanced on the GPU)"
 #endif
 #if LIMITER == FOURTH_ORDER_LIM \
-    || (SHOCK_FLATTENING != NO && (SHOCK_FLATTENING != MULTID || (RECONSTRUCTION == PARABOLIC && CT_EMF_AVERAGE == UCT_HLL)))
-  #error "libpluto_gpu: FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID (with PARABOLIC: not UCT_HLL) are not available on the GPU"
+    || (SHOCK_FLATTENING != NO && SHOCK_FLATTENING != MULTID)
+  #error "libpluto_gpu: FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID are not available on the GPU"
 #endif
 #if CHAR_LIMITING == YES && (DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || (TIME_STEPPING != RK2 && TIME_STEPPING != RK3 && CT_EN_CORRECTION == YES) \
                              || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EMF_AVERAGE == UCT_HLL)

@@ -167,8 +167,6 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
   if (cfg->rk_order != 2 && cfg->rk_order != 3) return fail ("rk_order must be 2 or 3");
   if (cfg->limiter < 0 || cfg->limiter > PLUTO_GPU_LIM_MC) return fail ("bad limiter");
   if (cfg->shock_flattening != 0 && cfg->shock_flattening != 1) return fail ("bad shock_flattening");
-  if (cfg->shock_flattening && cfg->recon == PLUTO_GPU_RECON_PARABOLIC && cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL)
-    return fail ("SHOCK_FLATTENING MULTID with PARABOLIC reconstruction is not available with CT_EMF_AVERAGE UCT_HLL");
   if (cfg->emf_average < 0 || cfg->emf_average > PLUTO_GPU_EMF_UCT_HLL) return fail ("bad emf_average");
   if (cfg->time_stepping < PLUTO_GPU_TS_RK || cfg->time_stepping > PLUTO_GPU_TS_CHAR_TRACING) return fail ("bad time_stepping");
   if (cfg->time_stepping == PLUTO_GPU_TS_CHAR_TRACING){

@@ -51,7 +51,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # non-uniform grids with SHOCK_FLATTENING, CHAR_LIMITING, CT_EN_CORRECTION, BODY_FORCE inside the corner-transport-upwind step
          "blast3d_nug_sfl", "blast2d_nug_cl_roe", "blast2d_nug_en", "blast2d_nug_ctu_bp",
          # PARABOLIC on non-uniform grids: the shim hands over the weights of PPM_CoefficientsGet
-         "rotor2d_nug_ppm", "blast3d_nug_ppm_roe", "blast2d_nug_ppm_sfl_rk3"]
+         "rotor2d_nug_ppm", "blast3d_nug_ppm_roe", "blast2d_nug_ppm_sfl_rk3",
+         # PARABOLIC + SHOCK_FLATTENING MULTID with the default average UCT_HLL
+         "blast3d_ppm_sfl_uct_hll", "blast2d_ppm_sfl_uct_hll_roe"]
 
 
 def _blast_params(g):

@@ -202,6 +202,11 @@ CASES = [
                                          grid=("2  -0.5  20  u  0.2  8  s  0.5", "3  -0.5  6  s  -0.3  12  u  0.3  6  s  0.5", None)), 6),
     ("blast2d_nug_ppm_sfl_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=3e-4, solver="roe", flatten=True,
                                           grid=("3  -0.5  8  s  -0.25  20  u  0.25  8  s  0.5", "2  -0.5  24  u  0.1  8  s  0.5", None)), 10),
+    # PARABOLIC + SHOCK_FLATTENING MULTID with the default average UCT_HLL
+    ("blast2d_ppm_sfl_uct_hll_roe", RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=3e-4, solver="roe", flatten=True,
+                                              emf="uct_hll"), 12),
+    ("blast3d_ppm_sfl_uct_hll", RefConfig(problem="blast", dims=3, n=(14, 12, 16), recon="ppm", first_dt=3e-4, cfl=0.3, flatten=True,
+                                          emf="uct_hll"), 10),
     ("blast2d_chtr_mc_hllc", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="hllc"), 10),
 ]
 

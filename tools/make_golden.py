@@ -145,6 +145,11 @@ CASES = {
     "blast3d_bf_uct_hll": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, grav=(0.3, -1.0, 0.5), emf="uct_hll"), 12),
     "rotor2d_ppm_rk3_bp_uct_hll_roe": (RefConfig(problem="rotor", dims=2, n=(36, 28, 1), recon="ppm", tstep="rk3", first_dt=2.5e-3,
                                                  grav=(0.05, -0.03, 0.0), potential=True, emf="uct_hll", solver="roe"), 10),
+    # PARABOLIC + SHOCK_FLATTENING MULTID with the default average UCT_HLL
+    "blast3d_ppm_sfl_uct_hll": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), recon="ppm", first_dt=6e-4, cfl=0.3, flatten=True,
+                                          emf="uct_hll"), 12),
+    "blast2d_ppm_sfl_uct_hll_roe": (RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=6e-4, solver="roe", flatten=True,
+                                              emf="uct_hll"), 12),
     # BODY_FORCE with SHOCK_FLATTENING MULTID
     "blast3d_sfl_bf": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, flatten=True, grav=(0.3, -1.0, 0.5)), 12),
     "blast3d_ctu_sfl_bf": (RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=6e-4, cfl=0.3, tstep="hancock", flatten=True,
