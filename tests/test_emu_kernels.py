@@ -130,7 +130,7 @@ def test_create_refuses_unsupported_combinations(emu_lib):
     from pluto_b200.stepper import PlutoGpuError
     ok = dict(dims=3, n=(8, 8, 8), dx=(0.1, 0.1, 0.1), lib_path=emu_lib)
     for bad, msg in [(dict(recon="ppm", ctu=True), "LINEAR"), (dict(emf="uct_hll", ctu=True), "UCT_HLL"),
-                     (dict(emf="uct_hll", en_corr=True), "CT_EN_CORRECTION"), (dict(recon="ppm", flatten=True, emf="uct_hll"), "SHOCK_FLATTENING"),
+                     (dict(emf="uct_hll", en_corr=True), "CT_EN_CORRECTION"), (dict(ctu="chtr"), "2-D only"),
                      (dict(rk_order=4), "rk_order"), (dict(n=(8, 3, 8)), "nghost")]:
         kw = dict(ok); kw.update(bad)
         with pytest.raises(PlutoGpuError, match=msg):
