@@ -97,7 +97,7 @@ typedef struct {
   double grav[3];
   int    char_limiting;    /* CHAR_LIMITING YES (Src/States/plm_states.c:448-706, PrimEigenvectors Src/MHD/eigenv.c:190-470):
                               slopes limited on the characteristic variables.  2-D (DIMENSIONS = COMPONENTS = 2), LINEAR,
-                              RK2 / RK3, no SHOCK_FLATTENING, no BODY_FORCE, not UCT_HLL.  Not in 3-D: the reference's
+                              RK2 / RK3 and the corner-transport-upwind steps, no SHOCK_FLATTENING.  Not in 3-D: the reference's
                               eigenvector scratch keeps entries of the previous sweep direction there, its own result
                               depends on the sweep order                        */
 } PlutoGpuConfig;

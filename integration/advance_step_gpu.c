@@ -110,8 +110,8 @@ int AdvanceStep (Data *d, Riemann_Solver *Riemann, timeStep *Dts, Grid *grid)
   #error "libpluto_gpu: FOURTH_ORDER_LIM and SHOCK_FLATTENING other than MULTID are not available on the GPU"
 #endif
 #if CHAR_LIMITING == YES && (DIMENSIONS != 2 || RECONSTRUCTION != LINEAR || (TIME_STEPPING != RK2 && TIME_STEPPING != RK3 && CT_EN_CORRECTION == YES) \
-                             || SHOCK_FLATTENING != NO || BODY_FORCE != NO || CT_EMF_AVERAGE == UCT_HLL)
-  #error "libpluto_gpu: CHAR_LIMITING YES is available in 2-D with LINEAR reconstruction and RK2 / RK3, without SHOCK_FLATTENING, BODY_FORCE and UCT_HLL (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
+                             || SHOCK_FLATTENING != NO)
+  #error "libpluto_gpu: CHAR_LIMITING YES is available in 2-D with LINEAR reconstruction, without SHOCK_FLATTENING (in 3-D the reference's own result depends on the sweep order: its eigenvector scratch is never cleared)"
 #endif
 
   if (gpu == NULL && gpum == NULL){

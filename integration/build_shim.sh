@@ -10,7 +10,7 @@ ROOT="$(cd "$HERE/.." && pwd)"
 PLUTO_DIR="${PLUTO_DIR:-/root/reference}"
 [ -d "$PLUTO_DIR/Src" ] || { echo "build_shim.sh: no reference sources (skipping)" >&2; exit 0; }
 [ -f "$ROOT/pluto_b200/lib/libpluto_gpu.so" ] || { echo "build_shim.sh: build libpluto_gpu.so first" >&2; exit 1; }
-VARIANTS="${*:-2d_plm 3d_plm 2d_ppm 3d_ppm 3d_plm_lvl_earith 2d_plm_lmc_earith 3d_plm_lmc_euct_hll 3d_plm_sfl 2d_plm_hancock 3d_plm_hancock 3d_plm_lvl_earith_en 2d_plm_en 3d_plm_hancock_en 3d_plm_bf 2d_ppm_rk3_bf 3d_plm_hancock_bf 2d_plm_hancock_bf 3d_plm_bp 2d_plm_hancock_bp 2d_plm_cl 2d_plm_rk3_lvl_cl 2d_plm_rk3 3d_plm_nuw 2d_plm_lmc_earith_nuw 2d_plm_chtr 2d_plm_chtr_lmc 2d_plm_chtr_lmc_euct0 2d_plm_hancock_lmc_earith_cl 2d_plm_chtr_cl 2d_ppm_sfl 3d_ppm_sfl 2d_ppm_rk3 3d_plm_euct_hll_bf 2d_ppm_rk3_euct_hll_bp 3d_plm_sfl_bf 3d_plm_hancock_sfl_bf 2d_ppm_sfl_bp 2d_ppm_rk3_sfl 2d_ppm_euct_hll_sfl 3d_ppm_euct_hll_sfl}"
+VARIANTS="${*:-2d_plm 3d_plm 2d_ppm 3d_ppm 3d_plm_lvl_earith 2d_plm_lmc_earith 3d_plm_lmc_euct_hll 3d_plm_sfl 2d_plm_hancock 3d_plm_hancock 3d_plm_lvl_earith_en 2d_plm_en 3d_plm_hancock_en 3d_plm_bf 2d_ppm_rk3_bf 3d_plm_hancock_bf 2d_plm_hancock_bf 3d_plm_bp 2d_plm_hancock_bp 2d_plm_cl 2d_plm_rk3_lvl_cl 2d_plm_rk3 3d_plm_nuw 2d_plm_lmc_earith_nuw 2d_plm_chtr 2d_plm_chtr_lmc 2d_plm_chtr_lmc_euct0 2d_plm_hancock_lmc_earith_cl 2d_plm_chtr_cl 2d_ppm_sfl 3d_ppm_sfl 2d_ppm_rk3 3d_plm_euct_hll_bf 2d_ppm_rk3_euct_hll_bp 3d_plm_sfl_bf 3d_plm_hancock_sfl_bf 2d_ppm_sfl_bp 2d_ppm_rk3_sfl 2d_ppm_euct_hll_sfl 3d_ppm_euct_hll_sfl 2d_plm_euct_hll_cl 2d_plm_cl_bf 2d_plm_hancock_cl_bf}"
 for VARIANT in $VARIANTS; do
   B="$ROOT/oracle/_build/$VARIANT"
   [ -f "$B/definitions.h" ] || "$ROOT/oracle/ref_build/build_ref.sh" "$VARIANT"

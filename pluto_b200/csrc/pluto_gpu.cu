@@ -193,10 +193,9 @@ int pluto_gpu_create (const PlutoGpuConfig *cfg, PlutoGpu **out)
     if (cfg->dims != 2)
       return fail ("CHAR_LIMITING YES is available in 2-D only (in 3-D the reference's eigenvector scratch, eigenv.c:190-560, keeps "
                    "entries of the previous sweep direction: its result depends on the sweep order and cannot be reproduced)");
-    if (cfg->recon != PLUTO_GPU_RECON_LINEAR || cfg->shock_flattening || cfg->body_force || cfg->emf_average == PLUTO_GPU_EMF_UCT_HLL
-        || (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->en_correction))
+    if (cfg->recon != PLUTO_GPU_RECON_LINEAR || cfg->shock_flattening || (cfg->time_stepping != PLUTO_GPU_TS_RK && cfg->en_correction))
       return fail ("CHAR_LIMITING YES is available with LINEAR reconstruction (RK2 / RK3 / HANCOCK / CHARACTERISTIC_TRACING), without "
-                   "SHOCK_FLATTENING, BODY_FORCE and UCT_HLL");
+                   "SHOCK_FLATTENING");
   }
   if (cfg->time_stepping != PLUTO_GPU_TS_RK){
     if (cfg->recon != PLUTO_GPU_RECON_LINEAR) return fail ("TIME_STEPPING HANCOCK needs LINEAR reconstruction (Src/pluto.h: RK only with PARABOLIC)");

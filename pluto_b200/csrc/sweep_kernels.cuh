@@ -1074,11 +1074,15 @@ static int launch_sweep_xy_t (int recon, const SweepArgs &a, cudaStream_t s, boo
       const unsigned nb = (unsigned)((nwarp1*b.nchunk*32 + TPB - 1)/TPB);                             \
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
 #define PG_LXY(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = a.flag != nullptr;  \
+      if (a.char_lim && P && C == 2){                  /* CHAR_LIMITING (2-D, LINEAR): with the UCT_HLL slopes and / or a body force */ \
+        if (bf){ if (a.avg == 3) PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, true, false, true, false, true>));               \
+                 else            PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, false, false, true, false, true>)); }            \
+        else   { if (a.avg == 3) PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, true, false, false, false, true>));              \
+                 else            PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, false, false, false, false, true>)); } } else     \
       if (bf){ if (a.avg == 3){ if (fl) PG_LXY2(R, C, true, true, true); else PG_LXY2(R, C, true, false, true); }                         \
                else           { if (fl) PG_LXY2(R, C, false, true, true); else PG_LXY2(R, C, false, false, true); } }                  \
       else if (a.avg == 3){ if (fl) PG_LXY1(R, C, true, true); else PG_LXY1(R, C, true, false); }                       \
       else if (fl)        PG_LXY1(R, C, false, true);                                                                  \
-      else if (a.char_lim && P && C == 2) PG_LXYK((sweep_xy_kernel<RECON_PLM, SOLVER, 2, false, false, false, false, true>)); \
       else if (a.tma)     PG_LXY3(R, C);                               /* TMA staging of the ring rows */              \
       else                PG_LXY1(R, C, false, false); } while (0)
   if      (recon == RECON_PLMW && nc == 3) PG_LXY1(RECON_PLMW, 3, false, false);      // grid weights: plain options only (checked at create)
@@ -1113,7 +1117,11 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
     const unsigned nb = (unsigned)((nwarp*32 + TPB - 1)/TPB);
     const size_t xsmem = (size_t)(TPB/32)*2*9*36*sizeof (double);
 #define PG_LX(R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = a.flag != nullptr;                  \
-      if (a.char_lim && P && C == 2) sweep_x_kernel<RECON_PLM, SOLVER, 2, false, false, false, true><<<nb, TPB, xsmem, s>>>(a); \
+      if (a.char_lim && P && C == 2){                                                                                  \
+        if (bf){ if (a.avg == 3) sweep_x_kernel<RECON_PLM, SOLVER, 2, true, false, true, true><<<nb, TPB, xsmem, s>>>(a);        \
+                 else            sweep_x_kernel<RECON_PLM, SOLVER, 2, false, false, true, true><<<nb, TPB, xsmem, s>>>(a); }     \
+        else   { if (a.avg == 3) sweep_x_kernel<RECON_PLM, SOLVER, 2, true, false, false, true><<<nb, TPB, xsmem, s>>>(a);       \
+                 else            sweep_x_kernel<RECON_PLM, SOLVER, 2, false, false, false, true><<<nb, TPB, xsmem, s>>>(a); } }   \
       else if (bf){ if (a.avg == 3){ if (fl) sweep_x_kernel<R, SOLVER, C, true, true, true><<<nb, TPB, xsmem, s>>>(a);          \
                                      else    sweep_x_kernel<R, SOLVER, C, true, false, true><<<nb, TPB, xsmem, s>>>(a); }    \
                     else           { if (fl) sweep_x_kernel<R, SOLVER, C, false, true, true><<<nb, TPB, xsmem, s>>>(a);      \
@@ -1146,7 +1154,10 @@ static int launch_sweep_t (int dir, int recon, const SweepArgs &a, cudaStream_t 
       kfn<<<nb, TPB, smem, s>>>(b); } while (0)
 #define PG_LM(DD, R, C) do { constexpr bool P = (R == RECON_PLM); const bool fl = a.flag != nullptr;               \
       if (a.char_lim && P && C == 2 && DD == 1){ smem = (size_t)march_slots (RECON_PLM, true)*TPB*sizeof (double);            \
-                                                 PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, false, true>)); } \
+        if (bf){ if (a.avg == 3) PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, true, false, true, true>));             \
+                 else            PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, true, true>)); }          \
+        else   { if (a.avg == 3) PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, true, false, false, true>));            \
+                 else            PG_LMK((sweep_march_kernel<1, RECON_PLM, SOLVER, 2, false, false, false, true>)); } }        \
       else if (bf){ if (a.avg == 3){ if (fl) PG_LM2(DD, R, C, true, true, true); else PG_LM2(DD, R, C, true, false, true); }   \
                     else           { if (fl) PG_LM2(DD, R, C, false, true, true); else PG_LM2(DD, R, C, false, false, true); } } \
       else if (a.avg == 3){ if (fl) PG_LM1(DD, R, C, true, true); else PG_LM1(DD, R, C, true, false); }                    \

@@ -53,7 +53,9 @@ CASES = ["ot2d_plm_hlld", "blast3d_plm_hlld", "rotor2d_ppm_roe", "ot3d_ppm_roe",
          # PARABOLIC on non-uniform grids: the shim hands over the weights of PPM_CoefficientsGet
          "rotor2d_nug_ppm", "blast3d_nug_ppm_roe", "blast2d_nug_ppm_sfl_rk3",
          # PARABOLIC + SHOCK_FLATTENING MULTID with the default average UCT_HLL
-         "blast3d_ppm_sfl_uct_hll", "blast2d_ppm_sfl_uct_hll_roe"]
+         "blast3d_ppm_sfl_uct_hll", "blast2d_ppm_sfl_uct_hll_roe",
+         # CHAR_LIMITING with UCT_HLL / BODY_FORCE
+         "ot2d_cl_uct_hll", "blast2d_cl_bf_roe", "blast2d_ctu_cl_bf"]
 
 
 def _blast_params(g):

@@ -207,6 +207,10 @@ CASES = [
                                               emf="uct_hll"), 12),
     ("blast3d_ppm_sfl_uct_hll", RefConfig(problem="blast", dims=3, n=(14, 12, 16), recon="ppm", first_dt=3e-4, cfl=0.3, flatten=True,
                                           emf="uct_hll"), 10),
+    # CHAR_LIMITING with the default average UCT_HLL and with BODY_FORCE (RK and Hancock)
+    ("ot2d_cl_uct_hll", RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, char_lim=True, emf="uct_hll"), 10),
+    ("blast2d_cl_bf_roe", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, solver="roe", char_lim=True, grav=(0.5, 0.25, 0.0)), 10),
+    ("blast2d_ctu_cl_bf", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="hancock", char_lim=True, grav=(0.5, 0.25, 0.0)), 10),
     ("blast2d_chtr_mc_hllc", RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=3e-4, tstep="chtr", limiter="mc", solver="hllc"), 10),
 ]
 

@@ -150,6 +150,10 @@ CASES = {
                                           emf="uct_hll"), 12),
     "blast2d_ppm_sfl_uct_hll_roe": (RefConfig(problem="blast", dims=2, n=(36, 32, 1), recon="ppm", first_dt=6e-4, solver="roe", flatten=True,
                                               emf="uct_hll"), 12),
+    # CHAR_LIMITING with the default average UCT_HLL and with BODY_FORCE (RK, Hancock)
+    "ot2d_cl_uct_hll": (RefConfig(problem="ot", dims=2, n=(32, 28, 1), first_dt=1.5e-2, char_lim=True, emf="uct_hll"), 12),
+    "blast2d_cl_bf_roe": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=6e-4, solver="roe", char_lim=True, grav=(0.5, 0.25, 0.0)), 12),
+    "blast2d_ctu_cl_bf": (RefConfig(problem="blast", dims=2, n=(28, 24, 1), first_dt=6e-4, tstep="hancock", char_lim=True, grav=(0.5, 0.25, 0.0)), 12),
     # BODY_FORCE with SHOCK_FLATTENING MULTID
     "blast3d_sfl_bf": (RefConfig(problem="blast", dims=3, n=(16, 12, 14), first_dt=6e-4, cfl=0.3, flatten=True, grav=(0.3, -1.0, 0.5)), 12),
     "blast3d_ctu_sfl_bf": (RefConfig(problem="blast", dims=3, n=(12, 14, 10), first_dt=6e-4, cfl=0.3, tstep="hancock", flatten=True,
