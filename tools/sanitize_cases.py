@@ -146,6 +146,21 @@ def fam_schemes3():
     run("blast", 3, (24, 20, 16), arith="fast", emf="uct_hll", grav=(0.3, -1.0, 0.5))
     run("blast", 3, (24, 20, 16), arith="fast", flatten=True, grav=(0.3, -1.0, 0.5), steps=6)
     run("blast", 3, (24, 20, 16), arith="fast", flatten=True, emf="uct_hll", grav=(0.3, -1.0, 0.5), steps=6)
+    run("ot", 2, (48, 40, 1), arith="fast", char_lim=True, emf="uct_hll", dt=1e-3)
+    run("blast", 2, (40, 32, 1), arith="fast", char_lim=True, emf="uct_hll", grav=(0.5, 0.25, 0.0), solver="roe")
+    run("blast", 2, (40, 32, 1), arith="exact", char_lim=True, grav=(0.5, 0.25, 0.0), ctu=True)
+    for dims, n, arith in ((3, (24, 20, 16), "fast"), (2, (48, 40, 1), "fast")):      # PARABOLIC + MULTID + UCT_HLL (+ body force)
+        st0, meta = problems.make("blast", dims, n)
+        s = GpuStepper(dims, n, meta["dx"], bc=meta["bc"], gamma=meta["gamma"], arith=arith, recon="ppm", flatten=True, emf="uct_hll",
+                       grav=(0.3, -1.0, 0.5)[:dims] + (0.0,)*(3 - dims))
+        s.set_plm_coeffs([[np.full(n[d] + 2*s.ng, c) for c in (2.0, 2.0, 1.0, 1.0, 0.5, 0.5)] for d in range(dims)])
+        s.set_state(st0)
+        dt = 1e-4
+        for _ in range(6):
+            info = s.advance(dt)
+            dt = s.next_dt(info.inv_dt_hyp, meta["cfl"], 1.1, dt)
+        assert all(np.isfinite(v).all() for v in s.get_state().values())
+        s.close()
     rng = np.random.default_rng(5)
     for dims, n, kw in ((3, (24, 20, 16), dict(arith="fast", flatten=True)), (2, (48, 40, 1), dict(arith="fast", en_corr=True)),
                         (3, (24, 20, 16), dict(arith="fast", ctu=True, grav=(0.3, -1.0, 0.5))),
